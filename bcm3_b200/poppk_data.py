@@ -1,0 +1,143 @@
+"""Host-side data model of the PopPK likelihood.
+
+Mirrors what ``LikelihoodPopPKTrajectory::Initialize`` leaves in the object
+after parsing ``likelihood.xml`` and the NetCDF trial group
+(reference: src/likelihoods/LikelihoodPopPKTrajectory.cpp:50-252).  The NetCDF
+reader itself is out of scope; a trial is handed in
+as numpy arrays with the same names and shapes as the NetCDF variables.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# pk_model type= strings, LikelihoodPopPKTrajectory.cpp:69-83
+PK_ONE = 0
+PK_TWO = 1
+PK_TYPES = {"one": PK_ONE, "two": PK_TWO}
+
+# VariableSet transforms, src/sampler/VariableSet.cpp:97-124
+TRANSFORM_NONE = 0
+TRANSFORM_LOG = 1
+TRANSFORM_LOG10 = 2
+TRANSFORM_LOGIT = 3
+
+# LikelihoodPopPKTrajectory.cpp:377-393
+MOLECULAR_WEIGHT = {
+    "lapatinib": 581.06,
+    "dacomitinib": 469.95,
+    "afatinib": 485.94,
+    "trametinib": 615.404,
+    "mirdametinib": 482.19,
+    "selumetinib": 457.68,
+}
+
+F32_1E_6 = float(np.float32(1e-6))  # the reference passes the float literal 1e-6f, cpp:238
+
+
+def num_pk_params(pk_type: int) -> int:
+    """cpp:99-104"""
+    return 4 if pk_type == PK_ONE else 6
+
+
+@dataclass
+class PopPKTrial:
+    """One NetCDF trial group (cpp:94-161)."""
+
+    drug: str
+    time: np.ndarray  # [T] hours
+    observed_concentration: np.ndarray  # [P, T] nM, NaN = missing
+    dose: np.ndarray  # [P]
+    dosing_interval: np.ndarray  # [P]
+    dose_after_dose_change: np.ndarray  # [P] NaN = none
+    dose_change_time: np.ndarray  # [P]
+    intermittent: np.ndarray  # [P] 0..3
+    treatment_interruptions: np.ndarray  # [P, 29] flags per day
+
+    @property
+    def num_patients(self) -> int:
+        return int(self.observed_concentration.shape[0])
+
+    @property
+    def num_timepoints(self) -> int:
+        return int(self.time.shape[0])
+
+
+@dataclass
+class PopPKProblem:
+    """Derived state of an initialised likelihood (cpp:122-252)."""
+
+    pk_type: int
+    trial: PopPKTrial
+    transforms: np.ndarray  # [nvar] int32
+    sd_ix: int
+    fixed_vod: float = math.nan
+    fixed_periphery_fwd: float = math.nan
+    fixed_periphery_bwd: float = math.nan
+    max_steps: int = 2000  # ODESolverCVODE.cpp:45
+    # derived
+    simulate_until: np.ndarray = field(init=False)
+    skipped_days: np.ndarray = field(init=False)
+    rtol: float = field(init=False)
+    atol: float = field(init=False)
+    mol_weight: float = field(init=False)
+
+    def __post_init__(self):
+        tr = self.trial
+        P, T = tr.num_patients, tr.num_timepoints
+        if tr.drug not in MOLECULAR_WEIGHT:
+            raise ValueError(f'Unknown drug "{tr.drug}"')  # cpp:391
+        self.mol_weight = MOLECULAR_WEIGHT[tr.drug]
+        fixed = sum(0 if math.isnan(v) else 1 for v in (self.fixed_vod, self.fixed_periphery_fwd, self.fixed_periphery_bwd))
+        expected = num_pk_params(self.pk_type) - fixed + 2 * (P + 1) + 2
+        self.transforms = np.ascontiguousarray(self.transforms, dtype=np.int32)
+        if self.transforms.shape[0] != expected:
+            raise ValueError("Incorrect number of variables in prior")  # cpp:127-130
+        if fixed:
+            # the reference indexes the variable vector positionally (cpp:267-272) even when
+            # a parameter is fixed in likelihood.xml; only the all-sampled layout is supported here
+            raise NotImplementedError("fixed volume_of_distribution / k_periphery_* attributes")
+
+        inter = np.asarray(tr.treatment_interruptions).reshape(P, 29) != 0
+        self.skipped_days = (inter.astype(np.uint64) << np.arange(29, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+
+        # simulate_until, cpp:163-184
+        time = np.asarray(tr.time, dtype=np.float64)
+        su = np.full(P, T, dtype=np.int32)
+        ge24 = np.nonzero(time >= 24.0)[0]
+        first_ge24 = int(ge24[0]) if ge24.size else None
+        day1 = inter[:, 1]
+        if first_ge24 is not None:
+            su[day1] = first_ge24
+        else:
+            # reference leaves simulate_until[j] value-initialised (0) when no timepoint is >= 24 h
+            su[day1] = 0
+        obs = np.asarray(tr.observed_concentration, dtype=np.float64)
+        notnan = ~np.isnan(obs)
+        has = notnan.any(axis=1)
+        first = np.argmax(notnan, axis=1)
+        late = has & (time[first] > 15 * 24)
+        su[late] = 0
+        self.simulate_until = su
+
+        dac = np.asarray(tr.dose_after_dose_change, dtype=np.float64)
+        dct = np.asarray(tr.dose_change_time, dtype=np.float64)
+        bad = ~np.isnan(dac) & np.isnan(dct)
+        if bad.any():
+            raise ValueError(f"Patient {int(np.nonzero(bad)[0][0])} has dose change, but time of dose change is not specified.")  # cpp:187-190
+        min_dose = float(np.min(tr.dose)) if P else float(np.finfo(np.float64).max)
+        if (~np.isnan(dac)).any():
+            min_dose = min(min_dose, float(np.nanmin(dac)))
+        # SetTolerance(1e-6f, minimum_dose * 1e-6f), cpp:238
+        self.rtol = F32_1E_6
+        self.atol = min_dose * F32_1E_6
+
+    @property
+    def num_variables(self) -> int:
+        return int(self.transforms.shape[0])
+
+    @property
+    def num_states(self) -> int:
+        return 2 if self.pk_type == PK_ONE else 3

@@ -1,0 +1,94 @@
+/* TEST INFRASTRUCTURE ONLY -- not part of the product.
+ *
+ * C interface shared by the two CPU checkers of the batched-likelihood path:
+ *   - oracle/_ref/libbcm3ref.so  : the reference's OWN compiled solver stack
+ *     (vendored CVODE 5.3.0 + src/odecommon, unmodified, compiled in place from
+ *     /root/reference by oracle/ref/build_ref.sh) plus a thin restatement of
+ *     the Boost/NetCDF-bound per-patient glue (oracle/ref/poppk_ref.cpp);
+ *   - oracle/liboracle.so        : a plain-C restatement of the whole path
+ *     (oracle/cvode_bdf.c + oracle/poppk_oracle.c), pinned against the former
+ *     through tests/golden/.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load either of them.
+ */
+#ifndef BCM3_ORACLE_API_H
+#define BCM3_ORACLE_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* pk_type values; reference enum EPKModelType, LikelihoodPopPKTrajectory.h */
+#define ORACLE_PK_ONE 0 /* "one": N=2, LikelihoodPopPKTrajectory.cpp:446-467 */
+#define ORACLE_PK_TWO 1 /* "two": N=3, LikelihoodPopPKTrajectory.cpp:469-494 */
+
+/* transform codes; reference VariableSet::TransformVariable, VariableSet.cpp:97-124 */
+#define ORACLE_TRANSFORM_NONE 0
+#define ORACLE_TRANSFORM_LOG 1   /* exp(x) */
+#define ORACLE_TRANSFORM_LOG10 2 /* fastpow10(x) */
+#define ORACLE_TRANSFORM_LOGIT 3
+
+/* What LikelihoodPopPKTrajectory::Initialize (cpp:50-252) leaves in the object
+ * after reading likelihood.xml + the NetCDF group. All arrays caller-owned. */
+typedef struct {
+	int32_t pk_type;
+	int32_t num_patients;   /* P */
+	int32_t num_timepoints; /* T */
+	int32_t num_variables;  /* nvar = npk - nfixed + 2*(P+1) + 2, cpp:127 */
+	int32_t sd_ix;          /* varset->GetVariableIndex("standard_deviation"), cpp:263 */
+	int32_t max_steps;      /* ODESolverCVODE::max_steps, 2000, ODESolverCVODE.cpp:45 */
+	double fixed_vod;       /* NaN when sampled, cpp:65 */
+	double fixed_periphery_fwd;
+	double fixed_periphery_bwd;
+	double mol_weight;      /* MW of the drug, cpp:377-393 */
+	double rtol;            /* (double)1e-6f, cpp:238 */
+	double atol;            /* minimum_dose * (double)1e-6f, cpp:238 */
+	const double* time;                   /* [T] */
+	const double* observed_concentration; /* [P][T], NaN = missing */
+	const double* dose;                   /* [P] */
+	const double* dosing_interval;        /* [P] */
+	const double* dose_after_dose_change; /* [P], NaN = no change */
+	const double* dose_change_time;       /* [P] */
+	const int32_t* intermittent;          /* [P] 0..3 */
+	const uint32_t* skipped_days;         /* [P] bit d set = day d skipped (29 days) */
+	const int32_t* simulate_until;        /* [P] number of leading timepoints simulated */
+	const int32_t* transforms;            /* [nvar] ORACLE_TRANSFORM_* */
+} oracle_poppk_problem;
+
+/* per-(chain, patient) solver counters, summed over the restarts of one solve */
+enum {
+	ORACLE_CNT_STEPS = 0, /* ODESolverCVODE current_step (accepted steps) */
+	ORACLE_CNT_NFE,
+	ORACLE_CNT_NSETUPS,
+	ORACLE_CNT_NJE,
+	ORACLE_CNT_NETF,
+	ORACLE_CNT_NCFN,
+	ORACLE_CNT_NNI,
+	ORACLE_CNT_OK, /* 1 = solve succeeded */
+	ORACLE_NUM_COUNTERS
+};
+
+/* Evaluate num_chains parameter vectors (values[c*nvar + i]) the way
+ * LikelihoodPopPKTrajectory::EvaluateLogProbability (cpp:259-444) does, one
+ * chain per worker thread as SamplerPTChain.cpp:315-326 schedules them.
+ *   logp      [C]            out
+ *   conc      [C][P][T]      out, optional: conversion*trajectory(1,i) (NaN where not simulated)
+ *   patient_ll[C][P]         out, optional: patient_logllh
+ *   counters  [C][P][ORACLE_NUM_COUNTERS] out, optional
+ * With conc/patient_ll/counters requested, the early `break` on logp == -inf
+ * (cpp:438) is NOT taken so that every patient is reported; logp is unaffected.
+ * Returns 0 on success. */
+int oracle_poppk_evaluate(const oracle_poppk_problem* prob, size_t num_chains, const double* values,
+                          double* logp, double* conc, double* patient_ll, int64_t* counters, int num_threads);
+
+/* "ref" or "port" */
+const char* oracle_kind(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
