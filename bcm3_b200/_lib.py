@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI in include/bcm3b200.h (libbcm3b200.so, built in-tree by __graft_entry__.build()).
+
+There is deliberately no fallback: if the shared library is missing the import of this module fails,
+and every compute entry point raises when no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libbcm3b200.so")
+
+# every symbol declared in include/bcm3b200.h
+EXPORTS = [
+    "bcm3b200_create",
+    "bcm3b200_set_data",
+    "bcm3b200_finalize",
+    "bcm3b200_evaluate_batch",
+    "bcm3b200_evaluate_batch_device",
+    "bcm3b200_combine_partials",
+    "bcm3b200_get_diagnostics",
+    "bcm3b200_set_option",
+    "bcm3b200_get_stat",
+    "bcm3b200_destroy",
+    "bcm3b200_last_error",
+    "bcm3b200_device_count",
+    "bcm3b200_host_alloc",
+    "bcm3b200_host_free",
+]
+
+
+class Bcm3B200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"bcm3b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, dp, ip = C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.bcm3b200_create.argtypes = [C.c_char_p, C.c_char_p, sz, C.c_int, C.POINTER(vp)]
+    lib.bcm3b200_set_data.argtypes = [vp, C.c_char_p, vp, C.POINTER(sz), C.c_int]
+    lib.bcm3b200_finalize.argtypes = [vp]
+    lib.bcm3b200_evaluate_batch.argtypes = [vp, sz, sz, vp, vp, vp]
+    lib.bcm3b200_evaluate_batch_device.argtypes = [vp, sz, sz, vp, vp, vp]
+    lib.bcm3b200_combine_partials.argtypes = [sz, vp, vp, vp]
+    lib.bcm3b200_get_diagnostics.argtypes = [vp, vp, vp, vp]
+    lib.bcm3b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.bcm3b200_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
+    lib.bcm3b200_destroy.argtypes = [vp]
+    lib.bcm3b200_destroy.restype = None
+    lib.bcm3b200_last_error.restype = C.c_char_p
+    lib.bcm3b200_device_count.restype = C.c_int
+    lib.bcm3b200_host_alloc.argtypes = [sz]
+    lib.bcm3b200_host_alloc.restype = vp
+    lib.bcm3b200_host_free.argtypes = [vp]
+    lib.bcm3b200_host_free.restype = None
+    for name in ("create", "set_data", "finalize", "evaluate_batch", "evaluate_batch_device", "combine_partials",
+                 "get_diagnostics", "set_option", "get_stat"):
+        getattr(lib, "bcm3b200_" + name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise Bcm3B200Error(rc, load().bcm3b200_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return int(load().bcm3b200_device_count())

@@ -1,0 +1,647 @@
+// bcm3b200.cu -- C ABI (include/bcm3b200.h) of the B200-native batched likelihood evaluator.
+//
+// Host side of the drop-in boundary: owns device buffers, streams and the static trial data, mirrors
+// LikelihoodPopPKTrajectory::Initialize (src/likelihoods/LikelihoodPopPKTrajectory.cpp:50-252) for the
+// derived quantities, and turns one batched call into kernel launches. No CPU fallback exists: without a
+// usable CUDA device every entry point that computes returns BCM3B200_ERR_CUDA.
+#include "../../include/bcm3b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "poppk_kernel.cuh"
+
+using namespace bcm3b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	return code;
+}
+
+#define CUDA_TRY(expr)                                                                                         \
+	do {                                                                                                       \
+		cudaError_t e_ = (expr);                                                                               \
+		if (e_ != cudaSuccess) return fail(BCM3B200_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+	} while (0)
+
+// the float literal of LikelihoodPopPKTrajectory.cpp:238, widened to double
+const double kTol = (double)1e-6f;
+
+double molecular_weight(const std::string& drug)
+{
+	// LikelihoodPopPKTrajectory.cpp:377-393
+	if (drug == "lapatinib") return 581.06;
+	if (drug == "dacomitinib") return 469.95;
+	if (drug == "afatinib") return 485.94;
+	if (drug == "trametinib") return 615.404;
+	if (drug == "mirdametinib") return 482.19;
+	if (drug == "selumetinib") return 457.68;
+	return std::numeric_limits<double>::quiet_NaN();
+}
+
+template <class T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	~DevBuf() { release(); }
+	void release()
+	{
+		if (p) cudaFree(p);
+		p = nullptr;
+		n = 0;
+	}
+	cudaError_t ensure(size_t count)
+	{
+		if (count <= n) return cudaSuccess;
+		release();
+		cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+		if (e == cudaSuccess) n = count;
+		return e;
+	}
+};
+
+struct Shard {
+	int device = 0;
+	int offset = 0; // global index of the first patient
+	int P = 0;      // patients in this shard
+	int P_pad = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	DevBuf<double> time, obs_t, dose, interval, dac, dct, values, block_partial, partial, diag_conc, diag_ll;
+	DevBuf<int32_t> intermittent, simulate_until, diag_counters;
+	DevBuf<uint32_t> skipped;
+	double* h_partial = nullptr; // pinned [3][C]
+	size_t h_partial_n = 0;
+	int last_C = 0;
+	~Shard()
+	{
+		if (h_partial) cudaFreeHost(h_partial);
+		if (ev0) cudaEventDestroy(ev0);
+		if (ev1) cudaEventDestroy(ev1);
+		if (stream) cudaStreamDestroy(stream);
+	}
+};
+
+struct Handle {
+	// description
+	int pk_type = PK_ONE;
+	std::string drug;
+	int P = 0, T = 0, nvar = 0, sd_ix = -1, max_steps = 2000;
+	int shard_rank = 0, shard_count = 1, device0 = 0, device_count = 1;
+	// host copies of the static data
+	std::map<std::string, std::vector<double>> data;
+	// derived
+	bool finalized = false;
+	double rtol = 0, atol = 0, mol_weight = 0;
+	int npk = 4;
+	int tr[SV_COUNT];
+	int ix[SV_COUNT];
+	std::vector<std::unique_ptr<Shard>> shards;
+	// options / stats
+	bool diagnostics = false;
+	int block_size = 0;
+	int64_t total_launches = 0, last_launches = 0, num_evaluations = 0;
+	double last_kernel_ms = 0;
+};
+
+bool parse_desc(const char* desc, size_t n, std::map<std::string, std::string>& kv)
+{
+	std::string s(desc, n);
+	size_t pos = 0;
+	while (pos < s.size()) {
+		size_t end = s.find(';', pos);
+		if (end == std::string::npos) end = s.size();
+		std::string item = s.substr(pos, end - pos);
+		pos = end + 1;
+		size_t a = item.find_first_not_of(" \t\n\r");
+		if (a == std::string::npos) continue;
+		size_t b = item.find_last_not_of(" \t\n\r\0", std::string::npos, 5);
+		item = item.substr(a, b - a + 1);
+		size_t eq = item.find('=');
+		if (eq == std::string::npos) return false;
+		kv[item.substr(0, eq)] = item.substr(eq + 1);
+	}
+	return true;
+}
+
+int get_int(const std::map<std::string, std::string>& kv, const char* key, int def, bool* present = nullptr)
+{
+	auto it = kv.find(key);
+	if (present) *present = it != kv.end();
+	if (it == kv.end()) return def;
+	return atoi(it->second.c_str());
+}
+
+int pick_block_size(const Handle& h, const Shard& s, size_t C)
+{
+	if (h.block_size) return h.block_size;
+	// keep >= 2 blocks per SM when the batch is small, otherwise 128 threads (4 warps) per block
+	int dev_sms = 148;
+	cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s.device);
+	size_t threads = (size_t)s.P * C;
+	if (threads >= (size_t)dev_sms * 2 * 128) return 128;
+	if (threads >= (size_t)dev_sms * 2 * 64) return 64;
+	return 32;
+}
+
+int finalize(Handle* h)
+{
+	if (h->finalized) return BCM3B200_OK;
+	const int P = h->P, T = h->T;
+	static const char* required[] = { "time", "observed_concentration", "dose", "dosing_interval", "dose_after_dose_change",
+		                              "dose_change_time", "intermittent", "treatment_interruptions", "transforms" };
+	for (const char* name : required) {
+		if (!h->data.count(name)) return fail(BCM3B200_ERR_STATE, "missing data \"%s\"", name);
+	}
+	h->mol_weight = molecular_weight(h->drug);
+	if (std::isnan(h->mol_weight)) return fail(BCM3B200_ERR_ARG, "Unknown drug \"%s\"", h->drug.c_str());
+	h->npk = (h->pk_type == PK_ONE) ? 4 : 6;
+	if (h->nvar != h->npk + 2 * (P + 1) + 2) return fail(BCM3B200_ERR_ARG, "Incorrect number of variables in prior"); // cpp:127-130
+	if (h->sd_ix < 0 || h->sd_ix + 1 >= h->nvar) return fail(BCM3B200_ERR_ARG, "sd_ix out of range");
+
+	const std::vector<double>& time = h->data["time"];
+	const std::vector<double>& obs = h->data["observed_concentration"];
+	const std::vector<double>& dose = h->data["dose"];
+	const std::vector<double>& dac = h->data["dose_after_dose_change"];
+	const std::vector<double>& dct = h->data["dose_change_time"];
+	const std::vector<double>& inter = h->data["treatment_interruptions"];
+	const std::vector<double>& transforms = h->data["transforms"];
+
+	// chain-level variable indices (positional, cpp:267-272,283-286) and their transforms
+	const int ix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, h->npk + 0, h->npk + 1, h->sd_ix, h->sd_ix + 1 };
+	for (int k = 0; k < SV_COUNT; k++) {
+		h->ix[k] = ix[k];
+		h->tr[k] = (int)transforms[ix[k]];
+	}
+
+	// simulate_until (cpp:163-184), skipped-day masks (cpp:154-161), minimum dose (cpp:197-203)
+	std::vector<int32_t> simulate_until(P);
+	std::vector<uint32_t> skipped(P);
+	double minimum_dose = std::numeric_limits<double>::max();
+	for (int j = 0; j < P; j++) {
+		uint32_t mask = 0;
+		for (int d = 0; d < 29; d++)
+			if (inter[(size_t)j * 29 + d] != 0.0) mask |= (1u << d);
+		skipped[j] = mask;
+		int su = 0;
+		if (mask & 2u) {
+			for (int i = 0; i < T; i++) {
+				if (time[i] >= 24.0) {
+					su = i;
+					break;
+				}
+			}
+		} else {
+			su = T;
+		}
+		for (int i = 0; i < T; i++) {
+			if (!std::isnan(obs[(size_t)j * T + i])) {
+				if (time[i] > 15 * 24) su = 0;
+				break;
+			}
+		}
+		simulate_until[j] = su;
+		if (!std::isnan(dac[j])) {
+			if (std::isnan(dct[j]))
+				return fail(BCM3B200_ERR_ARG, "Patient %d has dose change, but time of dose change is not specified.", j);
+		}
+		if (dose[j] < minimum_dose) minimum_dose = dose[j];
+		if (!std::isnan(dac[j]) && dac[j] < minimum_dose) minimum_dose = dac[j];
+	}
+	h->rtol = kTol;
+	h->atol = minimum_dose * kTol; // SetTolerance(1e-6f, minimum_dose * 1e-6f), cpp:238
+
+	// partition this handle's contiguous slice of patients over its devices
+	const long long lo = (long long)P * h->shard_rank / h->shard_count;
+	const long long hi = (long long)P * (h->shard_rank + 1) / h->shard_count;
+	const long long Pl = hi - lo;
+	h->shards.clear();
+	for (int d = 0; d < h->device_count; d++) {
+		std::unique_ptr<Shard> s(new Shard);
+		s->device = h->device0 + d;
+		s->offset = (int)(lo + Pl * d / h->device_count);
+		s->P = (int)(lo + Pl * (d + 1) / h->device_count) - s->offset;
+		s->P_pad = (s->P + 31) / 32 * 32;
+		CUDA_TRY(cudaSetDevice(s->device));
+		CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreate(&s->ev0));
+		CUDA_TRY(cudaEventCreate(&s->ev1));
+		const int Ps = s->P, off = s->offset;
+		const size_t Pa = (size_t)(Ps > 0 ? Ps : 1);
+		CUDA_TRY(s->time.ensure(T > 0 ? T : 1));
+		CUDA_TRY(cudaMemcpy(s->time.p, time.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+		// observations, transposed to time-major so that a warp reads 32 consecutive patients
+		std::vector<double> obs_t((size_t)T * s->P_pad, std::numeric_limits<double>::quiet_NaN());
+		for (int j = 0; j < Ps; j++)
+			for (int i = 0; i < T; i++) obs_t[(size_t)i * s->P_pad + j] = obs[(size_t)(off + j) * T + i];
+		CUDA_TRY(s->obs_t.ensure(obs_t.size() ? obs_t.size() : 1));
+		CUDA_TRY(cudaMemcpy(s->obs_t.p, obs_t.data(), sizeof(double) * obs_t.size(), cudaMemcpyHostToDevice));
+		auto up = [&](DevBuf<double>& b, const std::vector<double>& v) -> cudaError_t {
+			cudaError_t e = b.ensure(Pa);
+			if (e != cudaSuccess) return e;
+			return cudaMemcpy(b.p, v.data() + off, sizeof(double) * Ps, cudaMemcpyHostToDevice);
+		};
+		CUDA_TRY(up(s->dose, dose));
+		CUDA_TRY(up(s->interval, h->data["dosing_interval"]));
+		CUDA_TRY(up(s->dac, dac));
+		CUDA_TRY(up(s->dct, dct));
+		std::vector<int32_t> im(Pa);
+		const std::vector<double>& imd = h->data["intermittent"];
+		for (int j = 0; j < Ps; j++) im[j] = (int32_t)imd[off + j];
+		CUDA_TRY(s->intermittent.ensure(Pa));
+		CUDA_TRY(cudaMemcpy(s->intermittent.p, im.data(), sizeof(int32_t) * Ps, cudaMemcpyHostToDevice));
+		CUDA_TRY(s->skipped.ensure(Pa));
+		CUDA_TRY(cudaMemcpy(s->skipped.p, skipped.data() + off, sizeof(uint32_t) * Ps, cudaMemcpyHostToDevice));
+		CUDA_TRY(s->simulate_until.ensure(Pa));
+		CUDA_TRY(cudaMemcpy(s->simulate_until.p, simulate_until.data() + off, sizeof(int32_t) * Ps, cudaMemcpyHostToDevice));
+		h->shards.push_back(std::move(s));
+	}
+	h->finalized = true;
+	return BCM3B200_OK;
+}
+
+// enqueue K0+K1 and K3 for one shard; values already on the device in the layout (row_stride, col_patient0, ix)
+int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long long row_stride, long long col_patient0,
+                 const int* ix, double* d_partial, cudaStream_t stream)
+{
+	const int block = pick_block_size(*h, *s, C);
+	const int nblk = (s->P + block - 1) / block;
+	if (nblk == 0) {
+		// empty shard: neutral partial
+		std::vector<double> neutral(3 * C, std::numeric_limits<double>::infinity());
+		for (size_t c = 0; c < C; c++) neutral[c] = 0.0;
+		CUDA_TRY(cudaMemcpyAsync(d_partial, neutral.data(), sizeof(double) * 3 * C, cudaMemcpyHostToDevice, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		h->last_launches = 0;
+		return BCM3B200_OK;
+	}
+	CUDA_TRY(s->block_partial.ensure((size_t)nblk * C * 3));
+
+	PkArgs a;
+	a.time = s->time.p;
+	a.obs_t = s->obs_t.p;
+	a.dose = s->dose.p;
+	a.dosing_interval = s->interval.p;
+	a.dose_after_dose_change = s->dac.p;
+	a.dose_change_time = s->dct.p;
+	a.intermittent = s->intermittent.p;
+	a.skipped_days = s->skipped.p;
+	a.simulate_until = s->simulate_until.p;
+	a.P_local = s->P;
+	a.P_pad = s->P_pad;
+	a.patient_offset = s->offset;
+	a.T = h->T;
+	a.max_steps = h->max_steps;
+	a.rtol = h->rtol;
+	a.atol = h->atol;
+	a.conv_base = 1e6 / h->mol_weight;
+	a.values = d_values;
+	a.row_stride = row_stride;
+	a.col_patient0 = col_patient0;
+	for (int k = 0; k < SV_COUNT; k++) {
+		a.ix[k] = ix[k];
+		a.tr[k] = h->tr[k];
+	}
+	a.block_partial = s->block_partial.p;
+	a.diag_conc = nullptr;
+	a.diag_ll = nullptr;
+	a.diag_counters = nullptr;
+	if (h->diagnostics) {
+		CUDA_TRY(s->diag_conc.ensure(C * s->P * h->T));
+		CUDA_TRY(s->diag_ll.ensure(C * s->P));
+		CUDA_TRY(s->diag_counters.ensure(C * s->P * 8));
+		a.diag_conc = s->diag_conc.p;
+		a.diag_ll = s->diag_ll.p;
+		a.diag_counters = s->diag_counters.p;
+	}
+	s->last_C = (int)C;
+
+	const size_t smem = sizeof(double) * ((size_t)h->T + (size_t)h->T * block);
+	const size_t smem_min = sizeof(double) * 3 * ((block + 31) / 32);
+	const size_t smem_bytes = smem > smem_min ? smem : smem_min;
+	if (smem_bytes > 200 * 1024) return fail(BCM3B200_ERR_UNSUPPORTED, "too many timepoints (%d) for block size %d", h->T, block);
+	dim3 grid(nblk, (unsigned)C);
+	if (C > 65535) return fail(BCM3B200_ERR_UNSUPPORTED, "more than 65535 chains in one batch");
+
+#define LAUNCH(MODEL, DIAGV)                                                                                          \
+	do {                                                                                                              \
+		if (smem_bytes > 48 * 1024)                                                                                   \
+			CUDA_TRY(cudaFuncSetAttribute(poppk_kernel<MODEL, DIAGV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+			                              (int)smem_bytes));                                                          \
+		poppk_kernel<MODEL, DIAGV><<<grid, block, smem_bytes, stream>>>(a);                                           \
+	} while (0)
+	if (h->pk_type == PK_ONE) {
+		if (h->diagnostics) LAUNCH(PkOneModel, true);
+		else LAUNCH(PkOneModel, false);
+	} else {
+		if (h->diagnostics) LAUNCH(PkTwoModel, true);
+		else LAUNCH(PkTwoModel, false);
+	}
+#undef LAUNCH
+	CUDA_TRY(cudaGetLastError());
+	poppk_chain_reduce<<<(unsigned)C, 256, 0, stream>>>(s->block_partial.p, nblk, (int)C, d_partial);
+	CUDA_TRY(cudaGetLastError());
+	h->last_launches += 2;
+	h->total_launches += 2;
+	return BCM3B200_OK;
+}
+
+void combine(size_t C, const double* partial, double* logp, int* status)
+{
+	// serial semantics of cpp:427-440: the sum stops at the first -inf patient; a NaN before it poisons the sum
+	for (size_t c = 0; c < C; c++) {
+		const double s = partial[c], first_inf = partial[C + c], first_nan = partial[2 * C + c];
+		double v;
+		if (first_nan < first_inf) v = std::numeric_limits<double>::quiet_NaN();
+		else if (first_inf < std::numeric_limits<double>::infinity()) v = -std::numeric_limits<double>::infinity();
+		else v = s;
+		logp[c] = v;
+		if (status) status[c] = std::isnan(v) ? BCM3B200_STATUS_NAN : BCM3B200_STATUS_OK;
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+const char* bcm3b200_last_error(void) { return g_last_error.c_str(); }
+
+int bcm3b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_bytes, int device_count, void** handle)
+{
+	if (!model_kind || !handle) return fail(BCM3B200_ERR_ARG, "null argument");
+	*handle = nullptr;
+	if (strcmp(model_kind, "pop_pk_trajectory") != 0)
+		return fail(BCM3B200_ERR_UNSUPPORTED, "unknown model kind \"%s\"", model_kind);
+	std::map<std::string, std::string> kv;
+	if (model_desc && !parse_desc((const char*)model_desc, desc_bytes, kv)) return fail(BCM3B200_ERR_ARG, "malformed model description");
+	std::unique_ptr<Handle> h(new Handle);
+	const std::string type = kv.count("type") ? kv["type"] : "";
+	if (type == "one") h->pk_type = PK_ONE;
+	else if (type == "two") h->pk_type = PK_TWO;
+	else return fail(BCM3B200_ERR_UNSUPPORTED, "pk_model type \"%s\" is not supported (one, two)", type.c_str());
+	h->drug = kv.count("drug") ? kv["drug"] : "";
+	bool hasP, hasT, hasN, hasS;
+	h->P = get_int(kv, "num_patients", 0, &hasP);
+	h->T = get_int(kv, "num_timepoints", 0, &hasT);
+	h->nvar = get_int(kv, "num_variables", 0, &hasN);
+	h->sd_ix = get_int(kv, "sd_ix", -1, &hasS);
+	if (!hasP || !hasT || !hasN || !hasS || h->P < 0 || h->T < 0)
+		return fail(BCM3B200_ERR_ARG, "num_patients, num_timepoints, num_variables and sd_ix are required");
+	h->max_steps = get_int(kv, "max_steps", 2000);
+	h->shard_rank = get_int(kv, "shard_rank", 0);
+	h->shard_count = get_int(kv, "shard_count", 1);
+	h->device0 = get_int(kv, "device", 0);
+	h->device_count = device_count;
+	if (h->shard_count < 1 || h->shard_rank < 0 || h->shard_rank >= h->shard_count) return fail(BCM3B200_ERR_ARG, "bad shard_rank / shard_count");
+	if (device_count < 1) return fail(BCM3B200_ERR_ARG, "device_count must be >= 1");
+	const int ndev = bcm3b200_device_count();
+	if (ndev == 0) return fail(BCM3B200_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+	if (h->device0 < 0 || h->device0 + device_count > ndev)
+		return fail(BCM3B200_ERR_CUDA, "devices %d..%d requested but only %d visible", h->device0, h->device0 + device_count - 1, ndev);
+	*handle = h.release();
+	return BCM3B200_OK;
+}
+
+int bcm3b200_set_data(void* handle, const char* name, const double* data, const size_t* shape, int ndim)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !name || !data || !shape || ndim < 1 || ndim > 2) return fail(BCM3B200_ERR_ARG, "bad argument");
+	const size_t P = (size_t)h->P, T = (size_t)h->T;
+	const std::string n(name);
+	size_t want0 = 0, want1 = 0;
+	if (n == "time") want0 = T;
+	else if (n == "observed_concentration") { want0 = P; want1 = T; }
+	else if (n == "dose" || n == "dosing_interval" || n == "dose_after_dose_change" || n == "dose_change_time" || n == "intermittent") want0 = P;
+	else if (n == "treatment_interruptions") { want0 = P; want1 = 29; }
+	else if (n == "transforms") want0 = (size_t)h->nvar;
+	else return fail(BCM3B200_ERR_ARG, "unknown data name \"%s\"", name);
+	const int want_ndim = want1 ? 2 : 1;
+	if (ndim != want_ndim || shape[0] != want0 || (want1 && shape[1] != want1))
+		return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);
+	const size_t count = want0 * (want1 ? want1 : 1);
+	h->data[n].assign(data, data + count);
+	h->finalized = false;
+	return BCM3B200_OK;
+}
+
+int bcm3b200_finalize(void* handle)
+{
+	Handle* h = (Handle*)handle;
+	if (!h) return fail(BCM3B200_ERR_ARG, "null handle");
+	return finalize(h);
+}
+
+int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variables, const double* values, double* logp, int* status)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !values || !logp) return fail(BCM3B200_ERR_ARG, "null argument");
+	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
+	int rc = finalize(h);
+	if (rc != BCM3B200_OK) return rc;
+	const size_t C = num_chains;
+	if (C == 0) return BCM3B200_OK;
+	h->last_launches = 0;
+
+	// compact per-shard layout of the batch: [C][16 + 2 * P_shard]: chain-level entries first, then this
+	// shard's per-patient probabilities; one strided H2D copy per shard
+	static const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9 };
+	const int SH = 16;
+	std::vector<double> shared(C * SH, 0.0);
+	for (size_t c = 0; c < C; c++)
+		for (int k = 0; k < SV_COUNT; k++) {
+			if (h->ix[k] < h->nvar) shared[c * SH + k] = values[c * num_variables + h->ix[k]];
+		}
+	for (auto& sp : h->shards) {
+		Shard* s = sp.get();
+		CUDA_TRY(cudaSetDevice(s->device));
+		const size_t stride = SH + 2 * (size_t)s->P;
+		CUDA_TRY(s->values.ensure(C * stride));
+		CUDA_TRY(s->partial.ensure(3 * C));
+		if (s->h_partial_n < 3 * C) {
+			if (s->h_partial) cudaFreeHost(s->h_partial);
+			s->h_partial = nullptr;
+			CUDA_TRY(cudaMallocHost((void**)&s->h_partial, sizeof(double) * 3 * C));
+			s->h_partial_n = 3 * C;
+		}
+		CUDA_TRY(cudaMemcpy2DAsync(s->values.p, stride * sizeof(double), shared.data(), SH * sizeof(double), SH * sizeof(double), C,
+		                           cudaMemcpyHostToDevice, s->stream));
+		if (s->P > 0) {
+			const double* src = values + h->npk + 2 + 2 * (size_t)s->offset;
+			CUDA_TRY(cudaMemcpy2DAsync(s->values.p + SH, stride * sizeof(double), src, num_variables * sizeof(double),
+			                           2 * (size_t)s->P * sizeof(double), C, cudaMemcpyHostToDevice, s->stream));
+		}
+		CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+		rc = launch_shard(h, s, C, s->values.p, (long long)stride, SH, cix, s->partial.p, s->stream);
+		if (rc != BCM3B200_OK) return rc;
+		CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+		CUDA_TRY(cudaMemcpyAsync(s->h_partial, s->partial.p, sizeof(double) * 3 * C, cudaMemcpyDeviceToHost, s->stream));
+	}
+	// combine the shards in patient order
+	std::vector<double> total(3 * C, std::numeric_limits<double>::infinity());
+	for (size_t c = 0; c < C; c++) total[c] = 0.0;
+	double max_ms = 0.0;
+	for (auto& sp : h->shards) {
+		Shard* s = sp.get();
+		CUDA_TRY(cudaSetDevice(s->device));
+		CUDA_TRY(cudaStreamSynchronize(s->stream));
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess && ms > max_ms) max_ms = ms;
+		for (size_t c = 0; c < C; c++) {
+			total[c] += s->h_partial[c];
+			total[C + c] = std::fmin(total[C + c], s->h_partial[C + c]);
+			total[2 * C + c] = std::fmin(total[2 * C + c], s->h_partial[2 * C + c]);
+		}
+	}
+	h->last_kernel_ms = max_ms;
+	if (h->shard_count > 1) {
+		// partial of this handle's slice: report the slice-local outcome (see header)
+		combine(C, total.data(), logp, status);
+	} else {
+		combine(C, total.data(), logp, status);
+	}
+	h->num_evaluations += (int64_t)C;
+	return BCM3B200_OK;
+}
+
+int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_variables, const double* d_values, double* d_partial,
+                                   void* stream)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !d_values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
+	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
+	int rc = finalize(h);
+	if (rc != BCM3B200_OK) return rc;
+	if (h->shards.size() != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "device-buffer entry needs device_count == 1");
+	if (num_chains == 0) return BCM3B200_OK;
+	Shard* s = h->shards[0].get();
+	CUDA_TRY(cudaSetDevice(s->device));
+	h->last_launches = 0;
+	const long long col0 = (long long)h->npk + 2 + 2ll * s->offset;
+	rc = launch_shard(h, s, num_chains, d_values, (long long)num_variables, col0, h->ix, d_partial, (cudaStream_t)stream);
+	if (rc != BCM3B200_OK) return rc;
+	h->num_evaluations += (int64_t)num_chains;
+	return BCM3B200_OK;
+}
+
+int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* logp, int* status)
+{
+	if (!partial || !logp) return fail(BCM3B200_ERR_ARG, "null argument");
+	combine(num_chains, partial, logp, status);
+	return BCM3B200_OK;
+}
+
+int bcm3b200_get_diagnostics(void* handle, double* conc, double* patient_ll, int32_t* counters)
+{
+	Handle* h = (Handle*)handle;
+	if (!h) return fail(BCM3B200_ERR_ARG, "null handle");
+	if (!h->diagnostics || !h->finalized) return fail(BCM3B200_ERR_STATE, "diagnostics were not enabled before the last evaluate");
+	// layout over the handle's patients: [C][P_handle][...], shards are contiguous slices
+	size_t Ph = 0;
+	for (auto& sp : h->shards) Ph += (size_t)sp->P;
+	size_t base = 0;
+	for (auto& sp : h->shards) {
+		Shard* s = sp.get();
+		const size_t C = (size_t)s->last_C, Ps = (size_t)s->P, T = (size_t)h->T;
+		if (C == 0 || Ps == 0) {
+			base += Ps;
+			continue;
+		}
+		CUDA_TRY(cudaSetDevice(s->device));
+		CUDA_TRY(cudaDeviceSynchronize());
+		if (conc)
+			CUDA_TRY(cudaMemcpy2D(conc + base * T, Ph * T * sizeof(double), s->diag_conc.p, Ps * T * sizeof(double), Ps * T * sizeof(double), C,
+			                      cudaMemcpyDeviceToHost));
+		if (patient_ll)
+			CUDA_TRY(cudaMemcpy2D(patient_ll + base, Ph * sizeof(double), s->diag_ll.p, Ps * sizeof(double), Ps * sizeof(double), C,
+			                      cudaMemcpyDeviceToHost));
+		if (counters)
+			CUDA_TRY(cudaMemcpy2D(counters + base * 8, Ph * 8 * sizeof(int32_t), s->diag_counters.p, Ps * 8 * sizeof(int32_t),
+			                      Ps * 8 * sizeof(int32_t), C, cudaMemcpyDeviceToHost));
+		base += Ps;
+	}
+	return BCM3B200_OK;
+}
+
+int bcm3b200_set_option(void* handle, const char* name, int64_t value)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !name) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (!strcmp(name, "diagnostics")) h->diagnostics = value != 0;
+	else if (!strcmp(name, "block_size")) {
+		if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256) return fail(BCM3B200_ERR_ARG, "block_size must be 0, 32, 64, 128 or 256");
+		h->block_size = (int)value;
+	} else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
+	return BCM3B200_OK;
+}
+
+int bcm3b200_get_stat(void* handle, const char* name, int64_t* value)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !name || !value) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (!strcmp(name, "last_kernel_launches")) *value = h->last_launches;
+	else if (!strcmp(name, "total_kernel_launches")) *value = h->total_launches;
+	else if (!strcmp(name, "num_evaluations")) *value = h->num_evaluations;
+	else if (!strcmp(name, "last_kernel_us")) *value = (int64_t)(h->last_kernel_ms * 1000.0);
+	else if (!strcmp(name, "num_patients_local") || !strcmp(name, "patient_offset")) {
+		if (!h->finalized) return fail(BCM3B200_ERR_STATE, "not finalized");
+		int64_t n = 0;
+		for (auto& sp : h->shards) n += sp->P;
+		*value = !strcmp(name, "num_patients_local") ? n : (h->shards.empty() ? 0 : h->shards[0]->offset);
+	} else return fail(BCM3B200_ERR_ARG, "unknown stat \"%s\"", name);
+	return BCM3B200_OK;
+}
+
+void* bcm3b200_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		g_last_error = "cudaMallocHost failed";
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+void bcm3b200_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+void bcm3b200_destroy(void* handle)
+{
+	Handle* h = (Handle*)handle;
+	if (!h) return;
+	for (auto& sp : h->shards) cudaSetDevice(sp->device);
+	delete h;
+}
+
+} // extern "C"

@@ -1,0 +1,438 @@
+// poppk_kernel.cuh -- K0+K1+K3 of the PopPK path: one (chain, patient) ODE system per thread.
+//
+// Replaces, for all chains at once, the per-patient loop of
+//   LikelihoodPopPKTrajectory::EvaluateLogProbability   src/likelihoods/LikelihoodPopPKTrajectory.cpp:259-444
+// and under it ODESolver::SolveReturnSolution / ODESolverCVODE::Solve (src/odecommon/ODESolver.cpp:93-134,
+// ODESolverCVODE.cpp:322-463) with the CVODE-faithful integrator of bdf_thread.cuh.
+//
+// Launch shape: grid = (ceil(P_local / BLOCK), C); thread = patient, blockIdx.y = chain. A warp holds 32
+// consecutive patients of ONE chain, so parameter reads (double2 per lane) and observation reads
+// (time-major obs_t[T][P_pad]) are coalesced and the per-chain reduction is warp-local.
+// Control flow is organised so that a warp stays converged where it matters: all lanes run the
+// restart path (CVodeReInit + cvHin) together at the start of each dosing segment and then iterate
+// "one step attempt per loop trip" until every lane has reached its next discontinuity.
+#pragma once
+
+#include <cstdint>
+
+#include "bdf_thread.cuh"
+
+namespace bcm3b200 {
+
+enum : int { PK_ONE = 0, PK_TWO = 1 };
+enum : int { TR_NONE = 0, TR_LOG = 1, TR_LOG10 = 2, TR_LOGIT = 3 };
+
+// indices into PkArgs::ix / PkArgs::tr (the chain-level entries of the variable vector)
+enum : int {
+	SV_MEAN_ABSORPTION = 0, // values[0]            mean log10 k_absorption
+	SV_EXCRETION,           // values[1]
+	SV_MEAN_CLEARANCE,      // values[2]            mean log10 clearance
+	SV_VOD,                 // values[3]
+	SV_PERIPHERY_FWD,       // values[4]  (two-compartment)
+	SV_PERIPHERY_BWD,       // values[5]
+	SV_SIGMA_ABSORPTION,    // values[npk + 0]
+	SV_SIGMA_CLEARANCE,     // values[npk + 1]
+	SV_SD,                  // values[sd_ix]
+	SV_SD2,                 // values[sd_ix + 1]
+	SV_COUNT
+};
+
+struct PkArgs {
+	// static data of this shard (device pointers)
+	const double* time;            // [T]
+	const double* obs_t;           // [T][P_pad]  time-major observed concentrations, NaN = missing
+	const double* dose;            // [P_local]
+	const double* dosing_interval; // [P_local]
+	const double* dose_after_dose_change;
+	const double* dose_change_time;
+	const int32_t* intermittent;
+	const uint32_t* skipped_days;
+	const int32_t* simulate_until;
+	int P_local, P_pad, patient_offset, T, max_steps;
+	double rtol, atol, conv_base; // conv_base = 1e6 / MW
+	// the batch
+	const double* values; // [C][row_stride]
+	long long row_stride;
+	long long col_patient0; // column of patient_offset's first probability
+	int ix[SV_COUNT];
+	int tr[SV_COUNT];
+	// outputs
+	double* block_partial; // [C][gridDim.x][3]
+	double* diag_conc;     // [C][P_local][T] or null
+	double* diag_ll;       // [C][P_local] or null
+	int32_t* diag_counters; // [C][P_local][8] or null
+};
+
+// VariableSet::TransformVariable, src/sampler/VariableSet.cpp:97-124; bcm3::fastpow10, MathFunctions.h:13
+__device__ __forceinline__ double fastpow10(double x) { return exp(x * 2.3025850929940459); }
+__device__ __forceinline__ double transform_variable(int tr, double x)
+{
+	switch (tr) {
+	case TR_LOG:
+		return exp(x);
+	case TR_LOG10:
+		return fastpow10(x);
+	case TR_LOGIT:
+		if (x > 0) {
+			double z = exp(-x);
+			return 1.0 / (1.0 + z);
+		} else {
+			double z = exp(x);
+			return z / (1.0 + z);
+		}
+	default:
+		return x;
+	}
+}
+
+// bcm3::QuantileNormal(p, mu, sigma) = boost::math::quantile(normal(mu, sigma), p)
+// (ProbabilityDistributions.cpp:359-363): mu + sigma * Phi^-1(p)
+__device__ __forceinline__ double quantile_normal(double p, double mu, double sigma)
+{
+	double r = normcdfinv(p);
+	r *= sigma;
+	r += mu;
+	return r;
+}
+
+// bcm3::LogPdfTnu4, ProbabilityDistributions.cpp:216-224
+__device__ __forceinline__ double logpdf_tnu4(double x, double mu, double sigma)
+{
+	double xn = (x - mu) / sigma;
+	return -0.9808292530117262 - 2.5 * log1p(0.25 * xn * xn) - log(sigma);
+}
+
+// RHS / Jacobian: LikelihoodPopPKTrajectory.cpp:446-467 (one), :469-494 (two)
+struct PkOneModel {
+	static constexpr int N = 2;
+	double ka, kex, kel, kf, kb;
+	__device__ __forceinline__ void rhs(double, const double (&y)[2], double (&f)[2]) const
+	{
+		f[0] = -(ka + kex) * y[0];
+		f[1] = ka * y[0] - kel * y[1];
+	}
+	__device__ __forceinline__ void jac(double (&A)[4]) const
+	{
+		A[0 * 2 + 0] = -(ka + kex);
+		A[1 * 2 + 0] = ka;
+		A[1 * 2 + 1] = -kel;
+	}
+};
+struct PkTwoModel {
+	static constexpr int N = 3;
+	double ka, kex, kel, kf, kb;
+	__device__ __forceinline__ void rhs(double, const double (&y)[3], double (&f)[3]) const
+	{
+		f[0] = -(ka + kex) * y[0];
+		f[1] = ka * y[0] - kel * y[1] - kf * y[1] + kb * y[2];
+		f[2] = kf * y[1] - kb * y[2];
+	}
+	__device__ __forceinline__ void jac(double (&A)[9]) const
+	{
+		A[0 * 3 + 0] = -(ka + kex);
+		A[1 * 3 + 0] = ka;
+		A[1 * 3 + 1] = -(kel + kf);
+		A[1 * 3 + 2] = kb;
+		A[2 * 3 + 1] = kf;
+		A[2 * 3 + 2] = -kb;
+	}
+};
+
+// LikelihoodPopPKTrajectory::CheckGiveTreatment, cpp:644-671
+__device__ __forceinline__ bool check_give_treatment(double t, uint32_t skipped_days, int intermittent)
+{
+	bool give = true;
+	int day = static_cast<int>(floor(t / 24.0));
+	if (day >= 0 && day < 29 && ((skipped_days >> day) & 1u)) give = false;
+	if (intermittent == 1) {
+		double tw = t - 7.0 * 24.0 * floor(t / (7.0 * 24.0));
+		if (tw >= 5.0 * 24.0) give = false;
+	} else if (intermittent == 2) {
+		double tc = t - 28.0 * 24.0 * floor(t / (28.0 * 24.0));
+		if (tc >= 21.0 * 24.0) give = false;
+	} else if (intermittent == 3) {
+		double tw = t - 7.0 * 24.0 * floor(t / (7.0 * 24.0));
+		if (tw >= 4.0 * 24.0) give = false;
+	}
+	return give;
+}
+
+template <class Model, bool DIAG>
+__global__ void poppk_kernel(const PkArgs a)
+{
+	constexpr int N = Model::N;
+	constexpr unsigned FULL = 0xffffffffu;
+	extern __shared__ double smem[];
+	double* s_time = smem;            // [T]
+	double* s_sim = smem + a.T;       // [T][blockDim.x]  simulated central-compartment amounts at the output times
+
+	const int tid = threadIdx.x;
+	const int c = blockIdx.y;
+	const int jl = blockIdx.x * blockDim.x + tid; // patient index inside this shard
+	const bool valid = jl < a.P_local;
+	const int T = a.T;
+
+	for (int i = tid; i < T; i += blockDim.x) s_time[i] = a.time[i];
+	__syncthreads();
+
+	// ---- K0: parameters of this (chain, patient); cpp:263-295 ----
+	const double* vrow = a.values + (long long)c * a.row_stride;
+	Model model;
+	double sd, sd2, conversion;
+	{
+		double k_vod = transform_variable(a.tr[SV_VOD], vrow[a.ix[SV_VOD]]);
+		model.kex = transform_variable(a.tr[SV_EXCRETION], vrow[a.ix[SV_EXCRETION]]);
+		if (N == 3) {
+			model.kf = transform_variable(a.tr[SV_PERIPHERY_FWD], vrow[a.ix[SV_PERIPHERY_FWD]]);
+			model.kb = transform_variable(a.tr[SV_PERIPHERY_BWD], vrow[a.ix[SV_PERIPHERY_BWD]]);
+		} else {
+			model.kf = 0.0;
+			model.kb = 0.0;
+		}
+		sd = transform_variable(a.tr[SV_SD], vrow[a.ix[SV_SD]]);
+		sd2 = transform_variable(a.tr[SV_SD2], vrow[a.ix[SV_SD2]]);
+		double2 pp = make_double2(0.5, 0.5);
+		if (valid) pp = *reinterpret_cast<const double2*>(vrow + a.col_patient0 + 2ll * jl);
+		model.ka = fastpow10(quantile_normal(pp.x, vrow[a.ix[SV_MEAN_ABSORPTION]], vrow[a.ix[SV_SIGMA_ABSORPTION]]));
+		model.kel = fastpow10(quantile_normal(pp.y, vrow[a.ix[SV_MEAN_CLEARANCE]], vrow[a.ix[SV_SIGMA_CLEARANCE]])) / k_vod;
+		conversion = a.conv_base / k_vod;
+	}
+
+	double dose = 0.0, dosing_interval = 1.0, dose_after = 0.0, dose_change_time = 0.0;
+	int intermittent = 0, ntp = 0;
+	uint32_t skipped = 0;
+	if (valid) {
+		dose = a.dose[jl];
+		dosing_interval = a.dosing_interval[jl];
+		dose_after = a.dose_after_dose_change[jl];
+		dose_change_time = a.dose_change_time[jl];
+		intermittent = a.intermittent[jl];
+		skipped = a.skipped_days[jl];
+		ntp = a.simulate_until[jl];
+	}
+
+	// ---- K1: ODESolver::SolveReturnSolution + ODESolverCVODE::Solve ----
+	BdfThread<N, Model, DIAG> S;
+	S.create();
+
+	bool done = !valid || ntp <= 0;
+	bool failed = false;
+	int tpi = 0;
+	int current_step = 0;
+	double y[N];
+	y[0] = dose; // initial_conditions, cpp:366-373
+#pragma unroll
+	for (int i = 1; i < N; i++) y[i] = 0.0;
+
+	// ODESolver.cpp:109-118: output times at t ~ 0 take the initial condition
+	if (!done) {
+		while (s_time[tpi] < DBL_EPSILON) {
+			s_sim[tpi * blockDim.x + tid] = y[1];
+			tpi++;
+			if (tpi == ntp) {
+				done = true;
+				break;
+			}
+		}
+	}
+	const double end_time = (ntp > 0) ? s_time[ntp - 1] : 0.0;
+	double t = 0.0;
+	// SetDiscontinuity(dosing_interval, TreatmentCallback), cpp:362-363 (ignored for time <= 0, ODESolver.cpp:62-71)
+	double current_dose_time = dosing_interval;
+	double next_disc = (dosing_interval > 0.0) ? dosing_interval : NAN;
+	S.tstopset = !isnan(next_disc);
+	S.tstop = next_disc;
+
+#pragma unroll 1
+	for (;;) {
+		if (!__any_sync(FULL, !done)) break;
+
+		// CVodeReInit + first-call block, all lanes of the warp together
+		if (!done) {
+			if (!S.restart(t, y, end_time, model, a.rtol, a.atol)) {
+				failed = true;
+				done = true;
+			}
+		}
+		bool seg_end = false;
+		bool newstep = true;
+
+#pragma unroll 1
+		for (;;) {
+			const bool active = !done && !seg_end;
+			if (!__any_sync(FULL, active)) break;
+			if (active) {
+				bool ok = true;
+				if (newstep) {
+					ok = S.begin_step(a.rtol, a.atol);
+					newstep = false;
+				}
+				int r = BDF_ATTEMPT_FAILED;
+				if (ok) r = S.attempt(model);
+				if (r == BDF_ATTEMPT_FAILED) {
+					failed = true;
+					done = true;
+				} else if (r == BDF_ATTEMPT_DONE) {
+					double yout[N], tret;
+					const bool tstop_return = S.after_step(yout, tret);
+					t = tret;
+					current_step++;
+					// dense output at every requested time passed by this step, ODESolverCVODE.cpp:406-427
+					while (tpi < ntp && tret >= s_time[tpi]) {
+						double v[N];
+						if (!S.dky(s_time[tpi], v)) {
+							failed = true;
+							done = true;
+							break;
+						}
+						s_sim[tpi * blockDim.x + tid] = v[1];
+						tpi++;
+					}
+					if (!failed) {
+						if (t >= end_time) {
+							done = true; // ODESolverCVODE.cpp:436
+						} else if (current_step == a.max_steps) {
+							failed = true; // :440-446
+							done = true;
+						} else if (!isnan(next_disc) && (tstop_return || next_disc == t)) {
+							seg_end = true; // :448
+#pragma unroll
+							for (int i = 0; i < N; i++) y[i] = yout[i];
+						}
+					}
+					newstep = true;
+				}
+			}
+		}
+
+		// TreatmentCallback (cpp:673-690), then CVodeReInit(t, y) + CVodeSetStopTime at the top of the loop
+		if (!done && seg_end) {
+			current_dose_time += dosing_interval;
+			if (check_give_treatment(t, skipped, intermittent)) {
+				double d = dose;
+				if (t >= dose_change_time) d = dose_after;
+				y[0] = y[0] + d;
+			}
+			next_disc = current_dose_time;
+			if (!isnan(next_disc) && next_disc < INFINITY) {
+				S.tstop = next_disc;
+				S.tstopset = true;
+			}
+		}
+	}
+
+	// ---- observation model: Student-t4 log-pdf, cpp:409-424 ----
+	double ll = 0.0;
+	if (valid && ntp > 0) {
+		if (failed) {
+			ll = -INFINITY;
+		} else {
+			bool broken = false;
+			for (int i = 0; i < T; i++) {
+				if (i < ntp && !broken) {
+					double x = conversion * s_sim[i * blockDim.x + tid];
+					double yobs = a.obs_t[(long long)i * a.P_pad + jl];
+					if (!isnan(yobs)) ll += logpdf_tnu4(x, yobs, sd + sd2 * ((x < 0.0) ? 0.0 : x));
+					if (isnan(x)) {
+						ll = -INFINITY;
+						broken = true;
+					}
+				}
+			}
+		}
+	}
+
+	if (DIAG && valid) {
+		const long long cj = (long long)c * a.P_local + jl;
+		if (a.diag_ll) a.diag_ll[cj] = ll;
+		if (a.diag_conc) {
+			for (int i = 0; i < T; i++) {
+				double x = NAN;
+				if (i < ntp && !failed) x = conversion * s_sim[i * blockDim.x + tid];
+				a.diag_conc[cj * T + i] = x;
+			}
+		}
+		if (a.diag_counters) {
+			int32_t* k = a.diag_counters + cj * 8;
+			k[0] = current_step;
+			k[1] = S.cnt.nfe;
+			k[2] = S.cnt.nsetups;
+			k[3] = S.cnt.nje;
+			k[4] = S.cnt.netf;
+			k[5] = S.cnt.ncfn;
+			k[6] = S.cnt.nni;
+			k[7] = (ntp > 0 && !failed) ? 1 : 0;
+		}
+	}
+
+	// ---- K3 (first level): per-block partial of this chain, fixed reduction order ----
+	// (sum of finite terms, first patient index with -inf, first patient index with NaN)
+	const double big = INFINITY;
+	double vsum = 0.0, vinf = big, vnan = big;
+	if (valid) {
+		const double gidx = (double)(a.patient_offset + jl);
+		if (isnan(ll) || ll == INFINITY) vnan = gidx;
+		else if (ll == -INFINITY) vinf = gidx;
+		else vsum = ll;
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) {
+		vsum += __shfl_down_sync(FULL, vsum, off);
+		vinf = fmin(vinf, __shfl_down_sync(FULL, vinf, off));
+		vnan = fmin(vnan, __shfl_down_sync(FULL, vnan, off));
+	}
+	__syncthreads(); // s_sim is dead from here on; reuse the front of smem
+	const int warp = tid >> 5, lane = tid & 31, nwarp = (blockDim.x + 31) >> 5;
+	if (lane == 0) {
+		smem[warp * 3 + 0] = vsum;
+		smem[warp * 3 + 1] = vinf;
+		smem[warp * 3 + 2] = vnan;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		double s = 0.0, mi = big, mn = big;
+		for (int w = 0; w < nwarp; w++) {
+			s += smem[w * 3 + 0];
+			mi = fmin(mi, smem[w * 3 + 1]);
+			mn = fmin(mn, smem[w * 3 + 2]);
+		}
+		double* out = a.block_partial + ((long long)c * gridDim.x + blockIdx.x) * 3;
+		out[0] = s;
+		out[1] = mi;
+		out[2] = mn;
+	}
+}
+
+// K3 (second level): block partials -> partial[3][C], fixed order.
+__global__ void poppk_chain_reduce(const double* __restrict__ block_partial, int nblk, int C, double* __restrict__ partial)
+{
+	__shared__ double sh[3][256];
+	const int c = blockIdx.x;
+	const int tid = threadIdx.x;
+	double s = 0.0, mi = INFINITY, mn = INFINITY;
+	for (int b = tid; b < nblk; b += blockDim.x) {
+		const double* p = block_partial + ((long long)c * nblk + b) * 3;
+		s += p[0];
+		mi = fmin(mi, p[1]);
+		mn = fmin(mn, p[2]);
+	}
+	sh[0][tid] = s;
+	sh[1][tid] = mi;
+	sh[2][tid] = mn;
+	__syncthreads();
+	for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+		if (tid < off) {
+			sh[0][tid] += sh[0][tid + off];
+			sh[1][tid] = fmin(sh[1][tid], sh[1][tid + off]);
+			sh[2][tid] = fmin(sh[2][tid], sh[2][tid + off]);
+		}
+		__syncthreads();
+	}
+	if (tid == 0) {
+		partial[0 * C + c] = sh[0][0];
+		partial[1 * C + c] = sh[1][0];
+		partial[2 * C + c] = sh[2][0];
+	}
+}
+
+} // namespace bcm3b200

@@ -1,0 +1,127 @@
+/* bcm3b200.h -- C ABI of the B200-native batched likelihood evaluator.
+ *
+ * Drop-in boundary for ONE path of NKI-CCB/bcm3: evaluating
+ *   bcm3::Likelihood::EvaluateLogProbability(threadix, values, logp)      (src/sampler/Likelihood.h:29)
+ * for every parallel-tempered chain's proposal at once. The reference has no FFI for this
+ * path; the closest precedent is LikelihoodDLL (src/likelihoods/LikelihoodDLL.h:17-18:
+ * `initialize_likelihood` / `evaluate_log_probability`, resolved with dlsym,
+ * LikelihoodDLL.cpp:72-75) and the R bridge's all-pointer convention
+ * (src/bcmrbridge/interface.cpp:27-101). The entry points below are what a
+ * GPU-backed `bcm3::Likelihood` subclass binds (INTEGRATION.md shows the subclass).
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, row = chain.
+ * Return 0 = ok, < 0 = unrecoverable (maps to `return false` in the reference's
+ * bool convention). logp = -inf is a legal value (failed ODE solve,
+ * LikelihoodPopPKTrajectory.cpp:400-408); a NaN log-likelihood is reported through
+ * status[c] != 0 (the reference sampler treats NaN as an error, Sampler.cpp:172-178).
+ * There is no CPU fallback: every call fails with BCM3B200_ERR_CUDA when no device is usable.
+ */
+#ifndef BCM3B200_H
+#define BCM3B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCM3B200_OK 0
+#define BCM3B200_ERR_ARG (-1)     /* bad argument / unknown name / shape mismatch */
+#define BCM3B200_ERR_STATE (-2)   /* data missing or call out of order */
+#define BCM3B200_ERR_CUDA (-3)    /* CUDA runtime error (bcm3b200_last_error has the text) */
+#define BCM3B200_ERR_UNSUPPORTED (-4)
+
+/* per-chain status codes written by evaluate */
+#define BCM3B200_STATUS_OK 0
+#define BCM3B200_STATUS_NAN 1 /* log-likelihood is NaN: the reference aborts sampling on this (Sampler.cpp:172-178) */
+
+/* Create an evaluator.
+ *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62):
+ *                "pop_pk_trajectory"
+ *   model_desc : `key=value;...` text, desc_bytes long (no terminator needed). Keys for pop_pk_trajectory
+ *                mirror the <pk_model> attributes (LikelihoodPopPKTrajectory.cpp:58-87) plus sizes:
+ *                  type=one|two  drug=<name>  num_patients=<P>  num_timepoints=<T>
+ *                  num_variables=<nvar>  sd_ix=<index of "standard_deviation">  [max_steps=2000]
+ *                  [shard_rank=0] [shard_count=1]   contiguous slice of patients owned by this handle
+ *                  [device=0]                       first CUDA device ordinal
+ *   device_count: number of CUDA devices (device .. device+device_count-1) this handle spreads its patients
+ *                over inside this process; 1 for the one-process-per-GPU launch.
+ * Replaces: LikelihoodFactory::CreateLikelihood -> make_shared<LikelihoodPopPKTrajectory> + Initialize
+ *           (LikelihoodFactory.cpp:31-101). */
+int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_bytes, int device_count, void** handle);
+
+/* Attach one named static input (all as doubles; integer-valued inputs are passed as doubles).
+ * pop_pk_trajectory names and shapes = the NetCDF variables read at LikelihoodPopPKTrajectory.cpp:94-161
+ * (FULL arrays over all P patients even when the handle owns a shard):
+ *   "time"[T]  "observed_concentration"[P][T] (NaN = missing)  "dose"[P]  "dosing_interval"[P]
+ *   "dose_after_dose_change"[P] (NaN = none)  "dose_change_time"[P]  "intermittent"[P] (0..3)
+ *   "treatment_interruptions"[P][29] (0/1)
+ *   "transforms"[nvar] : VariableSet transform per variable, 0 none / 1 log / 2 log10 / 3 logit (VariableSet.cpp:97-124)
+ * Replaces: the NetCDFDataFile reads in LikelihoodPopPKTrajectory::Initialize. */
+int bcm3b200_set_data(void* handle, const char* name, const double* data, const size_t* shape, int ndim);
+
+/* Derive simulate_until / tolerances / skipped-day masks (LikelihoodPopPKTrajectory.cpp:163-204,238) and upload
+ * the static data to the device(s). Called implicitly by the first evaluate. Replaces: PostInitialize. */
+int bcm3b200_finalize(void* handle);
+
+/* Evaluate num_chains parameter vectors at once. HOST buffers:
+ *   values [num_chains][num_variables]  (row c = chain c's VectorReal `values`)
+ *   logp   [num_chains]  out
+ *   status [num_chains]  out, may be NULL
+ * With shard_count > 1 the result is this shard's partial (see bcm3b200_evaluate_batch_device for the
+ * exact combination rule); otherwise it equals the reference's EvaluateLogProbability per chain.
+ * Replaces: C calls of LikelihoodPopPKTrajectory::EvaluateLogProbability (cpp:259-444). */
+int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variables, const double* values, double* logp,
+                            int* status);
+
+/* Same evaluation on DEVICE buffers of the handle's first device, enqueued on `stream` (a cudaStream_t), no sync:
+ *   d_values  [num_chains][num_variables] device
+ *   d_partial [3][num_chains] device, out:
+ *       row 0: sum of the finite per-patient log-likelihoods of this shard
+ *       row 1: global index of the first patient whose log-likelihood is -inf (+inf if none)
+ *       row 2: global index of the first patient whose log-likelihood is NaN  (+inf if none)
+ * Combination across shards (NCCL all-reduce: SUM on row 0, MIN on rows 1-2) followed by
+ * bcm3b200_combine_partials reproduces the reference's serial `logp += patient_logllh; if (logp == -inf) break;`
+ * loop (cpp:427-440) exactly in its -inf / NaN outcome. */
+int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_variables, const double* d_values,
+                                   double* d_partial, void* stream);
+
+/* partial [3][num_chains] (host) -> logp[num_chains], status[num_chains] (may be NULL) */
+int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* logp, int* status);
+
+/* Diagnostics of the LAST evaluate on this handle, for parity checks against the reference
+ * (LikelihoodPopPKTrajectory::GetSimulatedConcentrations, .h:25; ODESolver::GetNumSteps, ODESolver.h:35).
+ * Must be enabled before the evaluate with bcm3b200_set_option(h, "diagnostics", 1).
+ *   conc       [num_chains][P_local][T] : conversion * trajectory(1, i), NaN where not simulated
+ *   patient_ll [num_chains][P_local]
+ *   counters   [num_chains][P_local][8] : steps, nfe, nsetups, nje, netf, ncfn, nni, ok
+ * Any pointer may be NULL. */
+int bcm3b200_get_diagnostics(void* handle, double* conc, double* patient_ll, int32_t* counters);
+
+/* options: "diagnostics" (0/1), "block_size" (0 = auto, 32/64/128/256) */
+int bcm3b200_set_option(void* handle, const char* name, int64_t value);
+
+/* stats: "num_patients_local", "patient_offset", "last_kernel_launches", "total_kernel_launches",
+ * "num_evaluations" (chains evaluated so far = the reference's num_likelihood_evaluations, Sampler.cpp:169),
+ * "last_kernel_us" (device time of the last host-buffer evaluate's kernels, microseconds, max over devices) */
+int bcm3b200_get_stat(void* handle, const char* name, int64_t* value);
+
+void bcm3b200_destroy(void* handle);
+
+/* Page-locked host memory for the caller's `values` / `logp` buffers: evaluate_batch copies straight from it
+ * with asynchronous DMA instead of staging pageable memory. Plain malloc'ed buffers work too, only slower. */
+void* bcm3b200_host_alloc(size_t bytes);
+void bcm3b200_host_free(void* p);
+
+/* text of the last error raised on the calling thread ("" if none) */
+const char* bcm3b200_last_error(void);
+
+/* number of usable CUDA devices (0 when there is no driver / no GPU) */
+int bcm3b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BCM3B200_H */
