@@ -18,6 +18,7 @@ EXPORTS = [
     "bcm3b200_finalize",
     "bcm3b200_evaluate_batch",
     "bcm3b200_evaluate_batch_device",
+    "bcm3b200_enqueue_batch",
     "bcm3b200_combine_partials",
     "bcm3b200_get_diagnostics",
     "bcm3b200_set_option",
@@ -25,6 +26,7 @@ EXPORTS = [
     "bcm3b200_destroy",
     "bcm3b200_last_error",
     "bcm3b200_device_count",
+    "bcm3b200_measure_fp64_peak",
     "bcm3b200_host_alloc",
     "bcm3b200_host_free",
 ]
@@ -55,6 +57,7 @@ def load() -> C.CDLL:
     lib.bcm3b200_finalize.argtypes = [vp]
     lib.bcm3b200_evaluate_batch.argtypes = [vp, sz, sz, vp, vp, vp]
     lib.bcm3b200_evaluate_batch_device.argtypes = [vp, sz, sz, vp, vp, vp]
+    lib.bcm3b200_enqueue_batch.argtypes = [vp, sz, sz, vp, vp, vp]
     lib.bcm3b200_combine_partials.argtypes = [sz, vp, vp, vp]
     lib.bcm3b200_get_diagnostics.argtypes = [vp, vp, vp, vp]
     lib.bcm3b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -63,11 +66,13 @@ def load() -> C.CDLL:
     lib.bcm3b200_destroy.restype = None
     lib.bcm3b200_last_error.restype = C.c_char_p
     lib.bcm3b200_device_count.restype = C.c_int
+    lib.bcm3b200_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.bcm3b200_measure_fp64_peak.restype = C.c_int
     lib.bcm3b200_host_alloc.argtypes = [sz]
     lib.bcm3b200_host_alloc.restype = vp
     lib.bcm3b200_host_free.argtypes = [vp]
     lib.bcm3b200_host_free.restype = None
-    for name in ("create", "set_data", "finalize", "evaluate_batch", "evaluate_batch_device", "combine_partials",
+    for name in ("create", "set_data", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials",
                  "get_diagnostics", "set_option", "get_stat"):
         getattr(lib, "bcm3b200_" + name).restype = C.c_int
     _lib = lib
@@ -77,6 +82,12 @@ def load() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise Bcm3B200Error(rc, load().bcm3b200_last_error().decode(errors="replace"))
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    v = C.c_double()
+    check(load().bcm3b200_measure_fp64_peak(device, C.byref(v)))
+    return float(v.value)
 
 
 def device_count() -> int:

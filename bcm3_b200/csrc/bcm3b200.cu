@@ -91,10 +91,13 @@ struct Shard {
 	DevBuf<uint32_t> skipped;
 	double* h_partial = nullptr; // pinned [3][C]
 	size_t h_partial_n = 0;
+	double* h_shared = nullptr; // pinned [C][16] staging of the chain-level entries
+	size_t h_shared_n = 0;
 	int last_C = 0;
 	~Shard()
 	{
 		if (h_partial) cudaFreeHost(h_partial);
+		if (h_shared) cudaFreeHost(h_shared);
 		if (ev0) cudaEventDestroy(ev0);
 		if (ev1) cudaEventDestroy(ev1);
 		if (stream) cudaStreamDestroy(stream);
@@ -379,9 +382,60 @@ void combine(size_t C, const double* partial, double* logp, int* status)
 	}
 }
 
+// FP64 FMA-chain microbenchmark: the roofline denominator for the BDF kernels (MEASURED_PEAKS.json has no FP64 entry).
+__global__ void fp64_peak_kernel(double* out, double a, double b, int iters)
+{
+	double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int u = 0; u < 16; u++) {
+			x0 = fma(x0, a, b);
+			x1 = fma(x1, a, b);
+			x2 = fma(x2, a, b);
+			x3 = fma(x3, a, b);
+			x4 = fma(x4, a, b);
+			x5 = fma(x5, a, b);
+			x6 = fma(x6, a, b);
+			x7 = fma(x7, a, b);
+		}
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 } // namespace
 
 extern "C" {
+
+int bcm3b200_measure_fp64_peak(int device, double* tflops)
+{
+	if (!tflops) return fail(BCM3B200_ERR_ARG, "null argument");
+	CUDA_TRY(cudaSetDevice(device));
+	int sms = 0;
+	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+	const int block = 256, grid = sms * 8, iters = 2048;
+	double* d = nullptr;
+	CUDA_TRY(cudaMalloc((void**)&d, sizeof(double) * block * grid));
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0));
+	CUDA_TRY(cudaEventCreate(&e1));
+	double best = 0.0;
+	for (int rep = 0; rep < 6; rep++) {
+		CUDA_TRY(cudaEventRecord(e0));
+		fp64_peak_kernel<<<grid, block>>>(d, 0.999999, 1e-9, iters);
+		CUDA_TRY(cudaEventRecord(e1));
+		CUDA_TRY(cudaEventSynchronize(e1));
+		float ms = 0.f;
+		CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+		const double flop = 2.0 * 8 * 16 * (double)iters * block * grid;
+		const double tf = flop / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	*tflops = best;
+	return BCM3B200_OK;
+}
 
 const char* bcm3b200_last_error(void) { return g_last_error.c_str(); }
 
@@ -460,6 +514,38 @@ int bcm3b200_finalize(void* handle)
 	return finalize(h);
 }
 
+// Upload this shard's slice of the host batch in the compact layout [C][16 + 2 * P_shard] (chain-level entries
+// first, then the shard's per-patient probabilities; two strided copies) and enqueue the kernels on `stream`.
+static int upload_and_launch(Handle* h, Shard* s, size_t C, size_t num_variables, const double* values, double* d_partial,
+                             cudaStream_t stream)
+{
+	static const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9 };
+	const int SH = 16;
+	const size_t stride = SH + 2 * (size_t)s->P;
+	CUDA_TRY(s->values.ensure(C * stride));
+	// chain-level entries: gathered into a small pinned staging block so that the copy is asynchronous
+	if (s->h_shared_n < C * SH) {
+		if (s->h_shared) cudaFreeHost(s->h_shared);
+		s->h_shared = nullptr;
+		CUDA_TRY(cudaMallocHost((void**)&s->h_shared, sizeof(double) * C * SH));
+		s->h_shared_n = C * SH;
+	}
+	for (size_t c = 0; c < C; c++)
+		for (int k = 0; k < SH; k++) s->h_shared[c * SH + k] = (k < SV_COUNT && h->ix[k] < h->nvar) ? values[c * num_variables + h->ix[k]] : 0.0;
+	CUDA_TRY(cudaMemcpy2DAsync(s->values.p, stride * sizeof(double), s->h_shared, SH * sizeof(double), SH * sizeof(double), C,
+	                           cudaMemcpyHostToDevice, stream));
+	if (s->P > 0) {
+		const double* src = values + h->npk + 2 + 2 * (size_t)s->offset;
+		CUDA_TRY(cudaMemcpy2DAsync(s->values.p + SH, stride * sizeof(double), src, num_variables * sizeof(double),
+		                           2 * (size_t)s->P * sizeof(double), C, cudaMemcpyHostToDevice, stream));
+	}
+	CUDA_TRY(cudaEventRecord(s->ev0, stream));
+	int rc = launch_shard(h, s, C, s->values.p, (long long)stride, SH, cix, d_partial, stream);
+	if (rc != BCM3B200_OK) return rc;
+	CUDA_TRY(cudaEventRecord(s->ev1, stream));
+	return BCM3B200_OK;
+}
+
 int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variables, const double* values, double* logp, int* status)
 {
 	Handle* h = (Handle*)handle;
@@ -471,20 +557,9 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
 	if (C == 0) return BCM3B200_OK;
 	h->last_launches = 0;
 
-	// compact per-shard layout of the batch: [C][16 + 2 * P_shard]: chain-level entries first, then this
-	// shard's per-patient probabilities; one strided H2D copy per shard
-	static const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9 };
-	const int SH = 16;
-	std::vector<double> shared(C * SH, 0.0);
-	for (size_t c = 0; c < C; c++)
-		for (int k = 0; k < SV_COUNT; k++) {
-			if (h->ix[k] < h->nvar) shared[c * SH + k] = values[c * num_variables + h->ix[k]];
-		}
 	for (auto& sp : h->shards) {
 		Shard* s = sp.get();
 		CUDA_TRY(cudaSetDevice(s->device));
-		const size_t stride = SH + 2 * (size_t)s->P;
-		CUDA_TRY(s->values.ensure(C * stride));
 		CUDA_TRY(s->partial.ensure(3 * C));
 		if (s->h_partial_n < 3 * C) {
 			if (s->h_partial) cudaFreeHost(s->h_partial);
@@ -492,17 +567,8 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
 			CUDA_TRY(cudaMallocHost((void**)&s->h_partial, sizeof(double) * 3 * C));
 			s->h_partial_n = 3 * C;
 		}
-		CUDA_TRY(cudaMemcpy2DAsync(s->values.p, stride * sizeof(double), shared.data(), SH * sizeof(double), SH * sizeof(double), C,
-		                           cudaMemcpyHostToDevice, s->stream));
-		if (s->P > 0) {
-			const double* src = values + h->npk + 2 + 2 * (size_t)s->offset;
-			CUDA_TRY(cudaMemcpy2DAsync(s->values.p + SH, stride * sizeof(double), src, num_variables * sizeof(double),
-			                           2 * (size_t)s->P * sizeof(double), C, cudaMemcpyHostToDevice, s->stream));
-		}
-		CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-		rc = launch_shard(h, s, C, s->values.p, (long long)stride, SH, cix, s->partial.p, s->stream);
+		rc = upload_and_launch(h, s, C, num_variables, values, s->partial.p, s->stream);
 		if (rc != BCM3B200_OK) return rc;
-		CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
 		CUDA_TRY(cudaMemcpyAsync(s->h_partial, s->partial.p, sizeof(double) * 3 * C, cudaMemcpyDeviceToHost, s->stream));
 	}
 	// combine the shards in patient order
@@ -522,13 +588,26 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
 		}
 	}
 	h->last_kernel_ms = max_ms;
-	if (h->shard_count > 1) {
-		// partial of this handle's slice: report the slice-local outcome (see header)
-		combine(C, total.data(), logp, status);
-	} else {
-		combine(C, total.data(), logp, status);
-	}
+	combine(C, total.data(), logp, status);
 	h->num_evaluations += (int64_t)C;
+	return BCM3B200_OK;
+}
+
+int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables, const double* values, double* d_partial, void* stream)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
+	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
+	int rc = finalize(h);
+	if (rc != BCM3B200_OK) return rc;
+	if (h->shards.size() != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "device-buffer entries need device_count == 1");
+	if (num_chains == 0) return BCM3B200_OK;
+	Shard* s = h->shards[0].get();
+	CUDA_TRY(cudaSetDevice(s->device));
+	h->last_launches = 0;
+	rc = upload_and_launch(h, s, num_chains, num_variables, values, d_partial, (cudaStream_t)stream);
+	if (rc != BCM3B200_OK) return rc;
+	h->num_evaluations += (int64_t)num_chains;
 	return BCM3B200_OK;
 }
 

@@ -1,0 +1,99 @@
+"""One process per GPU: patients sharded across ranks, per-chain partials combined with an all-reduce.
+
+The path shards naturally: given a chain's parameter vector every patient is independent, so
+rank g owns a contiguous slice of the patients for ALL chains and the only exchange is the reduction of the
+[3][C] partial block (bcm3b200.h): SUM of the finite per-patient terms, MIN of the first -inf / first NaN patient
+index.  Over NCCL that is two tiny all-reduces on the device, stream-ordered right behind the reduction kernel;
+the combination rule then reproduces the reference's serial loop (LikelihoodPopPKTrajectory.cpp:427-440)
+independently of the number of ranks.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(num_patients: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous balanced slice [lo, hi) of rank `rank` -- the same formula as the C ABI (bcm3b200.cu finalize)."""
+    lo = num_patients * rank // world_size
+    hi = num_patients * (rank + 1) // world_size
+    return lo, hi
+
+
+def combine_partials(partial: np.ndarray):
+    """partial[3][C] -> (logp[C], status[C]); numpy twin of bcm3b200_combine_partials for host-only use."""
+    s, first_inf, first_nan = partial[0], partial[1], partial[2]
+    logp = np.where(first_nan < first_inf, np.nan, np.where(np.isfinite(first_inf), -np.inf, s))
+    return logp, np.isnan(logp).astype(np.int32)
+
+
+def partial_from_patient_ll(patient_ll: np.ndarray, offset: int) -> np.ndarray:
+    """[C][P_shard] per-patient log-likelihoods -> the [3][C] partial block a shard contributes."""
+    ll = np.asarray(patient_ll, dtype=np.float64)
+    C, P = ll.shape
+    idx = (offset + np.arange(P, dtype=np.float64))[None, :]
+    nan = np.isnan(ll) | (ll == np.inf)
+    ninf = ll == -np.inf
+    fin = ~(nan | ninf)
+    out = np.empty((3, C))
+    out[0] = np.where(fin, ll, 0.0).sum(axis=1)
+    out[1] = np.where(ninf, idx, np.inf).min(axis=1, initial=np.inf)
+    out[2] = np.where(nan, idx, np.inf).min(axis=1, initial=np.inf)
+    return out
+
+
+def allreduce_partial(partial, group=None):
+    """In-place all-reduce of a torch tensor [3][C]: SUM on row 0, MIN on rows 1-2 (NCCL on device, gloo on host)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return partial
+    dist.all_reduce(partial[0], op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(partial[1:], op=dist.ReduceOp.MIN, group=group)
+    return partial
+
+
+class ShardedPopPKLikelihood:
+    """Rank-local GPU evaluator + the cross-rank reduction. Every rank ends up with the same logp[C]
+    (so the host-side, deterministic proposal / swap logic can run replicated)."""
+
+    def __init__(self, problem, rank: int, world_size: int, device: int, group=None, block_size: int = 0):
+        import torch
+
+        from .poppk import PopPKEvaluator
+
+        self.torch = torch
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.device = torch.device("cuda", device)
+        self.evaluator = PopPKEvaluator(problem, device=device, shard_rank=rank, shard_count=world_size, block_size=block_size)
+        self.nvar = problem.num_variables
+        self._partial = None
+        self._h_partial = None
+
+    def _buffers(self, C: int):
+        torch = self.torch
+        if self._partial is None or self._partial.shape[1] != C:
+            self._partial = torch.empty((3, C), dtype=torch.float64, device=self.device)
+            self._h_partial = torch.empty((3, C), dtype=torch.float64, pin_memory=True)
+        return self._partial, self._h_partial
+
+    def enqueue(self, values_host):
+        """values_host: torch CPU tensor [C][nvar] float64 (pinned for an asynchronous copy). Returns the device
+        partial after the all-reduce; nothing is synchronised."""
+        torch = self.torch
+        C = values_host.shape[0]
+        partial, _ = self._buffers(C)
+        stream = torch.cuda.current_stream(self.device)
+        self.evaluator.enqueue(values_host.data_ptr(), C, self.nvar, partial.data_ptr(), stream.cuda_stream)
+        allreduce_partial(partial, self.group)
+        return partial
+
+    def evaluate(self, values_host):
+        """Full end-to-end call: H2D of this rank's slice, kernels, all-reduce, D2H, combination."""
+        partial = self.enqueue(values_host)
+        _, h = self._buffers(values_host.shape[0])
+        h.copy_(partial, non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return combine_partials(h.numpy())
+
+    def close(self):
+        self.evaluator.close()

@@ -90,6 +90,11 @@ class PopPKEvaluator:
         _lib.check(self.lib.bcm3b200_evaluate_batch_device(self.handle, nC, nvar, d_values_ptr, d_partial_ptr, stream or None))
         self._last_C = nC
 
+    def enqueue(self, values_ptr: int, nC: int, nvar: int, d_partial_ptr: int, stream: int = 0) -> None:
+        """HOST values (ideally pinned) in, DEVICE partial [3][C] out, asynchronous on `stream`."""
+        _lib.check(self.lib.bcm3b200_enqueue_batch(self.handle, nC, nvar, values_ptr, d_partial_ptr, stream or None))
+        self._last_C = nC
+
     def combine_partials(self, partial: np.ndarray):
         partial = np.ascontiguousarray(partial, dtype=np.float64)
         nC = partial.shape[1]

@@ -63,6 +63,8 @@ def exact_linear_pk(pk_type, ka, kex, kel, kf, kb, dose, dosing_interval, times,
     (optionally masked by give_dose[P, ndoses]).  Returns [P, T].
     """
     P = ka.shape[0]
+    if P == 0:
+        return np.zeros((0, np.asarray(times).shape[0]))
     N = 2 if pk_type == PK_ONE else 3
     A = np.zeros((P, N, N))
     A[:, 0, 0] = -(ka + kex)

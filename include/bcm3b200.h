@@ -87,6 +87,14 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
 int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_variables, const double* d_values,
                                    double* d_partial, void* stream);
 
+/* HOST values in, DEVICE partial out, enqueued on `stream` without synchronising: copies only this handle's slice of
+ * the batch (chain-level entries + its patients' probabilities) host->device, then runs the kernels.
+ * `values` should be page-locked (bcm3b200_host_alloc) for the copy to overlap; it must stay untouched until the
+ * stream has passed the copy. d_partial as in bcm3b200_evaluate_batch_device. This is the entry the
+ * one-process-per-GPU launch uses: enqueue, NCCL all-reduce d_partial, read back 3*C doubles. */
+int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables, const double* values, double* d_partial,
+                           void* stream);
+
 /* partial [3][num_chains] (host) -> logp[num_chains], status[num_chains] (may be NULL) */
 int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* logp, int* status);
 
@@ -113,6 +121,10 @@ void bcm3b200_destroy(void* handle);
  * with asynchronous DMA instead of staging pageable memory. Plain malloc'ed buffers work too, only slower. */
 void* bcm3b200_host_alloc(size_t bytes);
 void bcm3b200_host_free(void* p);
+
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (dependent-chain-free DFMA microbenchmark, best of 5 after one
+ * warm-up): the denominator of the FP64 roofline fraction reported by bench.py. */
+int bcm3b200_measure_fp64_peak(int device, double* tflops);
 
 /* text of the last error raised on the calling thread ("" if none) */
 const char* bcm3b200_last_error(void);

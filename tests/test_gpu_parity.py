@@ -1,0 +1,200 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the golden vectors of the compiled reference,
+against the CPU checker on fresh seeded inputs, and through size-independent properties at BASELINE.json's full sizes.
+
+The bar (BASELINE.json north_star): relative error <= 1e-6 on every per-chain log-likelihood at matched rtol/atol."""
+import numpy as np
+import pytest
+
+from bcm3_b200 import synthetic as syn
+from bcm3_b200.poppk_data import PK_ONE, PK_TWO, PopPKProblem
+from tests.util import GOLDEN_NAMES, assert_matches_golden, counter_match_floor, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+LOGP_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def Evaluator(built):
+    from bcm3_b200 import _lib
+    from bcm3_b200.poppk import PopPKEvaluator
+
+    assert _lib.device_count() > 0, "no CUDA device: the GPU suite must run on the B200 box"
+    return PopPKEvaluator
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_matches_reference_golden(Evaluator, name):
+    prob, gold = load_golden(name)
+    ev = Evaluator(prob, diagnostics=True)
+    logp, status = ev.evaluate(gold["values"])
+    d = ev.diagnostics()
+    ev.close()
+    assert (status == 0).all()
+    assert_matches_golden(logp, d["conc"], d["counters"], gold, logp_tol=LOGP_RTOL, min_counter_match=counter_match_floor(name))
+    assert (np.isneginf(d["patient_ll"]) == np.isneginf(gold["patient_ll"])).all()
+    m = ~np.isnan(gold["conc"])
+    rel = rel_err(d["conc"][m], gold["conc"][m])
+    assert np.median(rel) < 1e-9
+    assert (rel > 1e-6).mean() < 1.5 * (1.0 - counter_match_floor(name))
+
+
+@pytest.mark.parametrize("pk,het,seed", [(PK_ONE, False, 101), (PK_ONE, True, 102), (PK_TWO, False, 103), (PK_TWO, True, 104)])
+def test_matches_cpu_checker_on_seeded_inputs(Evaluator, port, pk, het, seed):
+    prob = syn.make_poppk_problem(pk, P=777, T=9, t_end=96.0, heterogeneous=het, missing_fraction=0.1 if het else 0.0, seed=seed)
+    vals = syn.make_chain_values(prob, 5, seed=seed)
+    ev = Evaluator(prob, diagnostics=True)
+    logp, status = ev.evaluate(vals)
+    d = ev.diagnostics()
+    ev.close()
+    want = port.poppk_evaluate(prob, vals, threads=4, want_counters=True, want_patient_ll=True)
+    assert rel_err(logp, want["logp"]).max() <= LOGP_RTOL
+    same = (d["counters"].astype(np.int64) == want["counters"]).all(axis=2).mean()
+    assert same >= 0.97
+    # the sum the kernels reduce equals the sum of the per-patient terms they report
+    assert rel_err(logp, d["patient_ll"].sum(axis=1)).max() < 1e-12
+
+
+@pytest.mark.parametrize("block", [32, 64, 128, 256])
+def test_block_size_does_not_change_results(Evaluator, block):
+    prob, gold = load_golden("poppk_two_hetero")
+    ev = Evaluator(prob, block_size=block)
+    logp, _ = ev.evaluate(gold["values"])
+    ev.close()
+    assert rel_err(logp, gold["logp"]).max() <= LOGP_RTOL
+
+
+def test_edge_cases(Evaluator, port):
+    # empty trial, single patient, ragged sizes that do not fill a warp, timepoint at t = 0, all-missing observations
+    for P in (0, 1, 31, 33):
+        prob = syn.make_poppk_problem(PK_ONE, P=P, T=5, t_end=48.0, seed=7)
+        if P > 1:
+            prob.trial.time[0] = 0.0
+            prob.trial.observed_concentration[1, :] = np.nan
+            prob = PopPKProblem(pk_type=prob.pk_type, trial=prob.trial, transforms=prob.transforms, sd_ix=prob.sd_ix)
+        vals = syn.make_chain_values(prob, 3, seed=P)
+        ev = Evaluator(prob)
+        logp, status = ev.evaluate(vals)
+        ev.close()
+        want = port.poppk_evaluate(prob, vals)["logp"]
+        assert rel_err(logp, want).max() <= LOGP_RTOL, P
+        assert (status == 0).all()
+
+
+def test_nan_and_minus_infinity_semantics(Evaluator, port):
+    """A failed solve gives -inf (cpp:400-408); a NaN log-likelihood is flagged (Sampler.cpp:172-178); a NaN that the
+    reference's serial loop never reaches (it breaks at the first -inf, cpp:438) must not surface."""
+    from tests.util import make_nan_inf_case
+
+    prob, vals = make_nan_inf_case()
+    want = port.poppk_evaluate(prob, vals)["logp"]
+    assert want[0] == -np.inf and want[1] == -np.inf and np.isnan(want[2])
+    for block in (32, 64):
+        ev = Evaluator(prob, block_size=block)
+        logp, status = ev.evaluate(vals)
+        ev.close()
+        assert logp[0] == -np.inf and logp[1] == -np.inf and np.isnan(logp[2])
+        assert status.tolist() == [0, 0, 1]
+
+
+def test_chain_independence_and_determinism(Evaluator):
+    prob = syn.make_poppk_problem(PK_TWO, P=500, T=10, t_end=72.0, seed=21)
+    vals = syn.make_chain_values(prob, 6, seed=21)
+    ev = Evaluator(prob, block_size=64)
+    a, _ = ev.evaluate(vals)
+    b, _ = ev.evaluate(vals)
+    single = np.array([ev.evaluate(vals[c:c + 1])[0][0] for c in range(6)])
+    rev, _ = ev.evaluate(vals[::-1].copy())
+    ev.close()
+    assert np.array_equal(a, b)                # run-to-run bit-identical (fixed reduction order)
+    assert np.array_equal(a, single)           # a chain's result does not depend on its batch
+    assert np.array_equal(a, rev[::-1])
+
+
+def test_shards_add_up(Evaluator):
+    """Contiguous patient shards (what each rank of a multi-GPU run owns) recombine to the unsharded result."""
+    from bcm3_b200.parallel import combine_partials
+
+    prob = syn.make_poppk_problem(PK_ONE, P=1000, T=10, t_end=72.0, heterogeneous=True, seed=31)
+    vals = syn.make_chain_values(prob, 4, seed=31)
+    full = Evaluator(prob)
+    want, _ = full.evaluate(vals)
+    full.close()
+    import torch
+
+    total = None
+    for r in range(3):
+        ev = Evaluator(prob, shard_rank=r, shard_count=3)
+        d_vals = torch.from_numpy(vals).cuda()
+        d_partial = torch.empty((3, 4), dtype=torch.float64, device="cuda")
+        ev.evaluate_device(d_vals.data_ptr(), 4, prob.num_variables, d_partial.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        p = d_partial.cpu().numpy()
+        # the host-values entry must give the same partial as the device-values entry
+        pinned = torch.from_numpy(vals).pin_memory()
+        d_partial2 = torch.empty_like(d_partial)
+        ev.enqueue(pinned.data_ptr(), 4, prob.num_variables, d_partial2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(p, d_partial2.cpu().numpy())
+        ev.close()
+        total = p if total is None else np.stack([total[0] + p[0], np.minimum(total[1], p[1]), np.minimum(total[2], p[2])])
+    got, status = combine_partials(total)
+    assert rel_err(got, want).max() < 1e-13
+
+
+@pytest.mark.parametrize("pk,P,C", [(PK_ONE, 1000, 16), (PK_TWO, 100000, 64)])
+def test_full_size_properties(Evaluator, port, pk, P, C):
+    """BASELINE.json configs 2 and 5 at full size: (i) a random subsample of patients, evaluated alone by the CPU
+    checker, reproduces the per-patient terms; (ii) permuting the patients permutes nothing but the summation order;
+    (iii) the simulated concentrations stay within CVODE's own accuracy of the exact solution of the linear model."""
+    prob = syn.make_poppk_problem(pk, P=P, T=10, t_end=72.0, seed=1)
+    vals = syn.make_chain_values(prob, C)
+    diag = P * C <= 2_000_000
+    ev = Evaluator(prob, diagnostics=diag)
+    logp, status = ev.evaluate(vals)
+    assert (status == 0).all() and np.isfinite(logp).all()
+
+    # (ii) permutation of patients (observations, dosing data and per-patient variables move together)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(P)
+    tr = prob.trial
+    npk = 4 if pk == PK_ONE else 6
+    tr2 = type(tr)(drug=tr.drug, time=tr.time, observed_concentration=tr.observed_concentration[perm], dose=tr.dose[perm],
+                   dosing_interval=tr.dosing_interval[perm], dose_after_dose_change=tr.dose_after_dose_change[perm],
+                   dose_change_time=tr.dose_change_time[perm], intermittent=tr.intermittent[perm],
+                   treatment_interruptions=tr.treatment_interruptions[perm])
+    prob2 = PopPKProblem(pk_type=pk, trial=tr2, transforms=prob.transforms, sd_ix=prob.sd_ix)
+    vals2 = vals.copy()
+    pp = vals[:, npk + 2:npk + 2 + 2 * P].reshape(C, P, 2)
+    vals2[:, npk + 2:npk + 2 + 2 * P] = pp[:, perm, :].reshape(C, 2 * P)
+    ev2 = Evaluator(prob2, diagnostics=diag)  # same kernel instantiation as `ev`
+    logp2, _ = ev2.evaluate(vals2)
+    ev2.close()
+    assert rel_err(logp2, logp).max() < 1e-11
+
+    # (i) subsample against the CPU checker
+    sub = np.sort(rng.choice(P, size=min(P, 400), replace=False))
+    trs = type(tr)(drug=tr.drug, time=tr.time, observed_concentration=tr.observed_concentration[sub], dose=tr.dose[sub],
+                   dosing_interval=tr.dosing_interval[sub], dose_after_dose_change=tr.dose_after_dose_change[sub],
+                   dose_change_time=tr.dose_change_time[sub], intermittent=tr.intermittent[sub],
+                   treatment_interruptions=tr.treatment_interruptions[sub])
+    ns = len(sub)
+    nvs = npk + 2 * (ns + 1) + 2
+    probs = PopPKProblem(pk_type=pk, trial=trs, transforms=syn.poppk_transforms(pk, ns), sd_ix=nvs - 2)
+    # the tolerances depend on the minimum dose of the trial, identical here (constant dose)
+    assert probs.atol == prob.atol
+    cs = [0, C - 1]
+    vs = np.empty((len(cs), nvs))
+    vs[:, :npk + 2] = vals[cs, :npk + 2]
+    vs[:, npk + 2:npk + 2 + 2 * ns] = pp[cs][:, sub, :].reshape(len(cs), 2 * ns)
+    vs[:, nvs - 2:] = vals[cs, -2:]
+    want = port.poppk_evaluate(probs, vs, threads=4, want_patient_ll=True)
+    evs = Evaluator(probs)
+    got, _ = evs.evaluate(vs)
+    evs.close()
+    assert rel_err(got, want["logp"]).max() <= LOGP_RTOL
+    if diag:
+        d = ev.diagnostics()
+        assert np.abs(d["patient_ll"][cs][:, sub] - want["patient_ll"]).max() < 1e-2
+        assert rel_err(d["patient_ll"][cs][:, sub].sum(axis=1), want["logp"]).max() <= LOGP_RTOL
+    ev.close()

@@ -1,0 +1,76 @@
+"""Shared helpers of the test-suite."""
+import glob
+import os
+
+import numpy as np
+
+from bcm3_b200.poppk_data import PopPKProblem, PopPKTrial
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "poppk_*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    trial = PopPKTrial(
+        drug=str(z["drug"]), time=z["time"], observed_concentration=z["observed_concentration"], dose=z["dose"],
+        dosing_interval=z["dosing_interval"], dose_after_dose_change=z["dose_after_dose_change"],
+        dose_change_time=z["dose_change_time"], intermittent=z["intermittent"],
+        treatment_interruptions=z["treatment_interruptions"])
+    prob = PopPKProblem(pk_type=int(z["pk_type"]), trial=trial, transforms=z["transforms"], sd_ix=int(z["sd_ix"]))
+    return prob, {k: z[k] for k in ("values", "logp", "conc", "patient_ll", "counters")}
+
+
+def rel_err(a, b):
+    """Relative error that treats equal infinities / NaN patterns as exact."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    out = np.zeros_like(a)
+    fin = np.isfinite(a) & np.isfinite(b)
+    out[fin] = np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300)
+    bad = ~fin & ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    out[bad] = np.inf
+    return out
+
+
+def counter_match_floor(name):
+    """Round-off flips a step-size/order decision in roughly 0.5 % of the systems per 300 steps (the same rate is seen
+    between the reference and its own restatement), so long-horizon fixtures get a lower floor."""
+    return 0.90 if name.endswith("maxsteps") else 0.97
+
+
+def assert_matches_golden(got_logp, got_conc, got_counters, gold, logp_tol=1e-6, min_counter_match=0.97):
+    """The bar of BASELINE.json: per-chain log-likelihood within 1e-6 relative of the reference's CVODE path.
+    Step counters must coincide for (almost) all systems: equal counters mean the same step-size/order decisions."""
+    assert rel_err(got_logp, gold["logp"]).max() <= logp_tol
+    if got_conc is not None:
+        assert (np.isnan(got_conc) == np.isnan(gold["conc"])).all()
+    if got_counters is not None:
+        same = (np.asarray(got_counters, dtype=np.int64) == gold["counters"]).all(axis=-1)
+        assert same.mean() >= min_counter_match, f"only {same.mean():.3f} of the systems reproduce CVODE's counters"
+
+
+def make_nan_inf_case():
+    """A trial whose three chains end in -inf, -inf and NaN under the reference's serial loop
+    (LikelihoodPopPKTrajectory.cpp:427-440):
+      patient 40: dosing every 2 h over 240 h => exceeds max_steps => patient_logllh = -inf for every chain;
+      patient 5 (dose 1e4) / patient 50 (dose 1e5): with a NEGATIVE proportional sd the Student-t scale
+      sd + sd2*x turns negative for large concentrations => log(negative) = NaN.
+    chain 0: sd2 > 0            -> -inf
+    chain 1: sd2 = -0.002       -> NaN only at patient 50, after the -inf patient: never reached -> -inf
+    chain 2: sd2 = -0.01        -> NaN at patient 5, before the -inf patient -> NaN (the sampler aborts on it)"""
+    from bcm3_b200 import synthetic as syn
+    from bcm3_b200.poppk_data import PK_ONE, TRANSFORM_NONE
+
+    prob = syn.make_poppk_problem(PK_ONE, P=61, T=6, t_end=240.0, seed=77)
+    tr = prob.trial
+    tr.dosing_interval[40] = 2.0
+    tr.dose[5] = 1e4
+    tr.dose[50] = 1e5
+    transforms = prob.transforms.copy()
+    transforms[prob.sd_ix + 1] = TRANSFORM_NONE
+    prob = PopPKProblem(pk_type=PK_ONE, trial=tr, transforms=transforms, sd_ix=prob.sd_ix)
+    vals = syn.make_chain_values(prob, 3, seed=77)
+    vals[:, prob.sd_ix] = 3.0
+    vals[:, prob.sd_ix + 1] = [0.2, -0.002, -0.01]
+    return prob, vals
