@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libbcm3b200.so")
+LIB_PATH = os.environ.get("BCM3B200_LIB", os.path.join(PKG_DIR, "libbcm3b200.so"))  # override: kernel build experiments
 
 # every symbol declared in include/bcm3b200.h
 EXPORTS = [

@@ -157,10 +157,13 @@ int get_int(const std::map<std::string, std::string>& kv, const char* key, int d
 int pick_block_size(const Handle& h, const Shard& s, size_t C)
 {
 	if (h.block_size) return h.block_size;
-	// keep >= 2 blocks per SM when the batch is small, otherwise 128 threads (4 warps) per block
+	// Large batches: 256 threads = 8 warps per block, one block per SM at 255 registers per thread; the warps of a
+	// block run the integrator in lock-step (BCM3_BLOCK_LOCKSTEP) and share instruction fetches. Small batches are
+	// latency-bound: spread them over as many SMs as possible with small blocks.
 	int dev_sms = 148;
 	cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s.device);
 	size_t threads = (size_t)s.P * C;
+	if (threads >= (size_t)dev_sms * 2 * 256) return 256;
 	if (threads >= (size_t)dev_sms * 2 * 128) return 128;
 	if (threads >= (size_t)dev_sms * 2 * 64) return 64;
 	return 32;
@@ -676,7 +679,7 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 	if (!h || !name) return fail(BCM3B200_ERR_ARG, "null argument");
 	if (!strcmp(name, "diagnostics")) h->diagnostics = value != 0;
 	else if (!strcmp(name, "block_size")) {
-		if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256) return fail(BCM3B200_ERR_ARG, "block_size must be 0, 32, 64, 128 or 256");
+		if (value != 0 && (value < 32 || value > 1024 || value % 32 != 0)) return fail(BCM3B200_ERR_ARG, "block_size must be 0 or a multiple of 32 up to 1024");
 		h->block_size = (int)value;
 	} else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
 	return BCM3B200_OK;

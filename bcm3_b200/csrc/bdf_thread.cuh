@@ -103,11 +103,23 @@ struct BdfCounters {
 	int nfe, nsetups, nje, netf, ncfn, nni;
 };
 
-__device__ __forceinline__ double bdf_rpower_r(double base, double exponent)
+#ifndef BCM3_ROOT_INLINE
+#define BCM3_ROOT_INLINE __noinline__
+#endif
+// SUNRpowerR(base, 1/k) for k = 1..6 (sundials_math.c): the k-th root in CVODE's step-size formulas.
+// Evaluated as exp(log(base) / k) with the correctly rounded constant 1/k instead of pow(): a few ulp from pow's
+// result, i.e. the same size as the FMA-contraction differences between two builds of the reference itself, and
+// several times cheaper than the generic double-precision pow on the GPU.
+__device__ BCM3_ROOT_INLINE double bdf_root(double base, int k)
 {
-	// SUNRpowerR, sundials_math.c
 	if (base <= 0.0) return 0.0;
-	return pow(base, exponent);
+	double inv = 1.0;
+	inv = (k == 2) ? (1.0 / 2.0) : inv;
+	inv = (k == 3) ? (1.0 / 3.0) : inv;
+	inv = (k == 4) ? (1.0 / 4.0) : inv;
+	inv = (k == 5) ? (1.0 / 5.0) : inv;
+	inv = (k == 6) ? (1.0 / 6.0) : inv;
+	return exp(log(base) * inv);
 }
 
 template <int N, class Model, bool STATS>
@@ -140,7 +152,7 @@ struct BdfThread {
 			double p = x[i] * ewt[i];
 			sum += p * p;
 		}
-		return sqrt(sum / N);
+		return sqrt(sum * (1.0 / N));
 	}
 
 	// cvEwtSetSV, cvode.c:4268-4295 (atol > 0 so no N_VMin test)
@@ -464,7 +476,7 @@ struct BdfThread {
 	}
 
 	// One pass of cvStep's attempt loop.
-	__device__ __forceinline__ int attempt(const Model& model)
+	__device__ __forceinline__ int attempt(const Model& model, unsigned mask)
 	{
 		// l[] and tq[] never outlive one attempt: cvSetBDF rewrites l[0..q], tq[2], tq[4], tq[5] every time and
 		// tq[1], tq[3] are written (qwait == 1) in the same step that reads them (qwait == 0 after cvCompleteStep)
@@ -568,7 +580,10 @@ struct BdfThread {
 		}
 
 		// ---- cvNls / Newton ----
-		int nls_ret; // 0 ok, 1 recoverable convergence failure
+		// Both loops below are made warp-uniform with votes over `mask` (the lanes that entered this attempt):
+		// every lane stays in a loop until no lane needs another trip, so the warp is converged again when the
+		// loop ends and the step-completion code that follows runs once for all lanes, not once per exit path.
+		int nls_ret = 1; // 0 ok, 1 recoverable convergence failure
 		{
 			int convfail = ((nflag == BDF_FIRST_CALL) || (nflag == BDF_PREV_ERR_FAIL)) ? BDF_NO_FAILURES : BDF_FAIL_OTHER;
 			bool callSetup = (nflag == BDF_PREV_CONV_FAIL) || (nflag == BDF_PREV_ERR_FAIL) || (nst == 0) ||
@@ -577,76 +592,16 @@ struct BdfThread {
 			for (int i = 0; i < N; i++) acor[i] = 0.0;
 			const double tol = tq[4];
 			bool jbad = false;
+			bool need_pass = true;
 #pragma unroll 1
 			for (;;) {
-				double y[N], f[N], delta[N];
-				// cvNlsResidual
+				if (!__any_sync(mask, need_pass)) break;
+				double delta[N];
 #pragma unroll
-				for (int i = 0; i < N; i++) y[i] = zn[0][i] + acor[i];
-				model.rhs(tn, y, f);
-				if (STATS) cnt.nfe++;
-#pragma unroll
-				for (int i = 0; i < N; i++) delta[i] = rl1 * zn[1][i] + acor[i];
-#pragma unroll
-				for (int i = 0; i < N; i++) delta[i] += -gamma * f[i];
-
-				if (callSetup) {
-					// cvNlsLSetup + cvLsSetup
-					if (jbad) convfail = BDF_FAIL_BAD_J;
-					double dgamma = fabs((gamma / gammap) - 1.0);
-					bool jb = (nst == 0) || (nst > nstlj + BDF_MSBJ) || ((convfail == BDF_FAIL_BAD_J) && (dgamma < BDF_LS_DGMAX)) ||
-					          (convfail == BDF_FAIL_OTHER);
-					if (jb) {
-						nstlj = nst;
-						if (STATS) cnt.nje++;
-					}
-					linear_setup(model);
-					if (STATS) cnt.nsetups++;
-					nls_jcur = jb;
-					gamrat = 1.0;
-					gammap = gamma;
-					crate = 1.0;
-					nstlp = nst;
-				}
-
-				nls_ret = 1;
-#pragma unroll 1
-				for (int m = 0; m < BDF_NLS_MAXCOR; m++) {
-					if (STATS) cnt.nni++;
-					// delta <- A^-1 (-delta), scaled for a changed gamma (cvLsSolve)
-					double b[N];
-#pragma unroll
-					for (int i = 0; i < N; i++) b[i] = -delta[i];
-#pragma unroll
-					for (int i = 0; i < N; i++) {
-						double s = Minv[i * N + 0] * b[0];
-#pragma unroll
-						for (int j = 1; j < N; j++) s += Minv[i * N + j] * b[j];
-						delta[i] = s;
-					}
-					if (gamrat != 1.0) {
-						double sc = 2.0 / (1.0 + gamrat);
-#pragma unroll
-						for (int i = 0; i < N; i++) delta[i] *= sc;
-					}
-#pragma unroll
-					for (int i = 0; i < N; i++) acor[i] += delta[i];
-
-					// cvNlsConvTest
-					double del = wrms(delta);
-					if (m > 0) crate = fmax(BDF_CRDOWN * crate, del / delp);
-					double dcon = del * fmin(1.0, crate) / tol;
-					if (dcon <= 1.0) {
-						acnrm = (m == 0) ? del : wrms(acor);
-						nls_jcur = false;
-						nls_ret = 0;
-						break;
-					}
-					if ((m >= 1) && (del > BDF_RDIV * delp)) break;
-					delp = del;
-					if (m + 1 >= BDF_NLS_MAXCOR) break;
-
-					// next residual
+				for (int i = 0; i < N; i++) delta[i] = 0.0;
+				if (need_pass) {
+					// cvNlsResidual
+					double y[N], f[N];
 #pragma unroll
 					for (int i = 0; i < N; i++) y[i] = zn[0][i] + acor[i];
 					model.rhs(tn, y, f);
@@ -655,171 +610,253 @@ struct BdfThread {
 					for (int i = 0; i < N; i++) delta[i] = rl1 * zn[1][i] + acor[i];
 #pragma unroll
 					for (int i = 0; i < N; i++) delta[i] += -gamma * f[i];
+
+					if (callSetup) {
+						// cvNlsLSetup + cvLsSetup
+						if (jbad) convfail = BDF_FAIL_BAD_J;
+						double dgamma = fabs((gamma / gammap) - 1.0);
+						bool jb = (nst == 0) || (nst > nstlj + BDF_MSBJ) || ((convfail == BDF_FAIL_BAD_J) && (dgamma < BDF_LS_DGMAX)) ||
+						          (convfail == BDF_FAIL_OTHER);
+						if (jb) {
+							nstlj = nst;
+							if (STATS) cnt.nje++;
+						}
+						linear_setup(model);
+						if (STATS) cnt.nsetups++;
+						nls_jcur = jb;
+						gamrat = 1.0;
+						gammap = gamma;
+						crate = 1.0;
+						nstlp = nst;
+					}
 				}
-				if (nls_ret == 0) break;
-				if (!nls_jcur) {
-					// stale Jacobian data: redo with a forced setup (sunnonlinsol_newton.c:301-312)
-					callSetup = true;
-					jbad = true;
+
+				bool iter = need_pass;
+#pragma unroll 1
+				for (int m = 0; m < BDF_NLS_MAXCOR; m++) {
+					if (!__any_sync(mask, iter)) break;
+					if (iter) {
+						if (STATS) cnt.nni++;
+						// delta <- A^-1 (-delta), scaled for a changed gamma (cvLsSolve)
+						double b[N];
 #pragma unroll
-					for (int i = 0; i < N; i++) acor[i] = 0.0;
-					continue;
+						for (int i = 0; i < N; i++) b[i] = -delta[i];
+#pragma unroll
+						for (int i = 0; i < N; i++) {
+							double sx = Minv[i * N + 0] * b[0];
+#pragma unroll
+							for (int j = 1; j < N; j++) sx += Minv[i * N + j] * b[j];
+							delta[i] = sx;
+						}
+						if (gamrat != 1.0) {
+							double sc = 2.0 / (1.0 + gamrat);
+#pragma unroll
+							for (int i = 0; i < N; i++) delta[i] *= sc;
+						}
+#pragma unroll
+						for (int i = 0; i < N; i++) acor[i] += delta[i];
+
+						// cvNlsConvTest
+						double del = wrms(delta);
+						if (m > 0) crate = fmax(BDF_CRDOWN * crate, del / delp);
+						double dcon = del * fmin(1.0, crate) / tol;
+						if (dcon <= 1.0) {
+							acnrm = (m == 0) ? del : wrms(acor);
+							nls_jcur = false;
+							nls_ret = 0;
+							iter = false;
+						} else if ((m >= 1) && (del > BDF_RDIV * delp)) {
+							iter = false;
+						} else {
+							delp = del;
+							if (m + 1 >= BDF_NLS_MAXCOR) {
+								iter = false;
+							} else {
+								// next residual
+								double y[N], f[N];
+#pragma unroll
+								for (int i = 0; i < N; i++) y[i] = zn[0][i] + acor[i];
+								model.rhs(tn, y, f);
+								if (STATS) cnt.nfe++;
+#pragma unroll
+								for (int i = 0; i < N; i++) delta[i] = rl1 * zn[1][i] + acor[i];
+#pragma unroll
+								for (int i = 0; i < N; i++) delta[i] += -gamma * f[i];
+							}
+						}
+					}
 				}
-				break;
+
+				if (need_pass) {
+					if (nls_ret == 0 || nls_jcur) {
+						need_pass = false;
+					} else {
+						// stale Jacobian data: redo with a forced setup (sunnonlinsol_newton.c:301-312)
+						callSetup = true;
+						jbad = true;
+#pragma unroll
+						for (int i = 0; i < N; i++) acor[i] = 0.0;
+					}
+				}
 			}
 		}
 
-		// ---- cvHandleNFlag ----
+		int result;
 		if (nls_ret != 0) {
+			// ---- cvHandleNFlag ----
 			if (STATS) cnt.ncfn++;
 			restore();
 			ncf++;
 			etamax = 1.0;
 			// hmin = 0: |h| <= hmin * ONEPSM only for h == 0
-			if ((fabs(h) <= 0.0) || (ncf == BDF_MXNCF)) return BDF_ATTEMPT_FAILED;
-			eta = BDF_ETACF;
-			nflag = BDF_PREV_CONV_FAIL;
-			rescale();
-			return BDF_ATTEMPT_RETRY;
-		}
-
-		// ---- cvDoErrorTest ----
-		double dsm = acnrm * tq[2];
-		if (!(dsm <= 1.0)) {
-			nef++;
-			if (STATS) cnt.netf++;
-			nflag = BDF_PREV_ERR_FAIL;
-			restore();
-			if ((fabs(h) <= 0.0) || (nef == BDF_MXNEF)) return BDF_ATTEMPT_FAILED;
-			etamax = 1.0;
-			if (nef <= BDF_MXNEF1) {
-				eta = 1.0 / (bdf_rpower_r(BDF_BIAS2 * dsm, 1.0 / L) + BDF_ADDON);
-				eta = fmax(BDF_ETAMIN, eta);
-				if (nef >= BDF_SMALL_NEF) eta = fmin(eta, BDF_ETAMXF);
-				rescale();
-				return BDF_ATTEMPT_RETRY;
-			}
-			if (q > 1) {
-				eta = BDF_ETAMIN;
-				adjust_order(-1);
-				L = q;
-				q--;
-				qwait = L;
-				rescale();
-				return BDF_ATTEMPT_RETRY;
-			}
-			eta = BDF_ETAMIN;
-			h *= eta;
-			hscale = h;
-			qwait = BDF_LONG_WAIT;
-			double f[N];
-			model.rhs(tn, zn[0], f);
-			if (STATS) cnt.nfe++;
-#pragma unroll
-			for (int i = 0; i < N; i++) zn[1][i] = h * f[i];
-			return BDF_ATTEMPT_RETRY;
-		}
-
-		// ---- cvCompleteStep ----
-		nst++;
-		hu = h;
-		static_rfor<2, QMAX + 1>([&](auto I) {
-			constexpr int i = decltype(I)::value;
-			if (i <= q) tau[i] = tau[i - 1];
-		});
-		if ((q == 1) && (nst > 1)) tau[2] = tau[1];
-		tau[1] = h;
-		static_for<0, QMAX + 1>([&](auto J) {
-			constexpr int j = decltype(J)::value;
-			if (j <= q) {
-#pragma unroll
-				for (int i = 0; i < N; i++) zn[j][i] += l[j] * acor[i];
-			}
-		});
-		qwait--;
-		if ((qwait == 1) && (q != QMAX)) {
-#pragma unroll
-			for (int i = 0; i < N; i++) zn[QMAX][i] = acor[i];
-			saved_tq5 = tq[5];
-		}
-
-		// ---- cvPrepareNextStep ----
-		if (etamax == 1.0) {
-			qwait = (qwait > 2) ? qwait : 2;
-			qprime = q;
-			hprime = h;
-			eta = 1.0;
-		} else {
-			double etaq = 1.0 / (bdf_rpower_r(BDF_BIAS2 * dsm, 1.0 / L) + BDF_ADDON);
-			if (qwait != 0) {
-				eta = etaq;
-				qprime = q;
+			if ((fabs(h) <= 0.0) || (ncf == BDF_MXNCF)) {
+				result = BDF_ATTEMPT_FAILED;
 			} else {
-				qwait = 2;
-				// cvComputeEtaqm1
-				double etaqm1 = 0.0;
-				if (q > 1) {
-					double znq[N];
+				eta = BDF_ETACF;
+				nflag = BDF_PREV_CONV_FAIL;
+				rescale();
+				result = BDF_ATTEMPT_RETRY;
+			}
+		} else {
+			// ---- cvDoErrorTest ----
+			const double dsm = acnrm * tq[2];
+			if (!(dsm <= 1.0)) {
+				nef++;
+				if (STATS) cnt.netf++;
+				nflag = BDF_PREV_ERR_FAIL;
+				restore();
+				if ((fabs(h) <= 0.0) || (nef == BDF_MXNEF)) {
+					result = BDF_ATTEMPT_FAILED;
+				} else {
+					result = BDF_ATTEMPT_RETRY;
+					etamax = 1.0;
+					if (nef <= BDF_MXNEF1) {
+						eta = 1.0 / (bdf_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+						eta = fmax(BDF_ETAMIN, eta);
+						if (nef >= BDF_SMALL_NEF) eta = fmin(eta, BDF_ETAMXF);
+						rescale();
+					} else if (q > 1) {
+						eta = BDF_ETAMIN;
+						adjust_order(-1);
+						L = q;
+						q--;
+						qwait = L;
+						rescale();
+					} else {
+						eta = BDF_ETAMIN;
+						h *= eta;
+						hscale = h;
+						qwait = BDF_LONG_WAIT;
+						double f[N];
+						model.rhs(tn, zn[0], f);
+						if (STATS) cnt.nfe++;
 #pragma unroll
-					for (int i = 0; i < N; i++) znq[i] = zn[2][i];
-					static_for<3, QMAX + 1>([&](auto J) {
-						constexpr int j = decltype(J)::value;
-						if (j <= q) { // the last j <= q wins: znq = zn[q]
-#pragma unroll
-							for (int i = 0; i < N; i++) znq[i] = zn[j][i];
-						}
-					});
-					double ddn = wrms(znq) * tq[1];
-					etaqm1 = 1.0 / (bdf_rpower_r(BDF_BIAS1 * ddn, 1.0 / q) + BDF_ADDON);
-				}
-				// cvComputeEtaqp1
-				double etaqp1 = 0.0;
-				if (q != QMAX) {
-					if (saved_tq5 != 0.0) {
-						double base = h / tau[2];
-						double pw = 1.0;
-						static_for<1, QMAX + 1>([&](auto I) {
-							if (decltype(I)::value <= L) pw *= base;
-						});
-						double cquot = (tq[5] / saved_tq5) * pw;
-						double tmp[N];
-#pragma unroll
-						for (int i = 0; i < N; i++) tmp[i] = -cquot * zn[QMAX][i] + acor[i];
-						double dup = wrms(tmp) * tq[3];
-						etaqp1 = 1.0 / (bdf_rpower_r(BDF_BIAS3 * dup, 1.0 / (L + 1)) + BDF_ADDON);
+						for (int i = 0; i < N; i++) zn[1][i] = h * f[i];
 					}
 				}
-				// cvChooseEta
-				double etam = fmax(etaqm1, fmax(etaq, etaqp1));
-				if (etam < BDF_THRESH) {
-					eta = 1.0;
-					qprime = q;
-				} else if (etam == etaq) {
-					eta = etaq;
-					qprime = q;
-				} else if (etam == etaqm1) {
-					eta = etaqm1;
-					qprime = q - 1;
-				} else {
-					eta = etaqp1;
-					qprime = q + 1;
+			} else {
+				result = BDF_ATTEMPT_DONE;
+				// ---- cvCompleteStep ----
+				nst++;
+				hu = h;
+				static_rfor<2, QMAX + 1>([&](auto I) {
+					constexpr int i = decltype(I)::value;
+					if (i <= q) tau[i] = tau[i - 1];
+				});
+				if ((q == 1) && (nst > 1)) tau[2] = tau[1];
+				tau[1] = h;
+				static_for<0, QMAX + 1>([&](auto J) {
+					constexpr int j = decltype(J)::value;
+					if (j <= q) {
+#pragma unroll
+						for (int i = 0; i < N; i++) zn[j][i] += l[j] * acor[i];
+					}
+				});
+				qwait--;
+				if ((qwait == 1) && (q != QMAX)) {
 #pragma unroll
 					for (int i = 0; i < N; i++) zn[QMAX][i] = acor[i];
+					saved_tq5 = tq[5];
 				}
-			}
-			// cvSetEta (hmax_inv = 0)
-			if (eta < BDF_THRESH) {
-				eta = 1.0;
-				hprime = h;
-			} else {
-				eta = fmin(eta, etamax);
-				hprime = h * eta;
+
+				// ---- cvPrepareNextStep ----
+				if (etamax == 1.0) {
+					qwait = (qwait > 2) ? qwait : 2;
+					qprime = q;
+					hprime = h;
+					eta = 1.0;
+				} else {
+					const double etaq = 1.0 / (bdf_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+					eta = etaq;
+					qprime = q;
+					if (qwait == 0) {
+						qwait = 2;
+						// cvComputeEtaqm1
+						double etaqm1 = 0.0;
+						if (q > 1) {
+							double znq[N];
+#pragma unroll
+							for (int i = 0; i < N; i++) znq[i] = zn[2][i];
+							static_for<3, QMAX + 1>([&](auto J) {
+								constexpr int j = decltype(J)::value;
+								if (j <= q) { // the last j <= q wins: znq = zn[q]
+#pragma unroll
+									for (int i = 0; i < N; i++) znq[i] = zn[j][i];
+								}
+							});
+							double ddn = wrms(znq) * tq[1];
+							etaqm1 = 1.0 / (bdf_root(BDF_BIAS1 * ddn, q) + BDF_ADDON);
+						}
+						// cvComputeEtaqp1
+						double etaqp1 = 0.0;
+						if (q != QMAX) {
+							if (saved_tq5 != 0.0) {
+								double base = h / tau[2];
+								double pw = 1.0;
+								static_for<1, QMAX + 1>([&](auto I) {
+									if (decltype(I)::value <= L) pw *= base;
+								});
+								double cquot = (tq[5] / saved_tq5) * pw;
+								double tmp[N];
+#pragma unroll
+								for (int i = 0; i < N; i++) tmp[i] = -cquot * zn[QMAX][i] + acor[i];
+								double dup = wrms(tmp) * tq[3];
+								etaqp1 = 1.0 / (bdf_root(BDF_BIAS3 * dup, L + 1) + BDF_ADDON);
+							}
+						}
+						// cvChooseEta
+						double etam = fmax(etaqm1, fmax(etaq, etaqp1));
+						if (etam < BDF_THRESH) {
+							eta = 1.0;
+							qprime = q;
+						} else if (etam == etaq) {
+							eta = etaq;
+							qprime = q;
+						} else if (etam == etaqm1) {
+							eta = etaqm1;
+							qprime = q - 1;
+						} else {
+							eta = etaqp1;
+							qprime = q + 1;
+#pragma unroll
+							for (int i = 0; i < N; i++) zn[QMAX][i] = acor[i];
+						}
+					}
+					// cvSetEta (hmax_inv = 0)
+					if (eta < BDF_THRESH) {
+						eta = 1.0;
+						hprime = h;
+					} else {
+						eta = fmin(eta, etamax);
+						hprime = h * eta;
+					}
+				}
+				etamax = (nst <= BDF_SMALL_NST) ? BDF_ETAMX2 : BDF_ETAMX3;
+#pragma unroll
+				for (int i = 0; i < N; i++) acor[i] *= tq[2];
 			}
 		}
-		etamax = (nst <= BDF_SMALL_NST) ? BDF_ETAMX2 : BDF_ETAMX3;
-#pragma unroll
-		for (int i = 0; i < N; i++) acor[i] *= tq[2];
-		return BDF_ATTEMPT_DONE;
+		return result;
 	}
 
 	// CVodeGetDky(t, k = 0) for all components. Returns false on CV_BAD_T.
