@@ -1,0 +1,48 @@
+// Mirror of bcm3::Likelihood (src/sampler/Likelihood.h:9-35) with the ONE added entry of the batched design.
+#pragma once
+
+#include "Types.h"
+#include "VariableSet.h"
+#include "Xml.h"
+
+namespace bcm3 {
+
+class Likelihood {
+public:
+	virtual ~Likelihood() {}
+
+	bool SetLearningRate(Real lr)
+	{
+		if (!(lr > 0.0)) return false;
+		learning_rate = lr;
+		return true;
+	}
+	Real GetLearningRate() const { return learning_rate; }
+
+	// `likelihood_node` = the <bcm_likelihood> element (boost ptree in the reference)
+	virtual bool Initialize(std::shared_ptr<const VariableSet> varset, const XmlNode& likelihood_node) { (void)varset; (void)likelihood_node; return true; }
+	virtual bool PostInitialize() { return true; }
+	virtual bool IsReentrant() = 0;
+
+	//! As in the reference: evaluate one variable vector. False = unrecoverable, the sampler stops.
+	virtual bool EvaluateLogProbability(size_t threadix, const VectorReal& values, Real& logp) = 0;
+
+	//! NEW: evaluate all chains' proposals at once. values is nvar x C (column = chain), logp gets C entries.
+	//! The default loops over EvaluateLogProbability so every existing likelihood keeps working.
+	virtual bool EvaluateLogProbabilityBatch(const MatrixReal& values, VectorReal& logp)
+	{
+		logp.assign(values.cols(), -kInf);
+		VectorReal v(values.rows());
+		for (size_t c = 0; c < values.cols(); c++) {
+			v.assign(values.col(c), values.col(c) + values.rows());
+			if (!EvaluateLogProbability(0, v, logp[c])) return false;
+		}
+		return true;
+	}
+
+protected:
+	Likelihood() : learning_rate(1.0) {}
+	Real learning_rate;
+};
+
+} // namespace bcm3

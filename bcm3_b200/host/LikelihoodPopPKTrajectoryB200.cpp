@@ -1,0 +1,96 @@
+#include "LikelihoodPopPKTrajectoryB200.h"
+
+extern "C" {
+#include "bcm3b200.h"
+}
+
+using bcm3::Real;
+
+LikelihoodPopPKTrajectoryB200::LikelihoodPopPKTrajectoryB200(size_t, size_t) {}
+
+LikelihoodPopPKTrajectoryB200::~LikelihoodPopPKTrajectoryB200()
+{
+	if (handle) bcm3b200_destroy(handle);
+}
+
+bool LikelihoodPopPKTrajectoryB200::Initialize(std::shared_ptr<const bcm3::VariableSet> vs, const bcm3::XmlNode& node)
+{
+	varset = vs;
+	const bcm3::XmlNode* model = node.child("pk_model");
+	if (!model) {
+		last_error = "Error parsing likelihood file: no pk_model";
+		return false;
+	}
+	if (!model->has("drug") || !model->has("type")) {
+		last_error = "Error parsing likelihood file: pk_model needs drug and type";
+		return false;
+	}
+	drug = model->get("drug");
+	pk_type_str = model->get("type");
+	trial_name = model->get("trial");
+	pkdata_file = model->get("pkdata_file");
+	if (model->has("volume_of_distribution") || model->has("k_periphery_fwd") || model->has("k_periphery_bwd")) {
+		last_error = "fixed volume_of_distribution / k_periphery_* are not supported by the GPU path";
+		return false;
+	}
+	return true;
+}
+
+bool LikelihoodPopPKTrajectoryB200::PostInitialize()
+{
+	const size_t P = trial.dose.size(), T = trial.time.size(), nvar = varset->GetNumVariables();
+	const size_t sdix = varset->GetVariableIndex("standard_deviation"); // cpp:263
+	if (sdix == std::numeric_limits<size_t>::max()) {
+		last_error = "Could not find variable \"standard_deviation\"";
+		return false;
+	}
+	const std::string desc = "type=" + pk_type_str + ";drug=" + drug + ";num_patients=" + std::to_string(P) + ";num_timepoints=" +
+	                         std::to_string(T) + ";num_variables=" + std::to_string(nvar) + ";sd_ix=" + std::to_string(sdix) +
+	                         ";device=" + std::to_string(device0);
+	if (bcm3b200_create("pop_pk_trajectory", desc.data(), desc.size(), num_devices, &handle) != BCM3B200_OK) {
+		last_error = bcm3b200_last_error();
+		return false;
+	}
+	std::vector<double> transforms(nvar);
+	for (size_t i = 0; i < nvar; i++) transforms[i] = (double)varset->GetTransform(i);
+	auto set = [&](const char* name, const std::vector<double>& v, std::vector<size_t> shape) {
+		if (bcm3b200_set_data(handle, name, v.data(), shape.data(), (int)shape.size()) != BCM3B200_OK) {
+			last_error = bcm3b200_last_error();
+			return false;
+		}
+		return true;
+	};
+	bool ok = set("time", trial.time, { T }) && set("observed_concentration", trial.observed_concentration, { P, T }) &&
+	          set("dose", trial.dose, { P }) && set("dosing_interval", trial.dosing_interval, { P }) &&
+	          set("dose_after_dose_change", trial.dose_after_dose_change, { P }) && set("dose_change_time", trial.dose_change_time, { P }) &&
+	          set("intermittent", trial.intermittent, { P }) && set("treatment_interruptions", trial.treatment_interruptions, { P, 29 }) &&
+	          set("transforms", transforms, { nvar });
+	if (!ok) return false;
+	if (bcm3b200_finalize(handle) != BCM3B200_OK) {
+		last_error = bcm3b200_last_error();
+		return false;
+	}
+	return true;
+}
+
+bool LikelihoodPopPKTrajectoryB200::EvaluateLogProbability(size_t, const bcm3::VectorReal& values, Real& logp)
+{
+	int st = 0;
+	if (bcm3b200_evaluate_batch(handle, 1, values.size(), values.data(), &logp, &st) != BCM3B200_OK) {
+		last_error = bcm3b200_last_error();
+		return false;
+	}
+	return true; // a NaN stays in logp: the sampler turns it into an error (Sampler.cpp:172-178)
+}
+
+bool LikelihoodPopPKTrajectoryB200::EvaluateLogProbabilityBatch(const bcm3::MatrixReal& values, bcm3::VectorReal& logp)
+{
+	logp.assign(values.cols(), -bcm3::kInf);
+	status.assign(values.cols(), 0);
+	if (values.cols() == 0) return true;
+	if (bcm3b200_evaluate_batch(handle, values.cols(), values.rows(), values.data.data(), logp.data(), status.data()) != BCM3B200_OK) {
+		last_error = bcm3b200_last_error();
+		return false;
+	}
+	return true;
+}

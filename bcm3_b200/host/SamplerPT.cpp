@@ -1,0 +1,506 @@
+#include "SamplerPT.h"
+
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+namespace bcm3 {
+
+// ---------------------------------------------------------------------------------------------- settings
+bool SamplerPTSettings::LoadFromConfigFile(const std::string& filename, std::string* error)
+{
+	std::ifstream f(filename);
+	if (!f) {
+		if (error) *error = "cannot open " + filename;
+		return false;
+	}
+	std::stringstream ss;
+	ss << f.rdbuf();
+	return LoadFromConfigText(ss.str(), error);
+}
+
+bool SamplerPTSettings::LoadFromConfigText(const std::string& text, std::string* error)
+{
+	// boost::program_options INI style as in examples/banana/config.txt
+	std::map<std::string, std::string> kv;
+	std::istringstream in(text);
+	std::string line, section;
+	auto trim = [](std::string v) {
+		size_t a = v.find_first_not_of(" \t\r\n"), b = v.find_last_not_of(" \t\r\n");
+		return a == std::string::npos ? std::string() : v.substr(a, b - a + 1);
+	};
+	while (std::getline(in, line)) {
+		line = trim(line.substr(0, line.find('#')));
+		if (line.empty()) continue;
+		if (line.front() == '[' && line.back() == ']') {
+			section = line.substr(1, line.size() - 2);
+			continue;
+		}
+		size_t eq = line.find('=');
+		if (eq == std::string::npos) {
+			if (error) *error = "bad config line: " + line;
+			return false;
+		}
+		kv[section + "." + trim(line.substr(0, eq))] = trim(line.substr(eq + 1));
+	}
+	auto U = [&](const char* k, size_t& v) { if (kv.count(k)) v = (size_t)strtoull(kv[k].c_str(), nullptr, 10); };
+	auto R = [&](const char* k, Real& v) { if (kv.count(k)) v = strtod(kv[k].c_str(), nullptr); };
+	auto S = [&](const char* k, std::string& v) { if (kv.count(k)) v = kv[k]; };
+	U("sampler.num_samples", num_samples);
+	U("sampler.use_every_nth", use_every_nth);
+	if (kv.count("sampler.rngseed")) rngseed = strtoull(kv["sampler.rngseed"].c_str(), nullptr, 10);
+	U("ptmhsampler.num_chains", num_chains);
+	S("ptmhsampler.proposal_type", proposal_type);
+	S("ptmhsampler.swapping_scheme", swapping_scheme);
+	U("ptmhsampler.num_exploration_steps", num_exploration_steps);
+	U("ptmhsampler.max_history_size", max_history_size);
+	U("ptmhsampler.adapt_proposal_samples", adapt_proposal_samples);
+	U("ptmhsampler.adapt_proposal_times", adapt_proposal_times);
+	U("ptmhsampler.adapt_proposal_max_history_samples", adapt_proposal_max_history_samples);
+	U("ptmhsampler.stop_proposal_scaling", stop_proposal_scaling);
+	R("ptmhsampler.exchange_probability", exchange_probability);
+	R("ptmhsampler.temperature_schedule_power", temperature_schedule_power);
+	R("ptmhsampler.temperature_schedule_max", temperature_schedule_max);
+	U("ptmhsampler.initial_position_tries", initial_position_tries);
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------- history
+void SampleHistory::Initialize(size_t num_variables, size_t history_size, size_t sub)
+{
+	nvar = num_variables;
+	capacity = history_size;
+	subsampling = sub ? sub : 1;
+	sample_n = sample_n_s = 0;
+	samples.assign(nvar * capacity, 0.f);
+}
+
+void SampleHistory::AddSample(const VectorReal& sample)
+{
+	// SampleHistory.cpp:32-45
+	if (capacity == 0) return;
+	sample_n_s++;
+	if (sample_n_s == subsampling) {
+		size_t ix = sample_n % capacity;
+		for (size_t i = 0; i < nvar; i++) samples[ix * nvar + i] = (float)sample[i];
+		sample_n++;
+		sample_n_s = 0;
+	}
+}
+
+void SampleHistory::GetHistory(std::vector<VectorReal>& rows) const
+{
+	const size_t n = GetSampleCount();
+	rows.assign(n, VectorReal(nvar));
+	for (size_t r = 0; r < n; r++)
+		for (size_t i = 0; i < nvar; i++) rows[r][i] = (Real)samples[r * nvar + i];
+}
+
+// ---------------------------------------------------------------------------------------------- proposal
+bool ProposalGlobalCovariance::Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng)
+{
+	// Proposal::Initialize (Proposal.cpp:39-140) + ProposalGlobalCovariance::InitializeImpl (:66-112)
+	n = num_variables;
+	target_acceptance_rate = (n == 1) ? 0.44 : (n == 2) ? 0.35 : (n == 3) ? 0.3 : 0.234;
+	lower.resize(n);
+	upper.resize(n);
+	for (size_t i = 0; i < n; i++) {
+		lower[i] = prior.GetLowerBound(i);
+		upper[i] = prior.GetUpperBound(i);
+	}
+	std::vector<VectorReal> rows;
+	history.GetHistory(rows);
+	if (rows.size() > max_history_samples && max_history_samples > 0) {
+		std::vector<size_t> use;
+		size_t subsample = rows.size() / max_history_samples;
+		if (subsample > 1) {
+			use.resize(rows.size() / subsample);
+			for (size_t i = 0; i < use.size(); i++) use[i] = i * subsample;
+		} else {
+			use.resize(rows.size());
+			for (size_t i = 0; i < use.size(); i++) use[i] = i;
+		}
+		while (use.size() > max_history_samples) use.erase(use.begin() + rng.GetUnsignedInt((unsigned)use.size() - 1));
+		std::vector<VectorReal> sel;
+		for (size_t ix : use) sel.push_back(rows[ix]);
+		rows.swap(sel);
+	}
+	covariance.assign(n * n, 0.0);
+	if (rows.size() < 2) {
+		for (size_t j = 0; j < n; j++) {
+			Real var;
+			prior.EvaluateMarginalVariance(j, var);
+			covariance[j + j * n] = var;
+		}
+	} else {
+		VectorReal mean(n, 0.0);
+		for (auto& r : rows)
+			for (size_t i = 0; i < n; i++) mean[i] += r[i];
+		for (size_t i = 0; i < n; i++) mean[i] /= (Real)rows.size();
+		for (auto& r : rows)
+			for (size_t i = 0; i < n; i++)
+				for (size_t j = 0; j < n; j++) covariance[i + j * n] += (r[i] - mean[i]) * (r[j] - mean[j]);
+		for (Real& v : covariance) v /= (Real)(rows.size() - 1);
+		for (size_t j = 0; j < n; j++) {
+			Real var;
+			prior.EvaluateMarginalVariance(j, var);
+			covariance[j + j * n] = std::max(covariance[j + j * n], 1e-6 * var);
+		}
+	}
+	// Cholesky (covariance.llt())
+	chol.assign(n * n, 0.0);
+	for (size_t j = 0; j < n; j++) {
+		Real d = covariance[j + j * n];
+		for (size_t k = 0; k < j; k++) d -= chol[j + k * n] * chol[j + k * n];
+		if (!(d > 0.0)) return false;
+		chol[j + j * n] = sqrt(d);
+		for (size_t i = j + 1; i < n; i++) {
+			Real v = covariance[i + j * n];
+			for (size_t k = 0; k < j; k++) v -= chol[i + k * n] * chol[j + k * n];
+			chol[i + j * n] = v / chol[j + j * n];
+		}
+	}
+	return true;
+}
+
+void ProposalGlobalCovariance::Update(RNG& rng, bool scaling_frozen)
+{
+	// Proposal::Update, Proposal.cpp:196-211 (the draw happens regardless so that the stream does not depend on the flag)
+	Real learn_rate = 1.0 + rng.GetReal() * scaling_learning_rate;
+	if (scaling_frozen) return;
+	if (current_acceptance_rate_ema < 0.952381 * target_acceptance_rate) {
+		adaptive_scale /= learn_rate;
+		adaptive_scale = std::max(adaptive_scale, (Real)1e-4);
+	} else if (current_acceptance_rate_ema > 1.05 * target_acceptance_rate) {
+		adaptive_scale *= learn_rate;
+		adaptive_scale = std::min(adaptive_scale, (Real)10.0);
+	}
+}
+
+void ProposalGlobalCovariance::NotifyAccepted(bool accepted)
+{
+	// Proposal.cpp:213-222
+	const Real ema_alpha = 2.0 / (scaling_ema_period + 1);
+	current_acceptance_rate_ema += ((accepted ? 1.0 : 0.0) - current_acceptance_rate_ema) * ema_alpha;
+}
+
+Real ProposalGlobalCovariance::ReflectOnBounds(Real x, Real lb, Real ub)
+{
+	// Proposal.cpp:385-397
+	for (;;) {
+		if (x < lb) x = lb + (lb - x);
+		else if (x > ub) x = ub - (x - ub);
+		else break;
+	}
+	return x;
+}
+
+void ProposalGlobalCovariance::GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) const
+{
+	// ProposalGlobalCovariance.cpp:19-41 with t_dof = 0
+	VectorReal z(n);
+	for (size_t i = 0; i < n; i++) z[i] = rng.GetNormal();
+	proposed.assign(n, 0.0);
+	for (size_t i = 0; i < n; i++) {
+		Real v = 0.0;
+		for (size_t k = 0; k <= i; k++) v += chol[i + k * n] * z[k];
+		proposed[i] = ReflectOnBounds(current[i] + v * adaptive_scale, lower[i], upper[i]);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- sampler
+bool SamplerPT::Initialize()
+{
+	if (!varset || !prior || !likelihood) {
+		last_error = "variable set, prior and likelihood must be set";
+		return false;
+	}
+	if (s.proposal_type != "global_covariance") {
+		last_error = "proposal_type \"" + s.proposal_type + "\" is not part of the batched hot path; use global_covariance";
+		return false;
+	}
+	if (s.swapping_scheme != "deterministic_even_odd" && s.swapping_scheme != "stochastic_even_odd" && s.swapping_scheme != "stochastic_random") {
+		last_error = "Unknown swapping scheme \"" + s.swapping_scheme + "\"";
+		return false;
+	}
+	num_variables = varset->GetNumVariables();
+	if (s.num_chains < 1) return false;
+
+	// temperatures, SamplerPT.cpp:83-93: power law below temperature_max, chain 0 at temperature 0
+	temperatures.assign(s.num_chains, 0.0);
+	for (size_t i = 1; i + 1 < s.num_chains; i++) {
+		Real alpha = i / (Real)(s.num_chains - 1);
+		temperatures[i] = s.temperature_schedule_max * pow(alpha, s.temperature_schedule_power);
+	}
+	temperatures[s.num_chains - 1] = s.temperature_schedule_max;
+
+	if (s.adapt_proposal_samples > 0) {
+		// SamplerPT.cpp:75-78
+		proposal_scaling_ema_period = (size_t)ceil(s.adapt_proposal_samples * s.use_every_nth * (1.0 - s.exchange_probability) / 10);
+		proposal_scaling_learning_rate = pow(100.0, 1.0 / proposal_scaling_ema_period) - 1.0;
+	}
+
+	// history sizing, SamplerPT.cpp:113-126
+	size_t expected = s.adapt_proposal_samples * s.use_every_nth;
+	if (temperatures.size() > 1 && s.swapping_scheme == "deterministic_even_odd") expected *= (s.num_exploration_steps + 1);
+	size_t subsampling = 1, sample_history = expected;
+	if (sample_history > s.max_history_size) {
+		subsampling = (expected + s.max_history_size - 1) / s.max_history_size;
+		sample_history = expected / subsampling;
+	}
+
+	rng.Seed(s.rngseed, 0);
+	chains.assign(temperatures.size(), Chain());
+	for (size_t i = 0; i < chains.size(); i++) {
+		Chain& c = chains[i];
+		c.temperature = temperatures[i];
+		c.rng.Seed(s.rngseed, i + 1);
+		c.current_var_values.assign(num_variables, 0.0);
+		c.history.Initialize(num_variables, sample_history, subsampling);
+		if (!c.proposal.Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
+			last_error = "Proposal initialization failed.";
+			return false;
+		}
+		c.proposal.SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
+	}
+	previous_swap_even = false;
+	proposal_adaptations_done = 0;
+	proposal_scaling_adaptations_done = false;
+	samples.clear();
+	return true;
+}
+
+bool SamplerPT::EvaluateAll(const std::vector<size_t>& which, const MatrixReal& proposals, VectorReal& lpriors, VectorReal& llhs)
+{
+	// Sampler::EvaluatePriorLikelihood (Sampler.cpp:150-188) for the listed chains: priors on the host, likelihoods
+	// either in one batched call or one by one -- both give the same numbers for a likelihood whose batched entry is exact.
+	const size_t n = which.size();
+	lpriors.assign(n, -kInf);
+	llhs.assign(n, -kInf);
+	MatrixReal sub(num_variables, n);
+	for (size_t k = 0; k < n; k++) {
+		std::copy(proposals.col(which[k]), proposals.col(which[k]) + num_variables, sub.col(k));
+		if (!prior->EvaluateLogPDF(0, sub.col(k), lpriors[k])) {
+			last_error = "Prior evaluation failed";
+			return false;
+		}
+		if (lpriors[k] != lpriors[k]) {
+			last_error = "NAN in prior calculation";
+			return false;
+		}
+	}
+	if (s.batched) {
+		if (!likelihood->EvaluateLogProbabilityBatch(sub, llhs)) {
+			last_error = "Likelihood evaluation failed";
+			return false;
+		}
+		num_batched_calls++;
+	} else {
+		VectorReal v(num_variables);
+		for (size_t k = 0; k < n; k++) {
+			v.assign(sub.col(k), sub.col(k) + num_variables);
+			if (!likelihood->EvaluateLogProbability(0, v, llhs[k])) {
+				last_error = "Likelihood evaluation failed";
+				return false;
+			}
+		}
+	}
+	for (size_t k = 0; k < n; k++) {
+		llhs[k] *= likelihood->GetLearningRate(); // Sampler.cpp:168
+		num_likelihood_evaluations++;             // :169
+		if (llhs[k] != llhs[k]) {
+			last_error = "NAN in likelihood calculation";
+			return false;
+		}
+	}
+	return true;
+}
+
+bool SamplerPT::FindStartingPositions()
+{
+	// SamplerPTChain::FindStartingPosition (SamplerPTChain.cpp:188-215), all chains per try in one batch
+	std::vector<size_t> pending(chains.size());
+	for (size_t i = 0; i < chains.size(); i++) pending[i] = i;
+	MatrixReal proposals(num_variables, chains.size());
+	for (size_t t = 0; t < s.initial_position_tries && !pending.empty(); t++) {
+		for (size_t ci : pending) prior->Sample(proposals.col(ci), &chains[ci].rng);
+		VectorReal lp, ll;
+		if (!EvaluateAll(pending, proposals, lp, ll)) return false;
+		std::vector<size_t> still;
+		for (size_t k = 0; k < pending.size(); k++) {
+			Chain& c = chains[pending[k]];
+			c.current_var_values.assign(proposals.col(pending[k]), proposals.col(pending[k]) + num_variables);
+			c.lprior = lp[k];
+			c.llh = ll[k];
+			c.lpowerposterior = c.lprior + c.temperature * c.llh;
+			if (!(c.lpowerposterior > -kInf)) still.push_back(pending[k]);
+		}
+		pending.swap(still);
+	}
+	if (!pending.empty()) {
+		last_error = "Could not find starting position with power posterior != inf after " + std::to_string(s.initial_position_tries) + " tries";
+		return false;
+	}
+	return true;
+}
+
+bool SamplerPT::ExchangeMove(Chain& chain1, Chain& chain2)
+{
+	// SamplerPTChain::ExchangeMove, SamplerPTChain.cpp:328-381: uses cached lprior / llh only, no likelihood call
+	chain1.attempted_exchange++;
+	Real p1 = (chain1.temperature == 0.0) ? chain2.lprior : chain1.temperature * chain2.llh + chain2.lprior;
+	Real p2 = (chain2.temperature == 0.0) ? chain1.lprior : chain2.temperature * chain1.llh + chain1.lprior;
+	Real tp = exp((p1 + p2) - (chain1.lpowerposterior + chain2.lpowerposterior));
+	tp = std::min((Real)1.0, tp);
+	const bool swap = rng.GetReal() < tp;
+	if (swap) {
+		chain1.accepted_exchange++;
+		std::swap(chain1.current_var_values, chain2.current_var_values);
+		std::swap(chain1.llh, chain2.llh);
+		std::swap(chain1.lprior, chain2.lprior);
+		chain1.lpowerposterior = p1;
+		chain2.lpowerposterior = p2;
+	}
+	if (chain1.temperature != 0.0) chain1.history.AddSample(chain1.current_var_values);
+	if (chain2.temperature != 0.0) chain2.history.AddSample(chain2.current_var_values);
+	return swap;
+}
+
+void SamplerPT::DoExchangeMove()
+{
+	// SamplerPT.cpp:277-306
+	if (s.swapping_scheme == "stochastic_random") {
+		size_t ci = rng.GetUnsignedInt((unsigned)chains.size() - 2);
+		ExchangeMove(chains[ci], chains[ci + 1]);
+		return;
+	}
+	size_t start_ix;
+	if (previous_swap_even) {
+		start_ix = 1;
+		previous_swap_even = false;
+	} else {
+		start_ix = 0;
+		previous_swap_even = true;
+	}
+	for (size_t ci = start_ix; ci < chains.size(); ci += 2) {
+		size_t ix2 = ci + 1;
+		if (ix2 == chains.size()) ix2 = 0;
+		ExchangeMove(chains[ci], chains[ix2]);
+	}
+}
+
+bool SamplerPT::DoMutateMove()
+{
+	// SamplerPT::DoMutateMove (SamplerPT.cpp:308-319) + SamplerPTChain::MutateMove (SamplerPTChain.cpp:217-313), one_block:
+	// 1. every chain proposes (the T = 0 chain draws from the prior), host side, per-chain streams
+	const size_t C = chains.size();
+	MatrixReal proposals(num_variables, C);
+	std::vector<size_t> all(C);
+	for (size_t ci = 0; ci < C; ci++) {
+		Chain& c = chains[ci];
+		all[ci] = ci;
+		if (c.temperature == 0.0) {
+			prior->Sample(proposals.col(ci), &c.rng);
+		} else {
+			c.proposal.Update(c.rng, proposal_scaling_adaptations_done);
+			VectorReal np;
+			c.proposal.GetNewSample(c.current_var_values, np, c.rng);
+			std::copy(np.begin(), np.end(), proposals.col(ci));
+		}
+	}
+	// 2. ONE batched evaluation of all proposals
+	VectorReal lp, ll;
+	if (!EvaluateAll(all, proposals, lp, ll)) return false;
+	// 3. every chain tests and accepts / rejects
+	for (size_t ci = 0; ci < C; ci++) {
+		Chain& c = chains[ci];
+		if (c.temperature == 0.0) {
+			c.current_var_values.assign(proposals.col(ci), proposals.col(ci) + num_variables);
+			c.lprior = lp[ci];
+			c.llh = ll[ci];
+			c.lpowerposterior = (c.llh == -kInf) ? c.lprior : c.lprior + c.temperature * c.llh; // :230-236
+			c.attempted_mutate++;
+			c.accepted_mutate++;
+			continue;
+		}
+		const Real new_lpp = lp[ci] + c.temperature * ll[ci];
+		// TestSample, SamplerPTChain.cpp:465-482
+		c.attempted_mutate++;
+		bool accept = false;
+		if (new_lpp > -kInf) {
+			Real tp = exp(new_lpp - c.lpowerposterior + c.proposal.CalculateMHRatio());
+			tp = std::min((Real)1.0, tp);
+			accept = c.rng.GetReal() < tp;
+		}
+		if (accept) {
+			c.accepted_mutate++;
+			c.current_var_values.assign(proposals.col(ci), proposals.col(ci) + num_variables);
+			c.lprior = lp[ci];
+			c.llh = ll[ci];
+			c.lpowerposterior = new_lpp;
+		}
+		c.proposal.NotifyAccepted(accept);
+		c.history.AddSample(c.current_var_values);
+	}
+	return true;
+}
+
+void SamplerPT::EmitSample()
+{
+	// SamplerPT::EmitSample (SamplerPT.cpp:321-330): every fixed-temperature chain reports its state
+	for (const Chain& c : chains) samples.push_back(EmittedSample{ c.current_var_values, c.lprior, c.llh, c.temperature });
+}
+
+bool SamplerPT::AdaptProposals()
+{
+	for (Chain& c : chains) {
+		if (c.temperature == 0.0) continue;
+		Real keep_scale = c.proposal.GetScale();
+		(void)keep_scale;
+		if (!c.proposal.Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
+			last_error = "Proposal adaptation failed";
+			return false;
+		}
+		c.proposal.SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
+	}
+	return true;
+}
+
+bool SamplerPT::Run()
+{
+	// SamplerPT::RunImpl, SamplerPT.cpp:174-260
+	if (!FindStartingPositions()) return false;
+	const size_t total_samples = s.num_samples * s.use_every_nth;
+	for (size_t si = 0; si < total_samples; si++) {
+		const size_t sample_ix = si / s.use_every_nth;
+		bool result = true;
+		if (chains.size() > 1) {
+			if (s.swapping_scheme == "deterministic_even_odd") {
+				DoExchangeMove();
+				for (size_t ei = 0; ei < s.num_exploration_steps && result; ei++) result = DoMutateMove();
+			} else {
+				if (rng.GetReal() < s.exchange_probability) DoExchangeMove();
+				else result = DoMutateMove();
+			}
+		} else {
+			result = DoMutateMove();
+		}
+		if (!result) {
+			if (last_error.empty()) last_error = "Sample step failed";
+			return false;
+		}
+		if ((si + 1) % s.use_every_nth == 0) {
+			EmitSample();
+			if (s.adapt_proposal_samples > 0 && ((sample_ix + 1) % s.adapt_proposal_samples == 0) && si + 1 != total_samples &&
+			    proposal_adaptations_done < s.adapt_proposal_times) {
+				if (!AdaptProposals()) return false;
+				proposal_adaptations_done++;
+			}
+			if (s.stop_proposal_scaling > 0 && sample_ix > s.stop_proposal_scaling) proposal_scaling_adaptations_done = true;
+		}
+	}
+	return true;
+}
+
+} // namespace bcm3

@@ -1,0 +1,135 @@
+// Host PT driver: mirror of the reference's parallel-tempered Metropolis-Hastings sampler for the part that drives the
+// likelihood (src/sampler/SamplerPT.cpp:174-330, SamplerPTChain.cpp:188-381,465-482, Proposal.cpp:196-225,
+// ProposalGlobalCovariance.cpp:19-114, SampleHistory.cpp:32-67), restructured around ONE batched likelihood call per
+// mutate round:   propose for all chains -> EvaluateLogProbabilityBatch -> accept/reject for all chains.
+// Proposal generation, MH tests and temperature swaps stay on the host and are deterministic (RNG.h).
+// Blocking strategies other than one_block and the GMM / clustered proposals are out of scope.
+#pragma once
+
+#include <functional>
+
+#include "Likelihood.h"
+#include "Prior.h"
+#include "RNG.h"
+
+namespace bcm3 {
+
+struct SamplerPTSettings {
+	// [sampler]
+	size_t num_samples = 1000;
+	size_t use_every_nth = 1;
+	uint64_t rngseed = 0;
+	// [ptmhsampler] (defaults of SamplerPT::AddOptionsDescription, SamplerPT.cpp:147-172)
+	size_t num_chains = 6;
+	std::string proposal_type = "global_covariance";
+	std::string swapping_scheme = "deterministic_even_odd";
+	size_t num_exploration_steps = 1;
+	size_t max_history_size = 2000;
+	size_t adapt_proposal_samples = 2000;
+	size_t adapt_proposal_times = 2;
+	size_t adapt_proposal_max_history_samples = 2000;
+	size_t stop_proposal_scaling = 6000;
+	Real exchange_probability = 0.5;
+	Real temperature_schedule_power = 3.0;
+	Real temperature_schedule_max = 1.0;
+	size_t initial_position_tries = 100;
+	// evaluation mode: true = one EvaluateLogProbabilityBatch per mutate round, false = one EvaluateLogProbability per chain
+	bool batched = true;
+
+	bool LoadFromConfigFile(const std::string& filename, std::string* error = nullptr); // INI: [section] key=value
+	bool LoadFromConfigText(const std::string& text, std::string* error = nullptr);
+};
+
+class SampleHistory {
+public:
+	void Initialize(size_t num_variables, size_t history_size, size_t subsampling);
+	void AddSample(const VectorReal& sample);
+	size_t GetSampleCount() const { return sample_n < capacity ? sample_n : capacity; }
+	// rows = samples, columns = variables (stored as float like the reference, SampleHistory.cpp:41)
+	void GetHistory(std::vector<VectorReal>& rows) const;
+
+private:
+	size_t nvar = 0, capacity = 0, subsampling = 1, sample_n = 0, sample_n_s = 0;
+	std::vector<float> samples;
+};
+
+class ProposalGlobalCovariance {
+public:
+	bool Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng);
+	void SetScalingSchedule(size_t ema_period, Real learning_rate) { scaling_ema_period = ema_period; scaling_learning_rate = learning_rate; }
+	void Update(RNG& rng, bool scaling_frozen);
+	void GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) const;
+	Real CalculateMHRatio() const { return 0.0; }
+	void NotifyAccepted(bool accepted);
+	Real GetScale() const { return adaptive_scale; }
+	const std::vector<Real>& GetCovariance() const { return covariance; }
+
+private:
+	static Real ReflectOnBounds(Real x, Real lb, Real ub);
+	size_t n = 0;
+	std::vector<Real> covariance, chol; // n x n, column-major; chol lower-triangular
+	std::vector<Real> lower, upper;
+	size_t scaling_ema_period = 1000;
+	Real scaling_learning_rate = 0.05, target_acceptance_rate = 0.234, adaptive_scale = 1.0, current_acceptance_rate_ema = 0.23;
+};
+
+struct EmittedSample {
+	VectorReal values;
+	Real lprior, llh, temperature;
+};
+
+class SamplerPT {
+public:
+	SamplerPT(const SamplerPTSettings& settings) : s(settings) {}
+	void SetVariableSet(std::shared_ptr<const VariableSet> v) { varset = v; }
+	void SetPrior(std::shared_ptr<Prior> p) { prior = p; }
+	void SetLikelihood(std::shared_ptr<Likelihood> l) { likelihood = l; }
+	bool Initialize();
+	bool Run();
+
+	const std::vector<EmittedSample>& GetSamples() const { return samples; }
+	const VectorReal& GetTemperatures() const { return temperatures; }
+	size_t GetNumLikelihoodEvaluations() const { return num_likelihood_evaluations; }
+	size_t GetNumBatchedCalls() const { return num_batched_calls; }
+	Real GetMutateAcceptance(size_t chain) const { return chains[chain].attempted_mutate ? chains[chain].accepted_mutate / (Real)chains[chain].attempted_mutate : 0.0; }
+	Real GetExchangeAcceptance(size_t chain) const { return chains[chain].attempted_exchange ? chains[chain].accepted_exchange / (Real)chains[chain].attempted_exchange : 0.0; }
+	const std::string& LastError() const { return last_error; }
+
+private:
+	struct Chain {
+		Real temperature = 1.0;
+		VectorReal current_var_values;
+		Real lprior = -kInf, llh = -kInf, lpowerposterior = -kInf;
+		size_t attempted_mutate = 0, accepted_mutate = 0, attempted_exchange = 0, accepted_exchange = 0;
+		SampleHistory history;
+		ProposalGlobalCovariance proposal;
+		RNG rng;
+	};
+
+	bool EvaluateAll(const std::vector<size_t>& which, const MatrixReal& proposals, VectorReal& lpriors, VectorReal& llhs);
+	bool FindStartingPositions();
+	void DoExchangeMove();
+	bool ExchangeMove(Chain& chain1, Chain& chain2);
+	bool DoMutateMove();
+	void EmitSample();
+	bool AdaptProposals();
+
+	SamplerPTSettings s;
+	std::shared_ptr<const VariableSet> varset;
+	std::shared_ptr<Prior> prior;
+	std::shared_ptr<Likelihood> likelihood;
+	size_t num_variables = 0;
+	VectorReal temperatures;
+	std::vector<Chain> chains;
+	RNG rng; // exchange moves, prior draws of the start-up
+	bool previous_swap_even = false;
+	size_t proposal_adaptations_done = 0;
+	bool proposal_scaling_adaptations_done = false;
+	size_t proposal_scaling_ema_period = 1000;
+	Real proposal_scaling_learning_rate = 0.05;
+	size_t num_likelihood_evaluations = 0, num_batched_calls = 0;
+	std::vector<EmittedSample> samples;
+	std::string last_error;
+};
+
+} // namespace bcm3

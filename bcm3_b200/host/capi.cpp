@@ -1,0 +1,189 @@
+// C entry points of the host mirror (libbcm3host.so) so that the Python test-suite can drive the C++ sampler,
+// factory and likelihood classes exactly as a C++ program would.
+#include <cstring>
+
+#include "LikelihoodFactory.h"
+#include "LikelihoodPopPKTrajectoryB200.h"
+#include "SamplerPT.h"
+
+using namespace bcm3;
+
+namespace {
+
+void set_err(char* err, size_t errlen, const std::string& m)
+{
+	if (err && errlen) {
+		strncpy(err, m.c_str(), errlen - 1);
+		err[errlen - 1] = 0;
+	}
+}
+
+struct Setup {
+	std::shared_ptr<VariableSet> varset;
+	std::shared_ptr<Prior> prior;
+	std::shared_ptr<Likelihood> likelihood;
+};
+
+bool make_setup(const char* prior_xml, const char* likelihood_xml, Setup& s, std::string& error)
+{
+	XmlNode root;
+	if (!ParseXml(prior_xml, root, error)) return false;
+	const XmlNode* node = root.child("prior");
+	if (!node) node = root.child("variableset");
+	if (!node) {
+		error = "Incorrect prior XML format";
+		return false;
+	}
+	s.varset = std::make_shared<VariableSet>();
+	if (!s.varset->LoadFromNode(*node)) {
+		error = "Error parsing variable file";
+		return false;
+	}
+	s.prior = Prior::CreateFromNode(*node, s.varset);
+	if (!s.prior) {
+		error = "Error creating prior";
+		return false;
+	}
+	s.likelihood = LikelihoodFactory::CreateLikelihoodFromText(likelihood_xml, s.varset, 1, 1, &error);
+	return s.likelihood != nullptr;
+}
+
+int run(Setup& st, const char* config_text, int batched, unsigned long long seed, double* out, size_t max_rows, size_t* num_rows,
+        size_t* stats, char* err, size_t errlen)
+{
+	SamplerPTSettings settings;
+	std::string error;
+	if (!settings.LoadFromConfigText(config_text ? config_text : "", &error)) {
+		set_err(err, errlen, error);
+		return -1;
+	}
+	settings.batched = batched != 0;
+	settings.rngseed = seed;
+	SamplerPT sampler(settings);
+	sampler.SetVariableSet(st.varset);
+	sampler.SetPrior(st.prior);
+	sampler.SetLikelihood(st.likelihood);
+	if (!sampler.Initialize() || !sampler.Run()) {
+		set_err(err, errlen, sampler.LastError());
+		return -2;
+	}
+	const size_t nvar = st.varset->GetNumVariables();
+	const auto& samples = sampler.GetSamples();
+	size_t n = std::min(max_rows, samples.size());
+	for (size_t r = 0; r < n; r++) {
+		double* row = out + r * (nvar + 3);
+		row[0] = samples[r].temperature;
+		row[1] = samples[r].lprior;
+		row[2] = samples[r].llh;
+		for (size_t i = 0; i < nvar; i++) row[3 + i] = samples[r].values[i];
+	}
+	if (num_rows) *num_rows = samples.size();
+	if (stats) {
+		stats[0] = sampler.GetNumLikelihoodEvaluations();
+		stats[1] = sampler.GetNumBatchedCalls();
+		stats[2] = sampler.GetTemperatures().size();
+	}
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// Parallel-tempered run with a host likelihood (banana). out rows: [temperature, lprior, llh, values...].
+int bcm3host_run_pt(const char* prior_xml, const char* likelihood_xml, const char* config_text, int batched, unsigned long long seed,
+                    double* out, size_t max_rows, size_t* num_rows, size_t* stats, char* err, size_t errlen)
+{
+	Setup st;
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
+		set_err(err, errlen, error);
+		return -1;
+	}
+	if (!st.likelihood->PostInitialize()) {
+		set_err(err, errlen, "PostInitialize failed");
+		return -1;
+	}
+	return run(st, config_text, batched, seed, out, max_rows, num_rows, stats, err, errlen);
+}
+
+// Same with the GPU-backed pop_pk_trajectory likelihood; the trial arrays stand in for the NetCDF file.
+int bcm3host_run_pt_poppk(const char* prior_xml, const char* likelihood_xml, const char* config_text, int batched, unsigned long long seed,
+                          size_t P, size_t T, const double* time, const double* obs, const double* dose, const double* dosing_interval,
+                          const double* dose_after, const double* dose_change_time, const double* intermittent, const double* interruptions,
+                          int device, int device_count, double* out, size_t max_rows, size_t* num_rows, size_t* stats, char* err, size_t errlen)
+{
+	Setup st;
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
+		set_err(err, errlen, error);
+		return -1;
+	}
+	auto* ll = dynamic_cast<LikelihoodPopPKTrajectoryB200*>(st.likelihood.get());
+	if (!ll) {
+		set_err(err, errlen, "likelihood.xml is not of type pop_pk_trajectory");
+		return -1;
+	}
+	LikelihoodPopPKTrajectoryB200::TrialData td;
+	td.time.assign(time, time + T);
+	td.observed_concentration.assign(obs, obs + P * T);
+	td.dose.assign(dose, dose + P);
+	td.dosing_interval.assign(dosing_interval, dosing_interval + P);
+	td.dose_after_dose_change.assign(dose_after, dose_after + P);
+	td.dose_change_time.assign(dose_change_time, dose_change_time + P);
+	td.intermittent.assign(intermittent, intermittent + P);
+	td.treatment_interruptions.assign(interruptions, interruptions + P * 29);
+	ll->SetTrialData(td);
+	ll->SetDevices(device, device_count);
+	if (!ll->PostInitialize()) {
+		set_err(err, errlen, ll->LastError());
+		return -3;
+	}
+	return run(st, config_text, batched, seed, out, max_rows, num_rows, stats, err, errlen);
+}
+
+// Factory + plugin surface check: evaluate C variable vectors (values[C][nvar]) through EvaluateLogProbability (batched = 0)
+// or EvaluateLogProbabilityBatch (batched = 1) of the likelihood named by likelihood.xml (host likelihoods only).
+int bcm3host_evaluate(const char* prior_xml, const char* likelihood_xml, const double* values, size_t C, int batched, double* logp, char* err,
+                      size_t errlen)
+{
+	Setup st;
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
+		set_err(err, errlen, error);
+		return -1;
+	}
+	const size_t nvar = st.varset->GetNumVariables();
+	if (batched) {
+		MatrixReal m(nvar, C);
+		std::copy(values, values + nvar * C, m.data.begin());
+		VectorReal lp;
+		if (!st.likelihood->EvaluateLogProbabilityBatch(m, lp)) return -2;
+		std::copy(lp.begin(), lp.end(), logp);
+	} else {
+		for (size_t c = 0; c < C; c++) {
+			VectorReal v(values + c * nvar, values + (c + 1) * nvar);
+			if (!st.likelihood->EvaluateLogProbability(0, v, logp[c])) return -2;
+		}
+	}
+	return 0;
+}
+
+// VariableSet / Prior surface for tests: number of variables, transform codes, index lookup
+int bcm3host_varset_info(const char* prior_xml, const char* lookup_name, size_t* num_variables, int* transforms, size_t max_n, size_t* index)
+{
+	XmlNode root;
+	std::string error;
+	if (!ParseXml(prior_xml, root, error)) return -1;
+	const XmlNode* node = root.child("prior");
+	if (!node) node = root.child("variableset");
+	if (!node) return -1;
+	VariableSet vs;
+	if (!vs.LoadFromNode(*node)) return -1;
+	*num_variables = vs.GetNumVariables();
+	for (size_t i = 0; i < vs.GetNumVariables() && i < max_n; i++) transforms[i] = (int)vs.GetTransform(i);
+	if (lookup_name && index) *index = vs.GetVariableIndex(lookup_name);
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,84 @@
+"""ctypes binding of libbcm3host.so: the C++ mirror of the reference's plugin / sampler interface (bcm3_b200/host)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libbcm3host.so")
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build()")
+        # libbcm3host.so links against libbcm3b200.so next to it ($ORIGIN rpath)
+        _lib = C.CDLL(LIB_PATH)
+    return _lib
+
+
+def _err():
+    return C.create_string_buffer(1024)
+
+
+def run_pt(prior_xml: str, likelihood_xml: str, config_text: str, batched: bool = True, seed: int = 1, max_rows: int = 200000):
+    """Parallel-tempered run with a host likelihood. Returns (rows[n, 3 + nvar], stats dict)."""
+    lib = load()
+    nvar = varset_info(prior_xml)[0]
+    out = np.zeros((max_rows, nvar + 3))
+    nrows = C.c_size_t()
+    stats = (C.c_size_t * 3)()
+    err = _err()
+    rc = lib.bcm3host_run_pt(prior_xml.encode(), likelihood_xml.encode(), config_text.encode(), int(batched), C.c_ulonglong(seed),
+                             out.ctypes.data_as(C.c_void_p), C.c_size_t(max_rows), C.byref(nrows), stats, err, C.c_size_t(1024))
+    if rc != 0:
+        raise RuntimeError(f"bcm3host_run_pt failed ({rc}): {err.value.decode()}")
+    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])
+
+
+def run_pt_poppk(prior_xml: str, likelihood_xml: str, config_text: str, trial, batched: bool = True, seed: int = 1, device: int = 0,
+                 device_count: int = 1, max_rows: int = 100000):
+    lib = load()
+    nvar = varset_info(prior_xml)[0]
+    out = np.zeros((max_rows, nvar + 3))
+    nrows = C.c_size_t()
+    stats = (C.c_size_t * 3)()
+    err = _err()
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (
+        trial.time, trial.observed_concentration, trial.dose, trial.dosing_interval, trial.dose_after_dose_change,
+        trial.dose_change_time, trial.intermittent, trial.treatment_interruptions)]
+    ptrs = [a.ctypes.data_as(C.c_void_p) for a in arrs]
+    rc = lib.bcm3host_run_pt_poppk(prior_xml.encode(), likelihood_xml.encode(), config_text.encode(), int(batched), C.c_ulonglong(seed),
+                                   C.c_size_t(trial.num_patients), C.c_size_t(trial.num_timepoints), *ptrs, int(device), int(device_count),
+                                   out.ctypes.data_as(C.c_void_p), C.c_size_t(max_rows), C.byref(nrows), stats, err, C.c_size_t(1024))
+    if rc != 0:
+        raise RuntimeError(f"bcm3host_run_pt_poppk failed ({rc}): {err.value.decode()}")
+    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])
+
+
+def evaluate(prior_xml: str, likelihood_xml: str, values: np.ndarray, batched: bool):
+    lib = load()
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    logp = np.empty(values.shape[0])
+    err = _err()
+    rc = lib.bcm3host_evaluate(prior_xml.encode(), likelihood_xml.encode(), values.ctypes.data_as(C.c_void_p), C.c_size_t(values.shape[0]),
+                               int(batched), logp.ctypes.data_as(C.c_void_p), err, C.c_size_t(1024))
+    if rc != 0:
+        raise RuntimeError(f"bcm3host_evaluate failed ({rc}): {err.value.decode()}")
+    return logp
+
+
+def varset_info(prior_xml: str, lookup: str | None = None):
+    lib = load()
+    n = C.c_size_t()
+    idx = C.c_size_t()
+    tr = (C.c_int * 65536)()
+    rc = lib.bcm3host_varset_info(prior_xml.encode(), lookup.encode() if lookup else None, C.byref(n), tr, C.c_size_t(65536), C.byref(idx))
+    if rc != 0:
+        raise RuntimeError("bcm3host_varset_info failed")
+    return n.value, list(tr[: min(n.value, 65536)]), (idx.value if lookup else None)

@@ -1,0 +1,61 @@
+"""GPU suite: the C++ host mirror driving the GPU-backed pop_pk_trajectory likelihood through the reference's plugin
+surface (LikelihoodFactory type string, likelihood.xml, prior.xml, config.txt): a parallel-tempered run whose every
+mutate round is one batched call must equal the run that evaluates chain by chain."""
+import numpy as np
+import pytest
+
+from bcm3_b200 import synthetic as syn
+from bcm3_b200.poppk_data import PK_ONE, PK_TWO
+
+pytestmark = pytest.mark.gpu
+
+
+def poppk_prior_xml(pk, P):
+    two = pk == PK_TWO
+    lines = ['<?xml version="1.0" encoding="utf-8"?>', "<prior>",
+             '<variable name="mean_absorption" distribution="normal" mu="0.1" sigma="0.2"/>',
+             '<variable name="excretion" logspace="true" distribution="uniform" lower="-2.0" upper="-0.5"/>',
+             '<variable name="mean_clearance" distribution="normal" mu="0.9" sigma="0.2"/>',
+             '<variable name="volume_of_distribution" logspace="true" distribution="uniform" lower="1.2" upper="2.2"/>']
+    if two:
+        lines += ['<variable name="k_periphery_fwd" logspace="true" distribution="uniform" lower="-1.5" upper="0.5"/>',
+                  '<variable name="k_periphery_bwd" logspace="true" distribution="uniform" lower="-2.0" upper="0.0"/>']
+    lines += ['<variable name="sigma_absorption" distribution="uniform" lower="0.1" upper="0.6"/>',
+              '<variable name="sigma_clearance" distribution="uniform" lower="0.1" upper="0.6"/>',
+              f'<variable name="patient" repeat="{2 * P}" distribution="uniform" lower="0.02" upper="0.98"/>',
+              '<variable name="standard_deviation" logspace="true" distribution="uniform" lower="-1.0" upper="1.0"/>',
+              '<variable name="proportional_standard_deviation" logspace="true" distribution="uniform" lower="-1.5" upper="0.0"/>',
+              "</prior>"]
+    return "\n".join(lines)
+
+
+CONFIG = """[sampler]
+num_samples=40
+use_every_nth=2
+[ptmhsampler]
+num_chains=5
+proposal_type=global_covariance
+adapt_proposal_samples=20
+adapt_proposal_times=1
+"""
+
+
+@pytest.mark.parametrize("pk", [PK_ONE, PK_TWO])
+def test_pt_run_on_gpu_likelihood_batched_equals_serial(built, pk):
+    from bcm3_b200 import host_api
+
+    P = 40
+    prob = syn.make_poppk_problem(pk, P=P, T=8, t_end=48.0, seed=3)
+    prior = poppk_prior_xml(pk, P)
+    n, transforms, sdix = host_api.varset_info(prior, "standard_deviation")
+    assert n == prob.num_variables and sdix == prob.sd_ix and transforms == prob.transforms.tolist()
+    lik = f'<bcm_likelihood type="pop_pk_trajectory"><pk_model drug="lapatinib" type="{"one" if pk == PK_ONE else "two"}" trial="t" pkdata_file="unused.nc"/></bcm_likelihood>'
+    a, sa = host_api.run_pt_poppk(prior, lik, CONFIG, prob.trial, batched=True, seed=11)
+    b, sb = host_api.run_pt_poppk(prior, lik, CONFIG, prob.trial, batched=False, seed=11)
+    assert a.shape == (40 * 5, n + 3)
+    assert np.array_equal(a, b)
+    assert sa["batched_calls"] >= 80 and sb["batched_calls"] == 0 and sa["evaluations"] == sb["evaluations"]
+    assert np.isfinite(a[:, 2]).all()
+    # the posterior chain moved and its log-likelihood improved over the start
+    post = a[a[:, 0] == 1.0]
+    assert post[-1, 2] >= post[0, 2]

@@ -1,0 +1,100 @@
+"""CPU suite: the C++ host mirror (bcm3_b200/host) on BASELINE config 1 -- examples/banana, parallel-tempered MCMC with an
+analytic likelihood: the batched-evaluation plumbing must reproduce the serial sampler exactly for a fixed seed, and the
+posterior must match the analytic banana (TestLikelihoodBanana.cpp:42-55)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+# the reference's examples/banana/{prior.xml,likelihood.xml,config.txt}; proposal_type is global_covariance because the
+# GMM proposal machinery is outside the batched hot path
+PRIOR = """<?xml version="1.0" encoding="utf-8"?>
+<variableset>
+  <variable name="x1"   distribution="uniform" lower="-6.0" upper="4.0"/>
+  <variable name="x2"   distribution="uniform" lower="-6.0" upper="20.0"/>
+</variableset>"""
+LIKELIHOOD = """<bcm_likelihood type="banana" dimension="2" sd1="2.0" sd2="1.0">
+</bcm_likelihood>"""
+CONFIG = """[sampler]
+num_samples=8000
+use_every_nth=5
+
+[ptmhsampler]
+num_chains=6
+swapping_scheme=deterministic_even_odd
+num_exploration_steps=1
+max_history_size=5000
+proposal_type=global_covariance
+adapt_proposal_times=1
+adapt_proposal_samples=2000
+adapt_proposal_max_history_samples=5000
+stop_proposal_scaling=4000
+temperature_schedule_power=3.0
+"""
+
+
+@pytest.fixture(scope="module")
+def host(built):
+    from bcm3_b200 import host_api
+
+    host_api.load()
+    return host_api
+
+
+def test_variable_set_from_prior_xml(host):
+    xml = """<prior>
+      <variable name="mean_absorption" distribution="normal" mu="0" sigma="1"/>
+      <variable name="excretion" logspace="true" distribution="uniform" lower="-3" upper="1"/>
+      <variable name="patient" repeat="3" distribution="uniform" lower="0" upper="1"/>
+      <variable name="frac" logistic="true" distribution="normal" mu="0" sigma="2"/>
+    </prior>"""
+    n, transforms, idx = host.varset_info(xml, "patient_2")
+    assert n == 6 and transforms == [0, 2, 0, 0, 0, 3] and idx == 4
+    assert host.varset_info(xml, "nope")[2] == np.iinfo(np.uint64).max  # VariableSet.cpp:84-95
+
+
+def test_factory_and_default_batched_entry(host):
+    rng = np.random.default_rng(0)
+    vals = np.column_stack([rng.uniform(-6, 4, 50), rng.uniform(-6, 20, 50)])
+    serial = host.evaluate(PRIOR, LIKELIHOOD, vals, batched=False)
+    batch = host.evaluate(PRIOR, LIKELIHOOD, vals, batched=True)
+    assert np.array_equal(serial, batch)
+    want = stats.norm.logpdf(vals[:, 0], 0, 2.0) + stats.norm.logpdf(vals[:, 1], (1 + vals[:, 0]) ** 2, 1.0)
+    assert np.allclose(serial, want, rtol=1e-12, atol=1e-12)  # App. D #15: reference PdfNormal is itself only ~1e-14 accurate
+    with pytest.raises(RuntimeError, match="Unknown likelihood type"):
+        host.evaluate(PRIOR, '<bcm_likelihood type="nope"/>', vals, batched=True)
+
+
+def test_batched_run_equals_serial_run(host):
+    cfg = CONFIG.replace("num_samples=8000", "num_samples=600").replace("adapt_proposal_samples=2000", "adapt_proposal_samples=200")
+    a, sa = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=True, seed=7)
+    b, sb = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=False, seed=7)
+    assert a.shape == b.shape == (600 * 6, 5)
+    assert np.array_equal(a, b)  # same proposals, same decisions, same samples
+    assert sa["evaluations"] == sb["evaluations"]
+    assert sb["batched_calls"] == 0 and sa["batched_calls"] >= 600 * 5  # one batched call per mutate round
+    c, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=True, seed=8)
+    assert not np.array_equal(a, c)
+
+
+def test_banana_posterior(host):
+    rows, st = host.run_pt(PRIOR, LIKELIHOOD, CONFIG, batched=True, seed=20261018)
+    assert st["chains"] == 6
+    temps = np.unique(rows[:, 0])
+    assert len(temps) == 6 and temps[0] == 0.0 and temps[-1] == 1.0
+    assert np.allclose(temps[1:-1], [(i / 5) ** 3 for i in range(1, 5)])  # SamplerPT.cpp:83-93
+    post = rows[rows[:, 0] == 1.0][1000:, 3:]  # discard burn-in
+    x1, x2 = post[:, 0], post[:, 1]
+    # analytic marginal of x1 under the uniform prior box: N(0, 2) truncated to [-6, 4], further weighted by the mass of
+    # x2 | x1 ~ N((1 + x1)^2, 1) inside [-6, 20]
+    grid = np.linspace(-6, 4, 4001)
+    w = stats.norm.pdf(grid, 0, 2) * (stats.norm.cdf(20, (1 + grid) ** 2, 1) - stats.norm.cdf(-6, (1 + grid) ** 2, 1))
+    w /= np.trapezoid(w, grid)
+    m1 = np.trapezoid(w * grid, grid)
+    s1 = np.sqrt(np.trapezoid(w * (grid - m1) ** 2, grid))
+    assert abs(x1.mean() - m1) < 0.15 and abs(x1.std() - s1) < 0.15
+    # x2 - (1 + x1)^2 is (almost) standard normal
+    r = x2 - (1 + x1) ** 2
+    assert abs(r.mean()) < 0.1 and abs(r.std() - 1.0) < 0.1
+    # the T = 0 chain samples the prior
+    pri = rows[rows[:, 0] == 0.0][:, 3:]
+    assert abs(pri[:, 0].mean() - (-1.0)) < 0.15 and abs(pri[:, 1].mean() - 7.0) < 0.4
