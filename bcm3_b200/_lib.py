@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get("BCM3B200_LIB", os.path.join(PKG_DIR, "libbcm3b200.so"
 EXPORTS = [
     "bcm3b200_create",
     "bcm3b200_set_data",
+    "bcm3b200_set_text",
+    "bcm3b200_get_cell_diagnostics",
     "bcm3b200_finalize",
     "bcm3b200_evaluate_batch",
     "bcm3b200_evaluate_batch_device",
@@ -54,6 +56,8 @@ def load() -> C.CDLL:
     vp, sz, dp, ip = C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int)
     lib.bcm3b200_create.argtypes = [C.c_char_p, C.c_char_p, sz, C.c_int, C.POINTER(vp)]
     lib.bcm3b200_set_data.argtypes = [vp, C.c_char_p, vp, C.POINTER(sz), C.c_int]
+    lib.bcm3b200_set_text.argtypes = [vp, C.c_char_p, C.c_char_p, sz]
+    lib.bcm3b200_get_cell_diagnostics.argtypes = [vp, vp, vp, vp, vp]
     lib.bcm3b200_finalize.argtypes = [vp]
     lib.bcm3b200_evaluate_batch.argtypes = [vp, sz, sz, vp, vp, vp]
     lib.bcm3b200_evaluate_batch_device.argtypes = [vp, sz, sz, vp, vp, vp]
@@ -72,7 +76,7 @@ def load() -> C.CDLL:
     lib.bcm3b200_host_alloc.restype = vp
     lib.bcm3b200_host_free.argtypes = [vp]
     lib.bcm3b200_host_free.restype = None
-    for name in ("create", "set_data", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials",
+    for name in ("create", "set_data", "set_text", "get_cell_diagnostics", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials",
                  "get_diagnostics", "set_option", "get_stat"):
         getattr(lib, "bcm3b200_" + name).restype = C.c_int
     _lib = lib

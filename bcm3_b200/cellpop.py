@@ -1,0 +1,98 @@
+"""GPU-backed cell_population likelihood: host-side wrapper of the C ABI (include/bcm3b200.h, model kind
+"cell_population"). Mirrors CellPopulationLikelihood::EvaluateLogProbability (src/cellpop/CellPopulationLikelihood.cpp:82-101)
+for all chains at once."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .cellpop_data import CellPopProblem
+
+
+class CellPopEvaluator:
+    def __init__(self, problem: CellPopProblem, device: int = 0, compile_only: bool = False):
+        self.lib = _lib.load()
+        self.problem = p = problem
+        kv = dict(
+            num_species=p.num_species, num_constant_species=len(p.constant_species), num_variables=p.num_variables,
+            num_non_sampled=len(p.non_sampled_parameters), num_cells=p.num_cells, num_timepoints=p.num_timepoints,
+            num_replicates=p.num_replicates, variability_dim=p.variability_dim,
+            solver_relative_tolerance=repr(p.solver_relative_tolerance), solver_absolute_tolerance=repr(p.solver_absolute_tolerance),
+            solver_min_timestep=repr(p.solver_min_timestep), solver_max_steps=p.solver_max_steps, error_model=p.error_model,
+            weight=repr(p.weight), missing_simulation_time_stdev=repr(p.missing_simulation_time_stdev),
+            obs_species="+".join(str(s) for s in p.obs_species), device=device, compile_only=int(compile_only))
+        for name in ("entry_time", "stdev", "offset", "scale"):
+            ix = getattr(p, name + "_ix")
+            if ix is not None:
+                kv[name + "_ix"] = ix
+            else:
+                kv[name] = repr(float(getattr(p, name)))
+        desc = ";".join(f"{k}={v}" for k, v in kv.items()).encode()
+        h = C.c_void_p()
+        _lib.check(self.lib.bcm3b200_create(b"cell_population", desc, len(desc), 1, C.byref(h)))
+        self.handle = h
+        try:
+            self._set("initial_conditions", p.initial_conditions)
+            self._set("constant_species", p.constant_species)
+            self._set("non_sampled_parameters", p.non_sampled_parameters)
+            self._set("timepoints", p.timepoints)
+            self._set("observed", p.observed)
+            self._set("transforms", p.transforms)
+            if p.variability_dim:
+                self._set("sobol", np.asarray(p.sobol, dtype=np.float64).reshape(p.num_cells, p.variability_dim))
+                self._set("variability", p.variability_rows())
+            code = p.derivative_code.encode()
+            _lib.check(self.lib.bcm3b200_set_text(self.handle, b"derivative_code", code, len(code)))
+            _lib.check(self.lib.bcm3b200_finalize(self.handle))
+        except Exception:
+            self.close()
+            raise
+        self._last_C = 0
+
+    def _set(self, name: str, arr) -> None:
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        if a.size == 0 and a.ndim == 1:
+            shape = (C.c_size_t * 1)(0)
+            buf = np.zeros(1)
+            _lib.check(self.lib.bcm3b200_set_data(self.handle, name.encode(), buf.ctypes.data, shape, 1))
+            return
+        shape = (C.c_size_t * a.ndim)(*a.shape)
+        _lib.check(self.lib.bcm3b200_set_data(self.handle, name.encode(), a.ctypes.data, shape, a.ndim))
+
+    def evaluate(self, values: np.ndarray):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if values.ndim == 1:
+            values = values[None, :]
+        nC, nvar = values.shape
+        logp = np.empty(nC)
+        status = np.empty(nC, dtype=np.int32)
+        _lib.check(self.lib.bcm3b200_evaluate_batch(self.handle, nC, nvar, values.ctypes.data, logp.ctypes.data, status.ctypes.data))
+        self._last_C = nC
+        return logp, status
+
+    def get_stat(self, name: str) -> int:
+        v = C.c_int64()
+        _lib.check(self.lib.bcm3b200_get_stat(self.handle, name.encode(), C.byref(v)))
+        return int(v.value)
+
+    def diagnostics(self):
+        nC, nc, T = self._last_C, self.problem.num_cells, self.problem.num_timepoints
+        vals = np.empty((nC, T, nc))
+        status = np.empty((nC, nc), dtype=np.int32)
+        steps = np.empty((nC, nc), dtype=np.int32)
+        avg = np.empty((nC, T))
+        _lib.check(self.lib.bcm3b200_get_cell_diagnostics(self.handle, vals.ctypes.data, status.ctypes.data, steps.ctypes.data, avg.ctypes.data))
+        return dict(cell_values=vals, cell_status=status, cell_steps=steps, population_average=avg)
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.bcm3b200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,88 @@
+"""Host-side data model of the cell_population likelihood for the slice built in round 1:
+independent, non-dividing cells with per-cell quasi-random variability and ONE time_course_population_average data set.
+
+Mirrors what CellPopulationLikelihood / Experiment::Load leave in memory after parsing likelihood.xml, the SBML model and
+the NetCDF data (reference: src/cellpop/Experiment.cpp:404-633, CellPopulationLikelihood.cpp:27-80). The SBML reader and
+code generator stay on the reference side: the model enters as the TEXT its generator emits
+(SBMLModel::GenerateCode, src/sbml/SBMLModel.cpp:291-389).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+FLT_EPSILON = float(np.finfo(np.float32).eps)
+
+APPLY_TYPES = {  # VariabilityDescriptionVariable.cpp:139-157
+    "additive": 0, "additive_log": 1, "additive_log2": 2, "multiplicative": 3, "multiplicative_log": 4,
+    "multiplicative_log2": 5, "replace": 6,
+}
+
+
+@dataclass
+class Variability:
+    """One <variable> of a diagonal_gaussian <cell_variability> block (VariabilityDescriptionVariable.cpp:112-162)."""
+
+    apply: str
+    model_parameter: int | None = None          # index of the sampled variable it perturbs ...
+    initial_condition_species: int | None = None  # ... or index of the ODE species whose initial value it perturbs
+    scale_ix: int | None = None                 # scale = transformed variable[scale_ix] ...
+    scale_fixed: float = 0.0                    # ... or a constant; the quasi-random normal is multiplied by exp(scale)
+    negate: bool = False
+
+    def row(self):
+        is_ic = self.initial_condition_species is not None
+        target = self.initial_condition_species if is_ic else self.model_parameter
+        return [float(is_ic), float(target), float(APPLY_TYPES[self.apply]), float(-1 if self.scale_ix is None else self.scale_ix),
+                float(self.scale_fixed), float(self.negate)]
+
+
+@dataclass
+class CellPopProblem:
+    derivative_code: str                 # generated_derivative text in the reference generator's ABI
+    num_species: int
+    initial_conditions: np.ndarray       # [N]
+    transforms: np.ndarray               # [nvar] VariableSet transform codes
+    num_cells: int
+    timepoints: np.ndarray               # [T] data timepoints (sorted)
+    observed: np.ndarray                 # [R][T], NaN = missing
+    obs_species: list[int]               # species_name="a+b": indices of the summed ODE species
+    constant_species: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    non_sampled_parameters: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    sobol: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))  # [num_cells][D] uniforms in (0, 1)
+    variability: list[Variability] = field(default_factory=list)
+    entry_time_ix: int | None = None
+    entry_time: float = 0.0
+    error_model: str = "normal"
+    weight: float = 1.0
+    stdev_ix: int | None = None
+    stdev: float = 1.0
+    offset_ix: int | None = None
+    offset: float = 0.0
+    scale_ix: int | None = None
+    scale: float = 1.0
+    missing_simulation_time_stdev: float = 300.0
+    solver_relative_tolerance: float = 4 * FLT_EPSILON   # Experiment.cpp:415-416
+    solver_absolute_tolerance: float = 4 * FLT_EPSILON
+    solver_min_timestep: float = 1e-8                     # Experiment.cpp:412
+    solver_max_steps: int = 10000                         # Experiment.cpp:414
+
+    @property
+    def num_variables(self) -> int:
+        return int(self.transforms.shape[0])
+
+    @property
+    def num_timepoints(self) -> int:
+        return int(self.timepoints.shape[0])
+
+    @property
+    def num_replicates(self) -> int:
+        return int(self.observed.shape[0])
+
+    @property
+    def variability_dim(self) -> int:
+        return len(self.variability)
+
+    def variability_rows(self) -> np.ndarray:
+        return np.array([v.row() for v in self.variability], dtype=np.float64).reshape(len(self.variability), 6)

@@ -18,30 +18,13 @@
 #include <string>
 #include <vector>
 
+#include "common_host.cuh"
 #include "poppk_kernel.cuh"
+#include "cellpop_host.cuh"
 
 using namespace bcm3b200;
 
 namespace {
-
-thread_local std::string g_last_error;
-
-int fail(int code, const char* fmt, ...)
-{
-	char buf[1024];
-	va_list ap;
-	va_start(ap, fmt);
-	vsnprintf(buf, sizeof(buf), fmt, ap);
-	va_end(ap);
-	g_last_error = buf;
-	return code;
-}
-
-#define CUDA_TRY(expr)                                                                                         \
-	do {                                                                                                       \
-		cudaError_t e_ = (expr);                                                                               \
-		if (e_ != cudaSuccess) return fail(BCM3B200_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
-	} while (0)
 
 // the float literal of LikelihoodPopPKTrajectory.cpp:238, widened to double
 const double kTol = (double)1e-6f;
@@ -57,27 +40,6 @@ double molecular_weight(const std::string& drug)
 	if (drug == "selumetinib") return 457.68;
 	return std::numeric_limits<double>::quiet_NaN();
 }
-
-template <class T>
-struct DevBuf {
-	T* p = nullptr;
-	size_t n = 0;
-	~DevBuf() { release(); }
-	void release()
-	{
-		if (p) cudaFree(p);
-		p = nullptr;
-		n = 0;
-	}
-	cudaError_t ensure(size_t count)
-	{
-		if (count <= n) return cudaSuccess;
-		release();
-		cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-		if (e == cudaSuccess) n = count;
-		return e;
-	}
-};
 
 struct Shard {
 	int device = 0;
@@ -105,6 +67,7 @@ struct Shard {
 };
 
 struct Handle {
+	std::unique_ptr<CellPopState> cp; // set for model kind "cell_population"; the fields below are the PopPK evaluator
 	// description
 	int pk_type = PK_ONE;
 	std::string drug;
@@ -440,7 +403,7 @@ int bcm3b200_measure_fp64_peak(int device, double* tflops)
 	return BCM3B200_OK;
 }
 
-const char* bcm3b200_last_error(void) { return g_last_error.c_str(); }
+const char* bcm3b200_last_error(void) { return last_error_ref().c_str(); }
 
 int bcm3b200_device_count(void)
 {
@@ -456,11 +419,72 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 {
 	if (!model_kind || !handle) return fail(BCM3B200_ERR_ARG, "null argument");
 	*handle = nullptr;
-	if (strcmp(model_kind, "pop_pk_trajectory") != 0)
+	const bool is_cellpop = strcmp(model_kind, "cell_population") == 0;
+	if (!is_cellpop && strcmp(model_kind, "pop_pk_trajectory") != 0)
 		return fail(BCM3B200_ERR_UNSUPPORTED, "unknown model kind \"%s\"", model_kind);
 	std::map<std::string, std::string> kv;
 	if (model_desc && !parse_desc((const char*)model_desc, desc_bytes, kv)) return fail(BCM3B200_ERR_ARG, "malformed model description");
 	std::unique_ptr<Handle> h(new Handle);
+	if (is_cellpop) {
+		std::unique_ptr<CellPopState> cp(new CellPopState);
+		bool ok = true, present;
+		auto need = [&](const char* key) {
+			int v = get_int(kv, key, 0, &present);
+			ok = ok && present;
+			return v;
+		};
+		auto real = [&](const char* key, double def) { return kv.count(key) ? strtod(kv[key].c_str(), nullptr) : def; };
+		cp->N = need("num_species");
+		cp->nvar = need("num_variables");
+		cp->num_cells = need("num_cells");
+		cp->T = need("num_timepoints");
+		if (!ok || cp->N < 1 || cp->N > 64 || cp->num_cells < 0 || cp->T < 1)
+			return fail(BCM3B200_ERR_ARG, "num_species (1..64), num_variables, num_cells and num_timepoints are required");
+		cp->Nc = get_int(kv, "num_constant_species", 0);
+		cp->Nn = get_int(kv, "num_non_sampled", 0);
+		cp->R = get_int(kv, "num_replicates", 1);
+		cp->D = get_int(kv, "variability_dim", 0);
+		cp->entry_time_ix = get_int(kv, "entry_time_ix", -1);
+		cp->entry_time_fixed = real("entry_time", 0.0);
+		cp->rel_tol = real("solver_relative_tolerance", cp->rel_tol);
+		cp->abs_tol = real("solver_absolute_tolerance", cp->abs_tol);
+		cp->min_dt = real("solver_min_timestep", cp->min_dt);
+		cp->max_steps = get_int(kv, "solver_max_steps", cp->max_steps);
+		const std::string em = kv.count("error_model") ? kv["error_model"] : "normal";
+		if (em == "normal" || em == "additive_normal") cp->error_model = CP_ERR_NORMAL;
+		else if (em == "student_t4" || em == "t4") cp->error_model = CP_ERR_STUDENT_T4;
+		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4)", em.c_str());
+		cp->weight = real("weight", 1.0);
+		cp->stdev_ix = get_int(kv, "stdev_ix", -1);
+		cp->stdev_fixed = real("stdev", 1.0);
+		cp->offset_ix = get_int(kv, "offset_ix", -1);
+		cp->offset_fixed = real("offset", 0.0);
+		cp->scale_ix = get_int(kv, "scale_ix", -1);
+		cp->scale_fixed = real("scale", 1.0);
+		cp->missing_simulation_time_stdev = real("missing_simulation_time_stdev", 300.0);
+		if (kv.count("obs_species")) {
+			std::string v = kv["obs_species"];
+			size_t pos = 0;
+			while (pos <= v.size()) {
+				size_t e = v.find('+', pos);
+				if (e == std::string::npos) e = v.size();
+				if (e > pos) cp->obs_species.push_back(atoi(v.substr(pos, e - pos).c_str()));
+				pos = e + 1;
+			}
+		}
+		cp->shard_rank = get_int(kv, "shard_rank", 0);
+		cp->shard_count = get_int(kv, "shard_count", 1);
+		cp->device = get_int(kv, "device", 0);
+		if (device_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "cell_population needs device_count == 1");
+		if (get_int(kv, "compile_only", 0) == 0) {
+			const int ndev = bcm3b200_device_count();
+			if (ndev == 0) return fail(BCM3B200_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+			if (cp->device < 0 || cp->device >= ndev) return fail(BCM3B200_ERR_CUDA, "device %d requested but only %d visible", cp->device, ndev);
+		}
+		h->cp = std::move(cp);
+		*handle = h.release();
+		return BCM3B200_OK;
+	}
 	const std::string type = kv.count("type") ? kv["type"] : "";
 	if (type == "one") h->pk_type = PK_ONE;
 	else if (type == "two") h->pk_type = PK_TWO;
@@ -492,6 +516,25 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !name || !data || !shape || ndim < 1 || ndim > 2) return fail(BCM3B200_ERR_ARG, "bad argument");
+	if (h->cp) {
+		CellPopState& cp = *h->cp;
+		const std::string n(name);
+		size_t w0 = 0, w1 = 0;
+		if (n == "initial_conditions") w0 = cp.N;
+		else if (n == "constant_species") w0 = cp.Nc;
+		else if (n == "non_sampled_parameters") w0 = cp.Nn;
+		else if (n == "sobol") { w0 = cp.num_cells; w1 = cp.D; }
+		else if (n == "timepoints") w0 = cp.T;
+		else if (n == "observed") { w0 = cp.R; w1 = cp.T; }
+		else if (n == "transforms") w0 = cp.nvar;
+		else if (n == "variability") { w0 = cp.D; w1 = 6; }
+		else return fail(BCM3B200_ERR_ARG, "unknown data name \"%s\"", name);
+		const int want_ndim = w1 ? 2 : 1;
+		if (ndim != want_ndim || shape[0] != w0 || (w1 && shape[1] != w1)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);
+		cp.data[n].assign(data, data + w0 * (w1 ? w1 : 1));
+		cp.finalized = false;
+		return BCM3B200_OK;
+	}
 	const size_t P = (size_t)h->P, T = (size_t)h->T;
 	const std::string n(name);
 	size_t want0 = 0, want1 = 0;
@@ -510,10 +553,38 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 	return BCM3B200_OK;
 }
 
+int bcm3b200_set_text(void* handle, const char* name, const char* text, size_t text_bytes)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !name || !text) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (!h->cp) return fail(BCM3B200_ERR_ARG, "this model kind takes no text inputs");
+	if (strcmp(name, "derivative_code") != 0) return fail(BCM3B200_ERR_ARG, "unknown text name \"%s\"", name);
+	h->cp->derivative_code.assign(text, text_bytes);
+	h->cp->finalized = false;
+	return BCM3B200_OK;
+}
+
+int bcm3b200_get_cell_diagnostics(void* handle, double* cell_values, int32_t* cell_status, int32_t* cell_steps, double* population_average)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !h->cp) return fail(BCM3B200_ERR_ARG, "not a cell_population handle");
+	CellPopState& cp = *h->cp;
+	if (!cp.finalized || cp.last_C == 0) return fail(BCM3B200_ERR_STATE, "no evaluation yet");
+	CUDA_TRY(cudaSetDevice(cp.device));
+	CUDA_TRY(cudaDeviceSynchronize());
+	const size_t C = (size_t)cp.last_C, nc = (size_t)cp.cells_local, T = (size_t)cp.T;
+	if (cell_values) CUDA_TRY(cudaMemcpy(cell_values, cp.d_cellvals.p, sizeof(double) * C * T * nc, cudaMemcpyDeviceToHost));
+	if (cell_status) CUDA_TRY(cudaMemcpy(cell_status, cp.d_status.p, sizeof(int32_t) * C * nc, cudaMemcpyDeviceToHost));
+	if (cell_steps) CUDA_TRY(cudaMemcpy(cell_steps, cp.d_steps.p, sizeof(int32_t) * C * nc, cudaMemcpyDeviceToHost));
+	if (population_average) CUDA_TRY(cudaMemcpy(population_average, cp.d_avg.p, sizeof(double) * C * T, cudaMemcpyDeviceToHost));
+	return BCM3B200_OK;
+}
+
 int bcm3b200_finalize(void* handle)
 {
 	Handle* h = (Handle*)handle;
 	if (!h) return fail(BCM3B200_ERR_ARG, "null handle");
+	if (h->cp) return cellpop_finalize(*h->cp, bcm3b200_device_count() > 0);
 	return finalize(h);
 }
 
@@ -553,6 +624,7 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !values || !logp) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->cp) return cellpop_evaluate(*h->cp, num_chains, num_variables, values, logp, status);
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
 	if (rc != BCM3B200_OK) return rc;
@@ -600,6 +672,7 @@ int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->cp) return fail(BCM3B200_ERR_UNSUPPORTED, "device-partial entries are pop_pk_trajectory only");
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
 	if (rc != BCM3B200_OK) return rc;
@@ -619,6 +692,7 @@ int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_v
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !d_values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->cp) return fail(BCM3B200_ERR_UNSUPPORTED, "device-partial entries are pop_pk_trajectory only");
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
 	if (rc != BCM3B200_OK) return rc;
@@ -645,6 +719,7 @@ int bcm3b200_get_diagnostics(void* handle, double* conc, double* patient_ll, int
 {
 	Handle* h = (Handle*)handle;
 	if (!h) return fail(BCM3B200_ERR_ARG, "null handle");
+	if (h->cp) return fail(BCM3B200_ERR_UNSUPPORTED, "use bcm3b200_get_cell_diagnostics for cell_population");
 	if (!h->diagnostics || !h->finalized) return fail(BCM3B200_ERR_STATE, "diagnostics were not enabled before the last evaluate");
 	// layout over the handle's patients: [C][P_handle][...], shards are contiguous slices
 	size_t Ph = 0;
@@ -677,6 +752,11 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !name) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->cp) {
+		if (!strcmp(name, "diagnostics")) h->cp->diagnostics = value != 0;
+		else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
+		return BCM3B200_OK;
+	}
 	if (!strcmp(name, "diagnostics")) h->diagnostics = value != 0;
 	else if (!strcmp(name, "block_size")) {
 		if (value != 0 && (value < 32 || value > 1024 || value % 32 != 0)) return fail(BCM3B200_ERR_ARG, "block_size must be 0 or a multiple of 32 up to 1024");
@@ -689,6 +769,16 @@ int bcm3b200_get_stat(void* handle, const char* name, int64_t* value)
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !name || !value) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->cp) {
+		CellPopState& cp = *h->cp;
+		if (!strcmp(name, "last_kernel_launches")) *value = cp.last_launches;
+		else if (!strcmp(name, "total_kernel_launches")) *value = cp.total_launches;
+		else if (!strcmp(name, "num_evaluations")) *value = cp.num_evaluations;
+		else if (!strcmp(name, "last_kernel_us")) *value = (int64_t)(cp.last_kernel_ms * 1000.0);
+		else if (!strcmp(name, "num_cells_local")) *value = cp.cells_local;
+		else return fail(BCM3B200_ERR_ARG, "unknown stat \"%s\"", name);
+		return BCM3B200_OK;
+	}
 	if (!strcmp(name, "last_kernel_launches")) *value = h->last_launches;
 	else if (!strcmp(name, "total_kernel_launches")) *value = h->total_launches;
 	else if (!strcmp(name, "num_evaluations")) *value = h->num_evaluations;
@@ -706,7 +796,7 @@ void* bcm3b200_host_alloc(size_t bytes)
 {
 	void* p = nullptr;
 	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
-		g_last_error = "cudaMallocHost failed";
+		last_error_ref() = "cudaMallocHost failed";
 		cudaGetLastError();
 		return nullptr;
 	}

@@ -1,0 +1,57 @@
+// cellpop_args.h -- launch arguments shared by libbcm3b200.so and the per-model kernel library that is compiled
+// at PostInitialize time from the generated RHS text (the reference compiles and dlopens its generated code the
+// same way: src/cellpop/SolverCodeGenerator.cpp:390,407-414).
+#pragma once
+
+#include <stdint.h>
+
+#define CP_MAX_VARIABILITY 8
+
+// apply types, VariabilityDescriptionVariable.cpp:172-207
+enum {
+	CP_APPLY_ADDITIVE = 0,
+	CP_APPLY_ADDITIVE_LOG,
+	CP_APPLY_ADDITIVE_LOG2,
+	CP_APPLY_MULTIPLICATIVE,
+	CP_APPLY_MULTIPLICATIVE_LOG,
+	CP_APPLY_MULTIPLICATIVE_LOG2,
+	CP_APPLY_REPLACE
+};
+
+struct CpArgs {
+	// batch
+	int num_chains, num_cells, cell_offset; // cells of this shard, global index of the first one
+	const double* transformed;   // [C][nvar] transformed variables (VariableSet::TransformVariable applied)
+	int nvar;
+	// model
+	const double* initial_conditions; // [N]
+	const double* constant_species;   // [Nc]
+	const double* non_sampled;        // [Nn]
+	// per-cell variability (one diagonal_gaussian block): quasi-random uniforms, row = cell
+	const double* sobol; // [num_cells_total][D]
+	int D;
+	int var_scale_ix[CP_MAX_VARIABILITY];    // variable index of the scale, or -1
+	double var_scale_fixed[CP_MAX_VARIABILITY];
+	int var_apply[CP_MAX_VARIABILITY];
+	int var_negate[CP_MAX_VARIABILITY];
+	int var_slot[CP_MAX_VARIABILITY];        // override slot (parameter) or species index (initial condition)
+	int var_is_ic[CP_MAX_VARIABILITY];
+	// time
+	int entry_time_ix;     // variable index or -1
+	double entry_time_fixed;
+	const double* timepoints; // [T] absolute times, sorted
+	int T;
+	// solver (Experiment.cpp:411-416, Cell.cpp:70-74)
+	double rel_tol, abs_tol, min_dt;
+	int max_steps;
+	// observed species: sum of these ODE-integrated species per timepoint
+	int num_obs_species;
+	int obs_species[8];
+	// outputs
+	double* cell_values; // [C][T][num_cells]  (NaN where the cell does not exist at that time)
+	int32_t* cell_status; // [C][num_cells] 1 = ok, 0 = solver failure
+	int32_t* cell_steps;  // [C][num_cells] or null
+	int debug_report;     // 0: cell_steps = accepted steps; 1: RHS evaluations (nfe); 2: linear setups; 3: Jacobian evaluations
+};
+
+typedef int (*cellpop_launch_fn)(const CpArgs* args, void* stream);

@@ -1,0 +1,478 @@
+// cellpop_host.cuh -- host side of the cell_population evaluator inside libbcm3b200.so:
+//   * per-model kernel module: generated RHS text -> translation unit -> nvcc -> dlopen, the same mechanism the
+//     reference uses for its CPU code (src/cellpop/SolverCodeGenerator.cpp:32-100 writes code.cpp, :390 runs
+//     `cmake . ; make`, :407-414 dlopens the result), cached by content hash like its codegen_<name>/ directory;
+//   * model-independent kernels: variable transform (CellPopulationLikelihood.cpp:82-101), population average and
+//     data likelihood (DataLikelihoodTimeCoursePopulationAverage.cpp:85-197, DataLikelihoodTimeCourseBase.cpp:229-315).
+#pragma once
+
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+
+#include "cellpop_args.h"
+
+namespace bcm3b200 {
+
+enum : int { CP_ERR_NORMAL = 0, CP_ERR_STUDENT_T4 = 1 };
+
+struct CellPopState {
+	// description
+	int N = 0, Nc = 0, nvar = 0, Nn = 0, num_cells = 0, T = 0, R = 1, D = 0;
+	int entry_time_ix = -1;
+	double entry_time_fixed = 0.0;
+	double rel_tol = 4.0 * 1.1920928955078125e-07, abs_tol = 4.0 * 1.1920928955078125e-07; // 4 * FLT_EPSILON, Experiment.cpp:415-416
+	double min_dt = 1e-8;                                                                   // Experiment.cpp:412
+	int max_steps = 10000;                                                                  // Experiment.cpp:414
+	int error_model = CP_ERR_NORMAL;
+	double weight = 1.0;
+	int stdev_ix = -1, offset_ix = -1, scale_ix = -1;
+	double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0;
+	double missing_simulation_time_stdev = 300.0; // DataLikelihoodTimeCourseBase.cpp:22
+	std::vector<int> obs_species;
+	int shard_rank = 0, shard_count = 1, device = 0;
+	std::string derivative_code;
+	std::map<std::string, std::vector<double>> data;
+	// derived
+	bool finalized = false;
+	int cell_offset = 0, cells_local = 0;
+	void* module = nullptr;
+	cellpop_launch_fn launch = nullptr;
+	std::string module_path;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	DevBuf<double> d_ic, d_const, d_nonsampled, d_sobol, d_time, d_obs, d_values, d_transformed, d_cellvals, d_avg, d_logp;
+	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail;
+	bool diagnostics = false;
+	int last_C = 0;
+	double last_kernel_ms = 0.0;
+	int64_t total_launches = 0, last_launches = 0, num_evaluations = 0;
+	CpArgs args;
+
+	~CellPopState()
+	{
+		if (ev0) cudaEventDestroy(ev0);
+		if (ev1) cudaEventDestroy(ev1);
+		if (stream) cudaStreamDestroy(stream);
+		// the module stays loaded: unloading a library that registered CUDA kernels is not safe
+	}
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// model-independent kernels
+
+// transformed[c][i] = TransformVariable(i, values[c][i])
+__global__ void cellpop_transform_kernel(const double* __restrict__ values, const int32_t* __restrict__ transforms, int nvar, int C,
+                                         double* __restrict__ out)
+{
+	const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= (long long)nvar * C) return;
+	out[e] = transform_variable(transforms[e % nvar], values[e]);
+}
+
+// per (chain, timepoint): population size = cells that exist at that time (non-NaN value), average = sum_i x_i / size in
+// a fixed tree order; per chain: number of failed cells (block t == 0 only)
+__global__ void cellpop_average_kernel(const double* __restrict__ cell_values, const int32_t* __restrict__ status, int num_cells, int T,
+                                       double* __restrict__ avg, int32_t* __restrict__ count, int32_t* __restrict__ nfail)
+{
+	__shared__ double sh[256];
+	__shared__ int shi[256];
+	const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+	const double* v = cell_values + ((long long)c * T + t) * num_cells;
+	int n = 0;
+	for (int i = tid; i < num_cells; i += blockDim.x) n += isnan(v[i]) ? 0 : 1;
+	shi[tid] = n;
+	__syncthreads();
+	for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+		if (tid < off) shi[tid] += shi[tid + off];
+		__syncthreads();
+	}
+	const int pop = shi[0];
+	__syncthreads();
+	double s = 0.0;
+	for (int i = tid; i < num_cells; i += blockDim.x) {
+		const double x = v[i];
+		if (!isnan(x)) s += x / (double)pop; // NotifySimulatedValue divides every value by the population size, .cpp:161-197
+	}
+	sh[tid] = s;
+	__syncthreads();
+	for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+		if (tid < off) sh[tid] += sh[tid + off];
+		__syncthreads();
+	}
+	if (tid == 0) {
+		avg[c * T + t] = sh[0];
+		count[c * T + t] = pop;
+	}
+	if (t == 0) {
+		int f = 0;
+		const int32_t* st = status + (long long)c * num_cells;
+		for (int i = tid; i < num_cells; i += blockDim.x) f += st[i] ? 0 : 1;
+		__syncthreads();
+		shi[tid] = f;
+		__syncthreads();
+		for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+			if (tid < off) shi[tid] += shi[tid + off];
+			__syncthreads();
+		}
+		if (tid == 0) nfail[c] = shi[0];
+	}
+}
+
+struct CpLikArgs {
+	const double* avg;       // [C][T]
+	const int32_t* nfail;    // [C]
+	const double* transformed; // [C][nvar]
+	const double* timepoints;  // [T]
+	const double* observed;    // [R][T]
+	int T, R, nvar, error_model;
+	int stdev_ix, offset_ix, scale_ix;
+	double stdev_fixed, offset_fixed, scale_fixed, weight, missing_stdev;
+	double* logp; // [C]
+};
+
+// DataLikelihoodTimeCoursePopulationAverage::Evaluate (.cpp:85-159) for one species column; one thread per chain
+__global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C) return;
+	if (a.nfail[c] > 0) { // Simulate() failed for some cell: Experiment.cpp:356-358
+		a.logp[c] = -INFINITY;
+		return;
+	}
+	const double* tv = a.transformed + (long long)c * a.nvar;
+	const double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
+	const double offset = (a.offset_ix >= 0) ? tv[a.offset_ix] : a.offset_fixed;
+	const double scale = (a.scale_ix >= 0) ? tv[a.scale_ix] : a.scale_fixed;
+	const double minus_log_sigma = -log(stdev);
+	const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
+	double logp = 0.0;
+	for (int i = 0; i < a.T; i++) {
+		double x = a.avg[c * a.T + i];
+		x *= scale;
+		x += offset;
+		if (isnan(x)) {
+			// missing-value penalty, .cpp:121-144
+			double first_ok = a.timepoints[a.T - 1], last_ok = a.timepoints[0];
+			for (int m = 0; m < a.T; m++)
+				if (!isnan(a.avg[c * a.T + m] * scale + offset)) {
+					first_ok = a.timepoints[m];
+					break;
+				}
+			for (int m = a.T - 1; m >= 0; m--)
+				if (!isnan(a.avg[c * a.T + m] * scale + offset)) {
+					last_ok = a.timepoints[m];
+					break;
+				}
+			const double time_offset = fmin(fabs(a.timepoints[i] - first_ok), fabs(a.timepoints[i] - last_ok));
+			double pen;
+			if (a.error_model == CP_ERR_STUDENT_T4) {
+				pen = logpdf_tnu4(time_offset, 0.0, a.missing_stdev);
+			} else {
+				pen = -log(a.missing_stdev) - 0.91893853320467274178032973640562 - time_offset * time_offset / (2.0 * a.missing_stdev * a.missing_stdev);
+			}
+			for (int j = 0; j < a.R; j++)
+				if (!isnan(a.observed[j * a.T + i])) logp += pen;
+		} else {
+			for (int j = 0; j < a.R; j++) {
+				const double obs = a.observed[j * a.T + i];
+				if (isnan(obs)) continue;
+				// EvaluateValue(observed_data, x, 0): called with the arguments swapped: simulated := obs, observed := x
+				if (a.error_model == CP_ERR_STUDENT_T4) {
+					logp += logpdf_tnu4(x, obs, stdev);
+				} else {
+					const double d = x - obs;
+					logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
+				}
+			}
+		}
+	}
+	a.logp[c] = logp * a.weight;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-model module
+
+inline uint64_t fnv1a(const std::string& s)
+{
+	uint64_t h = 1469598103934665603ull;
+	for (unsigned char ch : s) {
+		h ^= ch;
+		h *= 1099511628211ull;
+	}
+	return h;
+}
+
+inline std::string library_dir()
+{
+	Dl_info info;
+	if (dladdr((void*)&fnv1a, &info) && info.dli_fname) {
+		std::string p(info.dli_fname);
+		size_t sl = p.find_last_of('/');
+		return sl == std::string::npos ? std::string(".") : p.substr(0, sl);
+	}
+	return ".";
+}
+
+// Turns the reference generator's text into a device function template and wraps it into a translation unit.
+inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>& override_vars, std::string& src)
+{
+	std::string code = cp.derivative_code;
+	// the (never installed) generated Jacobian uses host-only types: cut it off (Cell.cpp:57-76 never calls SetJacobianFunction)
+	size_t jac = code.find("EXPORT_PREFIX void generated_jacobian");
+	if (jac != std::string::npos) code = code.substr(0, jac);
+	const std::string sig = "EXPORT_PREFIX void generated_derivative(OdeReal* out, const OdeReal* species, const OdeReal* constant_species, "
+	                        "const OdeReal* parameters, const OdeReal* non_sampled_parameters)";
+	size_t at = code.find(sig);
+	if (at == std::string::npos)
+		return fail(BCM3B200_ERR_ARG, "derivative_code does not contain the reference generator's generated_derivative signature (SBMLModel.cpp:295)");
+	code.replace(at, sig.size(),
+	             "template <class SP, class PP>\n__device__ __forceinline__ void generated_derivative(OdeReal* out, const SP& species, "
+	             "const OdeReal* constant_species, const PP& parameters, const OdeReal* non_sampled_parameters)");
+	// std::numeric_limits in generated text (none emitted by the rate-law printer today, kept for safety)
+	std::ostringstream o;
+	o << "// generated by libbcm3b200 for a cell_population model -- do not edit\n";
+	o << "#include <cuda_runtime.h>\n#include <limits>\n";
+	o << "#define CP_N " << cp.N << "\n";
+	o << "#define CP_NUM_OVERRIDES " << override_vars.size() << "\n";
+	o << "#define CP_PARAM_OVERRIDE_BODY";
+	for (size_t s = 0; s < override_vars.size(); s++) o << " if (k == " << override_vars[s] << ") return ov[" << s << "];";
+	o << "\n#define CP_OVERRIDE_INIT";
+	for (size_t s = 0; s < override_vars.size(); s++) o << " S.params.ov[" << s << "] = tv[" << override_vars[s] << "];";
+	o << "\n";
+	// shared memory per warp grows with N^2: keep a block below ~96 KB
+	const size_t per_warp = sizeof(double) * ((size_t)13 * cp.N + 2 * (size_t)cp.N * (cp.N + 1) + 24) + sizeof(int) * cp.N;
+	int warps = 4;
+	while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+	o << "#define CP_WARPS_PER_BLOCK " << warps << "\n";
+	o << "#include \"cellpop_prelude.cuh\"\n";
+	o << code << "\n";
+	o << "#include \"cellpop_warp.cuh\"\n";
+	src = o.str();
+	return BCM3B200_OK;
+}
+
+inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& override_vars)
+{
+	std::string src;
+	int rc = cellpop_module_source(cp, override_vars, src);
+	if (rc != BCM3B200_OK) return rc;
+	const std::string csrc = library_dir() + "/csrc";
+	// -fmad=false: the generated rate laws are +,-,*,/,sqrt expressions; without FMA contraction every one of those is
+	// correctly rounded on the GPU exactly as in a host build of the same text with -ffp-contract=off, so the RHS -- the
+	// part whose rounding the stiff, switch-like models amplify most (two host builds of the reference's own generated
+	// code, with and without contraction, already differ by 3.5e-5 in single trajectories) -- is bit-identical to it.
+	// content hash over everything that determines the binary
+	std::string keyed = src + "|fmad=false";
+	for (const char* f : { "/cellpop_warp.cuh", "/cellpop_prelude.cuh", "/cellpop_args.h" }) {
+		std::ifstream in(csrc + f);
+		std::stringstream ss;
+		ss << in.rdbuf();
+		keyed += ss.str();
+	}
+	char hash[32];
+	snprintf(hash, sizeof(hash), "%016llx", (unsigned long long)fnv1a(keyed));
+	const char* env = getenv("BCM3B200_CACHE");
+	const std::string cache = env ? std::string(env) : (library_dir() + "/codegen_cache");
+	mkdir(cache.c_str(), 0755);
+	const std::string dir = cache + "/cellpop_" + hash;
+	mkdir(dir.c_str(), 0755);
+	const std::string so = dir + "/libcellpop_model.so";
+	if (access(so.c_str(), R_OK) != 0) {
+		{
+			std::ofstream f(dir + "/model.cu");
+			f << src;
+		}
+		const char* nvcc_env = getenv("NVCC");
+		const std::string nvcc = nvcc_env ? nvcc_env : "/usr/local/cuda/bin/nvcc";
+		const std::string tmp = so + ".tmp." + std::to_string((long)getpid());
+		const std::string cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 --shared -Xcompiler -fPIC -I" + csrc +
+		                        " -o " + tmp + " " + dir + "/model.cu > " + dir + "/build.log 2>&1";
+		if (system(cmd.c_str()) != 0) {
+			std::ifstream log(dir + "/build.log");
+			std::stringstream ss;
+			ss << log.rdbuf();
+			std::string text = ss.str();
+			if (text.size() > 700) text = text.substr(0, 700);
+			return fail(BCM3B200_ERR_STATE, "compiling the generated model failed (%s): %s", (dir + "/build.log").c_str(), text.c_str());
+		}
+		rename(tmp.c_str(), so.c_str());
+	}
+	cp.module = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+	if (!cp.module) return fail(BCM3B200_ERR_STATE, "dlopen(%s) failed: %s", so.c_str(), dlerror());
+	cp.launch = (cellpop_launch_fn)dlsym(cp.module, "cellpop_launch");
+	if (!cp.launch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_launch");
+	cp.module_path = so;
+	return BCM3B200_OK;
+}
+
+inline int cellpop_finalize(CellPopState& cp, bool need_device)
+{
+	if (cp.finalized) return BCM3B200_OK;
+	static const char* required[] = { "initial_conditions", "timepoints", "observed", "transforms" };
+	for (const char* n : required)
+		if (!cp.data.count(n)) return fail(BCM3B200_ERR_STATE, "missing data \"%s\"", n);
+	if (cp.derivative_code.empty()) return fail(BCM3B200_ERR_STATE, "missing text \"derivative_code\"");
+	if (cp.D > 0 && (!cp.data.count("sobol") || !cp.data.count("variability"))) return fail(BCM3B200_ERR_STATE, "variability needs \"sobol\" and \"variability\"");
+	if (cp.D > CP_MAX_VARIABILITY) return fail(BCM3B200_ERR_UNSUPPORTED, "more than %d variability dimensions", CP_MAX_VARIABILITY);
+	if (cp.obs_species.empty() || cp.obs_species.size() > 8) return fail(BCM3B200_ERR_ARG, "obs_species must name 1..8 species");
+	for (int s : cp.obs_species)
+		if (s < 0 || s >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species index out of range");
+
+	// variability rows: is_ic, target index, apply, scale_ix, scale_fixed, negate
+	CpArgs& a = cp.args;
+	memset(&a, 0, sizeof(a));
+	std::vector<int> override_vars;
+	for (int d = 0; d < cp.D; d++) {
+		const double* row = cp.data["variability"].data() + (size_t)d * 6;
+		a.var_is_ic[d] = row[0] != 0.0;
+		const int target = (int)row[1];
+		a.var_apply[d] = (int)row[2];
+		a.var_scale_ix[d] = (int)row[3];
+		a.var_scale_fixed[d] = row[4];
+		a.var_negate[d] = row[5] != 0.0;
+		if (a.var_apply[d] < 0 || a.var_apply[d] > CP_APPLY_REPLACE) return fail(BCM3B200_ERR_ARG, "bad variability apply type");
+		if (a.var_is_ic[d]) {
+			if (target < 0 || target >= cp.N) return fail(BCM3B200_ERR_ARG, "variability species index out of range");
+			a.var_slot[d] = target;
+		} else {
+			if (target < 0 || target >= cp.nvar) return fail(BCM3B200_ERR_ARG, "variability parameter index out of range");
+			int slot = -1;
+			for (size_t s = 0; s < override_vars.size(); s++)
+				if (override_vars[s] == target) slot = (int)s;
+			if (slot < 0) {
+				slot = (int)override_vars.size();
+				override_vars.push_back(target);
+			}
+			a.var_slot[d] = slot;
+		}
+	}
+	int rc = cellpop_build_module(cp, override_vars);
+	if (rc != BCM3B200_OK) return rc;
+	if (!need_device) return BCM3B200_OK; // compile-only (CPU container)
+
+	const long long lo = (long long)cp.num_cells * cp.shard_rank / cp.shard_count;
+	const long long hi = (long long)cp.num_cells * (cp.shard_rank + 1) / cp.shard_count;
+	cp.cell_offset = (int)lo;
+	cp.cells_local = (int)(hi - lo);
+	CUDA_TRY(cudaSetDevice(cp.device));
+	CUDA_TRY(cudaStreamCreateWithFlags(&cp.stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaEventCreate(&cp.ev0));
+	CUDA_TRY(cudaEventCreate(&cp.ev1));
+	auto up = [&](DevBuf<double>& b, const std::vector<double>& v) -> cudaError_t {
+		cudaError_t e = b.ensure(v.size() ? v.size() : 1);
+		if (e != cudaSuccess || v.empty()) return e;
+		return cudaMemcpy(b.p, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice);
+	};
+	CUDA_TRY(up(cp.d_ic, cp.data["initial_conditions"]));
+	CUDA_TRY(up(cp.d_const, cp.data["constant_species"]));
+	CUDA_TRY(up(cp.d_nonsampled, cp.data["non_sampled_parameters"]));
+	CUDA_TRY(up(cp.d_sobol, cp.data["sobol"]));
+	CUDA_TRY(up(cp.d_time, cp.data["timepoints"]));
+	CUDA_TRY(up(cp.d_obs, cp.data["observed"]));
+	std::vector<int32_t> tr(cp.nvar);
+	for (int i = 0; i < cp.nvar; i++) tr[i] = (int32_t)cp.data["transforms"][i];
+	CUDA_TRY(cp.d_transforms.ensure(cp.nvar ? cp.nvar : 1));
+	CUDA_TRY(cudaMemcpy(cp.d_transforms.p, tr.data(), sizeof(int32_t) * cp.nvar, cudaMemcpyHostToDevice));
+
+	a.num_cells = cp.cells_local;
+	a.cell_offset = cp.cell_offset;
+	a.nvar = cp.nvar;
+	a.initial_conditions = cp.d_ic.p;
+	a.constant_species = cp.d_const.p;
+	a.non_sampled = cp.d_nonsampled.p;
+	a.sobol = cp.d_sobol.p;
+	a.D = cp.D;
+	a.entry_time_ix = cp.entry_time_ix;
+	a.entry_time_fixed = cp.entry_time_fixed;
+	a.timepoints = cp.d_time.p;
+	a.T = cp.T;
+	a.rel_tol = cp.rel_tol;
+	a.abs_tol = cp.abs_tol;
+	a.min_dt = cp.min_dt;
+	a.max_steps = cp.max_steps;
+	a.num_obs_species = (int)cp.obs_species.size();
+	for (size_t k = 0; k < cp.obs_species.size(); k++) a.obs_species[k] = cp.obs_species[k];
+	cp.finalized = true;
+	return BCM3B200_OK;
+}
+
+inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const double* values, double* logp, int* status)
+{
+	if ((int)nvar != cp.nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", nvar, cp.nvar);
+	int rc = cellpop_finalize(cp, true);
+	if (rc != BCM3B200_OK) return rc;
+	if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "cell_population sharding is not implemented yet");
+	if (C == 0) return BCM3B200_OK;
+	CUDA_TRY(cudaSetDevice(cp.device));
+	const int T = cp.T, nc = cp.cells_local;
+	CUDA_TRY(cp.d_values.ensure(C * nvar));
+	CUDA_TRY(cp.d_transformed.ensure(C * nvar));
+	CUDA_TRY(cp.d_cellvals.ensure(C * (size_t)T * (nc ? nc : 1)));
+	CUDA_TRY(cp.d_status.ensure(C * (size_t)(nc ? nc : 1)));
+	CUDA_TRY(cp.d_steps.ensure(C * (size_t)(nc ? nc : 1)));
+	CUDA_TRY(cp.d_avg.ensure(C * (size_t)T));
+	CUDA_TRY(cp.d_count.ensure(C * (size_t)T));
+	CUDA_TRY(cp.d_nfail.ensure(C));
+	CUDA_TRY(cp.d_logp.ensure(C));
+	cudaStream_t st = cp.stream;
+	CUDA_TRY(cudaMemcpyAsync(cp.d_values.p, values, sizeof(double) * C * nvar, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaEventRecord(cp.ev0, st));
+	const long long ne = (long long)C * nvar;
+	cellpop_transform_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(cp.d_values.p, cp.d_transforms.p, (int)nvar, (int)C, cp.d_transformed.p);
+	CUDA_TRY(cudaGetLastError());
+	CpArgs a = cp.args;
+	a.num_chains = (int)C;
+	a.transformed = cp.d_transformed.p;
+	a.cell_values = cp.d_cellvals.p;
+	a.cell_status = cp.d_status.p;
+	a.cell_steps = cp.d_steps.p;
+	a.debug_report = getenv("BCM3B200_CELLPOP_REPORT") ? atoi(getenv("BCM3B200_CELLPOP_REPORT")) : 0;
+	cp.last_launches = 1;
+	if (nc > 0) {
+		int lrc = cp.launch(&a, (void*)st);
+		if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "cellpop kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+		cp.last_launches++;
+	}
+	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, nc, T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
+	CUDA_TRY(cudaGetLastError());
+	CpLikArgs la;
+	la.avg = cp.d_avg.p;
+	la.nfail = cp.d_nfail.p;
+	la.transformed = cp.d_transformed.p;
+	la.timepoints = cp.d_time.p;
+	la.observed = cp.d_obs.p;
+	la.T = T;
+	la.R = cp.R;
+	la.nvar = (int)nvar;
+	la.error_model = cp.error_model;
+	la.stdev_ix = cp.stdev_ix;
+	la.offset_ix = cp.offset_ix;
+	la.scale_ix = cp.scale_ix;
+	la.stdev_fixed = cp.stdev_fixed;
+	la.offset_fixed = cp.offset_fixed;
+	la.scale_fixed = cp.scale_fixed;
+	la.weight = cp.weight;
+	la.missing_stdev = cp.missing_simulation_time_stdev;
+	la.logp = cp.d_logp.p;
+	cellpop_datalik_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>(la, (int)C);
+	CUDA_TRY(cudaGetLastError());
+	cp.last_launches += 2;
+	cp.total_launches += cp.last_launches;
+	CUDA_TRY(cudaEventRecord(cp.ev1, st));
+	CUDA_TRY(cudaMemcpyAsync(logp, cp.d_logp.p, sizeof(double) * C, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, cp.ev0, cp.ev1) == cudaSuccess) cp.last_kernel_ms = ms;
+	if (status)
+		for (size_t c = 0; c < C; c++) status[c] = std::isnan(logp[c]) ? BCM3B200_STATUS_NAN : BCM3B200_STATUS_OK;
+	cp.last_C = (int)C;
+	cp.num_evaluations += (int64_t)C;
+	return BCM3B200_OK;
+}
+
+} // namespace bcm3b200

@@ -148,18 +148,28 @@ bool ProposalGlobalCovariance::Initialize(const SampleHistory& history, size_t m
 			covariance[j + j * n] = std::max(covariance[j + j * n], 1e-6 * var);
 		}
 	}
-	// Cholesky (covariance.llt())
-	chol.assign(n * n, 0.0);
-	for (size_t j = 0; j < n; j++) {
-		Real d = covariance[j + j * n];
-		for (size_t k = 0; k < j; k++) d -= chol[j + k * n] * chol[j + k * n];
-		if (!(d > 0.0)) return false;
-		chol[j + j * n] = sqrt(d);
-		for (size_t i = j + 1; i < n; i++) {
-			Real v = covariance[i + j * n];
-			for (size_t k = 0; k < j; k++) v -= chol[i + k * n] * chol[j + k * n];
-			chol[i + j * n] = v / chol[j + j * n];
+	// Cholesky (covariance.llt()). With fewer history samples than variables the empirical covariance is singular; Eigen's
+	// LLT would silently produce NaNs there, here the proposal falls back to the diagonal of the covariance.
+	auto cholesky = [&]() {
+		chol.assign(n * n, 0.0);
+		for (size_t j = 0; j < n; j++) {
+			Real d = covariance[j + j * n];
+			for (size_t k = 0; k < j; k++) d -= chol[j + k * n] * chol[j + k * n];
+			if (!(d > 1e-12 * covariance[j + j * n])) return false;
+			chol[j + j * n] = sqrt(d);
+			for (size_t i = j + 1; i < n; i++) {
+				Real v = covariance[i + j * n];
+				for (size_t k = 0; k < j; k++) v -= chol[i + k * n] * chol[j + k * n];
+				chol[i + j * n] = v / chol[j + j * n];
+			}
 		}
+		return true;
+	};
+	if (!cholesky()) {
+		for (size_t i = 0; i < n; i++)
+			for (size_t j = 0; j < n; j++)
+				if (i != j) covariance[i + j * n] = 0.0;
+		if (!cholesky()) return false;
 	}
 	return true;
 }

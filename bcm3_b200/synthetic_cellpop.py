@@ -1,0 +1,195 @@
+"""Synthetic cell_population workloads of the shapes BASELINE.json names (configs 3 and 4).
+
+The reference ships no SBML model and no data, so a model is synthesised here directly as the TEXT the reference's code
+generator would emit for it (src/sbml/SBMLModel.cpp:291-365: `ratelaws[r] = ...; out[i] = +ratelaws[..]-ratelaws[..];`,
+numeric constants printed with std::to_string's 6 decimals, helper calls hill_function_fixedn*, michaelis_menten_function,
+synthcap, tQSSA from the prelude of SolverCodeGenerator.cpp:122-295). The network is a signalling cascade with feedback:
+species i is produced in a saturating way from species i-1 and degraded linearly, rate constants spread over several
+decades so that the system is stiff. Nothing here touches the oracle or the GPU.
+"""
+from __future__ import annotations
+
+import math
+import re
+
+import numpy as np
+
+from .cellpop_data import CellPopProblem, Variability
+from .poppk_data import TRANSFORM_LOG10, TRANSFORM_NONE
+
+SIGNATURE = ("EXPORT_PREFIX void generated_derivative(OdeReal* out, const OdeReal* species, const OdeReal* constant_species, "
+             "const OdeReal* parameters, const OdeReal* non_sampled_parameters)")
+
+# sampled variables of the synthetic models (prior.xml order)
+VAR_K_IN, VAR_K_CASCADE, VAR_K_DEG, VAR_K_FEEDBACK, VAR_VARIABILITY_SCALE, VAR_STDEV = range(6)
+NUM_VARIABLES = 6
+
+
+def _lit(x: float) -> str:
+    """std::to_string(double): fixed, 6 decimals (SBMLRatelaws.cpp:757-763) -- the quirk that 1e-8 prints as 0.000000 is kept."""
+    return f"{x:.6f}"
+
+
+def cascade_code(N: int, seed: int = 0, rate_decades: float = 2.0):
+    """Returns (text, info) for an N-species cascade. Reaction 2i produces species i, reaction 2i+1 degrades it."""
+    rng = np.random.default_rng(seed)
+    lines = [SIGNATURE, "{", f"\tOdeReal ratelaws[{2 * N}];"]
+    for i in range(N):
+        speed = 10.0 ** rng.uniform(-rate_decades / 2, rate_decades / 2)  # time scale of this level
+        kscale = 4.0 * speed                                               # production gain over degradation ~ 4
+        K = rng.uniform(0.15, 0.35)
+        if i == 0:
+            prod = f"((parameters[{VAR_K_IN}]*constant_species[0])*synthcap(species[0]))"
+        else:
+            kind = i % 4
+            if kind == 1:
+                prod = f"(((parameters[{VAR_K_CASCADE}]*{_lit(kscale)})*species[{i - 1}])*(1.000000-species[{i}]))"
+            elif kind == 2:
+                prod = f"michaelis_menten_function((parameters[{VAR_K_CASCADE}]*{_lit(kscale)}),{_lit(K)},species[{i - 1}],(1.000000-species[{i}]))"
+            elif kind == 3:
+                prod = f"(((parameters[{VAR_K_CASCADE}]*{_lit(kscale)})*hill_function_fixedn2(species[{i - 1}],{_lit(K)}))*(1.000000-species[{i}]))"
+            else:
+                prod = f"tQSSA((parameters[{VAR_K_CASCADE}]*{_lit(kscale)}),{_lit(K)},species[{i - 1}],(1.000000-species[{i}]))"
+        lines.append(f"\tratelaws[{2 * i}] = {prod};")
+        dscale = speed
+        if i == 0 and N > 2:
+            # negative feedback from the end of the cascade onto the first species
+            deg = f"(((parameters[{VAR_K_DEG}]*{_lit(dscale)})*species[{i}])*(1.000000+(parameters[{VAR_K_FEEDBACK}]*species[{N - 1}])))"
+        else:
+            deg = f"((parameters[{VAR_K_DEG}]*{_lit(dscale)})*species[{i}])"
+        lines.append(f"\tratelaws[{2 * i + 1}] = {deg};")
+    for i in range(N):
+        lines.append(f"\tout[{i}] = +ratelaws[{2 * i}]-ratelaws[{2 * i + 1}];")
+    lines.append("}")
+    lines.append("")
+    # the generator also emits generated_jacobian(OdeMatrixReal& out, ...): present in real input, never used (Cell.cpp:57-76)
+    lines.append("EXPORT_PREFIX void generated_jacobian(OdeMatrixReal& out, const OdeReal* species, const OdeReal* constant_species, "
+                 "const OdeReal* parameters, const OdeReal* non_sampled_parameters)")
+    lines.append("{")
+    lines.append(f"\tout(0, 0) = -((parameters[{VAR_K_DEG}]*1.000000));")
+    lines.append("}")
+    return "\n".join(lines) + "\n"
+
+
+# ---- a Python evaluation of the generated text (only to synthesise observations) ---------------------------------
+def _py_helpers():
+    def hill(x, k, n):
+        if x <= 0:
+            return 0.0
+        return x ** n / (x ** n + k ** n)
+
+    def mm(kcat, KM, e, s):
+        if e <= 0:
+            return 0.0
+        if s + KM < 0.1 * KM:
+            bound = -KM + 0.1 * KM
+            offset = e * kcat * bound / (0.01 * KM) - e * kcat * bound / (KM + bound)
+            return e * kcat * s / (0.01 * KM) - offset
+        return kcat * e * s / (KM + s)
+
+    def tq(k, km, e, s):
+        ekms = e + km + s
+        return 0.5 * k * (ekms - math.sqrt(max(ekms * ekms - 4 * e * s, 0.0)))
+
+    return dict(
+        hill_function_fixedn2=lambda x, k: hill(x, k, 2), hill_function_fixedn4=lambda x, k: hill(x, k, 4),
+        michaelis_menten_function=mm, tQSSA=tq, synthcap=lambda x: 1.0 if x <= 0 else 1.0 - x ** 10)
+
+
+def python_rhs(code: str, N: int):
+    body = code[code.index("{") + 1: code.index("}")]
+    stmts = [s.strip() for s in body.split(";") if s.strip() and not s.strip().startswith("OdeReal ")]
+    src = "\n".join(stmts)
+    compiled = compile(src, "<generated_derivative>", "exec")
+    helpers = _py_helpers()
+    nr = int(re.search(r"ratelaws\[(\d+)\];", code).group(1))
+
+    def f(t, y, constant_species, parameters):
+        env = dict(helpers)
+        env.update(species=y, constant_species=constant_species, parameters=parameters, non_sampled_parameters=[],
+                   ratelaws=[0.0] * nr, out=[0.0] * N)
+        exec(compiled, env)
+        return env["out"]
+
+    return f
+
+
+def sobol_points(n: int, d: int) -> np.ndarray:
+    """Unscrambled Sobol points, skipping the all-zero first point (its normal quantile is -inf)."""
+    from scipy.stats import qmc
+
+    if d == 0:
+        return np.zeros((n, 0))
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pts = qmc.Sobol(d=d, scramble=False).random(n + 1)[1:]
+    return np.ascontiguousarray(pts)
+
+
+def default_values() -> np.ndarray:
+    """Reference ("true") values of the sampled variables, in the sampler's (untransformed) parametrisation."""
+    v = np.zeros(NUM_VARIABLES)
+    v[VAR_K_IN] = math.log10(0.8)
+    v[VAR_K_CASCADE] = math.log10(1.5)
+    v[VAR_K_DEG] = math.log10(0.6)
+    v[VAR_K_FEEDBACK] = math.log10(0.5)
+    v[VAR_VARIABILITY_SCALE] = math.log(0.25)  # log of the s.d. of the per-cell log-normal factors
+    v[VAR_STDEV] = math.log10(0.02)
+    return v
+
+
+def make_cellpop_problem(N: int = 12, num_cells: int = 10_000, T: int = 50, t_end: float = 8.0, seed: int = 1,
+                         rate_decades: float = 2.0, data_cells: int = 64, replicates: int = 1, missing_fraction: float = 0.0,
+                         two_species_readout: bool = False) -> CellPopProblem:
+    """cfg 3 (N~12, 10k cells) / cfg 4 (N~50, 100k cells, rate_decades=6) style experiment."""
+    from scipy.integrate import solve_ivp
+    from scipy.special import ndtri
+
+    code = cascade_code(N, seed=seed, rate_decades=rate_decades)
+    transforms = np.full(NUM_VARIABLES, TRANSFORM_LOG10, dtype=np.int32)
+    transforms[VAR_VARIABILITY_SCALE] = TRANSFORM_NONE
+    timepoints = t_end * (np.arange(T) + 1.0) / T
+    timepoints[0] = 0.0 if T > 4 else timepoints[0]  # one timepoint at the entry time: takes the initial condition
+    ic = np.zeros(N)
+    ic[0] = 0.05
+    const = np.array([1.0])
+    variability = [Variability(apply="multiplicative_log", model_parameter=VAR_K_IN, scale_ix=VAR_VARIABILITY_SCALE),
+                   Variability(apply="multiplicative_log", model_parameter=VAR_K_DEG, scale_ix=VAR_VARIABILITY_SCALE, negate=True),
+                   Variability(apply="additive", initial_condition_species=1, scale_fixed=math.log(0.01))]
+    sobol = sobol_points(num_cells, len(variability))
+    obs_species = [N - 1, N - 2] if two_species_readout else [N - 1]
+
+    # synthetic observations: population average of `data_cells` cells at the reference parameters + noise
+    v = default_values()
+    tv = np.where(transforms == TRANSFORM_LOG10, 10.0 ** v, v)
+    f = python_rhs(code, N)
+    acc = np.zeros(T)
+    rng = np.random.default_rng(seed + 1000)
+    u = sobol_points(data_cells, len(variability))
+    for ci in range(data_cells):
+        p = tv.copy()
+        y0 = ic.copy()
+        z = ndtri(u[ci]) * math.exp(tv[VAR_VARIABILITY_SCALE])
+        p[VAR_K_IN] *= math.exp(z[0])
+        p[VAR_K_DEG] *= math.exp(-z[1])
+        y0[1] += ndtri(u[ci][2]) * 0.01
+        sol = solve_ivp(lambda t, y: f(t, y, const, p), (0.0, float(timepoints[-1])), y0, method="LSODA", t_eval=timepoints, rtol=1e-7, atol=1e-9)
+        acc += sol.y[obs_species].sum(axis=0)
+    avg = acc / data_cells
+    observed = avg[None, :] + 0.02 * rng.standard_normal((replicates, T))
+    if missing_fraction > 0:
+        observed[rng.uniform(size=observed.shape) < missing_fraction] = np.nan
+    return CellPopProblem(derivative_code=code, num_species=N, initial_conditions=ic, transforms=transforms, num_cells=num_cells,
+                          timepoints=timepoints, observed=observed, obs_species=obs_species, constant_species=const, sobol=sobol,
+                          variability=variability, stdev_ix=VAR_STDEV)
+
+
+def make_chain_values(C: int, seed: int = 20261018) -> np.ndarray:
+    base = default_values()
+    out = np.empty((C, NUM_VARIABLES))
+    for c in range(C):
+        rng = np.random.default_rng(seed + c)
+        out[c] = base + rng.normal(0.0, 0.05, NUM_VARIABLES)
+    return out

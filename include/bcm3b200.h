@@ -37,8 +37,8 @@ extern "C" {
 #define BCM3B200_STATUS_NAN 1 /* log-likelihood is NaN: the reference aborts sampling on this (Sampler.cpp:172-178) */
 
 /* Create an evaluator.
- *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62):
- *                "pop_pk_trajectory"
+ *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62,81):
+ *                "pop_pk_trajectory" | "cell_population" (keys of the latter: see DESIGN.md section 9)
  *   model_desc : `key=value;...` text, desc_bytes long (no terminator needed). Keys for pop_pk_trajectory
  *                mirror the <pk_model> attributes (LikelihoodPopPKTrajectory.cpp:58-87) plus sizes:
  *                  type=one|two  drug=<name>  num_patients=<P>  num_timepoints=<T>
@@ -60,6 +60,14 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
  *   "transforms"[nvar] : VariableSet transform per variable, 0 none / 1 log / 2 log10 / 3 logit (VariableSet.cpp:97-124)
  * Replaces: the NetCDFDataFile reads in LikelihoodPopPKTrajectory::Initialize. */
 int bcm3b200_set_data(void* handle, const char* name, const double* data, const size_t* shape, int ndim);
+
+/* Attach one named text input. cell_population: "derivative_code" = the C++ text the reference's SBML code generator
+ * emits (SBMLModel::GenerateCode, src/sbml/SBMLModel.cpp:291-389; ABI derivative_fn of SolverCodeGenerator.h:6):
+ *   EXPORT_PREFIX void generated_derivative(OdeReal* out, const OdeReal* species, const OdeReal* constant_species,
+ *                                           const OdeReal* parameters, const OdeReal* non_sampled_parameters) {...}
+ * The library compiles it for the device at finalize, the way the reference compiles it for the host
+ * (SolverCodeGenerator.cpp:390,407-414). */
+int bcm3b200_set_text(void* handle, const char* name, const char* text, size_t text_bytes);
 
 /* Derive simulate_until / tolerances / skipped-day masks (LikelihoodPopPKTrajectory.cpp:163-204,238) and upload
  * the static data to the device(s). Called implicitly by the first evaluate. Replaces: PostInitialize. */
@@ -106,6 +114,13 @@ int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* 
  *   counters   [num_chains][P_local][8] : steps, nfe, nsetups, nje, netf, ncfn, nni, ok
  * Any pointer may be NULL. */
 int bcm3b200_get_diagnostics(void* handle, double* conc, double* patient_ll, int32_t* counters);
+
+/* cell_population diagnostics of the LAST evaluate (any pointer may be NULL):
+ *   cell_values [C][T][cells] observed-species value of every simulated cell at every data timepoint (NaN = cell absent)
+ *   cell_status [C][cells] 1 = solved, 0 = CVODE failure;  cell_steps [C][cells] accepted steps (ODESolver::GetNumSteps)
+ *   population_average [C][T] (DataLikelihoodTimeCoursePopulationAverage::population_average before offset/scale) */
+int bcm3b200_get_cell_diagnostics(void* handle, double* cell_values, int32_t* cell_status, int32_t* cell_steps,
+                                  double* population_average);
 
 /* options: "diagnostics" (0/1), "block_size" (0 = auto, 32/64/128/256) */
 int bcm3b200_set_option(void* handle, const char* name, int64_t value);

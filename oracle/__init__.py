@@ -67,6 +67,45 @@ def available(kind: str) -> bool:
     return os.path.exists(REF_LIB if kind == "ref" else PORT_LIB)
 
 
+class _CellPopProblem(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_species", "num_constant_species", "num_variables", "num_non_sampled", "num_cells",
+                                         "num_timepoints", "num_replicates", "variability_dim", "entry_time_ix", "max_steps",
+                                         "error_model", "stdev_ix", "offset_ix", "scale_ix", "num_obs_species")] + [
+        ("obs_species", C.c_int32 * 8)] + [(n, C.c_double) for n in ("entry_time", "rel_tol", "abs_tol", "min_dt", "weight", "stdev",
+                                                                     "offset", "scale", "missing_stdev")] + [
+        (n, C.c_void_p) for n in ("initial_conditions", "constant_species", "non_sampled", "sobol", "timepoints", "observed",
+                                  "variability", "transforms", "derivative")]
+
+
+_derivative_libs: dict[str, C.CDLL] = {}
+
+
+def compile_cellpop_derivative(code: str) -> C.CDLL:
+    """Compile the generated RHS text for the HOST the way the reference does (SolverCodeGenerator.cpp:100-300,390,407-414):
+    helper prelude + generated text -> shared library -> dlopen."""
+    import hashlib
+
+    key = hashlib.sha1((code + "|strict").encode()).hexdigest()[:16]
+    if key in _derivative_libs:
+        return _derivative_libs[key]
+    d = os.path.join(HERE, "_build", "cellpop_" + key)
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, "libgenerated_derivatives.so")
+    if not os.path.exists(so):
+        with open(os.path.join(d, "code.cpp"), "w") as f:
+            f.write('#include <limits>\n#include "cellpop_prelude.h"\n#define EXPORT_PREFIX extern "C"\n'
+                    "struct OdeMatrixReal { double dummy; double& operator()(int, int) { return dummy; } };\n\n")
+            f.write(code)
+        # strict IEEE (no FMA contraction): the device build of the same text uses -fmad=false, which makes the rate laws
+        # bit-identical on both sides; the reference's own flags (-O3 -march=native) would contract -- see DESIGN.md section 9
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++14", "-fPIC", "-shared", "-w", "-I", HERE, "-o", so + ".tmp",
+                        os.path.join(d, "code.cpp")], check=True)
+        os.replace(so + ".tmp", so)
+    lib = C.CDLL(so)
+    _derivative_libs[key] = lib
+    return lib
+
+
 class Oracle:
     def __init__(self, kind: str):
         path = REF_LIB if kind == "ref" else PORT_LIB
@@ -77,6 +116,8 @@ class Oracle:
         self.lib.oracle_poppk_evaluate.restype = C.c_int
         self.lib.oracle_poppk_evaluate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.oracle_cellpop_evaluate.restype = C.c_int
+        self.lib.oracle_cellpop_evaluate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         self.lib.oracle_kind.restype = C.c_char_p
         assert self.lib.oracle_kind().decode() == kind
 
@@ -125,6 +166,48 @@ class Oracle:
             raise RuntimeError(f"oracle_poppk_evaluate failed: {rc}")
         return dict(logp=logp, conc=conc, patient_ll=pll, counters=cnt)
 
+
+def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=False, want_steps=False, want_average=False):
+    """problem: bcm3_b200.cellpop_data.CellPopProblem; values [C, nvar]."""
+    p = problem
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if values.ndim == 1:
+        values = values[None, :]
+    nC = values.shape[0]
+    T, nc, D = p.num_timepoints, p.num_cells, p.variability_dim
+    dlib = compile_cellpop_derivative(p.derivative_code)
+    fn = C.cast(dlib.generated_derivative, C.c_void_p).value
+    keep = dict(
+        ic=np.ascontiguousarray(p.initial_conditions, dtype=np.float64), const=np.ascontiguousarray(p.constant_species, dtype=np.float64),
+        ns=np.ascontiguousarray(p.non_sampled_parameters, dtype=np.float64), sobol=np.ascontiguousarray(p.sobol, dtype=np.float64),
+        tp=np.ascontiguousarray(p.timepoints, dtype=np.float64), obs=np.ascontiguousarray(p.observed, dtype=np.float64),
+        var=np.ascontiguousarray(p.variability_rows(), dtype=np.float64), tr=np.ascontiguousarray(p.transforms, dtype=np.int32))
+    ptr = lambda a: a.ctypes.data if a.size else None
+    s = _CellPopProblem(
+        num_species=p.num_species, num_constant_species=len(keep["const"]), num_variables=p.num_variables, num_non_sampled=len(keep["ns"]),
+        num_cells=nc, num_timepoints=T, num_replicates=p.num_replicates, variability_dim=D,
+        entry_time_ix=-1 if p.entry_time_ix is None else p.entry_time_ix, max_steps=p.solver_max_steps,
+        error_model={"normal": 0, "additive_normal": 0, "student_t4": 1, "t4": 1}[p.error_model],
+        stdev_ix=-1 if p.stdev_ix is None else p.stdev_ix, offset_ix=-1 if p.offset_ix is None else p.offset_ix,
+        scale_ix=-1 if p.scale_ix is None else p.scale_ix, num_obs_species=len(p.obs_species),
+        obs_species=(C.c_int32 * 8)(*(list(p.obs_species) + [0] * (8 - len(p.obs_species)))),
+        entry_time=p.entry_time, rel_tol=p.solver_relative_tolerance, abs_tol=p.solver_absolute_tolerance, min_dt=p.solver_min_timestep,
+        weight=p.weight, stdev=p.stdev, offset=p.offset, scale=p.scale, missing_stdev=p.missing_simulation_time_stdev,
+        initial_conditions=ptr(keep["ic"]), constant_species=ptr(keep["const"]), non_sampled=ptr(keep["ns"]), sobol=ptr(keep["sobol"]),
+        timepoints=ptr(keep["tp"]), observed=ptr(keep["obs"]), variability=ptr(keep["var"]), transforms=ptr(keep["tr"]), derivative=fn)
+    logp = np.empty(nC)
+    cv = np.empty((nC, T, nc)) if want_cell_values else None
+    st = np.zeros((nC, nc), dtype=np.int32) if want_steps else None
+    avg = np.empty((nC, T)) if want_average else None
+    rc = self.lib.oracle_cellpop_evaluate(C.byref(s), nC, values.ctypes.data, logp.ctypes.data,
+                                          cv.ctypes.data if cv is not None else None, st.ctypes.data if st is not None else None,
+                                          avg.ctypes.data if avg is not None else None, int(threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle_cellpop_evaluate failed: {rc}")
+    return dict(logp=logp, cell_values=cv, cell_steps=st, population_average=avg)
+
+
+Oracle.cellpop_evaluate = _cellpop_evaluate
 
 _cache: dict[str, Oracle] = {}
 

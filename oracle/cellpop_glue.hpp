@@ -1,0 +1,197 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product.
+//
+// Restatement of the Boost/NetCDF-bound glue of the cell_population likelihood around an ODE solver adapter:
+//   CellPopulationLikelihood::EvaluateLogProbability   src/cellpop/CellPopulationLikelihood.cpp:82-101
+//   Experiment::EvaluateLogProbability / Simulate      src/cellpop/Experiment.cpp:239-372, 635-724
+//   CellPopulation::AddNewCell                         src/cellpop/CellPopulation.cpp:36-104 (Sobol row = cell index)
+//   Cell::Initialize / Simulate                        src/cellpop/Cell.cpp:150-273 (no events, no treatment trajectories)
+//   VariabilityDescription::GetPseudorandomVector      src/cellpop/VariabilityDescription.cpp:50-64 (diagonal_gaussian)
+//   VariabilityDescriptionVariable::Apply*             src/cellpop/VariabilityDescriptionVariable.cpp:80-110,172-207
+//   DataLikelihoodTimeCoursePopulationAverage          .cpp:85-197;  DataLikelihoodTimeCourseBase .cpp:229-315
+// Used twice: oracle/ref/cellpop_ref.cpp plugs in the reference's real ODESolverCVODE, oracle/cellpop_port.cpp plugs in
+// oracle/cvode_bdf.c. The adapter must provide
+//   bool solve(const double* y0, const double* cell_params, const double* timepoints_rel, int ntp, double* out /*[N][ntp] col-major*/, int& steps)
+// with the semantics of ODESolver::SolveReturnSolution.
+#pragma once
+
+#include <atomic>
+#include <cmath>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "oracle_api.h"
+
+namespace cellpop_glue {
+
+double ndtri(double p); // defined by the including translation unit
+
+inline double transform_variable(int tr, double x)
+{
+	switch (tr) {
+	case ORACLE_TRANSFORM_LOG: return exp(x);
+	case ORACLE_TRANSFORM_LOG10: return exp(x * 2.3025850929940459);
+	case ORACLE_TRANSFORM_LOGIT:
+		if (x > 0) { double z = exp(-x); return 1.0 / (1.0 + z); } else { double z = exp(x); return z / (1.0 + z); }
+	default: return x;
+	}
+}
+
+inline void apply_variability(double& x, double value, int apply)
+{
+	switch (apply) {
+	case 0: x += value; break;
+	case 1: x += exp(value); break;
+	case 2: x += pow(2.0, value); break;
+	case 3: x *= value; break;
+	case 4: x *= exp(value); break;
+	case 5: x *= pow(2.0, value); break;
+	case 6: x = value; break;
+	}
+}
+
+inline double logpdf_tnu4(double x, double mu, double sigma)
+{
+	double xn = (x - mu) / sigma;
+	return -0.9808292530117262 - 2.5 * log1p(0.25 * xn * xn) - log(sigma);
+}
+inline double logpdf_normal(double x, double mu, double sigma)
+{
+	double d = x - mu;
+	return -log(sigma) - 0.91893853320467274178032973640562 - d * d / (2.0 * sigma * sigma);
+}
+
+template <class Solver>
+void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, double* logp_out, double* cell_values, int32_t* cell_steps,
+                    double* pop_avg_out)
+{
+	const int N = pr.num_species, nvar = pr.num_variables, T = pr.num_timepoints, ncell = pr.num_cells, D = pr.variability_dim, R = pr.num_replicates;
+	const double nan = std::numeric_limits<double>::quiet_NaN();
+	std::vector<double> transformed(nvar);
+	for (int i = 0; i < nvar; i++) transformed[i] = transform_variable(pr.transforms[i], values[i]);
+	const double entry_time = (pr.entry_time_ix >= 0) ? transformed[pr.entry_time_ix] : pr.entry_time;
+
+	Solver solver(pr);
+	std::vector<double> population_average(T, 0.0), cell_params(nvar), y0(N), tp_rel(T), out((size_t)N * T);
+	std::vector<double> xs((size_t)T * ncell, nan); // value per (timepoint, cell)
+	bool result = true;
+
+	for (int ci = 0; ci < ncell && result; ci++) {
+		// Cell::Initialize
+		for (int i = 0; i < nvar; i++) cell_params[i] = transformed[i];
+		for (int i = 0; i < N; i++) y0[i] = pr.initial_conditions[i];
+		for (int d = 0; d < D; d++) {
+			const double* row = pr.variability + (size_t)d * 6;
+			const bool is_ic = row[0] != 0.0;
+			const int target = (int)row[1], apply = (int)row[2], scale_ix = (int)row[3];
+			const double scale = (scale_ix >= 0) ? transformed[scale_ix] : row[4];
+			double v = ndtri(pr.sobol[(size_t)ci * D + d]) * exp(scale);
+			if (row[5] != 0.0) v = -v;
+			if (is_ic) apply_variability(y0[target], v, apply);
+			else apply_variability(cell_params[target], v, apply);
+		}
+		// Cell::Simulate: output times relative to the creation time
+		const double creation_time = entry_time;
+		for (int i = 0; i < T; i++) tp_rel[i] = pr.timepoints[i] - creation_time;
+		int steps = 0;
+		if (!solver.solve(y0.data(), cell_params.data(), tp_rel.data(), T, out.data(), steps)) {
+			result = false; // Experiment::Simulate fails => logp = -inf (Experiment.cpp:356-358)
+		}
+		if (cell_steps) cell_steps[ci] = steps;
+		if (result) {
+			// Experiment.cpp:298-312 + Cell::GetInterpolatedSpeciesValue (Cell.cpp:280-360): exact stored timepoints only
+			for (int i = 0; i < T; i++) {
+				const double cell_time = pr.timepoints[i] - creation_time;
+				if (cell_time < 0.0 || cell_time > tp_rel[T - 1]) continue;
+				double x = 0.0;
+				for (int k = 0; k < pr.num_obs_species; k++) x += out[(size_t)pr.obs_species[k] + (size_t)i * N];
+				xs[(size_t)i * ncell + ci] = x;
+			}
+		}
+	}
+	if (cell_values)
+		for (size_t e = 0; e < xs.size(); e++) cell_values[e] = xs[e];
+
+	if (!result) {
+		*logp_out = -std::numeric_limits<double>::infinity();
+		if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = nan;
+		return;
+	}
+	// NotifySimulatedValue (.cpp:161-197): value / population size, accumulated cell by cell
+	for (int i = 0; i < T; i++) {
+		size_t pop = 0;
+		for (int ci = 0; ci < ncell; ci++) {
+			const double cell_time = pr.timepoints[i] - entry_time;
+			if (!(cell_time < 0.0 || cell_time > tp_rel[T - 1])) pop++; // CountCellsAtTime
+		}
+		for (int ci = 0; ci < ncell; ci++) {
+			const double x = xs[(size_t)i * ncell + ci];
+			if (x == x) population_average[i] += x / (double)pop;
+		}
+	}
+	if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = population_average[i];
+
+	// Evaluate (.cpp:85-159)
+	const double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
+	const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
+	const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
+	const double minus_log_sigma = -log(stdev), inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
+	for (int i = 0; i < T; i++) {
+		population_average[i] *= scale;
+		population_average[i] += offset;
+	}
+	double logp = 0.0;
+	for (int i = 0; i < T; i++) {
+		const double x = population_average[i];
+		if (std::isnan(x)) {
+			double first_ok = pr.timepoints[T - 1], last_ok = pr.timepoints[0];
+			for (int m = 0; m < T; m++) if (!std::isnan(population_average[m])) { first_ok = pr.timepoints[m]; break; }
+			for (int m = T - 1; m >= 0; m--) if (!std::isnan(population_average[m])) { last_ok = pr.timepoints[m]; break; }
+			const double time_offset = std::min(std::abs(pr.timepoints[i] - first_ok), std::abs(pr.timepoints[i] - last_ok));
+			const double pen = (pr.error_model == 1) ? logpdf_tnu4(time_offset, 0, pr.missing_stdev) : logpdf_normal(time_offset, 0, pr.missing_stdev);
+			for (int j = 0; j < R; j++) if (!std::isnan(pr.observed[(size_t)j * T + i])) logp += pen;
+		} else {
+			for (int j = 0; j < R; j++) {
+				const double obs = pr.observed[(size_t)j * T + i];
+				if (std::isnan(obs)) continue;
+				// EvaluateValue(observed_data(j, i), x, 0): first argument is named `simulated` (argument swap)
+				if (pr.error_model == 1) {
+					logp += logpdf_tnu4(x, obs, stdev);
+				} else {
+					const double d = x - obs;
+					logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
+				}
+			}
+		}
+	}
+	*logp_out = logp * pr.weight;
+}
+
+template <class Solver>
+int evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp, double* cell_values,
+             int32_t* cell_steps, double* population_average, int num_threads)
+{
+	if (!prob || !values || !logp || !prob->derivative) return -1;
+	const size_t T = prob->num_timepoints, nc = prob->num_cells, nvar = prob->num_variables;
+	if (num_threads < 1) num_threads = 1;
+	if ((size_t)num_threads > num_chains) num_threads = (int)num_chains;
+	std::atomic<size_t> next(0);
+	auto worker = [&]() {
+		for (;;) {
+			size_t c = next.fetch_add(1);
+			if (c >= num_chains) break;
+			evaluate_chain<Solver>(*prob, values + c * nvar, logp + c, cell_values ? cell_values + c * T * nc : nullptr,
+			                       cell_steps ? cell_steps + c * nc : nullptr, population_average ? population_average + c * T : nullptr);
+		}
+	};
+	if (num_threads == 1) {
+		worker();
+	} else {
+		std::vector<std::thread> th;
+		for (int i = 0; i < num_threads; i++) th.emplace_back(worker);
+		for (auto& t : th) t.join();
+	}
+	return 0;
+}
+
+} // namespace cellpop_glue

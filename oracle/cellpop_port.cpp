@@ -1,0 +1,83 @@
+// TEST INFRASTRUCTURE ONLY -- cell_population checker on top of the plain-C CVODE restatement (oracle/cvode_bdf.c)
+// with the difference-quotient Jacobian of ODESolverCVODE.cpp:496-537 (jac == NULL in bdf_create).
+#include <cstdlib>
+#include <cstring>
+
+#include "cellpop_glue.hpp"
+
+extern "C" {
+#include "cvode_bdf.h"
+double oracle_ndtri(double p);
+}
+
+namespace cellpop_glue {
+double ndtri(double p) { return oracle_ndtri(p); }
+}
+
+namespace {
+
+struct PortSolver {
+	const oracle_cellpop_problem& pr;
+	bdf_mem* m;
+	const double* cell_params = nullptr;
+	explicit PortSolver(const oracle_cellpop_problem& p) : pr(p), m(new bdf_mem) {}
+	~PortSolver() { delete m; }
+	static int rhs(double, const double* y, double* ydot, void* user)
+	{
+		PortSolver* s = (PortSolver*)user;
+		s->pr.derivative(ydot, y, s->pr.constant_species, s->cell_params, s->pr.non_sampled); // Cell::solver_rhs_fn, Cell.cpp:423-433
+		return 0;
+	}
+	// ODESolver::SolveReturnSolution (ODESolver.cpp:93-134) + ODESolverCVODE::Solve (ODESolverCVODE.cpp:322-463), no discontinuities
+	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps)
+	{
+		const int N = pr.num_species;
+		cell_params = params;
+		steps = 0;
+		int ti = 0;
+		while (tp[ti] < 2.220446049250313e-16) {
+			for (int i = 0; i < N; i++) out[i + (size_t)ti * N] = y0[i];
+			ti++;
+			if (ti == ntp) return true;
+		}
+		const double end_time = tp[ntp - 1];
+		bdf_create(m, N, &PortSolver::rhs, nullptr, this); // Cell::AllocateSolver happens once per cell object; state never leaks because
+		                                                    // CVodeReInit resets everything the first step reads
+		double atol[BDF_NMAX];
+		for (int i = 0; i < N; i++) atol[i] = pr.abs_tol;
+		bdf_set_tolerances(m, pr.rel_tol, atol);
+		m->hmin = pr.min_dt; // SetSolverParameter("min_dt"), Cell.cpp:72
+		double y[BDF_NMAX], tmp[BDF_NMAX];
+		for (int i = 0; i < N; i++) y[i] = y0[i];
+		bdf_reinit(m, 0.0, y);
+		int tpi = ti;
+		for (;;) {
+			double tret;
+			int result = bdf_step(m, end_time, y, &tret);
+			if (result < 0) return false;
+			steps++;
+			while (tret >= tp[tpi]) {
+				if (bdf_get_dky(m, tp[tpi], tmp) != BDF_SUCCESS) return false;
+				for (int i = 0; i < N; i++) out[i + (size_t)tpi * N] = tmp[i];
+				tpi++;
+				if (tpi >= ntp) break;
+			}
+			if (tret >= end_time) break;
+			if (steps == pr.max_steps) return false;
+		}
+		if (const char* rep = getenv("BCM3B200_CELLPOP_REPORT")) { // debugging aid: report another counter in place of the steps
+			int k = atoi(rep);
+			if (k == 1) steps = (int)m->nfe; else if (k == 2) steps = (int)m->nsetups; else if (k == 3) steps = (int)m->nje;
+		}
+		return true;
+	}
+};
+
+} // namespace
+
+extern "C" int oracle_cellpop_evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp,
+                                       double* cell_values, int32_t* cell_steps, double* population_average, int num_threads)
+{
+	if (prob && prob->num_species > BDF_NMAX) return -3;
+	return cellpop_glue::evaluate<PortSolver>(prob, num_chains, values, logp, cell_values, cell_steps, population_average, num_threads);
+}

@@ -84,6 +84,36 @@ enum {
 int oracle_poppk_evaluate(const oracle_poppk_problem* prob, size_t num_chains, const double* values,
                           double* logp, double* conc, double* patient_ll, int64_t* counters, int num_threads);
 
+/* ---- cell_population (rows a8-a12 of SURVEY.md section 8): independent non-dividing cells, one diagonal_gaussian
+ * variability block, one time_course_population_average data set ---- */
+typedef void (*oracle_derivative_fn)(double* out, const double* species, const double* constant_species, const double* parameters,
+                                     const double* non_sampled_parameters); /* SolverCodeGenerator.h:6 */
+
+typedef struct {
+	int32_t num_species, num_constant_species, num_variables, num_non_sampled, num_cells, num_timepoints, num_replicates, variability_dim;
+	int32_t entry_time_ix; /* -1: fixed */
+	int32_t max_steps;
+	int32_t error_model; /* 0 normal, 1 student_t4 */
+	int32_t stdev_ix, offset_ix, scale_ix; /* -1: fixed */
+	int32_t num_obs_species;
+	int32_t obs_species[8];
+	double entry_time, rel_tol, abs_tol, min_dt, weight, stdev, offset, scale, missing_stdev;
+	const double* initial_conditions;  /* [N] */
+	const double* constant_species;    /* [Nc] */
+	const double* non_sampled;         /* [Nn] */
+	const double* sobol;               /* [cells][D] */
+	const double* timepoints;          /* [T] */
+	const double* observed;            /* [R][T] */
+	const double* variability;         /* [D][6]: is_ic, target, apply, scale_ix, scale_fixed, negate */
+	const int32_t* transforms;         /* [nvar] */
+	oracle_derivative_fn derivative;   /* generated_derivative compiled for the host from the generated text */
+} oracle_cellpop_problem;
+
+/* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.
+ *   logp [C]; cell_values [C][T][cells] (optional); cell_steps [C][cells] (optional); population_average [C][T] (optional) */
+int oracle_cellpop_evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp,
+                            double* cell_values, int32_t* cell_steps, double* population_average, int num_threads);
+
 /* "ref" or "port" */
 const char* oracle_kind(void);
 

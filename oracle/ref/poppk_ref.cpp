@@ -309,6 +309,10 @@ void EvaluateChain(const oracle_poppk_problem& pr, const double* values, double*
 
 } // namespace
 
+namespace refglue {
+double ndtri(double p) { return ::ndtri(p); }
+}
+
 extern "C" int oracle_poppk_evaluate(const oracle_poppk_problem* prob, size_t num_chains, const double* values,
                                      double* logp, double* conc, double* patient_ll, int64_t* counters, int num_threads)
 {

@@ -1,0 +1,45 @@
+"""Generates tests/golden/cellpop_*.npz with the reference's own compiled solver stack (oracle/_ref: real ODESolverCVODE with
+its difference-quotient Jacobian and zero-skipping LU + vendored CVODE 5.3.0) driving the generated-derivative text compiled
+for the host. Run where /root/reference is mounted:  python tests/golden/make_golden_cellpop.py"""
+import dataclasses
+import zlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+from bcm3_b200 import synthetic_cellpop as sc  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: kwargs of make_cellpop_problem, C, tweaks
+    "cellpop_n12_normal": (dict(N=12, num_cells=48, T=16, data_cells=8, seed=21), 3, {}),
+    "cellpop_n12_t4_two_species": (dict(N=12, num_cells=40, T=12, data_cells=8, seed=22, replicates=3, missing_fraction=0.2,
+                                        two_species_readout=True), 3, dict(error_model="student_t4", offset=0.01, scale=1.1, weight=0.5)),
+    "cellpop_n5_late_entry": (dict(N=5, num_cells=33, T=10, data_cells=8, seed=23), 2, dict(entry_time=1.0)),
+    "cellpop_n24_stiff": (dict(N=24, num_cells=24, T=10, data_cells=4, seed=24, rate_decades=4.0), 2, {}),
+}
+
+
+def main():
+    ref = oracle.load("ref")
+    for name, (kw, C, tweaks) in CASES.items():
+        prob = dataclasses.replace(sc.make_cellpop_problem(**kw), **tweaks)
+        vals = sc.make_chain_values(C, seed=zlib.crc32(name.encode()) % 10000)
+        r = ref.cellpop_evaluate(prob, vals, threads=1, want_cell_values=True, want_steps=True, want_average=True)
+        out = {f.name: getattr(prob, f.name) for f in dataclasses.fields(prob) if f.name not in ("variability",)}
+        out = {k: (np.array(v) if not isinstance(v, np.ndarray) else v) for k, v in out.items() if v is not None}
+        out["variability_rows"] = prob.variability_rows()
+        out.update(values=vals, logp=r["logp"], cell_values=r["cell_values"], cell_steps=r["cell_steps"], population_average=r["population_average"])
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, "logp", r["logp"], "steps mean", r["cell_steps"].mean(), os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

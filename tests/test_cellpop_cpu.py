@@ -1,0 +1,88 @@
+"""CPU suite for the cell_population rows: the plain-C restatement against golden vectors made by
+the reference's own compiled ODESolverCVODE, the compiled reference against its own fixtures, the synthetic model generator,
+and the device translation unit of a generated model (cross-compiled, not run)."""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+
+from bcm3_b200 import synthetic_cellpop as sc
+from tests.util import CELLPOP_GOLDEN_NAMES, cellpop_logp_close, cellpop_rtol, load_cellpop_golden
+
+
+def test_cellpop_golden_fixtures_exist():
+    assert len(CELLPOP_GOLDEN_NAMES) >= 4
+
+
+@pytest.mark.parametrize("name", CELLPOP_GOLDEN_NAMES)
+def test_port_matches_reference_golden(port, name):
+    prob, gold = load_cellpop_golden(name)
+    r = port.cellpop_evaluate(prob, gold["values"], threads=2, want_cell_values=True, want_steps=True, want_average=True)
+    assert cellpop_logp_close(r["logp"], gold["logp"], prob.num_timepoints, prob.num_replicates, rtol=cellpop_rtol(name))
+    assert (np.isnan(r["cell_values"]) == np.isnan(gold["cell_values"])).all()
+    m = ~np.isnan(gold["cell_values"])
+    # single trajectories: tolerance level (rtol = atol = 4.8e-7 per step, a few hundred steps)
+    assert np.abs(r["cell_values"][m] - gold["cell_values"][m]).max() < 5e-5
+    assert np.abs(r["population_average"] - gold["population_average"]).max() < 5e-6
+    # step counts: identical for most cells; the stiff 24-species case flips more decisions
+    same = (r["cell_steps"] == gold["cell_steps"]).mean()
+    assert same >= (0.02 if "stiff" in name else 0.7)
+    assert abs(r["cell_steps"].mean() / gold["cell_steps"].mean() - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("name", CELLPOP_GOLDEN_NAMES)
+def test_compiled_reference_reproduces_golden(ref, name):
+    prob, gold = load_cellpop_golden(name)
+    r = ref.cellpop_evaluate(prob, gold["values"], threads=1, want_cell_values=True, want_steps=True)
+    assert np.array_equal(r["logp"], gold["logp"])
+    assert np.array_equal(r["cell_steps"], gold["cell_steps"])
+    assert np.array_equal(r["cell_values"], gold["cell_values"], equal_nan=True)
+
+
+def test_late_entry_cells_are_absent_before_entry(port):
+    prob, gold = load_cellpop_golden("cellpop_n5_late_entry")
+    before = prob.timepoints < prob.entry_time
+    assert before.any()
+    assert np.isnan(gold["cell_values"][:, before, :]).all() and not np.isnan(gold["cell_values"][:, ~before, :]).any()
+    assert np.all(gold["population_average"][:, before] == 0.0)  # nothing is notified for those timepoints
+
+
+def test_failed_cell_gives_minus_infinity(port):
+    prob, gold = load_cellpop_golden("cellpop_n12_normal")
+    p2 = dataclasses.replace(prob, solver_max_steps=20)  # ODESolverCVODE.cpp:440-446 => Simulate fails => -inf (Experiment.cpp:356-358)
+    r = port.cellpop_evaluate(p2, gold["values"])
+    assert np.all(r["logp"] == -np.inf)
+
+
+def test_generated_text_matches_generator_conventions():
+    code = sc.cascade_code(6, seed=3)
+    assert code.startswith(sc.SIGNATURE)
+    assert "OdeReal ratelaws[12];" in code and "out[5] = +ratelaws[10]-ratelaws[11];" in code
+    assert "EXPORT_PREFIX void generated_jacobian(OdeMatrixReal& out" in code
+    # std::to_string: every literal has exactly six decimals
+    import re
+
+    for lit in re.findall(r"\d+\.\d+", code):
+        assert len(lit.split(".")[1]) == 6
+
+
+def test_device_module_compiles_for_sm100a(built, tmp_path, monkeypatch):
+    """The per-model translation unit (prelude + generated text + cellpop_warp.cuh) cross-compiles with nvcc for sm_100a."""
+    from bcm3_b200.cellpop import CellPopEvaluator
+
+    monkeypatch.setenv("BCM3B200_CACHE", str(tmp_path))
+    prob, _ = load_cellpop_golden("cellpop_n5_late_entry")
+    ev = CellPopEvaluator(prob, compile_only=True)
+    ev.close()
+    built_dirs = [d for d in os.listdir(tmp_path) if d.startswith("cellpop_")]
+    assert len(built_dirs) == 1
+    assert os.path.exists(tmp_path / built_dirs[0] / "libcellpop_model.so")
+    src = open(tmp_path / built_dirs[0] / "model.cu").read()
+    assert "#define CP_N 5" in src and "template <class SP, class PP>" in src and "generated_jacobian" not in src
+    # a text without the generator's signature is rejected
+    bad = dataclasses.replace(prob, derivative_code="void f() {}")
+    from bcm3_b200 import _lib
+
+    with pytest.raises(_lib.Bcm3B200Error, match="generated_derivative signature"):
+        CellPopEvaluator(bad, compile_only=True)
