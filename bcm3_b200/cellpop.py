@@ -12,7 +12,7 @@ from .cellpop_data import CellPopProblem
 
 
 class CellPopEvaluator:
-    def __init__(self, problem: CellPopProblem, device: int = 0, compile_only: bool = False):
+    def __init__(self, problem: CellPopProblem, device: int = 0, compile_only: bool = False, kernel: str = "auto"):
         self.lib = _lib.load()
         self.problem = p = problem
         kv = dict(
@@ -45,6 +45,7 @@ class CellPopEvaluator:
                 self._set("variability", p.variability_rows())
             code = p.derivative_code.encode()
             _lib.check(self.lib.bcm3b200_set_text(self.handle, b"derivative_code", code, len(code)))
+            _lib.check(self.lib.bcm3b200_set_option(self.handle, b"cellpop_kernel", {"auto": 0, "warp": 1, "thread": 2}[kernel]))
             _lib.check(self.lib.bcm3b200_finalize(self.handle))
         except Exception:
             self.close()

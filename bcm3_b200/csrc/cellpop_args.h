@@ -55,3 +55,5 @@ struct CpArgs {
 };
 
 typedef int (*cellpop_launch_fn)(const CpArgs* args, void* stream);
+typedef int (*cellpop_thread_launch_fn)(const CpArgs* args, double* scratch, void* stream);
+typedef long long (*cellpop_thread_scratch_fn)(int num_chains, int num_cells);

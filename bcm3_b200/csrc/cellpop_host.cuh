@@ -42,6 +42,10 @@ struct CellPopState {
 	int cell_offset = 0, cells_local = 0;
 	void* module = nullptr;
 	cellpop_launch_fn launch = nullptr;
+	cellpop_thread_launch_fn thread_launch = nullptr;
+	cellpop_thread_scratch_fn thread_scratch = nullptr;
+	int kernel_choice = 0; // 0 auto (one cell per thread for N <= 20, per warp above), 1 warp, 2 thread
+	DevBuf<double> d_scratch;
 	std::string module_path;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -231,7 +235,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	if (at == std::string::npos)
 		return fail(BCM3B200_ERR_ARG, "derivative_code does not contain the reference generator's generated_derivative signature (SBMLModel.cpp:295)");
 	code.replace(at, sig.size(),
-	             "template <class SP, class PP>\n__device__ __forceinline__ void generated_derivative(OdeReal* out, const SP& species, "
+	             "template <class OUT, class SP, class PP>\n__device__ __forceinline__ void generated_derivative(OUT out, const SP& species, "
 	             "const OdeReal* constant_species, const PP& parameters, const OdeReal* non_sampled_parameters)");
 	// std::numeric_limits in generated text (none emitted by the rate-law printer today, kept for safety)
 	std::ostringstream o;
@@ -249,9 +253,12 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	int warps = 4;
 	while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
 	o << "#define CP_WARPS_PER_BLOCK " << warps << "\n";
+	// one cell per thread (small N): 12 N doubles of shared memory per thread
+	o << "#define CP_THREADS_PER_BLOCK " << ((size_t)12 * cp.N * 64 * sizeof(double) <= 112 * 1024 ? 64 : 32) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
 	o << code << "\n";
 	o << "#include \"cellpop_warp.cuh\"\n";
+	o << "#include \"cellpop_thread.cuh\"\n";
 	src = o.str();
 	return BCM3B200_OK;
 }
@@ -268,7 +275,7 @@ inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& overri
 	// code, with and without contraction, already differ by 3.5e-5 in single trajectories) -- is bit-identical to it.
 	// content hash over everything that determines the binary
 	std::string keyed = src + "|fmad=false";
-	for (const char* f : { "/cellpop_warp.cuh", "/cellpop_prelude.cuh", "/cellpop_args.h" }) {
+	for (const char* f : { "/cellpop_warp.cuh", "/cellpop_thread.cuh", "/cellpop_prelude.cuh", "/cellpop_args.h" }) {
 		std::ifstream in(csrc + f);
 		std::stringstream ss;
 		ss << in.rdbuf();
@@ -306,6 +313,9 @@ inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& overri
 	if (!cp.module) return fail(BCM3B200_ERR_STATE, "dlopen(%s) failed: %s", so.c_str(), dlerror());
 	cp.launch = (cellpop_launch_fn)dlsym(cp.module, "cellpop_launch");
 	if (!cp.launch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_launch");
+	cp.thread_launch = (cellpop_thread_launch_fn)dlsym(cp.module, "cellpop_thread_launch");
+	cp.thread_scratch = (cellpop_thread_scratch_fn)dlsym(cp.module, "cellpop_thread_scratch_doubles");
+	if (!cp.thread_launch || !cp.thread_scratch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_thread_launch");
 	cp.module_path = so;
 	return BCM3B200_OK;
 }
@@ -433,7 +443,17 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	a.cell_steps = cp.d_steps.p;
 	a.debug_report = getenv("BCM3B200_CELLPOP_REPORT") ? atoi(getenv("BCM3B200_CELLPOP_REPORT")) : 0;
 	cp.last_launches = 1;
-	if (nc > 0) {
+	const char* kenv = getenv("BCM3B200_CELLPOP_KERNEL");
+	int choice = cp.kernel_choice;
+	if (kenv && !strcmp(kenv, "warp")) choice = 1;
+	if (kenv && !strcmp(kenv, "thread")) choice = 2;
+	const bool use_thread = (choice == 2) || (choice == 0 && cp.N <= 20);
+	if (nc > 0 && use_thread) {
+		CUDA_TRY(cp.d_scratch.ensure((size_t)cp.thread_scratch((int)C, nc)));
+		int lrc = cp.thread_launch(&a, cp.d_scratch.p, (void*)st);
+		if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "cellpop thread kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+		cp.last_launches++;
+	} else if (nc > 0) {
 		int lrc = cp.launch(&a, (void*)st);
 		if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "cellpop kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
 		cp.last_launches++;

@@ -40,8 +40,11 @@ WORKLOADS = {
     "poppk_two_100k_x64": dict(pk="two", P=100_000, T=10, t_end=72.0, C=64, flop_per_system=64.5e3),
     # BASELINE.json configs[1]: PopPK one-compartment, 1k individuals x 10 samples, 16 temperatures
     "poppk_one_1k_x16": dict(pk="one", P=1000, T=10, t_end=72.0, C=16, flop_per_system=48.0e3),
+    # BASELINE.json configs[2]: cellpop small cell-cycle-like SBML-style model, 10k simulated cells, 16 temperatures, 1 GPU
+    "cellpop_12sp_10k_x16": dict(kind="cellpop", N=12, cells=10_000, T=50, C=16),
 }
 METRIC = "likelihood evals/sec (PopPK batched EvaluateLogProbability)"
+METRIC_CELLPOP = "likelihood evals/sec (cellpop batched EvaluateLogProbability)"
 UNIT = "evals/s"
 Q_MEAN = 4.3  # mean BDF order measured on the reference
 
@@ -93,6 +96,118 @@ def subsample_problem(prob, vals, P_sample: int):
     vs[:, :npk + 2 + 2 * P_sample] = vals[:, :npk + 2 + 2 * P_sample]
     vs[:, nvs - 2:] = vals[:, -2:]
     return ps, vs
+
+
+def cellpop_flop_per_system(N: int, steps: float, n_ratelaw_flops: float) -> float:
+    """SURVEY.md section 8(d) formula with the counter ratios the reference shows on this model family (measured with the
+    oracle: nfe/nst = 1.33, nni = nfe - 1, nsetups/nst = 0.122, nje/nst = 0.021), q = 4.3, DQ Jacobian and dense LU."""
+    q = Q_MEAN
+    A = N * (q * (q + 1) / 2 + 2 * (q + 1) + 4) + 60
+    nfe, nsetups, nje = 1.33 * steps, 0.122 * steps, 0.021 * steps
+    nni = nfe - 1
+    return float(steps * A + nfe * n_ratelaw_flops + nni * (2 * N * N + 9 * N) + nsetups * (2 * N * N + 2 * N ** 3 / 3) + nje * N * (n_ratelaw_flops + 2 * N))
+
+
+def run_cellpop(args, workload: str):
+    """cell_population workloads: single GPU (cells are not sharded across ranks yet)."""
+    import torch
+
+    from bcm3_b200 import _lib
+    from bcm3_b200 import synthetic_cellpop as sc
+    from bcm3_b200.cellpop import CellPopEvaluator
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[workload]
+    prob = sc.make_cellpop_problem(N=w["N"], num_cells=w["cells"], T=w["T"], data_cells=32, seed=1)
+    vals = sc.make_chain_values(w["C"])
+    C, nvar = vals.shape
+    if args.impl == "reference":
+        kind, chk = cpu_checker()
+        cores = max(1, min(C, os.cpu_count() or 1))
+        import dataclasses
+        times = []
+        for i in range(args.warmup + args.steps):
+            sample = min(w["cells"], 2000)
+            ps = dataclasses.replace(prob, num_cells=sample, sobol=prob.sobol[:sample])
+            t0 = time.perf_counter()
+            chk.cellpop_evaluate(ps, vals, threads=cores)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+        dt = statistics.mean(times)
+        value = (C / dt) * (sample / w["cells"])
+        print(json.dumps({"impl": "reference", "metric": METRIC_CELLPOP, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C,
+                                                                        "timepoints": w["T"]},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                                           "sample": f"all {C} chains x first {sample} of {w['cells']} cells in {dt:.1f} s on {cores} threads ({cpu_model_name()}); scaled by {sample}/{w['cells']}"},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    if not torch.cuda.is_available() or _lib.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    ev = CellPopEvaluator(prob, device=0)
+    h_vals = torch.from_numpy(vals).pin_memory()
+    h_logp = np.empty(C)
+    h_status = np.empty(C, dtype=np.int32)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")
+    fp64_peak = _lib.measure_fp64_peak(0)
+
+    def step():
+        _lib.check(ev.lib.bcm3b200_evaluate_batch(ev.handle, C, nvar, h_vals.data_ptr(), h_logp.ctypes.data, h_status.ctypes.data))
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    launches0 = ev.get_stat("total_kernel_launches")
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    kernel_ms, t_begin = [], time.perf_counter()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        e2e_s += time.perf_counter() - t0
+        kernel_ms.append(ev.get_stat("last_kernel_us") / 1e3)
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end)
+    launches = ev.get_stat("total_kernel_launches") - launches0
+    ev._last_C = C
+    steps_mean = float(ev.diagnostics()["cell_steps"].mean())
+    total_ms = sum(kernel_ms)
+    value = C * args.steps / (total_ms * 1e-3)
+    flop_sys = cellpop_flop_per_system(w["N"], steps_mean, 8.0 * 2 * w["N"])
+    k_ms = statistics.mean(kernel_ms)
+    achieved = flop_sys * C * w["cells"] / (k_ms * 1e-3) / 1e12
+    line = {"metric": METRIC_CELLPOP, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C, "timepoints": w["T"], "ode_solves_per_step": C * w["cells"],
+                       "mean_steps_per_solve": steps_mean, "l2": "256 MB memset between timed iterations"},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "kernel": "cellpop_thread_kernel" if w["N"] <= 20 else "cellpop_kernel", "kernel_ms": k_ms, "flop_per_system": flop_sys,
+                         "systems_per_launch": C * w["cells"], "peak_source": "measured live: bcm3b200_measure_fp64_peak"},
+            "e2e": {"value": C * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes), "d2h_bytes_per_step": int(C * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "check": {"logp0": float(h_logp[0]), "status_ok": bool((h_status == 0).all())}}
+    if not args.no_cpu_baseline:
+        import dataclasses
+        kind, chk = cpu_checker()
+        cores = max(1, min(C, os.cpu_count() or 1))
+        sample = min(w["cells"], 4000)
+        ps = dataclasses.replace(prob, num_cells=sample, sobol=prob.sobol[:sample])
+        t0 = time.perf_counter()
+        chk.cellpop_evaluate(ps, vals, threads=cores)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": (C / dt) * (sample / w["cells"]), "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"all {C} chains x first {sample} of {w['cells']} cells in {dt:.1f} s on {cores} threads ({cpu_model_name()}); scaled by {sample}/{w['cells']}"}
+    print(json.dumps(line))
+    ev.close()
 
 
 def cpu_checker():
@@ -245,6 +360,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     workload = args.workload
+
+    if WORKLOADS[workload].get("kind") == "cellpop":
+        run_cellpop(args, workload)
+        return
 
     if args.impl == "reference":
         run_reference(args, workload)

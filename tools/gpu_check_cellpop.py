@@ -6,10 +6,10 @@ import oracle
 from bcm3_b200 import synthetic_cellpop as sc
 from bcm3_b200.cellpop import CellPopEvaluator
 
-def run(N, cells, T, C, decades=2.0, kinds=("ref", "port")):
+def run(N, cells, T, C, decades=2.0, kinds=("ref", "port"), kernel="auto"):
     prob = sc.make_cellpop_problem(N=N, num_cells=cells, T=T, data_cells=8, rate_decades=decades)
     vals = sc.make_chain_values(C)
-    t0 = time.time(); ev = CellPopEvaluator(prob); print(f"N={N} cells={cells} T={T} C={C}: setup {time.time()-t0:.1f}s")
+    t0 = time.time(); ev = CellPopEvaluator(prob, kernel=kernel); print(f"kernel={kernel} N={N} cells={cells} T={T} C={C}: setup {time.time()-t0:.1f}s")
     for it in range(2):
         t0 = time.time(); logp, status = ev.evaluate(vals); dt = time.time() - t0
     d = ev.diagnostics()
@@ -28,8 +28,10 @@ def run(N, cells, T, C, decades=2.0, kinds=("ref", "port")):
     ev.close()
 
 if __name__ == "__main__":
-    run(12, 200, 20, 3)
-    run(12, 2000, 50, 8)
+    for k in ("thread", "warp"):
+        run(12, 200, 20, 3, kernel=k)
+        run(12, 2000, 50, 8, kernel=k, kinds=("port",))
     run(50, 200, 20, 2, decades=4.0)
     # timing at config-3 size
-    run(12, 10000, 50, 16, kinds=("ref",))
+    for k in ("thread", "warp"):
+        run(12, 10000, 50, 16, kinds=("ref",), kernel=k)
