@@ -45,7 +45,7 @@ class CellPopEvaluator:
                 self._set("variability", p.variability_rows())
             code = p.derivative_code.encode()
             _lib.check(self.lib.bcm3b200_set_text(self.handle, b"derivative_code", code, len(code)))
-            _lib.check(self.lib.bcm3b200_set_option(self.handle, b"cellpop_kernel", {"auto": 0, "warp": 1, "thread": 2}[kernel]))
+            _lib.check(self.lib.bcm3b200_set_option(self.handle, b"cellpop_kernel", {"auto": 0, "warp": 1, "thread": 2, "group": 3}[kernel]))
             _lib.check(self.lib.bcm3b200_finalize(self.handle))
         except Exception:
             self.close()

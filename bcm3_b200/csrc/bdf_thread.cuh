@@ -122,6 +122,28 @@ __device__ BCM3_ROOT_INLINE double bdf_root(double base, int k)
 	return exp(log(base) * inv);
 }
 
+// The same root without the double-precision log/exp pair: a single-precision seed exp2(log2(x) / k) (relative error
+// ~3e-7) refined by one Halley step for y^k = x in double precision (cubic convergence: ~(k^2 - 1) / 12 * e^3 < 1e-17),
+// so the result is within an ulp or two of pow(x, 1/k), like the exp/log form, at about a quarter of its instructions
+// and with no dependence on k in the control flow. Outside the single-precision range it falls back to exp/log.
+__device__ __forceinline__ double bdf_root_halley(double base, int k)
+{
+	if (base <= 0.0) return 0.0;
+	if (!(base > 1e-30 && base < 1e30)) return bdf_root(base, k);
+	const float kf = (float)k;
+	const double y = (double)exp2f(__fdividef(log2f((float)base), kf));
+	const double y2 = y * y, y3 = y2 * y, y4 = y2 * y2;
+	double yk = y2;
+	yk = (k == 3) ? y3 : yk;
+	yk = (k == 4) ? y4 : yk;
+	yk = (k == 5) ? y4 * y : yk;
+	yk = (k == 6) ? y3 * y3 : yk;
+	const double km = (double)(k - 1), kp = (double)(k + 1);
+	const double num = km * yk + kp * base;
+	const double den = kp * yk + km * base;
+	return y * (num / den);
+}
+
 template <int N, class Model, bool STATS>
 struct BdfThread {
 	static constexpr int QMAX = 5;

@@ -57,3 +57,6 @@ struct CpArgs {
 typedef int (*cellpop_launch_fn)(const CpArgs* args, void* stream);
 typedef int (*cellpop_thread_launch_fn)(const CpArgs* args, double* scratch, void* stream);
 typedef long long (*cellpop_thread_scratch_fn)(int num_chains, int num_cells);
+typedef int (*cellpop_group_launch_fn)(const CpArgs* args, double* scratch, void* stream);
+typedef long long (*cellpop_group_scratch_fn)(int num_chains, int num_cells);
+typedef int (*cellpop_group_info_fn)(int* lanes_per_cell, int* threads_per_block, int* smem_bytes_per_block);

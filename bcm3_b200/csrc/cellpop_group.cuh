@@ -1,0 +1,1352 @@
+// cellpop_group.cuh -- K0+K2 of the cellpop path: one ODE system (one simulated cell of one chain) per GROUP of G lanes
+// (G = 2..32, a power of two chosen per model so that every lane owns E = ceil(N / G) <= 3-4 components).
+//
+// Same algorithm and reference line map as bdf_thread.cuh / cellpop_warp.cuh (CVODE 5.3.0 BDF + modified Newton with the
+// difference-quotient Jacobian of ODESolverCVODE.cpp:496-537 and BCM3's partial-pivot LU,
+// EigenPartialPivLUSomewhatSparse.h:38-105). What is different is where things live:
+//
+//   * component i of every integrator vector belongs to lane (i mod G) of the group, slot (i div G): the Nordsieck array,
+//     weights and corrections are REGISTER arrays of E doubles indexed only by compile-time constants (the static_for
+//     loops of bdf_thread.cuh), so the vector work of a step costs no address arithmetic and no memory traffic;
+//   * norms are xor-butterfly reductions over the G lanes (every lane ends with the same bits, so all scalar
+//     bookkeeping -- step size, order, counters -- is replicated per lane and stays group-uniform without broadcasts);
+//   * the Newton matrix (LU factors) sits in SHARED memory, one padded row-major block per cell whose strides make the
+//     row-per-lane and column-per-lane access patterns of all groups of a half-warp bank-conflict free; the saved
+//     Jacobian sits in a global scratch block per resident group (touched only by linear setups);
+//   * the right-hand side is evaluated by every lane of the group from a shared copy of y (lanes keep their own
+//     components of the result); the N perturbed evaluations of the difference-quotient Jacobian are spread over the
+//     lanes, one column each; LU factorisation, permutation and the triangular solves are cooperative over the group;
+//   * cells are handed out from a global work queue to resident groups (grid = what fits on the GPU), so a group that
+//     finishes a cell picks up the next one instead of idling until the slowest cell of its block is done.
+//
+// Control flow is kept converged the way poppk_kernel does it: one step attempt per loop trip, the Newton loops made
+// warp-uniform with votes over the participating lanes, the warps of a block in lock-step.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+
+#include "bdf_thread.cuh"
+#include "cellpop_args.h"
+
+#ifndef CP_GROUP
+#define CP_GROUP 4
+#endif
+#ifndef CP_GROUP_WARPS
+#define CP_GROUP_WARPS 4
+#endif
+#ifndef CP_GROUP_MIN_BLOCKS
+#define CP_GROUP_MIN_BLOCKS 1
+#endif
+
+namespace cellpop_group {
+
+using bcm3b200::static_for;
+using bcm3b200::static_rfor;
+
+constexpr int N = CP_N;
+constexpr int G = CP_GROUP;
+constexpr int E = (N + G - 1) / G;
+constexpr bool PADDED = (E * G != N);
+constexpr int CPW = 32 / G; // cells per warp
+constexpr int WPB = CP_GROUP_WARPS;
+constexpr int BS = 32 * WPB;
+constexpr int QMAX = 5;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double UROUND = DBL_EPSILON;
+
+// Shared-memory block of one cell: M (N rows, stride RS), y (N), f (N), row permutation (N ints), cold scalars.
+// RS odd: the G lanes of a group touching G consecutive rows of one column hit distinct bank pairs. CS = RS * G (mod 16):
+// then bank pair (CS * g + RS * lg) mod 16 = RS * (G * g + lg) is a bijection over the 16 lanes of a half-warp.
+constexpr int RS = N | 1;
+constexpr int OFF_Y = N * RS;
+constexpr int OFF_F = OFF_Y + N;
+constexpr int OFF_PERM = OFF_F + N;
+constexpr int OFF_SCAL = OFF_PERM + (N + 1) / 2;
+// per-cell scalars that are touched a few times per step at most: kept out of the register file (every lane of the
+// group would hold a copy). Lanes of a group always store identical values, so no synchronisation is involved.
+enum { SC_TAU = 0 /* [1..5] */, SC_HU = 6, SC_SAVED_TQ5, SC_SAVED_T, SC_HSCALE, SC_ETAMAX, SC_CREATION, SC_END, SC_L /* [0..5] */, SC_TQ = SC_L + 6 /* [1..5] */, SC_COUNT = SC_TQ + 6 };
+constexpr int REGION_MIN = OFF_SCAL + SC_COUNT;
+constexpr int cell_stride()
+{
+	const int want = (RS * G) % 16;
+	int cs = REGION_MIN;
+	while (cs % 16 != want) cs++;
+	return cs;
+}
+constexpr int CS = cell_stride();
+
+enum { T_RETRY = 0, T_DONE = 1, T_FAILED = -1 };
+
+struct CellParameters {
+	const double* base;
+	double ov[CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1];
+	__device__ __forceinline__ double operator[](int k) const
+	{
+		CP_PARAM_OVERRIDE_BODY
+		return __ldg(base + k);
+	}
+};
+struct ConstVector {
+	const double* p;
+	__device__ __forceinline__ double operator[](int k) const { return __ldg(p + k); }
+};
+struct SpeciesShared {
+	const double* y;
+	__device__ __forceinline__ double operator[](int i) const { return y[i]; }
+};
+struct SpeciesPerturbed {
+	const double* y;
+	int j;
+	double yj;
+	__device__ __forceinline__ double operator[](int i) const { return (i == j) ? yj : y[i]; }
+};
+// `out[i] = value` of generated_derivative keeping only the components this lane owns (i is a literal in the generated text)
+struct OutOwned {
+	double* f;
+	int lg;
+	struct Ref {
+		double* f;
+		int lg, i;
+		__device__ __forceinline__ void operator=(double v) const
+		{
+			if ((i % G) == lg) f[i / G] = v;
+		}
+	};
+	__device__ __forceinline__ Ref operator[](int i) const { return Ref{ f, lg, i }; }
+};
+// `out[i] = value` of a perturbed evaluation: difference quotient of column j into the saved Jacobian and, already
+// scaled, into the Newton matrix (SUNMatScaleAddI(-gamma, A): A = -gamma * J, then the unit diagonal added)
+struct OutColumn {
+	double* Mcol;  // &M[0][j]
+	double* SJcol; // &SJ[0][j]
+	const double* fy;
+	double inc_inv, neg_gamma;
+	int j;
+	struct Ref {
+		const OutColumn& c;
+		int i;
+		__device__ __forceinline__ void operator=(double v) const
+		{
+			const double Jij = c.inc_inv * (v - c.fy[i]);
+			c.SJcol[i * N] = Jij;
+			double m = c.neg_gamma * Jij;
+			if (i == c.j) m += 1.0;
+			c.Mcol[i * RS] = m;
+		}
+	};
+	__device__ __forceinline__ Ref operator[](int i) const { return Ref{ *this, i }; }
+};
+
+#ifndef CP_GROUP_LOCKSTEP
+#define CP_GROUP_LOCKSTEP 1
+#endif
+#ifndef CP_GROUP_STATIC_LU_MAX
+#define CP_GROUP_STATIC_LU_MAX 0
+#endif
+
+__device__ __noinline__ double step_root(double base, int k) { return bcm3b200::bdf_root_halley(base, k); }
+
+// second half of N_VWrmsNorm: butterfly over the group, mean, square root -- one copy of the code for all call sites
+__device__ __noinline__ double norm_finish(double s, unsigned gmask)
+{
+#pragma unroll
+	for (int d = G / 2; d >= 1; d >>= 1) s += __shfl_xor_sync(gmask, s, d);
+	return sqrt(s / N);
+}
+
+struct GroupBdf {
+	// ---- distributed vectors (slot e = component lg + G * e) ----
+	double zn[6][E];
+	double ewt[E], acor[E];
+	// ---- replicated scalars ----
+	double tn, h, hprime, eta;
+	double gamma, gammap, gamrat, rl1, crate, delp, acnrm;
+	double* sc; // shared: tau[1..5], hu, saved_tq5, saved_t, hscale, etamax, creation/end time, l[] and tq[] across the Newton loop
+	int q, qprime, L, qwait, nst, nstlp, nstlj, nflag, ncf, nef;
+	bool nls_jcur;
+	int nfe, nsetups, nje;
+	// ---- placement ----
+	double* M;    // shared
+	double* ybuf; // shared, N
+	double* fbuf; // shared, N
+	int* perm;    // shared, N
+	double* SJ;   // global, N * N row-major
+	int lg;
+	unsigned gmask;
+	int gbase; // lane index (within the warp) of the group's lane 0
+	// ---- model ----
+	ConstVector constant_species, non_sampled;
+	CellParameters params;
+	double reltol, abstol, hmin;
+
+	__device__ __forceinline__ double& tau(int j) const { return sc[SC_TAU + j]; }
+	__device__ __forceinline__ double& hu() const { return sc[SC_HU]; }
+	__device__ __forceinline__ double& saved_tq5() const { return sc[SC_SAVED_TQ5]; }
+	__device__ __forceinline__ double& saved_t() const { return sc[SC_SAVED_T]; }
+	__device__ __forceinline__ double& hscale() const { return sc[SC_HSCALE]; }
+	__device__ __forceinline__ double& etamax() const { return sc[SC_ETAMAX]; }
+
+	__device__ __forceinline__ int idx(int e) const { return lg + G * e; }
+	__device__ __forceinline__ bool own(int e) const { return !PADDED || (lg + G * e < N); }
+	__device__ __forceinline__ void gsync() const { __syncwarp(gmask); }
+
+	__device__ __forceinline__ double gsum(double v) const
+	{
+#pragma unroll
+		for (int d = G / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
+		return v;
+	}
+	__device__ __forceinline__ double gmax(double v) const
+	{
+#pragma unroll
+		for (int d = G / 2; d >= 1; d >>= 1) {
+			const double o = __shfl_xor_sync(gmask, v, d);
+			v = (o > v) ? o : v;
+		}
+		return v;
+	}
+	// N_VWrmsNorm (nvector_serial_eigen.cpp:386-396); the sum runs lane-major instead of left to right
+	__device__ __forceinline__ double wrms(const double (&x)[E]) const
+	{
+		double s = 0.0;
+#pragma unroll
+		for (int e = 0; e < E; e++) {
+			const double p = x[e] * ewt[e];
+			s += p * p;
+		}
+		return norm_finish(s, gmask);
+	}
+	__device__ __forceinline__ void set_ewt()
+	{
+#pragma unroll
+		for (int e = 0; e < E; e++) ewt[e] = own(e) ? 1.0 / (reltol * fabs(zn[0][e]) + abstol) : 0.0;
+	}
+	// publish a distributed vector into the cell's shared y buffer
+	__device__ __forceinline__ void publish(double* buf, const double (&x)[E]) const
+	{
+		gsync(); // earlier readers of the buffer are done
+#pragma unroll
+		for (int e = 0; e < E; e++)
+			if (own(e)) buf[idx(e)] = x[e];
+		gsync();
+	}
+	// Cell::solver_rhs_fn (Cell.cpp:423-433) at the y held in ybuf; every lane evaluates, keeps its own components
+	__device__ __forceinline__ void rhs_shared(double (&f)[E])
+	{
+#pragma unroll
+		for (int e = 0; e < E; e++) f[e] = 0.0;
+		generated_derivative(OutOwned{ f, lg }, SpeciesShared{ ybuf }, constant_species, params, non_sampled);
+		nfe++;
+	}
+
+	// CVodeCreate zero state + CVodeReInit(0, y0) + the first-call block of CVode (cvode.c:586-665, 1068-1155)
+	__device__ __forceinline__ bool start(const double (&y0)[E], double tout)
+	{
+#pragma unroll
+		for (int j = 0; j < 6; j++) {
+			tau(j) = 0.0;
+#pragma unroll
+			for (int e = 0; e < E; e++) zn[j][e] = 0.0;
+		}
+#pragma unroll
+		for (int e = 0; e < E; e++) acor[e] = 0.0;
+		gammap = 0.0; crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5() = 0.0;
+		eta = gamma = gamrat = rl1 = 0.0;
+		hu() = 0.0;
+		nls_jcur = false; nstlj = 0; nfe = 0; nsetups = 0; nje = 0;
+		tn = 0.0; q = 1; L = 2; qwait = 2; etamax() = BDF_ETAMX1; nst = 0; nstlp = 0; qprime = 1;
+		saved_t() = 0.0; ncf = nef = 0; nflag = bcm3b200::BDF_FIRST_CALL;
+		h = hprime = 0.0;
+		hscale() = 0.0;
+#pragma unroll
+		for (int e = 0; e < E; e++) zn[0][e] = own(e) ? y0[e] : 0.0;
+		set_ewt();
+		publish(ybuf, zn[0]);
+		rhs_shared(zn[1]);
+		// cvHin (cvode.c:1884-1984), no tstop
+		const double tdiff = tout - tn;
+		if (tdiff == 0.0) return false;
+		const double sign = (tdiff > 0.0) ? 1.0 : -1.0;
+		const double tdist = fabs(tdiff);
+		const double tround = UROUND * fmax(fabs(tn), fabs(tout));
+		if (tdist < 2.0 * tround) return false;
+		const double hlb = BDF_HLB_FACTOR * tround;
+		double hub_inv = -INFINITY;
+#pragma unroll
+		for (int e = 0; e < E; e++) {
+			if (own(e)) {
+				double t2 = fabs(zn[0][e]);
+				double t1 = 1.0 / ewt[e];
+				t1 = BDF_HUB_FACTOR * t2 + t1;
+				t2 = fabs(zn[1][e]);
+				t1 = t2 / t1;
+				hub_inv = (t1 > hub_inv) ? t1 : hub_inv;
+			}
+		}
+		hub_inv = gmax(hub_inv);
+		double hub = BDF_HUB_FACTOR * tdist;
+		if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
+		double hg = sqrt(hlb * hub);
+		if (hub < hlb) {
+			h = (sign < 0.0) ? -hg : hg;
+		} else {
+			double hnew = hg;
+#pragma unroll 1
+			for (int count1 = 1; count1 <= BDF_MAX_ITERS; count1++) {
+				const double hgs = hg * sign;
+				double ytmp[E], ftmp[E];
+#pragma unroll
+				for (int e = 0; e < E; e++) ytmp[e] = hgs * zn[1][e] + zn[0][e];
+				publish(ybuf, ytmp);
+				rhs_shared(ftmp);
+				const double c = 1.0 / hgs;
+#pragma unroll
+				for (int e = 0; e < E; e++) ftmp[e] = c * (ftmp[e] - zn[1][e]);
+				const double yddnrm = wrms(ftmp);
+				hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
+				if (count1 == BDF_MAX_ITERS) break;
+				const double hrat = hnew / hg;
+				if ((hrat > 0.5) && (hrat < 2.0)) break;
+				if ((count1 > 1) && (hrat > 2.0)) {
+					hnew = hg;
+					break;
+				}
+				hg = hnew;
+			}
+			double h0 = BDF_H_BIAS * hnew;
+			if (h0 < hlb) h0 = hlb;
+			if (h0 > hub) h0 = hub;
+			if (sign < 0.0) h0 = -h0;
+			h = h0;
+		}
+		if (fabs(h) < hmin) h *= hmin / fabs(h);
+		hscale() = h;
+		hprime = h;
+#pragma unroll
+		for (int e = 0; e < E; e++) zn[1][e] *= h;
+		return true;
+	}
+
+	// cvRescale, cvode.c:2384-2400
+	__device__ __forceinline__ void rescale()
+	{
+		double c = eta;
+		static_for<1, QMAX + 1>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			if (j <= q) {
+#pragma unroll
+				for (int e = 0; e < E; e++) zn[j][e] *= c;
+				c = eta * c;
+			}
+		});
+		h = hscale() * eta;
+		hscale() = h;
+	}
+
+	// cvIncreaseBDF, cvode.c:2310-2340
+	__device__ __forceinline__ void increase_bdf()
+	{
+		double ll[6];
+#pragma unroll
+		for (int i = 0; i < 6; i++) ll[i] = 0.0;
+		double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
+		ll[2] = 1.0;
+		const double hs = hscale();
+		double hsum = hs;
+		static_for<1, QMAX - 1>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			if (j < q) {
+				hsum += tau(j + 1);
+				const double xi = hsum / hs;
+				prod *= xi;
+				alpha0 -= 1.0 / (j + 1);
+				alpha1 += 1.0 / xi;
+				static_rfor<2, j + 3>([&](auto I) {
+					constexpr int i = decltype(I)::value;
+					ll[i] = ll[i] * xiold + ll[i - 1];
+				});
+				xiold = xi;
+			}
+		});
+		const double A1 = (-alpha0 - alpha1) / prod;
+		double znL[E];
+#pragma unroll
+		for (int e = 0; e < E; e++) znL[e] = A1 * zn[QMAX][e];
+		static_for<2, QMAX + 1>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			if (j <= q) {
+#pragma unroll
+				for (int e = 0; e < E; e++) zn[j][e] += ll[j] * znL[e];
+			} else if (j <= L) {
+#pragma unroll
+				for (int e = 0; e < E; e++) zn[j][e] = znL[e];
+			}
+		});
+	}
+
+	// cvDecreaseBDF, cvode.c:2352-2374
+	__device__ __forceinline__ void decrease_bdf()
+	{
+		double ll[6];
+#pragma unroll
+		for (int i = 0; i < 6; i++) ll[i] = 0.0;
+		ll[2] = 1.0;
+		double hsum = 0.0;
+		const double hs = hscale();
+		static_for<1, QMAX - 1>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			if (j <= q - 2) {
+				hsum += tau(j);
+				const double xi = hsum / hs;
+				static_rfor<2, j + 3>([&](auto I) {
+					constexpr int i = decltype(I)::value;
+					ll[i] = ll[i] * xi + ll[i - 1];
+				});
+			}
+		});
+		double znq[E];
+#pragma unroll
+		for (int e = 0; e < E; e++) znq[e] = zn[2][e];
+		static_for<3, QMAX + 1>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			if (j <= q) {
+#pragma unroll
+				for (int e = 0; e < E; e++) znq[e] = zn[j][e];
+			}
+		});
+		if (q > 2) {
+			static_for<2, QMAX>([&](auto J) {
+				constexpr int j = decltype(J)::value;
+				if (j < q) {
+#pragma unroll
+					for (int e = 0; e < E; e++) zn[j][e] += (-ll[j]) * znq[e];
+				}
+			});
+		}
+	}
+
+	__device__ __forceinline__ void adjust_order(int deltaq)
+	{
+		if ((q == 2) && (deltaq != 1)) return;
+		if (deltaq == 1) increase_bdf();
+		else if (deltaq == -1) decrease_bdf();
+	}
+
+	// CVode loop head + cvStep head (cvode.c:1294-1337, 2094-2102). False on CV_TOO_MUCH_ACC.
+	__device__ __forceinline__ bool begin_step()
+	{
+		if (nst > 0) set_ewt();
+		if (UROUND * wrms(zn[0]) > 1.0) return false;
+		saved_t() = tn;
+		ncf = 0;
+		nef = 0;
+		nflag = bcm3b200::BDF_FIRST_CALL;
+		if ((nst > 0) && (hprime != h)) {
+			if (qprime != q) {
+				adjust_order(qprime - q);
+				q = qprime;
+				L = q + 1;
+				qwait = L;
+			}
+			rescale();
+		}
+		return true;
+	}
+
+	// cvRestore, cvode.c:2918-2927
+	__device__ __forceinline__ void restore()
+	{
+		tn = saved_t();
+		static_for<1, QMAX + 1>([&](auto K) {
+			constexpr int k = decltype(K)::value;
+			static_rfor<k, QMAX + 1>([&](auto J) {
+				constexpr int j = decltype(J)::value;
+				if (j <= q) {
+#pragma unroll
+					for (int e = 0; e < E; e++) zn[j - 1][e] = zn[j - 1][e] - zn[j][e];
+				}
+			});
+		});
+	}
+
+	// cvLsSetup: Newton matrix M = I - gamma J from a fresh difference-quotient Jacobian (jb) or the saved one, then LU
+	__device__ __forceinline__ void linear_setup(bool jb, const double (&y)[E], const double (&fy)[E])
+	{
+		const double neg_gamma = -gamma;
+		if (jb) {
+			// ODESolverCVODE::DifferenceQuotientJacobian (ODESolverCVODE.cpp:496-537); y is in ybuf, f(y) goes to fbuf
+			publish(fbuf, fy);
+			const double srur = sqrt(UROUND);
+			const double fnorm = wrms(fy);
+			const double minInc = (fnorm != 0.0) ? (1000.0 * fabs(h) * UROUND * N * fnorm) : 1.0;
+			// one instance of the right-hand side code for all slots: the slot's y and weight are picked with selects
+#pragma unroll 1
+			for (int e = 0; e < E; e++) {
+				double ye = y[0], we = ewt[0];
+				static_for<1, E>([&](auto J) {
+					constexpr int jj = decltype(J)::value;
+					if (e >= jj) {
+						ye = y[jj];
+						we = ewt[jj];
+					}
+				});
+				const int j = lg + G * e;
+				if (!PADDED || j < N) {
+					const double inc = fmax(srur * fabs(ye), minInc / we);
+					OutColumn col{ M + j, SJ + j, fbuf, 1.0 / inc, neg_gamma, j };
+					generated_derivative(col, SpeciesPerturbed{ ybuf, j, ye + inc }, constant_species, params, non_sampled);
+				}
+			}
+			nstlj = nst;
+			nje++;
+		} else {
+			gsync();
+#pragma unroll 1
+			for (int r = 0; r < N; r++) {
+#pragma unroll
+				for (int e = 0; e < E; e++) {
+					if (own(e)) {
+						const int c = idx(e);
+						double m = neg_gamma * SJ[r * N + c];
+						if (r == c) m += 1.0;
+						M[r * RS + c] = m;
+					}
+				}
+			}
+		}
+		if (lg == 0) {
+#pragma unroll
+			for (int i = 0; i < N; i++) perm[i] = i;
+		}
+		gsync();
+		// PartialPivLUExtended::compute_optimized (EigenPartialPivLUSomewhatSparse.h:38-105): lane = rows lg, lg + G, ...
+		if constexpr (N <= CP_GROUP_STATIC_LU_MAX) {
+			// fully unrolled: which slots still have rows below the pivot is known per (k, slot) at compile time, and every
+			// shared-memory access is [lane row base + constant]
+			double* const rowbase = M + lg * RS;
+			static_for<0, N>([&](auto K) {
+				constexpr int k = decltype(K)::value;
+				double best = -1.0;
+				int bi = N;
+				static_for<0, E>([&](auto EE) {
+					constexpr int e = decltype(EE)::value;
+					if constexpr (G * e + G - 1 >= k) {
+						const int i = lg + G * e;
+						if ((G * e >= k || i >= k) && own(e)) {
+							const double v = fabs(rowbase[G * e * RS + k]);
+							if (v > best) {
+								best = v;
+								bi = i;
+							}
+						}
+					}
+				});
+#pragma unroll
+				for (int d = G / 2; d >= 1; d >>= 1) {
+					const double ob = __shfl_xor_sync(gmask, best, d);
+					const int oi = __shfl_xor_sync(gmask, bi, d);
+					if (ob > best || (ob == best && oi < bi)) {
+						best = ob;
+						bi = oi;
+					}
+				}
+				double lik[E];
+#pragma unroll
+				for (int e = 0; e < E; e++) lik[e] = 0.0;
+				if (best != 0.0) { // group-uniform
+					if (bi != k) {
+#pragma unroll
+						for (int e = 0; e < E; e++) {
+							if (own(e)) {
+								const int c = idx(e);
+								const double t = M[k * RS + c];
+								M[k * RS + c] = M[bi * RS + c];
+								M[bi * RS + c] = t;
+							}
+						}
+						if (lg == 0) {
+							const int t = perm[k];
+							perm[k] = perm[bi];
+							perm[bi] = t;
+						}
+						gsync();
+					}
+					const double inv_coeff = 1.0 / M[k * RS + k];
+					static_for<0, E>([&](auto EE) {
+						constexpr int e = decltype(EE)::value;
+						if constexpr (G * e + G - 1 > k) {
+							const int i = lg + G * e;
+							if ((G * e > k || i > k) && own(e)) {
+								lik[e] = rowbase[G * e * RS + k] * inv_coeff;
+								rowbase[G * e * RS + k] = lik[e];
+							}
+						}
+					});
+				} else {
+					static_for<0, E>([&](auto EE) {
+						constexpr int e = decltype(EE)::value;
+						if constexpr (G * e + G - 1 > k) {
+							const int i = lg + G * e;
+							if ((G * e > k || i > k) && own(e)) lik[e] = rowbase[G * e * RS + k];
+						}
+					});
+				}
+				static_for<k + 1, N>([&](auto CC) {
+					constexpr int c = decltype(CC)::value;
+					const double a_kc = M[k * RS + c];
+					static_for<0, E>([&](auto EE) {
+						constexpr int e = decltype(EE)::value;
+						if constexpr (G * e + G - 1 > k) {
+							const int i = lg + G * e;
+							if ((G * e > k || i > k) && own(e)) rowbase[G * e * RS + c] = fma(-a_kc, lik[e], rowbase[G * e * RS + c]);
+						}
+					});
+				});
+				gsync();
+			});
+		} else
+#pragma unroll 1
+		for (int k = 0; k < N; k++) {
+			double best = -1.0;
+			int bi = N;
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				const int i = idx(e);
+				if (i >= k && own(e)) {
+					const double v = fabs(M[i * RS + k]);
+					if (v > best) {
+						best = v;
+						bi = i;
+					}
+				}
+			}
+#pragma unroll
+			for (int d = G / 2; d >= 1; d >>= 1) {
+				const double ob = __shfl_xor_sync(gmask, best, d);
+				const int oi = __shfl_xor_sync(gmask, bi, d);
+				if (ob > best || (ob == best && oi < bi)) {
+					best = ob;
+					bi = oi;
+				}
+			}
+			if (best != 0.0) { // group-uniform
+				if (bi != k) {
+#pragma unroll
+					for (int e = 0; e < E; e++) {
+						if (own(e)) {
+							const int c = idx(e);
+							const double t = M[k * RS + c];
+							M[k * RS + c] = M[bi * RS + c];
+							M[bi * RS + c] = t;
+						}
+					}
+					if (lg == 0) {
+						const int t = perm[k];
+						perm[k] = perm[bi];
+						perm[bi] = t;
+					}
+					gsync();
+				}
+				const double inv_coeff = 1.0 / M[k * RS + k];
+#pragma unroll
+				for (int e = 0; e < E; e++) {
+					const int i = idx(e);
+					if (i > k && own(e)) M[i * RS + k] *= inv_coeff;
+				}
+			}
+			double lik[E];
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				const int i = idx(e);
+				lik[e] = (i > k && own(e)) ? M[i * RS + k] : 0.0;
+			}
+#pragma unroll 1
+			for (int c = k + 1; c < N; c++) {
+				const double a_kc = M[k * RS + c];
+#pragma unroll
+				for (int e = 0; e < E; e++) {
+					const int i = idx(e);
+					if (i > k && own(e)) M[i * RS + c] = fma(-a_kc, lik[e], M[i * RS + c]);
+				}
+			}
+			gsync();
+		}
+		// the triangular solves multiply by the reciprocal pivots
+#pragma unroll
+		for (int e = 0; e < E; e++) {
+			if (own(e)) {
+				const int i = idx(e);
+				M[i * RS + i] = 1.0 / M[i * RS + i];
+			}
+		}
+		gsync();
+		nsetups++;
+	}
+
+	// x <- (P L U)^-1 x, cooperative: the pivot component is broadcast, every lane updates the components it owns.
+	// Real loops over k (the slot that holds component k is picked with selects): a twelfth of the unrolled code size.
+	__device__ __forceinline__ void lu_solve(double (&b)[E])
+	{
+		publish(ybuf, b);
+#pragma unroll
+		for (int e = 0; e < E; e++) b[e] = own(e) ? ybuf[perm[idx(e)]] : 0.0;
+		const double* const rowbase = M + lg * RS;
+#pragma unroll 1
+		for (int k = 0; k < N; k++) {
+			const int slot = k / G;
+			double bk = b[0];
+			static_for<1, E>([&](auto J) {
+				constexpr int j = decltype(J)::value;
+				if (slot >= j) bk = b[j];
+			});
+			const double xk = __shfl_sync(gmask, bk, gbase + (k % G));
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				const int i = lg + G * e;
+				if (i > k && own(e)) b[e] = fma(-xk, rowbase[G * e * RS + k], b[e]);
+			}
+		}
+#pragma unroll 1
+		for (int k = N - 1; k >= 0; k--) {
+			const int slot = k / G;
+			double bk = b[0];
+			static_for<1, E>([&](auto J) {
+				constexpr int j = decltype(J)::value;
+				if (slot >= j) bk = b[j];
+			});
+			const double xk = __shfl_sync(gmask, bk * M[k * RS + k], gbase + (k % G));
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				const int i = lg + G * e;
+				if (i < k) b[e] = fma(-xk, rowbase[G * e * RS + k], b[e]);
+				else if (i == k) b[e] = xk;
+			}
+		}
+	}
+
+	// cvNlsResidual at y = zn[0] + acor: y published to ybuf, f(y) in fy, delta = rl1 zn[1] + acor - gamma f
+	__device__ __forceinline__ void residual(double (&y)[E], double (&fy)[E], double (&delta)[E])
+	{
+#pragma unroll
+		for (int e = 0; e < E; e++) y[e] = zn[0][e] + acor[e];
+		publish(ybuf, y);
+		rhs_shared(fy);
+#pragma unroll
+		for (int e = 0; e < E; e++) {
+			double r = rl1 * zn[1][e] + acor[e];
+			r += -gamma * fy[e];
+			delta[e] = r;
+		}
+	}
+
+	// One pass of cvStep's attempt loop (structure of BdfThread::attempt); `mask` = lanes of the warp in this call.
+	__device__ __forceinline__ int attempt(unsigned mask)
+	{
+		double l[6], tq[6];
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			l[i] = 0.0;
+			tq[i] = 0.0;
+		}
+		// ---- cvPredict ----
+		tn += h;
+		static_for<1, QMAX + 1>([&](auto K) {
+			constexpr int k = decltype(K)::value;
+			static_rfor<k, QMAX + 1>([&](auto J) {
+				constexpr int j = decltype(J)::value;
+				if (j <= q) {
+#pragma unroll
+					for (int e = 0; e < E; e++) zn[j - 1][e] += zn[j][e];
+				}
+			});
+		});
+		// ---- cvSetBDF + cvSetTqBDF (cvode.c:2611-2686) ----
+		{
+			double xi_inv = 1.0, xistar_inv = 1.0, alpha0 = -1.0, alpha0_hat = -1.0;
+			double hsum = h;
+			l[0] = 1.0;
+			l[1] = 1.0;
+			if (q > 1) {
+				static_for<2, QMAX>([&](auto J) {
+					constexpr int j = decltype(J)::value;
+					if (j < q) {
+						hsum += tau(j - 1);
+						xi_inv = h / hsum;
+						alpha0 -= 1.0 / j;
+						static_rfor<1, j + 1>([&](auto I) {
+							constexpr int i = decltype(I)::value;
+							l[i] += l[i - 1] * xi_inv;
+						});
+					}
+				});
+				alpha0 -= 1.0 / q;
+				xistar_inv = -l[1] - alpha0;
+				hsum += tau(q - 1);
+				xi_inv = h / hsum;
+				alpha0_hat = -l[1] - xi_inv;
+				static_rfor<1, QMAX + 1>([&](auto I) {
+					constexpr int i = decltype(I)::value;
+					if (i <= q) l[i] += l[i - 1] * xistar_inv;
+				});
+			}
+			double lq = l[1];
+			static_for<2, QMAX + 1>([&](auto J) {
+				constexpr int j = decltype(J)::value;
+				if (j <= q) lq = l[j];
+			});
+			const double tauq = tau(q);
+			const double A1 = 1.0 - alpha0_hat + alpha0;
+			const double A2 = 1.0 + q * A1;
+			tq[2] = fabs(A1 / (alpha0 * A2));
+			tq[5] = fabs(A2 * xistar_inv / (lq * xi_inv));
+			if (qwait == 1) {
+				if (q > 1) {
+					const double C = xistar_inv / lq;
+					const double A3 = alpha0 + 1.0 / q;
+					const double A4 = alpha0_hat + xi_inv;
+					const double Cpinv = (1.0 - A4 + A3) / A3;
+					tq[1] = fabs(C * Cpinv);
+				} else {
+					tq[1] = 1.0;
+				}
+				hsum += tauq;
+				xi_inv = h / hsum;
+				const double A5 = alpha0 - (1.0 / (q + 1));
+				const double A6 = alpha0_hat - xi_inv;
+				const double Cppinv = (1.0 - A6 + A5) / A2;
+				tq[3] = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+			}
+			tq[4] = BDF_CORTES / tq[2];
+			rl1 = 1.0 / l[1];
+			gamma = h * rl1;
+			if (nst == 0) gammap = gamma;
+			gamrat = (nst > 0) ? gamma / gammap : 1.0;
+		}
+
+		// l[] and tq[1, 2, 3, 5] are not needed until the step is accepted: parked in shared memory over the Newton loop
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			sc[SC_L + i] = l[i];
+			sc[SC_TQ + i] = tq[i];
+		}
+		// ---- cvNls + Newton: both loops warp-uniform via votes ----
+		int nls_ret = 1;
+		{
+			const double tol = tq[4];
+			int convfail = ((nflag == bcm3b200::BDF_FIRST_CALL) || (nflag == bcm3b200::BDF_PREV_ERR_FAIL)) ? bcm3b200::BDF_NO_FAILURES : bcm3b200::BDF_FAIL_OTHER;
+			bool callSetup = (nflag == bcm3b200::BDF_PREV_CONV_FAIL) || (nflag == bcm3b200::BDF_PREV_ERR_FAIL) || (nst == 0) ||
+			                 (nst >= nstlp + BDF_MSBP) || (fabs(gamrat - 1.0) > BDF_DGMAX);
+#pragma unroll
+			for (int e = 0; e < E; e++) acor[e] = 0.0;
+			// One trip = one Newton iteration of SUNNonlinSolSolve_Newton (sunnonlinsol_newton.c:183-318): residual, the linear
+			// setup if this is the first iteration of a pass that asked for one, solve, convergence test. A failed pass with
+			// stale Jacobian data restarts at m = 0 with a forced setup (:301-312). One copy of the residual code serves all.
+			bool jbad = false, active = true;
+			int m = 0;
+#pragma unroll 1
+			for (;;) {
+				if (!__any_sync(mask, active)) break;
+				double y[E], fy[E], delta[E];
+#pragma unroll
+				for (int e = 0; e < E; e++) y[e] = fy[e] = delta[e] = 0.0;
+				if (active) residual(y, fy, delta);
+				const bool do_setup = active && (m == 0) && callSetup;
+				if (__any_sync(mask, do_setup)) {
+					if (do_setup) {
+						if (jbad) convfail = bcm3b200::BDF_FAIL_BAD_J;
+						const double dgamma = fabs((gamma / gammap) - 1.0);
+						const bool jb = (nst == 0) || (nst > nstlj + BDF_MSBJ) || ((convfail == bcm3b200::BDF_FAIL_BAD_J) && (dgamma < BDF_LS_DGMAX)) ||
+						                (convfail == bcm3b200::BDF_FAIL_OTHER);
+						linear_setup(jb, y, fy);
+						nls_jcur = jb;
+						gamrat = 1.0;
+						gammap = gamma;
+						crate = 1.0;
+						nstlp = nst;
+						callSetup = false;
+					}
+				}
+				if (active) {
+#pragma unroll
+					for (int e = 0; e < E; e++) delta[e] = -delta[e];
+					lu_solve(delta);
+					if (gamrat != 1.0) {
+						const double sc = 2.0 / (1.0 + gamrat);
+#pragma unroll
+						for (int e = 0; e < E; e++) delta[e] *= sc;
+					}
+#pragma unroll
+					for (int e = 0; e < E; e++) acor[e] += delta[e];
+					const double del = wrms(delta);
+					if (m > 0) crate = fmax(BDF_CRDOWN * crate, del / delp);
+					const double dcon = del * fmin(1.0, crate) / tol;
+					if (dcon <= 1.0) {
+						acnrm = (m == 0) ? del : wrms(acor);
+						nls_jcur = false;
+						nls_ret = 0;
+						active = false;
+					} else if (((m >= 1) && (del > BDF_RDIV * delp)) || (m + 1 >= BDF_NLS_MAXCOR)) {
+						// this pass failed
+						if (nls_jcur) {
+							active = false;
+						} else {
+							callSetup = true;
+							jbad = true;
+							m = 0;
+#pragma unroll
+							for (int e = 0; e < E; e++) acor[e] = 0.0;
+						}
+					} else {
+						delp = del;
+						m++;
+					}
+				}
+			}
+		}
+
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			l[i] = sc[SC_L + i];
+			tq[i] = sc[SC_TQ + i];
+		}
+		int result;
+		if (nls_ret != 0) {
+			// ---- cvHandleNFlag ----
+			restore();
+			ncf++;
+			etamax() = 1.0;
+			if ((fabs(h) <= hmin * BDF_ONEPSM) || (ncf == BDF_MXNCF)) {
+				result = T_FAILED;
+			} else {
+				eta = fmax(BDF_ETACF, hmin / fabs(h));
+				nflag = bcm3b200::BDF_PREV_CONV_FAIL;
+				rescale();
+				result = T_RETRY;
+			}
+		} else {
+			const double dsm = acnrm * tq[2];
+			if (!(dsm <= 1.0)) {
+				// ---- cvDoErrorTest, failure ----
+				nef++;
+				nflag = bcm3b200::BDF_PREV_ERR_FAIL;
+				restore();
+				if ((fabs(h) <= hmin * BDF_ONEPSM) || (nef == BDF_MXNEF)) {
+					result = T_FAILED;
+				} else {
+					result = T_RETRY;
+					etamax() = 1.0;
+					if (nef <= BDF_MXNEF1) {
+						eta = 1.0 / (step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+						eta = fmax(BDF_ETAMIN, fmax(eta, hmin / fabs(h)));
+						if (nef >= BDF_SMALL_NEF) eta = fmin(eta, BDF_ETAMXF);
+						rescale();
+					} else if (q > 1) {
+						eta = fmax(BDF_ETAMIN, hmin / fabs(h));
+						adjust_order(-1);
+						L = q;
+						q--;
+						qwait = L;
+						rescale();
+					} else {
+						eta = fmax(BDF_ETAMIN, hmin / fabs(h));
+						h *= eta;
+						hscale() = h;
+						qwait = BDF_LONG_WAIT;
+						double f[E];
+						publish(ybuf, zn[0]);
+						rhs_shared(f);
+#pragma unroll
+						for (int e = 0; e < E; e++) zn[1][e] = h * f[e];
+					}
+				}
+			} else {
+				result = T_DONE;
+				// ---- cvCompleteStep ----
+				nst++;
+				hu() = h;
+				for (int i = q; i >= 2; i--) tau(i) = tau(i - 1);
+				if ((q == 1) && (nst > 1)) tau(2) = tau(1);
+				tau(1) = h;
+				static_for<0, QMAX + 1>([&](auto J) {
+					constexpr int j = decltype(J)::value;
+					if (j <= q) {
+#pragma unroll
+						for (int e = 0; e < E; e++) zn[j][e] += l[j] * acor[e];
+					}
+				});
+				qwait--;
+				if ((qwait == 1) && (q != QMAX)) {
+#pragma unroll
+					for (int e = 0; e < E; e++) zn[QMAX][e] = acor[e];
+					saved_tq5() = tq[5];
+				}
+				// ---- cvPrepareNextStep ----
+				const double etamax_now = etamax();
+				if (etamax_now == 1.0) {
+					qwait = (qwait > 2) ? qwait : 2;
+					qprime = q;
+					hprime = h;
+					eta = 1.0;
+				} else {
+					const double etaq = 1.0 / (step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+					eta = etaq;
+					qprime = q;
+					if (qwait == 0) {
+						qwait = 2;
+						double etaqm1 = 0.0;
+						if (q > 1) {
+							double znq[E];
+#pragma unroll
+							for (int e = 0; e < E; e++) znq[e] = zn[2][e];
+							static_for<3, QMAX + 1>([&](auto J) {
+								constexpr int j = decltype(J)::value;
+								if (j <= q) {
+#pragma unroll
+									for (int e = 0; e < E; e++) znq[e] = zn[j][e];
+								}
+							});
+							const double ddn = wrms(znq) * tq[1];
+							etaqm1 = 1.0 / (step_root(BDF_BIAS1 * ddn, q) + BDF_ADDON);
+						}
+						double etaqp1 = 0.0;
+						if (q != QMAX) {
+							const double stq5 = saved_tq5();
+							if (stq5 != 0.0) {
+								const double base = h / tau(2);
+								double pw = 1.0;
+								static_for<1, QMAX + 1>([&](auto I) {
+									if (decltype(I)::value <= L) pw *= base;
+								});
+								const double cquot = (tq[5] / stq5) * pw;
+								double tmp[E];
+#pragma unroll
+								for (int e = 0; e < E; e++) tmp[e] = -cquot * zn[QMAX][e] + acor[e];
+								const double dup = wrms(tmp) * tq[3];
+								etaqp1 = 1.0 / (step_root(BDF_BIAS3 * dup, L + 1) + BDF_ADDON);
+							}
+						}
+						const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
+						if (etam < BDF_THRESH) {
+							eta = 1.0;
+							qprime = q;
+						} else if (etam == etaq) {
+							eta = etaq;
+							qprime = q;
+						} else if (etam == etaqm1) {
+							eta = etaqm1;
+							qprime = q - 1;
+						} else {
+							eta = etaqp1;
+							qprime = q + 1;
+#pragma unroll
+							for (int e = 0; e < E; e++) zn[QMAX][e] = acor[e];
+						}
+					}
+					if (eta < BDF_THRESH) {
+						eta = 1.0;
+						hprime = h;
+					} else {
+						eta = fmin(eta, etamax_now);
+						hprime = h * eta;
+					}
+				}
+				etamax() = BDF_ETAMX3;
+#pragma unroll
+				for (int e = 0; e < E; e++) acor[e] *= tq[2];
+			}
+		}
+		return result;
+	}
+
+	// CVodeGetDky(t, 0), cvode.c:1467-1524
+	__device__ __forceinline__ bool dky_ok(double t) const
+	{
+		const double hu_ = hu();
+		double tfuzz = BDF_FUZZ_FACTOR * UROUND * (fabs(tn) + fabs(hu_));
+		if (hu_ < 0.0) tfuzz = -tfuzz;
+		const double tp = tn - hu_ - tfuzz, tn1 = tn + tfuzz;
+		return !((t - tp) * (t - tn1) > 0.0);
+	}
+	// sum over the group of weight[e] * Dky component (weights = multiplicity of the component in the observed list)
+	__device__ __forceinline__ double dky_weighted(double t, const double (&weight)[E]) const
+	{
+		const double s = (t - tn) / h;
+		double acc[E];
+#pragma unroll
+		for (int e = 0; e < E; e++) acc[e] = 0.0;
+		bool first = true;
+		static_rfor<0, QMAX + 1>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			if (j <= q) {
+				double c = 1.0;
+#pragma unroll
+				for (int i = 0; i < j; i++) c *= s;
+				if (first) {
+#pragma unroll
+					for (int e = 0; e < E; e++) acc[e] = c * zn[j][e];
+					first = false;
+				} else {
+#pragma unroll
+					for (int e = 0; e < E; e++) acc[e] += c * zn[j][e];
+				}
+			}
+		});
+		double sv = 0.0;
+#pragma unroll
+		for (int e = 0; e < E; e++) sv += weight[e] * acc[e];
+		return gsum(sv);
+	}
+};
+
+__device__ __forceinline__ void apply_variability(double& x, double value, int apply)
+{
+	switch (apply) {
+	case CP_APPLY_ADDITIVE: x += value; break;
+	case CP_APPLY_ADDITIVE_LOG: x += exp(value); break;
+	case CP_APPLY_ADDITIVE_LOG2: x += pow(2.0, value); break;
+	case CP_APPLY_MULTIPLICATIVE: x *= value; break;
+	case CP_APPLY_MULTIPLICATIVE_LOG: x *= exp(value); break;
+	case CP_APPLY_MULTIPLICATIVE_LOG2: x *= pow(2.0, value); break;
+	case CP_APPLY_REPLACE: x = value; break;
+	default: break;
+	}
+}
+
+// Persistent grid: every group of G lanes takes (chain, cell) items from the queue until it is empty.
+__global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(const CpArgs a, double* __restrict__ saved_jacobians, unsigned long long* __restrict__ queue)
+{
+	extern __shared__ double smem_d[];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int gw = lane / G; // group within the warp
+
+	GroupBdf S;
+	S.lg = lane % G;
+	S.gbase = gw * G;
+	S.gmask = (G == 32) ? FULL : (((1u << G) - 1u) << S.gbase);
+	double* region = smem_d + (size_t)(warp * CPW + gw) * CS;
+	S.M = region;
+	S.ybuf = region + OFF_Y;
+	S.fbuf = region + OFF_F;
+	S.perm = reinterpret_cast<int*>(region + OFF_PERM);
+	S.sc = region + OFF_SCAL;
+	const long long group_id = (long long)blockIdx.x * (WPB * CPW) + warp * CPW + gw;
+	S.SJ = saved_jacobians + group_id * (N * N);
+	S.constant_species = ConstVector{ a.constant_species };
+	S.non_sampled = ConstVector{ a.non_sampled };
+	S.reltol = a.rel_tol;
+	S.abstol = a.abs_tol;
+	S.hmin = a.min_dt;
+
+	const int T = a.T;
+	const long long total = (long long)a.num_chains * a.num_cells;
+	const double nan = __longlong_as_double(0x7ff8000000000000ll);
+
+	// per-lane multiplicity of owned components in the observed-species list, 4 bits per slot
+	unsigned obs_count = 0;
+#pragma unroll
+	for (int e = 0; e < E; e++) {
+		int cnt = 0;
+		for (int k = 0; k < a.num_obs_species; k++) cnt += (a.obs_species[k] == S.idx(e)) ? 1 : 0;
+		obs_count |= (unsigned)cnt << (4 * e);
+	}
+	static_assert(E <= 8, "observed-species multiplicities are packed 4 bits per slot");
+
+	bool have = false, exhausted = false, ok = true, newstep = true;
+	int steps = 0, tpi = 0, c = 0, cell = 0;
+	double* out = nullptr;
+
+#pragma unroll 1
+	for (;;) {
+		if (!have && !exhausted) {
+			// ---- next item + K0: Cell::Initialize (Cell.cpp:150-191) ----
+			unsigned long long w = 0;
+			if (S.lg == 0) w = atomicAdd(queue, 1ull);
+			w = __shfl_sync(S.gmask, w, S.gbase);
+			if ((long long)w >= total) {
+				exhausted = true;
+			} else {
+				c = (int)(w / (unsigned long long)a.num_cells);
+				cell = (int)(w % (unsigned long long)a.num_cells);
+				const double* tv = a.transformed + (long long)c * a.nvar;
+				S.params.base = tv;
+				CP_OVERRIDE_INIT
+				// the per-cell parameter overrides are edited in a scratch copy: a run-time index into S itself would pin the
+				// whole integrator state in local memory
+				double ovl[CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1];
+#pragma unroll
+				for (int s = 0; s < (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1); s++) ovl[s] = S.params.ov[s];
+				double y0[E];
+#pragma unroll
+				for (int e = 0; e < E; e++) y0[e] = S.own(e) ? a.initial_conditions[S.idx(e)] : 0.0;
+				const long long gcell = (long long)a.cell_offset + cell;
+				for (int d = 0; d < a.D; d++) {
+					const double scale = (a.var_scale_ix[d] >= 0) ? tv[a.var_scale_ix[d]] : a.var_scale_fixed[d];
+					double v = normcdfinv(a.sobol[gcell * a.D + d]) * exp(scale);
+					if (a.var_negate[d]) v = -v;
+					if (a.var_is_ic[d]) {
+#pragma unroll
+						for (int e = 0; e < E; e++)
+							if (S.idx(e) == a.var_slot[d]) apply_variability(y0[e], v, a.var_apply[d]);
+					} else {
+						if (CP_NUM_OVERRIDES > 0) apply_variability(ovl[a.var_slot[d]], v, a.var_apply[d]);
+					}
+				}
+#pragma unroll
+				for (int s = 0; s < (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1); s++) S.params.ov[s] = ovl[s];
+				// ---- Cell::Simulate + ODESolver::SolveReturnSolution + ODESolverCVODE::Solve: the part before the first step ----
+				const double creation_time = (a.entry_time_ix >= 0) ? tv[a.entry_time_ix] : a.entry_time_fixed;
+				S.sc[SC_CREATION] = creation_time;
+				out = a.cell_values + ((long long)c * T) * a.num_cells + cell;
+				ok = true;
+				steps = 0;
+				tpi = 0;
+				newstep = true;
+				bool finished = false;
+				double sv0 = 0.0;
+#pragma unroll
+				for (int e = 0; e < E; e++) sv0 += (double)((obs_count >> (4 * e)) & 15u) * y0[e];
+				sv0 = S.gsum(sv0);
+				while (tpi < T && (a.timepoints[tpi] - creation_time) < DBL_EPSILON) {
+					const double cell_time = a.timepoints[tpi] - creation_time;
+					if (S.lg == 0) out[(long long)tpi * a.num_cells] = (cell_time < 0.0) ? nan : sv0;
+					tpi++;
+				}
+				if (tpi >= T) finished = true;
+				const double end_time = a.timepoints[T - 1] - creation_time;
+				S.sc[SC_END] = end_time;
+				if (!finished) {
+					if (!S.start(y0, end_time)) {
+						ok = false;
+						finished = true;
+					}
+				}
+				if (finished) {
+					if (S.lg == 0) {
+						if (!ok)
+							for (int k = tpi; k < T; k++) out[(long long)k * a.num_cells] = nan;
+						a.cell_status[(long long)c * a.num_cells + cell] = ok ? 1 : 0;
+						if (a.cell_steps) a.cell_steps[(long long)c * a.num_cells + cell] = 0;
+					}
+				} else {
+					have = true;
+				}
+			}
+		}
+#if CP_GROUP_LOCKSTEP
+		if (__syncthreads_or((have || !exhausted) ? 1 : 0) == 0) break;
+#else
+		if (!__any_sync(FULL, have || !exhausted)) break;
+#endif
+
+		bool done = !have;
+		if (!done && newstep) {
+			newstep = false;
+			if (!S.begin_step()) {
+				ok = false;
+				done = true;
+			}
+		}
+		const bool go = !done;
+		const unsigned mask = __ballot_sync(FULL, go);
+		if (go) {
+			const int r = S.attempt(mask);
+			if (r == T_FAILED) {
+				ok = false;
+				done = true;
+			} else if (r == T_DONE) {
+				steps++;
+				const double tret = S.tn;
+				const double creation_time = S.sc[SC_CREATION];
+				while (tpi < T && tret >= (a.timepoints[tpi] - creation_time)) {
+					const double tq = a.timepoints[tpi] - creation_time;
+					if (!S.dky_ok(tq)) {
+						ok = false;
+						done = true;
+						break;
+					}
+					double obs_weight[E];
+#pragma unroll
+					for (int e = 0; e < E; e++) obs_weight[e] = (double)((obs_count >> (4 * e)) & 15u);
+					const double sv = S.dky_weighted(tq, obs_weight);
+					if (S.lg == 0) out[(long long)tpi * a.num_cells] = sv;
+					tpi++;
+				}
+				if (ok) {
+					if (tret >= S.sc[SC_END]) done = true;
+					else if (steps == a.max_steps) {
+						ok = false;
+						done = true;
+					}
+				}
+				newstep = true;
+			}
+		}
+		if (have && done) {
+			if (S.lg == 0) {
+				if (!ok)
+					for (int k = tpi; k < T; k++) out[(long long)k * a.num_cells] = nan;
+				a.cell_status[(long long)c * a.num_cells + cell] = ok ? 1 : 0;
+				if (a.cell_steps)
+					a.cell_steps[(long long)c * a.num_cells + cell] = (a.debug_report == 1) ? S.nfe : (a.debug_report == 2) ? S.nsetups : (a.debug_report == 3) ? S.nje : steps;
+			}
+			have = false;
+		}
+	}
+}
+
+inline size_t smem_bytes() { return sizeof(double) * (size_t)CS * CPW * WPB; }
+
+inline int resident_blocks(int* err)
+{
+	static int blocks = 0;
+	if (blocks > 0) return blocks;
+	const size_t smem = smem_bytes();
+	cudaError_t e = cudaFuncSetAttribute(cellpop_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) { *err = (int)e; return 0; }
+	int per_sm = 0, dev = 0, sms = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cellpop_group_kernel, BS, smem);
+	if (e != cudaSuccess) { *err = (int)e; return 0; }
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (per_sm < 1) { *err = (int)cudaErrorLaunchOutOfResources; return 0; }
+	blocks = per_sm * sms;
+	return blocks;
+}
+
+} // namespace cellpop_group
+
+// scratch doubles: 2 for the queue counter + one saved Jacobian per resident group
+extern "C" long long cellpop_group_scratch_doubles(int num_chains, int num_cells)
+{
+	(void)num_chains;
+	(void)num_cells;
+	int err = 0;
+	const int blocks = cellpop_group::resident_blocks(&err);
+	if (blocks <= 0) return -(long long)(err ? err : 1);
+	return 2ll + (long long)blocks * cellpop_group::WPB * cellpop_group::CPW * CP_N * CP_N;
+}
+
+extern "C" int cellpop_group_launch(const CpArgs* args, double* scratch, void* stream)
+{
+	int err = 0;
+	int blocks = cellpop_group::resident_blocks(&err);
+	if (blocks <= 0) return err ? err : 1;
+	const long long total = (long long)args->num_chains * args->num_cells;
+	const long long per_block = cellpop_group::WPB * cellpop_group::CPW;
+	const long long needed = (total + per_block - 1) / per_block;
+	if (needed < blocks) blocks = (int)(needed > 0 ? needed : 1);
+	cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(double), (cudaStream_t)stream);
+	if (e != cudaSuccess) return (int)e;
+	cellpop_group::cellpop_group_kernel<<<blocks, cellpop_group::BS, cellpop_group::smem_bytes(), (cudaStream_t)stream>>>(
+	    *args, scratch + 2, reinterpret_cast<unsigned long long*>(scratch));
+	return (int)cudaGetLastError();
+}
+
+extern "C" int cellpop_group_info(int* lanes_per_cell, int* threads_per_block, int* smem_bytes_per_block)
+{
+	*lanes_per_cell = cellpop_group::G;
+	*threads_per_block = cellpop_group::BS;
+	*smem_bytes_per_block = (int)cellpop_group::smem_bytes();
+	return 0;
+}

@@ -44,7 +44,11 @@ struct CellPopState {
 	cellpop_launch_fn launch = nullptr;
 	cellpop_thread_launch_fn thread_launch = nullptr;
 	cellpop_thread_scratch_fn thread_scratch = nullptr;
-	int kernel_choice = 0; // 0 auto (one cell per thread for N <= 20, per warp above), 1 warp, 2 thread
+	cellpop_group_launch_fn group_launch = nullptr;
+	cellpop_group_scratch_fn group_scratch = nullptr;
+	cellpop_group_info_fn group_info = nullptr;
+	int kernel_choice = 0; // 0 auto (lane groups for N <= 96, one cell per warp above), 1 warp, 2 thread, 3 group
+	int group_lanes = 0;   // 0 auto: smallest power of two with ceil(N / G) <= 3
 	DevBuf<double> d_scratch;
 	std::string module_path;
 	cudaStream_t stream = nullptr;
@@ -235,8 +239,8 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	if (at == std::string::npos)
 		return fail(BCM3B200_ERR_ARG, "derivative_code does not contain the reference generator's generated_derivative signature (SBMLModel.cpp:295)");
 	code.replace(at, sig.size(),
-	             "template <class OUT, class SP, class PP>\n__device__ __forceinline__ void generated_derivative(OUT out, const SP& species, "
-	             "const OdeReal* constant_species, const PP& parameters, const OdeReal* non_sampled_parameters)");
+	             "template <class OUT, class SP, class CS, class PP, class NS>\n__device__ __forceinline__ void generated_derivative(OUT out, const SP& species, "
+	             "const CS& constant_species, const PP& parameters, const NS& non_sampled_parameters)");
 	// std::numeric_limits in generated text (none emitted by the rate-law printer today, kept for safety)
 	std::ostringstream o;
 	o << "// generated by libbcm3b200 for a cell_population model -- do not edit\n";
@@ -255,10 +259,27 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	o << "#define CP_WARPS_PER_BLOCK " << warps << "\n";
 	// one cell per thread (small N): 12 N doubles of shared memory per thread
 	o << "#define CP_THREADS_PER_BLOCK " << ((size_t)12 * cp.N * 64 * sizeof(double) <= 112 * 1024 ? 64 : 32) << "\n";
+	// lane groups: G lanes per cell, every lane owns at most 3 components; warps per block sized for >= 2 blocks per SM
+	int G = cp.group_lanes;
+	if (const char* genv = getenv("BCM3B200_CELLPOP_GROUP")) G = atoi(genv);
+	if (G != 2 && G != 4 && G != 8 && G != 16 && G != 32) {
+		G = 2;
+		while (G < 32 && (cp.N + G - 1) / G > 3) G <<= 1;
+	}
+	const size_t per_cell = sizeof(double) * ((size_t)cp.N * (cp.N | 1) + 3 * (size_t)cp.N + 16);
+	int gwarps = 4;
+	if (const char* wenv = getenv("BCM3B200_CELLPOP_GROUP_WARPS")) gwarps = atoi(wenv) > 0 ? atoi(wenv) : 4;
+	while (gwarps > 1 && per_cell * (32 / G) * gwarps > 100 * 1024) gwarps >>= 1;
+	o << "#define CP_GROUP " << G << "\n";
+	o << "#define CP_GROUP_WARPS " << gwarps << "\n";
+	if (const char* benv = getenv("BCM3B200_CELLPOP_GROUP_MIN_BLOCKS")) o << "#define CP_GROUP_MIN_BLOCKS " << atoi(benv) << "\n";
+	if (const char* lenv = getenv("BCM3B200_CELLPOP_GROUP_LOCKSTEP")) o << "#define CP_GROUP_LOCKSTEP " << atoi(lenv) << "\n";
+	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
 	o << code << "\n";
 	o << "#include \"cellpop_warp.cuh\"\n";
 	o << "#include \"cellpop_thread.cuh\"\n";
+	o << "#include \"cellpop_group.cuh\"\n";
 	src = o.str();
 	return BCM3B200_OK;
 }
@@ -275,7 +296,7 @@ inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& overri
 	// code, with and without contraction, already differ by 3.5e-5 in single trajectories) -- is bit-identical to it.
 	// content hash over everything that determines the binary
 	std::string keyed = src + "|fmad=false";
-	for (const char* f : { "/cellpop_warp.cuh", "/cellpop_thread.cuh", "/cellpop_prelude.cuh", "/cellpop_args.h" }) {
+	for (const char* f : { "/cellpop_warp.cuh", "/cellpop_thread.cuh", "/cellpop_group.cuh", "/bdf_thread.cuh", "/cellpop_prelude.cuh", "/cellpop_args.h" }) {
 		std::ifstream in(csrc + f);
 		std::stringstream ss;
 		ss << in.rdbuf();
@@ -316,6 +337,10 @@ inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& overri
 	cp.thread_launch = (cellpop_thread_launch_fn)dlsym(cp.module, "cellpop_thread_launch");
 	cp.thread_scratch = (cellpop_thread_scratch_fn)dlsym(cp.module, "cellpop_thread_scratch_doubles");
 	if (!cp.thread_launch || !cp.thread_scratch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_thread_launch");
+	cp.group_launch = (cellpop_group_launch_fn)dlsym(cp.module, "cellpop_group_launch");
+	cp.group_scratch = (cellpop_group_scratch_fn)dlsym(cp.module, "cellpop_group_scratch_doubles");
+	cp.group_info = (cellpop_group_info_fn)dlsym(cp.module, "cellpop_group_info");
+	if (!cp.group_launch || !cp.group_scratch || !cp.group_info) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_group_launch");
 	cp.module_path = so;
 	return BCM3B200_OK;
 }
@@ -447,8 +472,17 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	int choice = cp.kernel_choice;
 	if (kenv && !strcmp(kenv, "warp")) choice = 1;
 	if (kenv && !strcmp(kenv, "thread")) choice = 2;
-	const bool use_thread = (choice == 2) || (choice == 0 && cp.N <= 20);
-	if (nc > 0 && use_thread) {
+	if (kenv && !strcmp(kenv, "group")) choice = 3;
+	const bool use_group = (choice == 3) || (choice == 0 && cp.N <= 96);
+	const bool use_thread = (choice == 2);
+	if (nc > 0 && use_group) {
+		const long long need = cp.group_scratch((int)C, nc);
+		if (need < 0) return fail(BCM3B200_ERR_CUDA, "cellpop group kernel does not fit on this device: %s", cudaGetErrorString((cudaError_t)(-need)));
+		CUDA_TRY(cp.d_scratch.ensure((size_t)need));
+		int lrc = cp.group_launch(&a, cp.d_scratch.p, (void*)st);
+		if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "cellpop group kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+		cp.last_launches++;
+	} else if (nc > 0 && use_thread) {
 		CUDA_TRY(cp.d_scratch.ensure((size_t)cp.thread_scratch((int)C, nc)));
 		int lrc = cp.thread_launch(&a, cp.d_scratch.p, (void*)st);
 		if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "cellpop thread kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));

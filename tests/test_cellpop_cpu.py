@@ -79,7 +79,7 @@ def test_device_module_compiles_for_sm100a(built, tmp_path, monkeypatch):
     assert len(built_dirs) == 1
     assert os.path.exists(tmp_path / built_dirs[0] / "libcellpop_model.so")
     src = open(tmp_path / built_dirs[0] / "model.cu").read()
-    assert "#define CP_N 5" in src and "template <class OUT, class SP, class PP>" in src and "generated_jacobian" not in src
+    assert "#define CP_N 5" in src and "template <class OUT, class SP, class CS, class PP, class NS>" in src and "generated_jacobian" not in src
     # a text without the generator's signature is rejected
     bad = dataclasses.replace(prob, derivative_code="void f() {}")
     from bcm3_b200 import _lib

@@ -28,10 +28,10 @@ def run(N, cells, T, C, decades=2.0, kinds=("ref", "port"), kernel="auto"):
     ev.close()
 
 if __name__ == "__main__":
-    for k in ("thread", "warp"):
+    ks = sys.argv[1].split(",") if len(sys.argv) > 1 else ["group"]
+    for k in ks:
         run(12, 200, 20, 3, kernel=k)
+        run(5, 300, 20, 3, kernel=k)
         run(12, 2000, 50, 8, kernel=k, kinds=("port",))
-    run(50, 200, 20, 2, decades=4.0)
-    # timing at config-3 size
-    for k in ("thread", "warp"):
+        run(24, 500, 20, 2, decades=3.0, kernel=k)
         run(12, 10000, 50, 16, kinds=("ref",), kernel=k)
