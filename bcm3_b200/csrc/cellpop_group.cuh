@@ -25,6 +25,8 @@
 
 #include <cfloat>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 #include "bdf_thread.cuh"
 #include "cellpop_args.h"
@@ -65,8 +67,12 @@ constexpr int OFF_PERM = OFF_F + N;
 constexpr int OFF_SCAL = OFF_PERM + (N + 1) / 2;
 // per-cell scalars that are touched a few times per step at most: kept out of the register file (every lane of the
 // group would hold a copy). Lanes of a group always store identical values, so no synchronisation is involved.
-enum { SC_TAU = 0 /* [1..5] */, SC_HU = 6, SC_SAVED_TQ5, SC_SAVED_T, SC_HSCALE, SC_ETAMAX, SC_CREATION, SC_END, SC_L /* [0..5] */, SC_TQ = SC_L + 6 /* [1..5] */, SC_COUNT = SC_TQ + 6 };
-constexpr int REGION_MIN = OFF_SCAL + SC_COUNT;
+enum { SC_TAU = 0 /* [1..5] */, SC_HU = 6, SC_SAVED_TQ5, SC_SAVED_T, SC_HSCALE, SC_ETAMAX, SC_CREATION, SC_END, SC_HPRIME, SC_ETA, SC_GAMMAP, SC_CRATE, SC_DELP, SC_ACNRM,
+       SC_L /* [0..5] */, SC_TQ = SC_L + 6 /* [1..5] */,
+       SC_OV = SC_TQ + 6 /* per-cell parameter overrides */, SC_COUNT = SC_OV + (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1) };
+// Nordsieck columns 2..5, lane-private: element (j, e) of lane lg at OFF_ZNH + ((j - 2) * E + e) * G + lg
+constexpr int OFF_ZNH = OFF_SCAL + SC_COUNT;
+constexpr int REGION_MIN = OFF_ZNH + 4 * E * G;
 constexpr int cell_stride()
 {
 	const int want = (RS * G) % 16;
@@ -78,9 +84,14 @@ constexpr int CS = cell_stride();
 
 enum { T_RETRY = 0, T_DONE = 1, T_FAILED = -1 };
 
+// ---- the generated right-hand side: ONE instance for the whole kernel ----
+// Every use (Newton residual, the perturbed evaluations of the difference-quotient Jacobian, cvHin, the order-1 restart)
+// goes through rhs_eval(): y is read from shared memory with component j replaced by yj (j = -1: none), the result is
+// written to shared memory with a stride (1: the f buffer, RS: a column of the Newton matrix). Inlining the generated
+// code at each use costs ~750 instructions per copy, and the hot loop has to stay small.
 struct CellParameters {
-	const double* base;
-	double ov[CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1];
+	const double* base; // transformed variables of the chain
+	const double* ov;   // per-cell overrides (shared memory)
 	__device__ __forceinline__ double operator[](int k) const
 	{
 		CP_PARAM_OVERRIDE_BODY
@@ -91,52 +102,24 @@ struct ConstVector {
 	const double* p;
 	__device__ __forceinline__ double operator[](int k) const { return __ldg(p + k); }
 };
-struct SpeciesShared {
-	const double* y;
-	__device__ __forceinline__ double operator[](int i) const { return y[i]; }
-};
-struct SpeciesPerturbed {
+struct SpeciesAt {
 	const double* y;
 	int j;
 	double yj;
 	__device__ __forceinline__ double operator[](int i) const { return (i == j) ? yj : y[i]; }
 };
-// `out[i] = value` of generated_derivative keeping only the components this lane owns (i is a literal in the generated text)
-struct OutOwned {
-	double* f;
-	int lg;
-	struct Ref {
-		double* f;
-		int lg, i;
-		__device__ __forceinline__ void operator=(double v) const
-		{
-			if ((i % G) == lg) f[i / G] = v;
-		}
-	};
-	__device__ __forceinline__ Ref operator[](int i) const { return Ref{ f, lg, i }; }
+struct OutStrided {
+	double* p;
+	int stride;
+	__device__ __forceinline__ double& operator[](int i) const { return p[i * stride]; }
 };
-// `out[i] = value` of a perturbed evaluation: difference quotient of column j into the saved Jacobian and, already
-// scaled, into the Newton matrix (SUNMatScaleAddI(-gamma, A): A = -gamma * J, then the unit diagonal added)
-struct OutColumn {
-	double* Mcol;  // &M[0][j]
-	double* SJcol; // &SJ[0][j]
-	const double* fy;
-	double inc_inv, neg_gamma;
-	int j;
-	struct Ref {
-		const OutColumn& c;
-		int i;
-		__device__ __forceinline__ void operator=(double v) const
-		{
-			const double Jij = c.inc_inv * (v - c.fy[i]);
-			c.SJcol[i * N] = Jij;
-			double m = c.neg_gamma * Jij;
-			if (i == c.j) m += 1.0;
-			c.Mcol[i * RS] = m;
-		}
-	};
-	__device__ __forceinline__ Ref operator[](int i) const { return Ref{ *this, i }; }
-};
+__device__ __noinline__ void rhs_eval(unsigned y_off, int j, double yj, unsigned out_off, int out_stride, unsigned ov_off, const double* tv,
+                                      const double* constant_species, const double* non_sampled)
+{
+	extern __shared__ double smem_d[];
+	generated_derivative(OutStrided{ smem_d + out_off, out_stride }, SpeciesAt{ smem_d + y_off, j, yj }, ConstVector{ constant_species },
+	                     CellParameters{ tv, smem_d + ov_off }, ConstVector{ non_sampled });
+}
 
 #ifndef CP_GROUP_LOCKSTEP
 #define CP_GROUP_LOCKSTEP 1
@@ -157,11 +140,12 @@ __device__ __noinline__ double norm_finish(double s, unsigned gmask)
 
 struct GroupBdf {
 	// ---- distributed vectors (slot e = component lg + G * e) ----
-	double zn[6][E];
+	double zn01[2][E]; // Nordsieck columns 0 and 1; columns 2..5 are lane-private words of the cell's shared block
+	double* znh;
 	double ewt[E], acor[E];
 	// ---- replicated scalars ----
-	double tn, h, hprime, eta;
-	double gamma, gammap, gamrat, rl1, crate, delp, acnrm;
+	double tn, h;
+	double gamma, gamrat, rl1;
 	double* sc; // shared: tau[1..5], hu, saved_tq5, saved_t, hscale, etamax, creation/end time, l[] and tq[] across the Newton loop
 	int q, qprime, L, qwait, nst, nstlp, nstlj, nflag, ncf, nef;
 	bool nls_jcur;
@@ -172,12 +156,14 @@ struct GroupBdf {
 	double* fbuf; // shared, N
 	int* perm;    // shared, N
 	double* SJ;   // global, N * N row-major
+	unsigned region_off; // offset of the cell's shared block in doubles
 	int lg;
 	unsigned gmask;
 	int gbase; // lane index (within the warp) of the group's lane 0
 	// ---- model ----
-	ConstVector constant_species, non_sampled;
-	CellParameters params;
+	const double* constant_species;
+	const double* non_sampled;
+	const double* tv; // transformed variables of the cell's chain
 	double reltol, abstol, hmin;
 
 	__device__ __forceinline__ double& tau(int j) const { return sc[SC_TAU + j]; }
@@ -186,6 +172,18 @@ struct GroupBdf {
 	__device__ __forceinline__ double& saved_t() const { return sc[SC_SAVED_T]; }
 	__device__ __forceinline__ double& hscale() const { return sc[SC_HSCALE]; }
 	__device__ __forceinline__ double& etamax() const { return sc[SC_ETAMAX]; }
+	__device__ __forceinline__ double& hprime() const { return sc[SC_HPRIME]; }
+	__device__ __forceinline__ double& eta() const { return sc[SC_ETA]; }
+	__device__ __forceinline__ double& gammap() const { return sc[SC_GAMMAP]; }
+	__device__ __forceinline__ double& crate() const { return sc[SC_CRATE]; }
+	__device__ __forceinline__ double& delp() const { return sc[SC_DELP]; }
+	__device__ __forceinline__ double& acnrm() const { return sc[SC_ACNRM]; }
+	template <int J>
+	__device__ __forceinline__ double& Z(int e)
+	{
+		if constexpr (J < 2) return zn01[J][e];
+		else return znh[((J - 2) * E + e) * G];
+	}
 
 	__device__ __forceinline__ int idx(int e) const { return lg + G * e; }
 	__device__ __forceinline__ bool own(int e) const { return !PADDED || (lg + G * e < N); }
@@ -220,7 +218,7 @@ struct GroupBdf {
 	__device__ __forceinline__ void set_ewt()
 	{
 #pragma unroll
-		for (int e = 0; e < E; e++) ewt[e] = own(e) ? 1.0 / (reltol * fabs(zn[0][e]) + abstol) : 0.0;
+		for (int e = 0; e < E; e++) ewt[e] = own(e) ? 1.0 / (reltol * fabs(Z<0>(e)) + abstol) : 0.0;
 	}
 	// publish a distributed vector into the cell's shared y buffer
 	__device__ __forceinline__ void publish(double* buf, const double (&x)[E]) const
@@ -231,39 +229,40 @@ struct GroupBdf {
 			if (own(e)) buf[idx(e)] = x[e];
 		gsync();
 	}
-	// Cell::solver_rhs_fn (Cell.cpp:423-433) at the y held in ybuf; every lane evaluates, keeps its own components
+	// Cell::solver_rhs_fn (Cell.cpp:423-433) at the y held in ybuf: every lane of the group evaluates the whole vector into
+	// fbuf (identical stores) and reads back the components it owns
 	__device__ __forceinline__ void rhs_shared(double (&f)[E])
 	{
+		rhs_eval(region_off + OFF_Y, -1, 0.0, region_off + OFF_F, 1, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled);
 #pragma unroll
-		for (int e = 0; e < E; e++) f[e] = 0.0;
-		generated_derivative(OutOwned{ f, lg }, SpeciesShared{ ybuf }, constant_species, params, non_sampled);
+		for (int e = 0; e < E; e++) f[e] = own(e) ? fbuf[idx(e)] : 0.0;
 		nfe++;
 	}
 
 	// CVodeCreate zero state + CVodeReInit(0, y0) + the first-call block of CVode (cvode.c:586-665, 1068-1155)
 	__device__ __forceinline__ bool start(const double (&y0)[E], double tout)
 	{
-#pragma unroll
-		for (int j = 0; j < 6; j++) {
+		static_for<0, 6>([&](auto J) {
+			constexpr int j = decltype(J)::value;
 			tau(j) = 0.0;
 #pragma unroll
-			for (int e = 0; e < E; e++) zn[j][e] = 0.0;
-		}
+			for (int e = 0; e < E; e++) Z<j>(e) = 0.0;
+		});
 #pragma unroll
 		for (int e = 0; e < E; e++) acor[e] = 0.0;
-		gammap = 0.0; crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5() = 0.0;
-		eta = gamma = gamrat = rl1 = 0.0;
+		gammap() = 0.0; crate() = 1.0; delp() = 0.0; acnrm() = 0.0; saved_tq5() = 0.0;
+		eta() = gamma = gamrat = rl1 = 0.0;
 		hu() = 0.0;
 		nls_jcur = false; nstlj = 0; nfe = 0; nsetups = 0; nje = 0;
 		tn = 0.0; q = 1; L = 2; qwait = 2; etamax() = BDF_ETAMX1; nst = 0; nstlp = 0; qprime = 1;
 		saved_t() = 0.0; ncf = nef = 0; nflag = bcm3b200::BDF_FIRST_CALL;
-		h = hprime = 0.0;
+		h = hprime() = 0.0;
 		hscale() = 0.0;
 #pragma unroll
-		for (int e = 0; e < E; e++) zn[0][e] = own(e) ? y0[e] : 0.0;
+		for (int e = 0; e < E; e++) Z<0>(e) = own(e) ? y0[e] : 0.0;
 		set_ewt();
-		publish(ybuf, zn[0]);
-		rhs_shared(zn[1]);
+		publish(ybuf, zn01[0]);
+		rhs_shared(zn01[1]);
 		// cvHin (cvode.c:1884-1984), no tstop
 		const double tdiff = tout - tn;
 		if (tdiff == 0.0) return false;
@@ -276,10 +275,10 @@ struct GroupBdf {
 #pragma unroll
 		for (int e = 0; e < E; e++) {
 			if (own(e)) {
-				double t2 = fabs(zn[0][e]);
+				double t2 = fabs(Z<0>(e));
 				double t1 = 1.0 / ewt[e];
 				t1 = BDF_HUB_FACTOR * t2 + t1;
-				t2 = fabs(zn[1][e]);
+				t2 = fabs(Z<1>(e));
 				t1 = t2 / t1;
 				hub_inv = (t1 > hub_inv) ? t1 : hub_inv;
 			}
@@ -297,12 +296,12 @@ struct GroupBdf {
 				const double hgs = hg * sign;
 				double ytmp[E], ftmp[E];
 #pragma unroll
-				for (int e = 0; e < E; e++) ytmp[e] = hgs * zn[1][e] + zn[0][e];
+				for (int e = 0; e < E; e++) ytmp[e] = hgs * Z<1>(e) + Z<0>(e);
 				publish(ybuf, ytmp);
 				rhs_shared(ftmp);
 				const double c = 1.0 / hgs;
 #pragma unroll
-				for (int e = 0; e < E; e++) ftmp[e] = c * (ftmp[e] - zn[1][e]);
+				for (int e = 0; e < E; e++) ftmp[e] = c * (ftmp[e] - Z<1>(e));
 				const double yddnrm = wrms(ftmp);
 				hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
 				if (count1 == BDF_MAX_ITERS) break;
@@ -322,25 +321,25 @@ struct GroupBdf {
 		}
 		if (fabs(h) < hmin) h *= hmin / fabs(h);
 		hscale() = h;
-		hprime = h;
+		hprime() = h;
 #pragma unroll
-		for (int e = 0; e < E; e++) zn[1][e] *= h;
+		for (int e = 0; e < E; e++) Z<1>(e) *= h;
 		return true;
 	}
 
 	// cvRescale, cvode.c:2384-2400
 	__device__ __forceinline__ void rescale()
 	{
-		double c = eta;
+		double c = eta();
 		static_for<1, QMAX + 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j <= q) {
 #pragma unroll
-				for (int e = 0; e < E; e++) zn[j][e] *= c;
-				c = eta * c;
+				for (int e = 0; e < E; e++) Z<j>(e) *= c;
+				c = eta() * c;
 			}
 		});
-		h = hscale() * eta;
+		h = hscale() * eta();
 		hscale() = h;
 	}
 
@@ -372,15 +371,15 @@ struct GroupBdf {
 		const double A1 = (-alpha0 - alpha1) / prod;
 		double znL[E];
 #pragma unroll
-		for (int e = 0; e < E; e++) znL[e] = A1 * zn[QMAX][e];
+		for (int e = 0; e < E; e++) znL[e] = A1 * Z<QMAX>(e);
 		static_for<2, QMAX + 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j <= q) {
 #pragma unroll
-				for (int e = 0; e < E; e++) zn[j][e] += ll[j] * znL[e];
+				for (int e = 0; e < E; e++) Z<j>(e) += ll[j] * znL[e];
 			} else if (j <= L) {
 #pragma unroll
-				for (int e = 0; e < E; e++) zn[j][e] = znL[e];
+				for (int e = 0; e < E; e++) Z<j>(e) = znL[e];
 			}
 		});
 	}
@@ -407,12 +406,12 @@ struct GroupBdf {
 		});
 		double znq[E];
 #pragma unroll
-		for (int e = 0; e < E; e++) znq[e] = zn[2][e];
+		for (int e = 0; e < E; e++) znq[e] = Z<2>(e);
 		static_for<3, QMAX + 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j <= q) {
 #pragma unroll
-				for (int e = 0; e < E; e++) znq[e] = zn[j][e];
+				for (int e = 0; e < E; e++) znq[e] = Z<j>(e);
 			}
 		});
 		if (q > 2) {
@@ -420,7 +419,7 @@ struct GroupBdf {
 				constexpr int j = decltype(J)::value;
 				if (j < q) {
 #pragma unroll
-					for (int e = 0; e < E; e++) zn[j][e] += (-ll[j]) * znq[e];
+					for (int e = 0; e < E; e++) Z<j>(e) += (-ll[j]) * znq[e];
 				}
 			});
 		}
@@ -437,12 +436,12 @@ struct GroupBdf {
 	__device__ __forceinline__ bool begin_step()
 	{
 		if (nst > 0) set_ewt();
-		if (UROUND * wrms(zn[0]) > 1.0) return false;
+		if (UROUND * wrms(zn01[0]) > 1.0) return false;
 		saved_t() = tn;
 		ncf = 0;
 		nef = 0;
 		nflag = bcm3b200::BDF_FIRST_CALL;
-		if ((nst > 0) && (hprime != h)) {
+		if ((nst > 0) && (hprime() != h)) {
 			if (qprime != q) {
 				adjust_order(qprime - q);
 				q = qprime;
@@ -464,7 +463,7 @@ struct GroupBdf {
 				constexpr int j = decltype(J)::value;
 				if (j <= q) {
 #pragma unroll
-					for (int e = 0; e < E; e++) zn[j - 1][e] = zn[j - 1][e] - zn[j][e];
+					for (int e = 0; e < E; e++) Z<j - 1>(e) = Z<j - 1>(e) - Z<j>(e);
 				}
 			});
 		});
@@ -475,8 +474,8 @@ struct GroupBdf {
 	{
 		const double neg_gamma = -gamma;
 		if (jb) {
-			// ODESolverCVODE::DifferenceQuotientJacobian (ODESolverCVODE.cpp:496-537); y is in ybuf, f(y) goes to fbuf
-			publish(fbuf, fy);
+			// ODESolverCVODE::DifferenceQuotientJacobian (ODESolverCVODE.cpp:496-537); y is in ybuf and f(y) in fbuf (residual)
+			gsync();
 			const double srur = sqrt(UROUND);
 			const double fnorm = wrms(fy);
 			const double minInc = (fnorm != 0.0) ? (1000.0 * fabs(h) * UROUND * N * fnorm) : 1.0;
@@ -494,8 +493,18 @@ struct GroupBdf {
 				const int j = lg + G * e;
 				if (!PADDED || j < N) {
 					const double inc = fmax(srur * fabs(ye), minInc / we);
-					OutColumn col{ M + j, SJ + j, fbuf, 1.0 / inc, neg_gamma, j };
-					generated_derivative(col, SpeciesPerturbed{ ybuf, j, ye + inc }, constant_species, params, non_sampled);
+					// f(y + inc e_j) into column j of M, then the difference quotient into the saved Jacobian and, scaled
+					// (SUNMatScaleAddI(-gamma, A): A = -gamma * J, then the unit diagonal added), back into M
+					rhs_eval(region_off + OFF_Y, j, ye + inc, region_off + j, RS, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled);
+					const double inc_inv = 1.0 / inc;
+#pragma unroll 1
+					for (int i = 0; i < N; i++) {
+						const double Jij = inc_inv * (M[i * RS + j] - fbuf[i]);
+						SJ[i * N + j] = Jij;
+						double m = neg_gamma * Jij;
+						if (i == j) m += 1.0;
+						M[i * RS + j] = m;
+					}
 				}
 			}
 			nstlj = nst;
@@ -554,7 +563,7 @@ struct GroupBdf {
 				double lik[E];
 #pragma unroll
 				for (int e = 0; e < E; e++) lik[e] = 0.0;
-				if (best != 0.0) { // group-uniform
+				if (best > 0.0) { // group-uniform; a column of zeros (or of NaN: best stays -1) is left alone
 					if (bi != k) {
 #pragma unroll
 						for (int e = 0; e < E; e++) {
@@ -605,72 +614,75 @@ struct GroupBdf {
 				});
 				gsync();
 			});
-		} else
+		} else {
+			double* const rowbase = M + lg * RS;
 #pragma unroll 1
-		for (int k = 0; k < N; k++) {
-			double best = -1.0;
-			int bi = N;
+			for (int k = 0; k < N; k++) {
+				double best = -1.0;
+				int bi = N;
 #pragma unroll
-			for (int e = 0; e < E; e++) {
-				const int i = idx(e);
-				if (i >= k && own(e)) {
-					const double v = fabs(M[i * RS + k]);
-					if (v > best) {
-						best = v;
-						bi = i;
-					}
-				}
-			}
-#pragma unroll
-			for (int d = G / 2; d >= 1; d >>= 1) {
-				const double ob = __shfl_xor_sync(gmask, best, d);
-				const int oi = __shfl_xor_sync(gmask, bi, d);
-				if (ob > best || (ob == best && oi < bi)) {
-					best = ob;
-					bi = oi;
-				}
-			}
-			if (best != 0.0) { // group-uniform
-				if (bi != k) {
-#pragma unroll
-					for (int e = 0; e < E; e++) {
-						if (own(e)) {
-							const int c = idx(e);
-							const double t = M[k * RS + c];
-							M[k * RS + c] = M[bi * RS + c];
-							M[bi * RS + c] = t;
+				for (int e = 0; e < E; e++) {
+					const int i = lg + G * e;
+					if (i >= k && own(e)) {
+						const double v = fabs(rowbase[G * e * RS + k]);
+						if (v > best) {
+							best = v;
+							bi = i;
 						}
 					}
-					if (lg == 0) {
-						const int t = perm[k];
-						perm[k] = perm[bi];
-						perm[bi] = t;
+				}
+#pragma unroll
+				for (int d = G / 2; d >= 1; d >>= 1) {
+					const double ob = __shfl_xor_sync(gmask, best, d);
+					const int oi = __shfl_xor_sync(gmask, bi, d);
+					if (ob > best || (ob == best && oi < bi)) {
+						best = ob;
+						bi = oi;
 					}
-					gsync();
 				}
-				const double inv_coeff = 1.0 / M[k * RS + k];
+				double inv_coeff = 1.0;
+				if (best > 0.0) { // group-uniform; a column of zeros (or of NaN: best stays -1) is left alone
+					if (bi != k) {
+#pragma unroll
+						for (int e = 0; e < E; e++) {
+							if (own(e)) {
+								const int c = idx(e);
+								const double t = M[k * RS + c];
+								M[k * RS + c] = M[bi * RS + c];
+								M[bi * RS + c] = t;
+							}
+						}
+						if (lg == 0) {
+							const int t = perm[k];
+							perm[k] = perm[bi];
+							perm[bi] = t;
+						}
+						gsync();
+					}
+					inv_coeff = 1.0 / M[k * RS + k];
+				}
+				// multipliers of the rows this lane owns below the pivot
+				double lik[E];
 #pragma unroll
 				for (int e = 0; e < E; e++) {
-					const int i = idx(e);
-					if (i > k && own(e)) M[i * RS + k] *= inv_coeff;
+					const int i = lg + G * e;
+					lik[e] = 0.0;
+					if (i > k && own(e)) {
+						lik[e] = rowbase[G * e * RS + k] * inv_coeff;
+						rowbase[G * e * RS + k] = lik[e];
+					}
 				}
-			}
-			double lik[E];
-#pragma unroll
-			for (int e = 0; e < E; e++) {
-				const int i = idx(e);
-				lik[e] = (i > k && own(e)) ? M[i * RS + k] : 0.0;
-			}
 #pragma unroll 1
-			for (int c = k + 1; c < N; c++) {
-				const double a_kc = M[k * RS + c];
+				for (int c = k + 1; c < N; c++) {
+					const double a_kc = M[k * RS + c];
 #pragma unroll
-				for (int e = 0; e < E; e++) {
-					const int i = idx(e);
-					if (i > k && own(e)) M[i * RS + c] = fma(-a_kc, lik[e], M[i * RS + c]);
+					for (int e = 0; e < E; e++) {
+						const int i = lg + G * e;
+						if (i > k && own(e)) rowbase[G * e * RS + c] = fma(-a_kc, lik[e], rowbase[G * e * RS + c]);
+					}
 				}
+				gsync();
 			}
-			gsync();
 		}
 		// the triangular solves multiply by the reciprocal pivots
 #pragma unroll
@@ -685,7 +697,8 @@ struct GroupBdf {
 	}
 
 	// x <- (P L U)^-1 x, cooperative: the pivot component is broadcast, every lane updates the components it owns.
-	// Real loops over k (the slot that holds component k is picked with selects): a twelfth of the unrolled code size.
+	// Real loops over k (the slot that holds component k is picked with selects): the unrolled forms are faster per
+	// instruction but several times larger, and this kernel is bound by instruction fetch (hot code >> 32 KB L1.5 I-cache).
 	__device__ __forceinline__ void lu_solve(double (&b)[E])
 	{
 		publish(ybuf, b);
@@ -729,12 +742,12 @@ struct GroupBdf {
 	__device__ __forceinline__ void residual(double (&y)[E], double (&fy)[E], double (&delta)[E])
 	{
 #pragma unroll
-		for (int e = 0; e < E; e++) y[e] = zn[0][e] + acor[e];
+		for (int e = 0; e < E; e++) y[e] = Z<0>(e) + acor[e];
 		publish(ybuf, y);
 		rhs_shared(fy);
 #pragma unroll
 		for (int e = 0; e < E; e++) {
-			double r = rl1 * zn[1][e] + acor[e];
+			double r = rl1 * Z<1>(e) + acor[e];
 			r += -gamma * fy[e];
 			delta[e] = r;
 		}
@@ -757,7 +770,7 @@ struct GroupBdf {
 				constexpr int j = decltype(J)::value;
 				if (j <= q) {
 #pragma unroll
-					for (int e = 0; e < E; e++) zn[j - 1][e] += zn[j][e];
+					for (int e = 0; e < E; e++) Z<j - 1>(e) += Z<j>(e);
 				}
 			});
 		});
@@ -820,8 +833,8 @@ struct GroupBdf {
 			tq[4] = BDF_CORTES / tq[2];
 			rl1 = 1.0 / l[1];
 			gamma = h * rl1;
-			if (nst == 0) gammap = gamma;
-			gamrat = (nst > 0) ? gamma / gammap : 1.0;
+			if (nst == 0) gammap() = gamma;
+			gamrat = (nst > 0) ? gamma / gammap() : 1.0;
 		}
 
 		// l[] and tq[1, 2, 3, 5] are not needed until the step is accepted: parked in shared memory over the Newton loop
@@ -855,14 +868,14 @@ struct GroupBdf {
 				if (__any_sync(mask, do_setup)) {
 					if (do_setup) {
 						if (jbad) convfail = bcm3b200::BDF_FAIL_BAD_J;
-						const double dgamma = fabs((gamma / gammap) - 1.0);
+						const double dgamma = fabs((gamma / gammap()) - 1.0);
 						const bool jb = (nst == 0) || (nst > nstlj + BDF_MSBJ) || ((convfail == bcm3b200::BDF_FAIL_BAD_J) && (dgamma < BDF_LS_DGMAX)) ||
 						                (convfail == bcm3b200::BDF_FAIL_OTHER);
 						linear_setup(jb, y, fy);
 						nls_jcur = jb;
 						gamrat = 1.0;
-						gammap = gamma;
-						crate = 1.0;
+						gammap() = gamma;
+						crate() = 1.0;
 						nstlp = nst;
 						callSetup = false;
 					}
@@ -879,14 +892,14 @@ struct GroupBdf {
 #pragma unroll
 					for (int e = 0; e < E; e++) acor[e] += delta[e];
 					const double del = wrms(delta);
-					if (m > 0) crate = fmax(BDF_CRDOWN * crate, del / delp);
-					const double dcon = del * fmin(1.0, crate) / tol;
+					if (m > 0) crate() = fmax(BDF_CRDOWN * crate(), del / delp());
+					const double dcon = del * fmin(1.0, crate()) / tol;
 					if (dcon <= 1.0) {
-						acnrm = (m == 0) ? del : wrms(acor);
+						acnrm() = (m == 0) ? del : wrms(acor);
 						nls_jcur = false;
 						nls_ret = 0;
 						active = false;
-					} else if (((m >= 1) && (del > BDF_RDIV * delp)) || (m + 1 >= BDF_NLS_MAXCOR)) {
+					} else if (((m >= 1) && (del > BDF_RDIV * delp())) || (m + 1 >= BDF_NLS_MAXCOR)) {
 						// this pass failed
 						if (nls_jcur) {
 							active = false;
@@ -898,7 +911,7 @@ struct GroupBdf {
 							for (int e = 0; e < E; e++) acor[e] = 0.0;
 						}
 					} else {
-						delp = del;
+						delp() = del;
 						m++;
 					}
 				}
@@ -919,13 +932,13 @@ struct GroupBdf {
 			if ((fabs(h) <= hmin * BDF_ONEPSM) || (ncf == BDF_MXNCF)) {
 				result = T_FAILED;
 			} else {
-				eta = fmax(BDF_ETACF, hmin / fabs(h));
+				eta() = fmax(BDF_ETACF, hmin / fabs(h));
 				nflag = bcm3b200::BDF_PREV_CONV_FAIL;
 				rescale();
 				result = T_RETRY;
 			}
 		} else {
-			const double dsm = acnrm * tq[2];
+			const double dsm = acnrm() * tq[2];
 			if (!(dsm <= 1.0)) {
 				// ---- cvDoErrorTest, failure ----
 				nef++;
@@ -937,27 +950,27 @@ struct GroupBdf {
 					result = T_RETRY;
 					etamax() = 1.0;
 					if (nef <= BDF_MXNEF1) {
-						eta = 1.0 / (step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
-						eta = fmax(BDF_ETAMIN, fmax(eta, hmin / fabs(h)));
-						if (nef >= BDF_SMALL_NEF) eta = fmin(eta, BDF_ETAMXF);
+						eta() = 1.0 / (step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+						eta() = fmax(BDF_ETAMIN, fmax(eta(), hmin / fabs(h)));
+						if (nef >= BDF_SMALL_NEF) eta() = fmin(eta(), BDF_ETAMXF);
 						rescale();
 					} else if (q > 1) {
-						eta = fmax(BDF_ETAMIN, hmin / fabs(h));
+						eta() = fmax(BDF_ETAMIN, hmin / fabs(h));
 						adjust_order(-1);
 						L = q;
 						q--;
 						qwait = L;
 						rescale();
 					} else {
-						eta = fmax(BDF_ETAMIN, hmin / fabs(h));
-						h *= eta;
+						eta() = fmax(BDF_ETAMIN, hmin / fabs(h));
+						h *= eta();
 						hscale() = h;
 						qwait = BDF_LONG_WAIT;
 						double f[E];
-						publish(ybuf, zn[0]);
+						publish(ybuf, zn01[0]);
 						rhs_shared(f);
 #pragma unroll
-						for (int e = 0; e < E; e++) zn[1][e] = h * f[e];
+						for (int e = 0; e < E; e++) Z<1>(e) = h * f[e];
 					}
 				}
 			} else {
@@ -972,13 +985,13 @@ struct GroupBdf {
 					constexpr int j = decltype(J)::value;
 					if (j <= q) {
 #pragma unroll
-						for (int e = 0; e < E; e++) zn[j][e] += l[j] * acor[e];
+						for (int e = 0; e < E; e++) Z<j>(e) += l[j] * acor[e];
 					}
 				});
 				qwait--;
 				if ((qwait == 1) && (q != QMAX)) {
 #pragma unroll
-					for (int e = 0; e < E; e++) zn[QMAX][e] = acor[e];
+					for (int e = 0; e < E; e++) Z<QMAX>(e) = acor[e];
 					saved_tq5() = tq[5];
 				}
 				// ---- cvPrepareNextStep ----
@@ -986,11 +999,11 @@ struct GroupBdf {
 				if (etamax_now == 1.0) {
 					qwait = (qwait > 2) ? qwait : 2;
 					qprime = q;
-					hprime = h;
-					eta = 1.0;
+					hprime() = h;
+					eta() = 1.0;
 				} else {
 					const double etaq = 1.0 / (step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
-					eta = etaq;
+					eta() = etaq;
 					qprime = q;
 					if (qwait == 0) {
 						qwait = 2;
@@ -998,12 +1011,12 @@ struct GroupBdf {
 						if (q > 1) {
 							double znq[E];
 #pragma unroll
-							for (int e = 0; e < E; e++) znq[e] = zn[2][e];
+							for (int e = 0; e < E; e++) znq[e] = Z<2>(e);
 							static_for<3, QMAX + 1>([&](auto J) {
 								constexpr int j = decltype(J)::value;
 								if (j <= q) {
 #pragma unroll
-									for (int e = 0; e < E; e++) znq[e] = zn[j][e];
+									for (int e = 0; e < E; e++) znq[e] = Z<j>(e);
 								}
 							});
 							const double ddn = wrms(znq) * tq[1];
@@ -1021,34 +1034,34 @@ struct GroupBdf {
 								const double cquot = (tq[5] / stq5) * pw;
 								double tmp[E];
 #pragma unroll
-								for (int e = 0; e < E; e++) tmp[e] = -cquot * zn[QMAX][e] + acor[e];
+								for (int e = 0; e < E; e++) tmp[e] = -cquot * Z<QMAX>(e) + acor[e];
 								const double dup = wrms(tmp) * tq[3];
 								etaqp1 = 1.0 / (step_root(BDF_BIAS3 * dup, L + 1) + BDF_ADDON);
 							}
 						}
 						const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
 						if (etam < BDF_THRESH) {
-							eta = 1.0;
+							eta() = 1.0;
 							qprime = q;
 						} else if (etam == etaq) {
-							eta = etaq;
+							eta() = etaq;
 							qprime = q;
 						} else if (etam == etaqm1) {
-							eta = etaqm1;
+							eta() = etaqm1;
 							qprime = q - 1;
 						} else {
-							eta = etaqp1;
+							eta() = etaqp1;
 							qprime = q + 1;
 #pragma unroll
-							for (int e = 0; e < E; e++) zn[QMAX][e] = acor[e];
+							for (int e = 0; e < E; e++) Z<QMAX>(e) = acor[e];
 						}
 					}
-					if (eta < BDF_THRESH) {
-						eta = 1.0;
-						hprime = h;
+					if (eta() < BDF_THRESH) {
+						eta() = 1.0;
+						hprime() = h;
 					} else {
-						eta = fmin(eta, etamax_now);
-						hprime = h * eta;
+						eta() = fmin(eta(), etamax_now);
+						hprime() = h * eta();
 					}
 				}
 				etamax() = BDF_ETAMX3;
@@ -1069,7 +1082,7 @@ struct GroupBdf {
 		return !((t - tp) * (t - tn1) > 0.0);
 	}
 	// sum over the group of weight[e] * Dky component (weights = multiplicity of the component in the observed list)
-	__device__ __forceinline__ double dky_weighted(double t, const double (&weight)[E]) const
+	__device__ __forceinline__ double dky_weighted(double t, const double (&weight)[E])
 	{
 		const double s = (t - tn) / h;
 		double acc[E];
@@ -1084,11 +1097,11 @@ struct GroupBdf {
 				for (int i = 0; i < j; i++) c *= s;
 				if (first) {
 #pragma unroll
-					for (int e = 0; e < E; e++) acc[e] = c * zn[j][e];
+					for (int e = 0; e < E; e++) acc[e] = c * Z<j>(e);
 					first = false;
 				} else {
 #pragma unroll
-					for (int e = 0; e < E; e++) acc[e] += c * zn[j][e];
+					for (int e = 0; e < E; e++) acc[e] += c * Z<j>(e);
 				}
 			}
 		});
@@ -1120,23 +1133,25 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int gw = lane / G; // group within the warp
 
-	GroupBdf S;
-	S.lg = lane % G;
-	S.gbase = gw * G;
-	S.gmask = (G == 32) ? FULL : (((1u << G) - 1u) << S.gbase);
+	GroupBdf B;
+	B.lg = lane % G;
+	B.gbase = gw * G;
+	B.gmask = (G == 32) ? FULL : (((1u << G) - 1u) << B.gbase);
 	double* region = smem_d + (size_t)(warp * CPW + gw) * CS;
-	S.M = region;
-	S.ybuf = region + OFF_Y;
-	S.fbuf = region + OFF_F;
-	S.perm = reinterpret_cast<int*>(region + OFF_PERM);
-	S.sc = region + OFF_SCAL;
+	B.M = region;
+	B.ybuf = region + OFF_Y;
+	B.fbuf = region + OFF_F;
+	B.perm = reinterpret_cast<int*>(region + OFF_PERM);
+	B.sc = region + OFF_SCAL;
+	B.znh = region + OFF_ZNH + B.lg;
+	B.region_off = (unsigned)((warp * CPW + gw) * CS);
 	const long long group_id = (long long)blockIdx.x * (WPB * CPW) + warp * CPW + gw;
-	S.SJ = saved_jacobians + group_id * (N * N);
-	S.constant_species = ConstVector{ a.constant_species };
-	S.non_sampled = ConstVector{ a.non_sampled };
-	S.reltol = a.rel_tol;
-	S.abstol = a.abs_tol;
-	S.hmin = a.min_dt;
+	B.SJ = saved_jacobians + group_id * (N * N);
+	B.constant_species = a.constant_species;
+	B.non_sampled = a.non_sampled;
+	B.reltol = a.rel_tol;
+	B.abstol = a.abs_tol;
+	B.hmin = a.min_dt;
 
 	const int T = a.T;
 	const long long total = (long long)a.num_chains * a.num_cells;
@@ -1147,7 +1162,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 #pragma unroll
 	for (int e = 0; e < E; e++) {
 		int cnt = 0;
-		for (int k = 0; k < a.num_obs_species; k++) cnt += (a.obs_species[k] == S.idx(e)) ? 1 : 0;
+		for (int k = 0; k < a.num_obs_species; k++) cnt += (a.obs_species[k] == B.idx(e)) ? 1 : 0;
 		obs_count |= (unsigned)cnt << (4 * e);
 	}
 	static_assert(E <= 8, "observed-species multiplicities are packed 4 bits per slot");
@@ -1161,24 +1176,28 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 		if (!have && !exhausted) {
 			// ---- next item + K0: Cell::Initialize (Cell.cpp:150-191) ----
 			unsigned long long w = 0;
-			if (S.lg == 0) w = atomicAdd(queue, 1ull);
-			w = __shfl_sync(S.gmask, w, S.gbase);
+			if (B.lg == 0) w = atomicAdd(queue, 1ull);
+			w = __shfl_sync(B.gmask, w, B.gbase);
 			if ((long long)w >= total) {
 				exhausted = true;
 			} else {
 				c = (int)(w / (unsigned long long)a.num_cells);
 				cell = (int)(w % (unsigned long long)a.num_cells);
 				const double* tv = a.transformed + (long long)c * a.nvar;
-				S.params.base = tv;
+				B.tv = tv;
+				// per-cell parameter overrides: start from the chain's values (CP_OVERRIDE_INIT fills S.params.ov[]), apply the
+				// cell's variability, park them in the cell's shared block for CellParameters
+				struct {
+					struct {
+						double ov[CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1];
+					} params;
+				} S;
+				S.params.ov[0] = 0.0;
 				CP_OVERRIDE_INIT
-				// the per-cell parameter overrides are edited in a scratch copy: a run-time index into S itself would pin the
-				// whole integrator state in local memory
-				double ovl[CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1];
-#pragma unroll
-				for (int s = 0; s < (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1); s++) ovl[s] = S.params.ov[s];
+				double* const ovl = S.params.ov;
 				double y0[E];
 #pragma unroll
-				for (int e = 0; e < E; e++) y0[e] = S.own(e) ? a.initial_conditions[S.idx(e)] : 0.0;
+				for (int e = 0; e < E; e++) y0[e] = B.own(e) ? a.initial_conditions[B.idx(e)] : 0.0;
 				const long long gcell = (long long)a.cell_offset + cell;
 				for (int d = 0; d < a.D; d++) {
 					const double scale = (a.var_scale_ix[d] >= 0) ? tv[a.var_scale_ix[d]] : a.var_scale_fixed[d];
@@ -1187,16 +1206,17 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 					if (a.var_is_ic[d]) {
 #pragma unroll
 						for (int e = 0; e < E; e++)
-							if (S.idx(e) == a.var_slot[d]) apply_variability(y0[e], v, a.var_apply[d]);
+							if (B.idx(e) == a.var_slot[d]) apply_variability(y0[e], v, a.var_apply[d]);
 					} else {
 						if (CP_NUM_OVERRIDES > 0) apply_variability(ovl[a.var_slot[d]], v, a.var_apply[d]);
 					}
 				}
+				B.gsync();
 #pragma unroll
-				for (int s = 0; s < (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1); s++) S.params.ov[s] = ovl[s];
+				for (int s = 0; s < (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1); s++) B.sc[SC_OV + s] = ovl[s];
 				// ---- Cell::Simulate + ODESolver::SolveReturnSolution + ODESolverCVODE::Solve: the part before the first step ----
 				const double creation_time = (a.entry_time_ix >= 0) ? tv[a.entry_time_ix] : a.entry_time_fixed;
-				S.sc[SC_CREATION] = creation_time;
+				B.sc[SC_CREATION] = creation_time;
 				out = a.cell_values + ((long long)c * T) * a.num_cells + cell;
 				ok = true;
 				steps = 0;
@@ -1206,23 +1226,23 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				double sv0 = 0.0;
 #pragma unroll
 				for (int e = 0; e < E; e++) sv0 += (double)((obs_count >> (4 * e)) & 15u) * y0[e];
-				sv0 = S.gsum(sv0);
+				sv0 = B.gsum(sv0);
 				while (tpi < T && (a.timepoints[tpi] - creation_time) < DBL_EPSILON) {
 					const double cell_time = a.timepoints[tpi] - creation_time;
-					if (S.lg == 0) out[(long long)tpi * a.num_cells] = (cell_time < 0.0) ? nan : sv0;
+					if (B.lg == 0) out[(long long)tpi * a.num_cells] = (cell_time < 0.0) ? nan : sv0;
 					tpi++;
 				}
 				if (tpi >= T) finished = true;
 				const double end_time = a.timepoints[T - 1] - creation_time;
-				S.sc[SC_END] = end_time;
+				B.sc[SC_END] = end_time;
 				if (!finished) {
-					if (!S.start(y0, end_time)) {
+					if (!B.start(y0, end_time)) {
 						ok = false;
 						finished = true;
 					}
 				}
 				if (finished) {
-					if (S.lg == 0) {
+					if (B.lg == 0) {
 						if (!ok)
 							for (int k = tpi; k < T; k++) out[(long long)k * a.num_cells] = nan;
 						a.cell_status[(long long)c * a.num_cells + cell] = ok ? 1 : 0;
@@ -1242,7 +1262,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 		bool done = !have;
 		if (!done && newstep) {
 			newstep = false;
-			if (!S.begin_step()) {
+			if (!B.begin_step()) {
 				ok = false;
 				done = true;
 			}
@@ -1250,17 +1270,17 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 		const bool go = !done;
 		const unsigned mask = __ballot_sync(FULL, go);
 		if (go) {
-			const int r = S.attempt(mask);
+			const int r = B.attempt(mask);
 			if (r == T_FAILED) {
 				ok = false;
 				done = true;
 			} else if (r == T_DONE) {
 				steps++;
-				const double tret = S.tn;
-				const double creation_time = S.sc[SC_CREATION];
+				const double tret = B.tn;
+				const double creation_time = B.sc[SC_CREATION];
 				while (tpi < T && tret >= (a.timepoints[tpi] - creation_time)) {
 					const double tq = a.timepoints[tpi] - creation_time;
-					if (!S.dky_ok(tq)) {
+					if (!B.dky_ok(tq)) {
 						ok = false;
 						done = true;
 						break;
@@ -1268,12 +1288,12 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 					double obs_weight[E];
 #pragma unroll
 					for (int e = 0; e < E; e++) obs_weight[e] = (double)((obs_count >> (4 * e)) & 15u);
-					const double sv = S.dky_weighted(tq, obs_weight);
-					if (S.lg == 0) out[(long long)tpi * a.num_cells] = sv;
+					const double sv = B.dky_weighted(tq, obs_weight);
+					if (B.lg == 0) out[(long long)tpi * a.num_cells] = sv;
 					tpi++;
 				}
 				if (ok) {
-					if (tret >= S.sc[SC_END]) done = true;
+					if (tret >= B.sc[SC_END]) done = true;
 					else if (steps == a.max_steps) {
 						ok = false;
 						done = true;
@@ -1283,21 +1303,23 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 			}
 		}
 		if (have && done) {
-			if (S.lg == 0) {
+			if (B.lg == 0) {
 				if (!ok)
 					for (int k = tpi; k < T; k++) out[(long long)k * a.num_cells] = nan;
 				a.cell_status[(long long)c * a.num_cells + cell] = ok ? 1 : 0;
 				if (a.cell_steps)
-					a.cell_steps[(long long)c * a.num_cells + cell] = (a.debug_report == 1) ? S.nfe : (a.debug_report == 2) ? S.nsetups : (a.debug_report == 3) ? S.nje : steps;
+					a.cell_steps[(long long)c * a.num_cells + cell] = (a.debug_report == 1) ? B.nfe : (a.debug_report == 2) ? B.nsetups : (a.debug_report == 3) ? B.nje : steps;
 			}
 			have = false;
 		}
 	}
 }
 
-inline size_t smem_bytes() { return sizeof(double) * (size_t)CS * CPW * WPB; }
+// internal linkage on purpose: several model libraries live in one process, and a function-local static of an `inline`
+// function is a process-wide unique symbol -- the second model would reuse the first one's cached launch configuration
+static size_t smem_bytes() { return sizeof(double) * (size_t)CS * CPW * WPB; }
 
-inline int resident_blocks(int* err)
+static int resident_blocks(int* err)
 {
 	static int blocks = 0;
 	if (blocks > 0) return blocks;
@@ -1336,11 +1358,15 @@ extern "C" int cellpop_group_launch(const CpArgs* args, double* scratch, void* s
 	const long long per_block = cellpop_group::WPB * cellpop_group::CPW;
 	const long long needed = (total + per_block - 1) / per_block;
 	if (needed < blocks) blocks = (int)(needed > 0 ? needed : 1);
+	(void)cudaGetLastError();
 	cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(double), (cudaStream_t)stream);
-	if (e != cudaSuccess) return (int)e;
+	if (e != cudaSuccess) return (int)e + 10000;
 	cellpop_group::cellpop_group_kernel<<<blocks, cellpop_group::BS, cellpop_group::smem_bytes(), (cudaStream_t)stream>>>(
 	    *args, scratch + 2, reinterpret_cast<unsigned long long*>(scratch));
-	return (int)cudaGetLastError();
+	e = cudaGetLastError();
+	if (e != cudaSuccess && getenv("BCM3B200_DEBUG"))
+		fprintf(stderr, "cellpop_group_launch: %s (blocks %d threads %d smem %zu)\n", cudaGetErrorString(e), blocks, cellpop_group::BS, cellpop_group::smem_bytes());
+	return (int)e;
 }
 
 extern "C" int cellpop_group_info(int* lanes_per_cell, int* threads_per_block, int* smem_bytes_per_block)

@@ -48,6 +48,7 @@ struct CellPopState {
 	cellpop_group_scratch_fn group_scratch = nullptr;
 	cellpop_group_info_fn group_info = nullptr;
 	int kernel_choice = 0; // 0 auto (lane groups for N <= 96, one cell per warp above), 1 warp, 2 thread, 3 group
+	int built_kernel = 0;  // the one kernel the model library was compiled with (1, 2 or 3)
 	int group_lanes = 0;   // 0 auto: smallest power of two with ceil(N / G) <= 3
 	DevBuf<double> d_scratch;
 	std::string module_path;
@@ -227,6 +228,19 @@ inline std::string library_dir()
 }
 
 // Turns the reference generator's text into a device function template and wraps it into a translation unit.
+// which of the three mappings the model library is built with; fixed at finalize (option "cellpop_kernel" or the
+// BCM3B200_CELLPOP_KERNEL environment variable, else by size)
+inline int cellpop_resolve_kernel(const CellPopState& cp)
+{
+	int choice = cp.kernel_choice;
+	const char* kenv = getenv("BCM3B200_CELLPOP_KERNEL");
+	if (kenv && !strcmp(kenv, "warp")) choice = 1;
+	if (kenv && !strcmp(kenv, "thread")) choice = 2;
+	if (kenv && !strcmp(kenv, "group")) choice = 3;
+	if (choice < 1 || choice > 3) choice = (cp.N <= 96) ? 3 : 1;
+	return choice;
+}
+
 inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>& override_vars, std::string& src)
 {
 	std::string code = cp.derivative_code;
@@ -266,26 +280,36 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 		G = 2;
 		while (G < 32 && (cp.N + G - 1) / G > 3) G <<= 1;
 	}
-	const size_t per_cell = sizeof(double) * ((size_t)cp.N * (cp.N | 1) + 3 * (size_t)cp.N + 16);
-	int gwarps = 4;
-	if (const char* wenv = getenv("BCM3B200_CELLPOP_GROUP_WARPS")) gwarps = atoi(wenv) > 0 ? atoi(wenv) : 4;
-	while (gwarps > 1 && per_cell * (32 / G) * gwarps > 100 * 1024) gwarps >>= 1;
+	// block shape: as many cells per SM as its shared memory holds (the per-cell block of cellpop_group.cuh), two blocks
+	// per SM, at most 12 warps per SM -- above that the register budget (64K / threads) starts to force spills
+	const int Eg = (cp.N + G - 1) / G;
+	const size_t per_cell = sizeof(double) * ((size_t)cp.N * (cp.N | 1) + 3 * (size_t)cp.N + 64 + override_vars.size() + 4 * (size_t)Eg * G + 16);
+	const int cells_per_warp = 32 / G;
+	int warps_max = (int)((220 * 1024) / (per_cell * cells_per_warp));
+	if (warps_max > 12) warps_max = 12;
+	int gwarps = warps_max / 2, gblocks = 2;
+	if (gwarps < 1) {
+		gwarps = warps_max < 1 ? 1 : warps_max;
+		gblocks = 1;
+	}
+	if (const char* wenv = getenv("BCM3B200_CELLPOP_GROUP_WARPS")) gwarps = atoi(wenv) > 0 ? atoi(wenv) : gwarps;
+	if (const char* benv = getenv("BCM3B200_CELLPOP_GROUP_MIN_BLOCKS")) gblocks = atoi(benv) > 0 ? atoi(benv) : gblocks;
 	o << "#define CP_GROUP " << G << "\n";
 	o << "#define CP_GROUP_WARPS " << gwarps << "\n";
-	if (const char* benv = getenv("BCM3B200_CELLPOP_GROUP_MIN_BLOCKS")) o << "#define CP_GROUP_MIN_BLOCKS " << atoi(benv) << "\n";
+	o << "#define CP_GROUP_MIN_BLOCKS " << gblocks << "\n";
 	if (const char* lenv = getenv("BCM3B200_CELLPOP_GROUP_LOCKSTEP")) o << "#define CP_GROUP_LOCKSTEP " << atoi(lenv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
 	o << code << "\n";
-	o << "#include \"cellpop_warp.cuh\"\n";
-	o << "#include \"cellpop_thread.cuh\"\n";
-	o << "#include \"cellpop_group.cuh\"\n";
+	const int which = cellpop_resolve_kernel(cp);
+	o << (which == 1 ? "#include \"cellpop_warp.cuh\"\n" : which == 2 ? "#include \"cellpop_thread.cuh\"\n" : "#include \"cellpop_group.cuh\"\n");
 	src = o.str();
 	return BCM3B200_OK;
 }
 
 inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& override_vars)
 {
+	cp.built_kernel = cellpop_resolve_kernel(cp);
 	std::string src;
 	int rc = cellpop_module_source(cp, override_vars, src);
 	if (rc != BCM3B200_OK) return rc;
@@ -332,15 +356,19 @@ inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& overri
 	}
 	cp.module = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
 	if (!cp.module) return fail(BCM3B200_ERR_STATE, "dlopen(%s) failed: %s", so.c_str(), dlerror());
-	cp.launch = (cellpop_launch_fn)dlsym(cp.module, "cellpop_launch");
-	if (!cp.launch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_launch");
-	cp.thread_launch = (cellpop_thread_launch_fn)dlsym(cp.module, "cellpop_thread_launch");
-	cp.thread_scratch = (cellpop_thread_scratch_fn)dlsym(cp.module, "cellpop_thread_scratch_doubles");
-	if (!cp.thread_launch || !cp.thread_scratch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_thread_launch");
-	cp.group_launch = (cellpop_group_launch_fn)dlsym(cp.module, "cellpop_group_launch");
-	cp.group_scratch = (cellpop_group_scratch_fn)dlsym(cp.module, "cellpop_group_scratch_doubles");
-	cp.group_info = (cellpop_group_info_fn)dlsym(cp.module, "cellpop_group_info");
-	if (!cp.group_launch || !cp.group_scratch || !cp.group_info) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_group_launch");
+	if (cp.built_kernel == 1) {
+		cp.launch = (cellpop_launch_fn)dlsym(cp.module, "cellpop_launch");
+		if (!cp.launch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_launch");
+	} else if (cp.built_kernel == 2) {
+		cp.thread_launch = (cellpop_thread_launch_fn)dlsym(cp.module, "cellpop_thread_launch");
+		cp.thread_scratch = (cellpop_thread_scratch_fn)dlsym(cp.module, "cellpop_thread_scratch_doubles");
+		if (!cp.thread_launch || !cp.thread_scratch) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_thread_launch");
+	} else {
+		cp.group_launch = (cellpop_group_launch_fn)dlsym(cp.module, "cellpop_group_launch");
+		cp.group_scratch = (cellpop_group_scratch_fn)dlsym(cp.module, "cellpop_group_scratch_doubles");
+		cp.group_info = (cellpop_group_info_fn)dlsym(cp.module, "cellpop_group_info");
+		if (!cp.group_launch || !cp.group_scratch || !cp.group_info) return fail(BCM3B200_ERR_STATE, "generated module lacks cellpop_group_launch");
+	}
 	cp.module_path = so;
 	return BCM3B200_OK;
 }
@@ -468,13 +496,8 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	a.cell_steps = cp.d_steps.p;
 	a.debug_report = getenv("BCM3B200_CELLPOP_REPORT") ? atoi(getenv("BCM3B200_CELLPOP_REPORT")) : 0;
 	cp.last_launches = 1;
-	const char* kenv = getenv("BCM3B200_CELLPOP_KERNEL");
-	int choice = cp.kernel_choice;
-	if (kenv && !strcmp(kenv, "warp")) choice = 1;
-	if (kenv && !strcmp(kenv, "thread")) choice = 2;
-	if (kenv && !strcmp(kenv, "group")) choice = 3;
-	const bool use_group = (choice == 3) || (choice == 0 && cp.N <= 96);
-	const bool use_thread = (choice == 2);
+	const bool use_group = (cp.built_kernel == 3);
+	const bool use_thread = (cp.built_kernel == 2);
 	if (nc > 0 && use_group) {
 		const long long need = cp.group_scratch((int)C, nc);
 		if (need < 0) return fail(BCM3B200_ERR_CUDA, "cellpop group kernel does not fit on this device: %s", cudaGetErrorString((cudaError_t)(-need)));

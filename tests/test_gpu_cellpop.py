@@ -1,5 +1,6 @@
-"""GPU suite for the cell_population path: the warp-per-cell CUDA integrator (compiled per model from the generated RHS text)
-through the C ABI, against the golden vectors of the compiled reference and against the CPU checker on fresh inputs."""
+"""GPU suite for the cell_population path: the CUDA integrators (compiled per model from the generated RHS text; the lane-group
+mapping is the default, the one-cell-per-warp and one-cell-per-thread mappings are kept selectable) through the C ABI, against
+the golden vectors of the compiled reference and against the CPU checker on fresh inputs."""
 import numpy as np
 import pytest
 
@@ -20,8 +21,17 @@ def Evaluator(built):
 
 @pytest.mark.parametrize("name", CELLPOP_GOLDEN_NAMES)
 def test_matches_reference_golden(Evaluator, name):
+    _check_golden(Evaluator, name, "auto")
+
+
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_other_mappings_match_reference_golden(Evaluator, kernel):
+    _check_golden(Evaluator, "cellpop_n12_normal", kernel)
+
+
+def _check_golden(Evaluator, name, kernel):
     prob, gold = load_cellpop_golden(name)
-    ev = Evaluator(prob)
+    ev = Evaluator(prob, kernel=kernel)
     logp, status = ev.evaluate(gold["values"])
     d = ev.diagnostics()
     ev.close()
