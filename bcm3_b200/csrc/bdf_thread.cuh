@@ -126,7 +126,7 @@ __device__ BCM3_ROOT_INLINE double bdf_root(double base, int k)
 // ~3e-7) refined by one Halley step for y^k = x in double precision (cubic convergence: ~(k^2 - 1) / 12 * e^3 < 1e-17),
 // so the result is within an ulp or two of pow(x, 1/k), like the exp/log form, at about a quarter of its instructions
 // and with no dependence on k in the control flow. Outside the single-precision range it falls back to exp/log.
-__device__ __forceinline__ double bdf_root_halley(double base, int k)
+__device__ BCM3_ROOT_INLINE double bdf_root_halley(double base, int k)
 {
 	if (base <= 0.0) return 0.0;
 	if (!(base > 1e-30 && base < 1e30)) return bdf_root(base, k);
@@ -144,22 +144,66 @@ __device__ __forceinline__ double bdf_root_halley(double base, int k)
 	return y * (num / den);
 }
 
-template <int N, class Model, bool STATS>
+#ifndef BCM3_ROOT_EXPLOG
+#define bdf_step_root bdf_root_halley
+#else
+#define bdf_step_root bdf_root
+#endif
+
+// Where the state lives. Hot vectors and scalars (Nordsieck columns 0 and 1, weights, correction, t, h, gamma, ...) are
+// registers. Everything that is touched a few times per step at most -- Nordsieck columns 2..5, the step history tau,
+// the inverse Newton matrix, the step-size bookkeeping, and l[] / tq[] while the Newton loop runs -- sits in a
+// thread-private column of shared memory (word `slot` of thread `tid` at shared[slot * STRIDE + tid]: conflict-free),
+// which brings the kernel from 255 registers (8 warps per SM) to 168 (12 warps per SM) without spills.
+template <int N>
+struct BdfSlots {
+	enum : int {
+		ZNH = 0,                  // zn[2..5][N]
+		TAU = ZNH + 4 * N,        // tau[0..5] (tau[0] unused)
+		MINV = TAU + 6,           // N * N
+		HPRIME = MINV + N * N, HSCALE, ETA, ETAMAX, HU, GAMMAP, CRATE, DELP, ACNRM, SAVED_TQ5, SAVED_T, TSTOP,
+		LSTASH,                   // l[0..5]
+		TQSTASH = LSTASH + 6,     // tq[0..5]
+		COUNT = TQSTASH + 6
+	};
+};
+
+template <int N, class Model, bool STATS, int STRIDE>
 struct BdfThread {
 	static constexpr int QMAX = 5;
+	using SL = BdfSlots<N>;
 
-	double zn[6][N];
+	double zn01[2][N];
 	double ewt[N], acor[N];
-	double tau[6]; // tau[1..5]
-	double Minv[N * N]; // inverse of I - gamma*J, Minv[i * N + j]
-	double tn, h, hprime, hscale, eta, etamax, hu;
-	double gamma, gammap, gamrat, rl1, crate, delp, acnrm, saved_tq5;
-	double tstop;
-	double saved_t;
+	double tn, h;
+	double gamma, gamrat, rl1;
+	double* sh; // shared memory, already offset by the thread index
 	int q, qprime, L, qwait, nst, nstlp, nstlj;
 	int nflag, ncf, nef;
 	bool tstopset, nls_jcur;
 	BdfCounters cnt;
+
+	__device__ __forceinline__ double& slot(int k) const { return sh[k * STRIDE]; }
+	template <int J>
+	__device__ __forceinline__ double& Z(int i)
+	{
+		if constexpr (J < 2) return zn01[J][i];
+		else return sh[(SL::ZNH + (J - 2) * N + i) * STRIDE];
+	}
+	__device__ __forceinline__ double& tau(int j) const { return slot(SL::TAU + j); }
+	__device__ __forceinline__ double& Minv(int k) const { return slot(SL::MINV + k); }
+	__device__ __forceinline__ double& hprime() const { return slot(SL::HPRIME); }
+	__device__ __forceinline__ double& hscale() const { return slot(SL::HSCALE); }
+	__device__ __forceinline__ double& eta() const { return slot(SL::ETA); }
+	__device__ __forceinline__ double& etamax() const { return slot(SL::ETAMAX); }
+	__device__ __forceinline__ double& hu() const { return slot(SL::HU); }
+	__device__ __forceinline__ double& gammap() const { return slot(SL::GAMMAP); }
+	__device__ __forceinline__ double& crate() const { return slot(SL::CRATE); }
+	__device__ __forceinline__ double& delp() const { return slot(SL::DELP); }
+	__device__ __forceinline__ double& acnrm() const { return slot(SL::ACNRM); }
+	__device__ __forceinline__ double& saved_tq5() const { return slot(SL::SAVED_TQ5); }
+	__device__ __forceinline__ double& saved_t() const { return slot(SL::SAVED_T); }
+	__device__ __forceinline__ double& tstop() const { return slot(SL::TSTOP); }
 
 	__device__ __forceinline__ void count_reset()
 	{
@@ -181,37 +225,37 @@ struct BdfThread {
 	__device__ __forceinline__ void set_ewt(double rtol, double atol)
 	{
 #pragma unroll
-		for (int i = 0; i < N; i++) ewt[i] = 1.0 / (rtol * fabs(zn[0][i]) + atol);
+		for (int i = 0; i < N; i++) ewt[i] = 1.0 / (rtol * fabs(Z<0>(i)) + atol);
 	}
 
 	// persistent members that CVodeCreate zero-fills once and CVodeReInit never touches
 	__device__ __forceinline__ void create()
 	{
+		static_for<0, 6>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			tau(j) = 0.0;
 #pragma unroll
-		for (int j = 0; j < 6; j++) {
-			tau[j] = 0.0;
-#pragma unroll
-			for (int i = 0; i < N; i++) zn[j][i] = 0.0;
-		}
+			for (int i = 0; i < N; i++) Z<j>(i) = 0.0;
+		});
 #pragma unroll
 		for (int i = 0; i < N; i++) acor[i] = 0.0;
 #pragma unroll
-		for (int i = 0; i < N * N; i++) Minv[i] = 0.0;
-		gammap = 0.0;
-		crate = 1.0;
-		delp = 0.0;
-		acnrm = 0.0;
-		saved_tq5 = 0.0;
+		for (int i = 0; i < N * N; i++) Minv(i) = 0.0;
+		gammap() = 0.0;
+		crate() = 1.0;
+		delp() = 0.0;
+		acnrm() = 0.0;
+		saved_tq5() = 0.0;
 		tstopset = false;
-		tstop = 0.0;
-		h = hprime = hscale = eta = hu = gamma = gamrat = rl1 = 0.0;
+		tstop() = 0.0;
+		h = hprime() = hscale() = eta() = hu() = gamma = gamrat = rl1 = 0.0;
 		nls_jcur = false;
 		nstlj = 0;
 		count_reset();
 	}
 
 	// CVodeReInit(t0, y0) followed by the first-call block of CVode(tout, CV_ONE_STEP).
-	// tstop (if any) must have been set by the caller. Returns false where CVode returns < 0.
+	// tstop() (if any) must have been set by the caller. Returns false where CVode returns < 0.
 	__device__ __forceinline__ bool restart(double t0, const double (&y0)[N], double tout, const Model& model, double rtol,
 	                                        double atol)
 	{
@@ -219,12 +263,12 @@ struct BdfThread {
 		q = 1;
 		L = 2;
 		qwait = 2;
-		etamax = BDF_ETAMX1;
-		hu = 0.0;
+		etamax() = BDF_ETAMX1;
+		hu() = 0.0;
 		nst = 0;
 		nstlp = 0;
 #pragma unroll
-		for (int i = 0; i < N; i++) zn[0][i] = y0[i];
+		for (int i = 0; i < N; i++) Z<0>(i) = y0[i];
 
 		// cvInitialSetup: error weights; cvLsInitialize resets nstlj; SUNNonlinSolInitialize resets jcur
 		set_ewt(rtol, atol);
@@ -232,14 +276,14 @@ struct BdfThread {
 		nls_jcur = false;
 
 		// zn[1] = f(t0, y0)
-		model.rhs(tn, zn[0], zn[1]);
+		model.rhs(tn, zn01[0], zn01[1]);
 		if (STATS) cnt.nfe++;
 
 		if (tstopset) {
-			if ((tstop - tn) * (tout - tn) <= 0.0) return false; // CV_ILL_INPUT
+			if ((tstop() - tn) * (tout - tn) <= 0.0) return false; // CV_ILL_INPUT
 		}
 		double tout_hin = tout;
-		if (tstopset && (tout - tn) * (tout - tstop) > 0.0) tout_hin = tstop;
+		if (tstopset && (tout - tn) * (tout - tstop()) > 0.0) tout_hin = tstop();
 
 		// ---- cvHin ----
 		{
@@ -254,10 +298,10 @@ struct BdfThread {
 			double hub_inv = -INFINITY;
 #pragma unroll
 			for (int i = 0; i < N; i++) {
-				double t2 = fabs(zn[0][i]);
+				double t2 = fabs(Z<0>(i));
 				double t1 = 1.0 / ewt[i]; // N_VInv of the freshly computed weights
 				t1 = BDF_HUB_FACTOR * t2 + t1;
-				t2 = fabs(zn[1][i]);
+				t2 = fabs(Z<1>(i));
 				t1 = t2 / t1;
 				hub_inv = (t1 > hub_inv) ? t1 : hub_inv;
 			}
@@ -275,12 +319,12 @@ struct BdfThread {
 					// cvYddNorm
 					double ytmp[N], ftmp[N];
 #pragma unroll
-					for (int i = 0; i < N; i++) ytmp[i] = hgs * zn[1][i] + zn[0][i];
+					for (int i = 0; i < N; i++) ytmp[i] = hgs * Z<1>(i) + Z<0>(i);
 					model.rhs(tn + hgs, ytmp, ftmp);
 					if (STATS) cnt.nfe++;
 					double c = 1.0 / hgs;
 #pragma unroll
-					for (int i = 0; i < N; i++) ftmp[i] = c * (ftmp[i] - zn[1][i]);
+					for (int i = 0; i < N; i++) ftmp[i] = c * (ftmp[i] - Z<1>(i));
 					double yddnrm = wrms(ftmp);
 
 					hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
@@ -302,29 +346,29 @@ struct BdfThread {
 		}
 		// hmax_inv = 0, hmin = 0 (PopPK leaves CVODE's defaults)
 		if (tstopset) {
-			if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * BDF_UROUND);
+			if ((tn + h - tstop()) * h > 0.0) h = (tstop() - tn) * (1.0 - 4.0 * BDF_UROUND);
 		}
-		hscale = h;
-		hprime = h;
+		hscale() = h;
+		hprime() = h;
 #pragma unroll
-		for (int i = 0; i < N; i++) zn[1][i] *= h;
+		for (int i = 0; i < N; i++) Z<1>(i) *= h;
 		return true;
 	}
 
 	// cvRescale, cvode.c:2384-2400
 	__device__ __forceinline__ void rescale()
 	{
-		double c = eta;
+		double c = eta();
 		static_for<1, QMAX + 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j <= q) {
 #pragma unroll
-				for (int i = 0; i < N; i++) zn[j][i] *= c;
-				c = eta * c;
+				for (int i = 0; i < N; i++) Z<j>(i) *= c;
+				c = eta() * c;
 			}
 		});
-		h = hscale * eta;
-		hscale = h;
+		h = hscale() * eta();
+		hscale() = h;
 	}
 
 	// cvIncreaseBDF, cvode.c:2310-2340 (zn[L] <- A1 * saved acor in zn[qmax]; zn[2..q] += l[j] zn[L])
@@ -335,13 +379,13 @@ struct BdfThread {
 		for (int i = 0; i < 6; i++) ll[i] = 0.0;
 		double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
 		ll[2] = 1.0;
-		double hsum = hscale;
+		double hsum = hscale();
 		// an increase only happens for q < qmax, so j <= 3
 		static_for<1, QMAX - 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j < q) {
-				hsum += tau[j + 1];
-				double xi = hsum / hscale;
+				hsum += tau(j + 1);
+				double xi = hsum / hscale();
 				prod *= xi;
 				alpha0 -= 1.0 / (j + 1);
 				alpha1 += 1.0 / xi;
@@ -355,16 +399,16 @@ struct BdfThread {
 		double A1 = (-alpha0 - alpha1) / prod;
 		double znL[N];
 #pragma unroll
-		for (int i = 0; i < N; i++) znL[i] = A1 * zn[QMAX][i];
+		for (int i = 0; i < N; i++) znL[i] = A1 * Z<QMAX>(i);
 		// zn[j] += l[j] * zn[L] for j = 2..q, then the new column zn[L] (L = q + 1 <= 5)
 		static_for<2, QMAX + 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j <= q) {
 #pragma unroll
-				for (int i = 0; i < N; i++) zn[j][i] += ll[j] * znL[i];
+				for (int i = 0; i < N; i++) Z<j>(i) += ll[j] * znL[i];
 			} else if (j <= L) {
 #pragma unroll
-				for (int i = 0; i < N; i++) zn[j][i] = znL[i];
+				for (int i = 0; i < N; i++) Z<j>(i) = znL[i];
 			}
 		});
 	}
@@ -380,8 +424,8 @@ struct BdfThread {
 		static_for<1, QMAX - 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j <= q - 2) {
-				hsum += tau[j];
-				double xi = hsum / hscale;
+				hsum += tau(j);
+				double xi = hsum / hscale();
 				static_rfor<2, j + 3>([&](auto I) {
 					constexpr int i = decltype(I)::value;
 					ll[i] = ll[i] * xi + ll[i - 1];
@@ -391,12 +435,12 @@ struct BdfThread {
 		// znq = zn[q] (q >= 3 here): the last column with j <= q wins
 		double znq[N];
 #pragma unroll
-		for (int i = 0; i < N; i++) znq[i] = zn[2][i];
+		for (int i = 0; i < N; i++) znq[i] = Z<2>(i);
 		static_for<3, QMAX + 1>([&](auto J) {
 			constexpr int j = decltype(J)::value;
 			if (j <= q) {
 #pragma unroll
-				for (int i = 0; i < N; i++) znq[i] = zn[j][i];
+				for (int i = 0; i < N; i++) znq[i] = Z<j>(i);
 			}
 		});
 		if (q > 2) {
@@ -404,7 +448,7 @@ struct BdfThread {
 				constexpr int j = decltype(J)::value;
 				if (j < q) {
 #pragma unroll
-					for (int i = 0; i < N; i++) zn[j][i] += (-ll[j]) * znq[i];
+					for (int i = 0; i < N; i++) Z<j>(i) += (-ll[j]) * znq[i];
 				}
 			});
 		}
@@ -423,14 +467,14 @@ struct BdfThread {
 	__device__ __forceinline__ bool begin_step(double rtol, double atol)
 	{
 		if (nst > 0) set_ewt(rtol, atol);
-		double tolsf = BDF_UROUND * wrms(zn[0]);
+		double tolsf = BDF_UROUND * wrms(zn01[0]);
 		if (tolsf > 1.0) return false;
 
-		saved_t = tn;
+		saved_t() = tn;
 		ncf = 0;
 		nef = 0;
 		nflag = BDF_FIRST_CALL;
-		if ((nst > 0) && (hprime != h)) {
+		if ((nst > 0) && (hprime() != h)) {
 			// cvAdjustParams
 			if (qprime != q) {
 				adjust_order(qprime - q);
@@ -446,14 +490,14 @@ struct BdfThread {
 	// cvRestore, cvode.c:2918-2927
 	__device__ __forceinline__ void restore()
 	{
-		tn = saved_t;
+		tn = saved_t();
 		static_for<1, QMAX + 1>([&](auto K) {
 			constexpr int k = decltype(K)::value;
 			static_rfor<k, QMAX + 1>([&](auto J) {
 				constexpr int j = decltype(J)::value;
 				if (j <= q) { // implies k <= q
 #pragma unroll
-					for (int i = 0; i < N; i++) zn[j - 1][i] = zn[j - 1][i] - zn[j][i];
+					for (int i = 0; i < N; i++) Z<j - 1>(i) = Z<j - 1>(i) - Z<j>(i);
 				}
 			});
 		});
@@ -472,10 +516,10 @@ struct BdfThread {
 		for (int i = 0; i < N; i++) A[i * N + i] += 1.0;
 		if (N == 2) {
 			double invdet = 1.0 / (A[0] * A[3] - A[1] * A[2]);
-			Minv[0] = A[3] * invdet;
-			Minv[1] = -A[1] * invdet;
-			Minv[2] = -A[2] * invdet;
-			Minv[3] = A[0] * invdet;
+			Minv(0) = A[3] * invdet;
+			Minv(1) = -A[1] * invdet;
+			Minv(2) = -A[2] * invdet;
+			Minv(3) = A[0] * invdet;
 		} else {
 #define BDF_A(i, j) A[(i) * N + (j)]
 #define BDF_COF(i, j) \
@@ -483,15 +527,15 @@ struct BdfThread {
 			double c0 = BDF_COF(0, 0), c1 = BDF_COF(1, 0), c2 = BDF_COF(2, 0);
 			double det = c0 * BDF_A(0, 0) + c1 * BDF_A(1, 0) + c2 * BDF_A(2, 0);
 			double invdet = 1.0 / det;
-			Minv[0 * N + 0] = c0 * invdet;
-			Minv[0 * N + 1] = c1 * invdet;
-			Minv[0 * N + 2] = c2 * invdet;
-			Minv[1 * N + 0] = BDF_COF(0, 1) * invdet;
-			Minv[1 * N + 1] = BDF_COF(1, 1) * invdet;
-			Minv[1 * N + 2] = BDF_COF(2, 1) * invdet;
-			Minv[2 * N + 0] = BDF_COF(0, 2) * invdet;
-			Minv[2 * N + 1] = BDF_COF(1, 2) * invdet;
-			Minv[2 * N + 2] = BDF_COF(2, 2) * invdet;
+			Minv(0 * N + 0) = c0 * invdet;
+			Minv(0 * N + 1) = c1 * invdet;
+			Minv(0 * N + 2) = c2 * invdet;
+			Minv(1 * N + 0) = BDF_COF(0, 1) * invdet;
+			Minv(1 * N + 1) = BDF_COF(1, 1) * invdet;
+			Minv(1 * N + 2) = BDF_COF(2, 1) * invdet;
+			Minv(2 * N + 0) = BDF_COF(0, 2) * invdet;
+			Minv(2 * N + 1) = BDF_COF(1, 2) * invdet;
+			Minv(2 * N + 2) = BDF_COF(2, 2) * invdet;
 #undef BDF_COF
 #undef BDF_A
 		}
@@ -511,7 +555,7 @@ struct BdfThread {
 		// ---- cvPredict ----
 		tn += h;
 		if (tstopset) {
-			if ((tn - tstop) * h > 0.0) tn = tstop;
+			if ((tn - tstop()) * h > 0.0) tn = tstop();
 		}
 		static_for<1, QMAX + 1>([&](auto K) {
 			constexpr int k = decltype(K)::value;
@@ -519,7 +563,7 @@ struct BdfThread {
 				constexpr int j = decltype(J)::value;
 				if (j <= q) { // implies k <= q
 #pragma unroll
-					for (int i = 0; i < N; i++) zn[j - 1][i] += zn[j][i];
+					for (int i = 0; i < N; i++) Z<j - 1>(i) += Z<j>(i);
 				}
 			});
 		});
@@ -538,7 +582,7 @@ struct BdfThread {
 				static_for<2, QMAX>([&](auto J) {
 					constexpr int j = decltype(J)::value;
 					if (j < q) {
-						hsum += tau[j - 1];
+						hsum += tau(j - 1);
 						xi_inv = h / hsum;
 						alpha0 -= 1.0 / j;
 						static_rfor<1, j + 1>([&](auto I) {
@@ -549,13 +593,8 @@ struct BdfThread {
 				});
 				alpha0 -= 1.0 / q;
 				xistar_inv = -l[1] - alpha0;
-				// tau[q - 1]: the last j <= q - 1 wins
-				double tauqm1 = tau[1];
-				static_for<2, QMAX>([&](auto J) {
-					constexpr int j = decltype(J)::value;
-					if (j <= q - 1) tauqm1 = tau[j];
-				});
-				hsum += tauqm1;
+				// tau(q - 1): the last j <= q - 1 wins
+				hsum += tau(q - 1);
 				xi_inv = h / hsum;
 				alpha0_hat = -l[1] - xi_inv;
 				static_rfor<1, QMAX + 1>([&](auto I) {
@@ -563,15 +602,13 @@ struct BdfThread {
 					if (i <= q) l[i] += l[i - 1] * xistar_inv;
 				});
 			}
-			// l[q], tau[q]: the last j <= q wins
-			double lq = l[1], tauq = tau[1];
+			// l[q], tau(q): the last j <= q wins
+			double lq = l[1];
 			static_for<2, QMAX + 1>([&](auto J) {
 				constexpr int j = decltype(J)::value;
-				if (j <= q) {
-					lq = l[j];
-					tauq = tau[j];
-				}
+				if (j <= q) lq = l[j];
 			});
+			const double tauq = tau(q);
 			double A1 = 1.0 - alpha0_hat + alpha0;
 			double A2 = 1.0 + q * A1;
 			tq[2] = fabs(A1 / (alpha0 * A2));
@@ -597,14 +634,20 @@ struct BdfThread {
 			// cvSet tail
 			rl1 = 1.0 / l[1];
 			gamma = h * rl1;
-			if (nst == 0) gammap = gamma;
-			gamrat = (nst > 0) ? gamma / gammap : 1.0;
+			if (nst == 0) gammap() = gamma;
+			gamrat = (nst > 0) ? gamma / gammap() : 1.0;
 		}
 
 		// ---- cvNls / Newton ----
 		// Both loops below are made warp-uniform with votes over `mask` (the lanes that entered this attempt):
 		// every lane stays in a loop until no lane needs another trip, so the warp is converged again when the
 		// loop ends and the step-completion code that follows runs once for all lanes, not once per exit path.
+		// l[] and tq[1, 2, 3, 5] are not needed until the step is accepted: parked in shared memory over the Newton loop
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			slot(SL::LSTASH + i) = l[i];
+			slot(SL::TQSTASH + i) = tq[i];
+		}
 		int nls_ret = 1; // 0 ok, 1 recoverable convergence failure
 		{
 			int convfail = ((nflag == BDF_FIRST_CALL) || (nflag == BDF_PREV_ERR_FAIL)) ? BDF_NO_FAILURES : BDF_FAIL_OTHER;
@@ -625,18 +668,18 @@ struct BdfThread {
 					// cvNlsResidual
 					double y[N], f[N];
 #pragma unroll
-					for (int i = 0; i < N; i++) y[i] = zn[0][i] + acor[i];
+					for (int i = 0; i < N; i++) y[i] = Z<0>(i) + acor[i];
 					model.rhs(tn, y, f);
 					if (STATS) cnt.nfe++;
 #pragma unroll
-					for (int i = 0; i < N; i++) delta[i] = rl1 * zn[1][i] + acor[i];
+					for (int i = 0; i < N; i++) delta[i] = rl1 * Z<1>(i) + acor[i];
 #pragma unroll
 					for (int i = 0; i < N; i++) delta[i] += -gamma * f[i];
 
 					if (callSetup) {
 						// cvNlsLSetup + cvLsSetup
 						if (jbad) convfail = BDF_FAIL_BAD_J;
-						double dgamma = fabs((gamma / gammap) - 1.0);
+						double dgamma = fabs((gamma / gammap()) - 1.0);
 						bool jb = (nst == 0) || (nst > nstlj + BDF_MSBJ) || ((convfail == BDF_FAIL_BAD_J) && (dgamma < BDF_LS_DGMAX)) ||
 						          (convfail == BDF_FAIL_OTHER);
 						if (jb) {
@@ -647,8 +690,8 @@ struct BdfThread {
 						if (STATS) cnt.nsetups++;
 						nls_jcur = jb;
 						gamrat = 1.0;
-						gammap = gamma;
-						crate = 1.0;
+						gammap() = gamma;
+						crate() = 1.0;
 						nstlp = nst;
 					}
 				}
@@ -665,9 +708,9 @@ struct BdfThread {
 						for (int i = 0; i < N; i++) b[i] = -delta[i];
 #pragma unroll
 						for (int i = 0; i < N; i++) {
-							double sx = Minv[i * N + 0] * b[0];
+							double sx = Minv(i * N + 0) * b[0];
 #pragma unroll
-							for (int j = 1; j < N; j++) sx += Minv[i * N + j] * b[j];
+							for (int j = 1; j < N; j++) sx += Minv(i * N + j) * b[j];
 							delta[i] = sx;
 						}
 						if (gamrat != 1.0) {
@@ -680,28 +723,28 @@ struct BdfThread {
 
 						// cvNlsConvTest
 						double del = wrms(delta);
-						if (m > 0) crate = fmax(BDF_CRDOWN * crate, del / delp);
-						double dcon = del * fmin(1.0, crate) / tol;
+						if (m > 0) crate() = fmax(BDF_CRDOWN * crate(), del / delp());
+						double dcon = del * fmin(1.0, crate()) / tol;
 						if (dcon <= 1.0) {
-							acnrm = (m == 0) ? del : wrms(acor);
+							acnrm() = (m == 0) ? del : wrms(acor);
 							nls_jcur = false;
 							nls_ret = 0;
 							iter = false;
-						} else if ((m >= 1) && (del > BDF_RDIV * delp)) {
+						} else if ((m >= 1) && (del > BDF_RDIV * delp())) {
 							iter = false;
 						} else {
-							delp = del;
+							delp() = del;
 							if (m + 1 >= BDF_NLS_MAXCOR) {
 								iter = false;
 							} else {
 								// next residual
 								double y[N], f[N];
 #pragma unroll
-								for (int i = 0; i < N; i++) y[i] = zn[0][i] + acor[i];
+								for (int i = 0; i < N; i++) y[i] = Z<0>(i) + acor[i];
 								model.rhs(tn, y, f);
 								if (STATS) cnt.nfe++;
 #pragma unroll
-								for (int i = 0; i < N; i++) delta[i] = rl1 * zn[1][i] + acor[i];
+								for (int i = 0; i < N; i++) delta[i] = rl1 * Z<1>(i) + acor[i];
 #pragma unroll
 								for (int i = 0; i < N; i++) delta[i] += -gamma * f[i];
 							}
@@ -723,25 +766,30 @@ struct BdfThread {
 			}
 		}
 
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			l[i] = slot(SL::LSTASH + i);
+			tq[i] = slot(SL::TQSTASH + i);
+		}
 		int result;
 		if (nls_ret != 0) {
 			// ---- cvHandleNFlag ----
 			if (STATS) cnt.ncfn++;
 			restore();
 			ncf++;
-			etamax = 1.0;
+			etamax() = 1.0;
 			// hmin = 0: |h| <= hmin * ONEPSM only for h == 0
 			if ((fabs(h) <= 0.0) || (ncf == BDF_MXNCF)) {
 				result = BDF_ATTEMPT_FAILED;
 			} else {
-				eta = BDF_ETACF;
+				eta() = BDF_ETACF;
 				nflag = BDF_PREV_CONV_FAIL;
 				rescale();
 				result = BDF_ATTEMPT_RETRY;
 			}
 		} else {
 			// ---- cvDoErrorTest ----
-			const double dsm = acnrm * tq[2];
+			const double dsm = acnrm() * tq[2];
 			if (!(dsm <= 1.0)) {
 				nef++;
 				if (STATS) cnt.netf++;
@@ -751,65 +799,65 @@ struct BdfThread {
 					result = BDF_ATTEMPT_FAILED;
 				} else {
 					result = BDF_ATTEMPT_RETRY;
-					etamax = 1.0;
+					etamax() = 1.0;
 					if (nef <= BDF_MXNEF1) {
-						eta = 1.0 / (bdf_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
-						eta = fmax(BDF_ETAMIN, eta);
-						if (nef >= BDF_SMALL_NEF) eta = fmin(eta, BDF_ETAMXF);
+						eta() = 1.0 / (bdf_step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+						eta() = fmax(BDF_ETAMIN, eta());
+						if (nef >= BDF_SMALL_NEF) eta() = fmin(eta(), BDF_ETAMXF);
 						rescale();
 					} else if (q > 1) {
-						eta = BDF_ETAMIN;
+						eta() = BDF_ETAMIN;
 						adjust_order(-1);
 						L = q;
 						q--;
 						qwait = L;
 						rescale();
 					} else {
-						eta = BDF_ETAMIN;
-						h *= eta;
-						hscale = h;
+						eta() = BDF_ETAMIN;
+						h *= eta();
+						hscale() = h;
 						qwait = BDF_LONG_WAIT;
 						double f[N];
-						model.rhs(tn, zn[0], f);
+						model.rhs(tn, zn01[0], f);
 						if (STATS) cnt.nfe++;
 #pragma unroll
-						for (int i = 0; i < N; i++) zn[1][i] = h * f[i];
+						for (int i = 0; i < N; i++) Z<1>(i) = h * f[i];
 					}
 				}
 			} else {
 				result = BDF_ATTEMPT_DONE;
 				// ---- cvCompleteStep ----
 				nst++;
-				hu = h;
+				hu() = h;
 				static_rfor<2, QMAX + 1>([&](auto I) {
 					constexpr int i = decltype(I)::value;
-					if (i <= q) tau[i] = tau[i - 1];
+					if (i <= q) tau(i) = tau(i - 1);
 				});
-				if ((q == 1) && (nst > 1)) tau[2] = tau[1];
-				tau[1] = h;
+				if ((q == 1) && (nst > 1)) tau(2) = tau(1);
+				tau(1) = h;
 				static_for<0, QMAX + 1>([&](auto J) {
 					constexpr int j = decltype(J)::value;
 					if (j <= q) {
 #pragma unroll
-						for (int i = 0; i < N; i++) zn[j][i] += l[j] * acor[i];
+						for (int i = 0; i < N; i++) Z<j>(i) += l[j] * acor[i];
 					}
 				});
 				qwait--;
 				if ((qwait == 1) && (q != QMAX)) {
 #pragma unroll
-					for (int i = 0; i < N; i++) zn[QMAX][i] = acor[i];
-					saved_tq5 = tq[5];
+					for (int i = 0; i < N; i++) Z<QMAX>(i) = acor[i];
+					saved_tq5() = tq[5];
 				}
 
 				// ---- cvPrepareNextStep ----
-				if (etamax == 1.0) {
+				if (etamax() == 1.0) {
 					qwait = (qwait > 2) ? qwait : 2;
 					qprime = q;
-					hprime = h;
-					eta = 1.0;
+					hprime() = h;
+					eta() = 1.0;
 				} else {
-					const double etaq = 1.0 / (bdf_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
-					eta = etaq;
+					const double etaq = 1.0 / (bdf_step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+					eta() = etaq;
 					qprime = q;
 					if (qwait == 0) {
 						qwait = 2;
@@ -818,62 +866,62 @@ struct BdfThread {
 						if (q > 1) {
 							double znq[N];
 #pragma unroll
-							for (int i = 0; i < N; i++) znq[i] = zn[2][i];
+							for (int i = 0; i < N; i++) znq[i] = Z<2>(i);
 							static_for<3, QMAX + 1>([&](auto J) {
 								constexpr int j = decltype(J)::value;
 								if (j <= q) { // the last j <= q wins: znq = zn[q]
 #pragma unroll
-									for (int i = 0; i < N; i++) znq[i] = zn[j][i];
+									for (int i = 0; i < N; i++) znq[i] = Z<j>(i);
 								}
 							});
 							double ddn = wrms(znq) * tq[1];
-							etaqm1 = 1.0 / (bdf_root(BDF_BIAS1 * ddn, q) + BDF_ADDON);
+							etaqm1 = 1.0 / (bdf_step_root(BDF_BIAS1 * ddn, q) + BDF_ADDON);
 						}
 						// cvComputeEtaqp1
 						double etaqp1 = 0.0;
 						if (q != QMAX) {
-							if (saved_tq5 != 0.0) {
-								double base = h / tau[2];
+							if (saved_tq5() != 0.0) {
+								double base = h / tau(2);
 								double pw = 1.0;
 								static_for<1, QMAX + 1>([&](auto I) {
 									if (decltype(I)::value <= L) pw *= base;
 								});
-								double cquot = (tq[5] / saved_tq5) * pw;
+								double cquot = (tq[5] / saved_tq5()) * pw;
 								double tmp[N];
 #pragma unroll
-								for (int i = 0; i < N; i++) tmp[i] = -cquot * zn[QMAX][i] + acor[i];
+								for (int i = 0; i < N; i++) tmp[i] = -cquot * Z<QMAX>(i) + acor[i];
 								double dup = wrms(tmp) * tq[3];
-								etaqp1 = 1.0 / (bdf_root(BDF_BIAS3 * dup, L + 1) + BDF_ADDON);
+								etaqp1 = 1.0 / (bdf_step_root(BDF_BIAS3 * dup, L + 1) + BDF_ADDON);
 							}
 						}
 						// cvChooseEta
 						double etam = fmax(etaqm1, fmax(etaq, etaqp1));
 						if (etam < BDF_THRESH) {
-							eta = 1.0;
+							eta() = 1.0;
 							qprime = q;
 						} else if (etam == etaq) {
-							eta = etaq;
+							eta() = etaq;
 							qprime = q;
 						} else if (etam == etaqm1) {
-							eta = etaqm1;
+							eta() = etaqm1;
 							qprime = q - 1;
 						} else {
-							eta = etaqp1;
+							eta() = etaqp1;
 							qprime = q + 1;
 #pragma unroll
-							for (int i = 0; i < N; i++) zn[QMAX][i] = acor[i];
+							for (int i = 0; i < N; i++) Z<QMAX>(i) = acor[i];
 						}
 					}
 					// cvSetEta (hmax_inv = 0)
-					if (eta < BDF_THRESH) {
-						eta = 1.0;
-						hprime = h;
+					if (eta() < BDF_THRESH) {
+						eta() = 1.0;
+						hprime() = h;
 					} else {
-						eta = fmin(eta, etamax);
-						hprime = h * eta;
+						eta() = fmin(eta(), etamax());
+						hprime() = h * eta();
 					}
 				}
-				etamax = (nst <= BDF_SMALL_NST) ? BDF_ETAMX2 : BDF_ETAMX3;
+				etamax() = (nst <= BDF_SMALL_NST) ? BDF_ETAMX2 : BDF_ETAMX3;
 #pragma unroll
 				for (int i = 0; i < N; i++) acor[i] *= tq[2];
 			}
@@ -882,11 +930,11 @@ struct BdfThread {
 	}
 
 	// CVodeGetDky(t, k = 0) for all components. Returns false on CV_BAD_T.
-	__device__ __forceinline__ bool dky(double t, double (&out)[N]) const
+	__device__ __forceinline__ bool dky(double t, double (&out)[N])
 	{
-		double tfuzz = BDF_FUZZ_FACTOR * BDF_UROUND * (fabs(tn) + fabs(hu));
-		if (hu < 0.0) tfuzz = -tfuzz;
-		double tp = tn - hu - tfuzz;
+		double tfuzz = BDF_FUZZ_FACTOR * BDF_UROUND * (fabs(tn) + fabs(hu()));
+		if (hu() < 0.0) tfuzz = -tfuzz;
+		double tp = tn - hu() - tfuzz;
 		double tn1 = tn + tfuzz;
 		if ((t - tp) * (t - tn1) > 0.0) return false;
 		double s = (t - tn) / h;
@@ -904,11 +952,11 @@ struct BdfThread {
 				for (int i = 0; i < j; i++) c *= s;
 				if (first) {
 #pragma unroll
-					for (int i = 0; i < N; i++) acc[i] = c * zn[j][i];
+					for (int i = 0; i < N; i++) acc[i] = c * Z<j>(i);
 					first = false;
 				} else {
 #pragma unroll
-					for (int i = 0; i < N; i++) acc[i] += c * zn[j][i];
+					for (int i = 0; i < N; i++) acc[i] += c * Z<j>(i);
 				}
 			}
 		});
@@ -917,26 +965,26 @@ struct BdfThread {
 		return true;
 	}
 
-	// tstop handling after an accepted step (cvode.c:1410-1438). Returns true for CV_TSTOP_RETURN, in which
-	// case yout = Dky(tstop) and tret = tstop; otherwise yout = zn[0], tret = tn.
+	// tstop() handling after an accepted step (cvode.c:1410-1438). Returns true for CV_TSTOP_RETURN, in which
+	// case yout = Dky(tstop()) and tret = tstop(); otherwise yout = zn[0], tret = tn.
 	__device__ __forceinline__ bool after_step(double (&yout)[N], double& tret)
 	{
 		if (tstopset) {
 			double troundoff = BDF_FUZZ_FACTOR * BDF_UROUND * (fabs(tn) + fabs(h));
-			if (fabs(tn - tstop) <= troundoff) {
-				(void)dky(tstop, yout);
-				tret = tstop;
+			if (fabs(tn - tstop()) <= troundoff) {
+				(void)dky(tstop(), yout);
+				tret = tstop();
 				tstopset = false;
 				return true;
 			}
-			if ((tn + hprime - tstop) * h > 0.0) {
-				hprime = (tstop - tn) * (1.0 - 4.0 * BDF_UROUND);
-				eta = hprime / h;
+			if ((tn + hprime() - tstop()) * h > 0.0) {
+				hprime() = (tstop() - tn) * (1.0 - 4.0 * BDF_UROUND);
+				eta() = hprime() / h;
 			}
 		}
 		tret = tn;
 #pragma unroll
-		for (int i = 0; i < N; i++) yout[i] = zn[0][i];
+		for (int i = 0; i < N; i++) yout[i] = Z<0>(i);
 		return false;
 	}
 };

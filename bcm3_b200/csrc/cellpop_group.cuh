@@ -128,7 +128,7 @@ __device__ __noinline__ void rhs_eval(unsigned y_off, int j, double yj, unsigned
 #define CP_GROUP_STATIC_LU_MAX 0
 #endif
 
-__device__ __noinline__ double step_root(double base, int k) { return bcm3b200::bdf_root_halley(base, k); }
+__device__ __forceinline__ double step_root(double base, int k) { return bcm3b200::bdf_root_halley(base, k); }
 
 // second half of N_VWrmsNorm: butterfly over the group, mean, square root -- one copy of the code for all call sites
 __device__ __noinline__ double norm_finish(double s, unsigned gmask)

@@ -283,7 +283,15 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	// block shape: as many cells per SM as its shared memory holds (the per-cell block of cellpop_group.cuh), two blocks
 	// per SM, at most 12 warps per SM -- above that the register budget (64K / threads) starts to force spills
 	const int Eg = (cp.N + G - 1) / G;
-	const size_t per_cell = sizeof(double) * ((size_t)cp.N * (cp.N | 1) + 3 * (size_t)cp.N + 64 + override_vars.size() + 4 * (size_t)Eg * G + 16);
+	size_t per_cell;
+	{ // the constants of cellpop_group.cuh: RS, OFF_SCAL, SC_COUNT, OFF_ZNH, CS
+		const int RS = cp.N | 1;
+		const int off_scal = cp.N * RS + 2 * cp.N + (cp.N + 1) / 2;
+		const int sc_count = 31 + (override_vars.empty() ? 1 : (int)override_vars.size());
+		int cs = off_scal + sc_count + 4 * Eg * G;
+		while (cs % 16 != (RS * G) % 16) cs++;
+		per_cell = sizeof(double) * (size_t)cs;
+	}
 	const int cells_per_warp = 32 / G;
 	int warps_max = (int)((220 * 1024) / (per_cell * cells_per_warp));
 	if (warps_max > 12) warps_max = 12;

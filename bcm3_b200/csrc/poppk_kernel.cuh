@@ -169,8 +169,9 @@ __device__ __forceinline__ bool check_give_treatment(double t, uint32_t skipped_
 	return give;
 }
 
-template <class Model, bool DIAG>
-__global__ void poppk_kernel(const PkArgs a)
+// STRIDE = thread stride of the per-thread shared-memory state columns = the largest block this instantiation runs with
+template <class Model, bool DIAG, int STRIDE>
+__global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(const PkArgs a)
 {
 	constexpr int N = Model::N;
 	constexpr unsigned FULL = 0xffffffffu;
@@ -224,7 +225,8 @@ __global__ void poppk_kernel(const PkArgs a)
 	}
 
 	// ---- K1: ODESolver::SolveReturnSolution + ODESolverCVODE::Solve ----
-	BdfThread<N, Model, DIAG> S;
+	BdfThread<N, Model, DIAG, STRIDE> S;
+	S.sh = smem + a.T + (size_t)a.T * blockDim.x + tid; // after s_time and s_sim
 	S.create();
 
 	bool done = !valid || ntp <= 0;
@@ -253,7 +255,7 @@ __global__ void poppk_kernel(const PkArgs a)
 	double current_dose_time = dosing_interval;
 	double next_disc = (dosing_interval > 0.0) ? dosing_interval : NAN;
 	S.tstopset = !isnan(next_disc);
-	S.tstop = next_disc;
+	S.tstop() = next_disc;
 
 #pragma unroll 1
 	for (;;) {
@@ -331,7 +333,7 @@ __global__ void poppk_kernel(const PkArgs a)
 			}
 			next_disc = current_dose_time;
 			if (!isnan(next_disc) && next_disc < INFINITY) {
-				S.tstop = next_disc;
+				S.tstop() = next_disc;
 				S.tstopset = true;
 			}
 		}

@@ -55,7 +55,7 @@ def test_matches_cpu_checker_on_seeded_inputs(Evaluator, port, pk, het, seed):
     assert rel_err(logp, d["patient_ll"].sum(axis=1)).max() < 1e-12
 
 
-@pytest.mark.parametrize("block", [32, 64, 128, 256])
+@pytest.mark.parametrize("block", [32, 64, 128, 256, 384])
 def test_block_size_does_not_change_results(Evaluator, block):
     prob, gold = load_golden("poppk_two_hetero")
     ev = Evaluator(prob, block_size=block)

@@ -27,7 +27,22 @@ def timing(N, cells, T, C, reps=3, check=False, decades=2.0):
 
 if __name__ == "__main__":
     what = sys.argv[1]
-    if what == "sizes":
+    if what == "smoke":
+        prob = sc.make_cellpop_problem(N=12, num_cells=64, T=12, data_cells=4, seed=2)
+        vals = sc.make_chain_values(2)
+        r = oracle.load("ref").cellpop_evaluate(prob, vals, threads=2, want_cell_values=True, want_steps=True)
+        for k in ("group", "warp", "thread"):
+            ev = CellPopEvaluator(prob, kernel=k)
+            logp, st = ev.evaluate(vals)
+            d = ev.diagnostics()
+            ev.close()
+            diff = np.nanmax(np.abs(d["cell_values"] - r["cell_values"]), axis=1)  # [C][cells]
+            worst = np.argsort(diff.ravel())[-5:]
+            print(k, "logp", logp, "ref", r["logp"], "steps equal", (d["cell_steps"] == r["cell_steps"]).mean())
+            for w in worst:
+                c, cell = divmod(int(w), prob.num_cells)
+                print(f"   chain {c} cell {cell}: max |dv| {diff[c, cell]:.2e} steps gpu {d['cell_steps'][c, cell]} ref {r['cell_steps'][c, cell]}")
+    elif what == "sizes":
         for N in (3, 6, 7, 16, 24, 33, 50):
             timing(N, 300, 20, 2, reps=1, check=True, decades=3.0)
     else:
