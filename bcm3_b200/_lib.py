@@ -22,6 +22,7 @@ EXPORTS = [
     "bcm3b200_evaluate_batch_device",
     "bcm3b200_enqueue_batch",
     "bcm3b200_combine_partials",
+    "bcm3b200_cellpop_finish",
     "bcm3b200_get_diagnostics",
     "bcm3b200_set_option",
     "bcm3b200_get_stat",
@@ -63,6 +64,7 @@ def load() -> C.CDLL:
     lib.bcm3b200_evaluate_batch_device.argtypes = [vp, sz, sz, vp, vp, vp]
     lib.bcm3b200_enqueue_batch.argtypes = [vp, sz, sz, vp, vp, vp]
     lib.bcm3b200_combine_partials.argtypes = [sz, vp, vp, vp]
+    lib.bcm3b200_cellpop_finish.argtypes = [vp, sz, vp, vp, vp, vp]
     lib.bcm3b200_get_diagnostics.argtypes = [vp, vp, vp, vp]
     lib.bcm3b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.bcm3b200_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
@@ -76,7 +78,7 @@ def load() -> C.CDLL:
     lib.bcm3b200_host_alloc.restype = vp
     lib.bcm3b200_host_free.argtypes = [vp]
     lib.bcm3b200_host_free.restype = None
-    for name in ("create", "set_data", "set_text", "get_cell_diagnostics", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials",
+    for name in ("create", "set_data", "set_text", "get_cell_diagnostics", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials", "cellpop_finish",
                  "get_diagnostics", "set_option", "get_stat"):
         getattr(lib, "bcm3b200_" + name).restype = C.c_int
     _lib = lib

@@ -12,7 +12,8 @@ from .cellpop_data import CellPopProblem
 
 
 class CellPopEvaluator:
-    def __init__(self, problem: CellPopProblem, device: int = 0, compile_only: bool = False, kernel: str = "auto"):
+    def __init__(self, problem: CellPopProblem, device: int = 0, compile_only: bool = False, kernel: str = "auto",
+                 shard_rank: int = 0, shard_count: int = 1):
         self.lib = _lib.load()
         self.problem = p = problem
         kv = dict(
@@ -22,7 +23,8 @@ class CellPopEvaluator:
             solver_relative_tolerance=repr(p.solver_relative_tolerance), solver_absolute_tolerance=repr(p.solver_absolute_tolerance),
             solver_min_timestep=repr(p.solver_min_timestep), solver_max_steps=p.solver_max_steps, error_model=p.error_model,
             weight=repr(p.weight), missing_simulation_time_stdev=repr(p.missing_simulation_time_stdev),
-            obs_species="+".join(str(s) for s in p.obs_species), device=device, compile_only=int(compile_only))
+            obs_species="+".join(str(s) for s in p.obs_species), device=device, compile_only=int(compile_only),
+            shard_rank=shard_rank, shard_count=shard_count)
         for name in ("entry_time", "stdev", "offset", "scale"):
             ix = getattr(p, name + "_ix")
             if ix is not None:
@@ -71,6 +73,18 @@ class CellPopEvaluator:
         status = np.empty(nC, dtype=np.int32)
         _lib.check(self.lib.bcm3b200_evaluate_batch(self.handle, nC, nvar, values.ctypes.data, logp.ctypes.data, status.ctypes.data))
         self._last_C = nC
+        return logp, status
+
+    def enqueue(self, values_ptr: int, nC: int, nvar: int, d_partial_ptr: int, stream: int) -> None:
+        """Sharded handles: HOST values in, this shard's DEVICE partial [nC][2 T + 1] out, enqueued on `stream`."""
+        _lib.check(self.lib.bcm3b200_enqueue_batch(self.handle, nC, nvar, values_ptr, d_partial_ptr, stream))
+        self._last_C = nC
+
+    def finish(self, d_partial_ptr: int, nC: int, stream: int):
+        """Combined (summed over shards) partial -> logp, status. Synchronises the stream."""
+        logp = np.empty(nC)
+        status = np.empty(nC, dtype=np.int32)
+        _lib.check(self.lib.bcm3b200_cellpop_finish(self.handle, nC, d_partial_ptr, logp.ctypes.data, status.ctypes.data, stream))
         return logp, status
 
     def get_stat(self, name: str) -> int:

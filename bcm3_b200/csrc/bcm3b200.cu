@@ -683,7 +683,7 @@ int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
-	if (h->cp) return fail(BCM3B200_ERR_UNSUPPORTED, "device-partial entries are pop_pk_trajectory only");
+	if (h->cp) return cellpop_enqueue_partial(*h->cp, num_chains, num_variables, values, d_partial, (cudaStream_t)stream);
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
 	if (rc != BCM3B200_OK) return rc;
@@ -717,6 +717,14 @@ int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_v
 	if (rc != BCM3B200_OK) return rc;
 	h->num_evaluations += (int64_t)num_chains;
 	return BCM3B200_OK;
+}
+
+int bcm3b200_cellpop_finish(void* handle, size_t num_chains, const double* d_partial, double* logp, int* status, void* stream)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !d_partial || !logp) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (!h->cp) return fail(BCM3B200_ERR_ARG, "not a cell_population handle");
+	return cellpop_finish(*h->cp, num_chains, d_partial, logp, status, (cudaStream_t)stream);
 }
 
 int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* logp, int* status)
@@ -789,6 +797,7 @@ int bcm3b200_get_stat(void* handle, const char* name, int64_t* value)
 		else if (!strcmp(name, "num_evaluations")) *value = cp.num_evaluations;
 		else if (!strcmp(name, "last_kernel_us")) *value = (int64_t)(cp.last_kernel_ms * 1000.0);
 		else if (!strcmp(name, "num_cells_local")) *value = cp.cells_local;
+		else if (!strcmp(name, "partial_doubles_per_chain")) *value = 2 * cp.T + 1;
 		else return fail(BCM3B200_ERR_ARG, "unknown stat \"%s\"", name);
 		return BCM3B200_OK;
 	}

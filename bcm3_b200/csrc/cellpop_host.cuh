@@ -132,6 +132,72 @@ __global__ void cellpop_average_kernel(const double* __restrict__ cell_values, c
 	}
 }
 
+// Sharded form of the same reduction (cells split over ranks): per (chain, timepoint) the shard's raw sum and count of
+// existing cells, per chain its failed cells -- partial[c][0..T) sums, [T..2T) counts, [2T] failures, all as doubles so
+// that one SUM all-reduce combines the shards. Fixed tree order inside the shard.
+__global__ void cellpop_partial_kernel(const double* __restrict__ cell_values, const int32_t* __restrict__ status, int num_cells, int T,
+                                       double* __restrict__ partial)
+{
+	__shared__ double sh[256];
+	__shared__ int shi[256];
+	const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+	const double* v = cell_values + ((long long)c * T + t) * num_cells;
+	double s = 0.0;
+	int n = 0;
+	for (int i = tid; i < num_cells; i += blockDim.x) {
+		const double x = v[i];
+		if (!isnan(x)) {
+			s += x;
+			n++;
+		}
+	}
+	sh[tid] = s;
+	shi[tid] = n;
+	__syncthreads();
+	for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+		if (tid < off) {
+			sh[tid] += sh[tid + off];
+			shi[tid] += shi[tid + off];
+		}
+		__syncthreads();
+	}
+	double* out = partial + (long long)c * (2 * T + 1);
+	if (tid == 0) {
+		out[t] = sh[0];
+		out[T + t] = (double)shi[0];
+	}
+	if (t == 0) {
+		__syncthreads();
+		int f = 0;
+		const int32_t* st = status + (long long)c * num_cells;
+		for (int i = tid; i < num_cells; i += blockDim.x) f += st[i] ? 0 : 1;
+		shi[tid] = f;
+		__syncthreads();
+		for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+			if (tid < off) shi[tid] += shi[tid + off];
+			__syncthreads();
+		}
+		if (tid == 0) out[2 * T] = (double)shi[0];
+	}
+}
+
+// combined partial -> population average and failure count in the layout the data-likelihood kernel reads
+__global__ void cellpop_unpack_partial_kernel(const double* __restrict__ partial, int T, int C, double* __restrict__ avg, int32_t* __restrict__ count,
+                                              int32_t* __restrict__ nfail)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= C * (T + 1)) return;
+	const int c = i / (T + 1), t = i % (T + 1);
+	const double* in = partial + (long long)c * (2 * T + 1);
+	if (t < T) {
+		const double n = in[T + t];
+		avg[c * T + t] = (n > 0.0) ? in[t] / n : 0.0;
+		count[c * T + t] = (int32_t)n;
+	} else {
+		nfail[c] = (int32_t)in[2 * T];
+	}
+}
+
 struct CpLikArgs {
 	const double* avg;       // [C][T]
 	const int32_t* nfail;    // [C]
@@ -472,13 +538,12 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	return BCM3B200_OK;
 }
 
-inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const double* values, double* logp, int* status)
+// stage 1: upload the batch, transform, integrate every (chain, cell) of this shard -> cell_values / status on the device
+inline int cellpop_run_cells(CellPopState& cp, size_t C, size_t nvar, const double* values, cudaStream_t st)
 {
 	if ((int)nvar != cp.nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", nvar, cp.nvar);
 	int rc = cellpop_finalize(cp, true);
 	if (rc != BCM3B200_OK) return rc;
-	if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "cell_population sharding is not implemented yet");
-	if (C == 0) return BCM3B200_OK;
 	CUDA_TRY(cudaSetDevice(cp.device));
 	const int T = cp.T, nc = cp.cells_local;
 	CUDA_TRY(cp.d_values.ensure(C * nvar));
@@ -490,7 +555,6 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	CUDA_TRY(cp.d_count.ensure(C * (size_t)T));
 	CUDA_TRY(cp.d_nfail.ensure(C));
 	CUDA_TRY(cp.d_logp.ensure(C));
-	cudaStream_t st = cp.stream;
 	CUDA_TRY(cudaMemcpyAsync(cp.d_values.p, values, sizeof(double) * C * nvar, cudaMemcpyHostToDevice, st));
 	CUDA_TRY(cudaEventRecord(cp.ev0, st));
 	const long long ne = (long long)C * nvar;
@@ -523,17 +587,22 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 		if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "cellpop kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
 		cp.last_launches++;
 	}
-	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, nc, T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
-	CUDA_TRY(cudaGetLastError());
+	cp.last_C = (int)C;
+	return BCM3B200_OK;
+}
+
+// stage 3: data likelihood of every chain from the population averages in d_avg / d_nfail -> d_logp
+inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
+{
 	CpLikArgs la;
 	la.avg = cp.d_avg.p;
 	la.nfail = cp.d_nfail.p;
 	la.transformed = cp.d_transformed.p;
 	la.timepoints = cp.d_time.p;
 	la.observed = cp.d_obs.p;
-	la.T = T;
+	la.T = cp.T;
 	la.R = cp.R;
-	la.nvar = (int)nvar;
+	la.nvar = cp.nvar;
 	la.error_model = cp.error_model;
 	la.stdev_ix = cp.stdev_ix;
 	la.offset_ix = cp.offset_ix;
@@ -546,6 +615,22 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	la.logp = cp.d_logp.p;
 	cellpop_datalik_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>(la, (int)C);
 	CUDA_TRY(cudaGetLastError());
+	return BCM3B200_OK;
+}
+
+inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const double* values, double* logp, int* status)
+{
+	if (cp.shard_count != 1)
+		return fail(BCM3B200_ERR_UNSUPPORTED, "a sharded cell_population handle yields partials: use bcm3b200_enqueue_batch + bcm3b200_cellpop_finish");
+	if (C == 0) return BCM3B200_OK;
+	cudaStream_t st = cp.stream;
+	int rc = cellpop_run_cells(cp, C, nvar, values, st);
+	if (rc != BCM3B200_OK) return rc;
+	const int T = cp.T, nc = cp.cells_local;
+	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, nc, T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
+	CUDA_TRY(cudaGetLastError());
+	rc = cellpop_data_likelihood(cp, C, st);
+	if (rc != BCM3B200_OK) return rc;
 	cp.last_launches += 2;
 	cp.total_launches += cp.last_launches;
 	CUDA_TRY(cudaEventRecord(cp.ev1, st));
@@ -555,7 +640,42 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	if (cudaEventElapsedTime(&ms, cp.ev0, cp.ev1) == cudaSuccess) cp.last_kernel_ms = ms;
 	if (status)
 		for (size_t c = 0; c < C; c++) status[c] = std::isnan(logp[c]) ? BCM3B200_STATUS_NAN : BCM3B200_STATUS_OK;
-	cp.last_C = (int)C;
+	cp.num_evaluations += (int64_t)C;
+	return BCM3B200_OK;
+}
+
+// sharded stage 1+2: this shard's partial [C][2 T + 1] on the device, enqueued on `stream`
+inline int cellpop_enqueue_partial(CellPopState& cp, size_t C, size_t nvar, const double* values, double* d_partial, cudaStream_t st)
+{
+	if (C == 0) return BCM3B200_OK;
+	int rc = cellpop_run_cells(cp, C, nvar, values, st);
+	if (rc != BCM3B200_OK) return rc;
+	cellpop_partial_kernel<<<dim3(cp.T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, cp.cells_local, cp.T, d_partial);
+	CUDA_TRY(cudaGetLastError());
+	cp.last_launches += 1;
+	cp.total_launches += cp.last_launches;
+	return BCM3B200_OK;
+}
+
+// sharded stage 3: the combined (summed over shards) partial -> logp, on every rank
+inline int cellpop_finish(CellPopState& cp, size_t C, const double* d_partial, double* logp, int* status, cudaStream_t st)
+{
+	if (C == 0) return BCM3B200_OK;
+	if (!cp.finalized || cp.last_C != (int)C) return fail(BCM3B200_ERR_STATE, "bcm3b200_cellpop_finish without a matching bcm3b200_enqueue_batch");
+	CUDA_TRY(cudaSetDevice(cp.device));
+	const int n = (int)C * (cp.T + 1);
+	cellpop_unpack_partial_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_partial, cp.T, (int)C, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
+	CUDA_TRY(cudaGetLastError());
+	int rc = cellpop_data_likelihood(cp, C, st);
+	if (rc != BCM3B200_OK) return rc;
+	cp.total_launches += 2;
+	CUDA_TRY(cudaEventRecord(cp.ev1, st));
+	CUDA_TRY(cudaMemcpyAsync(logp, cp.d_logp.p, sizeof(double) * C, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, cp.ev0, cp.ev1) == cudaSuccess) cp.last_kernel_ms = ms;
+	if (status)
+		for (size_t c = 0; c < C; c++) status[c] = std::isnan(logp[c]) ? BCM3B200_STATUS_NAN : BCM3B200_STATUS_OK;
 	cp.num_evaluations += (int64_t)C;
 	return BCM3B200_OK;
 }

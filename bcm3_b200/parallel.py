@@ -97,3 +97,61 @@ class ShardedPopPKLikelihood:
 
     def close(self):
         self.evaluator.close()
+
+
+# ---- cell_population: the simulated cells are split over the ranks ----
+
+def cellpop_partial_from_cell_values(cell_values: np.ndarray, cell_status: np.ndarray) -> np.ndarray:
+    """CPU statement of cellpop_partial_kernel: cell_values [C][T][cells_local] (NaN = the cell does not exist at that
+    time), cell_status [C][cells_local] (1 ok) -> partial [C][2 T + 1] = sums, counts, failed cells."""
+    C, T, _ = cell_values.shape
+    partial = np.zeros((C, 2 * T + 1))
+    exists = ~np.isnan(cell_values)
+    partial[:, :T] = np.where(exists, cell_values, 0.0).sum(axis=2)
+    partial[:, T:2 * T] = exists.sum(axis=2)
+    partial[:, 2 * T] = (cell_status == 0).sum(axis=1)
+    return partial
+
+
+def cellpop_average_from_partial(partial: np.ndarray):
+    """Combined partial -> (population average [C][T], failed cells [C]); cellpop_unpack_partial_kernel."""
+    T = (partial.shape[1] - 1) // 2
+    n = partial[:, T:2 * T]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        avg = np.where(n > 0, partial[:, :T] / n, 0.0)
+    return avg, partial[:, 2 * T].astype(np.int64)
+
+
+class ShardedCellPopLikelihood:
+    """Rank-local GPU evaluator over this rank's slice of the simulated cells + one SUM all-reduce of the per-chain
+    partials; every rank ends up with the same logp[C]."""
+
+    def __init__(self, problem, rank: int, world_size: int, device: int, group=None, kernel: str = "auto"):
+        import torch
+
+        from .cellpop import CellPopEvaluator
+
+        self.torch = torch
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.device = torch.device("cuda", device)
+        self.evaluator = CellPopEvaluator(problem, device=device, kernel=kernel, shard_rank=rank, shard_count=world_size)
+        self.nvar = problem.num_variables
+        self.width = 2 * problem.num_timepoints + 1
+        self._partial = None
+
+    def evaluate(self, values_host):
+        """values_host: torch CPU tensor [C][nvar] float64. H2D, kernels, all-reduce, data likelihood, D2H of logp."""
+        torch = self.torch
+        C = values_host.shape[0]
+        if self._partial is None or self._partial.shape[0] != C:
+            self._partial = torch.empty((C, self.width), dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device)
+        self.evaluator.enqueue(values_host.data_ptr(), C, self.nvar, self._partial.data_ptr(), stream.cuda_stream)
+        if self.world_size > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self._partial, op=dist.ReduceOp.SUM, group=self.group)
+        return self.evaluator.finish(self._partial.data_ptr(), C, stream.cuda_stream)
+
+    def close(self):
+        self.evaluator.close()

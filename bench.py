@@ -117,12 +117,17 @@ def run_cellpop(args, workload: str):
     from bcm3_b200.cellpop import CellPopEvaluator
 
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank != 0 and (args.impl == "reference" or world == 1):
         return
     w = WORKLOADS[workload]
     prob = sc.make_cellpop_problem(N=w["N"], num_cells=w["cells"], T=w["T"], data_cells=32, seed=1)
     vals = sc.make_chain_values(w["C"])
     C, nvar = vals.shape
+    if args.impl != "reference" and world > 1:
+        run_cellpop_sharded(args, workload, prob, vals, rank, world, local_rank)
+        return
     if args.impl == "reference":
         kind, chk = cpu_checker()
         cores = max(1, min(C, os.cpu_count() or 1))
@@ -208,6 +213,74 @@ def run_cellpop(args, workload: str):
                                 "sample": f"all {C} chains x first {sample} of {w['cells']} cells in {dt:.1f} s on {cores} threads ({cpu_model_name()}); scaled by {sample}/{w['cells']}"}
     print(json.dumps(line))
     ev.close()
+
+
+def run_cellpop_sharded(args, workload, prob, vals, rank, world, local_rank):
+    """N > 1: the simulated cells are split over the ranks (strong scaling), one SUM all-reduce of [C][2 T + 1] doubles."""
+    import torch
+    import torch.distributed as dist
+
+    from bcm3_b200 import _lib
+    from bcm3_b200.parallel import ShardedCellPopLikelihood
+
+    w = WORKLOADS[workload]
+    C, nvar = vals.shape
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lk = ShardedCellPopLikelihood(prob, rank, world, local_rank)
+    h_vals = torch.from_numpy(vals).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        logp, status = lk.evaluate(h_vals)
+    barrier()
+    launches0 = lk.evaluator.get_stat("total_kernel_launches")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_begin = time.perf_counter()
+    wall = 0.0
+    for a, b in evs:
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        a.record(stream)
+        logp, status = lk.evaluate(h_vals)  # H2D of the batch, kernels, all-reduce, data likelihood, D2H of logp
+        b.record(stream)
+        wall += time.perf_counter() - t0
+    barrier()
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    torch.cuda.synchronize(dev)
+    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in evs), 1e3 * wall], dtype=torch.float64, device=dev)
+    nl = torch.tensor([float(lk.evaluator.get_stat("total_kernel_launches") - launches0)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        total_ms, wall_ms = float(tot[0].item()), float(tot[1].item())
+        line = {"metric": METRIC_CELLPOP, "value": C * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C, "timepoints": w["T"], "ode_solves_per_step": C * w["cells"],
+                           "sharding": f"cells over {world} ranks, NCCL SUM all-reduce of [{C}][{2 * w['T'] + 1}] doubles", "l2": "256 MB memset between timed iterations"},
+                "roofline": None,
+                "e2e": {"value": C * args.steps / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes) * world, "d2h_bytes_per_step": int(C * 8) * world,
+                        "ms_per_step": wall_ms / args.steps},
+                "gpu_launches": int(nl.item()), "clocks": clocks, "check": {"logp0": float(logp[0]), "status_ok": bool((status == 0).all())}}
+        print(json.dumps(line))
+    lk.close()
+    dist.destroy_process_group()
 
 
 def cpu_checker():

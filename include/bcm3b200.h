@@ -103,6 +103,16 @@ int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_v
 int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables, const double* values, double* d_partial,
                            void* stream);
 
+/* cell_population handles created with shard_count > 1 own a contiguous slice of the simulated cells (the reference
+ * walks them in one loop, Experiment.cpp:470-560 / DataLikelihoodTimeCourse.cpp:161-197). For those handles
+ * bcm3b200_enqueue_batch writes d_partial [num_chains][2 T + 1]: per timepoint the shard's sum of the existing cells'
+ * observed values and their count, then its number of failed cells, all as doubles. One SUM all-reduce of d_partial
+ * over the ranks followed by bcm3b200_cellpop_finish on every rank gives the population average (sum / count; the
+ * unsharded handle divides every cell by the population size before summing -- the two differ at round-off), the
+ * data likelihood and the -inf verdict for failed cells, exactly as the unsharded bcm3b200_evaluate_batch does.
+ * bcm3b200_get_stat(h, "partial_doubles_per_chain") = 2 T + 1. Synchronises `stream` before returning. */
+int bcm3b200_cellpop_finish(void* handle, size_t num_chains, const double* d_partial, double* logp, int* status, void* stream);
+
 /* partial [3][num_chains] (host) -> logp[num_chains], status[num_chains] (may be NULL) */
 int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* logp, int* status);
 

@@ -74,3 +74,36 @@ def test_failed_cell_and_chain_independence(Evaluator):
     single = np.array([ev.evaluate(gold["values"][c:c + 1])[0][0] for c in range(len(full))])
     ev.close()
     assert np.array_equal(full, single)
+
+
+def test_sharded_cells_reproduce_the_unsharded_result(Evaluator):
+    """Two handles owning half of the cells each (what two ranks hold), partials summed as the all-reduce would, the
+    finish step on each: same logp as the single handle, to round-off (sum / count versus sum of x / count)."""
+    import torch
+
+    prob, gold = load_cellpop_golden("cellpop_n5_late_entry")
+    vals = np.ascontiguousarray(gold["values"])
+    C = vals.shape[0]
+    ev = Evaluator(prob)
+    want, _ = ev.evaluate(vals)
+    ev.close()
+    shards = [Evaluator(prob, shard_rank=r, shard_count=2) for r in range(2)]
+    width = shards[0].get_stat("partial_doubles_per_chain")
+    assert width == 2 * prob.num_timepoints + 1
+    assert shards[0].get_stat("num_cells_local") + shards[1].get_stat("num_cells_local") == prob.num_cells
+    stream = torch.cuda.current_stream().cuda_stream
+    parts = []
+    for s in shards:
+        d = torch.empty((C, width), dtype=torch.float64, device="cuda:0")
+        s.enqueue(vals.ctypes.data, C, vals.shape[1], d.data_ptr(), stream)
+        parts.append(d)
+    torch.cuda.synchronize()
+    total = parts[0] + parts[1]
+    for s in shards:
+        logp, status = s.finish(total.data_ptr(), C, stream)
+        assert (status == 0).all()
+        assert np.abs(logp - want).max() <= 1e-9 * np.maximum(np.abs(want), 1.0).max()
+    with pytest.raises(Exception):
+        shards[0].evaluate(vals)  # a sharded handle only yields partials
+    for s in shards:
+        s.close()

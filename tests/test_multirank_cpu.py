@@ -85,3 +85,42 @@ def test_partial_block_matches_serial_loop():
         tot = np.stack([a[0] + b[0], np.minimum(a[1], b[1]), np.minimum(a[2], b[2])])
         got, _ = combine_partials(tot)
         assert (np.isnan(s) and np.isnan(got[0])) or s == got[0] or abs(s - got[0]) < 1e-12
+
+
+def _cellpop_worker(rank, world, port_no, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from bcm3_b200.parallel import cellpop_average_from_partial, cellpop_partial_from_cell_values, shard_bounds
+
+    from tests.util import load_cellpop_golden
+
+    prob, gold = load_cellpop_golden("cellpop_n5_late_entry")
+    full = oracle.load("port").cellpop_evaluate(prob, gold["values"], want_cell_values=True, want_average=True, want_steps=True)
+    lo, hi = shard_bounds(prob.num_cells, rank, world)
+    status = np.ones((gold["values"].shape[0], hi - lo), dtype=np.int32)
+    if rank == 1:
+        status[0, 0] = 0  # one failed cell on one rank must reach every rank
+    partial = torch.from_numpy(cellpop_partial_from_cell_values(full["cell_values"][:, :, lo:hi], status))
+    dist.all_reduce(partial, op=dist.ReduceOp.SUM)
+    avg, nfail = cellpop_average_from_partial(partial.numpy())
+    np.save(os.path.join(out_dir, f"avg_{rank}.npy"), avg)
+    np.save(os.path.join(out_dir, f"nfail_{rank}.npy"), nfail)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "want_avg.npy"), full["population_average"])
+    dist.destroy_process_group()
+
+
+def test_cell_population_shards_combine_to_the_population_average(built, tmp_path):
+    """Cells split over two ranks: per-timepoint sums and counts, one SUM all-reduce, average = sum / count on every rank
+    (cells that enter late are NaN before their entry time and must not be counted)."""
+    port_no = 31500 + (os.getpid() % 2000)
+    mp.start_processes(_cellpop_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    a, b = np.load(tmp_path / "avg_0.npy"), np.load(tmp_path / "avg_1.npy")
+    want = np.load(tmp_path / "want_avg.npy")
+    assert np.array_equal(a, b)
+    assert np.abs(a - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    assert np.load(tmp_path / "nfail_0.npy").tolist() == np.load(tmp_path / "nfail_1.npy").tolist()
+    assert np.load(tmp_path / "nfail_0.npy")[0] == 1
