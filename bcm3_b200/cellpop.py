@@ -25,7 +25,8 @@ class CellPopEvaluator:
             weight=repr(p.weight), missing_simulation_time_stdev=repr(p.missing_simulation_time_stdev),
             obs_species="+".join(str(s) for s in p.obs_species), device=device, compile_only=int(compile_only),
             shard_rank=shard_rank, shard_count=shard_count)
-        for name in ("entry_time", "stdev", "offset", "scale"):
+        kv["variability_distribution"] = p.variability_distribution
+        for name in ("entry_time", "stdev", "offset", "scale", "proportional_stdev"):
             ix = getattr(p, name + "_ix")
             if ix is not None:
                 kv[name + "_ix"] = ix
@@ -45,6 +46,8 @@ class CellPopEvaluator:
             if p.variability_dim:
                 self._set("sobol", np.asarray(p.sobol, dtype=np.float64).reshape(p.num_cells, p.variability_dim))
                 self._set("variability", p.variability_rows())
+                if p.variability_distribution == "full_gaussian" and p.variability_dim > 1:
+                    self._set("variability_covariance", p.covariance_rows())
             code = p.derivative_code.encode()
             _lib.check(self.lib.bcm3b200_set_text(self.handle, b"derivative_code", code, len(code)))
             _lib.check(self.lib.bcm3b200_set_option(self.handle, b"cellpop_kernel", {"auto": 0, "warp": 1, "thread": 2, "group": 3}[kernel]))

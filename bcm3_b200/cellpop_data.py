@@ -52,12 +52,16 @@ class CellPopProblem:
     non_sampled_parameters: np.ndarray = field(default_factory=lambda: np.zeros(0))
     sobol: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))  # [num_cells][D] uniforms in (0, 1)
     variability: list[Variability] = field(default_factory=list)
+    variability_distribution: str = "diagonal_gaussian"   # or "full_gaussian" (VariabilityDescription.cpp:50-139)
+    covariance: list = field(default_factory=list)        # full_gaussian: D (D - 1) / 2 entries, each a variable index (int) or a fixed float
     entry_time_ix: int | None = None
     entry_time: float = 0.0
     error_model: str = "normal"
     weight: float = 1.0
     stdev_ix: int | None = None
     stdev: float = 1.0
+    proportional_stdev_ix: int | None = None   # error_model proportional_normal / additive_proportional_normal
+    proportional_stdev: float = 1.0
     offset_ix: int | None = None
     offset: float = 0.0
     scale_ix: int | None = None
@@ -83,6 +87,17 @@ class CellPopProblem:
     @property
     def variability_dim(self) -> int:
         return len(self.variability)
+
+    def covariance_rows(self) -> np.ndarray:
+        """[D (D - 1) / 2][2]: variable index (or -1), fixed value -- entry (i - 1) i / 2 + k is the angle (in units of pi) of
+        row i, column k of the spherical Cholesky parametrisation."""
+        D = len(self.variability)
+        n = D * (D - 1) // 2
+        if self.variability_distribution != "full_gaussian":
+            return np.zeros((0, 2))
+        if len(self.covariance) != n:
+            raise ValueError(f"full_gaussian with {D} variables needs {n} covariance entries")
+        return np.array([[float(c), 0.0] if isinstance(c, (int, np.integer)) else [-1.0, float(c)] for c in self.covariance], dtype=np.float64).reshape(n, 2)
 
     def variability_rows(self) -> np.ndarray:
         return np.array([v.row() for v in self.variability], dtype=np.float64).reshape(len(self.variability), 6)

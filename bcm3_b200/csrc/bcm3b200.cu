@@ -464,7 +464,14 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		const std::string em = kv.count("error_model") ? kv["error_model"] : "normal";
 		if (em == "normal" || em == "additive_normal") cp->error_model = CP_ERR_NORMAL;
 		else if (em == "student_t4" || em == "t4") cp->error_model = CP_ERR_STUDENT_T4;
-		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4)", em.c_str());
+		else if (em == "proportional_normal") cp->error_model = CP_ERR_PROPORTIONAL_NORMAL;
+		else if (em == "additive_proportional_normal") cp->error_model = CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL;
+		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4, proportional_normal, additive_proportional_normal)", em.c_str());
+		cp->prop_stdev_ix = get_int(kv, "proportional_stdev_ix", -1);
+		cp->prop_stdev_fixed = real("proportional_stdev", 1.0);
+		const std::string vd = kv.count("variability_distribution") ? kv["variability_distribution"] : "diagonal_gaussian";
+		if (vd == "full_gaussian") cp->full_gaussian = true;
+		else if (vd != "diagonal_gaussian") return fail(BCM3B200_ERR_UNSUPPORTED, "variability_distribution \"%s\" is not supported (diagonal_gaussian, full_gaussian)", vd.c_str());
 		cp->weight = real("weight", 1.0);
 		cp->stdev_ix = get_int(kv, "stdev_ix", -1);
 		cp->stdev_fixed = real("stdev", 1.0);
@@ -539,6 +546,7 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 		else if (n == "observed") { w0 = cp.R; w1 = cp.T; }
 		else if (n == "transforms") w0 = cp.nvar;
 		else if (n == "variability") { w0 = cp.D; w1 = 6; }
+		else if (n == "variability_covariance") { w0 = (size_t)cp.D * (cp.D - 1) / 2; w1 = 2; }
 		else return fail(BCM3B200_ERR_ARG, "unknown data name \"%s\"", name);
 		const int want_ndim = w1 ? 2 : 1;
 		if (ndim != want_ndim || shape[0] != w0 || (w1 && shape[1] != w1)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);

@@ -36,6 +36,8 @@ struct CpArgs {
 	int var_negate[CP_MAX_VARIABILITY];
 	int var_slot[CP_MAX_VARIABILITY];        // override slot (parameter) or species index (initial condition)
 	int var_is_ic[CP_MAX_VARIABILITY];
+	int var_full;           // 1: full_gaussian -- v = L z with the chain's Cholesky factor (VariabilityDescription.cpp:99-131)
+	const double* var_chol; // [C][D][D] row-major lower triangle, written per batch by cellpop_cholesky_kernel
 	// time
 	int entry_time_ix;     // variable index or -1
 	double entry_time_fixed;
@@ -53,6 +55,22 @@ struct CpArgs {
 	int32_t* cell_steps;  // [C][num_cells] or null
 	int debug_report;     // 0: cell_steps = accepted steps; 1: RHS evaluations (nfe); 2: linear setups; 3: Jacobian evaluations
 };
+
+#ifdef __CUDACC__
+// VariabilityDescription::GetPseudorandomVector (VariabilityDescription.cpp:50-139): component d of the cell's vector
+__device__ __forceinline__ double cellpop_variability_value(const CpArgs& a, const double* tv, int c, long long gcell, int d)
+{
+	if (a.var_full) {
+		const double* L = a.var_chol + ((long long)c * a.D + d) * a.D;
+		double v = 0.0;
+		for (int j = 0; j <= d; j++) v += L[j] * normcdfinv(a.sobol[gcell * a.D + j]);
+		return v;
+	}
+	// diagonal_gaussian: the scale is on log scale (:54-64)
+	const double scale = (a.var_scale_ix[d] >= 0) ? tv[a.var_scale_ix[d]] : a.var_scale_fixed[d];
+	return normcdfinv(a.sobol[gcell * a.D + d]) * exp(scale);
+}
+#endif
 
 typedef int (*cellpop_launch_fn)(const CpArgs* args, void* stream);
 typedef int (*cellpop_thread_launch_fn)(const CpArgs* args, double* scratch, void* stream);

@@ -1200,8 +1200,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				for (int e = 0; e < E; e++) y0[e] = B.own(e) ? a.initial_conditions[B.idx(e)] : 0.0;
 				const long long gcell = (long long)a.cell_offset + cell;
 				for (int d = 0; d < a.D; d++) {
-					const double scale = (a.var_scale_ix[d] >= 0) ? tv[a.var_scale_ix[d]] : a.var_scale_fixed[d];
-					double v = normcdfinv(a.sobol[gcell * a.D + d]) * exp(scale);
+					double v = cellpop_variability_value(a, tv, c, gcell, d);
 					if (a.var_negate[d]) v = -v;
 					if (a.var_is_ic[d]) {
 #pragma unroll

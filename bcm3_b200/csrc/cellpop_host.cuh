@@ -18,7 +18,7 @@
 
 namespace bcm3b200 {
 
-enum : int { CP_ERR_NORMAL = 0, CP_ERR_STUDENT_T4 = 1 };
+enum : int { CP_ERR_NORMAL = 0, CP_ERR_STUDENT_T4 = 1, CP_ERR_PROPORTIONAL_NORMAL = 2, CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL = 3 };
 
 struct CellPopState {
 	// description
@@ -30,9 +30,10 @@ struct CellPopState {
 	int max_steps = 10000;                                                                  // Experiment.cpp:414
 	int error_model = CP_ERR_NORMAL;
 	double weight = 1.0;
-	int stdev_ix = -1, offset_ix = -1, scale_ix = -1;
-	double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0;
+	int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
+	double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0;
 	double missing_simulation_time_stdev = 300.0; // DataLikelihoodTimeCourseBase.cpp:22
+	bool full_gaussian = false;                   // <cell_variability distribution="full_gaussian">
 	std::vector<int> obs_species;
 	int shard_rank = 0, shard_count = 1, device = 0;
 	std::string derivative_code;
@@ -55,7 +56,8 @@ struct CellPopState {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<double> d_ic, d_const, d_nonsampled, d_sobol, d_time, d_obs, d_values, d_transformed, d_cellvals, d_avg, d_logp;
-	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail;
+	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail, d_cov_ix;
+	DevBuf<double> d_cov_fixed, d_chol;
 	bool diagnostics = false;
 	int last_C = 0;
 	double last_kernel_ms = 0.0;
@@ -198,6 +200,42 @@ __global__ void cellpop_unpack_partial_kernel(const double* __restrict__ partial
 	}
 }
 
+// Per chain: the Cholesky factor of the cell-variability covariance in the spherical parametrisation of
+// VariabilityDescription.cpp:99-131 -- L(i, j) = exp(scale_i) * prod_{k < j} sin(pi c_ik) * [j < i] cos(pi c_ij), c_ik =
+// covariance value (i - 1) i / 2 + k. One thread per chain; out [C][D][D] row-major, zeros above the diagonal.
+struct CpCholArgs {
+	int D, nvar;
+	int scale_ix[CP_MAX_VARIABILITY];
+	double scale_fixed[CP_MAX_VARIABILITY];
+	const int32_t* cov_ix;   // [D (D - 1) / 2] variable index or -1
+	const double* cov_fixed; // [D (D - 1) / 2]
+};
+__global__ void cellpop_cholesky_kernel(const CpCholArgs a, const double* __restrict__ transformed, int C, double* __restrict__ out)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C) return;
+	const double* tv = transformed + (long long)c * a.nvar;
+	double* L = out + (long long)c * a.D * a.D;
+	for (int i = 0; i < a.D; i++) {
+		const double exp_scale = exp((a.scale_ix[i] >= 0) ? tv[a.scale_ix[i]] : a.scale_fixed[i]);
+		for (int j = 0; j < a.D; j++) {
+			double l = 0.0;
+			if (j <= i) {
+				l = exp_scale;
+				for (int k = 0; k < i; k++) {
+					if (k <= j) {
+						const int e = (i - 1) * i / 2 + k;
+						const double cov_value = ((a.cov_ix[e] >= 0) ? tv[a.cov_ix[e]] : a.cov_fixed[e]) * 3.14159265358979323846;
+						if (k == j) l *= cos(cov_value);
+						else l *= sin(cov_value);
+					}
+				}
+			}
+			L[i * a.D + j] = l;
+		}
+	}
+}
+
 struct CpLikArgs {
 	const double* avg;       // [C][T]
 	const int32_t* nfail;    // [C]
@@ -205,8 +243,8 @@ struct CpLikArgs {
 	const double* timepoints;  // [T]
 	const double* observed;    // [R][T]
 	int T, R, nvar, error_model;
-	int stdev_ix, offset_ix, scale_ix;
-	double stdev_fixed, offset_fixed, scale_fixed, weight, missing_stdev;
+	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
+	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, weight, missing_stdev;
 	double* logp; // [C]
 };
 
@@ -223,6 +261,7 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 	const double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
 	const double offset = (a.offset_ix >= 0) ? tv[a.offset_ix] : a.offset_fixed;
 	const double scale = (a.scale_ix >= 0) ? tv[a.scale_ix] : a.scale_fixed;
+	const double prop_stdev = (a.prop_stdev_ix >= 0) ? tv[a.prop_stdev_ix] : a.prop_stdev_fixed;
 	const double minus_log_sigma = -log(stdev);
 	const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
 	double logp = 0.0;
@@ -259,6 +298,12 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 				// EvaluateValue(observed_data, x, 0): called with the arguments swapped: simulated := obs, observed := x
 				if (a.error_model == CP_ERR_STUDENT_T4) {
 					logp += logpdf_tnu4(x, obs, stdev);
+				} else if (a.error_model == CP_ERR_PROPORTIONAL_NORMAL || a.error_model == CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL) {
+					// DataLikelihoodTimeCourseBase.cpp:281-287 with the swapped arguments: the proportional part scales with the datum
+					double sigma = prop_stdev * fmax(obs, 0.0);
+					if (a.error_model == CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL) sigma = stdev + sigma;
+					const double d = x - obs;
+					logp += -log(sigma) - 0.91893853320467274178032973640562 - d * d / (2.0 * sigma * sigma);
 				} else {
 					const double d = x - obs;
 					logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
@@ -511,6 +556,22 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	CUDA_TRY(up(cp.d_sobol, cp.data["sobol"]));
 	CUDA_TRY(up(cp.d_time, cp.data["timepoints"]));
 	CUDA_TRY(up(cp.d_obs, cp.data["observed"]));
+	if (cp.full_gaussian) {
+		const size_t ncov = (size_t)cp.D * (cp.D - 1) / 2;
+		const std::vector<double>& cov = cp.data["variability_covariance"];
+		if (cov.size() != 2 * ncov) return fail(BCM3B200_ERR_STATE, "full_gaussian with %d variables needs \"variability_covariance\" of shape [%zu][2]", cp.D, ncov);
+		std::vector<int32_t> cix(ncov ? ncov : 1, -1);
+		std::vector<double> cfx(ncov ? ncov : 1, 0.0);
+		for (size_t e = 0; e < ncov; e++) {
+			cix[e] = (int32_t)cov[2 * e];
+			cfx[e] = cov[2 * e + 1];
+			if (cix[e] >= cp.nvar) return fail(BCM3B200_ERR_ARG, "covariance variable index out of range");
+		}
+		CUDA_TRY(cp.d_cov_ix.ensure(cix.size()));
+		CUDA_TRY(cp.d_cov_fixed.ensure(cfx.size()));
+		CUDA_TRY(cudaMemcpy(cp.d_cov_ix.p, cix.data(), sizeof(int32_t) * cix.size(), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(cp.d_cov_fixed.p, cfx.data(), sizeof(double) * cfx.size(), cudaMemcpyHostToDevice));
+	}
 	std::vector<int32_t> tr(cp.nvar);
 	for (int i = 0; i < cp.nvar; i++) tr[i] = (int32_t)cp.data["transforms"][i];
 	CUDA_TRY(cp.d_transforms.ensure(cp.nvar ? cp.nvar : 1));
@@ -561,6 +622,24 @@ inline int cellpop_run_cells(CellPopState& cp, size_t C, size_t nvar, const doub
 	cellpop_transform_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(cp.d_values.p, cp.d_transforms.p, (int)nvar, (int)C, cp.d_transformed.p);
 	CUDA_TRY(cudaGetLastError());
 	CpArgs a = cp.args;
+	a.var_full = 0;
+	a.var_chol = nullptr;
+	if (cp.full_gaussian && cp.D > 0) {
+		CUDA_TRY(cp.d_chol.ensure(C * (size_t)cp.D * cp.D));
+		CpCholArgs ca;
+		ca.D = cp.D;
+		ca.nvar = cp.nvar;
+		for (int d = 0; d < cp.D; d++) {
+			ca.scale_ix[d] = a.var_scale_ix[d];
+			ca.scale_fixed[d] = a.var_scale_fixed[d];
+		}
+		ca.cov_ix = cp.d_cov_ix.p;
+		ca.cov_fixed = cp.d_cov_fixed.p;
+		cellpop_cholesky_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>(ca, cp.d_transformed.p, (int)C, cp.d_chol.p);
+		CUDA_TRY(cudaGetLastError());
+		a.var_full = 1;
+		a.var_chol = cp.d_chol.p;
+	}
 	a.num_chains = (int)C;
 	a.transformed = cp.d_transformed.p;
 	a.cell_values = cp.d_cellvals.p;
@@ -608,6 +687,8 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	la.offset_ix = cp.offset_ix;
 	la.scale_ix = cp.scale_ix;
 	la.stdev_fixed = cp.stdev_fixed;
+	la.prop_stdev_ix = cp.prop_stdev_ix;
+	la.prop_stdev_fixed = cp.prop_stdev_fixed;
 	la.offset_fixed = cp.offset_fixed;
 	la.scale_fixed = cp.scale_fixed;
 	la.weight = cp.weight;

@@ -693,8 +693,7 @@ __global__ void __launch_bounds__(CP_THREADS_PER_BLOCK) cellpop_thread_kernel(co
 	for (int i = 0; i < N; i++) y[i] = a.initial_conditions[i];
 	const long long gcell = (long long)a.cell_offset + (valid ? cell : 0);
 	for (int d = 0; d < a.D; d++) {
-		const double scale = (a.var_scale_ix[d] >= 0) ? tv[a.var_scale_ix[d]] : a.var_scale_fixed[d];
-		double v = normcdfinv(a.sobol[gcell * a.D + d]) * exp(scale);
+		double v = cellpop_variability_value(a, tv, c, gcell, d);
 		if (a.var_negate[d]) v = -v;
 		if (a.var_is_ic[d]) {
 			double x = y[a.var_slot[d]];

@@ -869,9 +869,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS_PER_BLOCK) cellpop_kernel(const 
 	__syncwarp();
 	const long long gcell = (long long)a.cell_offset + cell;
 	for (int d = 0; d < a.D; d++) {
-		// VariabilityDescription::GetPseudorandomVector, diagonal_gaussian (VariabilityDescription.cpp:54-64)
-		const double scale = (a.var_scale_ix[d] >= 0) ? tv[a.var_scale_ix[d]] : a.var_scale_fixed[d];
-		double v = normcdfinv(a.sobol[gcell * a.D + d]) * exp(scale);
+		double v = cellpop_variability_value(a, tv, c, gcell, d);
 		if (a.var_negate[d]) v = -v;
 		if (a.var_is_ic[d]) {
 			if (lane == 0) {

@@ -194,7 +194,7 @@ def run_cellpop(args, workload: str):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C, "timepoints": w["T"], "ode_solves_per_step": C * w["cells"],
                        "mean_steps_per_solve": steps_mean, "l2": "256 MB memset between timed iterations"},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": ncu_traffic(workload),
                          "kernel": "cellpop_group_kernel" if w["N"] <= 96 else "cellpop_kernel", "kernel_ms": k_ms, "flop_per_system": flop_sys,
                          "systems_per_launch": C * w["cells"], "peak_source": "measured live: bcm3b200_measure_fp64_peak"},
             "e2e": {"value": C * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes), "d2h_bytes_per_step": int(C * 8), "ms_per_step": 1e3 * e2e_s / args.steps},

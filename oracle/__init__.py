@@ -70,10 +70,11 @@ def available(kind: str) -> bool:
 class _CellPopProblem(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("num_species", "num_constant_species", "num_variables", "num_non_sampled", "num_cells",
                                          "num_timepoints", "num_replicates", "variability_dim", "entry_time_ix", "max_steps",
-                                         "error_model", "stdev_ix", "offset_ix", "scale_ix", "num_obs_species")] + [
+                                         "error_model", "stdev_ix", "offset_ix", "scale_ix", "proportional_stdev_ix", "full_gaussian",
+                                         "num_obs_species")] + [
         ("obs_species", C.c_int32 * 8)] + [(n, C.c_double) for n in ("entry_time", "rel_tol", "abs_tol", "min_dt", "weight", "stdev",
-                                                                     "offset", "scale", "missing_stdev")] + [
-        (n, C.c_void_p) for n in ("initial_conditions", "constant_species", "non_sampled", "sobol", "timepoints", "observed",
+                                                                     "offset", "scale", "missing_stdev", "proportional_stdev")] + [
+        (n, C.c_void_p) for n in ("covariance", "initial_conditions", "constant_species", "non_sampled", "sobol", "timepoints", "observed",
                                   "variability", "transforms", "derivative")]
 
 
@@ -167,6 +168,9 @@ class Oracle:
         return dict(logp=logp, conc=conc, patient_ll=pll, counters=cnt)
 
 
+ERROR_MODELS = {"normal": 0, "additive_normal": 0, "student_t4": 1, "t4": 1, "proportional_normal": 2, "additive_proportional_normal": 3}
+
+
 def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=False, want_steps=False, want_average=False):
     """problem: bcm3_b200.cellpop_data.CellPopProblem; values [C, nvar]."""
     p = problem
@@ -181,13 +185,17 @@ def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=
         ic=np.ascontiguousarray(p.initial_conditions, dtype=np.float64), const=np.ascontiguousarray(p.constant_species, dtype=np.float64),
         ns=np.ascontiguousarray(p.non_sampled_parameters, dtype=np.float64), sobol=np.ascontiguousarray(p.sobol, dtype=np.float64),
         tp=np.ascontiguousarray(p.timepoints, dtype=np.float64), obs=np.ascontiguousarray(p.observed, dtype=np.float64),
-        var=np.ascontiguousarray(p.variability_rows(), dtype=np.float64), tr=np.ascontiguousarray(p.transforms, dtype=np.int32))
+        var=np.ascontiguousarray(p.variability_rows(), dtype=np.float64), tr=np.ascontiguousarray(p.transforms, dtype=np.int32),
+        cov=np.ascontiguousarray(p.covariance_rows(), dtype=np.float64))
     ptr = lambda a: a.ctypes.data if a.size else None
     s = _CellPopProblem(
         num_species=p.num_species, num_constant_species=len(keep["const"]), num_variables=p.num_variables, num_non_sampled=len(keep["ns"]),
         num_cells=nc, num_timepoints=T, num_replicates=p.num_replicates, variability_dim=D,
         entry_time_ix=-1 if p.entry_time_ix is None else p.entry_time_ix, max_steps=p.solver_max_steps,
-        error_model={"normal": 0, "additive_normal": 0, "student_t4": 1, "t4": 1}[p.error_model],
+        error_model=ERROR_MODELS[p.error_model],
+        proportional_stdev_ix=-1 if p.proportional_stdev_ix is None else p.proportional_stdev_ix,
+        full_gaussian=int(p.variability_distribution == "full_gaussian"), proportional_stdev=p.proportional_stdev,
+        covariance=ptr(keep["cov"]),
         stdev_ix=-1 if p.stdev_ix is None else p.stdev_ix, offset_ix=-1 if p.offset_ix is None else p.offset_ix,
         scale_ix=-1 if p.scale_ix is None else p.scale_ix, num_obs_species=len(p.obs_species),
         obs_species=(C.c_int32 * 8)(*(list(p.obs_species) + [0] * (8 - len(p.obs_species)))),

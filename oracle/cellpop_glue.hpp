@@ -71,6 +71,29 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	for (int i = 0; i < nvar; i++) transformed[i] = transform_variable(pr.transforms[i], values[i]);
 	const double entry_time = (pr.entry_time_ix >= 0) ? transformed[pr.entry_time_ix] : pr.entry_time;
 
+	// VariabilityDescription::GetPseudorandomVector, FullGaussian (VariabilityDescription.cpp:99-131): spherical
+	// parametrisation of the Cholesky factor, L(i, j) = exp(scale_i) * prod_{k < j} sin(pi c_ik) * [j < i] cos(pi c_ij)
+	std::vector<double> cholesky((size_t)D * D, 0.0);
+	if (pr.full_gaussian) {
+		for (int i = 0; i < D; i++) {
+			const double* row = pr.variability + (size_t)i * 6;
+			const int scale_ix = (int)row[3];
+			const double exp_scale = exp((scale_ix >= 0) ? transformed[scale_ix] : row[4]);
+			for (int j = 0; j <= i; j++) {
+				double l = exp_scale;
+				for (int k = 0; k < i; k++) {
+					if (k <= j) {
+						const double* cv = pr.covariance + (size_t)((i - 1) * i / 2 + k) * 2;
+						const double cov_value = (((int)cv[0] >= 0) ? transformed[(int)cv[0]] : cv[1]) * M_PI;
+						if (k == j) l *= cos(cov_value);
+						else l *= sin(cov_value);
+					}
+				}
+				cholesky[(size_t)i * D + j] = l;
+			}
+		}
+	}
+
 	Solver solver(pr);
 	std::vector<double> population_average(T, 0.0), cell_params(nvar), y0(N), tp_rel(T), out((size_t)N * T);
 	std::vector<double> xs((size_t)T * ncell, nan); // value per (timepoint, cell)
@@ -84,8 +107,14 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 			const double* row = pr.variability + (size_t)d * 6;
 			const bool is_ic = row[0] != 0.0;
 			const int target = (int)row[1], apply = (int)row[2], scale_ix = (int)row[3];
-			const double scale = (scale_ix >= 0) ? transformed[scale_ix] : row[4];
-			double v = ndtri(pr.sobol[(size_t)ci * D + d]) * exp(scale);
+			double v;
+			if (pr.full_gaussian) {
+				v = 0.0; // v = L z, row d
+				for (int j = 0; j <= d; j++) v += cholesky[(size_t)d * D + j] * ndtri(pr.sobol[(size_t)ci * D + j]);
+			} else {
+				const double scale = (scale_ix >= 0) ? transformed[scale_ix] : row[4];
+				v = ndtri(pr.sobol[(size_t)ci * D + d]) * exp(scale);
+			}
 			if (row[5] != 0.0) v = -v;
 			if (is_ic) apply_variability(y0[target], v, apply);
 			else apply_variability(cell_params[target], v, apply);
@@ -135,6 +164,7 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	const double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
 	const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
 	const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
+	const double prop_stdev = (pr.proportional_stdev_ix >= 0) ? transformed[pr.proportional_stdev_ix] : pr.proportional_stdev;
 	const double minus_log_sigma = -log(stdev), inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
 	for (int i = 0; i < T; i++) {
 		population_average[i] *= scale;
@@ -155,8 +185,13 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 				const double obs = pr.observed[(size_t)j * T + i];
 				if (std::isnan(obs)) continue;
 				// EvaluateValue(observed_data(j, i), x, 0): first argument is named `simulated` (argument swap)
+				// so inside EvaluateValue (DataLikelihoodTimeCourseBase.cpp:267-299) `simulated` = obs and `observed` = x
 				if (pr.error_model == 1) {
 					logp += logpdf_tnu4(x, obs, stdev);
+				} else if (pr.error_model == 2) {
+					logp += logpdf_normal(x, obs, prop_stdev * std::max(obs, 0.0));
+				} else if (pr.error_model == 3) {
+					logp += logpdf_normal(x, obs, stdev + prop_stdev * std::max(obs, 0.0));
 				} else {
 					const double d = x - obs;
 					logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;

@@ -84,8 +84,8 @@ enum {
 int oracle_poppk_evaluate(const oracle_poppk_problem* prob, size_t num_chains, const double* values,
                           double* logp, double* conc, double* patient_ll, int64_t* counters, int num_threads);
 
-/* ---- cell_population (rows a8-a12 of SURVEY.md section 8): independent non-dividing cells, one diagonal_gaussian
- * variability block, one time_course_population_average data set ---- */
+/* ---- cell_population (rows a8-a12 of SURVEY.md section 8): independent non-dividing cells, one cell_variability block
+ * (diagonal_gaussian or full_gaussian), one time_course_population_average data set ---- */
 typedef void (*oracle_derivative_fn)(double* out, const double* species, const double* constant_species, const double* parameters,
                                      const double* non_sampled_parameters); /* SolverCodeGenerator.h:6 */
 
@@ -93,11 +93,14 @@ typedef struct {
 	int32_t num_species, num_constant_species, num_variables, num_non_sampled, num_cells, num_timepoints, num_replicates, variability_dim;
 	int32_t entry_time_ix; /* -1: fixed */
 	int32_t max_steps;
-	int32_t error_model; /* 0 normal, 1 student_t4 */
+	int32_t error_model; /* 0 normal, 1 student_t4, 2 proportional_normal, 3 additive_proportional_normal */
 	int32_t stdev_ix, offset_ix, scale_ix; /* -1: fixed */
+	int32_t proportional_stdev_ix;         /* -1: fixed */
+	int32_t full_gaussian;                 /* 0: diagonal_gaussian, 1: full_gaussian (spherical Cholesky, VariabilityDescription.cpp:99-131) */
 	int32_t num_obs_species;
 	int32_t obs_species[8];
-	double entry_time, rel_tol, abs_tol, min_dt, weight, stdev, offset, scale, missing_stdev;
+	double entry_time, rel_tol, abs_tol, min_dt, weight, stdev, offset, scale, missing_stdev, proportional_stdev;
+	const double* covariance;          /* [D (D - 1) / 2][2]: variable index (or -1), fixed value; full_gaussian only */
 	const double* initial_conditions;  /* [N] */
 	const double* constant_species;    /* [Nc] */
 	const double* non_sampled;         /* [Nn] */

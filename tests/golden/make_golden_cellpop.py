@@ -23,16 +23,30 @@ CASES = {
                                         two_species_readout=True), 3, dict(error_model="student_t4", offset=0.01, scale=1.1, weight=0.5)),
     "cellpop_n5_late_entry": (dict(N=5, num_cells=33, T=10, data_cells=8, seed=23), 2, dict(entry_time=1.0)),
     "cellpop_n24_stiff": (dict(N=24, num_cells=24, T=10, data_cells=4, seed=24, rate_decades=4.0), 2, {}),
+    # <cell_variability distribution="full_gaussian"> (two fixed angles and one sampled) + additive_proportional_normal error model
+    "cellpop_n8_fullgauss_addprop": (dict(N=8, num_cells=64, T=12, data_cells=8, seed=25, replicates=2), 3,
+                                     dict(variability_distribution="full_gaussian", covariance=[0.3, sc.VAR_VARIABILITY_SCALE, 0.15],
+                                          error_model="additive_proportional_normal", proportional_stdev=0.1)),
+    "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
+                                dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
 
 
 def main():
     ref = oracle.load("ref")
+    only = sys.argv[1:]
     for name, (kw, C, tweaks) in CASES.items():
+        if only and name not in only:
+            continue
+        tweaks = dict(tweaks)
+        positive = tweaks.pop("_positive_data", False)
         prob = dataclasses.replace(sc.make_cellpop_problem(**kw), **tweaks)
+        if positive:  # a proportional error model has sigma = 0 (log-density NaN) at data <= 0
+            prob = dataclasses.replace(prob, observed=np.abs(prob.observed) + 0.05)
         vals = sc.make_chain_values(C, seed=zlib.crc32(name.encode()) % 10000)
         r = ref.cellpop_evaluate(prob, vals, threads=1, want_cell_values=True, want_steps=True, want_average=True)
-        out = {f.name: getattr(prob, f.name) for f in dataclasses.fields(prob) if f.name not in ("variability",)}
+        out = {f.name: getattr(prob, f.name) for f in dataclasses.fields(prob) if f.name not in ("variability", "covariance")}
+        out["covariance_rows"] = prob.covariance_rows()
         out = {k: (np.array(v) if not isinstance(v, np.ndarray) else v) for k, v in out.items() if v is not None}
         out["variability_rows"] = prob.variability_rows()
         out.update(values=vals, logp=r["logp"], cell_values=r["cell_values"], cell_steps=r["cell_steps"], population_average=r["population_average"])

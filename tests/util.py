@@ -91,6 +91,11 @@ def load_cellpop_golden(name):
                                        initial_condition_species=int(target) if is_ic else None,
                                        scale_ix=None if scale_ix < 0 else int(scale_ix), scale_fixed=float(scale_fixed), negate=bool(negate)))
     opt_int = lambda k: int(z[k]) if k in z.files else None
+    extra = {}
+    if "variability_distribution" in z.files:
+        extra = dict(variability_distribution=str(z["variability_distribution"]),
+                     covariance=[int(ix) if ix >= 0 else float(fx) for ix, fx in z["covariance_rows"]],
+                     proportional_stdev_ix=opt_int("proportional_stdev_ix"), proportional_stdev=float(z["proportional_stdev"]))
     prob = CellPopProblem(
         derivative_code=str(z["derivative_code"]), num_species=int(z["num_species"]), initial_conditions=z["initial_conditions"],
         transforms=z["transforms"], num_cells=int(z["num_cells"]), timepoints=z["timepoints"], observed=z["observed"],
@@ -100,7 +105,7 @@ def load_cellpop_golden(name):
         stdev_ix=opt_int("stdev_ix"), stdev=float(z["stdev"]), offset_ix=opt_int("offset_ix"), offset=float(z["offset"]),
         scale_ix=opt_int("scale_ix"), scale=float(z["scale"]), missing_simulation_time_stdev=float(z["missing_simulation_time_stdev"]),
         solver_relative_tolerance=float(z["solver_relative_tolerance"]), solver_absolute_tolerance=float(z["solver_absolute_tolerance"]),
-        solver_min_timestep=float(z["solver_min_timestep"]), solver_max_steps=int(z["solver_max_steps"]))
+        solver_min_timestep=float(z["solver_min_timestep"]), solver_max_steps=int(z["solver_max_steps"]), **extra)
     return prob, {k: z[k] for k in ("values", "logp", "cell_values", "cell_steps", "population_average")}
 
 
