@@ -391,8 +391,10 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 		G = 2;
 		while (G < 32 && (cp.N + G - 1) / G > 3) G <<= 1;
 	}
-	// block shape: as many cells per SM as its shared memory holds (the per-cell block of cellpop_group.cuh), two blocks
-	// per SM, at most 12 warps per SM -- above that the register budget (64K / threads) starts to force spills
+	// block shape: ONE block per SM holding as many cells as its shared memory allows (the per-cell block of
+	// cellpop_group.cuh), at most 12 warps -- above that the register budget (64K / threads) starts to force spills. One
+	// large lock-step block shares instruction fetches best: measured 130.6 ms (1 x 12 warps) vs 136.7 (2 x 6) vs 146.0
+	// (4 x 3) at config 3.
 	const int Eg = (cp.N + G - 1) / G;
 	size_t per_cell;
 	{ // the constants of cellpop_group.cuh: RS, OFF_SCAL, SC_COUNT, OFF_ZNH, CS
@@ -406,11 +408,8 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	const int cells_per_warp = 32 / G;
 	int warps_max = (int)((220 * 1024) / (per_cell * cells_per_warp));
 	if (warps_max > 12) warps_max = 12;
-	int gwarps = warps_max / 2, gblocks = 2;
-	if (gwarps < 1) {
-		gwarps = warps_max < 1 ? 1 : warps_max;
-		gblocks = 1;
-	}
+	if (warps_max < 1) warps_max = 1;
+	int gwarps = warps_max, gblocks = 1;
 	if (const char* wenv = getenv("BCM3B200_CELLPOP_GROUP_WARPS")) gwarps = atoi(wenv) > 0 ? atoi(wenv) : gwarps;
 	if (const char* benv = getenv("BCM3B200_CELLPOP_GROUP_MIN_BLOCKS")) gblocks = atoi(benv) > 0 ? atoi(benv) : gblocks;
 	o << "#define CP_GROUP " << G << "\n";

@@ -42,6 +42,8 @@ WORKLOADS = {
     "poppk_one_1k_x16": dict(pk="one", P=1000, T=10, t_end=72.0, C=16, flop_per_system=48.0e3),
     # BASELINE.json configs[2]: cellpop small cell-cycle-like SBML-style model, 10k simulated cells, 16 temperatures, 1 GPU
     "cellpop_12sp_10k_x16": dict(kind="cellpop", N=12, cells=10_000, T=50, C=16),
+    # BASELINE.json configs[3]: cellpop ~50-species stiff signalling cascade, 100k cells, 16 temperatures (sharded over GPUs when N > 1)
+    "cellpop_50sp_100k_x16": dict(kind="cellpop", N=50, cells=100_000, T=50, C=16, rate_decades=4.0),
 }
 METRIC = "likelihood evals/sec (PopPK batched EvaluateLogProbability)"
 METRIC_CELLPOP = "likelihood evals/sec (cellpop batched EvaluateLogProbability)"
@@ -122,7 +124,7 @@ def run_cellpop(args, workload: str):
     if rank != 0 and (args.impl == "reference" or world == 1):
         return
     w = WORKLOADS[workload]
-    prob = sc.make_cellpop_problem(N=w["N"], num_cells=w["cells"], T=w["T"], data_cells=32, seed=1)
+    prob = sc.make_cellpop_problem(N=w["N"], num_cells=w["cells"], T=w["T"], data_cells=32, seed=1, rate_decades=w.get("rate_decades", 2.0))
     vals = sc.make_chain_values(w["C"])
     C, nvar = vals.shape
     if args.impl != "reference" and world > 1:
@@ -134,7 +136,7 @@ def run_cellpop(args, workload: str):
         import dataclasses
         times = []
         for i in range(args.warmup + args.steps):
-            sample = min(w["cells"], 2000)
+            sample = min(w["cells"], 2000 if w["N"] <= 20 else 200)
             ps = dataclasses.replace(prob, num_cells=sample, sobol=prob.sobol[:sample])
             t0 = time.perf_counter()
             chk.cellpop_evaluate(ps, vals, threads=cores)
@@ -204,7 +206,7 @@ def run_cellpop(args, workload: str):
         import dataclasses
         kind, chk = cpu_checker()
         cores = max(1, min(C, os.cpu_count() or 1))
-        sample = min(w["cells"], 4000)
+        sample = min(w["cells"], 4000 if w["N"] <= 20 else 400)
         ps = dataclasses.replace(prob, num_cells=sample, sobol=prob.sobol[:sample])
         t0 = time.perf_counter()
         chk.cellpop_evaluate(ps, vals, threads=cores)
