@@ -3,6 +3,7 @@
 #include <fstream>
 #include <sstream>
 
+#include "CellPopulationLikelihoodB200.h"
 #include "LikelihoodPopPKTrajectoryB200.h"
 #include "TestLikelihoodBanana.h"
 
@@ -41,12 +42,17 @@ std::shared_ptr<Likelihood> LikelihoodFactory::CreateLikelihoodFromText(const st
 		ll = std::make_shared<TestLikelihoodBanana>(sampling_threads, evaluation_threads);
 	} else if (type == "pop_pk_trajectory") {
 		ll = std::make_shared<LikelihoodPopPKTrajectoryB200>(sampling_threads, evaluation_threads);
+	} else if (type == "cell_population") { // LikelihoodFactory.cpp:81
+		ll = std::make_shared<CellPopulationLikelihoodB200>(sampling_threads, evaluation_threads);
 	} else {
 		if (error) *error = "Unknown likelihood type \"" + type + "\"";
 		return ll;
 	}
 	if (!ll->Initialize(varset, *node)) {
-		if (error) *error = "Failed to initialize likelihood";
+		if (error) {
+			*error = "Failed to initialize likelihood";
+			if (auto* cp = dynamic_cast<CellPopulationLikelihoodB200*>(ll.get())) *error += ": " + cp->LastError();
+		}
 		ll.reset();
 	}
 	return ll;

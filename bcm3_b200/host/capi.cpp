@@ -2,6 +2,7 @@
 // factory and likelihood classes exactly as a C++ program would.
 #include <cstring>
 
+#include "CellPopulationLikelihoodB200.h"
 #include "LikelihoodFactory.h"
 #include "LikelihoodPopPKTrajectoryB200.h"
 #include "SamplerPT.h"
@@ -164,6 +165,68 @@ int bcm3host_evaluate(const char* prior_xml, const char* likelihood_xml, const d
 		for (size_t c = 0; c < C; c++) {
 			VectorReal v(values + c * nvar, values + (c + 1) * nvar);
 			if (!st.likelihood->EvaluateLogProbability(0, v, logp[c])) return -2;
+		}
+	}
+	return 0;
+}
+
+// cell_population through the plugin surface: likelihood.xml + the generated model, data set and quasi-random table that
+// the SBML / NetCDF readers would supply; evaluates values[C][nvar] batched (1) or chain by chain (0). compile_only = 1
+// stops after PostInitialize (CPU container: the model library is compiled, nothing runs); the descriptor handed to the
+// C ABI is returned in desc_out.
+int bcm3host_cellpop_evaluate(const char* prior_xml, const char* likelihood_xml, const char* derivative_code, size_t N,
+                              const char* const* species_names, const double* initial_conditions, size_t Nc, const double* constant_species,
+                              size_t T, size_t R, const double* timepoints, const double* observed, size_t sobol_count, const double* sobol,
+                              int device, int compile_only, const double* values, size_t C, int batched, double* logp, char* desc_out,
+                              size_t desc_len, char* err, size_t errlen)
+{
+	Setup st;
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
+		set_err(err, errlen, error);
+		return -1;
+	}
+	auto* ll = dynamic_cast<CellPopulationLikelihoodB200*>(st.likelihood.get());
+	if (!ll) {
+		set_err(err, errlen, "likelihood.xml is not of type cell_population");
+		return -1;
+	}
+	CellPopulationLikelihoodB200::Model m;
+	m.derivative_code = derivative_code;
+	for (size_t i = 0; i < N; i++) m.species_names.push_back(species_names[i]);
+	m.initial_conditions.assign(initial_conditions, initial_conditions + N);
+	m.constant_species.assign(constant_species, constant_species + Nc);
+	ll->SetModel(m);
+	CellPopulationLikelihoodB200::Data d;
+	d.timepoints.assign(timepoints, timepoints + T);
+	d.observed.assign(observed, observed + R * T);
+	d.num_replicates = R;
+	ll->SetData(d);
+	ll->SetSobolTable(std::vector<double>(sobol, sobol + sobol_count));
+	ll->SetDevice(device, compile_only != 0);
+	if (!ll->PostInitialize()) {
+		set_err(err, errlen, ll->LastError());
+		return -3;
+	}
+	set_err(desc_out, desc_len, ll->GetDescriptor());
+	if (compile_only) return 0;
+	const size_t nvar = st.varset->GetNumVariables();
+	if (batched) {
+		MatrixReal mat(nvar, C);
+		std::copy(values, values + nvar * C, mat.data.begin());
+		VectorReal lp;
+		if (!st.likelihood->EvaluateLogProbabilityBatch(mat, lp)) {
+			set_err(err, errlen, ll->LastError());
+			return -2;
+		}
+		std::copy(lp.begin(), lp.end(), logp);
+	} else {
+		for (size_t c = 0; c < C; c++) {
+			VectorReal v(values + c * nvar, values + (c + 1) * nvar);
+			if (!st.likelihood->EvaluateLogProbability(0, v, logp[c])) {
+				set_err(err, errlen, ll->LastError());
+				return -2;
+			}
 		}
 	}
 	return 0;

@@ -82,3 +82,29 @@ def varset_info(prior_xml: str, lookup: str | None = None):
     if rc != 0:
         raise RuntimeError("bcm3host_varset_info failed")
     return n.value, list(tr[: min(n.value, 65536)]), (idx.value if lookup else None)
+
+
+def cellpop_evaluate(prior_xml: str, likelihood_xml: str, problem, species_names, values=None, batched: bool = True, device: int = 0,
+                     compile_only: bool = False):
+    """CellPopulationLikelihoodB200 through LikelihoodFactory: likelihood.xml + the generated model / data set / quasi-random
+    table of `problem` (bcm3_b200.cellpop_data.CellPopProblem). Returns (logp or None, descriptor handed to the C ABI)."""
+    lib = load()
+    p = problem
+    names = (C.c_char_p * len(species_names))(*[s.encode() for s in species_names])
+    ic = np.ascontiguousarray(p.initial_conditions, dtype=np.float64)
+    cs = np.ascontiguousarray(p.constant_species, dtype=np.float64)
+    tp = np.ascontiguousarray(p.timepoints, dtype=np.float64)
+    obs = np.ascontiguousarray(p.observed, dtype=np.float64)
+    sob = np.ascontiguousarray(p.sobol, dtype=np.float64)
+    vals = np.zeros((1, p.num_variables)) if values is None else np.ascontiguousarray(values, dtype=np.float64)
+    logp = np.empty(vals.shape[0])
+    desc = C.create_string_buffer(4096)
+    err = _err()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.bcm3host_cellpop_evaluate(prior_xml.encode(), likelihood_xml.encode(), p.derivative_code.encode(), C.c_size_t(p.num_species), names,
+                                       vp(ic), C.c_size_t(cs.size), vp(cs), C.c_size_t(tp.size), C.c_size_t(obs.shape[0]), vp(tp), vp(obs),
+                                       C.c_size_t(sob.size), vp(sob), int(device), int(compile_only), vp(vals), C.c_size_t(vals.shape[0]),
+                                       int(batched), vp(logp), desc, C.c_size_t(4096), err, C.c_size_t(1024))
+    if rc != 0:
+        raise RuntimeError(f"bcm3host_cellpop_evaluate failed ({rc}): {err.value.decode()}")
+    return (None if compile_only else logp), desc.value.decode()

@@ -59,3 +59,22 @@ def test_pt_run_on_gpu_likelihood_batched_equals_serial(built, pk):
     # the posterior chain moved and its log-likelihood improved over the start
     post = a[a[:, 0] == 1.0]
     assert post[-1, 2] >= post[0, 2]
+
+
+def test_cell_population_plugin_matches_the_direct_abi_call(built):
+    """likelihood.xml -> LikelihoodFactory -> CellPopulationLikelihoodB200::EvaluateLogProbabilityBatch gives what the ABI
+    gives for the same problem, batched and chain by chain."""
+    from bcm3_b200 import host_api
+    from bcm3_b200 import synthetic_cellpop as sc
+    from bcm3_b200.cellpop import CellPopEvaluator
+    from tests.util import cellpop_xml
+
+    prob = sc.make_cellpop_problem(N=8, num_cells=96, T=10, data_cells=4, seed=9)
+    vals = sc.make_chain_values(3, seed=9)
+    ev = CellPopEvaluator(prob)
+    want, _ = ev.evaluate(vals)
+    ev.close()
+    prior, lik, species = cellpop_xml(prob)
+    batched, _ = host_api.cellpop_evaluate(prior, lik, prob, species, values=vals, batched=True)
+    serial, _ = host_api.cellpop_evaluate(prior, lik, prob, species, values=vals, batched=False)
+    assert np.array_equal(batched, want) and np.array_equal(serial, want)

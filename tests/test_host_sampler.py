@@ -98,3 +98,27 @@ def test_banana_posterior(host):
     # the T = 0 chain samples the prior
     pri = rows[rows[:, 0] == 0.0][:, 3:]
     assert abs(pri[:, 0].mean() - (-1.0)) < 0.15 and abs(pri[:, 1].mean() - 7.0) < 0.4
+
+
+def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path, monkeypatch):
+    """CellPopulationLikelihoodB200 behind LikelihoodFactory type="cell_population": Initialize reads the reference's
+    likelihood.xml attributes, PostInitialize hands descriptor + arrays + generated text to the C ABI (compile-only here)."""
+    from bcm3_b200 import host_api
+    from bcm3_b200 import synthetic_cellpop as sc
+    from tests.util import cellpop_xml
+
+    monkeypatch.setenv("BCM3B200_CACHE", str(tmp_path))
+    prob = sc.make_cellpop_problem(N=5, num_cells=16, T=6, data_cells=2, seed=3)
+    prior, lik, species = cellpop_xml(prob)
+    _, desc = host_api.cellpop_evaluate(prior, lik, prob, species, compile_only=True)
+    kv = dict(item.split("=", 1) for item in desc.split(";"))
+    assert kv["num_species"] == "5" and kv["num_cells"] == "16" and kv["num_timepoints"] == "6" and kv["variability_dim"] == "3"
+    assert kv["stdev_ix"] == "5" and kv["obs_species"] == "4" and kv["error_model"] == "normal" and float(kv["entry_time"]) == 0.0
+    assert kv["variability_distribution"] == "diagonal_gaussian" and "proportional_stdev" not in kv
+    # the reference's default is dividing cells (Experiment.cpp:488): refused, not silently ignored
+    with pytest.raises(RuntimeError, match="divide_cells"):
+        host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)
+    with pytest.raises(RuntimeError, match="not supported"):
+        host_api.cellpop_evaluate(prior, lik.replace("time_course_population_average", "time_course"), prob, species, compile_only=True)
+    with pytest.raises(RuntimeError, match="Could not find variable"):
+        host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="no_such_variable"'), prob, species, compile_only=True)

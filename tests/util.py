@@ -125,3 +125,31 @@ def cellpop_rtol(name):
     5e-6 there (4 % of the cells keep identical step counts) -- round-off decides step-size/order decisions early in a
     trajectory whose global error is ~1e-5."""
     return 2e-5 if "stiff" in name else 1e-6
+
+
+# ---- cell_population through the C++ plugin surface: prior.xml / likelihood.xml of the synthetic models ----
+CELLPOP_VARIABLE_NAMES = ["k_in", "k_cascade", "k_deg", "k_feedback", "variability_scale", "stdev"]
+
+
+def cellpop_xml(prob, **experiment_overrides):
+    """prior.xml and likelihood.xml (reference schema) describing bcm3_b200.synthetic_cellpop.make_cellpop_problem."""
+    import math
+
+    logspace = lambda n: 'logspace="true" ' if n != "variability_scale" else ""
+    prior = "<variableset>" + "".join(
+        f'<variable name="{n}" {logspace(n)}distribution="uniform" lower="-5" upper="5"/>' for n in CELLPOP_VARIABLE_NAMES) + "</variableset>"
+    species = [f"x{i}" for i in range(prob.num_species)]
+    exp = dict(name="synthetic", model_file="cascade.xml", entry_time="0", num_cells=str(prob.num_cells), max_cells=str(prob.num_cells),
+               divide_cells="false")
+    exp.update(experiment_overrides)
+    attrs = " ".join(f'{k}="{v}"' for k, v in exp.items())
+    obs = "+".join(species[s] for s in prob.obs_species)
+    lik = (f'<bcm_likelihood type="cell_population"><experiment {attrs}>'
+           '<cell_variability distribution="diagonal_gaussian">'
+           '<variable model_parameter="k_in" apply="multiplicative_log" scale="variability_scale"/>'
+           '<variable model_parameter="k_deg" apply="multiplicative_log" scale="variability_scale" negate="true"/>'
+           f'<variable initial_condition_species="x1" apply="additive" scale="{math.log(0.01)!r}"/>'
+           '</cell_variability>'
+           f'<data type="time_course_population_average" data_name="readout" species_name="{obs}" stdev="stdev"/>'
+           '</experiment></bcm_likelihood>')
+    return prior, lik, species
