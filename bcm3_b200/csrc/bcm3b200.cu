@@ -7,6 +7,7 @@
 #include "../../include/bcm3b200.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
 #include <cstdarg>
@@ -49,6 +50,9 @@ struct Shard {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<double> time, obs_t, dose, interval, dac, dct, values, block_partial, partial, diag_conc, diag_ll;
+	DevBuf<unsigned long long> rank_keys, rank_keys_sorted; // [C][P] (chain, ka) sort keys
+	DevBuf<int> rank_patients, order;                        // [C][P] patient indices before / after the sort
+	DevBuf<unsigned char> sort_temp;
 	DevBuf<int32_t> intermittent, simulate_until, diag_counters;
 	DevBuf<uint32_t> skipped;
 	double* h_partial = nullptr; // pinned [3][C]
@@ -85,6 +89,8 @@ struct Handle {
 	// options / stats
 	bool diagnostics = false;
 	int block_size = 0;
+	bool sort_patients = true;                    // option "sort_patients"
+	long long sort_min_systems = 148ll * 2 * 384; // option "sort_min_systems": rank patients when P * C reaches this
 	int64_t total_launches = 0, last_launches = 0, num_evaluations = 0;
 	double last_kernel_ms = 0;
 };
@@ -293,6 +299,28 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 		a.tr[k] = h->tr[k];
 	}
 	a.block_partial = s->block_partial.p;
+	a.order = nullptr;
+	// large batches: rank every chain's patients by absorption rate first (see poppk_kernel)
+	if (h->sort_patients && (long long)s->P * (long long)C >= h->sort_min_systems && s->P > 0) {
+		const size_t n = (size_t)s->P * C;
+		CUDA_TRY(s->rank_keys.ensure(n));
+		CUDA_TRY(s->rank_keys_sorted.ensure(n));
+		CUDA_TRY(s->rank_patients.ensure(n));
+		CUDA_TRY(s->order.ensure(n));
+		poppk_rank_kernel<<<dim3((s->P + 255) / 256, (unsigned)C), 256, 0, stream>>>(a, (int)C, s->rank_keys.p, s->rank_patients.p);
+		CUDA_TRY(cudaGetLastError());
+		int chain_bits = 1;
+		while (((size_t)1 << chain_bits) < C) chain_bits++;
+		size_t temp_bytes = 0;
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, s->rank_keys.p, s->rank_keys_sorted.p, s->rank_patients.p, s->order.p, (int)n, 0,
+		                                         32 + chain_bits, stream));
+		CUDA_TRY(s->sort_temp.ensure(temp_bytes ? temp_bytes : 1));
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->sort_temp.p, temp_bytes, s->rank_keys.p, s->rank_keys_sorted.p, s->rank_patients.p, s->order.p, (int)n, 0,
+		                                         32 + chain_bits, stream));
+		a.order = s->order.p;
+		h->last_launches += 1; // + the library's sort passes
+		h->total_launches += 1;
+	}
 	a.diag_conc = nullptr;
 	a.diag_ll = nullptr;
 	a.diag_counters = nullptr;
@@ -787,6 +815,8 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 		return BCM3B200_OK;
 	}
 	if (!strcmp(name, "diagnostics")) h->diagnostics = value != 0;
+	else if (!strcmp(name, "sort_patients")) h->sort_patients = value != 0;
+	else if (!strcmp(name, "sort_min_systems")) h->sort_min_systems = value;
 	else if (!strcmp(name, "block_size")) {
 		if (value != 0 && (value < 32 || value > 384 || value % 32 != 0)) return fail(BCM3B200_ERR_ARG, "block_size must be 0 or a multiple of 32 up to 384");
 		h->block_size = (int)value;

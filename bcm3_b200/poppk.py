@@ -21,7 +21,9 @@ class PopPKEvaluator:
     """Owns one ``bcm3b200`` handle for a PopPKProblem (optionally a contiguous shard of its patients)."""
 
     def __init__(self, problem: PopPKProblem, device: int = 0, device_count: int = 1, shard_rank: int = 0,
-                 shard_count: int = 1, diagnostics: bool = False, block_size: int = 0):
+                 shard_count: int = 1, diagnostics: bool = False, block_size: int = 0, sort_patients: bool | None = None):
+        """sort_patients: None = the library's policy (rank each chain's patients by absorption rate for large batches),
+        True = always, False = never."""
         self.lib = _lib.load()
         self.problem = problem
         tr = problem.trial
@@ -46,6 +48,10 @@ class PopPKEvaluator:
                 self.set_option("diagnostics", 1)
             if block_size:
                 self.set_option("block_size", block_size)
+            if sort_patients is not None:
+                self.set_option("sort_patients", int(sort_patients))
+                if sort_patients:
+                    self.set_option("sort_min_systems", 0)
             _lib.check(self.lib.bcm3b200_finalize(self.handle))
         except Exception:
             self.close()

@@ -198,3 +198,32 @@ def test_full_size_properties(Evaluator, port, pk, P, C):
         assert np.abs(d["patient_ll"][cs][:, sub] - want["patient_ll"]).max() < 1e-2
         assert rel_err(d["patient_ll"][cs][:, sub].sum(axis=1), want["logp"]).max() <= LOGP_RTOL
     ev.close()
+
+
+@pytest.mark.parametrize("name", ["poppk_two_hetero", "poppk_one_hetero", "poppk_one_maxsteps"])
+def test_ranking_patients_by_absorption_rate_does_not_change_results(Evaluator, name):
+    """Large batches integrate each chain's patients in order of ka (rank kernel + radix sort) so that the lanes of a warp
+    take similar numbers of steps; the per-patient results are the same, only the summation order changes."""
+    prob, gold = load_golden(name)
+    out = {}
+    for flag in (True, False):
+        ev = Evaluator(prob, sort_patients=flag, diagnostics=True)
+        logp, _ = ev.evaluate(gold["values"])
+        out[flag] = (logp, ev.diagnostics()["patient_ll"])
+        ev.close()
+    assert rel_err(out[True][0], gold["logp"]).max() <= LOGP_RTOL
+    assert np.array_equal(out[True][1], out[False][1], equal_nan=True)   # per-patient terms bit-identical
+    assert rel_err(out[True][0], out[False][0]).max() < 1e-12
+
+
+def test_ranked_large_batch_matches_the_cpu_checker(Evaluator, port):
+    """Above the library's own threshold (P * C >= 113 664 systems) the ranking is on by default."""
+    prob = syn.make_poppk_problem(PK_TWO, P=7200, T=10, t_end=72.0, seed=33, heterogeneous=True, missing_fraction=0.05)
+    vals = syn.make_chain_values(prob, 16, seed=33)
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    launches = ev.get_stat("last_kernel_launches")
+    ev.close()
+    want = port.poppk_evaluate(prob, vals, threads=8)["logp"]
+    assert launches == 3  # rank kernel + integrator + chain reduce (the sort passes are the library's)
+    assert (status == 0).all() and rel_err(logp, want).max() <= LOGP_RTOL
