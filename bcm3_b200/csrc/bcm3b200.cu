@@ -126,15 +126,15 @@ int get_int(const std::map<std::string, std::string>& kv, const char* key, int d
 int pick_block_size(const Handle& h, const Shard& s, size_t C)
 {
 	if (h.block_size) return h.block_size;
-	// Large batches: one block of 384 threads (12 warps) per SM at 168 registers per thread -- the cold part of the
-	// integrator state lives in shared memory (bdf_thread.cuh) -- with the warps of the block running the integrator in
-	// lock-step (BCM3_BLOCK_LOCKSTEP) so that they share instruction fetches: the hot loop is several times larger than
-	// the 32 KB instruction cache, and three independent blocks of 128 measured 3% slower than one block of 384.
-	// Small batches are latency-bound: spread them over as many SMs as possible with small blocks.
+	// Large batches: 12 warps per SM at 168 registers per thread -- the cold part of the integrator state lives in shared
+	// memory (bdf_thread.cuh) -- with the warps of a block running the integrator in lock-step (BCM3_BLOCK_LOCKSTEP) so that
+	// they share instruction fetches (the hot loop is several times larger than the 32 KB instruction cache). With the
+	// patients ranked by absorption rate the blocks are homogeneous in step count, and three blocks of 128 threads per SM
+	// (264.0 ms at config 5) schedule slightly better than one block of 384 (268.9 ms); unranked it was the other way round
+	// (355.7 vs 345.7 ms). Small batches are latency-bound: spread them over as many SMs as possible with small blocks.
 	int dev_sms = 148;
 	cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s.device);
 	size_t threads = (size_t)s.P * C;
-	if (threads >= (size_t)dev_sms * 2 * 384) return 384;
 	if (threads >= (size_t)dev_sms * 2 * 128) return 128;
 	if (threads >= (size_t)dev_sms * 2 * 64) return 64;
 	return 32;
