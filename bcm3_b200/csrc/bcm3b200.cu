@@ -83,6 +83,7 @@ struct Handle {
 	bool finalized = false;
 	double rtol = 0, atol = 0, mol_weight = 0;
 	int npk = 4;
+	int named_a_ix = -1, named_b_ix = -1; // n_transit / biphasic_uptake_time, mean_transit_time / mean_absorption2
 	int tr[SV_COUNT];
 	int ix[SV_COUNT];
 	std::vector<std::unique_ptr<Shard>> shards;
@@ -151,7 +152,11 @@ int finalize(Handle* h)
 	}
 	h->mol_weight = molecular_weight(h->drug);
 	if (std::isnan(h->mol_weight)) return fail(BCM3B200_ERR_ARG, "Unknown drug \"%s\"", h->drug.c_str());
-	h->npk = (h->pk_type == PK_ONE) ? 4 : 6;
+	static const int npk_of_type[6] = { 4, 6, 7, 7, 6, 8 }; // cpp:99-120 (7 for both biphasic types, as in the reference)
+	h->npk = npk_of_type[h->pk_type];
+	if (h->pk_type >= PK_ONE_BIPHASIC && (h->named_a_ix < 0 || h->named_b_ix < 0 || h->named_a_ix >= h->nvar || h->named_b_ix >= h->nvar))
+		return fail(BCM3B200_ERR_ARG, h->pk_type >= PK_ONE_TRANSIT ? "transit models need n_transit_ix and mean_transit_time_ix"
+		                                                           : "biphasic models need biphasic_uptake_time_ix and mean_absorption2_ix");
 	if (h->nvar != h->npk + 2 * (P + 1) + 2) return fail(BCM3B200_ERR_ARG, "Incorrect number of variables in prior"); // cpp:127-130
 	if (h->sd_ix < 0 || h->sd_ix + 1 >= h->nvar) return fail(BCM3B200_ERR_ARG, "sd_ix out of range");
 
@@ -164,7 +169,8 @@ int finalize(Handle* h)
 	const std::vector<double>& transforms = h->data["transforms"];
 
 	// chain-level variable indices (positional, cpp:267-272,283-286) and their transforms
-	const int ix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, h->npk + 0, h->npk + 1, h->sd_ix, h->sd_ix + 1 };
+	const int named_a = h->named_a_ix >= 0 ? h->named_a_ix : 0, named_b = h->named_b_ix >= 0 ? h->named_b_ix : 0;
+	const int ix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, h->npk + 0, h->npk + 1, h->sd_ix, h->sd_ix + 1, named_a, named_b };
 	for (int k = 0; k < SV_COUNT; k++) {
 		h->ix[k] = ix[k];
 		h->tr[k] = (int)transforms[ix[k]];
@@ -336,8 +342,9 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 
 	// s_time [T], s_sim [T][block], then the integrator's thread-private state columns [slots][stride]
 	if (block > 384) return fail(BCM3B200_ERR_ARG, "block_size above 384 is not supported");
-	const int stride = block <= 128 ? 128 : block <= 256 ? 256 : 384;
-	const int slots = (h->pk_type == PK_ONE) ? (int)BdfSlots<2>::COUNT : (int)BdfSlots<3>::COUNT;
+	const int stride = block <= 128 ? 128 : 384; // the two instantiations of the state-column stride
+	const bool two_cmt = (h->pk_type == PK_TWO || h->pk_type == PK_TWO_BIPHASIC || h->pk_type == PK_TWO_TRANSIT);
+	const int slots = two_cmt ? (int)BdfSlots<3>::COUNT : (int)BdfSlots<2>::COUNT;
 	const size_t smem_bytes = sizeof(double) * ((size_t)h->T + (size_t)h->T * block + (size_t)slots * stride);
 	if (smem_bytes > 200 * 1024) return fail(BCM3B200_ERR_UNSUPPORTED, "too many timepoints (%d) for block size %d", h->T, block);
 	dim3 grid(nblk, (unsigned)C);
@@ -353,16 +360,22 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 #define LAUNCH(MODEL, DIAGV)                                                                                          \
 	do {                                                                                                              \
 		if (stride == 128) LAUNCH_S(MODEL, DIAGV, 128);                                                               \
-		else if (stride == 256) LAUNCH_S(MODEL, DIAGV, 256);                                                          \
 		else LAUNCH_S(MODEL, DIAGV, 384);                                                                             \
 	} while (0)
-	if (h->pk_type == PK_ONE) {
-		if (h->diagnostics) LAUNCH(PkOneModel, true);
-		else LAUNCH(PkOneModel, false);
-	} else {
-		if (h->diagnostics) LAUNCH(PkTwoModel, true);
-		else LAUNCH(PkTwoModel, false);
+#define LAUNCH_D(MODEL)                        \
+	do {                                       \
+		if (h->diagnostics) LAUNCH(MODEL, true); \
+		else LAUNCH(MODEL, false);               \
+	} while (0)
+	switch (h->pk_type) {
+	case PK_ONE: LAUNCH_D(PkOneModel); break;
+	case PK_TWO: LAUNCH_D(PkTwoModel); break;
+	case PK_ONE_BIPHASIC: LAUNCH_D(PkOneBiphasicModel); break;
+	case PK_TWO_BIPHASIC: LAUNCH_D(PkTwoBiphasicModel); break;
+	case PK_ONE_TRANSIT: LAUNCH_D(PkOneTransitModel); break;
+	default: LAUNCH_D(PkTwoTransitModel); break;
 	}
+#undef LAUNCH_D
 #undef LAUNCH
 #undef LAUNCH_S
 	CUDA_TRY(cudaGetLastError());
@@ -534,7 +547,18 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 	const std::string type = kv.count("type") ? kv["type"] : "";
 	if (type == "one") h->pk_type = PK_ONE;
 	else if (type == "two") h->pk_type = PK_TWO;
-	else return fail(BCM3B200_ERR_UNSUPPORTED, "pk_model type \"%s\" is not supported (one, two)", type.c_str());
+	else if (type == "one_biphasic_uptake") h->pk_type = PK_ONE_BIPHASIC;
+	else if (type == "two_biphasic_uptake") h->pk_type = PK_TWO_BIPHASIC;
+	else if (type == "one_transit") h->pk_type = PK_ONE_TRANSIT;
+	else if (type == "two_transit") h->pk_type = PK_TWO_TRANSIT;
+	else return fail(BCM3B200_ERR_UNSUPPORTED, "Unknown PK model type \"%s\"", type.c_str()); // cpp:84-87
+	if (h->pk_type == PK_ONE_TRANSIT || h->pk_type == PK_TWO_TRANSIT) {
+		h->named_a_ix = get_int(kv, "n_transit_ix", -1);
+		h->named_b_ix = get_int(kv, "mean_transit_time_ix", -1);
+	} else if (h->pk_type == PK_ONE_BIPHASIC || h->pk_type == PK_TWO_BIPHASIC) {
+		h->named_a_ix = get_int(kv, "biphasic_uptake_time_ix", -1);
+		h->named_b_ix = get_int(kv, "mean_absorption2_ix", -1);
+	}
 	h->drug = kv.count("drug") ? kv["drug"] : "";
 	bool hasP, hasT, hasN, hasS;
 	h->P = get_int(kv, "num_patients", 0, &hasP);
@@ -640,7 +664,7 @@ int bcm3b200_finalize(void* handle)
 static int upload_and_launch(Handle* h, Shard* s, size_t C, size_t num_variables, const double* values, double* d_partial,
                              cudaStream_t stream)
 {
-	static const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9 };
+	static const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 };
 	const int SH = 16;
 	const size_t stride = SH + 2 * (size_t)s->P;
 	CUDA_TRY(s->values.ensure(C * stride));

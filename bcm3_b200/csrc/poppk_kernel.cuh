@@ -31,7 +31,9 @@
 
 namespace bcm3b200 {
 
-enum : int { PK_ONE = 0, PK_TWO = 1 };
+// pk_model type=, LikelihoodPopPKTrajectory.cpp:69-83
+enum : int { PK_ONE = 0, PK_TWO = 1, PK_ONE_BIPHASIC = 2, PK_TWO_BIPHASIC = 3, PK_ONE_TRANSIT = 4, PK_TWO_TRANSIT = 5 };
+enum : int { PKV_PLAIN = 0, PKV_BIPHASIC = 1, PKV_TRANSIT = 2 };
 enum : int { TR_NONE = 0, TR_LOG = 1, TR_LOG10 = 2, TR_LOGIT = 3 };
 
 // indices into PkArgs::ix / PkArgs::tr (the chain-level entries of the variable vector)
@@ -46,6 +48,8 @@ enum : int {
 	SV_SIGMA_CLEARANCE,     // values[npk + 1]
 	SV_SD,                  // values[sd_ix]
 	SV_SD2,                 // values[sd_ix + 1]
+	SV_NAMED_A,             // by name: n_transit (transit types) / biphasic_uptake_time (biphasic types), cpp:296-310
+	SV_NAMED_B,             // by name: mean_transit_time / mean_absorption2
 	SV_COUNT
 };
 
@@ -115,41 +119,65 @@ __device__ __forceinline__ double logpdf_tnu4(double x, double mu, double sigma)
 	return -0.9808292530117262 - 2.5 * log1p(0.25 * xn * xn) - log(sigma);
 }
 
-// RHS / Jacobian: LikelihoodPopPKTrajectory.cpp:446-467 (one), :469-494 (two)
-struct PkOneModel {
-	static constexpr int N = 2;
+// RHS / Jacobian of the six model types: LikelihoodPopPKTrajectory.cpp:446-467 (one), :469-494 (two), :496-571 (biphasic
+// uptake: the absorption rate switches between k_absorption and k_absorption2 at the discontinuities), :573-642 (transit:
+// no bolus, a gamma-shaped input k_tr * (k_tr s)^n e^(-k_tr s) / n! * dose into the depot, s = time since the last dose,
+// n! by Stirling's series exactly as the reference writes it).
+template <int NN, int VARIANT_>
+struct PkModel {
+	static constexpr int N = NN;
+	static constexpr int VARIANT = VARIANT_;
 	double ka, kex, kel, kf, kb;
-	__device__ __forceinline__ void rhs(double, const double (&y)[2], double (&f)[2]) const
+	// biphasic: ka2, switch flag; transit: k_transit, n_transit, log n!, last treatment time, the patient's doses
+	double ka2, k_transit, n_transit, log_n_factorial, last_treatment, dose, dose_after, dose_change_time;
+	bool biphasic_switch;
+
+	__device__ __forceinline__ double current_ka() const
 	{
-		f[0] = -(ka + kex) * y[0];
-		f[1] = ka * y[0] - kel * y[1];
+		if (VARIANT == PKV_BIPHASIC) return biphasic_switch ? ka : ka2;
+		return ka;
 	}
-	__device__ __forceinline__ void jac(double (&A)[4]) const
+	__device__ __forceinline__ void rhs(double t, const double (&y)[NN], double (&f)[NN]) const
 	{
-		A[0 * 2 + 0] = -(ka + kex);
-		A[1 * 2 + 0] = ka;
-		A[1 * 2 + 1] = -kel;
+		const double k = current_ka();
+		if (VARIANT == PKV_TRANSIT) {
+			double d = dose;
+			if (t >= dose_change_time) d = dose_after;
+			const double s = t - last_treatment;
+			double transit = exp((n_transit * log(k_transit * s) - k_transit * s) - log_n_factorial);
+			transit = k_transit * transit * d;
+			f[0] = transit - (k + kex) * y[0];
+		} else {
+			f[0] = -(k + kex) * y[0];
+		}
+		if (NN == 2) {
+			f[1] = k * y[0] - kel * y[1];
+		} else {
+			f[1] = k * y[0] - kel * y[1] - kf * y[1] + kb * y[2];
+			f[2] = kf * y[1] - kb * y[2];
+		}
+	}
+	__device__ __forceinline__ void jac(double (&A)[NN * NN]) const
+	{
+		const double k = current_ka();
+		A[0 * NN + 0] = -(k + kex);
+		A[1 * NN + 0] = k;
+		if (NN == 2) {
+			A[1 * NN + 1] = -kel;
+		} else {
+			A[1 * NN + 1] = -(kel + kf);
+			A[1 * NN + 2] = kb;
+			A[2 * NN + 1] = kf;
+			A[2 * NN + 2] = -kb;
+		}
 	}
 };
-struct PkTwoModel {
-	static constexpr int N = 3;
-	double ka, kex, kel, kf, kb;
-	__device__ __forceinline__ void rhs(double, const double (&y)[3], double (&f)[3]) const
-	{
-		f[0] = -(ka + kex) * y[0];
-		f[1] = ka * y[0] - kel * y[1] - kf * y[1] + kb * y[2];
-		f[2] = kf * y[1] - kb * y[2];
-	}
-	__device__ __forceinline__ void jac(double (&A)[9]) const
-	{
-		A[0 * 3 + 0] = -(ka + kex);
-		A[1 * 3 + 0] = ka;
-		A[1 * 3 + 1] = -(kel + kf);
-		A[1 * 3 + 2] = kb;
-		A[2 * 3 + 1] = kf;
-		A[2 * 3 + 2] = -kb;
-	}
-};
+typedef PkModel<2, PKV_PLAIN> PkOneModel;
+typedef PkModel<3, PKV_PLAIN> PkTwoModel;
+typedef PkModel<2, PKV_BIPHASIC> PkOneBiphasicModel;
+typedef PkModel<3, PKV_BIPHASIC> PkTwoBiphasicModel;
+typedef PkModel<2, PKV_TRANSIT> PkOneTransitModel;
+typedef PkModel<3, PKV_TRANSIT> PkTwoTransitModel;
 
 // LikelihoodPopPKTrajectory::CheckGiveTreatment, cpp:644-671
 __device__ __forceinline__ bool check_give_treatment(double t, uint32_t skipped_days, int intermittent)
@@ -235,6 +263,14 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 		model.ka = fastpow10(quantile_normal(pp.x, vrow[a.ix[SV_MEAN_ABSORPTION]], vrow[a.ix[SV_SIGMA_ABSORPTION]]));
 		model.kel = fastpow10(quantile_normal(pp.y, vrow[a.ix[SV_MEAN_CLEARANCE]], vrow[a.ix[SV_SIGMA_CLEARANCE]])) / k_vod;
 		conversion = a.conv_base / k_vod;
+		model.ka2 = model.k_transit = model.n_transit = model.log_n_factorial = model.last_treatment = 0.0;
+		model.biphasic_switch = true;
+		if (Model::VARIANT == PKV_TRANSIT) { // cpp:296-301
+			model.n_transit = transform_variable(a.tr[SV_NAMED_A], vrow[a.ix[SV_NAMED_A]]);
+			model.k_transit = (model.n_transit + 1) / transform_variable(a.tr[SV_NAMED_B], vrow[a.ix[SV_NAMED_B]]);
+			model.log_n_factorial = 0.9189385332046727 + (model.n_transit + 0.5) * log(model.n_transit) - model.n_transit + log(1 + 1 / (12.0 * model.n_transit));
+		}
+		if (Model::VARIANT == PKV_BIPHASIC) model.ka2 = transform_variable(a.tr[SV_NAMED_B], vrow[a.ix[SV_NAMED_B]]); // cpp:308-309
 	}
 
 #if BCM3_SORT_BLOCK_PATIENTS
@@ -282,6 +318,12 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 		skipped = a.skipped_days[jl];
 		ntp = a.simulate_until[jl];
 	}
+	model.dose = dose;
+	model.dose_after = dose_after;
+	model.dose_change_time = dose_change_time;
+	// biphasic: the switching time is clipped just below the dosing interval (cpp:304-306)
+	double biphasic_switch_time = 0.0;
+	if (Model::VARIANT == PKV_BIPHASIC) biphasic_switch_time = fmin(transform_variable(a.tr[SV_NAMED_A], vrow[a.ix[SV_NAMED_A]]), dosing_interval - 1e-2);
 
 	// ---- K1: ODESolver::SolveReturnSolution + ODESolverCVODE::Solve ----
 	BdfThread<N, Model, DIAG, STRIDE> S;
@@ -293,7 +335,7 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 	int tpi = 0;
 	int current_step = 0;
 	double y[N];
-	y[0] = dose; // initial_conditions, cpp:366-373
+	y[0] = (Model::VARIANT == PKV_TRANSIT) ? 0.0 : dose; // initial_conditions, cpp:366-373
 #pragma unroll
 	for (int i = 1; i < N; i++) y[i] = 0.0;
 
@@ -313,6 +355,10 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 	// SetDiscontinuity(dosing_interval, TreatmentCallback), cpp:362-363 (ignored for time <= 0, ODESolver.cpp:62-71)
 	double current_dose_time = dosing_interval;
 	double next_disc = (dosing_interval > 0.0) ? dosing_interval : NAN;
+	if (Model::VARIANT == PKV_BIPHASIC) { // cpp:357-360: first discontinuity = the switch to the second absorption phase
+		current_dose_time = 0.0;
+		next_disc = (biphasic_switch_time > 0.0) ? biphasic_switch_time : NAN;
+	}
 	S.tstopset = !isnan(next_disc);
 	S.tstop() = next_disc;
 
@@ -384,13 +430,29 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 
 		// TreatmentCallback (cpp:673-690), then CVodeReInit(t, y) + CVodeSetStopTime at the top of the loop
 		if (!done && seg_end) {
-			current_dose_time += dosing_interval;
-			if (check_give_treatment(t, skipped, intermittent)) {
+			if (Model::VARIANT != PKV_BIPHASIC) {
+				current_dose_time += dosing_interval;
+				if (check_give_treatment(t, skipped, intermittent)) {
+					double d = dose;
+					if (t >= dose_change_time) d = dose_after;
+					if (Model::VARIANT == PKV_TRANSIT) model.last_treatment = t;
+					else y[0] = y[0] + d;
+				}
+				next_disc = current_dose_time;
+			} else if (model.biphasic_switch) { // TreatmentCallbackBiphasic, cpp:692-718
+				model.biphasic_switch = false;
+				current_dose_time += dosing_interval;
+				next_disc = current_dose_time;
+			} else if (check_give_treatment(t, skipped, intermittent)) {
 				double d = dose;
 				if (t >= dose_change_time) d = dose_after;
 				y[0] = y[0] + d;
+				model.biphasic_switch = true;
+				next_disc = current_dose_time + biphasic_switch_time;
+			} else {
+				current_dose_time += dosing_interval;
+				next_disc = current_dose_time;
 			}
-			next_disc = current_dose_time;
 			if (!isnan(next_disc) && next_disc < INFINITY) {
 				S.tstop() = next_disc;
 				S.tstopset = true;

@@ -44,9 +44,24 @@ bool LikelihoodPopPKTrajectoryB200::PostInitialize()
 		last_error = "Could not find variable \"standard_deviation\"";
 		return false;
 	}
-	const std::string desc = "type=" + pk_type_str + ";drug=" + drug + ";num_patients=" + std::to_string(P) + ";num_timepoints=" +
-	                         std::to_string(T) + ";num_variables=" + std::to_string(nvar) + ";sd_ix=" + std::to_string(sdix) +
-	                         ";device=" + std::to_string(device0);
+	std::string desc = "type=" + pk_type_str + ";drug=" + drug + ";num_patients=" + std::to_string(P) + ";num_timepoints=" +
+	                   std::to_string(T) + ";num_variables=" + std::to_string(nvar) + ";sd_ix=" + std::to_string(sdix) +
+	                   ";device=" + std::to_string(device0);
+	// the variables the variants look up by name (cpp:296-310)
+	auto named = [&](const char* variable, const char* key) {
+		const size_t ix = varset->GetVariableIndex(variable);
+		if (ix == std::numeric_limits<size_t>::max()) {
+			last_error = std::string("Could not find variable \"") + variable + "\"";
+			return false;
+		}
+		desc += std::string(";") + key + "=" + std::to_string(ix);
+		return true;
+	};
+	if (pk_type_str == "one_transit" || pk_type_str == "two_transit") {
+		if (!named("n_transit", "n_transit_ix") || !named("mean_transit_time", "mean_transit_time_ix")) return false;
+	} else if (pk_type_str == "one_biphasic_uptake" || pk_type_str == "two_biphasic_uptake") {
+		if (!named("biphasic_uptake_time", "biphasic_uptake_time_ix") || !named("mean_absorption2", "mean_absorption2_ix")) return false;
+	}
 	if (bcm3b200_create("pop_pk_trajectory", desc.data(), desc.size(), num_devices, &handle) != BCM3B200_OK) {
 		last_error = bcm3b200_last_error();
 		return false;

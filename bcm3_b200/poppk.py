@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .poppk_data import PK_ONE, PopPKProblem
+from .poppk_data import PK_ONE, PK_TYPE_NAMES, PopPKProblem
 
 NUM_COUNTERS = 8
 
@@ -28,9 +28,13 @@ class PopPKEvaluator:
         self.problem = problem
         tr = problem.trial
         P, T = tr.num_patients, tr.num_timepoints
-        desc = (f"type={'one' if problem.pk_type == PK_ONE else 'two'};drug={tr.drug};num_patients={P};num_timepoints={T};"
+        desc = (f"type={PK_TYPE_NAMES[problem.pk_type]};drug={tr.drug};num_patients={P};num_timepoints={T};"
                 f"num_variables={problem.num_variables};sd_ix={problem.sd_ix};max_steps={problem.max_steps};"
-                f"shard_rank={shard_rank};shard_count={shard_count};device={device}").encode()
+                f"shard_rank={shard_rank};shard_count={shard_count};device={device}")
+        for name in ("n_transit_ix", "mean_transit_time_ix", "biphasic_uptake_time_ix", "mean_absorption2_ix"):
+            if getattr(problem, name) >= 0:
+                desc += f";{name}={getattr(problem, name)}"
+        desc = desc.encode()
         h = C.c_void_p()
         _lib.check(self.lib.bcm3b200_create(b"pop_pk_trajectory", desc, len(desc), device_count, C.byref(h)))
         self.handle = h

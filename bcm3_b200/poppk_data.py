@@ -16,7 +16,25 @@ import numpy as np
 # pk_model type= strings, LikelihoodPopPKTrajectory.cpp:69-83
 PK_ONE = 0
 PK_TWO = 1
-PK_TYPES = {"one": PK_ONE, "two": PK_TWO}
+PK_ONE_BIPHASIC = 2
+PK_TWO_BIPHASIC = 3
+PK_ONE_TRANSIT = 4
+PK_TWO_TRANSIT = 5
+PK_TYPES = {"one": PK_ONE, "two": PK_TWO, "one_biphasic_uptake": PK_ONE_BIPHASIC, "two_biphasic_uptake": PK_TWO_BIPHASIC,
+            "one_transit": PK_ONE_TRANSIT, "two_transit": PK_TWO_TRANSIT}
+PK_TYPE_NAMES = {v: k for k, v in PK_TYPES.items()}
+
+
+def is_two_compartment(pk_type: int) -> bool:
+    return pk_type in (PK_TWO, PK_TWO_BIPHASIC, PK_TWO_TRANSIT)
+
+
+def is_biphasic(pk_type: int) -> bool:
+    return pk_type in (PK_ONE_BIPHASIC, PK_TWO_BIPHASIC)
+
+
+def is_transit(pk_type: int) -> bool:
+    return pk_type in (PK_ONE_TRANSIT, PK_TWO_TRANSIT)
 
 # VariableSet transforms, src/sampler/VariableSet.cpp:97-124
 TRANSFORM_NONE = 0
@@ -38,8 +56,9 @@ F32_1E_6 = float(np.float32(1e-6))  # the reference passes the float literal 1e-
 
 
 def num_pk_params(pk_type: int) -> int:
-    """cpp:99-104"""
-    return 4 if pk_type == PK_ONE else 6
+    """cpp:99-120, as the reference has them (7 for BOTH biphasic types: the two-compartment one has no free slot for its
+    second named variable, which therefore has to alias another variable)."""
+    return {PK_ONE: 4, PK_TWO: 6, PK_ONE_BIPHASIC: 7, PK_TWO_BIPHASIC: 7, PK_ONE_TRANSIT: 6, PK_TWO_TRANSIT: 8}[pk_type]
 
 
 @dataclass
@@ -77,6 +96,11 @@ class PopPKProblem:
     fixed_periphery_fwd: float = math.nan
     fixed_periphery_bwd: float = math.nan
     max_steps: int = 2000  # ODESolverCVODE.cpp:45
+    # variables the variants look up by NAME (cpp:296-310): their indices in the variable vector
+    n_transit_ix: int = -1
+    mean_transit_time_ix: int = -1
+    biphasic_uptake_time_ix: int = -1
+    mean_absorption2_ix: int = -1
     # derived
     simulate_until: np.ndarray = field(init=False)
     skipped_days: np.ndarray = field(init=False)
@@ -95,6 +119,10 @@ class PopPKProblem:
         self.transforms = np.ascontiguousarray(self.transforms, dtype=np.int32)
         if self.transforms.shape[0] != expected:
             raise ValueError("Incorrect number of variables in prior")  # cpp:127-130
+        if is_transit(self.pk_type) and (self.n_transit_ix < 0 or self.mean_transit_time_ix < 0):
+            raise ValueError('transit models need the variables "n_transit" and "mean_transit_time"')
+        if is_biphasic(self.pk_type) and (self.biphasic_uptake_time_ix < 0 or self.mean_absorption2_ix < 0):
+            raise ValueError('biphasic models need the variables "biphasic_uptake_time" and "mean_absorption2"')
         if fixed:
             # the reference indexes the variable vector positionally (cpp:267-272) even when
             # a parameter is fixed in likelihood.xml; only the all-sampled layout is supported here

@@ -13,7 +13,14 @@ import numpy as np
 
 from .poppk_data import (
     PK_ONE,
+    PK_ONE_BIPHASIC,
+    PK_ONE_TRANSIT,
     PK_TWO,
+    PK_TWO_BIPHASIC,
+    PK_TWO_TRANSIT,
+    is_biphasic,
+    is_transit,
+    is_two_compartment,
     TRANSFORM_LOG10,
     TRANSFORM_NONE,
     PopPKProblem,
@@ -28,9 +35,28 @@ LN10 = 2.3025850929940459
 def population_defaults(pk_type: int) -> dict:
     """Population-level parameters of the synthetic configs (SURVEY.md 8d cfg 2/5)."""
     d = dict(mu_logka=0.1, log_kex=-1.3, mu_logcl=0.9, log_vd=1.7, sigma_ka=0.3, sigma_cl=0.3, log_sd=0.0, log_sd2=math.log10(0.2))
-    if pk_type == PK_TWO:
+    if is_two_compartment(pk_type):
         d.update(log_kf=-0.5, log_kb=-1.0)
+    if is_biphasic(pk_type):
+        d.update(log_uptake_time=0.3, log_ka2=-0.5)
+    if is_transit(pk_type):
+        d.update(log_n_transit=0.5, log_transit_time=0.3)
     return d
+
+
+def named_variable_indices(pk_type: int) -> dict:
+    """Where the synthetic prior puts the variables the variants look up by name (cpp:296-310). The reference counts 7
+    "pk params" for BOTH biphasic types (cpp:105-110), so the two-compartment one has a single free slot: its
+    mean_absorption2 aliases variable 1 (the excretion rate) here."""
+    if pk_type == PK_ONE_BIPHASIC:
+        return dict(biphasic_uptake_time_ix=4, mean_absorption2_ix=5)
+    if pk_type == PK_TWO_BIPHASIC:
+        return dict(biphasic_uptake_time_ix=6, mean_absorption2_ix=1)
+    if pk_type == PK_ONE_TRANSIT:
+        return dict(n_transit_ix=4, mean_transit_time_ix=5)
+    if pk_type == PK_TWO_TRANSIT:
+        return dict(n_transit_ix=6, mean_transit_time_ix=7)
+    return {}
 
 
 def poppk_transforms(pk_type: int, P: int) -> np.ndarray:
@@ -42,9 +68,11 @@ def poppk_transforms(pk_type: int, P: int) -> np.ndarray:
     tr = np.zeros(nvar, dtype=np.int32)
     tr[1] = TRANSFORM_LOG10
     tr[3] = TRANSFORM_LOG10
-    if pk_type == PK_TWO:
+    if is_two_compartment(pk_type):
         tr[4] = TRANSFORM_LOG10
         tr[5] = TRANSFORM_LOG10
+    for ix in named_variable_indices(pk_type).values():
+        tr[ix] = TRANSFORM_LOG10
     tr[nvar - 2] = TRANSFORM_LOG10
     tr[nvar - 1] = TRANSFORM_LOG10
     return tr
@@ -65,11 +93,11 @@ def exact_linear_pk(pk_type, ka, kex, kel, kf, kb, dose, dosing_interval, times,
     P = ka.shape[0]
     if P == 0:
         return np.zeros((0, np.asarray(times).shape[0]))
-    N = 2 if pk_type == PK_ONE else 3
+    N = 3 if is_two_compartment(pk_type) else 2
     A = np.zeros((P, N, N))
     A[:, 0, 0] = -(ka + kex)
     A[:, 1, 0] = ka
-    if pk_type == PK_ONE:
+    if N == 2:
         A[:, 1, 1] = -kel
     else:
         A[:, 1, 1] = -(kel + kf)
@@ -148,7 +176,7 @@ def make_poppk_problem(pk_type: int = PK_ONE, P: int = 1000, T: int = 10, t_end:
                        dose_after_dose_change=dac, dose_change_time=dct, intermittent=intermittent,
                        treatment_interruptions=interruptions)
     nvar = num_pk_params(pk_type) + 2 * (P + 1) + 2
-    return PopPKProblem(pk_type=pk_type, trial=trial, transforms=poppk_transforms(pk_type, P), sd_ix=nvar - 2)
+    return PopPKProblem(pk_type=pk_type, trial=trial, transforms=poppk_transforms(pk_type, P), sd_ix=nvar - 2, **named_variable_indices(pk_type))
 
 
 def make_chain_values(problem: PopPKProblem, C: int, seed: int = 20261018) -> np.ndarray:
@@ -165,9 +193,18 @@ def make_chain_values(problem: PopPKProblem, C: int, seed: int = 20261018) -> np
         v[1] = pop["log_kex"]
         v[2] = rng.normal(pop["mu_logcl"], 0.1)
         v[3] = pop["log_vd"]
-        if problem.pk_type == PK_TWO:
+        v[4:npk] = 0.0
+        if is_two_compartment(problem.pk_type):
             v[4] = pop["log_kf"]
             v[5] = pop["log_kb"]
+        named = named_variable_indices(problem.pk_type)
+        if is_biphasic(problem.pk_type):
+            v[named["biphasic_uptake_time_ix"]] = rng.normal(pop["log_uptake_time"], 0.05)
+            if named["mean_absorption2_ix"] >= 4:
+                v[named["mean_absorption2_ix"]] = rng.normal(pop["log_ka2"], 0.05)
+        if is_transit(problem.pk_type):
+            v[named["n_transit_ix"]] = rng.normal(pop["log_n_transit"], 0.05)
+            v[named["mean_transit_time_ix"]] = rng.normal(pop["log_transit_time"], 0.05)
         v[npk + 0] = pop["sigma_ka"]
         v[npk + 1] = pop["sigma_cl"]
         v[npk + 2: npk + 2 + 2 * P] = rng.uniform(0.02, 0.98, 2 * P)

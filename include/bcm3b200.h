@@ -41,8 +41,11 @@ extern "C" {
  *                "pop_pk_trajectory" | "cell_population" (keys of the latter: see DESIGN.md section 9)
  *   model_desc : `key=value;...` text, desc_bytes long (no terminator needed). Keys for pop_pk_trajectory
  *                mirror the <pk_model> attributes (LikelihoodPopPKTrajectory.cpp:58-87) plus sizes:
- *                  type=one|two  drug=<name>  num_patients=<P>  num_timepoints=<T>
+ *                  type=one|two|one_biphasic_uptake|two_biphasic_uptake|one_transit|two_transit  drug=<name>
+ *                  num_patients=<P>  num_timepoints=<T>
  *                  num_variables=<nvar>  sd_ix=<index of "standard_deviation">  [max_steps=2000]
+ *                  transit types:  n_transit_ix= mean_transit_time_ix=   (indices of the variables of those names,
+ *                  biphasic types: biphasic_uptake_time_ix= mean_absorption2_ix=    cpp:296-310)
  *                  [shard_rank=0] [shard_count=1]   contiguous slice of patients owned by this handle
  *                  [device=0]                       first CUDA device ordinal
  *   device_count: number of CUDA devices (device .. device+device_count-1) this handle spreads its patients

@@ -47,6 +47,10 @@ class _PopPKProblem(C.Structure):
         ("skipped_days", C.c_void_p),
         ("simulate_until", C.c_void_p),
         ("transforms", C.c_void_p),
+        ("n_transit_ix", C.c_int32),
+        ("mean_transit_time_ix", C.c_int32),
+        ("biphasic_uptake_time_ix", C.c_int32),
+        ("mean_absorption2_ix", C.c_int32),
     ]
 
 
@@ -153,6 +157,8 @@ class Oracle:
             dose_change_time=keep["dct"].ctypes.data, intermittent=keep["inter"].ctypes.data,
             skipped_days=keep["skipped"].ctypes.data, simulate_until=keep["su"].ctypes.data,
             transforms=keep["transforms"].ctypes.data,
+            n_transit_ix=problem.n_transit_ix, mean_transit_time_ix=problem.mean_transit_time_ix,
+            biphasic_uptake_time_ix=problem.biphasic_uptake_time_ix, mean_absorption2_ix=problem.mean_absorption2_ix,
         )
         logp = np.empty(nC, dtype=np.float64)
         conc = np.empty((nC, P, T), dtype=np.float64) if want_conc else None

@@ -24,6 +24,13 @@ extern "C" {
 /* pk_type values; reference enum EPKModelType, LikelihoodPopPKTrajectory.h */
 #define ORACLE_PK_ONE 0 /* "one": N=2, LikelihoodPopPKTrajectory.cpp:446-467 */
 #define ORACLE_PK_TWO 1 /* "two": N=3, LikelihoodPopPKTrajectory.cpp:469-494 */
+#define ORACLE_PK_ONE_BIPHASIC 2 /* "one_biphasic_uptake", cpp:496-529 */
+#define ORACLE_PK_TWO_BIPHASIC 3 /* "two_biphasic_uptake", cpp:531-571 */
+#define ORACLE_PK_ONE_TRANSIT 4  /* "one_transit", cpp:573-604 */
+#define ORACLE_PK_TWO_TRANSIT 5  /* "two_transit", cpp:606-642 */
+#define ORACLE_PK_IS_TWO(t) ((t) == ORACLE_PK_TWO || (t) == ORACLE_PK_TWO_BIPHASIC || (t) == ORACLE_PK_TWO_TRANSIT)
+#define ORACLE_PK_IS_BIPHASIC(t) ((t) == ORACLE_PK_ONE_BIPHASIC || (t) == ORACLE_PK_TWO_BIPHASIC)
+#define ORACLE_PK_IS_TRANSIT(t) ((t) == ORACLE_PK_ONE_TRANSIT || (t) == ORACLE_PK_TWO_TRANSIT)
 
 /* transform codes; reference VariableSet::TransformVariable, VariableSet.cpp:97-124 */
 #define ORACLE_TRANSFORM_NONE 0
@@ -56,6 +63,8 @@ typedef struct {
 	const uint32_t* skipped_days;         /* [P] bit d set = day d skipped (29 days) */
 	const int32_t* simulate_until;        /* [P] number of leading timepoints simulated */
 	const int32_t* transforms;            /* [nvar] ORACLE_TRANSFORM_* */
+	/* variables the variants look up by name (cpp:296-310); -1 when the model type does not use them */
+	int32_t n_transit_ix, mean_transit_time_ix, biphasic_uptake_time_ix, mean_absorption2_ix;
 } oracle_poppk_problem;
 
 /* per-(chain, patient) solver counters, summed over the restarts of one solve */

@@ -96,8 +96,56 @@ typedef struct {
 	unsigned intermittent;
 	uint32_t skipped_days;
 	double k_absorption, k_excretion, k_elimination, k_vod, k_periphery_fwd, k_periphery_bwd;
+	double k_transit, n_transit, k_biphasic_switch_time, k_absorption2, last_treatment;
+	int biphasic_switch;
+	int two, biphasic, transit; /* model type flags */
 	double current_dose_time;
 } patient_data;
+
+/* CalculateDerivative_* of the biphasic-uptake and transit types, cpp:496-642 (the plain types keep their own functions) */
+static int rhs_variant(double t, const double* y, double* dydt, void* user)
+{
+	const patient_data* pd = (const patient_data*)user;
+	double ka = pd->k_absorption;
+	if (pd->biphasic && !pd->biphasic_switch) ka = pd->k_absorption2;
+	if (pd->transit) {
+		double dose = pd->dose;
+		if (t >= pd->dose_change_time) dose = pd->dose_after_dose_change;
+		double t_since_treatment = t - pd->last_treatment;
+		double log_n_transit_factorial = 0.9189385332046727 + (pd->n_transit + 0.5) * log(pd->n_transit) - pd->n_transit + log(1 + 1 / (12.0 * pd->n_transit));
+		double transit = exp((pd->n_transit * log(pd->k_transit * t_since_treatment) - pd->k_transit * t_since_treatment) - log_n_transit_factorial);
+		transit = pd->k_transit * transit * dose;
+		dydt[0] = transit - (ka + pd->k_excretion) * y[0];
+	} else {
+		dydt[0] = -(ka + pd->k_excretion) * y[0];
+	}
+	if (!pd->two) {
+		dydt[1] = ka * y[0] - pd->k_elimination * y[1];
+	} else {
+		dydt[1] = ka * y[0] - pd->k_elimination * y[1] - pd->k_periphery_fwd * y[1] + pd->k_periphery_bwd * y[2];
+		dydt[2] = pd->k_periphery_fwd * y[1] - pd->k_periphery_bwd * y[2];
+	}
+	return 0;
+}
+static int jac_variant(double t, const double* y, const double* fy, double* J, void* user)
+{
+	const patient_data* pd = (const patient_data*)user;
+	(void)t; (void)y; (void)fy;
+	double ka = pd->k_absorption;
+	if (pd->biphasic && !pd->biphasic_switch) ka = pd->k_absorption2;
+	const int N = pd->two ? 3 : 2;
+	J[0 + 0 * N] = -(ka + pd->k_excretion);
+	J[1 + 0 * N] = ka;
+	if (!pd->two) {
+		J[1 + 1 * N] = -pd->k_elimination;
+	} else {
+		J[1 + 1 * N] = -(pd->k_elimination + pd->k_periphery_fwd);
+		J[1 + 2 * N] = pd->k_periphery_bwd;
+		J[2 + 1 * N] = pd->k_periphery_fwd;
+		J[2 + 2 * N] = -pd->k_periphery_bwd;
+	}
+	return 0;
+}
 
 /* cpp:446-455 */
 static int rhs_one(double t, const double* y, double* dydt, void* user)
@@ -188,6 +236,7 @@ static int solve_patient(bdf_mem* m, patient_data* pd, int N, const double* y0, 
 	/* cpp:362-363: SetDiscontinuity(dosing_interval, ...) is ignored for time <= 0 (ODESolver.cpp:62-71);
 	 * the stale value of a previous solve would be used by the reference -- not reproduced, inputs keep interval > 0 */
 	double next_disc = pd->dosing_interval > 0.0 ? pd->dosing_interval : NAN;
+	if (pd->biphasic) next_disc = pd->k_biphasic_switch_time > 0.0 ? pd->k_biphasic_switch_time : NAN; /* cpp:357-360 */
 
 	double y[BDF_NMAX];
 	for (int i = 0; i < N; i++) y[i] = y0[i];
@@ -226,15 +275,32 @@ static int solve_patient(bdf_mem* m, patient_data* pd, int N, const double* y0, 
 		}
 
 		if (!isnan(next_disc) && (result == BDF_TSTOP_RETURN || next_disc == t)) {
-			/* TreatmentCallback, cpp:673-690 */
 			if (cnt) add_counters(m, cnt);
-			pd->current_dose_time += pd->dosing_interval;
-			if (check_give_treatment(t, pd)) {
+			if (!pd->biphasic) {
+				/* TreatmentCallback, cpp:673-690 */
+				pd->current_dose_time += pd->dosing_interval;
+				if (check_give_treatment(t, pd)) {
+					double dose = pd->dose;
+					if (t >= pd->dose_change_time) dose = pd->dose_after_dose_change;
+					if (pd->transit) pd->last_treatment = t;
+					else y[0] = y[0] + dose;
+				}
+				next_disc = pd->current_dose_time;
+			} else if (pd->biphasic_switch) {
+				/* TreatmentCallbackBiphasic, cpp:692-718 */
+				pd->biphasic_switch = 0;
+				pd->current_dose_time += pd->dosing_interval;
+				next_disc = pd->current_dose_time;
+			} else if (check_give_treatment(t, pd)) {
 				double dose = pd->dose;
 				if (t >= pd->dose_change_time) dose = pd->dose_after_dose_change;
 				y[0] = y[0] + dose;
+				pd->biphasic_switch = 1;
+				next_disc = pd->current_dose_time + pd->k_biphasic_switch_time;
+			} else {
+				pd->current_dose_time += pd->dosing_interval;
+				next_disc = pd->current_dose_time;
 			}
-			next_disc = pd->current_dose_time;
 			bdf_reinit(m, t, y);
 			if (!isnan(next_disc) && next_disc < INFINITY) bdf_set_stop_time(m, next_disc);
 		}
@@ -247,15 +313,21 @@ static void evaluate_chain(const oracle_poppk_problem* pr, const double* values,
                            double* patient_ll, int64_t* counters)
 {
 	const int P = pr->num_patients, T = pr->num_timepoints;
-	const int two = pr->pk_type == ORACLE_PK_TWO;
+	const int two = ORACLE_PK_IS_TWO(pr->pk_type);
+	const int biphasic = ORACLE_PK_IS_BIPHASIC(pr->pk_type), transit = ORACLE_PK_IS_TRANSIT(pr->pk_type);
 	const int N = two ? 3 : 2;
-	const size_t npk = two ? 6 : 4;
+	static const size_t pk_params_of_type[6] = { 4, 6, 7, 7, 6, 8 }; /* cpp:99-120 */
+	const size_t npk = pk_params_of_type[pr->pk_type];
 	const int report_all = conc || patient_ll || counters;
 
 	patient_data pd;
 	memset(&pd, 0, sizeof(pd));
+	pd.two = two;
+	pd.biphasic = biphasic;
+	pd.transit = transit;
 	bdf_mem* m = (bdf_mem*)malloc(sizeof(bdf_mem));
-	bdf_create(m, N, two ? rhs_two : rhs_one, two ? jac_two : jac_one, &pd);
+	if (biphasic || transit) bdf_create(m, N, rhs_variant, jac_variant, &pd);
+	else bdf_create(m, N, two ? rhs_two : rhs_one, two ? jac_two : jac_one, &pd);
 	double atolv[3] = { pr->atol, pr->atol, pr->atol };
 	bdf_set_tolerances(m, pr->rtol, atolv);
 
@@ -294,9 +366,20 @@ static void evaluate_chain(const oracle_poppk_problem* pr, const double* values,
 				pd.k_periphery_bwd = pr->fixed_periphery_bwd;
 			}
 		}
-		pd.current_dose_time = pd.dosing_interval;
+		if (transit) { /* cpp:296-301 */
+			pd.n_transit = transform_variable(pr->transforms[pr->n_transit_ix], values[pr->n_transit_ix]);
+			pd.k_transit = (pd.n_transit + 1) / transform_variable(pr->transforms[pr->mean_transit_time_ix], values[pr->mean_transit_time_ix]);
+		}
+		if (biphasic) { /* cpp:302-310 */
+			pd.k_biphasic_switch_time = transform_variable(pr->transforms[pr->biphasic_uptake_time_ix], values[pr->biphasic_uptake_time_ix]);
+			if (pd.dosing_interval - 1e-2 < pd.k_biphasic_switch_time) pd.k_biphasic_switch_time = pd.dosing_interval - 1e-2;
+			pd.k_absorption2 = transform_variable(pr->transforms[pr->mean_absorption2_ix], values[pr->mean_absorption2_ix]);
+		}
+		pd.last_treatment = 0.0;
+		pd.biphasic_switch = 1;                                   /* cpp:358 */
+		pd.current_dose_time = biphasic ? 0.0 : pd.dosing_interval; /* cpp:359-362 */
 
-		double y0[3] = { pd.dose, 0.0, 0.0 };
+		double y0[3] = { transit ? 0.0 : pd.dose, 0.0, 0.0 }; /* cpp:366-373 */
 		double conversion = (1e6 / pr->mol_weight) / pd.k_vod;
 		int ntp = pr->simulate_until[j];
 
@@ -360,7 +443,7 @@ int oracle_poppk_evaluate(const oracle_poppk_problem* prob, size_t num_chains, c
                           double* conc, double* patient_ll, int64_t* counters, int num_threads)
 {
 	if (!prob || !values || !logp) return -1;
-	if (prob->pk_type != ORACLE_PK_ONE && prob->pk_type != ORACLE_PK_TWO) return -2;
+	if (prob->pk_type < ORACLE_PK_ONE || prob->pk_type > ORACLE_PK_TWO_TRANSIT) return -2;
 	if (num_threads < 1) num_threads = 1;
 	if ((size_t)num_threads > num_chains) num_threads = (int)num_chains;
 	size_t next = 0;

@@ -131,6 +131,8 @@ struct ParallelData {
 	unsigned int intermittent;
 	uint32_t skipped_days;
 	double k_absorption, k_excretion, k_elimination, k_vod, k_periphery_fwd, k_periphery_bwd;
+	double k_transit, n_transit, k_biphasic_switch_time, k_absorption2, last_treatment;
+	bool biphasic_switch;
 	double current_dose_time;
 	ProbedSolver* solver;
 	int64_t* counters; // may be null
@@ -161,8 +163,10 @@ void EvaluateChain(const oracle_poppk_problem& pr, const double* values, double*
 {
 	const int P = pr.num_patients;
 	const int T = pr.num_timepoints;
-	const bool two = pr.pk_type == ORACLE_PK_TWO;
-	const size_t num_pk_params = two ? 6 : 4;
+	const bool two = ORACLE_PK_IS_TWO(pr.pk_type);
+	const bool biphasic = ORACLE_PK_IS_BIPHASIC(pr.pk_type), transit = ORACLE_PK_IS_TRANSIT(pr.pk_type);
+	static const size_t pk_params_of_type[6] = { 4, 6, 7, 7, 6, 8 }; // cpp:99-120
+	const size_t num_pk_params = pk_params_of_type[pr.pk_type];
 	const size_t num_pk_pop_params = 2;
 	const bool report_all = conc || patient_ll || counters;
 
@@ -170,53 +174,82 @@ void EvaluateChain(const oracle_poppk_problem& pr, const double* values, double*
 	ProbedSolver solver;
 	pd.solver = &solver;
 
-	ODESolver::TDeriviativeFunction deriv;
-	ODESolver::TJacobianFunction jac;
-	if (!two) {
-		deriv = [&pd](OdeReal t, const OdeReal* y, OdeReal* dydt, void*) {
-			dydt[0] = -(pd.k_absorption + pd.k_excretion) * y[0];
-			dydt[1] = pd.k_absorption * y[0] - pd.k_elimination * y[1];
-			return true;
-		};
-		jac = [&pd](OdeReal t, const OdeReal* y, const OdeReal* dydt, OdeMatrixReal& jac, void*) {
-			jac(0, 0) = -(pd.k_absorption + pd.k_excretion);
-			jac(1, 0) = pd.k_absorption;
-			jac(1, 1) = -pd.k_elimination;
-			return true;
-		};
-	} else {
-		deriv = [&pd](OdeReal t, const OdeReal* y, OdeReal* dydt, void*) {
-			dydt[0] = -(pd.k_absorption + pd.k_excretion) * y[0];
-			dydt[1] = pd.k_absorption * y[0] - pd.k_elimination * y[1] - pd.k_periphery_fwd * y[1] + pd.k_periphery_bwd * y[2];
+	// CalculateDerivative_* / CalculateJacobian_* of all six model types (cpp:446-642): the biphasic types switch the
+	// absorption rate, the transit types replace the bolus by a gamma-shaped input into the depot
+	ODESolver::TDeriviativeFunction deriv = [&pd, two, biphasic, transit](OdeReal t, const OdeReal* y, OdeReal* dydt, void*) {
+		double ka = pd.k_absorption;
+		if (biphasic && !pd.biphasic_switch) ka = pd.k_absorption2;
+		double input = 0.0;
+		if (transit) {
+			Real dose = pd.dose;
+			if (t >= pd.dose_change_time) dose = pd.dose_after_dose_change;
+			Real t_since_treatment = t - pd.last_treatment;
+			Real log_n_transit_factorial = 0.9189385332046727 + (pd.n_transit + 0.5) * log(pd.n_transit) - pd.n_transit + log(1 + 1 / (12.0 * pd.n_transit));
+			Real tr = exp((pd.n_transit * log(pd.k_transit * t_since_treatment) - pd.k_transit * t_since_treatment) - log_n_transit_factorial);
+			input = pd.k_transit * tr * dose;
+		}
+		if (transit) dydt[0] = input - (ka + pd.k_excretion) * y[0];
+		else dydt[0] = -(ka + pd.k_excretion) * y[0];
+		if (!two) {
+			dydt[1] = ka * y[0] - pd.k_elimination * y[1];
+		} else {
+			dydt[1] = ka * y[0] - pd.k_elimination * y[1] - pd.k_periphery_fwd * y[1] + pd.k_periphery_bwd * y[2];
 			dydt[2] = pd.k_periphery_fwd * y[1] - pd.k_periphery_bwd * y[2];
-			return true;
-		};
-		jac = [&pd](OdeReal t, const OdeReal* y, const OdeReal* dydt, OdeMatrixReal& jac, void*) {
-			jac(0, 0) = -(pd.k_absorption + pd.k_excretion);
-			jac(1, 0) = pd.k_absorption;
+		}
+		return true;
+	};
+	ODESolver::TJacobianFunction jac = [&pd, two, biphasic](OdeReal t, const OdeReal* y, const OdeReal* dydt, OdeMatrixReal& jac, void*) {
+		double ka = pd.k_absorption;
+		if (biphasic && !pd.biphasic_switch) ka = pd.k_absorption2;
+		jac(0, 0) = -(ka + pd.k_excretion);
+		jac(1, 0) = ka;
+		if (!two) {
+			jac(1, 1) = -pd.k_elimination;
+		} else {
 			jac(1, 1) = -(pd.k_elimination + pd.k_periphery_fwd);
 			jac(1, 2) = pd.k_periphery_bwd;
 			jac(2, 1) = pd.k_periphery_fwd;
 			jac(2, 2) = -pd.k_periphery_bwd;
-			return true;
-		};
-	}
+		}
+		return true;
+	};
 	solver.SetDerivativeFunction(deriv);
 	solver.SetJacobianFunction(jac);
 	solver.Initialize(two ? 3 : 2, NULL, 0);
 	solver.SetSolverParameter("max_steps", pr.max_steps, 0.0);
 	solver.SetTolerance(pr.rtol, pr.atol);
 
-	ODESolver::TDiscontinuityCallback treatment_cb = [&pd](OdeReal t, void*) -> Real {
+	ODESolver::TDiscontinuityCallback treatment_cb = [&pd, transit](OdeReal t, void*) -> Real {
 		// LikelihoodPopPKTrajectory::TreatmentCallback, cpp:673-690 (called right before CVodeReInit)
 		if (pd.counters) pd.solver->AccumulateCounters(pd.counters);
 		pd.current_dose_time += pd.dosing_interval;
 		if (CheckGiveTreatment(t, pd)) {
 			double dose = pd.dose;
 			if (t >= pd.dose_change_time) dose = pd.dose_after_dose_change;
-			pd.solver->set_current_y(0, pd.solver->get_current_y(0) + dose);
+			if (transit) pd.last_treatment = t;
+			else pd.solver->set_current_y(0, pd.solver->get_current_y(0) + dose);
 		}
 		return pd.current_dose_time;
+	};
+	ODESolver::TDiscontinuityCallback treatment_cb_biphasic = [&pd](OdeReal t, void*) -> Real {
+		// LikelihoodPopPKTrajectory::TreatmentCallbackBiphasic, cpp:692-718
+		if (pd.counters) pd.solver->AccumulateCounters(pd.counters);
+		if (pd.biphasic_switch) {
+			pd.biphasic_switch = false;
+			pd.current_dose_time += pd.dosing_interval;
+			return pd.current_dose_time;
+		} else {
+			if (CheckGiveTreatment(t, pd)) {
+				double dose = pd.dose;
+				if (t >= pd.dose_change_time) dose = pd.dose_after_dose_change;
+				pd.solver->set_current_y(0, pd.solver->get_current_y(0) + dose);
+				pd.biphasic_switch = true;
+				return pd.current_dose_time + pd.k_biphasic_switch_time;
+			} else {
+				pd.current_dose_time += pd.dosing_interval;
+				return pd.current_dose_time;
+			}
+		}
 	};
 
 	Eigen::Map<const OdeVectorReal> time(pr.time, T);
@@ -260,12 +293,29 @@ void EvaluateChain(const oracle_poppk_problem& pr, const double* values, double*
 			}
 		}
 
-		pd.current_dose_time = pd.dosing_interval;
-		solver.SetDiscontinuity(pd.dosing_interval, treatment_cb, nullptr);
+		if (transit) { // cpp:296-301
+			pd.n_transit = TransformVariable(pr.transforms[pr.n_transit_ix], values[pr.n_transit_ix]);
+			pd.k_transit = (pd.n_transit + 1) / TransformVariable(pr.transforms[pr.mean_transit_time_ix], values[pr.mean_transit_time_ix]);
+		}
+		if (biphasic) { // cpp:302-310
+			pd.k_biphasic_switch_time = TransformVariable(pr.transforms[pr.biphasic_uptake_time_ix], values[pr.biphasic_uptake_time_ix]);
+			pd.k_biphasic_switch_time = std::min(pd.k_biphasic_switch_time, pd.dosing_interval - 1e-2);
+			pd.k_absorption2 = TransformVariable(pr.transforms[pr.mean_absorption2_ix], values[pr.mean_absorption2_ix]);
+		}
+		pd.last_treatment = 0.0;
+
+		if (biphasic) { // cpp:357-364
+			pd.biphasic_switch = true;
+			pd.current_dose_time = 0;
+			solver.SetDiscontinuity(pd.k_biphasic_switch_time, treatment_cb_biphasic, nullptr);
+		} else {
+			pd.current_dose_time = pd.dosing_interval;
+			solver.SetDiscontinuity(pd.dosing_interval, treatment_cb, nullptr);
+		}
 
 		OdeVectorReal initial_conditions(two ? 3 : 2);
 		initial_conditions.setZero();
-		initial_conditions[0] = pd.dose;
+		initial_conditions[0] = transit ? 0.0 : pd.dose; // cpp:366-373
 
 		double conversion = (1e6 / pr.mol_weight) / pd.k_vod;
 
@@ -317,7 +367,7 @@ extern "C" int oracle_poppk_evaluate(const oracle_poppk_problem* prob, size_t nu
                                      double* logp, double* conc, double* patient_ll, int64_t* counters, int num_threads)
 {
 	if (!prob || !values || !logp) return -1;
-	if (prob->pk_type != ORACLE_PK_ONE && prob->pk_type != ORACLE_PK_TWO) return -2;
+	if (prob->pk_type < ORACLE_PK_ONE || prob->pk_type > ORACLE_PK_TWO_TRANSIT) return -2;
 	const size_t P = (size_t)prob->num_patients, T = (size_t)prob->num_timepoints, nvar = (size_t)prob->num_variables;
 	if (num_threads < 1) num_threads = 1;
 	if ((size_t)num_threads > num_chains) num_threads = (int)num_chains;

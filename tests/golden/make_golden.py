@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 
 import oracle  # noqa: E402
 from bcm3_b200 import synthetic as syn  # noqa: E402
-from bcm3_b200.poppk_data import PK_ONE, PK_TWO  # noqa: E402
+from bcm3_b200.poppk_data import PK_ONE, PK_ONE_BIPHASIC, PK_ONE_TRANSIT, PK_TWO, PK_TWO_BIPHASIC, PK_TWO_TRANSIT  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -28,6 +28,11 @@ CASES = {
     "poppk_two_hetero": (PK_TWO, 96, 12, 120.0, True, 0.15, 3, 14),
     # long horizon: some patients exceed max_steps = 2000 => -inf (ODESolverCVODE.cpp:440-446)
     "poppk_one_maxsteps": (PK_ONE, 32, 8, 600.0, True, 0.0, 2, 15),
+    # the variants of LikelihoodPopPKTrajectory.cpp:496-642, 692-718
+    "poppk_one_biphasic": (PK_ONE_BIPHASIC, 64, 10, 96.0, True, 0.1, 3, 16),
+    "poppk_two_biphasic": (PK_TWO_BIPHASIC, 64, 10, 96.0, True, 0.1, 3, 17),
+    "poppk_one_transit": (PK_ONE_TRANSIT, 64, 10, 96.0, True, 0.1, 3, 18),
+    "poppk_two_transit": (PK_TWO_TRANSIT, 64, 10, 96.0, True, 0.1, 3, 19),
 }
 
 
@@ -37,12 +42,17 @@ def problem_arrays(prob):
         pk_type=np.int32(prob.pk_type), drug=np.array(tr.drug), time=tr.time, observed_concentration=tr.observed_concentration,
         dose=tr.dose, dosing_interval=tr.dosing_interval, dose_after_dose_change=tr.dose_after_dose_change,
         dose_change_time=tr.dose_change_time, intermittent=tr.intermittent, treatment_interruptions=tr.treatment_interruptions,
-        transforms=prob.transforms, sd_ix=np.int32(prob.sd_ix))
+        transforms=prob.transforms, sd_ix=np.int32(prob.sd_ix), n_transit_ix=np.int32(prob.n_transit_ix),
+        mean_transit_time_ix=np.int32(prob.mean_transit_time_ix), biphasic_uptake_time_ix=np.int32(prob.biphasic_uptake_time_ix),
+        mean_absorption2_ix=np.int32(prob.mean_absorption2_ix))
 
 
 def main():
     ref = oracle.load("ref")
+    only = sys.argv[1:]
     for name, (pk, P, T, t_end, het, miss, C, seed) in CASES.items():
+        if only and name not in only:
+            continue
         prob = syn.make_poppk_problem(pk, P=P, T=T, t_end=t_end, heterogeneous=het, missing_fraction=miss, seed=seed)
         if name.endswith("hetero"):
             # exercise simulate_until: day-1 interruption => only the first day; late first observation => nothing

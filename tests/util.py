@@ -17,7 +17,8 @@ def load_golden(name):
         dosing_interval=z["dosing_interval"], dose_after_dose_change=z["dose_after_dose_change"],
         dose_change_time=z["dose_change_time"], intermittent=z["intermittent"],
         treatment_interruptions=z["treatment_interruptions"])
-    prob = PopPKProblem(pk_type=int(z["pk_type"]), trial=trial, transforms=z["transforms"], sd_ix=int(z["sd_ix"]))
+    named = {k: int(z[k]) for k in ("n_transit_ix", "mean_transit_time_ix", "biphasic_uptake_time_ix", "mean_absorption2_ix") if k in z.files}
+    prob = PopPKProblem(pk_type=int(z["pk_type"]), trial=trial, transforms=z["transforms"], sd_ix=int(z["sd_ix"]), **named)
     return prob, {k: z[k] for k in ("values", "logp", "conc", "patient_ll", "counters")}
 
 
