@@ -54,6 +54,7 @@ struct CpArgs {
 	int32_t* cell_status; // [C][num_cells] 1 = ok, 0 = solver failure
 	int32_t* cell_steps;  // [C][num_cells] or null
 	int debug_report;     // 0: cell_steps = accepted steps; 1: RHS evaluations (nfe); 2: linear setups; 3: Jacobian evaluations
+	const int32_t* cell_order; // [num_cells] or null: the order in which the group kernel hands out this shard's cells
 };
 
 #ifdef __CUDACC__

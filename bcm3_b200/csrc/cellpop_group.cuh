@@ -124,6 +124,9 @@ __device__ __noinline__ void rhs_eval(unsigned y_off, int j, double yj, unsigned
 #ifndef CP_GROUP_LOCKSTEP
 #define CP_GROUP_LOCKSTEP 1
 #endif
+#ifndef CP_GROUP_BATCHED
+#define CP_GROUP_BATCHED 1
+#endif
 #ifndef CP_GROUP_STATIC_LU_MAX
 #define CP_GROUP_STATIC_LU_MAX 0
 #endif
@@ -1173,6 +1176,24 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 
 #pragma unroll 1
 	for (;;) {
+#if CP_GROUP_BATCHED
+		// A warp takes its next CPW items together, when all of its groups are idle. The items of a chain are handed out in
+		// `cell_order` (cells sorted along a space-filling curve through their quasi-random variability vectors), so the
+		// cells that share a warp have nearly the same parameters, start in the same trip and take nearly the same
+		// step-size, order, Newton and setup decisions in the same trips: the lanes of the warp diverge far less.
+		unsigned long long w = ~0ull;
+		bool fetched = false;
+		if (!exhausted && !__any_sync(FULL, have)) {
+			unsigned long long base = 0;
+			if (lane == 0) base = atomicAdd(queue, (unsigned long long)CPW);
+			base = __shfl_sync(FULL, base, 0);
+			w = base + (unsigned long long)gw;
+			fetched = true;
+			if ((long long)(base + CPW) >= total) exhausted = true; // the queue only grows: nothing left after this batch
+		}
+		if (fetched && (long long)w < total) {
+			{
+#else
 		if (!have && !exhausted) {
 			// ---- next item + K0: Cell::Initialize (Cell.cpp:150-191) ----
 			unsigned long long w = 0;
@@ -1181,8 +1202,10 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 			if ((long long)w >= total) {
 				exhausted = true;
 			} else {
+#endif
 				c = (int)(w / (unsigned long long)a.num_cells);
 				cell = (int)(w % (unsigned long long)a.num_cells);
+				if (a.cell_order) cell = a.cell_order[cell];
 				const double* tv = a.transformed + (long long)c * a.nvar;
 				B.tv = tv;
 				// per-cell parameter overrides: start from the chain's values (CP_OVERRIDE_INIT fills S.params.ov[]), apply the

@@ -10,6 +10,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <fstream>
 #include <sstream>
@@ -56,7 +57,7 @@ struct CellPopState {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<double> d_ic, d_const, d_nonsampled, d_sobol, d_time, d_obs, d_values, d_transformed, d_cellvals, d_avg, d_logp;
-	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail, d_cov_ix;
+	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail, d_cov_ix, d_cell_order;
 	DevBuf<double> d_cov_fixed, d_chol;
 	bool diagnostics = false;
 	int last_C = 0;
@@ -416,6 +417,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	o << "#define CP_GROUP_WARPS " << gwarps << "\n";
 	o << "#define CP_GROUP_MIN_BLOCKS " << gblocks << "\n";
 	if (const char* lenv = getenv("BCM3B200_CELLPOP_GROUP_LOCKSTEP")) o << "#define CP_GROUP_LOCKSTEP " << atoi(lenv) << "\n";
+	if (const char* benv2 = getenv("BCM3B200_CELLPOP_GROUP_BATCHED")) o << "#define CP_GROUP_BATCHED " << atoi(benv2) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
 	o << code << "\n";
@@ -576,6 +578,32 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	CUDA_TRY(cp.d_transforms.ensure(cp.nvar ? cp.nvar : 1));
 	CUDA_TRY(cudaMemcpy(cp.d_transforms.p, tr.data(), sizeof(int32_t) * cp.nvar, cudaMemcpyHostToDevice));
 
+	// Order in which the group kernel hands out this shard's cells: along a Morton (Z-order) curve through the first three
+	// coordinates of their quasi-random variability vectors, so that consecutive cells -- the ones that share a warp --
+	// have nearly the same per-cell parameters. Results do not depend on the order (every cell writes its own column of
+	// cell_values, which is reduced in cell order afterwards).
+	a.cell_order = nullptr;
+	if (cp.D > 0 && cp.cells_local > 1 && !getenv("BCM3B200_CELLPOP_NO_ORDER")) {
+		const std::vector<double>& sob = cp.data["sobol"];
+		const int dims = cp.D < 3 ? cp.D : 3;
+		std::vector<std::pair<uint32_t, int32_t>> keyed(cp.cells_local);
+		for (int i = 0; i < cp.cells_local; i++) {
+			uint32_t key = 0;
+			for (int d = 0; d < dims; d++) {
+				double u = sob[(size_t)(cp.cell_offset + i) * cp.D + d];
+				uint32_t qv = (uint32_t)(u < 0.0 ? 0.0 : (u >= 1.0 ? 1023.0 : u * 1024.0));
+				if (qv > 1023u) qv = 1023u;
+				for (int b = 0; b < 10; b++) key |= ((qv >> b) & 1u) << (b * dims + d);
+			}
+			keyed[i] = { key, (int32_t)i };
+		}
+		std::sort(keyed.begin(), keyed.end());
+		std::vector<int32_t> order(cp.cells_local);
+		for (int i = 0; i < cp.cells_local; i++) order[i] = keyed[i].second;
+		CUDA_TRY(cp.d_cell_order.ensure(order.size()));
+		CUDA_TRY(cudaMemcpy(cp.d_cell_order.p, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice));
+		a.cell_order = cp.d_cell_order.p;
+	}
 	a.num_cells = cp.cells_local;
 	a.cell_offset = cp.cell_offset;
 	a.nvar = cp.nvar;
