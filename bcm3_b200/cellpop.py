@@ -26,6 +26,8 @@ class CellPopEvaluator:
             obs_species="+".join(str(s) for s in p.obs_species), device=device, compile_only=int(compile_only),
             shard_rank=shard_rank, shard_count=shard_count)
         kv["variability_distribution"] = p.variability_distribution
+        if p.treatment_species is not None:
+            kv["treatment_species"] = p.treatment_species
         for name in ("entry_time", "stdev", "offset", "scale", "proportional_stdev"):
             ix = getattr(p, name + "_ix")
             if ix is not None:
@@ -43,6 +45,8 @@ class CellPopEvaluator:
             self._set("timepoints", p.timepoints)
             self._set("observed", p.observed)
             self._set("transforms", p.transforms)
+            if p.treatment_species is not None and len(p.treatment_times):
+                self._set("treatment_times", np.asarray(p.treatment_times, dtype=np.float64))
             if p.variability_dim:
                 self._set("sobol", np.asarray(p.sobol, dtype=np.float64).reshape(p.num_cells, p.variability_dim))
                 self._set("variability", p.variability_rows())

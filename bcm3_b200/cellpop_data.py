@@ -54,6 +54,10 @@ class CellPopProblem:
     variability: list[Variability] = field(default_factory=list)
     variability_distribution: str = "diagonal_gaussian"   # or "full_gaussian" (VariabilityDescription.cpp:50-139)
     covariance: list = field(default_factory=list)        # full_gaussian: D (D - 1) / 2 entries, each a variable index (int) or a fixed float
+    # one <treatment_trajectory type="pulses" species_name= times="t1,t2,..."/> (TreatmentTrajectoryPulses.cpp): index of the
+    # CONSTANT species it drives and the pulse times; None = no treatment
+    treatment_species: int | None = None
+    treatment_times: np.ndarray = field(default_factory=lambda: np.zeros(0))
     entry_time_ix: int | None = None
     entry_time: float = 0.0
     error_model: str = "normal"

@@ -508,6 +508,7 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		else if (em == "proportional_normal") cp->error_model = CP_ERR_PROPORTIONAL_NORMAL;
 		else if (em == "additive_proportional_normal") cp->error_model = CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL;
 		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4, proportional_normal, additive_proportional_normal)", em.c_str());
+		cp->treatment_species = get_int(kv, "treatment_species", -1);
 		cp->prop_stdev_ix = get_int(kv, "proportional_stdev_ix", -1);
 		cp->prop_stdev_fixed = real("proportional_stdev", 1.0);
 		const std::string vd = kv.count("variability_distribution") ? kv["variability_distribution"] : "diagonal_gaussian";
@@ -599,6 +600,7 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 		else if (n == "transforms") w0 = cp.nvar;
 		else if (n == "variability") { w0 = cp.D; w1 = 6; }
 		else if (n == "variability_covariance") { w0 = (size_t)cp.D * (cp.D - 1) / 2; w1 = 2; }
+		else if (n == "treatment_times") w0 = shape[0]; // any number of pulses
 		else return fail(BCM3B200_ERR_ARG, "unknown data name \"%s\"", name);
 		const int want_ndim = w1 ? 2 : 1;
 		if (ndim != want_ndim || shape[0] != w0 || (w1 && shape[1] != w1)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);

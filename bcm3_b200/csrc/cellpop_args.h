@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #define CP_MAX_VARIABILITY 8
+#define CP_GROUP_SCALARS 33 /* per-cell scalar slots of cellpop_group.cuh before the parameter overrides (enum SC_*) */
 
 // apply types, VariabilityDescriptionVariable.cpp:172-207
 enum {
@@ -55,6 +56,9 @@ struct CpArgs {
 	int32_t* cell_steps;  // [C][num_cells] or null
 	int debug_report;     // 0: cell_steps = accepted steps; 1: RHS evaluations (nfe); 2: linear setups; 3: Jacobian evaluations
 	const int32_t* cell_order; // [num_cells] or null: the order in which the group kernel hands out this shard's cells
+	// one <treatment_trajectory type="pulses"> (TreatmentTrajectoryPulses.cpp): constant species it drives (-1: none)
+	int treatment_species, treatment_num_pulses;
+	const double* treatment_times; // [treatment_num_pulses] sorted
 };
 
 #ifdef __CUDACC__

@@ -68,10 +68,12 @@ constexpr int OFF_SCAL = OFF_PERM + (N + 1) / 2;
 // per-cell scalars that are touched a few times per step at most: kept out of the register file (every lane of the
 // group would hold a copy). Lanes of a group always store identical values, so no synchronisation is involved.
 enum { SC_TAU = 0 /* [1..5] */, SC_HU = 6, SC_SAVED_TQ5, SC_SAVED_T, SC_HSCALE, SC_ETAMAX, SC_CREATION, SC_END, SC_HPRIME, SC_ETA, SC_GAMMAP, SC_CRATE, SC_DELP, SC_ACNRM,
+       SC_TSTOP, SC_NEXT_DISC,
        SC_L /* [0..5] */, SC_TQ = SC_L + 6 /* [1..5] */,
        SC_OV = SC_TQ + 6 /* per-cell parameter overrides */, SC_COUNT = SC_OV + (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1) };
 // Nordsieck columns 2..5, lane-private: element (j, e) of lane lg at OFF_ZNH + ((j - 2) * E + e) * G + lg
 constexpr int OFF_ZNH = OFF_SCAL + SC_COUNT;
+static_assert(SC_OV == CP_GROUP_SCALARS, "cellpop_host.cuh sizes the shared block with CP_GROUP_SCALARS");
 constexpr int REGION_MIN = OFF_ZNH + 4 * E * G;
 constexpr int cell_stride()
 {
@@ -102,6 +104,13 @@ struct ConstVector {
 	const double* p;
 	__device__ __forceinline__ double operator[](int k) const { return __ldg(p + k); }
 };
+// constant species with the one a pulsed treatment drives replaced by its current value (Cell::SetTreatmentConcentration)
+struct ConstSpecies {
+	const double* p;
+	int treat_ix;
+	double treat_value;
+	__device__ __forceinline__ double operator[](int k) const { return (k == treat_ix) ? treat_value : __ldg(p + k); }
+};
 struct SpeciesAt {
 	const double* y;
 	int j;
@@ -114,11 +123,11 @@ struct OutStrided {
 	__device__ __forceinline__ double& operator[](int i) const { return p[i * stride]; }
 };
 __device__ __noinline__ void rhs_eval(unsigned y_off, int j, double yj, unsigned out_off, int out_stride, unsigned ov_off, const double* tv,
-                                      const double* constant_species, const double* non_sampled)
+                                      const double* constant_species, const double* non_sampled, int treat_ix, double treat_value)
 {
 	extern __shared__ double smem_d[];
-	generated_derivative(OutStrided{ smem_d + out_off, out_stride }, SpeciesAt{ smem_d + y_off, j, yj }, ConstVector{ constant_species },
-	                     CellParameters{ tv, smem_d + ov_off }, ConstVector{ non_sampled });
+	generated_derivative(OutStrided{ smem_d + out_off, out_stride }, SpeciesAt{ smem_d + y_off, j, yj },
+	                     ConstSpecies{ constant_species, treat_ix, treat_value }, CellParameters{ tv, smem_d + ov_off }, ConstVector{ non_sampled });
 }
 
 #ifndef CP_GROUP_LOCKSTEP
@@ -168,6 +177,10 @@ struct GroupBdf {
 	const double* non_sampled;
 	const double* tv; // transformed variables of the cell's chain
 	double reltol, abstol, hmin;
+	// pulsed treatment (TreatmentTrajectoryPulses.cpp): constant species it drives (-1: none), sorted pulse times
+	int treat_ix, treat_n;
+	const double* treat_times;
+	bool tstopset;
 
 	__device__ __forceinline__ double& tau(int j) const { return sc[SC_TAU + j]; }
 	__device__ __forceinline__ double& hu() const { return sc[SC_HU]; }
@@ -181,6 +194,48 @@ struct GroupBdf {
 	__device__ __forceinline__ double& crate() const { return sc[SC_CRATE]; }
 	__device__ __forceinline__ double& delp() const { return sc[SC_DELP]; }
 	__device__ __forceinline__ double& acnrm() const { return sc[SC_ACNRM]; }
+	__device__ __forceinline__ double& tstop() const { return sc[SC_TSTOP]; }
+
+	// TreatmentTrajectoryPulses::GetConcentration(t, creation_time), .cpp:21-41
+	__device__ __forceinline__ double treatment_value(double t) const
+	{
+		if (treat_ix < 0) return 0.0;
+		const double global_time = t + sc[SC_CREATION];
+		for (int i = 0; i < treat_n; i++) {
+			const double t_in_pulse = global_time - __ldg(treat_times + i) - 2.0;
+			if (t_in_pulse >= 14.0) continue;
+			else if (t_in_pulse <= 0.0) return 0.0;
+			else if (t_in_pulse < 2.0) return t_in_pulse * 0.5;
+			else if (t_in_pulse < 10.0) return 1.0;
+			else return 1 - (t_in_pulse - 10.0) * 0.25;
+		}
+		return 0.0;
+	}
+	// TreatmentTrajectoryPulses::NextDiscontinuity, .cpp:52-71 (exact comparisons: `time` is a stop time this function returned)
+	__device__ __forceinline__ double next_discontinuity(double time) const
+	{
+		const double creation = sc[SC_CREATION];
+		for (int i = 0; i < treat_n; i++) {
+			const double tp = __ldg(treat_times + i);
+			if (time == tp - creation + 2.0) return tp - creation + 4.0;
+			else if (time == tp - creation + 4.0) return tp - creation + 10.0;
+			else if (time == tp - creation + 10.0) return tp - creation + 14.0;
+			else if (time == tp - creation + 14.0) {
+				if (i < treat_n - 1) return __ldg(treat_times + i + 1) - creation + 2.0;
+				return __longlong_as_double(0x7ff8000000000000ll);
+			}
+		}
+		return __longlong_as_double(0x7ff8000000000000ll);
+	}
+	// Cell::Simulate, Cell.cpp:212-229: the first discontinuity ahead of the cell, NaN if none
+	__device__ __forceinline__ double first_discontinuity() const
+	{
+		const double nan = __longlong_as_double(0x7ff8000000000000ll);
+		if (treat_ix < 0 || treat_n <= 0) return nan;
+		double d = __ldg(treat_times) - sc[SC_CREATION] + 2.0;
+		while (d < 0.0) d = next_discontinuity(d);
+		return (d > 0.0) ? d : nan; // NaN compares false
+	}
 	template <int J>
 	__device__ __forceinline__ double& Z(int e)
 	{
@@ -234,16 +289,17 @@ struct GroupBdf {
 	}
 	// Cell::solver_rhs_fn (Cell.cpp:423-433) at the y held in ybuf: every lane of the group evaluates the whole vector into
 	// fbuf (identical stores) and reads back the components it owns
-	__device__ __forceinline__ void rhs_shared(double (&f)[E])
+	__device__ __forceinline__ void rhs_shared(double t, double (&f)[E])
 	{
-		rhs_eval(region_off + OFF_Y, -1, 0.0, region_off + OFF_F, 1, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled);
+		rhs_eval(region_off + OFF_Y, -1, 0.0, region_off + OFF_F, 1, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled, treat_ix,
+		         treatment_value(t));
 #pragma unroll
 		for (int e = 0; e < E; e++) f[e] = own(e) ? fbuf[idx(e)] : 0.0;
 		nfe++;
 	}
 
-	// CVodeCreate zero state + CVodeReInit(0, y0) + the first-call block of CVode (cvode.c:586-665, 1068-1155)
-	__device__ __forceinline__ bool start(const double (&y0)[E], double tout)
+	// persistent members that CVodeCreate zero-fills once and CVodeReInit never touches
+	__device__ __forceinline__ void create()
 	{
 		static_for<0, 6>([&](auto J) {
 			constexpr int j = decltype(J)::value;
@@ -261,12 +317,27 @@ struct GroupBdf {
 		saved_t() = 0.0; ncf = nef = 0; nflag = bcm3b200::BDF_FIRST_CALL;
 		h = hprime() = 0.0;
 		hscale() = 0.0;
+		tstopset = false;
+		tstop() = 0.0;
+	}
+
+	// CVodeReInit(t0, y0) + the first-call block of CVode(tout, CV_ONE_STEP) (cvode.c:586-665, 1068-1155); a stop time, if
+	// any, has been set by the caller (CVodeSetStopTime). False where CVode returns < 0.
+	__device__ __forceinline__ bool restart(double t0, const double (&y0)[E], double tout_in)
+	{
+		tn = t0; q = 1; L = 2; qwait = 2; etamax() = BDF_ETAMX1; hu() = 0.0; nst = 0; nstlp = 0;
+		nstlj = 0; nls_jcur = false;
 #pragma unroll
 		for (int e = 0; e < E; e++) Z<0>(e) = own(e) ? y0[e] : 0.0;
 		set_ewt();
 		publish(ybuf, zn01[0]);
-		rhs_shared(zn01[1]);
-		// cvHin (cvode.c:1884-1984), no tstop
+		rhs_shared(tn, zn01[1]);
+		if (tstopset) {
+			if ((tstop() - tn) * (tout_in - tn) <= 0.0) return false; // CV_ILL_INPUT
+		}
+		double tout = tout_in;
+		if (tstopset && (tout - tn) * (tout - tstop()) > 0.0) tout = tstop();
+		// cvHin (cvode.c:1884-1984)
 		const double tdiff = tout - tn;
 		if (tdiff == 0.0) return false;
 		const double sign = (tdiff > 0.0) ? 1.0 : -1.0;
@@ -301,7 +372,7 @@ struct GroupBdf {
 #pragma unroll
 				for (int e = 0; e < E; e++) ytmp[e] = hgs * Z<1>(e) + Z<0>(e);
 				publish(ybuf, ytmp);
-				rhs_shared(ftmp);
+				rhs_shared(tn + hgs, ftmp);
 				const double c = 1.0 / hgs;
 #pragma unroll
 				for (int e = 0; e < E; e++) ftmp[e] = c * (ftmp[e] - Z<1>(e));
@@ -323,6 +394,9 @@ struct GroupBdf {
 			h = h0;
 		}
 		if (fabs(h) < hmin) h *= hmin / fabs(h);
+		if (tstopset) {
+			if ((tn + h - tstop()) * h > 0.0) h = (tstop() - tn) * (1.0 - 4.0 * UROUND);
+		}
 		hscale() = h;
 		hprime() = h;
 #pragma unroll
@@ -480,6 +554,7 @@ struct GroupBdf {
 			// ODESolverCVODE::DifferenceQuotientJacobian (ODESolverCVODE.cpp:496-537); y is in ybuf and f(y) in fbuf (residual)
 			gsync();
 			const double srur = sqrt(UROUND);
+			const double treat_now = treatment_value(tn);
 			const double fnorm = wrms(fy);
 			const double minInc = (fnorm != 0.0) ? (1000.0 * fabs(h) * UROUND * N * fnorm) : 1.0;
 			// one instance of the right-hand side code for all slots: the slot's y and weight are picked with selects
@@ -498,7 +573,8 @@ struct GroupBdf {
 					const double inc = fmax(srur * fabs(ye), minInc / we);
 					// f(y + inc e_j) into column j of M, then the difference quotient into the saved Jacobian and, scaled
 					// (SUNMatScaleAddI(-gamma, A): A = -gamma * J, then the unit diagonal added), back into M
-					rhs_eval(region_off + OFF_Y, j, ye + inc, region_off + j, RS, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled);
+					rhs_eval(region_off + OFF_Y, j, ye + inc, region_off + j, RS, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled, treat_ix,
+					         treat_now);
 					const double inc_inv = 1.0 / inc;
 #pragma unroll 1
 					for (int i = 0; i < N; i++) {
@@ -747,7 +823,7 @@ struct GroupBdf {
 #pragma unroll
 		for (int e = 0; e < E; e++) y[e] = Z<0>(e) + acor[e];
 		publish(ybuf, y);
-		rhs_shared(fy);
+		rhs_shared(tn, fy);
 #pragma unroll
 		for (int e = 0; e < E; e++) {
 			double r = rl1 * Z<1>(e) + acor[e];
@@ -767,6 +843,9 @@ struct GroupBdf {
 		}
 		// ---- cvPredict ----
 		tn += h;
+		if (tstopset) {
+			if ((tn - tstop()) * h > 0.0) tn = tstop();
+		}
 		static_for<1, QMAX + 1>([&](auto K) {
 			constexpr int k = decltype(K)::value;
 			static_rfor<k, QMAX + 1>([&](auto J) {
@@ -971,7 +1050,7 @@ struct GroupBdf {
 						qwait = BDF_LONG_WAIT;
 						double f[E];
 						publish(ybuf, zn01[0]);
-						rhs_shared(f);
+						rhs_shared(tn, f);
 #pragma unroll
 						for (int e = 0; e < E; e++) Z<1>(e) = h * f[e];
 					}
@@ -1084,6 +1163,52 @@ struct GroupBdf {
 		const double tp = tn - hu_ - tfuzz, tn1 = tn + tfuzz;
 		return !((t - tp) * (t - tn1) > 0.0);
 	}
+	// CVodeGetDky(t, 0) for the components this lane owns
+	__device__ __forceinline__ void dky_own(double t, double (&out)[E])
+	{
+		const double s = (t - tn) / h;
+#pragma unroll
+		for (int e = 0; e < E; e++) out[e] = 0.0;
+		bool first = true;
+		static_rfor<0, QMAX + 1>([&](auto J) {
+			constexpr int j = decltype(J)::value;
+			if (j <= q) {
+				double c = 1.0;
+#pragma unroll
+				for (int i = 0; i < j; i++) c *= s;
+				if (first) {
+#pragma unroll
+					for (int e = 0; e < E; e++) out[e] = c * Z<j>(e);
+					first = false;
+				} else {
+#pragma unroll
+					for (int e = 0; e < E; e++) out[e] += c * Z<j>(e);
+				}
+			}
+		});
+	}
+	// tstop handling after an accepted step (cvode.c:1410-1438). True for CV_TSTOP_RETURN: yout = Dky(tstop), tret = tstop;
+	// otherwise yout = zn[0], tret = tn.
+	__device__ __forceinline__ bool after_step(double (&yout)[E], double& tret)
+	{
+		if (tstopset) {
+			const double troundoff = BDF_FUZZ_FACTOR * UROUND * (fabs(tn) + fabs(h));
+			if (fabs(tn - tstop()) <= troundoff) {
+				dky_own(tstop(), yout);
+				tret = tstop();
+				tstopset = false;
+				return true;
+			}
+			if ((tn + hprime() - tstop()) * h > 0.0) {
+				hprime() = (tstop() - tn) * (1.0 - 4.0 * UROUND);
+				eta() = hprime() / h;
+			}
+		}
+		tret = tn;
+#pragma unroll
+		for (int e = 0; e < E; e++) yout[e] = Z<0>(e);
+		return false;
+	}
 	// sum over the group of weight[e] * Dky component (weights = multiplicity of the component in the observed list)
 	__device__ __forceinline__ double dky_weighted(double t, const double (&weight)[E])
 	{
@@ -1152,6 +1277,9 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 	B.SJ = saved_jacobians + group_id * (N * N);
 	B.constant_species = a.constant_species;
 	B.non_sampled = a.non_sampled;
+	B.treat_ix = a.treatment_species;
+	B.treat_n = a.treatment_num_pulses;
+	B.treat_times = a.treatment_times;
 	B.reltol = a.rel_tol;
 	B.abstol = a.abs_tol;
 	B.hmin = a.min_dt;
@@ -1258,7 +1386,15 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				const double end_time = a.timepoints[T - 1] - creation_time;
 				B.sc[SC_END] = end_time;
 				if (!finished) {
-					if (!B.start(y0, end_time)) {
+					// Cell::Simulate (Cell.cpp:212-229): SetDiscontinuity(first discontinuity ahead of the cell) = CVodeSetStopTime
+					B.create();
+					const double first_disc = B.first_discontinuity();
+					B.sc[SC_NEXT_DISC] = first_disc;
+					if (first_disc == first_disc) {
+						B.tstop() = first_disc;
+						B.tstopset = true;
+					}
+					if (!B.restart(0.0, y0, end_time)) {
 						ok = false;
 						finished = true;
 					}
@@ -1298,7 +1434,8 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				done = true;
 			} else if (r == T_DONE) {
 				steps++;
-				const double tret = B.tn;
+				double yout[E], tret;
+				const bool tstop_return = B.after_step(yout, tret);
 				const double creation_time = B.sc[SC_CREATION];
 				while (tpi < T && tret >= (a.timepoints[tpi] - creation_time)) {
 					const double tq = a.timepoints[tpi] - creation_time;
@@ -1319,6 +1456,21 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 					else if (steps == a.max_steps) {
 						ok = false;
 						done = true;
+					} else {
+						// ODESolverCVODE.cpp:448-461: at a discontinuity ask for the next one and CVodeReInit(t, y)
+						const double next_disc = B.sc[SC_NEXT_DISC];
+						if (next_disc == next_disc && (tstop_return || next_disc == tret)) {
+							const double nd = B.next_discontinuity(tret);
+							B.sc[SC_NEXT_DISC] = nd;
+							if (nd == nd && nd < INFINITY) {
+								B.tstop() = nd;
+								B.tstopset = true;
+							}
+							if (!B.restart(tret, yout, B.sc[SC_END])) {
+								ok = false;
+								done = true;
+							}
+						}
 					}
 				}
 				newstep = true;

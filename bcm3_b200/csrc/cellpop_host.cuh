@@ -35,6 +35,7 @@ struct CellPopState {
 	double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0;
 	double missing_simulation_time_stdev = 300.0; // DataLikelihoodTimeCourseBase.cpp:22
 	bool full_gaussian = false;                   // <cell_variability distribution="full_gaussian">
+	int treatment_species = -1;                   // <treatment_trajectory type="pulses" species_name=...>: constant species index
 	std::vector<int> obs_species;
 	int shard_rank = 0, shard_count = 1, device = 0;
 	std::string derivative_code;
@@ -58,7 +59,7 @@ struct CellPopState {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<double> d_ic, d_const, d_nonsampled, d_sobol, d_time, d_obs, d_values, d_transformed, d_cellvals, d_avg, d_logp;
 	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail, d_cov_ix, d_cell_order;
-	DevBuf<double> d_cov_fixed, d_chol;
+	DevBuf<double> d_cov_fixed, d_chol, d_treatment_times;
 	bool diagnostics = false;
 	int last_C = 0;
 	double last_kernel_ms = 0.0;
@@ -401,7 +402,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	{ // the constants of cellpop_group.cuh: RS, OFF_SCAL, SC_COUNT, OFF_ZNH, CS
 		const int RS = cp.N | 1;
 		const int off_scal = cp.N * RS + 2 * cp.N + (cp.N + 1) / 2;
-		const int sc_count = 31 + (override_vars.empty() ? 1 : (int)override_vars.size());
+		const int sc_count = CP_GROUP_SCALARS + (override_vars.empty() ? 1 : (int)override_vars.size());
 		int cs = off_scal + sc_count + 4 * Eg * G;
 		while (cs % 16 != (RS * G) % 16) cs++;
 		per_cell = sizeof(double) * (size_t)cs;
@@ -603,6 +604,20 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		CUDA_TRY(cp.d_cell_order.ensure(order.size()));
 		CUDA_TRY(cudaMemcpy(cp.d_cell_order.p, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice));
 		a.cell_order = cp.d_cell_order.p;
+	}
+	a.treatment_species = -1;
+	a.treatment_num_pulses = 0;
+	a.treatment_times = nullptr;
+	if (cp.treatment_species >= 0) {
+		if (cp.treatment_species >= cp.Nc) return fail(BCM3B200_ERR_ARG, "treatment_species is not a constant species of the model");
+		if (cp.built_kernel != 3) return fail(BCM3B200_ERR_UNSUPPORTED, "treatment trajectories need the lane-group kernel (cellpop_kernel = auto for N <= 96)");
+		std::vector<double> times = cp.data["treatment_times"];
+		std::sort(times.begin(), times.end()); // TreatmentTrajectoryPulses::Load, .cpp:17
+		CUDA_TRY(cp.d_treatment_times.ensure(times.size() ? times.size() : 1));
+		if (!times.empty()) CUDA_TRY(cudaMemcpy(cp.d_treatment_times.p, times.data(), sizeof(double) * times.size(), cudaMemcpyHostToDevice));
+		a.treatment_species = cp.treatment_species;
+		a.treatment_num_pulses = (int)times.size();
+		a.treatment_times = cp.d_treatment_times.p;
 	}
 	a.num_cells = cp.cells_local;
 	a.cell_offset = cp.cell_offset;

@@ -118,7 +118,19 @@ bool CellPopulationLikelihoodB200::Initialize(std::shared_ptr<const bcm3::Variab
 			if (!Resolve(c.get("scale", "1"), scale, "scale")) return false;
 			weight = c.get_real("weight", 1.0);
 			missing_stdev = c.get_real("missing_simulation_time_stdev", 300.0);
-		} else if (c.name == "treatment_trajectory" || c.name == "set_species" || c.name == "experiment_specific_parameter" || c.name == "set_parameter") {
+		} else if (c.name == "treatment_trajectory") {
+			// Experiment.cpp:566-590 + TreatmentTrajectoryPulses::Load
+			if (c.get("type") != "pulses") return Fail("treatment_trajectory type \"" + c.get("type") + "\" is not supported by the GPU path (pulses only)");
+			if (!treatment_species_name.empty()) return Fail("one treatment_trajectory per experiment is supported");
+			treatment_species_name = c.get("species_name");
+			std::stringstream ss(c.get("times"));
+			std::string tok;
+			while (std::getline(ss, tok, ',')) {
+				double v;
+				if (!parse_number(tok, v)) return Fail("treatment_trajectory times: cannot parse \"" + tok + "\"");
+				treatment_times.push_back(v);
+			}
+		} else if (c.name == "set_species" || c.name == "experiment_specific_parameter" || c.name == "set_parameter") {
 			return Fail("<" + c.name + "> is not supported by the GPU path");
 		}
 	}
@@ -163,6 +175,11 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 	ref("scale", scale);
 	d << ";obs_species=";
 	for (size_t k = 0; k < obs.size(); k++) d << (k ? "+" : "") << obs[k];
+	if (!treatment_species_name.empty()) {
+		auto it = std::find(model.constant_species_names.begin(), model.constant_species_names.end(), treatment_species_name);
+		if (it == model.constant_species_names.end()) return Fail("Treatment species \"" + treatment_species_name + "\" is not a constant species of the model");
+		d << ";treatment_species=" << (it - model.constant_species_names.begin());
+	}
 	descriptor = d.str();
 	if (bcm3b200_create("cell_population", descriptor.data(), descriptor.size(), 1, &handle) != BCM3B200_OK) return Fail(bcm3b200_last_error());
 
@@ -178,6 +195,7 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 	          set("non_sampled_parameters", model.non_sampled_parameters, { model.non_sampled_parameters.size() }) && set("timepoints", data.timepoints, { T }) &&
 	          set("observed", data.observed, { data.num_replicates, T }) && set("transforms", transforms, { nvar });
 	if (!ok) return false;
+	if (!treatment_species_name.empty() && !treatment_times.empty() && !set("treatment_times", treatment_times, { treatment_times.size() })) return false;
 	if (D > 0) {
 		std::vector<double> rows(D * 6);
 		for (size_t i = 0; i < D; i++) {

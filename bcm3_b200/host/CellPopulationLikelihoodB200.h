@@ -10,13 +10,14 @@
 //       </cell_variability>
 //       <data type="time_course_population_average" species_name="a[+b]" stdev=<variable|number> [proportional_stdev=]
 //             [offset=] [scale=] [error_model=] [weight=] [missing_simulation_time_stdev=]/>
+//       [<treatment_trajectory type="pulses" species_name=<constant species> times="t1,t2,..."/>]
 //     </experiment>
 //   </bcm_likelihood>
 //
 // The SBML reader/code generator and the NetCDF reader stay on the reference side: the generated model
 // (SetModel) and the data set (SetData) are supplied before PostInitialize(), which is where the reference compiles its
 // generated code too (Experiment::PostInitialize -> SolverCodeGenerator). Anything the device path does not implement
-// (cell division, several experiments / data sets, treatment trajectories, per-cell likelihood types) is refused here.
+// (cell division, several experiments / data sets, treatment trajectories from data, per-cell likelihood types) is refused here.
 #pragma once
 
 #include "Likelihood.h"
@@ -28,6 +29,7 @@ public:
 		std::vector<std::string> species_names;      // simulated species, in the generator's order
 		std::vector<double> initial_conditions;      // [N]
 		std::vector<double> constant_species;        // [Nc]
+		std::vector<std::string> constant_species_names; // needed only when a treatment trajectory drives one of them
 		std::vector<double> non_sampled_parameters;  // [Nn]
 	};
 	struct Data { // one time_course_population_average data set (DataLikelihoodTimeCourse.cpp:66-160)
@@ -83,6 +85,8 @@ private:
 	double solver_min_timestep = 1e-8, solver_abs_tol = 4.0 * 1.1920928955078125e-07, solver_rel_tol = 4.0 * 1.1920928955078125e-07;
 	long solver_max_steps = 10000;
 	std::vector<VarEntry> variables;
+	std::string treatment_species_name; // <treatment_trajectory type="pulses">
+	std::vector<double> treatment_times;
 	Model model;
 	Data data;
 	std::vector<double> sobol;

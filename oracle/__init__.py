@@ -79,7 +79,8 @@ class _CellPopProblem(C.Structure):
         ("obs_species", C.c_int32 * 8)] + [(n, C.c_double) for n in ("entry_time", "rel_tol", "abs_tol", "min_dt", "weight", "stdev",
                                                                      "offset", "scale", "missing_stdev", "proportional_stdev")] + [
         (n, C.c_void_p) for n in ("covariance", "initial_conditions", "constant_species", "non_sampled", "sobol", "timepoints", "observed",
-                                  "variability", "transforms", "derivative")]
+                                  "variability", "transforms", "derivative")] + [
+        ("treatment_species", C.c_int32), ("treatment_num_pulses", C.c_int32), ("treatment_times", C.c_void_p)]
 
 
 _derivative_libs: dict[str, C.CDLL] = {}
@@ -192,7 +193,8 @@ def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=
         ns=np.ascontiguousarray(p.non_sampled_parameters, dtype=np.float64), sobol=np.ascontiguousarray(p.sobol, dtype=np.float64),
         tp=np.ascontiguousarray(p.timepoints, dtype=np.float64), obs=np.ascontiguousarray(p.observed, dtype=np.float64),
         var=np.ascontiguousarray(p.variability_rows(), dtype=np.float64), tr=np.ascontiguousarray(p.transforms, dtype=np.int32),
-        cov=np.ascontiguousarray(p.covariance_rows(), dtype=np.float64))
+        cov=np.ascontiguousarray(p.covariance_rows(), dtype=np.float64),
+        treat=np.ascontiguousarray(np.sort(np.asarray(p.treatment_times, dtype=np.float64))))
     ptr = lambda a: a.ctypes.data if a.size else None
     s = _CellPopProblem(
         num_species=p.num_species, num_constant_species=len(keep["const"]), num_variables=p.num_variables, num_non_sampled=len(keep["ns"]),
@@ -202,6 +204,8 @@ def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=
         proportional_stdev_ix=-1 if p.proportional_stdev_ix is None else p.proportional_stdev_ix,
         full_gaussian=int(p.variability_distribution == "full_gaussian"), proportional_stdev=p.proportional_stdev,
         covariance=ptr(keep["cov"]),
+        treatment_species=-1 if p.treatment_species is None else p.treatment_species, treatment_num_pulses=len(keep["treat"]),
+        treatment_times=ptr(keep["treat"]),
         stdev_ix=-1 if p.stdev_ix is None else p.stdev_ix, offset_ix=-1 if p.offset_ix is None else p.offset_ix,
         scale_ix=-1 if p.scale_ix is None else p.scale_ix, num_obs_species=len(p.obs_species),
         obs_species=(C.c_int32 * 8)(*(list(p.obs_species) + [0] * (8 - len(p.obs_species)))),

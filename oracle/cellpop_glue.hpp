@@ -61,6 +61,52 @@ inline double logpdf_normal(double x, double mu, double sigma)
 	return -log(sigma) - 0.91893853320467274178032973640562 - d * d / (2.0 * sigma * sigma);
 }
 
+// TreatmentTrajectoryPulses::{GetConcentration, FirstDiscontinuity, NextDiscontinuity} (TreatmentTrajectoryPulses.cpp:21-71):
+// each pulse starts 2 h after its time point: linear rise over 2 h, plateau 8 h, linear decay over 4 h.
+inline double pulse_concentration(const oracle_cellpop_problem& pr, double time, double cell_creation_time)
+{
+	const double global_time = time + cell_creation_time;
+	for (int i = 0; i < pr.treatment_num_pulses; i++) {
+		const double t_in_pulse = global_time - pr.treatment_times[i] - 2.0;
+		if (t_in_pulse >= 14.0) continue;
+		else if (t_in_pulse <= 0.0) return 0.0;
+		else if (t_in_pulse < 2.0) return t_in_pulse * 0.5;
+		else if (t_in_pulse < 10.0) return 1.0;
+		else return 1 - (t_in_pulse - 10.0) * 0.25;
+	}
+	return 0.0;
+}
+inline double pulse_first_discontinuity(const oracle_cellpop_problem& pr, double cell_creation_time)
+{
+	if (pr.treatment_num_pulses > 0) return pr.treatment_times[0] - cell_creation_time + 2.0;
+	return std::numeric_limits<double>::quiet_NaN();
+}
+inline double pulse_next_discontinuity(const oracle_cellpop_problem& pr, double time, double cell_creation_time)
+{
+	for (int i = 0; i < pr.treatment_num_pulses; i++) {
+		const double* tp = pr.treatment_times;
+		if (time == tp[i] - cell_creation_time + 2.0) return tp[i] - cell_creation_time + 4.0;
+		else if (time == tp[i] - cell_creation_time + 4.0) return tp[i] - cell_creation_time + 10.0;
+		else if (time == tp[i] - cell_creation_time + 10.0) return tp[i] - cell_creation_time + 14.0;
+		else if (time == tp[i] - cell_creation_time + 14.0) {
+			if (i < pr.treatment_num_pulses - 1) return tp[i + 1] - cell_creation_time + 2.0;
+			else return std::numeric_limits<double>::quiet_NaN();
+		}
+	}
+	return std::numeric_limits<double>::quiet_NaN();
+}
+// Cell::Simulate, Cell.cpp:212-229: the first discontinuity that lies ahead of the cell (NaN: none)
+inline double first_discontinuity_ahead(const oracle_cellpop_problem& pr, double cell_creation_time)
+{
+	if (pr.treatment_species < 0) return std::numeric_limits<double>::quiet_NaN();
+	double discontinuity = pulse_first_discontinuity(pr, cell_creation_time);
+	if (!std::isnan(discontinuity)) {
+		while (discontinuity < 0.0) discontinuity = pulse_next_discontinuity(pr, discontinuity, cell_creation_time);
+	}
+	if (!std::isnan(discontinuity) && discontinuity > 0.0) return discontinuity;
+	return std::numeric_limits<double>::quiet_NaN();
+}
+
 template <class Solver>
 void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, double* logp_out, double* cell_values, int32_t* cell_steps,
                     double* pop_avg_out)
@@ -123,7 +169,7 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		const double creation_time = entry_time;
 		for (int i = 0; i < T; i++) tp_rel[i] = pr.timepoints[i] - creation_time;
 		int steps = 0;
-		if (!solver.solve(y0.data(), cell_params.data(), tp_rel.data(), T, out.data(), steps)) {
+		if (!solver.solve(y0.data(), cell_params.data(), tp_rel.data(), T, out.data(), steps, creation_time)) {
 			result = false; // Experiment::Simulate fails => logp = -inf (Experiment.cpp:356-358)
 		}
 		if (cell_steps) cell_steps[ci] = steps;

@@ -20,19 +20,29 @@ struct PortSolver {
 	const oracle_cellpop_problem& pr;
 	bdf_mem* m;
 	const double* cell_params = nullptr;
-	explicit PortSolver(const oracle_cellpop_problem& p) : pr(p), m(new bdf_mem) {}
+	double creation_time = 0.0;
+	std::vector<double> constant_species_y;
+	explicit PortSolver(const oracle_cellpop_problem& p)
+	    : pr(p), m(new bdf_mem), constant_species_y(p.constant_species, p.constant_species + p.num_constant_species)
+	{
+	}
 	~PortSolver() { delete m; }
-	static int rhs(double, const double* y, double* ydot, void* user)
+	static int rhs(double t, const double* y, double* ydot, void* user)
 	{
 		PortSolver* s = (PortSolver*)user;
-		s->pr.derivative(ydot, y, s->pr.constant_species, s->cell_params, s->pr.non_sampled); // Cell::solver_rhs_fn, Cell.cpp:423-433
+		// Cell::SetTreatmentConcentration + solver_rhs_fn, Cell.cpp:415-433
+		if (s->pr.treatment_species >= 0) s->constant_species_y[s->pr.treatment_species] = cellpop_glue::pulse_concentration(s->pr, t, s->creation_time);
+		s->pr.derivative(ydot, y, s->constant_species_y.data(), s->cell_params, s->pr.non_sampled);
 		return 0;
 	}
-	// ODESolver::SolveReturnSolution (ODESolver.cpp:93-134) + ODESolverCVODE::Solve (ODESolverCVODE.cpp:322-463), no discontinuities
-	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps)
+	// ODESolver::SolveReturnSolution (ODESolver.cpp:93-134) + ODESolverCVODE::Solve (ODESolverCVODE.cpp:322-463) with the
+	// discontinuities of a pulsed treatment (Cell.cpp:212-229, 444-460)
+	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps, double cell_creation_time)
 	{
 		const int N = pr.num_species;
 		cell_params = params;
+		creation_time = cell_creation_time;
+		double next_disc = cellpop_glue::first_discontinuity_ahead(pr, creation_time);
 		steps = 0;
 		int ti = 0;
 		while (tp[ti] < 2.220446049250313e-16) {
@@ -50,6 +60,7 @@ struct PortSolver {
 		double y[BDF_NMAX], tmp[BDF_NMAX];
 		for (int i = 0; i < N; i++) y[i] = y0[i];
 		bdf_reinit(m, 0.0, y);
+		if (!std::isnan(next_disc)) bdf_set_stop_time(m, next_disc);
 		int tpi = ti;
 		for (;;) {
 			double tret;
@@ -64,6 +75,11 @@ struct PortSolver {
 			}
 			if (tret >= end_time) break;
 			if (steps == pr.max_steps) return false;
+			if (!std::isnan(next_disc) && (result == BDF_TSTOP_RETURN || next_disc == tret)) { // ODESolverCVODE.cpp:448-461
+				next_disc = cellpop_glue::pulse_next_discontinuity(pr, tret, creation_time);
+				bdf_reinit(m, tret, y);
+				if (!std::isnan(next_disc) && next_disc < INFINITY) bdf_set_stop_time(m, next_disc);
+			}
 		}
 		if (const char* rep = getenv("BCM3B200_CELLPOP_REPORT")) { // debugging aid: report another counter in place of the steps
 			int k = atoi(rep);

@@ -119,6 +119,10 @@ typedef struct {
 	const double* variability;         /* [D][6]: is_ic, target, apply, scale_ix, scale_fixed, negate */
 	const int32_t* transforms;         /* [nvar] */
 	oracle_derivative_fn derivative;   /* generated_derivative compiled for the host from the generated text */
+	/* one <treatment_trajectory type="pulses"> (TreatmentTrajectoryPulses.cpp): the constant species it drives (-1: none)
+	 * and the sorted pulse times; its value is a function of time and every pulse adds four discontinuities */
+	int32_t treatment_species, treatment_num_pulses;
+	const double* treatment_times;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

@@ -18,11 +18,15 @@ struct RefSolver {
 	const oracle_cellpop_problem& pr;
 	ODESolverCVODE solver;
 	const double* cell_params = nullptr;
-	explicit RefSolver(const oracle_cellpop_problem& p) : pr(p)
+	double creation_time = 0.0;
+	std::vector<double> constant_species_y;
+	explicit RefSolver(const oracle_cellpop_problem& p) : pr(p), constant_species_y(p.constant_species, p.constant_species + p.num_constant_species)
 	{
 		// Cell::AllocateSolver, Cell.cpp:57-76 (no SetJacobianFunction => DifferenceQuotientJacobian)
-		solver.SetDerivativeFunction([this](OdeReal, const OdeReal* y, OdeReal* ydot, void*) {
-			pr.derivative(ydot, y, pr.constant_species, cell_params, pr.non_sampled);
+		solver.SetDerivativeFunction([this](OdeReal t, const OdeReal* y, OdeReal* ydot, void*) {
+			// Cell::SetTreatmentConcentration + solver_rhs_fn, Cell.cpp:415-433
+			if (pr.treatment_species >= 0) constant_species_y[pr.treatment_species] = cellpop_glue::pulse_concentration(pr, t, creation_time);
+			pr.derivative(ydot, y, constant_species_y.data(), cell_params, pr.non_sampled);
 			return true;
 		});
 		solver.Initialize((size_t)pr.num_species, nullptr, 0);
@@ -31,9 +35,16 @@ struct RefSolver {
 		solver.SetSolverParameter("max_dt", 0, std::numeric_limits<OdeReal>::infinity());
 		solver.SetSolverParameter("max_steps", pr.max_steps, std::numeric_limits<OdeReal>::quiet_NaN());
 	}
-	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps)
+	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps, double cell_creation_time)
 	{
 		cell_params = params;
+		creation_time = cell_creation_time;
+		// Cell::Simulate, Cell.cpp:212-229 + discontinuity_cb :444-460
+		const double first = cellpop_glue::first_discontinuity_ahead(pr, creation_time);
+		if (!std::isnan(first)) {
+			ODESolver::TDiscontinuityCallback cb = [this](OdeReal t, void*) -> Real { return cellpop_glue::pulse_next_discontinuity(pr, t, creation_time); };
+			solver.SetDiscontinuity(first, cb, nullptr);
+		}
 		Eigen::Map<const OdeVectorReal> ic(y0, pr.num_species);
 		OdeVectorReal initial = ic;
 		OdeVectorReal timepoints = Eigen::Map<const OdeVectorReal>(tp, ntp);

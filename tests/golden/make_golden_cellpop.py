@@ -27,6 +27,9 @@ CASES = {
     "cellpop_n8_fullgauss_addprop": (dict(N=8, num_cells=64, T=12, data_cells=8, seed=25, replicates=2), 3,
                                      dict(variability_distribution="full_gaussian", covariance=[0.3, sc.VAR_VARIABILITY_SCALE, 0.15],
                                           error_model="additive_proportional_normal", proportional_stdev=0.1)),
+    # <treatment_trajectory type="pulses"> driving the input (constant species 0): time-dependent RHS + 8 discontinuities, late entry
+    "cellpop_n8_treatment_pulses": (dict(N=8, num_cells=40, T=20, t_end=40.0, data_cells=4, seed=27), 2,
+                                    dict(treatment_species=0, treatment_times=np.array([20.0, 1.0]), obs_species=[0, 2], entry_time=4.0)),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }

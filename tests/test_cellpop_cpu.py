@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from bcm3_b200 import synthetic_cellpop as sc
-from tests.util import CELLPOP_GOLDEN_NAMES, cellpop_logp_close, cellpop_rtol, load_cellpop_golden
+from tests.util import CELLPOP_GOLDEN_NAMES, cellpop_step_match_floor, cellpop_logp_close, cellpop_rtol, load_cellpop_golden
 
 
 def test_cellpop_golden_fixtures_exist():
@@ -27,7 +27,7 @@ def test_port_matches_reference_golden(port, name):
     assert np.abs(r["population_average"] - gold["population_average"]).max() < 5e-6
     # step counts: identical for most cells; the stiff 24-species case flips more decisions
     same = (r["cell_steps"] == gold["cell_steps"]).mean()
-    assert same >= (0.02 if "stiff" in name else 0.7)
+    assert same >= cellpop_step_match_floor(name)
     assert abs(r["cell_steps"].mean() / gold["cell_steps"].mean() - 1.0) < 0.02
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from bcm3_b200 import synthetic_cellpop as sc
-from tests.util import CELLPOP_GOLDEN_NAMES, cellpop_logp_close, cellpop_rtol, load_cellpop_golden
+from tests.util import CELLPOP_GOLDEN_NAMES, cellpop_step_match_floor, cellpop_logp_close, cellpop_rtol, load_cellpop_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -42,7 +42,7 @@ def _check_golden(Evaluator, name, kernel):
     assert np.abs(d["cell_values"][m] - gold["cell_values"][m]).max() < 5e-5
     assert np.abs(d["population_average"] - gold["population_average"]).max() < 5e-6
     assert abs(d["cell_steps"].mean() / gold["cell_steps"].mean() - 1.0) < 0.02
-    assert (d["cell_steps"] == gold["cell_steps"]).mean() >= (0.02 if "stiff" in name else 0.7)
+    assert (d["cell_steps"] == gold["cell_steps"]).mean() >= cellpop_step_match_floor(name)
 
 
 def test_config3_shape_against_cpu_checker(Evaluator, port):

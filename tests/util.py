@@ -93,8 +93,10 @@ def load_cellpop_golden(name):
                                        scale_ix=None if scale_ix < 0 else int(scale_ix), scale_fixed=float(scale_fixed), negate=bool(negate)))
     opt_int = lambda k: int(z[k]) if k in z.files else None
     extra = {}
+    if "treatment_species" in z.files:
+        extra.update(treatment_species=int(z["treatment_species"]), treatment_times=z["treatment_times"])
     if "variability_distribution" in z.files:
-        extra = dict(variability_distribution=str(z["variability_distribution"]),
+        extra.update(variability_distribution=str(z["variability_distribution"]),
                      covariance=[int(ix) if ix >= 0 else float(fx) for ix, fx in z["covariance_rows"]],
                      proportional_stdev_ix=opt_int("proportional_stdev_ix"), proportional_stdev=float(z["proportional_stdev"]))
     prob = CellPopProblem(
@@ -118,6 +120,17 @@ def cellpop_logp_close(got, want, T, R, rtol=1e-6):
     got, want = np.asarray(got), np.asarray(want)
     scale = np.maximum(np.abs(want), 4.0 * T * R)
     return np.all(np.abs(got - want) <= rtol * scale)
+
+
+def cellpop_step_match_floor(name):
+    """Fraction of cells whose step count must equal the reference's: most of them on the plain fixtures; the stiff one and
+    the pulsed-treatment one (600 steps and 8 re-initialisations per cell) flip more round-off-sized decisions -- the
+    reference and its own restatement agree on 4 % / 21 % of the cells there while all values agree to ~1e-12."""
+    if "stiff" in name:
+        return 0.02
+    if "treatment" in name:
+        return 0.1
+    return 0.7
 
 
 def cellpop_rtol(name):
