@@ -35,6 +35,7 @@ struct CellPopState {
 	double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0;
 	double missing_simulation_time_stdev = 300.0; // DataLikelihoodTimeCourseBase.cpp:22
 	bool full_gaussian = false;                   // <cell_variability distribution="full_gaussian">
+	int steps_report = 0;                         // option "cellpop_steps_report": what get_cell_diagnostics returns as cell_steps (0 steps, 1 nfe, 2 nsetups, 3 nje)
 	int treatment_species = -1;                   // <treatment_trajectory type="pulses" species_name=...>: constant species index
 	std::vector<int> obs_species;
 	int shard_rank = 0, shard_count = 1, device = 0;
@@ -687,7 +688,7 @@ inline int cellpop_run_cells(CellPopState& cp, size_t C, size_t nvar, const doub
 	a.cell_values = cp.d_cellvals.p;
 	a.cell_status = cp.d_status.p;
 	a.cell_steps = cp.d_steps.p;
-	a.debug_report = getenv("BCM3B200_CELLPOP_REPORT") ? atoi(getenv("BCM3B200_CELLPOP_REPORT")) : 0;
+	a.debug_report = cp.steps_report;
 	cp.last_launches = 1;
 	const bool use_group = (cp.built_kernel == 3);
 	const bool use_thread = (cp.built_kernel == 2);

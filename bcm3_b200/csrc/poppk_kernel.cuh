@@ -203,8 +203,10 @@ __device__ __forceinline__ bool check_give_treatment(double t, uint32_t skipped_
 #define BCM3_SORT_BLOCK_PATIENTS 0 /* in-block ranking: measured +4 % only (the block still waits for its slowest warp) */
 #endif
 
-// Sort key of (chain, patient): chain in the high word, the bits of (float) ka -- positive, so they order like the value --
-// in the low word. Same expression as K0 of poppk_kernel.
+// Sort key of (chain, patient): chain in the high word; in the low word the bits of a positive float that orders the
+// patients by expected work: every dose restarts the integrator (about as many steps per dosing interval whatever its
+// length), so the number of dosing intervals inside the simulated window comes first, and within it the absorption rate
+// (ka as in K0 of poppk_kernel, squashed into [0, 1)).
 __global__ void poppk_rank_kernel(const PkArgs a, int C, unsigned long long* __restrict__ keys, int* __restrict__ patients)
 {
 	const int j = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
@@ -212,8 +214,17 @@ __global__ void poppk_rank_kernel(const PkArgs a, int C, unsigned long long* __r
 	const double* vrow = a.values + (long long)c * a.row_stride;
 	const double p = vrow[a.col_patient0 + 2ll * j];
 	const double ka = fastpow10(quantile_normal(p, vrow[a.ix[SV_MEAN_ABSORPTION]], vrow[a.ix[SV_SIGMA_ABSORPTION]]));
-	float kf = (float)ka;
-	if (!(kf >= 0.0f)) kf = INFINITY; // NaN / negative cannot happen for 10^x; keep the order total anyway
+	const int ntp = a.simulate_until[j];
+	const double end_time = (ntp > 0) ? a.time[ntp - 1] : 0.0;
+	const double interval = a.dosing_interval[j];
+	double intervals = (interval > 0.0) ? floor(end_time / interval) + 1.0 : 1.0;
+	if (!(intervals >= 1.0)) intervals = 1.0;
+	if (intervals > 1e6) intervals = 1e6;
+	double frac = (log10(ka) + 4.0) * 0.125; // ka in 1e-4 .. 1e4 per hour -> [0, 1)
+	if (!(frac >= 0.0)) frac = 0.0;
+	if (frac > 0.999) frac = 0.999;
+	float kf = (float)(intervals + frac);
+	if (!(kf >= 0.0f)) kf = INFINITY; // keep the order total whatever the inputs
 	const long long e = (long long)c * a.P_local + j;
 	keys[e] = ((unsigned long long)c << 32) | (unsigned long long)__float_as_uint(kf);
 	patients[e] = j;
