@@ -418,7 +418,13 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	o << "#define CP_GROUP " << G << "\n";
 	o << "#define CP_GROUP_WARPS " << gwarps << "\n";
 	o << "#define CP_GROUP_MIN_BLOCKS " << gblocks << "\n";
-	if (const char* lenv = getenv("BCM3B200_CELLPOP_GROUP_LOCKSTEP")) o << "#define CP_GROUP_LOCKSTEP " << atoi(lenv) << "\n";
+	// Block lock-step shares instruction fetches between the warps of a block but makes every trip as long as the slowest
+	// warp's. With 8 or more cells per warp the warps are statistically alike and sharing wins (N = 12: 130 vs 150 ms,
+	// N = 6: 13.5 vs 16.5 ms); with few cells per warp one linear setup (2 N^3 / 3 flops + N right-hand sides) stalls the
+	// whole block (N = 24: 217 vs 183 ms, N = 50: 299 vs 201 ms without it).
+	int lockstep = (G <= 4) ? 1 : 0;
+	if (const char* lenv = getenv("BCM3B200_CELLPOP_GROUP_LOCKSTEP")) lockstep = atoi(lenv);
+	o << "#define CP_GROUP_LOCKSTEP " << lockstep << "\n";
 	if (const char* benv2 = getenv("BCM3B200_CELLPOP_GROUP_BATCHED")) o << "#define CP_GROUP_BATCHED " << atoi(benv2) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
