@@ -122,8 +122,21 @@ struct OutStrided {
 	int stride;
 	__device__ __forceinline__ double& operator[](int i) const { return p[i * stride]; }
 };
-__device__ __noinline__ void rhs_eval(unsigned y_off, int j, double yj, unsigned out_off, int out_stride, unsigned ov_off, const double* tv,
-                                      const double* constant_species, const double* non_sampled, int treat_ix, double treat_value)
+struct SpeciesPlain {
+	const double* y;
+	__device__ __forceinline__ double operator[](int i) const { return y[i]; }
+};
+// Two instances: the plain one (every Newton residual: hot) reads y as it is; the perturbed one (difference-quotient
+// Jacobian columns: one evaluation in ~25) pays a compare-and-select per species read.
+__device__ __noinline__ void rhs_eval(unsigned y_off, unsigned out_off, unsigned ov_off, const double* tv, const double* constant_species,
+                                      const double* non_sampled, int treat_ix, double treat_value)
+{
+	extern __shared__ double smem_d[];
+	generated_derivative(OutStrided{ smem_d + out_off, 1 }, SpeciesPlain{ smem_d + y_off }, ConstSpecies{ constant_species, treat_ix, treat_value },
+	                     CellParameters{ tv, smem_d + ov_off }, ConstVector{ non_sampled });
+}
+__device__ __noinline__ void rhs_eval_perturbed(unsigned y_off, int j, double yj, unsigned out_off, int out_stride, unsigned ov_off, const double* tv,
+                                                const double* constant_species, const double* non_sampled, int treat_ix, double treat_value)
 {
 	extern __shared__ double smem_d[];
 	generated_derivative(OutStrided{ smem_d + out_off, out_stride }, SpeciesAt{ smem_d + y_off, j, yj },
@@ -291,8 +304,7 @@ struct GroupBdf {
 	// fbuf (identical stores) and reads back the components it owns
 	__device__ __forceinline__ void rhs_shared(double t, double (&f)[E])
 	{
-		rhs_eval(region_off + OFF_Y, -1, 0.0, region_off + OFF_F, 1, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled, treat_ix,
-		         treatment_value(t));
+		rhs_eval(region_off + OFF_Y, region_off + OFF_F, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled, treat_ix, treatment_value(t));
 #pragma unroll
 		for (int e = 0; e < E; e++) f[e] = own(e) ? fbuf[idx(e)] : 0.0;
 		nfe++;
@@ -573,8 +585,8 @@ struct GroupBdf {
 					const double inc = fmax(srur * fabs(ye), minInc / we);
 					// f(y + inc e_j) into column j of M, then the difference quotient into the saved Jacobian and, scaled
 					// (SUNMatScaleAddI(-gamma, A): A = -gamma * J, then the unit diagonal added), back into M
-					rhs_eval(region_off + OFF_Y, j, ye + inc, region_off + j, RS, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled, treat_ix,
-					         treat_now);
+					rhs_eval_perturbed(region_off + OFF_Y, j, ye + inc, region_off + j, RS, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled,
+					                   treat_ix, treat_now);
 					const double inc_inv = 1.0 / inc;
 #pragma unroll 1
 					for (int i = 0; i < N; i++) {

@@ -425,6 +425,11 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	int lockstep = (G <= 4) ? 1 : 0;
 	if (const char* lenv = getenv("BCM3B200_CELLPOP_GROUP_LOCKSTEP")) lockstep = atoi(lenv);
 	o << "#define CP_GROUP_LOCKSTEP " << lockstep << "\n";
+	// rate-law helpers: inlined for the small models that run in lock-step (N = 12: 131 vs 140 ms), real functions for the
+	// large ones, whose right-hand side alone would outgrow the instruction cache (N = 50: 161 vs 199 ms)
+	int helper_inline = lockstep;
+	if (const char* henv = getenv("BCM3B200_CELLPOP_HELPER_INLINE")) helper_inline = atoi(henv);
+	o << "#define CP_HELPER_INLINE " << helper_inline << "\n";
 	if (const char* benv2 = getenv("BCM3B200_CELLPOP_GROUP_BATCHED")) o << "#define CP_GROUP_BATCHED " << atoi(benv2) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";

@@ -10,11 +10,23 @@
 
 typedef double OdeReal;
 
+// The rate-law helpers are real functions by default: a 50-species model calls them ~100 times per right-hand side, and
+// inlined (divisions and square roots expand to dozens of instructions each) the right-hand side alone outgrows the
+// 32 KB instruction cache. CP_HELPER_INLINE=1 restores inlining.
+#ifndef CP_HELPER_INLINE
+#define CP_HELPER_INLINE 0
+#endif
+#if CP_HELPER_INLINE
+#define CP_HELPER __device__ __forceinline__
+#else
+#define CP_HELPER __device__ __noinline__
+#endif
+
 #define CP_REAL_MIN DBL_MIN /* std::numeric_limits<OdeReal>::min() */
 
 __device__ __forceinline__ OdeReal square(OdeReal x) { return x * x; }
 
-__device__ __forceinline__ OdeReal hill_function(OdeReal x, OdeReal k, OdeReal n)
+CP_HELPER OdeReal hill_function(OdeReal x, OdeReal k, OdeReal n)
 {
 	if (x <= 0.0) return 0.0;
 	OdeReal xn = pow(x, n);
@@ -24,7 +36,7 @@ __device__ __forceinline__ OdeReal hill_function(OdeReal x, OdeReal k, OdeReal n
 	if (xnpkn > 3e38f) return 1.0;
 	return xn / xnpkn;
 }
-__device__ __forceinline__ OdeReal hill_function_fixedn2(OdeReal x, OdeReal k)
+CP_HELPER OdeReal hill_function_fixedn2(OdeReal x, OdeReal k)
 {
 	if (x <= 0.0) return 0.0;
 	OdeReal x2 = x * x;
@@ -34,7 +46,7 @@ __device__ __forceinline__ OdeReal hill_function_fixedn2(OdeReal x, OdeReal k)
 	if (xnpkn > 3e38f) return 10.0;
 	return x2 / xnpkn;
 }
-__device__ __forceinline__ OdeReal hill_function_fixedn4(OdeReal x, OdeReal k)
+CP_HELPER OdeReal hill_function_fixedn4(OdeReal x, OdeReal k)
 {
 	if (x <= 0.0) return 0.0;
 	OdeReal x2 = x * x;
@@ -46,7 +58,7 @@ __device__ __forceinline__ OdeReal hill_function_fixedn4(OdeReal x, OdeReal k)
 	if (xnpkn > 3e38f) return 1.0;
 	return x4 / xnpkn;
 }
-__device__ __forceinline__ OdeReal hill_function_fixedn10(OdeReal x, OdeReal k)
+CP_HELPER OdeReal hill_function_fixedn10(OdeReal x, OdeReal k)
 {
 	if (x <= 0.0) return 0.0;
 	OdeReal x2 = x * x;
@@ -62,7 +74,7 @@ __device__ __forceinline__ OdeReal hill_function_fixedn10(OdeReal x, OdeReal k)
 	if (xnpkn > 3e38f) return 1.0;
 	return x10 / xnpkn;
 }
-__device__ __forceinline__ OdeReal hill_function_fixedn16(OdeReal x, OdeReal k)
+CP_HELPER OdeReal hill_function_fixedn16(OdeReal x, OdeReal k)
 {
 	if (x <= 0.0) return 0.0;
 	OdeReal x2 = x * x;
@@ -78,7 +90,7 @@ __device__ __forceinline__ OdeReal hill_function_fixedn16(OdeReal x, OdeReal k)
 	// the reference's `if (xnpkn > 3e38f) 1.0;` has no `return`: no effect
 	return x16 / xnpkn;
 }
-__device__ __forceinline__ OdeReal hill_function_fixedn100(OdeReal x, OdeReal k)
+CP_HELPER OdeReal hill_function_fixedn100(OdeReal x, OdeReal k)
 {
 	if (x <= 0.0) return 0.0;
 	OdeReal x2 = x * x;
@@ -100,7 +112,7 @@ __device__ __forceinline__ OdeReal hill_function_fixedn100(OdeReal x, OdeReal k)
 	if (xnpkn > 3e38f) return 1.0;
 	return x100 / xnpkn;
 }
-__device__ __forceinline__ OdeReal michaelis_menten_function(OdeReal kcat, OdeReal KM, OdeReal e, OdeReal s)
+CP_HELPER OdeReal michaelis_menten_function(OdeReal kcat, OdeReal KM, OdeReal e, OdeReal s)
 {
 	if (e <= 0) return 0.0;
 	if (s + KM < 0.1 * KM) {
@@ -110,7 +122,7 @@ __device__ __forceinline__ OdeReal michaelis_menten_function(OdeReal kcat, OdeRe
 	}
 	return kcat * e * s / (KM + s);
 }
-__device__ __forceinline__ OdeReal safepow(OdeReal x, OdeReal n)
+CP_HELPER OdeReal safepow(OdeReal x, OdeReal n)
 {
 	if (x <= 0) {
 		return 0.0;
@@ -118,7 +130,7 @@ __device__ __forceinline__ OdeReal safepow(OdeReal x, OdeReal n)
 		return pow(x, n);
 	}
 }
-__device__ __forceinline__ OdeReal synthcap(OdeReal x)
+CP_HELPER OdeReal synthcap(OdeReal x)
 {
 	if (x <= 0) {
 		return 1.0;
@@ -129,7 +141,7 @@ __device__ __forceinline__ OdeReal synthcap(OdeReal x)
 		return 1.0 - x8 * x2;
 	}
 }
-__device__ __forceinline__ OdeReal tQSSA(OdeReal k, OdeReal km, OdeReal e, OdeReal s)
+CP_HELPER OdeReal tQSSA(OdeReal k, OdeReal km, OdeReal e, OdeReal s)
 {
 	OdeReal ekms = e + km + s;
 	return 0.5 * k * (ekms - sqrt(ekms * ekms - 4 * e * s));
