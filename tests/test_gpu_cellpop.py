@@ -107,3 +107,21 @@ def test_sharded_cells_reproduce_the_unsharded_result(Evaluator):
         shards[0].evaluate(vals)  # a sharded handle only yields partials
     for s in shards:
         s.close()
+
+
+@pytest.mark.parametrize("N,decades,rtol", [(3, 2.0, 2e-6), (7, 2.0, 1e-6), (16, 3.0, 2e-5), (33, 3.0, 2e-5), (50, 4.0, 2e-5)])
+def test_lane_group_shapes_against_cpu_checker(Evaluator, port, N, decades, rtol):
+    """The lane-group mapping at sizes that exercise every shape: 2, 4 (padded), 8, 16 and 32 lanes per cell, with and
+    without block lock-step, inlined and called rate-law helpers. The stiff cases carry the tolerance at which the
+    reference and its own restatement agree there (tests/util.py::cellpop_rtol)."""
+    prob = sc.make_cellpop_problem(N=N, num_cells=96, T=12, data_cells=4, seed=40 + N, rate_decades=decades)
+    vals = sc.make_chain_values(2, seed=N)
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    d = ev.diagnostics()
+    ev.close()
+    want = port.cellpop_evaluate(prob, vals, threads=4, want_average=True, want_steps=True)
+    assert (status == 0).all() and (d["cell_status"] == 1).all()
+    assert cellpop_logp_close(logp, want["logp"], 12, 1, rtol=rtol)
+    assert np.abs(d["population_average"] - want["population_average"]).max() < 2e-5
+    assert abs(d["cell_steps"].mean() / want["cell_steps"].mean() - 1.0) < 0.02
