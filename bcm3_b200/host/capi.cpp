@@ -170,6 +170,44 @@ int bcm3host_evaluate(const char* prior_xml, const char* likelihood_xml, const d
 	return 0;
 }
 
+// likelihood.xml -> LikelihoodFactory -> CellPopulationLikelihoodB200, with the generated model, data set and quasi-random
+// table that the SBML / NetCDF readers would supply; PostInitialize included
+static bool make_cellpop(const char* prior_xml, const char* likelihood_xml, const char* derivative_code, size_t N, const char* const* species_names,
+                         const double* initial_conditions, size_t Nc, const double* constant_species, size_t T, size_t R, const double* timepoints,
+                         const double* observed, size_t sobol_count, const double* sobol, int device, int compile_only, Setup& st,
+                         CellPopulationLikelihoodB200*& ll, char* err, size_t errlen)
+{
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
+		set_err(err, errlen, error);
+		return false;
+	}
+	ll = dynamic_cast<CellPopulationLikelihoodB200*>(st.likelihood.get());
+	if (!ll) {
+		set_err(err, errlen, "likelihood.xml is not of type cell_population");
+		return false;
+	}
+	CellPopulationLikelihoodB200::Model m;
+	m.derivative_code = derivative_code;
+	for (size_t i = 0; i < N; i++) m.species_names.push_back(species_names[i]);
+	m.initial_conditions.assign(initial_conditions, initial_conditions + N);
+	m.constant_species.assign(constant_species, constant_species + Nc);
+	for (size_t i = 0; i < Nc; i++) m.constant_species_names.push_back("c" + std::to_string(i));
+	ll->SetModel(m);
+	CellPopulationLikelihoodB200::Data d;
+	d.timepoints.assign(timepoints, timepoints + T);
+	d.observed.assign(observed, observed + R * T);
+	d.num_replicates = R;
+	ll->SetData(d);
+	ll->SetSobolTable(std::vector<double>(sobol, sobol + sobol_count));
+	ll->SetDevice(device, compile_only != 0);
+	if (!ll->PostInitialize()) {
+		set_err(err, errlen, ll->LastError());
+		return false;
+	}
+	return true;
+}
+
 // cell_population through the plugin surface: likelihood.xml + the generated model, data set and quasi-random table that
 // the SBML / NetCDF readers would supply; evaluates values[C][nvar] batched (1) or chain by chain (0). compile_only = 1
 // stops after PostInitialize (CPU container: the model library is compiled, nothing runs); the descriptor handed to the
@@ -181,33 +219,10 @@ int bcm3host_cellpop_evaluate(const char* prior_xml, const char* likelihood_xml,
                               size_t desc_len, char* err, size_t errlen)
 {
 	Setup st;
-	std::string error;
-	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
-		set_err(err, errlen, error);
-		return -1;
-	}
-	auto* ll = dynamic_cast<CellPopulationLikelihoodB200*>(st.likelihood.get());
-	if (!ll) {
-		set_err(err, errlen, "likelihood.xml is not of type cell_population");
-		return -1;
-	}
-	CellPopulationLikelihoodB200::Model m;
-	m.derivative_code = derivative_code;
-	for (size_t i = 0; i < N; i++) m.species_names.push_back(species_names[i]);
-	m.initial_conditions.assign(initial_conditions, initial_conditions + N);
-	m.constant_species.assign(constant_species, constant_species + Nc);
-	ll->SetModel(m);
-	CellPopulationLikelihoodB200::Data d;
-	d.timepoints.assign(timepoints, timepoints + T);
-	d.observed.assign(observed, observed + R * T);
-	d.num_replicates = R;
-	ll->SetData(d);
-	ll->SetSobolTable(std::vector<double>(sobol, sobol + sobol_count));
-	ll->SetDevice(device, compile_only != 0);
-	if (!ll->PostInitialize()) {
-		set_err(err, errlen, ll->LastError());
+	CellPopulationLikelihoodB200* ll = nullptr;
+	if (!make_cellpop(prior_xml, likelihood_xml, derivative_code, N, species_names, initial_conditions, Nc, constant_species, T, R, timepoints, observed,
+	                  sobol_count, sobol, device, compile_only, st, ll, err, errlen))
 		return -3;
-	}
 	set_err(desc_out, desc_len, ll->GetDescriptor());
 	if (compile_only) return 0;
 	const size_t nvar = st.varset->GetNumVariables();
@@ -230,6 +245,20 @@ int bcm3host_cellpop_evaluate(const char* prior_xml, const char* likelihood_xml,
 		}
 	}
 	return 0;
+}
+
+// Parallel-tempered run on the GPU-backed cell_population likelihood (batched = one call per mutate round).
+int bcm3host_run_pt_cellpop(const char* prior_xml, const char* likelihood_xml, const char* config_text, int batched, unsigned long long seed,
+                            const char* derivative_code, size_t N, const char* const* species_names, const double* initial_conditions, size_t Nc,
+                            const double* constant_species, size_t T, size_t R, const double* timepoints, const double* observed, size_t sobol_count,
+                            const double* sobol, int device, double* out, size_t max_rows, size_t* num_rows, size_t* stats, char* err, size_t errlen)
+{
+	Setup st;
+	CellPopulationLikelihoodB200* ll = nullptr;
+	if (!make_cellpop(prior_xml, likelihood_xml, derivative_code, N, species_names, initial_conditions, Nc, constant_species, T, R, timepoints, observed,
+	                  sobol_count, sobol, device, 0, st, ll, err, errlen))
+		return -3;
+	return run(st, config_text, batched, seed, out, max_rows, num_rows, stats, err, errlen);
 }
 
 // VariableSet / Prior surface for tests: number of variables, transform codes, index lookup

@@ -108,3 +108,29 @@ def cellpop_evaluate(prior_xml: str, likelihood_xml: str, problem, species_names
     if rc != 0:
         raise RuntimeError(f"bcm3host_cellpop_evaluate failed ({rc}): {err.value.decode()}")
     return (None if compile_only else logp), desc.value.decode()
+
+
+def run_pt_cellpop(prior_xml: str, likelihood_xml: str, config_text: str, problem, species_names, batched: bool = True, seed: int = 1,
+                   device: int = 0, max_rows: int = 100000):
+    """Parallel-tempered run of the C++ sampler on CellPopulationLikelihoodB200 (one batched call per mutate round)."""
+    lib = load()
+    p = problem
+    nvar = varset_info(prior_xml)[0]
+    out = np.zeros((max_rows, nvar + 3))
+    nrows = C.c_size_t()
+    stats = (C.c_size_t * 3)()
+    err = _err()
+    names = (C.c_char_p * len(species_names))(*[s.encode() for s in species_names])
+    ic = np.ascontiguousarray(p.initial_conditions, dtype=np.float64)
+    cs = np.ascontiguousarray(p.constant_species, dtype=np.float64)
+    tp = np.ascontiguousarray(p.timepoints, dtype=np.float64)
+    obs = np.ascontiguousarray(p.observed, dtype=np.float64)
+    sob = np.ascontiguousarray(p.sobol, dtype=np.float64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.bcm3host_run_pt_cellpop(prior_xml.encode(), likelihood_xml.encode(), config_text.encode(), int(batched), C.c_ulonglong(seed),
+                                     p.derivative_code.encode(), C.c_size_t(p.num_species), names, vp(ic), C.c_size_t(cs.size), vp(cs),
+                                     C.c_size_t(tp.size), C.c_size_t(obs.shape[0]), vp(tp), vp(obs), C.c_size_t(sob.size), vp(sob), int(device),
+                                     vp(out), C.c_size_t(max_rows), C.byref(nrows), stats, err, C.c_size_t(1024))
+    if rc != 0:
+        raise RuntimeError(f"bcm3host_run_pt_cellpop failed ({rc}): {err.value.decode()}")
+    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])

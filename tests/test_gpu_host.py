@@ -78,3 +78,21 @@ def test_cell_population_plugin_matches_the_direct_abi_call(built):
     batched, _ = host_api.cellpop_evaluate(prior, lik, prob, species, values=vals, batched=True)
     serial, _ = host_api.cellpop_evaluate(prior, lik, prob, species, values=vals, batched=False)
     assert np.array_equal(batched, want) and np.array_equal(serial, want)
+
+
+def test_pt_run_on_gpu_cell_population_batched_equals_serial(built):
+    """The C++ sampler on the GPU-backed cell_population likelihood: one batched call per mutate round reproduces the
+    chain-by-chain run sample for sample (results do not depend on the batch a chain is evaluated in)."""
+    from bcm3_b200 import host_api
+    from bcm3_b200 import synthetic_cellpop as sc
+    from tests.util import cellpop_xml
+
+    prob = sc.make_cellpop_problem(N=8, num_cells=96, T=10, data_cells=4, seed=9)
+    prior, lik, species = cellpop_xml(prob)
+    prior = prior.replace('lower="-5" upper="5"', 'lower="-1.5" upper="0.5"')  # keep the start-up draws in a sane range
+    cfg = CONFIG.replace("num_samples=40", "num_samples=24").replace("num_chains=5", "num_chains=4")
+    a, sa = host_api.run_pt_cellpop(prior, lik, cfg, prob, species, batched=True, seed=5)
+    b, sb = host_api.run_pt_cellpop(prior, lik, cfg, prob, species, batched=False, seed=5)
+    assert a.shape == (24 * 4, prob.num_variables + 3)
+    assert np.array_equal(a, b, equal_nan=True)
+    assert sa["batched_calls"] >= 48 and sb["batched_calls"] == 0 and sa["evaluations"] == sb["evaluations"]
