@@ -217,7 +217,7 @@ def test_ranking_patients_by_absorption_rate_does_not_change_results(Evaluator, 
 
 
 def test_ranked_large_batch_matches_the_cpu_checker(Evaluator, port):
-    """Above the library's own threshold (P * C >= 113 664 systems) the ranking is on by default."""
+    """Above the library's own threshold (P * C >= 60 000 systems) the ranking is on by default."""
     prob = syn.make_poppk_problem(PK_TWO, P=7200, T=10, t_end=72.0, seed=33, heterogeneous=True, missing_fraction=0.05)
     vals = syn.make_chain_values(prob, 16, seed=33)
     ev = Evaluator(prob)
