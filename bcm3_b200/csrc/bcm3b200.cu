@@ -308,7 +308,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	a.block_partial = s->block_partial.p;
 	a.order = nullptr;
 	// large batches: rank every chain's patients by absorption rate first (see poppk_kernel)
-	if (h->sort_patients && (long long)s->P * (long long)C >= h->sort_min_systems && s->P > 0) {
+	if (h->sort_patients && (long long)s->P * (long long)C >= h->sort_min_systems && s->P > 0 && (long long)s->P * (long long)C < (1ll << 31)) {
 		const size_t n = (size_t)s->P * C;
 		CUDA_TRY(s->rank_keys.ensure(n));
 		CUDA_TRY(s->rank_keys_sorted.ensure(n));
