@@ -125,3 +125,51 @@ def test_lane_group_shapes_against_cpu_checker(Evaluator, port, N, decades, rtol
     assert cellpop_logp_close(logp, want["logp"], 12, 1, rtol=rtol)
     assert np.abs(d["population_average"] - want["population_average"]).max() < 2e-5
     assert abs(d["cell_steps"].mean() / want["cell_steps"].mean() - 1.0) < 0.02
+
+
+def test_config3_full_size_properties(Evaluator, port):
+    """BASELINE config 3 at full size (12 species, 10 000 cells, 50 timepoints, 16 chains), through properties that do not
+    need the checker to run the whole thing: (1) the first 192 cells' trajectories equal the checker's, (2) reversing the
+    order of the cells (rows of the quasi-random table) leaves every log-likelihood unchanged to round-off, (3) a chain's
+    result does not depend on the batch it is evaluated in, (4) two shards combine to the unsharded result."""
+    import dataclasses
+
+    import torch
+
+    prob = sc.make_cellpop_problem(N=12, num_cells=10_000, T=50, data_cells=32, seed=1)
+    vals = sc.make_chain_values(16)
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    d = ev.diagnostics()
+    single, _ = ev.evaluate(vals[5:6])
+    ev.close()
+    assert (status == 0).all() and (d["cell_status"] == 1).all() and np.isfinite(logp).all()
+    assert single[0] == logp[5]
+    # (1)
+    sub = dataclasses.replace(prob, num_cells=192, sobol=prob.sobol[:192])
+    want = port.cellpop_evaluate(sub, vals[:4], threads=4, want_cell_values=True, want_steps=True)
+    got = d["cell_values"][:4, :, :192]
+    assert (np.isnan(got) == np.isnan(want["cell_values"])).all()
+    m = ~np.isnan(got)
+    assert np.abs(got[m] - want["cell_values"][m]).max() < 5e-5
+    assert (d["cell_steps"][:4, :192] == want["cell_steps"]).mean() > 0.7
+    # (2)
+    ev = Evaluator(dataclasses.replace(prob, sobol=prob.sobol[::-1].copy()))
+    rev, _ = ev.evaluate(vals)
+    ev.close()
+    assert cellpop_logp_close(rev, logp, 50, 1, rtol=1e-9)
+    # (4)
+    shards = [Evaluator(prob, shard_rank=r, shard_count=2) for r in range(2)]
+    width = 2 * prob.num_timepoints + 1
+    stream = torch.cuda.current_stream().cuda_stream
+    parts = []
+    for s in shards:
+        part = torch.empty((16, width), dtype=torch.float64, device="cuda:0")
+        s.enqueue(vals.ctypes.data, 16, vals.shape[1], part.data_ptr(), stream)
+        parts.append(part)
+    torch.cuda.synchronize()
+    total = parts[0] + parts[1]
+    combined, _ = shards[0].finish(total.data_ptr(), 16, stream)
+    for s in shards:
+        s.close()
+    assert cellpop_logp_close(combined, logp, 50, 1, rtol=1e-9)
