@@ -26,6 +26,7 @@ class CellPopEvaluator:
             obs_species="+".join(str(s) for s in p.obs_species), device=device, compile_only=int(compile_only),
             shard_rank=shard_rank, shard_count=shard_count)
         kv["variability_distribution"] = p.variability_distribution
+        kv["relative_to_time_average"] = int(p.relative_to_time_average)
         if p.treatment_species is not None:
             kv["treatment_species"] = p.treatment_species
         for name in ("entry_time", "stdev", "offset", "scale", "proportional_stdev"):

@@ -61,6 +61,7 @@ class CellPopProblem:
     entry_time_ix: int | None = None
     entry_time: float = 0.0
     error_model: str = "normal"
+    relative_to_time_average: bool = False   # <data relative_to_time_average="true">: log of the value over its time average
     weight: float = 1.0
     stdev_ix: int | None = None
     stdev: float = 1.0

@@ -35,6 +35,7 @@ struct CellPopState {
 	double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0;
 	double missing_simulation_time_stdev = 300.0; // DataLikelihoodTimeCourseBase.cpp:22
 	bool full_gaussian = false;                   // <cell_variability distribution="full_gaussian">
+	bool relative_to_time_average = false;        // <data relative_to_time_average="true">
 	int steps_report = 0;                         // option "cellpop_steps_report": what get_cell_diagnostics returns as cell_steps (0 steps, 1 nfe, 2 nsetups, 3 nje)
 	int treatment_species = -1;                   // <treatment_trajectory type="pulses" species_name=...>: constant species index
 	std::vector<int> obs_species;
@@ -245,7 +246,7 @@ struct CpLikArgs {
 	const double* transformed; // [C][nvar]
 	const double* timepoints;  // [T]
 	const double* observed;    // [R][T]
-	int T, R, nvar, error_model;
+	int T, R, nvar, error_model, relative_to_time_average;
 	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
 	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, weight, missing_stdev;
 	double* logp; // [C]
@@ -267,21 +268,38 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 	const double prop_stdev = (a.prop_stdev_ix >= 0) ? tv[a.prop_stdev_ix] : a.prop_stdev_fixed;
 	const double minus_log_sigma = -log(stdev);
 	const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
+	// offset / scale of the population average (.cpp:105-115); with relative_to_time_average the logarithm of every value
+	// relative to the average over the timepoints
+	double time_average = 0.0;
+	if (a.relative_to_time_average) {
+		for (int i = 0; i < a.T; i++) time_average += a.avg[c * a.T + i] + offset;
+		time_average /= (double)a.T;
+	}
+	auto transformed_average = [&](int i) {
+		double x = a.avg[c * a.T + i];
+		if (a.relative_to_time_average) {
+			x += offset;
+			x = log(x / time_average);
+			x *= scale;
+		} else {
+			x *= scale;
+			x += offset;
+		}
+		return x;
+	};
 	double logp = 0.0;
 	for (int i = 0; i < a.T; i++) {
-		double x = a.avg[c * a.T + i];
-		x *= scale;
-		x += offset;
+		const double x = transformed_average(i);
 		if (isnan(x)) {
 			// missing-value penalty, .cpp:121-144
 			double first_ok = a.timepoints[a.T - 1], last_ok = a.timepoints[0];
 			for (int m = 0; m < a.T; m++)
-				if (!isnan(a.avg[c * a.T + m] * scale + offset)) {
+				if (!isnan(transformed_average(m))) {
 					first_ok = a.timepoints[m];
 					break;
 				}
 			for (int m = a.T - 1; m >= 0; m--)
-				if (!isnan(a.avg[c * a.T + m] * scale + offset)) {
+				if (!isnan(transformed_average(m))) {
 					last_ok = a.timepoints[m];
 					break;
 				}
@@ -741,6 +759,7 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	la.offset_ix = cp.offset_ix;
 	la.scale_ix = cp.scale_ix;
 	la.stdev_fixed = cp.stdev_fixed;
+	la.relative_to_time_average = cp.relative_to_time_average ? 1 : 0;
 	la.prop_stdev_ix = cp.prop_stdev_ix;
 	la.prop_stdev_fixed = cp.prop_stdev_fixed;
 	la.offset_fixed = cp.offset_fixed;

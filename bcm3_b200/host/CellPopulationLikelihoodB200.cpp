@@ -116,6 +116,7 @@ bool CellPopulationLikelihoodB200::Initialize(std::shared_ptr<const bcm3::Variab
 			}
 			if (!Resolve(c.get("offset", "0"), offset, "offset")) return false;
 			if (!Resolve(c.get("scale", "1"), scale, "scale")) return false;
+			relative_to_time_average = c.get_bool("relative_to_time_average", false);
 			weight = c.get_real("weight", 1.0);
 			missing_stdev = c.get_real("missing_simulation_time_stdev", 300.0);
 		} else if (c.name == "treatment_trajectory") {
@@ -162,7 +163,7 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 	  << model.non_sampled_parameters.size() << ";num_cells=" << num_cells << ";num_timepoints=" << T << ";num_replicates=" << data.num_replicates
 	  << ";variability_dim=" << D << ";variability_distribution=" << distribution << ";solver_relative_tolerance=" << solver_rel_tol
 	  << ";solver_absolute_tolerance=" << solver_abs_tol << ";solver_min_timestep=" << solver_min_timestep << ";solver_max_steps=" << solver_max_steps
-	  << ";error_model=" << error_model << ";weight=" << weight << ";missing_simulation_time_stdev=" << missing_stdev << ";device=" << device
+	  << ";relative_to_time_average=" << (relative_to_time_average ? 1 : 0) << ";error_model=" << error_model << ";weight=" << weight << ";missing_simulation_time_stdev=" << missing_stdev << ";device=" << device
 	  << ";compile_only=" << (compile_only ? 1 : 0);
 	auto ref = [&](const char* name, const ValueRef& r) {
 		if (r.ix >= 0) d << ";" << name << "_ix=" << r.ix;

@@ -80,7 +80,7 @@ private:
 	std::string experiment_name, model_file, distribution = "diagonal_gaussian", covar_base_name, species_name, error_model = "normal";
 	size_t num_cells = 1;
 	ValueRef entry_time, stdev, proportional_stdev, offset, scale;
-	bool have_proportional_stdev = false;
+	bool have_proportional_stdev = false, relative_to_time_average = false;
 	double weight = 1.0, missing_stdev = 300.0;
 	double solver_min_timestep = 1e-8, solver_abs_tol = 4.0 * 1.1920928955078125e-07, solver_rel_tol = 4.0 * 1.1920928955078125e-07;
 	long solver_max_steps = 10000;

@@ -212,9 +212,23 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
 	const double prop_stdev = (pr.proportional_stdev_ix >= 0) ? transformed[pr.proportional_stdev_ix] : pr.proportional_stdev;
 	const double minus_log_sigma = -log(stdev), inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
-	for (int i = 0; i < T; i++) {
-		population_average[i] *= scale;
-		population_average[i] += offset;
+	if (pr.relative_to_time_average) {
+		// .cpp:105-112: offset first, then the logarithm of every value relative to the average over the timepoints, then scale
+		double time_average = 0.0;
+		for (int i = 0; i < T; i++) {
+			population_average[i] += offset;
+			time_average += population_average[i];
+		}
+		time_average /= (double)T;
+		for (int i = 0; i < T; i++) {
+			population_average[i] = log(population_average[i] / time_average);
+			population_average[i] *= scale;
+		}
+	} else {
+		for (int i = 0; i < T; i++) {
+			population_average[i] *= scale;
+			population_average[i] += offset;
+		}
 	}
 	double logp = 0.0;
 	for (int i = 0; i < T; i++) {

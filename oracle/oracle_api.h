@@ -123,6 +123,7 @@ typedef struct {
 	 * and the sorted pulse times; its value is a function of time and every pulse adds four discontinuities */
 	int32_t treatment_species, treatment_num_pulses;
 	const double* treatment_times;
+	int32_t relative_to_time_average; /* <data relative_to_time_average="true">, DataLikelihoodTimeCoursePopulationAverage.cpp:105-115 */
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

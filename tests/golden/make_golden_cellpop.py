@@ -30,6 +30,9 @@ CASES = {
     # <treatment_trajectory type="pulses"> driving the input (constant species 0): time-dependent RHS + 8 discontinuities, late entry
     "cellpop_n8_treatment_pulses": (dict(N=8, num_cells=40, T=20, t_end=40.0, data_cells=4, seed=27), 2,
                                     dict(treatment_species=0, treatment_times=np.array([20.0, 1.0]), obs_species=[0, 2], entry_time=4.0)),
+    # <data relative_to_time_average="true">: log of the population average over its time average, then scaled
+    "cellpop_n6_relative": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=28, replicates=2), 2,
+                            dict(relative_to_time_average=True, offset=0.05, scale=0.8)),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }

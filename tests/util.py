@@ -93,6 +93,8 @@ def load_cellpop_golden(name):
                                        scale_ix=None if scale_ix < 0 else int(scale_ix), scale_fixed=float(scale_fixed), negate=bool(negate)))
     opt_int = lambda k: int(z[k]) if k in z.files else None
     extra = {}
+    if "relative_to_time_average" in z.files:
+        extra.update(relative_to_time_average=bool(z["relative_to_time_average"]))
     if "treatment_species" in z.files:
         extra.update(treatment_species=int(z["treatment_species"]), treatment_times=z["treatment_times"])
     if "variability_distribution" in z.files:
