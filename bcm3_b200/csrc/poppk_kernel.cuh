@@ -226,7 +226,8 @@ __global__ void poppk_rank_kernel(const PkArgs a, int C, unsigned long long* __r
 	float kf = (float)(intervals + frac);
 	if (!(kf >= 0.0f)) kf = INFINITY; // keep the order total whatever the inputs
 	const long long e = (long long)c * a.P_local + j;
-	keys[e] = ((unsigned long long)c << 32) | (unsigned long long)__float_as_uint(kf);
+	// descending work within the chain: the longest-running blocks are scheduled first (shorter tail at the end of the grid)
+	keys[e] = ((unsigned long long)c << 32) | (unsigned long long)(0xffffffffu - __float_as_uint(kf));
 	patients[e] = j;
 }
 
