@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common_host.cuh"
+#define BCM3_POPPK_AUX_KERNELS
 #include "poppk_kernel.cuh"
 #include "cellpop_host.cuh"
 
@@ -351,34 +352,11 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	dim3 grid(nblk, (unsigned)C);
 	if (C > 65535) return fail(BCM3B200_ERR_UNSUPPORTED, "more than 65535 chains in one batch");
 
-#define LAUNCH_S(MODEL, DIAGV, STRIDE)                                                                                \
-	do {                                                                                                              \
-		if (smem_bytes > 48 * 1024)                                                                                   \
-			CUDA_TRY(cudaFuncSetAttribute(poppk_kernel<MODEL, DIAGV, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-			                              (int)smem_bytes));                                                          \
-		poppk_kernel<MODEL, DIAGV, STRIDE><<<grid, block, smem_bytes, stream>>>(a);                                   \
-	} while (0)
-#define LAUNCH(MODEL, DIAGV)                                                                                          \
-	do {                                                                                                              \
-		if (stride == 128) LAUNCH_S(MODEL, DIAGV, 128);                                                               \
-		else LAUNCH_S(MODEL, DIAGV, 384);                                                                             \
-	} while (0)
-#define LAUNCH_D(MODEL)                        \
-	do {                                       \
-		if (h->diagnostics) LAUNCH(MODEL, true); \
-		else LAUNCH(MODEL, false);               \
-	} while (0)
-	switch (h->pk_type) {
-	case PK_ONE: LAUNCH_D(PkOneModel); break;
-	case PK_TWO: LAUNCH_D(PkTwoModel); break;
-	case PK_ONE_BIPHASIC: LAUNCH_D(PkOneBiphasicModel); break;
-	case PK_TWO_BIPHASIC: LAUNCH_D(PkTwoBiphasicModel); break;
-	case PK_ONE_TRANSIT: LAUNCH_D(PkOneTransitModel); break;
-	default: LAUNCH_D(PkTwoTransitModel); break;
-	}
-#undef LAUNCH_D
-#undef LAUNCH
-#undef LAUNCH_S
+	int lrc;
+	if (h->pk_type == PK_ONE || h->pk_type == PK_TWO) lrc = launch_poppk_plain(two_cmt, h->diagnostics, stride, grid, block, smem_bytes, stream, a);
+	else if (h->pk_type == PK_ONE_BIPHASIC || h->pk_type == PK_TWO_BIPHASIC) lrc = launch_poppk_biphasic(two_cmt, h->diagnostics, stride, grid, block, smem_bytes, stream, a);
+	else lrc = launch_poppk_transit(two_cmt, h->diagnostics, stride, grid, block, smem_bytes, stream, a);
+	if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "poppk_kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
 	CUDA_TRY(cudaGetLastError());
 	poppk_chain_reduce<<<(unsigned)C, 256, 0, stream>>>(s->block_partial.p, nblk, (int)C, d_partial);
 	CUDA_TRY(cudaGetLastError());

@@ -110,7 +110,7 @@ struct BdfCounters {
 // Evaluated as exp(log(base) / k) with the correctly rounded constant 1/k instead of pow(): a few ulp from pow's
 // result, i.e. the same size as the FMA-contraction differences between two builds of the reference itself, and
 // several times cheaper than the generic double-precision pow on the GPU.
-__device__ BCM3_ROOT_INLINE double bdf_root(double base, int k)
+static __device__ BCM3_ROOT_INLINE double bdf_root(double base, int k)
 {
 	if (base <= 0.0) return 0.0;
 	double inv = 1.0;
@@ -126,7 +126,7 @@ __device__ BCM3_ROOT_INLINE double bdf_root(double base, int k)
 // ~3e-7) refined by one Halley step for y^k = x in double precision (cubic convergence: ~(k^2 - 1) / 12 * e^3 < 1e-17),
 // so the result is within an ulp or two of pow(x, 1/k), like the exp/log form, at about a quarter of its instructions
 // and with no dependence on k in the control flow. Outside the single-precision range it falls back to exp/log.
-__device__ BCM3_ROOT_INLINE double bdf_root_halley(double base, int k)
+static __device__ BCM3_ROOT_INLINE double bdf_root_halley(double base, int k)
 {
 	if (base <= 0.0) return 0.0;
 	if (!(base > 1e-30 && base < 1e30)) return bdf_root(base, k);

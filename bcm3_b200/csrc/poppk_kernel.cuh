@@ -203,6 +203,14 @@ __device__ __forceinline__ bool check_give_treatment(double t, uint32_t skipped_
 #define BCM3_SORT_BLOCK_PATIENTS 0 /* in-block ranking: measured +4 % only (the block still waits for its slowest warp) */
 #endif
 
+// One translation unit per model family instantiates the integrator (poppk_inst_plain.cu, _biphasic.cu, _transit.cu: 8 kernels
+// each = one/two compartments x diagnostics x state-column stride) so that they compile in parallel and deterministically.
+// Returns a cudaError_t value.
+int launch_poppk_plain(bool two, bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a);
+int launch_poppk_biphasic(bool two, bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a);
+int launch_poppk_transit(bool two, bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a);
+
+#ifdef BCM3_POPPK_AUX_KERNELS /* compiled once, in bcm3b200.cu; the integrator instances live in poppk_inst_*.cu */
 // Sort key of (chain, patient): chain in the high word; in the low word the bits of a positive float that orders the
 // patients by expected work: every dose restarts the integrator (about as many steps per dosing interval whatever its
 // length), so the number of dosing intervals inside the simulated window comes first, and within it the absorption rate
@@ -230,6 +238,8 @@ __global__ void poppk_rank_kernel(const PkArgs a, int C, unsigned long long* __r
 	keys[e] = ((unsigned long long)c << 32) | (unsigned long long)(0xffffffffu - __float_as_uint(kf));
 	patients[e] = j;
 }
+
+#endif
 
 template <class Model, bool DIAG, int STRIDE>
 __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(const PkArgs a)
@@ -554,6 +564,7 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 	}
 }
 
+#ifdef BCM3_POPPK_AUX_KERNELS
 // K3 (second level): block partials -> partial[3][C], fixed order.
 __global__ void poppk_chain_reduce(const double* __restrict__ block_partial, int nblk, int C, double* __restrict__ partial)
 {
@@ -585,5 +596,6 @@ __global__ void poppk_chain_reduce(const double* __restrict__ block_partial, int
 		partial[2 * C + c] = sh[2][0];
 	}
 }
+#endif
 
 } // namespace bcm3b200
