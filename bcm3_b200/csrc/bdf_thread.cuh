@@ -772,59 +772,68 @@ struct BdfThread {
 			tq[i] = slot(SL::TQSTASH + i);
 		}
 		int result;
-		if (nls_ret != 0) {
-			// ---- cvHandleNFlag ----
-			if (STATS) cnt.ncfn++;
-			restore();
-			ncf++;
-			etamax() = 1.0;
-			// hmin = 0: |h| <= hmin * ONEPSM only for h == 0
-			if ((fabs(h) <= 0.0) || (ncf == BDF_MXNCF)) {
-				result = BDF_ATTEMPT_FAILED;
+		// Both failure paths (cvHandleNFlag :2865, cvDoErrorTest :2958) restore the Nordsieck array and, unless the step is
+		// abandoned, rescale it: written with ONE restore() and ONE rescale() site -- per warp a failure happens in half of
+		// the trips, so this is hot code, and the kernel is bound by its instruction footprint.
+		const double dsm = acnrm() * tq[2];
+		const bool conv_fail = (nls_ret != 0);
+		const bool err_fail = !conv_fail && !(dsm <= 1.0);
+		if (conv_fail || err_fail) {
+			bool do_rescale = false;
+			if (conv_fail) {
+				if (STATS) cnt.ncfn++;
+				ncf++;
 			} else {
-				eta() = BDF_ETACF;
-				nflag = BDF_PREV_CONV_FAIL;
-				rescale();
-				result = BDF_ATTEMPT_RETRY;
-			}
-		} else {
-			// ---- cvDoErrorTest ----
-			const double dsm = acnrm() * tq[2];
-			if (!(dsm <= 1.0)) {
 				nef++;
 				if (STATS) cnt.netf++;
 				nflag = BDF_PREV_ERR_FAIL;
-				restore();
-				if ((fabs(h) <= 0.0) || (nef == BDF_MXNEF)) {
+			}
+			restore();
+			if (conv_fail) {
+				// ---- cvHandleNFlag ----
+				etamax() = 1.0;
+				// hmin = 0: |h| <= hmin * ONEPSM only for h == 0
+				if ((fabs(h) <= 0.0) || (ncf == BDF_MXNCF)) {
 					result = BDF_ATTEMPT_FAILED;
 				} else {
+					eta() = BDF_ETACF;
+					nflag = BDF_PREV_CONV_FAIL;
+					do_rescale = true;
 					result = BDF_ATTEMPT_RETRY;
-					etamax() = 1.0;
-					if (nef <= BDF_MXNEF1) {
-						eta() = 1.0 / (bdf_step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
-						eta() = fmax(BDF_ETAMIN, eta());
-						if (nef >= BDF_SMALL_NEF) eta() = fmin(eta(), BDF_ETAMXF);
-						rescale();
-					} else if (q > 1) {
-						eta() = BDF_ETAMIN;
-						adjust_order(-1);
-						L = q;
-						q--;
-						qwait = L;
-						rescale();
-					} else {
-						eta() = BDF_ETAMIN;
-						h *= eta();
-						hscale() = h;
-						qwait = BDF_LONG_WAIT;
-						double f[N];
-						model.rhs(tn, zn01[0], f);
-						if (STATS) cnt.nfe++;
-#pragma unroll
-						for (int i = 0; i < N; i++) Z<1>(i) = h * f[i];
-					}
 				}
+			} else if ((fabs(h) <= 0.0) || (nef == BDF_MXNEF)) {
+				// ---- cvDoErrorTest ----
+				result = BDF_ATTEMPT_FAILED;
 			} else {
+				result = BDF_ATTEMPT_RETRY;
+				etamax() = 1.0;
+				if (nef <= BDF_MXNEF1) {
+					eta() = 1.0 / (bdf_step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+					eta() = fmax(BDF_ETAMIN, eta());
+					if (nef >= BDF_SMALL_NEF) eta() = fmin(eta(), BDF_ETAMXF);
+					do_rescale = true;
+				} else if (q > 1) {
+					eta() = BDF_ETAMIN;
+					adjust_order(-1);
+					L = q;
+					q--;
+					qwait = L;
+					do_rescale = true;
+				} else {
+					eta() = BDF_ETAMIN;
+					h *= eta();
+					hscale() = h;
+					qwait = BDF_LONG_WAIT;
+					double f[N];
+					model.rhs(tn, zn01[0], f);
+					if (STATS) cnt.nfe++;
+#pragma unroll
+					for (int i = 0; i < N; i++) Z<1>(i) = h * f[i];
+				}
+			}
+			if (do_rescale) rescale();
+		} else {
+			{
 				result = BDF_ATTEMPT_DONE;
 				// ---- cvCompleteStep ----
 				nst++;
