@@ -1018,56 +1018,64 @@ struct GroupBdf {
 			tq[i] = sc[SC_TQ + i];
 		}
 		int result;
-		if (nls_ret != 0) {
-			// ---- cvHandleNFlag ----
-			restore();
-			ncf++;
-			etamax() = 1.0;
-			if ((fabs(h) <= hmin * BDF_ONEPSM) || (ncf == BDF_MXNCF)) {
-				result = T_FAILED;
+		// Both failure paths (cvHandleNFlag, cvDoErrorTest) share ONE restore() and ONE rescale() site: per warp a failure
+		// happens in a large share of the trips, so this is hot code, and the kernel is bound by its instruction footprint.
+		const double dsm = acnrm() * tq[2];
+		const bool conv_fail = (nls_ret != 0);
+		const bool err_fail = !conv_fail && !(dsm <= 1.0);
+		if (conv_fail || err_fail) {
+			bool do_rescale = false;
+			if (conv_fail) {
+				ncf++;
 			} else {
-				eta() = fmax(BDF_ETACF, hmin / fabs(h));
-				nflag = bcm3b200::BDF_PREV_CONV_FAIL;
-				rescale();
-				result = T_RETRY;
-			}
-		} else {
-			const double dsm = acnrm() * tq[2];
-			if (!(dsm <= 1.0)) {
-				// ---- cvDoErrorTest, failure ----
 				nef++;
 				nflag = bcm3b200::BDF_PREV_ERR_FAIL;
-				restore();
-				if ((fabs(h) <= hmin * BDF_ONEPSM) || (nef == BDF_MXNEF)) {
+			}
+			restore();
+			if (conv_fail) {
+				// ---- cvHandleNFlag ----
+				etamax() = 1.0;
+				if ((fabs(h) <= hmin * BDF_ONEPSM) || (ncf == BDF_MXNCF)) {
 					result = T_FAILED;
 				} else {
+					eta() = fmax(BDF_ETACF, hmin / fabs(h));
+					nflag = bcm3b200::BDF_PREV_CONV_FAIL;
+					do_rescale = true;
 					result = T_RETRY;
-					etamax() = 1.0;
-					if (nef <= BDF_MXNEF1) {
-						eta() = 1.0 / (step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
-						eta() = fmax(BDF_ETAMIN, fmax(eta(), hmin / fabs(h)));
-						if (nef >= BDF_SMALL_NEF) eta() = fmin(eta(), BDF_ETAMXF);
-						rescale();
-					} else if (q > 1) {
-						eta() = fmax(BDF_ETAMIN, hmin / fabs(h));
-						adjust_order(-1);
-						L = q;
-						q--;
-						qwait = L;
-						rescale();
-					} else {
-						eta() = fmax(BDF_ETAMIN, hmin / fabs(h));
-						h *= eta();
-						hscale() = h;
-						qwait = BDF_LONG_WAIT;
-						double f[E];
-						publish(ybuf, zn01[0]);
-						rhs_shared(tn, f);
-#pragma unroll
-						for (int e = 0; e < E; e++) Z<1>(e) = h * f[e];
-					}
 				}
+			} else if ((fabs(h) <= hmin * BDF_ONEPSM) || (nef == BDF_MXNEF)) {
+				// ---- cvDoErrorTest, failure ----
+				result = T_FAILED;
 			} else {
+				result = T_RETRY;
+				etamax() = 1.0;
+				if (nef <= BDF_MXNEF1) {
+					eta() = 1.0 / (step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
+					eta() = fmax(BDF_ETAMIN, fmax(eta(), hmin / fabs(h)));
+					if (nef >= BDF_SMALL_NEF) eta() = fmin(eta(), BDF_ETAMXF);
+					do_rescale = true;
+				} else if (q > 1) {
+					eta() = fmax(BDF_ETAMIN, hmin / fabs(h));
+					adjust_order(-1);
+					L = q;
+					q--;
+					qwait = L;
+					do_rescale = true;
+				} else {
+					eta() = fmax(BDF_ETAMIN, hmin / fabs(h));
+					h *= eta();
+					hscale() = h;
+					qwait = BDF_LONG_WAIT;
+					double f[E];
+					publish(ybuf, zn01[0]);
+					rhs_shared(tn, f);
+#pragma unroll
+					for (int e = 0; e < E; e++) Z<1>(e) = h * f[e];
+				}
+			}
+			if (do_rescale) rescale();
+		} else {
+			{
 				result = T_DONE;
 				// ---- cvCompleteStep ----
 				nst++;
