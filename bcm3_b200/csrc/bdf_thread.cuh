@@ -180,6 +180,10 @@ struct BdfThread {
 	double* sh; // shared memory, already offset by the thread index
 	int q, qprime, L, qwait, nst, nstlp, nstlj;
 	int nflag, ncf, nef;
+	// cvAdjustOrder + cvRescale requested by begin_step (cvAdjustParams) or by a failed attempt: carried out at the top of the
+	// next attempt(), so that the kernel holds ONE copy of that code
+	int pending_adjust;
+	bool pending_rescale;
 	bool tstopset, nls_jcur;
 	BdfCounters cnt;
 
@@ -263,6 +267,8 @@ struct BdfThread {
 		q = 1;
 		L = 2;
 		qwait = 2;
+		pending_adjust = 0;
+		pending_rescale = false;
 		etamax() = BDF_ETAMX1;
 		hu() = 0.0;
 		nst = 0;
@@ -475,14 +481,9 @@ struct BdfThread {
 		nef = 0;
 		nflag = BDF_FIRST_CALL;
 		if ((nst > 0) && (hprime() != h)) {
-			// cvAdjustParams
-			if (qprime != q) {
-				adjust_order(qprime - q);
-				q = qprime;
-				L = q + 1;
-				qwait = L;
-			}
-			rescale();
+			// cvAdjustParams: order change, then rescale -- at the top of attempt()
+			pending_adjust = qprime - q;
+			pending_rescale = true;
 		}
 		return true;
 	}
@@ -551,6 +552,18 @@ struct BdfThread {
 		for (int i = 0; i < 6; i++) {
 			l[i] = 0.0;
 			tq[i] = 0.0;
+		}
+		// ---- pending cvAdjustOrder (q, L, qwait follow as in cvAdjustParams :2192-2204 / cvDoErrorTest :3017-3022) + cvRescale ----
+		if (pending_adjust != 0) {
+			adjust_order(pending_adjust);
+			q += pending_adjust;
+			L = q + 1;
+			qwait = L;
+			pending_adjust = 0;
+		}
+		if (pending_rescale) {
+			rescale();
+			pending_rescale = false;
 		}
 		// ---- cvPredict ----
 		tn += h;
@@ -779,7 +792,6 @@ struct BdfThread {
 		const bool conv_fail = (nls_ret != 0);
 		const bool err_fail = !conv_fail && !(dsm <= 1.0);
 		if (conv_fail || err_fail) {
-			bool do_rescale = false;
 			if (conv_fail) {
 				if (STATS) cnt.ncfn++;
 				ncf++;
@@ -798,7 +810,7 @@ struct BdfThread {
 				} else {
 					eta() = BDF_ETACF;
 					nflag = BDF_PREV_CONV_FAIL;
-					do_rescale = true;
+					pending_rescale = true;
 					result = BDF_ATTEMPT_RETRY;
 				}
 			} else if ((fabs(h) <= 0.0) || (nef == BDF_MXNEF)) {
@@ -811,14 +823,11 @@ struct BdfThread {
 					eta() = 1.0 / (bdf_step_root(BDF_BIAS2 * dsm, L) + BDF_ADDON);
 					eta() = fmax(BDF_ETAMIN, eta());
 					if (nef >= BDF_SMALL_NEF) eta() = fmin(eta(), BDF_ETAMXF);
-					do_rescale = true;
+					pending_rescale = true;
 				} else if (q > 1) {
 					eta() = BDF_ETAMIN;
-					adjust_order(-1);
-					L = q;
-					q--;
-					qwait = L;
-					do_rescale = true;
+					pending_adjust = -1;
+					pending_rescale = true;
 				} else {
 					eta() = BDF_ETAMIN;
 					h *= eta();
@@ -831,7 +840,6 @@ struct BdfThread {
 					for (int i = 0; i < N; i++) Z<1>(i) = h * f[i];
 				}
 			}
-			if (do_rescale) rescale();
 		} else {
 			{
 				result = BDF_ATTEMPT_DONE;
