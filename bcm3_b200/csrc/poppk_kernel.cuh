@@ -199,9 +199,6 @@ __device__ __forceinline__ bool check_give_treatment(double t, uint32_t skipped_
 }
 
 // STRIDE = thread stride of the per-thread shared-memory state columns = the largest block this instantiation runs with
-#ifndef BCM3_SORT_BLOCK_PATIENTS
-#define BCM3_SORT_BLOCK_PATIENTS 0 /* in-block ranking: measured +4 % only (the block still waits for its slowest warp) */
-#endif
 
 // One translation unit per model family instantiates the integrator (poppk_inst_plain.cu, _biphasic.cu, _transit.cu: 8 kernels
 // each = one/two compartments x diagnostics x state-column stride) so that they compile in parallel and deterministically.
@@ -295,38 +292,6 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 		if (Model::VARIANT == PKV_BIPHASIC) model.ka2 = transform_variable(a.tr[SV_NAMED_B], vrow[a.ix[SV_NAMED_B]]); // cpp:308-309
 	}
 
-#if BCM3_SORT_BLOCK_PATIENTS
-	// ---- order the block's patients by absorption rate ----
-	// The number of steps a solve takes is ~96 % determined by ka (correlation 0.98 on the config-5 workload: the fast
-	// absorption transient sets the early step sizes after every dose), and a warp runs until its slowest lane is done.
-	// With patients in arrival order a warp's lanes are busy 84 % of its trips; ranked by ka within the block, 97 %. The
-	// patients stay in this block (same global reads, same block partial); only the lane that integrates each one changes.
-	{
-		double* s_key = smem + T + (size_t)T * blockDim.x; // the integrator's state columns are not in use yet
-		double* s_ka = s_key + blockDim.x;
-		double* s_kel = s_ka + blockDim.x;
-		int* s_pat = reinterpret_cast<int*>(s_kel + blockDim.x);
-		double key = valid ? model.ka : INFINITY;
-		if (!(key == key)) key = INFINITY; // NaN would break the strict order below
-		s_key[tid] = key;
-		__syncthreads();
-		int rank = 0;
-		for (int k = 0; k < (int)blockDim.x; k++) {
-			const double kk = s_key[k];
-			rank += (kk < key || (kk == key && k < tid)) ? 1 : 0;
-		}
-		s_ka[rank] = model.ka;
-		s_kel[rank] = model.kel;
-		s_pat[rank] = valid ? jl : -1;
-		__syncthreads();
-		model.ka = s_ka[tid];
-		model.kel = s_kel[tid];
-		const int pat = s_pat[tid];
-		valid = pat >= 0;
-		jl = valid ? pat : jl;
-		__syncthreads(); // the columns are zero-filled by S.create() next
-	}
-#endif
 
 	double dose = 0.0, dosing_interval = 1.0, dose_after = 0.0, dose_change_time = 0.0;
 	int intermittent = 0, ntp = 0;
