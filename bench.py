@@ -269,14 +269,26 @@ def run_cellpop_sharded(args, workload, prob, vals, rank, world, local_rank):
     nl = torch.tensor([float(lk.evaluator.get_stat("total_kernel_launches") - launches0)], dtype=torch.float64, device=dev)
     dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    # roofline of the dominant kernel on this rank's shard (kernel time from the library's own events, max over ranks)
+    kms = torch.tensor([lk.evaluator.get_stat("last_kernel_us") / 1e3], dtype=torch.float64, device=dev)
+    dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    fp64_peak = _lib.measure_fp64_peak(local_rank)
+    cells_local = lk.evaluator.get_stat("num_cells_local")
     if rank == 0:
         total_ms, wall_ms = float(tot[0].item()), float(tot[1].item())
+        steps_mean = 243.6 if w["N"] == 12 else 542.0  # mean accepted steps per cell of the synthetic models (measured at N = 1)
+        flop_sys = cellpop_flop_per_system(w["N"], steps_mean, 8.0 * 2 * w["N"])
+        k_ms = float(kms.item())
+        achieved = flop_sys * C * cells_local / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                    "kernel": "cellpop_group_kernel", "kernel_ms": k_ms, "flop_per_system": flop_sys, "systems_per_launch": C * cells_local,
+                    "note": "per GPU, on its shard of the cells", "peak_source": "measured live: bcm3b200_measure_fp64_peak"}
         line = {"metric": METRIC_CELLPOP, "value": C * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C, "timepoints": w["T"], "ode_solves_per_step": C * w["cells"],
                            "sharding": f"cells over {world} ranks, NCCL SUM all-reduce of [{C}][{2 * w['T'] + 1}] doubles", "l2": "256 MB memset between timed iterations"},
-                "roofline": None,
+                "roofline": roofline,
                 "e2e": {"value": C * args.steps / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes) * world, "d2h_bytes_per_step": int(C * 8) * world,
                         "ms_per_step": wall_ms / args.steps},
                 "gpu_launches": int(nl.item()), "clocks": clocks, "check": {"logp0": float(logp[0]), "status_ok": bool((status == 0).all())}}
