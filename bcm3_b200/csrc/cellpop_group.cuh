@@ -19,6 +19,10 @@
 //   * cells are handed out from a global work queue to resident groups (grid = what fits on the GPU), so a group that
 //     finishes a cell picks up the next one instead of idling until the slowest cell of its block is done.
 //
+// The model library is compiled with -fmad=false so that the generated right-hand side rounds exactly like the checker's
+// (see cellpop_host.cuh); the integrator's own multiply-adds are written as explicit fma() -- the reference's host build
+// contracts them too.
+//
 // Control flow is kept converged the way poppk_kernel does it: one step attempt per loop trip, the Newton loops made
 // warp-uniform with votes over the participating lanes, the warps of a block in lock-step.
 #pragma once
@@ -282,7 +286,7 @@ struct GroupBdf {
 #pragma unroll
 		for (int e = 0; e < E; e++) {
 			const double p = x[e] * ewt[e];
-			s += p * p;
+			s = fma(p, p, s);
 		}
 		return norm_finish(s, gmask);
 	}
@@ -382,7 +386,7 @@ struct GroupBdf {
 				const double hgs = hg * sign;
 				double ytmp[E], ftmp[E];
 #pragma unroll
-				for (int e = 0; e < E; e++) ytmp[e] = hgs * Z<1>(e) + Z<0>(e);
+				for (int e = 0; e < E; e++) ytmp[e] = fma(hgs, Z<1>(e), Z<0>(e));
 				publish(ybuf, ytmp);
 				rhs_shared(tn + hgs, ftmp);
 				const double c = 1.0 / hgs;
@@ -465,7 +469,7 @@ struct GroupBdf {
 			constexpr int j = decltype(J)::value;
 			if (j <= q) {
 #pragma unroll
-				for (int e = 0; e < E; e++) Z<j>(e) += ll[j] * znL[e];
+				for (int e = 0; e < E; e++) Z<j>(e) = fma(ll[j], znL[e], Z<j>(e));
 			} else if (j <= L) {
 #pragma unroll
 				for (int e = 0; e < E; e++) Z<j>(e) = znL[e];
@@ -508,7 +512,7 @@ struct GroupBdf {
 				constexpr int j = decltype(J)::value;
 				if (j < q) {
 #pragma unroll
-					for (int e = 0; e < E; e++) Z<j>(e) += (-ll[j]) * znq[e];
+					for (int e = 0; e < E; e++) Z<j>(e) = fma(-ll[j], znq[e], Z<j>(e));
 				}
 			});
 		}
@@ -838,8 +842,8 @@ struct GroupBdf {
 		rhs_shared(tn, fy);
 #pragma unroll
 		for (int e = 0; e < E; e++) {
-			double r = rl1 * Z<1>(e) + acor[e];
-			r += -gamma * fy[e];
+			double r = fma(rl1, Z<1>(e), acor[e]);
+			r = fma(-gamma, fy[e], r);
 			delta[e] = r;
 		}
 	}
@@ -1087,7 +1091,7 @@ struct GroupBdf {
 					constexpr int j = decltype(J)::value;
 					if (j <= q) {
 #pragma unroll
-						for (int e = 0; e < E; e++) Z<j>(e) += l[j] * acor[e];
+						for (int e = 0; e < E; e++) Z<j>(e) = fma(l[j], acor[e], Z<j>(e));
 					}
 				});
 				qwait--;
@@ -1136,7 +1140,7 @@ struct GroupBdf {
 								const double cquot = (tq[5] / stq5) * pw;
 								double tmp[E];
 #pragma unroll
-								for (int e = 0; e < E; e++) tmp[e] = -cquot * Z<QMAX>(e) + acor[e];
+								for (int e = 0; e < E; e++) tmp[e] = fma(-cquot, Z<QMAX>(e), acor[e]);
 								const double dup = wrms(tmp) * tq[3];
 								etaqp1 = 1.0 / (step_root(BDF_BIAS3 * dup, L + 1) + BDF_ADDON);
 							}
@@ -1202,7 +1206,7 @@ struct GroupBdf {
 					first = false;
 				} else {
 #pragma unroll
-					for (int e = 0; e < E; e++) out[e] += c * Z<j>(e);
+					for (int e = 0; e < E; e++) out[e] = fma(c, Z<j>(e), out[e]);
 				}
 			}
 		});
@@ -1249,7 +1253,7 @@ struct GroupBdf {
 					first = false;
 				} else {
 #pragma unroll
-					for (int e = 0; e < E; e++) acc[e] += c * Z<j>(e);
+					for (int e = 0; e < E; e++) acc[e] = fma(c, Z<j>(e), acc[e]);
 				}
 			}
 		});
