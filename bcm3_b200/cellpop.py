@@ -29,6 +29,8 @@ class CellPopEvaluator:
         kv["relative_to_time_average"] = int(p.relative_to_time_average)
         if p.treatment_species is not None:
             kv["treatment_species"] = p.treatment_species
+        if p.simulation_end_time is not None:
+            kv["simulation_end_time"] = repr(float(p.simulation_end_time))
         for name in ("entry_time", "stdev", "offset", "scale", "proportional_stdev"):
             ix = getattr(p, name + "_ix")
             if ix is not None:

@@ -62,6 +62,9 @@ class CellPopProblem:
     entry_time: float = 0.0
     error_model: str = "normal"
     relative_to_time_average: bool = False   # <data relative_to_time_average="true">: log of the value over its time average
+    # the time the experiment integrates its cells to when it has further data sets that end later (Experiment.cpp:655-656);
+    # None: the last of `timepoints`
+    simulation_end_time: float | None = None
     weight: float = 1.0
     stdev_ix: int | None = None
     stdev: float = 1.0

@@ -502,6 +502,8 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		cp->scale_ix = get_int(kv, "scale_ix", -1);
 		cp->scale_fixed = real("scale", 1.0);
 		cp->missing_simulation_time_stdev = real("missing_simulation_time_stdev", 300.0);
+		cp->have_sim_end_time = kv.count("simulation_end_time") != 0;
+		cp->sim_end_time = real("simulation_end_time", 0.0);
 		if (kv.count("obs_species")) {
 			std::string v = kv["obs_species"];
 			size_t pos = 0;

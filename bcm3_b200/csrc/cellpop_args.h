@@ -44,6 +44,9 @@ struct CpArgs {
 	double entry_time_fixed;
 	const double* timepoints; // [T] absolute times, sorted
 	int T;
+	// absolute time every cell is integrated to: the last timepoint of ALL data sets of the experiment (Experiment.cpp:655-656);
+	// equals timepoints[T - 1] when this data set is the only or the longest one
+	double sim_end_time;
 	// solver (Experiment.cpp:411-416, Cell.cpp:70-74)
 	double rel_tol, abs_tol, min_dt;
 	int max_steps;

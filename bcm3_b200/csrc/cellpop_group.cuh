@@ -1406,8 +1406,8 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 					if (B.lg == 0) out[(long long)tpi * a.num_cells] = (cell_time < 0.0) ? nan : sv0;
 					tpi++;
 				}
-				if (tpi >= T) finished = true;
-				const double end_time = a.timepoints[T - 1] - creation_time;
+				const double end_time = a.sim_end_time - creation_time;
+				if (end_time < DBL_EPSILON) finished = true; // nothing to integrate: every requested time is at or before the cell's creation
 				B.sc[SC_END] = end_time;
 				if (!finished) {
 					// Cell::Simulate (Cell.cpp:212-229): SetDiscontinuity(first discontinuity ahead of the cell) = CVodeSetStopTime

@@ -34,6 +34,8 @@ struct CellPopState {
 	int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
 	double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0;
 	double missing_simulation_time_stdev = 300.0; // DataLikelihoodTimeCourseBase.cpp:22
+	bool have_sim_end_time = false; // descriptor key simulation_end_time: the experiment's last requested time over ALL its data sets
+	double sim_end_time = 0.0;
 	bool full_gaussian = false;                   // <cell_variability distribution="full_gaussian">
 	bool relative_to_time_average = false;        // <data relative_to_time_average="true">
 	int steps_report = 0;                         // option "cellpop_steps_report": what get_cell_diagnostics returns as cell_steps (0 steps, 1 nfe, 2 nsetups, 3 nje)
@@ -534,6 +536,7 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	if (cp.D > 0 && (!cp.data.count("sobol") || !cp.data.count("variability"))) return fail(BCM3B200_ERR_STATE, "variability needs \"sobol\" and \"variability\"");
 	if (cp.D > CP_MAX_VARIABILITY) return fail(BCM3B200_ERR_UNSUPPORTED, "more than %d variability dimensions", CP_MAX_VARIABILITY);
 	if (cp.obs_species.empty() || cp.obs_species.size() > 8) return fail(BCM3B200_ERR_ARG, "obs_species must name 1..8 species");
+	if (cp.have_sim_end_time && !(cp.sim_end_time >= cp.data["timepoints"].back())) return fail(BCM3B200_ERR_ARG, "simulation_end_time lies before the last timepoint");
 	for (int s : cp.obs_species)
 		if (s < 0 || s >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species index out of range");
 
@@ -661,6 +664,7 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	a.entry_time_fixed = cp.entry_time_fixed;
 	a.timepoints = cp.d_time.p;
 	a.T = cp.T;
+	a.sim_end_time = cp.have_sim_end_time ? cp.sim_end_time : cp.data["timepoints"].back();
 	a.rel_tol = cp.rel_tol;
 	a.abs_tol = cp.abs_tol;
 	a.min_dt = cp.min_dt;

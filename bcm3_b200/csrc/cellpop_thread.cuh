@@ -721,9 +721,9 @@ __global__ void __launch_bounds__(CP_THREADS_PER_BLOCK) cellpop_thread_kernel(co
 			out[(long long)tpi * a.num_cells] = (cell_time < 0.0) ? nan : sv;
 			tpi++;
 		}
-		if (tpi >= T) done = true;
 	}
-	const double end_time = a.timepoints[T - 1] - creation_time;
+	const double end_time = a.sim_end_time - creation_time;
+	if (end_time < DBL_EPSILON) done = true;
 	if (!done) {
 		if (!S.start(end_time)) {
 			ok = false;

@@ -909,8 +909,8 @@ __global__ void __launch_bounds__(32 * CP_WARPS_PER_BLOCK) cellpop_kernel(const 
 		if (lane == 0) out[(long long)ti * a.num_cells] = (cell_time < 0.0) ? nan : observe(m->y);
 		ti++;
 	}
-	if (ti < T) {
-		const double end_time = a.timepoints[T - 1] - creation_time;
+	if ((a.sim_end_time - creation_time) >= DBL_EPSILON) {
+		const double end_time = a.sim_end_time - creation_time;
 		S.reinit(0.0, m->y);
 		S.tstopset = false; // no treatment trajectories: no discontinuities
 		double t = 0.0;

@@ -9,15 +9,23 @@
 //         <variable (initial_condition_species=|model_parameter=) apply= scale=<variable|number> [negate=]/> ...
 //       </cell_variability>
 //       <data type="time_course_population_average" species_name="a[+b]" stdev=<variable|number> [proportional_stdev=]
-//             [offset=] [scale=] [error_model=] [weight=] [missing_simulation_time_stdev=]/>
+//             [offset=] [scale=] [error_model=] [weight=] [missing_simulation_time_stdev=] [relative_to_time_average=]/> ...
 //       [<treatment_trajectory type="pulses" species_name=<constant species> times="t1,t2,..."/>]
-//     </experiment>
+//     </experiment> ...
 //   </bcm_likelihood>
 //
+// Several <experiment> elements and several <data> elements per experiment are accepted: the log-likelihood is the sum over
+// experiments of the sum over their data sets (CellPopulationLikelihood.cpp:82-101, Experiment.cpp:346-355). Every data set is
+// one handle of the C ABI; the data sets of one experiment all integrate their cells to the experiment's common end time
+// (descriptor key simulation_end_time = the last time any of them requests, Experiment.cpp:190-214,655-656), which makes
+// each handle's trajectories the ones the reference's single simulation of that experiment produces. The cells of an
+// experiment are therefore integrated once per data set -- sharing one integration between the data sets of an experiment
+// is a device-side optimisation that is not built yet.
+//
 // The SBML reader/code generator and the NetCDF reader stay on the reference side: the generated model
-// (SetModel) and the data set (SetData) are supplied before PostInitialize(), which is where the reference compiles its
+// (SetModel) and the data sets (SetData) are supplied before PostInitialize(), which is where the reference compiles its
 // generated code too (Experiment::PostInitialize -> SolverCodeGenerator). Anything the device path does not implement
-// (cell division, several experiments / data sets, treatment trajectories from data, per-cell likelihood types) is refused here.
+// (cell division, treatment trajectories from data, per-cell likelihood types, experiment-specific parameters) is refused here.
 #pragma once
 
 #include "Likelihood.h"
@@ -42,19 +50,30 @@ public:
 	~CellPopulationLikelihoodB200() override;
 
 	bool Initialize(std::shared_ptr<const bcm3::VariableSet> varset, const bcm3::XmlNode& likelihood_node) override;
-	void SetModel(const Model& m) { model = m; }
-	void SetData(const Data& d) { data = d; }
-	// the quasi-random table of VariabilityPseudoRandomIterator.cpp:14-26, [num_cells][D] uniforms in (0, 1)
-	void SetSobolTable(const std::vector<double>& table) { sobol = table; }
+	size_t GetNumExperiments() const { return experiments.size(); }
+	size_t GetNumDataSets(size_t experiment) const { return experiments[experiment].data.size(); }
+	const std::string& GetExperimentName(size_t experiment) const { return experiments[experiment].name; }
+	const std::string& GetModelFile(size_t experiment) const { return experiments[experiment].model_file; }
+	// the generated model of one experiment / of every experiment (the usual case: all experiments share one model_file)
+	void SetModel(size_t experiment, const Model& m) { experiments[experiment].model = m; }
+	void SetModel(const Model& m)
+	{
+		for (auto& e : experiments) e.model = m;
+	}
+	void SetData(size_t experiment, size_t data_set, const Data& d) { experiments[experiment].data[data_set].data = d; }
+	void SetData(const Data& d) { SetData(0, 0, d); }
+	// the quasi-random table of VariabilityPseudoRandomIterator.cpp:14-26, [num_cells][D] uniforms in (0, 1); one per experiment
+	void SetSobolTable(size_t experiment, const std::vector<double>& table) { experiments[experiment].sobol = table; }
+	void SetSobolTable(const std::vector<double>& table) { SetSobolTable(0, table); }
 	void SetDevice(int dev, bool compile_only_ = false) { device = dev; compile_only = compile_only_; }
 	bool PostInitialize() override;
 	bool IsReentrant() override { return true; } // the reference's is not (CellPopulationLikelihood.h:22): one object per sampling thread
 	bool EvaluateLogProbability(size_t threadix, const bcm3::VectorReal& values, bcm3::Real& logp) override;
 	bool EvaluateLogProbabilityBatch(const bcm3::MatrixReal& values, bcm3::VectorReal& logp) override;
 
-	size_t GetNumCells() const { return num_cells; }
-	size_t GetVariabilityDimension() const { return variables.size(); }
-	const std::string& GetDescriptor() const { return descriptor; }
+	size_t GetNumCells(size_t experiment = 0) const { return experiments[experiment].num_cells; }
+	size_t GetVariabilityDimension(size_t experiment = 0) const { return experiments[experiment].variables.size(); }
+	const std::string& GetDescriptor(size_t experiment = 0, size_t data_set = 0) const { return experiments[experiment].data[data_set].descriptor; }
 	const std::string& LastError() const { return last_error; }
 
 private:
@@ -69,7 +88,31 @@ private:
 		ValueRef scale;
 		bool negate = false;
 	};
+	struct DataSet { // one <data> element = one handle of the C ABI
+		std::string species_name, error_model = "normal";
+		ValueRef stdev, proportional_stdev, offset, scale;
+		bool have_proportional_stdev = false, relative_to_time_average = false;
+		double weight = 1.0, missing_stdev = 300.0;
+		Data data;
+		std::string descriptor;
+		void* handle = nullptr;
+	};
+	struct Experiment {
+		std::string name, model_file, distribution = "diagonal_gaussian", covar_base_name;
+		size_t num_cells = 1;
+		ValueRef entry_time;
+		double solver_min_timestep = 1e-8, solver_abs_tol = 4.0 * 1.1920928955078125e-07, solver_rel_tol = 4.0 * 1.1920928955078125e-07;
+		long solver_max_steps = 10000;
+		std::vector<VarEntry> variables;
+		std::string treatment_species_name; // <treatment_trajectory type="pulses">
+		std::vector<double> treatment_times;
+		Model model;
+		std::vector<double> sobol;
+		std::vector<DataSet> data;
+	};
 	bool Resolve(const std::string& text, ValueRef& out, const char* what);
+	bool InitializeExperiment(const bcm3::XmlNode& node, Experiment& e);
+	bool CreateHandle(Experiment& e, DataSet& ds, double simulation_end_time);
 	bool Fail(const std::string& m)
 	{
 		last_error = m;
@@ -77,23 +120,10 @@ private:
 	}
 
 	std::shared_ptr<const bcm3::VariableSet> varset;
-	std::string experiment_name, model_file, distribution = "diagonal_gaussian", covar_base_name, species_name, error_model = "normal";
-	size_t num_cells = 1;
-	ValueRef entry_time, stdev, proportional_stdev, offset, scale;
-	bool have_proportional_stdev = false, relative_to_time_average = false;
-	double weight = 1.0, missing_stdev = 300.0;
-	double solver_min_timestep = 1e-8, solver_abs_tol = 4.0 * 1.1920928955078125e-07, solver_rel_tol = 4.0 * 1.1920928955078125e-07;
-	long solver_max_steps = 10000;
-	std::vector<VarEntry> variables;
-	std::string treatment_species_name; // <treatment_trajectory type="pulses">
-	std::vector<double> treatment_times;
-	Model model;
-	Data data;
-	std::vector<double> sobol;
-	std::string descriptor;
-	void* handle = nullptr;
+	std::vector<Experiment> experiments;
 	int device = 0;
 	bool compile_only = false;
 	std::vector<int> status;
+	std::vector<double> part; // one handle's per-chain results
 	std::string last_error;
 };

@@ -261,6 +261,122 @@ int bcm3host_run_pt_cellpop(const char* prior_xml, const char* likelihood_xml, c
 	return run(st, config_text, batched, seed, out, max_rows, num_rows, stats, err, errlen);
 }
 
+// ---- cell_population with several experiments / data sets: a session object, filled the way the reference's readers would ----
+struct CellpopSession {
+	Setup st;
+	CellPopulationLikelihoodB200* ll = nullptr;
+};
+
+void* bcm3host_cellpop_open(const char* prior_xml, const char* likelihood_xml, char* err, size_t errlen)
+{
+	auto* s = new CellpopSession;
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, s->st, error)) {
+		set_err(err, errlen, error);
+		delete s;
+		return nullptr;
+	}
+	s->ll = dynamic_cast<CellPopulationLikelihoodB200*>(s->st.likelihood.get());
+	if (!s->ll) {
+		set_err(err, errlen, "likelihood.xml is not of type cell_population");
+		delete s;
+		return nullptr;
+	}
+	return s;
+}
+
+void bcm3host_cellpop_close(void* session) { delete static_cast<CellpopSession*>(session); }
+
+// number of experiments; num_data[i] = data sets of experiment i (up to max_experiments entries)
+size_t bcm3host_cellpop_layout(void* session, size_t* num_data, size_t max_experiments)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	const size_t n = s->ll->GetNumExperiments();
+	for (size_t i = 0; i < n && i < max_experiments; i++) num_data[i] = s->ll->GetNumDataSets(i);
+	return n;
+}
+
+// experiment < 0: every experiment gets this model
+int bcm3host_cellpop_set_model(void* session, long experiment, const char* derivative_code, size_t N, const char* const* species_names,
+                               const double* initial_conditions, size_t Nc, const double* constant_species)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	if (experiment >= (long)s->ll->GetNumExperiments()) return -1;
+	CellPopulationLikelihoodB200::Model m;
+	m.derivative_code = derivative_code;
+	for (size_t i = 0; i < N; i++) m.species_names.push_back(species_names[i]);
+	m.initial_conditions.assign(initial_conditions, initial_conditions + N);
+	m.constant_species.assign(constant_species, constant_species + Nc);
+	for (size_t i = 0; i < Nc; i++) m.constant_species_names.push_back("c" + std::to_string(i));
+	if (experiment < 0) s->ll->SetModel(m);
+	else s->ll->SetModel((size_t)experiment, m);
+	return 0;
+}
+
+int bcm3host_cellpop_set_data(void* session, size_t experiment, size_t data_set, size_t T, size_t R, const double* timepoints, const double* observed)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	if (experiment >= s->ll->GetNumExperiments() || data_set >= s->ll->GetNumDataSets(experiment)) return -1;
+	CellPopulationLikelihoodB200::Data d;
+	d.timepoints.assign(timepoints, timepoints + T);
+	d.observed.assign(observed, observed + R * T);
+	d.num_replicates = R;
+	s->ll->SetData(experiment, data_set, d);
+	return 0;
+}
+
+int bcm3host_cellpop_set_sobol(void* session, size_t experiment, size_t count, const double* sobol)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	if (experiment >= s->ll->GetNumExperiments()) return -1;
+	s->ll->SetSobolTable(experiment, std::vector<double>(sobol, sobol + count));
+	return 0;
+}
+
+int bcm3host_cellpop_post_initialize(void* session, int device, int compile_only, char* err, size_t errlen)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	s->ll->SetDevice(device, compile_only != 0);
+	if (!s->ll->PostInitialize()) {
+		set_err(err, errlen, s->ll->LastError());
+		return -3;
+	}
+	return 0;
+}
+
+int bcm3host_cellpop_descriptor(void* session, size_t experiment, size_t data_set, char* out, size_t len)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	if (experiment >= s->ll->GetNumExperiments() || data_set >= s->ll->GetNumDataSets(experiment)) return -1;
+	set_err(out, len, s->ll->GetDescriptor(experiment, data_set));
+	return 0;
+}
+
+int bcm3host_cellpop_session_evaluate(void* session, const double* values, size_t C, int batched, double* logp, char* err, size_t errlen)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	const size_t nvar = s->st.varset->GetNumVariables();
+	if (batched) {
+		MatrixReal mat(nvar, C);
+		std::copy(values, values + nvar * C, mat.data.begin());
+		VectorReal lp;
+		if (!s->st.likelihood->EvaluateLogProbabilityBatch(mat, lp)) {
+			set_err(err, errlen, s->ll->LastError());
+			return -2;
+		}
+		std::copy(lp.begin(), lp.end(), logp);
+	} else {
+		for (size_t c = 0; c < C; c++) {
+			VectorReal v(values + c * nvar, values + (c + 1) * nvar);
+			if (!s->st.likelihood->EvaluateLogProbability(0, v, logp[c])) {
+				set_err(err, errlen, s->ll->LastError());
+				return -2;
+			}
+		}
+	}
+	return 0;
+}
+
 // VariableSet / Prior surface for tests: number of variables, transform codes, index lookup
 int bcm3host_varset_info(const char* prior_xml, const char* lookup_name, size_t* num_variables, int* transforms, size_t max_n, size_t* index)
 {

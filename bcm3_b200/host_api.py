@@ -134,3 +134,80 @@ def run_pt_cellpop(prior_xml: str, likelihood_xml: str, config_text: str, proble
     if rc != 0:
         raise RuntimeError(f"bcm3host_run_pt_cellpop failed ({rc}): {err.value.decode()}")
     return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])
+
+
+class CellPopSession:
+    """CellPopulationLikelihoodB200 with any number of <experiment> / <data> elements: likelihood.xml goes through
+    LikelihoodFactory, then the generated model, the data sets and the quasi-random tables are supplied the way the
+    reference's SBML / NetCDF readers would (`set_model`, `set_data`, `set_sobol`), then `post_initialize`."""
+
+    def __init__(self, prior_xml: str, likelihood_xml: str):
+        self.lib = lib = load()
+        lib.bcm3host_cellpop_open.restype = C.c_void_p
+        lib.bcm3host_cellpop_layout.restype = C.c_size_t
+        err = _err()
+        self.nvar = varset_info(prior_xml)[0]
+        self.handle = lib.bcm3host_cellpop_open(prior_xml.encode(), likelihood_xml.encode(), err, C.c_size_t(1024))
+        if not self.handle:
+            raise RuntimeError(f"bcm3host_cellpop_open failed: {err.value.decode()}")
+        nd = (C.c_size_t * 64)()
+        n = lib.bcm3host_cellpop_layout(C.c_void_p(self.handle), nd, C.c_size_t(64))
+        self.num_data_sets = [int(nd[i]) for i in range(n)]
+
+    def set_model(self, problem, species_names, experiment: int = -1) -> None:
+        p = problem
+        names = (C.c_char_p * len(species_names))(*[s.encode() for s in species_names])
+        ic = np.ascontiguousarray(p.initial_conditions, dtype=np.float64)
+        cs = np.ascontiguousarray(p.constant_species, dtype=np.float64)
+        rc = self.lib.bcm3host_cellpop_set_model(C.c_void_p(self.handle), C.c_long(experiment), p.derivative_code.encode(), C.c_size_t(p.num_species),
+                                                 names, ic.ctypes.data_as(C.c_void_p), C.c_size_t(cs.size), cs.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("bcm3host_cellpop_set_model: no such experiment")
+
+    def set_data(self, experiment: int, data_set: int, timepoints, observed) -> None:
+        tp = np.ascontiguousarray(timepoints, dtype=np.float64)
+        obs = np.ascontiguousarray(observed, dtype=np.float64)
+        obs = obs.reshape(-1, tp.size) if tp.size else obs.reshape(1, 0)
+        rc = self.lib.bcm3host_cellpop_set_data(C.c_void_p(self.handle), C.c_size_t(experiment), C.c_size_t(data_set), C.c_size_t(tp.size),
+                                                C.c_size_t(obs.shape[0]), tp.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("bcm3host_cellpop_set_data: no such experiment / data set")
+
+    def set_sobol(self, experiment: int, table) -> None:
+        sob = np.ascontiguousarray(table, dtype=np.float64)
+        rc = self.lib.bcm3host_cellpop_set_sobol(C.c_void_p(self.handle), C.c_size_t(experiment), C.c_size_t(sob.size), sob.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("bcm3host_cellpop_set_sobol: no such experiment")
+
+    def post_initialize(self, device: int = 0, compile_only: bool = False) -> None:
+        err = _err()
+        rc = self.lib.bcm3host_cellpop_post_initialize(C.c_void_p(self.handle), int(device), int(compile_only), err, C.c_size_t(1024))
+        if rc != 0:
+            raise RuntimeError(f"PostInitialize failed: {err.value.decode()}")
+
+    def descriptor(self, experiment: int, data_set: int) -> str:
+        buf = C.create_string_buffer(4096)
+        if self.lib.bcm3host_cellpop_descriptor(C.c_void_p(self.handle), C.c_size_t(experiment), C.c_size_t(data_set), buf, C.c_size_t(4096)) != 0:
+            raise RuntimeError("bcm3host_cellpop_descriptor: no such experiment / data set")
+        return buf.value.decode()
+
+    def evaluate(self, values, batched: bool = True) -> np.ndarray:
+        vals = np.ascontiguousarray(values, dtype=np.float64).reshape(-1, self.nvar)
+        logp = np.empty(vals.shape[0])
+        err = _err()
+        rc = self.lib.bcm3host_cellpop_session_evaluate(C.c_void_p(self.handle), vals.ctypes.data_as(C.c_void_p), C.c_size_t(vals.shape[0]),
+                                                        int(batched), logp.ctypes.data_as(C.c_void_p), err, C.c_size_t(1024))
+        if rc != 0:
+            raise RuntimeError(f"evaluate failed ({rc}): {err.value.decode()}")
+        return logp
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.bcm3host_cellpop_close(C.c_void_p(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

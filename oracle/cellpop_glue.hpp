@@ -141,7 +141,11 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	}
 
 	Solver solver(pr);
-	std::vector<double> population_average(T, 0.0), cell_params(nvar), y0(N), tp_rel(T), out((size_t)N * T);
+	// the solver integrates to the last output time it is given: when the experiment runs longer than this data set, one
+	// extra output time (whose values nobody reads) carries the experiment's end
+	const bool longer = pr.have_sim_end_time && pr.sim_end_time > pr.timepoints[T - 1];
+	const int Tsolve = T + (longer ? 1 : 0);
+	std::vector<double> population_average(T, 0.0), cell_params(nvar), y0(N), tp_rel(Tsolve), out((size_t)N * Tsolve);
 	std::vector<double> xs((size_t)T * ncell, nan); // value per (timepoint, cell)
 	bool result = true;
 
@@ -168,8 +172,9 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		// Cell::Simulate: output times relative to the creation time
 		const double creation_time = entry_time;
 		for (int i = 0; i < T; i++) tp_rel[i] = pr.timepoints[i] - creation_time;
+		if (longer) tp_rel[T] = pr.sim_end_time - creation_time;
 		int steps = 0;
-		if (!solver.solve(y0.data(), cell_params.data(), tp_rel.data(), T, out.data(), steps, creation_time)) {
+		if (!solver.solve(y0.data(), cell_params.data(), tp_rel.data(), Tsolve, out.data(), steps, creation_time)) {
 			result = false; // Experiment::Simulate fails => logp = -inf (Experiment.cpp:356-358)
 		}
 		if (cell_steps) cell_steps[ci] = steps;
@@ -177,7 +182,7 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 			// Experiment.cpp:298-312 + Cell::GetInterpolatedSpeciesValue (Cell.cpp:280-360): exact stored timepoints only
 			for (int i = 0; i < T; i++) {
 				const double cell_time = pr.timepoints[i] - creation_time;
-				if (cell_time < 0.0 || cell_time > tp_rel[T - 1]) continue;
+				if (cell_time < 0.0 || cell_time > tp_rel[Tsolve - 1]) continue;
 				double x = 0.0;
 				for (int k = 0; k < pr.num_obs_species; k++) x += out[(size_t)pr.obs_species[k] + (size_t)i * N];
 				xs[(size_t)i * ncell + ci] = x;
@@ -197,7 +202,7 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		size_t pop = 0;
 		for (int ci = 0; ci < ncell; ci++) {
 			const double cell_time = pr.timepoints[i] - entry_time;
-			if (!(cell_time < 0.0 || cell_time > tp_rel[T - 1])) pop++; // CountCellsAtTime
+			if (!(cell_time < 0.0 || cell_time > tp_rel[Tsolve - 1])) pop++; // CountCellsAtTime
 		}
 		for (int ci = 0; ci < ncell; ci++) {
 			const double x = xs[(size_t)i * ncell + ci];

@@ -124,6 +124,10 @@ typedef struct {
 	int32_t treatment_species, treatment_num_pulses;
 	const double* treatment_times;
 	int32_t relative_to_time_average; /* <data relative_to_time_average="true">, DataLikelihoodTimeCoursePopulationAverage.cpp:105-115 */
+	/* an experiment with several data sets integrates every cell to the last time ANY of them requests (Experiment.cpp:190-214,
+	 * 655-656); evaluating one data set of such an experiment needs that end time. 0: the last of `timepoints` */
+	int32_t have_sim_end_time;
+	double sim_end_time;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

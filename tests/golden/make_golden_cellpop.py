@@ -33,6 +33,10 @@ CASES = {
     # <data relative_to_time_average="true">: log of the population average over its time average, then scaled
     "cellpop_n6_relative": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=28, replicates=2), 2,
                             dict(relative_to_time_average=True, offset=0.05, scale=0.8)),
+    # one data set of an experiment whose other data sets run longer: cells are integrated to the experiment's last requested
+    # time (Experiment.cpp:190-214, 655-656), which enters CVODE's initial step -- late entry
+    "cellpop_n8_longer_experiment": (dict(N=8, num_cells=48, T=8, data_cells=8, seed=29), 2,
+                                     dict(simulation_end_time=13.5, entry_time=0.5)),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }

@@ -96,3 +96,31 @@ def test_pt_run_on_gpu_cell_population_batched_equals_serial(built):
     assert a.shape == (24 * 4, prob.num_variables + 3)
     assert np.array_equal(a, b, equal_nan=True)
     assert sa["batched_calls"] >= 48 and sb["batched_calls"] == 0 and sa["evaluations"] == sb["evaluations"]
+
+
+def test_cell_population_plugin_sums_experiments_and_data_sets(built):
+    """Two experiments, the first with two data sets (different species, timepoints, error model): the plugin's result is
+    the reference's sum over experiments of the sum over data sets (CellPopulationLikelihood.cpp:82-101, Experiment.cpp:346-355),
+    each term checked against the CPU checker run with the experiment's common simulation end."""
+    import oracle
+    from tests.util import cellpop_two_experiment_setup, open_cellpop_session, rel_err
+    from bcm3_b200 import synthetic_cellpop as sc
+
+    prior, lik, species, problems = cellpop_two_experiment_setup()
+    vals = sc.make_chain_values(4, seed=9)
+    s = open_cellpop_session(prior, lik, species, problems)
+    s.post_initialize()
+    batched = s.evaluate(vals, batched=True)
+    serial = s.evaluate(vals, batched=False)
+    s.close()
+    assert np.array_equal(batched, serial)
+    chk = oracle.load("ref" if oracle.available("ref") else "port")
+    terms = [[chk.cellpop_evaluate(p, vals)["logp"] for p in exp] for exp in problems]
+    want = sum((sum(exp[1:], 0.0 + exp[0]) for exp in terms), np.zeros(len(vals)))
+    assert np.isfinite(want).all()
+    assert rel_err(batched, want).max() <= 1e-6
+    # the shorter data set integrated only to its own last timepoint is NOT the same number: the end time enters CVODE's
+    # initial step (cvHin), which is why the descriptor carries simulation_end_time
+    import dataclasses
+    alone = chk.cellpop_evaluate(dataclasses.replace(problems[0][1], simulation_end_time=None), vals)["logp"]
+    assert not np.array_equal(alone, terms[0][1])

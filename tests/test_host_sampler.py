@@ -122,3 +122,29 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
         host_api.cellpop_evaluate(prior, lik.replace("time_course_population_average", "time_course"), prob, species, compile_only=True)
     with pytest.raises(RuntimeError, match="Could not find variable"):
         host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="no_such_variable"'), prob, species, compile_only=True)
+
+
+def test_cell_population_plugin_takes_several_experiments_and_data_sets(built, tmp_path, monkeypatch):
+    """One handle of the C ABI per <data> element; the data sets of an experiment carry the experiment's common simulation
+    end (the last time any of them requests, Experiment.cpp:190-214, 655-656) so that each reproduces the reference's one
+    simulation of that experiment."""
+    from tests.util import cellpop_two_experiment_setup, open_cellpop_session
+
+    monkeypatch.setenv("BCM3B200_CACHE", str(tmp_path))
+    prior, lik, species, problems = cellpop_two_experiment_setup()
+    s = open_cellpop_session(prior, lik, species, problems)
+    s.post_initialize(compile_only=True)
+    kv = lambda e, d: dict(item.split("=", 1) for item in s.descriptor(e, d).split(";"))
+    first, early, second = kv(0, 0), kv(0, 1), kv(1, 0)
+    assert "simulation_end_time" not in first and "simulation_end_time" not in second
+    assert float(early["simulation_end_time"]) == float(problems[0][0].timepoints[-1]) > float(problems[0][1].timepoints[-1])
+    assert early["num_timepoints"] == "6" and early["obs_species"] == "2+3" and early["error_model"] == "student_t4"
+    assert float(early["stdev"]) == 0.3 and float(early["weight"]) == 0.5 and first["stdev_ix"] == "5"
+    assert first["num_cells"] == "96" and second["num_cells"] == "64" and float(second["entry_time"]) == problems[1][0].entry_time
+    s.close()
+    # a data set that was never supplied is an error of PostInitialize, not a crash
+    s = open_cellpop_session(prior, lik, species, [[problems[0][0], problems[0][1]], problems[1]])
+    s.set_data(0, 1, [], np.zeros((1, 0)))
+    with pytest.raises(RuntimeError, match="consistent data set"):
+        s.post_initialize(compile_only=True)
+    s.close()

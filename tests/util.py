@@ -95,6 +95,8 @@ def load_cellpop_golden(name):
     extra = {}
     if "relative_to_time_average" in z.files:
         extra.update(relative_to_time_average=bool(z["relative_to_time_average"]))
+    if "simulation_end_time" in z.files:
+        extra.update(simulation_end_time=float(z["simulation_end_time"]))
     if "treatment_species" in z.files:
         extra.update(treatment_species=int(z["treatment_species"]), treatment_times=z["treatment_times"])
     if "variability_distribution" in z.files:
@@ -169,3 +171,55 @@ def cellpop_xml(prob, **experiment_overrides):
            f'<data type="time_course_population_average" data_name="readout" species_name="{obs}" stdev="stdev"/>'
            '</experiment></bcm_likelihood>')
     return prior, lik, species
+
+
+def cellpop_two_experiment_setup(seed=9):
+    """A likelihood.xml with two experiments -- the first with two data sets on different species, timepoints and error
+    models -- plus, for every <data> element, the single-data-set problem that reproduces it (for the direct ABI call and
+    the CPU checkers): data sets of one experiment share the experiment's simulation end (Experiment.cpp:190-214, 655-656).
+    Returns (prior, likelihood, species, [[problem per data set] per experiment])."""
+    import dataclasses
+    import math
+
+    from bcm3_b200 import synthetic_cellpop as sc
+
+    a = sc.make_cellpop_problem(N=8, num_cells=96, T=10, data_cells=4, seed=seed)
+    b = sc.make_cellpop_problem(N=8, num_cells=64, T=7, data_cells=3, seed=seed)  # same model (the seed fixes the rate laws), other cells and times
+    assert a.derivative_code == b.derivative_code
+    prior, _, species = cellpop_xml(a)
+    end = float(a.timepoints[-1])
+    rng = np.random.default_rng(seed)
+    a2 = dataclasses.replace(a, obs_species=[2, 3], timepoints=a.timepoints[:6].copy(),
+                             observed=np.abs(a.observed[:, :6] * 1.7 + 0.05 * rng.standard_normal(a.observed[:, :6].shape)),
+                             error_model="student_t4", stdev_ix=None, stdev=0.3, weight=0.5, simulation_end_time=end)
+    b1 = dataclasses.replace(b, entry_time=0.25 * float(b.timepoints[1]))
+    variability = ('<cell_variability distribution="diagonal_gaussian">'
+                   '<variable model_parameter="k_in" apply="multiplicative_log" scale="variability_scale"/>'
+                   '<variable model_parameter="k_deg" apply="multiplicative_log" scale="variability_scale" negate="true"/>'
+                   f'<variable initial_condition_species="x1" apply="additive" scale="{math.log(0.01)!r}"/>'
+                   '</cell_variability>')
+    obs = lambda p: "+".join(species[s] for s in p.obs_species)
+    lik = ('<bcm_likelihood type="cell_population">'
+           f'<experiment name="first" model_file="cascade.xml" entry_time="0" num_cells="{a.num_cells}" max_cells="{a.num_cells}" divide_cells="false">'
+           + variability +
+           f'<data type="time_course_population_average" data_name="readout" species_name="{obs(a)}" stdev="stdev"/>'
+           f'<data type="time_course_population_average" data_name="early" species_name="{obs(a2)}" stdev="0.3" error_model="student_t4" weight="0.5"/>'
+           '</experiment>'
+           f'<experiment name="second" model_file="cascade.xml" entry_time="{b1.entry_time!r}" num_cells="{b.num_cells}" max_cells="{b.num_cells}" divide_cells="false">'
+           + variability +
+           f'<data type="time_course_population_average" data_name="readout" species_name="{obs(b1)}" stdev="stdev"/>'
+           '</experiment></bcm_likelihood>')
+    return prior, lik, species, [[a, a2], [b1]]
+
+
+def open_cellpop_session(prior, lik, species, problems):
+    from bcm3_b200 import host_api
+
+    s = host_api.CellPopSession(prior, lik)
+    assert s.num_data_sets == [len(e) for e in problems]
+    s.set_model(problems[0][0], species)
+    for ei, exp in enumerate(problems):
+        s.set_sobol(ei, exp[0].sobol)
+        for di, p in enumerate(exp):
+            s.set_data(ei, di, p.timepoints, p.observed)
+    return s
