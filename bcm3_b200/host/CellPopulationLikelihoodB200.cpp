@@ -143,11 +143,31 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				if (!parse_number(tok, v)) return Fail("treatment_trajectory times: cannot parse \"" + tok + "\"");
 				e.treatment_times.push_back(v);
 			}
-		} else if (c.name == "set_species" || c.name == "experiment_specific_parameter" || c.name == "set_parameter") {
-			return Fail("<" + c.name + "> is not supported by the GPU path");
+		} else if (c.name == "experiment_specific_parameter") {
+			// Experiment.cpp:515-527
+			const size_t p = varset->GetVariableIndex(c.get("parameter_name")), r = varset->GetVariableIndex(c.get("replacement_parameter_name"));
+			const size_t none = std::numeric_limits<size_t>::max();
+			if (p == none) return Fail("experiment_specific_parameter: \"" + c.get("parameter_name") + "\" is not a variable");
+			if (r == none) return Fail("experiment_specific_parameter: replacement \"" + c.get("replacement_parameter_name") + "\" is not a variable");
+			if (varset->GetTransform(p) != varset->GetTransform(r))
+				return Fail("experiment_specific_parameter: \"" + c.get("parameter_name") + "\" and its replacement must share a variable transform on the GPU path");
+			e.specific_parameters.emplace_back(p, r);
+		} else if (c.name == "set_parameter") {
+			double v;
+			if (!c.has("parameter_name") || !parse_number(c.get("value"), v)) return Fail("set_parameter needs parameter_name and a numeric value");
+			e.fixed_parameters.emplace_back(c.get("parameter_name"), v);
+		} else if (c.name == "set_species") {
+			double v;
+			if (!c.has("species_name") || !parse_number(c.get("value"), v)) return Fail("set_species needs species_name and a numeric value");
+			e.set_species.push_back(c.get("species_name"));
 		}
 	}
 	if (e.data.empty()) return Fail("experiment \"" + e.name + "\" has no data");
+	// the reference evaluates its data likelihoods on the unreplaced values (Experiment.cpp:350)
+	for (const auto& sp : e.specific_parameters)
+		for (const auto& ds : e.data)
+			for (const ValueRef* r : { &ds.stdev, &ds.proportional_stdev, &ds.offset, &ds.scale })
+				if (r->ix == (long)sp.first) return Fail("experiment_specific_parameter replaces a variable that a data set of the experiment reads");
 	return true;
 }
 
@@ -163,6 +183,9 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 			if (!std::is_sorted(ds.data.timepoints.begin(), ds.data.timepoints.end())) return Fail("data set timepoints must be sorted");
 			end_time = std::max(end_time, ds.data.timepoints.back());
 		}
+		for (const auto& name : e.set_species) // Experiment.cpp:497-500
+			if (std::find(e.model.species_names.begin(), e.model.species_names.end(), name) == e.model.species_names.end())
+				return Fail("set_species: \"" + name + "\" is not a simulated species of the model");
 		for (auto& ds : e.data)
 			if (!CreateHandle(e, ds, end_time)) return false;
 	}
@@ -273,16 +296,28 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	return true;
 }
 
+// Experiment::Simulate (Experiment.cpp:635-642): transformed[parameter] = transformed[replacement] for the cells of this
+// experiment; with equal transforms that is the same as replacing the untransformed column
+const double* CellPopulationLikelihoodB200::ExperimentValues(const Experiment& e, const double* values, size_t C, size_t nvar)
+{
+	if (e.specific_parameters.empty()) return values;
+	replaced.assign(values, values + C * nvar);
+	for (size_t c = 0; c < C; c++)
+		for (const auto& sp : e.specific_parameters) replaced[c * nvar + sp.first] = replaced[c * nvar + sp.second];
+	return replaced.data();
+}
+
 bool CellPopulationLikelihoodB200::EvaluateLogProbability(size_t, const bcm3::VectorReal& values, Real& logp)
 {
 	// CellPopulationLikelihood.cpp:84-98 / Experiment.cpp:346-355: sums start from 0.0, data sets inside experiments
 	logp = 0.0;
 	for (auto& e : experiments) {
 		Real experiment_logp = 0.0;
+		const double* v = ExperimentValues(e, values.data(), 1, values.size());
 		for (auto& ds : e.data) {
 			int st = 0;
 			Real dl_logp = 0.0;
-			if (bcm3b200_evaluate_batch(ds.handle, 1, values.size(), values.data(), &dl_logp, &st) != BCM3B200_OK) return Fail(bcm3b200_last_error());
+			if (bcm3b200_evaluate_batch(ds.handle, 1, values.size(), v, &dl_logp, &st) != BCM3B200_OK) return Fail(bcm3b200_last_error());
 			experiment_logp += dl_logp;
 		}
 		logp += experiment_logp;
@@ -301,8 +336,9 @@ bool CellPopulationLikelihoodB200::EvaluateLogProbabilityBatch(const bcm3::Matri
 	std::vector<double> experiment_logp(C);
 	for (auto& e : experiments) {
 		std::fill(experiment_logp.begin(), experiment_logp.end(), 0.0);
+		const double* v = ExperimentValues(e, values.data.data(), C, values.rows());
 		for (auto& ds : e.data) {
-			if (bcm3b200_evaluate_batch(ds.handle, C, values.rows(), values.data.data(), part.data(), status.data()) != BCM3B200_OK) return Fail(bcm3b200_last_error());
+			if (bcm3b200_evaluate_batch(ds.handle, C, values.rows(), v, part.data(), status.data()) != BCM3B200_OK) return Fail(bcm3b200_last_error());
 			for (size_t c = 0; c < C; c++) experiment_logp[c] += part[c];
 		}
 		for (size_t c = 0; c < C; c++) logp[c] += experiment_logp[c];

@@ -11,6 +11,8 @@
 //       <data type="time_course_population_average" species_name="a[+b]" stdev=<variable|number> [proportional_stdev=]
 //             [offset=] [scale=] [error_model=] [weight=] [missing_simulation_time_stdev=] [relative_to_time_average=]/> ...
 //       [<treatment_trajectory type="pulses" species_name=<constant species> times="t1,t2,..."/>]
+//       [<experiment_specific_parameter parameter_name= replacement_parameter_name=/>] [<set_parameter parameter_name= value=/>]
+//       [<set_species species_name= value=/>]
 //     </experiment> ...
 //   </bcm_likelihood>
 //
@@ -25,8 +27,18 @@
 // The SBML reader/code generator and the NetCDF reader stay on the reference side: the generated model
 // (SetModel) and the data sets (SetData) are supplied before PostInitialize(), which is where the reference compiles its
 // generated code too (Experiment::PostInitialize -> SolverCodeGenerator). Anything the device path does not implement
-// (cell division, treatment trajectories from data, per-cell likelihood types, experiment-specific parameters) is refused here.
+// (cell division, treatment trajectories from data, per-cell likelihood types) is refused here.
+//
+// <experiment_specific_parameter> (Experiment.cpp:515-527, :640-642): the cells of the experiment see the replacement
+// variable's transformed value in place of the parameter's; done here by handing the experiment's handles a copy of the
+// chain values with that column replaced (both variables must share a transform, and no data set of the experiment may
+// read the replaced variable, because the reference's data likelihoods see the unreplaced values, Experiment.cpp:350).
+// <set_parameter> (:508-514) fixes a parameter in the cell model BEFORE code generation: it is recorded
+// (GetFixedParameters) for whoever supplies the generated model. <set_species> is read and then ignored, as in the
+// reference, whose use of it is compiled out (Cell.cpp:88-93 under #if 0).
 #pragma once
+
+#include <utility>
 
 #include "Likelihood.h"
 
@@ -71,6 +83,8 @@ public:
 	bool EvaluateLogProbability(size_t threadix, const bcm3::VectorReal& values, bcm3::Real& logp) override;
 	bool EvaluateLogProbabilityBatch(const bcm3::MatrixReal& values, bcm3::VectorReal& logp) override;
 
+	// <set_parameter> elements of the experiment: to be applied to the cell model before its code is generated
+	const std::vector<std::pair<std::string, double>>& GetFixedParameters(size_t experiment) const { return experiments[experiment].fixed_parameters; }
 	size_t GetNumCells(size_t experiment = 0) const { return experiments[experiment].num_cells; }
 	size_t GetVariabilityDimension(size_t experiment = 0) const { return experiments[experiment].variables.size(); }
 	const std::string& GetDescriptor(size_t experiment = 0, size_t data_set = 0) const { return experiments[experiment].data[data_set].descriptor; }
@@ -109,10 +123,15 @@ private:
 		Model model;
 		std::vector<double> sobol;
 		std::vector<DataSet> data;
+		std::vector<std::pair<size_t, size_t>> specific_parameters; // (parameter, replacement) variable indices
+		std::vector<std::pair<std::string, double>> fixed_parameters; // <set_parameter>
+		std::vector<std::string> set_species;                         // <set_species>: names only (validated, otherwise unused)
 	};
 	bool Resolve(const std::string& text, ValueRef& out, const char* what);
 	bool InitializeExperiment(const bcm3::XmlNode& node, Experiment& e);
 	bool CreateHandle(Experiment& e, DataSet& ds, double simulation_end_time);
+	// the [C][nvar] block the handles of `e` are given: `values` itself, or the copy with the experiment-specific columns replaced
+	const double* ExperimentValues(const Experiment& e, const double* values, size_t C, size_t nvar);
 	bool Fail(const std::string& m)
 	{
 		last_error = m;
@@ -125,5 +144,6 @@ private:
 	bool compile_only = false;
 	std::vector<int> status;
 	std::vector<double> part; // one handle's per-chain results
+	std::vector<double> replaced; // ExperimentValues scratch
 	std::string last_error;
 };

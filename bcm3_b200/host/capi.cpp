@@ -352,6 +352,19 @@ int bcm3host_cellpop_descriptor(void* session, size_t experiment, size_t data_se
 	return 0;
 }
 
+// k-th <set_parameter> of an experiment; returns the number of them
+size_t bcm3host_cellpop_fixed_parameter(void* session, size_t experiment, size_t k, char* name_out, size_t len, double* value)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	if (experiment >= s->ll->GetNumExperiments()) return 0;
+	const auto& fp = s->ll->GetFixedParameters(experiment);
+	if (k < fp.size()) {
+		set_err(name_out, len, fp[k].first);
+		*value = fp[k].second;
+	}
+	return fp.size();
+}
+
 int bcm3host_cellpop_session_evaluate(void* session, const double* values, size_t C, int batched, double* logp, char* err, size_t errlen)
 {
 	auto* s = static_cast<CellpopSession*>(session);

@@ -191,6 +191,18 @@ class CellPopSession:
             raise RuntimeError("bcm3host_cellpop_descriptor: no such experiment / data set")
         return buf.value.decode()
 
+    def fixed_parameters(self, experiment: int) -> list:
+        """The <set_parameter> elements of an experiment: [(name, value)], to be applied to the cell model before code generation."""
+        self.lib.bcm3host_cellpop_fixed_parameter.restype = C.c_size_t
+        out, k = [], 0
+        while True:
+            buf, v = C.create_string_buffer(256), C.c_double()
+            n = self.lib.bcm3host_cellpop_fixed_parameter(C.c_void_p(self.handle), C.c_size_t(experiment), C.c_size_t(k), buf, C.c_size_t(256), C.byref(v))
+            if k >= n:
+                return out
+            out.append((buf.value.decode(), v.value))
+            k += 1
+
     def evaluate(self, values, batched: bool = True) -> np.ndarray:
         vals = np.ascontiguousarray(values, dtype=np.float64).reshape(-1, self.nvar)
         logp = np.empty(vals.shape[0])

@@ -103,7 +103,7 @@ def test_cell_population_plugin_sums_experiments_and_data_sets(built):
     the reference's sum over experiments of the sum over data sets (CellPopulationLikelihood.cpp:82-101, Experiment.cpp:346-355),
     each term checked against the CPU checker run with the experiment's common simulation end."""
     import oracle
-    from tests.util import cellpop_two_experiment_setup, open_cellpop_session, rel_err
+    from tests.util import cellpop_two_experiment_setup, open_cellpop_session
     from bcm3_b200 import synthetic_cellpop as sc
 
     prior, lik, species, problems = cellpop_two_experiment_setup()
@@ -118,9 +118,52 @@ def test_cell_population_plugin_sums_experiments_and_data_sets(built):
     terms = [[chk.cellpop_evaluate(p, vals)["logp"] for p in exp] for exp in problems]
     want = sum((sum(exp[1:], 0.0 + exp[0]) for exp in terms), np.zeros(len(vals)))
     assert np.isfinite(want).all()
-    assert rel_err(batched, want).max() <= 1e-6
+    # every term within 1e-6 of the size of the sum it is made of (tests/util.py::cellpop_logp_close)
+    scale = sum(np.maximum(np.abs(t), 4.0 * p.num_timepoints * p.num_replicates) for exp, ts in zip(problems, terms) for p, t in zip(exp, ts))
+    assert np.all(np.abs(batched - want) <= 1e-6 * scale)
     # the shorter data set integrated only to its own last timepoint is NOT the same number: the end time enters CVODE's
     # initial step (cvHin), which is why the descriptor carries simulation_end_time
     import dataclasses
     alone = chk.cellpop_evaluate(dataclasses.replace(problems[0][1], simulation_end_time=None), vals)["logp"]
     assert not np.array_equal(alone, terms[0][1])
+
+
+def test_cell_population_experiment_specific_parameter(built):
+    """<experiment_specific_parameter>: the second experiment's cells see k_in_second where the model reads k_in
+    (Experiment.cpp:515-527, 640-642) -- the same as evaluating that experiment with the column replaced."""
+    from tests.util import cellpop_two_experiment_setup, open_cellpop_session
+    from bcm3_b200 import synthetic_cellpop as sc
+    from bcm3_b200.cellpop import CellPopEvaluator
+    import dataclasses
+
+    prior, lik, species, problems = cellpop_two_experiment_setup()
+    prior = prior.replace("</variableset>", '<variable name="k_in_second" logspace="true" distribution="uniform" lower="-5" upper="5"/></variableset>')
+    at = lik.index(">", lik.index('<experiment name="second"')) + 1
+    lik = lik[:at] + '<experiment_specific_parameter parameter_name="k_in" replacement_parameter_name="k_in_second"/>' + lik[at:]
+    base = sc.make_chain_values(3, seed=4)
+    vals = np.concatenate([base, base[:, :1] + 0.2], axis=1)  # the extra variable: another k_in
+    s = open_cellpop_session(prior, lik, species, problems)
+    s.post_initialize()
+    got = s.evaluate(vals, batched=True)
+    serial = s.evaluate(vals, batched=False)
+    s.close()
+    assert np.array_equal(got, serial)
+    want = np.zeros(len(vals))
+    for ei, exp in enumerate(problems):
+        v = vals.copy()
+        if ei == 1:
+            v[:, 0] = v[:, 6]
+        term = np.zeros(len(vals))
+        for p in exp:
+            tr = np.concatenate([p.transforms, p.transforms[:1]])
+            ev = CellPopEvaluator(dataclasses.replace(p, transforms=tr))
+            term = term + ev.evaluate(v)[0]
+            ev.close()
+        want = want + term
+    assert np.isfinite(want).all() and np.array_equal(got, want)
+    # and the replacement matters
+    s = open_cellpop_session(prior, lik.replace('<experiment_specific_parameter parameter_name="k_in" replacement_parameter_name="k_in_second"/>', ""),
+                             species, problems)
+    s.post_initialize()
+    assert not np.array_equal(s.evaluate(vals), got)
+    s.close()

@@ -148,3 +148,33 @@ def test_cell_population_plugin_takes_several_experiments_and_data_sets(built, t
     with pytest.raises(RuntimeError, match="consistent data set"):
         s.post_initialize(compile_only=True)
     s.close()
+
+
+def test_cell_population_plugin_experiment_specific_elements(built, tmp_path, monkeypatch):
+    """<experiment_specific_parameter>, <set_parameter>, <set_species> of Experiment::Load (Experiment.cpp:495-527)."""
+    from bcm3_b200 import host_api
+    from tests.util import cellpop_two_experiment_setup, open_cellpop_session
+
+    monkeypatch.setenv("BCM3B200_CACHE", str(tmp_path))
+    prior, lik, species, problems = cellpop_two_experiment_setup()
+    prior = prior.replace("</variableset>", '<variable name="k_in_second" logspace="true" distribution="uniform" lower="-5" upper="5"/>'
+                          '<variable name="shift" distribution="uniform" lower="-5" upper="5"/></variableset>')
+    head = '<experiment name="second"'
+    at = lik.index(">", lik.index(head)) + 1
+    extra = ('<experiment_specific_parameter parameter_name="k_in" replacement_parameter_name="k_in_second"/>'
+             '<set_parameter parameter_name="k_leak" value="0.125"/><set_species species_name="x3" value="2.0"/>')
+    s = open_cellpop_session(prior, lik[:at] + extra + lik[at:], species, problems)
+    assert s.fixed_parameters(0) == [] and s.fixed_parameters(1) == [("k_leak", 0.125)]
+    s.post_initialize(compile_only=True)
+    s.close()
+    bad = lambda text: host_api.CellPopSession(prior, lik[:at] + text + lik[at:])
+    with pytest.raises(RuntimeError, match="share a variable transform"):
+        bad('<experiment_specific_parameter parameter_name="k_in" replacement_parameter_name="shift"/>')
+    with pytest.raises(RuntimeError, match="is not a variable"):
+        bad('<experiment_specific_parameter parameter_name="k_in" replacement_parameter_name="nope"/>')
+    with pytest.raises(RuntimeError, match="a data set of the experiment reads"):
+        bad('<experiment_specific_parameter parameter_name="stdev" replacement_parameter_name="k_in_second"/>')
+    s = open_cellpop_session(prior, lik[:at] + '<set_species species_name="not_a_species" value="1"/>' + lik[at:], species, problems)
+    with pytest.raises(RuntimeError, match="not a simulated species"):
+        s.post_initialize(compile_only=True)
+    s.close()
