@@ -69,6 +69,13 @@ bool Prior::Sample(Real* values, RNG* rng) const
 Real Prior::GetLowerBound(size_t i) const { return marginals[i].kind == Marginal::Uniform ? marginals[i].a : -kInf; }
 Real Prior::GetUpperBound(size_t i) const { return marginals[i].kind == Marginal::Uniform ? marginals[i].b : kInf; }
 
+bool Prior::EvaluateMarginalMean(size_t i, Real& mean) const
+{
+	const Marginal& m = marginals[i];
+	mean = (m.kind == Marginal::Uniform) ? 0.5 * (m.a + m.b) : m.a;
+	return true;
+}
+
 bool Prior::EvaluateMarginalVariance(size_t i, Real& var) const
 {
 	const Marginal& m = marginals[i];

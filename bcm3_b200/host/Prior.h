@@ -22,6 +22,7 @@ public:
 	bool Sample(Real* values, RNG* rng) const;                                  // :159-179
 	Real GetLowerBound(size_t i) const;
 	Real GetUpperBound(size_t i) const;
+	bool EvaluateMarginalMean(size_t i, Real& mean) const; // PriorIndependence.cpp:181-193
 	bool EvaluateMarginalVariance(size_t i, Real& var) const;
 	size_t GetNumVariables() const { return marginals.size(); }
 

@@ -98,9 +98,9 @@ void SampleHistory::GetHistory(std::vector<VectorReal>& rows) const
 }
 
 // ---------------------------------------------------------------------------------------------- proposal
-bool ProposalGlobalCovariance::Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng)
+bool Proposal::Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng)
 {
-	// Proposal::Initialize (Proposal.cpp:39-140) + ProposalGlobalCovariance::InitializeImpl (:66-112)
+	// Proposal::Initialize (Proposal.cpp:39-140)
 	n = num_variables;
 	target_acceptance_rate = (n == 1) ? 0.44 : (n == 2) ? 0.35 : (n == 3) ? 0.3 : 0.234;
 	lower.resize(n);
@@ -126,6 +126,12 @@ bool ProposalGlobalCovariance::Initialize(const SampleHistory& history, size_t m
 		for (size_t ix : use) sel.push_back(rows[ix]);
 		rows.swap(sel);
 	}
+	return InitializeImpl(rows, prior, rng);
+}
+
+bool ProposalGlobalCovariance::InitializeImpl(const std::vector<VectorReal>& rows, const Prior& prior, RNG&)
+{
+	// ProposalGlobalCovariance::InitializeImpl (ProposalGlobalCovariance.cpp:66-112)
 	covariance.assign(n * n, 0.0);
 	if (rows.size() < 2) {
 		for (size_t j = 0; j < n; j++) {
@@ -195,7 +201,7 @@ void ProposalGlobalCovariance::NotifyAccepted(bool accepted)
 	current_acceptance_rate_ema += ((accepted ? 1.0 : 0.0) - current_acceptance_rate_ema) * ema_alpha;
 }
 
-Real ProposalGlobalCovariance::ReflectOnBounds(Real x, Real lb, Real ub)
+Real Proposal::ReflectOnBounds(Real x, Real lb, Real ub)
 {
 	// Proposal.cpp:385-397
 	for (;;) {
@@ -206,7 +212,7 @@ Real ProposalGlobalCovariance::ReflectOnBounds(Real x, Real lb, Real ub)
 	return x;
 }
 
-void ProposalGlobalCovariance::GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) const
+void ProposalGlobalCovariance::GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng)
 {
 	// ProposalGlobalCovariance.cpp:19-41 with t_dof = 0
 	VectorReal z(n);
@@ -219,6 +225,136 @@ void ProposalGlobalCovariance::GetNewSample(const VectorReal& current, VectorRea
 	}
 }
 
+// ---------------------------------------------------------------------------------------------- mixture proposal
+namespace {
+
+// lag-`lag` autocorrelation of a history column (SummaryStats.h acf)
+Real autocorrelation(const std::vector<VectorReal>& rows, size_t col, size_t lag, Real mu, Real var)
+{
+	const size_t n = rows.size();
+	Real c = 0.0;
+	for (size_t i = 0; i + lag < n; i++) c += (rows[i][col] - mu) * (rows[i + lag][col] - mu);
+	return c / ((Real)(n - lag) * var);
+}
+
+} // namespace
+
+bool ProposalGaussianMixture::InitializeImpl(const std::vector<VectorReal>& rows, const Prior& prior, RNG& rng)
+{
+	// ProposalGaussianMixture::InitializeImpl (ProposalGaussianMixture.cpp:117-251)
+	bool have = false;
+	const size_t ns = rows.size();
+	if (ns >= 2) {
+		// the smallest per-variable effective sample size scales the log-likelihood in the adjusted AIC and the
+		// regularisation of the covariance estimates
+		Real min_ess = kInf;
+		const int lag_max = std::max(5, (int)(10 * log10((Real)ns)));
+		for (size_t i = 0; i < n; i++) {
+			Real mu = 0.0, var = 0.0;
+			for (auto& r : rows) mu += r[i];
+			mu /= (Real)ns;
+			for (auto& r : rows) var += (r[i] - mu) * (r[i] - mu);
+			var /= (Real)(ns - 1);
+			Real rho = 0.0;
+			if (var > 0.0)
+				for (int lag = 1; lag < lag_max && (size_t)lag < ns; lag++) rho += autocorrelation(rows, i, (size_t)lag, mu, var);
+			min_ess = std::min(min_ess, (Real)ns / (1.0 + 2.0 * rho));
+		}
+		if (!(min_ess > 0.0)) min_ess = 1.0; // strongly anti-correlated or constant history
+		min_ess = std::min(min_ess, (Real)ns);
+		const Real aic_adjust = min_ess / (Real)ns;
+		Real best = kInf;
+		static const size_t num_components[7] = { 1, 2, 3, 4, 5, 8, 13 };
+		for (size_t k : num_components) {
+			if (min_ess < (Real)(k * (1 + std::min(n / 2, (size_t)10)))) continue; // not enough effective samples
+			GaussianMixture candidate;
+			if (!candidate.Fit(rows, k, rng, (Real)ns / min_ess)) continue;
+			const Real nparam = 0.5 * candidate.GetAIC() + candidate.GetLogLikelihood();
+			const Real score = adjusted_aic ? 2.0 * nparam - 2.0 * aic_adjust * candidate.GetLogLikelihood() : candidate.GetAIC();
+			if (score < best) {
+				gmm = candidate;
+				best = candidate.GetAIC(); // as the reference does, also when the adjusted score selects (:163-166)
+				have = true;
+			}
+		}
+	}
+	if (!have) {
+		// first initialisation, or no mixture could be fitted: one component with the prior's marginal variances
+		VectorReal mean(n, 0.0);
+		std::vector<Real> cov(n * n, 0.0);
+		for (size_t i = 0; i < n; i++) {
+			Real m = 0.0, v = 1.0;
+			if (!prior.EvaluateMarginalMean(i, m)) m = 0.0;
+			if (!prior.EvaluateMarginalVariance(i, v)) v = 1.0;
+			mean[i] = m;
+			cov[i + i * n] = v;
+		}
+		if (!gmm.Set({ mean }, { cov }, VectorReal(1, 1.0))) return false;
+	}
+	scales.assign(gmm.GetNumComponents(), 2.38 / sqrt((Real)n));
+	acceptance_rate_emas.assign(gmm.GetNumComponents(), target_acceptance_rate);
+	selected_component = -1;
+	return true;
+}
+
+void ProposalGaussianMixture::GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng)
+{
+	// ProposalGaussianMixture.cpp:21-45 with t_dof = 0
+	VectorReal resp;
+	gmm.CalculateResponsibilities(current, resp);
+	selected_component = (long)SampleIndex(rng, resp);
+	const std::vector<Real>& L = gmm.GetComponent((size_t)selected_component).chol;
+	VectorReal z(n);
+	for (size_t i = 0; i < n; i++) z[i] = rng.GetNormal();
+	proposed.assign(n, 0.0);
+	for (size_t i = 0; i < n; i++) {
+		Real v = 0.0;
+		for (size_t k = 0; k <= i; k++) v += L[i + k * n] * z[k];
+		proposed[i] = ReflectOnBounds(current[i] + v * scales[(size_t)selected_component], lower[i], upper[i]);
+	}
+}
+
+Real ProposalGaussianMixture::CalculateMHRatio(const VectorReal& current, const VectorReal& proposed) const
+{
+	// ProposalGaussianMixture.cpp:47-67: q(new | cur) = sum_k resp_k(cur) N(new - cur; 0, scale_k^2 Sigma_k), and the reverse
+	VectorReal fwd, rev, v(n);
+	gmm.CalculateResponsibilities(current, fwd);
+	gmm.CalculateResponsibilities(proposed, rev);
+	Real fwd_logp = -kInf, rev_logp = -kInf;
+	for (size_t k = 0; k < gmm.GetNumComponents(); k++) {
+		const GaussianMixture::Component& c = gmm.GetComponent(k);
+		for (size_t i = 0; i < n; i++) v[i] = (proposed[i] - current[i]) / scales[k];
+		GaussianMixture::SolveLower(c.chol, n, v);
+		Real q = 0.0;
+		for (size_t i = 0; i < n; i++) q += v[i] * v[i];
+		// the step density is even in the step, so forward and reverse share the quadratic form
+		const Real base = -log(scales[k] * scales[k]) + c.logC - 0.5 * q;
+		fwd_logp = GaussianMixture::LogSum(fwd_logp, base + log(fwd[k]));
+		rev_logp = GaussianMixture::LogSum(rev_logp, base + log(rev[k]));
+	}
+	return rev_logp - fwd_logp;
+}
+
+void ProposalGaussianMixture::Update(RNG& rng, bool scaling_frozen)
+{
+	// ProposalGaussianMixture.cpp:69-90: only the scale of the component that made the previous proposal moves
+	const Real learn_rate = 1.0 + rng.GetReal() * scaling_learning_rate * (Real)gmm.GetNumComponents();
+	if (scaling_frozen || selected_component < 0) return;
+	Real& scale = scales[(size_t)selected_component];
+	const Real ema = acceptance_rate_emas[(size_t)selected_component];
+	if (ema < target_acceptance_rate / (1.0 - scaling_learning_rate)) scale = std::max(scale / learn_rate, (Real)1e-4);
+	else if (ema > (1.0 + scaling_learning_rate) * target_acceptance_rate) scale = std::min(scale * learn_rate, (Real)10.0);
+}
+
+void ProposalGaussianMixture::NotifyAccepted(bool accepted)
+{
+	// ProposalGaussianMixture.cpp:92-104
+	if (selected_component < 0) return;
+	const Real ema_alpha = 2.0 / (scaling_ema_period + 1);
+	Real& ema = acceptance_rate_emas[(size_t)selected_component];
+	ema += ((accepted ? 1.0 : 0.0) - ema) * ema_alpha;
+}
+
 // ---------------------------------------------------------------------------------------------- sampler
 bool SamplerPT::Initialize()
 {
@@ -226,8 +362,8 @@ bool SamplerPT::Initialize()
 		last_error = "variable set, prior and likelihood must be set";
 		return false;
 	}
-	if (s.proposal_type != "global_covariance") {
-		last_error = "proposal_type \"" + s.proposal_type + "\" is not part of the batched hot path; use global_covariance";
+	if (!MakeProposal()) {
+		last_error = "proposal_type \"" + s.proposal_type + "\" is not supported (global_covariance, gaussian_mixture, gaussian_mixture_adjustedAIC)";
 		return false;
 	}
 	if (s.swapping_scheme != "deterministic_even_odd" && s.swapping_scheme != "stochastic_even_odd" && s.swapping_scheme != "stochastic_random") {
@@ -268,17 +404,27 @@ bool SamplerPT::Initialize()
 		c.rng.Seed(s.rngseed, i + 1);
 		c.current_var_values.assign(num_variables, 0.0);
 		c.history.Initialize(num_variables, sample_history, subsampling);
-		if (!c.proposal.Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
+		c.proposal = MakeProposal();
+		if (!c.proposal->Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
 			last_error = "Proposal initialization failed.";
 			return false;
 		}
-		c.proposal.SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
+		c.proposal->SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
 	}
 	previous_swap_even = false;
 	proposal_adaptations_done = 0;
 	proposal_scaling_adaptations_done = false;
 	samples.clear();
 	return true;
+}
+
+// SamplerPTChain.cpp:431-437
+std::shared_ptr<Proposal> SamplerPT::MakeProposal() const
+{
+	if (s.proposal_type == "global_covariance") return std::make_shared<ProposalGlobalCovariance>();
+	if (s.proposal_type == "gaussian_mixture") return std::make_shared<ProposalGaussianMixture>(false);
+	if (s.proposal_type == "gaussian_mixture_adjustedAIC") return std::make_shared<ProposalGaussianMixture>(true);
+	return nullptr;
 }
 
 bool SamplerPT::EvaluateAll(const std::vector<size_t>& which, const MatrixReal& proposals, VectorReal& lpriors, VectorReal& llhs)
@@ -413,9 +559,9 @@ bool SamplerPT::DoMutateMove()
 		if (c.temperature == 0.0) {
 			prior->Sample(proposals.col(ci), &c.rng);
 		} else {
-			c.proposal.Update(c.rng, proposal_scaling_adaptations_done);
+			c.proposal->Update(c.rng, proposal_scaling_adaptations_done);
 			VectorReal np;
-			c.proposal.GetNewSample(c.current_var_values, np, c.rng);
+			c.proposal->GetNewSample(c.current_var_values, np, c.rng);
 			std::copy(np.begin(), np.end(), proposals.col(ci));
 		}
 	}
@@ -439,7 +585,8 @@ bool SamplerPT::DoMutateMove()
 		c.attempted_mutate++;
 		bool accept = false;
 		if (new_lpp > -kInf) {
-			Real tp = exp(new_lpp - c.lpowerposterior + c.proposal.CalculateMHRatio());
+			const VectorReal proposed(proposals.col(ci), proposals.col(ci) + num_variables);
+			Real tp = exp(new_lpp - c.lpowerposterior + c.proposal->CalculateMHRatio(c.current_var_values, proposed));
 			tp = std::min((Real)1.0, tp);
 			accept = c.rng.GetReal() < tp;
 		}
@@ -450,7 +597,7 @@ bool SamplerPT::DoMutateMove()
 			c.llh = ll[ci];
 			c.lpowerposterior = new_lpp;
 		}
-		c.proposal.NotifyAccepted(accept);
+		c.proposal->NotifyAccepted(accept);
 		c.history.AddSample(c.current_var_values);
 	}
 	return true;
@@ -466,13 +613,11 @@ bool SamplerPT::AdaptProposals()
 {
 	for (Chain& c : chains) {
 		if (c.temperature == 0.0) continue;
-		Real keep_scale = c.proposal.GetScale();
-		(void)keep_scale;
-		if (!c.proposal.Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
+		if (!c.proposal->Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
 			last_error = "Proposal adaptation failed";
 			return false;
 		}
-		c.proposal.SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
+		c.proposal->SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
 	}
 	return true;
 }

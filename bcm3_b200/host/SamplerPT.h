@@ -3,11 +3,13 @@
 // ProposalGlobalCovariance.cpp:19-114, SampleHistory.cpp:32-67), restructured around ONE batched likelihood call per
 // mutate round:   propose for all chains -> EvaluateLogProbabilityBatch -> accept/reject for all chains.
 // Proposal generation, MH tests and temperature swaps stay on the host and are deterministic (RNG.h).
-// Blocking strategies other than one_block and the GMM / clustered proposals are out of scope.
+// Proposals: global_covariance and gaussian_mixture (the one examples/banana/config.txt asks for; ProposalGaussianMixture.cpp,
+// GMM.cpp). Blocking strategies other than one_block and the clustered proposal are out of scope.
 #pragma once
 
 #include <functional>
 
+#include "GaussianMixture.h"
 #include "Likelihood.h"
 #include "Prior.h"
 #include "RNG.h"
@@ -21,7 +23,7 @@ struct SamplerPTSettings {
 	uint64_t rngseed = 0;
 	// [ptmhsampler] (defaults of SamplerPT::AddOptionsDescription, SamplerPT.cpp:147-172)
 	size_t num_chains = 6;
-	std::string proposal_type = "global_covariance";
+	std::string proposal_type = "global_covariance"; // or gaussian_mixture / gaussian_mixture_adjustedAIC (SamplerPTChain.cpp:431-437)
 	std::string swapping_scheme = "deterministic_even_odd";
 	size_t num_exploration_steps = 1;
 	size_t max_history_size = 2000;
@@ -53,24 +55,65 @@ private:
 	std::vector<float> samples;
 };
 
-class ProposalGlobalCovariance {
+// Proposal (src/sampler/Proposal.{h,cpp}): what a chain asks of its proposal distribution for the one variable block
+class Proposal {
 public:
+	virtual ~Proposal() {}
+	// Proposal::Initialize (Proposal.cpp:39-140): bounds, target acceptance rate, the (sub)sampled history -> InitializeImpl
 	bool Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng);
 	void SetScalingSchedule(size_t ema_period, Real learning_rate) { scaling_ema_period = ema_period; scaling_learning_rate = learning_rate; }
-	void Update(RNG& rng, bool scaling_frozen);
-	void GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) const;
-	Real CalculateMHRatio() const { return 0.0; }
-	void NotifyAccepted(bool accepted);
+	virtual void Update(RNG& rng, bool scaling_frozen) = 0;
+	virtual void GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) = 0;
+	virtual Real CalculateMHRatio(const VectorReal& current, const VectorReal& proposed) const = 0; // log q(cur|new) - log q(new|cur)
+	virtual void NotifyAccepted(bool accepted) = 0;
+
+protected:
+	virtual bool InitializeImpl(const std::vector<VectorReal>& history_rows, const Prior& prior, RNG& rng) = 0;
+	static Real ReflectOnBounds(Real x, Real lb, Real ub);
+	size_t n = 0;
+	std::vector<Real> lower, upper;
+	size_t scaling_ema_period = 1000;
+	Real scaling_learning_rate = 0.05, target_acceptance_rate = 0.234; // proposal_t_dof = 0 (normal proposals) only
+};
+
+class ProposalGlobalCovariance : public Proposal {
+public:
+	void Update(RNG& rng, bool scaling_frozen) override;
+	void GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) override;
+	Real CalculateMHRatio(const VectorReal&, const VectorReal&) const override { return 0.0; }
+	void NotifyAccepted(bool accepted) override;
 	Real GetScale() const { return adaptive_scale; }
 	const std::vector<Real>& GetCovariance() const { return covariance; }
 
+protected:
+	bool InitializeImpl(const std::vector<VectorReal>& history_rows, const Prior& prior, RNG& rng) override;
+
 private:
-	static Real ReflectOnBounds(Real x, Real lb, Real ub);
-	size_t n = 0;
 	std::vector<Real> covariance, chol; // n x n, column-major; chol lower-triangular
-	std::vector<Real> lower, upper;
-	size_t scaling_ema_period = 1000;
-	Real scaling_learning_rate = 0.05, target_acceptance_rate = 0.234, adaptive_scale = 1.0, current_acceptance_rate_ema = 0.23;
+	Real adaptive_scale = 1.0, current_acceptance_rate_ema = 0.23;
+};
+
+// ProposalGaussianMixture (src/sampler/ProposalGaussianMixture.cpp): a mixture fitted to the chain's history; a proposal
+// picks the component by its responsibility for the current position, steps with that component's covariance and scale,
+// and the Metropolis-Hastings ratio accounts for the position-dependent choice
+class ProposalGaussianMixture : public Proposal {
+public:
+	explicit ProposalGaussianMixture(bool select_with_adjusted_aic) : adjusted_aic(select_with_adjusted_aic) {}
+	void Update(RNG& rng, bool scaling_frozen) override;
+	void GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) override;
+	Real CalculateMHRatio(const VectorReal& current, const VectorReal& proposed) const override;
+	void NotifyAccepted(bool accepted) override;
+	const GaussianMixture& GetMixture() const { return gmm; }
+	const VectorReal& GetScales() const { return scales; }
+
+protected:
+	bool InitializeImpl(const std::vector<VectorReal>& history_rows, const Prior& prior, RNG& rng) override;
+
+private:
+	GaussianMixture gmm;
+	VectorReal scales, acceptance_rate_emas;
+	long selected_component = -1;
+	bool adjusted_aic;
 };
 
 struct EmittedSample {
@@ -102,7 +145,7 @@ private:
 		Real lprior = -kInf, llh = -kInf, lpowerposterior = -kInf;
 		size_t attempted_mutate = 0, accepted_mutate = 0, attempted_exchange = 0, accepted_exchange = 0;
 		SampleHistory history;
-		ProposalGlobalCovariance proposal;
+		std::shared_ptr<Proposal> proposal;
 		RNG rng;
 	};
 
@@ -113,6 +156,7 @@ private:
 	bool DoMutateMove();
 	void EmitSample();
 	bool AdaptProposals();
+	std::shared_ptr<Proposal> MakeProposal() const;
 
 	SamplerPTSettings s;
 	std::shared_ptr<const VariableSet> varset;

@@ -390,6 +390,59 @@ int bcm3host_cellpop_session_evaluate(void* session, const double* values, size_
 	return 0;
 }
 
+// ---- GaussianMixture (the fit behind proposal_type=gaussian_mixture) for tests ----
+// samples[n][D] row-major. Outputs: weights[K], means[K][D], covariances[K][D][D], stats = { AIC, log-likelihood }.
+int bcm3host_gmm_fit(const double* samples, size_t n, size_t D, size_t K, unsigned long long seed, double ess_factor, double* weights,
+                     double* means, double* covariances, double* stats)
+{
+	std::vector<VectorReal> rows(n, VectorReal(D));
+	for (size_t r = 0; r < n; r++) rows[r].assign(samples + r * D, samples + (r + 1) * D);
+	RNG rng(seed, 0);
+	GaussianMixture g;
+	if (!g.Fit(rows, K, rng, ess_factor)) return -1;
+	for (size_t k = 0; k < K; k++) {
+		weights[k] = g.GetWeights()[k];
+		const auto& c = g.GetComponent(k);
+		std::copy(c.mean.begin(), c.mean.end(), means + k * D);
+		std::copy(c.covariance.begin(), c.covariance.end(), covariances + k * D * D);
+	}
+	stats[0] = g.GetAIC();
+	stats[1] = g.GetLogLikelihood();
+	return 0;
+}
+
+// mixture given explicitly: log pdf and responsibilities at x[m][D]
+int bcm3host_gmm_evaluate(size_t K, size_t D, const double* weights, const double* means, const double* covariances, const double* x, size_t m,
+                          double* logpdf, double* responsibilities)
+{
+	std::vector<VectorReal> mu(K, VectorReal(D));
+	std::vector<std::vector<Real>> cov(K, std::vector<Real>(D * D));
+	for (size_t k = 0; k < K; k++) {
+		mu[k].assign(means + k * D, means + (k + 1) * D);
+		cov[k].assign(covariances + k * D * D, covariances + (k + 1) * D * D);
+	}
+	GaussianMixture g;
+	if (!g.Set(mu, cov, VectorReal(weights, weights + K))) return -1;
+	VectorReal r;
+	for (size_t i = 0; i < m; i++) {
+		const VectorReal xi(x + i * D, x + (i + 1) * D);
+		logpdf[i] = g.LogPdf(xi);
+		g.CalculateResponsibilities(xi, r);
+		std::copy(r.begin(), r.end(), responsibilities + i * K);
+	}
+	return 0;
+}
+
+// symmetric eigen-decomposition of a[n][n]: values ascending, vectors column-major
+void bcm3host_symmetric_eigen(const double* a, size_t n, double* values, double* vectors)
+{
+	VectorReal v;
+	std::vector<Real> vec;
+	GaussianMixture::SymmetricEigen(std::vector<Real>(a, a + n * n), n, v, vec);
+	std::copy(v.begin(), v.end(), values);
+	std::copy(vec.begin(), vec.end(), vectors);
+}
+
 // VariableSet / Prior surface for tests: number of variables, transform codes, index lookup
 int bcm3host_varset_info(const char* prior_xml, const char* lookup_name, size_t* num_variables, int* transforms, size_t max_n, size_t* index)
 {

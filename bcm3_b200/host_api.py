@@ -136,6 +136,45 @@ def run_pt_cellpop(prior_xml: str, likelihood_xml: str, config_text: str, proble
     return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])
 
 
+def gmm_fit(samples, num_components: int, seed: int = 1, ess_factor: float = 1.0):
+    """GaussianMixture::Fit (the fit behind proposal_type=gaussian_mixture). Returns dict(weights, means, covariances, aic, logl) or None."""
+    lib = load()
+    x = np.ascontiguousarray(samples, dtype=np.float64)
+    n, D = x.shape
+    K = num_components
+    w, mu, cov, st = np.empty(K), np.empty((K, D)), np.empty((K, D, D)), np.empty(2)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.bcm3host_gmm_fit(vp(x), C.c_size_t(n), C.c_size_t(D), C.c_size_t(K), C.c_ulonglong(seed), C.c_double(ess_factor), vp(w), vp(mu), vp(cov), vp(st))
+    if rc != 0:
+        return None
+    return dict(weights=w, means=mu, covariances=cov, aic=st[0], logl=st[1])
+
+
+def gmm_evaluate(weights, means, covariances, x):
+    """log pdf [m] and responsibilities [m][K] of an explicit mixture at x[m][D]."""
+    lib = load()
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    mu = np.ascontiguousarray(means, dtype=np.float64)
+    cov = np.ascontiguousarray(covariances, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    K, D = mu.shape
+    lp, resp = np.empty(x.shape[0]), np.empty((x.shape[0], K))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.bcm3host_gmm_evaluate(C.c_size_t(K), C.c_size_t(D), vp(w), vp(mu), vp(cov), vp(x), C.c_size_t(x.shape[0]), vp(lp), vp(resp))
+    if rc != 0:
+        raise RuntimeError("mixture covariance is not positive definite")
+    return lp, resp
+
+
+def symmetric_eigen(a):
+    lib = load()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    vals, vecs = np.empty(n), np.empty((n, n))
+    lib.bcm3host_symmetric_eigen(a.ctypes.data_as(C.c_void_p), C.c_size_t(n), vals.ctypes.data_as(C.c_void_p), vecs.ctypes.data_as(C.c_void_p))
+    return vals, vecs.T  # column-major -> columns are eigenvectors
+
+
 class CellPopSession:
     """CellPopulationLikelihoodB200 with any number of <experiment> / <data> elements: likelihood.xml goes through
     LikelihoodFactory, then the generated model, the data sets and the quasi-random tables are supplied the way the

@@ -5,8 +5,8 @@ import numpy as np
 import pytest
 from scipy import stats
 
-# the reference's examples/banana/{prior.xml,likelihood.xml,config.txt}; proposal_type is global_covariance because the
-# GMM proposal machinery is outside the batched hot path
+# the reference's examples/banana/{prior.xml,likelihood.xml,config.txt}; CONFIG swaps the proposal for global_covariance,
+# GMM_CONFIG is the example's own (proposal_type=gaussian_mixture)
 PRIOR = """<?xml version="1.0" encoding="utf-8"?>
 <variableset>
   <variable name="x1"   distribution="uniform" lower="-6.0" upper="4.0"/>
@@ -30,6 +30,7 @@ adapt_proposal_max_history_samples=5000
 stop_proposal_scaling=4000
 temperature_schedule_power=3.0
 """
+GMM_CONFIG = CONFIG.replace("proposal_type=global_covariance", "proposal_type=gaussian_mixture")
 
 
 @pytest.fixture(scope="module")
@@ -178,3 +179,66 @@ def test_cell_population_plugin_experiment_specific_elements(built, tmp_path, mo
     with pytest.raises(RuntimeError, match="not a simulated species"):
         s.post_initialize(compile_only=True)
     s.close()
+
+
+def test_symmetric_eigen_and_mixture_density(host):
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((7, 7))
+    a = a @ a.T + 0.1 * np.eye(7)
+    vals, vecs = host.symmetric_eigen(a)
+    assert np.all(np.diff(vals) >= 0) and np.allclose(vals, np.linalg.eigvalsh(a), rtol=1e-12)
+    assert np.allclose(vecs @ np.diag(vals) @ vecs.T, a, atol=1e-12) and np.allclose(vecs.T @ vecs, np.eye(7), atol=1e-12)
+    w = np.array([0.3, 0.7])
+    mu = np.array([[0.0, 1.0, -1.0], [2.0, -1.0, 0.5]])
+    cov = np.stack([np.diag([1.0, 0.5, 2.0]), a[:3, :3]])
+    x = rng.standard_normal((20, 3)) * 2
+    lp, resp = host.gmm_evaluate(w, mu, cov, x)
+    comp = np.stack([np.log(w[k]) + stats.multivariate_normal(mu[k], cov[k]).logpdf(x) for k in range(2)], axis=1)
+    assert np.allclose(lp, np.logaddexp(comp[:, 0], comp[:, 1]), rtol=1e-12, atol=1e-12)
+    assert np.allclose(resp, np.exp(comp - lp[:, None]), atol=1e-12) and np.allclose(resp.sum(axis=1), 1.0)
+
+
+def test_mixture_fit_recovers_two_clusters(host):
+    """GMM::Fit (GMM.cpp:48-158): k-means++ start + EM with the shrunk covariance estimate; AIC prefers the true component count."""
+    rng = np.random.default_rng(11)
+    c0 = rng.multivariate_normal([-3.0, 0.0, 1.0], np.diag([0.5, 1.0, 0.2]), 1200)
+    c1 = rng.multivariate_normal([2.0, 2.0, -1.0], [[1.0, 0.6, 0.0], [0.6, 1.0, 0.0], [0.0, 0.0, 0.3]], 800)
+    x = rng.permutation(np.concatenate([c0, c1]))
+    one, two, three = (host.gmm_fit(x, k, seed=5) for k in (1, 2, 3))
+    assert np.allclose(one["means"][0], x.mean(axis=0), atol=1e-9)
+    # one component with ess_factor 1: the sample covariance up to the O(D / n) eigenvalue shrinkage
+    assert np.allclose(one["covariances"][0], np.cov(x.T), rtol=0.01, atol=0.01)
+    order = np.argsort(two["means"][:, 0])
+    assert np.allclose(two["weights"][order], [0.6, 0.4], atol=0.02)
+    assert np.allclose(two["means"][order], [[-3.0, 0.0, 1.0], [2.0, 2.0, -1.0]], atol=0.12)
+    assert abs(two["covariances"][order[1]][0, 1] - 0.6) < 0.1
+    assert two["aic"] < one["aic"] - 500 and two["aic"] < three["aic"] + 30 and two["logl"] > one["logl"]
+    lp, _ = host.gmm_evaluate(two["weights"], two["means"], two["covariances"], x)
+    assert np.isclose(lp.sum(), two["logl"], rtol=1e-3)  # the reported log-likelihood is the last expectation step's
+    assert host.gmm_fit(x[:10], 2) is None  # fewer than 2 D K samples (GMM.cpp:86-90)
+    assert host.gmm_fit(x, 2, seed=5)["aic"] == two["aic"]  # deterministic given the seed
+
+
+def test_gaussian_mixture_proposal_on_the_banana(host):
+    """BASELINE config 1 as the reference ships it: examples/banana/config.txt with proposal_type=gaussian_mixture."""
+    cfg = GMM_CONFIG.replace("num_samples=8000", "num_samples=600").replace("adapt_proposal_samples=2000", "adapt_proposal_samples=200")
+    a, sa = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=True, seed=7)
+    b, sb = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=False, seed=7)
+    assert np.array_equal(a, b) and sa["evaluations"] == sb["evaluations"]
+    g, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg.replace("gaussian_mixture", "global_covariance"), batched=True, seed=7)
+    assert not np.array_equal(a, g)
+    with pytest.raises(RuntimeError, match="proposal_type"):
+        host.run_pt(PRIOR, LIKELIHOOD, cfg.replace("gaussian_mixture", "clustered_covariance"), seed=7)
+    rows, st = host.run_pt(PRIOR, LIKELIHOOD, GMM_CONFIG, batched=True, seed=20261018)
+    post = rows[rows[:, 0] == 1.0][1000:, 3:]
+    x1, x2 = post[:, 0], post[:, 1]
+    grid = np.linspace(-6, 4, 4001)
+    w = stats.norm.pdf(grid, 0, 2) * (stats.norm.cdf(20, (1 + grid) ** 2, 1) - stats.norm.cdf(-6, (1 + grid) ** 2, 1))
+    w /= np.trapezoid(w, grid)
+    m1 = np.trapezoid(w * grid, grid)
+    s1 = np.sqrt(np.trapezoid(w * (grid - m1) ** 2, grid))
+    assert abs(x1.mean() - m1) < 0.15 and abs(x1.std() - s1) < 0.15
+    r = x2 - (1 + x1) ** 2
+    assert abs(r.mean()) < 0.1 and abs(r.std() - 1.0) < 0.1
+    adj, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg.replace("gaussian_mixture", "gaussian_mixture_adjustedAIC"), batched=True, seed=7)
+    assert adj.shape == a.shape and np.isfinite(adj[:, 2]).all()
