@@ -256,7 +256,20 @@ void GaussianMixture::MeanCovariance(const std::vector<VectorReal>& samples, con
 	}
 	n_eff = std::max(n_eff, (Real)D);
 	VectorReal sd(D);
-	for (size_t i = 0; i < D; i++) sd[i] = sqrt(cov[i + i * D]);
+	bool degenerate = false;
+	for (size_t i = 0; i < D; i++) {
+		sd[i] = sqrt(cov[i + i * D]);
+		if (!(sd[i] > 0.0) || !std::isfinite(sd[i])) degenerate = true;
+	}
+	if (degenerate) {
+		// a variable that did not move in the history has no correlation to shrink (the reference ends up with NaNs and a
+		// failed factorisation here): keep the variances, floor them like the regular path does
+		for (size_t j = 0; j < D; j++)
+			for (size_t i = 0; i < D; i++)
+				if (i != j) cov[i + j * D] = 0.0;
+		for (size_t i = 0; i < D; i++) cov[i + i * D] = (std::isfinite(cov[i + i * D]) && cov[i + i * D] > 0.0 ? cov[i + i * D] : 0.0) + 1e-8;
+		return;
+	}
 	std::vector<Real> corr(D * D);
 	for (size_t i = 0; i < D; i++) {
 		corr[i + i * D] = 1.0;
