@@ -298,7 +298,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 
 // Experiment::Simulate (Experiment.cpp:635-642): transformed[parameter] = transformed[replacement] for the cells of this
 // experiment; with equal transforms that is the same as replacing the untransformed column
-const double* CellPopulationLikelihoodB200::ExperimentValues(const Experiment& e, const double* values, size_t C, size_t nvar)
+const double* CellPopulationLikelihoodB200::ExperimentValues(const Experiment& e, const double* values, size_t C, size_t nvar, std::vector<double>& replaced)
 {
 	if (e.specific_parameters.empty()) return values;
 	replaced.assign(values, values + C * nvar);
@@ -313,7 +313,8 @@ bool CellPopulationLikelihoodB200::EvaluateLogProbability(size_t, const bcm3::Ve
 	logp = 0.0;
 	for (auto& e : experiments) {
 		Real experiment_logp = 0.0;
-		const double* v = ExperimentValues(e, values.data(), 1, values.size());
+		std::vector<double> scratch; // local: this entry may be called from several sampling threads (IsReentrant)
+		const double* v = ExperimentValues(e, values.data(), 1, values.size(), scratch);
 		for (auto& ds : e.data) {
 			int st = 0;
 			Real dl_logp = 0.0;
@@ -336,7 +337,7 @@ bool CellPopulationLikelihoodB200::EvaluateLogProbabilityBatch(const bcm3::Matri
 	std::vector<double> experiment_logp(C);
 	for (auto& e : experiments) {
 		std::fill(experiment_logp.begin(), experiment_logp.end(), 0.0);
-		const double* v = ExperimentValues(e, values.data.data(), C, values.rows());
+		const double* v = ExperimentValues(e, values.data.data(), C, values.rows(), replaced);
 		for (auto& ds : e.data) {
 			if (bcm3b200_evaluate_batch(ds.handle, C, values.rows(), v, part.data(), status.data()) != BCM3B200_OK) return Fail(bcm3b200_last_error());
 			for (size_t c = 0; c < C; c++) experiment_logp[c] += part[c];

@@ -131,7 +131,7 @@ private:
 	bool InitializeExperiment(const bcm3::XmlNode& node, Experiment& e);
 	bool CreateHandle(Experiment& e, DataSet& ds, double simulation_end_time);
 	// the [C][nvar] block the handles of `e` are given: `values` itself, or the copy with the experiment-specific columns replaced
-	const double* ExperimentValues(const Experiment& e, const double* values, size_t C, size_t nvar);
+	static const double* ExperimentValues(const Experiment& e, const double* values, size_t C, size_t nvar, std::vector<double>& scratch);
 	bool Fail(const std::string& m)
 	{
 		last_error = m;
@@ -143,7 +143,7 @@ private:
 	int device = 0;
 	bool compile_only = false;
 	std::vector<int> status;
-	std::vector<double> part; // one handle's per-chain results
-	std::vector<double> replaced; // ExperimentValues scratch
+	std::vector<double> part; // one handle's per-chain results (batched entry: one caller at a time, like the reference's sampler)
+	std::vector<double> replaced; // ExperimentValues scratch of the batched entry
 	std::string last_error;
 };
