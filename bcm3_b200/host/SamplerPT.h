@@ -23,7 +23,7 @@ struct SamplerPTSettings {
 	uint64_t rngseed = 0;
 	// [ptmhsampler] (defaults of SamplerPT::AddOptionsDescription, SamplerPT.cpp:147-172)
 	size_t num_chains = 6;
-	std::string proposal_type = "global_covariance"; // or gaussian_mixture / gaussian_mixture_adjustedAIC (SamplerPTChain.cpp:431-437)
+	std::string proposal_type = "gaussian_mixture"; // the reference default (SamplerPT.cpp:11,152); also global_covariance, gaussian_mixture_adjustedAIC (SamplerPTChain.cpp:431-437)
 	std::string swapping_scheme = "deterministic_even_odd";
 	size_t num_exploration_steps = 1;
 	size_t max_history_size = 2000;
