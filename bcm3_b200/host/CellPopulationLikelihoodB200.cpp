@@ -110,7 +110,7 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				if (ve.apply < 0) return Fail("Unknown cell variability apply type \"" + v.get("apply") + "\"");
 				if (!Resolve(v.get("scale", "0"), ve.scale, "scale")) return false;
 				ve.negate = v.get_bool("negate", false);
-				if (v.get_bool("only_initial_cells", false)) return Fail("only_initial_cells is not supported");
+				// only_initial_cells (VariabilityDescriptionVariable.cpp:66-110): without division every cell is an initial cell
 				e.variables.push_back(ve);
 			}
 		} else if (c.name == "data") {
