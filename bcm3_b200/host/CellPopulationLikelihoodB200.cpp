@@ -91,9 +91,13 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 	size_t num_variability = 0;
 	for (const auto& c : exp->children) {
 		if (c.name == "cell_variability") {
-			if (++num_variability > 1) return Fail("one cell_variability block per experiment is supported");
-			e.distribution = c.get("distribution", "diagonal_gaussian");
-			if (e.distribution != "diagonal_gaussian" && e.distribution != "full_gaussian") return Fail("Unknown cell_variability distribution \"" + e.distribution + "\"");
+			// Several blocks take successive quasi-random dimensions and are applied in order (Cell.cpp:163-175,
+			// VariabilityDescription.cpp:54-64): for diagonal_gaussian blocks that is one block with all their variables.
+			const std::string distribution = c.get("distribution", "diagonal_gaussian");
+			if (distribution != "diagonal_gaussian" && distribution != "full_gaussian") return Fail("Unknown cell_variability distribution \"" + distribution + "\"");
+			if (++num_variability > 1 && (distribution != "diagonal_gaussian" || e.distribution != "diagonal_gaussian"))
+				return Fail("several cell_variability blocks per experiment are supported only when all of them are diagonal_gaussian");
+			e.distribution = distribution;
 			e.covar_base_name = c.get("covar_base_name");
 			for (const auto& v : c.children) {
 				if (v.name != "variable") continue;

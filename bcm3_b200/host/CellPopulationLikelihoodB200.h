@@ -5,7 +5,7 @@
 //   <bcm_likelihood type="cell_population">
 //     <experiment name= model_file= entry_time=<variable|number> num_cells= max_cells= divide_cells="false"
 //                 [solver_min_timestep=] [solver_max_steps=] [solver_absolute_tolerance=] [solver_relative_tolerance=]>
-//       <cell_variability distribution="diagonal_gaussian|full_gaussian" [covar_base_name=]>
+//       <cell_variability distribution="diagonal_gaussian|full_gaussian" [covar_base_name=]>   (several diagonal_gaussian blocks allowed)
 //         <variable (initial_condition_species=|model_parameter=) apply= scale=<variable|number> [negate=]/> ...
 //       </cell_variability>
 //       <data type="time_course_population_average" species_name="a[+b]" stdev=<variable|number> [proportional_stdev=]

@@ -116,6 +116,13 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     assert kv["num_species"] == "5" and kv["num_cells"] == "16" and kv["num_timepoints"] == "6" and kv["variability_dim"] == "3"
     assert kv["stdev_ix"] == "5" and kv["obs_species"] == "4" and kv["error_model"] == "normal" and float(kv["entry_time"]) == 0.0
     assert kv["variability_distribution"] == "diagonal_gaussian" and "proportional_stdev" not in kv
+    # two diagonal_gaussian blocks = one block with all their variables (successive quasi-random dimensions, applied in order)
+    split = lik.replace('negate="true"/>', 'negate="true" only_initial_cells="true"/></cell_variability><cell_variability distribution="diagonal_gaussian">')
+    assert split.count("<cell_variability") == 2
+    assert host_api.cellpop_evaluate(prior, split, prob, species, compile_only=True)[1] == desc
+    with pytest.raises(RuntimeError, match="all of them are diagonal_gaussian"):
+        host_api.cellpop_evaluate(prior, split.replace('<cell_variability distribution="diagonal_gaussian">', '<cell_variability distribution="full_gaussian" covar_base_name="c">', 1),
+                                  prob, species, compile_only=True)
     # the reference's default is dividing cells (Experiment.cpp:488): refused, not silently ignored
     with pytest.raises(RuntimeError, match="divide_cells"):
         host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)
