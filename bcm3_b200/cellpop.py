@@ -27,6 +27,7 @@ class CellPopEvaluator:
             shard_rank=shard_rank, shard_count=shard_count)
         kv["variability_distribution"] = p.variability_distribution
         kv["relative_to_time_average"] = int(p.relative_to_time_average)
+        kv["stdev_relative_to_scale"] = int(p.stdev_relative_to_scale)
         if p.treatment_species is not None:
             kv["treatment_species"] = p.treatment_species
         if p.simulation_end_time is not None:

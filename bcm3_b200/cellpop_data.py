@@ -65,6 +65,7 @@ class CellPopProblem:
     # the time the experiment integrates its cells to when it has further data sets that end later (Experiment.cpp:655-656);
     # None: the last of `timepoints`
     simulation_end_time: float | None = None
+    stdev_relative_to_scale: bool = False    # <data stdev_relative_to_scale="true">: stdev *= data scale (DataLikelihoodBase.cpp:151-153)
     weight: float = 1.0
     stdev_ix: int | None = None
     stdev: float = 1.0

@@ -489,6 +489,7 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4, proportional_normal, additive_proportional_normal)", em.c_str());
 		cp->treatment_species = get_int(kv, "treatment_species", -1);
 		cp->relative_to_time_average = get_int(kv, "relative_to_time_average", 0) != 0;
+		cp->stdev_relative_to_scale = get_int(kv, "stdev_relative_to_scale", 0) != 0;
 		cp->prop_stdev_ix = get_int(kv, "proportional_stdev_ix", -1);
 		cp->prop_stdev_fixed = real("proportional_stdev", 1.0);
 		const std::string vd = kv.count("variability_distribution") ? kv["variability_distribution"] : "diagonal_gaussian";

@@ -38,6 +38,7 @@ struct CellPopState {
 	double sim_end_time = 0.0;
 	bool full_gaussian = false;                   // <cell_variability distribution="full_gaussian">
 	bool relative_to_time_average = false;        // <data relative_to_time_average="true">
+	bool stdev_relative_to_scale = false;         // <data stdev_relative_to_scale="true">: stdev *= data scale (DataLikelihoodBase.cpp:151-153)
 	int steps_report = 0;                         // option "cellpop_steps_report": what get_cell_diagnostics returns as cell_steps (0 steps, 1 nfe, 2 nsetups, 3 nje)
 	int treatment_species = -1;                   // <treatment_trajectory type="pulses" species_name=...>: constant species index
 	std::vector<int> obs_species;
@@ -248,7 +249,7 @@ struct CpLikArgs {
 	const double* transformed; // [C][nvar]
 	const double* timepoints;  // [T]
 	const double* observed;    // [R][T]
-	int T, R, nvar, error_model, relative_to_time_average;
+	int T, R, nvar, error_model, relative_to_time_average, stdev_relative_to_scale;
 	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
 	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, weight, missing_stdev;
 	double* logp; // [C]
@@ -264,9 +265,10 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 		return;
 	}
 	const double* tv = a.transformed + (long long)c * a.nvar;
-	const double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
+	double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
 	const double offset = (a.offset_ix >= 0) ? tv[a.offset_ix] : a.offset_fixed;
 	const double scale = (a.scale_ix >= 0) ? tv[a.scale_ix] : a.scale_fixed;
+	if (a.stdev_relative_to_scale) stdev *= scale; // GetCurrentSTDev, DataLikelihoodBase.cpp:151-153
 	const double prop_stdev = (a.prop_stdev_ix >= 0) ? tv[a.prop_stdev_ix] : a.prop_stdev_fixed;
 	const double minus_log_sigma = -log(stdev);
 	const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
@@ -764,6 +766,7 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	la.scale_ix = cp.scale_ix;
 	la.stdev_fixed = cp.stdev_fixed;
 	la.relative_to_time_average = cp.relative_to_time_average ? 1 : 0;
+	la.stdev_relative_to_scale = cp.stdev_relative_to_scale ? 1 : 0;
 	la.prop_stdev_ix = cp.prop_stdev_ix;
 	la.prop_stdev_fixed = cp.prop_stdev_fixed;
 	la.offset_fixed = cp.offset_fixed;

@@ -132,6 +132,11 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 			if (!Resolve(c.get("offset", "0"), ds.offset, "offset")) return false;
 			if (!Resolve(c.get("scale", "1"), ds.scale, "scale")) return false;
 			ds.relative_to_time_average = c.get_bool("relative_to_time_average", false);
+			ds.stdev_relative_to_scale = c.get_bool("stdev_relative_to_scale", false); // DataLikelihoodBase.cpp:48
+			// attributes of DataLikelihoodTimeCourseBase::Load (.cpp:41-57) that change the population average and are not built
+			if (c.get_bool("use_log_ratio", false)) return Fail("use_log_ratio is not supported by the GPU path");
+			if (c.get_bool("include_only_cells_that_went_through_mitosis", false)) return Fail("include_only_cells_that_went_through_mitosis is not supported by the GPU path");
+			// optimize_offset_scale, saturation_scale and value_relative_to_timepoint_ix act on the per-cell data types only
 			ds.weight = c.get_real("weight", 1.0);
 			ds.missing_stdev = c.get_real("missing_simulation_time_stdev", 300.0);
 			e.data.push_back(ds);
@@ -222,7 +227,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	  << model.non_sampled_parameters.size() << ";num_cells=" << num_cells << ";num_timepoints=" << T << ";num_replicates=" << data.num_replicates
 	  << ";variability_dim=" << D << ";variability_distribution=" << e.distribution << ";solver_relative_tolerance=" << e.solver_rel_tol
 	  << ";solver_absolute_tolerance=" << e.solver_abs_tol << ";solver_min_timestep=" << e.solver_min_timestep << ";solver_max_steps=" << e.solver_max_steps
-	  << ";relative_to_time_average=" << (ds.relative_to_time_average ? 1 : 0) << ";error_model=" << ds.error_model << ";weight=" << ds.weight
+	  << ";relative_to_time_average=" << (ds.relative_to_time_average ? 1 : 0) << ";stdev_relative_to_scale=" << (ds.stdev_relative_to_scale ? 1 : 0) << ";error_model=" << ds.error_model << ";weight=" << ds.weight
 	  << ";missing_simulation_time_stdev=" << ds.missing_stdev << ";device=" << device << ";compile_only=" << (compile_only ? 1 : 0);
 	if (simulation_end_time > data.timepoints.back()) d << ";simulation_end_time=" << simulation_end_time;
 	auto ref = [&](const char* name, const ValueRef& r) {

@@ -9,7 +9,8 @@
 //         <variable (initial_condition_species=|model_parameter=) apply= scale=<variable|number> [negate=]/> ...
 //       </cell_variability>
 //       <data type="time_course_population_average" species_name="a[+b]" stdev=<variable|number> [proportional_stdev=]
-//             [offset=] [scale=] [error_model=] [weight=] [missing_simulation_time_stdev=] [relative_to_time_average=]/> ...
+//             [offset=] [scale=] [error_model=] [weight=] [missing_simulation_time_stdev=] [relative_to_time_average=]
+//             [stdev_relative_to_scale=]/> ...
 //       [<treatment_trajectory type="pulses" species_name=<constant species> times="t1,t2,..."/>]
 //       [<experiment_specific_parameter parameter_name= replacement_parameter_name=/>] [<set_parameter parameter_name= value=/>]
 //       [<set_species species_name= value=/>]
@@ -105,7 +106,7 @@ private:
 	struct DataSet { // one <data> element = one handle of the C ABI
 		std::string species_name, error_model = "normal";
 		ValueRef stdev, proportional_stdev, offset, scale;
-		bool have_proportional_stdev = false, relative_to_time_average = false;
+		bool have_proportional_stdev = false, relative_to_time_average = false, stdev_relative_to_scale = false;
 		double weight = 1.0, missing_stdev = 300.0;
 		Data data;
 		std::string descriptor;

@@ -81,7 +81,8 @@ class _CellPopProblem(C.Structure):
         (n, C.c_void_p) for n in ("covariance", "initial_conditions", "constant_species", "non_sampled", "sobol", "timepoints", "observed",
                                   "variability", "transforms", "derivative")] + [
         ("treatment_species", C.c_int32), ("treatment_num_pulses", C.c_int32), ("treatment_times", C.c_void_p),
-        ("relative_to_time_average", C.c_int32), ("have_sim_end_time", C.c_int32), ("sim_end_time", C.c_double)]
+        ("relative_to_time_average", C.c_int32), ("have_sim_end_time", C.c_int32), ("sim_end_time", C.c_double),
+        ("stdev_relative_to_scale", C.c_int32)]
 
 
 _derivative_libs: dict[str, C.CDLL] = {}
@@ -208,6 +209,7 @@ def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=
         treatment_species=-1 if p.treatment_species is None else p.treatment_species, treatment_num_pulses=len(keep["treat"]),
         treatment_times=ptr(keep["treat"]), relative_to_time_average=int(p.relative_to_time_average),
         have_sim_end_time=int(p.simulation_end_time is not None), sim_end_time=float(p.simulation_end_time or 0.0),
+        stdev_relative_to_scale=int(p.stdev_relative_to_scale),
         stdev_ix=-1 if p.stdev_ix is None else p.stdev_ix, offset_ix=-1 if p.offset_ix is None else p.offset_ix,
         scale_ix=-1 if p.scale_ix is None else p.scale_ix, num_obs_species=len(p.obs_species),
         obs_species=(C.c_int32 * 8)(*(list(p.obs_species) + [0] * (8 - len(p.obs_species)))),

@@ -212,9 +212,10 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = population_average[i];
 
 	// Evaluate (.cpp:85-159)
-	const double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
+	double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
 	const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
 	const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
+	if (pr.stdev_relative_to_scale) stdev *= scale; // GetCurrentSTDev, DataLikelihoodBase.cpp:151-153
 	const double prop_stdev = (pr.proportional_stdev_ix >= 0) ? transformed[pr.proportional_stdev_ix] : pr.proportional_stdev;
 	const double minus_log_sigma = -log(stdev), inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
 	if (pr.relative_to_time_average) {

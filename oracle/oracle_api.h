@@ -128,6 +128,7 @@ typedef struct {
 	 * 655-656); evaluating one data set of such an experiment needs that end time. 0: the last of `timepoints` */
 	int32_t have_sim_end_time;
 	double sim_end_time;
+	int32_t stdev_relative_to_scale; /* <data stdev_relative_to_scale="true">: stdev *= data scale, DataLikelihoodBase.cpp:151-153 */
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

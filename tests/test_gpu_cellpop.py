@@ -173,3 +173,25 @@ def test_config3_full_size_properties(Evaluator, port):
     for s in shards:
         s.close()
     assert cellpop_logp_close(combined, logp, 50, 1, rtol=1e-9)
+
+
+def test_stdev_relative_to_scale(Evaluator, port):
+    """<data stdev_relative_to_scale="true"> (DataLikelihoodBase.cpp:151-153): the standard deviation is multiplied by the
+    data scale -- equal to the run that is given the product directly, and equal to the CPU checker."""
+    import dataclasses
+
+    base = sc.make_cellpop_problem(N=8, num_cells=96, T=10, data_cells=4, seed=9)
+    vals = sc.make_chain_values(3, seed=9)
+    prob = dataclasses.replace(base, scale=1.7, offset=0.02, stdev_ix=None, stdev=0.2, stdev_relative_to_scale=True)
+    ev = Evaluator(prob)
+    got, _ = ev.evaluate(vals)
+    ev.close()
+    ev = Evaluator(dataclasses.replace(prob, stdev=0.2 * 1.7, stdev_relative_to_scale=False))
+    same, _ = ev.evaluate(vals)
+    ev.close()
+    ev = Evaluator(dataclasses.replace(prob, stdev_relative_to_scale=False))
+    other, _ = ev.evaluate(vals)
+    ev.close()
+    assert np.allclose(got, same, rtol=1e-13, atol=0) and not np.allclose(got, other, rtol=1e-3)
+    want = port.cellpop_evaluate(prob, vals)["logp"]
+    assert cellpop_logp_close(got, want, prob.num_timepoints, prob.num_replicates, rtol=1e-6)

@@ -123,6 +123,12 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     with pytest.raises(RuntimeError, match="all of them are diagonal_gaussian"):
         host_api.cellpop_evaluate(prior, split.replace('<cell_variability distribution="diagonal_gaussian">', '<cell_variability distribution="full_gaussian" covar_base_name="c">', 1),
                                   prob, species, compile_only=True)
+    rel = host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" stdev_relative_to_scale="true" optimize_offset_scale="false"'),
+                                    prob, species, compile_only=True)[1]
+    assert "stdev_relative_to_scale=1" in rel and "stdev_relative_to_scale=0" in desc
+    for attribute in ("use_log_ratio", "include_only_cells_that_went_through_mitosis"):
+        with pytest.raises(RuntimeError, match=attribute):
+            host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', f'stdev="stdev" {attribute}="true"'), prob, species, compile_only=True)
     # the reference's default is dividing cells (Experiment.cpp:488): refused, not silently ignored
     with pytest.raises(RuntimeError, match="divide_cells"):
         host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)
