@@ -87,6 +87,13 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 	e.solver_abs_tol = exp->get_real("solver_absolute_tolerance", e.solver_abs_tol);
 	e.solver_rel_tol = exp->get_real("solver_relative_tolerance", e.solver_rel_tol);
 	if (!Resolve(exp->get("entry_time", "0"), e.entry_time, "entry_time")) return false;
+	// Experiment.cpp:413 -> CVodeSetMaxStep (ODESolverCVODE.cpp:156-161): the device integrators have no step-size ceiling
+	if (exp->has("solver_max_timestep") && std::isfinite(exp->get_real("solver_max_timestep", bcm3::kInf)))
+		return Fail("solver_max_timestep is not supported by the GPU path");
+	// Experiment.cpp:172-180: only meaningful for the synchronised per-cell data types (and it overwrites the fixed entry time there)
+	if (!exp->get("synchronization_time_offset").empty()) return Fail("synchronization_time_offset is not supported by the GPU path");
+	e.trailing_simulation_time = exp->get_real("trailing_simulation_time", 0.0); // Experiment.cpp:489, 655-656
+	if (!(e.trailing_simulation_time >= 0.0)) return Fail("trailing_simulation_time must not be negative");
 
 	size_t num_variability = 0;
 	for (const auto& c : exp->children) {
@@ -195,6 +202,13 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 		for (const auto& name : e.set_species) // Experiment.cpp:497-500
 			if (std::find(e.model.species_names.begin(), e.model.species_names.end(), name) == e.model.species_names.end())
 				return Fail("set_species: \"" + name + "\" is not a simulated species of the model");
+		// Cell::integration_step_cb (Cell.cpp:463-540): with these species in the model a cell's integration ends at a
+		// threshold crossing (death) or is extended past anaphase -- events the device path does not have. The other
+		// special species only record times for the per-cell data types.
+		for (const char* special : { "apoptosis", "chromatid_separation" })
+			if (std::find(e.model.species_names.begin(), e.model.species_names.end(), special) != e.model.species_names.end())
+				return Fail(std::string("the model has the species \"") + special + "\": threshold events are not supported by the GPU path");
+		end_time += e.trailing_simulation_time;
 		for (auto& ds : e.data)
 			if (!CreateHandle(e, ds, end_time)) return false;
 	}

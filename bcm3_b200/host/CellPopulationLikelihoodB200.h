@@ -4,7 +4,8 @@
 //
 //   <bcm_likelihood type="cell_population">
 //     <experiment name= model_file= entry_time=<variable|number> num_cells= max_cells= divide_cells="false"
-//                 [solver_min_timestep=] [solver_max_steps=] [solver_absolute_tolerance=] [solver_relative_tolerance=]>
+//                 [solver_min_timestep=] [solver_max_steps=] [solver_absolute_tolerance=] [solver_relative_tolerance=]
+//                 [trailing_simulation_time=]>
 //       <cell_variability distribution="diagonal_gaussian|full_gaussian" [covar_base_name=]>   (several diagonal_gaussian blocks allowed)
 //         <variable (initial_condition_species=|model_parameter=) apply= scale=<variable|number> [negate=]/> ...
 //       </cell_variability>
@@ -118,6 +119,7 @@ private:
 		ValueRef entry_time;
 		double solver_min_timestep = 1e-8, solver_abs_tol = 4.0 * 1.1920928955078125e-07, solver_rel_tol = 4.0 * 1.1920928955078125e-07;
 		long solver_max_steps = 10000;
+		double trailing_simulation_time = 0.0; // the cells are integrated this much past the last requested time
 		std::vector<VarEntry> variables;
 		std::string treatment_species_name; // <treatment_trajectory type="pulses">
 		std::vector<double> treatment_times;

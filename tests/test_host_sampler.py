@@ -129,6 +129,15 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     for attribute in ("use_log_ratio", "include_only_cells_that_went_through_mitosis"):
         with pytest.raises(RuntimeError, match=attribute):
             host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', f'stdev="stdev" {attribute}="true"'), prob, species, compile_only=True)
+    # trailing_simulation_time (Experiment.cpp:489, 655-656) moves the end of the integration past the last timepoint
+    trail = host_api.cellpop_evaluate(*cellpop_xml(prob, trailing_simulation_time="2.5")[:2], prob, species, compile_only=True)[1]
+    assert float(dict(i.split("=", 1) for i in trail.split(";"))["simulation_end_time"]) == float(prob.timepoints[-1]) + 2.5
+    for attrs, message in ((dict(solver_max_timestep="0.5"), "solver_max_timestep"), (dict(synchronization_time_offset="3"), "synchronization_time_offset")):
+        with pytest.raises(RuntimeError, match=message):
+            host_api.cellpop_evaluate(*cellpop_xml(prob, **attrs)[:2], prob, species, compile_only=True)
+    renamed = [("apoptosis" if s == "x2" else s) for s in species]
+    with pytest.raises(RuntimeError, match="threshold events"):
+        host_api.cellpop_evaluate(prior, lik, prob, renamed, compile_only=True)
     # the reference's default is dividing cells (Experiment.cpp:488): refused, not silently ignored
     with pytest.raises(RuntimeError, match="divide_cells"):
         host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)
