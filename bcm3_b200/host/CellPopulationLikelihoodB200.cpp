@@ -136,6 +136,9 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				ds.have_proportional_stdev = true;
 				if (!Resolve(c.get("proportional_stdev"), ds.proportional_stdev, "proportional_stdev")) return false;
 			}
+			// DataLikelihoodBase.cpp:64-69
+			if ((ds.error_model == "proportional_normal" || ds.error_model == "additive_proportional_normal") && !ds.have_proportional_stdev)
+				return Fail("Proportional error model is selected, but proportional stdev has not been specified.");
 			if (!Resolve(c.get("offset", "0"), ds.offset, "offset")) return false;
 			if (!Resolve(c.get("scale", "1"), ds.scale, "scale")) return false;
 			ds.relative_to_time_average = c.get_bool("relative_to_time_average", false);

@@ -138,6 +138,8 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     renamed = [("apoptosis" if s == "x2" else s) for s in species]
     with pytest.raises(RuntimeError, match="threshold events"):
         host_api.cellpop_evaluate(prior, lik, prob, renamed, compile_only=True)
+    with pytest.raises(RuntimeError, match="proportional stdev has not been specified"):
+        host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" error_model="proportional_normal"'), prob, species, compile_only=True)
     # the reference's default is dividing cells (Experiment.cpp:488): refused, not silently ignored
     with pytest.raises(RuntimeError, match="divide_cells"):
         host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)
