@@ -37,6 +37,10 @@ CASES = {
     # time (Experiment.cpp:190-214, 655-656), which enters CVODE's initial step -- late entry
     "cellpop_n8_longer_experiment": (dict(N=8, num_cells=48, T=8, data_cells=8, seed=29), 2,
                                      dict(simulation_end_time=13.5, entry_time=0.5)),
+    # the same with a pulsed treatment: discontinuities (re-initialisations) keep coming after the data set's last timepoint
+    "cellpop_n8_treatment_pulses_longer": (dict(N=8, num_cells=40, T=20, t_end=40.0, data_cells=4, seed=27), 2,
+                                           dict(treatment_species=0, treatment_times=np.array([20.0, 1.0, 45.0]), obs_species=[0, 2], entry_time=4.0,
+                                                simulation_end_time=55.0)),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
