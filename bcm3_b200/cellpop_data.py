@@ -30,11 +30,14 @@ class Variability:
     scale_ix: int | None = None                 # scale = transformed variable[scale_ix] ...
     scale_fixed: float = 0.0                    # ... or a constant; the quasi-random normal is multiplied by exp(scale)
     negate: bool = False
+    # <variable entry_time=...>: the reference reads it, gives it a quasi-random dimension and never applies it
+    # (VariabilityDescription::ApplyVariabilityEntryTime has no caller); kind 2 of the ABI's variability rows
+    entry_time: bool = False
 
     def row(self):
         is_ic = self.initial_condition_species is not None
-        target = self.initial_condition_species if is_ic else self.model_parameter
-        return [float(is_ic), float(target), float(APPLY_TYPES[self.apply]), float(-1 if self.scale_ix is None else self.scale_ix),
+        target = 0 if self.entry_time else (self.initial_condition_species if is_ic else self.model_parameter)
+        return [2.0 if self.entry_time else float(is_ic), float(target), float(APPLY_TYPES[self.apply]), float(-1 if self.scale_ix is None else self.scale_ix),
                 float(self.scale_fixed), float(self.negate)]
 
 

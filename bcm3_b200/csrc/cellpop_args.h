@@ -35,7 +35,7 @@ struct CpArgs {
 	double var_scale_fixed[CP_MAX_VARIABILITY];
 	int var_apply[CP_MAX_VARIABILITY];
 	int var_negate[CP_MAX_VARIABILITY];
-	int var_slot[CP_MAX_VARIABILITY];        // override slot (parameter) or species index (initial condition)
+	int var_slot[CP_MAX_VARIABILITY];        // override slot (parameter; -1: a dimension without a target) or species index (initial condition)
 	int var_is_ic[CP_MAX_VARIABILITY];
 	int var_full;           // 1: full_gaussian -- v = L z with the chain's Cholesky factor (VariabilityDescription.cpp:99-131)
 	const double* var_chol; // [C][D][D] row-major lower triangle, written per batch by cellpop_cholesky_kernel

@@ -1382,7 +1382,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 						for (int e = 0; e < E; e++)
 							if (B.idx(e) == a.var_slot[d]) apply_variability(y0[e], v, a.var_apply[d]);
 					} else {
-						if (CP_NUM_OVERRIDES > 0) apply_variability(ovl[a.var_slot[d]], v, a.var_apply[d]);
+						if (CP_NUM_OVERRIDES > 0 && a.var_slot[d] >= 0) apply_variability(ovl[a.var_slot[d]], v, a.var_apply[d]);
 					}
 				}
 				B.gsync();

@@ -548,14 +548,19 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	std::vector<int> override_vars;
 	for (int d = 0; d < cp.D; d++) {
 		const double* row = cp.data["variability"].data() + (size_t)d * 6;
-		a.var_is_ic[d] = row[0] != 0.0;
+		// row[0]: 0 = parameter, 1 = initial condition, 2 = entry time. The reference never applies an entry-time variable
+		// (VariabilityDescription::ApplyVariabilityEntryTime has no caller), but it takes its quasi-random dimension.
+		const bool no_target = ((int)row[0] == 2);
+		a.var_is_ic[d] = ((int)row[0] == 1);
 		const int target = (int)row[1];
 		a.var_apply[d] = (int)row[2];
 		a.var_scale_ix[d] = (int)row[3];
 		a.var_scale_fixed[d] = row[4];
 		a.var_negate[d] = row[5] != 0.0;
 		if (a.var_apply[d] < 0 || a.var_apply[d] > CP_APPLY_REPLACE) return fail(BCM3B200_ERR_ARG, "bad variability apply type");
-		if (a.var_is_ic[d]) {
+		if (no_target) {
+			a.var_slot[d] = -1;
+		} else if (a.var_is_ic[d]) {
 			if (target < 0 || target >= cp.N) return fail(BCM3B200_ERR_ARG, "variability species index out of range");
 			a.var_slot[d] = target;
 		} else {

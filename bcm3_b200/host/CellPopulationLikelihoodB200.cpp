@@ -114,8 +114,12 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 					ve.target = v.get("initial_condition_species");
 				} else if (v.has("model_parameter")) {
 					ve.target = v.get("model_parameter");
+				} else if (!v.get("entry_time").empty()) {
+					// VariabilityDescriptionVariable.cpp:116-117: the reference has no caller of ApplyVariabilityEntryTime, so
+					// the variable only occupies a quasi-random dimension
+					ve.entry_time = true;
 				} else {
-					return Fail("cell_variability variable needs initial_condition_species or model_parameter (entry_time variability is not supported)");
+					return Fail("Cell variability description has neither a initial_condition_species name nor a model_parameter name, nor entry_time");
 				}
 				ve.apply = apply_code(v.get("apply"));
 				if (ve.apply < 0) return Fail("Unknown cell variability apply type \"" + v.get("apply") + "\"");
@@ -284,8 +288,9 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		std::vector<double> rows(D * 6);
 		for (size_t i = 0; i < D; i++) {
 			const VarEntry& ve = e.variables[i];
-			size_t target;
-			if (ve.is_ic) {
+			size_t target = 0;
+			if (ve.entry_time) {
+			} else if (ve.is_ic) {
 				auto it = std::find(model.species_names.begin(), model.species_names.end(), ve.target);
 				if (it == model.species_names.end()) return Fail("Variability initial_condition_species \"" + ve.target + "\" is not a simulated species");
 				target = (size_t)(it - model.species_names.begin());
@@ -294,7 +299,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 				if (target == std::numeric_limits<size_t>::max()) return Fail("Variability model_parameter \"" + ve.target + "\" is not a sampled variable");
 			}
 			double* r = rows.data() + i * 6;
-			r[0] = ve.is_ic ? 1.0 : 0.0;
+			r[0] = ve.entry_time ? 2.0 : ve.is_ic ? 1.0 : 0.0;
 			r[1] = (double)target;
 			r[2] = (double)ve.apply;
 			r[3] = (double)ve.scale.ix;

@@ -7,7 +7,8 @@
 //                 [solver_min_timestep=] [solver_max_steps=] [solver_absolute_tolerance=] [solver_relative_tolerance=]
 //                 [trailing_simulation_time=]>
 //       <cell_variability distribution="diagonal_gaussian|full_gaussian" [covar_base_name=]>   (several diagonal_gaussian blocks allowed)
-//         <variable (initial_condition_species=|model_parameter=) apply= scale=<variable|number> [negate=]/> ...
+//         <variable (initial_condition_species=|model_parameter=|entry_time=) apply= scale=<variable|number> [negate=]
+//                   [only_initial_cells=]/> ...
 //       </cell_variability>
 //       <data type="time_course_population_average" species_name="a[+b]" stdev=<variable|number> [proportional_stdev=]
 //             [offset=] [scale=] [error_model=] [weight=] [missing_simulation_time_stdev=] [relative_to_time_average=]
@@ -99,6 +100,7 @@ private:
 	};
 	struct VarEntry {
 		bool is_ic = false;
+		bool entry_time = false; // read, given a quasi-random dimension, never applied -- as in the reference
 		std::string target;
 		int apply = 0;
 		ValueRef scale;

@@ -166,6 +166,7 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 				v = ndtri(pr.sobol[(size_t)ci * D + d]) * exp(scale);
 			}
 			if (row[5] != 0.0) v = -v;
+			if ((int)row[0] == 2) continue; // entry-time variable: takes a dimension, is never applied (no caller of ApplyVariabilityEntryTime)
 			if (is_ic) apply_variability(y0[target], v, apply);
 			else apply_variability(cell_params[target], v, apply);
 		}

@@ -195,3 +195,28 @@ def test_stdev_relative_to_scale(Evaluator, port):
     assert np.allclose(got, same, rtol=1e-13, atol=0) and not np.allclose(got, other, rtol=1e-3)
     want = port.cellpop_evaluate(prob, vals)["logp"]
     assert cellpop_logp_close(got, want, prob.num_timepoints, prob.num_replicates, rtol=1e-6)
+
+
+def test_entry_time_variability_takes_a_dimension_and_nothing_else(Evaluator, port):
+    """<variable entry_time=...> of a cell_variability block: the reference reads it and gives it a quasi-random dimension
+    but never applies it (VariabilityDescription::ApplyVariabilityEntryTime has no caller) -- the result equals the run
+    without that variable on the remaining columns of the table."""
+    import dataclasses
+    from bcm3_b200.cellpop_data import Variability
+
+    base = sc.make_cellpop_problem(N=8, num_cells=96, T=10, data_cells=4, seed=9)
+    vals = sc.make_chain_values(3, seed=9)
+    rng = np.random.default_rng(1)
+    extra = rng.uniform(0.05, 0.95, size=(base.num_cells, 1))
+    sobol = np.concatenate([base.sobol[:, :1], extra, base.sobol[:, 1:]], axis=1)
+    variability = [base.variability[0], Variability(apply="additive", entry_time=True, scale_fixed=0.3)] + list(base.variability[1:])
+    prob = dataclasses.replace(base, sobol=sobol, variability=variability)
+    for kernel in ("auto", "warp", "thread"):
+        ev = Evaluator(prob, kernel=kernel)
+        got, _ = ev.evaluate(vals)
+        ev.close()
+        ev = Evaluator(base, kernel=kernel)
+        want, _ = ev.evaluate(vals)
+        ev.close()
+        assert np.array_equal(got, want), kernel
+    assert np.array_equal(port.cellpop_evaluate(prob, vals)["logp"], port.cellpop_evaluate(base, vals)["logp"])

@@ -1,6 +1,8 @@
 """CPU suite: the C++ host mirror (bcm3_b200/host) on BASELINE config 1 -- examples/banana, parallel-tempered MCMC with an
 analytic likelihood: the batched-evaluation plumbing must reproduce the serial sampler exactly for a fixed seed, and the
 posterior must match the analytic banana (TestLikelihoodBanana.cpp:42-55)."""
+import dataclasses
+
 import numpy as np
 import pytest
 from scipy import stats
@@ -140,6 +142,12 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
         host_api.cellpop_evaluate(prior, lik, prob, renamed, compile_only=True)
     with pytest.raises(RuntimeError, match="proportional stdev has not been specified"):
         host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" error_model="proportional_normal"'), prob, species, compile_only=True)
+    # an entry_time variable occupies a quasi-random dimension (kind 2 of the variability rows) and needs a wider table
+    with_entry = lik.replace("</cell_variability>", '<variable entry_time="true" apply="additive" scale="0.3"/></cell_variability>')
+    with pytest.raises(RuntimeError, match="SetSobolTable"):
+        host_api.cellpop_evaluate(prior, with_entry, prob, species, compile_only=True)
+    wider = dataclasses.replace(prob, sobol=np.concatenate([prob.sobol, prob.sobol[:, :1]], axis=1))
+    assert "variability_dim=4" in host_api.cellpop_evaluate(prior, with_entry, wider, species, compile_only=True)[1]
     # the reference's default is dividing cells (Experiment.cpp:488): refused, not silently ignored
     with pytest.raises(RuntimeError, match="divide_cells"):
         host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)

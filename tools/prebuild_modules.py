@@ -31,7 +31,7 @@ def jobs():
     out += [("golden", "cellpop_n12_normal", "warp"), ("golden", "cellpop_n12_normal", "thread")]
     out += [("synthetic", dict(N=12, num_cells=8, T=50, data_cells=2, seed=5), "auto")]          # config-3 shape (bench, tests)
     out += [("synthetic", dict(N=12, num_cells=8, T=12, data_cells=2, seed=2), k) for k in ("auto", "warp")]  # smoke
-    out += [("synthetic", dict(N=8, num_cells=8, T=10, data_cells=2, seed=9), "auto")]           # host plugin test
+    out += [("synthetic", dict(N=8, num_cells=8, T=10, data_cells=2, seed=9), k) for k in ("auto", "warp", "thread")]  # host plugin tests, entry-time test
     out += [("synthetic", dict(N=n, num_cells=8, T=12, data_cells=2, seed=40 + n, rate_decades=d), "auto")
             for n, d in ((3, 2.0), (7, 2.0), (16, 3.0), (33, 3.0), (50, 4.0))]
     return out
