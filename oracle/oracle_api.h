@@ -116,7 +116,7 @@ typedef struct {
 	const double* sobol;               /* [cells][D] */
 	const double* timepoints;          /* [T] */
 	const double* observed;            /* [R][T] */
-	const double* variability;         /* [D][6]: is_ic, target, apply, scale_ix, scale_fixed, negate */
+	const double* variability;         /* [D][6]: kind (0 parameter, 1 initial condition, 2 entry time: dimension only), target, apply, scale_ix, scale_fixed, negate */
 	const int32_t* transforms;         /* [nvar] */
 	oracle_derivative_fn derivative;   /* generated_derivative compiled for the host from the generated text */
 	/* one <treatment_trajectory type="pulses"> (TreatmentTrajectoryPulses.cpp): the constant species it drives (-1: none)
