@@ -342,7 +342,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	}
 	s->last_C = (int)C;
 
-	// s_time [T], s_sim [T][block], then the integrator's thread-private state columns [slots][stride]
+	// the integrator's thread-private state columns [slots][stride] first, then s_time [T] and s_sim [T][block]
 	if (block > 384) return fail(BCM3B200_ERR_ARG, "block_size above 384 is not supported");
 	const int stride = block <= 128 ? 128 : 384; // the two instantiations of the state-column stride
 	const bool two_cmt = (h->pk_type == PK_TWO || h->pk_type == PK_TWO_BIPHASIC || h->pk_type == PK_TWO_TRANSIT);

@@ -243,9 +243,12 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 {
 	constexpr int N = Model::N;
 	constexpr unsigned FULL = 0xffffffffu;
+	// Dynamic shared memory: the integrator's per-thread state columns FIRST, at compile-time offsets (slot * STRIDE + tid:
+	// the hot loop addresses them with nothing but the thread index), then the output times and the simulated values,
+	// whose offsets depend on T and are only needed at output times.
 	extern __shared__ double smem[];
-	double* s_time = smem;            // [T]
-	double* s_sim = smem + a.T;       // [T][blockDim.x]  simulated central-compartment amounts at the output times
+	double* s_time = smem + BdfSlots<N>::COUNT * STRIDE; // [T]
+	double* s_sim = s_time + a.T;                         // [T][blockDim.x]  simulated central-compartment amounts at the output times
 
 	const int tid = threadIdx.x;
 	const int c = blockIdx.y;
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 
 	// ---- K1: ODESolver::SolveReturnSolution + ODESolverCVODE::Solve ----
 	BdfThread<N, Model, DIAG, STRIDE> S;
-	S.sh = smem + a.T + (size_t)a.T * blockDim.x + tid; // after s_time and s_sim
+	S.sh = smem + tid;
 	S.create();
 
 	bool done = !valid || ntp <= 0;
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 		vinf = fmin(vinf, __shfl_down_sync(FULL, vinf, off));
 		vnan = fmin(vnan, __shfl_down_sync(FULL, vnan, off));
 	}
-	__syncthreads(); // s_sim is dead from here on; reuse the front of smem
+	__syncthreads(); // the integrator state and s_sim are dead from here on; reuse the front of smem
 	const int warp = tid >> 5, lane = tid & 31, nwarp = (blockDim.x + 31) >> 5;
 	if (lane == 0) {
 		smem[warp * 3 + 0] = vsum;

@@ -35,6 +35,8 @@ for r in rows[2:]:
 src = {}
 root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bcm3_b200", "csrc")
 for f in os.listdir(root):
+    if not os.path.isfile(os.path.join(root, f)):
+        continue
     src[f] = open(os.path.join(root, f), errors="replace").read().split('\n')
 print(f"total warp instructions {tot}, samples {ts}, sass lines {len(rows) - 2}")
 for k, v in agg.most_common(top):
