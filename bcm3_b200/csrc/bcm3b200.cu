@@ -50,7 +50,7 @@ struct Shard {
 	int P_pad = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	DevBuf<double> time, obs_t, dose, interval, dac, dct, values, block_partial, partial, diag_conc, diag_ll;
+	DevBuf<double> time, obs_t, dose, interval, dac, dct, values, patient_ll, partial, diag_conc;
 	DevBuf<unsigned long long> rank_keys, rank_keys_sorted; // [C][P] (chain, ka) sort keys
 	DevBuf<int> rank_patients, order;                        // [C][P] patient indices before / after the sort
 	DevBuf<unsigned char> sort_temp;
@@ -58,13 +58,10 @@ struct Shard {
 	DevBuf<uint32_t> skipped;
 	double* h_partial = nullptr; // pinned [3][C]
 	size_t h_partial_n = 0;
-	double* h_shared = nullptr; // pinned [C][16] staging of the chain-level entries
-	size_t h_shared_n = 0;
 	int last_C = 0;
 	~Shard()
 	{
 		if (h_partial) cudaFreeHost(h_partial);
-		if (h_shared) cudaFreeHost(h_shared);
 		if (ev0) cudaEventDestroy(ev0);
 		if (ev1) cudaEventDestroy(ev1);
 		if (stream) cudaStreamDestroy(stream);
@@ -78,6 +75,9 @@ struct Handle {
 	std::string drug;
 	int P = 0, T = 0, nvar = 0, sd_ix = -1, max_steps = 2000;
 	int shard_rank = 0, shard_count = 1, device0 = 0, device_count = 1;
+	// <pk_model volume_of_distribution= k_periphery_fwd= k_periphery_bwd=>, NaN = sampled (cpp:64-67)
+	double fixed_vod = std::numeric_limits<double>::quiet_NaN(), fixed_periphery_fwd = std::numeric_limits<double>::quiet_NaN(),
+	       fixed_periphery_bwd = std::numeric_limits<double>::quiet_NaN();
 	// host copies of the static data
 	std::map<std::string, std::vector<double>> data;
 	// derived
@@ -159,7 +159,12 @@ int finalize(Handle* h)
 	if (h->pk_type >= PK_ONE_BIPHASIC && (h->named_a_ix < 0 || h->named_b_ix < 0 || h->named_a_ix >= h->nvar || h->named_b_ix >= h->nvar))
 		return fail(BCM3B200_ERR_ARG, h->pk_type >= PK_ONE_TRANSIT ? "transit models need n_transit_ix and mean_transit_time_ix"
 		                                                           : "biphasic models need biphasic_uptake_time_ix and mean_absorption2_ix");
-	if (h->nvar != h->npk + 2 * (P + 1) + 2) return fail(BCM3B200_ERR_ARG, "Incorrect number of variables in prior"); // cpp:127-130
+	// cpp:122-130: every fixed attribute takes one variable out of the prior -- and nothing else changes: the reference keeps
+	// reading the vector at the all-sampled positions (cpp:267-272, 283-286), which is reproduced here as it is
+	const int fixed_var_count = (std::isnan(h->fixed_vod) ? 0 : 1) + (std::isnan(h->fixed_periphery_fwd) ? 0 : 1) + (std::isnan(h->fixed_periphery_bwd) ? 0 : 1);
+	if (h->nvar != h->npk - fixed_var_count + 2 * (P + 1) + 2) return fail(BCM3B200_ERR_ARG, "Incorrect number of variables in prior");
+	if (P > 0 && h->npk + 2 * P + 1 >= h->nvar)
+		return fail(BCM3B200_ERR_ARG, "with these fixed pk_model attributes the reference reads past the end of the variable vector (cpp:283-286)");
 	if (h->sd_ix < 0 || h->sd_ix + 1 >= h->nvar) return fail(BCM3B200_ERR_ARG, "sd_ix out of range");
 
 	const std::vector<double>& time = h->data["time"];
@@ -279,7 +284,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 		h->last_launches = 0;
 		return BCM3B200_OK;
 	}
-	CUDA_TRY(s->block_partial.ensure((size_t)nblk * C * 3));
+	CUDA_TRY(s->patient_ll.ensure((size_t)s->P * C));
 
 	PkArgs a;
 	a.time = s->time.p;
@@ -299,6 +304,9 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	a.rtol = h->rtol;
 	a.atol = h->atol;
 	a.conv_base = 1e6 / h->mol_weight;
+	a.fixed_vod = h->fixed_vod;
+	a.fixed_periphery_fwd = h->fixed_periphery_fwd;
+	a.fixed_periphery_bwd = h->fixed_periphery_bwd;
 	a.values = d_values;
 	a.row_stride = row_stride;
 	a.col_patient0 = col_patient0;
@@ -306,7 +314,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 		a.ix[k] = ix[k];
 		a.tr[k] = h->tr[k];
 	}
-	a.block_partial = s->block_partial.p;
+	a.patient_ll = s->patient_ll.p;
 	a.order = nullptr;
 	// large batches: rank every chain's patients by absorption rate first (see poppk_kernel)
 	if (h->sort_patients && (long long)s->P * (long long)C >= h->sort_min_systems && s->P > 0 && (long long)s->P * (long long)C < (1ll << 31)) {
@@ -330,14 +338,11 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 		h->total_launches += 1;
 	}
 	a.diag_conc = nullptr;
-	a.diag_ll = nullptr;
 	a.diag_counters = nullptr;
 	if (h->diagnostics) {
 		CUDA_TRY(s->diag_conc.ensure(C * s->P * h->T));
-		CUDA_TRY(s->diag_ll.ensure(C * s->P));
 		CUDA_TRY(s->diag_counters.ensure(C * s->P * 8));
 		a.diag_conc = s->diag_conc.p;
-		a.diag_ll = s->diag_ll.p;
 		a.diag_counters = s->diag_counters.p;
 	}
 	s->last_C = (int)C;
@@ -358,7 +363,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	else lrc = launch_poppk_transit(two_cmt, h->diagnostics, stride, grid, block, smem_bytes, stream, a);
 	if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "poppk_kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
 	CUDA_TRY(cudaGetLastError());
-	poppk_chain_reduce<<<(unsigned)C, 256, 0, stream>>>(s->block_partial.p, nblk, (int)C, d_partial);
+	poppk_chain_reduce<<<(unsigned)C, 256, 0, stream>>>(s->patient_ll.p, s->P, s->offset, (int)C, d_partial);
 	CUDA_TRY(cudaGetLastError());
 	h->last_launches += 2;
 	h->total_launches += 2;
@@ -469,8 +474,10 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		cp->nvar = need("num_variables");
 		cp->num_cells = need("num_cells");
 		cp->T = need("num_timepoints");
-		if (!ok || cp->N < 1 || cp->N > 64 || cp->num_cells < 0 || cp->T < 1)
-			return fail(BCM3B200_ERR_ARG, "num_species (1..64), num_variables, num_cells and num_timepoints are required");
+		// 96 species = the lane-group kernel at 32 lanes x 3 components per lane with the Newton matrix (N x (N | 1) doubles,
+		// 74 KB at N = 96) in the cell's shared-memory block; larger models do not fit one SM's shared memory per cell
+		if (!ok || cp->N < 1 || cp->N > 96 || cp->num_cells < 0 || cp->T < 1)
+			return fail(BCM3B200_ERR_ARG, "num_species (1..96), num_variables, num_cells and num_timepoints are required");
 		cp->Nc = get_int(kv, "num_constant_species", 0);
 		cp->Nn = get_int(kv, "num_non_sampled", 0);
 		cp->R = get_int(kv, "num_replicates", 1);
@@ -531,8 +538,11 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 	const std::string type = kv.count("type") ? kv["type"] : "";
 	if (type == "one") h->pk_type = PK_ONE;
 	else if (type == "two") h->pk_type = PK_TWO;
-	else if (type == "one_biphasic_uptake") h->pk_type = PK_ONE_BIPHASIC;
-	else if (type == "two_biphasic_uptake") h->pk_type = PK_TWO_BIPHASIC;
+	// cpp:73-76: BOTH biphasic strings select the TWO-compartment biphasic model in the reference -- the same
+	// likelihood.xml must give the same log-likelihood here. The one-compartment biphasic right-hand side the reference
+	// also carries (cpp:496-530) is unreachable from its XML; it is kept under a name of its own.
+	else if (type == "one_biphasic_uptake" || type == "two_biphasic_uptake") h->pk_type = PK_TWO_BIPHASIC;
+	else if (type == "one_compartment_biphasic_uptake") h->pk_type = PK_ONE_BIPHASIC;
 	else if (type == "one_transit") h->pk_type = PK_ONE_TRANSIT;
 	else if (type == "two_transit") h->pk_type = PK_TWO_TRANSIT;
 	else return fail(BCM3B200_ERR_UNSUPPORTED, "Unknown PK model type \"%s\"", type.c_str()); // cpp:84-87
@@ -544,6 +554,9 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		h->named_b_ix = get_int(kv, "mean_absorption2_ix", -1);
 	}
 	h->drug = kv.count("drug") ? kv["drug"] : "";
+	if (kv.count("volume_of_distribution")) h->fixed_vod = strtod(kv["volume_of_distribution"].c_str(), nullptr);
+	if (kv.count("k_periphery_fwd")) h->fixed_periphery_fwd = strtod(kv["k_periphery_fwd"].c_str(), nullptr);
+	if (kv.count("k_periphery_bwd")) h->fixed_periphery_bwd = strtod(kv["k_periphery_bwd"].c_str(), nullptr);
 	bool hasP, hasT, hasN, hasS;
 	h->P = get_int(kv, "num_patients", 0, &hasP);
 	h->T = get_int(kv, "num_timepoints", 0, &hasT);
@@ -644,31 +657,30 @@ int bcm3b200_finalize(void* handle)
 	return finalize(h);
 }
 
-// Upload this shard's slice of the host batch in the compact layout [C][16 + 2 * P_shard] (chain-level entries
-// first, then the shard's per-patient probabilities; two strided copies) and enqueue the kernels on `stream`.
+// Upload this shard's slice of the host batch in the compact layout [C][16 + 2 * P_shard] and enqueue the kernels on
+// `stream`. Slots of a row: [0, npk + 2) = the head of the variable vector (the positional chain-level entries and the two
+// population spreads, cpp:267-272, 283-286), 10-11 = standard_deviation and its successor, 12-13 = the two variables the
+// variants find by name, 16.. = the shard's per-patient probabilities. Every piece is a strided copy straight from the
+// caller's buffer (asynchronous when that is page-locked): nothing is staged in the handle, so enqueueing a second batch
+// while the first is still in flight is safe as long as the caller leaves the first `values` alone until the stream has
+// passed its copies (stated in bcm3b200.h).
 static int upload_and_launch(Handle* h, Shard* s, size_t C, size_t num_variables, const double* values, double* d_partial,
                              cudaStream_t stream)
 {
-	static const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 };
 	const int SH = 16;
+	const int head = h->npk + 2;
+	const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, h->npk + 0, h->npk + 1, 10, 11, 12, 13 };
 	const size_t stride = SH + 2 * (size_t)s->P;
 	CUDA_TRY(s->values.ensure(C * stride));
-	// chain-level entries: gathered into a small pinned staging block so that the copy is asynchronous
-	if (s->h_shared_n < C * SH) {
-		if (s->h_shared) cudaFreeHost(s->h_shared);
-		s->h_shared = nullptr;
-		CUDA_TRY(cudaMallocHost((void**)&s->h_shared, sizeof(double) * C * SH));
-		s->h_shared_n = C * SH;
-	}
-	for (size_t c = 0; c < C; c++)
-		for (int k = 0; k < SH; k++) s->h_shared[c * SH + k] = (k < SV_COUNT && h->ix[k] < h->nvar) ? values[c * num_variables + h->ix[k]] : 0.0;
-	CUDA_TRY(cudaMemcpy2DAsync(s->values.p, stride * sizeof(double), s->h_shared, SH * sizeof(double), SH * sizeof(double), C,
-	                           cudaMemcpyHostToDevice, stream));
-	if (s->P > 0) {
-		const double* src = values + h->npk + 2 + 2 * (size_t)s->offset;
-		CUDA_TRY(cudaMemcpy2DAsync(s->values.p + SH, stride * sizeof(double), src, num_variables * sizeof(double),
-		                           2 * (size_t)s->P * sizeof(double), C, cudaMemcpyHostToDevice, stream));
-	}
+	auto piece = [&](int slot, size_t column, size_t count) -> cudaError_t {
+		return cudaMemcpy2DAsync(s->values.p + slot, stride * sizeof(double), values + column, num_variables * sizeof(double), count * sizeof(double), C,
+		                         cudaMemcpyHostToDevice, stream);
+	};
+	CUDA_TRY(piece(0, 0, (size_t)head));
+	CUDA_TRY(piece(10, (size_t)h->sd_ix, 2));
+	if (h->named_a_ix >= 0) CUDA_TRY(piece(12, (size_t)h->named_a_ix, 1));
+	if (h->named_b_ix >= 0) CUDA_TRY(piece(13, (size_t)h->named_b_ix, 1));
+	if (s->P > 0) CUDA_TRY(piece(SH, (size_t)h->npk + 2 + 2 * (size_t)s->offset, 2 * (size_t)s->P));
 	CUDA_TRY(cudaEventRecord(s->ev0, stream));
 	int rc = launch_shard(h, s, C, s->values.p, (long long)stride, SH, cix, d_partial, stream);
 	if (rc != BCM3B200_OK) return rc;
@@ -802,7 +814,7 @@ int bcm3b200_get_diagnostics(void* handle, double* conc, double* patient_ll, int
 			CUDA_TRY(cudaMemcpy2D(conc + base * T, Ph * T * sizeof(double), s->diag_conc.p, Ps * T * sizeof(double), Ps * T * sizeof(double), C,
 			                      cudaMemcpyDeviceToHost));
 		if (patient_ll)
-			CUDA_TRY(cudaMemcpy2D(patient_ll + base, Ph * sizeof(double), s->diag_ll.p, Ps * sizeof(double), Ps * sizeof(double), C,
+			CUDA_TRY(cudaMemcpy2D(patient_ll + base, Ph * sizeof(double), s->patient_ll.p, Ps * sizeof(double), Ps * sizeof(double), C,
 			                      cudaMemcpyDeviceToHost));
 		if (counters)
 			CUDA_TRY(cudaMemcpy2D(counters + base * 8, Ph * 8 * sizeof(int32_t), s->diag_counters.p, Ps * 8 * sizeof(int32_t),

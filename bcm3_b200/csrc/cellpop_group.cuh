@@ -1517,21 +1517,24 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 // function is a process-wide unique symbol -- the second model would reuse the first one's cached launch configuration
 static size_t smem_bytes() { return sizeof(double) * (size_t)CS * CPW * WPB; }
 
+// launch configuration per DEVICE: the shared-memory opt-in and the occupancy result are per-device state, and one process
+// may hold handles of the same model on several devices (the multi-device handle, several ranks' handles in tests)
 static int resident_blocks(int* err)
 {
-	static int blocks = 0;
-	if (blocks > 0) return blocks;
+	static int blocks_of_device[64] = { 0 };
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev >= 0 && dev < 64 && blocks_of_device[dev] > 0) return blocks_of_device[dev];
 	const size_t smem = smem_bytes();
 	cudaError_t e = cudaFuncSetAttribute(cellpop_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) { *err = (int)e; return 0; }
-	int per_sm = 0, dev = 0, sms = 0;
+	int per_sm = 0, sms = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cellpop_group_kernel, BS, smem);
 	if (e != cudaSuccess) { *err = (int)e; return 0; }
-	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	if (per_sm < 1) { *err = (int)cudaErrorLaunchOutOfResources; return 0; }
-	blocks = per_sm * sms;
-	return blocks;
+	if (dev >= 0 && dev < 64) blocks_of_device[dev] = per_sm * sms;
+	return per_sm * sms;
 }
 
 } // namespace cellpop_group

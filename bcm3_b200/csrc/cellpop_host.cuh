@@ -7,7 +7,10 @@
 #pragma once
 
 #include <dlfcn.h>
+#include <errno.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -49,6 +52,7 @@ struct CellPopState {
 	bool finalized = false;
 	int cell_offset = 0, cells_local = 0;
 	void* module = nullptr;
+	uint64_t module_key = 0; // hash of the module source the loaded library was built from
 	cellpop_launch_fn launch = nullptr;
 	cellpop_thread_launch_fn thread_launch = nullptr;
 	cellpop_thread_scratch_fn thread_scratch = nullptr;
@@ -490,24 +494,50 @@ inline int cellpop_build_module(CellPopState& cp, const std::vector<int>& overri
 	mkdir(dir.c_str(), 0755);
 	const std::string so = dir + "/libcellpop_model.so";
 	if (access(so.c_str(), R_OK) != 0) {
+		// Several ranks may build the same model at once: every process writes its own source, log and output names and
+		// renames the finished library into place. nvcc is started with an argument vector (fork + execv), never through a
+		// shell: $NVCC, $BCM3B200_CACHE and the install path may contain anything.
+		const std::string pid = std::to_string((long)getpid());
+		const std::string cu = dir + "/model." + pid + ".cu", log = dir + "/build." + pid + ".log", tmp = so + ".tmp." + pid;
 		{
-			std::ofstream f(dir + "/model.cu");
+			std::ofstream f(cu);
 			f << src;
 		}
 		const char* nvcc_env = getenv("NVCC");
 		const std::string nvcc = nvcc_env ? nvcc_env : "/usr/local/cuda/bin/nvcc";
-		const std::string tmp = so + ".tmp." + std::to_string((long)getpid());
-		const std::string cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 --shared -Xcompiler -fPIC -I" + csrc +
-		                        " -o " + tmp + " " + dir + "/model.cu > " + dir + "/build.log 2>&1";
-		if (system(cmd.c_str()) != 0) {
-			std::ifstream log(dir + "/build.log");
+		const std::string inc = "-I" + csrc;
+		std::vector<std::string> args = { nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17", "--shared",
+			                              "-Xcompiler", "-fPIC", inc, "-o", tmp, cu };
+		std::vector<char*> argv;
+		for (std::string& a : args) argv.push_back(&a[0]);
+		argv.push_back(nullptr);
+		int status = -1;
+		const pid_t child = fork();
+		if (child == 0) {
+			const int fd = open(log.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+			if (fd >= 0) {
+				dup2(fd, 1);
+				dup2(fd, 2);
+				close(fd);
+			}
+			execv(argv[0], argv.data());
+			_exit(127);
+		}
+		if (child > 0) {
+			while (waitpid(child, &status, 0) < 0 && errno == EINTR) {
+			}
+		}
+		if (child < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+			std::ifstream lf(log);
 			std::stringstream ss;
-			ss << log.rdbuf();
+			ss << lf.rdbuf();
 			std::string text = ss.str();
 			if (text.size() > 700) text = text.substr(0, 700);
-			return fail(BCM3B200_ERR_STATE, "compiling the generated model failed (%s): %s", (dir + "/build.log").c_str(), text.c_str());
+			return fail(BCM3B200_ERR_STATE, "compiling the generated model failed (%s, log %s): %s", nvcc.c_str(), log.c_str(), text.c_str());
 		}
 		rename(tmp.c_str(), so.c_str());
+		rename(cu.c_str(), (dir + "/model.cu").c_str());
+		rename(log.c_str(), (dir + "/build.log").c_str());
 	}
 	cp.module = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
 	if (!cp.module) return fail(BCM3B200_ERR_STATE, "dlopen(%s) failed: %s", so.c_str(), dlerror());
@@ -575,8 +605,19 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 			a.var_slot[d] = slot;
 		}
 	}
-	int rc = cellpop_build_module(cp, override_vars);
-	if (rc != BCM3B200_OK) return rc;
+	// set_data after a finalize clears `finalized`: the module (keyed by the model text and the override list) is loaded
+	// once per distinct source, streams and events are created once
+	{
+		std::string src;
+		int rc = cellpop_module_source(cp, override_vars, src);
+		if (rc != BCM3B200_OK) return rc;
+		const uint64_t key = fnv1a(src);
+		if (!cp.module || key != cp.module_key) {
+			rc = cellpop_build_module(cp, override_vars);
+			if (rc != BCM3B200_OK) return rc;
+			cp.module_key = key;
+		}
+	}
 	if (!need_device) return BCM3B200_OK; // compile-only (CPU container)
 
 	const long long lo = (long long)cp.num_cells * cp.shard_rank / cp.shard_count;
@@ -584,9 +625,9 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	cp.cell_offset = (int)lo;
 	cp.cells_local = (int)(hi - lo);
 	CUDA_TRY(cudaSetDevice(cp.device));
-	CUDA_TRY(cudaStreamCreateWithFlags(&cp.stream, cudaStreamNonBlocking));
-	CUDA_TRY(cudaEventCreate(&cp.ev0));
-	CUDA_TRY(cudaEventCreate(&cp.ev1));
+	if (!cp.stream) CUDA_TRY(cudaStreamCreateWithFlags(&cp.stream, cudaStreamNonBlocking));
+	if (!cp.ev0) CUDA_TRY(cudaEventCreate(&cp.ev0));
+	if (!cp.ev1) CUDA_TRY(cudaEventCreate(&cp.ev1));
 	auto up = [&](DevBuf<double>& b, const std::vector<double>& v) -> cudaError_t {
 		cudaError_t e = b.ensure(v.size() ? v.size() : 1);
 		if (e != cudaSuccess || v.empty()) return e;

@@ -66,6 +66,10 @@ struct PkArgs {
 	const int32_t* simulate_until;
 	int P_local, P_pad, patient_offset, T, max_steps;
 	double rtol, atol, conv_base; // conv_base = 1e6 / MW
+	// <pk_model volume_of_distribution= k_periphery_fwd= k_periphery_bwd=> (cpp:64-67): NaN = sampled. As in the reference the
+	// positional indices of the variable vector do not move when a parameter is fixed (cpp:267-272, 285-294), and the
+	// peripheral pair is taken from the attributes only when k_periphery_fwd is given (cpp:288).
+	double fixed_vod, fixed_periphery_fwd, fixed_periphery_bwd;
 	// the batch
 	const double* values; // [C][row_stride]
 	long long row_stride;
@@ -74,9 +78,8 @@ struct PkArgs {
 	int tr[SV_COUNT];
 	const int* order; // [C][P_local] or null: patient handled by thread r of chain c (patients ranked by absorption rate)
 	// outputs
-	double* block_partial; // [C][gridDim.x][3]
+	double* patient_ll;    // [C][P_local] log-likelihood of every (chain, patient), in patient order whatever the launch shape
 	double* diag_conc;     // [C][P_local][T] or null
-	double* diag_ll;       // [C][P_local] or null
 	int32_t* diag_counters; // [C][P_local][8] or null
 };
 
@@ -269,11 +272,16 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 	Model model;
 	double sd, sd2, conversion;
 	{
-		double k_vod = transform_variable(a.tr[SV_VOD], vrow[a.ix[SV_VOD]]);
+		double k_vod = isnan(a.fixed_vod) ? transform_variable(a.tr[SV_VOD], vrow[a.ix[SV_VOD]]) : a.fixed_vod;
 		model.kex = transform_variable(a.tr[SV_EXCRETION], vrow[a.ix[SV_EXCRETION]]);
 		if (N == 3) {
-			model.kf = transform_variable(a.tr[SV_PERIPHERY_FWD], vrow[a.ix[SV_PERIPHERY_FWD]]);
-			model.kb = transform_variable(a.tr[SV_PERIPHERY_BWD], vrow[a.ix[SV_PERIPHERY_BWD]]);
+			if (isnan(a.fixed_periphery_fwd)) {
+				model.kf = transform_variable(a.tr[SV_PERIPHERY_FWD], vrow[a.ix[SV_PERIPHERY_FWD]]);
+				model.kb = transform_variable(a.tr[SV_PERIPHERY_BWD], vrow[a.ix[SV_PERIPHERY_BWD]]);
+			} else {
+				model.kf = a.fixed_periphery_fwd;
+				model.kb = a.fixed_periphery_bwd;
+			}
 		} else {
 			model.kf = 0.0;
 			model.kb = 0.0;
@@ -281,7 +289,18 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 		sd = transform_variable(a.tr[SV_SD], vrow[a.ix[SV_SD]]);
 		sd2 = transform_variable(a.tr[SV_SD2], vrow[a.ix[SV_SD2]]);
 		double2 pp = make_double2(0.5, 0.5);
-		if (valid) pp = *reinterpret_cast<const double2*>(vrow + a.col_patient0 + 2ll * jl);
+		if (valid) {
+			// the patient's probability pair: one 16-byte load where the pair is 16-byte aligned (always in the compact layout
+			// of the host entries; in a caller's [C][nvar] device block only when c * nvar + npk + 2 is even and the block
+			// itself is 16-byte aligned -- uniform over the thread block), two 8-byte loads otherwise
+			const double* pair = vrow + a.col_patient0 + 2ll * jl;
+			if ((reinterpret_cast<uintptr_t>(pair) & 15u) == 0) {
+				pp = *reinterpret_cast<const double2*>(pair);
+			} else {
+				pp.x = pair[0];
+				pp.y = pair[1];
+			}
+		}
 		model.ka = fastpow10(quantile_normal(pp.x, vrow[a.ix[SV_MEAN_ABSORPTION]], vrow[a.ix[SV_SIGMA_ABSORPTION]]));
 		model.kel = fastpow10(quantile_normal(pp.y, vrow[a.ix[SV_MEAN_CLEARANCE]], vrow[a.ix[SV_SIGMA_CLEARANCE]])) / k_vod;
 		conversion = a.conv_base / k_vod;
@@ -471,9 +490,12 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 		}
 	}
 
+	// ---- K3 (first level): the patient's term goes to its own slot [chain][patient]; poppk_chain_reduce sums them in patient
+	// order, so a chain's log-likelihood has the same bits whatever the block size, the ranking or the batch it is part of ----
+	if (valid) a.patient_ll[(long long)c * a.P_local + jl] = ll;
+
 	if (DIAG && valid) {
 		const long long cj = (long long)c * a.P_local + jl;
-		if (a.diag_ll) a.diag_ll[cj] = ll;
 		if (a.diag_conc) {
 			for (int i = 0; i < T; i++) {
 				double x = NAN;
@@ -493,58 +515,25 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 			k[7] = (ntp > 0 && !failed) ? 1 : 0;
 		}
 	}
-
-	// ---- K3 (first level): per-block partial of this chain, fixed reduction order ----
-	// (sum of finite terms, first patient index with -inf, first patient index with NaN)
-	const double big = INFINITY;
-	double vsum = 0.0, vinf = big, vnan = big;
-	if (valid) {
-		const double gidx = (double)(a.patient_offset + jl);
-		if (isnan(ll) || ll == INFINITY) vnan = gidx;
-		else if (ll == -INFINITY) vinf = gidx;
-		else vsum = ll;
-	}
-#pragma unroll
-	for (int off = 16; off > 0; off >>= 1) {
-		vsum += __shfl_down_sync(FULL, vsum, off);
-		vinf = fmin(vinf, __shfl_down_sync(FULL, vinf, off));
-		vnan = fmin(vnan, __shfl_down_sync(FULL, vnan, off));
-	}
-	__syncthreads(); // the integrator state and s_sim are dead from here on; reuse the front of smem
-	const int warp = tid >> 5, lane = tid & 31, nwarp = (blockDim.x + 31) >> 5;
-	if (lane == 0) {
-		smem[warp * 3 + 0] = vsum;
-		smem[warp * 3 + 1] = vinf;
-		smem[warp * 3 + 2] = vnan;
-	}
-	__syncthreads();
-	if (tid == 0) {
-		double s = 0.0, mi = big, mn = big;
-		for (int w = 0; w < nwarp; w++) {
-			s += smem[w * 3 + 0];
-			mi = fmin(mi, smem[w * 3 + 1]);
-			mn = fmin(mn, smem[w * 3 + 2]);
-		}
-		double* out = a.block_partial + ((long long)c * gridDim.x + blockIdx.x) * 3;
-		out[0] = s;
-		out[1] = mi;
-		out[2] = mn;
-	}
 }
 
 #ifdef BCM3_POPPK_AUX_KERNELS
-// K3 (second level): block partials -> partial[3][C], fixed order.
-__global__ void poppk_chain_reduce(const double* __restrict__ block_partial, int nblk, int C, double* __restrict__ partial)
+// K3 (second level): patient_ll [C][P_local] -> partial[3][C] = (sum of the finite terms, global index of the first -inf
+// patient, global index of the first NaN patient). One block per chain; thread t adds patients t, t + 256, ... in order, then
+// a fixed tree: the order depends on P_local only (run-to-run and batch-to-batch identical bits).
+__global__ void poppk_chain_reduce(const double* __restrict__ patient_ll, int P_local, int patient_offset, int C, double* __restrict__ partial)
 {
 	__shared__ double sh[3][256];
 	const int c = blockIdx.x;
 	const int tid = threadIdx.x;
+	const double* v = patient_ll + (long long)c * P_local;
 	double s = 0.0, mi = INFINITY, mn = INFINITY;
-	for (int b = tid; b < nblk; b += blockDim.x) {
-		const double* p = block_partial + ((long long)c * nblk + b) * 3;
-		s += p[0];
-		mi = fmin(mi, p[1]);
-		mn = fmin(mn, p[2]);
+	for (int j = tid; j < P_local; j += blockDim.x) {
+		const double ll = v[j];
+		const double gidx = (double)(patient_offset + j);
+		if (isnan(ll) || ll == INFINITY) mn = fmin(mn, gidx);
+		else if (ll == -INFINITY) mi = fmin(mi, gidx);
+		else s += ll;
 	}
 	sh[0][tid] = s;
 	sh[1][tid] = mi;

@@ -29,10 +29,10 @@ bool LikelihoodPopPKTrajectoryB200::Initialize(std::shared_ptr<const bcm3::Varia
 	pk_type_str = model->get("type");
 	trial_name = model->get("trial");
 	pkdata_file = model->get("pkdata_file");
-	if (model->has("volume_of_distribution") || model->has("k_periphery_fwd") || model->has("k_periphery_bwd")) {
-		last_error = "fixed volume_of_distribution / k_periphery_* are not supported by the GPU path";
-		return false;
-	}
+	// cpp:64-67: parameters fixed in likelihood.xml instead of sampled; handed through as they are
+	fixed_attributes.clear();
+	for (const char* key : { "volume_of_distribution", "k_periphery_fwd", "k_periphery_bwd" })
+		if (model->has(key)) fixed_attributes += std::string(";") + key + "=" + model->get(key);
 	return true;
 }
 
@@ -46,7 +46,7 @@ bool LikelihoodPopPKTrajectoryB200::PostInitialize()
 	}
 	std::string desc = "type=" + pk_type_str + ";drug=" + drug + ";num_patients=" + std::to_string(P) + ";num_timepoints=" +
 	                   std::to_string(T) + ";num_variables=" + std::to_string(nvar) + ";sd_ix=" + std::to_string(sdix) +
-	                   ";device=" + std::to_string(device0);
+	                   ";device=" + std::to_string(device0) + fixed_attributes;
 	// the variables the variants look up by name (cpp:296-310)
 	auto named = [&](const char* variable, const char* key) {
 		const size_t ix = varset->GetVariableIndex(variable);

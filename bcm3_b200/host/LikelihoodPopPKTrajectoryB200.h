@@ -32,7 +32,7 @@ public:
 
 private:
 	std::shared_ptr<const bcm3::VariableSet> varset;
-	std::string drug, pk_type_str, trial_name, pkdata_file;
+	std::string drug, pk_type_str, trial_name, pkdata_file, fixed_attributes;
 	TrialData trial;
 	void* handle = nullptr;
 	int device0 = 0, num_devices = 1;

@@ -21,19 +21,25 @@ class PopPKEvaluator:
     """Owns one ``bcm3b200`` handle for a PopPKProblem (optionally a contiguous shard of its patients)."""
 
     def __init__(self, problem: PopPKProblem, device: int = 0, device_count: int = 1, shard_rank: int = 0,
-                 shard_count: int = 1, diagnostics: bool = False, block_size: int = 0, sort_patients: bool | None = None):
+                 shard_count: int = 1, diagnostics: bool = False, block_size: int = 0, sort_patients: bool | None = None,
+                 type_string: str | None = None):
         """sort_patients: None = the library's policy (rank each chain's patients by absorption rate for large batches),
-        True = always, False = never."""
+        True = always, False = never. type_string: the <pk_model type=> string to hand to the library instead of the one
+        derived from problem.pk_type (tests of the reference's string -> model mapping)."""
         self.lib = _lib.load()
         self.problem = problem
         tr = problem.trial
         P, T = tr.num_patients, tr.num_timepoints
-        desc = (f"type={PK_TYPE_NAMES[problem.pk_type]};drug={tr.drug};num_patients={P};num_timepoints={T};"
+        desc = (f"type={type_string or PK_TYPE_NAMES[problem.pk_type]};drug={tr.drug};num_patients={P};num_timepoints={T};"
                 f"num_variables={problem.num_variables};sd_ix={problem.sd_ix};max_steps={problem.max_steps};"
                 f"shard_rank={shard_rank};shard_count={shard_count};device={device}")
         for name in ("n_transit_ix", "mean_transit_time_ix", "biphasic_uptake_time_ix", "mean_absorption2_ix"):
             if getattr(problem, name) >= 0:
                 desc += f";{name}={getattr(problem, name)}"
+        for key, v in (("volume_of_distribution", problem.fixed_vod), ("k_periphery_fwd", problem.fixed_periphery_fwd),
+                       ("k_periphery_bwd", problem.fixed_periphery_bwd)):
+            if v == v:  # not NaN: fixed in likelihood.xml (cpp:64-67)
+                desc += f";{key}={v!r}"
         desc = desc.encode()
         h = C.c_void_p()
         _lib.check(self.lib.bcm3b200_create(b"pop_pk_trajectory", desc, len(desc), device_count, C.byref(h)))

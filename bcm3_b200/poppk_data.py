@@ -20,9 +20,13 @@ PK_ONE_BIPHASIC = 2
 PK_TWO_BIPHASIC = 3
 PK_ONE_TRANSIT = 4
 PK_TWO_TRANSIT = 5
-PK_TYPES = {"one": PK_ONE, "two": PK_TWO, "one_biphasic_uptake": PK_ONE_BIPHASIC, "two_biphasic_uptake": PK_TWO_BIPHASIC,
+# likelihood.xml strings -> model. As in the reference BOTH biphasic strings select the two-compartment biphasic model
+# (cpp:73-76); its one-compartment biphasic right-hand side (cpp:496-530) cannot be reached from XML.
+PK_TYPES = {"one": PK_ONE, "two": PK_TWO, "one_biphasic_uptake": PK_TWO_BIPHASIC, "two_biphasic_uptake": PK_TWO_BIPHASIC,
             "one_transit": PK_ONE_TRANSIT, "two_transit": PK_TWO_TRANSIT}
-PK_TYPE_NAMES = {v: k for k, v in PK_TYPES.items()}
+# model -> the C ABI's type= key (the one-compartment biphasic model has a name of its own there)
+PK_TYPE_NAMES = {PK_ONE: "one", PK_TWO: "two", PK_ONE_BIPHASIC: "one_compartment_biphasic_uptake", PK_TWO_BIPHASIC: "two_biphasic_uptake",
+                 PK_ONE_TRANSIT: "one_transit", PK_TWO_TRANSIT: "two_transit"}
 
 
 def is_two_compartment(pk_type: int) -> bool:
@@ -123,10 +127,11 @@ class PopPKProblem:
             raise ValueError('transit models need the variables "n_transit" and "mean_transit_time"')
         if is_biphasic(self.pk_type) and (self.biphasic_uptake_time_ix < 0 or self.mean_absorption2_ix < 0):
             raise ValueError('biphasic models need the variables "biphasic_uptake_time" and "mean_absorption2"')
-        if fixed:
-            # the reference indexes the variable vector positionally (cpp:267-272) even when
-            # a parameter is fixed in likelihood.xml; only the all-sampled layout is supported here
-            raise NotImplementedError("fixed volume_of_distribution / k_periphery_* attributes")
+        # fixed attributes: the reference keeps indexing the variable vector at the all-sampled positions (cpp:267-272,
+        # 283-286) although the prior is `fixed` variables shorter -- reproduced as it is; with all three fixed it would
+        # read past the end of the vector
+        if P > 0 and num_pk_params(self.pk_type) + 2 * P + 1 >= expected:
+            raise ValueError("with these fixed pk_model attributes the reference reads past the end of the variable vector")
 
         inter = np.asarray(tr.treatment_interruptions).reshape(P, 29) != 0
         self.skipped_days = (inter.astype(np.uint64) << np.arange(29, dtype=np.uint64)).sum(axis=1).astype(np.uint32)

@@ -42,6 +42,12 @@ extern "C" {
  *   model_desc : `key=value;...` text, desc_bytes long (no terminator needed). Keys for pop_pk_trajectory
  *                mirror the <pk_model> attributes (LikelihoodPopPKTrajectory.cpp:58-87) plus sizes:
  *                  type=one|two|one_biphasic_uptake|two_biphasic_uptake|one_transit|two_transit  drug=<name>
+ *                       (as in the reference BOTH biphasic strings select the two-compartment biphasic model, cpp:73-76;
+ *                        its one-compartment biphasic right-hand side, unreachable from the reference's XML, is
+ *                        available as type=one_compartment_biphasic_uptake)
+ *                  [volume_of_distribution=<v>] [k_periphery_fwd=<v>] [k_periphery_bwd=<v>]  fixed instead of sampled
+ *                       (cpp:64-67): each takes one variable out of the prior (cpp:122-130) while the vector is still read
+ *                       at the all-sampled positions, exactly as the reference does
  *                  num_patients=<P>  num_timepoints=<T>
  *                  num_variables=<nvar>  sd_ix=<index of "standard_deviation">  [max_steps=2000]
  *                  transit types:  n_transit_ix= mean_transit_time_ix=   (indices of the variables of those names,
@@ -87,7 +93,8 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
                             int* status);
 
 /* Same evaluation on DEVICE buffers of the handle's first device, enqueued on `stream` (a cudaStream_t), no sync:
- *   d_values  [num_chains][num_variables] device
+ *   d_values  [num_chains][num_variables] device (8-byte alignment is enough; rows whose per-patient block happens to be
+ *             16-byte aligned are read with 128-bit loads)
  *   d_partial [3][num_chains] device, out:
  *       row 0: sum of the finite per-patient log-likelihoods of this shard
  *       row 1: global index of the first patient whose log-likelihood is -inf (+inf if none)
@@ -101,7 +108,8 @@ int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_v
 /* HOST values in, DEVICE partial out, enqueued on `stream` without synchronising: copies only this handle's slice of
  * the batch (chain-level entries + its patients' probabilities) host->device, then runs the kernels.
  * `values` should be page-locked (bcm3b200_host_alloc) for the copy to overlap; it must stay untouched until the
- * stream has passed the copy. d_partial as in bcm3b200_evaluate_batch_device. This is the entry the
+ * stream has passed the copy (the library stages nothing of its own, so several batches may be in flight on one
+ * handle as long as each has its own `values` and `d_partial`). d_partial as in bcm3b200_evaluate_batch_device. This is the entry the
  * one-process-per-GPU launch uses: enqueue, NCCL all-reduce d_partial, read back 3*C doubles. */
 int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables, const double* values, double* d_partial,
                            void* stream);

@@ -88,12 +88,23 @@ class _CellPopProblem(C.Structure):
 _derivative_libs: dict[str, C.CDLL] = {}
 
 
+RHS_FLAGS = {
+    # strict IEEE (no FMA contraction): the device build of the same text uses -fmad=false, which makes the rate laws
+    # bit-identical on both sides
+    "strict": ["-O2", "-ffp-contract=off"],
+    # what the reference's own CMake build of the generated code does (-O3 -march=native, contraction on): only used to
+    # measure how far the reference moves under its own flags (tests/golden/measure_noise_floor.py)
+    "contracted": ["-O3", "-march=x86-64-v3"],
+}
+rhs_build = "strict"
+
+
 def compile_cellpop_derivative(code: str) -> C.CDLL:
     """Compile the generated RHS text for the HOST the way the reference does (SolverCodeGenerator.cpp:100-300,390,407-414):
     helper prelude + generated text -> shared library -> dlopen."""
     import hashlib
 
-    key = hashlib.sha1((code + "|strict").encode()).hexdigest()[:16]
+    key = hashlib.sha1((code + "|" + rhs_build).encode()).hexdigest()[:16]
     if key in _derivative_libs:
         return _derivative_libs[key]
     d = os.path.join(HERE, "_build", "cellpop_" + key)
@@ -104,9 +115,8 @@ def compile_cellpop_derivative(code: str) -> C.CDLL:
             f.write('#include <limits>\n#include "cellpop_prelude.h"\n#define EXPORT_PREFIX extern "C"\n'
                     "struct OdeMatrixReal { double dummy; double& operator()(int, int) { return dummy; } };\n\n")
             f.write(code)
-        # strict IEEE (no FMA contraction): the device build of the same text uses -fmad=false, which makes the rate laws
-        # bit-identical on both sides; the reference's own flags (-O3 -march=native) would contract -- see DESIGN.md section 9
-        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++14", "-fPIC", "-shared", "-w", "-I", HERE, "-o", so + ".tmp",
+        # default "strict": the reference's own flags (-O3 -march=native) would contract -- see DESIGN.md section 9
+        subprocess.run(["g++"] + RHS_FLAGS[rhs_build] + ["-std=c++14", "-fPIC", "-shared", "-w", "-I", HERE, "-o", so + ".tmp",
                         os.path.join(d, "code.cpp")], check=True)
         os.replace(so + ".tmp", so)
     lib = C.CDLL(so)
@@ -115,8 +125,8 @@ def compile_cellpop_derivative(code: str) -> C.CDLL:
 
 
 class Oracle:
-    def __init__(self, kind: str):
-        path = REF_LIB if kind == "ref" else PORT_LIB
+    def __init__(self, kind: str, path: str | None = None):
+        path = path or (REF_LIB if kind == "ref" else PORT_LIB)
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} not built (run `make -C oracle` / `make -C oracle/ref`)")
         self.kind = kind

@@ -35,3 +35,12 @@ def ref(built):
     if not oracle.available("ref"):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     return oracle.load("ref")
+
+
+@pytest.fixture(scope="session")
+def checker(built):
+    """The CPU checker for fresh (non-golden) inputs: the reference's own compiled CVODE/odecommon stack (oracle/_ref, built
+    in the container and shipped to the GPU box) whenever it is present, the plain-C restatement only as a stand-in."""
+    import oracle
+
+    return oracle.load("ref" if oracle.available("ref") else "port")

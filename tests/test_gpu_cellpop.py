@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 from bcm3_b200 import synthetic_cellpop as sc
-from tests.util import CELLPOP_GOLDEN_NAMES, cellpop_step_match_floor, cellpop_logp_close, cellpop_rtol, load_cellpop_golden
+from tests.util import (CELLPOP_GOLDEN_NAMES, assert_logp_parity, cellpop_step_match_floor, load_cellpop_golden, reference_noise_floor_cellpop,
+                        rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -36,16 +37,27 @@ def _check_golden(Evaluator, name, kernel):
     d = ev.diagnostics()
     ev.close()
     assert (status == 0).all() and (d["cell_status"] == 1).all()
-    assert cellpop_logp_close(logp, gold["logp"], prob.num_timepoints, prob.num_replicates, rtol=cellpop_rtol(name))
+    # the bar: PURE relative error <= 1e-6 per chain, or twice the reference's own measured irreproducibility on this fixture
+    # (tests/golden/measure_noise_floor.py) where that is larger
+    assert_logp_parity(logp, gold["logp"], gold["noise_floor"], name)
     assert (np.isnan(d["cell_values"]) == np.isnan(gold["cell_values"])).all()
     m = ~np.isnan(gold["cell_values"])
     assert np.abs(d["cell_values"][m] - gold["cell_values"][m]).max() < 5e-5
     assert np.abs(d["population_average"] - gold["population_average"]).max() < 5e-6
     assert abs(d["cell_steps"].mean() / gold["cell_steps"].mean() - 1.0) < 0.02
-    assert (d["cell_steps"] == gold["cell_steps"]).mean() >= cellpop_step_match_floor(name)
+    assert (d["cell_steps"] == gold["cell_steps"]).mean() >= cellpop_step_match_floor(gold)
 
 
-def test_config3_shape_against_cpu_checker(Evaluator, port):
+def _fresh_reference(checker, prob, vals, threads=8):
+    """(reference result, per-chain noise floor, step-match fraction of the reference's own builds) for fresh inputs; with only
+    the plain-C port present (no compiled reference) the floor is unknown and the bar is the plain 1e-6."""
+    m = reference_noise_floor_cellpop(prob, vals, threads=threads)
+    if m is not None:
+        return m
+    return checker.cellpop_evaluate(prob, vals, threads=threads, want_average=True, want_steps=True, want_cell_values=True), None, 0.5
+
+
+def test_config3_shape_against_cpu_checker(Evaluator, checker):
     """BASELINE config 3 shape at a size the checker finishes in seconds: 12 species, 2 000 cells, 50 timepoints, 8 chains."""
     prob = sc.make_cellpop_problem(N=12, num_cells=2000, T=50, data_cells=16, seed=5)
     vals = sc.make_chain_values(8, seed=5)
@@ -54,9 +66,9 @@ def test_config3_shape_against_cpu_checker(Evaluator, port):
     again, _ = ev.evaluate(vals)
     d = ev.diagnostics()
     ev.close()
-    want = port.cellpop_evaluate(prob, vals, threads=8, want_average=True, want_steps=True)
+    want, floor, _ = _fresh_reference(checker, prob, vals)
     assert np.array_equal(logp, again)  # deterministic
-    assert cellpop_logp_close(logp, want["logp"], 50, 1, rtol=1e-6)
+    assert_logp_parity(logp, want["logp"], floor, "config-3 shape")
     assert np.abs(d["population_average"] - want["population_average"]).max() < 1e-6
     assert abs(d["cell_steps"].mean() / want["cell_steps"].mean() - 1.0) < 0.01
 
@@ -109,25 +121,25 @@ def test_sharded_cells_reproduce_the_unsharded_result(Evaluator):
         s.close()
 
 
-@pytest.mark.parametrize("N,decades,rtol", [(3, 2.0, 2e-6), (7, 2.0, 1e-6), (16, 3.0, 2e-5), (33, 3.0, 2e-5), (50, 4.0, 2e-5)])
-def test_lane_group_shapes_against_cpu_checker(Evaluator, port, N, decades, rtol):
+@pytest.mark.parametrize("N,decades", [(3, 2.0), (7, 2.0), (16, 3.0), (33, 3.0), (50, 4.0)])
+def test_lane_group_shapes_against_cpu_checker(Evaluator, checker, N, decades):
     """The lane-group mapping at sizes that exercise every shape: 2, 4 (padded), 8, 16 and 32 lanes per cell, with and
-    without block lock-step, inlined and called rate-law helpers. The stiff cases carry the tolerance at which the
-    reference and its own restatement agree there (tests/util.py::cellpop_rtol)."""
+    without block lock-step, inlined and called rate-law helpers -- against the compiled reference, with the tolerance the
+    reference's own reproducibility on the very same inputs allows (measured here with its two builds)."""
     prob = sc.make_cellpop_problem(N=N, num_cells=96, T=12, data_cells=4, seed=40 + N, rate_decades=decades)
     vals = sc.make_chain_values(2, seed=N)
     ev = Evaluator(prob)
     logp, status = ev.evaluate(vals)
     d = ev.diagnostics()
     ev.close()
-    want = port.cellpop_evaluate(prob, vals, threads=4, want_average=True, want_steps=True)
+    want, floor, _ = _fresh_reference(checker, prob, vals, threads=4)
     assert (status == 0).all() and (d["cell_status"] == 1).all()
-    assert cellpop_logp_close(logp, want["logp"], 12, 1, rtol=rtol)
+    assert_logp_parity(logp, want["logp"], floor, f"N={N}")
     assert np.abs(d["population_average"] - want["population_average"]).max() < 2e-5
     assert abs(d["cell_steps"].mean() / want["cell_steps"].mean() - 1.0) < 0.02
 
 
-def test_config3_full_size_properties(Evaluator, port):
+def test_config3_full_size_properties(Evaluator, checker):
     """BASELINE config 3 at full size (12 species, 10 000 cells, 50 timepoints, 16 chains), through properties that do not
     need the checker to run the whole thing: (1) the first 192 cells' trajectories equal the checker's, (2) reversing the
     order of the cells (rows of the quasi-random table) leaves every log-likelihood unchanged to round-off, (3) a chain's
@@ -147,7 +159,7 @@ def test_config3_full_size_properties(Evaluator, port):
     assert single[0] == logp[5]
     # (1)
     sub = dataclasses.replace(prob, num_cells=192, sobol=prob.sobol[:192])
-    want = port.cellpop_evaluate(sub, vals[:4], threads=4, want_cell_values=True, want_steps=True)
+    want = checker.cellpop_evaluate(sub, vals[:4], threads=4, want_cell_values=True, want_steps=True)
     got = d["cell_values"][:4, :, :192]
     assert (np.isnan(got) == np.isnan(want["cell_values"])).all()
     m = ~np.isnan(got)
@@ -157,7 +169,7 @@ def test_config3_full_size_properties(Evaluator, port):
     ev = Evaluator(dataclasses.replace(prob, sobol=prob.sobol[::-1].copy()))
     rev, _ = ev.evaluate(vals)
     ev.close()
-    assert cellpop_logp_close(rev, logp, 50, 1, rtol=1e-9)
+    assert rel_err(rev, logp).max() < 1e-9
     # (4)
     shards = [Evaluator(prob, shard_rank=r, shard_count=2) for r in range(2)]
     width = 2 * prob.num_timepoints + 1
@@ -172,10 +184,10 @@ def test_config3_full_size_properties(Evaluator, port):
     combined, _ = shards[0].finish(total.data_ptr(), 16, stream)
     for s in shards:
         s.close()
-    assert cellpop_logp_close(combined, logp, 50, 1, rtol=1e-9)
+    assert rel_err(combined, logp).max() < 1e-9
 
 
-def test_stdev_relative_to_scale(Evaluator, port):
+def test_stdev_relative_to_scale(Evaluator, checker):
     """<data stdev_relative_to_scale="true"> (DataLikelihoodBase.cpp:151-153): the standard deviation is multiplied by the
     data scale -- equal to the run that is given the product directly, and equal to the CPU checker."""
     import dataclasses
@@ -193,11 +205,11 @@ def test_stdev_relative_to_scale(Evaluator, port):
     other, _ = ev.evaluate(vals)
     ev.close()
     assert np.allclose(got, same, rtol=1e-13, atol=0) and not np.allclose(got, other, rtol=1e-3)
-    want = port.cellpop_evaluate(prob, vals)["logp"]
-    assert cellpop_logp_close(got, want, prob.num_timepoints, prob.num_replicates, rtol=1e-6)
+    want, floor, _ = _fresh_reference(checker, prob, vals, threads=2)
+    assert_logp_parity(got, want["logp"], floor, "stdev_relative_to_scale")
 
 
-def test_entry_time_variability_takes_a_dimension_and_nothing_else(Evaluator, port):
+def test_entry_time_variability_takes_a_dimension_and_nothing_else(Evaluator, checker):
     """<variable entry_time=...> of a cell_variability block: the reference reads it and gives it a quasi-random dimension
     but never applies it (VariabilityDescription::ApplyVariabilityEntryTime has no caller) -- the result equals the run
     without that variable on the remaining columns of the table."""
@@ -219,4 +231,4 @@ def test_entry_time_variability_takes_a_dimension_and_nothing_else(Evaluator, po
         want, _ = ev.evaluate(vals)
         ev.close()
         assert np.array_equal(got, want), kernel
-    assert np.array_equal(port.cellpop_evaluate(prob, vals)["logp"], port.cellpop_evaluate(base, vals)["logp"])
+    assert np.array_equal(checker.cellpop_evaluate(prob, vals)["logp"], checker.cellpop_evaluate(base, vals)["logp"])

@@ -40,14 +40,14 @@ def test_matches_reference_golden(Evaluator, name):
 
 
 @pytest.mark.parametrize("pk,het,seed", [(PK_ONE, False, 101), (PK_ONE, True, 102), (PK_TWO, False, 103), (PK_TWO, True, 104)])
-def test_matches_cpu_checker_on_seeded_inputs(Evaluator, port, pk, het, seed):
+def test_matches_cpu_checker_on_seeded_inputs(Evaluator, checker, pk, het, seed):
     prob = syn.make_poppk_problem(pk, P=777, T=9, t_end=96.0, heterogeneous=het, missing_fraction=0.1 if het else 0.0, seed=seed)
     vals = syn.make_chain_values(prob, 5, seed=seed)
     ev = Evaluator(prob, diagnostics=True)
     logp, status = ev.evaluate(vals)
     d = ev.diagnostics()
     ev.close()
-    want = port.poppk_evaluate(prob, vals, threads=4, want_counters=True, want_patient_ll=True)
+    want = checker.poppk_evaluate(prob, vals, threads=4, want_counters=True, want_patient_ll=True)
     assert rel_err(logp, want["logp"]).max() <= LOGP_RTOL
     same = (d["counters"].astype(np.int64) == want["counters"]).all(axis=2).mean()
     assert same >= 0.97
@@ -64,7 +64,7 @@ def test_block_size_does_not_change_results(Evaluator, block):
     assert rel_err(logp, gold["logp"]).max() <= LOGP_RTOL
 
 
-def test_edge_cases(Evaluator, port):
+def test_edge_cases(Evaluator, checker):
     # empty trial, single patient, ragged sizes that do not fill a warp, timepoint at t = 0, all-missing observations
     for P in (0, 1, 31, 33):
         prob = syn.make_poppk_problem(PK_ONE, P=P, T=5, t_end=48.0, seed=7)
@@ -76,18 +76,18 @@ def test_edge_cases(Evaluator, port):
         ev = Evaluator(prob)
         logp, status = ev.evaluate(vals)
         ev.close()
-        want = port.poppk_evaluate(prob, vals)["logp"]
+        want = checker.poppk_evaluate(prob, vals)["logp"]
         assert rel_err(logp, want).max() <= LOGP_RTOL, P
         assert (status == 0).all()
 
 
-def test_nan_and_minus_infinity_semantics(Evaluator, port):
+def test_nan_and_minus_infinity_semantics(Evaluator, checker):
     """A failed solve gives -inf (cpp:400-408); a NaN log-likelihood is flagged (Sampler.cpp:172-178); a NaN that the
     reference's serial loop never reaches (it breaks at the first -inf, cpp:438) must not surface."""
     from tests.util import make_nan_inf_case
 
     prob, vals = make_nan_inf_case()
-    want = port.poppk_evaluate(prob, vals)["logp"]
+    want = checker.poppk_evaluate(prob, vals)["logp"]
     assert want[0] == -np.inf and want[1] == -np.inf and np.isnan(want[2])
     for block in (32, 64):
         ev = Evaluator(prob, block_size=block)
@@ -143,7 +143,7 @@ def test_shards_add_up(Evaluator):
 
 
 @pytest.mark.parametrize("pk,P,C", [(PK_ONE, 1000, 16), (PK_TWO, 100000, 64)])
-def test_full_size_properties(Evaluator, port, pk, P, C):
+def test_full_size_properties(Evaluator, checker, pk, P, C):
     """BASELINE.json configs 2 and 5 at full size: (i) a random subsample of patients, evaluated alone by the CPU
     checker, reproduces the per-patient terms; (ii) permuting the patients permutes nothing but the summation order;
     (iii) the simulated concentrations stay within CVODE's own accuracy of the exact solution of the linear model."""
@@ -188,7 +188,7 @@ def test_full_size_properties(Evaluator, port, pk, P, C):
     vs[:, :npk + 2] = vals[cs, :npk + 2]
     vs[:, npk + 2:npk + 2 + 2 * ns] = pp[cs][:, sub, :].reshape(len(cs), 2 * ns)
     vs[:, nvs - 2:] = vals[cs, -2:]
-    want = port.poppk_evaluate(probs, vs, threads=4, want_patient_ll=True)
+    want = checker.poppk_evaluate(probs, vs, threads=4, want_patient_ll=True)
     evs = Evaluator(probs)
     got, _ = evs.evaluate(vs)
     evs.close()
@@ -198,6 +198,11 @@ def test_full_size_properties(Evaluator, port, pk, P, C):
         assert np.abs(d["patient_ll"][cs][:, sub] - want["patient_ll"]).max() < 1e-2
         assert rel_err(d["patient_ll"][cs][:, sub].sum(axis=1), want["logp"]).max() <= LOGP_RTOL
     ev.close()
+
+    # (iv) WHOLE chains at full size against the reference: the first and the last chain over all P patients (at config 5
+    # the compiled reference needs ~10 s per chain on one host thread)
+    whole = checker.poppk_evaluate(prob, vals[cs], threads=2)["logp"]
+    assert rel_err(logp[cs], whole).max() <= LOGP_RTOL
 
 
 @pytest.mark.parametrize("name", ["poppk_two_hetero", "poppk_one_hetero", "poppk_one_maxsteps"])
@@ -216,14 +221,103 @@ def test_ranking_patients_by_absorption_rate_does_not_change_results(Evaluator, 
     assert rel_err(out[True][0], out[False][0]).max() < 1e-12
 
 
-def test_ranked_large_batch_matches_the_cpu_checker(Evaluator, port):
+def test_ranked_large_batch_matches_the_cpu_checker(Evaluator, checker):
     """Above the library's own threshold (P * C >= 60 000 systems) the ranking is on by default."""
     prob = syn.make_poppk_problem(PK_TWO, P=7200, T=10, t_end=72.0, seed=33, heterogeneous=True, missing_fraction=0.05)
     vals = syn.make_chain_values(prob, 16, seed=33)
     ev = Evaluator(prob)
     logp, status = ev.evaluate(vals)
     launches = ev.get_stat("last_kernel_launches")
+    # a chain evaluated alone falls below the ranking threshold and runs with another block size: its log-likelihood must
+    # still have the same BITS (patient terms are summed in patient order whatever the launch shape), or Metropolis-Hastings
+    # decisions could differ between a batched and a chain-by-chain run
+    single = np.array([ev.evaluate(vals[c:c + 1])[0][0] for c in (0, 7, 15)])
     ev.close()
-    want = port.poppk_evaluate(prob, vals, threads=8)["logp"]
+    assert np.array_equal(single, logp[[0, 7, 15]])
+    want = checker.poppk_evaluate(prob, vals, threads=8)["logp"]
     assert launches == 3  # rank kernel + integrator + chain reduce (the sort passes are the library's)
     assert (status == 0).all() and rel_err(logp, want).max() <= LOGP_RTOL
+
+
+def test_device_entry_with_odd_row_stride(Evaluator, checker):
+    """bcm3b200_evaluate_batch_device on a caller's [C][nvar] block: for the biphasic models nvar = 2 P + 11 is odd, so every
+    second chain's per-patient block is only 8-byte aligned (and so is a block that starts at an odd double): the kernel must
+    not assume 16-byte alignment there."""
+    import torch
+
+    prob, gold = load_golden("poppk_two_biphasic")
+    vals = np.ascontiguousarray(gold["values"])
+    C, nvar = vals.shape
+    assert nvar % 2 == 1
+    ev = Evaluator(prob)
+    want, _ = ev.evaluate(vals)
+    stream = torch.cuda.current_stream().cuda_stream
+    for shift in (0, 1):  # block at a 16-byte boundary / 8 bytes off it
+        flat = torch.zeros(C * nvar + 2, dtype=torch.float64, device="cuda")
+        d_vals = flat[shift:shift + C * nvar]
+        d_vals.copy_(torch.from_numpy(vals).reshape(-1))
+        assert (d_vals.data_ptr() % 16 == 0) == (shift == 0)
+        d_partial = torch.empty((3, C), dtype=torch.float64, device="cuda")
+        ev.evaluate_device(d_vals.data_ptr(), C, nvar, d_partial.data_ptr(), stream)
+        torch.cuda.synchronize()
+        got, status = ev.combine_partials(d_partial.cpu().numpy())
+        assert np.array_equal(got, want) and (status == 0).all()
+    ev.close()
+    assert rel_err(want, gold["logp"]).max() <= LOGP_RTOL
+
+
+def test_two_batches_in_flight_on_one_handle(Evaluator):
+    """bcm3b200_enqueue_batch does not synchronise: a second batch enqueued while the first is still queued behind its
+    kernels must not disturb it (the library stages nothing of its own between the caller's buffer and the device)."""
+    import torch
+
+    prob = syn.make_poppk_problem(PK_TWO, P=3000, T=10, t_end=72.0, seed=41)
+    a = syn.make_chain_values(prob, 8, seed=41)
+    b = syn.make_chain_values(prob, 8, seed=42)
+    ev = Evaluator(prob)
+    want_a, _ = ev.evaluate(a)
+    want_b, _ = ev.evaluate(b)
+    ha, hb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    pa = torch.empty((3, 8), dtype=torch.float64, device="cuda")
+    pb = torch.empty((3, 8), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    ev.enqueue(ha.data_ptr(), 8, a.shape[1], pa.data_ptr(), stream)
+    ev.enqueue(hb.data_ptr(), 8, b.shape[1], pb.data_ptr(), stream)
+    torch.cuda.synchronize()
+    got_a, _ = ev.combine_partials(pa.cpu().numpy())
+    got_b, _ = ev.combine_partials(pb.cpu().numpy())
+    ev.close()
+    assert np.array_equal(got_a, want_a) and np.array_equal(got_b, want_b) and not np.array_equal(want_a, want_b)
+
+
+def test_both_biphasic_type_strings_select_the_two_compartment_model(Evaluator):
+    """LikelihoodPopPKTrajectory.cpp:73-76: type="one_biphasic_uptake" selects PKMT_TwoCompartmentBiphasicUptake, exactly
+    like "two_biphasic_uptake" -- the same likelihood.xml must give the same log-likelihood here."""
+    prob, gold = load_golden("poppk_two_biphasic")
+    out = []
+    for type_string in ("one_biphasic_uptake", "two_biphasic_uptake"):
+        ev = Evaluator(prob, type_string=type_string)
+        out.append(ev.evaluate(gold["values"])[0])
+        ev.close()
+    assert np.array_equal(out[0], out[1])
+    assert rel_err(out[0], gold["logp"]).max() <= LOGP_RTOL
+
+
+@pytest.mark.parametrize("fixed", [dict(fixed_vod=45.0), dict(fixed_periphery_fwd=0.3, fixed_periphery_bwd=0.08), dict(fixed_vod=60.0, fixed_periphery_bwd=0.1)])
+def test_fixed_pk_model_attributes(Evaluator, checker, fixed):
+    """<pk_model volume_of_distribution= k_periphery_fwd= k_periphery_bwd=> (cpp:64-67, 122-130, 285-294): each fixed attribute
+    shortens the prior by one variable while the vector is still read at the all-sampled positions; k_periphery_bwd alone
+    counts as fixed but is not used (cpp:288 tests the forward rate only). Checked against the compiled reference glue."""
+    base = syn.make_poppk_problem(PK_TWO, P=300, T=8, t_end=72.0, heterogeneous=True, seed=51)
+    vals = syn.make_chain_values(base, 4, seed=51)
+    n = len(fixed)
+    prob = PopPKProblem(pk_type=PK_TWO, trial=base.trial, transforms=base.transforms[:-n], sd_ix=base.num_variables - n - 2, **fixed)
+    vals = np.ascontiguousarray(vals[:, :-n])
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    ev.close()
+    want = checker.poppk_evaluate(prob, vals, threads=4)["logp"]
+    assert np.isfinite(want).all() and (status == 0).all()
+    assert rel_err(logp, want).max() <= LOGP_RTOL
+    plain = checker.poppk_evaluate(base, syn.make_chain_values(base, 4, seed=51), threads=4)["logp"]  # nothing fixed
+    assert not np.allclose(plain, want, rtol=1e-3)
