@@ -832,6 +832,7 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 		if (!strcmp(name, "diagnostics")) h->cp->diagnostics = value != 0;
 		else if (!strcmp(name, "cellpop_kernel")) h->cp->kernel_choice = (int)value; // 0 auto, 1 one cell per warp, 2 one cell per thread, 3 one cell per lane group
 		else if (!strcmp(name, "cellpop_steps_report")) h->cp->steps_report = (int)value;
+		else if (!strcmp(name, "cellpop_rhs_lanes")) { h->cp->rhs_lanes = value != 0; h->cp->finalized = false; } // before finalize: lane-parallel right-hand side (default on)
 		else if (!strcmp(name, "cellpop_group_lanes")) h->cp->group_lanes = (int)value; // before finalize: lanes per cell of the group kernel (0 auto)
 		else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
 		return BCM3B200_OK;

@@ -78,7 +78,13 @@ enum { SC_TAU = 0 /* [1..5] */, SC_HU = 6, SC_SAVED_TQ5, SC_SAVED_T, SC_HSCALE, 
 // Nordsieck columns 2..5, lane-private: element (j, e) of lane lg at OFF_ZNH + ((j - 2) * E + e) * G + lg
 constexpr int OFF_ZNH = OFF_SCAL + SC_COUNT;
 static_assert(SC_OV == CP_GROUP_SCALARS, "cellpop_host.cuh sizes the shared block with CP_GROUP_SCALARS");
-constexpr int REGION_MIN = OFF_ZNH + 4 * E * G;
+// rate-law values of the lane-parallel right-hand side (one double per reaction), when the model has one
+#ifndef CP_RHS_LANES
+#define CP_RHS_LANES 0
+#define CP_NUM_RATELAWS 0
+#endif
+constexpr int OFF_RL = OFF_ZNH + 4 * E * G;
+constexpr int REGION_MIN = OFF_RL + CP_NUM_RATELAWS;
 constexpr int cell_stride()
 {
 	const int want = (RS * G) % 16;
@@ -147,6 +153,26 @@ __device__ __noinline__ void rhs_eval_perturbed(unsigned y_off, int j, double yj
 	                     ConstSpecies{ constant_species, treat_ix, treat_value }, CellParameters{ tv, smem_d + ov_off }, ConstVector{ non_sampled });
 }
 
+#if CP_RHS_LANES
+// The lane-parallel form (cellpop_host.cuh::cellpop_lane_rhs): the lanes of the cell's group evaluate different reactions at the
+// same time into the cell's rate-law buffer, then every lane assembles the species it owns and leaves them in the f
+// buffer. ONE instance for all uses, like rhs_eval. The caller has published y (with its group barriers).
+__device__ __noinline__ void rhs_eval_lanes(unsigned y_off, unsigned f_off, unsigned rl_off, unsigned ov_off, const double* tv, const double* constant_species,
+                                            const double* non_sampled, int treat_ix, double treat_value, int lg, unsigned gmask)
+{
+	extern __shared__ double smem_d[];
+	double* const rl = smem_d + rl_off;
+	generated_ratelaws_lanes<G>(lg, rl, SpeciesPlain{ smem_d + y_off }, ConstSpecies{ constant_species, treat_ix, treat_value }, CellParameters{ tv, smem_d + ov_off },
+	                            ConstVector{ non_sampled });
+	__syncwarp(gmask);
+#pragma unroll
+	for (int e = 0; e < E; e++) {
+		const int i = lg + G * e;
+		if (!PADDED || i < N) smem_d[f_off + i] = generated_assemble(i, rl);
+	}
+}
+#endif
+
 #ifndef CP_GROUP_LOCKSTEP
 #define CP_GROUP_LOCKSTEP 1
 #endif
@@ -155,6 +181,21 @@ __device__ __noinline__ void rhs_eval_perturbed(unsigned y_off, int j, double yj
 #endif
 #ifndef CP_GROUP_STATIC_LU_MAX
 #define CP_GROUP_STATIC_LU_MAX 0
+#endif
+// Large models (16 or 32 lanes per cell, one or two cells per warp): LU column updates visit only the columns whose pivot-row
+// entry is non-zero (as the reference's LU does), the triangular solves run slot by slot with compile-time slots, the pivot
+// search uses three warp-reduce instructions instead of log2(G) shuffle stages. Measured (B200, kernel ms): 50 species x
+// 6 000 cells x 16 chains 2 126 -> 1 464 with all of them and the lane-parallel right-hand side (each worth 4-24 %); with 4
+// lanes per cell (12 species, 8 cells per warp) every one of them LOSES (128 -> 178 ms: the per-group loops over the non-zero
+// columns and over the reactions of a shape diverge between the 8 groups of a warp), so small models keep the dense forms.
+#ifndef CP_LU_SKIP_ZEROS
+#define CP_LU_SKIP_ZEROS (CP_GROUP >= 16)
+#endif
+#ifndef CP_SOLVE_SLOTTED
+#define CP_SOLVE_SLOTTED (CP_GROUP >= 16)
+#endif
+#ifndef CP_PIVOT_REDUX
+#define CP_PIVOT_REDUX (CP_GROUP >= 16)
 #endif
 
 __device__ __forceinline__ double step_root(double base, int k) { return bcm3b200::bdf_root_halley(base, k); }
@@ -308,9 +349,14 @@ struct GroupBdf {
 	// fbuf (identical stores) and reads back the components it owns
 	__device__ __forceinline__ void rhs_shared(double t, double (&f)[E])
 	{
+#if CP_RHS_LANES
+		rhs_eval_lanes(region_off + OFF_Y, region_off + OFF_F, region_off + OFF_RL, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled, treat_ix,
+		               treatment_value(t), lg, gmask);
+#else
 		rhs_eval(region_off + OFF_Y, region_off + OFF_F, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled, treat_ix, treatment_value(t));
+#endif
 #pragma unroll
-		for (int e = 0; e < E; e++) f[e] = own(e) ? fbuf[idx(e)] : 0.0;
+		for (int e = 0; e < E; e++) f[e] = own(e) ? fbuf[idx(e)] : 0.0; // its own stores (lanes form) or identical stores of all lanes
 		nfe++;
 	}
 
@@ -619,6 +665,57 @@ struct GroupBdf {
 				}
 			}
 		}
+		if constexpr (N <= 3) {
+			// SUNLinSolSetup_Dense_Eigen for 2 and 3 states (sunlinsol_dense_eigen.cpp:111-145): an EXPLICIT inverse -- closed
+			// form for 2 x 2, cofactors for 3 x 3 (Eigen's compute_inverse), no pivoting -- and x = inverse * b in the solve.
+			// On a stiff I - gamma J that inverse is less accurate than a pivoted LU, and the Newton iterates inherit the
+			// difference (measured: population averages 1e-7 away from the reference with LU, 1e-10 with this), so it is
+			// reproduced: every lane computes the same inverse, lane 0 stores it over M. Products and differences are fused the
+			// way the thread integrator's build fuses them (bdf_thread.cuh::linear_setup, which this follows).
+			gsync();
+			double A[N * N], Ainv[N * N];
+#pragma unroll
+			for (int i = 0; i < N; i++)
+#pragma unroll
+				for (int j = 0; j < N; j++) A[i * N + j] = (N == 1) ? 1.0 : M[i * RS + j];
+			if constexpr (N == 1) {
+				Ainv[0] = 1.0 / M[0];
+			} else if constexpr (N == 2) {
+				const double invdet = 1.0 / fma(A[0], A[3], -(A[1] * A[2]));
+				Ainv[0] = A[3] * invdet;
+				Ainv[1] = -A[1] * invdet;
+				Ainv[2] = -A[2] * invdet;
+				Ainv[3] = A[0] * invdet;
+			} else {
+#define CPG_A(i, j) A[(i) * N + (j)]
+#define CPG_COF(i, j) \
+	fma(CPG_A(((i) + 1) % 3, ((j) + 1) % 3), CPG_A(((i) + 2) % 3, ((j) + 2) % 3), -(CPG_A(((i) + 1) % 3, ((j) + 2) % 3) * CPG_A(((i) + 2) % 3, ((j) + 1) % 3)))
+				const double c0 = CPG_COF(0, 0), c1 = CPG_COF(1, 0), c2 = CPG_COF(2, 0);
+				const double det = fma(c2, CPG_A(2, 0), fma(c1, CPG_A(1, 0), c0 * CPG_A(0, 0)));
+				const double invdet = 1.0 / det;
+				Ainv[0 * N + 0] = c0 * invdet;
+				Ainv[0 * N + 1] = c1 * invdet;
+				Ainv[0 * N + 2] = c2 * invdet;
+				Ainv[1 * N + 0] = CPG_COF(0, 1) * invdet;
+				Ainv[1 * N + 1] = CPG_COF(1, 1) * invdet;
+				Ainv[1 * N + 2] = CPG_COF(2, 1) * invdet;
+				Ainv[2 * N + 0] = CPG_COF(0, 2) * invdet;
+				Ainv[2 * N + 1] = CPG_COF(1, 2) * invdet;
+				Ainv[2 * N + 2] = CPG_COF(2, 2) * invdet;
+#undef CPG_COF
+#undef CPG_A
+			}
+			gsync();
+			if (lg == 0) {
+#pragma unroll
+				for (int i = 0; i < N; i++)
+#pragma unroll
+					for (int j = 0; j < N; j++) M[i * RS + j] = Ainv[i * N + j];
+			}
+			gsync();
+			nsetups++;
+			return;
+		}
 		if (lg == 0) {
 #pragma unroll
 			for (int i = 0; i < N; i++) perm[i] = i;
@@ -726,17 +823,34 @@ struct GroupBdf {
 						}
 					}
 				}
+				// largest |a_ik| of the group, the lowest row among equals (Eigen's maxCoeff visitor keeps the first)
+				bool have_pivot;
+				if constexpr (CP_PIVOT_REDUX) {
+					// three warp-reduce instructions instead of log2(G) shuffle stages: the bit pattern of a non-negative double
+					// orders like the number, so the maximum is found on the high word, then on the low word among the lanes
+					// that hold that high word, then the smallest row index among the lanes that hold both. A lane without a
+					// candidate (best = -1) and a NaN column (best stays -1) carry key 0, like a column of zeros.
+					const unsigned hi = (best > 0.0) ? (unsigned)__double2hiint(best) : 0u;
+					const unsigned lo = (best > 0.0) ? (unsigned)__double2loint(best) : 0u;
+					const unsigned mh = __reduce_max_sync(gmask, hi);
+					const unsigned ml = __reduce_max_sync(gmask, (hi == mh) ? lo : 0u);
+					const bool cand = (hi == mh) && (lo == ml);
+					bi = (int)__reduce_min_sync(gmask, cand ? (unsigned)bi : (unsigned)N);
+					have_pivot = (mh | ml) != 0u;
+				} else {
 #pragma unroll
-				for (int d = G / 2; d >= 1; d >>= 1) {
-					const double ob = __shfl_xor_sync(gmask, best, d);
-					const int oi = __shfl_xor_sync(gmask, bi, d);
-					if (ob > best || (ob == best && oi < bi)) {
-						best = ob;
-						bi = oi;
+					for (int d = G / 2; d >= 1; d >>= 1) {
+						const double ob = __shfl_xor_sync(gmask, best, d);
+						const int oi = __shfl_xor_sync(gmask, bi, d);
+						if (ob > best || (ob == best && oi < bi)) {
+							best = ob;
+							bi = oi;
+						}
 					}
+					have_pivot = best > 0.0;
 				}
 				double inv_coeff = 1.0;
-				if (best > 0.0) { // group-uniform; a column of zeros (or of NaN: best stays -1) is left alone
+				if (have_pivot) { // group-uniform; a column of zeros (or of NaN) is left alone
 					if (bi != k) {
 #pragma unroll
 						for (int e = 0; e < E; e++) {
@@ -767,6 +881,28 @@ struct GroupBdf {
 						rowbase[G * e * RS + k] = lik[e];
 					}
 				}
+#if CP_LU_SKIP_ZEROS
+				// Column updates, skipping the columns whose pivot-row entry is zero exactly as the reference's LU does
+				// (EigenPartialPivLUSomewhatSparse.h:88-93: `if (a_kj != 0.0)`): the lanes look at the pivot row together, one
+				// column per lane and slot, a vote gives the set of non-zero columns, and only those are visited. Signalling
+				// networks have a handful of non-zeros per row, so this turns the N^3 / 3 multiply-adds into ~N^2.
+#pragma unroll
+				for (int e = 0; e < E; e++) {
+					const int c0 = lg + G * e;
+					const double rk = (c0 > k && (!PADDED || c0 < N)) ? M[k * RS + c0] : 0.0;
+					unsigned nz = (__ballot_sync(gmask, rk != 0.0) & gmask) >> gbase;
+					while (nz) {
+						const int j = __ffs(nz) - 1;
+						nz &= nz - 1;
+						const double a_kc = __shfl_sync(gmask, rk, gbase + j);
+						const int c = j + G * e;
+#pragma unroll
+						for (int e2 = 0; e2 < E; e2++) {
+							if (lik[e2] != 0.0) rowbase[G * e2 * RS + c] = fma(-a_kc, lik[e2], rowbase[G * e2 * RS + c]);
+						}
+					}
+				}
+#else
 #pragma unroll 1
 				for (int c = k + 1; c < N; c++) {
 					const double a_kc = M[k * RS + c];
@@ -776,6 +912,7 @@ struct GroupBdf {
 						if (i > k && own(e)) rowbase[G * e * RS + c] = fma(-a_kc, lik[e], rowbase[G * e * RS + c]);
 					}
 				}
+#endif
 				gsync();
 			}
 		}
@@ -792,14 +929,67 @@ struct GroupBdf {
 	}
 
 	// x <- (P L U)^-1 x, cooperative: the pivot component is broadcast, every lane updates the components it owns.
-	// Real loops over k (the slot that holds component k is picked with selects): the unrolled forms are faster per
-	// instruction but several times larger, and this kernel is bound by instruction fetch (hot code >> 32 KB L1.5 I-cache).
+	// Real loops over the lanes inside compile-time slots: ~7 instructions per column (one shuffle pair, one load and one
+	// multiply-add per slot) where a single loop over k with run-time slot selection needed ~18.
 	__device__ __forceinline__ void lu_solve(double (&b)[E])
 	{
+		if constexpr (N <= 3) { // x = inverse * b, every row summed left to right (see linear_setup)
+			publish(ybuf, b);
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				if (own(e)) {
+					const int i = idx(e);
+					double sx = M[i * RS + 0] * ybuf[0];
+#pragma unroll
+					for (int j = 1; j < N; j++) sx = fma(M[i * RS + j], ybuf[j], sx);
+					b[e] = sx;
+				} else {
+					b[e] = 0.0;
+				}
+			}
+			return;
+		}
 		publish(ybuf, b);
 #pragma unroll
 		for (int e = 0; e < E; e++) b[e] = own(e) ? ybuf[perm[idx(e)]] : 0.0;
 		const double* const rowbase = M + lg * RS;
+#if CP_SOLVE_SLOTTED
+		// Forward substitution with the unit lower factor, column by column: slot by slot (compile time) and lane by lane
+		// inside a slot, so that the pivot component is a static register read by a shuffle and every lane touches its
+		// rows through [lane row base + constant]. Rows of the pivot's own slot take part only on the lanes behind it.
+		static_for<0, E>([&](auto S) {
+			constexpr int s = decltype(S)::value;
+			constexpr int KK = (G * (s + 1) <= N) ? G : (N - G * s);
+#pragma unroll 4
+			for (int kk = 0; kk < KK; kk++) {
+				const int k = G * s + kk;
+				const double xk = __shfl_sync(gmask, b[s], gbase + kk);
+				if (lg > kk && own(s)) b[s] = fma(-xk, rowbase[G * s * RS + k], b[s]);
+				static_for<s + 1, E>([&](auto EE) {
+					constexpr int e2 = decltype(EE)::value;
+					if (own(e2)) b[e2] = fma(-xk, rowbase[G * e2 * RS + k], b[e2]);
+				});
+			}
+		});
+		// Back substitution with the upper factor (reciprocal pivots on the diagonal): the lane that owns row k reads its
+		// diagonal entry with the same load the lanes above it use for their entry of column k.
+		static_rfor<0, E>([&](auto S) {
+			constexpr int s = decltype(S)::value;
+			constexpr int KK = (G * (s + 1) <= N) ? G : (N - G * s);
+#pragma unroll 4
+			for (int kk = KK - 1; kk >= 0; kk--) {
+				const int k = G * s + kk;
+				const double m_k = own(s) ? rowbase[G * s * RS + k] : 0.0;
+				const double xk = __shfl_sync(gmask, b[s] * m_k, gbase + kk);
+				if (lg < kk) b[s] = fma(-xk, m_k, b[s]);
+				else if (lg == kk) b[s] = xk;
+				static_for<0, s>([&](auto EE) {
+					constexpr int e2 = decltype(EE)::value;
+					b[e2] = fma(-xk, rowbase[G * e2 * RS + k], b[e2]);
+				});
+			}
+		});
+#else
 #pragma unroll 1
 		for (int k = 0; k < N; k++) {
 			const int slot = k / G;
@@ -831,6 +1021,7 @@ struct GroupBdf {
 				else if (i == k) b[e] = xk;
 			}
 		}
+#endif
 	}
 
 	// cvNlsResidual at y = zn[0] + acor: y published to ybuf, f(y) in fy, delta = rl1 zn[1] + acor - gamma f

@@ -62,6 +62,7 @@ struct CellPopState {
 	int kernel_choice = 0; // 0 auto (lane groups for N <= 96, one cell per warp above), 1 warp, 2 thread, 3 group
 	int built_kernel = 0;  // the one kernel the model library was compiled with (1, 2 or 3)
 	int group_lanes = 0;   // 0 auto: smallest power of two with ceil(N / G) <= 3
+	bool rhs_lanes = true; // option "cellpop_rhs_lanes": lane-parallel right-hand side where the generated text can be regrouped (cellpop_lane_rhs)
 	DevBuf<double> d_scratch;
 	std::string module_path;
 	cudaStream_t stream = nullptr;
@@ -343,6 +344,294 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 	a.logp[c] = logp * a.weight;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lane-parallel right-hand side.
+//
+// The reference's generator emits one statement per reaction, `ratelaws[r] = <expr>;`, then one per species,
+// `out[i] = +ratelaws[a]-2.000000*ratelaws[b]...;` (SBMLModel.cpp:291-365). Evaluated as it stands, that text is SCALAR
+// code: the lanes that share a cell all execute every rate law. Here the statements are regrouped by SHAPE -- the
+// expression with its array indices and numeric literals replaced by placeholders -- and every shape becomes one loop in
+// which the lanes of the cell's group evaluate different reactions of that shape at the same time, reading their indices and
+// literals from a table; the species sums are then assembled by the lane that owns the species, term by term in the order
+// of the text. Every rate law and every sum is the same sequence of IEEE operations on the same operands as in the
+// original text (the module is compiled with -fmad=false), so the result is bit-identical to the scalar evaluation --
+// tests/test_gpu_cellpop.py::test_lane_parallel_rhs_is_bit_identical checks exactly that.
+// Anything the parser does not recognise makes it give up, and the model runs the scalar text unchanged.
+struct LaneRhs {
+	bool ok = false;
+	int num_ratelaws = 0;
+	int num_shapes = 0;
+	std::string code; // tables + generated_ratelaws_lanes<G>() + generated_assemble()
+};
+
+namespace lane_rhs_detail {
+
+inline std::string trim(const std::string& s)
+{
+	size_t a = s.find_first_not_of(" \t\r\n");
+	if (a == std::string::npos) return "";
+	size_t b = s.find_last_not_of(" \t\r\n");
+	return s.substr(a, b - a + 1);
+}
+inline bool is_ident_start(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_'; }
+inline bool is_ident(char c) { return is_ident_start(c) || (c >= '0' && c <= '9'); }
+inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+
+struct Law {
+	int target = -1;
+	std::string shape;             // expression with \x01 (index) / \x02 (literal) placeholders
+	std::vector<int> idx;          // array indices in order of appearance
+	std::vector<std::string> lit;  // literal texts in order of appearance
+};
+
+// expression -> shape; false on anything unexpected
+inline bool scan(const std::string& e, Law& law)
+{
+	size_t i = 0;
+	while (i < e.size()) {
+		const char c = e[i];
+		if (is_ident_start(c)) {
+			size_t j = i;
+			while (j < e.size() && is_ident(e[j])) j++;
+			const std::string id = e.substr(i, j - i);
+			if (id == "ratelaws" || id == "out") return false; // a rate law that depends on another statement: keep the text order
+			if (id == "species" || id == "constant_species" || id == "parameters" || id == "non_sampled_parameters") {
+				if (j >= e.size() || e[j] != '[') return false;
+				size_t k = j + 1;
+				while (k < e.size() && is_digit(e[k])) k++;
+				if (k == j + 1 || k >= e.size() || e[k] != ']') return false;
+				law.idx.push_back(atoi(e.substr(j + 1, k - j - 1).c_str()));
+				law.shape += id + "[\x01]";
+				i = k + 1;
+			} else {
+				law.shape += id; // a helper or a math function
+				i = j;
+			}
+		} else if (is_digit(c)) {
+			size_t j = i;
+			while (j < e.size() && is_digit(e[j])) j++;
+			bool real = false;
+			if (j < e.size() && e[j] == '.') {
+				real = true;
+				j++;
+				while (j < e.size() && is_digit(e[j])) j++;
+			}
+			if (j < e.size() && (e[j] == 'e' || e[j] == 'E')) {
+				size_t k = j + 1;
+				if (k < e.size() && (e[k] == '+' || e[k] == '-')) k++;
+				if (k < e.size() && is_digit(e[k])) {
+					real = true;
+					while (k < e.size() && is_digit(e[k])) k++;
+					j = k;
+				}
+			}
+			if (j < e.size() && e[j] == 'f') return false; // single-precision literals: ODE_SINGLE_PRECISION builds are not supported
+			if (real) {
+				law.lit.push_back(e.substr(i, j - i));
+				law.shape += "\x02";
+			} else {
+				law.shape += e.substr(i, j - i); // an integer stays part of the shape
+			}
+			i = j;
+		} else {
+			if (c == '[' || c == ']' || c == ';' || c == '{' || c == '}' || c == '=' || c == '"') return false;
+			if (c != ' ' && c != '\t' && c != '\n' && c != '\r') law.shape += c;
+			i++;
+		}
+	}
+	return !law.shape.empty();
+}
+
+struct Term {
+	int law;
+	std::string coef; // signed literal text
+};
+
+// `+ratelaws[3]-2.000000*ratelaws[5]` | `0.0`
+inline bool parse_sum(const std::string& e, std::vector<Term>& terms)
+{
+	const std::string t = trim(e);
+	if (t == "0.0" || t == "0" || t == "0.000000") return true;
+	size_t i = 0;
+	while (i < t.size()) {
+		char sign = '+';
+		if (t[i] == '+' || t[i] == '-') sign = t[i++];
+		else if (i != 0) return false;
+		std::string coef = "1.0";
+		if (i < t.size() && is_digit(t[i])) {
+			size_t j = i;
+			while (j < t.size() && (is_digit(t[j]) || t[j] == '.')) j++;
+			if (j >= t.size() || t[j] != '*') return false;
+			coef = t.substr(i, j - i);
+			i = j + 1;
+		}
+		if (t.compare(i, 9, "ratelaws[") != 0) return false;
+		size_t j = i + 9;
+		size_t k = j;
+		while (k < t.size() && is_digit(t[k])) k++;
+		if (k == j || k >= t.size() || t[k] != ']') return false;
+		terms.push_back(Term{ atoi(t.substr(j, k - j).c_str()), std::string(1, sign) + coef });
+		i = k + 1;
+	}
+	return true;
+}
+
+} // namespace lane_rhs_detail
+
+inline LaneRhs cellpop_lane_rhs(const std::string& code_without_jacobian, int N)
+{
+	using namespace lane_rhs_detail;
+	LaneRhs out;
+	const size_t open = code_without_jacobian.find('{');
+	const size_t close = code_without_jacobian.rfind('}');
+	if (open == std::string::npos || close == std::string::npos || close <= open) return out;
+	const std::string body = code_without_jacobian.substr(open + 1, close - open - 1);
+	int NR = -1;
+	std::vector<Law> laws;
+	std::vector<std::vector<Term>> sums(N);
+	std::vector<bool> have_sum(N, false);
+	size_t pos = 0;
+	while (pos < body.size()) {
+		size_t end = body.find(';', pos);
+		if (end == std::string::npos) end = body.size();
+		const std::string st = trim(body.substr(pos, end - pos));
+		pos = end + 1;
+		if (st.empty()) continue;
+		if (st.compare(0, 17, "OdeReal ratelaws[") == 0) {
+			NR = atoi(st.c_str() + 17);
+			continue;
+		}
+		const bool is_law = st.compare(0, 9, "ratelaws[") == 0, is_out = st.compare(0, 4, "out[") == 0;
+		if (!is_law && !is_out) return out;
+		const size_t b0 = is_law ? 9 : 4;
+		size_t b1 = b0;
+		while (b1 < st.size() && is_digit(st[b1])) b1++;
+		if (b1 == b0 || b1 >= st.size() || st[b1] != ']') return out;
+		const int index = atoi(st.substr(b0, b1 - b0).c_str());
+		size_t eq = st.find('=', b1);
+		if (eq == std::string::npos || trim(st.substr(b1 + 1, eq - b1 - 1)) != "") return out;
+		const std::string expr = trim(st.substr(eq + 1));
+		if (is_law) {
+			Law law;
+			law.target = index;
+			if (!scan(expr, law)) return out;
+			laws.push_back(law);
+		} else {
+			if (index < 0 || index >= N || have_sum[index]) return out;
+			if (!parse_sum(expr, sums[index])) return out;
+			have_sum[index] = true;
+		}
+	}
+	if (NR <= 0 || (int)laws.size() != NR) return out;
+	{ // every rate law defined exactly once, every species assembled, every term refers to a rate law
+		std::vector<int> seen(NR, 0);
+		for (const Law& l : laws) {
+			if (l.target < 0 || l.target >= NR || seen[l.target]++) return out;
+		}
+		for (int i = 0; i < N; i++) {
+			if (!have_sum[i]) return out;
+			for (const Term& t : sums[i])
+				if (t.law < 0 || t.law >= NR) return out;
+		}
+	}
+	// group by shape, in order of first appearance
+	std::vector<std::string> shape_names;
+	std::vector<std::vector<int>> members;
+	for (size_t li = 0; li < laws.size(); li++) {
+		size_t sidx = 0;
+		while (sidx < shape_names.size() && shape_names[sidx] != laws[li].shape) sidx++;
+		if (sidx == shape_names.size()) {
+			shape_names.push_back(laws[li].shape);
+			members.emplace_back();
+		}
+		members[sidx].push_back((int)li);
+	}
+	std::ostringstream tab_idx, tab_lit, tab_target, fn;
+	int off_idx = 0, off_lit = 0, off_target = 0;
+	fn << "template <int G_, class SP, class CS, class PP, class NS>\n"
+	      "__device__ __forceinline__ void generated_ratelaws_lanes(int lg, double* ratelaws, const SP& species, const CS& constant_species, const PP& parameters, "
+	      "const NS& non_sampled_parameters)\n{\n";
+	for (size_t sidx = 0; sidx < shape_names.size(); sidx++) {
+		const std::vector<int>& mem = members[sidx];
+		const Law& first = laws[mem[0]];
+		const size_t ni = first.idx.size(), nk = first.lit.size();
+		// a placeholder whose value is the same in every member stays a constant of the code
+		std::vector<int> idx_slot(ni, -1), lit_slot(nk, -1);
+		int vi = 0, vk = 0;
+		for (size_t k = 0; k < ni; k++) {
+			bool same = true;
+			for (int m : mem) same = same && laws[m].idx[k] == first.idx[k];
+			if (!same) idx_slot[k] = vi++;
+		}
+		for (size_t k = 0; k < nk; k++) {
+			bool same = true;
+			for (int m : mem) same = same && laws[m].lit[k] == first.lit[k];
+			if (!same) lit_slot[k] = vk++;
+		}
+		std::string expr;
+		size_t ci = 0, ck = 0;
+		for (char c : first.shape) {
+			if (c == '\x01') {
+				expr += (idx_slot[ci] < 0) ? std::to_string(first.idx[ci]) : ("__ldg(I + " + std::to_string(idx_slot[ci]) + ")");
+				ci++;
+			} else if (c == '\x02') {
+				expr += (lit_slot[ck] < 0) ? first.lit[ck] : ("__ldg(K + " + std::to_string(lit_slot[ck]) + ")");
+				ck++;
+			} else {
+				expr += c;
+			}
+		}
+		fn << "\t// shape " << sidx << ": " << mem.size() << " reaction(s)\n";
+		fn << "\tfor (int m = lg; m < " << mem.size() << "; m += G_) {\n";
+		if (vi) fn << "\t\tconst int* I = cp_rl_idx + " << off_idx << " + m * " << vi << ";\n";
+		if (vk) fn << "\t\tconst double* K = cp_rl_lit + " << off_lit << " + m * " << vk << ";\n";
+		fn << "\t\tratelaws[__ldg(cp_rl_target + " << off_target << " + m)] = " << expr << ";\n\t}\n";
+		for (int m : mem) {
+			for (size_t k = 0; k < ni; k++)
+				if (idx_slot[k] >= 0) tab_idx << laws[m].idx[k] << ", ";
+			for (size_t k = 0; k < nk; k++)
+				if (lit_slot[k] >= 0) tab_lit << laws[m].lit[k] << ", ";
+			tab_target << laws[m].target << ", ";
+		}
+		off_idx += vi * (int)mem.size();
+		off_lit += vk * (int)mem.size();
+		off_target += (int)mem.size();
+	}
+	fn << "}\n";
+	std::ostringstream ob, ol, oc;
+	int nterms = 0;
+	for (int i = 0; i < N; i++) {
+		ob << nterms << ", ";
+		for (const Term& t : sums[i]) {
+			ol << t.law << ", ";
+			oc << t.coef << ", ";
+			nterms++;
+		}
+	}
+	ob << nterms;
+	std::ostringstream o;
+	o << "// ---- lane-parallel form of generated_derivative (" << shape_names.size() << " shapes, " << NR << " reactions), made by cellpop_lane_rhs ----\n";
+	o << "#define CP_RHS_LANES 1\n#define CP_NUM_RATELAWS " << NR << "\n";
+	o << "__device__ const int cp_rl_idx[] = { " << tab_idx.str() << "0 };\n";
+	o << "__device__ const double cp_rl_lit[] = { " << tab_lit.str() << "0.0 };\n";
+	o << "__device__ const int cp_rl_target[] = { " << tab_target.str() << "0 };\n";
+	o << "__device__ const int cp_out_begin[] = { " << ob.str() << " };\n";
+	o << "__device__ const int cp_out_law[] = { " << ol.str() << "0 };\n";
+	o << "__device__ const double cp_out_coef[] = { " << oc.str() << "0.0 };\n";
+	o << fn.str();
+	// out[i] = the signed terms of the text, left to right (a coefficient of 1 multiplies exactly)
+	o << "__device__ __forceinline__ double generated_assemble(int i, const double* ratelaws)\n{\n"
+	     "\tint t = __ldg(cp_out_begin + i);\n\tconst int t1 = __ldg(cp_out_begin + i + 1);\n\tif (t == t1) return 0.0;\n"
+	     "\tdouble acc = __ldg(cp_out_coef + t) * ratelaws[__ldg(cp_out_law + t)];\n"
+	     "\tfor (t++; t < t1; t++) acc = acc + __ldg(cp_out_coef + t) * ratelaws[__ldg(cp_out_law + t)];\n\treturn acc;\n}\n";
+	out.ok = true;
+	out.num_ratelaws = NR;
+	out.num_shapes = (int)shape_names.size();
+	out.code = o.str();
+	return out;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // per-model module
 
@@ -425,12 +714,21 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	// large lock-step block shares instruction fetches best: measured 130.6 ms (1 x 12 warps) vs 136.7 (2 x 6) vs 146.0
 	// (4 x 3) at config 3.
 	const int Eg = (cp.N + G - 1) / G;
+	// lane-parallel right-hand side (see cellpop_lane_rhs): the cell's shared block grows by one double per reaction
+	LaneRhs lanes;
+	{
+		const char* renv = getenv("BCM3B200_CELLPOP_RHS_LANES");
+		// default: models with 16 or 32 lanes per cell (measured: 50 species 1 933 -> 1 464 ms; with 4 lanes per cell and 8 cells
+		// per warp the per-shape loops diverge between the groups and the scalar text is faster, 143 vs 178 ms at 12 species)
+		const bool want = renv ? atoi(renv) != 0 : (cp.rhs_lanes && G >= 16);
+		if (want && cellpop_resolve_kernel(cp) == 3) lanes = cellpop_lane_rhs(code.substr(at), cp.N);
+	}
 	size_t per_cell;
-	{ // the constants of cellpop_group.cuh: RS, OFF_SCAL, SC_COUNT, OFF_ZNH, CS
+	{ // the constants of cellpop_group.cuh: RS, OFF_SCAL, SC_COUNT, OFF_ZNH, OFF_RL, CS
 		const int RS = cp.N | 1;
 		const int off_scal = cp.N * RS + 2 * cp.N + (cp.N + 1) / 2;
 		const int sc_count = CP_GROUP_SCALARS + (override_vars.empty() ? 1 : (int)override_vars.size());
-		int cs = off_scal + sc_count + 4 * Eg * G;
+		int cs = off_scal + sc_count + 4 * Eg * G + (lanes.ok ? lanes.num_ratelaws : 0);
 		while (cs % 16 != (RS * G) % 16) cs++;
 		per_cell = sizeof(double) * (size_t)cs;
 	}
@@ -458,9 +756,13 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	o << "#define CP_HELPER_INLINE " << helper_inline << "\n";
 	if (const char* benv2 = getenv("BCM3B200_CELLPOP_GROUP_BATCHED")) o << "#define CP_GROUP_BATCHED " << atoi(benv2) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
+	if (const char* senv = getenv("BCM3B200_CELLPOP_LU_SKIP_ZEROS")) o << "#define CP_LU_SKIP_ZEROS " << atoi(senv) << "\n";
+	if (const char* senv = getenv("BCM3B200_CELLPOP_SOLVE_SLOTTED")) o << "#define CP_SOLVE_SLOTTED " << atoi(senv) << "\n";
+	if (const char* senv = getenv("BCM3B200_CELLPOP_PIVOT_REDUX")) o << "#define CP_PIVOT_REDUX " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
 	o << code << "\n";
 	const int which = cellpop_resolve_kernel(cp);
+	if (lanes.ok) o << lanes.code << "\n";
 	o << (which == 1 ? "#include \"cellpop_warp.cuh\"\n" : which == 2 ? "#include \"cellpop_thread.cuh\"\n" : "#include \"cellpop_group.cuh\"\n");
 	src = o.str();
 	return BCM3B200_OK;

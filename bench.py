@@ -1,7 +1,12 @@
 #!/usr/bin/env python
-"""bench.py -- likelihood evaluations per second of the batched PopPK path (BASELINE.json metric).
+"""bench.py -- likelihood evaluations per second of the batched PopPK / cellpop paths (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload poppk_two_100k_x64|poppk_one_1k_x16] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload ...] [--impl reference] [--no-secondary]
+
+The ONE JSON line is the headline workload (default: BASELINE config 5, PopPK two-compartment, 100 000 individuals x 64
+chains); its "secondary" list carries the cell_population half of the metric, each entry a complete line of its own (value,
+e2e, roofline with oracle-counted FLOPs, cpu_baseline, clocks): BASELINE config 3 (12 species, 10 000 cells, 16 chains; N = 1
+only -- it is a one-GPU configuration) and config 4 (50 species, 100 000 cells, 16 chains, cells sharded over the --gpus N ranks).
 
 A "step" is one batched call: EvaluateLogProbability for all C tempered chains' proposals at once, i.e. C * P
 independent stiff ODE solves + the per-chain reduction. One evaluation = one chain's log-likelihood (the unit the
@@ -100,201 +105,165 @@ def subsample_problem(prob, vals, P_sample: int):
     return ps, vs
 
 
-def cellpop_flop_per_system(N: int, steps: float, n_ratelaw_flops: float) -> float:
-    """SURVEY.md section 8(d) formula with the counter ratios the reference shows on this model family (measured with the
-    oracle: nfe/nst = 1.33, nni = nfe - 1, nsetups/nst = 0.122, nje/nst = 0.021), q = 4.3, DQ Jacobian and dense LU."""
+# floating-point operations of one call of the prelude helpers (cellpop_prelude.cuh = SolverCodeGenerator.cpp:122-295), main branch
+HELPER_FLOPS = {"hill_function_fixedn2": 4, "hill_function_fixedn4": 6, "hill_function_fixedn10": 10, "hill_function_fixedn16": 10,
+                "hill_function_fixedn100": 18, "hill_function": 4 + 2 * 20, "michaelis_menten_function": 4, "safepow": 20, "synthcap": 5, "tQSSA": 9}
+
+
+def count_rhs_flops(code: str) -> int:
+    """F_rhs of SURVEY.md section 8(d) "counted from the generated text": the arithmetic operators of generated_derivative
+    (binary + - * /; a sign in front of a term of an `out[i] = +a-b` line counts as the addition it stands for) plus the
+    operation count of every helper call."""
+    import re
+
+    body = code[code.index("{") + 1:]
+    end = body.find("EXPORT_PREFIX void generated_jacobian")
+    if end >= 0:
+        body = body[:end]
+    body = re.sub(r"\[[^\]]*\]", "[]", body)          # indices are not arithmetic
+    body = re.sub(r"\d+\.\d+(e[+-]?\d+)?", "K", body)   # literals (no sign inside)
+    flops = body.count("*") + body.count("/") + body.count("+") + body.count("-")
+    flops -= len(re.findall(r"=\s*[+-]", body))         # the leading sign of an assembled sum is not an operation
+    for name, cost in HELPER_FLOPS.items():
+        flops += cost * len(re.findall(r"\b" + name + r"\(", body))
+    return int(flops)
+
+
+def cellpop_flop_per_system(N: int, cnt_mean: np.ndarray, f_rhs: float, nout: float) -> float:
+    """FLOP(system) from the ORACLE's counters of a sample of the same workload
+    (steps, nfe, nsetups, nje, netf, ncfn, nni, ok), with the difference-quotient Jacobian N (F_rhs + 2 N) and the dense LU 2 N^3 / 3."""
+    nst, nfe, nsetups, nje, nni = cnt_mean[0], cnt_mean[1], cnt_mean[2], cnt_mean[3], cnt_mean[6]
     q = Q_MEAN
     A = N * (q * (q + 1) / 2 + 2 * (q + 1) + 4) + 60
-    nfe, nsetups, nje = 1.33 * steps, 0.122 * steps, 0.021 * steps
-    nni = nfe - 1
-    return float(steps * A + nfe * n_ratelaw_flops + nni * (2 * N * N + 9 * N) + nsetups * (2 * N * N + 2 * N ** 3 / 3) + nje * N * (n_ratelaw_flops + 2 * N))
+    return float(nst * A + nfe * f_rhs + nni * (2 * N * N + 9 * N) + nsetups * (2 * N * N + 2 * N ** 3 / 3) + nje * N * (f_rhs + 2 * N) + nout * 2 * N * (q + 1))
 
 
-def run_cellpop(args, workload: str):
-    """cell_population workloads: single GPU (cells are not sharded across ranks yet)."""
+COUNTER_NAMES = ["steps", "nfe", "nsetups", "nje", "netf", "ncfn", "nni", "ok"]
+
+
+def cellpop_cpu_sample(prob, vals, sample: int, cores: int):
+    """The reference's CPU implementation on the first `sample` cells of the workload, all chains: evals/s scaled to the full
+    population (cells are i.i.d. quasi-random draws) and the solver's counters, from which the algorithmic FLOPs come."""
+    import dataclasses
+
+    kind, chk = cpu_checker()
+    ps = dataclasses.replace(prob, num_cells=sample, sobol=prob.sobol[:sample])
+    t0 = time.perf_counter()
+    r = chk.cellpop_counters(ps, vals, threads=cores)
+    dt = time.perf_counter() - t0
+    C = vals.shape[0]
+    cnt = r["counters"].reshape(-1, r["counters"].shape[-1]).mean(axis=0)
+    return dict(kind=kind, seconds=dt, evals_per_s=(C / dt) * (sample / prob.num_cells), counters_mean=cnt,
+                sample=f"all {C} chains x first {sample} of {prob.num_cells} cells in {dt:.1f} s on {cores} threads ({cpu_model_name()}); scaled by {sample}/{prob.num_cells}")
+
+
+def cellpop_line(args, workload: str, steps: int, warmup: int, ctx: dict):
+    """One complete JSON line (a dict, rank 0; None elsewhere) for a cell_population workload: single GPU, or the cells split over
+    the ranks of the torchrun launch (strong scaling, one SUM all-reduce of [C][2 T + 1] doubles)."""
     import torch
 
     from bcm3_b200 import _lib
     from bcm3_b200 import synthetic_cellpop as sc
-    from bcm3_b200.cellpop import CellPopEvaluator
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank != 0 and (args.impl == "reference" or world == 1):
-        return
+    rank, world, local_rank = ctx["rank"], ctx["world"], ctx["local_rank"]
     w = WORKLOADS[workload]
     prob = sc.make_cellpop_problem(N=w["N"], num_cells=w["cells"], T=w["T"], data_cells=32, seed=1, rate_decades=w.get("rate_decades", 2.0))
     vals = sc.make_chain_values(w["C"])
     C, nvar = vals.shape
-    if args.impl != "reference" and world > 1:
-        run_cellpop_sharded(args, workload, prob, vals, rank, world, local_rank)
-        return
+    cores = max(1, min(C, os.cpu_count() or 1))
+    f_rhs = count_rhs_flops(prob.derivative_code)
+    config = {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C, "timepoints": w["T"], "ode_solves_per_step": C * w["cells"],
+              "l2": "256 MB memset between timed iterations"}
+    base = {"metric": METRIC_CELLPOP, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+
     if args.impl == "reference":
-        kind, chk = cpu_checker()
-        cores = max(1, min(C, os.cpu_count() or 1))
-        import dataclasses
-        times = []
-        for i in range(args.warmup + args.steps):
-            sample = min(w["cells"], 2000 if w["N"] <= 20 else 200)
-            ps = dataclasses.replace(prob, num_cells=sample, sobol=prob.sobol[:sample])
-            t0 = time.perf_counter()
-            chk.cellpop_evaluate(ps, vals, threads=cores)
-            dt = time.perf_counter() - t0
-            if i >= args.warmup:
-                times.append(dt)
-        dt = statistics.mean(times)
-        value = (C / dt) * (sample / w["cells"])
-        print(json.dumps({"impl": "reference", "metric": METRIC_CELLPOP, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                          "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C,
-                                                                        "timepoints": w["T"]},
-                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                                           "sample": f"all {C} chains x first {sample} of {w['cells']} cells in {dt:.1f} s on {cores} threads ({cpu_model_name()}); scaled by {sample}/{w['cells']}"},
-                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
-        return
-    if not torch.cuda.is_available() or _lib.device_count() == 0:
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    ev = CellPopEvaluator(prob, device=0)
-    h_vals = torch.from_numpy(vals).pin_memory()
-    h_logp = np.empty(C)
-    h_status = np.empty(C, dtype=np.int32)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")
-    fp64_peak = _lib.measure_fp64_peak(0)
+        if rank != 0:
+            return None
+        sample = min(w["cells"], 2000 if w["N"] <= 20 else 200)
+        runs = [cellpop_cpu_sample(prob, vals, sample, cores) for _ in range(warmup + steps)][warmup:]
+        value = statistics.mean(r["evals_per_s"] for r in runs)
+        return dict(base, impl="reference", value=value, ms_per_step=1e3 * statistics.mean(r["seconds"] for r in runs), config=config,
+                    cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": runs[-1]["kind"], "sample": runs[-1]["sample"]},
+                    e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
 
-    def step():
-        _lib.check(ev.lib.bcm3b200_evaluate_batch(ev.handle, C, nvar, h_vals.data_ptr(), h_logp.ctypes.data, h_status.ctypes.data))
-
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step()
-    torch.cuda.synchronize()
-    launches0 = ev.get_stat("total_kernel_launches")
-    sampler = ClockSampler(0)
-    sampler.start()
-    time.sleep(0.25)
-    kernel_ms, t_begin = [], time.perf_counter()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step()
-        e2e_s += time.perf_counter() - t0
-        kernel_ms.append(ev.get_stat("last_kernel_us") / 1e3)
-    t_end = time.perf_counter()
-    clocks = sampler.stop(t_begin, t_end)
-    launches = ev.get_stat("total_kernel_launches") - launches0
-    ev._last_C = C
-    steps_mean = float(ev.diagnostics()["cell_steps"].mean())
-    total_ms = sum(kernel_ms)
-    value = C * args.steps / (total_ms * 1e-3)
-    flop_sys = cellpop_flop_per_system(w["N"], steps_mean, 8.0 * 2 * w["N"])
-    k_ms = statistics.mean(kernel_ms)
-    achieved = flop_sys * C * w["cells"] / (k_ms * 1e-3) / 1e12
-    line = {"metric": METRIC_CELLPOP, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C, "timepoints": w["T"], "ode_solves_per_step": C * w["cells"],
-                       "mean_steps_per_solve": steps_mean, "l2": "256 MB memset between timed iterations"},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": ncu_traffic(workload),
-                         "kernel": "cellpop_group_kernel" if w["N"] <= 96 else "cellpop_kernel", "kernel_ms": k_ms, "flop_per_system": flop_sys,
-                         "systems_per_launch": C * w["cells"], "peak_source": "measured live: bcm3b200_measure_fp64_peak"},
-            "e2e": {"value": C * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes), "d2h_bytes_per_step": int(C * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "check": {"logp0": float(h_logp[0]), "status_ok": bool((h_status == 0).all())}}
-    if not args.no_cpu_baseline:
-        import dataclasses
-        kind, chk = cpu_checker()
-        cores = max(1, min(C, os.cpu_count() or 1))
-        sample = min(w["cells"], 4000 if w["N"] <= 20 else 400)
-        ps = dataclasses.replace(prob, num_cells=sample, sobol=prob.sobol[:sample])
-        t0 = time.perf_counter()
-        chk.cellpop_evaluate(ps, vals, threads=cores)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": (C / dt) * (sample / w["cells"]), "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": f"all {C} chains x first {sample} of {w['cells']} cells in {dt:.1f} s on {cores} threads ({cpu_model_name()}); scaled by {sample}/{w['cells']}"}
-    print(json.dumps(line))
-    ev.close()
-
-
-def run_cellpop_sharded(args, workload, prob, vals, rank, world, local_rank):
-    """N > 1: the simulated cells are split over the ranks (strong scaling), one SUM all-reduce of [C][2 T + 1] doubles."""
-    import torch
-    import torch.distributed as dist
-
-    from bcm3_b200 import _lib
-    from bcm3_b200.parallel import ShardedCellPopLikelihood
-
-    w = WORKLOADS[workload]
-    C, nvar = vals.shape
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    lk = ShardedCellPopLikelihood(prob, rank, world, local_rank)
     h_vals = torch.from_numpy(vals).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    flush = ctx["flush"]
+    fp64_peak = ctx["fp64_peak"]
+    if world == 1:
+        from bcm3_b200.cellpop import CellPopEvaluator
 
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize(dev)
+        ev = CellPopEvaluator(prob, device=local_rank)
+        h_logp = np.empty(C)
+        h_status = np.empty(C, dtype=np.int32)
 
-    for _ in range(max(args.warmup, 3)):
+        def step():
+            _lib.check(ev.lib.bcm3b200_evaluate_batch(ev.handle, C, nvar, h_vals.data_ptr(), h_logp.ctypes.data, h_status.ctypes.data))
+            return h_logp, h_status
+        closer = ev
+    else:
+        from bcm3_b200.parallel import ShardedCellPopLikelihood
+
+        lk = ShardedCellPopLikelihood(prob, rank, world, local_rank)
+        ev = lk.evaluator
+
+        def step():
+            return lk.evaluate(h_vals)  # H2D of the batch, kernels, all-reduce, data likelihood, D2H of logp
+        closer = lk
+        config["sharding"] = f"cells over {world} ranks, SUM all-reduce of [{C}][{2 * w['T'] + 1}] doubles"
+
+    for _ in range(warmup):
         flush.zero_()
-        logp, status = lk.evaluate(h_vals)
-    barrier()
-    launches0 = lk.evaluator.get_stat("total_kernel_launches")
+        step()
+    ctx["barrier"]()
+    launches0 = ev.get_stat("total_kernel_launches")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    kernel_ms, wall = [], 0.0
+    ctx["barrier"]()
     t_begin = time.perf_counter()
-    wall = 0.0
-    for a, b in evs:
+    for _ in range(steps):
         flush.zero_()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        a.record(stream)
-        logp, status = lk.evaluate(h_vals)  # H2D of the batch, kernels, all-reduce, data likelihood, D2H of logp
-        b.record(stream)
+        logp, status = step()
         wall += time.perf_counter() - t0
-    barrier()
+        kernel_ms.append(ev.get_stat("last_kernel_us") / 1e3)
+    ctx["barrier"]()
     t_end = time.perf_counter()
     clocks = sampler.stop(t_begin, t_end) if sampler else None
-    torch.cuda.synchronize(dev)
-    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in evs), 1e3 * wall], dtype=torch.float64, device=dev)
-    nl = torch.tensor([float(lk.evaluator.get_stat("total_kernel_launches") - launches0)], dtype=torch.float64, device=dev)
-    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    dist.all_reduce(nl, op=dist.ReduceOp.SUM)
-    # roofline of the dominant kernel on this rank's shard (kernel time from the library's own events, max over ranks)
-    kms = torch.tensor([lk.evaluator.get_stat("last_kernel_us") / 1e3], dtype=torch.float64, device=dev)
-    dist.all_reduce(kms, op=dist.ReduceOp.MAX)
-    fp64_peak = _lib.measure_fp64_peak(local_rank)
-    cells_local = lk.evaluator.get_stat("num_cells_local")
-    if rank == 0:
-        total_ms, wall_ms = float(tot[0].item()), float(tot[1].item())
-        steps_mean = 243.6 if w["N"] == 12 else 542.0  # mean accepted steps per cell of the synthetic models (measured at N = 1)
-        flop_sys = cellpop_flop_per_system(w["N"], steps_mean, 8.0 * 2 * w["N"])
-        k_ms = float(kms.item())
-        achieved = flop_sys * C * cells_local / (k_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
-                    "kernel": "cellpop_group_kernel", "kernel_ms": k_ms, "flop_per_system": flop_sys, "systems_per_launch": C * cells_local,
-                    "note": "per GPU, on its shard of the cells", "peak_source": "measured live: bcm3b200_measure_fp64_peak"}
-        line = {"metric": METRIC_CELLPOP, "value": C * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "species": w["N"], "cells": w["cells"], "chains": C, "timepoints": w["T"], "ode_solves_per_step": C * w["cells"],
-                           "sharding": f"cells over {world} ranks, NCCL SUM all-reduce of [{C}][{2 * w['T'] + 1}] doubles", "l2": "256 MB memset between timed iterations"},
-                "roofline": roofline,
-                "e2e": {"value": C * args.steps / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes) * world, "d2h_bytes_per_step": int(C * 8) * world,
-                        "ms_per_step": wall_ms / args.steps},
-                "gpu_launches": int(nl.item()), "clocks": clocks, "check": {"logp0": float(logp[0]), "status_ok": bool((status == 0).all())}}
-        print(json.dumps(line))
-    lk.close()
-    dist.destroy_process_group()
+    launches = ev.get_stat("total_kernel_launches") - launches0
+    cells_local = ev.get_stat("num_cells_local")
+    # device time of a step = the library's own events around its kernels (host-buffer entry: the H2D of the 768-byte batch
+    # precedes the first event), max over ranks; e2e = wall clock around the call, max over ranks
+    tot = ctx["max_over_ranks"]([sum(kernel_ms), 1e3 * wall, statistics.mean(kernel_ms)])
+    nl = ctx["sum_over_ranks"]([float(launches)])[0]
+    closer.close()
+    if rank != 0:
+        return None
+    total_ms, wall_ms, k_ms = tot
+    line = dict(base, value=C * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, config=config,
+                e2e={"value": C * steps / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes) * world, "d2h_bytes_per_step": int(C * 8) * world,
+                     "ms_per_step": wall_ms / steps},
+                gpu_launches=int(nl), clocks=clocks, check={"logp0": float(logp[0]), "status_ok": bool((np.asarray(status) == 0).all())})
+    # CPU arm of the same run (rank 0's host cores) on a bounded sample; its counters give the ALGORITHMIC FLOPs of the roofline
+    sample = min(w["cells"], 4000 if w["N"] <= 20 else 400)
+    cb = cellpop_cpu_sample(prob, vals, sample, cores)
+    cnt = cb["counters_mean"]
+    flop_sys = cellpop_flop_per_system(w["N"], cnt, f_rhs, w["T"])
+    achieved = flop_sys * C * cells_local / (k_ms * 1e-3) / 1e12
+    line["cpu_baseline"] = {"value": cb["evals_per_s"], "unit": UNIT, "cores": cores, "kind": cb["kind"], "sample": cb["sample"]}
+    line["config"]["mean_steps_per_solve"] = float(cnt[0])
+    line["roofline"] = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": ncu_traffic(workload),
+                        "kernel": "cellpop_group_kernel", "kernel_ms": k_ms, "flop_per_system": flop_sys, "systems_per_launch": C * cells_local,
+                        "rhs_flops_from_generated_text": f_rhs, "oracle_counters_mean": {k: float(v) for k, v in zip(COUNTER_NAMES, cnt)},
+                        "flops_from": f"SURVEY 8(d) formula on the {cb['kind']} CPU run's counters of this run's sample ({sample} cells x {C} chains)",
+                        "note": "per GPU, on its shard of the cells" if world > 1 else "whole workload on one GPU",
+                        "peak_source": "measured live: bcm3b200_measure_fp64_peak (DFMA chains), MEASURED_PEAKS.json has no FP64 entry"}
+    return line
 
 
 def cpu_checker():
@@ -409,11 +378,8 @@ def ncu_traffic(workload: str):
         return None
 
 
-def run_reference(args, workload: str):
-    """--impl reference: the reference's own CPU implementation of the path on the box's host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def reference_line(args, workload: str):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     prob, vals = make_workload(workload)
     w = WORKLOADS[workload]
     target = 4.0  # seconds of CPU work per step
@@ -424,58 +390,31 @@ def run_reference(args, workload: str):
             times.append(last)
     value = statistics.mean(t["evals_per_s"] for t in times)
     ms = 1e3 * statistics.mean(t["seconds"] for t in times)
-    line = {
+    # the prefix sample is scaled linearly to the full population: checked here once with a sample of twice the size
+    double = time_cpu(prob, vals, 2 * target)
+    return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "pk_model": w["pk"], "individuals": w["P"], "chains": w["C"], "timepoints": w["T"],
                    "note": "each step = a bounded sample of the workload (all chains x a prefix of the individuals), evals/s scaled to the full size"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"],
+                         "build": "oracle/_ref: the reference's CVODE 5.3.0 + src/odecommon, -O3 -march=x86-64-v3 (the reference's own flag is -march=native)",
+                         "scaling_check": {"sample_individuals": [last["P_sample"], double["P_sample"]], "evals_per_s": [last["evals_per_s"], double["evals_per_s"]]}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="poppk_two_100k_x64", choices=sorted(WORKLOADS))
-    ap.add_argument("--block-size", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    workload = args.workload
-
-    if WORKLOADS[workload].get("kind") == "cellpop":
-        run_cellpop(args, workload)
-        return
-
-    if args.impl == "reference":
-        run_reference(args, workload)
-        return
-
+def poppk_line(args, workload: str, steps: int, warmup: int, ctx: dict):
+    """One complete JSON line (a dict, rank 0; None elsewhere) for a PopPK workload."""
     import torch
-    import torch.distributed as dist
 
-    from bcm3_b200 import _lib
     from bcm3_b200.parallel import ShardedPopPKLikelihood, combine_partials, shard_bounds
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
-    if not torch.cuda.is_available() or _lib.device_count() == 0:
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
+    rank, world, local_rank = ctx["rank"], ctx["world"], ctx["local_rank"]
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-
+    barrier = ctx["barrier"]
+    line = None
     w = WORKLOADS[workload]
     prob, vals = make_workload(workload)
     C, nvar = vals.shape
@@ -483,17 +422,12 @@ def main():
     lk = ShardedPopPKLikelihood(prob, rank, world, local_rank, block_size=args.block_size)
     ev = lk.evaluator
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     # inputs: pinned host copy (e2e) and a device-resident copy (value)
     h_vals = torch.from_numpy(vals).pin_memory()
     d_vals = torch.from_numpy(vals).to(dev)
     d_partial = torch.empty((3, C), dtype=torch.float64, device=dev)
     h_partial = torch.empty((3, C), dtype=torch.float64).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = ctx["flush"]
     stream = torch.cuda.current_stream(dev)
 
     def device_step():
@@ -503,10 +437,10 @@ def main():
 
             allreduce_partial(d_partial)
 
-    fp64_peak = _lib.measure_fp64_peak(local_rank)
+    fp64_peak = ctx["fp64_peak"]
 
     # ---- device-resident timing: W warm-up steps, then exactly K timed steps ----
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         flush.zero_()
         device_step()
     barrier()
@@ -515,7 +449,7 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     t_begin = time.perf_counter()
     for a, b in evs:
@@ -528,13 +462,8 @@ def main():
     clocks = sampler.stop(t_begin, t_end) if sampler else None
     launches = ev.get_stat("total_kernel_launches") - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    nl = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
-    total_ms = float(total_ms.item())
-    launches_all = int(nl.item())
+    total_ms = ctx["max_over_ranks"]([sum(step_ms)])[0]
+    launches_all = int(ctx["sum_over_ranks"]([float(launches)])[0])
     h_partial.copy_(d_partial)
     logp, status = combine_partials(h_partial.numpy())
 
@@ -559,14 +488,11 @@ def main():
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.zero_()
         out = e2e_step()
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
+    e2e_s = ctx["max_over_ranks"]([time.perf_counter() - t0])[0]
     e2e_logp = np.array(out, dtype=np.float64, copy=True)
 
     lo, hi = shard_bounds(P, rank, world)
@@ -575,8 +501,8 @@ def main():
 
     if rank == 0:
         N = 2 if w["pk"] == "one" else 3
-        value = C * args.steps / (total_ms * 1e-3)
-        ms_per_step = total_ms / args.steps
+        value = C * steps / (total_ms * 1e-3)
+        ms_per_step = total_ms / steps
         # roofline of the dominant kernel: algorithmic FLOPs per launch / its average duration
         flop_per_system = w["flop_per_system"]
         systems_per_launch = C * (hi - lo)
@@ -590,7 +516,7 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         bytes_per_launch = algorithmic_bytes_per_eval(hi - lo, T, nvar) * C
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "pk_model": w["pk"], "individuals": P, "chains": C, "timepoints": T, "t_end_h": w["t_end"],
                        "ode_solves_per_step": C * P, "sharding": f"individuals over {world} rank(s), NCCL all-reduce of [3][{C}] doubles",
@@ -602,8 +528,8 @@ def main():
                          "hbm": {"achieved": bytes_per_launch / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": bytes_per_launch,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-            "e2e": {"value": C * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e": {"value": C * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / steps},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "check": {"logp0": float(logp[0]), "status_ok": bool((status == 0).all()),
@@ -617,9 +543,95 @@ def main():
             line["roofline"]["flop_per_system_from_oracle_counters"] = algorithmic_flop_per_system(N, cnt, T)
             line["roofline"]["oracle_counters_mean"] = {k: float(v) for k, v in zip(
                 ["steps", "nfe", "nsetups", "nje", "netf", "ncfn", "nni", "ok"], cnt)}
-        print(json.dumps(line))
     lk.close()
+    return line
+
+
+def make_context(args):
+    """Process-wide state shared by the lines of one run: rank layout, torch.distributed (plumbing: barriers and max-over-ranks
+    of the timings), the L2 flush buffer, the FP64 peak of this GPU."""
+    import torch
+    import torch.distributed as dist
+
+    from bcm3_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = dict(rank=rank, world=world, local_rank=local_rank)
+    if args.impl == "reference":
+        return ctx
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available() or _lib.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reduce_over_ranks(values, op):
+        t = torch.tensor(list(values), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return [float(x) for x in t.tolist()]
+
+    ctx.update(barrier=barrier, max_over_ranks=lambda v: reduce_over_ranks(v, dist.ReduceOp.MAX),
+               sum_over_ranks=lambda v: reduce_over_ranks(v, dist.ReduceOp.SUM),
+               flush=torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev),  # > 126 MB L2
+               fp64_peak=_lib.measure_fp64_peak(local_rank))
+    return ctx
+
+
+# the cell_population half of BASELINE's metric, reported next to the PopPK headline: (workload, runs at N > 1, steps cap)
+SECONDARY = [("cellpop_12sp_10k_x16", False, 8), ("cellpop_50sp_100k_x16", True, 2)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="poppk_two_100k_x64", choices=sorted(WORKLOADS))
+    ap.add_argument("--block-size", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="only the headline workload")
+    args = ap.parse_args()
+    workload = args.workload
+    ctx = make_context(args)
+    rank, world = ctx["rank"], ctx["world"]
+    warmup = max(args.warmup, 3)
+
+    def one_line(name, steps):
+        if WORKLOADS[name].get("kind") == "cellpop":
+            return cellpop_line(args, name, steps, warmup if args.impl != "reference" else args.warmup, ctx)
+        if args.impl == "reference":
+            return reference_line(args, name) if rank == 0 else None
+        return poppk_line(args, name, steps, warmup, ctx)
+
+    line = one_line(workload, args.steps)
+    if workload == "poppk_two_100k_x64" and not args.no_secondary:
+        secondary = []
+        for name, multi_gpu, cap in SECONDARY:
+            if world > 1 and not multi_gpu:
+                continue
+            sec = one_line(name, min(args.steps, cap))
+            if sec is not None:
+                secondary.append(sec)
+        if line is not None:
+            line["secondary"] = secondary
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1 and args.impl != "reference":
+        import torch.distributed as dist
+
         dist.destroy_process_group()
 
 

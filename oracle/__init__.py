@@ -190,8 +190,8 @@ class Oracle:
 ERROR_MODELS = {"normal": 0, "additive_normal": 0, "student_t4": 1, "t4": 1, "proportional_normal": 2, "additive_proportional_normal": 3}
 
 
-def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=False, want_steps=False, want_average=False):
-    """problem: bcm3_b200.cellpop_data.CellPopProblem; values [C, nvar]."""
+def _cellpop_struct(problem, values):
+    """(struct, arrays it points into, values [C, nvar]) for a bcm3_b200.cellpop_data.CellPopProblem."""
     p = problem
     values = np.ascontiguousarray(values, dtype=np.float64)
     if values.ndim == 1:
@@ -227,6 +227,14 @@ def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=
         weight=p.weight, stdev=p.stdev, offset=p.offset, scale=p.scale, missing_stdev=p.missing_simulation_time_stdev,
         initial_conditions=ptr(keep["ic"]), constant_species=ptr(keep["const"]), non_sampled=ptr(keep["ns"]), sobol=ptr(keep["sobol"]),
         timepoints=ptr(keep["tp"]), observed=ptr(keep["obs"]), variability=ptr(keep["var"]), transforms=ptr(keep["tr"]), derivative=fn)
+    return s, keep, values
+
+
+def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=False, want_steps=False, want_average=False):
+    """problem: bcm3_b200.cellpop_data.CellPopProblem; values [C, nvar]."""
+    s, keep, values = _cellpop_struct(problem, values)
+    nC = values.shape[0]
+    T, nc = problem.num_timepoints, problem.num_cells
     logp = np.empty(nC)
     cv = np.empty((nC, T, nc)) if want_cell_values else None
     st = np.zeros((nC, nc), dtype=np.int32) if want_steps else None
@@ -239,7 +247,26 @@ def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=
     return dict(logp=logp, cell_values=cv, cell_steps=st, population_average=avg)
 
 
+
+
+def _cellpop_counters(self, problem, values, threads: int = 1):
+    """The solver's counters per cell, [C, cells, 8] = (steps, nfe, nsetups, nje, netf, ncfn, nni, ok) summed over the restarts of
+    each solve: what bench.py computes the algorithmic FLOPs of the cell_population workloads from."""
+    s, keep, values = _cellpop_struct(problem, values)
+    nC = values.shape[0]
+    fn = self.lib.oracle_cellpop_evaluate_counters
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    logp = np.empty(nC)
+    cnt = np.zeros((nC, problem.num_cells, NUM_COUNTERS), dtype=np.int64)
+    rc = fn(C.byref(s), nC, values.ctypes.data, logp.ctypes.data, cnt.ctypes.data, int(threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle_cellpop_evaluate_counters failed: {rc}")
+    return dict(logp=logp, counters=cnt)
+
+
 Oracle.cellpop_evaluate = _cellpop_evaluate
+Oracle.cellpop_counters = _cellpop_counters
 
 _cache: dict[str, Oracle] = {}
 

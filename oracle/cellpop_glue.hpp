@@ -109,7 +109,7 @@ inline double first_discontinuity_ahead(const oracle_cellpop_problem& pr, double
 
 template <class Solver>
 void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, double* logp_out, double* cell_values, int32_t* cell_steps,
-                    double* pop_avg_out)
+                    double* pop_avg_out, int64_t* cell_counters = nullptr)
 {
 	const int N = pr.num_species, nvar = pr.num_variables, T = pr.num_timepoints, ncell = pr.num_cells, D = pr.variability_dim, R = pr.num_replicates;
 	const double nan = std::numeric_limits<double>::quiet_NaN();
@@ -179,6 +179,12 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 			result = false; // Experiment::Simulate fails => logp = -inf (Experiment.cpp:356-358)
 		}
 		if (cell_steps) cell_steps[ci] = steps;
+		if (cell_counters) { // per cell: ORACLE_CNT_* (steps, nfe, nsetups, nje, netf, ncfn, nni, ok), summed over the restarts of the solve
+			int64_t* k = cell_counters + (size_t)ci * ORACLE_NUM_COUNTERS;
+			solver.counters(k);
+			k[ORACLE_CNT_STEPS] = steps;
+			k[ORACLE_CNT_OK] = result ? 1 : 0;
+		}
 		if (result) {
 			// Experiment.cpp:298-312 + Cell::GetInterpolatedSpeciesValue (Cell.cpp:280-360): exact stored timepoints only
 			for (int i = 0; i < T; i++) {
@@ -271,7 +277,7 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 
 template <class Solver>
 int evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp, double* cell_values,
-             int32_t* cell_steps, double* population_average, int num_threads)
+             int32_t* cell_steps, double* population_average, int num_threads, int64_t* cell_counters = nullptr)
 {
 	if (!prob || !values || !logp || !prob->derivative) return -1;
 	const size_t T = prob->num_timepoints, nc = prob->num_cells, nvar = prob->num_variables;
@@ -283,7 +289,8 @@ int evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double
 			size_t c = next.fetch_add(1);
 			if (c >= num_chains) break;
 			evaluate_chain<Solver>(*prob, values + c * nvar, logp + c, cell_values ? cell_values + c * T * nc : nullptr,
-			                       cell_steps ? cell_steps + c * nc : nullptr, population_average ? population_average + c * T : nullptr);
+			                       cell_steps ? cell_steps + c * nc : nullptr, population_average ? population_average + c * T : nullptr,
+			                       cell_counters ? cell_counters + c * nc * ORACLE_NUM_COUNTERS : nullptr);
 		}
 	};
 	if (num_threads == 1) {

@@ -22,6 +22,20 @@ struct PortSolver {
 	const double* cell_params = nullptr;
 	double creation_time = 0.0;
 	std::vector<double> constant_species_y;
+	int64_t cnt[ORACLE_NUM_COUNTERS] = { 0 };
+	void counters(int64_t* out)
+	{
+		for (int k = 0; k < ORACLE_NUM_COUNTERS; k++) out[k] = cnt[k];
+	}
+	void accumulate() // bdf_reinit zeroes the counters, as CVodeReInit does
+	{
+		cnt[ORACLE_CNT_NFE] += m->nfe;
+		cnt[ORACLE_CNT_NSETUPS] += m->nsetups;
+		cnt[ORACLE_CNT_NJE] += m->nje;
+		cnt[ORACLE_CNT_NETF] += m->netf;
+		cnt[ORACLE_CNT_NCFN] += m->ncfn;
+		cnt[ORACLE_CNT_NNI] += m->nni;
+	}
 	explicit PortSolver(const oracle_cellpop_problem& p)
 	    : pr(p), m(new bdf_mem), constant_species_y(p.constant_species, p.constant_species + p.num_constant_species)
 	{
@@ -44,6 +58,7 @@ struct PortSolver {
 		creation_time = cell_creation_time;
 		double next_disc = cellpop_glue::first_discontinuity_ahead(pr, creation_time);
 		steps = 0;
+		for (int k = 0; k < ORACLE_NUM_COUNTERS; k++) cnt[k] = 0;
 		int ti = 0;
 		while (tp[ti] < 2.220446049250313e-16) {
 			for (int i = 0; i < N; i++) out[i + (size_t)ti * N] = y0[i];
@@ -77,10 +92,12 @@ struct PortSolver {
 			if (steps == pr.max_steps) return false;
 			if (!std::isnan(next_disc) && (result == BDF_TSTOP_RETURN || next_disc == tret)) { // ODESolverCVODE.cpp:448-461
 				next_disc = cellpop_glue::pulse_next_discontinuity(pr, tret, creation_time);
+				accumulate();
 				bdf_reinit(m, tret, y);
 				if (!std::isnan(next_disc) && next_disc < INFINITY) bdf_set_stop_time(m, next_disc);
 			}
 		}
+		accumulate();
 		if (const char* rep = getenv("BCM3B200_CELLPOP_REPORT")) { // debugging aid: report another counter in place of the steps
 			int k = atoi(rep);
 			if (k == 1) steps = (int)m->nfe; else if (k == 2) steps = (int)m->nsetups; else if (k == 3) steps = (int)m->nje;
@@ -96,4 +113,11 @@ extern "C" int oracle_cellpop_evaluate(const oracle_cellpop_problem* prob, size_
 {
 	if (prob && prob->num_species > BDF_NMAX) return -3;
 	return cellpop_glue::evaluate<PortSolver>(prob, num_chains, values, logp, cell_values, cell_steps, population_average, num_threads);
+}
+
+extern "C" int oracle_cellpop_evaluate_counters(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp,
+                                                int64_t* counters, int num_threads)
+{
+	if (prob && prob->num_species > BDF_NMAX) return -3;
+	return cellpop_glue::evaluate<PortSolver>(prob, num_chains, values, logp, nullptr, nullptr, nullptr, num_threads, counters);
 }

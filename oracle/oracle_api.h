@@ -136,6 +136,12 @@ typedef struct {
 int oracle_cellpop_evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp,
                             double* cell_values, int32_t* cell_steps, double* population_average, int num_threads);
 
+/* The same evaluation, reporting the solver's counters per cell: counters [C][cells][ORACLE_NUM_COUNTERS] (steps, nfe, nsetups,
+ * nje, netf, ncfn, nni, ok; nfe counts the integrator's own right-hand-side evaluations -- the N per difference-quotient
+ * Jacobian are nje * N on top). bench.py computes the algorithmic FLOPs of the cell_population workloads from these. */
+int oracle_cellpop_evaluate_counters(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp,
+                                     int64_t* counters, int num_threads);
+
 /* "ref" or "port" */
 const char* oracle_kind(void);
 

@@ -14,9 +14,29 @@ double ndtri(double p) { return refglue::ndtri(p); }
 
 namespace {
 
+// subclass only to reach the protected cvode_mem for the statistics counters (CVodeReInit zeroes them: they are read before
+// every re-initialisation and at the end of the solve)
+struct CountingCVODE : public ODESolverCVODE {
+	void Accumulate(int64_t* cnt)
+	{
+		long v;
+		if (CVodeGetNumRhsEvals(cvode_mem, &v) == 0) cnt[ORACLE_CNT_NFE] += v;
+		if (CVodeGetNumLinSolvSetups(cvode_mem, &v) == 0) cnt[ORACLE_CNT_NSETUPS] += v;
+		if (CVodeGetNumErrTestFails(cvode_mem, &v) == 0) cnt[ORACLE_CNT_NETF] += v;
+		if (CVodeGetNumNonlinSolvConvFails(cvode_mem, &v) == 0) cnt[ORACLE_CNT_NCFN] += v;
+		if (CVodeGetNumNonlinSolvIters(cvode_mem, &v) == 0) cnt[ORACLE_CNT_NNI] += v;
+		if (CVodeGetNumJacEvals(cvode_mem, &v) == 0) cnt[ORACLE_CNT_NJE] += v;
+	}
+};
+
 struct RefSolver {
 	const oracle_cellpop_problem& pr;
-	ODESolverCVODE solver;
+	CountingCVODE solver;
+	int64_t cnt[ORACLE_NUM_COUNTERS] = { 0 };
+	void counters(int64_t* out)
+	{
+		for (int k = 0; k < ORACLE_NUM_COUNTERS; k++) out[k] = cnt[k];
+	}
 	const double* cell_params = nullptr;
 	double creation_time = 0.0;
 	std::vector<double> constant_species_y;
@@ -39,10 +59,14 @@ struct RefSolver {
 	{
 		cell_params = params;
 		creation_time = cell_creation_time;
+		for (int k = 0; k < ORACLE_NUM_COUNTERS; k++) cnt[k] = 0;
 		// Cell::Simulate, Cell.cpp:212-229 + discontinuity_cb :444-460
 		const double first = cellpop_glue::first_discontinuity_ahead(pr, creation_time);
 		if (!std::isnan(first)) {
-			ODESolver::TDiscontinuityCallback cb = [this](OdeReal t, void*) -> Real { return cellpop_glue::pulse_next_discontinuity(pr, t, creation_time); };
+			ODESolver::TDiscontinuityCallback cb = [this](OdeReal t, void*) -> Real {
+				solver.Accumulate(cnt); // the callback runs right before CVodeReInit (ODESolverCVODE.cpp:448-457)
+				return cellpop_glue::pulse_next_discontinuity(pr, t, creation_time);
+			};
 			solver.SetDiscontinuity(first, cb, nullptr);
 		}
 		Eigen::Map<const OdeVectorReal> ic(y0, pr.num_species);
@@ -51,6 +75,7 @@ struct RefSolver {
 		OdeMatrixReal output;
 		bool ok = solver.SolveReturnSolution(initial, &timepoints, &output);
 		steps = (int)solver.GetNumSteps();
+		solver.Accumulate(cnt);
 		if (ok) {
 			for (int t = 0; t < ntp; t++)
 				for (int i = 0; i < pr.num_species; i++) out[i + (size_t)t * pr.num_species] = output(i, t);
@@ -65,4 +90,10 @@ extern "C" int oracle_cellpop_evaluate(const oracle_cellpop_problem* prob, size_
                                        double* cell_values, int32_t* cell_steps, double* population_average, int num_threads)
 {
 	return cellpop_glue::evaluate<RefSolver>(prob, num_chains, values, logp, cell_values, cell_steps, population_average, num_threads);
+}
+
+extern "C" int oracle_cellpop_evaluate_counters(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp,
+                                                int64_t* counters, int num_threads)
+{
+	return cellpop_glue::evaluate<RefSolver>(prob, num_chains, values, logp, nullptr, nullptr, nullptr, num_threads, counters);
 }

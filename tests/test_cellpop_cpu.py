@@ -87,3 +87,78 @@ def test_device_module_compiles_for_sm100a(built, tmp_path, monkeypatch):
 
     with pytest.raises(_lib.Bcm3B200Error, match="generated_derivative signature"):
         CellPopEvaluator(bad, compile_only=True)
+
+
+def test_lane_parallel_rhs_text_is_bit_identical_on_the_host(built, tmp_path, monkeypatch):
+    """The library regroups the generated statements by expression shape so that the lanes of a cell's group evaluate
+    different reactions at the same time (cellpop_host.cuh::cellpop_lane_rhs). Here the regrouped text of a stiff 33-species
+    cascade (all rate-law shapes, stoichiometric coefficients added) is compiled for the HOST next to the original text, the
+    "lanes" run one after the other, and both must give the same BITS on random states."""
+    import ctypes
+    import subprocess
+
+    from bcm3_b200.cellpop import CellPopEvaluator
+
+    monkeypatch.setenv("BCM3B200_CACHE", str(tmp_path))
+    prob = sc.make_cellpop_problem(N=33, num_cells=8, T=6, data_cells=2, seed=73, rate_decades=3.0)
+    # give two species a sum with coefficients and a leading minus, and one an empty sum, as the generator can emit them
+    code = prob.derivative_code.replace("out[5] = +ratelaws[10]-ratelaws[11];", "out[5] = -2.000000*ratelaws[11]+ratelaws[10]+0.500000*ratelaws[3];")
+    code = code.replace("out[7] = +ratelaws[14]-ratelaws[15];", "out[7] = 0.0;")
+    assert code != prob.derivative_code
+    prob = dataclasses.replace(prob, derivative_code=code)
+    CellPopEvaluator(prob, compile_only=True).close()
+    (d,) = [d for d in os.listdir(tmp_path) if d.startswith("cellpop_")]
+    src = open(tmp_path / d / "model.cu").read()
+    assert "#define CP_RHS_LANES 1" in src and "#define CP_NUM_RATELAWS 66" in src
+    lanes = src[src.index("// ---- lane-parallel form"):src.index('#include "cellpop_group.cuh"')]
+    here = os.path.dirname(os.path.abspath(__file__))
+    harness = ('#include <cmath>\n#include <limits>\n#include <vector>\n#include "cellpop_prelude.h"\n#define EXPORT_PREFIX extern "C"\n'
+               "struct OdeMatrixReal { double dummy; double& operator()(int, int) { return dummy; } };\n" + code +
+               "\n#define __device__\n#define __forceinline__ inline\ntemplate <class T> static inline T __ldg(const T* p) { return *p; }\n" + lanes +
+               """
+template <int G> static void run(double* out, const double* y, const double* cs, const double* p, const double* ns, int N)
+{
+	std::vector<double> rl(CP_NUM_RATELAWS, std::numeric_limits<double>::quiet_NaN());
+	for (int lg = 0; lg < G; lg++) generated_ratelaws_lanes<G>(lg, rl.data(), y, cs, p, ns);
+	for (int i = 0; i < N; i++) out[i] = generated_assemble(i, rl.data());
+}
+extern "C" void lanes_eval(int G, double* out, const double* y, const double* cs, const double* p, const double* ns, int N)
+{
+	if (G == 2) run<2>(out, y, cs, p, ns, N); else if (G == 16) run<16>(out, y, cs, p, ns, N); else run<32>(out, y, cs, p, ns, N);
+}
+""")
+    (tmp_path / "harness.cpp").write_text(harness)
+    so = str(tmp_path / "harness.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++14", "-fPIC", "-shared", "-w", "-I", os.path.join(os.path.dirname(here), "oracle"),
+                    "-o", so, str(tmp_path / "harness.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(3)
+    N = 33
+    for trial in range(50):
+        y = rng.uniform(-0.05, 1.2, N) if trial % 3 else rng.uniform(-1.0, 3.0, N)  # includes the helpers' negative / saturated branches
+        cs = np.array([rng.uniform(0.0, 2.0)])
+        p = 10.0 ** rng.uniform(-1, 1, 6)
+        ns = np.zeros(1)
+        want = np.full(N, np.nan)
+        lib.generated_derivative(want.ctypes.data_as(dp), y.ctypes.data_as(dp), cs.ctypes.data_as(dp), p.ctypes.data_as(dp), ns.ctypes.data_as(dp))
+        for G in (2, 16, 32):
+            got = np.full(N, np.nan)
+            lib.lanes_eval(G, got.ctypes.data_as(dp), y.ctypes.data_as(dp), cs.ctypes.data_as(dp), p.ctypes.data_as(dp), ns.ctypes.data_as(dp), N)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (trial, G)
+    assert want[7] == 0.0
+
+
+def test_unrecognised_generated_text_keeps_the_scalar_form(built, tmp_path, monkeypatch):
+    """A statement the regrouping does not understand (here: a rate law that reads another rate law) makes it give up; the model
+    is then compiled from the text as it stands."""
+    from bcm3_b200.cellpop import CellPopEvaluator
+
+    monkeypatch.setenv("BCM3B200_CACHE", str(tmp_path))
+    prob, _ = load_cellpop_golden("cellpop_n5_late_entry")
+    code = prob.derivative_code.replace("\tratelaws[3] = ", "\tratelaws[3] = 0.0*ratelaws[2]+")
+    assert code != prob.derivative_code
+    CellPopEvaluator(dataclasses.replace(prob, derivative_code=code), compile_only=True).close()
+    (d,) = [d for d in os.listdir(tmp_path) if d.startswith("cellpop_")]
+    src = open(tmp_path / d / "model.cu").read()
+    assert "CP_RHS_LANES 1" not in src and "generated_ratelaws_lanes" not in src
