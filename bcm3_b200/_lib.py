@@ -22,6 +22,9 @@ EXPORTS = [
     "bcm3b200_evaluate_batch_device",
     "bcm3b200_enqueue_batch",
     "bcm3b200_combine_partials",
+    "bcm3b200_comm_unique_id",
+    "bcm3b200_comm_init",
+    "bcm3b200_exchange_partials",
     "bcm3b200_cellpop_finish",
     "bcm3b200_get_diagnostics",
     "bcm3b200_set_option",
@@ -44,10 +47,30 @@ class Bcm3B200Error(RuntimeError):
 _lib = None
 
 
+def _prefer_bundled_nccl() -> None:
+    """A Python process may import torch AFTER the library has loaded NCCL; torch must then find the NCCL it was built
+    against (the pip package nvidia-nccl, same soname as the system library). Point the library at that copy unless the
+    caller chose one (BCM3B200_NCCL_LIB). A C++ host has no such concern and gets the system libnccl.so.2."""
+    if os.environ.get("BCM3B200_NCCL_LIB"):
+        return
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["BCM3B200_NCCL_LIB"] = cand
+            return
+
+
 def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    _prefer_bundled_nccl()
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
@@ -64,6 +87,9 @@ def load() -> C.CDLL:
     lib.bcm3b200_evaluate_batch_device.argtypes = [vp, sz, sz, vp, vp, vp]
     lib.bcm3b200_enqueue_batch.argtypes = [vp, sz, sz, vp, vp, vp]
     lib.bcm3b200_combine_partials.argtypes = [sz, vp, vp, vp]
+    lib.bcm3b200_comm_unique_id.argtypes = [vp, sz]
+    lib.bcm3b200_comm_init.argtypes = [vp, vp, sz]
+    lib.bcm3b200_exchange_partials.argtypes = [vp, sz, vp, vp]
     lib.bcm3b200_cellpop_finish.argtypes = [vp, sz, vp, vp, vp, vp]
     lib.bcm3b200_get_diagnostics.argtypes = [vp, vp, vp, vp]
     lib.bcm3b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -78,7 +104,7 @@ def load() -> C.CDLL:
     lib.bcm3b200_host_alloc.restype = vp
     lib.bcm3b200_host_free.argtypes = [vp]
     lib.bcm3b200_host_free.restype = None
-    for name in ("create", "set_data", "set_text", "get_cell_diagnostics", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials", "cellpop_finish",
+    for name in ("create", "set_data", "set_text", "get_cell_diagnostics", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials", "cellpop_finish", "comm_unique_id", "comm_init", "exchange_partials",
                  "get_diagnostics", "set_option", "get_stat"):
         getattr(lib, "bcm3b200_" + name).restype = C.c_int
     _lib = lib
@@ -98,3 +124,13 @@ def measure_fp64_peak(device: int = 0) -> float:
 
 def device_count() -> int:
     return int(load().bcm3b200_device_count())
+
+
+COMM_ID_BYTES = 128  # BCM3B200_COMM_ID_BYTES
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0's call: the id every rank passes to comm_init (an ncclUniqueId as plain bytes)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    check(load().bcm3b200_comm_unique_id(buf, COMM_ID_BYTES))
+    return buf.raw

@@ -13,7 +13,7 @@ from .cellpop_data import CellPopProblem
 
 class CellPopEvaluator:
     def __init__(self, problem: CellPopProblem, device: int = 0, compile_only: bool = False, kernel: str = "auto",
-                 shard_rank: int = 0, shard_count: int = 1, rhs_lanes: bool | None = None):
+                 shard_rank: int = 0, shard_count: int = 1, rhs_lanes: bool | None = None, device_count: int = 1):
         """rhs_lanes: None = the library's default (the lane-parallel right-hand side wherever the generated text can be regrouped),
         False = evaluate the generated text as it stands (every lane of a cell's group runs every rate law)."""
         self.lib = _lib.load()
@@ -42,7 +42,7 @@ class CellPopEvaluator:
                 kv[name] = repr(float(getattr(p, name)))
         desc = ";".join(f"{k}={v}" for k, v in kv.items()).encode()
         h = C.c_void_p()
-        _lib.check(self.lib.bcm3b200_create(b"cell_population", desc, len(desc), 1, C.byref(h)))
+        _lib.check(self.lib.bcm3b200_create(b"cell_population", desc, len(desc), device_count, C.byref(h)))
         self.handle = h
         try:
             self._set("initial_conditions", p.initial_conditions)
@@ -101,6 +101,14 @@ class CellPopEvaluator:
         status = np.empty(nC, dtype=np.int32)
         _lib.check(self.lib.bcm3b200_cellpop_finish(self.handle, nC, d_partial_ptr, logp.ctypes.data, status.ctypes.data, stream))
         return logp, status
+
+    def comm_init(self, comm_id: bytes) -> None:
+        """Collective over the ranks (one process per GPU): attach the library's NCCL communicator; afterwards evaluate()
+        returns the complete result on every rank."""
+        _lib.check(self.lib.bcm3b200_comm_init(self.handle, comm_id, len(comm_id)))
+
+    def exchange(self, d_partial_ptr: int, nC: int, stream: int = 0) -> None:
+        _lib.check(self.lib.bcm3b200_exchange_partials(self.handle, nC, d_partial_ptr, stream or None))
 
     def get_stat(self, name: str) -> int:
         v = C.c_int64()

@@ -23,6 +23,7 @@
 #define BCM3_POPPK_AUX_KERNELS
 #include "poppk_kernel.cuh"
 #include "cellpop_host.cuh"
+#include "comm_host.cuh"
 
 using namespace bcm3b200;
 
@@ -70,6 +71,13 @@ struct Shard {
 
 struct Handle {
 	std::unique_ptr<CellPopState> cp; // set for model kind "cell_population"; the fields below are the PopPK evaluator
+	// cell_population with device_count > 1 in ONE process: the states of the further devices (cp is the first device's) and
+	// one NCCL end per device (ncclCommInitAll); the first device combines the gathered partials and finishes
+	std::vector<std::unique_ptr<CellPopState>> cp_more;
+	std::vector<std::unique_ptr<CommEnd>> dev_comm;
+	// one process per GPU: this rank's end of the communicator attached with bcm3b200_comm_init (both model kinds)
+	CommEnd comm;
+	DevBuf<double> xchg; // partial block of a host-buffer evaluate on a handle with a communicator
 	// description
 	int pk_type = PK_ONE;
 	std::string drug;
@@ -124,6 +132,84 @@ int get_int(const std::map<std::string, std::string>& kv, const char* key, int d
 	if (present) *present = it != kv.end();
 	if (it == kv.end()) return def;
 	return atoi(it->second.c_str());
+}
+
+std::vector<CellPopState*> cellpop_states(Handle* h)
+{
+	std::vector<CellPopState*> v;
+	if (h->cp) v.push_back(h->cp.get());
+	for (auto& m : h->cp_more) v.push_back(m.get());
+	return v;
+}
+
+// "key=value" description -> one cell_population state (bcm3b200.h lists the keys)
+int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<CellPopState>& out)
+{
+	std::unique_ptr<CellPopState> cp(new CellPopState);
+	bool ok = true, present;
+	auto need = [&](const char* key) {
+		int v = get_int(kv, key, 0, &present);
+		ok = ok && present;
+		return v;
+	};
+	auto real = [&](const char* key, double def) { return kv.count(key) ? strtod(kv[key].c_str(), nullptr) : def; };
+	cp->N = need("num_species");
+	cp->nvar = need("num_variables");
+	cp->num_cells = need("num_cells");
+	cp->T = need("num_timepoints");
+	// 96 species = the lane-group kernel at 32 lanes x 3 components per lane with the Newton matrix (N x (N | 1) doubles,
+	// 74 KB at N = 96) in the cell's shared-memory block; larger models do not fit one SM's shared memory per cell
+	if (!ok || cp->N < 1 || cp->N > 96 || cp->num_cells < 0 || cp->T < 1)
+		return fail(BCM3B200_ERR_ARG, "num_species (1..96), num_variables, num_cells and num_timepoints are required");
+	cp->Nc = get_int(kv, "num_constant_species", 0);
+	cp->Nn = get_int(kv, "num_non_sampled", 0);
+	cp->R = get_int(kv, "num_replicates", 1);
+	cp->D = get_int(kv, "variability_dim", 0);
+	cp->entry_time_ix = get_int(kv, "entry_time_ix", -1);
+	cp->entry_time_fixed = real("entry_time", 0.0);
+	cp->rel_tol = real("solver_relative_tolerance", cp->rel_tol);
+	cp->abs_tol = real("solver_absolute_tolerance", cp->abs_tol);
+	cp->min_dt = real("solver_min_timestep", cp->min_dt);
+	cp->max_steps = get_int(kv, "solver_max_steps", cp->max_steps);
+	const std::string em = kv.count("error_model") ? kv["error_model"] : "normal";
+	if (em == "normal" || em == "additive_normal") cp->error_model = CP_ERR_NORMAL;
+	else if (em == "student_t4" || em == "t4") cp->error_model = CP_ERR_STUDENT_T4;
+	else if (em == "proportional_normal") cp->error_model = CP_ERR_PROPORTIONAL_NORMAL;
+	else if (em == "additive_proportional_normal") cp->error_model = CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL;
+	else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4, proportional_normal, additive_proportional_normal)", em.c_str());
+	cp->treatment_species = get_int(kv, "treatment_species", -1);
+	cp->relative_to_time_average = get_int(kv, "relative_to_time_average", 0) != 0;
+	cp->stdev_relative_to_scale = get_int(kv, "stdev_relative_to_scale", 0) != 0;
+	cp->prop_stdev_ix = get_int(kv, "proportional_stdev_ix", -1);
+	cp->prop_stdev_fixed = real("proportional_stdev", 1.0);
+	const std::string vd = kv.count("variability_distribution") ? kv["variability_distribution"] : "diagonal_gaussian";
+	if (vd == "full_gaussian") cp->full_gaussian = true;
+	else if (vd != "diagonal_gaussian") return fail(BCM3B200_ERR_UNSUPPORTED, "variability_distribution \"%s\" is not supported (diagonal_gaussian, full_gaussian)", vd.c_str());
+	cp->weight = real("weight", 1.0);
+	cp->stdev_ix = get_int(kv, "stdev_ix", -1);
+	cp->stdev_fixed = real("stdev", 1.0);
+	cp->offset_ix = get_int(kv, "offset_ix", -1);
+	cp->offset_fixed = real("offset", 0.0);
+	cp->scale_ix = get_int(kv, "scale_ix", -1);
+	cp->scale_fixed = real("scale", 1.0);
+	cp->missing_simulation_time_stdev = real("missing_simulation_time_stdev", 300.0);
+	cp->have_sim_end_time = kv.count("simulation_end_time") != 0;
+	cp->sim_end_time = real("simulation_end_time", 0.0);
+	if (kv.count("obs_species")) {
+		std::string v = kv["obs_species"];
+		size_t pos = 0;
+		while (pos <= v.size()) {
+			size_t e = v.find('+', pos);
+			if (e == std::string::npos) e = v.size();
+			if (e > pos) cp->obs_species.push_back(atoi(v.substr(pos, e - pos).c_str()));
+			pos = e + 1;
+		}
+	}
+	cp->shard_rank = get_int(kv, "shard_rank", 0);
+	cp->shard_count = get_int(kv, "shard_count", 1);
+	cp->device = get_int(kv, "device", 0);
+	out = std::move(cp);
+	return BCM3B200_OK;
 }
 
 int pick_block_size(const Handle& h, const Shard& s, size_t C)
@@ -462,75 +548,38 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 	if (model_desc && !parse_desc((const char*)model_desc, desc_bytes, kv)) return fail(BCM3B200_ERR_ARG, "malformed model description");
 	std::unique_ptr<Handle> h(new Handle);
 	if (is_cellpop) {
-		std::unique_ptr<CellPopState> cp(new CellPopState);
-		bool ok = true, present;
-		auto need = [&](const char* key) {
-			int v = get_int(kv, key, 0, &present);
-			ok = ok && present;
-			return v;
-		};
-		auto real = [&](const char* key, double def) { return kv.count(key) ? strtod(kv[key].c_str(), nullptr) : def; };
-		cp->N = need("num_species");
-		cp->nvar = need("num_variables");
-		cp->num_cells = need("num_cells");
-		cp->T = need("num_timepoints");
-		// 96 species = the lane-group kernel at 32 lanes x 3 components per lane with the Newton matrix (N x (N | 1) doubles,
-		// 74 KB at N = 96) in the cell's shared-memory block; larger models do not fit one SM's shared memory per cell
-		if (!ok || cp->N < 1 || cp->N > 96 || cp->num_cells < 0 || cp->T < 1)
-			return fail(BCM3B200_ERR_ARG, "num_species (1..96), num_variables, num_cells and num_timepoints are required");
-		cp->Nc = get_int(kv, "num_constant_species", 0);
-		cp->Nn = get_int(kv, "num_non_sampled", 0);
-		cp->R = get_int(kv, "num_replicates", 1);
-		cp->D = get_int(kv, "variability_dim", 0);
-		cp->entry_time_ix = get_int(kv, "entry_time_ix", -1);
-		cp->entry_time_fixed = real("entry_time", 0.0);
-		cp->rel_tol = real("solver_relative_tolerance", cp->rel_tol);
-		cp->abs_tol = real("solver_absolute_tolerance", cp->abs_tol);
-		cp->min_dt = real("solver_min_timestep", cp->min_dt);
-		cp->max_steps = get_int(kv, "solver_max_steps", cp->max_steps);
-		const std::string em = kv.count("error_model") ? kv["error_model"] : "normal";
-		if (em == "normal" || em == "additive_normal") cp->error_model = CP_ERR_NORMAL;
-		else if (em == "student_t4" || em == "t4") cp->error_model = CP_ERR_STUDENT_T4;
-		else if (em == "proportional_normal") cp->error_model = CP_ERR_PROPORTIONAL_NORMAL;
-		else if (em == "additive_proportional_normal") cp->error_model = CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL;
-		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4, proportional_normal, additive_proportional_normal)", em.c_str());
-		cp->treatment_species = get_int(kv, "treatment_species", -1);
-		cp->relative_to_time_average = get_int(kv, "relative_to_time_average", 0) != 0;
-		cp->stdev_relative_to_scale = get_int(kv, "stdev_relative_to_scale", 0) != 0;
-		cp->prop_stdev_ix = get_int(kv, "proportional_stdev_ix", -1);
-		cp->prop_stdev_fixed = real("proportional_stdev", 1.0);
-		const std::string vd = kv.count("variability_distribution") ? kv["variability_distribution"] : "diagonal_gaussian";
-		if (vd == "full_gaussian") cp->full_gaussian = true;
-		else if (vd != "diagonal_gaussian") return fail(BCM3B200_ERR_UNSUPPORTED, "variability_distribution \"%s\" is not supported (diagonal_gaussian, full_gaussian)", vd.c_str());
-		cp->weight = real("weight", 1.0);
-		cp->stdev_ix = get_int(kv, "stdev_ix", -1);
-		cp->stdev_fixed = real("stdev", 1.0);
-		cp->offset_ix = get_int(kv, "offset_ix", -1);
-		cp->offset_fixed = real("offset", 0.0);
-		cp->scale_ix = get_int(kv, "scale_ix", -1);
-		cp->scale_fixed = real("scale", 1.0);
-		cp->missing_simulation_time_stdev = real("missing_simulation_time_stdev", 300.0);
-		cp->have_sim_end_time = kv.count("simulation_end_time") != 0;
-		cp->sim_end_time = real("simulation_end_time", 0.0);
-		if (kv.count("obs_species")) {
-			std::string v = kv["obs_species"];
-			size_t pos = 0;
-			while (pos <= v.size()) {
-				size_t e = v.find('+', pos);
-				if (e == std::string::npos) e = v.size();
-				if (e > pos) cp->obs_species.push_back(atoi(v.substr(pos, e - pos).c_str()));
-				pos = e + 1;
-			}
-		}
-		cp->shard_rank = get_int(kv, "shard_rank", 0);
-		cp->shard_count = get_int(kv, "shard_count", 1);
-		cp->device = get_int(kv, "device", 0);
-		if (device_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "cell_population needs device_count == 1");
-		if (get_int(kv, "compile_only", 0) == 0) {
+		std::unique_ptr<CellPopState> cp;
+		int mrc = make_cellpop_state(kv, cp);
+		if (mrc != BCM3B200_OK) return mrc;
+		if (device_count < 1) return fail(BCM3B200_ERR_ARG, "device_count must be >= 1");
+		if (cp->shard_count < 1 || cp->shard_rank < 0 || cp->shard_rank >= cp->shard_count) return fail(BCM3B200_ERR_ARG, "bad shard_rank / shard_count");
+		const bool compile_only = get_int(kv, "compile_only", 0) != 0;
+		if (!compile_only) {
 			const int ndev = bcm3b200_device_count();
 			if (ndev == 0) return fail(BCM3B200_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
-			if (cp->device < 0 || cp->device >= ndev) return fail(BCM3B200_ERR_CUDA, "device %d requested but only %d visible", cp->device, ndev);
+			if (cp->device < 0 || cp->device + device_count > ndev)
+				return fail(BCM3B200_ERR_CUDA, "devices %d..%d requested but only %d visible", cp->device, cp->device + device_count - 1, ndev);
 		}
+		if (device_count > 1) {
+			// the handle's slice of the cells is split once more over its devices: device d is shard rank * D + d of count * D
+			const int r0 = cp->shard_rank, cnt = cp->shard_count, dev0 = cp->device;
+			for (int d = 0; d < device_count; d++) {
+				std::unique_ptr<CellPopState> more;
+				if (d > 0) {
+					mrc = make_cellpop_state(kv, more);
+					if (mrc != BCM3B200_OK) return mrc;
+				}
+				CellPopState& st = d == 0 ? *cp : *more;
+				st.shard_rank = r0 * device_count + d;
+				st.shard_count = cnt * device_count;
+				st.device = dev0 + d;
+				if (d > 0) h->cp_more.push_back(std::move(more));
+			}
+		}
+		h->device0 = cp->device;
+		h->device_count = device_count;
+		h->shard_rank = get_int(kv, "shard_rank", 0);
+		h->shard_count = get_int(kv, "shard_count", 1);
 		h->cp = std::move(cp);
 		*handle = h.release();
 		return BCM3B200_OK;
@@ -600,8 +649,10 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 		else return fail(BCM3B200_ERR_ARG, "unknown data name \"%s\"", name);
 		const int want_ndim = w1 ? 2 : 1;
 		if (ndim != want_ndim || shape[0] != w0 || (w1 && shape[1] != w1)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);
-		cp.data[n].assign(data, data + w0 * (w1 ? w1 : 1));
-		cp.finalized = false;
+		for (CellPopState* st : cellpop_states(h)) {
+			st->data[n].assign(data, data + w0 * (w1 ? w1 : 1));
+			st->finalized = false;
+		}
 		return BCM3B200_OK;
 	}
 	const size_t P = (size_t)h->P, T = (size_t)h->T;
@@ -628,8 +679,10 @@ int bcm3b200_set_text(void* handle, const char* name, const char* text, size_t t
 	if (!h || !name || !text) return fail(BCM3B200_ERR_ARG, "null argument");
 	if (!h->cp) return fail(BCM3B200_ERR_ARG, "this model kind takes no text inputs");
 	if (strcmp(name, "derivative_code") != 0) return fail(BCM3B200_ERR_ARG, "unknown text name \"%s\"", name);
-	h->cp->derivative_code.assign(text, text_bytes);
-	h->cp->finalized = false;
+	for (CellPopState* st : cellpop_states(h)) {
+		st->derivative_code.assign(text, text_bytes);
+		st->finalized = false;
+	}
 	return BCM3B200_OK;
 }
 
@@ -653,8 +706,95 @@ int bcm3b200_finalize(void* handle)
 {
 	Handle* h = (Handle*)handle;
 	if (!h) return fail(BCM3B200_ERR_ARG, "null handle");
-	if (h->cp) return cellpop_finalize(*h->cp, bcm3b200_device_count() > 0);
+	if (h->cp) {
+		for (CellPopState* st : cellpop_states(h)) {
+			int rc = cellpop_finalize(*st, bcm3b200_device_count() > 0);
+			if (rc != BCM3B200_OK) return rc;
+		}
+		return BCM3B200_OK;
+	}
 	return finalize(h);
+}
+
+// cell_population, host buffers in, complete log-likelihoods out, for every way a handle can be spread:
+//   one device                          -> cellpop_evaluate
+//   one process per GPU + communicator  -> this rank's partial, all-gather + rank-order sum, finish (every rank gets logp)
+//   several devices in this process     -> every device's partial on its own stream, grouped all-gather over the
+//                                          ncclCommInitAll ends, the first device sums in device order and finishes
+static int cellpop_evaluate_handle(Handle* h, size_t C, size_t nvar, const double* values, double* logp, int* status)
+{
+	CellPopState& cp = *h->cp;
+	if (h->cp_more.empty() && !h->comm.active()) return cellpop_evaluate(cp, C, nvar, values, logp, status);
+	if (C == 0) return BCM3B200_OK;
+	const size_t width = 2 * (size_t)cp.T + 1, n = C * width;
+	if (h->cp_more.empty()) {
+		int rc = cellpop_finalize(cp, true);
+		if (rc != BCM3B200_OK) return rc;
+		CUDA_TRY(cudaSetDevice(cp.device));
+		CUDA_TRY(h->xchg.ensure(n));
+		rc = cellpop_enqueue_partial(cp, C, nvar, values, h->xchg.p, cp.stream);
+		if (rc != BCM3B200_OK) return rc;
+		rc = h->comm.gather_combine(h->xchg.p, n, n, h->xchg.p, cp.stream);
+		if (rc != BCM3B200_OK) return rc;
+		cp.total_launches += 2;
+		return cellpop_finish(cp, C, h->xchg.p, logp, status, cp.stream);
+	}
+	std::vector<CellPopState*> states = cellpop_states(h);
+	for (CellPopState* st : states) {
+		int rc = cellpop_finalize(*st, true);
+		if (rc != BCM3B200_OK) return rc;
+	}
+	if (h->dev_comm.empty()) {
+		NcclApi& api = NcclApi::get();
+		if (!api.ok()) return fail(BCM3B200_ERR_CUDA, "NCCL is needed to combine the devices of a cell_population handle and could not be loaded: %s", api.why.c_str());
+		std::vector<int> devs;
+		for (CellPopState* st : states) devs.push_back(st->device);
+		std::vector<ncclComm_t> comms(devs.size());
+		NCCL_TRY(api.CommInitAll(comms.data(), (int)devs.size(), devs.data()));
+		for (size_t d = 0; d < devs.size(); d++) {
+			std::unique_ptr<CommEnd> e(new CommEnd);
+			e->comm = comms[d];
+			e->world = (int)devs.size();
+			e->rank = (int)d;
+			h->dev_comm.push_back(std::move(e));
+		}
+	}
+	for (size_t d = 0; d < states.size(); d++) {
+		CellPopState& st = *states[d];
+		CUDA_TRY(cudaSetDevice(st.device));
+		CUDA_TRY(st.d_partial.ensure(n));
+		CUDA_TRY(h->dev_comm[d]->gathered.ensure(states.size() * n));
+		int rc = cellpop_enqueue_partial(st, C, nvar, values, st.d_partial.p, st.stream);
+		if (rc != BCM3B200_OK) return rc;
+	}
+	NCCL_TRY(NcclApi::get().GroupStart());
+	for (size_t d = 0; d < states.size(); d++) {
+		CUDA_TRY(cudaSetDevice(states[d]->device));
+		int rc = h->dev_comm[d]->gather(states[d]->d_partial.p, n, states[d]->stream);
+		if (rc != BCM3B200_OK) {
+			NcclApi::get().GroupEnd();
+			return rc;
+		}
+	}
+	NCCL_TRY(NcclApi::get().GroupEnd());
+	CUDA_TRY(cudaSetDevice(cp.device));
+	int rc = h->dev_comm[0]->combine(n, n, cp.d_partial.p, cp.stream);
+	if (rc != BCM3B200_OK) return rc;
+	cp.total_launches += 1;
+	rc = cellpop_finish(cp, C, cp.d_partial.p, logp, status, cp.stream);
+	if (rc != BCM3B200_OK) return rc;
+	double max_ms = cp.last_kernel_ms;
+	for (size_t d = 1; d < states.size(); d++) { // the other devices have nothing left but their end of the gather
+		CUDA_TRY(cudaSetDevice(states[d]->device));
+		CUDA_TRY(cudaEventRecord(states[d]->ev1, states[d]->stream));
+		CUDA_TRY(cudaStreamSynchronize(states[d]->stream));
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, states[d]->ev0, states[d]->ev1) == cudaSuccess && ms > max_ms) max_ms = ms;
+		cp.last_launches += states[d]->last_launches;
+	}
+	cp.last_kernel_ms = max_ms;
+	CUDA_TRY(cudaSetDevice(cp.device));
+	return BCM3B200_OK;
 }
 
 // Upload this shard's slice of the host batch in the compact layout [C][16 + 2 * P_shard] and enqueue the kernels on
@@ -692,13 +832,40 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !values || !logp) return fail(BCM3B200_ERR_ARG, "null argument");
-	if (h->cp) return cellpop_evaluate(*h->cp, num_chains, num_variables, values, logp, status);
+	if (h->cp) return cellpop_evaluate_handle(h, num_chains, num_variables, values, logp, status);
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
 	if (rc != BCM3B200_OK) return rc;
 	const size_t C = num_chains;
 	if (C == 0) return BCM3B200_OK;
 	h->last_launches = 0;
+	if (h->comm.active()) {
+		// one process per GPU with the communicator inside the library: this rank's slice, then ONE all-gather of the
+		// [3][C] blocks and their combination in rank order on the device, then 3 C doubles back -- the complete result on
+		// every rank, bit-identical between the ranks
+		Shard* s = h->shards[0].get();
+		CUDA_TRY(cudaSetDevice(s->device));
+		CUDA_TRY(s->partial.ensure(3 * C));
+		if (s->h_partial_n < 3 * C) {
+			if (s->h_partial) cudaFreeHost(s->h_partial);
+			s->h_partial = nullptr;
+			CUDA_TRY(cudaMallocHost((void**)&s->h_partial, sizeof(double) * 3 * C));
+			s->h_partial_n = 3 * C;
+		}
+		rc = upload_and_launch(h, s, C, num_variables, values, s->partial.p, s->stream);
+		if (rc != BCM3B200_OK) return rc;
+		rc = h->comm.gather_combine(s->partial.p, 3 * C, C, s->partial.p, s->stream);
+		if (rc != BCM3B200_OK) return rc;
+		h->last_launches += 2;
+		h->total_launches += 2;
+		CUDA_TRY(cudaMemcpyAsync(s->h_partial, s->partial.p, sizeof(double) * 3 * C, cudaMemcpyDeviceToHost, s->stream));
+		CUDA_TRY(cudaStreamSynchronize(s->stream));
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) h->last_kernel_ms = ms;
+		combine(C, s->h_partial, logp, status);
+		h->num_evaluations += (int64_t)C;
+		return BCM3B200_OK;
+	}
 
 	for (auto& sp : h->shards) {
 		Shard* s = sp.get();
@@ -740,7 +907,10 @@ int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
-	if (h->cp) return cellpop_enqueue_partial(*h->cp, num_chains, num_variables, values, d_partial, (cudaStream_t)stream);
+	if (h->cp) {
+		if (!h->cp_more.empty()) return fail(BCM3B200_ERR_UNSUPPORTED, "device-buffer entries need device_count == 1");
+		return cellpop_enqueue_partial(*h->cp, num_chains, num_variables, values, d_partial, (cudaStream_t)stream);
+	}
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
 	if (rc != BCM3B200_OK) return rc;
@@ -782,6 +952,52 @@ int bcm3b200_cellpop_finish(void* handle, size_t num_chains, const double* d_par
 	if (!h || !d_partial || !logp) return fail(BCM3B200_ERR_ARG, "null argument");
 	if (!h->cp) return fail(BCM3B200_ERR_ARG, "not a cell_population handle");
 	return cellpop_finish(*h->cp, num_chains, d_partial, logp, status, (cudaStream_t)stream);
+}
+
+int bcm3b200_comm_unique_id(void* id, size_t id_bytes)
+{
+	if (!id || id_bytes < sizeof(ncclUniqueId)) return fail(BCM3B200_ERR_ARG, "the id buffer needs %zu bytes (BCM3B200_COMM_ID_BYTES)", sizeof(ncclUniqueId));
+	NcclApi& api = NcclApi::get();
+	if (!api.ok()) return fail(BCM3B200_ERR_CUDA, "NCCL could not be loaded: %s", api.why.c_str());
+	ncclUniqueId uid;
+	NCCL_TRY(api.GetUniqueId(&uid));
+	memset(id, 0, id_bytes);
+	memcpy(id, &uid, sizeof(uid));
+	return BCM3B200_OK;
+}
+
+int bcm3b200_comm_init(void* handle, const void* id, size_t id_bytes)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !id || id_bytes < sizeof(ncclUniqueId)) return fail(BCM3B200_ERR_ARG, "bad argument");
+	if (h->device_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "a communicator joins handles with one device each (device_count == 1)");
+	if (h->comm.comm) return fail(BCM3B200_ERR_STATE, "this handle already has a communicator");
+	const int world = h->cp ? h->cp->shard_count : h->shard_count, rank = h->cp ? h->cp->shard_rank : h->shard_rank;
+	if (world == 1) return BCM3B200_OK; // nothing to exchange
+	NcclApi& api = NcclApi::get();
+	if (!api.ok()) return fail(BCM3B200_ERR_CUDA, "NCCL could not be loaded: %s", api.why.c_str());
+	CUDA_TRY(cudaSetDevice(h->cp ? h->cp->device : h->device0));
+	ncclUniqueId uid;
+	memcpy(&uid, id, sizeof(uid));
+	NCCL_TRY(api.CommInitRank(&h->comm.comm, world, uid, rank));
+	h->comm.world = world;
+	h->comm.rank = rank;
+	return BCM3B200_OK;
+}
+
+int bcm3b200_exchange_partials(void* handle, size_t num_chains, double* d_partial, void* stream)
+{
+	Handle* h = (Handle*)handle;
+	if (!h || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (num_chains == 0 || !h->comm.active()) return BCM3B200_OK;
+	CUDA_TRY(cudaSetDevice(h->cp ? h->cp->device : h->device0));
+	const size_t C = num_chains;
+	int rc;
+	if (h->cp) rc = h->comm.gather_combine(d_partial, C * (2 * (size_t)h->cp->T + 1), C * (2 * (size_t)h->cp->T + 1), d_partial, (cudaStream_t)stream);
+	else rc = h->comm.gather_combine(d_partial, 3 * C, C, d_partial, (cudaStream_t)stream);
+	if (rc != BCM3B200_OK) return rc;
+	(h->cp ? h->cp->total_launches : h->total_launches) += 2;
+	return BCM3B200_OK;
 }
 
 int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* logp, int* status)
@@ -829,12 +1045,14 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 	Handle* h = (Handle*)handle;
 	if (!h || !name) return fail(BCM3B200_ERR_ARG, "null argument");
 	if (h->cp) {
-		if (!strcmp(name, "diagnostics")) h->cp->diagnostics = value != 0;
-		else if (!strcmp(name, "cellpop_kernel")) h->cp->kernel_choice = (int)value; // 0 auto, 1 one cell per warp, 2 one cell per thread, 3 one cell per lane group
-		else if (!strcmp(name, "cellpop_steps_report")) h->cp->steps_report = (int)value;
-		else if (!strcmp(name, "cellpop_rhs_lanes")) { h->cp->rhs_lanes = value != 0; h->cp->finalized = false; } // before finalize: lane-parallel right-hand side (default on)
-		else if (!strcmp(name, "cellpop_group_lanes")) h->cp->group_lanes = (int)value; // before finalize: lanes per cell of the group kernel (0 auto)
-		else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
+		for (CellPopState* st : cellpop_states(h)) {
+			if (!strcmp(name, "diagnostics")) st->diagnostics = value != 0;
+			else if (!strcmp(name, "cellpop_kernel")) st->kernel_choice = (int)value; // 0 auto, 1 one cell per warp, 2 one cell per thread, 3 one cell per lane group
+			else if (!strcmp(name, "cellpop_steps_report")) st->steps_report = (int)value;
+			else if (!strcmp(name, "cellpop_rhs_lanes")) { st->rhs_lanes = value != 0; st->finalized = false; } // before finalize: lane-parallel right-hand side (default on)
+			else if (!strcmp(name, "cellpop_group_lanes")) st->group_lanes = (int)value; // before finalize: lanes per cell of the group kernel (0 auto)
+			else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
+		}
 		return BCM3B200_OK;
 	}
 	if (!strcmp(name, "diagnostics")) h->diagnostics = value != 0;
@@ -895,7 +1113,16 @@ void bcm3b200_destroy(void* handle)
 {
 	Handle* h = (Handle*)handle;
 	if (!h) return;
-	for (auto& sp : h->shards) cudaSetDevice(sp->device);
+	for (auto& sp : h->shards) {
+		cudaSetDevice(sp->device);
+		cudaDeviceSynchronize();
+	}
+	for (CellPopState* st : cellpop_states(h)) {
+		if (st->stream) {
+			cudaSetDevice(st->device);
+			cudaStreamSynchronize(st->stream);
+		}
+	}
 	delete h;
 }
 

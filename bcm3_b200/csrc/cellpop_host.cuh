@@ -69,7 +69,7 @@ struct CellPopState {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<double> d_ic, d_const, d_nonsampled, d_sobol, d_time, d_obs, d_values, d_transformed, d_cellvals, d_avg, d_logp;
 	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail, d_cov_ix, d_cell_order;
-	DevBuf<double> d_cov_fixed, d_chol, d_treatment_times;
+	DevBuf<double> d_cov_fixed, d_chol, d_treatment_times, d_partial;
 	bool diagnostics = false;
 	int last_C = 0;
 	double last_kernel_ms = 0.0;

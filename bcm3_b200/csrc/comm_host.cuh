@@ -45,12 +45,20 @@ struct NcclApi {
 private:
 	void load()
 	{
-		const char* names[] = { getenv("BCM3B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
-		for (const char* n : names) {
-			if (!n || !*n) continue;
-			lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+		// Order: an explicit override; the copy this process already carries (PyTorch bundles one under the same soname, and the
+		// dynamic loader resolves a later DT_NEEDED "libnccl.so.2" to whatever object of that soname is loaded first -- loading
+		// the system library ahead of `import torch` would hand torch a libnccl it was not built against); the system library.
+		if (const char* over = getenv("BCM3B200_NCCL_LIB")) {
+			if (*over) {
+				lib = dlopen(over, RTLD_NOW | RTLD_GLOBAL);
+				if (!lib) why = dlerror();
+			}
+		}
+		if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+		for (const char* n : { "libnccl.so.2", "libnccl.so" }) {
 			if (lib) break;
-			why = dlerror();
+			lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+			if (!lib) why = dlerror();
 		}
 		if (!lib) return;
 		bool all = true;

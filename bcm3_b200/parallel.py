@@ -1,11 +1,13 @@
-"""One process per GPU: patients sharded across ranks, per-chain partials combined with an all-reduce.
+"""One process per GPU: patients / cells sharded across ranks, per-chain partials combined inside the library.
 
 The path shards naturally: given a chain's parameter vector every patient is independent, so
-rank g owns a contiguous slice of the patients for ALL chains and the only exchange is the reduction of the
+rank g owns a contiguous slice of the patients for ALL chains and the only exchange is the combination of the
 [3][C] partial block (bcm3b200.h): SUM of the finite per-patient terms, MIN of the first -inf / first NaN patient
-index.  Over NCCL that is two tiny all-reduces on the device, stream-ordered right behind the reduction kernel;
-the combination rule then reproduces the reference's serial loop (LikelihoodPopPKTrajectory.cpp:427-440)
-independently of the number of ranks.
+index.  The exchange is the LIBRARY's (csrc/comm_host.cuh: one NCCL all-gather stream-ordered right behind the
+reduction kernel + a rank-order combination kernel, bit-identical on every rank); the combination rule then reproduces
+the reference's serial loop (LikelihoodPopPKTrajectory.cpp:427-440) independently of the number of ranks.
+torch.distributed is used for ONE thing here: handing rank 0's communicator id to the other ranks (a C++ host would use
+MPI_Bcast or a file for that).
 """
 from __future__ import annotations
 
@@ -41,6 +43,20 @@ def partial_from_patient_ll(patient_ll: np.ndarray, offset: int) -> np.ndarray:
     return out
 
 
+def share_comm_id(group=None) -> bytes | None:
+    """Rank 0 asks the library for a communicator id and the process group hands it to everyone (any backend: the id is
+    128 plain bytes). None when there is one rank only."""
+    import torch.distributed as dist
+
+    from . import _lib
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    box = [_lib.comm_unique_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return box[0]
+
+
 def allreduce_partial(partial, group=None):
     """In-place all-reduce of a torch tensor [3][C]: SUM on row 0, MIN on rows 1-2 (NCCL on device, gloo on host)."""
     import torch.distributed as dist
@@ -56,7 +72,7 @@ class ShardedPopPKLikelihood:
     """Rank-local GPU evaluator + the cross-rank reduction. Every rank ends up with the same logp[C]
     (so the host-side, deterministic proposal / swap logic can run replicated)."""
 
-    def __init__(self, problem, rank: int, world_size: int, device: int, group=None, block_size: int = 0):
+    def __init__(self, problem, rank: int, world_size: int, device: int, group=None, block_size: int = 0, library_comm: bool = True):
         import torch
 
         from .poppk import PopPKEvaluator
@@ -68,6 +84,10 @@ class ShardedPopPKLikelihood:
         self.nvar = problem.num_variables
         self._partial = None
         self._h_partial = None
+        # the library's own communicator (default); library_comm=False keeps the exchange in torch.distributed (two all-reduces)
+        self.library_comm = library_comm and world_size > 1
+        if self.library_comm:
+            self.evaluator.comm_init(share_comm_id(group))
 
     def _buffers(self, C: int):
         torch = self.torch
@@ -84,11 +104,17 @@ class ShardedPopPKLikelihood:
         partial, _ = self._buffers(C)
         stream = torch.cuda.current_stream(self.device)
         self.evaluator.enqueue(values_host.data_ptr(), C, self.nvar, partial.data_ptr(), stream.cuda_stream)
-        allreduce_partial(partial, self.group)
+        if self.library_comm:
+            self.evaluator.exchange(partial.data_ptr(), C, stream.cuda_stream)
+        else:
+            allreduce_partial(partial, self.group)
         return partial
 
     def evaluate(self, values_host):
-        """Full end-to-end call: H2D of this rank's slice, kernels, all-reduce, D2H, combination."""
+        """Full end-to-end call: H2D of this rank's slice, kernels, exchange, D2H, combination. With the library's
+        communicator this is ONE C-ABI call (bcm3b200_evaluate_batch), exactly what a C++ host makes."""
+        if self.library_comm:
+            return self.evaluator.evaluate(values_host.numpy())
         partial = self.enqueue(values_host)
         _, h = self._buffers(values_host.shape[0])
         h.copy_(partial, non_blocking=True)
@@ -126,7 +152,7 @@ class ShardedCellPopLikelihood:
     """Rank-local GPU evaluator over this rank's slice of the simulated cells + one SUM all-reduce of the per-chain
     partials; every rank ends up with the same logp[C]."""
 
-    def __init__(self, problem, rank: int, world_size: int, device: int, group=None, kernel: str = "auto"):
+    def __init__(self, problem, rank: int, world_size: int, device: int, group=None, kernel: str = "auto", library_comm: bool = True):
         import torch
 
         from .cellpop import CellPopEvaluator
@@ -138,11 +164,16 @@ class ShardedCellPopLikelihood:
         self.nvar = problem.num_variables
         self.width = 2 * problem.num_timepoints + 1
         self._partial = None
+        self.library_comm = library_comm and world_size > 1
+        if self.library_comm:
+            self.evaluator.comm_init(share_comm_id(group))
 
     def evaluate(self, values_host):
         """values_host: torch CPU tensor [C][nvar] float64. H2D, kernels, all-reduce, data likelihood, D2H of logp."""
         torch = self.torch
         C = values_host.shape[0]
+        if self.library_comm:  # one C-ABI call: partial, all-gather + rank-order sum, data likelihood, logp back
+            return self.evaluator.evaluate(values_host.numpy())
         if self._partial is None or self._partial.shape[0] != C:
             self._partial = torch.empty((C, self.width), dtype=torch.float64, device=self.device)
         stream = torch.cuda.current_stream(self.device)

@@ -111,6 +111,15 @@ class PopPKEvaluator:
         _lib.check(self.lib.bcm3b200_enqueue_batch(self.handle, nC, nvar, values_ptr, d_partial_ptr, stream or None))
         self._last_C = nC
 
+    def comm_init(self, comm_id: bytes) -> None:
+        """Collective over the ranks (one process per GPU): attach the library's NCCL communicator; afterwards evaluate()
+        returns the complete result on every rank. comm_id: _lib.comm_unique_id() of rank 0, handed round by the caller."""
+        _lib.check(self.lib.bcm3b200_comm_init(self.handle, comm_id, len(comm_id)))
+
+    def exchange(self, d_partial_ptr: int, nC: int, stream: int = 0) -> None:
+        """In-place all-gather + rank-order combination of a device partial block, asynchronous on `stream`."""
+        _lib.check(self.lib.bcm3b200_exchange_partials(self.handle, nC, d_partial_ptr, stream or None))
+
     def combine_partials(self, partial: np.ndarray):
         partial = np.ascontiguousarray(partial, dtype=np.float64)
         nC = partial.shape[1]

@@ -14,14 +14,14 @@ reference counts in Sampler.cpp:129-134).
 
   value  device-timed (CUDA events on the launching stream), parameter vectors already resident in HBM
   e2e    the same steps through the reference-facing call with HOST buffers: pinned host values -> H2D of the
-         rank's slice -> kernels -> (NCCL all-reduce) -> D2H of the result, wall-clock with a device sync
+         rank's slice -> kernels -> (the library's NCCL all-gather + rank-order combination) -> D2H of the result, wall-clock with a device sync
   roofline       dominant kernel (poppk_kernel) against the FP64 FMA peak measured live on this GPU
   cpu_baseline   the reference's CPU implementation (oracle/_ref = its own compiled CVODE stack; else the plain-C
                  port) timed on the box's host cores on a bounded sample of the same workload (rank 0, N=1 only)
 
 --impl reference times only that CPU implementation, one bounded sample per step, same metric and config.
 N > 1: launched by torchrun, one rank per GPU; patients are sharded across ranks (strong scaling on the named
-workload), per-chain partials combined by an NCCL all-reduce; time = max over ranks.
+workload), per-chain partials combined inside the library (NCCL all-gather + rank-order combination); time = max over ranks.
 """
 from __future__ import annotations
 
@@ -159,7 +159,7 @@ def cellpop_cpu_sample(prob, vals, sample: int, cores: int):
 
 def cellpop_line(args, workload: str, steps: int, warmup: int, ctx: dict):
     """One complete JSON line (a dict, rank 0; None elsewhere) for a cell_population workload: single GPU, or the cells split over
-    the ranks of the torchrun launch (strong scaling, one SUM all-reduce of [C][2 T + 1] doubles)."""
+    the ranks of the torchrun launch (strong scaling, one all-gather + rank-order sum of [C][2 T + 1] doubles inside the library)."""
     import torch
 
     from bcm3_b200 import _lib
@@ -209,9 +209,9 @@ def cellpop_line(args, workload: str, steps: int, warmup: int, ctx: dict):
         ev = lk.evaluator
 
         def step():
-            return lk.evaluate(h_vals)  # H2D of the batch, kernels, all-reduce, data likelihood, D2H of logp
+            return lk.evaluate(h_vals)  # ONE C-ABI call: H2D of the batch, kernels, library exchange, data likelihood, D2H of logp
         closer = lk
-        config["sharding"] = f"cells over {world} ranks, SUM all-reduce of [{C}][{2 * w['T'] + 1}] doubles"
+        config["sharding"] = f"cells over {world} ranks; library exchange: NCCL all-gather of [{C}][{2 * w['T'] + 1}] doubles per rank + rank-order sum"
 
     for _ in range(warmup):
         flush.zero_()
@@ -432,10 +432,8 @@ def poppk_line(args, workload: str, steps: int, warmup: int, ctx: dict):
 
     def device_step():
         ev.evaluate_device(d_vals.data_ptr(), C, nvar, d_partial.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            from bcm3_b200.parallel import allreduce_partial
-
-            allreduce_partial(d_partial)
+        if world > 1:  # the library's exchange: one NCCL all-gather + rank-order combination, on the same stream
+            ev.exchange(d_partial.data_ptr(), C, stream.cuda_stream)
 
     fp64_peak = ctx["fp64_peak"]
 
@@ -519,7 +517,7 @@ def poppk_line(args, workload: str, steps: int, warmup: int, ctx: dict):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "pk_model": w["pk"], "individuals": P, "chains": C, "timepoints": T, "t_end_h": w["t_end"],
-                       "ode_solves_per_step": C * P, "sharding": f"individuals over {world} rank(s), NCCL all-reduce of [3][{C}] doubles",
+                       "ode_solves_per_step": C * P, "sharding": f"individuals over {world} rank(s); library exchange: NCCL all-gather of [3][{C}] doubles per rank + rank-order combination",
                        "l2": "256 MB memset between timed iterations", "block_size": args.block_size or "auto"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": ncu_traffic(workload), "kernel": "poppk_kernel", "kernel_ms": k_ms,

@@ -54,7 +54,7 @@ extern "C" {
  *                  biphasic types: biphasic_uptake_time_ix= mean_absorption2_ix=    cpp:296-310)
  *                  [shard_rank=0] [shard_count=1]   contiguous slice of patients owned by this handle
  *                  [device=0]                       first CUDA device ordinal
- *   device_count: number of CUDA devices (device .. device+device_count-1) this handle spreads its patients
+ *   device_count: number of CUDA devices (device .. device+device_count-1) this handle spreads its patients / cells
  *                over inside this process; 1 for the one-process-per-GPU launch.
  * Replaces: LikelihoodFactory::CreateLikelihood -> make_shared<LikelihoodPopPKTrajectory> + Initialize
  *           (LikelihoodFactory.cpp:31-101). */
@@ -123,6 +123,29 @@ int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables
  * data likelihood and the -inf verdict for failed cells, exactly as the unsharded bcm3b200_evaluate_batch does.
  * bcm3b200_get_stat(h, "partial_doubles_per_chain") = 2 T + 1. Synchronises `stream` before returning. */
 int bcm3b200_cellpop_finish(void* handle, size_t num_chains, const double* d_partial, double* logp, int* status, void* stream);
+
+/* ---- the exchange step inside the library (NCCL over NVLink / NVSwitch) ----
+ * One process per GPU: every rank creates its handle with shard_rank = its rank and shard_count = the number of ranks,
+ * rank 0 obtains an id with bcm3b200_comm_unique_id and hands it to the other ranks by whatever means the host program has
+ * (MPI_Bcast, a file, a socket: it is BCM3B200_COMM_ID_BYTES of plain bytes = an ncclUniqueId), then EVERY rank calls
+ * bcm3b200_comm_init (collective). From then on
+ *   bcm3b200_evaluate_batch        returns the COMPLETE per-chain log-likelihoods on every rank (both model kinds): this
+ *                                  rank's slice, one all-gather of the per-rank partial blocks stream-ordered behind the
+ *                                  reduction kernel, their combination in rank order on the device -- bit-identical on all
+ *                                  ranks and from run to run, which an all-reduce does not promise --, 3 C doubles back;
+ *   bcm3b200_exchange_partials     is that exchange alone, in place on a device block produced by bcm3b200_enqueue_batch /
+ *                                  bcm3b200_evaluate_batch_device ([3][C] for pop_pk_trajectory: SUM row 0, MIN rows 1-2;
+ *                                  [C][2 T + 1] for cell_population: SUM), enqueued on `stream`, no synchronisation.
+ * Without a communicator (shard_count == 1, or bcm3b200_comm_init never called) the exchange is a no-op and a sharded
+ * handle yields its partial as described above. NCCL is loaded at run time (libnccl.so.2; BCM3B200_NCCL_LIB overrides).
+ * Replaces: nothing in the reference (its evaluation threads share one address space, SamplerPT.cpp:438-475); this is the
+ * ownership row of the multi-GPU design.
+ * cell_population handles created with device_count > 1 spread their cells over the devices of ONE process and combine
+ * them the same way over ncclCommInitAll communicators inside bcm3b200_evaluate_batch. */
+#define BCM3B200_COMM_ID_BYTES 128
+int bcm3b200_comm_unique_id(void* id, size_t id_bytes);
+int bcm3b200_comm_init(void* handle, const void* id, size_t id_bytes);
+int bcm3b200_exchange_partials(void* handle, size_t num_chains, double* d_partial, void* stream);
 
 /* partial [3][num_chains] (host) -> logp[num_chains], status[num_chains] (may be NULL) */
 int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* logp, int* status);

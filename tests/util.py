@@ -125,7 +125,8 @@ def parity_tolerance(noise_floor=None):
     reference itself is reproducible at that level, and twice the reference's own measured irreproducibility elsewhere.
 
     `noise_floor` (per chain) is how far the reference's result moves between builds of its own sources that differ only in
-    compiler flags (FMA contraction of the solver / of the generated right-hand side): tests/golden/measure_noise_floor.py
+    compiler flags (FMA contraction of the solver / of the generated right-hand side) and when its inputs move by one unit in
+    the last place: tests/golden/measure_noise_floor.py
     stores it in every golden fixture, reference_noise_floor_cellpop() measures it for fresh inputs. It is ONE draw of a
     round-off-driven quantity (a step-size decision flips or it does not), so the bound is twice the draw, not the draw."""
     if noise_floor is None:
@@ -144,7 +145,8 @@ def assert_logp_parity(got, want, noise_floor=None, what=""):
 
 def reference_noise_floor_cellpop(prob, vals, threads=4):
     """The same measurement as tests/golden/measure_noise_floor.py for fresh inputs: the compiled reference (A) against its
-    -ffp-contract=off build (B) and against itself with the generated right-hand side compiled with contraction (C).
+    -ffp-contract=off build (B), against itself with the generated right-hand side compiled with contraction (C) and against
+    itself at inputs one unit in the last place away (D).
     Returns (logp_A result dict, per-chain floor, fraction of cells with identical step counts between the builds), or
     None when the reference builds are not present (container without /root/reference and without a shipped oracle/_ref)."""
     import oracle
@@ -163,6 +165,12 @@ def reference_noise_floor_cellpop(prob, vals, threads=4):
         oracle.rhs_build = "strict"
     floor = np.maximum(rel_err(rb["logp"], ra["logp"]), rel_err(rc["logp"], ra["logp"]))
     steps = min((ra["cell_steps"] == rb["cell_steps"]).mean(), (ra["cell_steps"] == rc["cell_steps"]).mean())
+    # (D) the reference at inputs moved by one unit in the last place, both directions: its own conditioning. Small models give
+    # the compiler nothing to contract, so A == B == C there says nothing about how sensitive the step decisions are.
+    for direction in (np.inf, -np.inf):
+        rd = a.cellpop_evaluate(prob, np.nextafter(np.asarray(vals, dtype=np.float64), direction), threads=threads, want_steps=True)
+        floor = np.maximum(floor, rel_err(rd["logp"], ra["logp"]))
+        steps = min(steps, (ra["cell_steps"] == rd["cell_steps"]).mean())
     return ra, floor, float(steps)
 
 
@@ -177,13 +185,25 @@ def _strict_oracle(path):
     return _strict_cache[path]
 
 
-def cellpop_step_match_floor(gold_or_fraction):
-    """Fraction of cells whose accepted-step count must equal the reference's: half of the fraction on which the reference's
-    own builds agree with each other (`noise_floor_step_match`: 0.06 on the stiff fixture, 0.12-0.24 with pulsed treatments,
-    0.7-0.98 elsewhere) -- equal step counts mean the same step-size/order decisions, and a round-off-sized difference flips
-    them at the reference's own rate."""
-    frac = gold_or_fraction["noise_floor_step_match"] if isinstance(gold_or_fraction, dict) else gold_or_fraction
-    return 0.5 * float(frac)
+def cellpop_step_match_floor(gold_or_fraction, num_solves=None):
+    """Fraction of cells whose accepted-step count must equal the reference's. Equal step counts mean the same step-size/order
+    decisions, and a round-off-sized difference flips them at the reference's own rate: `noise_floor_step_match` is the
+    fraction on which the reference's own builds agree with each other (0.06 on the stiff fixture, 0.12-0.24 with pulsed
+    treatments, 0.7-0.98 elsewhere). The expected agreement of an independent implementation is taken as half of that, and the
+    assertion allows the binomial scatter of the count over the fixture's solves (two standard deviations): on the stiff
+    fixture (48 solves, 3 of which agree between the reference's builds) that leaves no requirement at all -- step counts
+    cannot demonstrate control-flow fidelity there; the mean step count (asserted separately, 2 %) and the parity of the
+    result are what is checked."""
+    if isinstance(gold_or_fraction, dict):
+        frac = float(gold_or_fraction["noise_floor_step_match"])
+        if num_solves is None and "cell_steps" in gold_or_fraction:
+            num_solves = int(np.asarray(gold_or_fraction["cell_steps"]).size)
+    else:
+        frac = float(gold_or_fraction)
+    q = 0.5 * frac
+    if not num_solves:
+        return q
+    return max(0.0, q - 2.0 * np.sqrt(q * (1.0 - q) / num_solves))
 
 
 # ---- cell_population through the C++ plugin surface: prior.xml / likelihood.xml of the synthetic models ----
