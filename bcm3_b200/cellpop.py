@@ -14,8 +14,9 @@ from .cellpop_data import CellPopProblem
 class CellPopEvaluator:
     def __init__(self, problem: CellPopProblem, device: int = 0, compile_only: bool = False, kernel: str = "auto",
                  shard_rank: int = 0, shard_count: int = 1, rhs_lanes: bool | None = None, device_count: int = 1):
-        """rhs_lanes: None = the library's default (the lane-parallel right-hand side wherever the generated text can be regrouped),
-        False = evaluate the generated text as it stands (every lane of a cell's group runs every rate law)."""
+        """rhs_lanes: None = the library's default (the lane-parallel right-hand side for models with 16 or 32 lanes per cell),
+        False = evaluate the generated text as it stands (every lane of a cell's group runs every rate law), "always" = regroup
+        the text whenever it can be parsed, whatever the number of lanes per cell."""
         self.lib = _lib.load()
         self.problem = p = problem
         kv = dict(
@@ -62,7 +63,7 @@ class CellPopEvaluator:
             _lib.check(self.lib.bcm3b200_set_text(self.handle, b"derivative_code", code, len(code)))
             _lib.check(self.lib.bcm3b200_set_option(self.handle, b"cellpop_kernel", {"auto": 0, "warp": 1, "thread": 2, "group": 3}[kernel]))
             if rhs_lanes is not None:
-                _lib.check(self.lib.bcm3b200_set_option(self.handle, b"cellpop_rhs_lanes", int(rhs_lanes)))
+                _lib.check(self.lib.bcm3b200_set_option(self.handle, b"cellpop_rhs_lanes", 2 if rhs_lanes == "always" else int(bool(rhs_lanes))))
             _lib.check(self.lib.bcm3b200_finalize(self.handle))
         except Exception:
             self.close()

@@ -1049,7 +1049,7 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 			if (!strcmp(name, "diagnostics")) st->diagnostics = value != 0;
 			else if (!strcmp(name, "cellpop_kernel")) st->kernel_choice = (int)value; // 0 auto, 1 one cell per warp, 2 one cell per thread, 3 one cell per lane group
 			else if (!strcmp(name, "cellpop_steps_report")) st->steps_report = (int)value;
-			else if (!strcmp(name, "cellpop_rhs_lanes")) { st->rhs_lanes = value != 0; st->finalized = false; } // before finalize: lane-parallel right-hand side (default on)
+			else if (!strcmp(name, "cellpop_rhs_lanes")) { st->rhs_lanes = (int)value; st->finalized = false; } // before finalize: lane-parallel right-hand side, 0 never / 1 where it pays (default) / 2 always
 			else if (!strcmp(name, "cellpop_group_lanes")) st->group_lanes = (int)value; // before finalize: lanes per cell of the group kernel (0 auto)
 			else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
 		}

@@ -62,7 +62,7 @@ struct CellPopState {
 	int kernel_choice = 0; // 0 auto (lane groups for N <= 96, one cell per warp above), 1 warp, 2 thread, 3 group
 	int built_kernel = 0;  // the one kernel the model library was compiled with (1, 2 or 3)
 	int group_lanes = 0;   // 0 auto: smallest power of two with ceil(N / G) <= 3
-	bool rhs_lanes = true; // option "cellpop_rhs_lanes": lane-parallel right-hand side where the generated text can be regrouped (cellpop_lane_rhs)
+	int rhs_lanes = 1;     // option "cellpop_rhs_lanes": lane-parallel right-hand side (cellpop_lane_rhs): 0 never, 1 where it pays (16 or 32 lanes per cell), 2 wherever the text can be regrouped
 	DevBuf<double> d_scratch;
 	std::string module_path;
 	cudaStream_t stream = nullptr;
@@ -720,7 +720,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 		const char* renv = getenv("BCM3B200_CELLPOP_RHS_LANES");
 		// default: models with 16 or 32 lanes per cell (measured: 50 species 1 933 -> 1 464 ms; with 4 lanes per cell and 8 cells
 		// per warp the per-shape loops diverge between the groups and the scalar text is faster, 143 vs 178 ms at 12 species)
-		const bool want = renv ? atoi(renv) != 0 : (cp.rhs_lanes && G >= 16);
+		const bool want = renv ? atoi(renv) != 0 : (cp.rhs_lanes == 2 || (cp.rhs_lanes == 1 && G >= 16));
 		if (want && cellpop_resolve_kernel(cp) == 3) lanes = cellpop_lane_rhs(code.substr(at), cp.N);
 	}
 	size_t per_cell;

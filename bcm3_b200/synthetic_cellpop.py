@@ -92,7 +92,9 @@ def _py_helpers():
         return 0.5 * k * (ekms - math.sqrt(max(ekms * ekms - 4 * e * s, 0.0)))
 
     return dict(
-        hill_function_fixedn2=lambda x, k: hill(x, k, 2), hill_function_fixedn4=lambda x, k: hill(x, k, 4),
+        hill_function=hill, hill_function_fixedn2=lambda x, k: hill(x, k, 2), hill_function_fixedn4=lambda x, k: hill(x, k, 4),
+        hill_function_fixedn10=lambda x, k: hill(x, k, 10), hill_function_fixedn16=lambda x, k: hill(x, k, 16),
+        hill_function_fixedn100=lambda x, k: hill(x, k, 100), safepow=lambda x, n: 0.0 if x < 0 else x ** n, exp=math.exp, log=math.log,
         michaelis_menten_function=mm, tQSSA=tq, synthcap=lambda x: 1.0 if x <= 0 else 1.0 - x ** 10)
 
 
@@ -104,9 +106,9 @@ def python_rhs(code: str, N: int):
     helpers = _py_helpers()
     nr = int(re.search(r"ratelaws\[(\d+)\];", code).group(1))
 
-    def f(t, y, constant_species, parameters):
+    def f(t, y, constant_species, parameters, non_sampled_parameters=()):
         env = dict(helpers)
-        env.update(species=y, constant_species=constant_species, parameters=parameters, non_sampled_parameters=[],
+        env.update(species=y, constant_species=constant_species, parameters=parameters, non_sampled_parameters=non_sampled_parameters,
                    ratelaws=[0.0] * nr, out=[0.0] * N)
         exec(compiled, env)
         return env["out"]

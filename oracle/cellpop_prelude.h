@@ -1,8 +1,8 @@
 // TEST INFRASTRUCTURE ONLY -- cellpop_prelude.h -- host restatement of the helper functions the reference prepends to its generated
 // derivative code (src/cellpop/SolverCodeGenerator.cpp:122-295), including their quirks (SURVEY.md App. D #6:
-// hill_function_fixedn2 returns 10.0 on overflow, hill_function_fixedn16 has a no-op overflow test). Only the
-// helpers used by generated_derivative are needed: the generated Jacobian is never installed by the reference
-// (src/cellpop/Cell.cpp:57-76), so its *_derivative helpers are omitted.
+// hill_function_fixedn2 returns 10.0 on overflow, hill_function_fixedn16 has a no-op overflow test). The
+// *_derivative helpers are only called by generated_jacobian, which the reference compiles into the same file and never
+// installs (src/cellpop/Cell.cpp:57-76); they are here so that real generator output compiles as it does on the reference side.
 #pragma once
 
 #include <cfloat>
@@ -133,4 +133,51 @@ static inline OdeReal tQSSA(OdeReal k, OdeReal km, OdeReal e, OdeReal s)
 {
 	OdeReal ekms = e + km + s;
 	return 0.5 * k * (ekms - sqrt(ekms * ekms - 4 * e * s));
+}
+
+// ---- helpers of generated_jacobian (SolverCodeGenerator.cpp:218-230, 241-258, 268-279, 285-294); compiled, never called ----
+static inline OdeReal hill_function_derivative(OdeReal x, OdeReal k, OdeReal n)
+{
+	if (x <= 0.0) return 0.0;
+	OdeReal xn = pow(x, n);
+	OdeReal kn = pow(k, n);
+	OdeReal denom = (square(xn + kn));
+	if (denom < CP_REAL_MIN) return 0.0;
+	if (denom > 3e38f) return 0.0;
+	OdeReal xnm1 = pow(x, n - 1);
+	return kn * n * xnm1 / denom;
+}
+static inline OdeReal michaelis_menten_derivative_enzyme(OdeReal kcat, OdeReal KM, OdeReal e, OdeReal s)
+{
+	if (e <= 0) return 0.0;
+	if (s + KM < 0.1 * KM) {
+		OdeReal bound = -KM + 0.1 * KM;
+		OdeReal offset = (kcat * bound / (0.01 * KM) - kcat * bound / (KM + bound));
+		return kcat * s / (0.01 * KM) - offset;
+	}
+	return kcat * s / (KM + s);
+}
+static inline OdeReal michaelis_menten_derivative_substrate(OdeReal kcat, OdeReal KM, OdeReal e, OdeReal s)
+{
+	if (e <= 0) return 0.0;
+	if (s + KM <= 0.1 * KM) return e * kcat / (0.01 * KM);
+	return e * kcat * KM / (square(KM + s));
+}
+static inline OdeReal synthcap_derivative(OdeReal x, OdeReal dx)
+{
+	if (x <= 0) return 0.0;
+	OdeReal x2 = x * x;
+	OdeReal x4 = x2 * x2;
+	OdeReal x8 = x4 * x4;
+	return -10.0 * x8 * x * dx;
+}
+static inline OdeReal tQSSA_derivative_enzyme(OdeReal k, OdeReal km, OdeReal e, OdeReal s)
+{
+	OdeReal ekms = e + km + s;
+	return k * (0.5 - 0.5 * (km - s + e) / (sqrt(ekms * ekms - 4 * e * s)));
+}
+static inline OdeReal tQSSA_derivative_substrate(OdeReal k, OdeReal km, OdeReal e, OdeReal s)
+{
+	OdeReal ekms = e + km + s;
+	return k * (0.5 - 0.5 * (km + s - e) / (sqrt(ekms * ekms - 4 * e * s)));
 }

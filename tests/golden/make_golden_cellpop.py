@@ -41,6 +41,10 @@ CASES = {
     "cellpop_n8_treatment_pulses_longer": (dict(N=8, num_cells=40, T=20, t_end=40.0, data_cells=4, seed=27), 2,
                                            dict(treatment_species=0, treatment_times=np.array([20.0, 1.0, 45.0]), obs_species=[0, 2], entry_time=4.0,
                                                 simulation_end_time=55.0)),
+    # the model text is the OUTPUT OF THE REFERENCE'S OWN SBML CODE GENERATOR (tests/golden/make_golden_sbml.py): 13 species, 24
+    # reactions, hill_function with a non-integer exponent, the fixed-exponent variants 2/4/10/16/100, michaelis_menten_function,
+    # tQSSA, safepow, synthcap, exp, a division, a non-sampled parameter, three constant species, stoichiometry 2
+    "cellpop_sbml_cell_cycle": (dict(_builder="sbml_cell_cycle", num_cells=48, T=14), 3, {}),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
@@ -54,10 +58,18 @@ def main():
             continue
         tweaks = dict(tweaks)
         positive = tweaks.pop("_positive_data", False)
-        prob = dataclasses.replace(sc.make_cellpop_problem(**kw), **tweaks)
+        kw = dict(kw)
+        if kw.pop("_builder", None) == "sbml_cell_cycle":
+            from tests.util import sbml_cell_cycle_problem, sbml_cell_cycle_values
+
+            prob = sbml_cell_cycle_problem(**kw)
+            fixed_values = sbml_cell_cycle_values(C)
+        else:
+            prob = dataclasses.replace(sc.make_cellpop_problem(**kw), **tweaks)
+            fixed_values = None
         if positive:  # a proportional error model has sigma = 0 (log-density NaN) at data <= 0
             prob = dataclasses.replace(prob, observed=np.abs(prob.observed) + 0.05)
-        vals = sc.make_chain_values(C, seed=zlib.crc32(name.encode()) % 10000)
+        vals = fixed_values if fixed_values is not None else sc.make_chain_values(C, seed=zlib.crc32(name.encode()) % 10000)
         r = ref.cellpop_evaluate(prob, vals, threads=1, want_cell_values=True, want_steps=True, want_average=True)
         out = {f.name: getattr(prob, f.name) for f in dataclasses.fields(prob) if f.name not in ("variability", "covariance")}
         out["covariance_rows"] = prob.covariance_rows()

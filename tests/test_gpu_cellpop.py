@@ -1,6 +1,8 @@
 """GPU suite for the cell_population path: the CUDA integrators (compiled per model from the generated RHS text; the lane-group
 mapping is the default, the one-cell-per-warp and one-cell-per-thread mappings are kept selectable) through the C ABI, against
 the golden vectors of the compiled reference and against the CPU checker on fresh inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -139,6 +141,30 @@ def test_lane_group_shapes_against_cpu_checker(Evaluator, checker, N, decades):
     assert abs(d["cell_steps"].mean() / want["cell_steps"].mean() - 1.0) < 0.02
 
 
+@pytest.mark.parametrize("case", ["cellpop_sbml_cell_cycle", "cellpop_n24_stiff", "fresh_n33"])
+def test_lane_parallel_rhs_is_bit_identical(Evaluator, case):
+    """The regrouped right-hand side (cellpop_host.cuh::cellpop_lane_rhs: lanes evaluate different reactions of one shape at the
+    same time, species sums assembled term by term in the order of the text) performs the same IEEE operations on the same
+    operands as the generated text evaluated as it stands: every trajectory value and every step count must be the same bits.
+    Includes the fixture whose text came out of the reference's own generator (21 shapes for 24 reactions)."""
+    if case == "fresh_n33":
+        prob = sc.make_cellpop_problem(N=33, num_cells=64, T=12, data_cells=4, seed=73, rate_decades=3.0)
+        vals = sc.make_chain_values(2, seed=33)
+    else:
+        prob, gold = load_cellpop_golden(case)
+        vals = gold["values"]
+    out = []
+    for lanes in (False, "always"):
+        ev = Evaluator(prob, rhs_lanes=lanes)
+        logp, _ = ev.evaluate(vals)
+        d = ev.diagnostics()
+        ev.close()
+        out.append((logp, d))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1]["cell_values"], out[1][1]["cell_values"], equal_nan=True)
+    assert np.array_equal(out[0][1]["cell_steps"], out[1][1]["cell_steps"])
+
+
 def test_config3_full_size_properties(Evaluator, checker):
     """BASELINE config 3 at full size (12 species, 10 000 cells, 50 timepoints, 16 chains), through properties that do not
     need the checker to run the whole thing: (1) the first 192 cells' trajectories equal the checker's, (2) reversing the
@@ -185,6 +211,43 @@ def test_config3_full_size_properties(Evaluator, checker):
     for s in shards:
         s.close()
     assert rel_err(combined, logp).max() < 1e-9
+
+
+def test_config4_full_size_against_the_reference(Evaluator, checker):
+    """BASELINE.json config 4 as named: ~50-species stiff network, 100 000 cells, 16 chains. (1) ONE WHOLE CHAIN at full size
+    -- every one of the 100 000 cells integrated by the compiled reference on the host cores -- against the GPU's per-chain
+    log-likelihood and population average; (2) the first 200 cells' trajectories of two chains; (3) the whole 16-chain batch
+    runs, and a chain's result does not depend on the batch it is evaluated in."""
+    import dataclasses
+
+    prob = sc.make_cellpop_problem(N=50, num_cells=100_000, T=50, data_cells=32, seed=1, rate_decades=4.0)
+    vals = sc.make_chain_values(16)
+    threads = max(1, os.cpu_count() or 1)
+    ev = Evaluator(prob)
+    one, status = ev.evaluate(vals[3:4])
+    d = ev.diagnostics()
+    assert status[0] == 0 and (d["cell_status"] == 1).all()
+    # (1): the floor is the reference's own movement under its compiler flags and 1-ulp inputs, on this very input
+    m = reference_noise_floor_cellpop(prob, vals[3:4], threads=threads)
+    if m is None:
+        want, floor = checker.cellpop_evaluate(prob, vals[3:4], threads=threads, want_average=True, want_steps=True), None
+    else:
+        want, floor, _ = m
+    assert_logp_parity(one, want["logp"], floor, "config 4, one whole chain")
+    assert np.abs(d["population_average"] - want["population_average"]).max() < 1e-6
+    assert abs(d["cell_steps"].mean() / want["cell_steps"].mean() - 1.0) < 0.005
+    # (2)
+    sub = dataclasses.replace(prob, num_cells=200, sobol=prob.sobol[:200])
+    ws = checker.cellpop_evaluate(sub, vals[[3]], threads=threads, want_cell_values=True)
+    got = d["cell_values"][:, :, :200]
+    assert (np.isnan(got) == np.isnan(ws["cell_values"])).all()
+    mk = ~np.isnan(got)
+    assert np.abs(got[mk] - ws["cell_values"][mk]).max() < 5e-5
+    # (3)
+    logp, status = ev.evaluate(vals)
+    ev.close()
+    assert (status == 0).all() and np.isfinite(logp).all()
+    assert logp[3] == one[0]
 
 
 def test_stdev_relative_to_scale(Evaluator, checker):

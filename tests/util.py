@@ -206,6 +206,71 @@ def cellpop_step_match_floor(gold_or_fraction, num_solves=None):
     return max(0.0, q - 2.0 * np.sqrt(q * (1.0 - q) / num_solves))
 
 
+# ---- the fixture whose model text came out of the reference's own SBML code generator (tests/golden/make_golden_sbml.py) ----
+def sbml_cell_cycle_problem(num_cells=48, T=14, t_end=30.0, data_cells=8, seed=31):
+    """13-species cell-cycle network, `derivative_code` = tests/golden/sbml_cell_cycle_generated.txt verbatim (species order,
+    printed constants and helper calls as SBMLModel::GenerateCode chose them). The read-out is CycE + CycEp27
+    (species_name="CycE+CycEp27"), per-cell variability on k_syn and k_deg and on the initial amount of Rb."""
+    import math
+
+    from scipy.integrate import solve_ivp
+    from scipy.special import ndtri
+
+    from bcm3_b200 import synthetic_cellpop as sc
+    from bcm3_b200.cellpop_data import CellPopProblem, Variability
+    from bcm3_b200.poppk_data import TRANSFORM_LOG10, TRANSFORM_NONE
+
+    text = open(os.path.join(GOLDEN_DIR, "sbml_cell_cycle_generated.txt")).read()
+    header = {}
+    for line in text.splitlines():
+        if line.startswith("// ") and ":" in line:
+            key, _, rest = line[3:].partition(":")
+            header[key.strip()] = rest.split()
+    species = header["ode_species"]
+    ic = np.array([float(x) for x in header["ode_initial"]])
+    const = np.array([float(x) for x in header["constant_initial"]])
+    code = text[text.index("EXPORT_PREFIX"):]
+    N = len(species)
+    names = header["variables"]
+    transforms = np.full(len(names), TRANSFORM_LOG10, dtype=np.int32)
+    transforms[names.index("variability_scale")] = TRANSFORM_NONE
+    timepoints = t_end * np.arange(T) / (T - 1.0)
+    variability = [Variability(apply="multiplicative_log", model_parameter=names.index("k_syn"), scale_ix=names.index("variability_scale")),
+                   Variability(apply="multiplicative_log", model_parameter=names.index("k_deg"), scale_ix=names.index("variability_scale"), negate=True),
+                   Variability(apply="additive", initial_condition_species=species.index("Rb"), scale_fixed=math.log(0.02))]
+    sobol = sc.sobol_points(num_cells, len(variability))
+    obs = [species.index("CycE"), species.index("CycEp27")]
+    non_sampled = np.array([0.01])  # basal
+    v = sbml_cell_cycle_values(1)[0]
+    tv = np.where(transforms == TRANSFORM_LOG10, 10.0 ** v, v)
+    f = sc.python_rhs(code, N)
+    acc = np.zeros(T)
+    rng = np.random.default_rng(seed)
+    u = sc.sobol_points(data_cells, len(variability))
+    for ci in range(data_cells):
+        p = tv.copy()
+        y0 = ic.copy()
+        z = ndtri(u[ci]) * math.exp(tv[names.index("variability_scale")])
+        p[names.index("k_syn")] *= math.exp(z[0])
+        p[names.index("k_deg")] *= math.exp(-z[1])
+        y0[species.index("Rb")] += ndtri(u[ci][2]) * 0.02
+        sol = solve_ivp(lambda t, y: f(t, y, const, p, non_sampled), (0.0, float(timepoints[-1])), y0, method="LSODA", t_eval=timepoints, rtol=1e-7, atol=1e-9)
+        acc += sol.y[obs].sum(axis=0)
+    observed = (acc / data_cells)[None, :] + 0.01 * rng.standard_normal((1, T))
+    return CellPopProblem(derivative_code=code, num_species=N, initial_conditions=ic, transforms=transforms, num_cells=num_cells, timepoints=timepoints,
+                          observed=observed, obs_species=obs, constant_species=const, non_sampled_parameters=non_sampled, sobol=sobol,
+                          variability=variability, stdev_ix=names.index("stdev"))
+
+
+def sbml_cell_cycle_values(C, seed=77):
+    """[C][6] sampled values (k_syn, k_deg, k_act, k_inh as log10; variability_scale natural log of the s.d.; stdev log10)."""
+    import math
+
+    base = np.array([math.log10(0.6), math.log10(0.4), math.log10(1.2), math.log10(0.8), math.log(0.2), math.log10(0.02)])
+    rng = np.random.default_rng(seed)
+    return base[None, :] + rng.normal(0.0, 0.05, (C, 6))
+
+
 # ---- cell_population through the C++ plugin surface: prior.xml / likelihood.xml of the synthetic models ----
 CELLPOP_VARIABLE_NAMES = ["k_in", "k_cascade", "k_deg", "k_feedback", "variability_scale", "stdev"]
 
