@@ -35,6 +35,16 @@ class CellPopEvaluator:
             kv["treatment_species"] = p.treatment_species
         if p.simulation_end_time is not None:
             kv["simulation_end_time"] = repr(float(p.simulation_end_time))
+        if np.isfinite(p.solver_max_timestep):
+            kv["solver_max_timestep"] = repr(float(p.solver_max_timestep))
+        if p.divide_cells:
+            kv["divide_cells"] = 1
+            kv["max_cells"] = int(p.max_cells)
+            if p.cytokinesis_species is not None:
+                kv["cytokinesis_species"] = int(p.cytokinesis_species)
+            kv["division_reset_species"] = "+".join(str(int(i)) for i in p.division_reset_species)
+        if p.apoptosis_species is not None:
+            kv["apoptosis_species"] = int(p.apoptosis_species)
         for name in ("entry_time", "stdev", "offset", "scale", "proportional_stdev"):
             ix = getattr(p, name + "_ix")
             if ix is not None:
@@ -55,7 +65,7 @@ class CellPopEvaluator:
             if p.treatment_species is not None and len(p.treatment_times):
                 self._set("treatment_times", np.asarray(p.treatment_times, dtype=np.float64))
             if p.variability_dim:
-                self._set("sobol", np.asarray(p.sobol, dtype=np.float64).reshape(p.num_cells, p.variability_dim))
+                self._set("sobol", np.asarray(p.sobol, dtype=np.float64).reshape(-1, p.variability_dim))
                 self._set("variability", p.variability_rows())
                 if p.variability_distribution == "full_gaussian" and p.variability_dim > 1:
                     self._set("variability_covariance", p.covariance_rows())
@@ -117,7 +127,7 @@ class CellPopEvaluator:
         return int(v.value)
 
     def diagnostics(self):
-        nC, nc, T = self._last_C, self.problem.num_cells, self.problem.num_timepoints
+        nC, nc, T = self._last_C, self.get_stat("cell_columns"), self.problem.num_timepoints
         vals = np.empty((nC, T, nc))
         status = np.empty((nC, nc), dtype=np.int32)
         steps = np.empty((nC, nc), dtype=np.int32)

@@ -33,11 +33,14 @@ class Variability:
     # <variable entry_time=...>: the reference reads it, gives it a quasi-random dimension and never applies it
     # (VariabilityDescription::ApplyVariabilityEntryTime has no caller); kind 2 of the ABI's variability rows
     entry_time: bool = False
+    # <variable only_initial_cells="true">: applied to cells whose "initial cell" flag is set only -- not to daughters, and (a
+    # quirk of Experiment.cpp:662-670) not to the single initial cell of a num_cells="1" experiment; + 4 on the kind column
+    only_initial_cells: bool = False
 
     def row(self):
         is_ic = self.initial_condition_species is not None
         target = 0 if self.entry_time else (self.initial_condition_species if is_ic else self.model_parameter)
-        return [2.0 if self.entry_time else float(is_ic), float(target), float(APPLY_TYPES[self.apply]), float(-1 if self.scale_ix is None else self.scale_ix),
+        return [(2.0 if self.entry_time else float(is_ic)) + (4.0 if self.only_initial_cells else 0.0), float(target), float(APPLY_TYPES[self.apply]), float(-1 if self.scale_ix is None else self.scale_ix),
                 float(self.scale_fixed), float(self.negate)]
 
 
@@ -82,7 +85,23 @@ class CellPopProblem:
     solver_relative_tolerance: float = 4 * FLT_EPSILON   # Experiment.cpp:415-416
     solver_absolute_tolerance: float = 4 * FLT_EPSILON
     solver_min_timestep: float = 1e-8                     # Experiment.cpp:412
+    solver_max_timestep: float = float("inf")             # Experiment.cpp:413 -> CVodeSetMaxStep (0 / inf: no ceiling)
     solver_max_steps: int = 10000                         # Experiment.cpp:414
+    # <experiment divide_cells="true" max_cells=>: a cell whose ODE species "cytokinesis" exceeds 1 after a step ends there and two
+    # daughters start from its state with seven named species reset (Experiment.cpp:726-782, Cell.cpp:119-148, 463-538);
+    # a cell whose "apoptosis" species exceeds 1 ends. Species are given by index; `sobol` then has more rows than num_cells
+    # (the reference makes 100 * num_cells): daughters of the cell with row r take rows num_cells + 2 r + child.
+    divide_cells: bool = False
+    max_cells: int = 0
+    cytokinesis_species: int | None = None
+    apoptosis_species: int | None = None
+    # indices of cytokinesis, nuclear_envelope, G1S_break, G2_break, spindle_components, assembled_spindle, chromatid_separation
+    division_reset_species: tuple = ()
+
+    @property
+    def capacity(self) -> int:
+        """Number of cell columns of every per-cell output: max_cells for a dividing population, num_cells otherwise."""
+        return int(self.max_cells) if self.divide_cells else int(self.num_cells)
 
     @property
     def num_variables(self) -> int:

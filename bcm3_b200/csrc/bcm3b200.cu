@@ -170,6 +170,7 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 	cp->rel_tol = real("solver_relative_tolerance", cp->rel_tol);
 	cp->abs_tol = real("solver_absolute_tolerance", cp->abs_tol);
 	cp->min_dt = real("solver_min_timestep", cp->min_dt);
+	cp->max_dt = real("solver_max_timestep", cp->max_dt);
 	cp->max_steps = get_int(kv, "solver_max_steps", cp->max_steps);
 	const std::string em = kv.count("error_model") ? kv["error_model"] : "normal";
 	if (em == "normal" || em == "additive_normal") cp->error_model = CP_ERR_NORMAL;
@@ -208,6 +209,23 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 	cp->shard_rank = get_int(kv, "shard_rank", 0);
 	cp->shard_count = get_int(kv, "shard_count", 1);
 	cp->device = get_int(kv, "device", 0);
+	// dividing / dying cells (Experiment.cpp:488-489 divide_cells, max_cells; Cell.cpp:40-55 the species found by name)
+	cp->divide_cells = get_int(kv, "divide_cells", 0) != 0;
+	cp->max_cells = get_int(kv, "max_cells", cp->num_cells);
+	cp->cytokinesis_ix = get_int(kv, "cytokinesis_species", -1);
+	cp->apoptosis_ix = get_int(kv, "apoptosis_species", -1);
+	cp->sobol_rows = cp->num_cells;
+	if (kv.count("division_reset_species")) {
+		std::string v = kv["division_reset_species"];
+		size_t pos = 0;
+		int k = 0;
+		while (pos <= v.size() && k < 7) {
+			size_t e = v.find('+', pos);
+			if (e == std::string::npos) e = v.size();
+			if (e > pos) cp->reset_ix[k++] = atoi(v.substr(pos, e - pos).c_str());
+			pos = e + 1;
+		}
+	}
 	out = std::move(cp);
 	return BCM3B200_OK;
 }
@@ -639,7 +657,12 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 		if (n == "initial_conditions") w0 = cp.N;
 		else if (n == "constant_species") w0 = cp.Nc;
 		else if (n == "non_sampled_parameters") w0 = cp.Nn;
-		else if (n == "sobol") { w0 = cp.num_cells; w1 = cp.D; }
+		else if (n == "sobol") {
+			// a dividing population takes rows beyond its initial cells (daughters of row r: num_cells + 2 r + child,
+			// CellPopulation.cpp:75; the reference makes 100 * num_cells rows, VariabilityPseudoRandomIterator.cpp:17)
+			w0 = (cp.divide_cells && shape[0] >= (size_t)cp.num_cells) ? shape[0] : (size_t)cp.num_cells;
+			w1 = cp.D;
+		}
 		else if (n == "timepoints") w0 = cp.T;
 		else if (n == "observed") { w0 = cp.R; w1 = cp.T; }
 		else if (n == "transforms") w0 = cp.nvar;
@@ -651,6 +674,7 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 		if (ndim != want_ndim || shape[0] != w0 || (w1 && shape[1] != w1)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);
 		for (CellPopState* st : cellpop_states(h)) {
 			st->data[n].assign(data, data + w0 * (w1 ? w1 : 1));
+			if (n == "sobol") st->sobol_rows = (int)w0;
 			st->finalized = false;
 		}
 		return BCM3B200_OK;
@@ -694,7 +718,7 @@ int bcm3b200_get_cell_diagnostics(void* handle, double* cell_values, int32_t* ce
 	if (!cp.finalized || cp.last_C == 0) return fail(BCM3B200_ERR_STATE, "no evaluation yet");
 	CUDA_TRY(cudaSetDevice(cp.device));
 	CUDA_TRY(cudaDeviceSynchronize());
-	const size_t C = (size_t)cp.last_C, nc = (size_t)cp.cells_local, T = (size_t)cp.T;
+	const size_t C = (size_t)cp.last_C, nc = (size_t)cp.capacity(), T = (size_t)cp.T; // max_cells columns for a dividing population
 	if (cell_values) CUDA_TRY(cudaMemcpy(cell_values, cp.d_cellvals.p, sizeof(double) * C * T * nc, cudaMemcpyDeviceToHost));
 	if (cell_status) CUDA_TRY(cudaMemcpy(cell_status, cp.d_status.p, sizeof(int32_t) * C * nc, cudaMemcpyDeviceToHost));
 	if (cell_steps) CUDA_TRY(cudaMemcpy(cell_steps, cp.d_steps.p, sizeof(int32_t) * C * nc, cudaMemcpyDeviceToHost));
@@ -1076,6 +1100,7 @@ int bcm3b200_get_stat(void* handle, const char* name, int64_t* value)
 		else if (!strcmp(name, "num_evaluations")) *value = cp.num_evaluations;
 		else if (!strcmp(name, "last_kernel_us")) *value = (int64_t)(cp.last_kernel_ms * 1000.0);
 		else if (!strcmp(name, "num_cells_local")) *value = cp.cells_local;
+		else if (!strcmp(name, "cell_columns")) *value = cp.capacity();
 		else if (!strcmp(name, "partial_doubles_per_chain")) *value = 2 * cp.T + 1;
 		else return fail(BCM3B200_ERR_ARG, "unknown stat \"%s\"", name);
 		return BCM3B200_OK;

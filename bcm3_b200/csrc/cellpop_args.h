@@ -49,6 +49,7 @@ struct CpArgs {
 	double sim_end_time;
 	// solver (Experiment.cpp:411-416, Cell.cpp:70-74)
 	double rel_tol, abs_tol, min_dt;
+	double max_dt_inv; // CVodeSetMaxStep(solver_max_timestep): 1 / hmax, 0 = no ceiling (Experiment.cpp:413, Cell.cpp:73, cvode_io.c:344-376)
 	int max_steps;
 	// observed species: sum of these ODE-integrated species per timepoint
 	int num_obs_species;
@@ -62,6 +63,24 @@ struct CpArgs {
 	// one <treatment_trajectory type="pulses"> (TreatmentTrajectoryPulses.cpp): constant species it drives (-1: none)
 	int treatment_species, treatment_num_pulses;
 	const double* treatment_times; // [treatment_num_pulses] sorted
+	// ---- dividing and dying cells (group kernel built with CP_DIVISION; Experiment.cpp:726-782, CellPopulation.cpp:36-104,
+	// Cell.cpp:119-148, 463-538, the branch without stored integration points). The population is integrated one generation at
+	// a time: `items` lists the (chain, slot) pairs of the generation, the per-cell records say when a cell was created, which
+	// quasi-random row it takes and which cell it inherits its state from; a cell whose "cytokinesis" / "apoptosis" species
+	// exceeds 1 after an accepted step ends there and leaves its state behind for its daughters.
+	int var_only_initial[CP_MAX_VARIABILITY]; // <variable only_initial_cells="true">: skipped unless the cell's "initial cell" flag is set
+	int initial_flag;     // the flag of the experiment's first cells: 1 when num_cells > 1, 0 for a single cell (Experiment.cpp:662-670); daughters: 0
+	int cell_stride;      // cell columns of cell_values / cell_status / cell_steps and of the records below (num_cells when nothing divides)
+	int cytokinesis_ix, apoptosis_ix; // ODE species indices, -1: none
+	int reset_ix[7];      // species a daughter resets to 0, 1, 1, 1, 0, 0, 0 (Cell.cpp:127-133)
+	const int32_t* items; // [num_items][2] (chain, slot), or null: every cell of every chain
+	int num_items;
+	const double* cell_creation; // [C][stride] absolute creation time
+	const int32_t* cell_row;     // [C][stride] quasi-random row
+	const int32_t* cell_parent;  // [C][stride] slot of the parent, -1: an initial cell
+	double* cell_end_y;          // [C][stride][N] y after the step that ended a dividing cell
+	double* cell_end_time;       // [C][stride] absolute time at which the cell's integration ended (division, death or the end of the experiment)
+	int32_t* cell_event;         // [C][stride] 0 none, 1 divided, 2 died
 };
 
 #ifdef __CUDACC__

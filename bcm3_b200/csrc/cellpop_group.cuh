@@ -176,6 +176,11 @@ __device__ __noinline__ void rhs_eval_lanes(unsigned y_off, unsigned f_off, unsi
 #ifndef CP_GROUP_LOCKSTEP
 #define CP_GROUP_LOCKSTEP 1
 #endif
+// 1: dividing / dying cells (CpArgs: items, per-cell records, event species). The model library of an experiment without
+// divide_cells and without an "apoptosis" species is built with 0 and contains none of that code.
+#ifndef CP_DIVISION
+#define CP_DIVISION 0
+#endif
 #ifndef CP_GROUP_BATCHED
 #define CP_GROUP_BATCHED 1
 #endif
@@ -234,7 +239,7 @@ struct GroupBdf {
 	const double* constant_species;
 	const double* non_sampled;
 	const double* tv; // transformed variables of the cell's chain
-	double reltol, abstol, hmin;
+	double reltol, abstol, hmin, hmax_inv;
 	// pulsed treatment (TreatmentTrajectoryPulses.cpp): constant species it drives (-1: none), sorted pulse times
 	int treat_ix, treat_n;
 	const double* treat_times;
@@ -454,6 +459,10 @@ struct GroupBdf {
 			if (h0 > hub) h0 = hub;
 			if (sign < 0.0) h0 = -h0;
 			h = h0;
+		}
+		if (hmax_inv > 0.0) { // cvode.c:1121-1122 (a step-size ceiling is rare: the division stays out of the common path)
+			const double rh = fabs(h) * hmax_inv;
+			if (rh > 1.0) h /= rh;
 		}
 		if (fabs(h) < hmin) h *= hmin / fabs(h);
 		if (tstopset) {
@@ -1358,6 +1367,7 @@ struct GroupBdf {
 						hprime() = h;
 					} else {
 						eta() = fmin(eta(), etamax_now);
+						if (hmax_inv > 0.0) eta() /= fmax(1.0, fabs(h) * hmax_inv * eta()); // cvSetEta, cvode.c:3142-3143 (dividing by 1 changes nothing)
 						hprime() = h * eta();
 					}
 				}
@@ -1498,9 +1508,15 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 	B.reltol = a.rel_tol;
 	B.abstol = a.abs_tol;
 	B.hmin = a.min_dt;
+	B.hmax_inv = a.max_dt_inv;
 
 	const int T = a.T;
+#if CP_DIVISION
+	const long long total = a.items ? (long long)a.num_items : (long long)a.num_chains * a.num_cells;
+#else
 	const long long total = (long long)a.num_chains * a.num_cells;
+#endif
+	const long long stride = a.cell_stride; // cell columns of the per-cell outputs
 	const double nan = __longlong_as_double(0x7ff8000000000000ll);
 
 	// per-lane multiplicity of owned components in the observed-species list, 4 bits per slot
@@ -1546,9 +1562,19 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				exhausted = true;
 			} else {
 #endif
-				c = (int)(w / (unsigned long long)a.num_cells);
-				cell = (int)(w % (unsigned long long)a.num_cells);
-				if (a.cell_order) cell = a.cell_order[cell];
+#if CP_DIVISION
+				int parent = -1;
+				if (a.items) { // one generation of a dividing population: (chain, slot) pairs
+					c = a.items[2 * w];
+					cell = a.items[2 * w + 1];
+					parent = a.cell_parent[(long long)c * stride + cell];
+				} else
+#endif
+				{
+					c = (int)(w / (unsigned long long)a.num_cells);
+					cell = (int)(w % (unsigned long long)a.num_cells);
+					if (a.cell_order) cell = a.cell_order[cell];
+				}
 				const double* tv = a.transformed + (long long)c * a.nvar;
 				B.tv = tv;
 				// per-cell parameter overrides: start from the chain's values (CP_OVERRIDE_INIT fills S.params.ov[]), apply the
@@ -1564,8 +1590,32 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				double y0[E];
 #pragma unroll
 				for (int e = 0; e < E; e++) y0[e] = B.own(e) ? a.initial_conditions[B.idx(e)] : 0.0;
-				const long long gcell = (long long)a.cell_offset + cell;
+				long long gcell = (long long)a.cell_offset + cell;
+#if CP_DIVISION
+				bool initial_flag = a.initial_flag != 0;
+				if (a.items) {
+					gcell = a.cell_row[(long long)c * stride + cell];
+					if (parent >= 0) {
+						// Cell::SetInitialConditionsFromOtherCell (Cell.cpp:119-148): the parent's state at its division, seven species reset
+						initial_flag = false;
+						const double* py = a.cell_end_y + ((long long)c * stride + parent) * N;
+#pragma unroll
+						for (int e = 0; e < E; e++) {
+							if (B.own(e)) {
+								double v = py[B.idx(e)];
+#pragma unroll
+								for (int k = 0; k < 7; k++)
+									if (B.idx(e) == a.reset_ix[k]) v = (k >= 1 && k <= 3) ? 1.0 : 0.0;
+								y0[e] = v;
+							}
+						}
+					}
+				}
+#endif
 				for (int d = 0; d < a.D; d++) {
+#if CP_DIVISION
+					if (a.var_only_initial[d] && !initial_flag) continue; // VariabilityDescriptionVariable.cpp:66-110
+#endif
 					double v = cellpop_variability_value(a, tv, c, gcell, d);
 					if (a.var_negate[d]) v = -v;
 					if (a.var_is_ic[d]) {
@@ -1580,9 +1630,12 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 #pragma unroll
 				for (int s = 0; s < (CP_NUM_OVERRIDES > 0 ? CP_NUM_OVERRIDES : 1); s++) B.sc[SC_OV + s] = ovl[s];
 				// ---- Cell::Simulate + ODESolver::SolveReturnSolution + ODESolverCVODE::Solve: the part before the first step ----
-				const double creation_time = (a.entry_time_ix >= 0) ? tv[a.entry_time_ix] : a.entry_time_fixed;
+				double creation_time = (a.entry_time_ix >= 0) ? tv[a.entry_time_ix] : a.entry_time_fixed;
+#if CP_DIVISION
+				if (a.items) creation_time = a.cell_creation[(long long)c * stride + cell];
+#endif
 				B.sc[SC_CREATION] = creation_time;
-				out = a.cell_values + ((long long)c * T) * a.num_cells + cell;
+				out = a.cell_values + ((long long)c * T) * stride + cell;
 				ok = true;
 				steps = 0;
 				tpi = 0;
@@ -1594,7 +1647,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				sv0 = B.gsum(sv0);
 				while (tpi < T && (a.timepoints[tpi] - creation_time) < DBL_EPSILON) {
 					const double cell_time = a.timepoints[tpi] - creation_time;
-					if (B.lg == 0) out[(long long)tpi * a.num_cells] = (cell_time < 0.0) ? nan : sv0;
+					if (B.lg == 0) out[(long long)tpi * stride] = (cell_time < 0.0) ? nan : sv0;
 					tpi++;
 				}
 				const double end_time = a.sim_end_time - creation_time;
@@ -1617,9 +1670,15 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				if (finished) {
 					if (B.lg == 0) {
 						if (!ok)
-							for (int k = tpi; k < T; k++) out[(long long)k * a.num_cells] = nan;
-						a.cell_status[(long long)c * a.num_cells + cell] = ok ? 1 : 0;
-						if (a.cell_steps) a.cell_steps[(long long)c * a.num_cells + cell] = 0;
+							for (int k = tpi; k < T; k++) out[(long long)k * stride] = nan;
+						a.cell_status[(long long)c * stride + cell] = ok ? 1 : 0;
+						if (a.cell_steps) a.cell_steps[(long long)c * stride + cell] = 0;
+#if CP_DIVISION
+						if (a.items) {
+							a.cell_event[(long long)c * stride + cell] = 0;
+							a.cell_end_time[(long long)c * stride + cell] = a.sim_end_time;
+						}
+#endif
 					}
 				} else {
 					have = true;
@@ -1663,10 +1722,45 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 #pragma unroll
 					for (int e = 0; e < E; e++) obs_weight[e] = (double)((obs_count >> (4 * e)) & 15u);
 					const double sv = B.dky_weighted(tq, obs_weight);
-					if (B.lg == 0) out[(long long)tpi * a.num_cells] = sv;
+					if (B.lg == 0) out[(long long)tpi * stride] = sv;
 					tpi++;
 				}
+#if CP_DIVISION
+				// Cell::integration_step_cb (Cell.cpp:463-538, the branch without stored integration points), called by the solver
+				// after the outputs of the step and before its own end test (ODESolverCVODE.cpp:431-441): a cell whose
+				// "cytokinesis" (divide_cells) or "apoptosis" species has passed 1 ends at this step, with this state
 				if (ok) {
+					int ev = 0;
+					if (a.cytokinesis_ix >= 0 || a.apoptosis_ix >= 0) {
+						double ycyt = 0.0, yapo = 0.0;
+#pragma unroll
+						for (int e = 0; e < E; e++) {
+							if (B.idx(e) == a.cytokinesis_ix) ycyt = yout[e];
+							if (B.idx(e) == a.apoptosis_ix) yapo = yout[e];
+						}
+						if (a.cytokinesis_ix >= 0) ycyt = __shfl_sync(B.gmask, ycyt, B.gbase + a.cytokinesis_ix % G);
+						if (a.apoptosis_ix >= 0) yapo = __shfl_sync(B.gmask, yapo, B.gbase + a.apoptosis_ix % G);
+						if (a.cytokinesis_ix >= 0 && ycyt > 1.0) ev |= 1;
+						if (a.apoptosis_ix >= 0 && yapo > 1.0) ev |= 2;
+					}
+					if (ev) {
+						const long long rec = (long long)c * stride + cell;
+						if (ev & 1) {
+#pragma unroll
+							for (int e = 0; e < E; e++)
+								if (B.own(e)) a.cell_end_y[rec * N + B.idx(e)] = yout[e];
+						}
+						if (B.lg == 0) {
+							a.cell_event[rec] = ev;
+							a.cell_end_time[rec] = tret + creation_time;
+							for (int k = tpi; k < T; k++) out[(long long)k * stride] = nan; // the cell does not exist after the event
+						}
+						tpi = T;
+						done = true;
+					}
+				}
+#endif
+				if (ok && !done) {
 					if (tret >= B.sc[SC_END]) done = true;
 					else if (steps == a.max_steps) {
 						ok = false;
@@ -1694,10 +1788,10 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 		if (have && done) {
 			if (B.lg == 0) {
 				if (!ok)
-					for (int k = tpi; k < T; k++) out[(long long)k * a.num_cells] = nan;
-				a.cell_status[(long long)c * a.num_cells + cell] = ok ? 1 : 0;
+					for (int k = tpi; k < T; k++) out[(long long)k * stride] = nan;
+				a.cell_status[(long long)c * stride + cell] = ok ? 1 : 0;
 				if (a.cell_steps)
-					a.cell_steps[(long long)c * a.num_cells + cell] = (a.debug_report == 1) ? B.nfe : (a.debug_report == 2) ? B.nsetups : (a.debug_report == 3) ? B.nje : steps;
+					a.cell_steps[(long long)c * stride + cell] = (a.debug_report == 1) ? B.nfe : (a.debug_report == 2) ? B.nsetups : (a.debug_report == 3) ? B.nje : steps;
 			}
 			have = false;
 		}
@@ -1746,7 +1840,7 @@ extern "C" int cellpop_group_launch(const CpArgs* args, double* scratch, void* s
 	int err = 0;
 	int blocks = cellpop_group::resident_blocks(&err);
 	if (blocks <= 0) return err ? err : 1;
-	const long long total = (long long)args->num_chains * args->num_cells;
+	const long long total = args->items ? (long long)args->num_items : (long long)args->num_chains * args->num_cells;
 	const long long per_block = cellpop_group::WPB * cellpop_group::CPW;
 	const long long needed = (total + per_block - 1) / per_block;
 	if (needed < blocks) blocks = (int)(needed > 0 ? needed : 1);

@@ -31,6 +31,7 @@ struct CellPopState {
 	double entry_time_fixed = 0.0;
 	double rel_tol = 4.0 * 1.1920928955078125e-07, abs_tol = 4.0 * 1.1920928955078125e-07; // 4 * FLT_EPSILON, Experiment.cpp:415-416
 	double min_dt = 1e-8;                                                                   // Experiment.cpp:412
+	double max_dt = std::numeric_limits<double>::infinity();                                // Experiment.cpp:413 solver_max_timestep
 	int max_steps = 10000;                                                                  // Experiment.cpp:414
 	int error_model = CP_ERR_NORMAL;
 	double weight = 1.0;
@@ -46,6 +47,16 @@ struct CellPopState {
 	int treatment_species = -1;                   // <treatment_trajectory type="pulses" species_name=...>: constant species index
 	std::vector<int> obs_species;
 	int shard_rank = 0, shard_count = 1, device = 0;
+	// <experiment divide_cells="true" max_cells=> and the species the reference's cell events are built around (by index):
+	// Experiment.cpp:726-782, Cell.cpp:119-148, 463-538
+	bool divide_cells = false;
+	int max_cells = 0, cytokinesis_ix = -1, apoptosis_ix = -1, sobol_rows = 0;
+	int reset_ix[7] = { -1, -1, -1, -1, -1, -1, -1 };
+	bool division() const { return (divide_cells && cytokinesis_ix >= 0) || apoptosis_ix >= 0; } // the model library carries the event code
+	int capacity() const { return division() ? (divide_cells ? max_cells : cells_local) : cells_local; }
+	DevBuf<double> d_creation, d_end_y, d_end_time;
+	DevBuf<int32_t> d_row, d_parent, d_event, d_items, d_wave, d_item_offsets;
+	std::vector<int32_t> h_wave;
 	std::string derivative_code;
 	std::map<std::string, std::vector<double>> data;
 	// derived
@@ -210,6 +221,110 @@ __global__ void cellpop_unpack_partial_kernel(const double* __restrict__ partial
 	} else {
 		nfail[c] = (int32_t)in[2 * T];
 	}
+}
+
+// ---- dividing populations: one generation at a time (Experiment::ParallelSimulation / SimulateCell, Experiment.cpp:691-782) ----
+// wave [C][4]: first slot of the generation being integrated, one past its last slot, overflow flag, unused
+
+// Generation 0: the experiment's initial cells (Experiment.cpp:662-670) and the reset of every per-cell record
+__global__ void cellpop_division_init_kernel(int C, int n0, int stride, const double* __restrict__ transformed, int nvar, int entry_time_ix,
+                                             double entry_time_fixed, int row0, double* __restrict__ creation, int32_t* __restrict__ row,
+                                             int32_t* __restrict__ parent, int32_t* __restrict__ event, int32_t* __restrict__ status,
+                                             int32_t* __restrict__ steps, int32_t* __restrict__ items, int32_t* __restrict__ wave)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (long long)C * stride) return;
+	const int c = (int)(i / stride), slot = (int)(i % stride);
+	event[i] = 0;
+	status[i] = 1;
+	steps[i] = 0;
+	parent[i] = -1;
+	row[i] = row0 + slot;
+	creation[i] = (entry_time_ix >= 0) ? transformed[(long long)c * nvar + entry_time_ix] : entry_time_fixed;
+	if (slot < n0) {
+		items[2 * ((long long)c * n0 + slot)] = c;
+		items[2 * ((long long)c * n0 + slot) + 1] = slot;
+	}
+	if (slot == 0) {
+		wave[4 * c] = 0;
+		wave[4 * c + 1] = n0;
+		wave[4 * c + 2] = 0;
+		wave[4 * c + 3] = 0;
+	}
+}
+
+// After a generation: every cell of it that divided before the end of the experiment gets two daughters, in the order of the
+// parents -- the order in which the reference's loop over the population appends them (CellPopulation::AddNewCell,
+// CellPopulation.cpp:36-104). One block per chain. A daughter without a free cell object or quasi-random row fails the
+// evaluation of the chain (AddNewCell returns max, SimulateCell returns false).
+__global__ void cellpop_spawn_kernel(int stride, int n0, int sobol_rows, double target_time, const int32_t* __restrict__ event,
+                                     const double* __restrict__ end_time, double* __restrict__ creation, int32_t* __restrict__ row,
+                                     int32_t* __restrict__ parent, int32_t* __restrict__ wave)
+{
+	__shared__ int sh[256];
+	__shared__ int base, overflow;
+	const int c = blockIdx.x, tid = threadIdx.x;
+	const int begin = wave[4 * c], end = wave[4 * c + 1];
+	const long long o = (long long)c * stride;
+	if (tid == 0) {
+		base = 0;
+		overflow = wave[4 * c + 2];
+	}
+	__syncthreads();
+	for (int s0 = begin; s0 < end; s0 += blockDim.x) {
+		const int slot = s0 + tid;
+		const bool divides = slot < end && (event[o + slot] & 1) && end_time[o + slot] < target_time;
+		sh[tid] = divides ? 1 : 0;
+		__syncthreads();
+		for (int off = 1; off < blockDim.x; off <<= 1) { // inclusive scan
+			const int v = (tid >= off) ? sh[tid - off] : 0;
+			__syncthreads();
+			sh[tid] += v;
+			__syncthreads();
+		}
+		const int rank = base + sh[tid] - (divides ? 1 : 0);
+		if (divides) {
+			for (int child = 0; child < 2; child++) {
+				const int d = end + 2 * rank + child;
+				const long long r = (long long)n0 + 2ll * row[o + slot] + child; // CellPopulation.cpp:75
+				if (d >= stride || r >= sobol_rows) {
+					overflow = 1;
+				} else {
+					creation[o + d] = end_time[o + slot];
+					row[o + d] = (int32_t)r;
+					parent[o + d] = slot;
+				}
+			}
+		}
+		__syncthreads();
+		if (tid == 0) base += sh[blockDim.x - 1];
+		__syncthreads();
+	}
+	if (tid == 0) {
+		int next_end = end + 2 * base;
+		if (next_end > stride) next_end = stride;
+		wave[4 * c] = end;
+		wave[4 * c + 1] = overflow ? end : next_end; // a failed chain integrates nothing more
+		wave[4 * c + 2] = overflow;
+	}
+}
+
+// the (chain, slot) list of the next generation; offsets [C] = exclusive prefix of the generations' sizes (host)
+__global__ void cellpop_items_kernel(int C, const int32_t* __restrict__ wave, const int32_t* __restrict__ offsets, int32_t* __restrict__ items)
+{
+	const int c = blockIdx.x;
+	const int begin = wave[4 * c], n = wave[4 * c + 1] - begin;
+	for (int k = threadIdx.x; k < n; k += blockDim.x) {
+		items[2 * ((long long)offsets[c] + k)] = c;
+		items[2 * ((long long)offsets[c] + k) + 1] = begin + k;
+	}
+}
+
+// a chain whose population outgrew max_cells (or the quasi-random table) counts as failed: logp = -inf (Experiment.cpp:356-358)
+__global__ void cellpop_overflow_kernel(int C, const int32_t* __restrict__ wave, int32_t* __restrict__ nfail)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < C && wave[4 * c + 2]) nfail[c] += 1;
 }
 
 // Per chain: the Cholesky factor of the cell-variability covariance in the spherical parametrisation of
@@ -754,6 +869,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	int helper_inline = lockstep;
 	if (const char* henv = getenv("BCM3B200_CELLPOP_HELPER_INLINE")) helper_inline = atoi(henv);
 	o << "#define CP_HELPER_INLINE " << helper_inline << "\n";
+	if (cp.division()) o << "#define CP_DIVISION 1\n";
 	if (const char* benv2 = getenv("BCM3B200_CELLPOP_GROUP_BATCHED")) o << "#define CP_GROUP_BATCHED " << atoi(benv2) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_LU_SKIP_ZEROS")) o << "#define CP_LU_SKIP_ZEROS " << atoi(senv) << "\n";
@@ -873,6 +989,17 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	if (cp.have_sim_end_time && !(cp.sim_end_time >= cp.data["timepoints"].back())) return fail(BCM3B200_ERR_ARG, "simulation_end_time lies before the last timepoint");
 	for (int s : cp.obs_species)
 		if (s < 0 || s >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species index out of range");
+	if (cp.division()) {
+		if (cp.cytokinesis_ix >= cp.N || cp.apoptosis_ix >= cp.N) return fail(BCM3B200_ERR_ARG, "cytokinesis_species / apoptosis_species index out of range");
+		if (cp.divide_cells && cp.cytokinesis_ix >= 0) {
+			if (cp.max_cells < cp.num_cells) return fail(BCM3B200_ERR_ARG, "max_cells is smaller than num_cells");
+			for (int k = 0; k < 7; k++)
+				if (cp.reset_ix[k] < 0 || cp.reset_ix[k] >= cp.N)
+					return fail(BCM3B200_ERR_ARG, "divide_cells needs division_reset_species = the seven species a daughter resets (Cell.cpp:127-133)");
+		}
+		if (cellpop_resolve_kernel(cp) != 3) return fail(BCM3B200_ERR_UNSUPPORTED, "dividing / dying cells need the lane-group kernel (cellpop_kernel = auto, N <= 96)");
+		if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "a dividing population is not split over ranks (the max_cells cap is population-wide)");
+	}
 
 	// variability rows: is_ic, target index, apply, scale_ix, scale_fixed, negate
 	CpArgs& a = cp.args;
@@ -882,8 +1009,10 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		const double* row = cp.data["variability"].data() + (size_t)d * 6;
 		// row[0]: 0 = parameter, 1 = initial condition, 2 = entry time. The reference never applies an entry-time variable
 		// (VariabilityDescription::ApplyVariabilityEntryTime has no caller), but it takes its quasi-random dimension.
-		const bool no_target = ((int)row[0] == 2);
-		a.var_is_ic[d] = ((int)row[0] == 1);
+		const int kind = (int)row[0] & 3;
+		a.var_only_initial[d] = ((int)row[0] & 4) ? 1 : 0; // <variable only_initial_cells="true">
+		const bool no_target = (kind == 2);
+		a.var_is_ic[d] = (kind == 1);
 		const int target = (int)row[1];
 		a.var_apply[d] = (int)row[2];
 		a.var_scale_ix[d] = (int)row[3];
@@ -1003,6 +1132,13 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		a.treatment_times = cp.d_treatment_times.p;
 	}
 	a.num_cells = cp.cells_local;
+	a.cell_stride = cp.capacity();
+	a.initial_flag = cp.num_cells > 1 ? 1 : 0; // Experiment.cpp:662-670
+	a.cytokinesis_ix = (cp.divide_cells && cp.division()) ? cp.cytokinesis_ix : -1;
+	a.apoptosis_ix = cp.division() ? cp.apoptosis_ix : -1;
+	for (int k = 0; k < 7; k++) a.reset_ix[k] = cp.reset_ix[k];
+	a.items = nullptr;
+	a.num_items = 0;
 	a.cell_offset = cp.cell_offset;
 	a.nvar = cp.nvar;
 	a.initial_conditions = cp.d_ic.p;
@@ -1018,6 +1154,10 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	a.rel_tol = cp.rel_tol;
 	a.abs_tol = cp.abs_tol;
 	a.min_dt = cp.min_dt;
+	// CVodeSetMaxStep (cvode_io.c:344-376): 0 and infinity mean no ceiling; a ceiling below the minimum step is an error
+	a.max_dt_inv = (cp.max_dt > 0.0 && std::isfinite(cp.max_dt)) ? 1.0 / cp.max_dt : 0.0;
+	if (cp.max_dt < 0.0 || a.max_dt_inv * cp.min_dt > 1.0) return fail(BCM3B200_ERR_ARG, "solver_max_timestep is negative or below solver_min_timestep");
+	if (a.max_dt_inv > 0.0 && cp.built_kernel != 3) return fail(BCM3B200_ERR_UNSUPPORTED, "solver_max_timestep needs the lane-group kernel (cellpop_kernel = auto, N <= 96)");
 	a.max_steps = cp.max_steps;
 	a.num_obs_species = (int)cp.obs_species.size();
 	for (size_t k = 0; k < cp.obs_species.size(); k++) a.obs_species[k] = cp.obs_species[k];
@@ -1033,11 +1173,12 @@ inline int cellpop_run_cells(CellPopState& cp, size_t C, size_t nvar, const doub
 	if (rc != BCM3B200_OK) return rc;
 	CUDA_TRY(cudaSetDevice(cp.device));
 	const int T = cp.T, nc = cp.cells_local;
+	const size_t cols = (size_t)(cp.capacity() ? cp.capacity() : 1); // cell columns of the per-cell outputs
 	CUDA_TRY(cp.d_values.ensure(C * nvar));
 	CUDA_TRY(cp.d_transformed.ensure(C * nvar));
-	CUDA_TRY(cp.d_cellvals.ensure(C * (size_t)T * (nc ? nc : 1)));
-	CUDA_TRY(cp.d_status.ensure(C * (size_t)(nc ? nc : 1)));
-	CUDA_TRY(cp.d_steps.ensure(C * (size_t)(nc ? nc : 1)));
+	CUDA_TRY(cp.d_cellvals.ensure(C * (size_t)T * cols));
+	CUDA_TRY(cp.d_status.ensure(C * cols));
+	CUDA_TRY(cp.d_steps.ensure(C * cols));
 	CUDA_TRY(cp.d_avg.ensure(C * (size_t)T));
 	CUDA_TRY(cp.d_count.ensure(C * (size_t)T));
 	CUDA_TRY(cp.d_nfail.ensure(C));
@@ -1075,7 +1216,67 @@ inline int cellpop_run_cells(CellPopState& cp, size_t C, size_t nvar, const doub
 	cp.last_launches = 1;
 	const bool use_group = (cp.built_kernel == 3);
 	const bool use_thread = (cp.built_kernel == 2);
-	if (nc > 0 && use_group) {
+	if (nc > 0 && use_group && cp.division()) {
+		// One generation at a time (Experiment::ParallelSimulation, Experiment.cpp:691-724): the cells of a generation are
+		// independent work items of one launch; the daughters of those that divided form the next generation.
+		const int stride = cp.capacity();
+		const size_t recs = C * (size_t)stride;
+		CUDA_TRY(cp.d_creation.ensure(recs));
+		CUDA_TRY(cp.d_end_time.ensure(recs));
+		CUDA_TRY(cp.d_end_y.ensure(recs * (size_t)cp.N));
+		CUDA_TRY(cp.d_row.ensure(recs));
+		CUDA_TRY(cp.d_parent.ensure(recs));
+		CUDA_TRY(cp.d_event.ensure(recs));
+		CUDA_TRY(cp.d_items.ensure(2 * recs));
+		CUDA_TRY(cp.d_wave.ensure(4 * C));
+		CUDA_TRY(cp.d_item_offsets.ensure(C));
+		cp.h_wave.resize(4 * C);
+		CUDA_TRY(cudaMemsetAsync(cp.d_cellvals.p, 0xFF, sizeof(double) * C * (size_t)T * stride, st)); // all-ones = NaN: the cell does not exist
+		cellpop_division_init_kernel<<<(unsigned)((recs + 255) / 256), 256, 0, st>>>((int)C, nc, stride, cp.d_transformed.p, (int)nvar, cp.entry_time_ix,
+		                                                                            cp.entry_time_fixed, cp.cell_offset, cp.d_creation.p, cp.d_row.p,
+		                                                                            cp.d_parent.p, cp.d_event.p, cp.d_status.p, cp.d_steps.p, cp.d_items.p,
+		                                                                            cp.d_wave.p);
+		CUDA_TRY(cudaGetLastError());
+		cp.last_launches++;
+		a.cell_stride = stride;
+		a.items = cp.d_items.p;
+		a.cell_creation = cp.d_creation.p;
+		a.cell_row = cp.d_row.p;
+		a.cell_parent = cp.d_parent.p;
+		a.cell_end_y = cp.d_end_y.p;
+		a.cell_end_time = cp.d_end_time.p;
+		a.cell_event = cp.d_event.p;
+		const long long need = cp.group_scratch((int)C, nc);
+		if (need < 0) return fail(BCM3B200_ERR_CUDA, "cellpop group kernel does not fit on this device: %s", cudaGetErrorString((cudaError_t)(-need)));
+		CUDA_TRY(cp.d_scratch.ensure((size_t)need));
+		long long items = (long long)C * nc;
+		for (int generation = 0; items > 0; generation++) {
+			if (generation > 64) return fail(BCM3B200_ERR_STATE, "more than 64 generations of dividing cells");
+			a.num_items = (int)items;
+			int lrc = cp.group_launch(&a, cp.d_scratch.p, (void*)st);
+			if (lrc != 0) return fail(BCM3B200_ERR_CUDA, "cellpop group kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+			cp.last_launches++;
+			if (!cp.divide_cells || cp.cytokinesis_ix < 0) break; // cells only die: one generation
+			cellpop_spawn_kernel<<<(unsigned)C, 256, 0, st>>>(stride, cp.num_cells, cp.sobol_rows, a.sim_end_time, cp.d_event.p, cp.d_end_time.p, cp.d_creation.p,
+			                                                 cp.d_row.p, cp.d_parent.p, cp.d_wave.p);
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaMemcpyAsync(cp.h_wave.data(), cp.d_wave.p, sizeof(int32_t) * 4 * C, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+			std::vector<int32_t> offsets(C);
+			items = 0;
+			for (size_t c = 0; c < C; c++) {
+				offsets[c] = (int32_t)items;
+				items += cp.h_wave[4 * c + 1] - cp.h_wave[4 * c];
+			}
+			cp.last_launches++;
+			if (items == 0) break;
+			CUDA_TRY(cudaMemcpyAsync(cp.d_item_offsets.p, offsets.data(), sizeof(int32_t) * C, cudaMemcpyHostToDevice, st));
+			cellpop_items_kernel<<<(unsigned)C, 256, 0, st>>>((int)C, cp.d_wave.p, cp.d_item_offsets.p, cp.d_items.p);
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaStreamSynchronize(st)); // `offsets` is a stack buffer
+			cp.last_launches++;
+		}
+	} else if (nc > 0 && use_group) {
 		const long long need = cp.group_scratch((int)C, nc);
 		if (need < 0) return fail(BCM3B200_ERR_CUDA, "cellpop group kernel does not fit on this device: %s", cudaGetErrorString((cudaError_t)(-need)));
 		CUDA_TRY(cp.d_scratch.ensure((size_t)need));
@@ -1136,8 +1337,13 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	int rc = cellpop_run_cells(cp, C, nvar, values, st);
 	if (rc != BCM3B200_OK) return rc;
 	const int T = cp.T, nc = cp.cells_local;
-	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, nc, T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
+	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, cp.capacity(), T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
 	CUDA_TRY(cudaGetLastError());
+	if (cp.division() && cp.divide_cells && nc > 0) {
+		cellpop_overflow_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>((int)C, cp.d_wave.p, cp.d_nfail.p);
+		CUDA_TRY(cudaGetLastError());
+		cp.last_launches++;
+	}
 	rc = cellpop_data_likelihood(cp, C, st);
 	if (rc != BCM3B200_OK) return rc;
 	cp.last_launches += 2;

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <limits>
 #include <sstream>
@@ -77,19 +78,20 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 	const bcm3::XmlNode* exp = &xml;
 	e.name = exp->get("name");
 	e.model_file = exp->get("model_file");
-	if (exp->get_bool("divide_cells", true)) return Fail("divide_cells=\"true\" (the reference's default, Experiment.cpp:488) is not supported by the GPU path: set divide_cells=\"false\"");
+	e.divide_cells = exp->get_bool("divide_cells", true); // Experiment.cpp:488: true unless said otherwise
 	e.num_cells = (size_t)exp->get_int("num_cells", 1);
-	const size_t max_cells = (size_t)exp->get_int("max_cells", 20);
-	if (e.num_cells > max_cells) return Fail("num_cells exceeds max_cells");
+	e.max_cells = (size_t)exp->get_int("max_cells", 20);
+	if (e.num_cells > e.max_cells) return Fail("num_cells exceeds max_cells");
+	// Cell.cpp:489-497: a non-zero value extends a cell's integration past the end of the experiment from a threshold-crossing
+	// time that only exists with stored integration points (per-cell data types)
+	if (exp->get_real("simulate_past_chromatid_separation_time", 0.0) != 0.0) return Fail("simulate_past_chromatid_separation_time is not supported by the GPU path");
 	if (exp->get("solver_type", "CVODE") != "CVODE") return Fail("only solver_type=\"CVODE\" is supported");
 	e.solver_min_timestep = exp->get_real("solver_min_timestep", e.solver_min_timestep);
 	e.solver_max_steps = exp->get_int("solver_max_steps", e.solver_max_steps);
 	e.solver_abs_tol = exp->get_real("solver_absolute_tolerance", e.solver_abs_tol);
 	e.solver_rel_tol = exp->get_real("solver_relative_tolerance", e.solver_rel_tol);
 	if (!Resolve(exp->get("entry_time", "0"), e.entry_time, "entry_time")) return false;
-	// Experiment.cpp:413 -> CVodeSetMaxStep (ODESolverCVODE.cpp:156-161): the device integrators have no step-size ceiling
-	if (exp->has("solver_max_timestep") && std::isfinite(exp->get_real("solver_max_timestep", bcm3::kInf)))
-		return Fail("solver_max_timestep is not supported by the GPU path");
+	e.solver_max_timestep = exp->get_real("solver_max_timestep", bcm3::kInf); // Experiment.cpp:413 -> CVodeSetMaxStep
 	// Experiment.cpp:172-180: only meaningful for the synchronised per-cell data types (and it overwrites the fixed entry time there)
 	if (!exp->get("synchronization_time_offset").empty()) return Fail("synchronization_time_offset is not supported by the GPU path");
 	e.trailing_simulation_time = exp->get_real("trailing_simulation_time", 0.0); // Experiment.cpp:489, 655-656
@@ -125,7 +127,8 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				if (ve.apply < 0) return Fail("Unknown cell variability apply type \"" + v.get("apply") + "\"");
 				if (!Resolve(v.get("scale", "0"), ve.scale, "scale")) return false;
 				ve.negate = v.get_bool("negate", false);
-				// only_initial_cells (VariabilityDescriptionVariable.cpp:66-110): without division every cell is an initial cell
+				// VariabilityDescriptionVariable.cpp:132-136: defaults to true for an entry-time variable, false otherwise
+				ve.only_initial_cells = v.get_bool("only_initial_cells", ve.entry_time);
 				e.variables.push_back(ve);
 			}
 		} else if (c.name == "data") {
@@ -196,9 +199,51 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 
 // Experiment::PostInitialize (Experiment.cpp:120-232): every data set becomes one handle; the experiment's simulation end is
 // the last time any of its data sets requests (:190-214, :655-656)
+bool CellPopulationLikelihoodB200::AddNonSampledParameters(const std::vector<std::string>& variable_names)
+{
+	non_sampled_names = variable_names;
+	have_non_sampled_names = true;
+	// Experiment.cpp:134-135: values unknown until SetNonSampledParameters
+	for (auto& e : experiments) e.model.non_sampled_parameters.assign(variable_names.size(), std::numeric_limits<double>::quiet_NaN());
+	return true;
+}
+
+void CellPopulationLikelihoodB200::SetNonSampledParameters(const bcm3::VectorReal& values)
+{
+	for (auto& e : experiments) {
+		e.model.non_sampled_parameters.assign(values.begin(), values.end());
+		for (auto& ds : e.data) {
+			if (!ds.handle || values.empty()) continue;
+			const size_t shape[1] = { values.size() };
+			if (bcm3b200_set_data(ds.handle, "non_sampled_parameters", values.data(), shape, 1) != BCM3B200_OK) last_error = bcm3b200_last_error();
+		}
+	}
+}
+
+void CellPopulationLikelihoodB200::OutputEvaluationStatistics(const std::string& path) const
+{
+	FILE* f = fopen((path + "/cellpop_evaluation_statistics.txt").c_str(), "w");
+	if (!f) return;
+	fprintf(f, "experiment\tdata_set\tevaluations\tkernel_launches\n");
+	for (const auto& e : experiments) {
+		for (size_t k = 0; k < e.data.size(); k++) {
+			int64_t evals = 0, launches = 0;
+			if (e.data[k].handle) {
+				bcm3b200_get_stat(e.data[k].handle, "num_evaluations", &evals);
+				bcm3b200_get_stat(e.data[k].handle, "total_kernel_launches", &launches);
+			}
+			fprintf(f, "%s\t%zu\t%lld\t%lld\n", e.name.c_str(), k, (long long)evals, (long long)launches);
+		}
+	}
+	fclose(f);
+}
+
 bool CellPopulationLikelihoodB200::PostInitialize()
 {
 	for (auto& e : experiments) {
+		if (have_non_sampled_names && e.model.non_sampled_parameters.size() != non_sampled_names.size())
+			return Fail("the model of experiment \"" + e.name + "\" was generated for " + std::to_string(e.model.non_sampled_parameters.size()) +
+			            " non-sampled parameters, AddNonSampledParameters named " + std::to_string(non_sampled_names.size()));
 		double end_time = -std::numeric_limits<double>::infinity();
 		for (const auto& ds : e.data) {
 			const size_t T = ds.data.timepoints.size();
@@ -212,9 +257,9 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 		// Cell::integration_step_cb (Cell.cpp:463-540): with these species in the model a cell's integration ends at a
 		// threshold crossing (death) or is extended past anaphase -- events the device path does not have. The other
 		// special species only record times for the per-cell data types.
-		for (const char* special : { "apoptosis", "chromatid_separation" })
-			if (std::find(e.model.species_names.begin(), e.model.species_names.end(), special) != e.model.species_names.end())
-				return Fail(std::string("the model has the species \"") + special + "\": threshold events are not supported by the GPU path");
+		// Built: division at "cytokinesis" > 1 (divide_cells), death at "apoptosis" > 1, both without stored integration points.
+		// "chromatid_separation" only moves the end of the integration when simulate_past_chromatid_separation_time is set
+		// (refused above); the remaining special species only record times for the per-cell data types.
 		end_time += e.trailing_simulation_time;
 		for (auto& ds : e.data)
 			if (!CreateHandle(e, ds, end_time)) return false;
@@ -229,7 +274,16 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	const size_t N = model.species_names.size(), nvar = varset->GetNumVariables(), T = data.timepoints.size(), D = e.variables.size();
 	const size_t num_cells = e.num_cells;
 	if (N == 0 || model.initial_conditions.size() != N || model.derivative_code.empty()) return Fail("SetModel() has not supplied the generated model");
-	if (D > 0 && e.sobol.size() != num_cells * D) return Fail("SetSobolTable(): expected num_cells x variability dimension entries");
+	auto species_index = [&](const char* name) -> long {
+		auto it = std::find(model.species_names.begin(), model.species_names.end(), name);
+		return it == model.species_names.end() ? -1 : (long)(it - model.species_names.begin());
+	};
+	// Cell::Cell looks these up by name (Cell.cpp:40-55); a model without "cytokinesis" never divides
+	const long cytokinesis = species_index("cytokinesis"), apoptosis = species_index("apoptosis");
+	const bool divides = e.divide_cells && cytokinesis >= 0;
+	if (D > 0 && (divides ? (e.sobol.size() < num_cells * D || e.sobol.size() % D != 0) : e.sobol.size() != num_cells * D))
+		return Fail(divides ? "SetSobolTable(): a dividing population needs at least num_cells rows (the reference makes 100 x num_cells)"
+		                    : "SetSobolTable(): expected num_cells x variability dimension entries");
 
 	// species_name="a+b": the summed simulated species
 	std::vector<size_t> obs;
@@ -251,6 +305,19 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	  << ";relative_to_time_average=" << (ds.relative_to_time_average ? 1 : 0) << ";stdev_relative_to_scale=" << (ds.stdev_relative_to_scale ? 1 : 0) << ";error_model=" << ds.error_model << ";weight=" << ds.weight
 	  << ";missing_simulation_time_stdev=" << ds.missing_stdev << ";device=" << device << ";compile_only=" << (compile_only ? 1 : 0);
 	if (simulation_end_time > data.timepoints.back()) d << ";simulation_end_time=" << simulation_end_time;
+	if (std::isfinite(e.solver_max_timestep)) d << ";solver_max_timestep=" << e.solver_max_timestep;
+	if (divides) {
+		// Cell::SetInitialConditionsFromOtherCell (Cell.cpp:127-133) resets these seven species by name and does not check that
+		// they exist: a dividing model without one of them is an error here
+		d << ";divide_cells=1;max_cells=" << e.max_cells << ";cytokinesis_species=" << cytokinesis << ";division_reset_species=";
+		const char* reset_names[7] = { "cytokinesis", "nuclear_envelope", "G1S_break", "G2_break", "spindle_components", "assembled_spindle", "chromatid_separation" };
+		for (int k = 0; k < 7; k++) {
+			const long ix = species_index(reset_names[k]);
+			if (ix < 0) return Fail(std::string("divide_cells: the model has no species \"") + reset_names[k] + "\" (Cell.cpp:127-133 resets it in every daughter)");
+			d << (k ? "+" : "") << ix;
+		}
+	}
+	if (apoptosis >= 0) d << ";apoptosis_species=" << apoptosis;
 	auto ref = [&](const char* name, const ValueRef& r) {
 		if (r.ix >= 0) d << ";" << name << "_ix=" << r.ix;
 		else d << ";" << name << "=" << r.fixed;
@@ -299,14 +366,14 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 				if (target == std::numeric_limits<size_t>::max()) return Fail("Variability model_parameter \"" + ve.target + "\" is not a sampled variable");
 			}
 			double* r = rows.data() + i * 6;
-			r[0] = ve.entry_time ? 2.0 : ve.is_ic ? 1.0 : 0.0;
+			r[0] = (ve.entry_time ? 2.0 : ve.is_ic ? 1.0 : 0.0) + (ve.only_initial_cells ? 4.0 : 0.0);
 			r[1] = (double)target;
 			r[2] = (double)ve.apply;
 			r[3] = (double)ve.scale.ix;
 			r[4] = ve.scale.fixed;
 			r[5] = ve.negate ? 1.0 : 0.0;
 		}
-		if (!set("sobol", e.sobol, { num_cells, D }) || !set("variability", rows, { D, 6 })) return false;
+		if (!set("sobol", e.sobol, { divides ? e.sobol.size() / D : num_cells, D }) || !set("variability", rows, { D, 6 })) return false;
 		if (e.distribution == "full_gaussian" && D > 1) {
 			// covariance values are variables named <covar_base_name><k+1>_<i+1>, k < i (VariabilityDescription.cpp:203-216)
 			std::vector<double> cov(D * (D - 1));

@@ -81,6 +81,14 @@ public:
 	void SetSobolTable(size_t experiment, const std::vector<double>& table) { experiments[experiment].sobol = table; }
 	void SetSobolTable(const std::vector<double>& table) { SetSobolTable(0, table); }
 	void SetDevice(int dev, bool compile_only_ = false) { device = dev; compile_only = compile_only_; }
+	// CellPopulationLikelihood.cpp:46-61 -> Experiment.cpp:132-143: the names become non_sampled_parameters[i] of the generated
+	// code (the generator is on the reference side: the Model handed to SetModel must have been generated with the same names),
+	// the values start as NaN and are replaced between evaluations (bcmopt/main.cpp:231)
+	bool AddNonSampledParameters(const std::vector<std::string>& variable_names) override;
+	void SetNonSampledParameters(const bcm3::VectorReal& values) override;
+	const std::vector<std::string>& GetNonSampledParameterNames() const { return non_sampled_names; }
+	// CellPopulationLikelihood.cpp:73-80 (the reference's body is compiled out): evaluation and launch counts per data set
+	void OutputEvaluationStatistics(const std::string& path) const override;
 	bool PostInitialize() override;
 	bool IsReentrant() override { return true; } // the reference's is not (CellPopulationLikelihood.h:22): one object per sampling thread
 	bool EvaluateLogProbability(size_t threadix, const bcm3::VectorReal& values, bcm3::Real& logp) override;
@@ -101,6 +109,7 @@ private:
 	struct VarEntry {
 		bool is_ic = false;
 		bool entry_time = false; // read, given a quasi-random dimension, never applied -- as in the reference
+		bool only_initial_cells = false; // not applied to daughters (nor to the single cell of a num_cells="1" experiment)
 		std::string target;
 		int apply = 0;
 		ValueRef scale;
@@ -117,8 +126,10 @@ private:
 	};
 	struct Experiment {
 		std::string name, model_file, distribution = "diagonal_gaussian", covar_base_name;
-		size_t num_cells = 1;
+		size_t num_cells = 1, max_cells = 20;
+		bool divide_cells = true; // Experiment.cpp:488
 		ValueRef entry_time;
+		double solver_max_timestep = std::numeric_limits<double>::infinity();
 		double solver_min_timestep = 1e-8, solver_abs_tol = 4.0 * 1.1920928955078125e-07, solver_rel_tol = 4.0 * 1.1920928955078125e-07;
 		long solver_max_steps = 10000;
 		double trailing_simulation_time = 0.0; // the cells are integrated this much past the last requested time
@@ -144,6 +155,8 @@ private:
 	}
 
 	std::shared_ptr<const bcm3::VariableSet> varset;
+	std::vector<std::string> non_sampled_names;
+	bool have_non_sampled_names = false;
 	std::vector<Experiment> experiments;
 	int device = 0;
 	bool compile_only = false;

@@ -13,7 +13,7 @@ public:
 
 	bool SetLearningRate(Real lr)
 	{
-		if (!(lr > 0.0)) return false;
+		if (lr < 0.0 || lr > 1.0) return false; // Likelihood.cpp:17-20
 		learning_rate = lr;
 		return true;
 	}
@@ -21,8 +21,14 @@ public:
 
 	// `likelihood_node` = the <bcm_likelihood> element (boost ptree in the reference)
 	virtual bool Initialize(std::shared_ptr<const VariableSet> varset, const XmlNode& likelihood_node) { (void)varset; (void)likelihood_node; return true; }
+	// The optimiser's hooks (src/sampler/Likelihood.h:18-19, used by bcmopt/main.cpp:156-234): parameters that are not
+	// sampled but set from outside between evaluations. Defaults as in Likelihood.cpp:31-38.
+	virtual bool AddNonSampledParameters(const std::vector<std::string>& variable_names) { (void)variable_names; return true; }
+	virtual void SetNonSampledParameters(const VectorReal& values) { (void)values; }
 	virtual bool PostInitialize() { return true; }
 	virtual bool IsReentrant() = 0;
+	// Likelihood.h:22, called once after sampling (bcminf/main.cpp:133)
+	virtual void OutputEvaluationStatistics(const std::string& path) const { (void)path; }
 
 	//! As in the reference: evaluate one variable vector. False = unrecoverable, the sampler stops.
 	virtual bool EvaluateLogProbability(size_t threadix, const VectorReal& values, Real& logp) = 0;

@@ -297,6 +297,23 @@ size_t bcm3host_cellpop_layout(void* session, size_t* num_data, size_t max_exper
 }
 
 // experiment < 0: every experiment gets this model
+int bcm3host_cellpop_set_model_ns(void* session, long experiment, const char* derivative_code, size_t N, const char* const* species_names,
+                                  const double* initial_conditions, size_t Nc, const double* constant_species, size_t Nn, const double* non_sampled)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	if (experiment >= (long)s->ll->GetNumExperiments()) return -1;
+	CellPopulationLikelihoodB200::Model m;
+	m.derivative_code = derivative_code;
+	for (size_t i = 0; i < N; i++) m.species_names.push_back(species_names[i]);
+	m.initial_conditions.assign(initial_conditions, initial_conditions + N);
+	m.constant_species.assign(constant_species, constant_species + Nc);
+	for (size_t i = 0; i < Nc; i++) m.constant_species_names.push_back("c" + std::to_string(i));
+	m.non_sampled_parameters.assign(non_sampled, non_sampled + Nn);
+	if (experiment < 0) s->ll->SetModel(m);
+	else s->ll->SetModel((size_t)experiment, m);
+	return 0;
+}
+
 int bcm3host_cellpop_set_model(void* session, long experiment, const char* derivative_code, size_t N, const char* const* species_names,
                                const double* initial_conditions, size_t Nc, const double* constant_species)
 {
@@ -310,6 +327,28 @@ int bcm3host_cellpop_set_model(void* session, long experiment, const char* deriv
 	for (size_t i = 0; i < Nc; i++) m.constant_species_names.push_back("c" + std::to_string(i));
 	if (experiment < 0) s->ll->SetModel(m);
 	else s->ll->SetModel((size_t)experiment, m);
+	return 0;
+}
+
+// Likelihood::AddNonSampledParameters / SetNonSampledParameters / OutputEvaluationStatistics through the session
+int bcm3host_cellpop_add_non_sampled(void* session, size_t count, const char* const* names)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	std::vector<std::string> v;
+	for (size_t i = 0; i < count; i++) v.push_back(names[i]);
+	return s->ll->AddNonSampledParameters(v) ? 0 : -1;
+}
+
+int bcm3host_cellpop_set_non_sampled(void* session, size_t count, const double* values)
+{
+	auto* s = static_cast<CellpopSession*>(session);
+	s->ll->SetNonSampledParameters(bcm3::VectorReal(values, values + count));
+	return 0;
+}
+
+int bcm3host_cellpop_output_statistics(void* session, const char* path)
+{
+	static_cast<CellpopSession*>(session)->ll->OutputEvaluationStatistics(path);
 	return 0;
 }
 

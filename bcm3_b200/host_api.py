@@ -203,6 +203,34 @@ class CellPopSession:
         if rc != 0:
             raise RuntimeError("bcm3host_cellpop_set_model: no such experiment")
 
+    def set_model_with_non_sampled(self, problem, species_names, experiment: int = -1) -> None:
+        """set_model that also hands over the model's non-sampled parameter values (SBMLModel::AddNonSampledParameters side)."""
+        p = problem
+        names = (C.c_char_p * p.num_species)(*[n.encode() for n in species_names])
+        ic = np.ascontiguousarray(p.initial_conditions, dtype=np.float64)
+        cs = np.ascontiguousarray(p.constant_species, dtype=np.float64)
+        ns = np.ascontiguousarray(p.non_sampled_parameters, dtype=np.float64)
+        rc = self.lib.bcm3host_cellpop_set_model_ns(C.c_void_p(self.handle), C.c_long(experiment), p.derivative_code.encode(), C.c_size_t(p.num_species), names,
+                                                    ic.ctypes.data_as(C.c_void_p), C.c_size_t(cs.size), cs.ctypes.data_as(C.c_void_p), C.c_size_t(ns.size),
+                                                    ns.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("bcm3host_cellpop_set_model_ns: no such experiment")
+
+    def add_non_sampled_parameters(self, names) -> None:
+        """bcm3::Likelihood::AddNonSampledParameters (Likelihood.h:18)."""
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        if self.lib.bcm3host_cellpop_add_non_sampled(C.c_void_p(self.handle), C.c_size_t(len(names)), arr) != 0:
+            raise RuntimeError("AddNonSampledParameters failed")
+
+    def set_non_sampled_parameters(self, values) -> None:
+        """bcm3::Likelihood::SetNonSampledParameters (Likelihood.h:19)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self.lib.bcm3host_cellpop_set_non_sampled(C.c_void_p(self.handle), C.c_size_t(v.size), v.ctypes.data_as(C.c_void_p))
+
+    def output_evaluation_statistics(self, path: str) -> None:
+        """bcm3::Likelihood::OutputEvaluationStatistics (Likelihood.h:22)."""
+        self.lib.bcm3host_cellpop_output_statistics(C.c_void_p(self.handle), path.encode())
+
     def set_data(self, experiment: int, data_set: int, timepoints, observed) -> None:
         tp = np.ascontiguousarray(timepoints, dtype=np.float64)
         obs = np.ascontiguousarray(observed, dtype=np.float64)

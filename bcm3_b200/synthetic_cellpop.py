@@ -71,6 +71,70 @@ def cascade_code(N: int, seed: int = 0, rate_decades: float = 2.0):
     return "\n".join(lines) + "\n"
 
 
+DIVISION_SPECIES = ("cytokinesis", "nuclear_envelope", "G1S_break", "G2_break", "spindle_components", "assembled_spindle", "chromatid_separation")
+DIVISION_RESET_VALUES = (0.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0)  # Cell::SetInitialConditionsFromOtherCell, Cell.cpp:127-133
+
+
+def division_code(M: int, seed: int = 0, rate_decades: float = 1.0, with_apoptosis: bool = False):
+    """An M-species cascade (cascade_code) followed by the seven species the reference's dividing cells are built around
+    (Cell.cpp:119-148, 463-538) -- cytokinesis, nuclear_envelope, G1S_break, G2_break, spindle_components, assembled_spindle,
+    chromatid_separation, in that order at indices M .. M + 6 -- and optionally `apoptosis` at M + 7. The cascade's last species
+    releases the G1/S break, that releases the G2 break, the nuclear envelope breaks down, the spindle assembles, chromatids
+    separate and cytokinesis accumulates until it passes 1: the cell divides, the daughters start with the seven species reset."""
+    base = cascade_code(M, seed=seed, rate_decades=rate_decades)
+    body = base[base.index("{") + 1: base.index("}")]
+    laws = [ln for ln in body.split("\n") if ln.strip().startswith("ratelaws[")]
+    outs = [ln for ln in body.split("\n") if ln.strip().startswith("out[")]
+    K, L = VAR_K_CASCADE, M - 1
+    cyt, ne, g1s, g2, sc_, asp, chs = (M + i for i in range(7))
+    r0 = 2 * M
+    extra = [
+        f"(((parameters[{K}]*1.500000)*species[{g1s}])*species[{L}])",                                   # r0+0: G1S_break released by the cascade
+        f"(((parameters[{K}]*2.000000)*species[{g2}])*(1.000000-species[{g1s}]))",                       # r0+1: G2_break released after G1/S
+        f"(((parameters[{K}]*3.000000)*species[{ne}])*(1.000000-species[{g2}]))",                        # r0+2: nuclear envelope breakdown
+        f"((parameters[{K}]*1.000000)*(1.000000-species[{g2}]))",                                         # r0+3: spindle components made
+        f"(((parameters[{K}]*4.000000)*species[{sc_}])*(1.000000-species[{ne}]))",                       # r0+4: spindle assembly
+        f"(((parameters[{K}]*2.000000)*hill_function_fixedn4(species[{asp}],0.300000))*(1.000000-species[{chs}]))",  # r0+5: chromatid separation
+        f"((parameters[{K}]*1.200000)*hill_function_fixedn2(species[{chs}],0.500000))",                  # r0+6: cytokinesis accumulates
+    ]
+    if with_apoptosis:
+        extra.append(f"((parameters[{VAR_K_DEG}]*0.110000)*(1.000000+species[0]))")                   # r0+7: slow death signal
+    nr = r0 + len(extra)
+    lines = [SIGNATURE, "{", f"\tOdeReal ratelaws[{nr}];"] + laws + [f"\tratelaws[{r0 + i}] = {e};" for i, e in enumerate(extra)] + outs
+    lines += [f"\tout[{cyt}] = +ratelaws[{r0 + 6}];", f"\tout[{ne}] = -ratelaws[{r0 + 2}];", f"\tout[{g1s}] = -ratelaws[{r0 + 0}];",
+              f"\tout[{g2}] = -ratelaws[{r0 + 1}];", f"\tout[{sc_}] = +ratelaws[{r0 + 3}]-ratelaws[{r0 + 4}];", f"\tout[{asp}] = +ratelaws[{r0 + 4}];",
+              f"\tout[{chs}] = +ratelaws[{r0 + 5}];"]
+    if with_apoptosis:
+        lines.append(f"\tout[{M + 7}] = +ratelaws[{r0 + 7}];")
+    lines.append("}")
+    return "\n".join(lines) + "\n"
+
+
+def make_dividing_problem(M: int = 5, num_cells: int = 24, max_cells: int = 160, T: int = 16, t_end: float = 12.0, seed: int = 3,
+                          with_apoptosis: bool = False, data_cells: int = 4) -> CellPopProblem:
+    """<experiment divide_cells="true" num_cells= max_cells=> around division_code: the read-out is the population average of the
+    cascade's last species; observations are synthetic (a smooth curve plus noise: their values only shift the likelihood)."""
+    N = M + 7 + (1 if with_apoptosis else 0)
+    code = division_code(M, seed=seed, with_apoptosis=with_apoptosis)
+    transforms = np.full(NUM_VARIABLES, TRANSFORM_LOG10, dtype=np.int32)
+    transforms[VAR_VARIABILITY_SCALE] = TRANSFORM_NONE
+    timepoints = t_end * np.arange(T) / (T - 1.0)
+    ic = np.zeros(N)
+    ic[0] = 0.05
+    for k, v in enumerate(DIVISION_RESET_VALUES):
+        ic[M + k] = v
+    variability = [Variability(apply="multiplicative_log", model_parameter=VAR_K_CASCADE, scale_ix=VAR_VARIABILITY_SCALE),
+                   Variability(apply="multiplicative_log", model_parameter=VAR_K_DEG, scale_ix=VAR_VARIABILITY_SCALE, negate=True),
+                   Variability(apply="additive", initial_condition_species=1, scale_fixed=math.log(0.01), only_initial_cells=True)]
+    sobol = sobol_points(100 * num_cells, len(variability))  # VariabilityPseudoRandomIterator.cpp:17
+    rng = np.random.default_rng(seed + 500)
+    observed = (0.8 * (1.0 - np.exp(-timepoints / 2.0)))[None, :] + 0.02 * rng.standard_normal((1, T))
+    return CellPopProblem(derivative_code=code, num_species=N, initial_conditions=ic, transforms=transforms, num_cells=num_cells, timepoints=timepoints,
+                          observed=observed, obs_species=[M - 1], constant_species=np.array([1.0]), sobol=sobol, variability=variability,
+                          stdev_ix=VAR_STDEV, divide_cells=True, max_cells=max_cells, cytokinesis_species=M,
+                          apoptosis_species=(M + 7) if with_apoptosis else None, division_reset_species=tuple(M + k for k in range(7)))
+
+
 # ---- a Python evaluation of the generated text (only to synthesise observations) ---------------------------------
 def _py_helpers():
     def hill(x, k, n):

@@ -82,7 +82,8 @@ class _CellPopProblem(C.Structure):
                                   "variability", "transforms", "derivative")] + [
         ("treatment_species", C.c_int32), ("treatment_num_pulses", C.c_int32), ("treatment_times", C.c_void_p),
         ("relative_to_time_average", C.c_int32), ("have_sim_end_time", C.c_int32), ("sim_end_time", C.c_double),
-        ("stdev_relative_to_scale", C.c_int32)]
+        ("stdev_relative_to_scale", C.c_int32), ("divide_cells", C.c_int32), ("max_cells", C.c_int32), ("sobol_rows", C.c_int32),
+        ("cytokinesis_ix", C.c_int32), ("apoptosis_ix", C.c_int32), ("reset_ix", C.c_int32 * 7), ("max_dt", C.c_double)]
 
 
 _derivative_libs: dict[str, C.CDLL] = {}
@@ -220,6 +221,10 @@ def _cellpop_struct(problem, values):
         treatment_times=ptr(keep["treat"]), relative_to_time_average=int(p.relative_to_time_average),
         have_sim_end_time=int(p.simulation_end_time is not None), sim_end_time=float(p.simulation_end_time or 0.0),
         stdev_relative_to_scale=int(p.stdev_relative_to_scale),
+        divide_cells=int(p.divide_cells), max_cells=p.capacity, sobol_rows=int(keep["sobol"].shape[0]) if keep["sobol"].ndim == 2 else 0,
+        cytokinesis_ix=-1 if p.cytokinesis_species is None else p.cytokinesis_species,
+        apoptosis_ix=-1 if p.apoptosis_species is None else p.apoptosis_species,
+        reset_ix=(C.c_int32 * 7)(*(list(p.division_reset_species) if p.divide_cells else [0] * 7)), max_dt=float(p.solver_max_timestep),
         stdev_ix=-1 if p.stdev_ix is None else p.stdev_ix, offset_ix=-1 if p.offset_ix is None else p.offset_ix,
         scale_ix=-1 if p.scale_ix is None else p.scale_ix, num_obs_species=len(p.obs_species),
         obs_species=(C.c_int32 * 8)(*(list(p.obs_species) + [0] * (8 - len(p.obs_species)))),
@@ -234,9 +239,9 @@ def _cellpop_evaluate(self, problem, values, threads: int = 1, want_cell_values=
     """problem: bcm3_b200.cellpop_data.CellPopProblem; values [C, nvar]."""
     s, keep, values = _cellpop_struct(problem, values)
     nC = values.shape[0]
-    T, nc = problem.num_timepoints, problem.num_cells
+    T, nc = problem.num_timepoints, problem.capacity
     logp = np.empty(nC)
-    cv = np.empty((nC, T, nc)) if want_cell_values else None
+    cv = np.full((nC, T, nc), np.nan) if want_cell_values else None
     st = np.zeros((nC, nc), dtype=np.int32) if want_steps else None
     avg = np.empty((nC, T)) if want_average else None
     rc = self.lib.oracle_cellpop_evaluate(C.byref(s), nC, values.ctypes.data, logp.ctypes.data,
@@ -258,7 +263,7 @@ def _cellpop_counters(self, problem, values, threads: int = 1):
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     logp = np.empty(nC)
-    cnt = np.zeros((nC, problem.num_cells, NUM_COUNTERS), dtype=np.int64)
+    cnt = np.zeros((nC, problem.capacity, NUM_COUNTERS), dtype=np.int64)
     rc = fn(C.byref(s), nC, values.ctypes.data, logp.ctypes.data, cnt.ctypes.data, int(threads))
     if rc != 0:
         raise RuntimeError(f"oracle_cellpop_evaluate_counters failed: {rc}")

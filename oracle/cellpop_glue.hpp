@@ -10,13 +10,18 @@
 //   DataLikelihoodTimeCoursePopulationAverage          .cpp:85-197;  DataLikelihoodTimeCourseBase .cpp:229-315
 // Used twice: oracle/ref/cellpop_ref.cpp plugs in the reference's real ODESolverCVODE, oracle/cellpop_port.cpp plugs in
 // oracle/cvode_bdf.c. The adapter must provide
-//   bool solve(const double* y0, const double* cell_params, const double* timepoints_rel, int ntp, double* out /*[N][ntp] col-major*/, int& steps)
-// with the semantics of ODESolver::SolveReturnSolution.
+//   bool solve(const double* y0, const double* cell_params, const double* timepoints_rel, int ntp, double* out /*[N][ntp] col-major*/, int& steps,
+//              double creation_time, SolveEvents* events)
+// with the semantics of ODESolver::SolveReturnSolution and, after every accepted step, of Cell::integration_step_cb
+// (events->after_step: true = stop). Dividing cells: Experiment.cpp:726-782, CellPopulation.cpp:36-104, Cell.cpp:119-148.
 #pragma once
 
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <limits>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -107,11 +112,41 @@ inline double first_discontinuity_ahead(const oracle_cellpop_problem& pr, double
 	return std::numeric_limits<double>::quiet_NaN();
 }
 
+// What the integration-step callback of a cell reports (Cell::integration_step_cb, Cell.cpp:463-538, the branch without stored
+// integration points): the integration ended at the step that took "cytokinesis" / "apoptosis" above 1, at cell time t_event
+// with state y_event (the solver's y at the end of that step).
+struct SolveEvents {
+	int cytokinesis_ix = -1, apoptosis_ix = -1;
+	bool divided = false, died = false;
+	double t_event = 0.0;
+	std::vector<double> y_event;
+	// true = stop integrating
+	bool after_step(double t, const double* y, int N)
+	{
+		bool stop = false;
+		if (cytokinesis_ix >= 0 && y[cytokinesis_ix] > 1.0) {
+			divided = true;
+			stop = true;
+		}
+		if (apoptosis_ix >= 0 && y[apoptosis_ix] > 1.0) {
+			died = true;
+			stop = true;
+		}
+		if (stop) {
+			t_event = t;
+			y_event.assign(y, y + N);
+		}
+		return stop;
+	}
+};
+
 template <class Solver>
 void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, double* logp_out, double* cell_values, int32_t* cell_steps,
-                    double* pop_avg_out, int64_t* cell_counters = nullptr)
+                    double* pop_avg_out, int64_t* cell_counters = nullptr, int cell_threads = 1)
 {
-	const int N = pr.num_species, nvar = pr.num_variables, T = pr.num_timepoints, ncell = pr.num_cells, D = pr.variability_dim, R = pr.num_replicates;
+	const int N = pr.num_species, nvar = pr.num_variables, T = pr.num_timepoints, ninit = pr.num_cells, D = pr.variability_dim, R = pr.num_replicates;
+	const bool dividing = pr.divide_cells != 0;
+	const int ncell = dividing ? pr.max_cells : ninit; // capacity = number of cell columns of the outputs
 	const double nan = std::numeric_limits<double>::quiet_NaN();
 	std::vector<double> transformed(nvar);
 	for (int i = 0; i < nvar; i++) transformed[i] = transform_variable(pr.transforms[i], values[i]);
@@ -140,62 +175,149 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		}
 	}
 
-	Solver solver(pr);
 	// the solver integrates to the last output time it is given: when the experiment runs longer than this data set, one
 	// extra output time (whose values nobody reads) carries the experiment's end
 	const bool longer = pr.have_sim_end_time && pr.sim_end_time > pr.timepoints[T - 1];
 	const int Tsolve = T + (longer ? 1 : 0);
-	std::vector<double> population_average(T, 0.0), cell_params(nvar), y0(N), tp_rel(Tsolve), out((size_t)N * Tsolve);
+	const double target_time = longer ? pr.sim_end_time : pr.timepoints[T - 1]; // Experiment::Simulate's simulation_end_time
+	std::vector<double> population_average(T, 0.0);
 	std::vector<double> xs((size_t)T * ncell, nan); // value per (timepoint, cell)
+
+	// The population (CellPopulation): cells in creation order. Initial cells take the quasi-random rows 0 .. ninit - 1, the
+	// daughters of the cell with row r take ninit + 2 r + child (CellPopulation.cpp:56-80).
+	struct CellRec {
+		double creation = 0.0, sim_end = 0.0; // sim_end: cell time up to which the cell exists (Cell::simulation_end_time)
+		long row = 0;
+		int parent = -1;
+		bool initial = false, ok = true, divided = false, died = false;
+		std::vector<double> y0, end_y;
+		double achieved = 0.0;
+	};
+	std::vector<CellRec> cells;
+	cells.reserve(ncell);
+	for (int ci = 0; ci < ninit; ci++) {
+		CellRec c;
+		c.creation = entry_time;
+		c.row = ci;
+		c.initial = ninit > 1; // Experiment.cpp:662-670: the flag handed to Cell::Initialize is false for a single initial cell
+		c.y0.assign(pr.initial_conditions, pr.initial_conditions + N);
+		cells.push_back(std::move(c));
+	}
 	bool result = true;
 
-	for (int ci = 0; ci < ncell && result; ci++) {
-		// Cell::Initialize
-		for (int i = 0; i < nvar; i++) cell_params[i] = transformed[i];
-		for (int i = 0; i < N; i++) y0[i] = pr.initial_conditions[i];
+	// Cell::Initialize + Cell::Simulate of one cell; everything it writes is its own (cell record, its column of xs, its counters)
+	auto simulate_cell = [&](Solver& solver, int ci) {
+		CellRec& c = cells[ci];
+		std::vector<double> cell_params(transformed), y0(c.y0), tp_rel(Tsolve), out((size_t)N * Tsolve);
 		for (int d = 0; d < D; d++) {
 			const double* row = pr.variability + (size_t)d * 6;
-			const bool is_ic = row[0] != 0.0;
+			const int kind = (int)row[0] & 3;
+			const bool only_initial = ((int)row[0] & 4) != 0; // VariabilityDescriptionVariable.cpp:66-110
+			const bool is_ic = kind == 1;
 			const int target = (int)row[1], apply = (int)row[2], scale_ix = (int)row[3];
 			double v;
 			if (pr.full_gaussian) {
 				v = 0.0; // v = L z, row d
-				for (int j = 0; j <= d; j++) v += cholesky[(size_t)d * D + j] * ndtri(pr.sobol[(size_t)ci * D + j]);
+				for (int j = 0; j <= d; j++) v += cholesky[(size_t)d * D + j] * ndtri(pr.sobol[(size_t)c.row * D + j]);
 			} else {
 				const double scale = (scale_ix >= 0) ? transformed[scale_ix] : row[4];
-				v = ndtri(pr.sobol[(size_t)ci * D + d]) * exp(scale);
+				v = ndtri(pr.sobol[(size_t)c.row * D + d]) * exp(scale);
 			}
 			if (row[5] != 0.0) v = -v;
-			if ((int)row[0] == 2) continue; // entry-time variable: takes a dimension, is never applied (no caller of ApplyVariabilityEntryTime)
+			if (kind == 2) continue; // entry-time variable: takes a dimension, is never applied (no caller of ApplyVariabilityEntryTime)
+			if (only_initial && !c.initial) continue;
 			if (is_ic) apply_variability(y0[target], v, apply);
 			else apply_variability(cell_params[target], v, apply);
 		}
 		// Cell::Simulate: output times relative to the creation time
-		const double creation_time = entry_time;
+		const double creation_time = c.creation;
 		for (int i = 0; i < T; i++) tp_rel[i] = pr.timepoints[i] - creation_time;
 		if (longer) tp_rel[T] = pr.sim_end_time - creation_time;
 		int steps = 0;
-		if (!solver.solve(y0.data(), cell_params.data(), tp_rel.data(), Tsolve, out.data(), steps, creation_time)) {
-			result = false; // Experiment::Simulate fails => logp = -inf (Experiment.cpp:356-358)
-		}
+		SolveEvents ev;
+		if (dividing) ev.cytokinesis_ix = pr.cytokinesis_ix;
+		ev.apoptosis_ix = pr.apoptosis_ix;
+		c.ok = solver.solve(y0.data(), cell_params.data(), tp_rel.data(), Tsolve, out.data(), steps, creation_time, &ev);
+		c.divided = ev.divided;
+		c.died = ev.died;
+		// Cell.cpp:243-256: a cell that divided or died exists up to the event, any other up to the last requested time
+		c.sim_end = (ev.divided || ev.died) ? ev.t_event : std::max(target_time - creation_time, tp_rel[Tsolve - 1]);
+		c.achieved = ((ev.divided || ev.died) ? ev.t_event : tp_rel[Tsolve - 1]) + creation_time;
+		if (ev.divided) c.end_y = ev.y_event;
 		if (cell_steps) cell_steps[ci] = steps;
 		if (cell_counters) { // per cell: ORACLE_CNT_* (steps, nfe, nsetups, nje, netf, ncfn, nni, ok), summed over the restarts of the solve
 			int64_t* k = cell_counters + (size_t)ci * ORACLE_NUM_COUNTERS;
 			solver.counters(k);
 			k[ORACLE_CNT_STEPS] = steps;
-			k[ORACLE_CNT_OK] = result ? 1 : 0;
+			k[ORACLE_CNT_OK] = c.ok ? 1 : 0;
 		}
-		if (result) {
+		if (c.ok) {
 			// Experiment.cpp:298-312 + Cell::GetInterpolatedSpeciesValue (Cell.cpp:280-360): exact stored timepoints only
 			for (int i = 0; i < T; i++) {
 				const double cell_time = pr.timepoints[i] - creation_time;
-				if (cell_time < 0.0 || cell_time > tp_rel[Tsolve - 1]) continue;
+				if (cell_time < 0.0 || cell_time > c.sim_end) continue;
 				double x = 0.0;
 				for (int k = 0; k < pr.num_obs_species; k++) x += out[(size_t)pr.obs_species[k] + (size_t)i * N];
 				xs[(size_t)i * ncell + ci] = x;
 			}
 		}
+	};
+
+	// Experiment::ParallelSimulation + SimulateCell (Experiment.cpp:691-782), one generation at a time: the cells of a generation
+	// are independent, and creating the daughters in the order of their parents afterwards gives the cell indices the
+	// reference's single-threaded loop gives (it walks the population by index and appends daughters at the end).
+	std::vector<std::unique_ptr<Solver>> solvers;
+	for (int t = 0; t < std::max(1, cell_threads); t++) solvers.emplace_back(new Solver(pr));
+	size_t wave_begin = 0;
+	while (result && wave_begin < cells.size()) {
+		const size_t wave_end = cells.size();
+		if (solvers.size() == 1) {
+			for (size_t ci = wave_begin; ci < wave_end; ci++) simulate_cell(*solvers[0], (int)ci);
+		} else {
+			std::atomic<size_t> next(wave_begin);
+			std::vector<std::thread> th;
+			for (size_t t = 0; t < solvers.size(); t++) {
+				th.emplace_back([&, t]() {
+					for (;;) {
+						const size_t ci = next.fetch_add(1);
+						if (ci >= wave_end) break;
+						simulate_cell(*solvers[t], (int)ci);
+					}
+				});
+			}
+			for (auto& t : th) t.join();
+		}
+		for (size_t ci = wave_begin; ci < wave_end && result; ci++) {
+			const CellRec& c = cells[ci];
+			if (!c.ok) {
+				result = false; // Experiment::Simulate fails => logp = -inf (Experiment.cpp:356-358)
+				if (getenv("ORACLE_CELLPOP_DEBUG")) fprintf(stderr, "cell %zu (row %ld, parent %d, created %.6g) failed in the solver\n", ci, c.row, c.parent, c.creation);
+				break;
+			}
+			if (dividing && c.divided && c.achieved < target_time) {
+				for (int child = 0; child < 2; child++) {
+					CellRec d;
+					d.creation = c.achieved;
+					d.parent = (int)ci;
+					d.row = (long)ninit + c.row * 2 + child;
+					d.initial = false;
+					// CellPopulation::AddNewCell: no free cell object, or no quasi-random row left => the evaluation fails
+					if ((int)cells.size() >= ncell || d.row >= (long)pr.sobol_rows) {
+						if (getenv("ORACLE_CELLPOP_DEBUG")) fprintf(stderr, "no room for a daughter of cell %zu: %zu cells of %d, row %ld of %d\n", ci, cells.size(), ncell, d.row, pr.sobol_rows);
+						result = false;
+						break;
+					}
+					// Cell::SetInitialConditionsFromOtherCell (Cell.cpp:119-148): the parent's state, seven species reset
+					d.y0 = c.end_y;
+					static const double reset_value[7] = { 0.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0 };
+					for (int k = 0; k < 7; k++) d.y0[pr.reset_ix[k]] = reset_value[k];
+					cells.push_back(std::move(d));
+				}
+			}
+		}
+		wave_begin = wave_end;
 	}
+	const int nactive = (int)cells.size();
 	if (cell_values)
 		for (size_t e = 0; e < xs.size(); e++) cell_values[e] = xs[e];
 
@@ -204,16 +326,17 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = nan;
 		return;
 	}
-	// NotifySimulatedValue (.cpp:161-197): value / population size, accumulated cell by cell
+	// NotifySimulatedValue (.cpp:161-197): value / population size, accumulated cell by cell; CountCellsAtTime (CellPopulation.cpp:
+	// 106-121, Cell::CellAliveAtTime Cell.cpp:362-396): the cells whose life span [0, simulation_end_time] covers the time
 	for (int i = 0; i < T; i++) {
 		size_t pop = 0;
-		for (int ci = 0; ci < ncell; ci++) {
-			const double cell_time = pr.timepoints[i] - entry_time;
-			if (!(cell_time < 0.0 || cell_time > tp_rel[Tsolve - 1])) pop++; // CountCellsAtTime
+		for (int ci = 0; ci < nactive; ci++) {
+			const double cell_time = pr.timepoints[i] - cells[ci].creation;
+			if (!(cell_time < 0.0 || cell_time > cells[ci].sim_end)) pop++;
 		}
-		for (int ci = 0; ci < ncell; ci++) {
+		for (int ci = 0; ci < nactive; ci++) {
 			const double x = xs[(size_t)i * ncell + ci];
-			if (x == x) population_average[i] += x / (double)pop;
+			if (x == x) population_average[i] += x / (double)pop; // the accumulator starts at zero (Reset, .cpp:77-83)
 		}
 	}
 	if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = population_average[i];
@@ -280,9 +403,15 @@ int evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double
              int32_t* cell_steps, double* population_average, int num_threads, int64_t* cell_counters = nullptr)
 {
 	if (!prob || !values || !logp || !prob->derivative) return -1;
-	const size_t T = prob->num_timepoints, nc = prob->num_cells, nvar = prob->num_variables;
+	const size_t T = prob->num_timepoints, nc = prob->divide_cells ? prob->max_cells : prob->num_cells, nvar = prob->num_variables;
 	if (num_threads < 1) num_threads = 1;
-	if ((size_t)num_threads > num_chains) num_threads = (int)num_chains;
+	// threads that the chains cannot use go to the cells of a chain (results do not depend on the split: every cell writes its
+	// own column, the sums run in cell order afterwards)
+	int cell_threads = 1;
+	if ((size_t)num_threads > num_chains) {
+		cell_threads = (int)((size_t)num_threads / (num_chains ? num_chains : 1));
+		num_threads = (int)num_chains;
+	}
 	std::atomic<size_t> next(0);
 	auto worker = [&]() {
 		for (;;) {
@@ -290,7 +419,7 @@ int evaluate(const oracle_cellpop_problem* prob, size_t num_chains, const double
 			if (c >= num_chains) break;
 			evaluate_chain<Solver>(*prob, values + c * nvar, logp + c, cell_values ? cell_values + c * T * nc : nullptr,
 			                       cell_steps ? cell_steps + c * nc : nullptr, population_average ? population_average + c * T : nullptr,
-			                       cell_counters ? cell_counters + c * nc * ORACLE_NUM_COUNTERS : nullptr);
+			                       cell_counters ? cell_counters + c * nc * ORACLE_NUM_COUNTERS : nullptr, cell_threads);
 		}
 	};
 	if (num_threads == 1) {

@@ -51,7 +51,8 @@ struct PortSolver {
 	}
 	// ODESolver::SolveReturnSolution (ODESolver.cpp:93-134) + ODESolverCVODE::Solve (ODESolverCVODE.cpp:322-463) with the
 	// discontinuities of a pulsed treatment (Cell.cpp:212-229, 444-460)
-	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps, double cell_creation_time)
+	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps, double cell_creation_time,
+	           cellpop_glue::SolveEvents* events)
 	{
 		const int N = pr.num_species;
 		cell_params = params;
@@ -72,6 +73,7 @@ struct PortSolver {
 		for (int i = 0; i < N; i++) atol[i] = pr.abs_tol;
 		bdf_set_tolerances(m, pr.rel_tol, atol);
 		m->hmin = pr.min_dt; // SetSolverParameter("min_dt"), Cell.cpp:72
+		m->hmax_inv = (pr.max_dt > 0.0 && std::isfinite(pr.max_dt)) ? 1.0 / pr.max_dt : 0.0; // "max_dt" -> CVodeSetMaxStep, cvode_io.c:344-376
 		double y[BDF_NMAX], tmp[BDF_NMAX];
 		for (int i = 0; i < N; i++) y[i] = y0[i];
 		bdf_reinit(m, 0.0, y);
@@ -88,6 +90,7 @@ struct PortSolver {
 				tpi++;
 				if (tpi >= ntp) break;
 			}
+			if (events->after_step(tret, y, N)) break; // integration_step_cb, ODESolverCVODE.cpp:431-436
 			if (tret >= end_time) break;
 			if (steps == pr.max_steps) return false;
 			if (!std::isnan(next_disc) && (result == BDF_TSTOP_RETURN || next_disc == tret)) { // ODESolverCVODE.cpp:448-461

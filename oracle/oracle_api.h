@@ -129,6 +129,15 @@ typedef struct {
 	int32_t have_sim_end_time;
 	double sim_end_time;
 	int32_t stdev_relative_to_scale; /* <data stdev_relative_to_scale="true">: stdev *= data scale, DataLikelihoodBase.cpp:151-153 */
+	/* Dividing and dying cells (Experiment.cpp:726-782, CellPopulation.cpp:36-104, Cell.cpp:119-148, 463-538), the path without
+	 * stored integration points: after every accepted step a cell whose "cytokinesis" species exceeds 1 ends there and two
+	 * daughters start from its state (seven named species reset) with quasi-random rows num_cells + 2 * row(parent) + child;
+	 * a cell whose "apoptosis" species exceeds 1 ends there. With divide_cells the per-cell output arrays have max_cells
+	 * columns and the quasi-random table has sobol_rows rows (the reference makes 100 * num_cells). */
+	int32_t divide_cells, max_cells, sobol_rows;
+	int32_t cytokinesis_ix, apoptosis_ix; /* ODE species indices, -1: the model has no such species */
+	int32_t reset_ix[7];                  /* cytokinesis, nuclear_envelope, G1S_break, G2_break, spindle_components, assembled_spindle, chromatid_separation */
+	double max_dt; /* <experiment solver_max_timestep=> -> SetSolverParameter("max_dt") -> CVodeSetMaxStep (Cell.cpp:73); infinity: none */
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

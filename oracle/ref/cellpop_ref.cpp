@@ -52,13 +52,20 @@ struct RefSolver {
 		solver.Initialize((size_t)pr.num_species, nullptr, 0);
 		solver.SetTolerance(pr.rel_tol, pr.abs_tol);
 		solver.SetSolverParameter("min_dt", 0, pr.min_dt);
-		solver.SetSolverParameter("max_dt", 0, std::numeric_limits<OdeReal>::infinity());
+		solver.SetSolverParameter("max_dt", 0, pr.max_dt); // Cell.cpp:73 (infinity unless the experiment sets solver_max_timestep)
 		solver.SetSolverParameter("max_steps", pr.max_steps, std::numeric_limits<OdeReal>::quiet_NaN());
 	}
-	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps, double cell_creation_time)
+	bool solve(const double* y0, const double* params, const double* tp, int ntp, double* out, int& steps, double cell_creation_time,
+	           cellpop_glue::SolveEvents* events)
 	{
 		cell_params = params;
 		creation_time = cell_creation_time;
+		solver.Restart(); // Cell::Initialize, Cell.cpp:187
+		// Cell::AllocateSolver installs the callback once (Cell.cpp:64-66); here it is re-pointed at this cell's record
+		ODESolver::TIntegrationStepCallback step_cb = [this, events](OdeReal t, const OdeReal* y, Real& end_time, void*) -> bool {
+			return !events->after_step(t, y, pr.num_species);
+		};
+		solver.SetIntegrationStepCallback(step_cb);
 		for (int k = 0; k < ORACLE_NUM_COUNTERS; k++) cnt[k] = 0;
 		// Cell::Simulate, Cell.cpp:212-229 + discontinuity_cb :444-460
 		const double first = cellpop_glue::first_discontinuity_ahead(pr, creation_time);

@@ -45,6 +45,11 @@ CASES = {
     # reactions, hill_function with a non-integer exponent, the fixed-exponent variants 2/4/10/16/100, michaelis_menten_function,
     # tQSSA, safepow, synthcap, exp, a division, a non-sampled parameter, three constant species, stoichiometry 2
     "cellpop_sbml_cell_cycle": (dict(_builder="sbml_cell_cycle", num_cells=48, T=14), 3, {}),
+    # <experiment divide_cells="true">: 16 initial cells, two generations of daughters within the experiment (Experiment.cpp:726-782,
+    # Cell.cpp:119-148, 463-538); a variability variable with only_initial_cells="true"
+    "cellpop_dividing_two_generations": (dict(_builder="dividing", M=5, num_cells=16, max_cells=400, t_end=5.5, T=16), 3, {}),
+    # the same with an "apoptosis" species: some cells die before or instead of dividing
+    "cellpop_dividing_with_apoptosis": (dict(_builder="dividing", M=5, num_cells=16, max_cells=400, t_end=5.5, T=16, with_apoptosis=True), 3, {}),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
@@ -59,7 +64,11 @@ def main():
         tweaks = dict(tweaks)
         positive = tweaks.pop("_positive_data", False)
         kw = dict(kw)
-        if kw.pop("_builder", None) == "sbml_cell_cycle":
+        builder = kw.pop("_builder", None)
+        if builder == "dividing":
+            prob = sc.make_dividing_problem(**kw)
+            fixed_values = sc.make_chain_values(C, seed=5)
+        elif builder == "sbml_cell_cycle":
             from tests.util import sbml_cell_cycle_problem, sbml_cell_cycle_values
 
             prob = sbml_cell_cycle_problem(**kw)

@@ -1,6 +1,8 @@
 """GPU suite: the C++ host mirror driving the GPU-backed pop_pk_trajectory likelihood through the reference's plugin
 surface (LikelihoodFactory type string, likelihood.xml, prior.xml, config.txt): a parallel-tempered run whose every
 mutate round is one batched call must equal the run that evaluates chain by chain."""
+import math
+
 import numpy as np
 import pytest
 
@@ -170,3 +172,72 @@ def test_cell_population_experiment_specific_parameter(built):
     s.post_initialize()
     assert not np.array_equal(s.evaluate(vals), got)
     s.close()
+
+
+def test_cell_population_plugin_with_real_generator_output_and_non_sampled_parameters(built, tmp_path):
+    """The plugin on the fixture whose model text the reference's own SBML code generator emitted, through the three
+    bcm3::Likelihood virtuals of Likelihood.h:18-22: AddNonSampledParameters names `basal`, SetNonSampledParameters replaces
+    its value between evaluations (bcmopt/main.cpp:231) -- equal to the direct ABI call on a problem that carries that value --
+    and OutputEvaluationStatistics writes its report."""
+    import dataclasses
+
+    from bcm3_b200 import host_api
+    from bcm3_b200.cellpop import CellPopEvaluator
+    from tests.util import sbml_cell_cycle_problem, sbml_cell_cycle_values
+
+    prob = sbml_cell_cycle_problem(num_cells=64, T=10)
+    vals = sbml_cell_cycle_values(3)
+    species = ["Cdc20", "Cdh1", "CycA", "CycB", "CycD", "CycD2", "CycE", "CycEp27", "E2F", "Emi1", "Rb", "p27", "pRb"]
+    names = ["k_syn", "k_deg", "k_act", "k_inh", "variability_scale", "stdev"]
+    prior = "<variableset>" + "".join(
+        f'<variable name="{n}" {"" if n == "variability_scale" else "logspace=" + chr(34) + "true" + chr(34) + " "}distribution="uniform" lower="-5" upper="5"/>'
+        for n in names) + "</variableset>"
+    lik = (f'<bcm_likelihood type="cell_population"><experiment name="cycle" model_file="cell_cycle.xml" entry_time="0" num_cells="{prob.num_cells}" '
+           f'max_cells="{prob.num_cells}" divide_cells="false"><cell_variability distribution="diagonal_gaussian">'
+           '<variable model_parameter="k_syn" apply="multiplicative_log" scale="variability_scale"/>'
+           '<variable model_parameter="k_deg" apply="multiplicative_log" scale="variability_scale" negate="true"/>'
+           f'<variable initial_condition_species="Rb" apply="additive" scale="{float(np.log(0.02))!r}"/></cell_variability>'
+           '<data type="time_course_population_average" data_name="readout" species_name="CycE+CycEp27" stdev="stdev"/>'
+           '</experiment></bcm_likelihood>')
+    s = host_api.CellPopSession(prior, lik)
+    s.add_non_sampled_parameters(["basal"])
+    s.set_model_with_non_sampled(prob, species)
+    s.set_data(0, 0, prob.timepoints, prob.observed)
+    s.set_sobol(0, prob.sobol)
+    s.post_initialize()
+    for basal in (0.01, 0.05):
+        s.set_non_sampled_parameters([basal])
+        got = s.evaluate(vals)
+        ev = CellPopEvaluator(dataclasses.replace(prob, non_sampled_parameters=np.array([basal])))
+        want, _ = ev.evaluate(vals)
+        ev.close()
+        assert np.array_equal(got, want)
+    s.output_evaluation_statistics(str(tmp_path))
+    s.close()
+    report = (tmp_path / "cellpop_evaluation_statistics.txt").read_text().splitlines()
+    assert report[0].split("\t") == ["experiment", "data_set", "evaluations", "kernel_launches"] and report[1].split("\t")[:3] == ["cycle", "0", "6"]
+
+
+def test_cell_population_plugin_with_dividing_cells(built):
+    """likelihood.xml with the reference's default divide_cells="true" and a model that has the cell-cycle species: the plugin
+    finds them by name (Cell.cpp:40-55, 127-133), the evaluation equals the direct ABI call on the same problem."""
+    from bcm3_b200 import host_api
+    from bcm3_b200 import synthetic_cellpop as sc
+    from bcm3_b200.cellpop import CellPopEvaluator
+    from tests.util import cellpop_xml
+
+    M = 5
+    prob = sc.make_dividing_problem(M=M, num_cells=16, max_cells=400, t_end=5.5, T=16)
+    vals = sc.make_chain_values(3, seed=5)
+    ev = CellPopEvaluator(prob)
+    want, _ = ev.evaluate(vals)
+    ev.close()
+    prior, lik, species = cellpop_xml(prob, max_cells="400")
+    lik = lik.replace(' divide_cells="false"', "").replace('model_parameter="k_in"', 'model_parameter="k_cascade"')
+    assert f'scale="{math.log(0.01)!r}"/>' in lik
+    lik = lik.replace(f'scale="{math.log(0.01)!r}"/>', f'scale="{math.log(0.01)!r}" only_initial_cells="true"/>')
+    species = species[:M] + list(sc.DIVISION_SPECIES)
+    lik = lik.replace(f'species_name="x{prob.num_species - 1}"', f'species_name="x{M - 1}"')
+    got, desc = host_api.cellpop_evaluate(prior, lik, prob, species, values=vals, batched=True)
+    assert "divide_cells=1" in desc and f"cytokinesis_species={M}" in desc
+    assert np.array_equal(got, want)

@@ -134,12 +134,15 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     # trailing_simulation_time (Experiment.cpp:489, 655-656) moves the end of the integration past the last timepoint
     trail = host_api.cellpop_evaluate(*cellpop_xml(prob, trailing_simulation_time="2.5")[:2], prob, species, compile_only=True)[1]
     assert float(dict(i.split("=", 1) for i in trail.split(";"))["simulation_end_time"]) == float(prob.timepoints[-1]) + 2.5
-    for attrs, message in ((dict(solver_max_timestep="0.5"), "solver_max_timestep"), (dict(synchronization_time_offset="3"), "synchronization_time_offset")):
+    assert "solver_max_timestep=0.5" in host_api.cellpop_evaluate(*cellpop_xml(prob, solver_max_timestep="0.5")[:2], prob, species, compile_only=True)[1]
+    for attrs, message in ((dict(synchronization_time_offset="3"), "synchronization_time_offset"),):
         with pytest.raises(RuntimeError, match=message):
             host_api.cellpop_evaluate(*cellpop_xml(prob, **attrs)[:2], prob, species, compile_only=True)
+    # a species named "apoptosis" ends a cell's life when it passes 1 (Cell.cpp:516-534): handed on by index
     renamed = [("apoptosis" if s == "x2" else s) for s in species]
-    with pytest.raises(RuntimeError, match="threshold events"):
-        host_api.cellpop_evaluate(prior, lik, prob, renamed, compile_only=True)
+    assert "apoptosis_species=2" in host_api.cellpop_evaluate(prior, lik, prob, renamed, compile_only=True)[1]
+    with pytest.raises(RuntimeError, match="simulate_past_chromatid_separation_time"):
+        host_api.cellpop_evaluate(*cellpop_xml(prob, simulate_past_chromatid_separation_time="3")[:2], prob, species, compile_only=True)
     with pytest.raises(RuntimeError, match="proportional stdev has not been specified"):
         host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" error_model="proportional_normal"'), prob, species, compile_only=True)
     # an entry_time variable occupies a quasi-random dimension (kind 2 of the variability rows) and needs a wider table
@@ -148,9 +151,12 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
         host_api.cellpop_evaluate(prior, with_entry, prob, species, compile_only=True)
     wider = dataclasses.replace(prob, sobol=np.concatenate([prob.sobol, prob.sobol[:, :1]], axis=1))
     assert "variability_dim=4" in host_api.cellpop_evaluate(prior, with_entry, wider, species, compile_only=True)[1]
-    # the reference's default is dividing cells (Experiment.cpp:488): refused, not silently ignored
-    with pytest.raises(RuntimeError, match="divide_cells"):
-        host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)
+    # the reference's default is dividing cells (Experiment.cpp:488); a model without a "cytokinesis" species never divides
+    # (Cell.cpp:499), so the default and divide_cells="false" describe the same evaluator ...
+    assert host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, species, compile_only=True)[1] == desc
+    # ... and one with "cytokinesis" needs all seven species a daughter resets (Cell.cpp:127-133 looks them up unchecked)
+    with pytest.raises(RuntimeError, match="nuclear_envelope"):
+        host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, [("cytokinesis" if s == "x2" else s) for s in species], compile_only=True)
     with pytest.raises(RuntimeError, match="not supported"):
         host_api.cellpop_evaluate(prior, lik.replace("time_course_population_average", "time_course"), prob, species, compile_only=True)
     with pytest.raises(RuntimeError, match="Could not find variable"):

@@ -87,10 +87,13 @@ def load_cellpop_golden(name):
     inv_apply = {v: k for k, v in APPLY_TYPES.items()}
     variability = []
     for row in z["variability_rows"]:
-        is_ic, target, apply, scale_ix, scale_fixed, negate = row
-        variability.append(Variability(apply=inv_apply[int(apply)], model_parameter=None if is_ic else int(target),
-                                       initial_condition_species=int(target) if is_ic else None,
-                                       scale_ix=None if scale_ix < 0 else int(scale_ix), scale_fixed=float(scale_fixed), negate=bool(negate)))
+        kind_flags, target, apply, scale_ix, scale_fixed, negate = row
+        kind, only_initial = int(kind_flags) & 3, bool(int(kind_flags) & 4)
+        is_ic = kind == 1
+        variability.append(Variability(apply=inv_apply[int(apply)], model_parameter=None if (is_ic or kind == 2) else int(target),
+                                       initial_condition_species=int(target) if is_ic else None, entry_time=(kind == 2),
+                                       scale_ix=None if scale_ix < 0 else int(scale_ix), scale_fixed=float(scale_fixed), negate=bool(negate),
+                                       only_initial_cells=only_initial))
     opt_int = lambda k: int(z[k]) if k in z.files else None
     extra = {}
     if "relative_to_time_average" in z.files:
@@ -99,6 +102,11 @@ def load_cellpop_golden(name):
         extra.update(simulation_end_time=float(z["simulation_end_time"]))
     if "treatment_species" in z.files:
         extra.update(treatment_species=int(z["treatment_species"]), treatment_times=z["treatment_times"])
+    if "divide_cells" in z.files and bool(z["divide_cells"]):
+        extra.update(divide_cells=True, max_cells=int(z["max_cells"]), cytokinesis_species=opt_int("cytokinesis_species"),
+                     division_reset_species=tuple(int(i) for i in z["division_reset_species"]))
+    if "apoptosis_species" in z.files:
+        extra.update(apoptosis_species=int(z["apoptosis_species"]))
     if "variability_distribution" in z.files:
         extra.update(variability_distribution=str(z["variability_distribution"]),
                      covariance=[int(ix) if ix >= 0 else float(fx) for ix, fx in z["covariance_rows"]],
