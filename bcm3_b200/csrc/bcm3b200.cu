@@ -24,6 +24,7 @@
 #include "poppk_kernel.cuh"
 #include "cellpop_host.cuh"
 #include "comm_host.cuh"
+#include "pharmaco_host.cuh"
 
 using namespace bcm3b200;
 
@@ -70,6 +71,7 @@ struct Shard {
 };
 
 struct Handle {
+	std::unique_ptr<PharmacoState> ph; // set for model kind "pharmaco_population" (matrix-exponential PK, no ODE solver)
 	std::unique_ptr<CellPopState> cp; // set for model kind "cell_population"; the fields below are the PopPK evaluator
 	// cell_population with device_count > 1 in ONE process: the states of the further devices (cp is the first device's) and
 	// one NCCL end per device (ncclCommInitAll); the first device combines the gathered partials and finishes
@@ -559,12 +561,47 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 {
 	if (!model_kind || !handle) return fail(BCM3B200_ERR_ARG, "null argument");
 	*handle = nullptr;
-	const bool is_cellpop = strcmp(model_kind, "cell_population") == 0;
-	if (!is_cellpop && strcmp(model_kind, "pop_pk_trajectory") != 0)
+	const bool is_cellpop = strcmp(model_kind, "cell_population") == 0, is_pharmaco = strcmp(model_kind, "pharmaco_population") == 0;
+	if (!is_cellpop && !is_pharmaco && strcmp(model_kind, "pop_pk_trajectory") != 0)
 		return fail(BCM3B200_ERR_UNSUPPORTED, "unknown model kind \"%s\"", model_kind);
 	std::map<std::string, std::string> kv;
 	if (model_desc && !parse_desc((const char*)model_desc, desc_bytes, kv)) return fail(BCM3B200_ERR_ARG, "malformed model description");
 	std::unique_ptr<Handle> h(new Handle);
+	if (is_pharmaco) {
+		std::unique_ptr<PharmacoState> ph(new PharmacoState);
+		bool hasP, hasT, hasN;
+		ph->P = get_int(kv, "num_patients", 0, &hasP);
+		ph->T = get_int(kv, "num_timepoints", 0, &hasT);
+		ph->nvar = get_int(kv, "num_variables", 0, &hasN);
+		if (!hasP || !hasT || !hasN || ph->P < 0 || ph->T < 0) return fail(BCM3B200_ERR_ARG, "num_patients, num_timepoints and num_variables are required");
+		ph->drug = kv.count("drug") ? kv["drug"] : "";
+		ph->use_peripheral = get_int(kv, "peripheral_compartment", 0) != 0;
+		ph->num_transit = get_int(kv, "num_transit_compartments", 0);
+		ph->use_bioavailability = get_int(kv, "bioavailability", 0) != 0;
+		static const char* roles[] = { "additive_sd", "proportional_sd", "mean_absorption", "mean_excretion", "mean_clearance", "mean_volume_of_distribution",
+			                           "sigma_absorption", "sigma_excretion", "sigma_clearance", "sigma_volume_of_distribution", "sigma_transit_time",
+			                           "peripheral_forward_rate", "peripheral_backward_rate", "mean_transit_time" };
+		for (const char* role : roles) {
+			const int ix = get_int(kv, (std::string(role) + "_ix").c_str(), -1);
+			if (ix >= ph->nvar) return fail(BCM3B200_ERR_ARG, "%s_ix out of range", role);
+			ph->ix[role] = ix;
+		}
+		ph->shard_rank = get_int(kv, "shard_rank", 0);
+		ph->shard_count = get_int(kv, "shard_count", 1);
+		ph->device = get_int(kv, "device", 0);
+		if (ph->shard_count < 1 || ph->shard_rank < 0 || ph->shard_rank >= ph->shard_count) return fail(BCM3B200_ERR_ARG, "bad shard_rank / shard_count");
+		if (device_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "pharmaco_population needs device_count == 1 (one process per GPU + bcm3b200_comm_init to use several)");
+		const int ndev = bcm3b200_device_count();
+		if (ndev == 0) return fail(BCM3B200_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+		if (ph->device < 0 || ph->device >= ndev) return fail(BCM3B200_ERR_CUDA, "device %d requested but only %d visible", ph->device, ndev);
+		h->shard_rank = ph->shard_rank;
+		h->shard_count = ph->shard_count;
+		h->device0 = ph->device;
+		h->device_count = 1;
+		h->ph = std::move(ph);
+		*handle = h.release();
+		return BCM3B200_OK;
+	}
 	if (is_cellpop) {
 		std::unique_ptr<CellPopState> cp;
 		int mrc = make_cellpop_state(kv, cp);
@@ -650,6 +687,27 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !name || !data || !shape || ndim < 1 || ndim > 2) return fail(BCM3B200_ERR_ARG, "bad argument");
+	if (h->ph) {
+		PharmacoState& ph = *h->ph;
+		const size_t P = (size_t)ph.P, T = (size_t)ph.T;
+		const std::string n(name);
+		size_t want0 = 0, want1 = 0;
+		if (n == "time") want0 = T;
+		else if (n == "observed_concentration") { want0 = P; want1 = T; }
+		else if (n == "dose" || n == "dosing_interval" || n == "dose_after_dose_change" || n == "dose_change_time" || n == "intermittent") want0 = P;
+		else if (n == "treatment_interruptions") { want0 = P; want1 = 29; }
+		else if (n == "transforms") want0 = (size_t)ph.nvar;
+		else {
+			bool known = false;
+			for (const char* arr : kPharmacoPatientArrays) known = known || n == arr;
+			if (!known) return fail(BCM3B200_ERR_ARG, "unknown data name \"%s\"", name);
+			want0 = P;
+		}
+		if (ndim != (want1 ? 2 : 1) || shape[0] != want0 || (want1 && shape[1] != want1)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);
+		ph.data[n].assign(data, data + want0 * (want1 ? want1 : 1));
+		ph.finalized = false;
+		return BCM3B200_OK;
+	}
 	if (h->cp) {
 		CellPopState& cp = *h->cp;
 		const std::string n(name);
@@ -730,6 +788,7 @@ int bcm3b200_finalize(void* handle)
 {
 	Handle* h = (Handle*)handle;
 	if (!h) return fail(BCM3B200_ERR_ARG, "null handle");
+	if (h->ph) return pharmaco_finalize(*h->ph, molecular_weight(h->ph->drug));
 	if (h->cp) {
 		for (CellPopState* st : cellpop_states(h)) {
 			int rc = cellpop_finalize(*st, bcm3b200_device_count() > 0);
@@ -738,6 +797,38 @@ int bcm3b200_finalize(void* handle)
 		return BCM3B200_OK;
 	}
 	return finalize(h);
+}
+
+// pharmaco_population, host buffers in, log-likelihoods out: this handle's slice of the patients, then (with a communicator)
+// the all-gather + rank-order combination of the [3][C] blocks, exactly as for pop_pk_trajectory
+static int pharmaco_evaluate_handle(Handle* h, size_t C, size_t nvar, const double* values, double* logp, int* status)
+{
+	PharmacoState& ph = *h->ph;
+	int rc = pharmaco_finalize(ph, molecular_weight(ph.drug));
+	if (rc != BCM3B200_OK) return rc;
+	if (C == 0) return BCM3B200_OK;
+	CUDA_TRY(cudaSetDevice(ph.device));
+	CUDA_TRY(ph.d_partial.ensure(3 * C));
+	if (ph.h_partial_n < 3 * C) {
+		if (ph.h_partial) cudaFreeHost(ph.h_partial);
+		ph.h_partial = nullptr;
+		CUDA_TRY(cudaMallocHost((void**)&ph.h_partial, sizeof(double) * 3 * C));
+		ph.h_partial_n = 3 * C;
+	}
+	rc = pharmaco_enqueue(ph, C, nvar, values, ph.d_partial.p, ph.stream);
+	if (rc != BCM3B200_OK) return rc;
+	if (h->comm.active()) {
+		rc = h->comm.gather_combine(ph.d_partial.p, 3 * C, C, ph.d_partial.p, ph.stream);
+		if (rc != BCM3B200_OK) return rc;
+		ph.total_launches += 2;
+	}
+	CUDA_TRY(cudaMemcpyAsync(ph.h_partial, ph.d_partial.p, sizeof(double) * 3 * C, cudaMemcpyDeviceToHost, ph.stream));
+	CUDA_TRY(cudaStreamSynchronize(ph.stream));
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, ph.ev0, ph.ev1) == cudaSuccess) ph.last_kernel_ms = ms;
+	pharmaco_combine(C, ph.h_partial, logp, status);
+	ph.num_evaluations += (int64_t)C;
+	return BCM3B200_OK;
 }
 
 // cell_population, host buffers in, complete log-likelihoods out, for every way a handle can be spread:
@@ -856,6 +947,7 @@ int bcm3b200_evaluate_batch(void* handle, size_t num_chains, size_t num_variable
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !values || !logp) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->ph) return pharmaco_evaluate_handle(h, num_chains, num_variables, values, logp, status);
 	if (h->cp) return cellpop_evaluate_handle(h, num_chains, num_variables, values, logp, status);
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
@@ -931,6 +1023,14 @@ int bcm3b200_enqueue_batch(void* handle, size_t num_chains, size_t num_variables
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->ph) {
+		int prc = pharmaco_finalize(*h->ph, molecular_weight(h->ph->drug));
+		if (prc != BCM3B200_OK) return prc;
+		if (num_chains == 0) return BCM3B200_OK;
+		prc = pharmaco_enqueue(*h->ph, num_chains, num_variables, values, d_partial, (cudaStream_t)stream);
+		if (prc == BCM3B200_OK) h->ph->num_evaluations += (int64_t)num_chains;
+		return prc;
+	}
 	if (h->cp) {
 		if (!h->cp_more.empty()) return fail(BCM3B200_ERR_UNSUPPORTED, "device-buffer entries need device_count == 1");
 		return cellpop_enqueue_partial(*h->cp, num_chains, num_variables, values, d_partial, (cudaStream_t)stream);
@@ -954,7 +1054,7 @@ int bcm3b200_evaluate_batch_device(void* handle, size_t num_chains, size_t num_v
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !d_values || !d_partial) return fail(BCM3B200_ERR_ARG, "null argument");
-	if (h->cp) return fail(BCM3B200_ERR_UNSUPPORTED, "device-partial entries are pop_pk_trajectory only");
+	if (h->cp || h->ph) return fail(BCM3B200_ERR_UNSUPPORTED, "the device-values entry is pop_pk_trajectory only");
 	if ((int)num_variables != h->nvar) return fail(BCM3B200_ERR_ARG, "num_variables %zu != %d", num_variables, h->nvar);
 	int rc = finalize(h);
 	if (rc != BCM3B200_OK) return rc;
@@ -996,7 +1096,7 @@ int bcm3b200_comm_init(void* handle, const void* id, size_t id_bytes)
 	if (!h || !id || id_bytes < sizeof(ncclUniqueId)) return fail(BCM3B200_ERR_ARG, "bad argument");
 	if (h->device_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "a communicator joins handles with one device each (device_count == 1)");
 	if (h->comm.comm) return fail(BCM3B200_ERR_STATE, "this handle already has a communicator");
-	const int world = h->cp ? h->cp->shard_count : h->shard_count, rank = h->cp ? h->cp->shard_rank : h->shard_rank;
+	const int world = h->cp ? h->cp->shard_count : h->shard_count, rank = h->cp ? h->cp->shard_rank : h->shard_rank; // pharmaco: copied into the handle
 	if (world == 1) return BCM3B200_OK; // nothing to exchange
 	NcclApi& api = NcclApi::get();
 	if (!api.ok()) return fail(BCM3B200_ERR_CUDA, "NCCL could not be loaded: %s", api.why.c_str());
@@ -1036,6 +1136,20 @@ int bcm3b200_get_diagnostics(void* handle, double* conc, double* patient_ll, int
 	Handle* h = (Handle*)handle;
 	if (!h) return fail(BCM3B200_ERR_ARG, "null handle");
 	if (h->cp) return fail(BCM3B200_ERR_UNSUPPORTED, "use bcm3b200_get_cell_diagnostics for cell_population");
+	if (h->ph) {
+		PharmacoState& ph = *h->ph;
+		if (!ph.finalized || ph.last_C == 0) return fail(BCM3B200_ERR_STATE, "no evaluation yet");
+		if (counters) return fail(BCM3B200_ERR_UNSUPPORTED, "pharmaco_population has no solver counters (matrix exponential, no ODE solver)");
+		CUDA_TRY(cudaSetDevice(ph.device));
+		CUDA_TRY(cudaDeviceSynchronize());
+		const size_t C = (size_t)ph.last_C, Pl = (size_t)ph.P_local;
+		if (patient_ll && Pl) CUDA_TRY(cudaMemcpy(patient_ll, ph.d_patient_ll.p, sizeof(double) * C * Pl, cudaMemcpyDeviceToHost));
+		if (conc) {
+			if (!ph.diagnostics) return fail(BCM3B200_ERR_STATE, "diagnostics were not enabled before the last evaluate");
+			if (Pl) CUDA_TRY(cudaMemcpy(conc, ph.d_conc.p, sizeof(double) * C * Pl * ph.T, cudaMemcpyDeviceToHost));
+		}
+		return BCM3B200_OK;
+	}
 	if (!h->diagnostics || !h->finalized) return fail(BCM3B200_ERR_STATE, "diagnostics were not enabled before the last evaluate");
 	// layout over the handle's patients: [C][P_handle][...], shards are contiguous slices
 	size_t Ph = 0;
@@ -1068,6 +1182,11 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !name) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->ph) {
+		if (!strcmp(name, "diagnostics")) h->ph->diagnostics = value != 0;
+		else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
+		return BCM3B200_OK;
+	}
 	if (h->cp) {
 		for (CellPopState* st : cellpop_states(h)) {
 			if (!strcmp(name, "diagnostics")) st->diagnostics = value != 0;
@@ -1093,6 +1212,19 @@ int bcm3b200_get_stat(void* handle, const char* name, int64_t* value)
 {
 	Handle* h = (Handle*)handle;
 	if (!h || !name || !value) return fail(BCM3B200_ERR_ARG, "null argument");
+	if (h->ph) {
+		PharmacoState& ph = *h->ph;
+		if (!strcmp(name, "last_kernel_launches")) *value = ph.last_launches;
+		else if (!strcmp(name, "total_kernel_launches")) *value = ph.total_launches;
+		else if (!strcmp(name, "num_evaluations")) *value = ph.num_evaluations;
+		else if (!strcmp(name, "last_kernel_us")) *value = (int64_t)(ph.last_kernel_ms * 1000.0);
+		else if (!strcmp(name, "num_patients_local") || !strcmp(name, "patient_offset")) {
+			if (!ph.finalized) return fail(BCM3B200_ERR_STATE, "not finalized");
+			*value = !strcmp(name, "num_patients_local") ? ph.P_local : ph.offset;
+		} else if (!strcmp(name, "num_compartments")) *value = ph.N;
+		else return fail(BCM3B200_ERR_ARG, "unknown stat \"%s\"", name);
+		return BCM3B200_OK;
+	}
 	if (h->cp) {
 		CellPopState& cp = *h->cp;
 		if (!strcmp(name, "last_kernel_launches")) *value = cp.last_launches;
@@ -1147,6 +1279,10 @@ void bcm3b200_destroy(void* handle)
 			cudaSetDevice(st->device);
 			cudaStreamSynchronize(st->stream);
 		}
+	}
+	if (h->ph && h->ph->stream) {
+		cudaSetDevice(h->ph->device);
+		cudaStreamSynchronize(h->ph->stream);
 	}
 	delete h;
 }

@@ -58,6 +58,10 @@ constexpr int CPW = 32 / G; // cells per warp
 constexpr int WPB = CP_GROUP_WARPS;
 constexpr int BS = 32 * WPB;
 constexpr int QMAX = 5;
+#ifndef CP_SJ_UNROLL
+#define CP_SJ_UNROLL 1
+#endif
+constexpr int SJ_UNROLL = CP_SJ_UNROLL; // rows of the saved Jacobian in flight when the Newton matrix is rebuilt from it
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double UROUND = DBL_EPSILON;
 
@@ -201,6 +205,9 @@ __device__ __noinline__ void rhs_eval_lanes(unsigned y_off, unsigned f_off, unsi
 #endif
 #ifndef CP_PIVOT_REDUX
 #define CP_PIVOT_REDUX (CP_GROUP >= 16)
+#endif
+#ifndef CP_SJ_UNROLL
+#define CP_SJ_UNROLL 1
 #endif
 
 __device__ __forceinline__ double step_root(double base, int k) { return bcm3b200::bdf_root_halley(base, k); }
@@ -661,7 +668,9 @@ struct GroupBdf {
 			nje++;
 		} else {
 			gsync();
-#pragma unroll 1
+			// M = I - gamma * (saved Jacobian), row by row; the saved Jacobian is in global memory: with CP_SJ_UNROLL > 1 several
+			// rows' loads are in flight at once instead of one round trip per row
+#pragma unroll SJ_UNROLL
 			for (int r = 0; r < N; r++) {
 #pragma unroll
 				for (int e = 0; e < E; e++) {
@@ -1485,6 +1494,19 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 	extern __shared__ double smem_d[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int gw = lane / G; // group within the warp
+#if CP_RHS_LANES && CP_TABLES_SHARED
+	{ // the tables of the lane-parallel right-hand side: one copy per block, behind the cells' blocks
+		double* td = smem_d + CP_TAB_BASE;
+		for (int i = tid; i < CP_TAB_NLIT; i += BS) td[i] = cp_rl_lit[i];
+		for (int i = tid; i < CP_TAB_NCOEF; i += BS) td[CP_TAB_NLIT + i] = cp_out_coef[i];
+		int* ti = reinterpret_cast<int*>(td + CP_TAB_NLIT + CP_TAB_NCOEF);
+		for (int i = tid; i < CP_TAB_NIDX; i += BS) ti[i] = cp_rl_idx[i];
+		for (int i = tid; i < CP_TAB_NTARGET; i += BS) ti[CP_TAB_NIDX + i] = cp_rl_target[i];
+		for (int i = tid; i < CP_TAB_NBEGIN; i += BS) ti[CP_TAB_NIDX + CP_TAB_NTARGET + i] = cp_out_begin[i];
+		for (int i = tid; i < CP_TAB_NLAW; i += BS) ti[CP_TAB_NIDX + CP_TAB_NTARGET + CP_TAB_NBEGIN + i] = cp_out_law[i];
+		__syncthreads();
+	}
+#endif
 
 	GroupBdf B;
 	B.lg = lane % G;
@@ -1800,7 +1822,13 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 
 // internal linkage on purpose: several model libraries live in one process, and a function-local static of an `inline`
 // function is a process-wide unique symbol -- the second model would reuse the first one's cached launch configuration
-static size_t smem_bytes() { return sizeof(double) * (size_t)CS * CPW * WPB; }
+#if CP_RHS_LANES && CP_TABLES_SHARED
+constexpr int TABLE_DOUBLES = CP_TAB_NLIT + CP_TAB_NCOEF + (CP_TAB_NIDX + CP_TAB_NTARGET + CP_TAB_NBEGIN + CP_TAB_NLAW + 1) / 2;
+static_assert(CP_TAB_BASE == CS * CPW * WPB, "cellpop_host.cuh places the tables right behind the cells' blocks");
+#else
+constexpr int TABLE_DOUBLES = 0;
+#endif
+static size_t smem_bytes() { return sizeof(double) * ((size_t)CS * CPW * WPB + TABLE_DOUBLES); }
 
 // launch configuration per DEVICE: the shared-memory opt-in and the occupancy result are per-device state, and one process
 // may hold handles of the same model on several devices (the multi-device handle, several ranks' handles in tests)

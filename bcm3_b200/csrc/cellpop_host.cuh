@@ -477,6 +477,7 @@ struct LaneRhs {
 	bool ok = false;
 	int num_ratelaws = 0;
 	int num_shapes = 0;
+	int table_doubles = 0; // size of the tables when they are copied into shared memory
 	std::string code; // tables + generated_ratelaws_lanes<G>() + generated_assemble()
 };
 
@@ -688,10 +689,10 @@ inline LaneRhs cellpop_lane_rhs(const std::string& code_without_jacobian, int N)
 		size_t ci = 0, ck = 0;
 		for (char c : first.shape) {
 			if (c == '\x01') {
-				expr += (idx_slot[ci] < 0) ? std::to_string(first.idx[ci]) : ("__ldg(I + " + std::to_string(idx_slot[ci]) + ")");
+				expr += (idx_slot[ci] < 0) ? std::to_string(first.idx[ci]) : ("CP_IDX(I + " + std::to_string(idx_slot[ci]) + ")");
 				ci++;
 			} else if (c == '\x02') {
-				expr += (lit_slot[ck] < 0) ? first.lit[ck] : ("__ldg(K + " + std::to_string(lit_slot[ck]) + ")");
+				expr += (lit_slot[ck] < 0) ? first.lit[ck] : ("CP_LIT(K + " + std::to_string(lit_slot[ck]) + ")");
 				ck++;
 			} else {
 				expr += c;
@@ -699,9 +700,9 @@ inline LaneRhs cellpop_lane_rhs(const std::string& code_without_jacobian, int N)
 		}
 		fn << "\t// shape " << sidx << ": " << mem.size() << " reaction(s)\n";
 		fn << "\tfor (int m = lg; m < " << mem.size() << "; m += G_) {\n";
-		if (vi) fn << "\t\tconst int* I = cp_rl_idx + " << off_idx << " + m * " << vi << ";\n";
-		if (vk) fn << "\t\tconst double* K = cp_rl_lit + " << off_lit << " + m * " << vk << ";\n";
-		fn << "\t\tratelaws[__ldg(cp_rl_target + " << off_target << " + m)] = " << expr << ";\n\t}\n";
+		if (vi) fn << "\t\tconst int I = " << off_idx << " + m * " << vi << ";\n";
+		if (vk) fn << "\t\tconst int K = " << off_lit << " + m * " << vk << ";\n";
+		fn << "\t\tratelaws[CP_TARGET(" << off_target << " + m)] = " << expr << ";\n\t}\n";
 		for (int m : mem) {
 			for (size_t k = 0; k < ni; k++)
 				if (idx_slot[k] >= 0) tab_idx << laws[m].idx[k] << ", ";
@@ -728,18 +729,36 @@ inline LaneRhs cellpop_lane_rhs(const std::string& code_without_jacobian, int N)
 	std::ostringstream o;
 	o << "// ---- lane-parallel form of generated_derivative (" << shape_names.size() << " shapes, " << NR << " reactions), made by cellpop_lane_rhs ----\n";
 	o << "#define CP_RHS_LANES 1\n#define CP_NUM_RATELAWS " << NR << "\n";
+	// Tables: literals and coefficients (doubles), then indices, targets, sum boundaries and sum terms (ints). With
+	// CP_TABLES_SHARED (set by cellpop_module_source when they fit behind the cells' blocks) the kernel copies them into shared
+	// memory once per block and the accessors read that copy; otherwise they are read through the read-only cache.
+	const int n_lit = off_lit + 1, n_coef = nterms + 1, n_idx = off_idx + 1, n_target = off_target + 1, n_begin = N + 1, n_law = nterms + 1;
+	o << "#define CP_TAB_NLIT " << n_lit << "\n#define CP_TAB_NCOEF " << n_coef << "\n#define CP_TAB_NIDX " << n_idx << "\n#define CP_TAB_NTARGET " << n_target
+	  << "\n#define CP_TAB_NBEGIN " << n_begin << "\n#define CP_TAB_NLAW " << n_law << "\n";
 	o << "__device__ const int cp_rl_idx[] = { " << tab_idx.str() << "0 };\n";
 	o << "__device__ const double cp_rl_lit[] = { " << tab_lit.str() << "0.0 };\n";
 	o << "__device__ const int cp_rl_target[] = { " << tab_target.str() << "0 };\n";
 	o << "__device__ const int cp_out_begin[] = { " << ob.str() << " };\n";
 	o << "__device__ const int cp_out_law[] = { " << ol.str() << "0 };\n";
 	o << "__device__ const double cp_out_coef[] = { " << oc.str() << "0.0 };\n";
+	o << "#ifndef CP_TABLES_SHARED\n#define CP_TABLES_SHARED 0\n#endif\n"
+	     "#if CP_TABLES_SHARED\n"
+	     "extern __shared__ double smem_d[];\n"
+	     "#define CP_TAB_INTS (reinterpret_cast<const int*>(smem_d + CP_TAB_BASE + CP_TAB_NLIT + CP_TAB_NCOEF))\n"
+	     "#define CP_LIT(k) (smem_d[CP_TAB_BASE + (k)])\n#define CP_COEF(k) (smem_d[CP_TAB_BASE + CP_TAB_NLIT + (k)])\n"
+	     "#define CP_IDX(k) (CP_TAB_INTS[(k)])\n#define CP_TARGET(k) (CP_TAB_INTS[CP_TAB_NIDX + (k)])\n"
+	     "#define CP_BEGIN(k) (CP_TAB_INTS[CP_TAB_NIDX + CP_TAB_NTARGET + (k)])\n#define CP_LAW(k) (CP_TAB_INTS[CP_TAB_NIDX + CP_TAB_NTARGET + CP_TAB_NBEGIN + (k)])\n"
+	     "#else\n"
+	     "#define CP_LIT(k) __ldg(cp_rl_lit + (k))\n#define CP_COEF(k) __ldg(cp_out_coef + (k))\n#define CP_IDX(k) __ldg(cp_rl_idx + (k))\n"
+	     "#define CP_TARGET(k) __ldg(cp_rl_target + (k))\n#define CP_BEGIN(k) __ldg(cp_out_begin + (k))\n#define CP_LAW(k) __ldg(cp_out_law + (k))\n"
+	     "#endif\n";
 	o << fn.str();
 	// out[i] = the signed terms of the text, left to right (a coefficient of 1 multiplies exactly)
 	o << "__device__ __forceinline__ double generated_assemble(int i, const double* ratelaws)\n{\n"
-	     "\tint t = __ldg(cp_out_begin + i);\n\tconst int t1 = __ldg(cp_out_begin + i + 1);\n\tif (t == t1) return 0.0;\n"
-	     "\tdouble acc = __ldg(cp_out_coef + t) * ratelaws[__ldg(cp_out_law + t)];\n"
-	     "\tfor (t++; t < t1; t++) acc = acc + __ldg(cp_out_coef + t) * ratelaws[__ldg(cp_out_law + t)];\n\treturn acc;\n}\n";
+	     "\tint t = CP_BEGIN(i);\n\tconst int t1 = CP_BEGIN(i + 1);\n\tif (t == t1) return 0.0;\n"
+	     "\tdouble acc = CP_COEF(t) * ratelaws[CP_LAW(t)];\n"
+	     "\tfor (t++; t < t1; t++) acc = acc + CP_COEF(t) * ratelaws[CP_LAW(t)];\n\treturn acc;\n}\n";
+	out.table_doubles = n_lit + n_coef + (n_idx + n_target + n_begin + n_law + 1) / 2;
 	out.ok = true;
 	out.num_ratelaws = NR;
 	out.num_shapes = (int)shape_names.size();
@@ -856,6 +875,13 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	if (const char* benv = getenv("BCM3B200_CELLPOP_GROUP_MIN_BLOCKS")) gblocks = atoi(benv) > 0 ? atoi(benv) : gblocks;
 	o << "#define CP_GROUP " << G << "\n";
 	o << "#define CP_GROUP_WARPS " << gwarps << "\n";
+	if (lanes.ok) {
+		// the tables of the lane-parallel right-hand side go behind the cells' blocks when the 227 KB of a block have room for them
+		const size_t cells_bytes = per_cell * cells_per_warp * gwarps, table_bytes = sizeof(double) * (size_t)lanes.table_doubles;
+		bool shared_tables = cells_bytes + table_bytes <= 227 * 1024;
+		if (const char* tenv = getenv("BCM3B200_CELLPOP_TABLES_SHARED")) shared_tables = shared_tables && atoi(tenv) != 0;
+		if (shared_tables) o << "#define CP_TABLES_SHARED 1\n#define CP_TAB_BASE " << (cells_bytes / sizeof(double)) << "\n";
+	}
 	o << "#define CP_GROUP_MIN_BLOCKS " << gblocks << "\n";
 	// Block lock-step shares instruction fetches between the warps of a block but makes every trip as long as the slowest
 	// warp's. With 8 or more cells per warp the warps are statistically alike and sharing wins (N = 12: 130 vs 150 ms,
@@ -875,6 +901,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	if (const char* senv = getenv("BCM3B200_CELLPOP_LU_SKIP_ZEROS")) o << "#define CP_LU_SKIP_ZEROS " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_SOLVE_SLOTTED")) o << "#define CP_SOLVE_SLOTTED " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_PIVOT_REDUX")) o << "#define CP_PIVOT_REDUX " << atoi(senv) << "\n";
+	if (const char* senv = getenv("BCM3B200_CELLPOP_SJ_UNROLL")) o << "#define CP_SJ_UNROLL " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
 	o << code << "\n";
 	const int which = cellpop_resolve_kernel(cp);

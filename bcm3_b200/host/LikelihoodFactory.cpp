@@ -5,6 +5,7 @@
 
 #include "CellPopulationLikelihoodB200.h"
 #include "LikelihoodPopPKTrajectoryB200.h"
+#include "PharmacoLikelihoodPopulationB200.h"
 #include "TestLikelihoodBanana.h"
 
 namespace bcm3 {
@@ -42,6 +43,8 @@ std::shared_ptr<Likelihood> LikelihoodFactory::CreateLikelihoodFromText(const st
 		ll = std::make_shared<TestLikelihoodBanana>(sampling_threads, evaluation_threads);
 	} else if (type == "pop_pk_trajectory") {
 		ll = std::make_shared<LikelihoodPopPKTrajectoryB200>(sampling_threads, evaluation_threads);
+	} else if (type == "pharmaco_population") { // LikelihoodFactory.cpp:66
+		ll = std::make_shared<PharmacoLikelihoodPopulationB200>(sampling_threads, evaluation_threads);
 	} else if (type == "cell_population") { // LikelihoodFactory.cpp:81
 		ll = std::make_shared<CellPopulationLikelihoodB200>(sampling_threads, evaluation_threads);
 	} else {
@@ -52,6 +55,7 @@ std::shared_ptr<Likelihood> LikelihoodFactory::CreateLikelihoodFromText(const st
 		if (error) {
 			*error = "Failed to initialize likelihood";
 			if (auto* cp = dynamic_cast<CellPopulationLikelihoodB200*>(ll.get())) *error += ": " + cp->LastError();
+			if (auto* ph = dynamic_cast<PharmacoLikelihoodPopulationB200*>(ll.get())) *error += ": " + ph->LastError();
 		}
 		ll.reset();
 	}

@@ -38,6 +38,29 @@ public:
 		return mu + sigma * r * std::cos(6.283185307179586 * u2);
 	}
 
+	// RNG::GetGamma (src/utils/RNG.cpp:84-111): Marsaglia-Tsang, shape k, SCALE theta
+	double GetGamma(double k, double theta)
+	{
+		if (k < 1) {
+			const double u = GetReal();
+			return GetGamma(1.0 + k, theta) * std::pow(u, 1.0 / k);
+		}
+		const double d = k - 0.33333333333333333333333333333333;
+		const double c = 0.33333333333333333333333333333333 / std::sqrt(d);
+		double x, v, u;
+		for (;;) {
+			do {
+				x = GetNormal(0.0, 1.0);
+				v = 1.0 + c * x;
+			} while (v <= 0.0);
+			v = v * v * v;
+			u = GetReal();
+			if (u < 1 - 0.0331 * x * x * x * x) break;
+			if (std::log(u) < 0.5 * x * x + d * (1 - v + std::log(v))) break;
+		}
+		return theta * d * v;
+	}
+
 private:
 	static uint64_t mix(uint64_t z)
 	{

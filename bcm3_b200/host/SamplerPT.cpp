@@ -62,6 +62,7 @@ bool SamplerPTSettings::LoadFromConfigText(const std::string& text, std::string*
 	R("ptmhsampler.exchange_probability", exchange_probability);
 	R("ptmhsampler.temperature_schedule_power", temperature_schedule_power);
 	R("ptmhsampler.temperature_schedule_max", temperature_schedule_max);
+	R("ptmhsampler.proposal_t_dof", proposal_t_dof);
 	U("ptmhsampler.initial_position_tries", initial_position_tries);
 	return true;
 }
@@ -214,14 +215,15 @@ Real Proposal::ReflectOnBounds(Real x, Real lb, Real ub)
 
 void ProposalGlobalCovariance::GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng)
 {
-	// ProposalGlobalCovariance.cpp:19-41 with t_dof = 0
+	// ProposalGlobalCovariance.cpp:19-41
+	const Real t_scale = TScale(rng);
 	VectorReal z(n);
 	for (size_t i = 0; i < n; i++) z[i] = rng.GetNormal();
 	proposed.assign(n, 0.0);
 	for (size_t i = 0; i < n; i++) {
 		Real v = 0.0;
 		for (size_t k = 0; k <= i; k++) v += chol[i + k * n] * z[k];
-		proposed[i] = ReflectOnBounds(current[i] + v * adaptive_scale, lower[i], upper[i]);
+		proposed[i] = ReflectOnBounds(current[i] + v * (t_scale * adaptive_scale), lower[i], upper[i]);
 	}
 }
 
@@ -299,10 +301,11 @@ bool ProposalGaussianMixture::InitializeImpl(const std::vector<VectorReal>& rows
 
 void ProposalGaussianMixture::GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng)
 {
-	// ProposalGaussianMixture.cpp:21-45 with t_dof = 0
+	// ProposalGaussianMixture.cpp:21-45 (the Metropolis-Hastings ratio below ignores the t scale, as the reference's does)
 	VectorReal resp;
 	gmm.CalculateResponsibilities(current, resp);
 	selected_component = (long)SampleIndex(rng, resp);
+	const Real t_scale = TScale(rng);
 	const std::vector<Real>& L = gmm.GetComponent((size_t)selected_component).chol;
 	VectorReal z(n);
 	for (size_t i = 0; i < n; i++) z[i] = rng.GetNormal();
@@ -310,7 +313,7 @@ void ProposalGaussianMixture::GetNewSample(const VectorReal& current, VectorReal
 	for (size_t i = 0; i < n; i++) {
 		Real v = 0.0;
 		for (size_t k = 0; k <= i; k++) v += L[i + k * n] * z[k];
-		proposed[i] = ReflectOnBounds(current[i] + v * scales[(size_t)selected_component], lower[i], upper[i]);
+		proposed[i] = ReflectOnBounds(current[i] + v * (t_scale * scales[(size_t)selected_component]), lower[i], upper[i]);
 	}
 }
 
@@ -410,6 +413,7 @@ bool SamplerPT::Initialize()
 			return false;
 		}
 		c.proposal->SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
+		c.proposal->SetTDof(s.proposal_t_dof);
 	}
 	previous_swap_even = false;
 	proposal_adaptations_done = 0;
@@ -618,6 +622,7 @@ bool SamplerPT::AdaptProposals()
 			return false;
 		}
 		c.proposal->SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
+		c.proposal->SetTDof(s.proposal_t_dof);
 	}
 	return true;
 }

@@ -34,6 +34,7 @@ struct SamplerPTSettings {
 	Real exchange_probability = 0.5;
 	Real temperature_schedule_power = 3.0;
 	Real temperature_schedule_max = 1.0;
+	Real proposal_t_dof = 0.0; // ptmhsampler.proposal_t_dof: 0 = normal proposals (SamplerPT.cpp:169)
 	size_t initial_position_tries = 100;
 	// evaluation mode: true = one EvaluateLogProbabilityBatch per mutate round, false = one EvaluateLogProbability per chain
 	bool batched = true;
@@ -62,6 +63,9 @@ public:
 	// Proposal::Initialize (Proposal.cpp:39-140): bounds, target acceptance rate, the (sub)sampled history -> InitializeImpl
 	bool Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng);
 	void SetScalingSchedule(size_t ema_period, Real learning_rate) { scaling_ema_period = ema_period; scaling_learning_rate = learning_rate; }
+	// ptmhsampler.proposal_t_dof (SamplerPT.cpp:63,169; Proposal.cpp:45): > 0 scales every step by 1 / sqrt(w), w drawn as
+	// rng.GetGamma(t_dof / 2, t_dof / 2) -- the second argument is the SCALE of RNG::GetGamma, as the reference passes it
+	void SetTDof(Real dof) { t_dof = dof; }
 	virtual void Update(RNG& rng, bool scaling_frozen) = 0;
 	virtual void GetNewSample(const VectorReal& current, VectorReal& proposed, RNG& rng) = 0;
 	virtual Real CalculateMHRatio(const VectorReal& current, const VectorReal& proposed) const = 0; // log q(cur|new) - log q(new|cur)
@@ -73,7 +77,9 @@ protected:
 	size_t n = 0;
 	std::vector<Real> lower, upper;
 	size_t scaling_ema_period = 1000;
-	Real scaling_learning_rate = 0.05, target_acceptance_rate = 0.234; // proposal_t_dof = 0 (normal proposals) only
+	Real scaling_learning_rate = 0.05, target_acceptance_rate = 0.234;
+	Real t_dof = 0.0;
+	Real TScale(RNG& rng) const { return t_dof > 0.0 ? 1.0 / std::sqrt(rng.GetGamma(0.5 * t_dof, 0.5 * t_dof)) : 1.0; }
 };
 
 class ProposalGlobalCovariance : public Proposal {

@@ -5,6 +5,7 @@
 #include "CellPopulationLikelihoodB200.h"
 #include "LikelihoodFactory.h"
 #include "LikelihoodPopPKTrajectoryB200.h"
+#include "PharmacoLikelihoodPopulationB200.h"
 #include "SamplerPT.h"
 
 using namespace bcm3;
@@ -141,6 +142,61 @@ int bcm3host_run_pt_poppk(const char* prior_xml, const char* likelihood_xml, con
 		return -3;
 	}
 	return run(st, config_text, batched, seed, out, max_rows, num_rows, stats, err, errlen);
+}
+
+// likelihood.xml type="pharmaco_population" -> LikelihoodFactory -> PharmacoLikelihoodPopulationB200 with the trial arrays the NetCDF
+// reader would supply; evaluates C variable vectors batched or one by one
+int bcm3host_pharmaco_evaluate(const char* prior_xml, const char* likelihood_xml, size_t P, size_t T, const double* time, const double* obs,
+                               const double* dose, const double* dosing_interval, const double* dose_after, const double* dose_change_time,
+                               const double* intermittent, const double* interruptions, int device, const double* values, size_t C, int batched,
+                               double* logp, char* err, size_t errlen)
+{
+	Setup st;
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
+		set_err(err, errlen, error);
+		return -1;
+	}
+	auto* ll = dynamic_cast<PharmacoLikelihoodPopulationB200*>(st.likelihood.get());
+	if (!ll) {
+		set_err(err, errlen, "likelihood.xml is not of type pharmaco_population");
+		return -1;
+	}
+	PharmacoLikelihoodPopulationB200::TrialData td;
+	td.time.assign(time, time + T);
+	td.observed_concentration.assign(obs, obs + P * T);
+	td.dose.assign(dose, dose + P);
+	td.dosing_interval.assign(dosing_interval, dosing_interval + P);
+	td.dose_after_dose_change.assign(dose_after, dose_after + P);
+	td.dose_change_time.assign(dose_change_time, dose_change_time + P);
+	td.intermittent.assign(intermittent, intermittent + P);
+	td.treatment_interruptions.assign(interruptions, interruptions + P * 29);
+	ll->SetTrialData(td);
+	ll->SetDevice(device);
+	if (!ll->PostInitialize()) {
+		set_err(err, errlen, ll->LastError());
+		return -3;
+	}
+	const size_t nvar = st.varset->GetNumVariables();
+	if (batched) {
+		MatrixReal m(nvar, C);
+		std::copy(values, values + nvar * C, m.data.begin());
+		VectorReal lp;
+		if (!st.likelihood->EvaluateLogProbabilityBatch(m, lp)) {
+			set_err(err, errlen, ll->LastError());
+			return -2;
+		}
+		std::copy(lp.begin(), lp.end(), logp);
+	} else {
+		for (size_t c = 0; c < C; c++) {
+			VectorReal v(values + c * nvar, values + (c + 1) * nvar);
+			if (!st.likelihood->EvaluateLogProbability(0, v, logp[c])) {
+				set_err(err, errlen, ll->LastError());
+				return -2;
+			}
+		}
+	}
+	return 0;
 }
 
 // Factory + plugin surface check: evaluate C variable vectors (values[C][nvar]) through EvaluateLogProbability (batched = 0)

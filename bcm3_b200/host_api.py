@@ -73,6 +73,25 @@ def evaluate(prior_xml: str, likelihood_xml: str, values: np.ndarray, batched: b
     return logp
 
 
+def pharmaco_evaluate(prior_xml: str, likelihood_xml: str, trial, values, batched: bool = True, device: int = 0):
+    """likelihood.xml type="pharmaco_population" through LikelihoodFactory and the plugin class; the trial arrays are what the NetCDF
+    reader would supply (PharmacoPatient.cpp:24-46)."""
+    lib = load()
+    vals = np.ascontiguousarray(values, dtype=np.float64)
+    P, T = trial.num_patients, trial.num_timepoints
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    keep = [arr(trial.time), arr(trial.observed_concentration), arr(trial.dose), arr(trial.dosing_interval), arr(trial.dose_after_dose_change),
+            arr(trial.dose_change_time), arr(trial.intermittent), arr(trial.treatment_interruptions)]
+    logp = np.empty(vals.shape[0])
+    err = C.create_string_buffer(1024)
+    rc = lib.bcm3host_pharmaco_evaluate(prior_xml.encode(), likelihood_xml.encode(), C.c_size_t(P), C.c_size_t(T), *[k.ctypes.data_as(C.c_void_p) for k in keep],
+                                        int(device), vals.ctypes.data_as(C.c_void_p), C.c_size_t(vals.shape[0]), int(batched),
+                                        logp.ctypes.data_as(C.c_void_p), err, C.c_size_t(1024))
+    if rc != 0:
+        raise RuntimeError(f"bcm3host_pharmaco_evaluate failed ({rc}): {err.value.decode()}")
+    return logp
+
+
 def varset_info(prior_xml: str, lookup: str | None = None):
     lib = load()
     n = C.c_size_t()

@@ -37,8 +37,24 @@ extern "C" {
 #define BCM3B200_STATUS_NAN 1 /* log-likelihood is NaN: the reference aborts sampling on this (Sampler.cpp:172-178) */
 
 /* Create an evaluator.
- *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62,81):
- *                "pop_pk_trajectory" | "cell_population" (keys of the latter: see DESIGN.md section 9)
+ *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62,66,81):
+ *                "pop_pk_trajectory" | "cell_population" (keys of the latter: see DESIGN.md section 9) | "pharmaco_population"
+ *                pharmaco_population = PharmacoLikelihoodPopulation (src/pharmaco/PharmacoLikelihoodPopulation.cpp:43-340): the
+ *                population PK model advanced with the matrix exponential (PharmacokineticModel.cpp:111-247), no ODE solver.
+ *                  drug=<name> num_patients=<P> num_timepoints=<T> num_variables=<nvar>
+ *                  [peripheral_compartment=0|1] [num_transit_compartments=<k>] [bioavailability=0|1]   (<pk_model> attributes, cpp:51-56)
+ *                  <role>_ix=<index of the prior variable>, roles (variable names of cpp:104-186): additive_sd, proportional_sd,
+ *                       mean_absorption, mean_excretion, mean_clearance, mean_volume_of_distribution, sigma_absorption,
+ *                       sigma_excretion, sigma_clearance, sigma_volume_of_distribution, sigma_transit_time,
+ *                       peripheral_forward_rate, peripheral_backward_rate, mean_transit_time -- absent = not in the prior
+ *                  [shard_rank=0] [shard_count=1] [device=0]
+ *                Data: the trial arrays of pop_pk_trajectory below (the same NetCDF group, Patient::Load PharmacoPatient.cpp:8-116)
+ *                plus, for every marginal the prior switches on, the indices of the per-patient variables p<i>_<name>
+ *                (InitializePatientMarginals, cpp:342-354) as "patient_absorption_ix" | "patient_excretion_ix" |
+ *                "patient_clearance_ix" | "patient_volume_of_distribution_ix" | "patient_transit_time_ix" |
+ *                "patient_bioavailability_ix", each [P]. Entry points: finalize, evaluate_batch (with a communicator: the
+ *                complete result on every rank), enqueue_batch (d_partial [3][C] as for pop_pk_trajectory, except that a NaN
+ *                term anywhere makes the chain NaN), exchange_partials, get_diagnostics (conc, patient_ll; no counters).
  *   model_desc : `key=value;...` text, desc_bytes long (no terminator needed). Keys for pop_pk_trajectory
  *                mirror the <pk_model> attributes (LikelihoodPopPKTrajectory.cpp:58-87) plus sizes:
  *                  type=one|two|one_biphasic_uptake|two_biphasic_uptake|one_transit|two_transit  drug=<name>

@@ -270,6 +270,68 @@ def _cellpop_counters(self, problem, values, threads: int = 1):
     return dict(logp=logp, counters=cnt)
 
 
+class _PharmacoProblem(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_patients", "num_timepoints", "num_variables", "use_peripheral", "num_transit", "use_bioavailability",
+                                         "additive_sd_ix", "proportional_sd_ix", "mean_absorption_ix", "mean_excretion_ix", "mean_clearance_ix",
+                                         "mean_vod_ix", "sigma_absorption_ix", "sigma_excretion_ix", "sigma_clearance_ix", "sigma_vod_ix",
+                                         "sigma_transit_ix", "periph_fwd_ix", "periph_bwd_ix", "mean_transit_time_ix")] + [
+        ("mol_weight", C.c_double)] + [(n, C.c_void_p) for n in (
+            "transforms", "p_absorption_ix", "p_excretion_ix", "p_clearance_ix", "p_vod_ix", "p_transit_ix", "p_bioavailability_ix", "time",
+            "observed_concentration", "dose", "dosing_interval", "dose_after_dose_change", "dose_change_time", "intermittent", "skipped_days")]
+
+
+def _pharmaco_evaluate(self, problem, values, threads: int = 1, want_conc=False, want_patient_ll=False):
+    """problem: bcm3_b200.pharmaco.PharmacoProblem; values [C, nvar]."""
+    p, tr = problem, problem.trial
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if values.ndim == 1:
+        values = values[None, :]
+    nC = values.shape[0]
+    P, T = tr.num_patients, tr.num_timepoints
+    skipped = np.zeros(P, dtype=np.uint32)
+    for d in range(29):
+        skipped |= (np.asarray(tr.treatment_interruptions)[:, d] != 0).astype(np.uint32) << np.uint32(d)
+    keep = dict(tr=np.ascontiguousarray(p.transforms, dtype=np.int32), time=np.ascontiguousarray(tr.time, dtype=np.float64),
+                obs=np.ascontiguousarray(tr.observed_concentration, dtype=np.float64), dose=np.ascontiguousarray(tr.dose, dtype=np.float64),
+                interval=np.ascontiguousarray(tr.dosing_interval, dtype=np.float64), dac=np.ascontiguousarray(tr.dose_after_dose_change, dtype=np.float64),
+                dct=np.ascontiguousarray(tr.dose_change_time, dtype=np.float64), inter=np.ascontiguousarray(tr.intermittent, dtype=np.int32), skipped=skipped)
+    pix = {k: np.ascontiguousarray(v, dtype=np.int32) for k, v in p.patient_indices().items()}
+    ptr = lambda a: a.ctypes.data
+    r = p.role_indices()
+    s = _PharmacoProblem(
+        num_patients=P, num_timepoints=T, num_variables=p.num_variables, use_peripheral=int(p.peripheral_compartment),
+        num_transit=int(p.num_transit_compartments), use_bioavailability=int(p.bioavailability), additive_sd_ix=r["additive_sd"],
+        proportional_sd_ix=r["proportional_sd"], mean_absorption_ix=r["mean_absorption"], mean_excretion_ix=r["mean_excretion"],
+        mean_clearance_ix=r["mean_clearance"], mean_vod_ix=r["mean_volume_of_distribution"],
+        sigma_absorption_ix=r["sigma_absorption"] if "patient_absorption_ix" in pix else -1,
+        sigma_excretion_ix=r["sigma_excretion"] if "patient_excretion_ix" in pix else -1,
+        sigma_clearance_ix=r["sigma_clearance"] if "patient_clearance_ix" in pix else -1,
+        sigma_vod_ix=r["sigma_volume_of_distribution"] if "patient_volume_of_distribution_ix" in pix else -1,
+        sigma_transit_ix=r["sigma_transit_time"] if "patient_transit_time_ix" in pix else -1,
+        periph_fwd_ix=r["peripheral_forward_rate"], periph_bwd_ix=r["peripheral_backward_rate"], mean_transit_time_ix=r["mean_transit_time"],
+        mol_weight=p.mol_weight, transforms=ptr(keep["tr"]),
+        p_absorption_ix=ptr(pix["patient_absorption_ix"]) if "patient_absorption_ix" in pix else None,
+        p_excretion_ix=ptr(pix["patient_excretion_ix"]) if "patient_excretion_ix" in pix else None,
+        p_clearance_ix=ptr(pix["patient_clearance_ix"]) if "patient_clearance_ix" in pix else None,
+        p_vod_ix=ptr(pix["patient_volume_of_distribution_ix"]) if "patient_volume_of_distribution_ix" in pix else None,
+        p_transit_ix=ptr(pix["patient_transit_time_ix"]) if "patient_transit_time_ix" in pix else None,
+        p_bioavailability_ix=ptr(pix["patient_bioavailability_ix"]) if "patient_bioavailability_ix" in pix else None,
+        time=ptr(keep["time"]), observed_concentration=ptr(keep["obs"]), dose=ptr(keep["dose"]), dosing_interval=ptr(keep["interval"]),
+        dose_after_dose_change=ptr(keep["dac"]), dose_change_time=ptr(keep["dct"]), intermittent=ptr(keep["inter"]), skipped_days=ptr(keep["skipped"]))
+    logp = np.empty(nC)
+    conc = np.empty((nC, P, T)) if want_conc else None
+    pll = np.empty((nC, P)) if want_patient_ll else None
+    fn = self.lib.oracle_pharmaco_evaluate
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = fn(C.byref(s), nC, values.ctypes.data, logp.ctypes.data, conc.ctypes.data if conc is not None else None,
+            pll.ctypes.data if pll is not None else None, int(threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle_pharmaco_evaluate failed: {rc}")
+    return dict(logp=logp, conc=conc, patient_ll=pll)
+
+
+Oracle.pharmaco_evaluate = _pharmaco_evaluate
 Oracle.cellpop_evaluate = _cellpop_evaluate
 Oracle.cellpop_counters = _cellpop_counters
 

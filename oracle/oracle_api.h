@@ -151,6 +151,32 @@ int oracle_cellpop_evaluate(const oracle_cellpop_problem* prob, size_t num_chain
 int oracle_cellpop_evaluate_counters(const oracle_cellpop_problem* prob, size_t num_chains, const double* values, double* logp,
                                      int64_t* counters, int num_threads);
 
+/* ---- pharmaco_population: PharmacoLikelihoodPopulation (src/pharmaco/PharmacoLikelihoodPopulation.cpp:202-340) around the
+ * matrix-exponential compartment model PharmacokineticModel (src/pharmaco/PharmacokineticModel.cpp:111-247) ---- */
+typedef struct {
+	int32_t num_patients, num_timepoints, num_variables;
+	int32_t use_peripheral, num_transit, use_bioavailability;
+	/* variable indices, -1 = not in the prior (PostInitialize, cpp:102-188) */
+	int32_t additive_sd_ix, proportional_sd_ix, mean_absorption_ix, mean_excretion_ix, mean_clearance_ix, mean_vod_ix;
+	int32_t sigma_absorption_ix, sigma_excretion_ix, sigma_clearance_ix, sigma_vod_ix, sigma_transit_ix;
+	int32_t periph_fwd_ix, periph_bwd_ix, mean_transit_time_ix;
+	double mol_weight;
+	const int32_t* transforms;              /* [nvar] */
+	/* p<i>_<name> variable indices per patient (InitializePatientMarginals, cpp:342-354), NULL where the prior has no sigma */
+	const int32_t *p_absorption_ix, *p_excretion_ix, *p_clearance_ix, *p_vod_ix, *p_transit_ix, *p_bioavailability_ix;
+	/* the trial as the NetCDF file holds it (Patient::Load, PharmacoPatient.cpp:8-116) */
+	const double* time;                     /* [T] */
+	const double* observed_concentration;   /* [P][T], NaN = missing */
+	const double *dose, *dosing_interval, *dose_after_dose_change, *dose_change_time; /* [P] */
+	const int32_t* intermittent;            /* [P] */
+	const uint32_t* skipped_days;           /* [P] bit d = day d skipped */
+} oracle_pharmaco_problem;
+
+/* logp [C]; conc [C][P][T] optional (conversion * simulated concentration at the observations that have a value, NaN elsewhere);
+ * patient_ll [C][P] optional */
+int oracle_pharmaco_evaluate(const oracle_pharmaco_problem* prob, size_t num_chains, const double* values, double* logp, double* conc,
+                             double* patient_ll, int num_threads);
+
 /* "ref" or "port" */
 const char* oracle_kind(void);
 

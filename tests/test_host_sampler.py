@@ -280,3 +280,17 @@ def test_gaussian_mixture_proposal_on_the_banana(host):
     assert abs(r.mean()) < 0.1 and abs(r.std() - 1.0) < 0.1
     adj, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg.replace("gaussian_mixture", "gaussian_mixture_adjustedAIC"), batched=True, seed=7)
     assert adj.shape == a.shape and np.isfinite(adj[:, 2]).all()
+
+
+def test_t_distributed_proposals_on_the_banana(host):
+    """ptmhsampler.proposal_t_dof > 0 (SamplerPT.cpp:63,169; ProposalGlobalCovariance.cpp:23-29): every step is scaled by
+    1 / sqrt(w), w a gamma draw -- heavier-tailed proposals, the same posterior. Batched and serial runs stay identical."""
+    cfg = CONFIG.replace("num_samples=8000", "num_samples=4000").replace("[ptmhsampler]", "[ptmhsampler]\nproposal_t_dof=4")
+    rows, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=True, seed=11)
+    plain, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg.replace("proposal_t_dof=4", "proposal_t_dof=0"), batched=True, seed=11)
+    assert not np.array_equal(rows, plain)  # the option is read and changes the proposals
+    serial, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=False, seed=11)
+    assert np.array_equal(rows, serial)
+    post = rows[rows[:, 0] == 1.0][800:, 3:]
+    r = post[:, 1] - (1 + post[:, 0]) ** 2
+    assert abs(r.mean()) < 0.15 and abs(r.std() - 1.0) < 0.15

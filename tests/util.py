@@ -77,6 +77,23 @@ def make_nan_inf_case():
     return prob, vals
 
 
+PHARMACO_GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "pharmaco_*.npz")))
+
+
+def load_pharmaco_golden(name):
+    from bcm3_b200.pharmaco import PharmacoProblem
+    from bcm3_b200.poppk_data import PopPKTrial
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    trial = PopPKTrial(drug=str(z["drug"]), time=z["time"], observed_concentration=z["observed_concentration"], dose=z["dose"],
+                       dosing_interval=z["dosing_interval"], dose_after_dose_change=z["dose_after_dose_change"], dose_change_time=z["dose_change_time"],
+                       intermittent=z["intermittent"], treatment_interruptions=z["treatment_interruptions"])
+    prob = PharmacoProblem(trial=trial, variable_names=[str(n) for n in z["variable_names"]], transforms=z["transforms"],
+                           peripheral_compartment=bool(z["peripheral_compartment"]), num_transit_compartments=int(z["num_transit_compartments"]),
+                           bioavailability=bool(z["bioavailability"]))
+    return prob, {k: z[k] for k in ("values", "logp", "conc", "patient_ll")}
+
+
 CELLPOP_GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "cellpop_*.npz")))
 
 
