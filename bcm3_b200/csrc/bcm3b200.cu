@@ -102,6 +102,7 @@ struct Handle {
 	bool diagnostics = false;
 	int block_size = 0;
 	bool sort_patients = true;                    // option "sort_patients"
+	bool chain_fastest_grid = true;               // option "chain_fastest_grid": with ranked patients, launch all chains' expensive blocks first
 	long long sort_min_systems = 60000;           // option "sort_min_systems": rank patients when P * C reaches this (measured:
 	                                              // 80 k systems 5.59 -> 4.75 ms, 40 k and below no gain; tools/rank_check.py)
 	int64_t total_launches = 0, last_launches = 0, num_evaluations = 0;
@@ -211,6 +212,46 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 	cp->shard_rank = get_int(kv, "shard_rank", 0);
 	cp->shard_count = get_int(kv, "shard_count", 1);
 	cp->device = get_int(kv, "device", 0);
+	// further data sets of the same experiment: the data-set keys again with the suffix @1, @2, @3
+	const int num_data_sets = get_int(kv, "num_data_sets", 1);
+	if (num_data_sets < 1 || num_data_sets > 4) return fail(BCM3B200_ERR_UNSUPPORTED, "num_data_sets must be 1..4");
+	for (int k = 1; k < num_data_sets; k++) {
+		std::unique_ptr<CellPopState::MoreData> m(new CellPopState::MoreData);
+		const std::string sfx = "@" + std::to_string(k);
+		auto key = [&](const char* base) { return std::string(base) + sfx; };
+		auto realk = [&](const char* base, double def) { return kv.count(key(base)) ? strtod(kv[key(base)].c_str(), nullptr) : def; };
+		m->T = get_int(kv, key("num_timepoints").c_str(), 0);
+		m->R = get_int(kv, key("num_replicates").c_str(), 1);
+		const std::string emk = kv.count(key("error_model")) ? kv[key("error_model")] : "normal";
+		if (emk == "normal" || emk == "additive_normal") m->error_model = CP_ERR_NORMAL;
+		else if (emk == "student_t4" || emk == "t4") m->error_model = CP_ERR_STUDENT_T4;
+		else if (emk == "proportional_normal") m->error_model = CP_ERR_PROPORTIONAL_NORMAL;
+		else if (emk == "additive_proportional_normal") m->error_model = CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL;
+		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported", emk.c_str());
+		m->stdev_ix = get_int(kv, key("stdev_ix").c_str(), -1);
+		m->stdev_fixed = realk("stdev", 1.0);
+		m->offset_ix = get_int(kv, key("offset_ix").c_str(), -1);
+		m->offset_fixed = realk("offset", 0.0);
+		m->scale_ix = get_int(kv, key("scale_ix").c_str(), -1);
+		m->scale_fixed = realk("scale", 1.0);
+		m->prop_stdev_ix = get_int(kv, key("proportional_stdev_ix").c_str(), -1);
+		m->prop_stdev_fixed = realk("proportional_stdev", 1.0);
+		m->weight = realk("weight", 1.0);
+		m->missing_stdev = realk("missing_simulation_time_stdev", 300.0);
+		m->relative_to_time_average = get_int(kv, key("relative_to_time_average").c_str(), 0) != 0;
+		m->stdev_relative_to_scale = get_int(kv, key("stdev_relative_to_scale").c_str(), 0) != 0;
+		if (kv.count(key("obs_species"))) {
+			std::string v = kv[key("obs_species")];
+			size_t pos = 0;
+			while (pos <= v.size()) {
+				size_t e = v.find('+', pos);
+				if (e == std::string::npos) e = v.size();
+				if (e > pos) m->obs_species.push_back(atoi(v.substr(pos, e - pos).c_str()));
+				pos = e + 1;
+			}
+		}
+		cp->more.push_back(std::move(m));
+	}
 	// dividing / dying cells (Experiment.cpp:488-489 divide_cells, max_cells; Cell.cpp:40-55 the species found by name)
 	cp->divide_cells = get_int(kv, "divide_cells", 0) != 0;
 	cp->max_cells = get_int(kv, "max_cells", cp->num_cells);
@@ -422,6 +463,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	}
 	a.patient_ll = s->patient_ll.p;
 	a.order = nullptr;
+	a.chain_fastest = 0;
 	// large batches: rank every chain's patients by absorption rate first (see poppk_kernel)
 	if (h->sort_patients && (long long)s->P * (long long)C >= h->sort_min_systems && s->P > 0 && (long long)s->P * (long long)C < (1ll << 31)) {
 		const size_t n = (size_t)s->P * C;
@@ -440,6 +482,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 		CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->sort_temp.p, temp_bytes, s->rank_keys.p, s->rank_keys_sorted.p, s->rank_patients.p, s->order.p, (int)n, 0,
 		                                         32 + chain_bits, stream));
 		a.order = s->order.p;
+		a.chain_fastest = (h->chain_fastest_grid && nblk <= 65535) ? 1 : 0;
 		h->last_launches += 1; // + the library's sort passes
 		h->total_launches += 1;
 	}
@@ -460,8 +503,8 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	const int slots = two_cmt ? (int)BdfSlots<3>::COUNT : (int)BdfSlots<2>::COUNT;
 	const size_t smem_bytes = sizeof(double) * ((size_t)h->T + (size_t)h->T * block + (size_t)slots * stride);
 	if (smem_bytes > 200 * 1024) return fail(BCM3B200_ERR_UNSUPPORTED, "too many timepoints (%d) for block size %d", h->T, block);
-	dim3 grid(nblk, (unsigned)C);
 	if (C > 65535) return fail(BCM3B200_ERR_UNSUPPORTED, "more than 65535 chains in one batch");
+	const dim3 grid = a.chain_fastest ? dim3((unsigned)C, nblk) : dim3(nblk, (unsigned)C);
 
 	int lrc;
 	if (h->pk_type == PK_ONE || h->pk_type == PK_TWO) lrc = launch_poppk_plain(two_cmt, h->diagnostics, stride, grid, block, smem_bytes, stream, a);
@@ -727,6 +770,20 @@ int bcm3b200_set_data(void* handle, const char* name, const double* data, const 
 		else if (n == "variability") { w0 = cp.D; w1 = 6; }
 		else if (n == "variability_covariance") { w0 = (size_t)cp.D * (cp.D - 1) / 2; w1 = 2; }
 		else if (n == "treatment_times") w0 = shape[0]; // any number of pulses
+		else if ((n.rfind("timepoints@", 0) == 0 || n.rfind("observed@", 0) == 0) && n.size() > 1) {
+			// a further data set of the experiment (num_data_sets > 1)
+			const int k = atoi(n.c_str() + n.find('@') + 1);
+			if (k < 1 || k > (int)cp.more.size()) return fail(BCM3B200_ERR_ARG, "\"%s\": the handle was created with %zu data set(s)", name, cp.more.size() + 1);
+			const bool is_time = n[0] == 't';
+			const size_t Tk = (size_t)cp.more[k - 1]->T, Rk = (size_t)cp.more[k - 1]->R;
+			if (is_time ? (ndim != 1 || shape[0] != Tk) : (ndim != 2 || shape[0] != Rk || shape[1] != Tk)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);
+			for (CellPopState* st : cellpop_states(h)) {
+				std::vector<double>& dst = is_time ? st->more[k - 1]->timepoints : st->more[k - 1]->observed;
+				dst.assign(data, data + (is_time ? Tk : Rk * Tk));
+				st->finalized = false;
+			}
+			return BCM3B200_OK;
+		}
 		else return fail(BCM3B200_ERR_ARG, "unknown data name \"%s\"", name);
 		const int want_ndim = w1 ? 2 : 1;
 		if (ndim != want_ndim || shape[0] != w0 || (w1 && shape[1] != w1)) return fail(BCM3B200_ERR_ARG, "shape mismatch for \"%s\"", name);
@@ -776,7 +833,7 @@ int bcm3b200_get_cell_diagnostics(void* handle, double* cell_values, int32_t* ce
 	if (!cp.finalized || cp.last_C == 0) return fail(BCM3B200_ERR_STATE, "no evaluation yet");
 	CUDA_TRY(cudaSetDevice(cp.device));
 	CUDA_TRY(cudaDeviceSynchronize());
-	const size_t C = (size_t)cp.last_C, nc = (size_t)cp.capacity(), T = (size_t)cp.T; // max_cells columns for a dividing population
+	const size_t C = (size_t)cp.last_C, nc = (size_t)cp.capacity(), T = (size_t)cp.rows(); // max_cells columns for a dividing population; every data set's timepoints
 	if (cell_values) CUDA_TRY(cudaMemcpy(cell_values, cp.d_cellvals.p, sizeof(double) * C * T * nc, cudaMemcpyDeviceToHost));
 	if (cell_status) CUDA_TRY(cudaMemcpy(cell_status, cp.d_status.p, sizeof(int32_t) * C * nc, cudaMemcpyDeviceToHost));
 	if (cell_steps) CUDA_TRY(cudaMemcpy(cell_steps, cp.d_steps.p, sizeof(int32_t) * C * nc, cudaMemcpyDeviceToHost));
@@ -841,7 +898,7 @@ static int cellpop_evaluate_handle(Handle* h, size_t C, size_t nvar, const doubl
 	CellPopState& cp = *h->cp;
 	if (h->cp_more.empty() && !h->comm.active()) return cellpop_evaluate(cp, C, nvar, values, logp, status);
 	if (C == 0) return BCM3B200_OK;
-	const size_t width = 2 * (size_t)cp.T + 1, n = C * width;
+	const size_t width = 2 * (size_t)cp.rows() + 1, n = C * width;
 	if (h->cp_more.empty()) {
 		int rc = cellpop_finalize(cp, true);
 		if (rc != BCM3B200_OK) return rc;
@@ -1117,7 +1174,7 @@ int bcm3b200_exchange_partials(void* handle, size_t num_chains, double* d_partia
 	CUDA_TRY(cudaSetDevice(h->cp ? h->cp->device : h->device0));
 	const size_t C = num_chains;
 	int rc;
-	if (h->cp) rc = h->comm.gather_combine(d_partial, C * (2 * (size_t)h->cp->T + 1), C * (2 * (size_t)h->cp->T + 1), d_partial, (cudaStream_t)stream);
+	if (h->cp) rc = h->comm.gather_combine(d_partial, C * (2 * (size_t)h->cp->rows() + 1), C * (2 * (size_t)h->cp->rows() + 1), d_partial, (cudaStream_t)stream);
 	else rc = h->comm.gather_combine(d_partial, 3 * C, C, d_partial, (cudaStream_t)stream);
 	if (rc != BCM3B200_OK) return rc;
 	(h->cp ? h->cp->total_launches : h->total_launches) += 2;
@@ -1201,6 +1258,7 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 	if (!strcmp(name, "diagnostics")) h->diagnostics = value != 0;
 	else if (!strcmp(name, "sort_patients")) h->sort_patients = value != 0;
 	else if (!strcmp(name, "sort_min_systems")) h->sort_min_systems = value;
+	else if (!strcmp(name, "chain_fastest_grid")) h->chain_fastest_grid = value != 0;
 	else if (!strcmp(name, "block_size")) {
 		if (value != 0 && (value < 32 || value > 384 || value % 32 != 0)) return fail(BCM3B200_ERR_ARG, "block_size must be 0 or a multiple of 32 up to 384");
 		h->block_size = (int)value;
@@ -1233,7 +1291,8 @@ int bcm3b200_get_stat(void* handle, const char* name, int64_t* value)
 		else if (!strcmp(name, "last_kernel_us")) *value = (int64_t)(cp.last_kernel_ms * 1000.0);
 		else if (!strcmp(name, "num_cells_local")) *value = cp.cells_local;
 		else if (!strcmp(name, "cell_columns")) *value = cp.capacity();
-		else if (!strcmp(name, "partial_doubles_per_chain")) *value = 2 * cp.T + 1;
+		else if (!strcmp(name, "partial_doubles_per_chain")) *value = 2 * cp.rows() + 1;
+		else if (!strcmp(name, "value_rows")) *value = cp.rows();
 		else return fail(BCM3B200_ERR_ARG, "unknown stat \"%s\"", name);
 		return BCM3B200_OK;
 	}

@@ -54,8 +54,16 @@ struct CpArgs {
 	// observed species: sum of these ODE-integrated species per timepoint
 	int num_obs_species;
 	int obs_species[8];
+	// Several data sets of one experiment share its cells' integration (group kernel built with CP_NUM_DATASETS = K > 1,
+	// Experiment.cpp:190-214, 298-312): `timepoints` is then the sorted union of their timepoints, tp_rows [T][K] says which row
+	// of cell_values the value of data set k at union time u goes to (-1: data set k does not ask for that time), and every data
+	// set sums its own observed species. num_rows = rows of cell_values per chain (= T with one data set).
+	int num_data_sets, num_rows;
+	const int32_t* tp_rows;
+	int num_obs_species_more[3];
+	int obs_species_more[3][8];
 	// outputs
-	double* cell_values; // [C][T][num_cells]  (NaN where the cell does not exist at that time)
+	double* cell_values; // [C][num_rows][cell_stride]  (NaN where the cell does not exist at that time)
 	int32_t* cell_status; // [C][num_cells] 1 = ok, 0 = solver failure
 	int32_t* cell_steps;  // [C][num_cells] or null
 	int debug_report;     // 0: cell_steps = accepted steps; 1: RHS evaluations (nfe); 2: linear setups; 3: Jacobian evaluations

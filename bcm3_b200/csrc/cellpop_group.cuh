@@ -69,7 +69,13 @@ constexpr double UROUND = DBL_EPSILON;
 // RS odd: the G lanes of a group touching G consecutive rows of one column hit distinct bank pairs. CS = RS * G (mod 16):
 // then bank pair (CS * g + RS * lg) mod 16 = RS * (G * g + lg) is a bijection over the 16 lanes of a half-warp.
 constexpr int RS = N | 1;
-constexpr int OFF_Y = N * RS;
+// CP_M_GLOBAL = 1: the Newton matrix of a cell lives in a global-memory block per resident group (served by L1 / L2) instead
+// of the cell's shared block -- 20 KB of the 24.6 KB per cell at 50 species, the difference between 9 and 12 warps per SM
+#ifndef CP_M_GLOBAL
+#define CP_M_GLOBAL 0
+#endif
+constexpr int M_SHARED = CP_M_GLOBAL ? 0 : N * RS;
+constexpr int OFF_Y = M_SHARED;
 constexpr int OFF_F = OFF_Y + N;
 constexpr int OFF_PERM = OFF_F + N;
 constexpr int OFF_SCAL = OFF_PERM + (N + 1) / 2;
@@ -149,11 +155,11 @@ __device__ __noinline__ void rhs_eval(unsigned y_off, unsigned out_off, unsigned
 	generated_derivative(OutStrided{ smem_d + out_off, 1 }, SpeciesPlain{ smem_d + y_off }, ConstSpecies{ constant_species, treat_ix, treat_value },
 	                     CellParameters{ tv, smem_d + ov_off }, ConstVector{ non_sampled });
 }
-__device__ __noinline__ void rhs_eval_perturbed(unsigned y_off, int j, double yj, unsigned out_off, int out_stride, unsigned ov_off, const double* tv,
+__device__ __noinline__ void rhs_eval_perturbed(unsigned y_off, int j, double yj, double* out, int out_stride, unsigned ov_off, const double* tv,
                                                 const double* constant_species, const double* non_sampled, int treat_ix, double treat_value)
 {
 	extern __shared__ double smem_d[];
-	generated_derivative(OutStrided{ smem_d + out_off, out_stride }, SpeciesAt{ smem_d + y_off, j, yj },
+	generated_derivative(OutStrided{ out, out_stride }, SpeciesAt{ smem_d + y_off, j, yj },
 	                     ConstSpecies{ constant_species, treat_ix, treat_value }, CellParameters{ tv, smem_d + ov_off }, ConstVector{ non_sampled });
 }
 
@@ -184,6 +190,10 @@ __device__ __noinline__ void rhs_eval_lanes(unsigned y_off, unsigned f_off, unsi
 // divide_cells and without an "apoptosis" species is built with 0 and contains none of that code.
 #ifndef CP_DIVISION
 #define CP_DIVISION 0
+#endif
+// number of data sets that share the cells' integration (CpArgs::tp_rows); 1 = the plain layout, no indirection
+#ifndef CP_NUM_DATASETS
+#define CP_NUM_DATASETS 1
 #endif
 #ifndef CP_GROUP_BATCHED
 #define CP_GROUP_BATCHED 1
@@ -233,7 +243,7 @@ struct GroupBdf {
 	bool nls_jcur;
 	int nfe, nsetups, nje;
 	// ---- placement ----
-	double* M;    // shared
+	double* M;    // shared (global with CP_M_GLOBAL)
 	double* ybuf; // shared, N
 	double* fbuf; // shared, N
 	int* perm;    // shared, N
@@ -651,7 +661,7 @@ struct GroupBdf {
 					const double inc = fmax(srur * fabs(ye), minInc / we);
 					// f(y + inc e_j) into column j of M, then the difference quotient into the saved Jacobian and, scaled
 					// (SUNMatScaleAddI(-gamma, A): A = -gamma * J, then the unit diagonal added), back into M
-					rhs_eval_perturbed(region_off + OFF_Y, j, ye + inc, region_off + j, RS, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled,
+					rhs_eval_perturbed(region_off + OFF_Y, j, ye + inc, M + j, RS, region_off + OFF_SCAL + SC_OV, tv, constant_species, non_sampled,
 					                   treat_ix, treat_now);
 					const double inc_inv = 1.0 / inc;
 #pragma unroll 1
@@ -1513,14 +1523,18 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 	B.gbase = gw * G;
 	B.gmask = (G == 32) ? FULL : (((1u << G) - 1u) << B.gbase);
 	double* region = smem_d + (size_t)(warp * CPW + gw) * CS;
+	const long long group_id = (long long)blockIdx.x * (WPB * CPW) + warp * CPW + gw;
+#if CP_M_GLOBAL
+	B.M = saved_jacobians + (long long)gridDim.x * (WPB * CPW) * (N * N) + group_id * (N * RS);
+#else
 	B.M = region;
+#endif
 	B.ybuf = region + OFF_Y;
 	B.fbuf = region + OFF_F;
 	B.perm = reinterpret_cast<int*>(region + OFF_PERM);
 	B.sc = region + OFF_SCAL;
 	B.znh = region + OFF_ZNH + B.lg;
 	B.region_off = (unsigned)((warp * CPW + gw) * CS);
-	const long long group_id = (long long)blockIdx.x * (WPB * CPW) + warp * CPW + gw;
 	B.SJ = saved_jacobians + group_id * (N * N);
 	B.constant_species = a.constant_species;
 	B.non_sampled = a.non_sampled;
@@ -1550,6 +1564,35 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 		obs_count |= (unsigned)cnt << (4 * e);
 	}
 	static_assert(E <= 8, "observed-species multiplicities are packed 4 bits per slot");
+	constexpr int ND = CP_NUM_DATASETS;
+	static_assert(ND >= 1 && ND <= 4, "up to four data sets share one integration");
+	unsigned obs_words[ND];
+	obs_words[0] = obs_count;
+#pragma unroll
+	for (int d = 1; d < ND; d++) {
+		unsigned w = 0;
+#pragma unroll
+		for (int e = 0; e < E; e++) {
+			int cnt = 0;
+			for (int k = 0; k < a.num_obs_species_more[d - 1]; k++) cnt += (a.obs_species_more[d - 1][k] == B.idx(e)) ? 1 : 0;
+			w |= (unsigned)cnt << (4 * e);
+		}
+		obs_words[d] = w;
+	}
+	// every union timepoint from `from` on: the cell has no value there (lane 0 of the group writes)
+	auto fill_nan = [&](double* out, int from) {
+		for (int u = from; u < a.T; u++) {
+			if constexpr (ND == 1) {
+				out[(long long)u * stride] = nan;
+			} else {
+#pragma unroll
+				for (int d = 0; d < ND; d++) {
+					const int r = a.tp_rows[u * ND + d];
+					if (r >= 0) out[(long long)r * stride] = nan;
+				}
+			}
+		}
+	};
 
 	bool have = false, exhausted = false, ok = true, newstep = true;
 	int steps = 0, tpi = 0, c = 0, cell = 0;
@@ -1657,19 +1700,33 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				if (a.items) creation_time = a.cell_creation[(long long)c * stride + cell];
 #endif
 				B.sc[SC_CREATION] = creation_time;
-				out = a.cell_values + ((long long)c * T) * stride + cell;
+				out = a.cell_values + ((long long)c * a.num_rows) * stride + cell;
 				ok = true;
 				steps = 0;
 				tpi = 0;
 				newstep = true;
 				bool finished = false;
-				double sv0 = 0.0;
+				double sv0[ND];
 #pragma unroll
-				for (int e = 0; e < E; e++) sv0 += (double)((obs_count >> (4 * e)) & 15u) * y0[e];
-				sv0 = B.gsum(sv0);
+				for (int d = 0; d < ND; d++) {
+					double v = 0.0;
+#pragma unroll
+					for (int e = 0; e < E; e++) v += (double)((obs_words[d] >> (4 * e)) & 15u) * y0[e];
+					sv0[d] = B.gsum(v);
+				}
 				while (tpi < T && (a.timepoints[tpi] - creation_time) < DBL_EPSILON) {
 					const double cell_time = a.timepoints[tpi] - creation_time;
-					if (B.lg == 0) out[(long long)tpi * stride] = (cell_time < 0.0) ? nan : sv0;
+					if (B.lg == 0) {
+						if constexpr (ND == 1) {
+							out[(long long)tpi * stride] = (cell_time < 0.0) ? nan : sv0[0];
+						} else {
+#pragma unroll
+							for (int d = 0; d < ND; d++) {
+								const int r = a.tp_rows[tpi * ND + d];
+								if (r >= 0) out[(long long)r * stride] = (cell_time < 0.0) ? nan : sv0[d];
+							}
+						}
+					}
 					tpi++;
 				}
 				const double end_time = a.sim_end_time - creation_time;
@@ -1691,8 +1748,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				}
 				if (finished) {
 					if (B.lg == 0) {
-						if (!ok)
-							for (int k = tpi; k < T; k++) out[(long long)k * stride] = nan;
+						if (!ok) fill_nan(out, tpi);
 						a.cell_status[(long long)c * stride + cell] = ok ? 1 : 0;
 						if (a.cell_steps) a.cell_steps[(long long)c * stride + cell] = 0;
 #if CP_DIVISION
@@ -1740,11 +1796,17 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 						done = true;
 						break;
 					}
-					double obs_weight[E];
 #pragma unroll
-					for (int e = 0; e < E; e++) obs_weight[e] = (double)((obs_count >> (4 * e)) & 15u);
-					const double sv = B.dky_weighted(tq, obs_weight);
-					if (B.lg == 0) out[(long long)tpi * stride] = sv;
+					for (int d = 0; d < ND; d++) {
+						int r = tpi;
+						if constexpr (ND > 1) r = a.tp_rows[tpi * ND + d];
+						if (r < 0) continue; // group-uniform: this data set does not ask for this time
+						double obs_weight[E];
+#pragma unroll
+						for (int e = 0; e < E; e++) obs_weight[e] = (double)((obs_words[d] >> (4 * e)) & 15u);
+						const double sv = B.dky_weighted(tq, obs_weight);
+						if (B.lg == 0) out[(long long)r * stride] = sv;
+					}
 					tpi++;
 				}
 #if CP_DIVISION
@@ -1775,7 +1837,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 						if (B.lg == 0) {
 							a.cell_event[rec] = ev;
 							a.cell_end_time[rec] = tret + creation_time;
-							for (int k = tpi; k < T; k++) out[(long long)k * stride] = nan; // the cell does not exist after the event
+							fill_nan(out, tpi); // the cell does not exist after the event
 						}
 						tpi = T;
 						done = true;
@@ -1809,8 +1871,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 		}
 		if (have && done) {
 			if (B.lg == 0) {
-				if (!ok)
-					for (int k = tpi; k < T; k++) out[(long long)k * stride] = nan;
+				if (!ok) fill_nan(out, tpi);
 				a.cell_status[(long long)c * stride + cell] = ok ? 1 : 0;
 				if (a.cell_steps)
 					a.cell_steps[(long long)c * stride + cell] = (a.debug_report == 1) ? B.nfe : (a.debug_report == 2) ? B.nsetups : (a.debug_report == 3) ? B.nje : steps;
@@ -1860,7 +1921,7 @@ extern "C" long long cellpop_group_scratch_doubles(int num_chains, int num_cells
 	int err = 0;
 	const int blocks = cellpop_group::resident_blocks(&err);
 	if (blocks <= 0) return -(long long)(err ? err : 1);
-	return 2ll + (long long)blocks * cellpop_group::WPB * cellpop_group::CPW * CP_N * CP_N;
+	return 2ll + (long long)blocks * cellpop_group::WPB * cellpop_group::CPW * (CP_N * CP_N + (CP_M_GLOBAL ? CP_N * cellpop_group::RS : 0));
 }
 
 extern "C" int cellpop_group_launch(const CpArgs* args, double* scratch, void* stream)

@@ -53,6 +53,28 @@ struct CellPopState {
 	int max_cells = 0, cytokinesis_ix = -1, apoptosis_ix = -1, sobol_rows = 0;
 	int reset_ix[7] = { -1, -1, -1, -1, -1, -1, -1 };
 	bool division() const { return (divide_cells && cytokinesis_ix >= 0) || apoptosis_ix >= 0; } // the model library carries the event code
+	// Further data sets of the same experiment (descriptor keys with the suffix @1, @2, @3; data "timepoints@k", "observed@k"):
+	// they share the integration of the experiment's cells (Experiment.cpp:190-214, 298-312) -- the kernel interpolates at the
+	// union of all timepoints and every data set sums its own species -- and their log-likelihoods are added in order (:346-355)
+	struct MoreData {
+		int T = 0, R = 1, error_model = CP_ERR_NORMAL;
+		int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
+		double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0, weight = 1.0, missing_stdev = 300.0;
+		bool relative_to_time_average = false, stdev_relative_to_scale = false;
+		std::vector<int> obs_species;
+		std::vector<double> timepoints, observed;
+		DevBuf<double> d_time, d_obs;
+	};
+	std::vector<std::unique_ptr<MoreData>> more;
+	int rows() const // rows of cell_values / population averages per chain: every data set's timepoints one after the other
+	{
+		int r = T;
+		for (const auto& m : more) r += m->T;
+		return r;
+	}
+	int TU = 0; // timepoints the kernel interpolates at (the sorted union; = T with one data set)
+	DevBuf<double> d_union_time;
+	DevBuf<int32_t> d_tp_rows;
 	int capacity() const { return division() ? (divide_cells ? max_cells : cells_local) : cells_local; }
 	DevBuf<double> d_creation, d_end_y, d_end_time;
 	DevBuf<int32_t> d_row, d_parent, d_event, d_items, d_wave, d_item_offsets;
@@ -364,7 +386,8 @@ __global__ void cellpop_cholesky_kernel(const CpCholArgs a, const double* __rest
 }
 
 struct CpLikArgs {
-	const double* avg;       // [C][T]
+	int avg_stride, avg_row0, accumulate; // the data set's averages are avg[c * avg_stride + avg_row0 + i]; accumulate: logp[c] += instead of =
+	const double* avg;       // [C][avg_stride]
 	const int32_t* nfail;    // [C]
 	const double* transformed; // [C][nvar]
 	const double* timepoints;  // [T]
@@ -384,6 +407,7 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 		a.logp[c] = -INFINITY;
 		return;
 	}
+	const double* avg = a.avg + (long long)c * a.avg_stride + a.avg_row0;
 	const double* tv = a.transformed + (long long)c * a.nvar;
 	double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
 	const double offset = (a.offset_ix >= 0) ? tv[a.offset_ix] : a.offset_fixed;
@@ -396,11 +420,11 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 	// relative to the average over the timepoints
 	double time_average = 0.0;
 	if (a.relative_to_time_average) {
-		for (int i = 0; i < a.T; i++) time_average += a.avg[c * a.T + i] + offset;
+		for (int i = 0; i < a.T; i++) time_average += avg[i] + offset;
 		time_average /= (double)a.T;
 	}
 	auto transformed_average = [&](int i) {
-		double x = a.avg[c * a.T + i];
+		double x = avg[i];
 		if (a.relative_to_time_average) {
 			x += offset;
 			x = log(x / time_average);
@@ -456,7 +480,8 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 			}
 		}
 	}
-	a.logp[c] = logp * a.weight;
+	// Experiment.cpp:346-355: the data sets' log-likelihoods are added in order
+	a.logp[c] = a.accumulate ? a.logp[c] + logp * a.weight : logp * a.weight;
 }
 
 
@@ -857,10 +882,14 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 		const bool want = renv ? atoi(renv) != 0 : (cp.rhs_lanes == 2 || (cp.rhs_lanes == 1 && G >= 16));
 		if (want && cellpop_resolve_kernel(cp) == 3) lanes = cellpop_lane_rhs(code.substr(at), cp.N);
 	}
+	// Newton matrices in global memory instead of the cells' shared blocks (CP_M_GLOBAL of cellpop_group.cuh): an experiment
+	// switch, see DESIGN.md section 9
+	bool m_global = false;
+	if (const char* menv = getenv("BCM3B200_CELLPOP_M_GLOBAL")) m_global = atoi(menv) != 0;
 	size_t per_cell;
 	{ // the constants of cellpop_group.cuh: RS, OFF_SCAL, SC_COUNT, OFF_ZNH, OFF_RL, CS
 		const int RS = cp.N | 1;
-		const int off_scal = cp.N * RS + 2 * cp.N + (cp.N + 1) / 2;
+		const int off_scal = (m_global ? 0 : cp.N * RS) + 2 * cp.N + (cp.N + 1) / 2;
 		const int sc_count = CP_GROUP_SCALARS + (override_vars.empty() ? 1 : (int)override_vars.size());
 		int cs = off_scal + sc_count + 4 * Eg * G + (lanes.ok ? lanes.num_ratelaws : 0);
 		while (cs % 16 != (RS * G) % 16) cs++;
@@ -874,12 +903,16 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	if (const char* wenv = getenv("BCM3B200_CELLPOP_GROUP_WARPS")) gwarps = atoi(wenv) > 0 ? atoi(wenv) : gwarps;
 	if (const char* benv = getenv("BCM3B200_CELLPOP_GROUP_MIN_BLOCKS")) gblocks = atoi(benv) > 0 ? atoi(benv) : gblocks;
 	o << "#define CP_GROUP " << G << "\n";
+	if (m_global) o << "#define CP_M_GLOBAL 1\n";
 	o << "#define CP_GROUP_WARPS " << gwarps << "\n";
 	if (lanes.ok) {
-		// the tables of the lane-parallel right-hand side go behind the cells' blocks when the 227 KB of a block have room for them
+		// The tables of the lane-parallel right-hand side can be copied behind the cells' blocks when the 227 KB of a block have
+		// room for them (BCM3B200_CELLPOP_TABLES_SHARED=1). Measured on B200, 50 species x 6 000 cells x 16 chains: 1 476 ms
+		// with the copy in shared memory vs 1 459 ms through the read-only cache (long-scoreboard stalls 3.3 -> 2.4 cycles per
+		// issue, instruction-fetch stalls 3.0 -> 4.3: nothing gained), so the default stays the read-only cache.
 		const size_t cells_bytes = per_cell * cells_per_warp * gwarps, table_bytes = sizeof(double) * (size_t)lanes.table_doubles;
-		bool shared_tables = cells_bytes + table_bytes <= 227 * 1024;
-		if (const char* tenv = getenv("BCM3B200_CELLPOP_TABLES_SHARED")) shared_tables = shared_tables && atoi(tenv) != 0;
+		bool shared_tables = false;
+		if (const char* tenv = getenv("BCM3B200_CELLPOP_TABLES_SHARED")) shared_tables = atoi(tenv) != 0 && cells_bytes + table_bytes <= 227 * 1024;
 		if (shared_tables) o << "#define CP_TABLES_SHARED 1\n#define CP_TAB_BASE " << (cells_bytes / sizeof(double)) << "\n";
 	}
 	o << "#define CP_GROUP_MIN_BLOCKS " << gblocks << "\n";
@@ -896,6 +929,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	if (const char* henv = getenv("BCM3B200_CELLPOP_HELPER_INLINE")) helper_inline = atoi(henv);
 	o << "#define CP_HELPER_INLINE " << helper_inline << "\n";
 	if (cp.division()) o << "#define CP_DIVISION 1\n";
+	if (!cp.more.empty()) o << "#define CP_NUM_DATASETS " << (1 + cp.more.size()) << "\n";
 	if (const char* benv2 = getenv("BCM3B200_CELLPOP_GROUP_BATCHED")) o << "#define CP_GROUP_BATCHED " << atoi(benv2) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_GROUP_STATIC_LU_MAX")) o << "#define CP_GROUP_STATIC_LU_MAX " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_LU_SKIP_ZEROS")) o << "#define CP_LU_SKIP_ZEROS " << atoi(senv) << "\n";
@@ -1016,6 +1050,18 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	if (cp.have_sim_end_time && !(cp.sim_end_time >= cp.data["timepoints"].back())) return fail(BCM3B200_ERR_ARG, "simulation_end_time lies before the last timepoint");
 	for (int s : cp.obs_species)
 		if (s < 0 || s >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species index out of range");
+	if (!cp.more.empty()) {
+		if (cp.more.size() > 3) return fail(BCM3B200_ERR_UNSUPPORTED, "more than four data sets per handle");
+		if (cellpop_resolve_kernel(cp) != 3) return fail(BCM3B200_ERR_UNSUPPORTED, "several data sets per handle need the lane-group kernel (cellpop_kernel = auto, N <= 96)");
+		for (size_t k = 0; k < cp.more.size(); k++) {
+			const CellPopState::MoreData& m = *cp.more[k];
+			if (m.T < 1 || (int)m.timepoints.size() != m.T || (int)m.observed.size() != m.R * m.T)
+				return fail(BCM3B200_ERR_STATE, "data set %zu: \"timepoints@%zu\" / \"observed@%zu\" missing or of the wrong shape", k + 1, k + 1, k + 1);
+			if (m.obs_species.empty() || m.obs_species.size() > 8) return fail(BCM3B200_ERR_ARG, "obs_species@%zu must name 1..8 species", k + 1);
+			for (int sp : m.obs_species)
+				if (sp < 0 || sp >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species@%zu index out of range", k + 1);
+		}
+	}
 	if (cp.division()) {
 		if (cp.cytokinesis_ix >= cp.N || cp.apoptosis_ix >= cp.N) return fail(BCM3B200_ERR_ARG, "cytokinesis_species / apoptosis_species index out of range");
 		if (cp.divide_cells && cp.cytokinesis_ix >= 0) {
@@ -1177,7 +1223,52 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	a.entry_time_fixed = cp.entry_time_fixed;
 	a.timepoints = cp.d_time.p;
 	a.T = cp.T;
-	a.sim_end_time = cp.have_sim_end_time ? cp.sim_end_time : cp.data["timepoints"].back();
+	cp.TU = cp.T;
+	a.num_data_sets = 1 + (int)cp.more.size();
+	a.num_rows = cp.rows();
+	a.tp_rows = nullptr;
+	double last_requested = cp.data["timepoints"].back();
+	if (!cp.more.empty()) {
+		// the union of the data sets' timepoints (exact comparisons: equal times are one interpolation) and, per union time and data
+		// set, the row of cell_values the value goes to
+		const int K = 1 + (int)cp.more.size();
+		std::vector<double> all(cp.data["timepoints"]);
+		for (const auto& m : cp.more) {
+			all.insert(all.end(), m->timepoints.begin(), m->timepoints.end());
+			last_requested = std::max(last_requested, m->timepoints.back());
+		}
+		std::sort(all.begin(), all.end());
+		all.erase(std::unique(all.begin(), all.end()), all.end());
+		std::vector<int32_t> rows(all.size() * K, -1);
+		int row0 = 0;
+		for (int k = 0; k < K; k++) {
+			const std::vector<double>& tp = k == 0 ? cp.data["timepoints"] : cp.more[k - 1]->timepoints;
+			for (size_t i = 0; i < tp.size(); i++) {
+				if (i > 0 && !(tp[i] > tp[i - 1])) return fail(BCM3B200_ERR_ARG, "several data sets per handle need strictly increasing timepoints in every one of them");
+				const size_t u = (size_t)(std::lower_bound(all.begin(), all.end(), tp[i]) - all.begin());
+				rows[u * K + k] = row0 + (int)i;
+			}
+			row0 += (int)tp.size();
+		}
+		CUDA_TRY(cp.d_union_time.ensure(all.size()));
+		CUDA_TRY(cudaMemcpy(cp.d_union_time.p, all.data(), sizeof(double) * all.size(), cudaMemcpyHostToDevice));
+		CUDA_TRY(cp.d_tp_rows.ensure(rows.size()));
+		CUDA_TRY(cudaMemcpy(cp.d_tp_rows.p, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice));
+		a.timepoints = cp.d_union_time.p;
+		a.T = cp.TU = (int)all.size();
+		a.tp_rows = cp.d_tp_rows.p;
+		for (size_t k = 0; k < cp.more.size(); k++) {
+			CellPopState::MoreData& m = *cp.more[k];
+			a.num_obs_species_more[k] = (int)m.obs_species.size();
+			for (size_t i = 0; i < m.obs_species.size(); i++) a.obs_species_more[k][i] = m.obs_species[i];
+			CUDA_TRY(m.d_time.ensure(m.timepoints.size()));
+			CUDA_TRY(cudaMemcpy(m.d_time.p, m.timepoints.data(), sizeof(double) * m.timepoints.size(), cudaMemcpyHostToDevice));
+			CUDA_TRY(m.d_obs.ensure(m.observed.size()));
+			CUDA_TRY(cudaMemcpy(m.d_obs.p, m.observed.data(), sizeof(double) * m.observed.size(), cudaMemcpyHostToDevice));
+		}
+	}
+	// the cells are integrated to the last time any data set of the experiment requests (Experiment.cpp:655-656)
+	a.sim_end_time = cp.have_sim_end_time ? std::max(cp.sim_end_time, last_requested) : last_requested;
 	a.rel_tol = cp.rel_tol;
 	a.abs_tol = cp.abs_tol;
 	a.min_dt = cp.min_dt;
@@ -1199,7 +1290,7 @@ inline int cellpop_run_cells(CellPopState& cp, size_t C, size_t nvar, const doub
 	int rc = cellpop_finalize(cp, true);
 	if (rc != BCM3B200_OK) return rc;
 	CUDA_TRY(cudaSetDevice(cp.device));
-	const int T = cp.T, nc = cp.cells_local;
+	const int T = cp.rows(), nc = cp.cells_local; // rows of per-cell values per chain
 	const size_t cols = (size_t)(cp.capacity() ? cp.capacity() : 1); // cell columns of the per-cell outputs
 	CUDA_TRY(cp.d_values.ensure(C * nvar));
 	CUDA_TRY(cp.d_transformed.ensure(C * nvar));
@@ -1329,6 +1420,9 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 {
 	CpLikArgs la;
 	la.avg = cp.d_avg.p;
+	la.avg_stride = cp.rows();
+	la.avg_row0 = 0;
+	la.accumulate = 0;
 	la.nfail = cp.d_nfail.p;
 	la.transformed = cp.d_transformed.p;
 	la.timepoints = cp.d_time.p;
@@ -1352,6 +1446,34 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	la.logp = cp.d_logp.p;
 	cellpop_datalik_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>(la, (int)C);
 	CUDA_TRY(cudaGetLastError());
+	// the further data sets of the experiment, from their own rows of the averages, added in order
+	int row0 = cp.T;
+	for (const auto& mp : cp.more) {
+		const CellPopState::MoreData& m = *mp;
+		la.avg_row0 = row0;
+		la.accumulate = 1;
+		la.timepoints = m.d_time.p;
+		la.observed = m.d_obs.p;
+		la.T = m.T;
+		la.R = m.R;
+		la.error_model = m.error_model;
+		la.stdev_ix = m.stdev_ix;
+		la.offset_ix = m.offset_ix;
+		la.scale_ix = m.scale_ix;
+		la.stdev_fixed = m.stdev_fixed;
+		la.relative_to_time_average = m.relative_to_time_average ? 1 : 0;
+		la.stdev_relative_to_scale = m.stdev_relative_to_scale ? 1 : 0;
+		la.prop_stdev_ix = m.prop_stdev_ix;
+		la.prop_stdev_fixed = m.prop_stdev_fixed;
+		la.offset_fixed = m.offset_fixed;
+		la.scale_fixed = m.scale_fixed;
+		la.weight = m.weight;
+		la.missing_stdev = m.missing_stdev;
+		cellpop_datalik_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>(la, (int)C);
+		CUDA_TRY(cudaGetLastError());
+		cp.last_launches++;
+		row0 += m.T;
+	}
 	return BCM3B200_OK;
 }
 
@@ -1363,7 +1485,7 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	cudaStream_t st = cp.stream;
 	int rc = cellpop_run_cells(cp, C, nvar, values, st);
 	if (rc != BCM3B200_OK) return rc;
-	const int T = cp.T, nc = cp.cells_local;
+	const int T = cp.rows(), nc = cp.cells_local;
 	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, cp.capacity(), T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
 	CUDA_TRY(cudaGetLastError());
 	if (cp.division() && cp.divide_cells && nc > 0) {
@@ -1392,7 +1514,7 @@ inline int cellpop_enqueue_partial(CellPopState& cp, size_t C, size_t nvar, cons
 	if (C == 0) return BCM3B200_OK;
 	int rc = cellpop_run_cells(cp, C, nvar, values, st);
 	if (rc != BCM3B200_OK) return rc;
-	cellpop_partial_kernel<<<dim3(cp.T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, cp.cells_local, cp.T, d_partial);
+	cellpop_partial_kernel<<<dim3(cp.rows(), (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, cp.cells_local, cp.rows(), d_partial);
 	CUDA_TRY(cudaGetLastError());
 	cp.last_launches += 1;
 	cp.total_launches += cp.last_launches;
@@ -1405,8 +1527,8 @@ inline int cellpop_finish(CellPopState& cp, size_t C, const double* d_partial, d
 	if (C == 0) return BCM3B200_OK;
 	if (!cp.finalized || cp.last_C != (int)C) return fail(BCM3B200_ERR_STATE, "bcm3b200_cellpop_finish without a matching bcm3b200_enqueue_batch");
 	CUDA_TRY(cudaSetDevice(cp.device));
-	const int n = (int)C * (cp.T + 1);
-	cellpop_unpack_partial_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_partial, cp.T, (int)C, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
+	const int n = (int)C * (cp.rows() + 1);
+	cellpop_unpack_partial_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_partial, cp.rows(), (int)C, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
 	CUDA_TRY(cudaGetLastError());
 	int rc = cellpop_data_likelihood(cp, C, st);
 	if (rc != BCM3B200_OK) return rc;

@@ -77,6 +77,10 @@ struct PkArgs {
 	int ix[SV_COUNT];
 	int tr[SV_COUNT];
 	const int* order; // [C][P_local] or null: patient handled by thread r of chain c (patients ranked by absorption rate)
+	// 1: grid = (C, blocks per chain) -- the block index that runs fastest is the CHAIN, so with ranked patients (most work
+	// first within every chain) the grid as a whole runs from the most expensive blocks of all chains to the cheapest ones and
+	// its tail is made of the shortest blocks; 0: grid = (blocks per chain, C)
+	int chain_fastest;
 	// outputs
 	double* patient_ll;    // [C][P_local] log-likelihood of every (chain, patient), in patient order whatever the launch shape
 	double* diag_conc;     // [C][P_local][T] or null
@@ -254,8 +258,8 @@ __global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(
 	double* s_sim = s_time + a.T;                         // [T][blockDim.x]  simulated central-compartment amounts at the output times
 
 	const int tid = threadIdx.x;
-	const int c = blockIdx.y;
-	int jl = blockIdx.x * blockDim.x + tid; // patient index inside this shard
+	const int c = a.chain_fastest ? blockIdx.x : blockIdx.y;
+	int jl = (a.chain_fastest ? blockIdx.y : blockIdx.x) * blockDim.x + tid; // patient index inside this shard
 	bool valid = jl < a.P_local;
 	// Patients ranked by absorption rate for this chain (poppk_rank_kernel + radix sort): the number of steps a solve takes
 	// is ~96 % determined by ka (correlation 0.98 on the config-5 workload: the absorption transient sets the step sizes

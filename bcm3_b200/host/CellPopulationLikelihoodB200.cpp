@@ -261,13 +261,24 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 		// "chromatid_separation" only moves the end of the integration when simulate_past_chromatid_separation_time is set
 		// (refused above); the remaining special species only record times for the per-cell data types.
 		end_time += e.trailing_simulation_time;
-		for (auto& ds : e.data)
-			if (!CreateHandle(e, ds, end_time)) return false;
+		// One integration per experiment, shared by its data sets (Experiment.cpp:190-214, 298-312): up to four data sets per
+		// handle -- the first of a group owns it, the others ride along. Needs strictly increasing timepoints and the lane-group
+		// kernel (N <= 96); otherwise, and with share_integration off, one handle per data set as before.
+		bool can_share = share_integration && e.model.species_names.size() <= 96;
+		for (const auto& ds : e.data)
+			for (size_t i = 1; i < ds.data.timepoints.size(); i++) can_share = can_share && ds.data.timepoints[i] > ds.data.timepoints[i - 1];
+		for (size_t k = 0; k < e.data.size();) {
+			std::vector<DataSet*> followers;
+			const size_t group = can_share ? std::min<size_t>(4, e.data.size() - k) : 1;
+			for (size_t j = 1; j < group; j++) followers.push_back(&e.data[k + j]);
+			if (!CreateHandle(e, e.data[k], end_time, followers)) return false;
+			k += group;
+		}
 	}
 	return true;
 }
 
-bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, double simulation_end_time)
+bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, double simulation_end_time, const std::vector<DataSet*>& followers)
 {
 	const Model& model = e.model;
 	const Data& data = ds.data;
@@ -287,15 +298,17 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 
 	// species_name="a+b": the summed simulated species
 	std::vector<size_t> obs;
-	{
-		std::stringstream ss(ds.species_name);
+	auto observed_species = [&](const std::string& names, std::vector<size_t>& out) {
+		std::stringstream ss(names);
 		std::string part;
 		while (std::getline(ss, part, '+')) {
 			auto it = std::find(model.species_names.begin(), model.species_names.end(), part);
 			if (it == model.species_names.end()) return Fail("Species \"" + part + "\" of the data set is not a simulated species of the model");
-			obs.push_back((size_t)(it - model.species_names.begin()));
+			out.push_back((size_t)(it - model.species_names.begin()));
 		}
-	}
+		return true;
+	};
+	if (!observed_species(ds.species_name, obs)) return false;
 	std::ostringstream d;
 	d.precision(17);
 	d << "num_species=" << N << ";num_constant_species=" << model.constant_species.size() << ";num_variables=" << nvar << ";num_non_sampled="
@@ -329,6 +342,27 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	ref("scale", ds.scale);
 	d << ";obs_species=";
 	for (size_t k = 0; k < obs.size(); k++) d << (k ? "+" : "") << obs[k];
+	// the experiment's further data sets that share this handle's integration: the data-set keys again, suffixed @1, @2, ...
+	if (!followers.empty()) d << ";num_data_sets=" << (1 + followers.size());
+	for (size_t j = 0; j < followers.size(); j++) {
+		const DataSet& f = *followers[j];
+		const std::string sfx = "@" + std::to_string(j + 1);
+		std::vector<size_t> fobs;
+		if (!observed_species(f.species_name, fobs)) return false;
+		d << ";num_timepoints" << sfx << "=" << f.data.timepoints.size() << ";num_replicates" << sfx << "=" << f.data.num_replicates << ";relative_to_time_average" << sfx
+		  << "=" << (f.relative_to_time_average ? 1 : 0) << ";stdev_relative_to_scale" << sfx << "=" << (f.stdev_relative_to_scale ? 1 : 0) << ";error_model" << sfx << "="
+		  << f.error_model << ";weight" << sfx << "=" << f.weight << ";missing_simulation_time_stdev" << sfx << "=" << f.missing_stdev;
+		auto fref = [&](const char* name, const ValueRef& r) {
+			if (r.ix >= 0) d << ";" << name << "_ix" << sfx << "=" << r.ix;
+			else d << ";" << name << sfx << "=" << r.fixed;
+		};
+		fref("stdev", f.stdev);
+		if (f.have_proportional_stdev) fref("proportional_stdev", f.proportional_stdev);
+		fref("offset", f.offset);
+		fref("scale", f.scale);
+		d << ";obs_species" << sfx << "=";
+		for (size_t k = 0; k < fobs.size(); k++) d << (k ? "+" : "") << fobs[k];
+	}
 	if (!e.treatment_species_name.empty()) {
 		auto it = std::find(model.constant_species_names.begin(), model.constant_species_names.end(), e.treatment_species_name);
 		if (it == model.constant_species_names.end()) return Fail("Treatment species \"" + e.treatment_species_name + "\" is not a constant species of the model");
@@ -350,6 +384,13 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	          set("non_sampled_parameters", model.non_sampled_parameters, { model.non_sampled_parameters.size() }) && set("timepoints", data.timepoints, { T }) &&
 	          set("observed", data.observed, { data.num_replicates, T }) && set("transforms", transforms, { nvar });
 	if (!ok) return false;
+	for (size_t j = 0; j < followers.size(); j++) {
+		const Data& fd = followers[j]->data;
+		const std::string sfx = "@" + std::to_string(j + 1);
+		if (!set(("timepoints" + sfx).c_str(), fd.timepoints, { fd.timepoints.size() }) ||
+		    !set(("observed" + sfx).c_str(), fd.observed, { fd.num_replicates, fd.timepoints.size() }))
+			return false;
+	}
 	if (!e.treatment_species_name.empty() && !e.treatment_times.empty() && !set("treatment_times", e.treatment_times, { e.treatment_times.size() })) return false;
 	if (D > 0) {
 		std::vector<double> rows(D * 6);
@@ -414,6 +455,7 @@ bool CellPopulationLikelihoodB200::EvaluateLogProbability(size_t, const bcm3::Ve
 		std::vector<double> scratch; // local: this entry may be called from several sampling threads (IsReentrant)
 		const double* v = ExperimentValues(e, values.data(), 1, values.size(), scratch);
 		for (auto& ds : e.data) {
+			if (!ds.handle) continue; // rides along with the first data set of its group
 			int st = 0;
 			Real dl_logp = 0.0;
 			if (bcm3b200_evaluate_batch(ds.handle, 1, values.size(), v, &dl_logp, &st) != BCM3B200_OK) return Fail(bcm3b200_last_error());
@@ -437,6 +479,7 @@ bool CellPopulationLikelihoodB200::EvaluateLogProbabilityBatch(const bcm3::Matri
 		std::fill(experiment_logp.begin(), experiment_logp.end(), 0.0);
 		const double* v = ExperimentValues(e, values.data.data(), C, values.rows(), replaced);
 		for (auto& ds : e.data) {
+			if (!ds.handle) continue; // rides along with the first data set of its group
 			if (bcm3b200_evaluate_batch(ds.handle, C, values.rows(), v, part.data(), status.data()) != BCM3B200_OK) return Fail(bcm3b200_last_error());
 			for (size_t c = 0; c < C; c++) experiment_logp[c] += part[c];
 		}

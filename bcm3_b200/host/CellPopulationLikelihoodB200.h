@@ -81,6 +81,8 @@ public:
 	void SetSobolTable(size_t experiment, const std::vector<double>& table) { experiments[experiment].sobol = table; }
 	void SetSobolTable(const std::vector<double>& table) { SetSobolTable(0, table); }
 	void SetDevice(int dev, bool compile_only_ = false) { device = dev; compile_only = compile_only_; }
+	// false: one handle (and one integration of the experiment's cells) per <data> element instead of one per experiment
+	void SetShareIntegration(bool share) { share_integration = share; }
 	// CellPopulationLikelihood.cpp:46-61 -> Experiment.cpp:132-143: the names become non_sampled_parameters[i] of the generated
 	// code (the generator is on the reference side: the Model handed to SetModel must have been generated with the same names),
 	// the values start as NaN and are replaced between evaluations (bcmopt/main.cpp:231)
@@ -145,7 +147,7 @@ private:
 	};
 	bool Resolve(const std::string& text, ValueRef& out, const char* what);
 	bool InitializeExperiment(const bcm3::XmlNode& node, Experiment& e);
-	bool CreateHandle(Experiment& e, DataSet& ds, double simulation_end_time);
+	bool CreateHandle(Experiment& e, DataSet& ds, double simulation_end_time, const std::vector<DataSet*>& followers);
 	// the [C][nvar] block the handles of `e` are given: `values` itself, or the copy with the experiment-specific columns replaced
 	static const double* ExperimentValues(const Experiment& e, const double* values, size_t C, size_t nvar, std::vector<double>& scratch);
 	bool Fail(const std::string& m)
@@ -159,7 +161,7 @@ private:
 	bool have_non_sampled_names = false;
 	std::vector<Experiment> experiments;
 	int device = 0;
-	bool compile_only = false;
+	bool compile_only = false, share_integration = true;
 	std::vector<int> status;
 	std::vector<double> part; // one handle's per-chain results (batched entry: one caller at a time, like the reference's sampler)
 	std::vector<double> replaced; // ExperimentValues scratch of the batched entry

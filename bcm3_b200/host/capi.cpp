@@ -439,6 +439,9 @@ int bcm3host_cellpop_post_initialize(void* session, int device, int compile_only
 	return 0;
 }
 
+// 0: one handle (one integration of the cells) per <data> element; 1 (default): one per experiment, shared by its data sets
+void bcm3host_cellpop_share_integration(void* session, int share) { static_cast<CellpopSession*>(session)->ll->SetShareIntegration(share != 0); }
+
 int bcm3host_cellpop_descriptor(void* session, size_t experiment, size_t data_set, char* out, size_t len)
 {
 	auto* s = static_cast<CellpopSession*>(session);

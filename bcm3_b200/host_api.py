@@ -265,6 +265,11 @@ class CellPopSession:
         if rc != 0:
             raise RuntimeError("bcm3host_cellpop_set_sobol: no such experiment")
 
+    def share_integration(self, share: bool) -> None:
+        """False: one handle -- one integration of the experiment's cells -- per <data> element (the default shares one per experiment)."""
+        self.lib.bcm3host_cellpop_share_integration.restype = None
+        self.lib.bcm3host_cellpop_share_integration(C.c_void_p(self.handle), int(share))
+
     def post_initialize(self, device: int = 0, compile_only: bool = False) -> None:
         err = _err()
         rc = self.lib.bcm3host_cellpop_post_initialize(C.c_void_p(self.handle), int(device), int(compile_only), err, C.c_size_t(1024))

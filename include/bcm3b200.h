@@ -152,6 +152,7 @@ int bcm3b200_cellpop_finish(void* handle, size_t num_chains, const double* d_par
  *   bcm3b200_exchange_partials     is that exchange alone, in place on a device block produced by bcm3b200_enqueue_batch /
  *                                  bcm3b200_evaluate_batch_device ([3][C] for pop_pk_trajectory: SUM row 0, MIN rows 1-2;
  *                                  [C][2 T + 1] for cell_population: SUM), enqueued on `stream`, no synchronisation.
+ * Every rank must make the same calls with the same num_chains (the exchange is a collective).
  * Without a communicator (shard_count == 1, or bcm3b200_comm_init never called) the exchange is a no-op and a sharded
  * handle yields its partial as described above. NCCL is loaded at run time (libnccl.so.2; BCM3B200_NCCL_LIB overrides).
  * Replaces: nothing in the reference (its evaluation threads share one address space, SamplerPT.cpp:438-475); this is the

@@ -133,6 +133,27 @@ def test_cell_population_plugin_sums_experiments_and_data_sets(built):
     assert not np.array_equal(alone, terms[0][1])
 
 
+def test_shared_integration_gives_the_same_bits_as_one_handle_per_data_set(built):
+    """One integration per experiment shared by its data sets (the kernel interpolates at the union of their timepoints and sums
+    every data set's own species) against one handle -- one integration of the same cells -- per <data> element: the same
+    accepted steps, the same Nordsieck polynomial at every output time, the same sums: bit-identical log-likelihoods. Half the
+    integrator launches for the two-data-set experiment."""
+    from bcm3_b200 import synthetic_cellpop as sc
+    from tests.util import cellpop_two_experiment_setup, open_cellpop_session
+
+    prior, lik, species, problems = cellpop_two_experiment_setup()
+    vals = sc.make_chain_values(4, seed=9)
+    out = {}
+    for share in (True, False):
+        s = open_cellpop_session(prior, lik, species, problems)
+        s.share_integration(share)
+        s.post_initialize()
+        out[share] = s.evaluate(vals, batched=True)
+        s.close()
+    assert np.isfinite(out[True]).all()
+    assert np.array_equal(out[True], out[False])
+
+
 def test_cell_population_experiment_specific_parameter(built):
     """<experiment_specific_parameter>: the second experiment's cells see k_in_second where the model reads k_in
     (Experiment.cpp:515-527, 640-642) -- the same as evaluating that experiment with the column replaced."""

@@ -47,7 +47,7 @@ def test_fresh_inputs_against_cpu_checker(Evaluator, checker, kw):
     assert single[0] == got[3]  # a chain's result does not depend on its batch
 
 
-def test_shards_add_up_and_failures_propagate(Evaluator):
+def test_shards_add_up_and_failures_propagate(Evaluator, checker):
     prob = ph.make_pharmaco_problem(P=301, T=10, seed=5)
     vals = ph.make_pharmaco_values(prob, 4, seed=7)
     ev = Evaluator(prob)
@@ -59,13 +59,15 @@ def test_shards_add_up_and_failures_propagate(Evaluator):
         parts.append(e.evaluate(vals)[0])
         e.close()
     assert rel_err(np.sum(parts, axis=0), want).max() < 1e-13
-    # a NaN volume of distribution poisons one chain only; an absurd clearance gives -inf concentrations-> -inf
+    # a NaN volume of distribution makes every simulated concentration of that chain NaN: the reference turns a NaN or infinite
+    # concentration into a log-likelihood of -inf (cpp:224-227), not NaN, and the other chains are untouched
     bad = vals.copy()
     bad[1, prob.index("mean_volume_of_distribution")] = np.nan
     ev = Evaluator(prob)
     got, status = ev.evaluate(bad)
     ev.close()
-    assert status[1] == 1 and np.isnan(got[1]) and np.array_equal(got[[0, 2, 3]], want[[0, 2, 3]])
+    ref = checker.pharmaco_evaluate(prob, bad, threads=2)["logp"]
+    assert np.isneginf(ref[1]) and np.isneginf(got[1]) and status[1] == 0 and np.array_equal(got[[0, 2, 3]], want[[0, 2, 3]])
 
 
 def test_plugin_through_the_factory(built):

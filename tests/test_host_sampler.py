@@ -164,14 +164,23 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
 
 
 def test_cell_population_plugin_takes_several_experiments_and_data_sets(built, tmp_path, monkeypatch):
-    """One handle of the C ABI per <data> element; the data sets of an experiment carry the experiment's common simulation
-    end (the last time any of them requests, Experiment.cpp:190-214, 655-656) so that each reproduces the reference's one
-    simulation of that experiment."""
+    """One handle of the C ABI per experiment, shared by its data sets (the default), or one per <data> element; either way the
+    data sets of an experiment carry the experiment's common simulation end (the last time any of them requests,
+    Experiment.cpp:190-214, 655-656) so that each reproduces the reference's one simulation of that experiment."""
     from tests.util import cellpop_two_experiment_setup, open_cellpop_session
 
     monkeypatch.setenv("BCM3B200_CACHE", str(tmp_path))
     prior, lik, species, problems = cellpop_two_experiment_setup()
+    # shared integration: the first data set's handle carries the second one as data set @1
     s = open_cellpop_session(prior, lik, species, problems)
+    s.post_initialize(compile_only=True)
+    shared = dict(item.split("=", 1) for item in s.descriptor(0, 0).split(";"))
+    assert shared["num_data_sets"] == "2" and shared["num_timepoints@1"] == "6" and shared["obs_species@1"] == "2+3" and shared["error_model@1"] == "student_t4"
+    assert float(shared["stdev@1"]) == 0.3 and float(shared["weight@1"]) == 0.5 and shared["stdev_ix"] == "5" and "simulation_end_time" not in shared
+    assert s.descriptor(0, 1) == "" and "num_data_sets" not in s.descriptor(1, 0)
+    s.close()
+    s = open_cellpop_session(prior, lik, species, problems)
+    s.share_integration(False)
     s.post_initialize(compile_only=True)
     kv = lambda e, d: dict(item.split("=", 1) for item in s.descriptor(e, d).split(";"))
     first, early, second = kv(0, 0), kv(0, 1), kv(1, 0)

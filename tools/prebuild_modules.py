@@ -15,6 +15,13 @@ from bcm3_b200 import synthetic_cellpop as sc
 from bcm3_b200.cellpop import CellPopEvaluator
 from tests.util import load_cellpop_golden
 kind, arg, kernel = {kind!r}, {arg!r}, {kernel!r}
+if kind == "plugin":  # the host plugin's two-experiment set-up, one integration per experiment (arg) or per data set
+    from tests.util import cellpop_two_experiment_setup, open_cellpop_session
+    s = open_cellpop_session(*cellpop_two_experiment_setup())
+    s.share_integration(arg)
+    s.post_initialize(compile_only=True)
+    s.close()
+    sys.exit(0)
 if kind == "golden":
     prob, _ = load_cellpop_golden(arg)
 else:
@@ -34,6 +41,7 @@ def jobs():
     out += [("synthetic", dict(N=8, num_cells=8, T=10, data_cells=2, seed=9), k) for k in ("auto", "warp", "thread")]  # host plugin tests, entry-time test
     out += [("synthetic", dict(N=n, num_cells=8, T=12, data_cells=2, seed=40 + n, rate_decades=d), "auto")
             for n, d in ((3, 2.0), (7, 2.0), (16, 3.0), (33, 3.0), (50, 4.0))]
+    out += [("plugin", True, "auto"), ("plugin", False, "auto")]
     return out
 
 
