@@ -38,7 +38,31 @@ extern "C" {
 
 /* Create an evaluator.
  *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62,66,81):
- *                "pop_pk_trajectory" | "cell_population" (keys of the latter: see DESIGN.md section 9) | "pharmaco_population"
+ *                "pop_pk_trajectory" | "cell_population" | "pharmaco_population"
+ *                cell_population = CellPopulationLikelihood (src/likelihoods/cellpop/CellPopulationLikelihood.cpp:27-101) with
+ *                one Experiment (Experiment.cpp:404-633) per handle:
+ *                  num_species num_constant_species num_variables num_non_sampled num_cells num_timepoints num_replicates
+ *                  variability_dim variability_distribution=diagonal_gaussian|full_gaussian  entry_time | entry_time_ix
+ *                  solver_relative_tolerance solver_absolute_tolerance solver_min_timestep solver_max_timestep solver_max_steps
+ *                  error_model=normal|student_t4|proportional_normal|additive_proportional_normal  weight
+ *                  relative_to_time_average stdev_relative_to_scale missing_simulation_time_stdev simulation_end_time
+ *                  stdev | stdev_ix, proportional_stdev | proportional_stdev_ix, offset | offset_ix, scale | scale_ix
+ *                  obs_species=<i>+<j>+...  treatment_species=<constant species index>
+ *                  divide_cells=0|1 max_cells cytokinesis_species apoptosis_species division_reset_species=<7 indices, '+'>
+ *                       (Experiment.cpp:726-782, CellPopulation.cpp:36-104, Cell.cpp:119-148: a cell whose cytokinesis species
+ *                        passes 1 is replaced by two daughters, one whose apoptosis species passes 1 ends; a chain that
+ *                        outgrows max_cells or the quasi-random table evaluates to -inf; such handles cannot be sharded)
+ *                  num_data_sets=<D <= 4>: the experiment's further <data> elements share this handle's ONE integration of
+ *                       the cells; data set k >= 1 repeats num_timepoints, num_replicates, obs_species, error_model, weight,
+ *                       the stdev/offset/scale keys and the relative_to/missing keys with the suffix @k ("stdev_ix@1=5")
+ *                       and supplies "timepoints@k", "observed@k"; the result is the sum over the data sets in order
+ *                  [shard_rank=0] [shard_count=1] [device=0]
+ *                Data: initial_conditions[N] constant_species non_sampled_parameters timepoints[T] observed[R][T]
+ *                transforms[nvar] sobol[rows][D] (the quasi-random table, VariabilityPseudoRandomIterator.cpp:14-26; rows >=
+ *                num_cells, dividing populations draw the daughters' rows from it) variability[D][6] (kind: 0 parameter,
+ *                1 initial condition, 2 entry time, +16 = only_initial_cells; target; apply; scale variable; fixed scale; negate)
+ *                variability_covariance[D(D-1)/2][2] treatment_times[pulses]. Text: derivative_code (bcm3b200_set_text).
+ *                DESIGN.md section 9 has the meaning of every key with the reference line it restates.
  *                pharmaco_population = PharmacoLikelihoodPopulation (src/pharmaco/PharmacoLikelihoodPopulation.cpp:43-340): the
  *                population PK model advanced with the matrix exponential (PharmacokineticModel.cpp:111-247), no ODE solver.
  *                  drug=<name> num_patients=<P> num_timepoints=<T> num_variables=<nvar>
@@ -176,19 +200,28 @@ int bcm3b200_combine_partials(size_t num_chains, const double* partial, double* 
  * Any pointer may be NULL. */
 int bcm3b200_get_diagnostics(void* handle, double* conc, double* patient_ll, int32_t* counters);
 
-/* cell_population diagnostics of the LAST evaluate (any pointer may be NULL):
- *   cell_values [C][T][cells] observed-species value of every simulated cell at every data timepoint (NaN = cell absent)
+/* cell_population diagnostics of the LAST evaluate (any pointer may be NULL), with rows = stat "value_rows" (the timepoints of
+ * all data sets of the handle one after the other; T for one data set) and cells = stat "cell_columns" (this handle's cells;
+ * max_cells for a dividing population):
+ *   cell_values [C][rows][cells] observed-species value of every simulated cell at every data timepoint (NaN = cell absent)
  *   cell_status [C][cells] 1 = solved, 0 = CVODE failure;  cell_steps [C][cells] accepted steps (ODESolver::GetNumSteps)
- *   population_average [C][T] (DataLikelihoodTimeCoursePopulationAverage::population_average before offset/scale) */
+ *   population_average [C][rows] (DataLikelihoodTimeCoursePopulationAverage::population_average before offset/scale) */
 int bcm3b200_get_cell_diagnostics(void* handle, double* cell_values, int32_t* cell_status, int32_t* cell_steps,
                                   double* population_average);
 
-/* options: "diagnostics" (0/1), "block_size" (0 = auto, 32/64/128/256) */
+/* options: "diagnostics" (0/1, all kinds);
+ *   pop_pk_trajectory: "block_size" (0 = auto, else a multiple of 32 up to 384), "sort_patients" (0/1: patients ranked by
+ *     expected cost, results unchanged), "sort_min_systems", "chain_fastest_grid" (0/1: block order of the ranked launch);
+ *   cell_population: "cellpop_kernel" (0 auto, 1 one cell per warp, 2 per thread, 3 per lane group), "cellpop_group_lanes"
+ *     (0 auto), "cellpop_rhs_lanes" (0 never, 1 where it pays, 2 always: lane-parallel form of the generated right-hand
+ *     side, bit-identical to the text as it stands) -- the last two before finalize; "cellpop_steps_report". */
 int bcm3b200_set_option(void* handle, const char* name, int64_t value);
 
 /* stats: "num_patients_local", "patient_offset", "last_kernel_launches", "total_kernel_launches",
  * "num_evaluations" (chains evaluated so far = the reference's num_likelihood_evaluations, Sampler.cpp:169),
- * "last_kernel_us" (device time of the last host-buffer evaluate's kernels, microseconds, max over devices) */
+ * "last_kernel_us" (device time of the last host-buffer evaluate's kernels, microseconds, max over devices);
+ * cell_population: "num_cells_local", "cell_columns", "value_rows", "partial_doubles_per_chain" (= 2 value_rows + 1);
+ * pharmaco_population: "num_compartments". */
 int bcm3b200_get_stat(void* handle, const char* name, int64_t* value);
 
 void bcm3b200_destroy(void* handle);
