@@ -497,12 +497,12 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	s->last_C = (int)C;
 
 	// the integrator's thread-private state columns [slots][stride] first, then s_time [T] and s_sim [T][block]
-	if (block > 384) return fail(BCM3B200_ERR_ARG, "block_size above 384 is not supported");
-	const int stride = block <= 128 ? 128 : 384; // the two instantiations of the state-column stride
+	if (block > BCM3_POPPK_STRIDE_BIG) return fail(BCM3B200_ERR_ARG, "block_size above %d is not supported", BCM3_POPPK_STRIDE_BIG);
+	const int stride = block <= BCM3_POPPK_STRIDE_SMALL ? BCM3_POPPK_STRIDE_SMALL : BCM3_POPPK_STRIDE_BIG; // the two instantiations of the state-column stride
 	const bool two_cmt = (h->pk_type == PK_TWO || h->pk_type == PK_TWO_BIPHASIC || h->pk_type == PK_TWO_TRANSIT);
 	const int slots = two_cmt ? (int)BdfSlots<3>::COUNT : (int)BdfSlots<2>::COUNT;
 	const size_t smem_bytes = sizeof(double) * ((size_t)h->T + (size_t)h->T * block + (size_t)slots * stride);
-	if (smem_bytes > 200 * 1024) return fail(BCM3B200_ERR_UNSUPPORTED, "too many timepoints (%d) for block size %d", h->T, block);
+	if (smem_bytes > 226 * 1024) return fail(BCM3B200_ERR_UNSUPPORTED, "too many timepoints (%d) for block size %d", h->T, block);
 	if (C > 65535) return fail(BCM3B200_ERR_UNSUPPORTED, "more than 65535 chains in one batch");
 	const dim3 grid = a.chain_fastest ? dim3((unsigned)C, nblk) : dim3(nblk, (unsigned)C);
 
@@ -1260,7 +1260,7 @@ int bcm3b200_set_option(void* handle, const char* name, int64_t value)
 	else if (!strcmp(name, "sort_min_systems")) h->sort_min_systems = value;
 	else if (!strcmp(name, "chain_fastest_grid")) h->chain_fastest_grid = value != 0;
 	else if (!strcmp(name, "block_size")) {
-		if (value != 0 && (value < 32 || value > 384 || value % 32 != 0)) return fail(BCM3B200_ERR_ARG, "block_size must be 0 or a multiple of 32 up to 384");
+		if (value != 0 && (value < 32 || value > BCM3_POPPK_STRIDE_BIG || value % 32 != 0)) return fail(BCM3B200_ERR_ARG, "block_size must be 0 or a multiple of 32 up to %d", BCM3_POPPK_STRIDE_BIG);
 		h->block_size = (int)value;
 	} else return fail(BCM3B200_ERR_ARG, "unknown option \"%s\"", name);
 	return BCM3B200_OK;

@@ -183,6 +183,9 @@ __device__ __noinline__ void rhs_eval_lanes(unsigned y_off, unsigned f_off, unsi
 }
 #endif
 
+#ifndef CP_GROUP_LOCKSTEP_EVERY
+#define CP_GROUP_LOCKSTEP_EVERY 1
+#endif
 #ifndef CP_GROUP_LOCKSTEP
 #define CP_GROUP_LOCKSTEP 1
 #endif
@@ -1596,6 +1599,7 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 
 	bool have = false, exhausted = false, ok = true, newstep = true;
 	int steps = 0, tpi = 0, c = 0, cell = 0;
+	unsigned trip = 0;
 	double* out = nullptr;
 
 #pragma unroll 1
@@ -1764,7 +1768,11 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 			}
 		}
 #if CP_GROUP_LOCKSTEP
-		if (__syncthreads_or((have || !exhausted) ? 1 : 0) == 0) break;
+		// block lock-step: the warps of the block meet before every CP_GROUP_LOCKSTEP_EVERY-th trip (and leave the loop only
+		// there, together), so that they run the same code at nearly the same time and share instruction fetches
+		if (CP_GROUP_LOCKSTEP_EVERY == 1 || (trip++ % CP_GROUP_LOCKSTEP_EVERY) == 0) {
+			if (__syncthreads_or((have || !exhausted) ? 1 : 0) == 0) break;
+		}
 #else
 		if (!__any_sync(FULL, have || !exhausted)) break;
 #endif

@@ -19,8 +19,9 @@ static int launch_one(dim3 grid, int block, size_t smem_bytes, cudaStream_t stre
 template <class Model>
 static int launch_model(bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a)
 {
-	if (diagnostics) return stride == 128 ? launch_one<Model, true, 128>(grid, block, smem_bytes, stream, a) : launch_one<Model, true, 384>(grid, block, smem_bytes, stream, a);
-	return stride == 128 ? launch_one<Model, false, 128>(grid, block, smem_bytes, stream, a) : launch_one<Model, false, 384>(grid, block, smem_bytes, stream, a);
+	constexpr int SMALL = BCM3_POPPK_STRIDE_SMALL, BIG = BCM3_POPPK_STRIDE_BIG;
+	if (diagnostics) return stride == SMALL ? launch_one<Model, true, SMALL>(grid, block, smem_bytes, stream, a) : launch_one<Model, true, BIG>(grid, block, smem_bytes, stream, a);
+	return stride == SMALL ? launch_one<Model, false, SMALL>(grid, block, smem_bytes, stream, a) : launch_one<Model, false, BIG>(grid, block, smem_bytes, stream, a);
 }
 
 int launch_poppk_plain(bool two, bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a)

@@ -210,6 +210,23 @@ __device__ __forceinline__ bool check_give_treatment(double t, uint32_t skipped_
 // One translation unit per model family instantiates the integrator (poppk_inst_plain.cu, _biphasic.cu, _transit.cu: 8 kernels
 // each = one/two compartments x diagnostics x state-column stride) so that they compile in parallel and deterministically.
 // Returns a cudaError_t value.
+// the two instantiations of the state-column stride (= the largest block size each serves) and the blocks per SM each is
+// compiled for: registers per thread follow from threads x blocks (168 at 3 x 128 and 1 x 384)
+#ifndef BCM3_POPPK_STRIDE_SMALL
+#define BCM3_POPPK_STRIDE_SMALL 128
+#endif
+#ifndef BCM3_POPPK_SMALL_BLOCKS
+#define BCM3_POPPK_SMALL_BLOCKS 3
+#endif
+#ifndef BCM3_POPPK_STRIDE_BIG
+#define BCM3_POPPK_STRIDE_BIG 384
+#endif
+#ifndef BCM3_POPPK_BIG_BLOCKS
+#define BCM3_POPPK_BIG_BLOCKS 1
+#endif
+#ifndef BCM3_POPPK_KERNEL_ATTR /* experiments: -DBCM3_POPPK_KERNEL_ATTR=__maxnreg__(152) */
+#define BCM3_POPPK_KERNEL_ATTR __launch_bounds__(STRIDE, (STRIDE <= BCM3_POPPK_STRIDE_SMALL) ? BCM3_POPPK_SMALL_BLOCKS : BCM3_POPPK_BIG_BLOCKS)
+#endif
 int launch_poppk_plain(bool two, bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a);
 int launch_poppk_biphasic(bool two, bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a);
 int launch_poppk_transit(bool two, bool diagnostics, int stride, dim3 grid, int block, size_t smem_bytes, cudaStream_t stream, const PkArgs& a);
@@ -246,7 +263,7 @@ __global__ void poppk_rank_kernel(const PkArgs a, int C, unsigned long long* __r
 #endif
 
 template <class Model, bool DIAG, int STRIDE>
-__global__ void __launch_bounds__(STRIDE, (STRIDE <= 128) ? 3 : 1) poppk_kernel(const PkArgs a)
+__global__ void BCM3_POPPK_KERNEL_ATTR poppk_kernel(const PkArgs a)
 {
 	constexpr int N = Model::N;
 	constexpr unsigned FULL = 0xffffffffu;

@@ -52,6 +52,7 @@ bool SamplerPTSettings::LoadFromConfigText(const std::string& text, std::string*
 	if (kv.count("sampler.rngseed")) rngseed = strtoull(kv["sampler.rngseed"].c_str(), nullptr, 10);
 	U("ptmhsampler.num_chains", num_chains);
 	S("ptmhsampler.proposal_type", proposal_type);
+	S("ptmhsampler.blocking_strategy", blocking_strategy);
 	S("ptmhsampler.swapping_scheme", swapping_scheme);
 	U("ptmhsampler.num_exploration_steps", num_exploration_steps);
 	U("ptmhsampler.max_history_size", max_history_size);
@@ -98,20 +99,174 @@ void SampleHistory::GetHistory(std::vector<VectorReal>& rows) const
 		for (size_t i = 0; i < nvar; i++) rows[r][i] = (Real)samples[r * nvar + i];
 }
 
+void SampleHistory::GetHistory(const std::vector<size_t>& variable_indices, std::vector<VectorReal>& rows) const
+{
+	const size_t n = GetSampleCount();
+	rows.assign(n, VectorReal(variable_indices.size()));
+	for (size_t r = 0; r < n; r++)
+		for (size_t i = 0; i < variable_indices.size(); i++) rows[r][i] = (Real)samples[r * nvar + variable_indices[i]];
+}
+
+MatrixReal SampleHistory::GetEmpiricalCorrelation() const
+{
+	// cor() of SummaryStats.h on the float history cast to Real: centred columns, covariance / (sd_i sd_j); a variable
+	// that never moved has no correlation (NaN), as there
+	const size_t n = GetSampleCount();
+	MatrixReal c(nvar, nvar, kNaN);
+	if (n < 2) return c;
+	std::vector<Real> mean(nvar, 0.0);
+	for (size_t r = 0; r < n; r++)
+		for (size_t i = 0; i < nvar; i++) mean[i] += (Real)samples[r * nvar + i];
+	for (size_t i = 0; i < nvar; i++) mean[i] /= (Real)n;
+	MatrixReal cov(nvar, nvar, 0.0);
+	for (size_t r = 0; r < n; r++)
+		for (size_t j = 0; j < nvar; j++) {
+			const Real dj = (Real)samples[r * nvar + j] - mean[j];
+			for (size_t i = j; i < nvar; i++) cov(i, j) += ((Real)samples[r * nvar + i] - mean[i]) * dj;
+		}
+	for (size_t j = 0; j < nvar; j++)
+		for (size_t i = j; i < nvar; i++) {
+			const Real v = (cov(i, j) / (Real)(n - 1)) / (sqrt(cov(i, i) / (Real)(n - 1)) * sqrt(cov(j, j) / (Real)(n - 1)));
+			c(i, j) = v;
+			c(j, i) = v;
+		}
+	return c;
+}
+
+// ---------------------------------------------------------------------------------------------- variable blocks
+std::vector<std::vector<size_t>> TreeClusterCompleteLinkage(const MatrixReal& distance, Real cut_height)
+{
+	// The merge list: n - 1 nodes in the order in which complete linkage joins the closest pair of clusters. The tie-breaking
+	// has to be the C Clustering Library's (cluster.c: find_closest_pair scans the lower triangle row by row and keeps the
+	// FIRST minimum; pmlcluster keeps the merged cluster in the smaller slot and moves the last slot into the freed one),
+	// or equal distances would give other blocks than the reference's.
+	const int n = (int)distance.cols();
+	std::vector<std::vector<size_t>> clusters;
+	if (n < 1) return clusters;
+	struct Node { int left, right; Real distance; };
+	std::vector<Node> nodes;
+	{
+		std::vector<std::vector<Real>> d(n);
+		for (int i = 0; i < n; i++) {
+			d[i].resize(i);
+			for (int j = 0; j < i; j++) d[i][j] = distance(j, i);
+		}
+		std::vector<int> id(n);
+		for (int j = 0; j < n; j++) id[j] = j;
+		for (int m = n; m > 1; m--) {
+			int is = 1, js = 0;
+			Real best = d[1][0];
+			for (int i = 1; i < m; i++)
+				for (int j = 0; j < i; j++)
+					if (d[i][j] < best) {
+						best = d[i][j];
+						is = i;
+						js = j;
+					}
+			// the joined cluster lives in slot js: its distance to every other slot is the larger of the two
+			for (int j = 0; j < js; j++) d[js][j] = std::max(d[is][j], d[js][j]);
+			for (int j = js + 1; j < is; j++) d[j][js] = std::max(d[is][j], d[j][js]);
+			for (int j = is + 1; j < m; j++) d[j][js] = std::max(d[j][is], d[j][js]);
+			// slot is takes over the last slot
+			for (int j = 0; j < is; j++) d[is][j] = d[m - 1][j];
+			for (int j = is + 1; j < m - 1; j++) d[j][is] = d[m - 1][j];
+			nodes.push_back(Node{ id[is], id[js], best });
+			id[js] = m - n - 1; // node k is referred to as -(k + 1)
+			id[is] = id[m - 1];
+		}
+	}
+	// The cut (Clustering.cpp:61-96): walking the merge list, a node below the cut height joins its two sides, one above
+	// it leaves each side that is a single item as a cluster of its own. cluster_of[item] = position in `clusters`.
+	std::vector<int> cluster_of(n, -1);
+	auto any_item = [&](int el) { // an item below a node (all of them are in one cluster when the node was joined)
+		while (el < 0) {
+			const Node& nd = nodes[(size_t)(-el) - 1];
+			el = nd.left >= 0 ? nd.left : nd.right;
+		}
+		return el;
+	};
+	auto add_item = [&](int item, int ci) {
+		clusters[ci].push_back((size_t)item);
+		cluster_of[item] = ci;
+	};
+	for (const Node& nd : nodes) {
+		if (nd.distance < cut_height) {
+			if (nd.left >= 0 && nd.right >= 0) {
+				clusters.emplace_back();
+				add_item(nd.left, (int)clusters.size() - 1);
+				add_item(nd.right, (int)clusters.size() - 1);
+			} else if (nd.left >= 0) {
+				add_item(nd.left, cluster_of[any_item(nd.right)]);
+			} else if (nd.right >= 0) {
+				add_item(nd.right, cluster_of[any_item(nd.left)]);
+			} else {
+				const int keep = cluster_of[any_item(nd.left)], drop = cluster_of[any_item(nd.right)];
+				for (size_t item : clusters[drop]) add_item((int)item, keep);
+				clusters.erase(clusters.begin() + drop);
+				for (int& c : cluster_of)
+					if (c > drop) c--;
+			}
+		} else {
+			if (nd.left >= 0) {
+				clusters.emplace_back();
+				add_item(nd.left, (int)clusters.size() - 1);
+			}
+			if (nd.right >= 0) {
+				clusters.emplace_back();
+				add_item(nd.right, (int)clusters.size() - 1);
+			}
+		}
+	}
+	for (auto& c : clusters) std::sort(c.begin(), c.end()); // std::set order
+	return clusters;
+}
+
+bool GetVariableBlocks(const std::string& strategy, const SampleHistory& history, size_t num_variables, std::vector<std::vector<size_t>>& blocks)
+{
+	blocks.clear();
+	auto singletons = [&]() {
+		blocks.resize(num_variables);
+		for (size_t i = 0; i < num_variables; i++) blocks[i].assign(1, i);
+	};
+	if (strategy == "one_block") {
+		blocks.resize(1);
+		for (size_t i = 0; i < num_variables; i++) blocks[0].push_back(i);
+	} else if (strategy == "no_blocking") {
+		singletons();
+	} else if (strategy == "Turek") {
+		// Turek et al. automated blocking: variables whose |correlation| in the chain's history exceeds 0.5 share a block
+		// (distance 1 - |r|, complete linkage, cut at 0.5). One variable: the reference's merge list is empty and it ends up
+		// with no block at all; here it is one block.
+		if (history.GetSampleCount() > 2 && num_variables > 1) {
+			const MatrixReal r = history.GetEmpiricalCorrelation();
+			MatrixReal dist(num_variables, num_variables, 0.0);
+			for (size_t j = 0; j < num_variables; j++)
+				for (size_t i = 0; i < num_variables; i++) dist(i, j) = 1.0 - fabs(r(i, j));
+			blocks = TreeClusterCompleteLinkage(dist, 0.5);
+		} else {
+			singletons();
+		}
+	} else {
+		return false;
+	}
+	return true;
+}
+
 // ---------------------------------------------------------------------------------------------- proposal
-bool Proposal::Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng)
+bool Proposal::Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, const std::vector<size_t>& variable_indices, RNG& rng)
 {
 	// Proposal::Initialize (Proposal.cpp:39-140)
-	n = num_variables;
+	var_ix = variable_indices;
+	n = var_ix.size();
 	target_acceptance_rate = (n == 1) ? 0.44 : (n == 2) ? 0.35 : (n == 3) ? 0.3 : 0.234;
 	lower.resize(n);
 	upper.resize(n);
 	for (size_t i = 0; i < n; i++) {
-		lower[i] = prior.GetLowerBound(i);
-		upper[i] = prior.GetUpperBound(i);
+		lower[i] = prior.GetLowerBound(var_ix[i]);
+		upper[i] = prior.GetUpperBound(var_ix[i]);
 	}
 	std::vector<VectorReal> rows;
-	history.GetHistory(rows);
+	history.GetHistory(var_ix, rows);
 	if (rows.size() > max_history_samples && max_history_samples > 0) {
 		std::vector<size_t> use;
 		size_t subsample = rows.size() / max_history_samples;
@@ -137,7 +292,7 @@ bool ProposalGlobalCovariance::InitializeImpl(const std::vector<VectorReal>& row
 	if (rows.size() < 2) {
 		for (size_t j = 0; j < n; j++) {
 			Real var;
-			prior.EvaluateMarginalVariance(j, var);
+			prior.EvaluateMarginalVariance(var_ix[j], var);
 			covariance[j + j * n] = var;
 		}
 	} else {
@@ -151,7 +306,7 @@ bool ProposalGlobalCovariance::InitializeImpl(const std::vector<VectorReal>& row
 		for (Real& v : covariance) v /= (Real)(rows.size() - 1);
 		for (size_t j = 0; j < n; j++) {
 			Real var;
-			prior.EvaluateMarginalVariance(j, var);
+			prior.EvaluateMarginalVariance(var_ix[j], var);
 			covariance[j + j * n] = std::max(covariance[j + j * n], 1e-6 * var);
 		}
 	}
@@ -286,8 +441,8 @@ bool ProposalGaussianMixture::InitializeImpl(const std::vector<VectorReal>& rows
 		std::vector<Real> cov(n * n, 0.0);
 		for (size_t i = 0; i < n; i++) {
 			Real m = 0.0, v = 1.0;
-			if (!prior.EvaluateMarginalMean(i, m)) m = 0.0;
-			if (!prior.EvaluateMarginalVariance(i, v)) v = 1.0;
+			if (!prior.EvaluateMarginalMean(var_ix[i], m)) m = 0.0;
+			if (!prior.EvaluateMarginalVariance(var_ix[i], v)) v = 1.0;
 			mean[i] = m;
 			cov[i + i * n] = v;
 		}
@@ -369,6 +524,11 @@ bool SamplerPT::Initialize()
 		last_error = "proposal_type \"" + s.proposal_type + "\" is not supported (global_covariance, gaussian_mixture, gaussian_mixture_adjustedAIC)";
 		return false;
 	}
+	if (s.blocking_strategy != "one_block" && s.blocking_strategy != "no_blocking" && s.blocking_strategy != "Turek") {
+		last_error = s.blocking_strategy == "clustered_autoblock" ? "blocking_strategy \"clustered_autoblock\" (clustered sample history) is not supported: one_block, no_blocking, Turek"
+		                                                          : "Unknown blocking strategy \"" + s.blocking_strategy + "\"";
+		return false;
+	}
 	if (s.swapping_scheme != "deterministic_even_odd" && s.swapping_scheme != "stochastic_even_odd" && s.swapping_scheme != "stochastic_random") {
 		last_error = "Unknown swapping scheme \"" + s.swapping_scheme + "\"";
 		return false;
@@ -407,13 +567,10 @@ bool SamplerPT::Initialize()
 		c.rng.Seed(s.rngseed, i + 1);
 		c.current_var_values.assign(num_variables, 0.0);
 		c.history.Initialize(num_variables, sample_history, subsampling);
-		c.proposal = MakeProposal();
-		if (!c.proposal->Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
-			last_error = "Proposal initialization failed.";
+		if (!AdaptChainProposal(c)) { // SamplerPTChain::Initialize ends with AdaptProposal on the empty history (SamplerPTChain.cpp:95)
+			if (last_error.empty()) last_error = "Proposal initialization failed.";
 			return false;
 		}
-		c.proposal->SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
-		c.proposal->SetTDof(s.proposal_t_dof);
 	}
 	previous_swap_even = false;
 	proposal_adaptations_done = 0;
@@ -552,58 +709,74 @@ void SamplerPT::DoExchangeMove()
 
 bool SamplerPT::DoMutateMove()
 {
-	// SamplerPT::DoMutateMove (SamplerPT.cpp:308-319) + SamplerPTChain::MutateMove (SamplerPTChain.cpp:217-313), one_block:
-	// 1. every chain proposes (the T = 0 chain draws from the prior), host side, per-chain streams
+	// SamplerPT::DoMutateMove (SamplerPT.cpp:308-319) + SamplerPTChain::MutateMove (SamplerPTChain.cpp:217-313). A chain updates
+	// its variable blocks one after the other, each with a likelihood evaluation at the vector that differs from the chain's
+	// current one in that block only; the chains are independent of each other, so round b evaluates block b of EVERY chain
+	// that has one in ONE batched call (the T = 0 chain draws from the prior in round 0 and has no further rounds).
 	const size_t C = chains.size();
-	MatrixReal proposals(num_variables, C);
-	std::vector<size_t> all(C);
-	for (size_t ci = 0; ci < C; ci++) {
-		Chain& c = chains[ci];
-		all[ci] = ci;
-		if (c.temperature == 0.0) {
-			prior->Sample(proposals.col(ci), &c.rng);
-		} else {
-			c.proposal->Update(c.rng, proposal_scaling_adaptations_done);
-			VectorReal np;
-			c.proposal->GetNewSample(c.current_var_values, np, c.rng);
-			std::copy(np.begin(), np.end(), proposals.col(ci));
+	size_t rounds = 1;
+	for (const Chain& c : chains) rounds = std::max(rounds, c.blocks.size());
+	std::vector<VectorReal> block_current(C), block_new(C);
+	for (size_t round = 0; round < rounds; round++) {
+		// 1. every participating chain proposes, host side, per-chain streams
+		std::vector<size_t> which;
+		for (size_t ci = 0; ci < C; ci++)
+			if (chains[ci].temperature == 0.0 ? round == 0 : round < chains[ci].blocks.size()) which.push_back(ci);
+		MatrixReal proposals(num_variables, which.size());
+		for (size_t k = 0; k < which.size(); k++) {
+			const size_t ci = which[k];
+			Chain& c = chains[ci];
+			if (c.temperature == 0.0) {
+				prior->Sample(proposals.col(k), &c.rng);
+				continue;
+			}
+			Chain::Block& b = c.blocks[round];
+			b.proposal->Update(c.rng, proposal_scaling_adaptations_done);
+			block_current[ci].resize(b.variable_indices.size());
+			for (size_t i = 0; i < b.variable_indices.size(); i++) block_current[ci][i] = c.current_var_values[b.variable_indices[i]];
+			b.proposal->GetNewSample(block_current[ci], block_new[ci], c.rng);
+			std::copy(c.current_var_values.begin(), c.current_var_values.end(), proposals.col(k));
+			for (size_t i = 0; i < b.variable_indices.size(); i++) proposals(b.variable_indices[i], k) = block_new[ci][i];
 		}
-	}
-	// 2. ONE batched evaluation of all proposals
-	VectorReal lp, ll;
-	if (!EvaluateAll(all, proposals, lp, ll)) return false;
-	// 3. every chain tests and accepts / rejects
-	for (size_t ci = 0; ci < C; ci++) {
-		Chain& c = chains[ci];
-		if (c.temperature == 0.0) {
-			c.current_var_values.assign(proposals.col(ci), proposals.col(ci) + num_variables);
-			c.lprior = lp[ci];
-			c.llh = ll[ci];
-			c.lpowerposterior = (c.llh == -kInf) ? c.lprior : c.lprior + c.temperature * c.llh; // :230-236
+		// 2. ONE batched evaluation of all proposals of this round
+		VectorReal lp, ll;
+		std::vector<size_t> slots(which.size());
+		for (size_t k = 0; k < which.size(); k++) slots[k] = k; // columns of `proposals`
+		if (!EvaluateAll(slots, proposals, lp, ll)) return false;
+		// 3. every chain tests and accepts / rejects
+		for (size_t k = 0; k < which.size(); k++) {
+			Chain& c = chains[which[k]];
+			if (c.temperature == 0.0) {
+				c.current_var_values.assign(proposals.col(k), proposals.col(k) + num_variables);
+				c.lprior = lp[k];
+				c.llh = ll[k];
+				c.lpowerposterior = (c.llh == -kInf) ? c.lprior : c.lprior + c.temperature * c.llh; // :230-236
+				c.attempted_mutate++;
+				c.accepted_mutate++;
+				continue;
+			}
+			Chain::Block& b = c.blocks[round];
+			const Real new_lpp = lp[k] + c.temperature * ll[k];
+			// TestSample, SamplerPTChain.cpp:465-482
 			c.attempted_mutate++;
-			c.accepted_mutate++;
-			continue;
+			bool accept = false;
+			if (new_lpp > -kInf) {
+				Real tp = exp(new_lpp - c.lpowerposterior + b.proposal->CalculateMHRatio(block_current[which[k]], block_new[which[k]]));
+				tp = std::min((Real)1.0, tp);
+				accept = c.rng.GetReal() < tp;
+			}
+			if (accept) {
+				c.accepted_mutate++;
+				c.current_var_values.assign(proposals.col(k), proposals.col(k) + num_variables);
+				c.lprior = lp[k];
+				c.llh = ll[k];
+				c.lpowerposterior = new_lpp;
+			}
+			b.proposal->NotifyAccepted(accept);
 		}
-		const Real new_lpp = lp[ci] + c.temperature * ll[ci];
-		// TestSample, SamplerPTChain.cpp:465-482
-		c.attempted_mutate++;
-		bool accept = false;
-		if (new_lpp > -kInf) {
-			const VectorReal proposed(proposals.col(ci), proposals.col(ci) + num_variables);
-			Real tp = exp(new_lpp - c.lpowerposterior + c.proposal->CalculateMHRatio(c.current_var_values, proposed));
-			tp = std::min((Real)1.0, tp);
-			accept = c.rng.GetReal() < tp;
-		}
-		if (accept) {
-			c.accepted_mutate++;
-			c.current_var_values.assign(proposals.col(ci), proposals.col(ci) + num_variables);
-			c.lprior = lp[ci];
-			c.llh = ll[ci];
-			c.lpowerposterior = new_lpp;
-		}
-		c.proposal->NotifyAccepted(accept);
-		c.history.AddSample(c.current_var_values);
 	}
+	for (Chain& c : chains)
+		if (c.temperature != 0.0) c.history.AddSample(c.current_var_values);
 	return true;
 }
 
@@ -613,17 +786,36 @@ void SamplerPT::EmitSample()
 	for (const Chain& c : chains) samples.push_back(EmittedSample{ c.current_var_values, c.lprior, c.llh, c.temperature });
 }
 
-bool SamplerPT::AdaptProposals()
+bool SamplerPT::AdaptChainProposal(Chain& c)
 {
-	for (Chain& c : chains) {
-		if (c.temperature == 0.0) continue;
-		if (!c.proposal->Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, num_variables, c.rng)) {
+	// SamplerPTChain::AdaptProposal (SamplerPTChain.cpp:109-170): nothing for the chain that samples the prior; the blocking
+	// strategy's blocks from the history, a fresh proposal per block from the history of its variables, history discarded
+	if (c.temperature == 0.0) return true;
+	std::vector<std::vector<size_t>> blocks;
+	if (!GetVariableBlocks(s.blocking_strategy, c.history, num_variables, blocks)) {
+		last_error = "Unknown blocking strategy \"" + s.blocking_strategy + "\"";
+		return false;
+	}
+	c.blocks.clear();
+	c.blocks.resize(blocks.size());
+	for (size_t b = 0; b < blocks.size(); b++) {
+		c.blocks[b].variable_indices = blocks[b];
+		c.blocks[b].proposal = MakeProposal();
+		if (!c.blocks[b].proposal->Initialize(c.history, s.adapt_proposal_max_history_samples, *prior, blocks[b], c.rng)) {
 			last_error = "Proposal adaptation failed";
 			return false;
 		}
-		c.proposal->SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
-		c.proposal->SetTDof(s.proposal_t_dof);
+		c.blocks[b].proposal->SetScalingSchedule(proposal_scaling_ema_period, proposal_scaling_learning_rate);
+		c.blocks[b].proposal->SetTDof(s.proposal_t_dof);
 	}
+	c.history.Reset();
+	return true;
+}
+
+bool SamplerPT::AdaptProposals()
+{
+	for (Chain& c : chains)
+		if (!AdaptChainProposal(c)) return false;
 	return true;
 }
 

@@ -4,7 +4,10 @@
 // mutate round:   propose for all chains -> EvaluateLogProbabilityBatch -> accept/reject for all chains.
 // Proposal generation, MH tests and temperature swaps stay on the host and are deterministic (RNG.h).
 // Proposals: global_covariance and gaussian_mixture (the one examples/banana/config.txt asks for; ProposalGaussianMixture.cpp,
-// GMM.cpp). Blocking strategies other than one_block and the clustered proposal are out of scope.
+// GMM.cpp). Blocking strategies one_block, no_blocking and Turek (BlockingStrategy*.cpp): a chain's mutate move updates its
+// variable blocks one after the other, each with its own proposal and its own likelihood evaluation
+// (SamplerPTChain.cpp:249-307); batched, block index b of ALL chains is one EvaluateLogProbabilityBatch. The clustered
+// strategy and proposal (clustered_autoblock, SampleHistoryClustering) are refused.
 #pragma once
 
 #include <functional>
@@ -24,6 +27,7 @@ struct SamplerPTSettings {
 	// [ptmhsampler] (defaults of SamplerPT::AddOptionsDescription, SamplerPT.cpp:147-172)
 	size_t num_chains = 6;
 	std::string proposal_type = "gaussian_mixture"; // the reference default (SamplerPT.cpp:11,152); also global_covariance, gaussian_mixture_adjustedAIC (SamplerPTChain.cpp:431-437)
+	std::string blocking_strategy = "one_block";     // one_block | no_blocking | Turek (SamplerPT.cpp:10,151; SamplerPTChain.cpp:66-77)
 	std::string swapping_scheme = "deterministic_even_odd";
 	size_t num_exploration_steps = 1;
 	size_t max_history_size = 2000;
@@ -47,9 +51,15 @@ class SampleHistory {
 public:
 	void Initialize(size_t num_variables, size_t history_size, size_t subsampling);
 	void AddSample(const VectorReal& sample);
+	void Reset() { sample_n = 0; sample_n_s = 0; } // SampleHistory.cpp:26-30: an adaptation discards the history it used
 	size_t GetSampleCount() const { return sample_n < capacity ? sample_n : capacity; }
 	// rows = samples, columns = variables (stored as float like the reference, SampleHistory.cpp:41)
 	void GetHistory(std::vector<VectorReal>& rows) const;
+	void GetHistory(const std::vector<size_t>& variable_indices, std::vector<VectorReal>& rows) const; // SampleHistory.cpp:58-68
+	// Pearson correlation of the variables over the stored samples, num_variables x num_variables column-major
+	// (SampleHistory.cpp:76-81 -> cor(), SummaryStats.h)
+	MatrixReal GetEmpiricalCorrelation() const;
+	size_t GetNumVariables() const { return nvar; }
 
 private:
 	size_t nvar = 0, capacity = 0, subsampling = 1, sample_n = 0, sample_n_s = 0;
@@ -57,11 +67,20 @@ private:
 };
 
 // Proposal (src/sampler/Proposal.{h,cpp}): what a chain asks of its proposal distribution for the one variable block
+// Complete-linkage hierarchical clustering of `n` items from their n x n distance matrix, cut at `cut_height`
+// (bcm3::TreeCluster, utils/Clustering.cpp:35-99, around the C Clustering Library's pairwise-maximum-linkage treecluster):
+// the clusters in the order in which the reference's walk over the merge list creates them, members ascending.
+std::vector<std::vector<size_t>> TreeClusterCompleteLinkage(const MatrixReal& distance, Real cut_height);
+
+// BlockingStrategy::GetBlocks (BlockingStrategyOneBlock.cpp, BlockingStrategyNoBlocking.cpp, BlockingStrategyTurek.cpp:8-40)
+bool GetVariableBlocks(const std::string& strategy, const SampleHistory& history, size_t num_variables, std::vector<std::vector<size_t>>& blocks);
+
 class Proposal {
 public:
 	virtual ~Proposal() {}
-	// Proposal::Initialize (Proposal.cpp:39-140): bounds, target acceptance rate, the (sub)sampled history -> InitializeImpl
-	bool Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, size_t num_variables, RNG& rng);
+	// Proposal::Initialize (Proposal.cpp:39-140): the block's variables, their bounds, target acceptance rate, the (sub)sampled
+	// history of those variables -> InitializeImpl
+	bool Initialize(const SampleHistory& history, size_t max_history_samples, const Prior& prior, const std::vector<size_t>& variable_indices, RNG& rng);
 	void SetScalingSchedule(size_t ema_period, Real learning_rate) { scaling_ema_period = ema_period; scaling_learning_rate = learning_rate; }
 	// ptmhsampler.proposal_t_dof (SamplerPT.cpp:63,169; Proposal.cpp:45): > 0 scales every step by 1 / sqrt(w), w drawn as
 	// rng.GetGamma(t_dof / 2, t_dof / 2) -- the second argument is the SCALE of RNG::GetGamma, as the reference passes it
@@ -75,6 +94,7 @@ protected:
 	virtual bool InitializeImpl(const std::vector<VectorReal>& history_rows, const Prior& prior, RNG& rng) = 0;
 	static Real ReflectOnBounds(Real x, Real lb, Real ub);
 	size_t n = 0;
+	std::vector<size_t> var_ix; // the block's variables (indices into the prior / variable set)
 	std::vector<Real> lower, upper;
 	size_t scaling_ema_period = 1000;
 	Real scaling_learning_rate = 0.05, target_acceptance_rate = 0.234;
@@ -140,6 +160,12 @@ public:
 	const VectorReal& GetTemperatures() const { return temperatures; }
 	size_t GetNumLikelihoodEvaluations() const { return num_likelihood_evaluations; }
 	size_t GetNumBatchedCalls() const { return num_batched_calls; }
+	std::vector<std::vector<size_t>> GetBlocks(size_t chain) const
+	{
+		std::vector<std::vector<size_t>> out;
+		for (auto& b : chains[chain].blocks) out.push_back(b.variable_indices);
+		return out;
+	}
 	Real GetMutateAcceptance(size_t chain) const { return chains[chain].attempted_mutate ? chains[chain].accepted_mutate / (Real)chains[chain].attempted_mutate : 0.0; }
 	Real GetExchangeAcceptance(size_t chain) const { return chains[chain].attempted_exchange ? chains[chain].accepted_exchange / (Real)chains[chain].attempted_exchange : 0.0; }
 	const std::string& LastError() const { return last_error; }
@@ -151,9 +177,14 @@ private:
 		Real lprior = -kInf, llh = -kInf, lpowerposterior = -kInf;
 		size_t attempted_mutate = 0, accepted_mutate = 0, attempted_exchange = 0, accepted_exchange = 0;
 		SampleHistory history;
-		std::shared_ptr<Proposal> proposal;
+		struct Block { // SamplerPTChain::Block, SamplerPTChain.h
+			std::vector<size_t> variable_indices;
+			std::shared_ptr<Proposal> proposal;
+		};
+		std::vector<Block> blocks;
 		RNG rng;
 	};
+	bool AdaptChainProposal(Chain& c);
 
 	bool EvaluateAll(const std::vector<size_t>& which, const MatrixReal& proposals, VectorReal& lpriors, VectorReal& llhs);
 	bool FindStartingPositions();

@@ -84,6 +84,7 @@ int run(Setup& st, const char* config_text, int batched, unsigned long long seed
 		stats[0] = sampler.GetNumLikelihoodEvaluations();
 		stats[1] = sampler.GetNumBatchedCalls();
 		stats[2] = sampler.GetTemperatures().size();
+		stats[3] = sampler.GetBlocks(sampler.GetTemperatures().size() - 1).size(); // variable blocks of the posterior chain at the end
 	}
 	return 0;
 }
@@ -490,6 +491,19 @@ int bcm3host_cellpop_session_evaluate(void* session, const double* values, size_
 
 // ---- GaussianMixture (the fit behind proposal_type=gaussian_mixture) for tests ----
 // samples[n][D] row-major. Outputs: weights[K], means[K][D], covariances[K][D][D], stats = { AIC, log-likelihood }.
+// TreeClusterCompleteLinkage for tests: cluster[i] = index of item i's block (blocks in the order the sampler would use them)
+int bcm3host_tree_cluster(const double* distance, size_t n, double cut_height, int* cluster)
+{
+	MatrixReal d(n, n);
+	for (size_t j = 0; j < n; j++)
+		for (size_t i = 0; i < n; i++) d(i, j) = distance[i * n + j];
+	const auto blocks = TreeClusterCompleteLinkage(d, cut_height);
+	for (size_t i = 0; i < n; i++) cluster[i] = -1;
+	for (size_t b = 0; b < blocks.size(); b++)
+		for (size_t item : blocks[b]) cluster[item] = (int)b;
+	return (int)blocks.size();
+}
+
 int bcm3host_gmm_fit(const double* samples, size_t n, size_t D, size_t K, unsigned long long seed, double ess_factor, double* weights,
                      double* means, double* covariances, double* stats)
 {

@@ -32,13 +32,13 @@ def run_pt(prior_xml: str, likelihood_xml: str, config_text: str, batched: bool 
     nvar = varset_info(prior_xml)[0]
     out = np.zeros((max_rows, nvar + 3))
     nrows = C.c_size_t()
-    stats = (C.c_size_t * 3)()
+    stats = (C.c_size_t * 4)()
     err = _err()
     rc = lib.bcm3host_run_pt(prior_xml.encode(), likelihood_xml.encode(), config_text.encode(), int(batched), C.c_ulonglong(seed),
                              out.ctypes.data_as(C.c_void_p), C.c_size_t(max_rows), C.byref(nrows), stats, err, C.c_size_t(1024))
     if rc != 0:
         raise RuntimeError(f"bcm3host_run_pt failed ({rc}): {err.value.decode()}")
-    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])
+    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2], blocks=stats[3])
 
 
 def run_pt_poppk(prior_xml: str, likelihood_xml: str, config_text: str, trial, batched: bool = True, seed: int = 1, device: int = 0,
@@ -47,7 +47,7 @@ def run_pt_poppk(prior_xml: str, likelihood_xml: str, config_text: str, trial, b
     nvar = varset_info(prior_xml)[0]
     out = np.zeros((max_rows, nvar + 3))
     nrows = C.c_size_t()
-    stats = (C.c_size_t * 3)()
+    stats = (C.c_size_t * 4)()
     err = _err()
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (
         trial.time, trial.observed_concentration, trial.dose, trial.dosing_interval, trial.dose_after_dose_change,
@@ -58,7 +58,16 @@ def run_pt_poppk(prior_xml: str, likelihood_xml: str, config_text: str, trial, b
                                    out.ctypes.data_as(C.c_void_p), C.c_size_t(max_rows), C.byref(nrows), stats, err, C.c_size_t(1024))
     if rc != 0:
         raise RuntimeError(f"bcm3host_run_pt_poppk failed ({rc}): {err.value.decode()}")
-    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])
+    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2], blocks=stats[3])
+
+
+def tree_cluster(distance: np.ndarray, cut_height: float) -> np.ndarray:
+    """Complete-linkage clustering cut at a height, as the Turek blocking strategy uses it: block index of every item."""
+    lib = load()
+    d = np.ascontiguousarray(distance, dtype=np.float64)
+    out = np.empty(d.shape[0], dtype=np.int32)
+    lib.bcm3host_tree_cluster(d.ctypes.data_as(C.c_void_p), C.c_size_t(d.shape[0]), C.c_double(cut_height), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def evaluate(prior_xml: str, likelihood_xml: str, values: np.ndarray, batched: bool):
@@ -137,7 +146,7 @@ def run_pt_cellpop(prior_xml: str, likelihood_xml: str, config_text: str, proble
     nvar = varset_info(prior_xml)[0]
     out = np.zeros((max_rows, nvar + 3))
     nrows = C.c_size_t()
-    stats = (C.c_size_t * 3)()
+    stats = (C.c_size_t * 4)()
     err = _err()
     names = (C.c_char_p * len(species_names))(*[s.encode() for s in species_names])
     ic = np.ascontiguousarray(p.initial_conditions, dtype=np.float64)
@@ -152,7 +161,7 @@ def run_pt_cellpop(prior_xml: str, likelihood_xml: str, config_text: str, proble
                                      vp(out), C.c_size_t(max_rows), C.byref(nrows), stats, err, C.c_size_t(1024))
     if rc != 0:
         raise RuntimeError(f"bcm3host_run_pt_cellpop failed ({rc}): {err.value.decode()}")
-    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2])
+    return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2], blocks=stats[3])
 
 
 def gmm_fit(samples, num_components: int, seed: int = 1, ess_factor: float = 1.0):

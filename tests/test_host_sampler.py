@@ -303,3 +303,53 @@ def test_t_distributed_proposals_on_the_banana(host):
     post = rows[rows[:, 0] == 1.0][800:, 3:]
     r = post[:, 1] - (1 + post[:, 0]) ** 2
     assert abs(r.mean()) < 0.15 and abs(r.std() - 1.0) < 0.15
+
+
+def test_complete_linkage_clustering_against_scipy(host):
+    """TreeClusterCompleteLinkage (bcm3::TreeCluster around the C Clustering Library's pairwise-maximum-linkage tree) against
+    scipy's complete linkage cut at the same height: the same partition."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from scipy.spatial.distance import squareform
+
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 7, 12, 25):
+        for trial in range(4):
+            x = rng.normal(size=(n, 3))
+            d = np.abs(x[:, None, :] - x[None, :, :]).sum(-1)
+            d = d / d.max()
+            got = host.tree_cluster(d, 0.5)
+            want = fcluster(linkage(squareform(d, checks=False), method="complete"), t=0.5 - 1e-12, criterion="distance")
+            assert got.min() == 0 and len(np.unique(got)) == got.max() + 1
+            # same partition: items share a block here iff they share one there
+            assert np.array_equal(got[:, None] == got[None, :], want[:, None] == want[None, :])
+    # everything further apart than the cut: singletons; everything closer: one block
+    assert len(np.unique(host.tree_cluster(np.full((5, 5), 0.9) - 0.9 * np.eye(5), 0.5))) == 5
+    assert len(np.unique(host.tree_cluster(np.full((5, 5), 0.1) - 0.1 * np.eye(5), 0.5))) == 1
+
+
+def test_blocking_strategies_on_the_banana(host):
+    """ptmhsampler.blocking_strategy (SamplerPT.cpp:48,151; SamplerPTChain.cpp:66-77,249-307): no_blocking updates one variable
+    at a time (two likelihood evaluations per mutate move of a two-variable chain, block b of all chains in one batched call),
+    Turek joins variables whose history correlates above 0.5. Batched and serial runs stay identical, the posterior is the
+    banana's either way."""
+    base = CONFIG.replace("num_samples=8000", "num_samples=3000")
+    one, s_one = host.run_pt(PRIOR, LIKELIHOOD, base, batched=True, seed=3)
+    assert s_one["blocks"] == 1
+    for strategy, blocks in (("no_blocking", 2), ("Turek", None)):
+        cfg = base.replace("[ptmhsampler]", f"[ptmhsampler]\nblocking_strategy={strategy}")
+        rows, st = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=True, seed=3)
+        serial, st_serial = host.run_pt(PRIOR, LIKELIHOOD, cfg, batched=False, seed=3)
+        assert np.array_equal(rows, serial) and st["evaluations"] == st_serial["evaluations"]
+        if blocks is not None:
+            assert st["blocks"] == blocks
+            # 5 tempered chains x 2 blocks + the prior chain's one draw per mutate move, against 6 evaluations with one block
+            assert st["evaluations"] > 1.7 * s_one["evaluations"] and st["batched_calls"] > 1.9 * s_one["batched_calls"]
+        else:
+            assert st["blocks"] in (1, 2)
+        post = rows[rows[:, 0] == 1.0][600:, 3:]
+        r = post[:, 1] - (1 + post[:, 0]) ** 2
+        assert abs(r.mean()) < 0.2 and abs(r.std() - 1.0) < 0.2
+    with pytest.raises(RuntimeError, match="clustered_autoblock"):
+        host.run_pt(PRIOR, LIKELIHOOD, base.replace("[ptmhsampler]", "[ptmhsampler]\nblocking_strategy=clustered_autoblock"))
+    with pytest.raises(RuntimeError, match="Unknown blocking strategy"):
+        host.run_pt(PRIOR, LIKELIHOOD, base.replace("[ptmhsampler]", "[ptmhsampler]\nblocking_strategy=nope"))
