@@ -102,6 +102,7 @@ struct Handle {
 	bool diagnostics = false;
 	int block_size = 0;
 	bool sort_patients = true;                    // option "sort_patients"
+	bool single = false;                          // model kind "pharmacokinetic_trajectory": one patient, the chain's variables are its rates
 	bool chain_fastest_grid = true;               // option "chain_fastest_grid": with ranked patients, launch all chains' expensive blocks first
 	long long sort_min_systems = 60000;           // option "sort_min_systems": rank patients when P * C reaches this (measured:
 	                                              // 80 k systems 5.59 -> 4.75 ms, 40 k and below no gain; tools/rank_check.py)
@@ -309,9 +310,19 @@ int finalize(Handle* h)
 	// cpp:122-130: every fixed attribute takes one variable out of the prior -- and nothing else changes: the reference keeps
 	// reading the vector at the all-sampled positions (cpp:267-272, 283-286), which is reproduced here as it is
 	const int fixed_var_count = (std::isnan(h->fixed_vod) ? 0 : 1) + (std::isnan(h->fixed_periphery_fwd) ? 0 : 1) + (std::isnan(h->fixed_periphery_bwd) ? 0 : 1);
-	if (h->nvar != h->npk - fixed_var_count + 2 * (P + 1) + 2) return fail(BCM3B200_ERR_ARG, "Incorrect number of variables in prior");
-	if (P > 0 && h->npk + 2 * P + 1 >= h->nvar)
-		return fail(BCM3B200_ERR_ARG, "with these fixed pk_model attributes the reference reads past the end of the variable vector (cpp:283-286)");
+	const bool two_cmt_model = (h->pk_type == PK_TWO || h->pk_type == PK_TWO_BIPHASIC || h->pk_type == PK_TWO_TRANSIT);
+	if (h->single) {
+		// the single-patient likelihood checks no variable count (its check is compiled out, LikelihoodPharmacokineticTrajectory.cpp:128-151);
+		// every position it reads (its cpp:264-305) has to exist
+		int last = 3;
+		if (two_cmt_model && std::isnan(h->fixed_periphery_fwd)) last = 5;
+		if (h->pk_type == PK_ONE_BIPHASIC || h->pk_type == PK_TWO_BIPHASIC) last = 7;
+		if (h->nvar <= last) return fail(BCM3B200_ERR_ARG, "the model reads variable %d, the prior has %d", last, h->nvar);
+	} else {
+		if (h->nvar != h->npk - fixed_var_count + 2 * (P + 1) + 2) return fail(BCM3B200_ERR_ARG, "Incorrect number of variables in prior");
+		if (P > 0 && h->npk + 2 * P + 1 >= h->nvar)
+			return fail(BCM3B200_ERR_ARG, "with these fixed pk_model attributes the reference reads past the end of the variable vector (cpp:283-286)");
+	}
 	if (h->sd_ix < 0 || h->sd_ix + 1 >= h->nvar) return fail(BCM3B200_ERR_ARG, "sd_ix out of range");
 
 	const std::vector<double>& time = h->data["time"];
@@ -324,7 +335,8 @@ int finalize(Handle* h)
 
 	// chain-level variable indices (positional, cpp:267-272,283-286) and their transforms
 	const int named_a = h->named_a_ix >= 0 ? h->named_a_ix : 0, named_b = h->named_b_ix >= 0 ? h->named_b_ix : 0;
-	const int ix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, h->npk + 0, h->npk + 1, h->sd_ix, h->sd_ix + 1, named_a, named_b };
+	const int sigma0 = h->single ? 0 : h->npk; // no population spreads in the single-patient likelihood: slots unused
+	const int ix[SV_COUNT] = { 0, 1, 2, 3, h->single && h->nvar <= 4 ? 0 : 4, h->single && h->nvar <= 5 ? 0 : 5, sigma0, h->single ? 0 : h->npk + 1, h->sd_ix, h->sd_ix + 1, named_a, named_b };
 	for (int k = 0; k < SV_COUNT; k++) {
 		h->ix[k] = ix[k];
 		h->tr[k] = (int)transforms[ix[k]];
@@ -356,8 +368,9 @@ int finalize(Handle* h)
 				break;
 			}
 		}
+		if (h->single) su = T; // the whole time vector (LikelihoodPharmacokineticTrajectory.cpp:341)
 		simulate_until[j] = su;
-		if (!std::isnan(dac[j])) {
+		if (!std::isnan(dac[j]) && !h->single) {
 			if (std::isnan(dct[j]))
 				return fail(BCM3B200_ERR_ARG, "Patient %d has dose change, but time of dose change is not specified.", j);
 		}
@@ -366,6 +379,7 @@ int finalize(Handle* h)
 	}
 	h->rtol = kTol;
 	h->atol = minimum_dose * kTol; // SetTolerance(1e-6f, minimum_dose * 1e-6f), cpp:238
+	if (h->single) h->atol = dose[0] * kTol; // SetTolerance(1e-6f, dose * 1e-6f), LikelihoodPharmacokineticTrajectory.cpp:226
 
 	// partition this handle's contiguous slice of patients over its devices
 	const long long lo = (long long)P * h->shard_rank / h->shard_count;
@@ -404,6 +418,8 @@ int finalize(Handle* h)
 		std::vector<int32_t> im(Pa);
 		const std::vector<double>& imd = h->data["intermittent"];
 		for (int j = 0; j < Ps; j++) im[j] = (int32_t)imd[off + j];
+		if (h->single) // the single-patient likelihood keeps the schedule in a bool (its cpp:184-186): any schedule is schedule 1
+			for (int j = 0; j < Ps; j++) im[j] = im[j] != 0 ? 1 : 0;
 		CUDA_TRY(s->intermittent.ensure(Pa));
 		CUDA_TRY(cudaMemcpy(s->intermittent.p, im.data(), sizeof(int32_t) * Ps, cudaMemcpyHostToDevice));
 		CUDA_TRY(s->skipped.ensure(Pa));
@@ -464,6 +480,7 @@ int launch_shard(Handle* h, Shard* s, size_t C, const double* d_values, long lon
 	a.patient_ll = s->patient_ll.p;
 	a.order = nullptr;
 	a.chain_fastest = 0;
+	a.single = h->single ? 1 : 0;
 	// large batches: rank every chain's patients by absorption rate first (see poppk_kernel)
 	if (h->sort_patients && (long long)s->P * (long long)C >= h->sort_min_systems && s->P > 0 && (long long)s->P * (long long)C < (1ll << 31)) {
 		const size_t n = (size_t)s->P * C;
@@ -605,7 +622,8 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 	if (!model_kind || !handle) return fail(BCM3B200_ERR_ARG, "null argument");
 	*handle = nullptr;
 	const bool is_cellpop = strcmp(model_kind, "cell_population") == 0, is_pharmaco = strcmp(model_kind, "pharmaco_population") == 0;
-	if (!is_cellpop && !is_pharmaco && strcmp(model_kind, "pop_pk_trajectory") != 0)
+	const bool is_single = strcmp(model_kind, "pharmacokinetic_trajectory") == 0;
+	if (!is_cellpop && !is_pharmaco && !is_single && strcmp(model_kind, "pop_pk_trajectory") != 0)
 		return fail(BCM3B200_ERR_UNSUPPORTED, "unknown model kind \"%s\"", model_kind);
 	std::map<std::string, std::string> kv;
 	if (model_desc && !parse_desc((const char*)model_desc, desc_bytes, kv)) return fail(BCM3B200_ERR_ARG, "malformed model description");
@@ -700,6 +718,13 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		h->named_a_ix = get_int(kv, "biphasic_uptake_time_ix", -1);
 		h->named_b_ix = get_int(kv, "mean_absorption2_ix", -1);
 	}
+	h->single = is_single;
+	if (is_single && (h->pk_type == PK_ONE_BIPHASIC || h->pk_type == PK_TWO_BIPHASIC)) {
+		// LikelihoodPharmacokineticTrajectory.cpp:302-303: the single-patient likelihood reads the switching time and the second
+		// absorption rate at positions 6 and 7, not by name
+		h->named_a_ix = 6;
+		h->named_b_ix = 7;
+	}
 	h->drug = kv.count("drug") ? kv["drug"] : "";
 	if (kv.count("volume_of_distribution")) h->fixed_vod = strtod(kv["volume_of_distribution"].c_str(), nullptr);
 	if (kv.count("k_periphery_fwd")) h->fixed_periphery_fwd = strtod(kv["k_periphery_fwd"].c_str(), nullptr);
@@ -711,6 +736,8 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 	h->sd_ix = get_int(kv, "sd_ix", -1, &hasS);
 	if (!hasP || !hasT || !hasN || !hasS || h->P < 0 || h->T < 0)
 		return fail(BCM3B200_ERR_ARG, "num_patients, num_timepoints, num_variables and sd_ix are required");
+	if (is_single && (h->P != 1 || device_count != 1 || get_int(kv, "shard_count", 1) != 1))
+		return fail(BCM3B200_ERR_ARG, "pharmacokinetic_trajectory is the likelihood of ONE patient: num_patients=1, one device, no shards");
 	h->max_steps = get_int(kv, "max_steps", 2000);
 	h->shard_rank = get_int(kv, "shard_rank", 0);
 	h->shard_count = get_int(kv, "shard_count", 1);
@@ -980,8 +1007,8 @@ static int upload_and_launch(Handle* h, Shard* s, size_t C, size_t num_variables
                              cudaStream_t stream)
 {
 	const int SH = 16;
-	const int head = h->npk + 2;
-	const int cix[SV_COUNT] = { 0, 1, 2, 3, 4, 5, h->npk + 0, h->npk + 1, 10, 11, 12, 13 };
+	const int head = h->single ? std::min(h->nvar, 10) : h->npk + 2;
+	const int cix[SV_COUNT] = { h->ix[0], h->ix[1], h->ix[2], h->ix[3], h->ix[4], h->ix[5], h->ix[6], h->ix[7], 10, 11, 12, 13 };
 	const size_t stride = SH + 2 * (size_t)s->P;
 	CUDA_TRY(s->values.ensure(C * stride));
 	auto piece = [&](int slot, size_t column, size_t count) -> cudaError_t {
@@ -992,7 +1019,7 @@ static int upload_and_launch(Handle* h, Shard* s, size_t C, size_t num_variables
 	CUDA_TRY(piece(10, (size_t)h->sd_ix, 2));
 	if (h->named_a_ix >= 0) CUDA_TRY(piece(12, (size_t)h->named_a_ix, 1));
 	if (h->named_b_ix >= 0) CUDA_TRY(piece(13, (size_t)h->named_b_ix, 1));
-	if (s->P > 0) CUDA_TRY(piece(SH, (size_t)h->npk + 2 + 2 * (size_t)s->offset, 2 * (size_t)s->P));
+	if (s->P > 0 && !h->single) CUDA_TRY(piece(SH, (size_t)h->npk + 2 + 2 * (size_t)s->offset, 2 * (size_t)s->P));
 	CUDA_TRY(cudaEventRecord(s->ev0, stream));
 	int rc = launch_shard(h, s, C, s->values.p, (long long)stride, SH, cix, d_partial, stream);
 	if (rc != BCM3B200_OK) return rc;

@@ -81,6 +81,7 @@ struct PkArgs {
 	// first within every chain) the grid as a whole runs from the most expensive blocks of all chains to the cheapest ones and
 	// its tail is made of the shortest blocks; 0: grid = (blocks per chain, C)
 	int chain_fastest;
+	int single; // 1: pharmacokinetic_trajectory -- the one patient's parameters are the chain's variables themselves (LikelihoodPharmacokineticTrajectory.cpp:259-330)
 	// outputs
 	double* patient_ll;    // [C][P_local] log-likelihood of every (chain, patient), in patient order whatever the launch shape
 	double* diag_conc;     // [C][P_local][T] or null
@@ -310,7 +311,7 @@ __global__ void BCM3_POPPK_KERNEL_ATTR poppk_kernel(const PkArgs a)
 		sd = transform_variable(a.tr[SV_SD], vrow[a.ix[SV_SD]]);
 		sd2 = transform_variable(a.tr[SV_SD2], vrow[a.ix[SV_SD2]]);
 		double2 pp = make_double2(0.5, 0.5);
-		if (valid) {
+		if (valid && !a.single) {
 			// the patient's probability pair: one 16-byte load where the pair is 16-byte aligned (always in the compact layout
 			// of the host entries; in a caller's [C][nvar] device block only when c * nvar + npk + 2 is even and the block
 			// itself is 16-byte aligned -- uniform over the thread block), two 8-byte loads otherwise
@@ -322,8 +323,13 @@ __global__ void BCM3_POPPK_KERNEL_ATTR poppk_kernel(const PkArgs a)
 				pp.y = pair[1];
 			}
 		}
-		model.ka = fastpow10(quantile_normal(pp.x, vrow[a.ix[SV_MEAN_ABSORPTION]], vrow[a.ix[SV_SIGMA_ABSORPTION]]));
-		model.kel = fastpow10(quantile_normal(pp.y, vrow[a.ix[SV_MEAN_CLEARANCE]], vrow[a.ix[SV_SIGMA_CLEARANCE]])) / k_vod;
+		if (a.single) { // LikelihoodPharmacokineticTrajectory.cpp:276-279: no population level, the variables are the rates
+			model.ka = transform_variable(a.tr[SV_MEAN_ABSORPTION], vrow[a.ix[SV_MEAN_ABSORPTION]]);
+			model.kel = transform_variable(a.tr[SV_MEAN_CLEARANCE], vrow[a.ix[SV_MEAN_CLEARANCE]]) / k_vod;
+		} else {
+			model.ka = fastpow10(quantile_normal(pp.x, vrow[a.ix[SV_MEAN_ABSORPTION]], vrow[a.ix[SV_SIGMA_ABSORPTION]]));
+			model.kel = fastpow10(quantile_normal(pp.y, vrow[a.ix[SV_MEAN_CLEARANCE]], vrow[a.ix[SV_SIGMA_CLEARANCE]])) / k_vod;
+		}
 		conversion = a.conv_base / k_vod;
 		model.ka2 = model.k_transit = model.n_transit = model.log_n_factorial = model.last_treatment = 0.0;
 		model.biphasic_switch = true;
@@ -353,7 +359,10 @@ __global__ void BCM3_POPPK_KERNEL_ATTR poppk_kernel(const PkArgs a)
 	model.dose_change_time = dose_change_time;
 	// biphasic: the switching time is clipped just below the dosing interval (cpp:304-306)
 	double biphasic_switch_time = 0.0;
-	if (Model::VARIANT == PKV_BIPHASIC) biphasic_switch_time = fmin(transform_variable(a.tr[SV_NAMED_A], vrow[a.ix[SV_NAMED_A]]), dosing_interval - 1e-2);
+	if (Model::VARIANT == PKV_BIPHASIC) {
+		biphasic_switch_time = transform_variable(a.tr[SV_NAMED_A], vrow[a.ix[SV_NAMED_A]]);
+		if (!a.single) biphasic_switch_time = fmin(biphasic_switch_time, dosing_interval - 1e-2); // the single-patient likelihood does not clip (its cpp:302)
+	}
 
 	// ---- K1: ODESolver::SolveReturnSolution + ODESolverCVODE::Solve ----
 	BdfThread<N, Model, DIAG, STRIDE> S;
@@ -502,7 +511,7 @@ __global__ void BCM3_POPPK_KERNEL_ATTR poppk_kernel(const PkArgs a)
 					double x = conversion * s_sim[i * blockDim.x + tid];
 					double yobs = a.obs_t[(long long)i * a.P_pad + jl];
 					if (!isnan(yobs)) ll += logpdf_tnu4(x, yobs, sd + sd2 * ((x < 0.0) ? 0.0 : x));
-					if (isnan(x)) {
+					if (isnan(x) && !a.single) { // cpp:419-422; the single-patient likelihood has no such test (NaN stays NaN)
 						ll = -INFINITY;
 						broken = true;
 					}

@@ -6,7 +6,7 @@ extern "C" {
 
 using bcm3::Real;
 
-LikelihoodPopPKTrajectoryB200::LikelihoodPopPKTrajectoryB200(size_t, size_t) {}
+LikelihoodPopPKTrajectoryB200::LikelihoodPopPKTrajectoryB200(size_t, size_t, bool single_patient) : single(single_patient) {}
 
 LikelihoodPopPKTrajectoryB200::~LikelihoodPopPKTrajectoryB200()
 {
@@ -29,6 +29,7 @@ bool LikelihoodPopPKTrajectoryB200::Initialize(std::shared_ptr<const bcm3::Varia
 	pk_type_str = model->get("type");
 	trial_name = model->get("trial");
 	pkdata_file = model->get("pkdata_file");
+	if (single && model->has("patient")) patient_id = model->get("patient"); // LikelihoodPharmacokineticTrajectory.cpp:96
 	// cpp:64-67: parameters fixed in likelihood.xml instead of sampled; handed through as they are
 	fixed_attributes.clear();
 	for (const char* key : { "volume_of_distribution", "k_periphery_fwd", "k_periphery_bwd" })
@@ -38,6 +39,37 @@ bool LikelihoodPopPKTrajectoryB200::Initialize(std::shared_ptr<const bcm3::Varia
 
 bool LikelihoodPopPKTrajectoryB200::PostInitialize()
 {
+	if (single) {
+		// LikelihoodPharmacokineticTrajectory.cpp:111-114, 161-166: the patient has to be named and has to be in the trial
+		if (patient_id.empty()) {
+			last_error = "Patient ID has not been specified in either the likelihood or as command-line option.";
+			return false;
+		}
+		size_t ix = trial.dose.size();
+		if (!patient_ids.empty()) {
+			for (size_t i = 0; i < patient_ids.size(); i++)
+				if (patient_ids[i] == patient_id) ix = i;
+		} else {
+			char* end = nullptr;
+			const unsigned long long v = strtoull(patient_id.c_str(), &end, 10);
+			if (end && *end == 0 && end != patient_id.c_str()) ix = (size_t)v;
+		}
+		if (ix >= trial.dose.size()) {
+			last_error = "Cannot find patient \"" + patient_id + "\" in data file";
+			return false;
+		}
+		const size_t Tn = trial.time.size();
+		TrialData one;
+		one.time = trial.time;
+		one.observed_concentration.assign(trial.observed_concentration.begin() + ix * Tn, trial.observed_concentration.begin() + (ix + 1) * Tn);
+		one.dose.assign(1, trial.dose[ix]);
+		one.dosing_interval.assign(1, trial.dosing_interval[ix]);
+		one.dose_after_dose_change.assign(1, trial.dose_after_dose_change[ix]);
+		one.dose_change_time.assign(1, trial.dose_change_time[ix]);
+		one.intermittent.assign(1, trial.intermittent[ix]);
+		one.treatment_interruptions.assign(trial.treatment_interruptions.begin() + ix * 29, trial.treatment_interruptions.begin() + (ix + 1) * 29);
+		trial = one;
+	}
 	const size_t P = trial.dose.size(), T = trial.time.size(), nvar = varset->GetNumVariables();
 	const size_t sdix = varset->GetVariableIndex("standard_deviation"); // cpp:263
 	if (sdix == std::numeric_limits<size_t>::max()) {
@@ -59,10 +91,10 @@ bool LikelihoodPopPKTrajectoryB200::PostInitialize()
 	};
 	if (pk_type_str == "one_transit" || pk_type_str == "two_transit") {
 		if (!named("n_transit", "n_transit_ix") || !named("mean_transit_time", "mean_transit_time_ix")) return false;
-	} else if (pk_type_str == "one_biphasic_uptake" || pk_type_str == "two_biphasic_uptake") {
+	} else if (!single && (pk_type_str == "one_biphasic_uptake" || pk_type_str == "two_biphasic_uptake")) { // positional (6, 7) in the single-patient likelihood
 		if (!named("biphasic_uptake_time", "biphasic_uptake_time_ix") || !named("mean_absorption2", "mean_absorption2_ix")) return false;
 	}
-	if (bcm3b200_create("pop_pk_trajectory", desc.data(), desc.size(), num_devices, &handle) != BCM3B200_OK) {
+	if (bcm3b200_create(single ? "pharmacokinetic_trajectory" : "pop_pk_trajectory", desc.data(), desc.size(), num_devices, &handle) != BCM3B200_OK) {
 		last_error = bcm3b200_last_error();
 		return false;
 	}

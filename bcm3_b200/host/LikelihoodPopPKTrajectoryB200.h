@@ -2,6 +2,10 @@
 // C ABI (include/bcm3b200.h). likelihood.xml surface: <bcm_likelihood type="pop_pk_trajectory"><pk_model drug=
 // type= trial= pkdata_file= .../> as in the reference (cpp:58-87). The NetCDF reader is out of scope (SURVEY 8f row
 // 3): the trial arrays are supplied with SetTrialData() before PostInitialize().
+// The same class, constructed with single_patient = true, is the drop-in for LikelihoodPharmacokineticTrajectory
+// (src/likelihoods/LikelihoodPharmacokineticTrajectory.{h,cpp}; type="pharmacokinetic_trajectory"): <pk_model ... patient=>
+// names ONE patient of the trial (its cpp:96, 161-166: looked up in the "patients" dimension -- SetPatientIDs() supplies that
+// dimension; without it the attribute is the patient's index), whose rates the chain's variables are.
 #pragma once
 
 #include "Likelihood.h"
@@ -16,7 +20,9 @@ public:
 		std::vector<double> treatment_interruptions; // [P][29]
 	};
 
-	LikelihoodPopPKTrajectoryB200(size_t sampling_threads, size_t evaluation_threads);
+	LikelihoodPopPKTrajectoryB200(size_t sampling_threads, size_t evaluation_threads, bool single_patient = false);
+	void SetPatientIDs(const std::vector<std::string>& ids) { patient_ids = ids; }
+	void SetPatientID(const std::string& patient) { patient_id = patient; } // LikelihoodPharmacokineticTrajectory::SetPatientID / the pk.patient option
 	~LikelihoodPopPKTrajectoryB200() override;
 
 	bool Initialize(std::shared_ptr<const bcm3::VariableSet> varset, const bcm3::XmlNode& likelihood_node) override;
@@ -32,7 +38,9 @@ public:
 
 private:
 	std::shared_ptr<const bcm3::VariableSet> varset;
-	std::string drug, pk_type_str, trial_name, pkdata_file, fixed_attributes;
+	std::string drug, pk_type_str, trial_name, pkdata_file, fixed_attributes, patient_id;
+	std::vector<std::string> patient_ids;
+	bool single = false;
 	TrialData trial;
 	void* handle = nullptr;
 	int device0 = 0, num_devices = 1;

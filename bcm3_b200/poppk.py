@@ -42,7 +42,8 @@ class PopPKEvaluator:
                 desc += f";{key}={v!r}"
         desc = desc.encode()
         h = C.c_void_p()
-        _lib.check(self.lib.bcm3b200_create(b"pop_pk_trajectory", desc, len(desc), device_count, C.byref(h)))
+        kind = b"pharmacokinetic_trajectory" if getattr(problem, "single", False) else b"pop_pk_trajectory"
+        _lib.check(self.lib.bcm3b200_create(kind, desc, len(desc), device_count, C.byref(h)))
         self.handle = h
         try:
             self._set("time", tr.time)

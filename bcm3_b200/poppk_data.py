@@ -105,6 +105,10 @@ class PopPKProblem:
     mean_transit_time_ix: int = -1
     biphasic_uptake_time_ix: int = -1
     mean_absorption2_ix: int = -1
+    # True: likelihood.xml type="pharmacokinetic_trajectory" (src/likelihoods/LikelihoodPharmacokineticTrajectory.cpp) -- ONE
+    # patient of the trial, no population level: variables 0..5 are the rates themselves (its cpp:264-290), the biphasic pair
+    # sits at positions 6 and 7 (its cpp:302-303), the whole time vector is simulated, no variable-count check (compiled out)
+    single: bool = False
     # derived
     simulate_until: np.ndarray = field(init=False)
     skipped_days: np.ndarray = field(init=False)
@@ -121,6 +125,15 @@ class PopPKProblem:
         fixed = sum(0 if math.isnan(v) else 1 for v in (self.fixed_vod, self.fixed_periphery_fwd, self.fixed_periphery_bwd))
         expected = num_pk_params(self.pk_type) - fixed + 2 * (P + 1) + 2
         self.transforms = np.ascontiguousarray(self.transforms, dtype=np.int32)
+        if self.single:
+            if P != 1:
+                raise ValueError("pharmacokinetic_trajectory is the likelihood of one patient")
+            if is_biphasic(self.pk_type):
+                self.biphasic_uptake_time_ix, self.mean_absorption2_ix = 6, 7
+            last = 7 if is_biphasic(self.pk_type) else (5 if is_two_compartment(self.pk_type) and math.isnan(self.fixed_periphery_fwd) else 3)
+            if self.transforms.shape[0] <= max(last, self.sd_ix + 1):
+                raise ValueError("the prior is shorter than the positions the likelihood reads")
+            expected = self.transforms.shape[0]
         if self.transforms.shape[0] != expected:
             raise ValueError("Incorrect number of variables in prior")  # cpp:127-130
         if is_transit(self.pk_type) and (self.n_transit_ix < 0 or self.mean_transit_time_ix < 0):
@@ -130,7 +143,7 @@ class PopPKProblem:
         # fixed attributes: the reference keeps indexing the variable vector at the all-sampled positions (cpp:267-272,
         # 283-286) although the prior is `fixed` variables shorter -- reproduced as it is; with all three fixed it would
         # read past the end of the vector
-        if P > 0 and num_pk_params(self.pk_type) + 2 * P + 1 >= expected:
+        if P > 0 and not self.single and num_pk_params(self.pk_type) + 2 * P + 1 >= expected:
             raise ValueError("with these fixed pk_model attributes the reference reads past the end of the variable vector")
 
         inter = np.asarray(tr.treatment_interruptions).reshape(P, 29) != 0
@@ -153,12 +166,14 @@ class PopPKProblem:
         first = np.argmax(notnan, axis=1)
         late = has & (time[first] > 15 * 24)
         su[late] = 0
+        if self.single:
+            su[:] = T
         self.simulate_until = su
 
         dac = np.asarray(tr.dose_after_dose_change, dtype=np.float64)
         dct = np.asarray(tr.dose_change_time, dtype=np.float64)
         bad = ~np.isnan(dac) & np.isnan(dct)
-        if bad.any():
+        if bad.any() and not self.single:
             raise ValueError(f"Patient {int(np.nonzero(bad)[0][0])} has dose change, but time of dose change is not specified.")  # cpp:187-190
         min_dose = float(np.min(tr.dose)) if P else float(np.finfo(np.float64).max)
         if (~np.isnan(dac)).any():
@@ -166,6 +181,8 @@ class PopPKProblem:
         # SetTolerance(1e-6f, minimum_dose * 1e-6f), cpp:238
         self.rtol = F32_1E_6
         self.atol = min_dose * F32_1E_6
+        if self.single:
+            self.atol = float(tr.dose[0]) * F32_1E_6  # SetTolerance(1e-6f, dose * 1e-6f), LikelihoodPharmacokineticTrajectory.cpp:226
 
     @property
     def num_variables(self) -> int:

@@ -211,3 +211,44 @@ def make_chain_values(problem: PopPKProblem, C: int, seed: int = 20261018) -> np
         v[nvar - 2] = pop["log_sd"]
         v[nvar - 1] = pop["log_sd2"]
     return out
+
+
+# ---- pharmacokinetic_trajectory: the likelihood of ONE patient (LikelihoodPharmacokineticTrajectory.cpp) ----
+SINGLE_NVAR = 10  # prior layout: ka, kex, clearance, Vd, kf, kb, (switch time | n_transit), (ka2 | mean_transit_time), standard_deviation, sd2
+
+
+def make_single_patient_problem(pk_type: int = PK_TWO, T: int = 12, t_end: float = 96.0, seed: int = 1, heterogeneous: bool = True,
+                                missing_fraction: float = 0.1, **fixed) -> PopPKProblem:
+    """One patient of a synthetic trial with the prior a pharmacokinetic_trajectory model directory has: every variable is a
+    rate in log10 space (positions as the likelihood reads them, its cpp:264-305), the named transit pair at 6 and 7."""
+    pop = make_poppk_problem(pk_type, P=1, T=T, t_end=t_end, seed=seed, heterogeneous=heterogeneous, missing_fraction=missing_fraction)
+    named = {}
+    if is_transit(pk_type):
+        named = dict(n_transit_ix=6, mean_transit_time_ix=7)
+    if is_biphasic(pk_type):
+        named = dict(biphasic_uptake_time_ix=6, mean_absorption2_ix=7)
+    transforms = np.full(SINGLE_NVAR, TRANSFORM_LOG10, dtype=np.int32)
+    return PopPKProblem(pk_type=pk_type, trial=pop.trial, transforms=transforms, sd_ix=SINGLE_NVAR - 2, single=True, **named, **fixed)
+
+
+def make_single_patient_values(problem: PopPKProblem, C: int, seed: int = 20261018) -> np.ndarray:
+    pop = population_defaults(problem.pk_type)
+    out = np.zeros((C, SINGLE_NVAR))
+    for c in range(C):
+        rng = np.random.default_rng(seed + c)
+        v = out[c]
+        v[0] = rng.normal(pop["mu_logka"], 0.3)
+        v[1] = rng.normal(pop["log_kex"], 0.1)
+        v[2] = rng.normal(pop["mu_logcl"], 0.3)
+        v[3] = rng.normal(pop["log_vd"], 0.1)
+        v[4] = rng.normal(pop.get("log_kf", -0.5), 0.1)
+        v[5] = rng.normal(pop.get("log_kb", -1.0), 0.1)
+        if is_biphasic(problem.pk_type):
+            v[6] = rng.normal(pop["log_uptake_time"], 0.05)
+            v[7] = rng.normal(pop["log_ka2"], 0.05)
+        if is_transit(problem.pk_type):
+            v[6] = rng.normal(pop["log_n_transit"], 0.05)
+            v[7] = rng.normal(pop["log_transit_time"], 0.05)
+        v[8] = pop["log_sd"]
+        v[9] = pop["log_sd2"]
+    return out

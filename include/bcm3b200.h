@@ -38,7 +38,16 @@ extern "C" {
 
 /* Create an evaluator.
  *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62,66,81):
- *                "pop_pk_trajectory" | "cell_population" | "pharmaco_population"
+ *                "pop_pk_trajectory" | "pharmacokinetic_trajectory" | "cell_population" | "pharmaco_population"
+ *                pharmacokinetic_trajectory = LikelihoodPharmacokineticTrajectory (LikelihoodFactory.cpp:60,
+ *                src/likelihoods/LikelihoodPharmacokineticTrajectory.cpp:259-352), the likelihood of ONE patient on the same
+ *                models, solver and dosing logic: the keys and data of pop_pk_trajectory below with num_patients=1 (the host
+ *                picks the patient its <pk_model patient=> names out of the trial), and these differences, all the
+ *                reference's: variables 0 and 2 are the absorption rate and the clearance themselves (no population level, its
+ *                cpp:276-279), the biphasic pair is read at positions 6 and 7 and the switching time is not clipped (its
+ *                cpp:302-303), every timepoint is simulated, any "intermittent" value acts as schedule 1 (a bool, its
+ *                cpp:184-186), no variable-count check, absolute tolerance dose * 1e-6f, a NaN concentration stays NaN.
+ *                A batch is one ODE system per chain.
  *                cell_population = CellPopulationLikelihood (src/likelihoods/cellpop/CellPopulationLikelihood.cpp:27-101) with
  *                one Experiment (Experiment.cpp:404-633) per handle:
  *                  num_species num_constant_species num_variables num_non_sampled num_cells num_timepoints num_replicates

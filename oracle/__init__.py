@@ -51,6 +51,7 @@ class _PopPKProblem(C.Structure):
         ("mean_transit_time_ix", C.c_int32),
         ("biphasic_uptake_time_ix", C.c_int32),
         ("mean_absorption2_ix", C.c_int32),
+        ("single", C.c_int32),
     ]
 
 
@@ -173,6 +174,7 @@ class Oracle:
             transforms=keep["transforms"].ctypes.data,
             n_transit_ix=problem.n_transit_ix, mean_transit_time_ix=problem.mean_transit_time_ix,
             biphasic_uptake_time_ix=problem.biphasic_uptake_time_ix, mean_absorption2_ix=problem.mean_absorption2_ix,
+            single=1 if getattr(problem, "single", False) else 0,
         )
         logp = np.empty(nC, dtype=np.float64)
         conc = np.empty((nC, P, T), dtype=np.float64) if want_conc else None

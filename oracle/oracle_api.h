@@ -65,6 +65,11 @@ typedef struct {
 	const int32_t* transforms;            /* [nvar] ORACLE_TRANSFORM_* */
 	/* variables the variants look up by name (cpp:296-310); -1 when the model type does not use them */
 	int32_t n_transit_ix, mean_transit_time_ix, biphasic_uptake_time_ix, mean_absorption2_ix;
+	/* 1: LikelihoodPharmacokineticTrajectory (src/likelihoods/LikelihoodPharmacokineticTrajectory.cpp:259-352), the likelihood
+	 * of ONE patient (P = 1): absorption and elimination are variables 0 and 2 themselves instead of population quantiles
+	 * (its cpp:276-279), the biphasic switching time is not clipped (its cpp:302), the dosing schedule is a bool (its
+	 * cpp:184-186: any intermittent value acts as 1), a NaN concentration is not turned into -inf (its cpp:343-350) */
+	int32_t single;
 } oracle_poppk_problem;
 
 /* per-(chain, patient) solver counters, summed over the restarts of one solve */

@@ -351,12 +351,17 @@ static void evaluate_chain(const oracle_poppk_problem* pr, const double* values,
 		pd.dose_after_dose_change = pr->dose_after_dose_change[j];
 		pd.dose_change_time = pr->dose_change_time[j];
 		pd.intermittent = (unsigned)pr->intermittent[j];
+		if (pr->single) pd.intermittent = pr->intermittent[j] ? 1u : 0u;
 		pd.skipped_days = pr->skipped_days[j];
 
-		pd.k_absorption = fastpow10(quantile_normal(values[npk + 2 * (j + 1) + 0], values[0], values[npk + 0]));
+		if (!pr->single) pd.k_absorption = fastpow10(quantile_normal(values[npk + 2 * (j + 1) + 0], values[0], values[npk + 0]));
 		pd.k_excretion = transform_variable(pr->transforms[1], values[1]);
 		pd.k_vod = isnan(pr->fixed_vod) ? transform_variable(pr->transforms[3], values[3]) : pr->fixed_vod;
-		pd.k_elimination = fastpow10(quantile_normal(values[npk + 2 * (j + 1) + 1], values[2], values[npk + 1])) / pd.k_vod;
+		if (pr->single) {
+			pd.k_absorption = transform_variable(pr->transforms[0], values[0]);
+			pd.k_elimination = transform_variable(pr->transforms[2], values[2]) / pd.k_vod;
+		} else
+			pd.k_elimination = fastpow10(quantile_normal(values[npk + 2 * (j + 1) + 1], values[2], values[npk + 1])) / pd.k_vod;
 		if (two) {
 			if (isnan(pr->fixed_periphery_fwd)) {
 				pd.k_periphery_fwd = transform_variable(pr->transforms[4], values[4]);
@@ -372,7 +377,7 @@ static void evaluate_chain(const oracle_poppk_problem* pr, const double* values,
 		}
 		if (biphasic) { /* cpp:302-310 */
 			pd.k_biphasic_switch_time = transform_variable(pr->transforms[pr->biphasic_uptake_time_ix], values[pr->biphasic_uptake_time_ix]);
-			if (pd.dosing_interval - 1e-2 < pd.k_biphasic_switch_time) pd.k_biphasic_switch_time = pd.dosing_interval - 1e-2;
+			if (!pr->single && pd.dosing_interval - 1e-2 < pd.k_biphasic_switch_time) pd.k_biphasic_switch_time = pd.dosing_interval - 1e-2;
 			pd.k_absorption2 = transform_variable(pr->transforms[pr->mean_absorption2_ix], values[pr->mean_absorption2_ix]);
 		}
 		pd.last_treatment = 0.0;
@@ -395,7 +400,7 @@ static void evaluate_chain(const oracle_poppk_problem* pr, const double* values,
 					double yobs = pr->observed_concentration[(size_t)j * T + i];
 					if (conc) conc[(size_t)j * T + i] = x;
 					if (!isnan(yobs)) patient_logllh += logpdf_tnu4(x, yobs, sd + sd2 * (x > 0.0 ? x : 0.0));
-					if (isnan(x)) {
+					if (isnan(x) && !pr->single) {
 						patient_logllh = -INFINITY;
 						break;
 					}

@@ -276,13 +276,18 @@ void EvaluateChain(const oracle_poppk_problem& pr, const double* values, double*
 		pd.dose_after_dose_change = pr.dose_after_dose_change[j];
 		pd.dose_change_time = pr.dose_change_time[j];
 		pd.intermittent = (unsigned int)pr.intermittent[j];
+		if (pr.single) pd.intermittent = pr.intermittent[j] ? 1u : 0u;
 		pd.skipped_days = pr.skipped_days[j];
 		pd.counters = counters ? counters + (size_t)j * ORACLE_NUM_COUNTERS : nullptr;
 
-		pd.k_absorption = bcm3::fastpow10(QuantileNormal(values[num_pk_params + num_pk_pop_params * (j + 1) + 0], values[0], values[num_pk_params + 0]));
+		if (!pr.single) pd.k_absorption = bcm3::fastpow10(QuantileNormal(values[num_pk_params + num_pk_pop_params * (j + 1) + 0], values[0], values[num_pk_params + 0]));
 		pd.k_excretion = TransformVariable(pr.transforms[1], values[1]);
 		pd.k_vod = std::isnan(pr.fixed_vod) ? TransformVariable(pr.transforms[3], values[3]) : pr.fixed_vod;
-		pd.k_elimination = bcm3::fastpow10(QuantileNormal(values[num_pk_params + num_pk_pop_params * (j + 1) + 1], values[2], values[num_pk_params + 1])) / pd.k_vod;
+		if (pr.single) {
+			pd.k_absorption = TransformVariable(pr.transforms[0], values[0]);
+			pd.k_elimination = TransformVariable(pr.transforms[2], values[2]) / pd.k_vod;
+		} else
+			pd.k_elimination = bcm3::fastpow10(QuantileNormal(values[num_pk_params + num_pk_pop_params * (j + 1) + 1], values[2], values[num_pk_params + 1])) / pd.k_vod;
 		if (two) {
 			if (std::isnan(pr.fixed_periphery_fwd)) {
 				pd.k_periphery_fwd = TransformVariable(pr.transforms[4], values[4]);
@@ -299,7 +304,7 @@ void EvaluateChain(const oracle_poppk_problem& pr, const double* values, double*
 		}
 		if (biphasic) { // cpp:302-310
 			pd.k_biphasic_switch_time = TransformVariable(pr.transforms[pr.biphasic_uptake_time_ix], values[pr.biphasic_uptake_time_ix]);
-			pd.k_biphasic_switch_time = std::min(pd.k_biphasic_switch_time, pd.dosing_interval - 1e-2);
+			if (!pr.single) pd.k_biphasic_switch_time = std::min(pd.k_biphasic_switch_time, pd.dosing_interval - 1e-2);
 			pd.k_absorption2 = TransformVariable(pr.transforms[pr.mean_absorption2_ix], values[pr.mean_absorption2_ix]);
 		}
 		pd.last_treatment = 0.0;
@@ -340,7 +345,7 @@ void EvaluateChain(const oracle_poppk_problem& pr, const double* values, double*
 					if (!std::isnan(y)) {
 						patient_logllh += LogPdfTnu4(x, y, sd + sd2 * std::max(x, 0.0));
 					}
-					if (std::isnan(x)) {
+					if (std::isnan(x) && !pr.single) {
 						patient_logllh = -inf;
 						break;
 					}

@@ -63,6 +63,42 @@ def test_pt_run_on_gpu_likelihood_batched_equals_serial(built, pk):
     assert post[-1, 2] >= post[0, 2]
 
 
+def test_single_patient_plugin_pt_run_and_parity(built):
+    """likelihood.xml type="pharmacokinetic_trajectory" (LikelihoodFactory.cpp:60): <pk_model patient=> picks one patient of the
+    trial; a parallel-tempered run with the no_blocking strategy (one variable, one batched call per block) equals the serial
+    run, and the plugin's log-likelihoods are the direct ABI call's on that patient."""
+    from bcm3_b200 import host_api
+    from bcm3_b200.poppk import PopPKEvaluator
+    from bcm3_b200.poppk_data import PopPKProblem, PopPKTrial
+
+    pop = syn.make_poppk_problem(PK_TWO, P=3, T=10, t_end=96.0, seed=9, heterogeneous=True)
+    names = ["absorption", "excretion", "clearance", "volume_of_distribution", "k_periphery_fwd", "k_periphery_bwd", "spare_a", "spare_b",
+             "standard_deviation", "proportional_standard_deviation"]
+    centres = [0.1, -1.3, 0.9, 1.7, -0.5, -1.0, 0.0, 0.0, 0.0, -0.7]
+    prior = "\n".join(['<?xml version="1.0" encoding="utf-8"?>', "<prior>"] +
+                      [f'<variable name="{n}" logspace="true" distribution="uniform" lower="{c - 0.5}" upper="{c + 0.5}"/>' for n, c in zip(names, centres)] +
+                      ["</prior>"])
+    lik = '<bcm_likelihood type="pharmacokinetic_trajectory"><pk_model drug="lapatinib" type="two" trial="t" patient="1"/></bcm_likelihood>'
+    cfg = CONFIG.replace("[ptmhsampler]", "[ptmhsampler]\nblocking_strategy=no_blocking")
+    a, sa = host_api.run_pt_poppk(prior, lik, cfg, pop.trial, batched=True, seed=5)
+    b, sb = host_api.run_pt_poppk(prior, lik, cfg, pop.trial, batched=False, seed=5)
+    assert np.array_equal(a, b) and sa["evaluations"] == sb["evaluations"] and sa["blocks"] == 10
+    assert sa["batched_calls"] >= 80 * 10 and np.isfinite(a[:, 2]).all()
+    # the same patient through the ABI directly
+    tr = pop.trial
+    one = PopPKTrial(drug=tr.drug, time=tr.time, observed_concentration=tr.observed_concentration[1:2], dose=tr.dose[1:2], dosing_interval=tr.dosing_interval[1:2],
+                     dose_after_dose_change=tr.dose_after_dose_change[1:2], dose_change_time=tr.dose_change_time[1:2], intermittent=tr.intermittent[1:2],
+                     treatment_interruptions=tr.treatment_interruptions[1:2])
+    prob = PopPKProblem(pk_type=PK_TWO, trial=one, transforms=np.full(10, 2, dtype=np.int32), sd_ix=8, single=True)
+    post = a[a[:, 0] == 1.0]
+    ev = PopPKEvaluator(prob)
+    logp, _ = ev.evaluate(post[:, 3:])
+    ev.close()
+    assert np.array_equal(logp, post[:, 2])
+    with pytest.raises(RuntimeError, match="Cannot find patient"):
+        host_api.run_pt_poppk(prior, lik.replace('patient="1"', 'patient="7"'), cfg, pop.trial)
+
+
 def test_cell_population_plugin_matches_the_direct_abi_call(built):
     """likelihood.xml -> LikelihoodFactory -> CellPopulationLikelihoodB200::EvaluateLogProbabilityBatch gives what the ABI
     gives for the same problem, batched and chain by chain."""

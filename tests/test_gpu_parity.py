@@ -321,3 +321,54 @@ def test_fixed_pk_model_attributes(Evaluator, checker, fixed):
     assert rel_err(logp, want).max() <= LOGP_RTOL
     plain = checker.poppk_evaluate(base, syn.make_chain_values(base, 4, seed=51), threads=4)["logp"]  # nothing fixed
     assert not np.allclose(plain, want, rtol=1e-3)
+
+
+# ---- pharmacokinetic_trajectory: the likelihood of one patient, a batch = one ODE system per chain ----
+from tests.util import SINGLE_GOLDEN_NAMES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", SINGLE_GOLDEN_NAMES)
+def test_single_patient_matches_reference_golden(Evaluator, name):
+    """likelihood.xml type="pharmacokinetic_trajectory" (LikelihoodPharmacokineticTrajectory.cpp:259-352) on the same kernel:
+    the chain's variables are the patient's rates, every timepoint is simulated; goldens from the compiled reference."""
+    prob, gold = load_golden(name)
+    ev = Evaluator(prob, diagnostics=True)
+    logp, status = ev.evaluate(gold["values"])
+    d = ev.diagnostics()
+    ev.close()
+    assert (status == 0).all()
+    assert (np.isneginf(logp) == np.isneginf(gold["logp"])).all()
+    assert rel_err(logp, gold["logp"]).max() < LOGP_RTOL
+    assert (d["counters"] == gold["counters"]).all(axis=-1).mean() >= 0.8  # 5 systems: at most one may differ in a counter
+    m = ~np.isnan(gold["conc"]) & np.isfinite(gold["logp"])[:, None, None]
+    assert np.median(rel_err(d["conc"][m], gold["conc"][m])) < 1e-9
+
+
+@pytest.mark.parametrize("pk", [PK_ONE, PK_TWO])
+def test_single_patient_fresh_inputs_and_nan(Evaluator, checker, pk):
+    """64 chains on a fresh patient against the checker. A NaN rate makes the solver fail: -inf, as in the reference; a NaN
+    standard deviation gives a NaN log-likelihood (status 1) that the reference's sampler turns into an error (Sampler.cpp:172-178)."""
+    prob = syn.make_single_patient_problem(pk, seed=77 + pk, T=16, t_end=144.0)
+    vals = syn.make_single_patient_values(prob, 64, seed=5)
+    vals[3, 2] = np.nan
+    vals[5, 8] = np.nan
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    ev.close()
+    want = checker.poppk_evaluate(prob, vals, threads=4)["logp"]
+    assert np.isneginf(logp[3]) and np.isneginf(want[3]) and status[3] == 0
+    assert np.isnan(logp[5]) and np.isnan(want[5]) and status[5] == 1
+    ok = ~np.isin(np.arange(64), (3, 5))
+    assert (status[ok] == 0).all() and rel_err(logp[ok], want[ok]).max() < LOGP_RTOL
+
+
+def test_single_patient_refuses_a_population(Evaluator):
+    import dataclasses
+
+    from bcm3_b200._lib import Bcm3B200Error
+
+    pop = syn.make_poppk_problem(PK_ONE, P=2, T=6)
+    prob = syn.make_single_patient_problem(PK_ONE)
+    prob.trial = dataclasses.replace(pop.trial)
+    with pytest.raises(Bcm3B200Error, match="ONE patient"):
+        Evaluator(prob)

@@ -101,3 +101,48 @@ def test_edge_cases(port):
     assert np.all(r["conc"][0, :, 0] == 0.0)
     assert r["patient_ll"][0, 1] == 0.0
     assert np.isfinite(r["logp"]).all()
+
+
+# ---- pharmacokinetic_trajectory: the likelihood of one patient (LikelihoodPharmacokineticTrajectory.cpp) ----
+from tests.util import SINGLE_GOLDEN_NAMES  # noqa: E402
+
+
+def test_single_patient_fixtures_exist():
+    assert len(SINGLE_GOLDEN_NAMES) >= 6
+
+
+@pytest.mark.parametrize("name", SINGLE_GOLDEN_NAMES)
+def test_single_patient_port_matches_reference_golden(port, name):
+    """The plain-C restatement against the compiled reference: the chain's variables are the patient's rates, the whole time
+    vector is simulated, any intermittent schedule acts as schedule 1, the biphasic switching time is not clipped."""
+    prob, gold = load_golden(name)
+    assert prob.single and prob.trial.num_patients == 1
+    r = port.poppk_evaluate(prob, gold["values"], threads=2, want_conc=True, want_counters=True)
+    assert (np.isneginf(r["logp"]) == np.isneginf(gold["logp"])).all()
+    assert rel_err(r["logp"], gold["logp"]).max() < 1e-7
+    assert (r["counters"] == gold["counters"]).all(axis=-1).mean() >= 0.8  # 5 systems per fixture: at most one may differ in a counter
+    m = ~np.isnan(gold["conc"]) & np.isfinite(gold["logp"])[:, None, None]
+    assert np.median(rel_err(r["conc"][m], gold["conc"][m])) < 1e-9
+
+
+@pytest.mark.parametrize("name", SINGLE_GOLDEN_NAMES)
+def test_single_patient_reference_reproduces_golden(ref, name):
+    prob, gold = load_golden(name)
+    r = ref.poppk_evaluate(prob, gold["values"], threads=1, want_conc=True, want_counters=True)
+    assert np.array_equal(r["logp"], gold["logp"]) and np.array_equal(r["counters"], gold["counters"])
+
+
+def test_single_patient_differs_from_the_population_likelihood_where_the_reference_does(port):
+    """Same trial arrays, same numbers in the variable vector: the two likelihood types read them differently."""
+    from bcm3_b200.poppk_data import PK_TWO_BIPHASIC
+
+    prob = syn.make_single_patient_problem(PK_TWO_BIPHASIC, seed=6)
+    vals = syn.make_single_patient_values(prob, 3)
+    a = port.poppk_evaluate(prob, vals)["logp"]
+    # the schedule is a bool in this likelihood (its cpp:184-186): 2 and 3 act as 1
+    for schedule in (2, 3):
+        prob.trial.intermittent[:] = schedule
+        b = port.poppk_evaluate(prob, vals)["logp"]
+        prob.trial.intermittent[:] = 1
+        assert np.array_equal(b, port.poppk_evaluate(prob, vals)["logp"])
+    assert np.isfinite(a).all()

@@ -10,6 +10,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "poppk_*.npz")))
 
 
+SINGLE_GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "pksingle_*.npz")))
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     trial = PopPKTrial(
@@ -18,6 +21,9 @@ def load_golden(name):
         dose_change_time=z["dose_change_time"], intermittent=z["intermittent"],
         treatment_interruptions=z["treatment_interruptions"])
     named = {k: int(z[k]) for k in ("n_transit_ix", "mean_transit_time_ix", "biphasic_uptake_time_ix", "mean_absorption2_ix") if k in z.files}
+    if "single" in z.files:  # pharmacokinetic_trajectory fixtures (tests/golden/make_golden_single.py)
+        named.update(single=bool(z["single"]), fixed_vod=float(z["fixed_vod"]), fixed_periphery_fwd=float(z["fixed_periphery_fwd"]),
+                     fixed_periphery_bwd=float(z["fixed_periphery_bwd"]))
     prob = PopPKProblem(pk_type=int(z["pk_type"]), trial=trial, transforms=z["transforms"], sd_ix=int(z["sd_ix"]), **named)
     return prob, {k: z[k] for k in ("values", "logp", "conc", "patient_ll", "counters", "noise_floor", "noise_floor_counter_match") if k in z.files}
 
