@@ -621,7 +621,8 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 {
 	if (!model_kind || !handle) return fail(BCM3B200_ERR_ARG, "null argument");
 	*handle = nullptr;
-	const bool is_cellpop = strcmp(model_kind, "cell_population") == 0, is_pharmaco = strcmp(model_kind, "pharmaco_population") == 0;
+	const bool is_pharmaco_single = strcmp(model_kind, "pharmaco_single") == 0;
+	const bool is_cellpop = strcmp(model_kind, "cell_population") == 0, is_pharmaco = strcmp(model_kind, "pharmaco_population") == 0 || is_pharmaco_single;
 	const bool is_single = strcmp(model_kind, "pharmacokinetic_trajectory") == 0;
 	if (!is_cellpop && !is_pharmaco && !is_single && strcmp(model_kind, "pop_pk_trajectory") != 0)
 		return fail(BCM3B200_ERR_UNSUPPORTED, "unknown model kind \"%s\"", model_kind);
@@ -639,13 +640,31 @@ int bcm3b200_create(const char* model_kind, const void* model_desc, size_t desc_
 		ph->use_peripheral = get_int(kv, "peripheral_compartment", 0) != 0;
 		ph->num_transit = get_int(kv, "num_transit_compartments", 0);
 		ph->use_bioavailability = get_int(kv, "bioavailability", 0) != 0;
-		static const char* roles[] = { "additive_sd", "proportional_sd", "mean_absorption", "mean_excretion", "mean_clearance", "mean_volume_of_distribution",
-			                           "sigma_absorption", "sigma_excretion", "sigma_clearance", "sigma_volume_of_distribution", "sigma_transit_time",
-			                           "peripheral_forward_rate", "peripheral_backward_rate", "mean_transit_time" };
-		for (const char* role : roles) {
-			const int ix = get_int(kv, (std::string(role) + "_ix").c_str(), -1);
-			if (ix >= ph->nvar) return fail(BCM3B200_ERR_ARG, "%s_ix out of range", role);
-			ph->ix[role] = ix;
+		ph->single = is_pharmaco_single;
+		if (is_pharmaco_single) {
+			// PharmacoLikelihoodSingle: <pk_model biphasic_absorption= metabolite=> (cpp:44-45), variables by the names of cpp:75-146
+			ph->use_biphasic = get_int(kv, "biphasic_absorption", 0) != 0;
+			ph->use_metabolite = get_int(kv, "metabolite", 0) != 0;
+			ph->use_bioavailability = 0;
+			static const char* keys[][2] = { { "additive_sd", "additive_sd" }, { "proportional_sd", "proportional_sd" }, { "absorption", "mean_absorption" },
+				                             { "excretion", "mean_excretion" }, { "clearance", "mean_clearance" }, { "volume_of_distribution", "mean_volume_of_distribution" },
+				                             { "peripheral_forward_rate", "peripheral_forward_rate" }, { "peripheral_backward_rate", "peripheral_backward_rate" },
+				                             { "mean_transit_time", "mean_transit_time" }, { "direct_absorption", "direct_absorption" },
+				                             { "metabolite_conversion_rate", "metabolite_conversion_rate" } };
+			for (auto& k : keys) {
+				const int ix = get_int(kv, (std::string(k[0]) + "_ix").c_str(), -1);
+				if (ix >= ph->nvar) return fail(BCM3B200_ERR_ARG, "%s_ix out of range", k[0]);
+				ph->ix[k[1]] = ix;
+			}
+		} else {
+			static const char* roles[] = { "additive_sd", "proportional_sd", "mean_absorption", "mean_excretion", "mean_clearance", "mean_volume_of_distribution",
+				                           "sigma_absorption", "sigma_excretion", "sigma_clearance", "sigma_volume_of_distribution", "sigma_transit_time",
+				                           "peripheral_forward_rate", "peripheral_backward_rate", "mean_transit_time" };
+			for (const char* role : roles) {
+				const int ix = get_int(kv, (std::string(role) + "_ix").c_str(), -1);
+				if (ix >= ph->nvar) return fail(BCM3B200_ERR_ARG, "%s_ix out of range", role);
+				ph->ix[role] = ix;
+			}
 		}
 		ph->shard_rank = get_int(kv, "shard_rank", 0);
 		ph->shard_count = get_int(kv, "shard_count", 1);

@@ -23,6 +23,8 @@ struct PharmacoState {
 	std::string drug;
 	int P = 0, T = 0, nvar = 0;
 	int use_peripheral = 0, num_transit = 0, use_bioavailability = 0;
+	bool single = false; // model kind "pharmaco_single"
+	int use_biphasic = 0, use_metabolite = 0;
 	std::map<std::string, int> ix; // variable indices by role, -1 = absent
 	int shard_rank = 0, shard_count = 1, device = 0;
 	std::map<std::string, std::vector<double>> data;
@@ -73,13 +75,21 @@ inline int pharmaco_finalize(PharmacoState& ph, double mol_weight)
 	if (ph.var("additive_sd") < 0 && ph.var("proportional_sd") < 0)
 		return fail(BCM3B200_ERR_ARG, "Neither \"additive_error_standard_deviation\" nor \"proportional_error_standard_deviation\" has been specified in the prior");
 	for (const char* role : { "mean_absorption", "mean_clearance", "mean_volume_of_distribution" })
-		if (ph.var(role) < 0) return fail(BCM3B200_ERR_ARG, "Could not find variable \"%s\"", role);
+		if (ph.var(role) < 0) return fail(BCM3B200_ERR_ARG, "Could not find variable \"%s\"", ph.single ? role + 5 : role);
+	if (ph.single) {
+		// PharmacoLikelihoodSingle::PostInitialize, PharmacoLikelihoodSingle.cpp:75-150
+		if (P != 1) return fail(BCM3B200_ERR_ARG, "pharmaco_single is the likelihood of ONE patient: num_patients=1");
+		if (ph.use_biphasic && ph.var("direct_absorption") < 0)
+			return fail(BCM3B200_ERR_ARG, "Biphasic absorption was specified, but direct absorption rate has not been specified in prior.");
+		if (ph.use_metabolite && ph.var("metabolite_conversion_rate") < 0)
+			return fail(BCM3B200_ERR_ARG, "Use of metabolite was specified, but metabolite conversion rate has not been specified in prior.");
+	}
 	if (ph.use_peripheral && (ph.var("peripheral_forward_rate") < 0 || ph.var("peripheral_backward_rate") < 0))
 		return fail(BCM3B200_ERR_ARG, "Peripheral compartment was specified, but forward or backward rates have not both been specified in prior");
 	if (ph.num_transit > 0 && ph.var("mean_transit_time") < 0)
 		return fail(BCM3B200_ERR_ARG, "Transit compartments were specified, but mean transit time has not been specified in prior");
-	ph.N = 2 + (ph.use_peripheral ? 1 : 0) + ph.num_transit;
-	if (ph.N > 8) return fail(BCM3B200_ERR_UNSUPPORTED, "more than 8 compartments (2 + peripheral + transit)");
+	ph.N = 2 + (ph.use_peripheral ? 1 : 0) + (ph.use_metabolite ? 1 : 0) + ph.num_transit;
+	if (ph.N > 8) return fail(BCM3B200_ERR_UNSUPPORTED, "more than 8 compartments (2 + peripheral + metabolite + transit)");
 	struct Marginal {
 		const char* sigma_role;
 		int array;
@@ -206,6 +216,11 @@ inline int pharmaco_finalize(PharmacoState& ph, double mol_weight)
 	a.use_peripheral = ph.use_peripheral;
 	a.num_transit = ph.num_transit;
 	a.use_bioavailability = ph.use_bioavailability;
+	a.single = ph.single ? 1 : 0;
+	a.use_biphasic = ph.use_biphasic;
+	a.use_metabolite = ph.use_metabolite;
+	a.direct_absorption_ix = ph.var("direct_absorption");
+	a.metabolite_conversion_ix = ph.var("metabolite_conversion_rate");
 	a.conv_base = 1e6 / ph.mol_weight;
 	a.treat_begin = ph.d_treat_begin.p;
 	a.treat_time = ph.d_treat_time.p;

@@ -29,6 +29,10 @@ struct PhArgs {
 	int sigma_absorption_ix, sigma_excretion_ix, sigma_clearance_ix, sigma_vod_ix, sigma_transit_ix;
 	int periph_fwd_ix, periph_bwd_ix, mean_transit_time_ix;
 	int use_peripheral, num_transit, use_bioavailability;
+	// model kind "pharmaco_single" (PharmacoLikelihoodSingle.cpp): ONE patient whose rates are the chain's variables themselves
+	// (mean_*_ix hold the indices of "absorption", "excretion", "clearance", "volume_of_distribution"), optionally with the
+	// direct-absorption route and the metabolite compartment that only this likelihood switches on
+	int single, use_biphasic, use_metabolite, direct_absorption_ix, metabolite_conversion_ix;
 	// per-patient marginal variables p<i>_<name> (InitializePatientMarginals, cpp:342-354): [P] variable indices, or null
 	const int32_t *p_absorption_ix, *p_excretion_ix, *p_clearance_ix, *p_vod_ix, *p_transit_ix, *p_bioavailability_ix;
 	double conv_base; // 1e6 / molecular weight (cpp:339)
@@ -240,15 +244,17 @@ __device__ __noinline__ void ph_expm(const PhMat<N>& M, PhMat<N>& R)
 	}
 }
 
-// PharmacokineticModel::ConstructMatrix, PharmacokineticModel.cpp:188-247 (no metabolite, no biphasic absorption: the
-// population likelihood never enables them)
+// PharmacokineticModel::ConstructMatrix, PharmacokineticModel.cpp:188-247 (the metabolite compartment and the direct
+// absorption route are switched on by the single-patient likelihood only)
 template <int N>
 __device__ __forceinline__ void ph_construct(PhMat<N>& A, double absorption, double excretion, double elimination, bool periph, double kf, double kb,
-                                             int ntransit, double transit_rate)
+                                             int ntransit, double transit_rate, bool biphasic = false, double direct_absorption = 0.0,
+                                             bool metabolite = false, double metabolite_conversion = 0.0, double metabolite_elimination = 0.0)
 {
 #pragma unroll
 	for (int i = 0; i < N * N; i++) A.m[i] = 0.0;
-	const int first_transit = periph ? 3 : 2;
+	const int metabolite_ix = periph ? 3 : 2;
+	const int first_transit = metabolite_ix + (metabolite ? 1 : 0);
 	A(0, 0) -= excretion;
 	A(0, 0) -= absorption;
 	if (ntransit > 0) {
@@ -280,6 +286,19 @@ __device__ __forceinline__ void ph_construct(PhMat<N>& A, double absorption, dou
 			A(2, 2) -= kb;
 		}
 	}
+	if (biphasic) { // :233-236
+		A(0, 0) -= direct_absorption;
+		A(1, 0) += direct_absorption;
+	}
+	if (metabolite) { // :238-242
+		A(1, 1) -= metabolite_conversion;
+#pragma unroll
+		for (int i = 2; i < N; i++)
+			if (i == metabolite_ix) {
+				A(i, 1) += metabolite_conversion;
+				A(i, i) -= metabolite_elimination;
+			}
+	}
 	A(1, 1) -= elimination;
 }
 
@@ -300,10 +319,11 @@ __global__ void __launch_bounds__(128) pharmaco_kernel(const PhArgs a)
 	// ---- SetupSimulation, cpp:259-340 ----
 	const double additive_sd = a.additive_sd_ix >= 0 ? tv(a.additive_sd_ix) : 0.0;
 	const double proportional_sd = a.proportional_sd_ix >= 0 ? tv(a.proportional_sd_ix) : 0.0;
-	const double absorption = marginal(a.mean_absorption_ix, a.sigma_absorption_ix, a.p_absorption_ix);
-	const double excretion = a.mean_excretion_ix >= 0 ? marginal(a.mean_excretion_ix, a.sigma_excretion_ix, a.p_excretion_ix) : 0.0;
-	const double clearance = marginal(a.mean_clearance_ix, a.sigma_clearance_ix, a.p_clearance_ix);
-	const double vod = marginal(a.mean_vod_ix, a.sigma_vod_ix, a.p_vod_ix);
+	// pharmaco_single (PharmacoLikelihoodSingle.cpp:163-178): the variables, transformed, are the rates
+	const double absorption = a.single ? tv(a.mean_absorption_ix) : marginal(a.mean_absorption_ix, a.sigma_absorption_ix, a.p_absorption_ix);
+	const double excretion = a.mean_excretion_ix >= 0 ? (a.single ? tv(a.mean_excretion_ix) : marginal(a.mean_excretion_ix, a.sigma_excretion_ix, a.p_excretion_ix)) : 0.0;
+	const double clearance = a.single ? tv(a.mean_clearance_ix) : marginal(a.mean_clearance_ix, a.sigma_clearance_ix, a.p_clearance_ix);
+	const double vod = a.single ? tv(a.mean_vod_ix) : marginal(a.mean_vod_ix, a.sigma_vod_ix, a.p_vod_ix);
 	double kf = 0.0, kb = 0.0, transit_rate = 0.0, bioavailability = 1.0;
 	if (a.use_peripheral) {
 		kf = tv(a.periph_fwd_ix);
@@ -317,7 +337,10 @@ __global__ void __launch_bounds__(128) pharmaco_kernel(const PhArgs a)
 	if (a.use_bioavailability) bioavailability = v[a.p_bioavailability_ix[j]];
 	const double conversion = a.conv_base / vod;
 	PhMat<N> A;
-	ph_construct(A, absorption, excretion, clearance / vod, a.use_peripheral != 0, kf, kb, a.num_transit, transit_rate);
+	const double direct_absorption = a.use_biphasic ? tv(a.direct_absorption_ix) : 0.0;             // Single.cpp:192-195
+	const double metabolite_conversion = a.use_metabolite ? tv(a.metabolite_conversion_ix) : 0.0;   // :196-199; elimination fixed at 1 (:143)
+	ph_construct(A, absorption, excretion, clearance / vod, a.use_peripheral != 0, kf, kb, a.num_transit, transit_rate, a.use_biphasic != 0, direct_absorption,
+	             a.use_metabolite != 0, metabolite_conversion, 1.0);
 
 	// ---- PharmacokineticModel::Solve, PharmacokineticModel.cpp:111-177 ----
 	const int t0 = a.treat_begin[j], t1 = a.treat_begin[j + 1], o0 = a.obs_begin[j], o1 = a.obs_begin[j + 1];

@@ -45,6 +45,8 @@ std::shared_ptr<Likelihood> LikelihoodFactory::CreateLikelihoodFromText(const st
 		ll = std::make_shared<LikelihoodPopPKTrajectoryB200>(sampling_threads, evaluation_threads);
 	} else if (type == "pharmacokinetic_trajectory") { // LikelihoodFactory.cpp:60
 		ll = std::make_shared<LikelihoodPopPKTrajectoryB200>(sampling_threads, evaluation_threads, true);
+	} else if (type == "pharmaco_single") { // LikelihoodFactory.cpp:64
+		ll = std::make_shared<PharmacoLikelihoodPopulationB200>(sampling_threads, evaluation_threads, true);
 	} else if (type == "pharmaco_population") { // LikelihoodFactory.cpp:66
 		ll = std::make_shared<PharmacoLikelihoodPopulationB200>(sampling_threads, evaluation_threads);
 	} else if (type == "cell_population") { // LikelihoodFactory.cpp:81

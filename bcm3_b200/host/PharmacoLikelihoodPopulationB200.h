@@ -3,6 +3,9 @@
 // <pk_model drug= trial= peripheral_compartment= num_transit_compartments= bioavailability= likelihood_cache_size=/> as in the
 // reference (cpp:47-62); variables are found by name in the prior (PostInitialize, cpp:102-188). The NetCDF reader is out of
 // scope: the trial arrays of pkdata.nc are supplied with SetTrialData() before PostInitialize().
+// Constructed with single_patient = true the class is the drop-in for PharmacoLikelihoodSingle (src/pharmaco/
+// PharmacoLikelihoodSingle.{h,cpp}; type="pharmaco_single", model kind "pharmaco_single"): <pk_model ... patient= biphasic_absorption=
+// metabolite=>, the variables "absorption", "clearance", "volume_of_distribution", ... are the patient's rates themselves.
 #pragma once
 
 #include "Likelihood.h"
@@ -12,7 +15,9 @@ class PharmacoLikelihoodPopulationB200 : public bcm3::Likelihood {
 public:
 	typedef LikelihoodPopPKTrajectoryB200::TrialData TrialData; // the same NetCDF group (Patient::Load, PharmacoPatient.cpp:24-46)
 
-	PharmacoLikelihoodPopulationB200(size_t sampling_threads, size_t evaluation_threads);
+	PharmacoLikelihoodPopulationB200(size_t sampling_threads, size_t evaluation_threads, bool single_patient = false);
+	void SetPatientIDs(const std::vector<std::string>& ids) { patient_ids = ids; } // the "patients" dimension of the trial (PharmacoPatient.cpp:14-18)
+	void SetPatientID(const std::string& patient) { patient_id = patient; }        // the pharmacosingle.patient option
 	~PharmacoLikelihoodPopulationB200() override;
 
 	bool Initialize(std::shared_ptr<const bcm3::VariableSet> varset, const bcm3::XmlNode& likelihood_node) override;
@@ -26,7 +31,9 @@ public:
 
 private:
 	std::shared_ptr<const bcm3::VariableSet> varset;
-	std::string drug, trial_name;
+	std::string drug, trial_name, patient_id;
+	std::vector<std::string> patient_ids;
+	bool single = false, use_biphasic = false, use_metabolite = false;
 	bool use_peripheral = false, use_bioavailability = false;
 	size_t num_transit = 0;
 	TrialData trial;

@@ -24,6 +24,15 @@ ROLES = {
     "sigma_clearance": "sigma_clearance", "sigma_volume_of_distribution": "sigma_volume_of_distribution", "sigma_transit_time": "sigma_transit_time",
     "peripheral_forward_rate": "peripheral_forward_rate", "peripheral_backward_rate": "peripheral_backward_rate", "mean_transit_time": "mean_transit_time",
 }
+# model kind pharmaco_single (PharmacoLikelihoodSingle.cpp:75-146): key of the C ABI's descriptor -> (variable name in prior.xml, internal role)
+SINGLE_ROLES = {
+    "additive_sd": ("additive_error_standard_deviation", "additive_sd"), "proportional_sd": ("proportional_error_standard_deviation", "proportional_sd"),
+    "absorption": ("absorption", "mean_absorption"), "excretion": ("excretion", "mean_excretion"), "clearance": ("clearance", "mean_clearance"),
+    "volume_of_distribution": ("volume_of_distribution", "mean_volume_of_distribution"),
+    "peripheral_forward_rate": ("peripheral_forward_rate", "peripheral_forward_rate"), "peripheral_backward_rate": ("peripheral_backward_rate", "peripheral_backward_rate"),
+    "mean_transit_time": ("mean_transit_time", "mean_transit_time"), "direct_absorption": ("direct_absorption", "direct_absorption"),
+    "metabolite_conversion_rate": ("metabolite_conversion_rate", "metabolite_conversion_rate"),
+}
 # per-patient marginals p<i>_<name> (InitializePatientMarginals, cpp:342-354): ABI array name -> (variable suffix, the sigma that switches it on)
 PATIENT_ARRAYS = {
     "patient_absorption_ix": ("absorption", "sigma_absorption"), "patient_excretion_ix": ("excretion", "sigma_excretion"),
@@ -40,6 +49,11 @@ class PharmacoProblem:
     peripheral_compartment: bool = False
     num_transit_compartments: int = 0
     bioavailability: bool = False
+    # likelihood.xml type="pharmaco_single" (src/pharmaco/PharmacoLikelihoodSingle.cpp): ONE patient, the variables are its rates;
+    # <pk_model biphasic_absorption= metabolite=> exist for this likelihood only
+    single: bool = False
+    biphasic_absorption: bool = False
+    metabolite: bool = False
 
     @property
     def num_variables(self) -> int:
@@ -53,12 +67,26 @@ class PharmacoProblem:
         return self.variable_names.index(name) if name in self.variable_names else -1
 
     def role_indices(self) -> dict:
+        if self.single:  # internal roles (the checker's struct); sigma roles do not exist
+            out = {role: -1 for role in ROLES}
+            out.update(direct_absorption=-1, metabolite_conversion_rate=-1)
+            for name, role in SINGLE_ROLES.values():
+                out[role] = self.index(name)
+            return out
         return {role: self.index(name) for role, name in ROLES.items()}
+
+    def descriptor_indices(self) -> dict:
+        """key -> variable index as the C ABI's descriptor names them."""
+        if self.single:
+            return {key: self.index(name) for key, (name, _) in SINGLE_ROLES.items()}
+        return self.role_indices()
 
     def patient_indices(self) -> dict:
         """ABI array name -> [P] variable indices, for the marginals the prior switches on."""
         P = self.trial.num_patients
         out = {}
+        if self.single:
+            return out
         for array, (suffix, sigma) in PATIENT_ARRAYS.items():
             on = self.bioavailability if sigma is None else (self.index(sigma) >= 0)
             if suffix == "excretion":
@@ -81,12 +109,14 @@ class PharmacoEvaluator:
         desc = (f"drug={tr.drug};num_patients={P};num_timepoints={T};num_variables={p.num_variables};peripheral_compartment={int(p.peripheral_compartment)};"
                 f"num_transit_compartments={int(p.num_transit_compartments)};bioavailability={int(p.bioavailability)};"
                 f"shard_rank={shard_rank};shard_count={shard_count};device={device}")
-        for role, ix in p.role_indices().items():
+        for role, ix in p.descriptor_indices().items():
             if ix >= 0:
                 desc += f";{role}_ix={ix}"
+        if p.single:
+            desc += f";biphasic_absorption={int(p.biphasic_absorption)};metabolite={int(p.metabolite)}"
         desc = desc.encode()
         h = C.c_void_p()
-        _lib.check(self.lib.bcm3b200_create(b"pharmaco_population", desc, len(desc), 1, C.byref(h)))
+        _lib.check(self.lib.bcm3b200_create(b"pharmaco_single" if p.single else b"pharmaco_population", desc, len(desc), 1, C.byref(h)))
         self.handle = h
         try:
             for name in ("time", "observed_concentration", "dose", "dosing_interval", "dose_after_dose_change", "dose_change_time", "intermittent",
@@ -197,4 +227,39 @@ def make_pharmaco_values(problem: PharmacoProblem, C: int, seed: int = 20261018)
                 out[c, i] = rng.uniform(0.5, 1.0)
             else:
                 out[c, i] = rng.uniform(0.02, 0.98)  # a patient's quantile
+    return out
+
+
+def make_pharmaco_single_problem(T: int = 12, peripheral: bool = False, num_transit: int = 0, biphasic_absorption: bool = False, metabolite: bool = False,
+                                 excretion: bool = True, missing_fraction: float = 0.1, seed: int = 1) -> PharmacoProblem:
+    """One patient of a synthetic trial with the prior of a pharmaco_single model directory: every variable a rate in log10 space."""
+    from . import synthetic as syn
+    from .poppk_data import PK_ONE, PK_TWO
+
+    base = syn.make_poppk_problem(PK_TWO if peripheral else PK_ONE, P=1, T=T, t_end=120.0, seed=seed, heterogeneous=True, missing_fraction=missing_fraction)
+    names = ["absorption", "clearance", "volume_of_distribution", "additive_error_standard_deviation", "proportional_error_standard_deviation"]
+    if excretion:
+        names.append("excretion")
+    if peripheral:
+        names += ["peripheral_forward_rate", "peripheral_backward_rate"]
+    if num_transit > 0:
+        names.append("mean_transit_time")
+    if biphasic_absorption:
+        names.append("direct_absorption")
+    if metabolite:
+        names.append("metabolite_conversion_rate")
+    return PharmacoProblem(trial=base.trial, variable_names=names, transforms=np.full(len(names), TRANSFORM_LOG10, dtype=np.int32), peripheral_compartment=peripheral,
+                           num_transit_compartments=num_transit, single=True, biphasic_absorption=biphasic_absorption, metabolite=metabolite)
+
+
+def make_pharmaco_single_values(problem: PharmacoProblem, C: int, seed: int = 20261018) -> np.ndarray:
+    out = np.empty((C, problem.num_variables))
+    for c in range(C):
+        rng = np.random.default_rng(seed + c)
+        v = dict(absorption=rng.normal(-0.3, 0.3), clearance=rng.normal(0.7, 0.3), volume_of_distribution=rng.normal(1.8, 0.1),
+                 additive_error_standard_deviation=rng.normal(0.3, 0.05), proportional_error_standard_deviation=rng.normal(-0.7, 0.05),
+                 excretion=rng.normal(-1.5, 0.2), peripheral_forward_rate=rng.normal(-0.8, 0.2), peripheral_backward_rate=rng.normal(-1.0, 0.2),
+                 mean_transit_time=rng.normal(0.3, 0.1), direct_absorption=rng.normal(-1.0, 0.2), metabolite_conversion_rate=rng.normal(-1.2, 0.2))
+        for i, n in enumerate(problem.variable_names):
+            out[c, i] = v[n]
     return out

@@ -38,7 +38,14 @@ extern "C" {
 
 /* Create an evaluator.
  *   model_kind : the reference's likelihood.xml type string (LikelihoodFactory.cpp:62,66,81):
- *                "pop_pk_trajectory" | "pharmacokinetic_trajectory" | "cell_population" | "pharmaco_population"
+ *                "pop_pk_trajectory" | "pharmacokinetic_trajectory" | "cell_population" | "pharmaco_population" | "pharmaco_single"
+ *                pharmaco_single = PharmacoLikelihoodSingle (LikelihoodFactory.cpp:64, src/pharmaco/PharmacoLikelihoodSingle.cpp): the
+ *                matrix-exponential model of pharmaco_population for ONE patient (num_patients=1, trial data as below), whose
+ *                rates are the chain's variables themselves: keys drug num_patients num_timepoints num_variables
+ *                [peripheral_compartment] [num_transit_compartments] [biphasic_absorption=0|1] [metabolite=0|1] (cpp:39-50) and
+ *                <name>_ix for additive_sd, proportional_sd, absorption, excretion, clearance, volume_of_distribution,
+ *                peripheral_forward_rate, peripheral_backward_rate, mean_transit_time, direct_absorption,
+ *                metabolite_conversion_rate (the variable names of cpp:75-146; the metabolite's elimination is fixed at 1).
  *                pharmacokinetic_trajectory = LikelihoodPharmacokineticTrajectory (LikelihoodFactory.cpp:60,
  *                src/likelihoods/LikelihoodPharmacokineticTrajectory.cpp:259-352), the likelihood of ONE patient on the same
  *                models, solver and dosing logic: the keys and data of pop_pk_trajectory below with num_patients=1 (the host

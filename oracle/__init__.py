@@ -279,7 +279,8 @@ class _PharmacoProblem(C.Structure):
                                          "sigma_transit_ix", "periph_fwd_ix", "periph_bwd_ix", "mean_transit_time_ix")] + [
         ("mol_weight", C.c_double)] + [(n, C.c_void_p) for n in (
             "transforms", "p_absorption_ix", "p_excretion_ix", "p_clearance_ix", "p_vod_ix", "p_transit_ix", "p_bioavailability_ix", "time",
-            "observed_concentration", "dose", "dosing_interval", "dose_after_dose_change", "dose_change_time", "intermittent", "skipped_days")]
+            "observed_concentration", "dose", "dosing_interval", "dose_after_dose_change", "dose_change_time", "intermittent", "skipped_days")] + [
+        (n, C.c_int32) for n in ("single", "use_biphasic", "use_metabolite", "direct_absorption_ix", "metabolite_conversion_ix")]
 
 
 def _pharmaco_evaluate(self, problem, values, threads: int = 1, want_conc=False, want_patient_ll=False):
@@ -319,7 +320,9 @@ def _pharmaco_evaluate(self, problem, values, threads: int = 1, want_conc=False,
         p_transit_ix=ptr(pix["patient_transit_time_ix"]) if "patient_transit_time_ix" in pix else None,
         p_bioavailability_ix=ptr(pix["patient_bioavailability_ix"]) if "patient_bioavailability_ix" in pix else None,
         time=ptr(keep["time"]), observed_concentration=ptr(keep["obs"]), dose=ptr(keep["dose"]), dosing_interval=ptr(keep["interval"]),
-        dose_after_dose_change=ptr(keep["dac"]), dose_change_time=ptr(keep["dct"]), intermittent=ptr(keep["inter"]), skipped_days=ptr(keep["skipped"]))
+        dose_after_dose_change=ptr(keep["dac"]), dose_change_time=ptr(keep["dct"]), intermittent=ptr(keep["inter"]), skipped_days=ptr(keep["skipped"]),
+        single=int(getattr(p, "single", False)), use_biphasic=int(getattr(p, "biphasic_absorption", False)), use_metabolite=int(getattr(p, "metabolite", False)),
+        direct_absorption_ix=r.get("direct_absorption", -1), metabolite_conversion_ix=r.get("metabolite_conversion_rate", -1))
     logp = np.empty(nC)
     conc = np.empty((nC, P, T)) if want_conc else None
     pll = np.empty((nC, P)) if want_patient_ll else None

@@ -175,6 +175,10 @@ typedef struct {
 	const double *dose, *dosing_interval, *dose_after_dose_change, *dose_change_time; /* [P] */
 	const int32_t* intermittent;            /* [P] */
 	const uint32_t* skipped_days;           /* [P] bit d = day d skipped */
+	/* 1: PharmacoLikelihoodSingle (src/pharmaco/PharmacoLikelihoodSingle.cpp:153-221), ONE patient (P = 1): mean_*_ix are the
+	 * indices of "absorption", "excretion", "clearance", "volume_of_distribution", used through the variable transform; the
+	 * direct-absorption route and the metabolite compartment (elimination fixed at 1, cpp:143) can be switched on */
+	int32_t single, use_biphasic, use_metabolite, direct_absorption_ix, metabolite_conversion_ix;
 } oracle_pharmaco_problem;
 
 /* logp [C]; conc [C][P][T] optional (conversion * simulated concentration at the observations that have a value, NaN elsewhere);

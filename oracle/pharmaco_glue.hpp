@@ -8,6 +8,8 @@
 // Used twice: oracle/ref/pharmaco_ref.cpp plugs in the reference's own PharmacokineticModel (compiled from its source with
 // Eigen's matrix exponential), oracle/pharmaco_port.cpp a plain restatement. The adapter provides
 //   void configure(bool peripheral, int num_transit);
+//   void configure_single(bool biphasic_absorption, bool metabolite); void set_single(direct_absorption_rate, metabolite_conversion_rate);
+//     -- PharmacoLikelihoodSingle (src/pharmaco/PharmacoLikelihoodSingle.cpp), the one-patient form of the same likelihood
 //   bool solve(absorption, excretion, elimination, kf, kb, transit_rate, bioavailability, treat_times, treat_doses, obs_times, out)
 #pragma once
 
@@ -94,6 +96,7 @@ void evaluate_chain(const oracle_pharmaco_problem& pr, const std::vector<Patient
 	};
 	Model model;
 	model.configure(pr.use_peripheral != 0, pr.num_transit);
+	model.configure_single(pr.single && pr.use_biphasic, pr.single && pr.use_metabolite); // PharmacoLikelihoodSingle.cpp:127-149
 	double logp = 0.0;
 	const double additive_sd = pr.additive_sd_ix >= 0 ? tv(pr.additive_sd_ix) : 0.0;
 	const double proportional_sd = pr.proportional_sd_ix >= 0 ? tv(pr.proportional_sd_ix) : 0.0;
@@ -101,10 +104,12 @@ void evaluate_chain(const oracle_pharmaco_problem& pr, const std::vector<Patient
 	for (int j = 0; j < P; j++) {
 		const PatientData& pt = patients[j];
 		// SetupSimulation
-		const double absorption = marginal(pr.mean_absorption_ix, pr.sigma_absorption_ix, pr.p_absorption_ix, j);
-		const double excretion = pr.mean_excretion_ix >= 0 ? marginal(pr.mean_excretion_ix, pr.sigma_excretion_ix, pr.p_excretion_ix, j) : 0.0;
-		const double clearance = marginal(pr.mean_clearance_ix, pr.sigma_clearance_ix, pr.p_clearance_ix, j);
-		const double vod = marginal(pr.mean_vod_ix, pr.sigma_vod_ix, pr.p_vod_ix, j);
+		// PharmacoLikelihoodSingle.cpp:163-178: the single-patient likelihood takes the transformed variables as the rates
+		const double absorption = pr.single ? tv(pr.mean_absorption_ix) : marginal(pr.mean_absorption_ix, pr.sigma_absorption_ix, pr.p_absorption_ix, j);
+		const double excretion = pr.mean_excretion_ix >= 0 ? (pr.single ? tv(pr.mean_excretion_ix) : marginal(pr.mean_excretion_ix, pr.sigma_excretion_ix, pr.p_excretion_ix, j)) : 0.0;
+		const double clearance = pr.single ? tv(pr.mean_clearance_ix) : marginal(pr.mean_clearance_ix, pr.sigma_clearance_ix, pr.p_clearance_ix, j);
+		const double vod = pr.single ? tv(pr.mean_vod_ix) : marginal(pr.mean_vod_ix, pr.sigma_vod_ix, pr.p_vod_ix, j);
+		if (pr.single) model.set_single(pr.use_biphasic ? tv(pr.direct_absorption_ix) : 0.0, pr.use_metabolite ? tv(pr.metabolite_conversion_ix) : 0.0); // :192-199
 		double kf = nan, kb = nan, transit_rate = nan, bioavailability = 1.0;
 		if (pr.use_peripheral) {
 			kf = tv(pr.periph_fwd_ix);

@@ -127,12 +127,26 @@ struct PortModel {
 		peripheral = use_peripheral;
 		num_transit = transit;
 	}
+	bool biphasic = false, metabolite = false;
+	double direct_absorption = 0.0, metabolite_conversion = 0.0;
+	void configure_single(bool use_biphasic, bool use_metabolite)
+	{
+		biphasic = use_biphasic;
+		metabolite = use_metabolite;
+	}
+	void set_single(double direct_absorption_rate, double metabolite_conversion_rate)
+	{
+		direct_absorption = direct_absorption_rate;
+		metabolite_conversion = metabolite_conversion_rate;
+	}
 	bool solve(double absorption, double excretion, double elimination, double kf, double kb, double transit_rate, double bioavailability,
 	           const std::vector<double>& tt, const std::vector<double>& td, const std::vector<double>& ot, std::vector<double>& out)
 	{
 		// ConstructMatrix, PharmacokineticModel.cpp:188-247
 		int n = 2;
 		if (peripheral) n++;
+		const int metabolite_ix = n;
+		if (metabolite) n++;
 		const int first_transit = n;
 		n += num_transit;
 		Mat A((size_t)n * n, 0.0);
@@ -157,6 +171,15 @@ struct PortModel {
 			a(2, 1) += kf;
 			a(1, 2) += kb;
 			a(2, 2) -= kb;
+		}
+		if (biphasic) {
+			a(0, 0) -= direct_absorption;
+			a(1, 0) += direct_absorption;
+		}
+		if (metabolite) {
+			a(1, 1) -= metabolite_conversion;
+			a(metabolite_ix, 1) += metabolite_conversion;
+			a(metabolite_ix, metabolite_ix) -= 1.0; // metabolite elimination, fixed (PharmacoLikelihoodSingle.cpp:143)
 		}
 		a(1, 1) -= elimination;
 		// Solve, :111-177

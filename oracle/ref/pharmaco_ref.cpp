@@ -27,6 +27,21 @@ struct RefModel {
 		model.SetUsePeripheralCompartment(use_peripheral);
 		model.SetNumTransitCompartments((size_t)transit);
 	}
+	bool biphasic = false, metabolite = false;
+	void configure_single(bool use_biphasic, bool use_metabolite)
+	{
+		// PharmacoLikelihoodSingle::PostInitialize, PharmacoLikelihoodSingle.cpp:127-149
+		biphasic = use_biphasic;
+		metabolite = use_metabolite;
+		model.SetUseBiphasicAbsorption(use_biphasic);
+		if (use_metabolite) model.SetMetaboliteElimination(1.0);
+		model.SetUseMetabolite(use_metabolite);
+	}
+	void set_single(double direct_absorption_rate, double metabolite_conversion_rate)
+	{
+		if (biphasic) model.SetDirectAbsorptionRate(direct_absorption_rate);
+		if (metabolite) model.SetMetaboliteConversionRate(metabolite_conversion_rate);
+	}
 	bool solve(double absorption, double excretion, double elimination, double kf, double kb, double transit_rate, double bioavailability,
 	           const std::vector<double>& tt, const std::vector<double>& td, const std::vector<double>& ot, std::vector<double>& out)
 	{

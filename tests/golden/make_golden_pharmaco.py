@@ -22,13 +22,26 @@ CASES = {
     # two transit compartments: the reference links the chain only for more than two (PharmacokineticModel.cpp:215)
     "pharmaco_transit2_quirk": dict(P=24, T=8, num_transit=2, seed=7),
 }
+# likelihood.xml type="pharmaco_single" (src/pharmaco/PharmacoLikelihoodSingle.cpp): one patient, the variables are its rates
+SINGLE_CASES = {
+    "pharmaco_single_plain": dict(seed=3),
+    "pharmaco_single_peripheral_no_excretion": dict(peripheral=True, excretion=False, seed=4),
+    "pharmaco_single_transit3": dict(num_transit=3, seed=5),
+    "pharmaco_single_biphasic": dict(biphasic_absorption=True, seed=6),
+    "pharmaco_single_metabolite": dict(metabolite=True, seed=7),
+    "pharmaco_single_everything": dict(peripheral=True, num_transit=3, biphasic_absorption=True, metabolite=True, seed=8),
+}
 
 
 def main():
     ref = oracle.load("ref")
-    for name, kw in CASES.items():
-        prob = ph.make_pharmaco_problem(**kw)
-        vals = ph.make_pharmaco_values(prob, 3, seed=100 + kw["seed"])
+    for name, kw in list(CASES.items()) + list(SINGLE_CASES.items()):
+        if name in SINGLE_CASES:
+            prob = ph.make_pharmaco_single_problem(**kw)
+            vals = ph.make_pharmaco_single_values(prob, 6, seed=100 + kw["seed"])
+        else:
+            prob = ph.make_pharmaco_problem(**kw)
+            vals = ph.make_pharmaco_values(prob, 3, seed=100 + kw["seed"])
         r = ref.pharmaco_evaluate(prob, vals, threads=1, want_conc=True, want_patient_ll=True)
         tr = prob.trial
         out = dict(drug=np.array(tr.drug), time=tr.time, observed_concentration=tr.observed_concentration, dose=tr.dose,
@@ -36,6 +49,7 @@ def main():
                    intermittent=tr.intermittent, treatment_interruptions=tr.treatment_interruptions, variable_names=np.array(prob.variable_names),
                    transforms=prob.transforms, peripheral_compartment=np.array(prob.peripheral_compartment),
                    num_transit_compartments=np.array(prob.num_transit_compartments), bioavailability=np.array(prob.bioavailability),
+                   single=np.array(prob.single), biphasic_absorption=np.array(prob.biphasic_absorption), metabolite=np.array(prob.metabolite),
                    values=vals, logp=r["logp"], conc=r["conc"], patient_ll=r["patient_ll"])
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)

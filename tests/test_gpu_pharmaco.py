@@ -89,3 +89,43 @@ def test_plugin_through_the_factory(built):
     for batched in (True, False):
         got = host_api.pharmaco_evaluate(prior, lik, prob.trial, vals, batched=batched)
         assert np.array_equal(got, want)
+
+
+# ---- pharmaco_single: PharmacoLikelihoodSingle, one patient (the goldens pharmaco_single_* run with the parametrised tests above) ----
+@pytest.mark.parametrize("kw", [dict(), dict(peripheral=True, num_transit=4, metabolite=True), dict(biphasic_absorption=True, excretion=False)])
+def test_single_patient_fresh_inputs(Evaluator, checker, kw):
+    prob = ph.make_pharmaco_single_problem(T=16, seed=31, **kw)
+    vals = ph.make_pharmaco_single_values(prob, 64, seed=7)
+    vals[5, 0] = np.nan  # a NaN absorption rate: NaN state, Solve returns false, -inf (PharmacoLikelihoodSingle.cpp:215-217)
+    want = checker.pharmaco_evaluate(prob, vals, threads=4)["logp"]
+    ev = Evaluator(prob)
+    got, status = ev.evaluate(vals)
+    ev.close()
+    assert np.isneginf(got[5]) and np.isneginf(want[5]) and (status == 0).all()
+    assert rel_err(got, want).max() <= 1e-10
+
+
+def test_single_patient_plugin_through_the_factory(built):
+    """likelihood.xml type="pharmaco_single" -> LikelihoodFactory -> the plugin picks <pk_model patient=> out of the trial."""
+    from bcm3_b200 import host_api
+    from bcm3_b200 import synthetic as syn
+    from bcm3_b200.poppk_data import PK_TWO
+
+    trial = syn.make_poppk_problem(PK_TWO, P=4, T=12, t_end=120.0, seed=12, heterogeneous=True, missing_fraction=0.1).trial
+    one = ph.make_pharmaco_single_problem(peripheral=True, biphasic_absorption=True, metabolite=True)
+    pick = lambda a: np.asarray(a)[2:3]
+    one.trial = type(trial)(drug=trial.drug, time=trial.time, observed_concentration=pick(trial.observed_concentration), dose=pick(trial.dose),
+                            dosing_interval=pick(trial.dosing_interval), dose_after_dose_change=pick(trial.dose_after_dose_change),
+                            dose_change_time=pick(trial.dose_change_time), intermittent=pick(trial.intermittent),
+                            treatment_interruptions=pick(trial.treatment_interruptions))
+    vals = ph.make_pharmaco_single_values(one, 5, seed=3)
+    ev = ph.PharmacoEvaluator(one)
+    want, _ = ev.evaluate(vals)
+    ev.close()
+    prior = "<variableset>" + "".join(f'<variable name="{n}" logspace="true" distribution="uniform" lower="-5" upper="5"/>' for n in one.variable_names) + "</variableset>"
+    lik = ('<bcm_likelihood type="pharmaco_single"><pk_model drug="lapatinib" trial="synthetic" patient="2" peripheral_compartment="true" '
+           'biphasic_absorption="true" metabolite="true"/></bcm_likelihood>')
+    for batched in (True, False):
+        assert np.array_equal(host_api.pharmaco_evaluate(prior, lik, trial, vals, batched=batched), want)
+    with pytest.raises(RuntimeError, match="Cannot find patient"):
+        host_api.pharmaco_evaluate(prior, lik.replace('patient="2"', 'patient="9"'), trial, vals)

@@ -96,7 +96,7 @@ def load_pharmaco_golden(name):
                        intermittent=z["intermittent"], treatment_interruptions=z["treatment_interruptions"])
     prob = PharmacoProblem(trial=trial, variable_names=[str(n) for n in z["variable_names"]], transforms=z["transforms"],
                            peripheral_compartment=bool(z["peripheral_compartment"]), num_transit_compartments=int(z["num_transit_compartments"]),
-                           bioavailability=bool(z["bioavailability"]))
+                           bioavailability=bool(z["bioavailability"]), **{k: bool(z[k]) for k in ("single", "biphasic_absorption", "metabolite") if k in z.files})
     return prob, {k: z[k] for k in ("values", "logp", "conc", "patient_ll")}
 
 
