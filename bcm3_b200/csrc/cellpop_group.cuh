@@ -219,6 +219,18 @@ __device__ __noinline__ void rhs_eval_lanes(unsigned y_off, unsigned f_off, unsi
 #ifndef CP_PIVOT_REDUX
 #define CP_PIVOT_REDUX (CP_GROUP >= 16)
 #endif
+// Triangular solves that leave out the columns of L (below the diagonal) and of U (above it) that hold nothing but zeros:
+// the factorisation's own votes say which columns those are (the multipliers of a pivot step, the non-zero entries of a
+// finished pivot row), kept as one bit per column. A skipped column would have subtracted x_k * 0 from every component, so
+// the result has the same bits. In a signalling network most columns of U are empty above the diagonal (a cascade: all
+// but the fill-in column), and every skipped column is one shuffle + multiply-add link less in the solve's dependent chain.
+// Measured (B200, 50 species x 6 000 cells x 16 chains, same bits): 1 536 ms with it, 1 500 ms without -- the run-time loops
+// over the set bits cost more than the skipped columns save (the pivoting of a stiff I - gamma J fills U's superdiagonal,
+// and the compile-time slotted loops are unrolled four columns deep); N = 24: 377 vs 377 ms. An experiment switch, off.
+// profiles/r02_cellpop50_variants_solve_skip.log
+#ifndef CP_SOLVE_SKIP
+#define CP_SOLVE_SKIP 0
+#endif
 #ifndef CP_SJ_UNROLL
 #define CP_SJ_UNROLL 1
 #endif
@@ -245,6 +257,9 @@ struct GroupBdf {
 	int q, qprime, L, qwait, nst, nstlp, nstlj, nflag, ncf, nef;
 	bool nls_jcur;
 	int nfe, nsetups, nje;
+#if CP_SOLVE_SKIP
+	unsigned lmask[E], umask[E]; // bit kk of slot s: column G * s + kk of L / U has a non-zero entry off the diagonal
+#endif
 	// ---- placement ----
 	double* M;    // shared (global with CP_M_GLOBAL)
 	double* ybuf; // shared, N
@@ -754,6 +769,10 @@ struct GroupBdf {
 		gsync();
 		// PartialPivLUExtended::compute_optimized (EigenPartialPivLUSomewhatSparse.h:38-105): lane = rows lg, lg + G, ...
 		if constexpr (N <= CP_GROUP_STATIC_LU_MAX) {
+#if CP_SOLVE_SKIP
+#pragma unroll
+			for (int e = 0; e < E; e++) lmask[e] = umask[e] = 0xffffffffu;
+#endif
 			// fully unrolled: which slots still have rows below the pivot is known per (k, slot) at compile time, and every
 			// shared-memory access is [lane row base + constant]
 			double* const rowbase = M + lg * RS;
@@ -839,6 +858,10 @@ struct GroupBdf {
 			});
 		} else {
 			double* const rowbase = M + lg * RS;
+#if CP_SOLVE_SKIP
+#pragma unroll
+			for (int e = 0; e < E; e++) lmask[e] = umask[e] = 0u;
+#endif
 #pragma unroll 1
 			for (int k = 0; k < N; k++) {
 				double best = -1.0;
@@ -912,6 +935,20 @@ struct GroupBdf {
 						rowbase[G * e * RS + k] = lik[e];
 					}
 				}
+#if CP_SOLVE_SKIP
+				{
+					bool any = false;
+#pragma unroll
+					for (int e = 0; e < E; e++) any = any || (lik[e] != 0.0);
+					if (__ballot_sync(gmask, any) & gmask) {
+						const unsigned bit = 1u << (k % G);
+						static_for<0, E>([&](auto S) {
+							constexpr int s = decltype(S)::value;
+							if (k / G == s) lmask[s] |= bit;
+						});
+					}
+				}
+#endif
 #if CP_LU_SKIP_ZEROS
 				// Column updates, skipping the columns whose pivot-row entry is zero exactly as the reference's LU does
 				// (EigenPartialPivLUSomewhatSparse.h:88-93: `if (a_kj != 0.0)`): the lanes look at the pivot row together, one
@@ -922,6 +959,9 @@ struct GroupBdf {
 					const int c0 = lg + G * e;
 					const double rk = (c0 > k && (!PADDED || c0 < N)) ? M[k * RS + c0] : 0.0;
 					unsigned nz = (__ballot_sync(gmask, rk != 0.0) & gmask) >> gbase;
+#if CP_SOLVE_SKIP
+					umask[e] |= nz; // row k of U is final: its non-zero columns
+#endif
 					while (nz) {
 						const int j = __ffs(nz) - 1;
 						nz &= nz - 1;
@@ -984,7 +1024,48 @@ struct GroupBdf {
 #pragma unroll
 		for (int e = 0; e < E; e++) b[e] = own(e) ? ybuf[perm[idx(e)]] : 0.0;
 		const double* const rowbase = M + lg * RS;
-#if CP_SOLVE_SLOTTED
+#if CP_SOLVE_SKIP
+		// As the slotted form below, visiting only the columns with an entry off the diagonal (see CP_SOLVE_SKIP).
+		static_for<0, E>([&](auto S) {
+			constexpr int s = decltype(S)::value;
+			constexpr int KK = (G * (s + 1) <= N) ? G : (N - G * s);
+			unsigned m = lmask[s] & (KK >= 32 ? 0xffffffffu : ((1u << (KK & 31)) - 1u));
+#pragma unroll 1
+			while (m) {
+				const int kk = __ffs(m) - 1;
+				m &= m - 1;
+				const int k = G * s + kk;
+				const double xk = __shfl_sync(gmask, b[s], gbase + kk);
+				if (lg > kk && own(s)) b[s] = fma(-xk, rowbase[G * s * RS + k], b[s]);
+				static_for<s + 1, E>([&](auto EE) {
+					constexpr int e2 = decltype(EE)::value;
+					if (own(e2)) b[e2] = fma(-xk, rowbase[G * e2 * RS + k], b[e2]);
+				});
+			}
+		});
+		static_rfor<0, E>([&](auto S) {
+			constexpr int s = decltype(S)::value;
+			constexpr int KK = (G * (s + 1) <= N) ? G : (N - G * s);
+			const unsigned cols = umask[s] & (KK >= 32 ? 0xffffffffu : ((1u << (KK & 31)) - 1u));
+			unsigned m = cols;
+#pragma unroll 1
+			while (m) {
+				const int kk = 31 - __clz(m);
+				m &= ~(1u << kk);
+				const int k = G * s + kk;
+				const double m_k = own(s) ? rowbase[G * s * RS + k] : 0.0;
+				const double xk = __shfl_sync(gmask, b[s] * m_k, gbase + kk);
+				if (lg < kk) b[s] = fma(-xk, m_k, b[s]);
+				else if (lg == kk) b[s] = xk;
+				static_for<0, s>([&](auto EE) {
+					constexpr int e2 = decltype(EE)::value;
+					b[e2] = fma(-xk, rowbase[G * e2 * RS + k], b[e2]);
+				});
+			}
+			// a column without entries above the diagonal: nobody else needs x_k, the owner scales its component
+			if (own(s) && !((cols >> lg) & 1u)) b[s] = b[s] * rowbase[G * s * RS + G * s + lg];
+		});
+#elif CP_SOLVE_SLOTTED
 		// Forward substitution with the unit lower factor, column by column: slot by slot (compile time) and lane by lane
 		// inside a slot, so that the pivot component is a static register read by a shuffle and every lane touches its
 		// rows through [lane row base + constant]. Rows of the pivot's own slot take part only on the lanes behind it.
