@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("BCM3B200_LIB", os.path.join(PKG_DIR, "libbcm3b200.so"
 # every symbol declared in include/bcm3b200.h
 EXPORTS = [
     "bcm3b200_create",
+    "bcm3b200_match_cells",
     "bcm3b200_set_data",
     "bcm3b200_set_text",
     "bcm3b200_get_cell_diagnostics",
@@ -104,6 +105,8 @@ def load() -> C.CDLL:
     lib.bcm3b200_host_alloc.restype = vp
     lib.bcm3b200_host_free.argtypes = [vp]
     lib.bcm3b200_host_free.restype = None
+    lib.bcm3b200_match_cells.argtypes = [C.c_int, vp, vp]
+    lib.bcm3b200_match_cells.restype = C.c_int
     for name in ("create", "set_data", "set_text", "get_cell_diagnostics", "finalize", "evaluate_batch", "evaluate_batch_device", "enqueue_batch", "combine_partials", "cellpop_finish", "comm_unique_id", "comm_init", "exchange_partials",
                  "get_diagnostics", "set_option", "get_stat"):
         getattr(lib, "bcm3b200_" + name).restype = C.c_int
@@ -114,6 +117,19 @@ def load() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise Bcm3B200Error(rc, load().bcm3b200_last_error().decode(errors="replace"))
+
+
+def match_cells(cost):
+    """The simulated cell (column) the per-cell time_course likelihood assigns to every observed cell (row) of a complete [n][n]
+    cost matrix: bcm3b200_match_cells, host code only. None when no perfect matching was found."""
+    import numpy as np
+
+    cost = np.ascontiguousarray(cost, dtype=np.float64)
+    n = cost.shape[0]
+    assert cost.shape == (n, n)
+    out = np.full(n, -1, dtype=np.int32)
+    rc = load().bcm3b200_match_cells(n, cost.ctypes.data, out.ctypes.data)
+    return out if rc == 0 else None
 
 
 def measure_fp64_peak(device: int = 0) -> float:

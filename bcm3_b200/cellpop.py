@@ -29,6 +29,8 @@ class CellPopEvaluator:
             obs_species="+".join(str(s) for s in p.obs_species), device=device, compile_only=int(compile_only),
             shard_rank=shard_rank, shard_count=shard_count)
         kv["variability_distribution"] = p.variability_distribution
+        if p.data_kind != "time_course_population_average":
+            kv["data_kind"] = p.data_kind
         kv["relative_to_time_average"] = int(p.relative_to_time_average)
         kv["stdev_relative_to_scale"] = int(p.stdev_relative_to_scale)
         if p.treatment_species is not None:

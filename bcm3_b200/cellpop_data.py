@@ -67,6 +67,10 @@ class CellPopProblem:
     entry_time_ix: int | None = None
     entry_time: float = 0.0
     error_model: str = "normal"
+    # <data type=>: "time_course_population_average" (observed [replicates][T]) or "time_course" -- per-cell trajectories:
+    # observed [observed cells][T], as many observed as simulated cells, every observed cell matched to one simulated cell by
+    # minimum-cost perfect matching (DataLikelihoodTimeCourse.cpp:230-365); synchronize="none", no parent information, one marker
+    data_kind: str = "time_course_population_average"
     relative_to_time_average: bool = False   # <data relative_to_time_average="true">: log of the value over its time average
     # the time the experiment integrates its cells to when it has further data sets that end later (Experiment.cpp:655-656);
     # None: the last of `timepoints`

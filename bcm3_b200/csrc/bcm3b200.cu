@@ -182,6 +182,11 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 	else if (em == "proportional_normal") cp->error_model = CP_ERR_PROPORTIONAL_NORMAL;
 	else if (em == "additive_proportional_normal") cp->error_model = CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL;
 	else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported (normal, student_t4, proportional_normal, additive_proportional_normal)", em.c_str());
+	{
+		const std::string dk = kv.count("data_kind") ? kv["data_kind"] : "time_course_population_average";
+		if (dk == "time_course") cp->data_kind = 1;
+		else if (dk != "time_course_population_average") return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind \"%s\" is not supported (time_course_population_average, time_course)", dk.c_str());
+	}
 	cp->treatment_species = get_int(kv, "treatment_species", -1);
 	cp->relative_to_time_average = get_int(kv, "relative_to_time_average", 0) != 0;
 	cp->stdev_relative_to_scale = get_int(kv, "stdev_relative_to_scale", 0) != 0;
@@ -229,6 +234,11 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 		else if (emk == "proportional_normal") m->error_model = CP_ERR_PROPORTIONAL_NORMAL;
 		else if (emk == "additive_proportional_normal") m->error_model = CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL;
 		else return fail(BCM3B200_ERR_UNSUPPORTED, "error_model \"%s\" is not supported", emk.c_str());
+		{
+			const std::string dk = kv.count(key("data_kind")) ? kv[key("data_kind")] : "time_course_population_average";
+			if (dk == "time_course") m->data_kind = 1;
+			else if (dk != "time_course_population_average") return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind \"%s\" is not supported", dk.c_str());
+		}
 		m->stdev_ix = get_int(kv, key("stdev_ix").c_str(), -1);
 		m->stdev_fixed = realk("stdev", 1.0);
 		m->offset_ix = get_int(kv, key("offset_ix").c_str(), -1);
@@ -1393,3 +1403,15 @@ void bcm3b200_destroy(void* handle)
 }
 
 } // extern "C"
+
+int bcm3b200_match_cells(int n, const double* cost, int32_t* match)
+{
+	if (n < 0 || (n > 0 && (!cost || !match))) return fail(BCM3B200_ERR_ARG, "bad argument");
+	const std::vector<int> m = payor_matching_complete(n, cost);
+	if ((int)m.size() != n) {
+		for (int i = 0; i < n; i++) match[i] = -1;
+		return n == 0 ? BCM3B200_OK : fail(BCM3B200_ERR_STATE, "no perfect matching found");
+	}
+	for (int i = 0; i < n; i++) match[i] = m[i];
+	return BCM3B200_OK;
+}

@@ -14,11 +14,14 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 #include "cellpop_args.h"
+#include "matching_host.cuh"
 
 namespace bcm3b200 {
 
@@ -26,6 +29,11 @@ enum : int { CP_ERR_NORMAL = 0, CP_ERR_STUDENT_T4 = 1, CP_ERR_PROPORTIONAL_NORMA
 
 struct CellPopState {
 	// description
+	// <data type=>: 0 = time_course_population_average; 1 = time_course -- one observed trajectory per cell ("observed" is
+	// [observed cells][T], num_replicates = observed cells = num_cells), every observed cell matched to one simulated cell
+	// (DataLikelihoodTimeCourse.cpp:230-365): the [observed x simulated] log-likelihood block is a kernel, the matching runs
+	// on the host (matching_host.cuh)
+	int data_kind = 0;
 	int N = 0, Nc = 0, nvar = 0, Nn = 0, num_cells = 0, T = 0, R = 1, D = 0;
 	int entry_time_ix = -1;
 	double entry_time_fixed = 0.0;
@@ -57,7 +65,7 @@ struct CellPopState {
 	// they share the integration of the experiment's cells (Experiment.cpp:190-214, 298-312) -- the kernel interpolates at the
 	// union of all timepoints and every data set sums its own species -- and their log-likelihoods are added in order (:346-355)
 	struct MoreData {
-		int T = 0, R = 1, error_model = CP_ERR_NORMAL;
+		int T = 0, R = 1, error_model = CP_ERR_NORMAL, data_kind = 0;
 		int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
 		double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0, weight = 1.0, missing_stdev = 300.0;
 		bool relative_to_time_average = false, stdev_relative_to_scale = false;
@@ -102,7 +110,15 @@ struct CellPopState {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<double> d_ic, d_const, d_nonsampled, d_sobol, d_time, d_obs, d_values, d_transformed, d_cellvals, d_avg, d_logp;
 	DevBuf<int32_t> d_transforms, d_status, d_steps, d_count, d_nfail, d_cov_ix, d_cell_order;
-	DevBuf<double> d_cov_fixed, d_chol, d_treatment_times, d_partial;
+	DevBuf<double> d_cov_fixed, d_chol, d_treatment_times, d_partial, d_cell_lik;
+	std::vector<double> h_cell_lik; // [C][observed][simulated] of the time_course data set being matched
+	bool any_time_course() const
+	{
+		if (data_kind == 1) return true;
+		for (const auto& m : more)
+			if (m->data_kind == 1) return true;
+		return false;
+	}
 	bool diagnostics = false;
 	int last_C = 0;
 	double last_kernel_ms = 0.0;
@@ -396,6 +412,7 @@ struct CpLikArgs {
 	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
 	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, weight, missing_stdev;
 	double* logp; // [C]
+	int kind;     // 1: a per-cell time_course data set -- its term is added on the host after the matching, here it is 0
 };
 
 // DataLikelihoodTimeCoursePopulationAverage::Evaluate (.cpp:85-159) for one species column; one thread per chain
@@ -405,6 +422,10 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 	if (c >= C) return;
 	if (a.nfail[c] > 0) { // Simulate() failed for some cell: Experiment.cpp:356-358
 		a.logp[c] = -INFINITY;
+		return;
+	}
+	if (a.kind == 1) {
+		if (!a.accumulate) a.logp[c] = 0.0;
 		return;
 	}
 	const double* avg = a.avg + (long long)c * a.avg_stride + a.avg_row0;
@@ -484,6 +505,75 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 	a.logp[c] = a.accumulate ? a.logp[c] + logp * a.weight : logp * a.weight;
 }
 
+// DataLikelihoodTimeCourse::CalculateCellLikelihood (.cpp:431-505) for every (observed cell i, simulated cell j) pair of a chain:
+// lik[c][i][j] = sum over the timepoints with an observation of the log-density of the observed value around the simulated
+// cell's (scaled, shifted) trajectory; a simulated value that is missing pays CalculateMissingValueLikelihood (.cpp:566-588).
+// One thread per pair, j fastest: the trajectory reads of a warp are one coalesced row segment, the observed value is a
+// broadcast. cell_values is the kernel's [C][rows][cell_stride] block, row0 the data set's first row.
+struct CpCellLikArgs {
+	const double* cell_values;
+	int rows, cell_stride, row0, T, n_obs, n_sim, nvar, error_model, stdev_relative_to_scale;
+	const double* transformed;
+	const double* timepoints; // [T]
+	const double* observed;   // [n_obs][T]
+	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
+	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, missing_stdev;
+	double* lik; // [C][n_obs][n_sim]
+};
+__global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, c = blockIdx.z;
+	if (j >= a.n_sim) return;
+	const double* tv = a.transformed + (long long)c * a.nvar;
+	double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
+	const double offset = (a.offset_ix >= 0) ? tv[a.offset_ix] : a.offset_fixed;
+	const double scale = (a.scale_ix >= 0) ? tv[a.scale_ix] : a.scale_fixed;
+	if (a.stdev_relative_to_scale) stdev *= scale;
+	const double prop_stdev = (a.prop_stdev_ix >= 0) ? tv[a.prop_stdev_ix] : a.prop_stdev_fixed;
+	const double minus_log_sigma = -log(stdev);
+	const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
+	const double* traj = a.cell_values + ((long long)c * a.rows + a.row0) * a.cell_stride + j;
+	auto value = [&](int k) { // .cpp:236-241: *= data scale, += data offset
+		double v = traj[(long long)k * a.cell_stride];
+		v *= scale;
+		v += offset;
+		return v;
+	};
+	const double* obs = a.observed + (long long)i * a.T;
+	double cell_logp = 0.0;
+	for (int k = 0; k < a.T; k++) {
+		const double y = obs[k];
+		if (isnan(y)) continue;
+		const double x = value(k);
+		if (isnan(x)) {
+			double first_ok = a.timepoints[a.T - 1], last_ok = a.timepoints[0];
+			for (int m = 0; m < a.T; m++)
+				if (!isnan(value(m))) {
+					first_ok = a.timepoints[m];
+					break;
+				}
+			for (int m = a.T - 1; m >= 0; m--)
+				if (!isnan(value(m))) {
+					last_ok = a.timepoints[m];
+					break;
+				}
+			const double time_offset = fmin(fabs(a.timepoints[k] - first_ok), fabs(a.timepoints[k] - last_ok));
+			if (a.error_model == CP_ERR_STUDENT_T4) cell_logp += logpdf_tnu4(time_offset, 0.0, a.missing_stdev);
+			else cell_logp += -log(a.missing_stdev) - 0.91893853320467274178032973640562 - time_offset * time_offset / (2.0 * a.missing_stdev * a.missing_stdev);
+		} else if (a.error_model == CP_ERR_NORMAL) {
+			const double d = y - x;
+			cell_logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
+		} else if (a.error_model == CP_ERR_STUDENT_T4) {
+			cell_logp += logpdf_tnu4(y, x, stdev);
+		} else { // .cpp:272-283: sigma from the simulated value
+			double sigma = prop_stdev * fmax(x, 0.0);
+			if (a.error_model == CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL) sigma += stdev;
+			const double d = y - x;
+			cell_logp += -log(sigma) - 0.91893853320467274178032973640562 - d * d * (1.0 / (2.0 * (sigma * sigma)));
+		}
+	}
+	a.lik[((long long)c * a.n_obs + i) * a.n_sim + j] = cell_logp;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Lane-parallel right-hand side.
@@ -1064,6 +1154,18 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 				if (sp < 0 || sp >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species@%zu index out of range", k + 1);
 		}
 	}
+	if (cp.any_time_course()) {
+		// what the per-cell likelihood is built for: no parent information (non-dividing cells), all cells on one
+		// device, as many observed as simulated cells (the reference refuses anything else, DataLikelihoodTimeCourse.cpp:178-187)
+		if (cp.division()) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course with dividing / dying cells (parent information) is not built");
+		if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course is not split over ranks (every observed cell is compared with every simulated cell)");
+		if (cp.num_cells > 4096) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course with more than 4096 cells (the matching is O(n^3) on the host)");
+		if (cp.data_kind == 1 && (cp.R != cp.num_cells || cp.relative_to_time_average))
+			return fail(BCM3B200_ERR_ARG, "data_kind time_course needs num_replicates (observed cells) = num_cells and no relative_to_time_average");
+		for (size_t k = 0; k < cp.more.size(); k++)
+			if (cp.more[k]->data_kind == 1 && (cp.more[k]->R != cp.num_cells || cp.more[k]->relative_to_time_average))
+				return fail(BCM3B200_ERR_ARG, "data_kind@%zu time_course needs num_replicates@%zu (observed cells) = num_cells and no relative_to_time_average", k + 1, k + 1);
+	}
 	if (cp.division()) {
 		if (cp.cytokinesis_ix >= cp.N || cp.apoptosis_ix >= cp.N) return fail(BCM3B200_ERR_ARG, "cytokinesis_species / apoptosis_species index out of range");
 		if (cp.divide_cells && cp.cytokinesis_ix >= 0) {
@@ -1446,6 +1548,7 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	la.weight = cp.weight;
 	la.missing_stdev = cp.missing_simulation_time_stdev;
 	la.logp = cp.d_logp.p;
+	la.kind = cp.data_kind;
 	cellpop_datalik_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>(la, (int)C);
 	CUDA_TRY(cudaGetLastError());
 	// the further data sets of the experiment, from their own rows of the averages, added in order
@@ -1471,10 +1574,122 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 		la.scale_fixed = m.scale_fixed;
 		la.weight = m.weight;
 		la.missing_stdev = m.missing_stdev;
+		la.kind = m.data_kind;
 		cellpop_datalik_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>(la, (int)C);
 		CUDA_TRY(cudaGetLastError());
 		cp.last_launches++;
 		row0 += m.T;
+	}
+	return BCM3B200_OK;
+}
+
+// The per-cell time_course data sets of the handle (DataLikelihoodTimeCourse::Evaluate, .cpp:230-365): the [observed x
+// simulated] block of cell log-likelihoods on the device, then per chain on the host the reference's admission rules (a NaN
+// anywhere or an observed cell without enough finite entries: -inf), the matching (matching_host.cuh) and the sum of the matched
+// entries in observed-cell order, times the data set's weight. The terms are added to logp [C] (host) after the
+// population-average data sets' terms, data set by data set.
+inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st, double* logp)
+{
+	int row0 = 0;
+	for (int k = -1; k < (int)cp.more.size(); k++) {
+		const CellPopState::MoreData* m = (k >= 0) ? cp.more[(size_t)k].get() : nullptr;
+		const int T = m ? m->T : cp.T;
+		const int kind = m ? m->data_kind : cp.data_kind;
+		if (kind == 1) {
+			const int n = cp.cells_local;
+			CpCellLikArgs a;
+			a.cell_values = cp.d_cellvals.p;
+			a.rows = cp.rows();
+			a.cell_stride = cp.capacity();
+			a.row0 = row0;
+			a.T = T;
+			a.n_obs = n;
+			a.n_sim = n;
+			a.nvar = cp.nvar;
+			a.error_model = m ? m->error_model : cp.error_model;
+			a.stdev_relative_to_scale = (m ? m->stdev_relative_to_scale : cp.stdev_relative_to_scale) ? 1 : 0;
+			a.transformed = cp.d_transformed.p;
+			a.timepoints = m ? m->d_time.p : cp.d_time.p;
+			a.observed = m ? m->d_obs.p : cp.d_obs.p;
+			a.stdev_ix = m ? m->stdev_ix : cp.stdev_ix;
+			a.offset_ix = m ? m->offset_ix : cp.offset_ix;
+			a.scale_ix = m ? m->scale_ix : cp.scale_ix;
+			a.prop_stdev_ix = m ? m->prop_stdev_ix : cp.prop_stdev_ix;
+			a.stdev_fixed = m ? m->stdev_fixed : cp.stdev_fixed;
+			a.offset_fixed = m ? m->offset_fixed : cp.offset_fixed;
+			a.scale_fixed = m ? m->scale_fixed : cp.scale_fixed;
+			a.prop_stdev_fixed = m ? m->prop_stdev_fixed : cp.prop_stdev_fixed;
+			a.missing_stdev = m ? m->missing_stdev : cp.missing_simulation_time_stdev;
+			const double weight = m ? m->weight : cp.weight;
+			const size_t block = (size_t)n * n;
+			CUDA_TRY(cp.d_cell_lik.ensure(C * block));
+			a.lik = cp.d_cell_lik.p;
+			if (n > 0) {
+				cellpop_cell_likelihood_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)n, (unsigned)C), 128, 0, st>>>(a);
+				CUDA_TRY(cudaGetLastError());
+				cp.last_launches++;
+				cp.total_launches++;
+			}
+			cp.h_cell_lik.resize(C * block);
+			CUDA_TRY(cudaMemcpyAsync(cp.h_cell_lik.data(), cp.d_cell_lik.p, sizeof(double) * C * block, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+			auto chain_term = [&](size_t c) {
+				const double ninf = -std::numeric_limits<double>::infinity();
+				if (!(logp[c] > ninf)) return; // already -inf (a failed cell, an earlier data set) or NaN: nothing to add to
+				const double* L = cp.h_cell_lik.data() + c * block;
+				for (int i = 0; i < n; i++) {
+					int finite_count = 0;
+					for (int j = 0; j < n; j++) {
+						const double v = L[(size_t)i * n + j];
+						if (v != v) { // .cpp:301-304
+							logp[c] = ninf;
+							return;
+						}
+						if (v > ninf) finite_count++;
+					}
+					if (finite_count < n) { // .cpp:316-320
+						logp[c] = ninf;
+						return;
+					}
+				}
+				std::vector<double> cost(block);
+				for (size_t e = 0; e < block; e++) cost[e] = -L[e];
+				const std::vector<int> match = payor_matching_complete(n, cost.data());
+				if ((int)match.size() != n) {
+					logp[c] = ninf;
+					return;
+				}
+				double term = 0.0;
+				for (int i = 0; i < n; i++) {
+					if (match[i] < 0) {
+						logp[c] = ninf;
+						return;
+					}
+					term += L[(size_t)i * n + match[i]];
+				}
+				logp[c] += term * weight;
+			};
+			// the matching is O(n^3) scalar work per chain: the chains go to the host's cores
+			size_t workers = std::thread::hardware_concurrency();
+			if (workers < 1) workers = 1;
+			if (workers > C) workers = C;
+			if (workers <= 1 || n < 32) {
+				for (size_t c = 0; c < C; c++) chain_term(c);
+			} else {
+				std::atomic<size_t> next(0);
+				std::vector<std::thread> th;
+				for (size_t w = 0; w < workers; w++)
+					th.emplace_back([&]() {
+						for (;;) {
+							const size_t c = next.fetch_add(1);
+							if (c >= C) break;
+							chain_term(c);
+						}
+					});
+				for (auto& t : th) t.join();
+			}
+		}
+		row0 += T;
 	}
 	return BCM3B200_OK;
 }
@@ -1504,6 +1719,10 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	CUDA_TRY(cudaStreamSynchronize(st));
 	float ms = 0.f;
 	if (cudaEventElapsedTime(&ms, cp.ev0, cp.ev1) == cudaSuccess) cp.last_kernel_ms = ms;
+	if (cp.any_time_course()) {
+		rc = cellpop_time_course_terms(cp, C, st, logp);
+		if (rc != BCM3B200_OK) return rc;
+	}
 	if (status)
 		for (size_t c = 0; c < C; c++) status[c] = std::isnan(logp[c]) ? BCM3B200_STATUS_NAN : BCM3B200_STATUS_OK;
 	cp.num_evaluations += (int64_t)C;

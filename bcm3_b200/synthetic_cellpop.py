@@ -252,6 +252,40 @@ def make_cellpop_problem(N: int = 12, num_cells: int = 10_000, T: int = 50, t_en
                           variability=variability, stdev_ix=VAR_STDEV)
 
 
+def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end: float = 8.0, seed: int = 41, noise: float = 0.03,
+                             missing_fraction: float = 0.0, two_species_readout: bool = False, rate_decades: float = 2.0) -> CellPopProblem:
+    """<data type="time_course">: one observed trajectory per cell (live-cell imaging), as many observed as simulated cells. The
+    observations are the trajectories of `num_cells` cells at the reference parameters (their own quasi-random draws, in a shuffled
+    order) plus noise: the likelihood has to find out which simulated cell goes with which observed one."""
+    from scipy.integrate import solve_ivp
+    from scipy.special import ndtri
+
+    base = make_cellpop_problem(N=N, num_cells=num_cells, T=T, t_end=t_end, seed=seed, data_cells=2, two_species_readout=two_species_readout,
+                                rate_decades=rate_decades)
+    v = default_values()
+    tv = np.where(base.transforms == TRANSFORM_LOG10, 10.0 ** v, v)
+    f = python_rhs(base.derivative_code, N)
+    rng = np.random.default_rng(seed + 2000)
+    u = sobol_points(2 * num_cells, len(base.variability))[num_cells:]  # other draws than the simulated cells will take
+    observed = np.empty((num_cells, T))
+    for ci in range(num_cells):
+        p = tv.copy()
+        y0 = base.initial_conditions.copy()
+        z = ndtri(u[ci]) * math.exp(tv[VAR_VARIABILITY_SCALE])
+        p[VAR_K_IN] *= math.exp(z[0])
+        p[VAR_K_DEG] *= math.exp(-z[1])
+        y0[1] += ndtri(u[ci][2]) * 0.01
+        sol = solve_ivp(lambda t, y: f(t, y, base.constant_species, p), (0.0, float(base.timepoints[-1])), y0, method="LSODA", t_eval=base.timepoints,
+                        rtol=1e-7, atol=1e-9)
+        observed[ci] = sol.y[base.obs_species].sum(axis=0)
+    observed = observed[rng.permutation(num_cells)] + noise * rng.standard_normal(observed.shape)
+    if missing_fraction > 0:
+        observed[rng.uniform(size=observed.shape) < missing_fraction] = np.nan
+    import dataclasses
+
+    return dataclasses.replace(base, observed=observed, data_kind="time_course", stdev_ix=None, stdev=noise * 1.5)
+
+
 def make_chain_values(C: int, seed: int = 20261018) -> np.ndarray:
     base = default_values()
     out = np.empty((C, NUM_VARIABLES))

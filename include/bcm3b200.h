@@ -257,6 +257,14 @@ const char* bcm3b200_last_error(void);
 /* number of usable CUDA devices (0 when there is no driver / no GPU) */
 int bcm3b200_device_count(void);
 
+/* The host-side step of the per-cell time_course likelihood (cell_population, data_kind = time_course), exported for callers
+ * and tests that want it on its own: the assignment of n observed cells (rows of cost [n][n]) to n simulated cells (columns)
+ * that the reference's hungarianMinimumWeightPerfectMatching returns for the complete edge list
+ * (dependencies/hungarian2/hungarian.cpp as DataLikelihoodTimeCourse.cpp:323 calls it -- not always the minimum-cost
+ * matching, see bcm3_b200/csrc/matching_host.cuh). match [n]: the column of every row; BCM3B200_ERR_STATE (match = -1) when no
+ * perfect matching was found. Pure host code: needs no device. */
+int bcm3b200_match_cells(int n, const double* cost, int32_t* match);
+
 #ifdef __cplusplus
 }
 #endif

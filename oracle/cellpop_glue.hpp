@@ -30,6 +30,10 @@
 namespace cellpop_glue {
 
 double ndtri(double p); // defined by the including translation unit
+// minimum-cost perfect matching of n_left left nodes (rows of cost [n_left][n_right]) to right nodes, with the call shape of the
+// reference's hungarianMinimumWeightPerfectMatching(n, n_right, edges, edge_count): defined by the including translation unit
+// (oracle/ref: the reference's own dependencies/hungarian2/hungarian.cpp; oracle/cellpop_port.cpp: a restatement)
+std::vector<int> hungarian_match(int n, int n_right, int n_left, const std::vector<double>& cost);
 
 inline double transform_variable(int tr, double x)
 {
@@ -340,6 +344,98 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		}
 	}
 	if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = population_average[i];
+
+	if (pr.data_kind == 1) {
+		// <data type="time_course">: DataLikelihoodTimeCourse::Evaluate (.cpp:230-365) with CalculateCellLikelihood (.cpp:431-505) and
+		// CalculateMissingValueLikelihood (.cpp:566-588) -- synchronize="none", no parent information, one marker, no offset/scale
+		// optimisation, no saturation. The trajectory of simulated cell j is column j of xs (NotifySimulatedValue .cpp:367-404 adds the
+		// species of a sum); observed cell i is row i of `observed`.
+		const int n_obs = R, n_sim = nactive;
+		double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
+		const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
+		const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
+		if (pr.stdev_relative_to_scale) stdev *= scale;
+		const double prop_stdev = (pr.proportional_stdev_ix >= 0) ? transformed[pr.proportional_stdev_ix] : pr.proportional_stdev;
+		std::vector<double> traj((size_t)T * n_sim), min_log_sigma, inv_two_sigma_sq_cell;
+		for (int k = 0; k < T; k++)
+			for (int j = 0; j < n_sim; j++) {
+				double v = xs[(size_t)k * ncell + j];
+				v *= scale; // .cpp:236-241
+				v += offset;
+				traj[(size_t)k * n_sim + j] = v;
+			}
+		if (pr.error_model == 2 || pr.error_model == 3) { // .cpp:272-283
+			min_log_sigma.resize(traj.size());
+			inv_two_sigma_sq_cell.resize(traj.size());
+			for (size_t e = 0; e < traj.size(); e++) {
+				double sigma = prop_stdev * std::max(traj[e], 0.0);
+				if (pr.error_model == 3) sigma += stdev;
+				min_log_sigma[e] = -log(sigma);
+				inv_two_sigma_sq_cell[e] = 1.0 / (2.0 * (sigma * sigma));
+			}
+		}
+		auto missing_value = [&](int j, int k) { // .cpp:566-588
+			double first_ok = pr.timepoints[T - 1], last_ok = pr.timepoints[0];
+			for (int m = 0; m < T; m++) if (!std::isnan(traj[(size_t)m * n_sim + j])) { first_ok = pr.timepoints[m]; break; }
+			for (int m = T - 1; m >= 0; m--) if (!std::isnan(traj[(size_t)m * n_sim + j])) { last_ok = pr.timepoints[m]; break; }
+			const double time_offset = std::min(std::abs(pr.timepoints[k] - first_ok), std::abs(pr.timepoints[k] - last_ok));
+			return (pr.error_model == 1) ? logpdf_tnu4(time_offset, 0, pr.missing_stdev) : logpdf_normal(time_offset, 0, pr.missing_stdev);
+		};
+		const int n = std::max(n_obs, n_sim);
+		std::vector<double> cell_likelihoods((size_t)n * n, 0.0);
+		const double minus_log_sigma = -log(stdev), inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
+		for (int i = 0; i < n_obs; i++) {
+			int finite_count = 0;
+			for (int j = 0; j < n_sim; j++) {
+				double cell_logp = 0.0;
+				for (int k = 0; k < T; k++) {
+					const double y = pr.observed[(size_t)i * T + k];
+					if (std::isnan(y)) continue;
+					const double x = traj[(size_t)k * n_sim + j]; // offset 0 + scale 1 * trajectory without optimize_offset_scale
+					if (std::isnan(x)) {
+						cell_logp += missing_value(j, k);
+					} else if (pr.error_model == 0) {
+						const double d = y - x;
+						cell_logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
+					} else if (pr.error_model == 1) {
+						cell_logp += logpdf_tnu4(y, x, stdev);
+					} else {
+						const double d = y - x;
+						cell_logp += min_log_sigma[(size_t)k * n_sim + j] - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq_cell[(size_t)k * n_sim + j];
+					}
+				}
+				cell_likelihoods[(size_t)i * n + j] = cell_logp;
+				if (cell_logp != cell_logp) { // .cpp:301-304
+					*logp_out = -std::numeric_limits<double>::infinity();
+					return;
+				}
+				if (cell_logp > -std::numeric_limits<double>::infinity()) finite_count++;
+			}
+			if (finite_count < n_obs) { // .cpp:316-320
+				*logp_out = -std::numeric_limits<double>::infinity();
+				return;
+			}
+		}
+		std::vector<double> cost((size_t)n_obs * n_sim);
+		for (int i = 0; i < n_obs; i++)
+			for (int j = 0; j < n_sim; j++) cost[(size_t)i * n_sim + j] = -cell_likelihoods[(size_t)i * n + j];
+		const std::vector<int> matching = hungarian_match(n, n_sim, n_obs, cost); // .cpp:323
+		if ((int)matching.size() != n_obs) {
+			*logp_out = -std::numeric_limits<double>::infinity();
+			return;
+		}
+		double logp = 0.0;
+		for (int i = 0; i < n_obs; i++) {
+			const int j = matching[i];
+			if (j == -1) {
+				*logp_out = -std::numeric_limits<double>::infinity();
+				return;
+			}
+			logp += cell_likelihoods[(size_t)i * n + j];
+		}
+		*logp_out = logp * pr.weight;
+		return;
+	}
 
 	// Evaluate (.cpp:85-159)
 	double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;

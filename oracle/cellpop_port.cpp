@@ -12,6 +12,21 @@ double oracle_ndtri(double p);
 
 namespace cellpop_glue {
 double ndtri(double p) { return oracle_ndtri(p); }
+
+// The matching of observed to simulated cells. The reference's Hungarian implementation (dependencies/hungarian2/hungarian.cpp)
+// does not return the optimal matching as the reference calls it (an integer test in its initialisation, see
+// bcm3_b200/csrc/matching_host.cuh), so "any optimal matching" is not a checker for it. oracle/_ref links the reference's own
+// compiled implementation and is the anchor (golden fixtures, tests/test_cellpop_cpu.py compares the restatement with it on
+// random matrices); this port build has no access to the reference and takes the product's restatement -- for this one step
+// the port checks the cost matrix and the plumbing around the matching, not the matching.
+}
+#include "../bcm3_b200/csrc/matching_host.cuh"
+namespace cellpop_glue {
+std::vector<int> hungarian_match(int n, int n_right, int n_left, const std::vector<double>& cost)
+{
+	if (n_left != n_right || n != n_left) return std::vector<int>();
+	return bcm3b200::payor_matching_complete(n, cost.data());
+}
 }
 
 namespace {
@@ -123,4 +138,12 @@ extern "C" int oracle_cellpop_evaluate_counters(const oracle_cellpop_problem* pr
 {
 	if (prob && prob->num_species > BDF_NMAX) return -3;
 	return cellpop_glue::evaluate<PortSolver>(prob, num_chains, values, logp, nullptr, nullptr, nullptr, num_threads, counters);
+}
+
+extern "C" int oracle_hungarian_match(int n, const double* cost, int32_t* match)
+{
+	std::vector<double> c(cost, cost + (size_t)n * n);
+	const std::vector<int> m = cellpop_glue::hungarian_match(n, n, n, c);
+	for (int i = 0; i < n; i++) match[i] = ((int)m.size() == n) ? m[i] : -1;
+	return 0;
 }

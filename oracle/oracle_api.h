@@ -143,6 +143,10 @@ typedef struct {
 	int32_t cytokinesis_ix, apoptosis_ix; /* ODE species indices, -1: the model has no such species */
 	int32_t reset_ix[7];                  /* cytokinesis, nuclear_envelope, G1S_break, G2_break, spindle_components, assembled_spindle, chromatid_separation */
 	double max_dt; /* <experiment solver_max_timestep=> -> SetSolverParameter("max_dt") -> CVodeSetMaxStep (Cell.cpp:73); infinity: none */
+	/* 0: <data type="time_course_population_average">; 1: <data type="time_course"> -- per-cell trajectories, one observed cell per
+	 * row of `observed` ([num_replicates = observed cells][T]), every observed cell matched to one simulated cell by minimum-cost
+	 * perfect matching (DataLikelihoodTimeCourse.cpp:230-365, 431-505; synchronize="none", no parent information, one marker) */
+	int32_t data_kind;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.
@@ -185,6 +189,11 @@ typedef struct {
  * patient_ll [C][P] optional */
 int oracle_pharmaco_evaluate(const oracle_pharmaco_problem* prob, size_t num_chains, const double* values, double* logp, double* conc,
                              double* patient_ll, int num_threads);
+
+/* hungarianMinimumWeightPerfectMatching (dependencies/hungarian2/hungarian.cpp) on a complete cost matrix [n][n], the edge list
+ * in row order as DataLikelihoodTimeCourse::Evaluate builds it (.cpp:288-323); match [n], -1 everywhere without a matching.
+ * "ref": the reference's compiled function; "port": the product's restatement (see oracle/cellpop_port.cpp). */
+int oracle_hungarian_match(int n, const double* cost, int32_t* match);
 
 /* "ref" or "port" */
 const char* oracle_kind(void);

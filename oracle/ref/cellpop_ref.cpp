@@ -8,8 +8,24 @@
 namespace refglue {
 double ndtri(double p); // poppk_ref.cpp
 }
+#include "hungarian.h" // the reference's dependencies/hungarian2 (compiled in place by the Makefile)
+
 namespace cellpop_glue {
 double ndtri(double p) { return refglue::ndtri(p); }
+// the edge list exactly as DataLikelihoodTimeCourse::Evaluate builds it (.cpp:288-323): every (observed, simulated) pair in row order
+std::vector<int> hungarian_match(int n, int n_right, int n_left, const std::vector<double>& cost)
+{
+	std::vector<WeightedBipartiteEdge> edges((size_t)n_left * n_right);
+	int edge_count = 0;
+	for (int i = 0; i < n_left; i++)
+		for (int j = 0; j < n_right; j++) {
+			edges[edge_count].left = i;
+			edges[edge_count].right = j;
+			edges[edge_count].cost = cost[(size_t)i * n_right + j];
+			edge_count++;
+		}
+	return hungarianMinimumWeightPerfectMatching(n, n_right, edges, edge_count);
+}
 }
 
 namespace {
@@ -103,4 +119,14 @@ extern "C" int oracle_cellpop_evaluate_counters(const oracle_cellpop_problem* pr
                                                 int64_t* counters, int num_threads)
 {
 	return cellpop_glue::evaluate<RefSolver>(prob, num_chains, values, logp, nullptr, nullptr, nullptr, num_threads, counters);
+}
+
+/* the reference's compiled hungarianMinimumWeightPerfectMatching on a complete [n][n] cost matrix, edges in row order as
+ * DataLikelihoodTimeCourse::Evaluate builds them; match [n] (-1 everywhere when it returns no matching). */
+extern "C" int oracle_hungarian_match(int n, const double* cost, int32_t* match)
+{
+	std::vector<double> c(cost, cost + (size_t)n * n);
+	const std::vector<int> m = cellpop_glue::hungarian_match(n, n, n, c);
+	for (int i = 0; i < n; i++) match[i] = ((int)m.size() == n) ? m[i] : -1;
+	return 0;
 }

@@ -50,6 +50,14 @@ CASES = {
     "cellpop_dividing_two_generations": (dict(_builder="dividing", M=5, num_cells=16, max_cells=400, t_end=5.5, T=16), 3, {}),
     # the same with an "apoptosis" species: some cells die before or instead of dividing
     "cellpop_dividing_with_apoptosis": (dict(_builder="dividing", M=5, num_cells=16, max_cells=400, t_end=5.5, T=16, with_apoptosis=True), 3, {}),
+    # <data type="time_course">: one observed trajectory per cell, every observed cell matched to one simulated cell by the
+    # reference's own Hungarian implementation (DataLikelihoodTimeCourse.cpp:230-365, dependencies/hungarian2 compiled into oracle/_ref)
+    "cellpop_time_course_n8_normal": (dict(_builder="time_course", N=8, num_cells=24, T=12, seed=41), 3, {}),
+    "cellpop_time_course_n6_t4_missing": (dict(_builder="time_course", N=6, num_cells=40, T=10, seed=42, missing_fraction=0.15,
+                                               two_species_readout=True), 3,
+                                          dict(error_model="student_t4", offset=0.01, scale=1.1, weight=0.5)),
+    "cellpop_time_course_n6_addprop": (dict(_builder="time_course", N=6, num_cells=33, T=10, seed=43), 2,
+                                       dict(error_model="additive_proportional_normal", proportional_stdev=0.1, _positive_data=True)),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
@@ -68,6 +76,9 @@ def main():
         if builder == "dividing":
             prob = sc.make_dividing_problem(**kw)
             fixed_values = sc.make_chain_values(C, seed=5)
+        elif builder == "time_course":
+            prob = dataclasses.replace(sc.make_time_course_problem(**kw), **tweaks)
+            fixed_values = None
         elif builder == "sbml_cell_cycle":
             from tests.util import sbml_cell_cycle_problem, sbml_cell_cycle_values
 

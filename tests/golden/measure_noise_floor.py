@@ -40,7 +40,10 @@ def resave(name, **extra):
 def main():
     a = oracle.load("ref")
     b = oracle.Oracle("ref", STRICT)
+    only = sys.argv[1:]  # fixture names: measure just these
     for name in GOLDEN_NAMES:
+        if only and name not in only:
+            continue
         prob, gold = load_golden(name)
         la = a.poppk_evaluate(prob, gold["values"], threads=2, want_counters=True)
         lb = b.poppk_evaluate(prob, gold["values"], threads=2, want_counters=True)
@@ -52,6 +55,8 @@ def main():
         resave(name, noise_floor=floor, noise_floor_counter_match=np.float64(same))
         print(f"{name:40s} floor {floor.max():.2e}  systems with identical counters between the two builds {same:.4f}")
     for name in CELLPOP_GOLDEN_NAMES:
+        if only and name not in only:
+            continue
         prob, gold = load_cellpop_golden(name)
         oracle.rhs_build = "strict"
         ra = a.cellpop_evaluate(prob, gold["values"], threads=1, want_steps=True, want_cell_values=True)

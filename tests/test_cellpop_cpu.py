@@ -162,3 +162,65 @@ def test_unrecognised_generated_text_keeps_the_scalar_form(built, tmp_path, monk
     (d,) = [d for d in os.listdir(tmp_path) if d.startswith("cellpop_")]
     src = open(tmp_path / d / "model.cu").read()
     assert "CP_RHS_LANES 1" not in src and "generated_ratelaws_lanes" not in src
+
+
+# ---- the per-cell time_course likelihood's matching (bcm3b200_match_cells: host code, no device needed) ----
+
+def _matching_cases():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matching_cases.npz"))
+    costs, matches, at_c, at_m = z["costs"], z["matches"], 0, 0
+    for n in z["sizes"]:
+        n = int(n)
+        yield costs[at_c:at_c + n * n].reshape(n, n), matches[at_m:at_m + n]
+        at_c += n * n
+        at_m += n
+
+
+def test_matching_reproduces_the_reference_matchings():
+    """The product's restatement of the reference's Hungarian implementation (bcm3_b200/csrc/matching_host.cuh) against matchings
+    the reference's own compiled function returned (tests/golden/make_golden_matching.py) -- 90 matrices, a fifth of which the
+    reference does NOT match optimally: the matching is part of the likelihood's value, so it is the reference's that counts."""
+    from bcm3_b200 import _lib
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matching_cases.npz"))
+    assert int(z["suboptimal"]) > 0  # the fixture does exercise the quirk
+    count = 0
+    for cost, want in _matching_cases():
+        got = _lib.match_cells(cost)
+        assert got is not None and np.array_equal(got, want)
+        assert sorted(got.tolist()) == list(range(len(got)))  # a perfect matching
+        count += 1
+    assert count == 90
+
+
+def test_matching_against_the_compiled_reference_on_fresh_matrices(ref):
+    from bcm3_b200 import _lib
+
+    rng = np.random.default_rng(7)
+    for trial in range(150):
+        n = int(rng.integers(1, 60))
+        cost = rng.normal(0.0, rng.uniform(0.2, 50.0), (n, n)) + rng.uniform(-500.0, 500.0)
+        if trial % 3 == 0:
+            cost = np.round(cost)
+        assert np.array_equal(_lib.match_cells(cost), ref.hungarian_match(cost))
+
+
+def test_time_course_likelihood_is_the_matched_sum_not_the_optimum(ref):
+    """DataLikelihoodTimeCourse::Evaluate sums the cell likelihoods of the matching its Hungarian call returns (.cpp:323-336); on
+    this fixture that is below the optimal assignment's sum -- the checker and the golden carry the reference's value."""
+    from scipy.optimize import linear_sum_assignment
+
+    prob, gold = load_cellpop_golden("cellpop_time_course_n8_normal")
+    assert prob.data_kind == "time_course" and prob.observed.shape == (prob.num_cells, prob.num_timepoints)
+    sim = gold["cell_values"]  # [C][T][cells]
+    n, sd = prob.num_cells, prob.stdev
+    below = 0
+    for c in range(sim.shape[0]):
+        d = prob.observed[:, :, None] - sim[c][None, :, :]                      # [observed][T][simulated]
+        lik = (-np.log(sd) - 0.9189385332046727 - d * d / (2 * sd * sd)).sum(axis=1)
+        match = ref.hungarian_match(-lik)
+        assert abs(lik[np.arange(n), match].sum() * prob.weight - gold["logp"][c]) <= 1e-9 * abs(gold["logp"][c])
+        r, col = linear_sum_assignment(-lik)
+        assert lik[r, col].sum() >= lik[np.arange(n), match].sum() - 1e-9
+        below += lik[r, col].sum() > lik[np.arange(n), match].sum() + 1e-6
+    assert below > 0

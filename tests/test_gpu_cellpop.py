@@ -1,6 +1,7 @@
 """GPU suite for the cell_population path: the CUDA integrators (compiled per model from the generated RHS text; the lane-group
 mapping is the default, the one-cell-per-warp and one-cell-per-thread mappings are kept selectable) through the C ABI, against
 the golden vectors of the compiled reference and against the CPU checker on fresh inputs."""
+import dataclasses
 import os
 
 import numpy as np
@@ -353,3 +354,40 @@ def test_solver_max_timestep(Evaluator, checker):
     assert (status == 0).all()
     assert_logp_parity(got, want["logp"], floor, "solver_max_timestep")
     assert abs(d["cell_steps"].mean() / want["cell_steps"].mean() - 1.0) < 0.01
+
+
+# ---- <data type="time_course">: per-cell trajectories, every observed cell matched to one simulated cell ----
+
+def test_time_course_fresh_problem_against_the_reference(Evaluator, checker):
+    """160 cells with an observed trajectory each (missing values, Student-t error model): the [observed x simulated] block of
+    cell log-likelihoods comes from the device, the matching from the host restatement of the reference's Hungarian call; the
+    checker runs the reference's own compiled solver and (oracle/_ref) its own compiled matching."""
+    prob = dataclasses.replace(sc.make_time_course_problem(N=8, num_cells=160, T=14, seed=51, missing_fraction=0.1), error_model="student_t4",
+                               scale=1.05, offset=-0.01, weight=0.7)
+    vals = sc.make_chain_values(5, seed=51)
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    again, _ = ev.evaluate(vals)
+    ev.close()
+    want, floor, _ = _fresh_reference(checker, prob, vals)
+    assert (status == 0).all() and np.isfinite(logp).all()
+    assert np.array_equal(logp, again)
+    assert_logp_parity(logp, want["logp"], floor, "time_course, 160 cells")
+
+
+def test_time_course_failed_cell_gives_minus_infinity(Evaluator):
+    prob = dataclasses.replace(sc.make_time_course_problem(N=6, num_cells=16, T=8, seed=52), solver_max_steps=15)
+    ev = Evaluator(prob)
+    logp, _ = ev.evaluate(sc.make_chain_values(2, seed=52))
+    ev.close()
+    assert np.all(logp == -np.inf)  # Simulate() fails => the experiment's likelihood is -inf (Experiment.cpp:356-358)
+
+
+def test_time_course_refuses_what_is_not_built(Evaluator):
+    from bcm3_b200._lib import Bcm3B200Error
+
+    prob = sc.make_time_course_problem(N=6, num_cells=16, T=8, seed=53)
+    with pytest.raises(Bcm3B200Error):  # fewer observed than simulated cells: the reference refuses it too (DataLikelihoodTimeCourse.cpp:178-187)
+        Evaluator(dataclasses.replace(prob, observed=prob.observed[:10])).close()
+    with pytest.raises(Bcm3B200Error):  # every observed cell is compared with every simulated cell: not split over ranks
+        Evaluator(prob, shard_rank=0, shard_count=2).close()

@@ -298,3 +298,43 @@ def test_cell_population_plugin_with_dividing_cells(built):
     got, desc = host_api.cellpop_evaluate(prior, lik, prob, species, values=vals, batched=True)
     assert "divide_cells=1" in desc and f"cytokinesis_species={M}" in desc
     assert np.array_equal(got, want)
+
+
+def test_cell_population_time_course_and_population_average_in_one_experiment(built):
+    """<data type="time_course"> (per-cell trajectories + matching) next to a population average over the same cells: one
+    integration, the plugin's result is the sum of the two data sets' terms as the reference adds them (Experiment.cpp:346-355),
+    each term from the CPU checker."""
+    import dataclasses
+    import math
+    import oracle
+    from bcm3_b200 import synthetic_cellpop as sc
+    from tests.util import cellpop_xml, open_cellpop_session, parity_tolerance
+
+    tc = sc.make_time_course_problem(N=8, num_cells=32, T=10, seed=61)
+    avg = dataclasses.replace(tc, data_kind="time_course_population_average", observed=np.nanmean(tc.observed, axis=0)[None, :] * 1.02,
+                              obs_species=[2, 3], stdev=0.05, error_model="student_t4")
+    prior, _, species = cellpop_xml(tc)
+    obs = lambda p: "+".join(species[s] for s in p.obs_species)
+    lik = ('<bcm_likelihood type="cell_population">'
+           f'<experiment name="imaging" model_file="cascade.xml" entry_time="0" num_cells="{tc.num_cells}" max_cells="{tc.num_cells}" divide_cells="false">'
+           '<cell_variability distribution="diagonal_gaussian">'
+           '<variable model_parameter="k_in" apply="multiplicative_log" scale="variability_scale"/>'
+           '<variable model_parameter="k_deg" apply="multiplicative_log" scale="variability_scale" negate="true"/>'
+           f'<variable initial_condition_species="x1" apply="additive" scale="{math.log(0.01)!r}"/>'
+           '</cell_variability>'
+           f'<data type="time_course" data_name="cells" species_name="{obs(tc)}" stdev="{tc.stdev!r}"/>'
+           f'<data type="time_course_population_average" data_name="bulk" species_name="{obs(avg)}" stdev="0.05" error_model="student_t4"/>'
+           '</experiment></bcm_likelihood>')
+    vals = sc.make_chain_values(3, seed=61)
+    out = {}
+    for share in (True, False):
+        s = open_cellpop_session(prior, lik, species, [[tc, avg]])
+        s.share_integration(share)
+        s.post_initialize()
+        out[share] = s.evaluate(vals, batched=True)
+        s.close()
+    chk = oracle.load("ref" if oracle.available("ref") else "port")
+    want = chk.cellpop_evaluate(tc, vals)["logp"] + chk.cellpop_evaluate(avg, vals)["logp"]
+    assert np.isfinite(want).all()
+    for share in (True, False):
+        assert np.all(np.abs(out[share] - want) <= parity_tolerance(None) * np.abs(want)), (share, out[share], want)

@@ -123,6 +123,8 @@ def load_cellpop_golden(name):
         extra.update(relative_to_time_average=bool(z["relative_to_time_average"]))
     if "simulation_end_time" in z.files:
         extra.update(simulation_end_time=float(z["simulation_end_time"]))
+    if "data_kind" in z.files:
+        extra.update(data_kind=str(z["data_kind"]))
     if "treatment_species" in z.files:
         extra.update(treatment_species=int(z["treatment_species"]), treatment_times=z["treatment_times"])
     if "divide_cells" in z.files and bool(z["divide_cells"]):
