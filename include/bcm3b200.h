@@ -68,8 +68,16 @@ extern "C" {
  *                       (Experiment.cpp:726-782, CellPopulation.cpp:36-104, Cell.cpp:119-148: a cell whose cytokinesis species
  *                        passes 1 is replaced by two daughters, one whose apoptosis species passes 1 ends; a chain that
  *                        outgrows max_cells or the quasi-random table evaluates to -inf; such handles cannot be sharded)
+ *                  data_kind=time_course_population_average|time_course (the <data type=>; default the population average).
+ *                       time_course = DataLikelihoodTimeCourse (src/cellpop/DataLikelihoodTimeCourse.cpp:230-365, 431-505,
+ *                        566-588) with synchronize="none", one marker and no parent information: "observed" holds one
+ *                        trajectory per OBSERVED CELL ([num_replicates = observed cells][T], NaN = missing), there are as
+ *                        many observed as simulated cells (the reference refuses anything else, .cpp:178-187), every pair's
+ *                        log-likelihood is computed on the device and the observed cells are matched to the simulated ones
+ *                        on the host exactly as the reference's Hungarian call does (bcm3b200_match_cells below); such
+ *                        handles cannot be sharded or combined with divide_cells
  *                  num_data_sets=<D <= 4>: the experiment's further <data> elements share this handle's ONE integration of
- *                       the cells; data set k >= 1 repeats num_timepoints, num_replicates, obs_species, error_model, weight,
+ *                       the cells; data set k >= 1 repeats num_timepoints, num_replicates, obs_species, error_model, weight, data_kind,
  *                       the stdev/offset/scale keys and the relative_to/missing keys with the suffix @k ("stdev_ix@1=5")
  *                       and supplies "timepoints@k", "observed@k"; the result is the sum over the data sets in order
  *                  [shard_rank=0] [shard_count=1] [device=0]
