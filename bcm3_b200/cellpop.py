@@ -31,6 +31,8 @@ class CellPopEvaluator:
         kv["variability_distribution"] = p.variability_distribution
         if p.data_kind != "time_course_population_average":
             kv["data_kind"] = p.data_kind
+        if p.value_relative_to_timepoint_ix is not None:
+            kv["value_relative_to_timepoint_ix"] = int(p.value_relative_to_timepoint_ix)
         kv["relative_to_time_average"] = int(p.relative_to_time_average)
         kv["stdev_relative_to_scale"] = int(p.stdev_relative_to_scale)
         if p.treatment_species is not None:

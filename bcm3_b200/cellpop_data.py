@@ -71,6 +71,10 @@ class CellPopProblem:
     # observed [observed cells][T], as many observed as simulated cells, every observed cell matched to one simulated cell by
     # minimum-cost perfect matching (DataLikelihoodTimeCourse.cpp:230-365); synchronize="none", no parent information, one marker
     data_kind: str = "time_course_population_average"
+    # "time_points" (DataLikelihoodTimePoints.cpp): observed [observed cell slots][T], NaN = no such cell at that timepoint -- at
+    # every timepoint the observed cells present are matched to simulated cells (snapshots of different cells per time);
+    # value_relative_to_timepoint_ix (DataLikelihoodBase.cpp:49): the simulated value relative to its own value at that timepoint
+    value_relative_to_timepoint_ix: int | None = None
     relative_to_time_average: bool = False   # <data relative_to_time_average="true">: log of the value over its time average
     # the time the experiment integrates its cells to when it has further data sets that end later (Experiment.cpp:655-656);
     # None: the last of `timepoints`

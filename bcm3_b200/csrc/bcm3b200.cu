@@ -185,7 +185,9 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 	{
 		const std::string dk = kv.count("data_kind") ? kv["data_kind"] : "time_course_population_average";
 		if (dk == "time_course") cp->data_kind = 1;
-		else if (dk != "time_course_population_average") return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind \"%s\" is not supported (time_course_population_average, time_course)", dk.c_str());
+		else if (dk == "time_points") cp->data_kind = 2;
+		else if (dk != "time_course_population_average") return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind \"%s\" is not supported (time_course_population_average, time_course, time_points)", dk.c_str());
+		cp->value_relative_to_timepoint_ix = get_int(kv, "value_relative_to_timepoint_ix", -1);
 	}
 	cp->treatment_species = get_int(kv, "treatment_species", -1);
 	cp->relative_to_time_average = get_int(kv, "relative_to_time_average", 0) != 0;
@@ -237,7 +239,9 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 		{
 			const std::string dk = kv.count(key("data_kind")) ? kv[key("data_kind")] : "time_course_population_average";
 			if (dk == "time_course") m->data_kind = 1;
+			else if (dk == "time_points") m->data_kind = 2;
 			else if (dk != "time_course_population_average") return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind \"%s\" is not supported", dk.c_str());
+			m->value_relative_to_timepoint_ix = get_int(kv, key("value_relative_to_timepoint_ix").c_str(), -1);
 		}
 		m->stdev_ix = get_int(kv, key("stdev_ix").c_str(), -1);
 		m->stdev_fixed = realk("stdev", 1.0);

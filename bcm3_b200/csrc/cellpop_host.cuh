@@ -33,7 +33,10 @@ struct CellPopState {
 	// [observed cells][T], num_replicates = observed cells = num_cells), every observed cell matched to one simulated cell
 	// (DataLikelihoodTimeCourse.cpp:230-365): the [observed x simulated] log-likelihood block is a kernel, the matching runs
 	// on the host (matching_host.cuh)
+	// 2 = time_points (DataLikelihoodTimePoints.cpp:209-345): "observed" is [observed cell slots][T], NaN = no such cell at that
+	// timepoint; at every timepoint the observed cells present are matched to the simulated cells that have a value there
 	int data_kind = 0;
+	int value_relative_to_timepoint_ix = -1; // time_points: simulated value = (x + offset) / x(that timepoint) * scale (DataLikelihoodBase.cpp:49)
 	int N = 0, Nc = 0, nvar = 0, Nn = 0, num_cells = 0, T = 0, R = 1, D = 0;
 	int entry_time_ix = -1;
 	double entry_time_fixed = 0.0;
@@ -65,7 +68,7 @@ struct CellPopState {
 	// they share the integration of the experiment's cells (Experiment.cpp:190-214, 298-312) -- the kernel interpolates at the
 	// union of all timepoints and every data set sums its own species -- and their log-likelihoods are added in order (:346-355)
 	struct MoreData {
-		int T = 0, R = 1, error_model = CP_ERR_NORMAL, data_kind = 0;
+		int T = 0, R = 1, error_model = CP_ERR_NORMAL, data_kind = 0, value_relative_to_timepoint_ix = -1;
 		int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
 		double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0, weight = 1.0, missing_stdev = 300.0;
 		bool relative_to_time_average = false, stdev_relative_to_scale = false;
@@ -114,9 +117,9 @@ struct CellPopState {
 	std::vector<double> h_cell_lik; // [C][observed][simulated] of the time_course data set being matched
 	bool any_time_course() const
 	{
-		if (data_kind == 1) return true;
+		if (data_kind != 0) return true;
 		for (const auto& m : more)
-			if (m->data_kind == 1) return true;
+			if (m->data_kind != 0) return true;
 		return false;
 	}
 	bool diagnostics = false;
@@ -412,7 +415,7 @@ struct CpLikArgs {
 	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
 	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, weight, missing_stdev;
 	double* logp; // [C]
-	int kind;     // 1: a per-cell time_course data set -- its term is added on the host after the matching, here it is 0
+	int kind;     // 1 / 2: a per-cell time_course / time_points data set -- its term is added on the host after the matching, here it is 0
 };
 
 // DataLikelihoodTimeCoursePopulationAverage::Evaluate (.cpp:85-159) for one species column; one thread per chain
@@ -424,7 +427,7 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 		a.logp[c] = -INFINITY;
 		return;
 	}
-	if (a.kind == 1) {
+	if (a.kind != 0) {
 		if (!a.accumulate) a.logp[c] = 0.0;
 		return;
 	}
@@ -519,6 +522,10 @@ struct CpCellLikArgs {
 	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
 	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, missing_stdev;
 	double* lik; // [C][n_obs][n_sim]
+	// time_points (DataLikelihoodTimePoints.cpp:255-290): only timepoint `only_k` (>= 0), the simulated value optionally relative
+	// to the cell's own value at timepoint `rel_k`, LogPdfNormal's division form; a simulated value that is missing gives NaN
+	// (the host leaves such cells out of the matching)
+	int only_k, rel_k;
 };
 __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 {
@@ -541,6 +548,28 @@ __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 	};
 	const double* obs = a.observed + (long long)i * a.T;
 	double cell_logp = 0.0;
+	if (a.only_k >= 0) {
+		const int k = a.only_k;
+		double x = traj[(long long)k * a.cell_stride];
+		if (a.rel_k >= 0) {
+			x += offset;
+			x /= traj[(long long)a.rel_k * a.cell_stride];
+			x *= scale;
+		} else {
+			x *= scale;
+			x += offset;
+		}
+		const double y = obs[k];
+		if (a.error_model == CP_ERR_NORMAL) {
+			const double two_sigma_sq = 2.0 * stdev * stdev, d = y - x;
+			cell_logp = -log(stdev) - 0.91893853320467274178032973640562 - d * d / two_sigma_sq;
+		} else {
+			cell_logp = logpdf_tnu4(y, x, stdev);
+		}
+		if (isnan(x)) cell_logp = NAN;
+		a.lik[((long long)c * a.n_obs + i) * a.n_sim + j] = cell_logp;
+		return;
+	}
 	for (int k = 0; k < a.T; k++) {
 		const double y = obs[k];
 		if (isnan(y)) continue;
@@ -1157,14 +1186,28 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	if (cp.any_time_course()) {
 		// what the per-cell likelihood is built for: no parent information (non-dividing cells), all cells on one
 		// device, as many observed as simulated cells (the reference refuses anything else, DataLikelihoodTimeCourse.cpp:178-187)
-		if (cp.division()) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course with dividing / dying cells (parent information) is not built");
-		if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course is not split over ranks (every observed cell is compared with every simulated cell)");
-		if (cp.num_cells > 4096) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course with more than 4096 cells (the matching is O(n^3) on the host)");
-		if (cp.data_kind == 1 && (cp.R != cp.num_cells || cp.relative_to_time_average))
-			return fail(BCM3B200_ERR_ARG, "data_kind time_course needs num_replicates (observed cells) = num_cells and no relative_to_time_average");
-		for (size_t k = 0; k < cp.more.size(); k++)
-			if (cp.more[k]->data_kind == 1 && (cp.more[k]->R != cp.num_cells || cp.more[k]->relative_to_time_average))
-				return fail(BCM3B200_ERR_ARG, "data_kind@%zu time_course needs num_replicates@%zu (observed cells) = num_cells and no relative_to_time_average", k + 1, k + 1);
+		if (cp.division()) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with dividing / dying cells is not built");
+		if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points is not split over ranks (every observed cell is compared with every simulated cell)");
+		if (cp.num_cells > 4096) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with more than 4096 cells (the matching is O(n^3) on the host)");
+		auto check_kind = [&](int kind, int R, int T, bool relative, int error_model, int rel_ix) -> int {
+			if (kind == 1 && (R != cp.num_cells || relative))
+				return fail(BCM3B200_ERR_ARG, "data_kind time_course needs num_replicates (observed cells) = num_cells and no relative_to_time_average");
+			if (kind == 2) {
+				if (R < 1 || R > cp.num_cells || relative)
+					return fail(BCM3B200_ERR_ARG, "data_kind time_points needs 1 <= num_replicates (observed cell slots) <= num_cells and no relative_to_time_average");
+				if (error_model != CP_ERR_NORMAL && error_model != CP_ERR_STUDENT_T4)
+					return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_points knows the normal and student_t4 error models (DataLikelihoodTimePoints.cpp:280-287)");
+				if (rel_ix >= T) return fail(BCM3B200_ERR_ARG, "value_relative_to_timepoint_ix out of range");
+			}
+			return BCM3B200_OK;
+		};
+		int rck = check_kind(cp.data_kind, cp.R, cp.T, cp.relative_to_time_average, cp.error_model, cp.value_relative_to_timepoint_ix);
+		if (rck != BCM3B200_OK) return rck;
+		for (size_t k = 0; k < cp.more.size(); k++) {
+			const CellPopState::MoreData& mk = *cp.more[k];
+			rck = check_kind(mk.data_kind, mk.R, mk.T, mk.relative_to_time_average, mk.error_model, mk.value_relative_to_timepoint_ix);
+			if (rck != BCM3B200_OK) return rck;
+		}
 	}
 	if (cp.division()) {
 		if (cp.cytokinesis_ix >= cp.N || cp.apoptosis_ix >= cp.N) return fail(BCM3B200_ERR_ARG, "cytokinesis_species / apoptosis_species index out of range");
@@ -1583,27 +1626,54 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	return BCM3B200_OK;
 }
 
-// The per-cell time_course data sets of the handle (DataLikelihoodTimeCourse::Evaluate, .cpp:230-365): the [observed x
+// The per-cell data sets of the handle. time_course (DataLikelihoodTimeCourse::Evaluate, .cpp:230-365): the [observed x
 // simulated] block of cell log-likelihoods on the device, then per chain on the host the reference's admission rules (a NaN
 // anywhere or an observed cell without enough finite entries: -inf), the matching (matching_host.cuh) and the sum of the matched
-// entries in observed-cell order, times the data set's weight. The terms are added to logp [C] (host) after the
-// population-average data sets' terms, data set by data set.
+// entries in observed-cell order. time_points (DataLikelihoodTimePoints::Evaluate, DataLikelihoodTimePoints.cpp:209-345): the same
+// per TIMEPOINT -- the observed cells present at that time against the simulated cells that have a value there, one block,
+// one matching and one partial sum per timepoint, accumulated in time order. Times the data set's weight; the terms are added
+// to logp [C] (host) after the population-average data sets' terms, data set by data set. Chains go to the host's cores.
+template <class F>
+inline void cellpop_for_each_chain(size_t C, bool parallel, F&& f)
+{
+	size_t workers = std::thread::hardware_concurrency();
+	if (workers < 1) workers = 1;
+	if (workers > C) workers = C;
+	if (!parallel || workers <= 1) {
+		for (size_t c = 0; c < C; c++) f(c);
+		return;
+	}
+	std::atomic<size_t> next(0);
+	std::vector<std::thread> th;
+	for (size_t w = 0; w < workers; w++)
+		th.emplace_back([&]() {
+			for (;;) {
+				const size_t c = next.fetch_add(1);
+				if (c >= C) break;
+				f(c);
+			}
+		});
+	for (auto& t : th) t.join();
+}
+
 inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st, double* logp)
 {
+	const double ninf = -std::numeric_limits<double>::infinity();
 	int row0 = 0;
 	for (int k = -1; k < (int)cp.more.size(); k++) {
 		const CellPopState::MoreData* m = (k >= 0) ? cp.more[(size_t)k].get() : nullptr;
 		const int T = m ? m->T : cp.T;
 		const int kind = m ? m->data_kind : cp.data_kind;
-		if (kind == 1) {
+		if (kind != 0) {
 			const int n = cp.cells_local;
+			const int n_obs = m ? m->R : cp.R; // time_course: = n; time_points: the observed cell slots (<= n)
 			CpCellLikArgs a;
 			a.cell_values = cp.d_cellvals.p;
 			a.rows = cp.rows();
 			a.cell_stride = cp.capacity();
 			a.row0 = row0;
 			a.T = T;
-			a.n_obs = n;
+			a.n_obs = n_obs;
 			a.n_sim = n;
 			a.nvar = cp.nvar;
 			a.error_model = m ? m->error_model : cp.error_model;
@@ -1620,73 +1690,110 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			a.scale_fixed = m ? m->scale_fixed : cp.scale_fixed;
 			a.prop_stdev_fixed = m ? m->prop_stdev_fixed : cp.prop_stdev_fixed;
 			a.missing_stdev = m ? m->missing_stdev : cp.missing_simulation_time_stdev;
+			a.only_k = -1;
+			a.rel_k = (kind == 2) ? (m ? m->value_relative_to_timepoint_ix : cp.value_relative_to_timepoint_ix) : -1;
 			const double weight = m ? m->weight : cp.weight;
-			const size_t block = (size_t)n * n;
-			CUDA_TRY(cp.d_cell_lik.ensure(C * block));
+			const size_t block = (size_t)n_obs * n;
+			CUDA_TRY(cp.d_cell_lik.ensure(C * block ? C * block : 1));
 			a.lik = cp.d_cell_lik.p;
-			if (n > 0) {
-				cellpop_cell_likelihood_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)n, (unsigned)C), 128, 0, st>>>(a);
+			cp.h_cell_lik.resize(C * block);
+			auto run_block = [&]() -> int { // the block for a.only_k (or all timepoints) to the host
+				if (block == 0) return BCM3B200_OK;
+				cellpop_cell_likelihood_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)n_obs, (unsigned)C), 128, 0, st>>>(a);
 				CUDA_TRY(cudaGetLastError());
 				cp.last_launches++;
 				cp.total_launches++;
-			}
-			cp.h_cell_lik.resize(C * block);
-			CUDA_TRY(cudaMemcpyAsync(cp.h_cell_lik.data(), cp.d_cell_lik.p, sizeof(double) * C * block, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaStreamSynchronize(st));
-			auto chain_term = [&](size_t c) {
-				const double ninf = -std::numeric_limits<double>::infinity();
-				if (!(logp[c] > ninf)) return; // already -inf (a failed cell, an earlier data set) or NaN: nothing to add to
-				const double* L = cp.h_cell_lik.data() + c * block;
-				for (int i = 0; i < n; i++) {
-					int finite_count = 0;
-					for (int j = 0; j < n; j++) {
-						const double v = L[(size_t)i * n + j];
-						if (v != v) { // .cpp:301-304
+				CUDA_TRY(cudaMemcpyAsync(cp.h_cell_lik.data(), cp.d_cell_lik.p, sizeof(double) * C * block, cudaMemcpyDeviceToHost, st));
+				CUDA_TRY(cudaStreamSynchronize(st));
+				return BCM3B200_OK;
+			};
+			if (kind == 1) {
+				int rc = run_block();
+				if (rc != BCM3B200_OK) return rc;
+				cellpop_for_each_chain(C, n >= 32, [&](size_t c) {
+					if (!(logp[c] > ninf)) return; // already -inf (a failed cell, an earlier data set) or NaN: nothing to add to
+					const double* L = cp.h_cell_lik.data() + c * block;
+					for (int i = 0; i < n; i++) {
+						int finite_count = 0;
+						for (int j = 0; j < n; j++) {
+							const double v = L[(size_t)i * n + j];
+							if (v != v) { // .cpp:301-304
+								logp[c] = ninf;
+								return;
+							}
+							if (v > ninf) finite_count++;
+						}
+						if (finite_count < n) { // .cpp:316-320
 							logp[c] = ninf;
 							return;
 						}
-						if (v > ninf) finite_count++;
 					}
-					if (finite_count < n) { // .cpp:316-320
+					std::vector<double> cost(block);
+					for (size_t e = 0; e < block; e++) cost[e] = -L[e];
+					const std::vector<int> match = payor_matching_complete(n, cost.data());
+					if ((int)match.size() != n) {
 						logp[c] = ninf;
 						return;
 					}
-				}
-				std::vector<double> cost(block);
-				for (size_t e = 0; e < block; e++) cost[e] = -L[e];
-				const std::vector<int> match = payor_matching_complete(n, cost.data());
-				if ((int)match.size() != n) {
-					logp[c] = ninf;
-					return;
-				}
-				double term = 0.0;
-				for (int i = 0; i < n; i++) {
-					if (match[i] < 0) {
-						logp[c] = ninf;
-						return;
+					double term = 0.0;
+					for (int i = 0; i < n; i++) {
+						if (match[i] < 0) {
+							logp[c] = ninf;
+							return;
+						}
+						term += L[(size_t)i * n + match[i]];
 					}
-					term += L[(size_t)i * n + match[i]];
-				}
-				logp[c] += term * weight;
-			};
-			// the matching is O(n^3) scalar work per chain: the chains go to the host's cores
-			size_t workers = std::thread::hardware_concurrency();
-			if (workers < 1) workers = 1;
-			if (workers > C) workers = C;
-			if (workers <= 1 || n < 32) {
-				for (size_t c = 0; c < C; c++) chain_term(c);
+					logp[c] += term * weight;
+				});
 			} else {
-				std::atomic<size_t> next(0);
-				std::vector<std::thread> th;
-				for (size_t w = 0; w < workers; w++)
-					th.emplace_back([&]() {
-						for (;;) {
-							const size_t c = next.fetch_add(1);
-							if (c >= C) break;
-							chain_term(c);
+				const std::vector<double>& observed = m ? m->observed : cp.data["observed"];
+				std::vector<double> term(C, 0.0);
+				std::vector<char> dead(C, 0);
+				for (int ti = 0; ti < T; ti++) {
+					std::vector<int> rows;
+					for (int i = 0; i < n_obs; i++)
+						if (std::isfinite(observed[(size_t)i * T + ti])) rows.push_back(i);
+					if (rows.empty()) continue; // .cpp:229-231
+					a.only_k = ti;
+					int rc = run_block();
+					if (rc != BCM3B200_OK) return rc;
+					const int fd = (int)rows.size();
+					cellpop_for_each_chain(C, fd >= 32, [&](size_t c) {
+						if (dead[c] || !(logp[c] > ninf)) return;
+						const double* L = cp.h_cell_lik.data() + c * block;
+						// the simulated cells with a value at this timepoint (and at the reference timepoint), .cpp:234-239: the block holds
+						// NaN for the others in every row
+						std::vector<int> cols;
+						const double* first = L + (size_t)rows[0] * n;
+						for (int j = 0; j < n; j++)
+							if (first[j] == first[j]) cols.push_back(j);
+						if ((int)cols.size() < fd) { // .cpp:241-245
+							dead[c] = 1;
+							return;
+						}
+						// the reference's Hungarian call keeps the edges to the first fd right nodes (hungarian.cpp:81)
+						std::vector<double> cost((size_t)fd * fd);
+						for (int p = 0; p < fd; p++)
+							for (int q = 0; q < fd; q++) cost[(size_t)p * fd + q] = -L[(size_t)rows[p] * n + cols[q]];
+						const std::vector<int> match = payor_matching_complete(fd, cost.data());
+						if ((int)match.size() != fd) {
+							dead[c] = 1;
+							return;
+						}
+						for (int p = 0; p < fd; p++) {
+							if (match[p] < 0) {
+								dead[c] = 1;
+								return;
+							}
+							term[c] += L[(size_t)rows[p] * n + cols[match[p]]];
 						}
 					});
-				for (auto& t : th) t.join();
+				}
+				for (size_t c = 0; c < C; c++) {
+					if (!(logp[c] > ninf)) continue;
+					if (dead[c]) logp[c] = ninf;
+					else logp[c] += term[c] * weight;
+				}
 			}
 		}
 		row0 += T;

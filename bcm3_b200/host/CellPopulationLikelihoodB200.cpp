@@ -135,10 +135,19 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 			// DataLikelihoodBase::Create (DataLikelihoodBase.cpp:17-36) + DataLikelihoodTimeCoursePopulationAverage::Load
 			// DataLikelihoodTimeCourse::Load (.cpp:20-215) for the per-cell type: what it can do beyond the slice built here is refused
 			const std::string type = c.get("type");
-			if (type != "time_course_population_average" && type != "time_course")
-				return Fail("data type \"" + type + "\" is not supported by the GPU path (time_course_population_average, time_course)");
+			if (type != "time_course_population_average" && type != "time_course" && type != "time_points")
+				return Fail("data type \"" + type + "\" is not supported by the GPU path (time_course_population_average, time_course, time_points)");
 			DataSet ds;
 			ds.type = type;
+			if (type == "time_points") {
+				// DataLikelihoodTimePoints::Load (DataLikelihoodTimePoints.cpp:20-43) + DataLikelihoodBase.cpp:49
+				const std::string sync = c.get("synchronize", "");
+				if (!sync.empty() && sync != "none") return Fail("time_points data with synchronize=\"" + sync + "\" needs stored integration points: not supported by the GPU path");
+				if (c.get_bool("relative_to_time_average", false)) return Fail("relative_to_time_average belongs to time_course_population_average data");
+				const std::string em = c.get("error_model", "normal");
+				if (em != "normal" && em != "student_t4") return Fail("time_points data knows the normal and student_t4 error models (DataLikelihoodTimePoints.cpp:280-287)");
+				ds.value_relative_to_timepoint_ix = (long)c.get_real("value_relative_to_timepoint_ix", -1.0);
+			}
 			if (type == "time_course") {
 				const std::string sync = c.get("synchronize", "");
 				if (!sync.empty() && sync != "none") return Fail("time_course data with synchronize=\"" + sync + "\" needs stored integration points: not supported by the GPU path");
@@ -328,7 +337,8 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	  << ";solver_absolute_tolerance=" << e.solver_abs_tol << ";solver_min_timestep=" << e.solver_min_timestep << ";solver_max_steps=" << e.solver_max_steps
 	  << ";relative_to_time_average=" << (ds.relative_to_time_average ? 1 : 0) << ";stdev_relative_to_scale=" << (ds.stdev_relative_to_scale ? 1 : 0) << ";error_model=" << ds.error_model << ";weight=" << ds.weight
 	  << ";missing_simulation_time_stdev=" << ds.missing_stdev << ";device=" << device << ";compile_only=" << (compile_only ? 1 : 0);
-	if (ds.type == "time_course") d << ";data_kind=time_course";
+	if (ds.type != "time_course_population_average") d << ";data_kind=" << ds.type;
+	if (ds.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix=" << ds.value_relative_to_timepoint_ix;
 	if (simulation_end_time > data.timepoints.back()) d << ";simulation_end_time=" << simulation_end_time;
 	if (std::isfinite(e.solver_max_timestep)) d << ";solver_max_timestep=" << e.solver_max_timestep;
 	if (divides) {
@@ -364,7 +374,8 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		d << ";num_timepoints" << sfx << "=" << f.data.timepoints.size() << ";num_replicates" << sfx << "=" << f.data.num_replicates << ";relative_to_time_average" << sfx
 		  << "=" << (f.relative_to_time_average ? 1 : 0) << ";stdev_relative_to_scale" << sfx << "=" << (f.stdev_relative_to_scale ? 1 : 0) << ";error_model" << sfx << "="
 		  << f.error_model << ";weight" << sfx << "=" << f.weight << ";missing_simulation_time_stdev" << sfx << "=" << f.missing_stdev;
-		if (f.type == "time_course") d << ";data_kind" << sfx << "=time_course";
+		if (f.type != "time_course_population_average") d << ";data_kind" << sfx << "=" << f.type;
+		if (f.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix" << sfx << "=" << f.value_relative_to_timepoint_ix;
 		auto fref = [&](const char* name, const ValueRef& r) {
 			if (r.ix >= 0) d << ";" << name << "_ix" << sfx << "=" << r.ix;
 			else d << ";" << name << sfx << "=" << r.fixed;

@@ -119,7 +119,8 @@ private:
 	};
 	struct DataSet { // one <data> element = one handle of the C ABI
 		std::string species_name, error_model = "normal";
-		std::string type = "time_course_population_average"; // or "time_course": per-cell trajectories + matching (DataLikelihoodTimeCourse.cpp)
+		std::string type = "time_course_population_average"; // or "time_course" / "time_points": per-cell data + matching (DataLikelihoodTimeCourse.cpp, DataLikelihoodTimePoints.cpp)
+		long value_relative_to_timepoint_ix = -1;             // time_points, DataLikelihoodBase.cpp:49
 		ValueRef stdev, proportional_stdev, offset, scale;
 		bool have_proportional_stdev = false, relative_to_time_average = false, stdev_relative_to_scale = false;
 		double weight = 1.0, missing_stdev = 300.0;

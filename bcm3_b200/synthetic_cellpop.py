@@ -286,6 +286,26 @@ def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end
     return dataclasses.replace(base, observed=observed, data_kind="time_course", stdev_ix=None, stdev=noise * 1.5)
 
 
+def make_time_points_problem(N: int = 8, num_cells: int = 24, T: int = 8, t_end: float = 8.0, seed: int = 45, noise: float = 0.03,
+                             min_fraction: float = 0.4, relative_to: int | None = None) -> CellPopProblem:
+    """<data type="time_points">: snapshots -- at every timepoint a different number of observed cells (fixed-cell imaging, flow
+    cytometry), each value matched to one simulated cell at that time. `observed` is [num_cells slots][T]; the slots a timepoint
+    does not fill are NaN, in no particular order."""
+    import dataclasses
+
+    tc = make_time_course_problem(N=N, num_cells=num_cells, T=T, t_end=t_end, seed=seed, noise=noise)
+    rng = np.random.default_rng(seed + 3000)
+    observed = tc.observed.copy()
+    for ti in range(T):
+        keep = int(rng.integers(max(1, int(min_fraction * num_cells)), num_cells + 1))
+        drop = rng.permutation(num_cells)[keep:]
+        observed[drop, ti] = np.nan
+    if relative_to is not None:
+        ref = np.nanmean(tc.observed[:, relative_to])
+        observed = observed / ref
+    return dataclasses.replace(tc, observed=observed, data_kind="time_points", value_relative_to_timepoint_ix=relative_to)
+
+
 def make_chain_values(C: int, seed: int = 20261018) -> np.ndarray:
     base = default_values()
     out = np.empty((C, NUM_VARIABLES))

@@ -68,7 +68,12 @@ extern "C" {
  *                       (Experiment.cpp:726-782, CellPopulation.cpp:36-104, Cell.cpp:119-148: a cell whose cytokinesis species
  *                        passes 1 is replaced by two daughters, one whose apoptosis species passes 1 ends; a chain that
  *                        outgrows max_cells or the quasi-random table evaluates to -inf; such handles cannot be sharded)
- *                  data_kind=time_course_population_average|time_course (the <data type=>; default the population average).
+ *                  data_kind=time_course_population_average|time_course|time_points (the <data type=>; default the population average).
+ *                       time_points = DataLikelihoodTimePoints (src/cellpop/DataLikelihoodTimePoints.cpp:209-345), synchronize="none",
+ *                        one marker: "observed" is [num_replicates = observed cell slots <= num_cells][T], NaN = no such cell at
+ *                        that timepoint; at every timepoint the observed cells present are matched to the simulated cells that
+ *                        have a value there (normal | student_t4); value_relative_to_timepoint_ix=<t> (DataLikelihoodBase.cpp:49):
+ *                        the simulated value is (x + offset) / x(timepoint t) * scale instead of x * scale + offset
  *                       time_course = DataLikelihoodTimeCourse (src/cellpop/DataLikelihoodTimeCourse.cpp:230-365, 431-505,
  *                        566-588) with synchronize="none", one marker and no parent information: "observed" holds one
  *                        trajectory per OBSERVED CELL ([num_replicates = observed cells][T], NaN = missing), there are as

@@ -84,7 +84,8 @@ class _CellPopProblem(C.Structure):
         ("treatment_species", C.c_int32), ("treatment_num_pulses", C.c_int32), ("treatment_times", C.c_void_p),
         ("relative_to_time_average", C.c_int32), ("have_sim_end_time", C.c_int32), ("sim_end_time", C.c_double),
         ("stdev_relative_to_scale", C.c_int32), ("divide_cells", C.c_int32), ("max_cells", C.c_int32), ("sobol_rows", C.c_int32),
-        ("cytokinesis_ix", C.c_int32), ("apoptosis_ix", C.c_int32), ("reset_ix", C.c_int32 * 7), ("max_dt", C.c_double), ("data_kind", C.c_int32)]
+        ("cytokinesis_ix", C.c_int32), ("apoptosis_ix", C.c_int32), ("reset_ix", C.c_int32 * 7), ("max_dt", C.c_double), ("data_kind", C.c_int32),
+        ("value_relative_to_timepoint_ix", C.c_int32)]
 
 
 _derivative_libs: dict[str, C.CDLL] = {}
@@ -227,7 +228,8 @@ def _cellpop_struct(problem, values):
         cytokinesis_ix=-1 if p.cytokinesis_species is None else p.cytokinesis_species,
         apoptosis_ix=-1 if p.apoptosis_species is None else p.apoptosis_species,
         reset_ix=(C.c_int32 * 7)(*(list(p.division_reset_species) if p.divide_cells else [0] * 7)), max_dt=float(p.solver_max_timestep),
-        data_kind=int(getattr(p, "data_kind", "time_course_population_average") == "time_course"),
+        data_kind={"time_course_population_average": 0, "time_course": 1, "time_points": 2}[getattr(p, "data_kind", "time_course_population_average")],
+        value_relative_to_timepoint_ix=-1 if getattr(p, "value_relative_to_timepoint_ix", None) is None else int(p.value_relative_to_timepoint_ix),
         stdev_ix=-1 if p.stdev_ix is None else p.stdev_ix, offset_ix=-1 if p.offset_ix is None else p.offset_ix,
         scale_ix=-1 if p.scale_ix is None else p.scale_ix, num_obs_species=len(p.obs_species),
         obs_species=(C.c_int32 * 8)(*(list(p.obs_species) + [0] * (8 - len(p.obs_species)))),

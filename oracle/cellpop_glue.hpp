@@ -437,6 +437,67 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		return;
 	}
 
+	if (pr.data_kind == 2) {
+		// <data type="time_points">: DataLikelihoodTimePoints::Evaluate (DataLikelihoodTimePoints.cpp:209-345) -- at every timepoint
+		// its own set of observed cells (row i of `observed`, NaN = no such cell at that time), matched to the simulated cells that
+		// have a value there. synchronize="none", one marker. The Hungarian call is rectangular (observed cells x simulated cells with
+		// a value); the reference's implementation keeps only the edges whose right node index lies below the number of LEFT nodes
+		// (hungarian.cpp:81), i.e. the first simulated cells -- the adapter hands it the edge list as Evaluate builds it.
+		double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
+		const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
+		const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
+		if (pr.stdev_relative_to_scale) stdev *= scale;
+		const int rel = pr.value_relative_to_timepoint_ix;
+		const int n_sim_all = ncell; // cell_trajectories has one entry per cell object (GetMaxNumberOfCells)
+		double logp = 0.0;
+		for (int ti = 0; ti < T; ti++) {
+			std::vector<int> rows, cols;
+			for (int i = 0; i < R; i++) if (std::isfinite(pr.observed[(size_t)i * T + ti])) rows.push_back(i);
+			if (rows.empty()) continue;
+			for (int j = 0; j < n_sim_all; j++)
+				if (!std::isnan(xs[(size_t)ti * ncell + j]) && (rel < 0 || !std::isnan(xs[(size_t)rel * ncell + j]))) cols.push_back(j);
+			if (cols.size() < rows.size()) { // .cpp:241-245
+				*logp_out = -std::numeric_limits<double>::infinity();
+				return;
+			}
+			const int fd = (int)rows.size(), fs = (int)cols.size();
+			std::vector<double> lik((size_t)fd * fs), cost((size_t)fd * fs);
+			for (int a = 0; a < fd; a++)
+				for (int b = 0; b < fs; b++) {
+					double x = xs[(size_t)ti * ncell + cols[b]];
+					if (rel >= 0) {
+						x += offset;
+						x /= xs[(size_t)rel * ncell + cols[b]];
+						x *= scale;
+					} else {
+						x *= scale;
+						x += offset;
+					}
+					const double y = pr.observed[(size_t)rows[a] * T + ti];
+					double cell_logp = 0.0;
+					if (pr.error_model == 0) cell_logp += logpdf_normal(y, x, stdev);
+					else if (pr.error_model == 1) cell_logp += logpdf_tnu4(y, x, stdev);
+					else cell_logp = nan; // assert(false) in the reference: the other error models do not exist for this data type
+					lik[(size_t)a * fs + b] = cell_logp;
+					cost[(size_t)a * fs + b] = -cell_logp;
+				}
+			const std::vector<int> matching = hungarian_match(fd, fs, fd, cost); // .cpp:306-307
+			if ((int)matching.size() != fd) {
+				*logp_out = -std::numeric_limits<double>::infinity();
+				return;
+			}
+			for (int a = 0; a < fd; a++) {
+				if (matching[a] == -1) {
+					*logp_out = -std::numeric_limits<double>::infinity();
+					return;
+				}
+				logp += lik[(size_t)a * fs + matching[a]];
+			}
+		}
+		*logp_out = logp * pr.weight;
+		return;
+	}
+
 	// Evaluate (.cpp:85-159)
 	double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
 	const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;

@@ -24,8 +24,14 @@ double ndtri(double p) { return oracle_ndtri(p); }
 namespace cellpop_glue {
 std::vector<int> hungarian_match(int n, int n_right, int n_left, const std::vector<double>& cost)
 {
-	if (n_left != n_right || n != n_left) return std::vector<int>();
-	return bcm3b200::payor_matching_complete(n, cost.data());
+	// the reference's implementation keeps the edges whose right node index is below n (hungarian.cpp:81): with more right than
+	// left nodes that is the complete graph on the first n right nodes
+	if (n != n_left || n_right < n_left) return std::vector<int>();
+	if (n_right == n_left) return bcm3b200::payor_matching_complete(n, cost.data());
+	std::vector<double> square((size_t)n * n);
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < n; j++) square[(size_t)i * n + j] = cost[(size_t)i * n_right + j];
+	return bcm3b200::payor_matching_complete(n, square.data());
 }
 }
 

@@ -143,10 +143,15 @@ typedef struct {
 	int32_t cytokinesis_ix, apoptosis_ix; /* ODE species indices, -1: the model has no such species */
 	int32_t reset_ix[7];                  /* cytokinesis, nuclear_envelope, G1S_break, G2_break, spindle_components, assembled_spindle, chromatid_separation */
 	double max_dt; /* <experiment solver_max_timestep=> -> SetSolverParameter("max_dt") -> CVodeSetMaxStep (Cell.cpp:73); infinity: none */
-	/* 0: <data type="time_course_population_average">; 1: <data type="time_course"> -- per-cell trajectories, one observed cell per
+	/* 0: <data type="time_course_population_average">; 2: see below; 1: <data type="time_course"> -- per-cell trajectories, one observed cell per
 	 * row of `observed` ([num_replicates = observed cells][T]), every observed cell matched to one simulated cell by minimum-cost
 	 * perfect matching (DataLikelihoodTimeCourse.cpp:230-365, 431-505; synchronize="none", no parent information, one marker) */
 	int32_t data_kind;
+	/* data_kind 2: <data type="time_points"> (DataLikelihoodTimePoints.cpp:209-345) -- `observed` [observed cell slots][T], NaN =
+	 * no such cell at that timepoint; at every timepoint the observed cells present are matched to simulated cells.
+	 * value_relative_to_timepoint_ix (DataLikelihoodBase.cpp:49; -1: none): the simulated value is (x + offset) / x(that
+	 * timepoint) * scale instead of x * scale + offset */
+	int32_t value_relative_to_timepoint_ix;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

@@ -58,6 +58,13 @@ CASES = {
                                           dict(error_model="student_t4", offset=0.01, scale=1.1, weight=0.5)),
     "cellpop_time_course_n6_addprop": (dict(_builder="time_course", N=6, num_cells=33, T=10, seed=43), 2,
                                        dict(error_model="additive_proportional_normal", proportional_stdev=0.1, _positive_data=True)),
+    # <data type="time_points">: at every timepoint its own set of observed cells, matched to the simulated cells (rectangular
+    # Hungarian calls: fewer observed than simulated cells at most timepoints), DataLikelihoodTimePoints.cpp:209-345
+    "cellpop_time_points_n8_normal": (dict(_builder="time_points", N=8, num_cells=24, T=8, seed=45), 3, {}),
+    # value_relative_to_timepoint_ix (DataLikelihoodBase.cpp:49): simulated values relative to the cell's own value at timepoint 2;
+    # Student-t error model, offset / scale / weight
+    "cellpop_time_points_n6_t4_relative": (dict(_builder="time_points", N=6, num_cells=30, T=9, seed=46, relative_to=2), 3,
+                                           dict(error_model="student_t4", offset=0.01, scale=1.1, weight=0.5, stdev=0.01)),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
@@ -78,6 +85,9 @@ def main():
             fixed_values = sc.make_chain_values(C, seed=5)
         elif builder == "time_course":
             prob = dataclasses.replace(sc.make_time_course_problem(**kw), **tweaks)
+            fixed_values = None
+        elif builder == "time_points":
+            prob = dataclasses.replace(sc.make_time_points_problem(**kw), **tweaks)
             fixed_values = None
         elif builder == "sbml_cell_cycle":
             from tests.util import sbml_cell_cycle_problem, sbml_cell_cycle_values

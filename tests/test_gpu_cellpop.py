@@ -391,3 +391,42 @@ def test_time_course_refuses_what_is_not_built(Evaluator):
         Evaluator(dataclasses.replace(prob, observed=prob.observed[:10])).close()
     with pytest.raises(Bcm3B200Error):  # every observed cell is compared with every simulated cell: not split over ranks
         Evaluator(prob, shard_rank=0, shard_count=2).close()
+
+
+# ---- <data type="time_points">: at every timepoint its own set of observed cells ----
+
+def test_time_points_fresh_problem_against_the_reference(Evaluator, checker):
+    """120 simulated cells, 48-120 observed cells per timepoint (rectangular matchings), values relative to timepoint 1."""
+    prob = dataclasses.replace(sc.make_time_points_problem(N=8, num_cells=120, T=10, seed=55, relative_to=1), weight=1.3, scale=0.9, stdev=0.02)
+    vals = sc.make_chain_values(4, seed=55)
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    again, _ = ev.evaluate(vals)
+    ev.close()
+    want, floor, _ = _fresh_reference(checker, prob, vals)
+    assert (status == 0).all() and np.isfinite(logp).all()
+    assert np.array_equal(logp, again)
+    assert_logp_parity(logp, want["logp"], floor, "time_points, 120 cells")
+
+
+def test_time_points_without_enough_simulated_cells_is_minus_infinity(Evaluator, checker):
+    """Cells that enter at t = 1: at the timepoints before that no simulated cell has a value while the data has cells:
+    DataLikelihoodTimePoints.cpp:241-245 gives -inf."""
+    prob = dataclasses.replace(sc.make_time_points_problem(N=6, num_cells=16, T=8, seed=56), entry_time=1.5)
+    assert (prob.timepoints < 1.5).any()
+    vals = sc.make_chain_values(2, seed=56)
+    ev = Evaluator(prob)
+    logp, _ = ev.evaluate(vals)
+    ev.close()
+    assert np.all(logp == -np.inf)
+    assert np.all(checker.cellpop_evaluate(prob, vals)["logp"] == -np.inf)
+    # with the early observations removed the same problem is finite and agrees
+    obs = prob.observed.copy()
+    obs[:, prob.timepoints < 1.5] = np.nan
+    p2 = dataclasses.replace(prob, observed=obs)
+    ev = Evaluator(p2)
+    logp, _ = ev.evaluate(vals)
+    ev.close()
+    want, floor, _ = _fresh_reference(checker, p2, vals)
+    assert np.isfinite(logp).all()
+    assert_logp_parity(logp, want["logp"], floor, "time_points, late entry")

@@ -125,6 +125,8 @@ def load_cellpop_golden(name):
         extra.update(simulation_end_time=float(z["simulation_end_time"]))
     if "data_kind" in z.files:
         extra.update(data_kind=str(z["data_kind"]))
+    if "value_relative_to_timepoint_ix" in z.files:
+        extra.update(value_relative_to_timepoint_ix=int(z["value_relative_to_timepoint_ix"]))
     if "treatment_species" in z.files:
         extra.update(treatment_species=int(z["treatment_species"]), treatment_times=z["treatment_times"])
     if "divide_cells" in z.files and bool(z["divide_cells"]):
