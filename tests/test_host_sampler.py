@@ -158,7 +158,19 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     with pytest.raises(RuntimeError, match="nuclear_envelope"):
         host_api.cellpop_evaluate(prior, lik.replace(' divide_cells="false"', ""), prob, [("cytokinesis" if s == "x2" else s) for s in species], compile_only=True)
     with pytest.raises(RuntimeError, match="not supported"):
+        host_api.cellpop_evaluate(prior, lik.replace("time_course_population_average", "duration"), prob, species, compile_only=True)
+    # the per-cell types are taken when they do not need stored integration points ...
+    with pytest.raises(RuntimeError, match="stored integration points"):
+        host_api.cellpop_evaluate(prior, lik.replace('type="time_course_population_average"', 'type="time_course" synchronize="mitosis"'), prob, species, compile_only=True)
+    with pytest.raises(RuntimeError, match="stored integration points"):
+        host_api.cellpop_evaluate(prior, lik.replace('type="time_course_population_average"', 'type="time_points" synchronize="anaphase"'), prob, species, compile_only=True)
+    with pytest.raises(RuntimeError, match="optimize_offset_scale"):
+        host_api.cellpop_evaluate(prior, lik.replace('type="time_course_population_average"', 'type="time_course" optimize_offset_scale="true"'), prob, species, compile_only=True)
+    # ... and a time_course data set needs one observed trajectory per simulated cell (here: 1 row of data for 16 cells)
+    with pytest.raises(RuntimeError, match="num_cells"):
         host_api.cellpop_evaluate(prior, lik.replace("time_course_population_average", "time_course"), prob, species, compile_only=True)
+    tp = host_api.cellpop_evaluate(prior, lik.replace('type="time_course_population_average"', 'type="time_points" value_relative_to_timepoint_ix="2"'), prob, species, compile_only=True)[1]
+    assert "data_kind=time_points" in tp and "value_relative_to_timepoint_ix=2" in tp
     with pytest.raises(RuntimeError, match="Could not find variable"):
         host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="no_such_variable"'), prob, species, compile_only=True)
 
