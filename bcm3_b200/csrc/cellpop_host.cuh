@@ -526,10 +526,11 @@ struct CpCellLikArgs {
 	// to the cell's own value at timepoint `rel_k`, LogPdfNormal's division form; a simulated value that is missing gives NaN
 	// (the host leaves such cells out of the matching)
 	int only_k, rel_k;
+	int c0; // first chain of this launch: grid z = chains c0 .. c0 + gridDim.z - 1, lik holds those chains only
 };
 __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 {
-	const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, c = blockIdx.z;
+	const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, cz = blockIdx.z, c = a.c0 + cz;
 	if (j >= a.n_sim) return;
 	const double* tv = a.transformed + (long long)c * a.nvar;
 	double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
@@ -567,7 +568,7 @@ __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 			cell_logp = logpdf_tnu4(y, x, stdev);
 		}
 		if (isnan(x)) cell_logp = NAN;
-		a.lik[((long long)c * a.n_obs + i) * a.n_sim + j] = cell_logp;
+		a.lik[((long long)cz * a.n_obs + i) * a.n_sim + j] = cell_logp;
 		return;
 	}
 	for (int k = 0; k < a.T; k++) {
@@ -601,7 +602,7 @@ __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 			cell_logp += -log(sigma) - 0.91893853320467274178032973640562 - d * d * (1.0 / (2.0 * (sigma * sigma)));
 		}
 	}
-	a.lik[((long long)c * a.n_obs + i) * a.n_sim + j] = cell_logp;
+	a.lik[((long long)cz * a.n_obs + i) * a.n_sim + j] = cell_logp;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1694,25 +1695,35 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			a.rel_k = (kind == 2) ? (m ? m->value_relative_to_timepoint_ix : cp.value_relative_to_timepoint_ix) : -1;
 			const double weight = m ? m->weight : cp.weight;
 			const size_t block = (size_t)n_obs * n;
-			CUDA_TRY(cp.d_cell_lik.ensure(C * block ? C * block : 1));
+			// the blocks of at most ~1 GiB worth of chains at a time (4 096 cells: 128 MiB per chain)
+			size_t budget = (size_t)1 << 27; // doubles
+			if (const char* benv = getenv("BCM3B200_CELL_LIKELIHOOD_DOUBLES")) budget = (size_t)strtoull(benv, nullptr, 10); // tests: force small chunks
+			size_t chunk = block ? budget / block : C;
+			if (chunk < 1) chunk = 1;
+			if (chunk > C) chunk = C;
+			CUDA_TRY(cp.d_cell_lik.ensure(chunk * block ? chunk * block : 1));
 			a.lik = cp.d_cell_lik.p;
-			cp.h_cell_lik.resize(C * block);
-			auto run_block = [&]() -> int { // the block for a.only_k (or all timepoints) to the host
+			cp.h_cell_lik.resize(chunk * block);
+			for (size_t c0 = 0; c0 < C; c0 += chunk) {
+			const size_t Cc = std::min(chunk, C - c0);
+			a.c0 = (int)c0;
+			auto run_block = [&]() -> int { // the block for a.only_k (or all timepoints) of chains c0 .. c0 + Cc - 1 to the host
 				if (block == 0) return BCM3B200_OK;
-				cellpop_cell_likelihood_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)n_obs, (unsigned)C), 128, 0, st>>>(a);
+				cellpop_cell_likelihood_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)n_obs, (unsigned)Cc), 128, 0, st>>>(a);
 				CUDA_TRY(cudaGetLastError());
 				cp.last_launches++;
 				cp.total_launches++;
-				CUDA_TRY(cudaMemcpyAsync(cp.h_cell_lik.data(), cp.d_cell_lik.p, sizeof(double) * C * block, cudaMemcpyDeviceToHost, st));
+				CUDA_TRY(cudaMemcpyAsync(cp.h_cell_lik.data(), cp.d_cell_lik.p, sizeof(double) * Cc * block, cudaMemcpyDeviceToHost, st));
 				CUDA_TRY(cudaStreamSynchronize(st));
 				return BCM3B200_OK;
 			};
 			if (kind == 1) {
 				int rc = run_block();
 				if (rc != BCM3B200_OK) return rc;
-				cellpop_for_each_chain(C, n >= 32, [&](size_t c) {
+				cellpop_for_each_chain(Cc, n >= 32, [&](size_t cc) {
+					const size_t c = c0 + cc;
 					if (!(logp[c] > ninf)) return; // already -inf (a failed cell, an earlier data set) or NaN: nothing to add to
-					const double* L = cp.h_cell_lik.data() + c * block;
+					const double* L = cp.h_cell_lik.data() + cc * block;
 					for (int i = 0; i < n; i++) {
 						int finite_count = 0;
 						for (int j = 0; j < n; j++) {
@@ -1747,8 +1758,8 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 				});
 			} else {
 				const std::vector<double>& observed = m ? m->observed : cp.data["observed"];
-				std::vector<double> term(C, 0.0);
-				std::vector<char> dead(C, 0);
+				std::vector<double> term(Cc, 0.0);
+				std::vector<char> dead(Cc, 0);
 				for (int ti = 0; ti < T; ti++) {
 					std::vector<int> rows;
 					for (int i = 0; i < n_obs; i++)
@@ -1758,8 +1769,8 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 					int rc = run_block();
 					if (rc != BCM3B200_OK) return rc;
 					const int fd = (int)rows.size();
-					cellpop_for_each_chain(C, fd >= 32, [&](size_t c) {
-						if (dead[c] || !(logp[c] > ninf)) return;
+					cellpop_for_each_chain(Cc, fd >= 32, [&](size_t c) {
+						if (dead[c] || !(logp[c0 + c] > ninf)) return;
 						const double* L = cp.h_cell_lik.data() + c * block;
 						// the simulated cells with a value at this timepoint (and at the reference timepoint), .cpp:234-239: the block holds
 						// NaN for the others in every row
@@ -1789,12 +1800,13 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 						}
 					});
 				}
-				for (size_t c = 0; c < C; c++) {
-					if (!(logp[c] > ninf)) continue;
-					if (dead[c]) logp[c] = ninf;
-					else logp[c] += term[c] * weight;
+				for (size_t c = 0; c < Cc; c++) {
+					if (!(logp[c0 + c] > ninf)) continue;
+					if (dead[c]) logp[c0 + c] = ninf;
+					else logp[c0 + c] += term[c] * weight;
 				}
 			}
+			} // chain chunks
 		}
 		row0 += T;
 	}

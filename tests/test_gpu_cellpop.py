@@ -430,3 +430,16 @@ def test_time_points_without_enough_simulated_cells_is_minus_infinity(Evaluator,
     want, floor, _ = _fresh_reference(checker, p2, vals)
     assert np.isfinite(logp).all()
     assert_logp_parity(logp, want["logp"], floor, "time_points, late entry")
+
+
+@pytest.mark.parametrize("name", ["cellpop_time_course_n6_t4_missing", "cellpop_time_points_n8_normal"])
+def test_per_cell_blocks_in_chunks_of_chains_give_the_same_bits(Evaluator, name, monkeypatch):
+    """The [observed x simulated] blocks go to the host a bounded number of chains at a time (1 GiB); one chain at a time here."""
+    prob, gold = load_cellpop_golden(name)
+    ev = Evaluator(prob)
+    whole, _ = ev.evaluate(gold["values"])
+    monkeypatch.setenv("BCM3B200_CELL_LIKELIHOOD_DOUBLES", str(prob.num_cells * prob.num_cells))
+    chunked, _ = ev.evaluate(gold["values"])
+    ev.close()
+    assert np.array_equal(whole, chunked)
+    assert_logp_parity(chunked, gold["logp"], gold["noise_floor"], name)
