@@ -31,6 +31,9 @@ class CellPopEvaluator:
         kv["variability_distribution"] = p.variability_distribution
         if p.data_kind != "time_course_population_average":
             kv["data_kind"] = p.data_kind
+        if p.optimize_offset_scale:
+            kv.update(optimize_offset_scale=1, optimize_offset_min=repr(float(p.optimize_offset_range[0])), optimize_offset_max=repr(float(p.optimize_offset_range[1])),
+                      optimize_scale_min=repr(float(p.optimize_scale_range[0])), optimize_scale_max=repr(float(p.optimize_scale_range[1])))
         if p.value_relative_to_timepoint_ix is not None:
             kv["value_relative_to_timepoint_ix"] = int(p.value_relative_to_timepoint_ix)
         kv["relative_to_time_average"] = int(p.relative_to_time_average)

@@ -75,6 +75,11 @@ class CellPopProblem:
     # every timepoint the observed cells present are matched to simulated cells (snapshots of different cells per time);
     # value_relative_to_timepoint_ix (DataLikelihoodBase.cpp:49): the simulated value relative to its own value at that timepoint
     value_relative_to_timepoint_ix: int | None = None
+    # time_course: <data optimize_offset_scale="true" ...> (DataLikelihoodTimeCourseBase.cpp:43-57, 317-322): every observed
+    # trajectory is regressed on every simulated one, offset and scale clamped to these ranges (the reference's defaults)
+    optimize_offset_scale: bool = False
+    optimize_offset_range: tuple = (-1.0, 1.0)
+    optimize_scale_range: tuple = (0.1, 10.0)
     relative_to_time_average: bool = False   # <data relative_to_time_average="true">: log of the value over its time average
     # the time the experiment integrates its cells to when it has further data sets that end later (Experiment.cpp:655-656);
     # None: the last of `timepoints`

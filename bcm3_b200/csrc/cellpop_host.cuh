@@ -36,6 +36,9 @@ struct CellPopState {
 	// 2 = time_points (DataLikelihoodTimePoints.cpp:209-345): "observed" is [observed cell slots][T], NaN = no such cell at that
 	// timepoint; at every timepoint the observed cells present are matched to the simulated cells that have a value there
 	int data_kind = 0;
+	// time_course: <data optimize_offset_scale=...> (DataLikelihoodTimeCourseBase.cpp:43-57, 317-322)
+	bool optimize_offset_scale = false;
+	double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
 	int value_relative_to_timepoint_ix = -1; // time_points: simulated value = (x + offset) / x(that timepoint) * scale (DataLikelihoodBase.cpp:49)
 	int N = 0, Nc = 0, nvar = 0, Nn = 0, num_cells = 0, T = 0, R = 1, D = 0;
 	int entry_time_ix = -1;
@@ -69,6 +72,8 @@ struct CellPopState {
 	// union of all timepoints and every data set sums its own species -- and their log-likelihoods are added in order (:346-355)
 	struct MoreData {
 		int T = 0, R = 1, error_model = CP_ERR_NORMAL, data_kind = 0, value_relative_to_timepoint_ix = -1;
+		bool optimize_offset_scale = false;
+		double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
 		int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
 		double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0, weight = 1.0, missing_stdev = 300.0;
 		bool relative_to_time_average = false, stdev_relative_to_scale = false;
@@ -526,6 +531,10 @@ struct CpCellLikArgs {
 	// to the cell's own value at timepoint `rel_k`, LogPdfNormal's division form; a simulated value that is missing gives NaN
 	// (the host leaves such cells out of the matching)
 	int only_k, rel_k;
+	// time_course with optimize_offset_scale: the observed trajectory regressed on the simulated one per pair (OptimizeOffsetScale,
+	// DataLikelihoodTimeCourseBase.cpp:317-322 = bcm3::linear_regress_columns, Correlation.cpp:158-200, + the clamps)
+	int optimize;
+	double opt_offset_min, opt_offset_max, opt_scale_min, opt_scale_max;
 	int c0; // first chain of this launch: grid z = chains c0 .. c0 + gridDim.z - 1, lik holds those chains only
 };
 __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
@@ -571,10 +580,36 @@ __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 		a.lik[((long long)cz * a.n_obs + i) * a.n_sim + j] = cell_logp;
 		return;
 	}
+	double opt_offset = 0.0, opt_scale = 1.0;
+	if (a.optimize) {
+		double mu_x = 0.0, mu_y = 0.0, xvar_calc = 0.0, cov_calc = 0.0, empirical_n = 0.0;
+		for (int k = 0; k < a.T; k++) {
+			const double xv = value(k), yv = obs[k];
+			if (isnan(xv) || isnan(yv)) continue;
+			empirical_n += 1.0;
+			const double invN = 1.0 / empirical_n, mu_x_nm1 = mu_x, mu_y_nm1 = mu_y;
+			mu_x += (xv - mu_x) * invN;
+			mu_y += (yv - mu_y) * invN;
+			if (empirical_n > 1) {
+				const double ratio = (empirical_n - 1) / empirical_n, dx = xv - mu_x_nm1, dy = yv - mu_y_nm1;
+				xvar_calc += dx * dx * ratio;
+				cov_calc += dx * dy * ratio;
+			}
+		}
+		if (empirical_n >= 2) {
+			opt_scale = cov_calc / xvar_calc;
+			opt_offset = mu_y - mu_x * opt_scale;
+		}
+		// std::min(std::max(v, lo), hi): a NaN slope (no variance in the simulated trajectory) stays NaN
+		opt_scale = (opt_scale < a.opt_scale_min) ? a.opt_scale_min : opt_scale;
+		opt_scale = (a.opt_scale_max < opt_scale) ? a.opt_scale_max : opt_scale;
+		opt_offset = (opt_offset < a.opt_offset_min) ? a.opt_offset_min : opt_offset;
+		opt_offset = (a.opt_offset_max < opt_offset) ? a.opt_offset_max : opt_offset;
+	}
 	for (int k = 0; k < a.T; k++) {
 		const double y = obs[k];
 		if (isnan(y)) continue;
-		const double x = value(k);
+		const double x = opt_offset + opt_scale * value(k);
 		if (isnan(x)) {
 			double first_ok = a.timepoints[a.T - 1], last_ok = a.timepoints[0];
 			for (int m = 0; m < a.T; m++)
@@ -1190,6 +1225,21 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		if (cp.division()) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with dividing / dying cells is not built");
 		if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points is not split over ranks (every observed cell is compared with every simulated cell)");
 		if (cp.num_cells > 4096) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with more than 4096 cells (the matching is O(n^3) on the host)");
+		auto check_optimize = [&](int kind, bool optimize, int error_model) -> int {
+			if (!optimize) return BCM3B200_OK;
+			if (kind != 1) return fail(BCM3B200_ERR_ARG, "optimize_offset_scale belongs to data_kind time_course");
+			// the reference's proportional models read per-cell sigma tables that it only fills WITHOUT optimize_offset_scale
+			// (DataLikelihoodTimeCourse.cpp:221-224, 272-283, 473-481): undefined there, refused here
+			if (error_model == CP_ERR_PROPORTIONAL_NORMAL || error_model == CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL)
+				return fail(BCM3B200_ERR_UNSUPPORTED, "optimize_offset_scale with a proportional error model is undefined in the reference");
+			return BCM3B200_OK;
+		};
+		int rco = check_optimize(cp.data_kind, cp.optimize_offset_scale, cp.error_model);
+		if (rco != BCM3B200_OK) return rco;
+		for (size_t k = 0; k < cp.more.size(); k++) {
+			rco = check_optimize(cp.more[k]->data_kind, cp.more[k]->optimize_offset_scale, cp.more[k]->error_model);
+			if (rco != BCM3B200_OK) return rco;
+		}
 		auto check_kind = [&](int kind, int R, int T, bool relative, int error_model, int rel_ix) -> int {
 			if (kind == 1 && (R != cp.num_cells || relative))
 				return fail(BCM3B200_ERR_ARG, "data_kind time_course needs num_replicates (observed cells) = num_cells and no relative_to_time_average");
@@ -1691,6 +1741,11 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			a.scale_fixed = m ? m->scale_fixed : cp.scale_fixed;
 			a.prop_stdev_fixed = m ? m->prop_stdev_fixed : cp.prop_stdev_fixed;
 			a.missing_stdev = m ? m->missing_stdev : cp.missing_simulation_time_stdev;
+			a.optimize = (kind == 1 && (m ? m->optimize_offset_scale : cp.optimize_offset_scale)) ? 1 : 0;
+			a.opt_offset_min = m ? m->optimize_offset_min : cp.optimize_offset_min;
+			a.opt_offset_max = m ? m->optimize_offset_max : cp.optimize_offset_max;
+			a.opt_scale_min = m ? m->optimize_scale_min : cp.optimize_scale_min;
+			a.opt_scale_max = m ? m->optimize_scale_max : cp.optimize_scale_max;
 			a.only_k = -1;
 			a.rel_k = (kind == 2) ? (m ? m->value_relative_to_timepoint_ix : cp.value_relative_to_timepoint_ix) : -1;
 			const double weight = m ? m->weight : cp.weight;

@@ -151,7 +151,15 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 			if (type == "time_course") {
 				const std::string sync = c.get("synchronize", "");
 				if (!sync.empty() && sync != "none") return Fail("time_course data with synchronize=\"" + sync + "\" needs stored integration points: not supported by the GPU path");
-				if (c.get_bool("optimize_offset_scale", false)) return Fail("optimize_offset_scale is not supported by the GPU path");
+				// DataLikelihoodTimeCourseBase::Load, .cpp:43-57
+				ds.optimize_offset_scale = c.get_bool("optimize_offset_scale", false);
+				ds.optimize_offset_min = c.get_real("optimize_offset_min", -1.0);
+				ds.optimize_offset_max = c.get_real("optimize_offset_max", 1.0);
+				ds.optimize_scale_min = c.get_real("optimize_scale_min", 0.1);
+				ds.optimize_scale_max = c.get_real("optimize_scale_max", 10.0);
+				const std::string em = c.get("error_model", "normal");
+				if (ds.optimize_offset_scale && (em == "proportional_normal" || em == "additive_proportional_normal"))
+					return Fail("optimize_offset_scale with a proportional error model is undefined in the reference (its per-cell sigma tables are not filled): not supported");
 				if (!c.get("saturation_scale", "").empty()) return Fail("saturation_scale is not supported by the GPU path");
 				if (c.get_bool("relative_to_time_average", false)) return Fail("relative_to_time_average belongs to time_course_population_average data");
 			}
@@ -339,6 +347,9 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	  << ";missing_simulation_time_stdev=" << ds.missing_stdev << ";device=" << device << ";compile_only=" << (compile_only ? 1 : 0);
 	if (ds.type != "time_course_population_average") d << ";data_kind=" << ds.type;
 	if (ds.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix=" << ds.value_relative_to_timepoint_ix;
+	if (ds.optimize_offset_scale)
+		d << ";optimize_offset_scale=1;optimize_offset_min=" << ds.optimize_offset_min << ";optimize_offset_max=" << ds.optimize_offset_max
+		  << ";optimize_scale_min=" << ds.optimize_scale_min << ";optimize_scale_max=" << ds.optimize_scale_max;
 	if (simulation_end_time > data.timepoints.back()) d << ";simulation_end_time=" << simulation_end_time;
 	if (std::isfinite(e.solver_max_timestep)) d << ";solver_max_timestep=" << e.solver_max_timestep;
 	if (divides) {
@@ -376,6 +387,9 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		  << f.error_model << ";weight" << sfx << "=" << f.weight << ";missing_simulation_time_stdev" << sfx << "=" << f.missing_stdev;
 		if (f.type != "time_course_population_average") d << ";data_kind" << sfx << "=" << f.type;
 		if (f.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix" << sfx << "=" << f.value_relative_to_timepoint_ix;
+		if (f.optimize_offset_scale)
+			d << ";optimize_offset_scale" << sfx << "=1;optimize_offset_min" << sfx << "=" << f.optimize_offset_min << ";optimize_offset_max" << sfx << "=" << f.optimize_offset_max
+			  << ";optimize_scale_min" << sfx << "=" << f.optimize_scale_min << ";optimize_scale_max" << sfx << "=" << f.optimize_scale_max;
 		auto fref = [&](const char* name, const ValueRef& r) {
 			if (r.ix >= 0) d << ";" << name << "_ix" << sfx << "=" << r.ix;
 			else d << ";" << name << sfx << "=" << r.fixed;

@@ -388,10 +388,35 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 			int finite_count = 0;
 			for (int j = 0; j < n_sim; j++) {
 				double cell_logp = 0.0;
+				double opt_offset = 0.0, opt_scale = 1.0;
+				if (pr.optimize_offset_scale) {
+					// OptimizeOffsetScale (DataLikelihoodTimeCourseBase.cpp:317-322) = bcm3::linear_regress_columns(simulated, observed)
+					// (Correlation.cpp:158-200: running means, NaN pairs skipped) + the clamps
+					double mu_x = 0.0, mu_y = 0.0, xvar_calc = 0.0, cov_calc = 0.0, empirical_n = 0.0;
+					for (int k = 0; k < T; k++) {
+						const double xv = traj[(size_t)k * n_sim + j], yv = pr.observed[(size_t)i * T + k];
+						if (std::isnan(xv) || std::isnan(yv)) continue;
+						empirical_n += 1.0;
+						const double invN = 1.0 / empirical_n, mu_x_nm1 = mu_x, mu_y_nm1 = mu_y;
+						mu_x += (xv - mu_x) * invN;
+						mu_y += (yv - mu_y) * invN;
+						if (empirical_n > 1) {
+							const double ratio = (empirical_n - 1) / empirical_n, dx = xv - mu_x_nm1, dy = yv - mu_y_nm1;
+							xvar_calc += dx * dx * ratio;
+							cov_calc += dx * dy * ratio;
+						}
+					}
+					if (empirical_n >= 2) {
+						opt_scale = cov_calc / xvar_calc;
+						opt_offset = mu_y - mu_x * opt_scale;
+					}
+					opt_scale = std::min(std::max(opt_scale, pr.optimize_scale_min), pr.optimize_scale_max);
+					opt_offset = std::min(std::max(opt_offset, pr.optimize_offset_min), pr.optimize_offset_max);
+				}
 				for (int k = 0; k < T; k++) {
 					const double y = pr.observed[(size_t)i * T + k];
 					if (std::isnan(y)) continue;
-					const double x = traj[(size_t)k * n_sim + j]; // offset 0 + scale 1 * trajectory without optimize_offset_scale
+					const double x = opt_offset + opt_scale * traj[(size_t)k * n_sim + j]; // .cpp:461
 					if (std::isnan(x)) {
 						cell_logp += missing_value(j, k);
 					} else if (pr.error_model == 0) {

@@ -152,6 +152,11 @@ typedef struct {
 	 * value_relative_to_timepoint_ix (DataLikelihoodBase.cpp:49; -1: none): the simulated value is (x + offset) / x(that
 	 * timepoint) * scale instead of x * scale + offset */
 	int32_t value_relative_to_timepoint_ix;
+	/* time_course: <data optimize_offset_scale="true" optimize_offset_min= optimize_offset_max= optimize_scale_min= optimize_scale_max=>
+	 * (DataLikelihoodTimeCourseBase.cpp:43-57, 317-322): for every (observed, simulated) pair the observed trajectory is regressed
+	 * on the simulated one (bcm3::linear_regress_columns, Correlation.cpp:158-200), offset and scale clamped to their ranges */
+	int32_t optimize_offset_scale;
+	double optimize_offset_min, optimize_offset_max, optimize_scale_min, optimize_scale_max;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

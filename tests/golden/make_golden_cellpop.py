@@ -58,6 +58,11 @@ CASES = {
                                           dict(error_model="student_t4", offset=0.01, scale=1.1, weight=0.5)),
     "cellpop_time_course_n6_addprop": (dict(_builder="time_course", N=6, num_cells=33, T=10, seed=43), 2,
                                        dict(error_model="additive_proportional_normal", proportional_stdev=0.1, _positive_data=True)),
+    # optimize_offset_scale: the observed trajectories are in arbitrary fluorescence units (x 2.7 + 0.4 here); every (observed,
+    # simulated) pair is regressed first, offset and scale clamped (the offset clamp of +-0.3 bites for some pairs)
+    "cellpop_time_course_n8_optimize": (dict(_builder="time_course", N=8, num_cells=24, T=12, seed=44, missing_fraction=0.1), 3,
+                                        dict(optimize_offset_scale=True, optimize_offset_range=(-0.3, 0.3), optimize_scale_range=(0.1, 10.0),
+                                             _affine_data=(0.4, 2.7), stdev=0.08)),
     # <data type="time_points">: at every timepoint its own set of observed cells, matched to the simulated cells (rectangular
     # Hungarian calls: fewer observed than simulated cells at most timepoints), DataLikelihoodTimePoints.cpp:209-345
     "cellpop_time_points_n8_normal": (dict(_builder="time_points", N=8, num_cells=24, T=8, seed=45), 3, {}),
@@ -78,6 +83,7 @@ def main():
             continue
         tweaks = dict(tweaks)
         positive = tweaks.pop("_positive_data", False)
+        affine = tweaks.pop("_affine_data", None)
         kw = dict(kw)
         builder = kw.pop("_builder", None)
         if builder == "dividing":
@@ -97,6 +103,8 @@ def main():
         else:
             prob = dataclasses.replace(sc.make_cellpop_problem(**kw), **tweaks)
             fixed_values = None
+        if affine is not None:
+            prob = dataclasses.replace(prob, observed=affine[0] + affine[1] * prob.observed)
         if positive:  # a proportional error model has sigma = 0 (log-density NaN) at data <= 0
             prob = dataclasses.replace(prob, observed=np.abs(prob.observed) + 0.05)
         vals = fixed_values if fixed_values is not None else sc.make_chain_values(C, seed=zlib.crc32(name.encode()) % 10000)

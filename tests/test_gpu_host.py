@@ -338,3 +338,38 @@ def test_cell_population_time_course_and_population_average_in_one_experiment(bu
     assert np.isfinite(want).all()
     for share in (True, False):
         assert np.all(np.abs(out[share] - want) <= parity_tolerance(None) * np.abs(want)), (share, out[share], want)
+
+
+def test_cell_population_plugin_time_course_with_offset_scale_optimisation(built):
+    """<data type="time_course" optimize_offset_scale="true" ...> through the plugin: observations in arbitrary units, every
+    (observed, simulated) pair regressed before it is scored (DataLikelihoodTimeCourseBase.cpp:317-322); against the CPU checker."""
+    import dataclasses
+    import math
+    import oracle
+    from bcm3_b200 import synthetic_cellpop as sc
+    from tests.util import cellpop_xml, open_cellpop_session, parity_tolerance
+
+    tc = sc.make_time_course_problem(N=8, num_cells=40, T=12, seed=63, missing_fraction=0.05)
+    tc = dataclasses.replace(tc, observed=0.1 + 3.0 * tc.observed, optimize_offset_scale=True, optimize_offset_range=(-0.5, 0.5),
+                             optimize_scale_range=(0.2, 5.0), stdev=0.1)
+    prior, _, species = cellpop_xml(tc)
+    obs = "+".join(species[s] for s in tc.obs_species)
+    lik = ('<bcm_likelihood type="cell_population">'
+           f'<experiment name="imaging" model_file="cascade.xml" entry_time="0" num_cells="{tc.num_cells}" max_cells="{tc.num_cells}" divide_cells="false">'
+           '<cell_variability distribution="diagonal_gaussian">'
+           '<variable model_parameter="k_in" apply="multiplicative_log" scale="variability_scale"/>'
+           '<variable model_parameter="k_deg" apply="multiplicative_log" scale="variability_scale" negate="true"/>'
+           f'<variable initial_condition_species="x1" apply="additive" scale="{math.log(0.01)!r}"/>'
+           '</cell_variability>'
+           f'<data type="time_course" data_name="cells" species_name="{obs}" stdev="0.1" optimize_offset_scale="true" optimize_offset_min="-0.5" '
+           'optimize_offset_max="0.5" optimize_scale_min="0.2" optimize_scale_max="5.0"/>'
+           '</experiment></bcm_likelihood>')
+    vals = sc.make_chain_values(3, seed=63)
+    s = open_cellpop_session(prior, lik, species, [[tc]])
+    s.post_initialize()
+    got = s.evaluate(vals, batched=True)
+    s.close()
+    chk = oracle.load("ref" if oracle.available("ref") else "port")
+    want = chk.cellpop_evaluate(tc, vals)["logp"]
+    assert np.isfinite(want).all()
+    assert np.all(np.abs(got - want) <= parity_tolerance(None) * np.abs(want)), (got, want)

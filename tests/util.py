@@ -125,6 +125,9 @@ def load_cellpop_golden(name):
         extra.update(simulation_end_time=float(z["simulation_end_time"]))
     if "data_kind" in z.files:
         extra.update(data_kind=str(z["data_kind"]))
+    if "optimize_offset_scale" in z.files and bool(z["optimize_offset_scale"]):
+        extra.update(optimize_offset_scale=True, optimize_offset_range=tuple(float(v) for v in z["optimize_offset_range"]),
+                     optimize_scale_range=tuple(float(v) for v in z["optimize_scale_range"]))
     if "value_relative_to_timepoint_ix" in z.files:
         extra.update(value_relative_to_timepoint_ix=int(z["value_relative_to_timepoint_ix"]))
     if "treatment_species" in z.files:
