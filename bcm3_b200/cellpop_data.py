@@ -78,6 +78,9 @@ class CellPopProblem:
     # time_course: <data optimize_offset_scale="true" ...> (DataLikelihoodTimeCourseBase.cpp:43-57, 317-322): every observed
     # trajectory is regressed on every simulated one, offset and scale clamped to these ranges (the reference's defaults)
     optimize_offset_scale: bool = False
+    # time_course: <data saturation_scale="variable"> (DataLikelihoodTimeCourse.cpp:243-254): index of the variable s of the signal
+    # saturation s / (1 + exp(-x)) - s / 2 applied to the scaled and shifted trajectories
+    saturation_scale_ix: int | None = None
     optimize_offset_range: tuple = (-1.0, 1.0)
     optimize_scale_range: tuple = (0.1, 10.0)
     relative_to_time_average: bool = False   # <data relative_to_time_average="true">: log of the value over its time average

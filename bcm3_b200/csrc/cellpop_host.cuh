@@ -39,6 +39,7 @@ struct CellPopState {
 	// time_course: <data optimize_offset_scale=...> (DataLikelihoodTimeCourseBase.cpp:43-57, 317-322)
 	bool optimize_offset_scale = false;
 	double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
+	int saturation_scale_ix = -1; // time_course: <data saturation_scale="variable">, DataLikelihoodTimeCourse.cpp:243-254
 	int value_relative_to_timepoint_ix = -1; // time_points: simulated value = (x + offset) / x(that timepoint) * scale (DataLikelihoodBase.cpp:49)
 	int N = 0, Nc = 0, nvar = 0, Nn = 0, num_cells = 0, T = 0, R = 1, D = 0;
 	int entry_time_ix = -1;
@@ -74,6 +75,7 @@ struct CellPopState {
 		int T = 0, R = 1, error_model = CP_ERR_NORMAL, data_kind = 0, value_relative_to_timepoint_ix = -1;
 		bool optimize_offset_scale = false;
 		double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
+		int saturation_scale_ix = -1;
 		int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
 		double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0, weight = 1.0, missing_stdev = 300.0;
 		bool relative_to_time_average = false, stdev_relative_to_scale = false;
@@ -535,6 +537,7 @@ struct CpCellLikArgs {
 	// DataLikelihoodTimeCourseBase.cpp:317-322 = bcm3::linear_regress_columns, Correlation.cpp:158-200, + the clamps)
 	int optimize;
 	double opt_offset_min, opt_offset_max, opt_scale_min, opt_scale_max;
+	int saturation_ix; // >= 0: signal saturation s / (1 + exp(-x)) - s / 2 with s = that transformed variable (.cpp:243-254)
 	int c0; // first chain of this launch: grid z = chains c0 .. c0 + gridDim.z - 1, lik holds those chains only
 };
 __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
@@ -554,6 +557,15 @@ __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 		double v = traj[(long long)k * a.cell_stride];
 		v *= scale;
 		v += offset;
+		if (a.saturation_ix >= 0) {
+			const double s = tv[a.saturation_ix];
+			v *= -1.0;
+			v = exp(v);
+			v += 1.0;
+			v = 1.0 / v;
+			v *= s;
+			v -= 0.5 * s;
+		}
 		return v;
 	};
 	const double* obs = a.observed + (long long)i * a.T;
@@ -1225,6 +1237,9 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		if (cp.division()) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with dividing / dying cells is not built");
 		if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points is not split over ranks (every observed cell is compared with every simulated cell)");
 		if (cp.num_cells > 4096) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with more than 4096 cells (the matching is O(n^3) on the host)");
+		if (cp.saturation_scale_ix >= cp.nvar) return fail(BCM3B200_ERR_ARG, "saturation_scale_ix out of range");
+		for (size_t k = 0; k < cp.more.size(); k++)
+			if (cp.more[k]->saturation_scale_ix >= cp.nvar) return fail(BCM3B200_ERR_ARG, "saturation_scale_ix@%zu out of range", k + 1);
 		auto check_optimize = [&](int kind, bool optimize, int error_model) -> int {
 			if (!optimize) return BCM3B200_OK;
 			if (kind != 1) return fail(BCM3B200_ERR_ARG, "optimize_offset_scale belongs to data_kind time_course");
@@ -1746,6 +1761,7 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			a.opt_offset_max = m ? m->optimize_offset_max : cp.optimize_offset_max;
 			a.opt_scale_min = m ? m->optimize_scale_min : cp.optimize_scale_min;
 			a.opt_scale_max = m ? m->optimize_scale_max : cp.optimize_scale_max;
+			a.saturation_ix = (kind == 1) ? (m ? m->saturation_scale_ix : cp.saturation_scale_ix) : -1;
 			a.only_k = -1;
 			a.rel_k = (kind == 2) ? (m ? m->value_relative_to_timepoint_ix : cp.value_relative_to_timepoint_ix) : -1;
 			const double weight = m ? m->weight : cp.weight;

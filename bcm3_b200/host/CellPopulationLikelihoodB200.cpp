@@ -160,7 +160,14 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				const std::string em = c.get("error_model", "normal");
 				if (ds.optimize_offset_scale && (em == "proportional_normal" || em == "additive_proportional_normal"))
 					return Fail("optimize_offset_scale with a proportional error model is undefined in the reference (its per-cell sigma tables are not filled): not supported");
-				if (!c.get("saturation_scale", "").empty()) return Fail("saturation_scale is not supported by the GPU path");
+				if (!c.get("saturation_scale", "").empty()) {
+					// DataLikelihoodTimeCourseBase::PostInitialize (.cpp:120-133) accepts a variable name or a number, but a number is
+					// overwritten with DBL_MAX at every evaluation (PrepateEvaluation, .cpp:243-246): only the variable form works
+					const size_t ix = varset->GetVariableIndex(c.get("saturation_scale"));
+					if (ix == std::numeric_limits<size_t>::max())
+						return Fail("saturation_scale must name a variable (the reference overwrites a numeric saturation scale with the largest double at every evaluation)");
+					ds.saturation_scale_ix = (long)ix;
+				}
 				if (c.get_bool("relative_to_time_average", false)) return Fail("relative_to_time_average belongs to time_course_population_average data");
 			}
 			ds.species_name = c.get("species_name");
@@ -347,6 +354,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	  << ";missing_simulation_time_stdev=" << ds.missing_stdev << ";device=" << device << ";compile_only=" << (compile_only ? 1 : 0);
 	if (ds.type != "time_course_population_average") d << ";data_kind=" << ds.type;
 	if (ds.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix=" << ds.value_relative_to_timepoint_ix;
+	if (ds.saturation_scale_ix >= 0) d << ";saturation_scale_ix=" << ds.saturation_scale_ix;
 	if (ds.optimize_offset_scale)
 		d << ";optimize_offset_scale=1;optimize_offset_min=" << ds.optimize_offset_min << ";optimize_offset_max=" << ds.optimize_offset_max
 		  << ";optimize_scale_min=" << ds.optimize_scale_min << ";optimize_scale_max=" << ds.optimize_scale_max;
@@ -387,6 +395,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		  << f.error_model << ";weight" << sfx << "=" << f.weight << ";missing_simulation_time_stdev" << sfx << "=" << f.missing_stdev;
 		if (f.type != "time_course_population_average") d << ";data_kind" << sfx << "=" << f.type;
 		if (f.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix" << sfx << "=" << f.value_relative_to_timepoint_ix;
+		if (f.saturation_scale_ix >= 0) d << ";saturation_scale_ix" << sfx << "=" << f.saturation_scale_ix;
 		if (f.optimize_offset_scale)
 			d << ";optimize_offset_scale" << sfx << "=1;optimize_offset_min" << sfx << "=" << f.optimize_offset_min << ";optimize_offset_max" << sfx << "=" << f.optimize_offset_max
 			  << ";optimize_scale_min" << sfx << "=" << f.optimize_scale_min << ";optimize_scale_max" << sfx << "=" << f.optimize_scale_max;

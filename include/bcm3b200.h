@@ -83,7 +83,8 @@ extern "C" {
  *                        handles cannot be sharded or combined with divide_cells.
  *                        optimize_offset_scale=1 [optimize_offset_min=-1 optimize_offset_max=1 optimize_scale_min=0.1
  *                        optimize_scale_max=10] (DataLikelihoodTimeCourseBase.cpp:43-57, 317-322): every pair regresses the
- *                        observed on the simulated trajectory first (normal | student_t4 only)
+ *                        observed on the simulated trajectory first (normal | student_t4 only);
+ *                        saturation_scale_ix=<variable>: the signal saturation of DataLikelihoodTimeCourse.cpp:243-254
  *                  num_data_sets=<D <= 4>: the experiment's further <data> elements share this handle's ONE integration of
  *                       the cells; data set k >= 1 repeats num_timepoints, num_replicates, obs_species, error_model, weight, data_kind,
  *                       the stdev/offset/scale keys and the relative_to/missing keys with the suffix @k ("stdev_ix@1=5")

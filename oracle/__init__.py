@@ -86,7 +86,8 @@ class _CellPopProblem(C.Structure):
         ("stdev_relative_to_scale", C.c_int32), ("divide_cells", C.c_int32), ("max_cells", C.c_int32), ("sobol_rows", C.c_int32),
         ("cytokinesis_ix", C.c_int32), ("apoptosis_ix", C.c_int32), ("reset_ix", C.c_int32 * 7), ("max_dt", C.c_double), ("data_kind", C.c_int32),
         ("value_relative_to_timepoint_ix", C.c_int32), ("optimize_offset_scale", C.c_int32), ("optimize_offset_min", C.c_double),
-        ("optimize_offset_max", C.c_double), ("optimize_scale_min", C.c_double), ("optimize_scale_max", C.c_double)]
+        ("optimize_offset_max", C.c_double), ("optimize_scale_min", C.c_double), ("optimize_scale_max", C.c_double),
+        ("saturation_scale_ix", C.c_int32)]
 
 
 _derivative_libs: dict[str, C.CDLL] = {}
@@ -231,6 +232,7 @@ def _cellpop_struct(problem, values):
         reset_ix=(C.c_int32 * 7)(*(list(p.division_reset_species) if p.divide_cells else [0] * 7)), max_dt=float(p.solver_max_timestep),
         data_kind={"time_course_population_average": 0, "time_course": 1, "time_points": 2}[getattr(p, "data_kind", "time_course_population_average")],
         value_relative_to_timepoint_ix=-1 if getattr(p, "value_relative_to_timepoint_ix", None) is None else int(p.value_relative_to_timepoint_ix),
+        saturation_scale_ix=-1 if getattr(p, "saturation_scale_ix", None) is None else int(p.saturation_scale_ix),
         optimize_offset_scale=int(bool(getattr(p, "optimize_offset_scale", False))),
         optimize_offset_min=float(getattr(p, "optimize_offset_range", (-1.0, 1.0))[0]), optimize_offset_max=float(getattr(p, "optimize_offset_range", (-1.0, 1.0))[1]),
         optimize_scale_min=float(getattr(p, "optimize_scale_range", (0.1, 10.0))[0]), optimize_scale_max=float(getattr(p, "optimize_scale_range", (0.1, 10.0))[1]),

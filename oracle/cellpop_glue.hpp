@@ -362,6 +362,15 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 				double v = xs[(size_t)k * ncell + j];
 				v *= scale; // .cpp:236-241
 				v += offset;
+				if (pr.saturation_scale_ix >= 0) { // .cpp:243-254, operation by operation
+					const double saturation_scale = transformed[pr.saturation_scale_ix];
+					v *= -1.0;
+					v = exp(v);
+					v += 1.0;
+					v = 1.0 / v;
+					v *= saturation_scale;
+					v -= 0.5 * saturation_scale;
+				}
 				traj[(size_t)k * n_sim + j] = v;
 			}
 		if (pr.error_model == 2 || pr.error_model == 3) { // .cpp:272-283

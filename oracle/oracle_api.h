@@ -157,6 +157,11 @@ typedef struct {
 	 * on the simulated one (bcm3::linear_regress_columns, Correlation.cpp:158-200), offset and scale clamped to their ranges */
 	int32_t optimize_offset_scale;
 	double optimize_offset_min, optimize_offset_max, optimize_scale_min, optimize_scale_max;
+	/* time_course: <data saturation_scale="variable">: the scaled and shifted trajectories pass through
+	 * s / (1 + exp(-x)) - s / 2 with s = that variable (DataLikelihoodTimeCourse.cpp:243-254); -1: none. (A NUMERIC saturation_scale
+	 * is parsed by the reference and then overwritten with DBL_MAX in PrepateEvaluation, DataLikelihoodTimeCourseBase.cpp:243-246:
+	 * only the variable form is usable there, and only it exists here.) */
+	int32_t saturation_scale_ix;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

@@ -63,6 +63,10 @@ CASES = {
     "cellpop_time_course_n8_optimize": (dict(_builder="time_course", N=8, num_cells=24, T=12, seed=44, missing_fraction=0.1), 3,
                                         dict(optimize_offset_scale=True, optimize_offset_range=(-0.3, 0.3), optimize_scale_range=(0.1, 10.0),
                                              _affine_data=(0.4, 2.7), stdev=0.08)),
+    # saturation_scale="k_feedback": the scaled trajectories pass through s / (1 + exp(-x)) - s / 2 (DataLikelihoodTimeCourse.cpp:243-254);
+    # the data went through the same curve with s = 0.5
+    "cellpop_time_course_n6_saturation": (dict(_builder="time_course", N=6, num_cells=20, T=10, seed=47), 3,
+                                          dict(saturation_scale_ix=sc.VAR_K_FEEDBACK, scale=4.0, _saturated_data=(4.0, 0.5), stdev=0.01)),
     # <data type="time_points">: at every timepoint its own set of observed cells, matched to the simulated cells (rectangular
     # Hungarian calls: fewer observed than simulated cells at most timepoints), DataLikelihoodTimePoints.cpp:209-345
     "cellpop_time_points_n8_normal": (dict(_builder="time_points", N=8, num_cells=24, T=8, seed=45), 3, {}),
@@ -84,6 +88,7 @@ def main():
         tweaks = dict(tweaks)
         positive = tweaks.pop("_positive_data", False)
         affine = tweaks.pop("_affine_data", None)
+        saturated = tweaks.pop("_saturated_data", None)
         kw = dict(kw)
         builder = kw.pop("_builder", None)
         if builder == "dividing":
@@ -103,6 +108,8 @@ def main():
         else:
             prob = dataclasses.replace(sc.make_cellpop_problem(**kw), **tweaks)
             fixed_values = None
+        if saturated is not None:
+            prob = dataclasses.replace(prob, observed=saturated[1] / (1.0 + np.exp(-saturated[0] * prob.observed)) - 0.5 * saturated[1])
         if affine is not None:
             prob = dataclasses.replace(prob, observed=affine[0] + affine[1] * prob.observed)
         if positive:  # a proportional error model has sigma = 0 (log-density NaN) at data <= 0

@@ -167,7 +167,7 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     with pytest.raises(RuntimeError, match="optimize_offset_scale"):
         host_api.cellpop_evaluate(prior, lik.replace('type="time_course_population_average"', 'type="time_course" optimize_offset_scale="true" error_model="proportional_normal" proportional_stdev="0.1"'),
                                   prob, species, compile_only=True)
-    with pytest.raises(RuntimeError, match="saturation_scale"):
+    with pytest.raises(RuntimeError, match="saturation_scale must name a variable"):  # a number: unusable in the reference (overwritten with DBL_MAX)
         host_api.cellpop_evaluate(prior, lik.replace('type="time_course_population_average"', 'type="time_course" saturation_scale="2.0"'), prob, species, compile_only=True)
     # ... and a time_course data set needs one observed trajectory per simulated cell (here: 1 row of data for 16 cells)
     with pytest.raises(RuntimeError, match="num_cells"):

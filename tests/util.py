@@ -128,6 +128,8 @@ def load_cellpop_golden(name):
     if "optimize_offset_scale" in z.files and bool(z["optimize_offset_scale"]):
         extra.update(optimize_offset_scale=True, optimize_offset_range=tuple(float(v) for v in z["optimize_offset_range"]),
                      optimize_scale_range=tuple(float(v) for v in z["optimize_scale_range"]))
+    if "saturation_scale_ix" in z.files:
+        extra.update(saturation_scale_ix=int(z["saturation_scale_ix"]))
     if "value_relative_to_timepoint_ix" in z.files:
         extra.update(value_relative_to_timepoint_ix=int(z["value_relative_to_timepoint_ix"]))
     if "treatment_species" in z.files:
