@@ -60,6 +60,20 @@ class CellPopEvaluator:
                 kv[name + "_ix"] = ix
             else:
                 kv[name] = repr(float(getattr(p, name)))
+        # further markers of a per-cell data set: data sets @1, @2, ... of the handle that name data set 0 as theirs (marker_of)
+        if p.extra_markers:
+            kv["num_data_sets"] = 1 + len(p.extra_markers)
+            for k, mk in enumerate(p.extra_markers, start=1):
+                kv[f"marker_of@{k}"] = 0
+                kv[f"num_timepoints@{k}"] = p.num_timepoints
+                kv[f"num_replicates@{k}"] = int(np.asarray(mk.observed).shape[0])
+                kv[f"obs_species@{k}"] = "+".join(str(s) for s in mk.obs_species)
+                for name in ("stdev", "offset", "scale", "proportional_stdev"):
+                    ix = getattr(mk, name + "_ix")
+                    if ix is not None:
+                        kv[f"{name}_ix@{k}"] = ix
+                    else:
+                        kv[f"{name}@{k}"] = repr(float(getattr(mk, name)))
         desc = ";".join(f"{k}={v}" for k, v in kv.items()).encode()
         h = C.c_void_p()
         _lib.check(self.lib.bcm3b200_create(b"cell_population", desc, len(desc), device_count, C.byref(h)))
@@ -70,6 +84,9 @@ class CellPopEvaluator:
             self._set("non_sampled_parameters", p.non_sampled_parameters)
             self._set("timepoints", p.timepoints)
             self._set("observed", p.observed)
+            for k, mk in enumerate(p.extra_markers, start=1):
+                self._set(f"timepoints@{k}", p.timepoints)
+                self._set(f"observed@{k}", np.asarray(mk.observed, dtype=np.float64))
             self._set("transforms", p.transforms)
             if p.treatment_species is not None and len(p.treatment_times):
                 self._set("treatment_times", np.asarray(p.treatment_times, dtype=np.float64))
@@ -136,13 +153,18 @@ class CellPopEvaluator:
         return int(v.value)
 
     def diagnostics(self):
-        nC, nc, T = self._last_C, self.get_stat("cell_columns"), self.problem.num_timepoints
-        vals = np.empty((nC, T, nc))
+        # the library writes "value_rows" rows per chain: every data set's (and every further marker's) timepoints one after the other;
+        # the first num_timepoints rows are this problem's first marker
+        nC, nc, T, rows = self._last_C, self.get_stat("cell_columns"), self.problem.num_timepoints, self.get_stat("value_rows")
+        vals = np.empty((nC, rows, nc))
         status = np.empty((nC, nc), dtype=np.int32)
         steps = np.empty((nC, nc), dtype=np.int32)
-        avg = np.empty((nC, T))
+        avg = np.empty((nC, rows))
         _lib.check(self.lib.bcm3b200_get_cell_diagnostics(self.handle, vals.ctypes.data, status.ctypes.data, steps.ctypes.data, avg.ctypes.data))
-        return dict(cell_values=vals, cell_status=status, cell_steps=steps, population_average=avg)
+        out = dict(cell_values=np.ascontiguousarray(vals[:, :T]), cell_status=status, cell_steps=steps, population_average=np.ascontiguousarray(avg[:, :T]))
+        if rows > T:
+            out["marker_values"] = [np.ascontiguousarray(vals[:, T * l:T * (l + 1)]) for l in range(1, rows // T)]
+        return out
 
     def close(self) -> None:
         if getattr(self, "handle", None):

@@ -45,6 +45,23 @@ class Variability:
 
 
 @dataclass
+class Marker:
+    """A further marker of a per-cell data set -- species_name="a+b;c", stdev="s1;s2" ...: the entries after a ';'
+    (DataLikelihoodTimeCourseBase.cpp:79-87, DataLikelihoodBase.cpp:130-233). Error model, weight and the switches are the data set's."""
+
+    obs_species: list
+    observed: np.ndarray                  # [observed cells][T], NaN = missing
+    stdev_ix: int | None = None
+    stdev: float = 1.0
+    proportional_stdev_ix: int | None = None
+    proportional_stdev: float = 1.0
+    offset_ix: int | None = None
+    offset: float = 0.0
+    scale_ix: int | None = None
+    scale: float = 1.0
+
+
+@dataclass
 class CellPopProblem:
     derivative_code: str                 # generated_derivative text in the reference generator's ABI
     num_species: int
@@ -81,6 +98,8 @@ class CellPopProblem:
     # time_course: <data saturation_scale="variable"> (DataLikelihoodTimeCourse.cpp:243-254): index of the variable s of the signal
     # saturation s / (1 + exp(-x)) - s / 2 applied to the scaled and shifted trajectories
     saturation_scale_ix: int | None = None
+    # per-cell data kinds: the markers after the first one (which is obs_species / observed / stdev ... of this problem)
+    extra_markers: list = field(default_factory=list)
     optimize_offset_range: tuple = (-1.0, 1.0)
     optimize_scale_range: tuple = (0.1, 10.0)
     relative_to_time_average: bool = False   # <data relative_to_time_average="true">: log of the value over its time average

@@ -76,6 +76,10 @@ struct CellPopState {
 		bool optimize_offset_scale = false;
 		double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
 		int saturation_scale_ix = -1;
+		// >= 0: not a data set of its own but a further MARKER (species_name="a;b": the part after a ';') of the per-cell data set
+		// with that index (0 = the handle's first data set, j = more[j - 1]): its rows, observed block and stdev / offset / scale
+		// entries enter that data set's cell likelihoods (DataLikelihoodTimeCourse.cpp:449-489, DataLikelihoodTimePoints.cpp:264-289)
+		int marker_of = -1;
 		int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
 		double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0, weight = 1.0, missing_stdev = 300.0;
 		bool relative_to_time_average = false, stdev_relative_to_scale = false;
@@ -516,25 +520,31 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 }
 
 // DataLikelihoodTimeCourse::CalculateCellLikelihood (.cpp:431-505) for every (observed cell i, simulated cell j) pair of a chain:
-// lik[c][i][j] = sum over the timepoints with an observation of the log-density of the observed value around the simulated
-// cell's (scaled, shifted) trajectory; a simulated value that is missing pays CalculateMissingValueLikelihood (.cpp:566-588).
-// One thread per pair, j fastest: the trajectory reads of a warp are one coalesced row segment, the observed value is a
-// broadcast. cell_values is the kernel's [C][rows][cell_stride] block, row0 the data set's first row.
+// lik[c][i][j] = sum over the markers and over the timepoints with an observation of the log-density of the observed value
+// around the simulated cell's (scaled, shifted) trajectory; a simulated value that is missing pays
+// CalculateMissingValueLikelihood (.cpp:566-588). One thread per pair, j fastest: the trajectory reads of a warp are one
+// coalesced row segment, the observed value is a broadcast. cell_values is the kernel's [C][rows][cell_stride] block; every
+// marker (species_name="a+b;c": the entries between the ';') has its own rows, observed block and stdev / offset / scale.
+struct CpMarkerArgs {
+	int row0, stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
+	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed;
+	const double* observed; // [n_obs][T]
+};
 struct CpCellLikArgs {
 	const double* cell_values;
-	int rows, cell_stride, row0, T, n_obs, n_sim, nvar, error_model, stdev_relative_to_scale;
+	int rows, cell_stride, T, n_obs, n_sim, nvar, error_model, stdev_relative_to_scale;
 	const double* transformed;
 	const double* timepoints; // [T]
-	const double* observed;   // [n_obs][T]
-	int stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
-	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed, missing_stdev;
+	int L;                    // markers, 1..4
+	CpMarkerArgs mk[4];
+	double missing_stdev;
 	double* lik; // [C][n_obs][n_sim]
 	// time_points (DataLikelihoodTimePoints.cpp:255-290): only timepoint `only_k` (>= 0), the simulated value optionally relative
-	// to the cell's own value at timepoint `rel_k`, LogPdfNormal's division form; a simulated value that is missing gives NaN
-	// (the host leaves such cells out of the matching)
+	// to the cell's own value at timepoint `rel_k`, LogPdfNormal's division form; a simulated value that is missing in marker 0
+	// gives NaN (the host leaves such cells out of the matching)
 	int only_k, rel_k;
-	// time_course with optimize_offset_scale: the observed trajectory regressed on the simulated one per pair (OptimizeOffsetScale,
-	// DataLikelihoodTimeCourseBase.cpp:317-322 = bcm3::linear_regress_columns, Correlation.cpp:158-200, + the clamps)
+	// time_course with optimize_offset_scale: the observed trajectory regressed on the simulated one per pair and marker
+	// (OptimizeOffsetScale, DataLikelihoodTimeCourseBase.cpp:317-322 = bcm3::linear_regress_columns, Correlation.cpp:158-200, + the clamps)
 	int optimize;
 	double opt_offset_min, opt_offset_max, opt_scale_min, opt_scale_max;
 	int saturation_ix; // >= 0: signal saturation s / (1 + exp(-x)) - s / 2 with s = that transformed variable (.cpp:243-254)
@@ -545,110 +555,116 @@ __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 	const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, cz = blockIdx.z, c = a.c0 + cz;
 	if (j >= a.n_sim) return;
 	const double* tv = a.transformed + (long long)c * a.nvar;
-	double stdev = (a.stdev_ix >= 0) ? tv[a.stdev_ix] : a.stdev_fixed;
-	const double offset = (a.offset_ix >= 0) ? tv[a.offset_ix] : a.offset_fixed;
-	const double scale = (a.scale_ix >= 0) ? tv[a.scale_ix] : a.scale_fixed;
-	if (a.stdev_relative_to_scale) stdev *= scale;
-	const double prop_stdev = (a.prop_stdev_ix >= 0) ? tv[a.prop_stdev_ix] : a.prop_stdev_fixed;
-	const double minus_log_sigma = -log(stdev);
-	const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
-	const double* traj = a.cell_values + ((long long)c * a.rows + a.row0) * a.cell_stride + j;
-	auto value = [&](int k) { // .cpp:236-241: *= data scale, += data offset
-		double v = traj[(long long)k * a.cell_stride];
-		v *= scale;
-		v += offset;
-		if (a.saturation_ix >= 0) {
-			const double s = tv[a.saturation_ix];
-			v *= -1.0;
-			v = exp(v);
-			v += 1.0;
-			v = 1.0 / v;
-			v *= s;
-			v -= 0.5 * s;
-		}
-		return v;
-	};
-	const double* obs = a.observed + (long long)i * a.T;
 	double cell_logp = 0.0;
-	if (a.only_k >= 0) {
-		const int k = a.only_k;
-		double x = traj[(long long)k * a.cell_stride];
-		if (a.rel_k >= 0) {
-			x += offset;
-			x /= traj[(long long)a.rel_k * a.cell_stride];
-			x *= scale;
-		} else {
-			x *= scale;
-			x += offset;
+	bool no_value = false; // time_points: the simulated cell has no value in marker 0
+	for (int l = 0; l < a.L; l++) {
+		const CpMarkerArgs& mk = a.mk[l];
+		double stdev = (mk.stdev_ix >= 0) ? tv[mk.stdev_ix] : mk.stdev_fixed;
+		const double offset = (mk.offset_ix >= 0) ? tv[mk.offset_ix] : mk.offset_fixed;
+		const double scale = (mk.scale_ix >= 0) ? tv[mk.scale_ix] : mk.scale_fixed;
+		if (a.stdev_relative_to_scale) stdev *= scale;
+		const double prop_stdev = (mk.prop_stdev_ix >= 0) ? tv[mk.prop_stdev_ix] : mk.prop_stdev_fixed;
+		const double* traj = a.cell_values + ((long long)c * a.rows + mk.row0) * a.cell_stride + j;
+		const double* obs = mk.observed + (long long)i * a.T;
+		if (a.only_k >= 0) {
+			const int k = a.only_k;
+			double x = traj[(long long)k * a.cell_stride];
+			if (a.rel_k >= 0) {
+				x += offset;
+				x /= traj[(long long)a.rel_k * a.cell_stride];
+				x *= scale;
+			} else {
+				x *= scale;
+				x += offset;
+			}
+			if (l == 0 && (isnan(traj[(long long)k * a.cell_stride]) || (a.rel_k >= 0 && isnan(traj[(long long)a.rel_k * a.cell_stride])))) no_value = true;
+			const double y = obs[k];
+			if (isnan(y)) continue; // DataLikelihoodTimePoints.cpp:275-279
+			if (a.error_model == CP_ERR_NORMAL) {
+				const double two_sigma_sq = 2.0 * stdev * stdev, d = y - x;
+				cell_logp += -log(stdev) - 0.91893853320467274178032973640562 - d * d / two_sigma_sq;
+			} else {
+				cell_logp += logpdf_tnu4(y, x, stdev);
+			}
+			continue;
 		}
-		const double y = obs[k];
-		if (a.error_model == CP_ERR_NORMAL) {
-			const double two_sigma_sq = 2.0 * stdev * stdev, d = y - x;
-			cell_logp = -log(stdev) - 0.91893853320467274178032973640562 - d * d / two_sigma_sq;
-		} else {
-			cell_logp = logpdf_tnu4(y, x, stdev);
+		const double minus_log_sigma = -log(stdev);
+		const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
+		auto value = [&](int k) { // .cpp:236-254: *= data scale, += data offset, the signal saturation
+			double v = traj[(long long)k * a.cell_stride];
+			v *= scale;
+			v += offset;
+			if (a.saturation_ix >= 0) {
+				const double s = tv[a.saturation_ix];
+				v *= -1.0;
+				v = exp(v);
+				v += 1.0;
+				v = 1.0 / v;
+				v *= s;
+				v -= 0.5 * s;
+			}
+			return v;
+		};
+		double opt_offset = 0.0, opt_scale = 1.0;
+		if (a.optimize) {
+			double mu_x = 0.0, mu_y = 0.0, xvar_calc = 0.0, cov_calc = 0.0, empirical_n = 0.0;
+			for (int k = 0; k < a.T; k++) {
+				const double xv = value(k), yv = obs[k];
+				if (isnan(xv) || isnan(yv)) continue;
+				empirical_n += 1.0;
+				const double invN = 1.0 / empirical_n, mu_x_nm1 = mu_x, mu_y_nm1 = mu_y;
+				mu_x += (xv - mu_x) * invN;
+				mu_y += (yv - mu_y) * invN;
+				if (empirical_n > 1) {
+					const double ratio = (empirical_n - 1) / empirical_n, dx = xv - mu_x_nm1, dy = yv - mu_y_nm1;
+					xvar_calc += dx * dx * ratio;
+					cov_calc += dx * dy * ratio;
+				}
+			}
+			if (empirical_n >= 2) {
+				opt_scale = cov_calc / xvar_calc;
+				opt_offset = mu_y - mu_x * opt_scale;
+			}
+			// std::min(std::max(v, lo), hi): a NaN slope (no variance in the simulated trajectory) stays NaN
+			opt_scale = (opt_scale < a.opt_scale_min) ? a.opt_scale_min : opt_scale;
+			opt_scale = (a.opt_scale_max < opt_scale) ? a.opt_scale_max : opt_scale;
+			opt_offset = (opt_offset < a.opt_offset_min) ? a.opt_offset_min : opt_offset;
+			opt_offset = (a.opt_offset_max < opt_offset) ? a.opt_offset_max : opt_offset;
 		}
-		if (isnan(x)) cell_logp = NAN;
-		a.lik[((long long)cz * a.n_obs + i) * a.n_sim + j] = cell_logp;
-		return;
-	}
-	double opt_offset = 0.0, opt_scale = 1.0;
-	if (a.optimize) {
-		double mu_x = 0.0, mu_y = 0.0, xvar_calc = 0.0, cov_calc = 0.0, empirical_n = 0.0;
 		for (int k = 0; k < a.T; k++) {
-			const double xv = value(k), yv = obs[k];
-			if (isnan(xv) || isnan(yv)) continue;
-			empirical_n += 1.0;
-			const double invN = 1.0 / empirical_n, mu_x_nm1 = mu_x, mu_y_nm1 = mu_y;
-			mu_x += (xv - mu_x) * invN;
-			mu_y += (yv - mu_y) * invN;
-			if (empirical_n > 1) {
-				const double ratio = (empirical_n - 1) / empirical_n, dx = xv - mu_x_nm1, dy = yv - mu_y_nm1;
-				xvar_calc += dx * dx * ratio;
-				cov_calc += dx * dy * ratio;
+			const double y = obs[k];
+			if (isnan(y)) continue;
+			const double x = opt_offset + opt_scale * value(k);
+			if (isnan(x)) {
+				double first_ok = a.timepoints[a.T - 1], last_ok = a.timepoints[0];
+				for (int m = 0; m < a.T; m++)
+					if (!isnan(value(m))) {
+						first_ok = a.timepoints[m];
+						break;
+					}
+				for (int m = a.T - 1; m >= 0; m--)
+					if (!isnan(value(m))) {
+						last_ok = a.timepoints[m];
+						break;
+					}
+				const double time_offset = fmin(fabs(a.timepoints[k] - first_ok), fabs(a.timepoints[k] - last_ok));
+				if (a.error_model == CP_ERR_STUDENT_T4) cell_logp += logpdf_tnu4(time_offset, 0.0, a.missing_stdev);
+				else cell_logp += -log(a.missing_stdev) - 0.91893853320467274178032973640562 - time_offset * time_offset / (2.0 * a.missing_stdev * a.missing_stdev);
+			} else if (a.error_model == CP_ERR_NORMAL) {
+				const double d = y - x;
+				cell_logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
+			} else if (a.error_model == CP_ERR_STUDENT_T4) {
+				cell_logp += logpdf_tnu4(y, x, stdev);
+			} else { // .cpp:272-283: sigma from the simulated value
+				double sigma = prop_stdev * fmax(x, 0.0);
+				if (a.error_model == CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL) sigma += stdev;
+				const double d = y - x;
+				cell_logp += -log(sigma) - 0.91893853320467274178032973640562 - d * d * (1.0 / (2.0 * (sigma * sigma)));
 			}
 		}
-		if (empirical_n >= 2) {
-			opt_scale = cov_calc / xvar_calc;
-			opt_offset = mu_y - mu_x * opt_scale;
-		}
-		// std::min(std::max(v, lo), hi): a NaN slope (no variance in the simulated trajectory) stays NaN
-		opt_scale = (opt_scale < a.opt_scale_min) ? a.opt_scale_min : opt_scale;
-		opt_scale = (a.opt_scale_max < opt_scale) ? a.opt_scale_max : opt_scale;
-		opt_offset = (opt_offset < a.opt_offset_min) ? a.opt_offset_min : opt_offset;
-		opt_offset = (a.opt_offset_max < opt_offset) ? a.opt_offset_max : opt_offset;
+		if (cell_logp == -INFINITY) break; // .cpp:485-488
 	}
-	for (int k = 0; k < a.T; k++) {
-		const double y = obs[k];
-		if (isnan(y)) continue;
-		const double x = opt_offset + opt_scale * value(k);
-		if (isnan(x)) {
-			double first_ok = a.timepoints[a.T - 1], last_ok = a.timepoints[0];
-			for (int m = 0; m < a.T; m++)
-				if (!isnan(value(m))) {
-					first_ok = a.timepoints[m];
-					break;
-				}
-			for (int m = a.T - 1; m >= 0; m--)
-				if (!isnan(value(m))) {
-					last_ok = a.timepoints[m];
-					break;
-				}
-			const double time_offset = fmin(fabs(a.timepoints[k] - first_ok), fabs(a.timepoints[k] - last_ok));
-			if (a.error_model == CP_ERR_STUDENT_T4) cell_logp += logpdf_tnu4(time_offset, 0.0, a.missing_stdev);
-			else cell_logp += -log(a.missing_stdev) - 0.91893853320467274178032973640562 - time_offset * time_offset / (2.0 * a.missing_stdev * a.missing_stdev);
-		} else if (a.error_model == CP_ERR_NORMAL) {
-			const double d = y - x;
-			cell_logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
-		} else if (a.error_model == CP_ERR_STUDENT_T4) {
-			cell_logp += logpdf_tnu4(y, x, stdev);
-		} else { // .cpp:272-283: sigma from the simulated value
-			double sigma = prop_stdev * fmax(x, 0.0);
-			if (a.error_model == CP_ERR_ADDITIVE_PROPORTIONAL_NORMAL) sigma += stdev;
-			const double d = y - x;
-			cell_logp += -log(sigma) - 0.91893853320467274178032973640562 - d * d * (1.0 / (2.0 * (sigma * sigma)));
-		}
-	}
+	if (no_value) cell_logp = NAN;
 	a.lik[((long long)cz * a.n_obs + i) * a.n_sim + j] = cell_logp;
 }
 
@@ -1240,6 +1256,19 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		if (cp.saturation_scale_ix >= cp.nvar) return fail(BCM3B200_ERR_ARG, "saturation_scale_ix out of range");
 		for (size_t k = 0; k < cp.more.size(); k++)
 			if (cp.more[k]->saturation_scale_ix >= cp.nvar) return fail(BCM3B200_ERR_ARG, "saturation_scale_ix@%zu out of range", k + 1);
+		for (size_t k = 0; k < cp.more.size(); k++) {
+			const CellPopState::MoreData& mk = *cp.more[k];
+			if (mk.marker_of < 0) continue;
+			if (mk.marker_of > (int)k) return fail(BCM3B200_ERR_ARG, "marker_of@%zu must name an earlier data set", k + 1);
+			const bool of_first = (mk.marker_of == 0);
+			const CellPopState::MoreData* parent = of_first ? nullptr : cp.more[(size_t)mk.marker_of - 1].get();
+			if (parent && parent->marker_of >= 0) return fail(BCM3B200_ERR_ARG, "marker_of@%zu names a marker, not a data set", k + 1);
+			const int pkind = of_first ? cp.data_kind : parent->data_kind, pT = of_first ? cp.T : parent->T, pR = of_first ? cp.R : parent->R;
+			const std::vector<double>& ptime = of_first ? cp.data["timepoints"] : parent->timepoints;
+			if (pkind == 0) return fail(BCM3B200_ERR_ARG, "marker_of@%zu: several markers exist for the per-cell data kinds only", k + 1);
+			if (mk.T != pT || mk.R != pR || mk.timepoints != ptime)
+				return fail(BCM3B200_ERR_ARG, "marker_of@%zu: a marker shares the timepoints and the observed cells of its data set", k + 1);
+		}
 		auto check_optimize = [&](int kind, bool optimize, int error_model) -> int {
 			if (!optimize) return BCM3B200_OK;
 			if (kind != 1) return fail(BCM3B200_ERR_ARG, "optimize_offset_scale belongs to data_kind time_course");
@@ -1271,6 +1300,7 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		if (rck != BCM3B200_OK) return rck;
 		for (size_t k = 0; k < cp.more.size(); k++) {
 			const CellPopState::MoreData& mk = *cp.more[k];
+			if (mk.marker_of >= 0) continue;
 			rck = check_kind(mk.data_kind, mk.R, mk.T, mk.relative_to_time_average, mk.error_model, mk.value_relative_to_timepoint_ix);
 			if (rck != BCM3B200_OK) return rck;
 		}
@@ -1664,6 +1694,10 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	int row0 = cp.T;
 	for (const auto& mp : cp.more) {
 		const CellPopState::MoreData& m = *mp;
+		if (m.marker_of >= 0) { // a further marker of a per-cell data set: no term of its own
+			row0 += m.T;
+			continue;
+		}
 		la.avg_row0 = row0;
 		la.accumulate = 1;
 		la.timepoints = m.d_time.p;
@@ -1730,6 +1764,10 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 		const CellPopState::MoreData* m = (k >= 0) ? cp.more[(size_t)k].get() : nullptr;
 		const int T = m ? m->T : cp.T;
 		const int kind = m ? m->data_kind : cp.data_kind;
+		if (m && m->marker_of >= 0) { // rows of a further marker: used by the data set it belongs to
+			row0 += T;
+			continue;
+		}
 		if (kind != 0) {
 			const int n = cp.cells_local;
 			const int n_obs = m ? m->R : cp.R; // time_course: = n; time_points: the observed cell slots (<= n)
@@ -1737,7 +1775,6 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			a.cell_values = cp.d_cellvals.p;
 			a.rows = cp.rows();
 			a.cell_stride = cp.capacity();
-			a.row0 = row0;
 			a.T = T;
 			a.n_obs = n_obs;
 			a.n_sim = n;
@@ -1746,15 +1783,41 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			a.stdev_relative_to_scale = (m ? m->stdev_relative_to_scale : cp.stdev_relative_to_scale) ? 1 : 0;
 			a.transformed = cp.d_transformed.p;
 			a.timepoints = m ? m->d_time.p : cp.d_time.p;
-			a.observed = m ? m->d_obs.p : cp.d_obs.p;
-			a.stdev_ix = m ? m->stdev_ix : cp.stdev_ix;
-			a.offset_ix = m ? m->offset_ix : cp.offset_ix;
-			a.scale_ix = m ? m->scale_ix : cp.scale_ix;
-			a.prop_stdev_ix = m ? m->prop_stdev_ix : cp.prop_stdev_ix;
-			a.stdev_fixed = m ? m->stdev_fixed : cp.stdev_fixed;
-			a.offset_fixed = m ? m->offset_fixed : cp.offset_fixed;
-			a.scale_fixed = m ? m->scale_fixed : cp.scale_fixed;
-			a.prop_stdev_fixed = m ? m->prop_stdev_fixed : cp.prop_stdev_fixed;
+			// marker 0: the data set itself; then the entries of `more` that name it as their data set
+			std::vector<const std::vector<double>*> observed_of_marker;
+			a.L = 1;
+			a.mk[0].row0 = row0;
+			a.mk[0].observed = m ? m->d_obs.p : cp.d_obs.p;
+			a.mk[0].stdev_ix = m ? m->stdev_ix : cp.stdev_ix;
+			a.mk[0].offset_ix = m ? m->offset_ix : cp.offset_ix;
+			a.mk[0].scale_ix = m ? m->scale_ix : cp.scale_ix;
+			a.mk[0].prop_stdev_ix = m ? m->prop_stdev_ix : cp.prop_stdev_ix;
+			a.mk[0].stdev_fixed = m ? m->stdev_fixed : cp.stdev_fixed;
+			a.mk[0].offset_fixed = m ? m->offset_fixed : cp.offset_fixed;
+			a.mk[0].scale_fixed = m ? m->scale_fixed : cp.scale_fixed;
+			a.mk[0].prop_stdev_fixed = m ? m->prop_stdev_fixed : cp.prop_stdev_fixed;
+			observed_of_marker.push_back(m ? &m->observed : &cp.data["observed"]);
+			{
+				int r = cp.T;
+				for (size_t q = 0; q < cp.more.size(); q++) {
+					const CellPopState::MoreData& f = *cp.more[q];
+					if (f.marker_of == k + 1 && a.L < 4) {
+						CpMarkerArgs& mk = a.mk[a.L++];
+						mk.row0 = r;
+						mk.observed = f.d_obs.p;
+						mk.stdev_ix = f.stdev_ix;
+						mk.offset_ix = f.offset_ix;
+						mk.scale_ix = f.scale_ix;
+						mk.prop_stdev_ix = f.prop_stdev_ix;
+						mk.stdev_fixed = f.stdev_fixed;
+						mk.offset_fixed = f.offset_fixed;
+						mk.scale_fixed = f.scale_fixed;
+						mk.prop_stdev_fixed = f.prop_stdev_fixed;
+						observed_of_marker.push_back(&f.observed);
+					}
+					r += f.T;
+				}
+			}
 			a.missing_stdev = m ? m->missing_stdev : cp.missing_simulation_time_stdev;
 			a.optimize = (kind == 1 && (m ? m->optimize_offset_scale : cp.optimize_offset_scale)) ? 1 : 0;
 			a.opt_offset_min = m ? m->optimize_offset_min : cp.optimize_offset_min;
@@ -1828,13 +1891,15 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 					logp[c] += term * weight;
 				});
 			} else {
-				const std::vector<double>& observed = m ? m->observed : cp.data["observed"];
 				std::vector<double> term(Cc, 0.0);
 				std::vector<char> dead(Cc, 0);
 				for (int ti = 0; ti < T; ti++) {
-					std::vector<int> rows;
-					for (int i = 0; i < n_obs; i++)
-						if (std::isfinite(observed[(size_t)i * T + ti])) rows.push_back(i);
+					std::vector<int> rows; // the observed cells with a finite value in any marker, .cpp:222-227
+					for (int i = 0; i < n_obs; i++) {
+						bool any = false;
+						for (const std::vector<double>* ob : observed_of_marker) any = any || std::isfinite((*ob)[(size_t)i * T + ti]);
+						if (any) rows.push_back(i);
+					}
 					if (rows.empty()) continue; // .cpp:229-231
 					a.only_k = ti;
 					int rc = run_block();

@@ -170,19 +170,44 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				}
 				if (c.get_bool("relative_to_time_average", false)) return Fail("relative_to_time_average belongs to time_course_population_average data");
 			}
-			ds.species_name = c.get("species_name");
-			if (ds.species_name.find(';') != std::string::npos) return Fail("one observed quantity per data set is supported");
+			// species_name="a+b;c": several MARKERS per cell (DataLikelihoodTimeCourseBase.cpp:79-87), each with the entry of the
+			// ';'-separated stdev / proportional_stdev / offset / scale lists that has its index -- or the only entry when a list
+			// has one (DataLikelihoodBase.cpp:75-119, 130-233). Per-cell data types only; every marker after the first becomes a
+			// data set of its own here (SetData supplies its observed block) that names the first as its owner.
+			auto split_list = [](const std::string& text) {
+				std::vector<std::string> out;
+				std::stringstream ss(text);
+				std::string part;
+				while (std::getline(ss, part, ';')) {
+					const size_t b = part.find_first_not_of(" \t"), en = part.find_last_not_of(" \t");
+					out.push_back(b == std::string::npos ? std::string() : part.substr(b, en - b + 1));
+				}
+				if (out.empty()) out.push_back(std::string());
+				return out;
+			};
+			const std::vector<std::string> marker_species = split_list(c.get("species_name"));
+			if (marker_species.size() > 1 && type == "time_course_population_average") return Fail("one observed quantity per population-average data set is supported");
+			if (marker_species.size() > 4) return Fail("more than four markers per data set are not supported by the GPU path");
+			auto list_entry = [&](const char* attr, const char* def, size_t l, std::string& out) {
+				const std::vector<std::string> tokens = split_list(c.get(attr, def));
+				if (tokens.size() == 1) out = tokens[0];
+				else if (l < tokens.size()) out = tokens[l];
+				else return Fail(std::string("the ") + attr + " list is shorter than the list of markers (DataLikelihoodBase.cpp: Out of bounds)");
+				return true;
+			};
+			ds.species_name = marker_species[0];
 			ds.error_model = c.get("error_model", "normal");
-			if (!Resolve(c.get("stdev", "1"), ds.stdev, "stdev")) return false;
+			std::string entry;
+			if (!list_entry("stdev", "1", 0, entry) || !Resolve(entry, ds.stdev, "stdev")) return false;
 			if (c.has("proportional_stdev")) {
 				ds.have_proportional_stdev = true;
-				if (!Resolve(c.get("proportional_stdev"), ds.proportional_stdev, "proportional_stdev")) return false;
+				if (!list_entry("proportional_stdev", "1", 0, entry) || !Resolve(entry, ds.proportional_stdev, "proportional_stdev")) return false;
 			}
 			// DataLikelihoodBase.cpp:64-69
 			if ((ds.error_model == "proportional_normal" || ds.error_model == "additive_proportional_normal") && !ds.have_proportional_stdev)
 				return Fail("Proportional error model is selected, but proportional stdev has not been specified.");
-			if (!Resolve(c.get("offset", "0"), ds.offset, "offset")) return false;
-			if (!Resolve(c.get("scale", "1"), ds.scale, "scale")) return false;
+			if (!list_entry("offset", "0", 0, entry) || !Resolve(entry, ds.offset, "offset")) return false;
+			if (!list_entry("scale", "1", 0, entry) || !Resolve(entry, ds.scale, "scale")) return false;
 			ds.relative_to_time_average = c.get_bool("relative_to_time_average", false);
 			ds.stdev_relative_to_scale = c.get_bool("stdev_relative_to_scale", false); // DataLikelihoodBase.cpp:48
 			// attributes of DataLikelihoodTimeCourseBase::Load (.cpp:41-57) that change the population average and are not built
@@ -192,6 +217,17 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 			ds.weight = c.get_real("weight", 1.0);
 			ds.missing_stdev = c.get_real("missing_simulation_time_stdev", 300.0);
 			e.data.push_back(ds);
+			const long owner = (long)e.data.size() - 1;
+			for (size_t l = 1; l < marker_species.size(); l++) {
+				DataSet mk = ds;
+				mk.marker_of = owner;
+				mk.species_name = marker_species[l];
+				if (!list_entry("stdev", "1", l, entry) || !Resolve(entry, mk.stdev, "stdev")) return false;
+				if (mk.have_proportional_stdev && (!list_entry("proportional_stdev", "1", l, entry) || !Resolve(entry, mk.proportional_stdev, "proportional_stdev"))) return false;
+				if (!list_entry("offset", "0", l, entry) || !Resolve(entry, mk.offset, "offset")) return false;
+				if (!list_entry("scale", "1", l, entry) || !Resolve(entry, mk.scale, "scale")) return false;
+				e.data.push_back(mk);
+			}
 		} else if (c.name == "treatment_trajectory") {
 			// Experiment.cpp:566-590 + TreatmentTrajectoryPulses::Load
 			if (c.get("type") != "pulses") return Fail("treatment_trajectory type \"" + c.get("type") + "\" is not supported by the GPU path (pulses only)");
@@ -302,10 +338,25 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 		bool can_share = share_integration && e.model.species_names.size() <= 96;
 		for (const auto& ds : e.data)
 			for (size_t i = 1; i < ds.data.timepoints.size(); i++) can_share = can_share && ds.data.timepoints[i] > ds.data.timepoints[i - 1];
+		// a data set and its further markers (marker_of) always share a handle: they are ONE likelihood
+		auto with_markers = [&](size_t k) { // number of entries of e.data that data set k and its markers occupy
+			size_t n = 1;
+			while (k + n < e.data.size() && e.data[k + n].marker_of == (long)k) n++;
+			return n;
+		};
 		for (size_t k = 0; k < e.data.size();) {
 			std::vector<DataSet*> followers;
-			const size_t group = can_share ? std::min<size_t>(4, e.data.size() - k) : 1;
-			for (size_t j = 1; j < group; j++) followers.push_back(&e.data[k + j]);
+			size_t group = with_markers(k);
+			if (group > 4) return Fail("a data set with more than three further markers does not fit one handle");
+			while (can_share && k + group < e.data.size() && group + with_markers(k + group) <= 4) group += with_markers(k + group);
+			for (size_t j = 1; j < group; j++) {
+				followers.push_back(&e.data[k + j]);
+				if (e.data[k + j].marker_of >= 0) {
+					const DataSet& owner = e.data[(size_t)e.data[k + j].marker_of];
+					if (e.data[k + j].data.timepoints != owner.data.timepoints || e.data[k + j].data.num_replicates != owner.data.num_replicates)
+						return Fail("SetData(): a marker shares the timepoints and the observed cells of the data set it belongs to");
+				}
+			}
 			if (!CreateHandle(e, e.data[k], end_time, followers)) return false;
 			k += group;
 		}
@@ -396,6 +447,13 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		if (f.type != "time_course_population_average") d << ";data_kind" << sfx << "=" << f.type;
 		if (f.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix" << sfx << "=" << f.value_relative_to_timepoint_ix;
 		if (f.saturation_scale_ix >= 0) d << ";saturation_scale_ix" << sfx << "=" << f.saturation_scale_ix;
+		if (f.marker_of >= 0) { // position of the owner inside this handle: 0 = ds, q + 1 = followers[q]
+			long at = (&e.data[(size_t)f.marker_of] == &ds) ? 0 : -1;
+			for (size_t q = 0; q < followers.size() && at < 0; q++)
+				if (followers[q] == &e.data[(size_t)f.marker_of]) at = (long)q + 1;
+			if (at < 0) return Fail("internal: a marker and its data set ended up in different handles");
+			d << ";marker_of" << sfx << "=" << at;
+		}
 		if (f.optimize_offset_scale)
 			d << ";optimize_offset_scale" << sfx << "=1;optimize_offset_min" << sfx << "=" << f.optimize_offset_min << ";optimize_offset_max" << sfx << "=" << f.optimize_offset_max
 			  << ";optimize_scale_min" << sfx << "=" << f.optimize_scale_min << ";optimize_scale_max" << sfx << "=" << f.optimize_scale_max;

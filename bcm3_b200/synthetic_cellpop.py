@@ -253,7 +253,8 @@ def make_cellpop_problem(N: int = 12, num_cells: int = 10_000, T: int = 50, t_en
 
 
 def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end: float = 8.0, seed: int = 41, noise: float = 0.03,
-                             missing_fraction: float = 0.0, two_species_readout: bool = False, rate_decades: float = 2.0) -> CellPopProblem:
+                             missing_fraction: float = 0.0, two_species_readout: bool = False, rate_decades: float = 2.0,
+                             extra_marker_species: tuple = ()) -> CellPopProblem:
     """<data type="time_course">: one observed trajectory per cell (live-cell imaging), as many observed as simulated cells. The
     observations are the trajectories of `num_cells` cells at the reference parameters (their own quasi-random draws, in a shuffled
     order) plus noise: the likelihood has to find out which simulated cell goes with which observed one."""
@@ -268,6 +269,7 @@ def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end
     rng = np.random.default_rng(seed + 2000)
     u = sobol_points(2 * num_cells, len(base.variability))[num_cells:]  # other draws than the simulated cells will take
     observed = np.empty((num_cells, T))
+    marker_observed = [np.empty((num_cells, T)) for _ in extra_marker_species]
     for ci in range(num_cells):
         p = tv.copy()
         y0 = base.initial_conditions.copy()
@@ -278,22 +280,35 @@ def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end
         sol = solve_ivp(lambda t, y: f(t, y, base.constant_species, p), (0.0, float(base.timepoints[-1])), y0, method="LSODA", t_eval=base.timepoints,
                         rtol=1e-7, atol=1e-9)
         observed[ci] = sol.y[base.obs_species].sum(axis=0)
-    observed = observed[rng.permutation(num_cells)] + noise * rng.standard_normal(observed.shape)
+        for mo, sp in zip(marker_observed, extra_marker_species):
+            mo[ci] = sol.y[list(sp)].sum(axis=0)
+    order = rng.permutation(num_cells)
+    observed = observed[order] + noise * rng.standard_normal(observed.shape)
     if missing_fraction > 0:
         observed[rng.uniform(size=observed.shape) < missing_fraction] = np.nan
     import dataclasses
 
-    return dataclasses.replace(base, observed=observed, data_kind="time_course", stdev_ix=None, stdev=noise * 1.5)
+    from .cellpop_data import Marker
+
+    # further markers (species_name="a;b;c"): the same observed cells in the same order, every marker with its own scale and noise
+    markers = []
+    for l, (mo, sp) in enumerate(zip(marker_observed, extra_marker_species), start=1):
+        scale = 1.0 + 0.4 * l
+        mobs = scale * mo[order] + 0.02 * l + noise * scale * rng.standard_normal(mo.shape)
+        if missing_fraction > 0:
+            mobs[rng.uniform(size=mobs.shape) < missing_fraction] = np.nan
+        markers.append(Marker(obs_species=list(sp), observed=mobs, stdev=noise * 1.5 * scale, scale=scale, offset=0.02 * l))
+    return dataclasses.replace(base, observed=observed, data_kind="time_course", stdev_ix=None, stdev=noise * 1.5, extra_markers=markers)
 
 
 def make_time_points_problem(N: int = 8, num_cells: int = 24, T: int = 8, t_end: float = 8.0, seed: int = 45, noise: float = 0.03,
-                             min_fraction: float = 0.4, relative_to: int | None = None) -> CellPopProblem:
+                             min_fraction: float = 0.4, relative_to: int | None = None, extra_marker_species: tuple = ()) -> CellPopProblem:
     """<data type="time_points">: snapshots -- at every timepoint a different number of observed cells (fixed-cell imaging, flow
     cytometry), each value matched to one simulated cell at that time. `observed` is [num_cells slots][T]; the slots a timepoint
     does not fill are NaN, in no particular order."""
     import dataclasses
 
-    tc = make_time_course_problem(N=N, num_cells=num_cells, T=T, t_end=t_end, seed=seed, noise=noise)
+    tc = make_time_course_problem(N=N, num_cells=num_cells, T=T, t_end=t_end, seed=seed, noise=noise, extra_marker_species=extra_marker_species)
     rng = np.random.default_rng(seed + 3000)
     observed = tc.observed.copy()
     for ti in range(T):
@@ -303,7 +318,12 @@ def make_time_points_problem(N: int = 8, num_cells: int = 24, T: int = 8, t_end:
     if relative_to is not None:
         ref = np.nanmean(tc.observed[:, relative_to])
         observed = observed / ref
-    return dataclasses.replace(tc, observed=observed, data_kind="time_points", value_relative_to_timepoint_ix=relative_to)
+    markers = []
+    for mk in tc.extra_markers:  # a cell that is absent at a timepoint is absent in every marker; a few values missing on top of that
+        mobs = np.where(np.isnan(observed), np.nan, mk.observed)
+        mobs[rng.uniform(size=mobs.shape) < 0.05] = np.nan
+        markers.append(dataclasses.replace(mk, observed=mobs))
+    return dataclasses.replace(tc, observed=observed, data_kind="time_points", value_relative_to_timepoint_ix=relative_to, extra_markers=markers)
 
 
 def make_chain_values(C: int, seed: int = 20261018) -> np.ndarray:

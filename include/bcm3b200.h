@@ -85,6 +85,14 @@ extern "C" {
  *                        optimize_scale_max=10] (DataLikelihoodTimeCourseBase.cpp:43-57, 317-322): every pair regresses the
  *                        observed on the simulated trajectory first (normal | student_t4 only);
  *                        saturation_scale_ix=<variable>: the signal saturation of DataLikelihoodTimeCourse.cpp:243-254
+ *                       several MARKERS per cell (species_name="a+b;c" with ';'-separated stdev / offset / scale lists,
+ *                        DataLikelihoodTimeCourseBase.cpp:79-87, DataLikelihoodBase.cpp:130-233): every marker after the first is
+ *                        passed as a further data set of the handle (num_data_sets, suffix @k: num_timepoints, num_replicates,
+ *                        obs_species, the stdev / offset / scale keys, "timepoints@k", "observed@k") that carries
+ *                        marker_of@k=<index of the per-cell data set it belongs to, 0 = the first>; it has the timepoints and
+ *                        observed cells of that data set and no term of its own -- its values enter that data set's cell
+ *                        likelihoods (time_course: all markers summed per pair; time_points: a simulated cell counts when
+ *                        marker 0 has a value, missing observations of a marker are skipped)
  *                  num_data_sets=<D <= 4>: the experiment's further <data> elements share this handle's ONE integration of
  *                       the cells; data set k >= 1 repeats num_timepoints, num_replicates, obs_species, error_model, weight, data_kind,
  *                       the stdev/offset/scale keys and the relative_to/missing keys with the suffix @k ("stdev_ix@1=5")

@@ -186,6 +186,8 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	const double target_time = longer ? pr.sim_end_time : pr.timepoints[T - 1]; // Experiment::Simulate's simulation_end_time
 	std::vector<double> population_average(T, 0.0);
 	std::vector<double> xs((size_t)T * ncell, nan); // value per (timepoint, cell)
+	const int L = 1 + ((pr.data_kind != 0) ? pr.num_extra_markers : 0); // markers of a per-cell data set
+	std::vector<std::vector<double>> xs_marker((size_t)(L - 1), std::vector<double>((size_t)T * ncell, nan));
 
 	// The population (CellPopulation): cells in creation order. Initial cells take the quasi-random rows 0 .. ninit - 1, the
 	// daughters of the cell with row r take ninit + 2 r + child (CellPopulation.cpp:56-80).
@@ -263,6 +265,12 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 				double x = 0.0;
 				for (int k = 0; k < pr.num_obs_species; k++) x += out[(size_t)pr.obs_species[k] + (size_t)i * N];
 				xs[(size_t)i * ncell + ci] = x;
+				for (int l = 1; l < L; l++) {
+					const oracle_cellpop_marker& mk = pr.extra_markers[l - 1];
+					double xm = 0.0;
+					for (int k = 0; k < mk.num_obs_species; k++) xm += out[(size_t)mk.obs_species[k] + (size_t)i * N];
+					xs_marker[(size_t)(l - 1)][(size_t)i * ncell + ci] = xm;
+				}
 			}
 		}
 	};
@@ -345,108 +353,146 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	}
 	if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = population_average[i];
 
+	// per-marker view of a per-cell data set: marker 0 is the problem's own entries, the others come from extra_markers
+	struct MarkerView {
+		const double* xs;       // [T][ncell] species sum per (timepoint, cell)
+		const double* observed; // [observed cells][T]
+		double stdev, offset, scale, prop_stdev;
+	};
+	std::vector<MarkerView> markers;
+	if (pr.data_kind != 0) {
+		for (int l = 0; l < L; l++) {
+			MarkerView mv;
+			if (l == 0) {
+				mv.xs = xs.data();
+				mv.observed = pr.observed;
+				mv.stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
+				mv.offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
+				mv.scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
+				mv.prop_stdev = (pr.proportional_stdev_ix >= 0) ? transformed[pr.proportional_stdev_ix] : pr.proportional_stdev;
+			} else {
+				const oracle_cellpop_marker& mk = pr.extra_markers[l - 1];
+				mv.xs = xs_marker[(size_t)(l - 1)].data();
+				mv.observed = mk.observed;
+				mv.stdev = (mk.stdev_ix >= 0) ? transformed[mk.stdev_ix] : mk.stdev;
+				mv.offset = (mk.offset_ix >= 0) ? transformed[mk.offset_ix] : mk.offset;
+				mv.scale = (mk.scale_ix >= 0) ? transformed[mk.scale_ix] : mk.scale;
+				mv.prop_stdev = (mk.proportional_stdev_ix >= 0) ? transformed[mk.proportional_stdev_ix] : mk.proportional_stdev;
+			}
+			if (pr.stdev_relative_to_scale) mv.stdev *= mv.scale; // GetCurrentSTDev(.., i), DataLikelihoodBase.cpp:151-153
+			markers.push_back(mv);
+		}
+	}
+
 	if (pr.data_kind == 1) {
 		// <data type="time_course">: DataLikelihoodTimeCourse::Evaluate (.cpp:230-365) with CalculateCellLikelihood (.cpp:431-505) and
-		// CalculateMissingValueLikelihood (.cpp:566-588) -- synchronize="none", no parent information, one marker, no offset/scale
-		// optimisation, no saturation. The trajectory of simulated cell j is column j of xs (NotifySimulatedValue .cpp:367-404 adds the
-		// species of a sum); observed cell i is row i of `observed`.
+		// CalculateMissingValueLikelihood (.cpp:566-588) -- synchronize="none", no parent information. The trajectory of simulated
+		// cell j for marker l is column j of that marker's xs (NotifySimulatedValue .cpp:367-404 adds the species of a sum);
+		// observed cell i is row i of the marker's `observed`.
 		const int n_obs = R, n_sim = nactive;
-		double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
-		const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
-		const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
-		if (pr.stdev_relative_to_scale) stdev *= scale;
-		const double prop_stdev = (pr.proportional_stdev_ix >= 0) ? transformed[pr.proportional_stdev_ix] : pr.proportional_stdev;
-		std::vector<double> traj((size_t)T * n_sim), min_log_sigma, inv_two_sigma_sq_cell;
-		for (int k = 0; k < T; k++)
-			for (int j = 0; j < n_sim; j++) {
-				double v = xs[(size_t)k * ncell + j];
-				v *= scale; // .cpp:236-241
-				v += offset;
-				if (pr.saturation_scale_ix >= 0) { // .cpp:243-254, operation by operation
-					const double saturation_scale = transformed[pr.saturation_scale_ix];
-					v *= -1.0;
-					v = exp(v);
-					v += 1.0;
-					v = 1.0 / v;
-					v *= saturation_scale;
-					v -= 0.5 * saturation_scale;
+		std::vector<std::vector<double>> traj((size_t)L), min_log_sigma((size_t)L), inv_two_sigma_sq_cell((size_t)L);
+		for (int l = 0; l < L; l++) {
+			const MarkerView& mv = markers[(size_t)l];
+			traj[(size_t)l].resize((size_t)T * n_sim);
+			for (int k = 0; k < T; k++)
+				for (int j = 0; j < n_sim; j++) {
+					double v = mv.xs[(size_t)k * ncell + j];
+					v *= mv.scale; // .cpp:236-241
+					v += mv.offset;
+					if (pr.saturation_scale_ix >= 0) { // .cpp:243-254, operation by operation
+						const double saturation_scale = transformed[pr.saturation_scale_ix];
+						v *= -1.0;
+						v = exp(v);
+						v += 1.0;
+						v = 1.0 / v;
+						v *= saturation_scale;
+						v -= 0.5 * saturation_scale;
+					}
+					traj[(size_t)l][(size_t)k * n_sim + j] = v;
 				}
-				traj[(size_t)k * n_sim + j] = v;
-			}
-		if (pr.error_model == 2 || pr.error_model == 3) { // .cpp:272-283
-			min_log_sigma.resize(traj.size());
-			inv_two_sigma_sq_cell.resize(traj.size());
-			for (size_t e = 0; e < traj.size(); e++) {
-				double sigma = prop_stdev * std::max(traj[e], 0.0);
-				if (pr.error_model == 3) sigma += stdev;
-				min_log_sigma[e] = -log(sigma);
-				inv_two_sigma_sq_cell[e] = 1.0 / (2.0 * (sigma * sigma));
+			if (pr.error_model == 2 || pr.error_model == 3) { // .cpp:272-283
+				min_log_sigma[(size_t)l].resize(traj[(size_t)l].size());
+				inv_two_sigma_sq_cell[(size_t)l].resize(traj[(size_t)l].size());
+				for (size_t e = 0; e < traj[(size_t)l].size(); e++) {
+					double sigma = mv.prop_stdev * std::max(traj[(size_t)l][e], 0.0);
+					if (pr.error_model == 3) sigma += mv.stdev;
+					min_log_sigma[(size_t)l][e] = -log(sigma);
+					inv_two_sigma_sq_cell[(size_t)l][e] = 1.0 / (2.0 * (sigma * sigma));
+				}
 			}
 		}
-		auto missing_value = [&](int j, int k) { // .cpp:566-588
+		auto missing_value = [&](int l, int j, int k) { // .cpp:566-588
+			const std::vector<double>& tr = traj[(size_t)l];
 			double first_ok = pr.timepoints[T - 1], last_ok = pr.timepoints[0];
-			for (int m = 0; m < T; m++) if (!std::isnan(traj[(size_t)m * n_sim + j])) { first_ok = pr.timepoints[m]; break; }
-			for (int m = T - 1; m >= 0; m--) if (!std::isnan(traj[(size_t)m * n_sim + j])) { last_ok = pr.timepoints[m]; break; }
+			for (int m = 0; m < T; m++) if (!std::isnan(tr[(size_t)m * n_sim + j])) { first_ok = pr.timepoints[m]; break; }
+			for (int m = T - 1; m >= 0; m--) if (!std::isnan(tr[(size_t)m * n_sim + j])) { last_ok = pr.timepoints[m]; break; }
 			const double time_offset = std::min(std::abs(pr.timepoints[k] - first_ok), std::abs(pr.timepoints[k] - last_ok));
 			return (pr.error_model == 1) ? logpdf_tnu4(time_offset, 0, pr.missing_stdev) : logpdf_normal(time_offset, 0, pr.missing_stdev);
 		};
 		const int n = std::max(n_obs, n_sim);
 		std::vector<double> cell_likelihoods((size_t)n * n, 0.0);
-		const double minus_log_sigma = -log(stdev), inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
+		const double ninf = -std::numeric_limits<double>::infinity();
 		for (int i = 0; i < n_obs; i++) {
 			int finite_count = 0;
 			for (int j = 0; j < n_sim; j++) {
 				double cell_logp = 0.0;
-				double opt_offset = 0.0, opt_scale = 1.0;
-				if (pr.optimize_offset_scale) {
-					// OptimizeOffsetScale (DataLikelihoodTimeCourseBase.cpp:317-322) = bcm3::linear_regress_columns(simulated, observed)
-					// (Correlation.cpp:158-200: running means, NaN pairs skipped) + the clamps
-					double mu_x = 0.0, mu_y = 0.0, xvar_calc = 0.0, cov_calc = 0.0, empirical_n = 0.0;
+				for (int l = 0; l < L; l++) {
+					const MarkerView& mv = markers[(size_t)l];
+					const std::vector<double>& tr = traj[(size_t)l];
+					double opt_offset = 0.0, opt_scale = 1.0;
+					if (pr.optimize_offset_scale) {
+						// OptimizeOffsetScale (DataLikelihoodTimeCourseBase.cpp:317-322) = bcm3::linear_regress_columns(simulated, observed)
+						// (Correlation.cpp:158-200: running means, NaN pairs skipped) + the clamps
+						double mu_x = 0.0, mu_y = 0.0, xvar_calc = 0.0, cov_calc = 0.0, empirical_n = 0.0;
+						for (int k = 0; k < T; k++) {
+							const double xv = tr[(size_t)k * n_sim + j], yv = mv.observed[(size_t)i * T + k];
+							if (std::isnan(xv) || std::isnan(yv)) continue;
+							empirical_n += 1.0;
+							const double invN = 1.0 / empirical_n, mu_x_nm1 = mu_x, mu_y_nm1 = mu_y;
+							mu_x += (xv - mu_x) * invN;
+							mu_y += (yv - mu_y) * invN;
+							if (empirical_n > 1) {
+								const double ratio = (empirical_n - 1) / empirical_n, dx = xv - mu_x_nm1, dy = yv - mu_y_nm1;
+								xvar_calc += dx * dx * ratio;
+								cov_calc += dx * dy * ratio;
+							}
+						}
+						if (empirical_n >= 2) {
+							opt_scale = cov_calc / xvar_calc;
+							opt_offset = mu_y - mu_x * opt_scale;
+						}
+						opt_scale = std::min(std::max(opt_scale, pr.optimize_scale_min), pr.optimize_scale_max);
+						opt_offset = std::min(std::max(opt_offset, pr.optimize_offset_min), pr.optimize_offset_max);
+					}
+					const double minus_log_sigma = -log(mv.stdev), inv_two_sigma_sq = 1.0 / (2.0 * mv.stdev * mv.stdev); // .cpp:452-453
 					for (int k = 0; k < T; k++) {
-						const double xv = traj[(size_t)k * n_sim + j], yv = pr.observed[(size_t)i * T + k];
-						if (std::isnan(xv) || std::isnan(yv)) continue;
-						empirical_n += 1.0;
-						const double invN = 1.0 / empirical_n, mu_x_nm1 = mu_x, mu_y_nm1 = mu_y;
-						mu_x += (xv - mu_x) * invN;
-						mu_y += (yv - mu_y) * invN;
-						if (empirical_n > 1) {
-							const double ratio = (empirical_n - 1) / empirical_n, dx = xv - mu_x_nm1, dy = yv - mu_y_nm1;
-							xvar_calc += dx * dx * ratio;
-							cov_calc += dx * dy * ratio;
+						const double y = mv.observed[(size_t)i * T + k];
+						if (std::isnan(y)) continue;
+						const double x = opt_offset + opt_scale * tr[(size_t)k * n_sim + j]; // .cpp:461
+						if (std::isnan(x)) {
+							cell_logp += missing_value(l, j, k);
+						} else if (pr.error_model == 0) {
+							const double d = y - x;
+							cell_logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
+						} else if (pr.error_model == 1) {
+							cell_logp += logpdf_tnu4(y, x, mv.stdev);
+						} else {
+							const double d = y - x;
+							cell_logp += min_log_sigma[(size_t)l][(size_t)k * n_sim + j] - 0.91893853320467274178032973640562 -
+							             d * d * inv_two_sigma_sq_cell[(size_t)l][(size_t)k * n_sim + j];
 						}
 					}
-					if (empirical_n >= 2) {
-						opt_scale = cov_calc / xvar_calc;
-						opt_offset = mu_y - mu_x * opt_scale;
-					}
-					opt_scale = std::min(std::max(opt_scale, pr.optimize_scale_min), pr.optimize_scale_max);
-					opt_offset = std::min(std::max(opt_offset, pr.optimize_offset_min), pr.optimize_offset_max);
-				}
-				for (int k = 0; k < T; k++) {
-					const double y = pr.observed[(size_t)i * T + k];
-					if (std::isnan(y)) continue;
-					const double x = opt_offset + opt_scale * traj[(size_t)k * n_sim + j]; // .cpp:461
-					if (std::isnan(x)) {
-						cell_logp += missing_value(j, k);
-					} else if (pr.error_model == 0) {
-						const double d = y - x;
-						cell_logp += minus_log_sigma - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq;
-					} else if (pr.error_model == 1) {
-						cell_logp += logpdf_tnu4(y, x, stdev);
-					} else {
-						const double d = y - x;
-						cell_logp += min_log_sigma[(size_t)k * n_sim + j] - 0.91893853320467274178032973640562 - d * d * inv_two_sigma_sq_cell[(size_t)k * n_sim + j];
-					}
+					if (cell_logp == ninf) break; // .cpp:485-488: negative infinity -- no need to go further
 				}
 				cell_likelihoods[(size_t)i * n + j] = cell_logp;
 				if (cell_logp != cell_logp) { // .cpp:301-304
-					*logp_out = -std::numeric_limits<double>::infinity();
+					*logp_out = ninf;
 					return;
 				}
-				if (cell_logp > -std::numeric_limits<double>::infinity()) finite_count++;
+				if (cell_logp > ninf) finite_count++;
 			}
 			if (finite_count < n_obs) { // .cpp:316-320
-				*logp_out = -std::numeric_limits<double>::infinity();
+				*logp_out = ninf;
 				return;
 			}
 		}
@@ -455,14 +501,14 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 			for (int j = 0; j < n_sim; j++) cost[(size_t)i * n_sim + j] = -cell_likelihoods[(size_t)i * n + j];
 		const std::vector<int> matching = hungarian_match(n, n_sim, n_obs, cost); // .cpp:323
 		if ((int)matching.size() != n_obs) {
-			*logp_out = -std::numeric_limits<double>::infinity();
+			*logp_out = ninf;
 			return;
 		}
 		double logp = 0.0;
 		for (int i = 0; i < n_obs; i++) {
 			const int j = matching[i];
 			if (j == -1) {
-				*logp_out = -std::numeric_limits<double>::infinity();
+				*logp_out = ninf;
 				return;
 			}
 			logp += cell_likelihoods[(size_t)i * n + j];
@@ -474,19 +520,19 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	if (pr.data_kind == 2) {
 		// <data type="time_points">: DataLikelihoodTimePoints::Evaluate (DataLikelihoodTimePoints.cpp:209-345) -- at every timepoint
 		// its own set of observed cells (row i of `observed`, NaN = no such cell at that time), matched to the simulated cells that
-		// have a value there. synchronize="none", one marker. The Hungarian call is rectangular (observed cells x simulated cells with
-		// a value); the reference's implementation keeps only the edges whose right node index lies below the number of LEFT nodes
-		// (hungarian.cpp:81), i.e. the first simulated cells -- the adapter hands it the edge list as Evaluate builds it.
-		double stdev = (pr.stdev_ix >= 0) ? transformed[pr.stdev_ix] : pr.stdev;
-		const double offset = (pr.offset_ix >= 0) ? transformed[pr.offset_ix] : pr.offset;
-		const double scale = (pr.scale_ix >= 0) ? transformed[pr.scale_ix] : pr.scale;
-		if (pr.stdev_relative_to_scale) stdev *= scale;
+		// have a value there (in marker 0). synchronize="none". The Hungarian call is rectangular (observed cells x simulated cells
+		// with a value); the reference's implementation keeps only the edges whose right node index lies below the number of LEFT
+		// nodes (hungarian.cpp:81), i.e. the first simulated cells -- the adapter hands it the edge list as Evaluate builds it.
 		const int rel = pr.value_relative_to_timepoint_ix;
 		const int n_sim_all = ncell; // cell_trajectories has one entry per cell object (GetMaxNumberOfCells)
 		double logp = 0.0;
 		for (int ti = 0; ti < T; ti++) {
 			std::vector<int> rows, cols;
-			for (int i = 0; i < R; i++) if (std::isfinite(pr.observed[(size_t)i * T + ti])) rows.push_back(i);
+			for (int i = 0; i < R; i++) { // a row with any finite value in any marker, .cpp:222-227
+				bool any = false;
+				for (int l = 0; l < L; l++) any = any || std::isfinite(markers[(size_t)l].observed[(size_t)i * T + ti]);
+				if (any) rows.push_back(i);
+			}
 			if (rows.empty()) continue;
 			for (int j = 0; j < n_sim_all; j++)
 				if (!std::isnan(xs[(size_t)ti * ncell + j]) && (rel < 0 || !std::isnan(xs[(size_t)rel * ncell + j]))) cols.push_back(j);
@@ -496,36 +542,40 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 			}
 			const int fd = (int)rows.size(), fs = (int)cols.size();
 			std::vector<double> lik((size_t)fd * fs), cost((size_t)fd * fs);
-			for (int a = 0; a < fd; a++)
-				for (int b = 0; b < fs; b++) {
-					double x = xs[(size_t)ti * ncell + cols[b]];
-					if (rel >= 0) {
-						x += offset;
-						x /= xs[(size_t)rel * ncell + cols[b]];
-						x *= scale;
-					} else {
-						x *= scale;
-						x += offset;
-					}
-					const double y = pr.observed[(size_t)rows[a] * T + ti];
+			for (int a2 = 0; a2 < fd; a2++)
+				for (int b2 = 0; b2 < fs; b2++) {
 					double cell_logp = 0.0;
-					if (pr.error_model == 0) cell_logp += logpdf_normal(y, x, stdev);
-					else if (pr.error_model == 1) cell_logp += logpdf_tnu4(y, x, stdev);
-					else cell_logp = nan; // assert(false) in the reference: the other error models do not exist for this data type
-					lik[(size_t)a * fs + b] = cell_logp;
-					cost[(size_t)a * fs + b] = -cell_logp;
+					for (int l = 0; l < L; l++) {
+						const MarkerView& mv = markers[(size_t)l];
+						double x = mv.xs[(size_t)ti * ncell + cols[b2]];
+						if (rel >= 0) {
+							x += mv.offset;
+							x /= mv.xs[(size_t)rel * ncell + cols[b2]];
+							x *= mv.scale;
+						} else {
+							x *= mv.scale;
+							x += mv.offset;
+						}
+						const double y = mv.observed[(size_t)rows[a2] * T + ti];
+						if (std::isnan(y)) continue; // .cpp:275-279: the other markers' missing values are ignored
+						if (pr.error_model == 0) cell_logp += logpdf_normal(y, x, mv.stdev);
+						else if (pr.error_model == 1) cell_logp += logpdf_tnu4(y, x, mv.stdev);
+						else cell_logp = nan; // assert(false) in the reference: the other error models do not exist for this data type
+					}
+					lik[(size_t)a2 * fs + b2] = cell_logp;
+					cost[(size_t)a2 * fs + b2] = -cell_logp;
 				}
 			const std::vector<int> matching = hungarian_match(fd, fs, fd, cost); // .cpp:306-307
 			if ((int)matching.size() != fd) {
 				*logp_out = -std::numeric_limits<double>::infinity();
 				return;
 			}
-			for (int a = 0; a < fd; a++) {
-				if (matching[a] == -1) {
+			for (int a2 = 0; a2 < fd; a2++) {
+				if (matching[a2] == -1) {
 					*logp_out = -std::numeric_limits<double>::infinity();
 					return;
 				}
-				logp += lik[(size_t)a * fs + matching[a]];
+				logp += lik[(size_t)a2 * fs + matching[a2]];
 			}
 		}
 		*logp_out = logp * pr.weight;

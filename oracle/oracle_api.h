@@ -103,6 +103,16 @@ int oracle_poppk_evaluate(const oracle_poppk_problem* prob, size_t num_chains, c
 typedef void (*oracle_derivative_fn)(double* out, const double* species, const double* constant_species, const double* parameters,
                                      const double* non_sampled_parameters); /* SolverCodeGenerator.h:6 */
 
+/* A further MARKER of a per-cell data set (species_name="a+b;c": the part after a ';', DataLikelihoodTimeCourseBase.cpp:79-87):
+ * its own observed block, species sum and stdev / offset / scale entries (DataLikelihoodBase.cpp:130-233: lists separated by ';') */
+typedef struct {
+	int32_t num_obs_species;
+	int32_t obs_species[8];
+	int32_t stdev_ix, offset_ix, scale_ix, proportional_stdev_ix; /* -1: fixed */
+	double stdev, offset, scale, proportional_stdev;
+	const double* observed; /* [observed cells][T] */
+} oracle_cellpop_marker;
+
 typedef struct {
 	int32_t num_species, num_constant_species, num_variables, num_non_sampled, num_cells, num_timepoints, num_replicates, variability_dim;
 	int32_t entry_time_ix; /* -1: fixed */
@@ -162,6 +172,9 @@ typedef struct {
 	 * is parsed by the reference and then overwritten with DBL_MAX in PrepateEvaluation, DataLikelihoodTimeCourseBase.cpp:243-246:
 	 * only the variable form is usable there, and only it exists here.) */
 	int32_t saturation_scale_ix;
+	/* per-cell data kinds: the markers after the first (which is obs_species / observed / stdev ... above) */
+	int32_t num_extra_markers;
+	const oracle_cellpop_marker* extra_markers;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

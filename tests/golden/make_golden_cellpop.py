@@ -67,6 +67,10 @@ CASES = {
     # the data went through the same curve with s = 0.5
     "cellpop_time_course_n6_saturation": (dict(_builder="time_course", N=6, num_cells=20, T=10, seed=47), 3,
                                           dict(saturation_scale_ix=sc.VAR_K_FEEDBACK, scale=4.0, _saturated_data=(4.0, 0.5), stdev=0.01)),
+    # species_name="a;b+c;d": three markers per cell, each with its own scale, offset and stdev (DataLikelihoodBase.cpp:130-233), missing values
+    "cellpop_time_course_n8_three_markers": (dict(_builder="time_course", N=8, num_cells=20, T=10, seed=48, missing_fraction=0.1,
+                                                  extra_marker_species=((5, 6), (3,))), 3, dict(error_model="student_t4", weight=0.8)),
+    "cellpop_time_points_n8_two_markers": (dict(_builder="time_points", N=8, num_cells=24, T=8, seed=49, extra_marker_species=((4,),)), 3, {}),
     # <data type="time_points">: at every timepoint its own set of observed cells, matched to the simulated cells (rectangular
     # Hungarian calls: fewer observed than simulated cells at most timepoints), DataLikelihoodTimePoints.cpp:209-345
     "cellpop_time_points_n8_normal": (dict(_builder="time_points", N=8, num_cells=24, T=8, seed=45), 3, {}),
@@ -116,7 +120,13 @@ def main():
             prob = dataclasses.replace(prob, observed=np.abs(prob.observed) + 0.05)
         vals = fixed_values if fixed_values is not None else sc.make_chain_values(C, seed=zlib.crc32(name.encode()) % 10000)
         r = ref.cellpop_evaluate(prob, vals, threads=1, want_cell_values=True, want_steps=True, want_average=True)
-        out = {f.name: getattr(prob, f.name) for f in dataclasses.fields(prob) if f.name not in ("variability", "covariance")}
+        out = {f.name: getattr(prob, f.name) for f in dataclasses.fields(prob) if f.name not in ("variability", "covariance", "extra_markers")}
+        if prob.extra_markers:  # [marker][...]: species lists padded with -1, one row of (stdev_ix, stdev, proportional_stdev_ix, proportional_stdev, offset_ix, offset, scale_ix, scale)
+            opt = lambda v: -1.0 if v is None else float(v)
+            out["marker_obs_species"] = np.array([list(m.obs_species) + [-1] * (8 - len(m.obs_species)) for m in prob.extra_markers], dtype=np.int64)
+            out["marker_observed"] = np.stack([np.asarray(m.observed, dtype=np.float64) for m in prob.extra_markers])
+            out["marker_parameters"] = np.array([[opt(m.stdev_ix), m.stdev, opt(m.proportional_stdev_ix), m.proportional_stdev, opt(m.offset_ix), m.offset,
+                                                  opt(m.scale_ix), m.scale] for m in prob.extra_markers], dtype=np.float64)
         out["covariance_rows"] = prob.covariance_rows()
         out = {k: (np.array(v) if not isinstance(v, np.ndarray) else v) for k, v in out.items() if v is not None}
         out["variability_rows"] = prob.variability_rows()

@@ -373,3 +373,50 @@ def test_cell_population_plugin_time_course_with_offset_scale_optimisation(built
     want = chk.cellpop_evaluate(tc, vals)["logp"]
     assert np.isfinite(want).all()
     assert np.all(np.abs(got - want) <= parity_tolerance(None) * np.abs(want)), (got, want)
+
+
+def test_cell_population_plugin_time_course_with_three_markers(built):
+    """species_name="a;b+c;d" with ';'-separated stdev / offset / scale lists: three markers per cell in one likelihood (the plugin
+    hands every further marker to the library as a data set that names the first as its owner); against the CPU checker."""
+    import math
+    import oracle
+    from bcm3_b200 import synthetic_cellpop as sc
+    from tests.util import cellpop_xml, open_cellpop_session, parity_tolerance
+    import dataclasses
+
+    tc = sc.make_time_course_problem(N=8, num_cells=28, T=10, seed=65, missing_fraction=0.08, extra_marker_species=((5, 6), (3,)))
+    prior, _, species = cellpop_xml(tc)
+    names = lambda sp: "+".join(species[s] for s in sp)
+    mk = tc.extra_markers
+    species_attr = ";".join([names(tc.obs_species)] + [names(m.obs_species) for m in mk])
+    lst = lambda f: ";".join(repr(float(v)) for v in f)
+    lik = ('<bcm_likelihood type="cell_population">'
+           f'<experiment name="imaging" model_file="cascade.xml" entry_time="0" num_cells="{tc.num_cells}" max_cells="{tc.num_cells}" divide_cells="false">'
+           '<cell_variability distribution="diagonal_gaussian">'
+           '<variable model_parameter="k_in" apply="multiplicative_log" scale="variability_scale"/>'
+           '<variable model_parameter="k_deg" apply="multiplicative_log" scale="variability_scale" negate="true"/>'
+           f'<variable initial_condition_species="x1" apply="additive" scale="{math.log(0.01)!r}"/>'
+           '</cell_variability>'
+           f'<data type="time_course" data_name="cells" species_name="{species_attr}" stdev="{lst([tc.stdev] + [m.stdev for m in mk])}" '
+           f'offset="{lst([tc.offset] + [m.offset for m in mk])}" scale="{lst([tc.scale] + [m.scale for m in mk])}" error_model="student_t4"/>'
+           '</experiment></bcm_likelihood>')
+    tc = dataclasses.replace(tc, error_model="student_t4")
+    vals = sc.make_chain_values(3, seed=65)
+    from bcm3_b200 import host_api
+
+    s = host_api.CellPopSession(prior, lik)
+    assert s.num_data_sets == [3]  # the three markers: every one takes its observed block through set_data
+    s.set_model(tc, species)
+    s.set_sobol(0, tc.sobol)
+    s.set_data(0, 0, tc.timepoints, tc.observed)
+    for l, m in enumerate(mk, start=1):
+        s.set_data(0, l, tc.timepoints, m.observed)
+    s.post_initialize()
+    got = s.evaluate(vals, batched=True)
+    serial = s.evaluate(vals, batched=False)
+    s.close()
+    assert np.array_equal(got, serial)
+    chk = oracle.load("ref" if oracle.available("ref") else "port")
+    want = chk.cellpop_evaluate(tc, vals)["logp"]
+    assert np.isfinite(want).all()
+    assert np.all(np.abs(got - want) <= parity_tolerance(None) * np.abs(want)), (got, want)

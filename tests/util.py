@@ -128,6 +128,15 @@ def load_cellpop_golden(name):
     if "optimize_offset_scale" in z.files and bool(z["optimize_offset_scale"]):
         extra.update(optimize_offset_scale=True, optimize_offset_range=tuple(float(v) for v in z["optimize_offset_range"]),
                      optimize_scale_range=tuple(float(v) for v in z["optimize_scale_range"]))
+    if "marker_observed" in z.files:
+        from bcm3_b200.cellpop_data import Marker
+
+        opt = lambda v: None if v < 0 else int(v)
+        extra.update(extra_markers=[
+            Marker(obs_species=[int(sp) for sp in z["marker_obs_species"][l] if sp >= 0], observed=z["marker_observed"][l],
+                   stdev_ix=opt(q[0]), stdev=float(q[1]), proportional_stdev_ix=opt(q[2]), proportional_stdev=float(q[3]),
+                   offset_ix=opt(q[4]), offset=float(q[5]), scale_ix=opt(q[6]), scale=float(q[7]))
+            for l, q in enumerate(z["marker_parameters"])])
     if "saturation_scale_ix" in z.files:
         extra.update(saturation_scale_ix=int(z["saturation_scale_ix"]))
     if "value_relative_to_timepoint_ix" in z.files:
