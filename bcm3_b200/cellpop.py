@@ -60,9 +60,21 @@ class CellPopEvaluator:
                 kv[name + "_ix"] = ix
             else:
                 kv[name] = repr(float(getattr(p, name)))
-        # further markers of a per-cell data set: data sets @1, @2, ... of the handle that name data set 0 as theirs (marker_of)
-        if p.extra_markers:
-            kv["num_data_sets"] = 1 + len(p.extra_markers)
+        # further markers of a per-cell data set: data sets @1, @2, ... of the handle that name data set 0 as theirs (marker_of);
+        # after them the denominators of log ratios (use_log_ratio): value rows only, flagged denominator_of = the entry they divide
+        self._denominators = []
+        if p.log_ratio_denominator is not None:
+            self._denominators.append((0, int(p.log_ratio_denominator)))
+        for k, mk in enumerate(p.extra_markers, start=1):
+            if mk.log_ratio_denominator is not None:
+                self._denominators.append((k, int(mk.log_ratio_denominator)))
+        if p.extra_markers or self._denominators:
+            kv["num_data_sets"] = 1 + len(p.extra_markers) + len(self._denominators)
+            for q, (owner, species) in enumerate(self._denominators, start=1 + len(p.extra_markers)):
+                kv[f"denominator_of@{q}"] = owner
+                kv[f"num_timepoints@{q}"] = p.num_timepoints
+                kv[f"num_replicates@{q}"] = 1
+                kv[f"obs_species@{q}"] = species
             for k, mk in enumerate(p.extra_markers, start=1):
                 kv[f"marker_of@{k}"] = 0
                 kv[f"num_timepoints@{k}"] = p.num_timepoints
@@ -87,6 +99,9 @@ class CellPopEvaluator:
             for k, mk in enumerate(p.extra_markers, start=1):
                 self._set(f"timepoints@{k}", p.timepoints)
                 self._set(f"observed@{k}", np.asarray(mk.observed, dtype=np.float64))
+            for q in range(1 + len(p.extra_markers), 1 + len(p.extra_markers) + len(self._denominators)):
+                self._set(f"timepoints@{q}", p.timepoints)
+                self._set(f"observed@{q}", np.zeros((1, p.num_timepoints)))  # a denominator has no observations of its own
             self._set("transforms", p.transforms)
             if p.treatment_species is not None and len(p.treatment_times):
                 self._set("treatment_times", np.asarray(p.treatment_times, dtype=np.float64))
@@ -162,7 +177,7 @@ class CellPopEvaluator:
         avg = np.empty((nC, rows))
         _lib.check(self.lib.bcm3b200_get_cell_diagnostics(self.handle, vals.ctypes.data, status.ctypes.data, steps.ctypes.data, avg.ctypes.data))
         out = dict(cell_values=np.ascontiguousarray(vals[:, :T]), cell_status=status, cell_steps=steps, population_average=np.ascontiguousarray(avg[:, :T]))
-        if rows > T:
+        if rows > T:  # further markers, then the denominators of log ratios
             out["marker_values"] = [np.ascontiguousarray(vals[:, T * l:T * (l + 1)]) for l in range(1, rows // T)]
         return out
 

@@ -59,6 +59,7 @@ class Marker:
     offset: float = 0.0
     scale_ix: int | None = None
     scale: float = 1.0
+    log_ratio_denominator: int | None = None  # use_log_ratio: species b of "a/b" (obs_species = [a])
 
 
 @dataclass
@@ -98,6 +99,9 @@ class CellPopProblem:
     # time_course: <data saturation_scale="variable"> (DataLikelihoodTimeCourse.cpp:243-254): index of the variable s of the signal
     # saturation s / (1 + exp(-x)) - s / 2 applied to the scaled and shifted trajectories
     saturation_scale_ix: int | None = None
+    # time_course: <data use_log_ratio="true" species_name="a/b"> (DataLikelihoodTimeCourse.cpp:380-397): the cell's value is
+    # log10(a / b), b replaced by 1e-16 when smaller; obs_species = [a], this = b. With markers, every marker is a ratio.
+    log_ratio_denominator: int | None = None
     # per-cell data kinds: the markers after the first one (which is obs_species / observed / stdev ... of this problem)
     extra_markers: list = field(default_factory=list)
     optimize_offset_range: tuple = (-1.0, 1.0)

@@ -250,6 +250,7 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 			m->value_relative_to_timepoint_ix = get_int(kv, key("value_relative_to_timepoint_ix").c_str(), -1);
 			m->saturation_scale_ix = get_int(kv, key("saturation_scale_ix").c_str(), -1);
 			m->marker_of = get_int(kv, key("marker_of").c_str(), -1);
+			m->denominator_of = get_int(kv, key("denominator_of").c_str(), -1);
 			m->optimize_offset_scale = get_int(kv, key("optimize_offset_scale").c_str(), 0) != 0;
 			m->optimize_offset_min = realk("optimize_offset_min", -1.0);
 			m->optimize_offset_max = realk("optimize_offset_max", 1.0);

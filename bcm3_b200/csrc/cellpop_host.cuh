@@ -80,6 +80,10 @@ struct CellPopState {
 		// with that index (0 = the handle's first data set, j = more[j - 1]): its rows, observed block and stdev / offset / scale
 		// entries enter that data set's cell likelihoods (DataLikelihoodTimeCourse.cpp:449-489, DataLikelihoodTimePoints.cpp:264-289)
 		int marker_of = -1;
+		// >= 0: the rows of this entry hold the DENOMINATOR of the log ratio (use_log_ratio, species_name="a/b",
+		// DataLikelihoodTimeCourse.cpp:380-397) of the time_course data set or marker with that index (same numbering)
+		int denominator_of = -1;
+		bool rides() const { return marker_of >= 0 || denominator_of >= 0; } // value rows for another entry, no term of its own
 		int stdev_ix = -1, offset_ix = -1, scale_ix = -1, prop_stdev_ix = -1;
 		double stdev_fixed = 1.0, offset_fixed = 0.0, scale_fixed = 1.0, prop_stdev_fixed = 1.0, weight = 1.0, missing_stdev = 300.0;
 		bool relative_to_time_average = false, stdev_relative_to_scale = false;
@@ -527,6 +531,7 @@ __global__ void cellpop_datalik_kernel(const CpLikArgs a, int C)
 // marker (species_name="a+b;c": the entries between the ';') has its own rows, observed block and stdev / offset / scale.
 struct CpMarkerArgs {
 	int row0, stdev_ix, offset_ix, scale_ix, prop_stdev_ix;
+	int den_row0; // >= 0: use_log_ratio -- the value is 0.4342944819032518 * log(rows(row0) / rows(den_row0)), denominator >= 1e-16
 	double stdev_fixed, offset_fixed, scale_fixed, prop_stdev_fixed;
 	const double* observed; // [n_obs][T]
 };
@@ -590,8 +595,13 @@ __global__ void cellpop_cell_likelihood_kernel(const CpCellLikArgs a)
 		}
 		const double minus_log_sigma = -log(stdev);
 		const double inv_two_sigma_sq = 1.0 / (2.0 * stdev * stdev);
-		auto value = [&](int k) { // .cpp:236-254: *= data scale, += data offset, the signal saturation
+		const double* dtraj = (mk.den_row0 >= 0) ? a.cell_values + ((long long)c * a.rows + mk.den_row0) * a.cell_stride + j : nullptr;
+		auto value = [&](int k) { // NotifySimulatedValue's log ratio (.cpp:380-397), then .cpp:236-254: *= data scale, += data offset, the signal saturation
 			double v = traj[(long long)k * a.cell_stride];
+			if (dtraj) {
+				const double den = dtraj[(long long)k * a.cell_stride];
+				v = 0.4342944819032518276511289189166 * ((den < 1e-16) ? log(v / 1e-16) : log(v / den));
+			}
 			v *= scale;
 			v += offset;
 			if (a.saturation_ix >= 0) {
@@ -1257,6 +1267,19 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		for (size_t k = 0; k < cp.more.size(); k++)
 			if (cp.more[k]->saturation_scale_ix >= cp.nvar) return fail(BCM3B200_ERR_ARG, "saturation_scale_ix@%zu out of range", k + 1);
 		for (size_t k = 0; k < cp.more.size(); k++) {
+			const CellPopState::MoreData& dn = *cp.more[k];
+			if (dn.denominator_of < 0) continue;
+			if (dn.marker_of >= 0 || dn.denominator_of > (int)k) return fail(BCM3B200_ERR_ARG, "denominator_of@%zu must name an earlier data set or marker", k + 1);
+			const bool of_first = (dn.denominator_of == 0);
+			const CellPopState::MoreData* owner = of_first ? nullptr : cp.more[(size_t)dn.denominator_of - 1].get();
+			if (owner && owner->denominator_of >= 0) return fail(BCM3B200_ERR_ARG, "denominator_of@%zu names a denominator", k + 1);
+			const int okind = of_first ? cp.data_kind : (owner->marker_of >= 0 ? (owner->marker_of == 0 ? cp.data_kind : cp.more[(size_t)owner->marker_of - 1]->data_kind) : owner->data_kind);
+			if (okind != 1) return fail(BCM3B200_ERR_ARG, "denominator_of@%zu: the log ratio exists for data_kind time_course only (DataLikelihoodTimeCourse.cpp:380-397)", k + 1);
+			const std::vector<double>& otime = of_first ? cp.data["timepoints"] : owner->timepoints;
+			if (dn.timepoints != otime) return fail(BCM3B200_ERR_ARG, "denominator_of@%zu: a denominator shares the timepoints of its numerator", k + 1);
+			if (dn.obs_species.size() != 1) return fail(BCM3B200_ERR_ARG, "denominator_of@%zu: the ratio of exactly two species (DataLikelihoodTimeCourseBase.cpp:178-181)", k + 1);
+		}
+		for (size_t k = 0; k < cp.more.size(); k++) {
 			const CellPopState::MoreData& mk = *cp.more[k];
 			if (mk.marker_of < 0) continue;
 			if (mk.marker_of > (int)k) return fail(BCM3B200_ERR_ARG, "marker_of@%zu must name an earlier data set", k + 1);
@@ -1300,7 +1323,7 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 		if (rck != BCM3B200_OK) return rck;
 		for (size_t k = 0; k < cp.more.size(); k++) {
 			const CellPopState::MoreData& mk = *cp.more[k];
-			if (mk.marker_of >= 0) continue;
+			if (mk.rides()) continue;
 			rck = check_kind(mk.data_kind, mk.R, mk.T, mk.relative_to_time_average, mk.error_model, mk.value_relative_to_timepoint_ix);
 			if (rck != BCM3B200_OK) return rck;
 		}
@@ -1694,7 +1717,7 @@ inline int cellpop_data_likelihood(CellPopState& cp, size_t C, cudaStream_t st)
 	int row0 = cp.T;
 	for (const auto& mp : cp.more) {
 		const CellPopState::MoreData& m = *mp;
-		if (m.marker_of >= 0) { // a further marker of a per-cell data set: no term of its own
+		if (m.rides()) { // a further marker (or a ratio's denominator) of a per-cell data set: no term of its own
 			row0 += m.T;
 			continue;
 		}
@@ -1764,7 +1787,7 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 		const CellPopState::MoreData* m = (k >= 0) ? cp.more[(size_t)k].get() : nullptr;
 		const int T = m ? m->T : cp.T;
 		const int kind = m ? m->data_kind : cp.data_kind;
-		if (m && m->marker_of >= 0) { // rows of a further marker: used by the data set it belongs to
+		if (m && m->rides()) { // rows of a further marker / of a denominator: used by the data set they belong to
 			row0 += T;
 			continue;
 		}
@@ -1785,8 +1808,17 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			a.timepoints = m ? m->d_time.p : cp.d_time.p;
 			// marker 0: the data set itself; then the entries of `more` that name it as their data set
 			std::vector<const std::vector<double>*> observed_of_marker;
+			auto denominator_rows = [&](int entry) { // first row of the entry of `more` that is the denominator of `entry`, or -1
+				int r = cp.T;
+				for (size_t q = 0; q < cp.more.size(); q++) {
+					if (cp.more[q]->denominator_of == entry) return r;
+					r += cp.more[q]->T;
+				}
+				return -1;
+			};
 			a.L = 1;
 			a.mk[0].row0 = row0;
+			a.mk[0].den_row0 = (kind == 1) ? denominator_rows(k + 1) : -1;
 			a.mk[0].observed = m ? m->d_obs.p : cp.d_obs.p;
 			a.mk[0].stdev_ix = m ? m->stdev_ix : cp.stdev_ix;
 			a.mk[0].offset_ix = m ? m->offset_ix : cp.offset_ix;
@@ -1804,6 +1836,7 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 					if (f.marker_of == k + 1 && a.L < 4) {
 						CpMarkerArgs& mk = a.mk[a.L++];
 						mk.row0 = r;
+						mk.den_row0 = (kind == 1) ? denominator_rows((int)q + 1) : -1;
 						mk.observed = f.d_obs.p;
 						mk.stdev_ix = f.stdev_ix;
 						mk.offset_ix = f.offset_ix;

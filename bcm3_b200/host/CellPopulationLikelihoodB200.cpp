@@ -211,7 +211,29 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 			ds.relative_to_time_average = c.get_bool("relative_to_time_average", false);
 			ds.stdev_relative_to_scale = c.get_bool("stdev_relative_to_scale", false); // DataLikelihoodBase.cpp:48
 			// attributes of DataLikelihoodTimeCourseBase::Load (.cpp:41-57) that change the population average and are not built
-			if (c.get_bool("use_log_ratio", false)) return Fail("use_log_ratio is not supported by the GPU path");
+			// use_log_ratio (DataLikelihoodTimeCourseBase.cpp:142-147, 171-201): per-cell time_course data only, every marker "a/b"
+			const bool use_log_ratio = c.get_bool("use_log_ratio", false);
+			if (use_log_ratio && type != "time_course") return Fail("use_log_ratio is supported for time_course data only (DataLikelihoodTimeCourse.cpp:380-397)");
+			auto split_ratio = [&](DataSet& target) {
+				const size_t slash = target.species_name.find('/');
+				if (use_log_ratio) {
+					if (slash == std::string::npos) return Fail("use_log_ratio is specified as true, but the species_name does not contain a division");
+					target.denominator_name = target.species_name.substr(slash + 1);
+					target.species_name = target.species_name.substr(0, slash);
+					auto trim = [](std::string& t) {
+						const size_t b = t.find_first_not_of(" \t"), en = t.find_last_not_of(" \t");
+						t = (b == std::string::npos) ? std::string() : t.substr(b, en - b + 1);
+					};
+					trim(target.denominator_name);
+					trim(target.species_name);
+					if (target.denominator_name.find('/') != std::string::npos || target.species_name.find('+') != std::string::npos || target.denominator_name.find('+') != std::string::npos)
+						return Fail("only division of exactly two species is supported");
+				} else if (slash != std::string::npos) {
+					return Fail("simulated species reference has a division, but use_log_ratio has not been specified; only log ratios are supported for now");
+				}
+				return true;
+			};
+			if (!split_ratio(ds)) return false;
 			if (c.get_bool("include_only_cells_that_went_through_mitosis", false)) return Fail("include_only_cells_that_went_through_mitosis is not supported by the GPU path");
 			// optimize_offset_scale, saturation_scale and value_relative_to_timepoint_ix act on the per-cell data types only
 			ds.weight = c.get_real("weight", 1.0);
@@ -222,6 +244,8 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				DataSet mk = ds;
 				mk.marker_of = owner;
 				mk.species_name = marker_species[l];
+				mk.denominator_name.clear();
+				if (!split_ratio(mk)) return false;
 				if (!list_entry("stdev", "1", l, entry) || !Resolve(entry, mk.stdev, "stdev")) return false;
 				if (mk.have_proportional_stdev && (!list_entry("proportional_stdev", "1", l, entry) || !Resolve(entry, mk.proportional_stdev, "proportional_stdev"))) return false;
 				if (!list_entry("offset", "0", l, entry) || !Resolve(entry, mk.offset, "offset")) return false;
@@ -344,11 +368,16 @@ bool CellPopulationLikelihoodB200::PostInitialize()
 			while (k + n < e.data.size() && e.data[k + n].marker_of == (long)k) n++;
 			return n;
 		};
+		auto slots = [&](size_t k, size_t n) { // value-row blocks of the handle that entries k .. k + n - 1 need: one each + one per log-ratio denominator
+			size_t v = n;
+			for (size_t j = 0; j < n; j++) v += e.data[k + j].denominator_name.empty() ? 0 : 1;
+			return v;
+		};
 		for (size_t k = 0; k < e.data.size();) {
 			std::vector<DataSet*> followers;
 			size_t group = with_markers(k);
-			if (group > 4) return Fail("a data set with more than three further markers does not fit one handle");
-			while (can_share && k + group < e.data.size() && group + with_markers(k + group) <= 4) group += with_markers(k + group);
+			if (slots(k, group) > 4) return Fail("a data set with its further markers and log-ratio denominators needs more than the four value blocks of a handle");
+			while (can_share && k + group < e.data.size() && slots(k, group + with_markers(k + group)) <= 4) group += with_markers(k + group);
 			for (size_t j = 1; j < group; j++) {
 				followers.push_back(&e.data[k + j]);
 				if (e.data[k + j].marker_of >= 0) {
@@ -435,7 +464,21 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	d << ";obs_species=";
 	for (size_t k = 0; k < obs.size(); k++) d << (k ? "+" : "") << obs[k];
 	// the experiment's further data sets that share this handle's integration: the data-set keys again, suffixed @1, @2, ...
-	if (!followers.empty()) d << ";num_data_sets=" << (1 + followers.size());
+	// log-ratio denominators: further value-row blocks of the handle after the followers, each flagged with the entry it divides
+	std::vector<std::pair<size_t, size_t>> denominators; // (entry of the handle, species index)
+	for (size_t j = 0; j <= followers.size(); j++) {
+		const DataSet& owner = (j == 0) ? ds : *followers[j - 1];
+		if (owner.denominator_name.empty()) continue;
+		std::vector<size_t> den;
+		if (!observed_species(owner.denominator_name, den)) return false;
+		denominators.emplace_back(j, den[0]);
+	}
+	if (!followers.empty() || !denominators.empty()) d << ";num_data_sets=" << (1 + followers.size() + denominators.size());
+	for (size_t q = 0; q < denominators.size(); q++) {
+		const std::string sfx = "@" + std::to_string(1 + followers.size() + q);
+		d << ";denominator_of" << sfx << "=" << denominators[q].first << ";num_timepoints" << sfx << "=" << T << ";num_replicates" << sfx << "=1;obs_species" << sfx << "="
+		  << denominators[q].second;
+	}
 	for (size_t j = 0; j < followers.size(); j++) {
 		const DataSet& f = *followers[j];
 		const std::string sfx = "@" + std::to_string(j + 1);
@@ -495,6 +538,12 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		if (!set(("timepoints" + sfx).c_str(), fd.timepoints, { fd.timepoints.size() }) ||
 		    !set(("observed" + sfx).c_str(), fd.observed, { fd.num_replicates, fd.timepoints.size() }))
 			return false;
+	}
+	for (size_t q = 0; q < denominators.size(); q++) { // value rows only: the timepoints of its numerator, no observations
+		const Data& od = (denominators[q].first == 0) ? data : followers[denominators[q].first - 1]->data;
+		const std::string sfx = "@" + std::to_string(1 + followers.size() + q);
+		const std::vector<double> none(od.timepoints.size(), 0.0);
+		if (!set(("timepoints" + sfx).c_str(), od.timepoints, { od.timepoints.size() }) || !set(("observed" + sfx).c_str(), none, { 1, od.timepoints.size() })) return false;
 	}
 	if (!e.treatment_species_name.empty() && !e.treatment_times.empty() && !set("treatment_times", e.treatment_times, { e.treatment_times.size() })) return false;
 	if (D > 0) {

@@ -254,7 +254,7 @@ def make_cellpop_problem(N: int = 12, num_cells: int = 10_000, T: int = 50, t_en
 
 def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end: float = 8.0, seed: int = 41, noise: float = 0.03,
                              missing_fraction: float = 0.0, two_species_readout: bool = False, rate_decades: float = 2.0,
-                             extra_marker_species: tuple = ()) -> CellPopProblem:
+                             extra_marker_species: tuple = (), log_ratio_denominator: int | None = None) -> CellPopProblem:
     """<data type="time_course">: one observed trajectory per cell (live-cell imaging), as many observed as simulated cells. The
     observations are the trajectories of `num_cells` cells at the reference parameters (their own quasi-random draws, in a shuffled
     order) plus noise: the likelihood has to find out which simulated cell goes with which observed one."""
@@ -280,6 +280,9 @@ def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end
         sol = solve_ivp(lambda t, y: f(t, y, base.constant_species, p), (0.0, float(base.timepoints[-1])), y0, method="LSODA", t_eval=base.timepoints,
                         rtol=1e-7, atol=1e-9)
         observed[ci] = sol.y[base.obs_species].sum(axis=0)
+        if log_ratio_denominator is not None:  # use_log_ratio: a ratiometric reporter, species_name="a/b"
+            with np.errstate(divide="ignore", invalid="ignore"):  # both species are 0 at t = 0: the caller leaves that timepoint out
+                observed[ci] = np.log10(observed[ci] / np.maximum(sol.y[log_ratio_denominator], 1e-16))
         for mo, sp in zip(marker_observed, extra_marker_species):
             mo[ci] = sol.y[list(sp)].sum(axis=0)
     order = rng.permutation(num_cells)
@@ -298,7 +301,8 @@ def make_time_course_problem(N: int = 8, num_cells: int = 24, T: int = 12, t_end
         if missing_fraction > 0:
             mobs[rng.uniform(size=mobs.shape) < missing_fraction] = np.nan
         markers.append(Marker(obs_species=list(sp), observed=mobs, stdev=noise * 1.5 * scale, scale=scale, offset=0.02 * l))
-    return dataclasses.replace(base, observed=observed, data_kind="time_course", stdev_ix=None, stdev=noise * 1.5, extra_markers=markers)
+    return dataclasses.replace(base, observed=observed, data_kind="time_course", stdev_ix=None, stdev=noise * 1.5, extra_markers=markers,
+                               log_ratio_denominator=log_ratio_denominator)
 
 
 def make_time_points_problem(N: int = 8, num_cells: int = 24, T: int = 8, t_end: float = 8.0, seed: int = 45, noise: float = 0.03,

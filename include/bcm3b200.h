@@ -93,6 +93,10 @@ extern "C" {
  *                        observed cells of that data set and no term of its own -- its values enter that data set's cell
  *                        likelihoods (time_course: all markers summed per pair; time_points: a simulated cell counts when
  *                        marker 0 has a value, missing observations of a marker are skipped)
+ *                       use_log_ratio (time_course, species_name="a/b", DataLikelihoodTimeCourse.cpp:380-397): obs_species = a; the
+ *                        denominator b is one more entry of the handle (suffix @k: num_timepoints, num_replicates=1, obs_species=b,
+ *                        "timepoints@k", an all-zero "observed@k") that carries denominator_of@k=<index of the data set or
+ *                        marker it divides>: the cell's value is 0.4342944819032518 * log(a / max-guarded b) before scale / offset
  *                  num_data_sets=<D <= 4>: the experiment's further <data> elements share this handle's ONE integration of
  *                       the cells; data set k >= 1 repeats num_timepoints, num_replicates, obs_species, error_model, weight, data_kind,
  *                       the stdev/offset/scale keys and the relative_to/missing keys with the suffix @k ("stdev_ix@1=5")

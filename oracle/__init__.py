@@ -75,7 +75,7 @@ def available(kind: str) -> bool:
 class _CellPopMarker(C.Structure):
     _fields_ = [("num_obs_species", C.c_int32), ("obs_species", C.c_int32 * 8), ("stdev_ix", C.c_int32), ("offset_ix", C.c_int32),
                 ("scale_ix", C.c_int32), ("proportional_stdev_ix", C.c_int32), ("stdev", C.c_double), ("offset", C.c_double),
-                ("scale", C.c_double), ("proportional_stdev", C.c_double), ("observed", C.c_void_p)]
+                ("scale", C.c_double), ("proportional_stdev", C.c_double), ("observed", C.c_void_p), ("log_ratio_denominator", C.c_int32)]
 
 
 class _CellPopProblem(C.Structure):
@@ -93,7 +93,7 @@ class _CellPopProblem(C.Structure):
         ("cytokinesis_ix", C.c_int32), ("apoptosis_ix", C.c_int32), ("reset_ix", C.c_int32 * 7), ("max_dt", C.c_double), ("data_kind", C.c_int32),
         ("value_relative_to_timepoint_ix", C.c_int32), ("optimize_offset_scale", C.c_int32), ("optimize_offset_min", C.c_double),
         ("optimize_offset_max", C.c_double), ("optimize_scale_min", C.c_double), ("optimize_scale_max", C.c_double),
-        ("saturation_scale_ix", C.c_int32), ("num_extra_markers", C.c_int32), ("extra_markers", C.c_void_p)]
+        ("saturation_scale_ix", C.c_int32), ("num_extra_markers", C.c_int32), ("extra_markers", C.c_void_p), ("log_ratio_denominator", C.c_int32)]
 
 
 _derivative_libs: dict[str, C.CDLL] = {}
@@ -226,7 +226,8 @@ def _cellpop_struct(problem, values):
     keep["markers"] = (_CellPopMarker * max(1, len(extra)))(*[
         _CellPopMarker(num_obs_species=len(m.obs_species), obs_species=(C.c_int32 * 8)(*(list(m.obs_species) + [0] * (8 - len(m.obs_species)))),
                        stdev_ix=opt(m.stdev_ix), offset_ix=opt(m.offset_ix), scale_ix=opt(m.scale_ix), proportional_stdev_ix=opt(m.proportional_stdev_ix),
-                       stdev=m.stdev, offset=m.offset, scale=m.scale, proportional_stdev=m.proportional_stdev, observed=o.ctypes.data)
+                       stdev=m.stdev, offset=m.offset, scale=m.scale, proportional_stdev=m.proportional_stdev, observed=o.ctypes.data,
+                       log_ratio_denominator=opt(getattr(m, "log_ratio_denominator", None)))
         for m, o in zip(extra, keep["marker_obs"])])
     s = _CellPopProblem(
         num_species=p.num_species, num_constant_species=len(keep["const"]), num_variables=p.num_variables, num_non_sampled=len(keep["ns"]),
@@ -247,6 +248,7 @@ def _cellpop_struct(problem, values):
         data_kind={"time_course_population_average": 0, "time_course": 1, "time_points": 2}[getattr(p, "data_kind", "time_course_population_average")],
         value_relative_to_timepoint_ix=-1 if getattr(p, "value_relative_to_timepoint_ix", None) is None else int(p.value_relative_to_timepoint_ix),
         saturation_scale_ix=-1 if getattr(p, "saturation_scale_ix", None) is None else int(p.saturation_scale_ix),
+        log_ratio_denominator=opt(getattr(p, "log_ratio_denominator", None)),
         num_extra_markers=len(extra), extra_markers=C.cast(keep["markers"], C.c_void_p).value if extra else None,
         optimize_offset_scale=int(bool(getattr(p, "optimize_offset_scale", False))),
         optimize_offset_min=float(getattr(p, "optimize_offset_range", (-1.0, 1.0))[0]), optimize_offset_max=float(getattr(p, "optimize_offset_range", (-1.0, 1.0))[1]),

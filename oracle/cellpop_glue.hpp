@@ -264,11 +264,18 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 				if (cell_time < 0.0 || cell_time > c.sim_end) continue;
 				double x = 0.0;
 				for (int k = 0; k < pr.num_obs_species; k++) x += out[(size_t)pr.obs_species[k] + (size_t)i * N];
+				// use_log_ratio (NotifySimulatedValue, DataLikelihoodTimeCourse.cpp:380-397): the numerator is notified first (val = a), the
+				// denominator then turns it into bcm3::log10(a / b), b replaced by 1e-16 when it is smaller (MathFunctions.h:11)
+				auto log_ratio = [](double num, double den) {
+					return 0.4342944819032518276511289189166 * ((den < 1e-16) ? log(num / 1e-16) : log(num / den));
+				};
+				if (pr.data_kind == 1 && pr.log_ratio_denominator >= 0) x = log_ratio(x, out[(size_t)pr.log_ratio_denominator + (size_t)i * N]);
 				xs[(size_t)i * ncell + ci] = x;
 				for (int l = 1; l < L; l++) {
 					const oracle_cellpop_marker& mk = pr.extra_markers[l - 1];
 					double xm = 0.0;
 					for (int k = 0; k < mk.num_obs_species; k++) xm += out[(size_t)mk.obs_species[k] + (size_t)i * N];
+					if (pr.data_kind == 1 && mk.log_ratio_denominator >= 0) xm = log_ratio(xm, out[(size_t)mk.log_ratio_denominator + (size_t)i * N]);
 					xs_marker[(size_t)(l - 1)][(size_t)i * ncell + ci] = xm;
 				}
 			}

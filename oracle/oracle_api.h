@@ -111,6 +111,7 @@ typedef struct {
 	int32_t stdev_ix, offset_ix, scale_ix, proportional_stdev_ix; /* -1: fixed */
 	double stdev, offset, scale, proportional_stdev;
 	const double* observed; /* [observed cells][T] */
+	int32_t log_ratio_denominator; /* use_log_ratio: species index of the denominator of "a/b" (obs_species = {a}), -1: none */
 } oracle_cellpop_marker;
 
 typedef struct {
@@ -175,6 +176,10 @@ typedef struct {
 	/* per-cell data kinds: the markers after the first (which is obs_species / observed / stdev ... above) */
 	int32_t num_extra_markers;
 	const oracle_cellpop_marker* extra_markers;
+	/* time_course: <data use_log_ratio="true" species_name="a/b"> (DataLikelihoodTimeCourseBase.cpp:142-147, 171-201;
+	 * DataLikelihoodTimeCourse.cpp:380-397): the cell's value is log10(a / b) = 0.4342944819032518 * log(a / b) with b replaced by
+	 * 1e-16 when it is smaller; obs_species = {a}, this = b (-1: no ratio). Every marker of the data set is a ratio then. */
+	int32_t log_ratio_denominator;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

@@ -70,6 +70,10 @@ CASES = {
     # species_name="a;b+c;d": three markers per cell, each with its own scale, offset and stdev (DataLikelihoodBase.cpp:130-233), missing values
     "cellpop_time_course_n8_three_markers": (dict(_builder="time_course", N=8, num_cells=20, T=10, seed=48, missing_fraction=0.1,
                                                   extra_marker_species=((5, 6), (3,))), 3, dict(error_model="student_t4", weight=0.8)),
+    # use_log_ratio="true" species_name="x7/x3": a ratiometric reporter, the cell's value is log10 of the ratio (the first timepoint, where
+    # the downstream species still are 0, is left out of the data: log10(0 / 0) there)
+    "cellpop_time_course_n8_log_ratio": (dict(_builder="time_course", N=8, num_cells=20, T=10, seed=50, log_ratio_denominator=3, noise=0.05), 3,
+                                         dict(_drop_first_timepoint=True)),
     "cellpop_time_points_n8_two_markers": (dict(_builder="time_points", N=8, num_cells=24, T=8, seed=49, extra_marker_species=((4,),)), 3, {}),
     # <data type="time_points">: at every timepoint its own set of observed cells, matched to the simulated cells (rectangular
     # Hungarian calls: fewer observed than simulated cells at most timepoints), DataLikelihoodTimePoints.cpp:209-345
@@ -93,6 +97,7 @@ def main():
         positive = tweaks.pop("_positive_data", False)
         affine = tweaks.pop("_affine_data", None)
         saturated = tweaks.pop("_saturated_data", None)
+        drop_first = tweaks.pop("_drop_first_timepoint", False)
         kw = dict(kw)
         builder = kw.pop("_builder", None)
         if builder == "dividing":
@@ -112,6 +117,10 @@ def main():
         else:
             prob = dataclasses.replace(sc.make_cellpop_problem(**kw), **tweaks)
             fixed_values = None
+        if drop_first:
+            obs = prob.observed.copy()
+            obs[:, 0] = np.nan
+            prob = dataclasses.replace(prob, observed=obs)
         if saturated is not None:
             prob = dataclasses.replace(prob, observed=saturated[1] / (1.0 + np.exp(-saturated[0] * prob.observed)) - 0.5 * saturated[1])
         if affine is not None:

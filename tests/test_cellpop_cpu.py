@@ -22,10 +22,12 @@ def test_port_matches_reference_golden(port, name):
     # pure relative error per chain, bounded by the north-star 1e-6 or the reference's own measured reproducibility
     assert_logp_parity(r["logp"], gold["logp"], gold["noise_floor"], name)
     assert (np.isnan(r["cell_values"]) == np.isnan(gold["cell_values"])).all()
-    m = ~np.isnan(gold["cell_values"])
-    # single trajectories: tolerance level (rtol = atol = 4.8e-7 per step, a few hundred steps)
-    assert np.abs(r["cell_values"][m] - gold["cell_values"][m]).max() < 5e-5
-    assert np.abs(r["population_average"] - gold["population_average"]).max() < 5e-6
+    m = np.isfinite(gold["cell_values"])  # a log ratio is -inf where both species still are 0
+    assert (np.isfinite(r["cell_values"]) == m).all()
+    # single trajectories: tolerance level (rtol = atol = 4.8e-7 per step, a few hundred steps); a log ratio divides by small numbers
+    assert np.abs(r["cell_values"][m] - gold["cell_values"][m]).max() < (5e-4 if prob.log_ratio_denominator is not None else 5e-5)
+    avg_ok = np.isfinite(gold["population_average"])
+    assert np.abs(r["population_average"][avg_ok] - gold["population_average"][avg_ok]).max() < (5e-4 if prob.log_ratio_denominator is not None else 5e-6)
     # step counts: identical for most cells; the stiff 24-species case flips more decisions
     same = (r["cell_steps"] == gold["cell_steps"]).mean()
     assert same >= cellpop_step_match_floor(gold)

@@ -420,3 +420,45 @@ def test_cell_population_plugin_time_course_with_three_markers(built):
     want = chk.cellpop_evaluate(tc, vals)["logp"]
     assert np.isfinite(want).all()
     assert np.all(np.abs(got - want) <= parity_tolerance(None) * np.abs(want)), (got, want)
+
+
+def test_cell_population_plugin_time_course_log_ratio_with_two_markers(built):
+    """use_log_ratio="true" species_name="x7/x3;x6/x2": two ratiometric markers per cell (DataLikelihoodTimeCourse.cpp:380-397) -- the
+    plugin adds the denominators as value-row blocks of the handle; against the CPU checker."""
+    import dataclasses
+    import math
+    import oracle
+    from bcm3_b200 import host_api, synthetic_cellpop as sc
+    from bcm3_b200.cellpop_data import Marker
+    from tests.util import cellpop_xml, parity_tolerance
+
+    tc = sc.make_time_course_problem(N=8, num_cells=24, T=10, seed=67, log_ratio_denominator=3, noise=0.05)
+    obs = tc.observed.copy()
+    obs[:, 0] = np.nan  # both species still are 0 at the first timepoint
+    rng = np.random.default_rng(67)
+    second = Marker(obs_species=[6], observed=np.where(np.isnan(obs), np.nan, 0.3 + 0.1 * rng.standard_normal(obs.shape)), stdev=0.4, log_ratio_denominator=2)
+    tc = dataclasses.replace(tc, observed=obs, extra_markers=[second])
+    prior, _, species = cellpop_xml(tc)
+    lik = ('<bcm_likelihood type="cell_population">'
+           f'<experiment name="fret" model_file="cascade.xml" entry_time="0" num_cells="{tc.num_cells}" max_cells="{tc.num_cells}" divide_cells="false">'
+           '<cell_variability distribution="diagonal_gaussian">'
+           '<variable model_parameter="k_in" apply="multiplicative_log" scale="variability_scale"/>'
+           '<variable model_parameter="k_deg" apply="multiplicative_log" scale="variability_scale" negate="true"/>'
+           f'<variable initial_condition_species="x1" apply="additive" scale="{math.log(0.01)!r}"/>'
+           '</cell_variability>'
+           f'<data type="time_course" data_name="ratio" use_log_ratio="true" species_name="x7 / x3; x6/x2" stdev="{tc.stdev!r};0.4"/>'
+           '</experiment></bcm_likelihood>')
+    vals = sc.make_chain_values(3, seed=67)
+    s = host_api.CellPopSession(prior, lik)
+    assert s.num_data_sets == [2]
+    s.set_model(tc, species)
+    s.set_sobol(0, tc.sobol)
+    s.set_data(0, 0, tc.timepoints, tc.observed)
+    s.set_data(0, 1, tc.timepoints, second.observed)
+    s.post_initialize()
+    got = s.evaluate(vals, batched=True)
+    s.close()
+    chk = oracle.load("ref" if oracle.available("ref") else "port")
+    want = chk.cellpop_evaluate(tc, vals)["logp"]
+    assert np.isfinite(want).all()
+    assert np.all(np.abs(got - want) <= parity_tolerance(None) * np.abs(want)), (got, want)
