@@ -34,6 +34,8 @@ class CellPopEvaluator:
         if p.optimize_offset_scale:
             kv.update(optimize_offset_scale=1, optimize_offset_min=repr(float(p.optimize_offset_range[0])), optimize_offset_max=repr(float(p.optimize_offset_range[1])),
                       optimize_scale_min=repr(float(p.optimize_scale_range[0])), optimize_scale_max=repr(float(p.optimize_scale_range[1])))
+        if p.use_only_nondivided:
+            kv["use_only_nondivided"] = 1
         if p.saturation_scale_ix is not None:
             kv["saturation_scale_ix"] = int(p.saturation_scale_ix)
         if p.value_relative_to_timepoint_ix is not None:

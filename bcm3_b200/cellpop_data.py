@@ -102,6 +102,7 @@ class CellPopProblem:
     # time_course: <data use_log_ratio="true" species_name="a/b"> (DataLikelihoodTimeCourse.cpp:380-397): the cell's value is
     # log10(a / b), b replaced by 1e-16 when smaller; obs_species = [a], this = b. With markers, every marker is a ratio.
     log_ratio_denominator: int | None = None
+    use_only_nondivided: bool = False  # time_points, dividing population: daughters are left out (DataLikelihoodTimePoints.cpp:349-351)
     # per-cell data kinds: the markers after the first one (which is obs_species / observed / stdev ... of this problem)
     extra_markers: list = field(default_factory=list)
     optimize_offset_range: tuple = (-1.0, 1.0)

@@ -40,6 +40,7 @@ struct CellPopState {
 	bool optimize_offset_scale = false;
 	double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
 	int saturation_scale_ix = -1; // time_course: <data saturation_scale="variable">, DataLikelihoodTimeCourse.cpp:243-254
+	bool use_only_nondivided = false; // time_points with dividing cells: daughters are left out (DataLikelihoodTimePoints.cpp:349-351)
 	int value_relative_to_timepoint_ix = -1; // time_points: simulated value = (x + offset) / x(that timepoint) * scale (DataLikelihoodBase.cpp:49)
 	int N = 0, Nc = 0, nvar = 0, Nn = 0, num_cells = 0, T = 0, R = 1, D = 0;
 	int entry_time_ix = -1;
@@ -76,6 +77,7 @@ struct CellPopState {
 		bool optimize_offset_scale = false;
 		double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
 		int saturation_scale_ix = -1;
+		bool use_only_nondivided = false;
 		// >= 0: not a data set of its own but a further MARKER (species_name="a;b": the part after a ';') of the per-cell data set
 		// with that index (0 = the handle's first data set, j = more[j - 1]): its rows, observed block and stdev / offset / scale
 		// entries enter that data set's cell likelihoods (DataLikelihoodTimeCourse.cpp:449-489, DataLikelihoodTimePoints.cpp:264-289)
@@ -1260,9 +1262,13 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	if (cp.any_time_course()) {
 		// what the per-cell likelihood is built for: no parent information (non-dividing cells), all cells on one
 		// device, as many observed as simulated cells (the reference refuses anything else, DataLikelihoodTimeCourse.cpp:178-187)
-		if (cp.division()) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with dividing / dying cells is not built");
+		if (cp.division()) { // snapshots of a dividing population are fine; per-cell trajectories would need the parent information
+			bool only_snapshots = (cp.data_kind != 1);
+			for (const auto& mp : cp.more) only_snapshots = only_snapshots && (mp->data_kind != 1);
+			if (!only_snapshots) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course with dividing / dying cells (parent information) is not built");
+		}
 		if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points is not split over ranks (every observed cell is compared with every simulated cell)");
-		if (cp.num_cells > 4096) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with more than 4096 cells (the matching is O(n^3) on the host)");
+		if ((cp.divide_cells ? cp.max_cells : cp.num_cells) > 4096) return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_course / time_points with more than 4096 cells (the matching is O(n^3) on the host)");
 		if (cp.saturation_scale_ix >= cp.nvar) return fail(BCM3B200_ERR_ARG, "saturation_scale_ix out of range");
 		for (size_t k = 0; k < cp.more.size(); k++)
 			if (cp.more[k]->saturation_scale_ix >= cp.nvar) return fail(BCM3B200_ERR_ARG, "saturation_scale_ix@%zu out of range", k + 1);
@@ -1311,8 +1317,8 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 			if (kind == 1 && (R != cp.num_cells || relative))
 				return fail(BCM3B200_ERR_ARG, "data_kind time_course needs num_replicates (observed cells) = num_cells and no relative_to_time_average");
 			if (kind == 2) {
-				if (R < 1 || R > cp.num_cells || relative)
-					return fail(BCM3B200_ERR_ARG, "data_kind time_points needs 1 <= num_replicates (observed cell slots) <= num_cells and no relative_to_time_average");
+				if (R < 1 || R > (cp.divide_cells ? cp.max_cells : cp.num_cells) || relative) // DataLikelihoodTimePoints.cpp:137-140
+					return fail(BCM3B200_ERR_ARG, "data_kind time_points needs 1 <= num_replicates (observed cell slots) <= num_cells (max_cells when dividing) and no relative_to_time_average");
 				if (error_model != CP_ERR_NORMAL && error_model != CP_ERR_STUDENT_T4)
 					return fail(BCM3B200_ERR_UNSUPPORTED, "data_kind time_points knows the normal and student_t4 error models (DataLikelihoodTimePoints.cpp:280-287)");
 				if (rel_ix >= T) return fail(BCM3B200_ERR_ARG, "value_relative_to_timepoint_ix out of range");
@@ -1792,8 +1798,11 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 			continue;
 		}
 		if (kind != 0) {
-			const int n = cp.cells_local;
+			// simulated cell columns: the cells of the handle; with a dividing population (time_points only) every cell slot up to
+			// max_cells -- a slot that was never filled, or a cell outside its life span, holds NaN and is left out per timepoint
+			const int n = (kind == 2) ? cp.capacity() : cp.cells_local;
 			const int n_obs = m ? m->R : cp.R; // time_course: = n; time_points: the observed cell slots (<= n)
+			const int newborn_from = (kind == 2 && (m ? m->use_only_nondivided : cp.use_only_nondivided)) ? cp.num_cells : n;
 			CpCellLikArgs a;
 			a.cell_values = cp.d_cellvals.p;
 			a.rows = cp.rows();
@@ -1945,7 +1954,7 @@ inline int cellpop_time_course_terms(CellPopState& cp, size_t C, cudaStream_t st
 						// NaN for the others in every row
 						std::vector<int> cols;
 						const double* first = L + (size_t)rows[0] * n;
-						for (int j = 0; j < n; j++)
+						for (int j = 0; j < newborn_from; j++)
 							if (first[j] == first[j]) cols.push_back(j);
 						if ((int)cols.size() < fd) { // .cpp:241-245
 							dead[c] = 1;

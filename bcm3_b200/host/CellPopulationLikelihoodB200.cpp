@@ -147,6 +147,7 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				const std::string em = c.get("error_model", "normal");
 				if (em != "normal" && em != "student_t4") return Fail("time_points data knows the normal and student_t4 error models (DataLikelihoodTimePoints.cpp:280-287)");
 				ds.value_relative_to_timepoint_ix = (long)c.get_real("value_relative_to_timepoint_ix", -1.0);
+				ds.use_only_nondivided = c.get_bool("use_only_nondivided", false); // .cpp:27: daughters of a dividing population are left out
 			}
 			if (type == "time_course") {
 				const std::string sync = c.get("synchronize", "");
@@ -434,6 +435,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	  << ";missing_simulation_time_stdev=" << ds.missing_stdev << ";device=" << device << ";compile_only=" << (compile_only ? 1 : 0);
 	if (ds.type != "time_course_population_average") d << ";data_kind=" << ds.type;
 	if (ds.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix=" << ds.value_relative_to_timepoint_ix;
+	if (ds.use_only_nondivided) d << ";use_only_nondivided=1";
 	if (ds.saturation_scale_ix >= 0) d << ";saturation_scale_ix=" << ds.saturation_scale_ix;
 	if (ds.optimize_offset_scale)
 		d << ";optimize_offset_scale=1;optimize_offset_min=" << ds.optimize_offset_min << ";optimize_offset_max=" << ds.optimize_offset_max
@@ -489,6 +491,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		  << f.error_model << ";weight" << sfx << "=" << f.weight << ";missing_simulation_time_stdev" << sfx << "=" << f.missing_stdev;
 		if (f.type != "time_course_population_average") d << ";data_kind" << sfx << "=" << f.type;
 		if (f.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix" << sfx << "=" << f.value_relative_to_timepoint_ix;
+		if (f.use_only_nondivided) d << ";use_only_nondivided" << sfx << "=1";
 		if (f.saturation_scale_ix >= 0) d << ";saturation_scale_ix" << sfx << "=" << f.saturation_scale_ix;
 		if (f.marker_of >= 0) { // position of the owner inside this handle: 0 = ds, q + 1 = followers[q]
 			long at = (&e.data[(size_t)f.marker_of] == &ds) ? 0 : -1;

@@ -73,7 +73,8 @@ extern "C" {
  *                        one marker: "observed" is [num_replicates = observed cell slots <= num_cells][T], NaN = no such cell at
  *                        that timepoint; at every timepoint the observed cells present are matched to the simulated cells that
  *                        have a value there (normal | student_t4); value_relative_to_timepoint_ix=<t> (DataLikelihoodBase.cpp:49):
- *                        the simulated value is (x + offset) / x(timepoint t) * scale instead of x * scale + offset
+ *                        the simulated value is (x + offset) / x(timepoint t) * scale instead of x * scale + offset;
+ *                        works with divide_cells (num_replicates <= max_cells; use_only_nondivided=1 leaves the daughters out)
  *                       time_course = DataLikelihoodTimeCourse (src/cellpop/DataLikelihoodTimeCourse.cpp:230-365, 431-505,
  *                        566-588) with synchronize="none", one marker and no parent information: "observed" holds one
  *                        trajectory per OBSERVED CELL ([num_replicates = observed cells][T], NaN = missing), there are as

@@ -541,8 +541,10 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 				if (any) rows.push_back(i);
 			}
 			if (rows.empty()) continue;
-			for (int j = 0; j < n_sim_all; j++)
+			for (int j = 0; j < n_sim_all; j++) {
+				if (pr.use_only_nondivided && j >= ninit) continue; // NotifySimulatedValue skips newborn cells: their entries stay NaN
 				if (!std::isnan(xs[(size_t)ti * ncell + j]) && (rel < 0 || !std::isnan(xs[(size_t)rel * ncell + j]))) cols.push_back(j);
+			}
 			if (cols.size() < rows.size()) { // .cpp:241-245
 				*logp_out = -std::numeric_limits<double>::infinity();
 				return;

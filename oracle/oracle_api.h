@@ -180,6 +180,9 @@ typedef struct {
 	 * DataLikelihoodTimeCourse.cpp:380-397): the cell's value is log10(a / b) = 0.4342944819032518 * log(a / b) with b replaced by
 	 * 1e-16 when it is smaller; obs_species = {a}, this = b (-1: no ratio). Every marker of the data set is a ratio then. */
 	int32_t log_ratio_denominator;
+	/* time_points: <data use_only_nondivided="true"> (DataLikelihoodTimePoints.cpp:27, 349-351): the daughters of a dividing
+	 * population (cell index >= num_cells) are left out of this data set */
+	int32_t use_only_nondivided;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

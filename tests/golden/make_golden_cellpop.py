@@ -82,6 +82,11 @@ CASES = {
     # Student-t error model, offset / scale / weight
     "cellpop_time_points_n6_t4_relative": (dict(_builder="time_points", N=6, num_cells=30, T=9, seed=46, relative_to=2), 3,
                                            dict(error_model="student_t4", offset=0.01, scale=1.1, weight=0.5, stdev=0.01)),
+    # <data type="time_points"> on a DIVIDING population: snapshots with more observed cells at the later timepoints (two generations of
+    # daughters); a cell slot that is not filled, or a cell outside its life span, has no value and is left out per timepoint
+    "cellpop_time_points_dividing": (dict(_builder="dividing_snapshots", M=5, num_cells=16, max_cells=400, t_end=5.5, T=12), 3, {}),
+    # the same with use_only_nondivided="true": only the 16 initial cells are matched (DataLikelihoodTimePoints.cpp:349-351)
+    "cellpop_time_points_dividing_nondivided": (dict(_builder="dividing_snapshots", M=5, num_cells=16, max_cells=400, t_end=5.5, T=12, nondivided=True), 3, {}),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
@@ -100,7 +105,23 @@ def main():
         drop_first = tweaks.pop("_drop_first_timepoint", False)
         kw = dict(kw)
         builder = kw.pop("_builder", None)
-        if builder == "dividing":
+        if builder == "dividing_snapshots":
+            # observations: values of cells that exist at each timepoint in the reference's own simulation at the reference parameters
+            nondivided = kw.pop("nondivided", False)
+            base = sc.make_dividing_problem(**kw)
+            sim = ref.cellpop_evaluate(base, sc.default_values()[None, :], threads=1, want_cell_values=True)["cell_values"][0]  # [T][max_cells]
+            rng = np.random.default_rng(77)
+            T = base.num_timepoints
+            slots = 40
+            observed = np.full((slots, T), np.nan)
+            for ti in range(T):
+                alive = np.flatnonzero(~np.isnan(sim[ti, :base.num_cells] if nondivided else sim[ti]))
+                take = rng.permutation(alive)[:max(1, min(len(alive) // 2, slots, int(rng.integers(4, 14))))]
+                where = rng.permutation(slots)[:len(take)]
+                observed[where, ti] = sim[ti, take] + 0.02 * rng.standard_normal(len(take))
+            prob = dataclasses.replace(base, data_kind="time_points", observed=observed, stdev_ix=None, stdev=0.03, use_only_nondivided=nondivided)
+            fixed_values = sc.make_chain_values(C, seed=5)
+        elif builder == "dividing":
             prob = sc.make_dividing_problem(**kw)
             fixed_values = sc.make_chain_values(C, seed=5)
         elif builder == "time_course":

@@ -66,13 +66,19 @@ def main():
         oracle.rhs_build = "strict"
         assert np.array_equal(ra["logp"], gold["logp"])
         la = ra["logp"]
-        f_solver = np.abs(la - rb["logp"]) / np.abs(la)
-        f_rhs = np.abs(la - rc["logp"]) / np.abs(la)
+
+        def rel(other):  # relative difference per chain; a chain that is -inf in both runs (a failed evaluation) counts as identical
+            with np.errstate(invalid="ignore"):
+                d = np.abs(la - other) / np.abs(la)
+            return np.where(np.isinf(la) & (la == other), 0.0, d)
+
+        f_solver = rel(rb["logp"])
+        f_rhs = rel(rc["logp"])
         f_ulp = np.zeros_like(la)
         steps_ulp = 1.0
         for direction in (np.inf, -np.inf):
             rd = a.cellpop_evaluate(prob, np.nextafter(gold["values"], direction), threads=1, want_steps=True)
-            f_ulp = np.maximum(f_ulp, np.abs(la - rd["logp"]) / np.abs(la))
+            f_ulp = np.maximum(f_ulp, rel(rd["logp"]))
             steps_ulp = min(steps_ulp, (ra["cell_steps"] == rd["cell_steps"]).mean())
         floor = np.maximum(np.maximum(f_solver, f_rhs), f_ulp)
         m = ~np.isnan(ra["cell_values"])

@@ -137,6 +137,8 @@ def load_cellpop_golden(name):
                    stdev_ix=opt(q[0]), stdev=float(q[1]), proportional_stdev_ix=opt(q[2]), proportional_stdev=float(q[3]),
                    offset_ix=opt(q[4]), offset=float(q[5]), scale_ix=opt(q[6]), scale=float(q[7]))
             for l, q in enumerate(z["marker_parameters"])])
+    if "use_only_nondivided" in z.files and bool(z["use_only_nondivided"]):
+        extra.update(use_only_nondivided=True)
     if "log_ratio_denominator" in z.files:
         extra.update(log_ratio_denominator=int(z["log_ratio_denominator"]))
     if "saturation_scale_ix" in z.files:
