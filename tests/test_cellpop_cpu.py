@@ -226,3 +226,18 @@ def test_time_course_likelihood_is_the_matched_sum_not_the_optimum(ref):
         assert lik[r, col].sum() >= lik[np.arange(n), match].sum() - 1e-9
         below += lik[r, col].sum() > lik[np.arange(n), match].sum() + 1e-6
     assert below > 0
+
+
+def test_matching_edge_cases():
+    from bcm3_b200 import _lib
+
+    assert np.array_equal(_lib.match_cells(np.array([[3.5]])), [0])
+    assert np.array_equal(_lib.match_cells(np.array([[-1e9]])), [0])
+    two = _lib.match_cells(np.array([[0.0, 5.0], [5.0, 0.0]]))
+    assert np.array_equal(two, [0, 1])
+    # all entries equal: every matching is optimal, the restatement returns the reference's (the identity: greedy over the tight edges)
+    assert np.array_equal(_lib.match_cells(np.zeros((7, 7))), np.arange(7))
+    # costs that differ by less than 1 are all "tight" for the reference's integer test: the greedy first pass decides
+    # -- the smallest example of the quirk: the reference's compiled function answers [0, 1] (cost 1.1) where [1, 0] costs 0.1
+    c = np.array([[0.2, 0.0], [0.1, 0.9]])
+    assert np.array_equal(_lib.match_cells(c), [0, 1])

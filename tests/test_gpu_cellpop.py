@@ -455,3 +455,14 @@ def test_per_cell_blocks_in_chunks_of_chains_give_the_same_bits(Evaluator, name,
     ev.close()
     assert np.array_equal(whole, chunked)
     assert_logp_parity(chunked, gold["logp"], gold["noise_floor"], name)
+
+
+def test_time_course_with_a_single_cell(Evaluator, checker):
+    prob = sc.make_time_course_problem(N=6, num_cells=1, T=8, seed=58)
+    vals = sc.make_chain_values(3, seed=58)
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    ev.close()
+    want, floor, _ = _fresh_reference(checker, prob, vals)
+    assert (status == 0).all() and np.isfinite(logp).all()
+    assert_logp_parity(logp, want["logp"], floor, "time_course, one cell")
