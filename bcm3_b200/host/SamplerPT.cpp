@@ -784,6 +784,9 @@ void SamplerPT::EmitSample()
 {
 	// SamplerPT::EmitSample (SamplerPT.cpp:321-330): every fixed-temperature chain reports its state
 	for (const Chain& c : chains) samples.push_back(EmittedSample{ c.current_var_values, c.lprior, c.llh, c.temperature });
+	// handler by handler, chain by chain, weight 1 (SamplerPT.cpp:323-329)
+	for (const auto& handler : sample_handlers)
+		for (const Chain& c : chains) handler->ReceiveSample(c.current_var_values, c.lprior, c.llh, c.temperature, 1.0);
 }
 
 bool SamplerPT::AdaptChainProposal(Chain& c)

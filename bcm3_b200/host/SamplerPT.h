@@ -17,6 +17,8 @@
 #include "Prior.h"
 #include "RNG.h"
 
+#include "SampleHandler.h"
+
 namespace bcm3 {
 
 struct SamplerPTSettings {
@@ -153,6 +155,7 @@ public:
 	void SetVariableSet(std::shared_ptr<const VariableSet> v) { varset = v; }
 	void SetPrior(std::shared_ptr<Prior> p) { prior = p; }
 	void SetLikelihood(std::shared_ptr<Likelihood> l) { likelihood = l; }
+	void AddSampleHandler(std::shared_ptr<SampleHandler> handler) { sample_handlers.push_back(handler); } // Sampler.cpp:49-52
 	bool Initialize();
 	bool Run();
 
@@ -209,6 +212,7 @@ private:
 	size_t proposal_scaling_ema_period = 1000;
 	Real proposal_scaling_learning_rate = 0.05;
 	size_t num_likelihood_evaluations = 0, num_batched_calls = 0;
+	std::vector<std::shared_ptr<SampleHandler>> sample_handlers;
 	std::vector<EmittedSample> samples;
 	std::string last_error;
 };

@@ -50,8 +50,15 @@ bool make_setup(const char* prior_xml, const char* likelihood_xml, Setup& s, std
 	return s.likelihood != nullptr;
 }
 
+// optional sinks of a run: a SampleHandlerTSV file and a SampleHandlerStoreMaxAPosteriori whose result goes to map_out
+// [lposterior, llikelihood, values...]
+struct RunSinks {
+	const char* tsv_file = nullptr;
+	double* map_out = nullptr;
+};
+
 int run(Setup& st, const char* config_text, int batched, unsigned long long seed, double* out, size_t max_rows, size_t* num_rows,
-        size_t* stats, char* err, size_t errlen)
+        size_t* stats, char* err, size_t errlen, const RunSinks* sinks = nullptr)
 {
 	SamplerPTSettings settings;
 	std::string error;
@@ -65,6 +72,23 @@ int run(Setup& st, const char* config_text, int batched, unsigned long long seed
 	sampler.SetVariableSet(st.varset);
 	sampler.SetPrior(st.prior);
 	sampler.SetLikelihood(st.likelihood);
+	std::shared_ptr<SampleHandlerTSV> tsv;
+	std::shared_ptr<SampleHandlerStoreMaxAPosteriori> map;
+	if (sinks && sinks->tsv_file && sinks->tsv_file[0]) { // as bcminf installs its NetCDF handler (bcminf/main.cpp:96-99)
+		tsv = std::make_shared<SampleHandlerTSV>();
+		tsv->SetFile(sinks->tsv_file);
+		std::vector<std::string> names;
+		for (size_t i = 0; i < st.varset->GetNumVariables(); i++) names.push_back(st.varset->GetVariableName(i));
+		if (!tsv->Initialize(settings.num_samples, names, VectorReal())) {
+			set_err(err, errlen, std::string("Failed to open output file \"") + sinks->tsv_file + "\"");
+			return -4;
+		}
+		sampler.AddSampleHandler(tsv);
+	}
+	if (sinks && sinks->map_out) {
+		map = std::make_shared<SampleHandlerStoreMaxAPosteriori>();
+		sampler.AddSampleHandler(map);
+	}
 	if (!sampler.Initialize() || !sampler.Run()) {
 		set_err(err, errlen, sampler.LastError());
 		return -2;
@@ -80,6 +104,11 @@ int run(Setup& st, const char* config_text, int batched, unsigned long long seed
 		for (size_t i = 0; i < nvar; i++) row[3 + i] = samples[r].values[i];
 	}
 	if (num_rows) *num_rows = samples.size();
+	if (map) {
+		sinks->map_out[0] = map->GetMAPlposterior();
+		sinks->map_out[1] = map->GetMAPllikelihood();
+		for (size_t i = 0; i < nvar && i < (size_t)map->GetMAP().size(); i++) sinks->map_out[2 + i] = map->GetMAP()[i];
+	}
 	if (stats) {
 		stats[0] = sampler.GetNumLikelihoodEvaluations();
 		stats[1] = sampler.GetNumBatchedCalls();
@@ -108,6 +137,28 @@ int bcm3host_run_pt(const char* prior_xml, const char* likelihood_xml, const cha
 		return -1;
 	}
 	return run(st, config_text, batched, seed, out, max_rows, num_rows, stats, err, errlen);
+}
+
+// The same run with the reference's sample sinks attached: SampleHandlerTSV writing to tsv_file (may be NULL) and
+// SampleHandlerStoreMaxAPosteriori reporting into map_out [2 + nvar] = lposterior, llikelihood, values (may be NULL).
+int bcm3host_run_pt_with_handlers(const char* prior_xml, const char* likelihood_xml, const char* config_text, int batched, unsigned long long seed,
+                                  const char* tsv_file, double* map_out, double* out, size_t max_rows, size_t* num_rows, size_t* stats, char* err,
+                                  size_t errlen)
+{
+	Setup st;
+	std::string error;
+	if (!make_setup(prior_xml, likelihood_xml, st, error)) {
+		set_err(err, errlen, error);
+		return -1;
+	}
+	if (!st.likelihood->PostInitialize()) {
+		set_err(err, errlen, "PostInitialize failed");
+		return -1;
+	}
+	RunSinks sinks;
+	sinks.tsv_file = tsv_file;
+	sinks.map_out = map_out;
+	return run(st, config_text, batched, seed, out, max_rows, num_rows, stats, err, errlen, &sinks);
 }
 
 // Same with the GPU-backed pop_pk_trajectory likelihood; the trial arrays stand in for the NetCDF file.

@@ -41,6 +41,26 @@ def run_pt(prior_xml: str, likelihood_xml: str, config_text: str, batched: bool 
     return out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2], blocks=stats[3])
 
 
+def run_pt_with_handlers(prior_xml: str, likelihood_xml: str, config_text: str, tsv_file: str | None = None, batched: bool = True, seed: int = 1,
+                         max_rows: int = 200000):
+    """run_pt with the reference's sample sinks attached: a SampleHandlerTSV file (posterior-chain samples as tab-separated text) and
+    a SampleHandlerStoreMaxAPosteriori. Returns (rows, stats, map) with map = dict(lposterior, llikelihood, values)."""
+    lib = load()
+    nvar = varset_info(prior_xml)[0]
+    out = np.zeros((max_rows, nvar + 3))
+    best = np.zeros(2 + nvar)
+    nrows = C.c_size_t()
+    stats = (C.c_size_t * 4)()
+    err = _err()
+    rc = lib.bcm3host_run_pt_with_handlers(prior_xml.encode(), likelihood_xml.encode(), config_text.encode(), int(batched), C.c_ulonglong(seed),
+                                           (tsv_file or "").encode(), best.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                           C.c_size_t(max_rows), C.byref(nrows), stats, err, C.c_size_t(1024))
+    if rc != 0:
+        raise RuntimeError(f"bcm3host_run_pt_with_handlers failed ({rc}): {err.value.decode()}")
+    return (out[: min(nrows.value, max_rows)], dict(evaluations=stats[0], batched_calls=stats[1], chains=stats[2], blocks=stats[3]),
+            dict(lposterior=best[0], llikelihood=best[1], values=best[2:].copy()))
+
+
 def run_pt_poppk(prior_xml: str, likelihood_xml: str, config_text: str, trial, batched: bool = True, seed: int = 1, device: int = 0,
                  device_count: int = 1, max_rows: int = 100000):
     lib = load()

@@ -368,3 +368,30 @@ def test_blocking_strategies_on_the_banana(host):
         host.run_pt(PRIOR, LIKELIHOOD, base.replace("[ptmhsampler]", "[ptmhsampler]\nblocking_strategy=clustered_autoblock"))
     with pytest.raises(RuntimeError, match="Unknown blocking strategy"):
         host.run_pt(PRIOR, LIKELIHOOD, base.replace("[ptmhsampler]", "[ptmhsampler]\nblocking_strategy=nope"))
+
+
+def test_sample_handlers_tsv_and_max_a_posteriori(host, tmp_path):
+    """The reference's sample sinks on the sampler mirror (Sampler::AddSampleHandler): SampleHandlerTSV writes the posterior chain's
+    samples in the reference's text format -- "%.6g", tab-separated, and its line structure: the weight on a line of its own
+    (SampleHandlerTSV.cpp:45-47) -- and SampleHandlerStoreMaxAPosteriori keeps the best log-posterior over ALL temperatures."""
+    cfg = CONFIG.replace("num_samples=8000", "num_samples=300").replace("adapt_proposal_samples=2000", "adapt_proposal_samples=100")
+    path = tmp_path / "samples.tsv"
+    rows, stats, best = host.run_pt_with_handlers(PRIOR, LIKELIHOOD, cfg, tsv_file=str(path), seed=11)
+    plain, _ = host.run_pt(PRIOR, LIKELIHOOD, cfg, seed=11)
+    assert np.array_equal(rows, plain)  # the handlers only listen
+    lines = path.read_text().split("\n")
+    assert lines[0] == "x1\tx2\tlog prior\tlog likelihood\tweight"
+    body = [l for l in lines[1:] if l != ""]
+    posterior = rows[rows[:, 0] == 1.0]  # [temperature, lprior, llh, values...]
+    assert len(posterior) == 300 and len(body) == 2 * len(posterior)
+    for r, (sample_line, weight_line) in zip(posterior, zip(body[0::2], body[1::2])):
+        want = "\t".join("%.6g" % v for v in (r[3], r[4], r[1], r[2]))
+        assert sample_line == want
+        assert weight_line == "1"
+    # maximum a posteriori over every emitted sample, the heated chains included
+    lpost = rows[:, 1] + rows[:, 2]
+    k = int(np.argmax(lpost))
+    assert best["lposterior"] == lpost[k] and best["llikelihood"] == rows[k, 2]
+    assert np.array_equal(best["values"], rows[k, 3:])
+    with pytest.raises(RuntimeError, match="Failed to open output file"):
+        host.run_pt_with_handlers(PRIOR, LIKELIHOOD, cfg, tsv_file=str(tmp_path / "no_such_dir" / "x.tsv"), seed=11)
