@@ -1247,6 +1247,15 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 	if (cp.have_sim_end_time && !(cp.sim_end_time >= cp.data["timepoints"].back())) return fail(BCM3B200_ERR_ARG, "simulation_end_time lies before the last timepoint");
 	for (int s : cp.obs_species)
 		if (s < 0 || s >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species index out of range");
+	// the data likelihoods read transformed[c][ix] on the device: an index past the variables would be an out-of-bounds read
+	{
+		auto bad = [&](int ix) { return ix >= cp.nvar; };
+		if (bad(cp.stdev_ix) || bad(cp.offset_ix) || bad(cp.scale_ix) || bad(cp.prop_stdev_ix) || bad(cp.entry_time_ix))
+			return fail(BCM3B200_ERR_ARG, "stdev_ix / offset_ix / scale_ix / proportional_stdev_ix / entry_time_ix out of range");
+		for (size_t k = 0; k < cp.more.size(); k++)
+			if (bad(cp.more[k]->stdev_ix) || bad(cp.more[k]->offset_ix) || bad(cp.more[k]->scale_ix) || bad(cp.more[k]->prop_stdev_ix))
+				return fail(BCM3B200_ERR_ARG, "stdev_ix@%zu / offset_ix@%zu / scale_ix@%zu / proportional_stdev_ix@%zu out of range", k + 1, k + 1, k + 1, k + 1);
+	}
 	if (!cp.more.empty()) {
 		if (cp.more.size() > 3) return fail(BCM3B200_ERR_UNSUPPORTED, "more than four data sets per handle");
 		if (cellpop_resolve_kernel(cp) != 3) return fail(BCM3B200_ERR_UNSUPPORTED, "several data sets per handle need the lane-group kernel (cellpop_kernel = auto, N <= 96)");

@@ -241,3 +241,18 @@ def test_matching_edge_cases():
     # -- the smallest example of the quirk: the reference's compiled function answers [0, 1] (cost 1.1) where [1, 0] costs 0.1
     c = np.array([[0.2, 0.0], [0.1, 0.9]])
     assert np.array_equal(_lib.match_cells(c), [0, 1])
+
+
+def test_variable_indices_of_the_data_likelihood_are_validated():
+    """stdev_ix & co. are read on the device as transformed[chain][ix]: an index past the variables is refused at finalize."""
+    from bcm3_b200._lib import Bcm3B200Error
+    from bcm3_b200.cellpop import CellPopEvaluator
+
+    prob = sc.make_cellpop_problem(N=6, num_cells=4, T=6, data_cells=2, seed=3)
+    for field in ("stdev_ix", "offset_ix", "scale_ix"):
+        with pytest.raises(Bcm3B200Error, match="out of range"):
+            CellPopEvaluator(dataclasses.replace(prob, **{field: prob.num_variables}), compile_only=True).close()
+    tc = sc.make_time_course_problem(N=6, num_cells=4, T=6, seed=3, extra_marker_species=((2,),))
+    tc.extra_markers[0].scale_ix = 50
+    with pytest.raises(Bcm3B200Error, match="out of range"):
+        CellPopEvaluator(tc, compile_only=True).close()
