@@ -34,6 +34,10 @@ class CellPopEvaluator:
         if p.optimize_offset_scale:
             kv.update(optimize_offset_scale=1, optimize_offset_min=repr(float(p.optimize_offset_range[0])), optimize_offset_max=repr(float(p.optimize_offset_range[1])),
                       optimize_scale_min=repr(float(p.optimize_scale_range[0])), optimize_scale_max=repr(float(p.optimize_scale_range[1])))
+        if p.nuclear_envelope_species is not None:
+            kv["nuclear_envelope_species"] = int(p.nuclear_envelope_species)
+        if p.include_only_cells_that_went_through_mitosis:
+            kv["include_only_cells_that_went_through_mitosis"] = 1
         if p.use_only_nondivided:
             kv["use_only_nondivided"] = 1
         if p.saturation_scale_ix is not None:

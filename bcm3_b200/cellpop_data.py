@@ -102,6 +102,10 @@ class CellPopProblem:
     # time_course: <data use_log_ratio="true" species_name="a/b"> (DataLikelihoodTimeCourse.cpp:380-397): the cell's value is
     # log10(a / b), b replaced by 1e-16 when smaller; obs_species = [a], this = b. With markers, every marker is a ratio.
     log_ratio_denominator: int | None = None
+    # population average over the cells that entered mitosis only: the model's "nuclear_envelope" species (by index) fell below 0.5
+    # after some accepted step (Cell.cpp:487-492; DataLikelihoodTimeCoursePopulationAverage.cpp:171-176)
+    include_only_cells_that_went_through_mitosis: bool = False
+    nuclear_envelope_species: int | None = None
     use_only_nondivided: bool = False  # time_points, dividing population: daughters are left out (DataLikelihoodTimePoints.cpp:349-351)
     # per-cell data kinds: the markers after the first one (which is obs_species / observed / stdev ... of this problem)
     extra_markers: list = field(default_factory=list)

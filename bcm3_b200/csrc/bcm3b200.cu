@@ -190,6 +190,8 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 		cp->value_relative_to_timepoint_ix = get_int(kv, "value_relative_to_timepoint_ix", -1);
 		cp->saturation_scale_ix = get_int(kv, "saturation_scale_ix", -1);
 		cp->use_only_nondivided = get_int(kv, "use_only_nondivided", 0) != 0;
+		cp->include_only_mitotic = get_int(kv, "include_only_cells_that_went_through_mitosis", 0) != 0;
+		cp->nuclear_envelope_ix = get_int(kv, "nuclear_envelope_species", -1);
 		cp->optimize_offset_scale = get_int(kv, "optimize_offset_scale", 0) != 0;
 		cp->optimize_offset_min = real("optimize_offset_min", -1.0);
 		cp->optimize_offset_max = real("optimize_offset_max", 1.0);
@@ -251,6 +253,7 @@ int make_cellpop_state(std::map<std::string, std::string>& kv, std::unique_ptr<C
 			m->value_relative_to_timepoint_ix = get_int(kv, key("value_relative_to_timepoint_ix").c_str(), -1);
 			m->saturation_scale_ix = get_int(kv, key("saturation_scale_ix").c_str(), -1);
 			m->use_only_nondivided = get_int(kv, key("use_only_nondivided").c_str(), 0) != 0;
+			m->include_only_mitotic = get_int(kv, key("include_only_cells_that_went_through_mitosis").c_str(), 0) != 0;
 			m->marker_of = get_int(kv, key("marker_of").c_str(), -1);
 			m->denominator_of = get_int(kv, key("denominator_of").c_str(), -1);
 			m->optimize_offset_scale = get_int(kv, key("optimize_offset_scale").c_str(), 0) != 0;

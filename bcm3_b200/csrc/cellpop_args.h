@@ -89,6 +89,10 @@ struct CpArgs {
 	double* cell_end_y;          // [C][stride][N] y after the step that ended a dividing cell
 	double* cell_end_time;       // [C][stride] absolute time at which the cell's integration ended (division, death or the end of the experiment)
 	int32_t* cell_event;         // [C][stride] 0 none, 1 divided, 2 died
+	// Cell::EnteredMitosis (Cell.h:27; Cell.cpp:487-492): the cell's "nuclear_envelope" species was below 0.5 after some accepted
+	// step. nuclear_envelope_ix = its ODE species index (-1: not tracked), cell_mitotic [C][stride] receives the flag (null: none)
+	int nuclear_envelope_ix;
+	int32_t* cell_mitotic;
 };
 
 #ifdef __CUDACC__

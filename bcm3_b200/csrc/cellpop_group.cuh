@@ -1680,6 +1680,9 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 
 	bool have = false, exhausted = false, ok = true, newstep = true;
 	int steps = 0, tpi = 0, c = 0, cell = 0;
+#if CP_DIVISION
+	bool mitotic = false; // Cell::EnteredMitosis of the cell being integrated
+#endif
 	unsigned trip = 0;
 	double* out = nullptr;
 
@@ -1788,6 +1791,9 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				out = a.cell_values + ((long long)c * a.num_rows) * stride + cell;
 				ok = true;
 				steps = 0;
+#if CP_DIVISION
+				mitotic = false;
+#endif
 				tpi = 0;
 				newstep = true;
 				bool finished = false;
@@ -1902,6 +1908,14 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 				// Cell::integration_step_cb (Cell.cpp:463-538, the branch without stored integration points), called by the solver
 				// after the outputs of the step and before its own end test (ODESolverCVODE.cpp:431-441): a cell whose
 				// "cytokinesis" (divide_cells) or "apoptosis" species has passed 1 ends at this step, with this state
+				if (ok && a.nuclear_envelope_ix >= 0 && !mitotic) { // Cell.cpp:487-492
+					double yne = 1.0;
+#pragma unroll
+					for (int e = 0; e < E; e++)
+						if (B.idx(e) == a.nuclear_envelope_ix) yne = yout[e];
+					yne = __shfl_sync(B.gmask, yne, B.gbase + a.nuclear_envelope_ix % G);
+					if (yne < 0.5) mitotic = true;
+				}
 				if (ok) {
 					int ev = 0;
 					if (a.cytokinesis_ix >= 0 || a.apoptosis_ix >= 0) {
@@ -1962,6 +1976,9 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 			if (B.lg == 0) {
 				if (!ok) fill_nan(out, tpi);
 				a.cell_status[(long long)c * stride + cell] = ok ? 1 : 0;
+#if CP_DIVISION
+				if (a.cell_mitotic) a.cell_mitotic[(long long)c * stride + cell] = mitotic ? 1 : 0;
+#endif
 				if (a.cell_steps)
 					a.cell_steps[(long long)c * stride + cell] = (a.debug_report == 1) ? B.nfe : (a.debug_report == 2) ? B.nsetups : (a.debug_report == 3) ? B.nje : steps;
 			}

@@ -40,6 +40,19 @@ struct CellPopState {
 	bool optimize_offset_scale = false;
 	double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
 	int saturation_scale_ix = -1; // time_course: <data saturation_scale="variable">, DataLikelihoodTimeCourse.cpp:243-254
+	// <data include_only_cells_that_went_through_mitosis="true"> (population average, DataLikelihoodTimeCoursePopulationAverage.cpp:
+	// 171-176) needs Cell::EnteredMitosis: the "nuclear_envelope" species (descriptor key nuclear_envelope_species) below 0.5 after
+	// some accepted step (Cell.cpp:487-492) -- tracked by the event code of the kernel (CP_DIVISION builds)
+	bool include_only_mitotic = false;
+	int nuclear_envelope_ix = -1;
+	bool track_mitosis() const
+	{
+		if (nuclear_envelope_ix < 0) return false;
+		if (include_only_mitotic) return true;
+		for (const auto& m : more)
+			if (m->include_only_mitotic) return true;
+		return false;
+	}
 	bool use_only_nondivided = false; // time_points with dividing cells: daughters are left out (DataLikelihoodTimePoints.cpp:349-351)
 	int value_relative_to_timepoint_ix = -1; // time_points: simulated value = (x + offset) / x(that timepoint) * scale (DataLikelihoodBase.cpp:49)
 	int N = 0, Nc = 0, nvar = 0, Nn = 0, num_cells = 0, T = 0, R = 1, D = 0;
@@ -68,7 +81,7 @@ struct CellPopState {
 	bool divide_cells = false;
 	int max_cells = 0, cytokinesis_ix = -1, apoptosis_ix = -1, sobol_rows = 0;
 	int reset_ix[7] = { -1, -1, -1, -1, -1, -1, -1 };
-	bool division() const { return (divide_cells && cytokinesis_ix >= 0) || apoptosis_ix >= 0; } // the model library carries the event code
+	bool division() const { return (divide_cells && cytokinesis_ix >= 0) || apoptosis_ix >= 0 || track_mitosis(); } // the model library carries the event code
 	// Further data sets of the same experiment (descriptor keys with the suffix @1, @2, @3; data "timepoints@k", "observed@k"):
 	// they share the integration of the experiment's cells (Experiment.cpp:190-214, 298-312) -- the kernel interpolates at the
 	// union of all timepoints and every data set sums its own species -- and their log-likelihoods are added in order (:346-355)
@@ -77,7 +90,7 @@ struct CellPopState {
 		bool optimize_offset_scale = false;
 		double optimize_offset_min = -1.0, optimize_offset_max = 1.0, optimize_scale_min = 0.1, optimize_scale_max = 10.0;
 		int saturation_scale_ix = -1;
-		bool use_only_nondivided = false;
+		bool use_only_nondivided = false, include_only_mitotic = false;
 		// >= 0: not a data set of its own but a further MARKER (species_name="a;b": the part after a ';') of the per-cell data set
 		// with that index (0 = the handle's first data set, j = more[j - 1]): its rows, observed block and stdev / offset / scale
 		// entries enter that data set's cell likelihoods (DataLikelihoodTimeCourse.cpp:449-489, DataLikelihoodTimePoints.cpp:264-289)
@@ -105,7 +118,7 @@ struct CellPopState {
 	DevBuf<int32_t> d_tp_rows;
 	int capacity() const { return division() ? (divide_cells ? max_cells : cells_local) : cells_local; }
 	DevBuf<double> d_creation, d_end_y, d_end_time;
-	DevBuf<int32_t> d_row, d_parent, d_event, d_items, d_wave, d_item_offsets;
+	DevBuf<int32_t> d_row, d_parent, d_event, d_items, d_wave, d_item_offsets, d_mitotic, d_row_only_mitotic;
 	std::vector<int32_t> h_wave;
 	std::string derivative_code;
 	std::map<std::string, std::vector<double>> data;
@@ -168,15 +181,19 @@ __global__ void cellpop_transform_kernel(const double* __restrict__ values, cons
 
 // per (chain, timepoint): population size = cells that exist at that time (non-NaN value), average = sum_i x_i / size in
 // a fixed tree order; per chain: number of failed cells (block t == 0 only)
+// mitotic [C][num_cells] / row_only_mitotic [T] (both or neither): rows with the flag average the cells that entered mitosis only,
+// over the number of such cells that exist at the timepoint (DataLikelihoodTimeCoursePopulationAverage.cpp:171-176)
 __global__ void cellpop_average_kernel(const double* __restrict__ cell_values, const int32_t* __restrict__ status, int num_cells, int T,
-                                       double* __restrict__ avg, int32_t* __restrict__ count, int32_t* __restrict__ nfail)
+                                       double* __restrict__ avg, int32_t* __restrict__ count, int32_t* __restrict__ nfail,
+                                       const int32_t* __restrict__ mitotic = nullptr, const int32_t* __restrict__ row_only_mitotic = nullptr)
 {
 	__shared__ double sh[256];
 	__shared__ int shi[256];
 	const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
 	const double* v = cell_values + ((long long)c * T + t) * num_cells;
+	const int32_t* mit = (mitotic && row_only_mitotic && row_only_mitotic[t]) ? mitotic + (long long)c * num_cells : nullptr;
 	int n = 0;
-	for (int i = tid; i < num_cells; i += blockDim.x) n += isnan(v[i]) ? 0 : 1;
+	for (int i = tid; i < num_cells; i += blockDim.x) n += (isnan(v[i]) || (mit && !mit[i])) ? 0 : 1;
 	shi[tid] = n;
 	__syncthreads();
 	for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
@@ -188,7 +205,7 @@ __global__ void cellpop_average_kernel(const double* __restrict__ cell_values, c
 	double s = 0.0;
 	for (int i = tid; i < num_cells; i += blockDim.x) {
 		const double x = v[i];
-		if (!isnan(x)) s += x / (double)pop; // NotifySimulatedValue divides every value by the population size, .cpp:161-197
+		if (!isnan(x) && !(mit && !mit[i])) s += x / (double)pop; // NotifySimulatedValue divides every value by the population size, .cpp:161-197
 	}
 	sh[tid] = s;
 	__syncthreads();
@@ -1268,6 +1285,17 @@ inline int cellpop_finalize(CellPopState& cp, bool need_device)
 				if (sp < 0 || sp >= cp.N) return fail(BCM3B200_ERR_ARG, "obs_species@%zu index out of range", k + 1);
 		}
 	}
+	{
+		bool wants = cp.include_only_mitotic;
+		for (const auto& mp : cp.more) wants = wants || mp->include_only_mitotic;
+		if (wants) {
+			if (cp.nuclear_envelope_ix < 0 || cp.nuclear_envelope_ix >= cp.N)
+				return fail(BCM3B200_ERR_ARG, "include_only_cells_that_went_through_mitosis needs nuclear_envelope_species = the index of the model's \"nuclear_envelope\" species");
+			if (cp.data_kind != 0 && cp.include_only_mitotic) return fail(BCM3B200_ERR_ARG, "include_only_cells_that_went_through_mitosis acts on population averages only");
+			if (cp.shard_count != 1) return fail(BCM3B200_ERR_UNSUPPORTED, "include_only_cells_that_went_through_mitosis is not split over ranks");
+			if (cellpop_resolve_kernel(cp) != 3) return fail(BCM3B200_ERR_UNSUPPORTED, "include_only_cells_that_went_through_mitosis needs the lane-group kernel (cellpop_kernel = auto, N <= 96)");
+		}
+	}
 	if (cp.any_time_course()) {
 		// what the per-cell likelihood is built for: no parent information (non-dividing cells), all cells on one
 		// device, as many observed as simulated cells (the reference refuses anything else, DataLikelihoodTimeCourse.cpp:178-187)
@@ -1631,6 +1659,26 @@ inline int cellpop_run_cells(CellPopState& cp, size_t C, size_t nvar, const doub
 		CUDA_TRY(cp.d_item_offsets.ensure(C));
 		cp.h_wave.resize(4 * C);
 		CUDA_TRY(cudaMemsetAsync(cp.d_cellvals.p, 0xFF, sizeof(double) * C * (size_t)T * stride, st)); // all-ones = NaN: the cell does not exist
+		a.nuclear_envelope_ix = -1;
+		a.cell_mitotic = nullptr;
+		if (cp.track_mitosis()) {
+			CUDA_TRY(cp.d_mitotic.ensure(recs));
+			CUDA_TRY(cudaMemsetAsync(cp.d_mitotic.p, 0, sizeof(int32_t) * recs, st));
+			a.nuclear_envelope_ix = cp.nuclear_envelope_ix;
+			a.cell_mitotic = cp.d_mitotic.p;
+			// which rows of the value block belong to data sets that average the mitotic cells only
+			std::vector<int32_t> only((size_t)T, 0);
+			int r = 0;
+			for (int k = -1; k < (int)cp.more.size(); k++) {
+				const int Tk = (k < 0) ? cp.T : cp.more[(size_t)k]->T;
+				const bool flag = (k < 0) ? cp.include_only_mitotic : cp.more[(size_t)k]->include_only_mitotic;
+				for (int i = 0; i < Tk; i++) only[(size_t)(r + i)] = flag ? 1 : 0;
+				r += Tk;
+			}
+			CUDA_TRY(cp.d_row_only_mitotic.ensure((size_t)T));
+			CUDA_TRY(cudaMemcpyAsync(cp.d_row_only_mitotic.p, only.data(), sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, st));
+			CUDA_TRY(cudaStreamSynchronize(st)); // `only` is a local
+		}
 		cellpop_division_init_kernel<<<(unsigned)((recs + 255) / 256), 256, 0, st>>>((int)C, nc, stride, cp.d_transformed.p, (int)nvar, cp.entry_time_ix,
 		                                                                            cp.entry_time_fixed, cp.cell_offset, cp.d_creation.p, cp.d_row.p,
 		                                                                            cp.d_parent.p, cp.d_event.p, cp.d_status.p, cp.d_steps.p, cp.d_items.p,
@@ -2009,7 +2057,8 @@ inline int cellpop_evaluate(CellPopState& cp, size_t C, size_t nvar, const doubl
 	int rc = cellpop_run_cells(cp, C, nvar, values, st);
 	if (rc != BCM3B200_OK) return rc;
 	const int T = cp.rows(), nc = cp.cells_local;
-	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, cp.capacity(), T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p);
+	cellpop_average_kernel<<<dim3(T, (unsigned)C), 256, 0, st>>>(cp.d_cellvals.p, cp.d_status.p, cp.capacity(), T, cp.d_avg.p, cp.d_count.p, cp.d_nfail.p,
+	                                                             cp.track_mitosis() ? cp.d_mitotic.p : nullptr, cp.track_mitosis() ? cp.d_row_only_mitotic.p : nullptr);
 	CUDA_TRY(cudaGetLastError());
 	if (cp.division() && cp.divide_cells && nc > 0) {
 		cellpop_overflow_kernel<<<(unsigned)((C + 63) / 64), 64, 0, st>>>((int)C, cp.d_wave.p, cp.d_nfail.p);

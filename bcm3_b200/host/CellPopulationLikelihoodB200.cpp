@@ -235,7 +235,8 @@ bool CellPopulationLikelihoodB200::InitializeExperiment(const bcm3::XmlNode& xml
 				return true;
 			};
 			if (!split_ratio(ds)) return false;
-			if (c.get_bool("include_only_cells_that_went_through_mitosis", false)) return Fail("include_only_cells_that_went_through_mitosis is not supported by the GPU path");
+			// DataLikelihoodTimeCourseBase.cpp:44; it acts in DataLikelihoodTimeCoursePopulationAverage::NotifySimulatedValue only (.cpp:171-176)
+			ds.include_only_mitotic = c.get_bool("include_only_cells_that_went_through_mitosis", false) && type == "time_course_population_average";
 			// optimize_offset_scale, saturation_scale and value_relative_to_timepoint_ix act on the per-cell data types only
 			ds.weight = c.get_real("weight", 1.0);
 			ds.missing_stdev = c.get_real("missing_simulation_time_stdev", 300.0);
@@ -435,6 +436,16 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 	  << ";missing_simulation_time_stdev=" << ds.missing_stdev << ";device=" << device << ";compile_only=" << (compile_only ? 1 : 0);
 	if (ds.type != "time_course_population_average") d << ";data_kind=" << ds.type;
 	if (ds.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix=" << ds.value_relative_to_timepoint_ix;
+	{
+		bool wants_mitosis = ds.include_only_mitotic;
+		for (const DataSet* f : followers) wants_mitosis = wants_mitosis || f->include_only_mitotic;
+		if (wants_mitosis) { // Cell::Cell finds the species by name (Cell.cpp:40-55); without it no cell ever "enters mitosis"
+			const long ne = species_index("nuclear_envelope");
+			if (ne < 0) return Fail("include_only_cells_that_went_through_mitosis: the model has no species \"nuclear_envelope\" (Cell.cpp:487-492)");
+			d << ";nuclear_envelope_species=" << ne;
+		}
+	}
+	if (ds.include_only_mitotic) d << ";include_only_cells_that_went_through_mitosis=1";
 	if (ds.use_only_nondivided) d << ";use_only_nondivided=1";
 	if (ds.saturation_scale_ix >= 0) d << ";saturation_scale_ix=" << ds.saturation_scale_ix;
 	if (ds.optimize_offset_scale)
@@ -491,6 +502,7 @@ bool CellPopulationLikelihoodB200::CreateHandle(Experiment& e, DataSet& ds, doub
 		  << f.error_model << ";weight" << sfx << "=" << f.weight << ";missing_simulation_time_stdev" << sfx << "=" << f.missing_stdev;
 		if (f.type != "time_course_population_average") d << ";data_kind" << sfx << "=" << f.type;
 		if (f.value_relative_to_timepoint_ix >= 0) d << ";value_relative_to_timepoint_ix" << sfx << "=" << f.value_relative_to_timepoint_ix;
+		if (f.include_only_mitotic) d << ";include_only_cells_that_went_through_mitosis" << sfx << "=1";
 		if (f.use_only_nondivided) d << ";use_only_nondivided" << sfx << "=1";
 		if (f.saturation_scale_ix >= 0) d << ";saturation_scale_ix" << sfx << "=" << f.saturation_scale_ix;
 		if (f.marker_of >= 0) { // position of the owner inside this handle: 0 = ds, q + 1 = followers[q]

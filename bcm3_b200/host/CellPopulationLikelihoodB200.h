@@ -122,6 +122,7 @@ private:
 		std::string type = "time_course_population_average"; // or "time_course" / "time_points": per-cell data + matching (DataLikelihoodTimeCourse.cpp, DataLikelihoodTimePoints.cpp)
 		long value_relative_to_timepoint_ix = -1;             // time_points, DataLikelihoodBase.cpp:49
 		bool use_only_nondivided = false;                     // time_points, DataLikelihoodTimePoints.cpp:27
+		bool include_only_mitotic = false;                    // population average, include_only_cells_that_went_through_mitosis
 		long saturation_scale_ix = -1;                        // time_course, <data saturation_scale="variable">
 		std::string denominator_name;                         // use_log_ratio: species b of species_name="a/b" (species_name then holds a)
 		long marker_of = -1;                                  // >= 0: a further marker (species_name="a;b") of the data set with that index in Experiment::data

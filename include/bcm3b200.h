@@ -98,6 +98,9 @@ extern "C" {
  *                        denominator b is one more entry of the handle (suffix @k: num_timepoints, num_replicates=1, obs_species=b,
  *                        "timepoints@k", an all-zero "observed@k") that carries denominator_of@k=<index of the data set or
  *                        marker it divides>: the cell's value is 0.4342944819032518 * log(a / max-guarded b) before scale / offset
+ *                  include_only_cells_that_went_through_mitosis=0|1 (population average, DataLikelihoodTimeCoursePopulationAverage.cpp:
+ *                       171-176) with nuclear_envelope_species=<index>: only the cells whose nuclear envelope species fell below
+ *                       0.5 after some accepted step (Cell.cpp:487-492, Cell.h:27) are averaged, over their own number
  *                  num_data_sets=<D <= 4>: the experiment's further <data> elements share this handle's ONE integration of
  *                       the cells; data set k >= 1 repeats num_timepoints, num_replicates, obs_species, error_model, weight, data_kind,
  *                       the stdev/offset/scale keys and the relative_to/missing keys with the suffix @k ("stdev_ix@1=5")

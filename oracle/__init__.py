@@ -93,7 +93,8 @@ class _CellPopProblem(C.Structure):
         ("cytokinesis_ix", C.c_int32), ("apoptosis_ix", C.c_int32), ("reset_ix", C.c_int32 * 7), ("max_dt", C.c_double), ("data_kind", C.c_int32),
         ("value_relative_to_timepoint_ix", C.c_int32), ("optimize_offset_scale", C.c_int32), ("optimize_offset_min", C.c_double),
         ("optimize_offset_max", C.c_double), ("optimize_scale_min", C.c_double), ("optimize_scale_max", C.c_double),
-        ("saturation_scale_ix", C.c_int32), ("num_extra_markers", C.c_int32), ("extra_markers", C.c_void_p), ("log_ratio_denominator", C.c_int32), ("use_only_nondivided", C.c_int32)]
+        ("saturation_scale_ix", C.c_int32), ("num_extra_markers", C.c_int32), ("extra_markers", C.c_void_p), ("log_ratio_denominator", C.c_int32), ("use_only_nondivided", C.c_int32), ("include_only_mitotic", C.c_int32),
+        ("nuclear_envelope_ix", C.c_int32)]
 
 
 _derivative_libs: dict[str, C.CDLL] = {}
@@ -249,6 +250,8 @@ def _cellpop_struct(problem, values):
         value_relative_to_timepoint_ix=-1 if getattr(p, "value_relative_to_timepoint_ix", None) is None else int(p.value_relative_to_timepoint_ix),
         saturation_scale_ix=-1 if getattr(p, "saturation_scale_ix", None) is None else int(p.saturation_scale_ix),
         log_ratio_denominator=opt(getattr(p, "log_ratio_denominator", None)), use_only_nondivided=int(bool(getattr(p, "use_only_nondivided", False))),
+        include_only_mitotic=int(bool(getattr(p, "include_only_cells_that_went_through_mitosis", False))),
+        nuclear_envelope_ix=opt(getattr(p, "nuclear_envelope_species", None)),
         num_extra_markers=len(extra), extra_markers=C.cast(keep["markers"], C.c_void_p).value if extra else None,
         optimize_offset_scale=int(bool(getattr(p, "optimize_offset_scale", False))),
         optimize_offset_min=float(getattr(p, "optimize_offset_range", (-1.0, 1.0))[0]), optimize_offset_max=float(getattr(p, "optimize_offset_range", (-1.0, 1.0))[1]),

@@ -121,6 +121,10 @@ inline double first_discontinuity_ahead(const oracle_cellpop_problem& pr, double
 // with state y_event (the solver's y at the end of that step).
 struct SolveEvents {
 	int cytokinesis_ix = -1, apoptosis_ix = -1;
+	// Cell.cpp:487-492: the first accepted step after which the nuclear envelope species is below 0.5 sets the breakdown time (to
+	// whatever get_threshold_crossing_time returns: always a number), and with it Cell::EnteredMitosis (Cell.h:27)
+	int nuclear_envelope_ix = -1;
+	bool entered_mitosis = false;
 	bool divided = false, died = false;
 	double t_event = 0.0;
 	std::vector<double> y_event;
@@ -128,6 +132,7 @@ struct SolveEvents {
 	bool after_step(double t, const double* y, int N)
 	{
 		bool stop = false;
+		if (nuclear_envelope_ix >= 0 && y[nuclear_envelope_ix] < 0.5) entered_mitosis = true;
 		if (cytokinesis_ix >= 0 && y[cytokinesis_ix] > 1.0) {
 			divided = true;
 			stop = true;
@@ -195,7 +200,7 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		double creation = 0.0, sim_end = 0.0; // sim_end: cell time up to which the cell exists (Cell::simulation_end_time)
 		long row = 0;
 		int parent = -1;
-		bool initial = false, ok = true, divided = false, died = false;
+		bool initial = false, ok = true, divided = false, died = false, entered_mitosis = false;
 		std::vector<double> y0, end_y;
 		double achieved = 0.0;
 	};
@@ -243,9 +248,11 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 		SolveEvents ev;
 		if (dividing) ev.cytokinesis_ix = pr.cytokinesis_ix;
 		ev.apoptosis_ix = pr.apoptosis_ix;
+		ev.nuclear_envelope_ix = pr.nuclear_envelope_ix;
 		c.ok = solver.solve(y0.data(), cell_params.data(), tp_rel.data(), Tsolve, out.data(), steps, creation_time, &ev);
 		c.divided = ev.divided;
 		c.died = ev.died;
+		c.entered_mitosis = ev.entered_mitosis;
 		// Cell.cpp:243-256: a cell that divided or died exists up to the event, any other up to the last requested time
 		c.sim_end = (ev.divided || ev.died) ? ev.t_event : std::max(target_time - creation_time, tp_rel[Tsolve - 1]);
 		c.achieved = ((ev.divided || ev.died) ? ev.t_event : tp_rel[Tsolve - 1]) + creation_time;
@@ -348,14 +355,15 @@ void evaluate_chain(const oracle_cellpop_problem& pr, const double* values, doub
 	// NotifySimulatedValue (.cpp:161-197): value / population size, accumulated cell by cell; CountCellsAtTime (CellPopulation.cpp:
 	// 106-121, Cell::CellAliveAtTime Cell.cpp:362-396): the cells whose life span [0, simulation_end_time] covers the time
 	for (int i = 0; i < T; i++) {
+		const bool only_mitotic = pr.include_only_mitotic != 0; // .cpp:171-176: these cells only, over their own number
 		size_t pop = 0;
 		for (int ci = 0; ci < nactive; ci++) {
 			const double cell_time = pr.timepoints[i] - cells[ci].creation;
-			if (!(cell_time < 0.0 || cell_time > cells[ci].sim_end)) pop++;
+			if (!(cell_time < 0.0 || cell_time > cells[ci].sim_end) && (!only_mitotic || cells[ci].entered_mitosis)) pop++;
 		}
 		for (int ci = 0; ci < nactive; ci++) {
 			const double x = xs[(size_t)i * ncell + ci];
-			if (x == x) population_average[i] += x / (double)pop; // the accumulator starts at zero (Reset, .cpp:77-83)
+			if (x == x && (!only_mitotic || cells[ci].entered_mitosis)) population_average[i] += x / (double)pop; // the accumulator starts at zero (Reset, .cpp:77-83)
 		}
 	}
 	if (pop_avg_out) for (int i = 0; i < T; i++) pop_avg_out[i] = population_average[i];

@@ -183,6 +183,11 @@ typedef struct {
 	/* time_points: <data use_only_nondivided="true"> (DataLikelihoodTimePoints.cpp:27, 349-351): the daughters of a dividing
 	 * population (cell index >= num_cells) are left out of this data set */
 	int32_t use_only_nondivided;
+	/* <data include_only_cells_that_went_through_mitosis="true"> (population average, DataLikelihoodTimeCourseBase.cpp:44,
+	 * DataLikelihoodTimeCoursePopulationAverage.cpp:171-176): only the cells that entered mitosis -- whose "nuclear_envelope"
+	 * species (index nuclear_envelope_ix) was below 0.5 after some accepted step (Cell.cpp:487-492, Cell.h:27) -- are averaged, over
+	 * the number of such cells alive at the timepoint (CellPopulation.cpp:106-121) */
+	int32_t include_only_mitotic, nuclear_envelope_ix;
 } oracle_cellpop_problem;
 
 /* CellPopulationLikelihood::EvaluateLogProbability (CellPopulationLikelihood.cpp:82-101) for num_chains vectors.

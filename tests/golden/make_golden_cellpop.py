@@ -87,6 +87,10 @@ CASES = {
     "cellpop_time_points_dividing": (dict(_builder="dividing_snapshots", M=5, num_cells=16, max_cells=400, t_end=5.5, T=12), 3, {}),
     # the same with use_only_nondivided="true": only the 16 initial cells are matched (DataLikelihoodTimePoints.cpp:349-351)
     "cellpop_time_points_dividing_nondivided": (dict(_builder="dividing_snapshots", M=5, num_cells=16, max_cells=400, t_end=5.5, T=12, nondivided=True), 3, {}),
+    # include_only_cells_that_went_through_mitosis="true": the population average over the cells whose nuclear envelope species fell
+    # below 0.5 after some accepted step (Cell::EnteredMitosis), over the number of such cells alive at the timepoint
+    "cellpop_dividing_mitotic_only": (dict(_builder="dividing", M=5, num_cells=16, max_cells=400, t_end=5.5, T=16), 3,
+                                      dict(include_only_cells_that_went_through_mitosis=True, nuclear_envelope_species=6)),
     "cellpop_n6_proportional": (dict(N=6, num_cells=32, T=10, data_cells=8, seed=26), 2,
                                 dict(error_model="proportional_normal", proportional_stdev=0.25, _positive_data=True)),
 }
@@ -105,7 +109,10 @@ def main():
         drop_first = tweaks.pop("_drop_first_timepoint", False)
         kw = dict(kw)
         builder = kw.pop("_builder", None)
-        if builder == "dividing_snapshots":
+        if builder == "dividing" and tweaks:
+            prob = dataclasses.replace(sc.make_dividing_problem(**kw), **tweaks)
+            fixed_values = sc.make_chain_values(C, seed=5)
+        elif builder == "dividing_snapshots":
             # observations: values of cells that exist at each timepoint in the reference's own simulation at the reference parameters
             nondivided = kw.pop("nondivided", False)
             base = sc.make_dividing_problem(**kw)

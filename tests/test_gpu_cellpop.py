@@ -466,3 +466,22 @@ def test_time_course_with_a_single_cell(Evaluator, checker):
     want, floor, _ = _fresh_reference(checker, prob, vals)
     assert (status == 0).all() and np.isfinite(logp).all()
     assert_logp_parity(logp, want["logp"], floor, "time_course, one cell")
+
+
+def test_mitotic_only_average_on_non_dividing_cells(Evaluator, checker):
+    """include_only_cells_that_went_through_mitosis without division: the event code of the kernel only records which cells'
+    nuclear envelope species fell below 0.5 after some accepted step; the average runs over those cells."""
+    base = sc.make_dividing_problem(M=5, num_cells=40, max_cells=40, t_end=1.5, T=12, seed=7)  # by t = 1.5 only some cells have entered mitosis
+    prob = dataclasses.replace(base, divide_cells=False, max_cells=0, cytokinesis_species=None, division_reset_species=(),
+                               sobol=base.sobol[:40], include_only_cells_that_went_through_mitosis=True, nuclear_envelope_species=6)
+    vals = sc.make_chain_values(4, seed=9)
+    ev = Evaluator(prob)
+    logp, status = ev.evaluate(vals)
+    d = ev.diagnostics()
+    ev.close()
+    want, floor, _ = _fresh_reference(checker, prob, vals)
+    everyone = checker.cellpop_evaluate(dataclasses.replace(prob, include_only_cells_that_went_through_mitosis=False), vals)["logp"]
+    assert (status == 0).all() and np.isfinite(logp).all()
+    assert not np.allclose(want["logp"], everyone)  # some cells have not entered mitosis by the end: the two averages differ
+    assert_logp_parity(logp, want["logp"], floor, "mitotic cells only")
+    assert np.abs(d["population_average"] - want["population_average"]).max() < 5e-5

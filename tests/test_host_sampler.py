@@ -128,9 +128,14 @@ def test_cell_population_plugin_parses_the_reference_xml_surface(built, tmp_path
     rel = host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" stdev_relative_to_scale="true" optimize_offset_scale="false"'),
                                     prob, species, compile_only=True)[1]
     assert "stdev_relative_to_scale=1" in rel and "stdev_relative_to_scale=0" in desc
-    for attribute in ("use_log_ratio", "include_only_cells_that_went_through_mitosis"):
-        with pytest.raises(RuntimeError, match=attribute):
-            host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', f'stdev="stdev" {attribute}="true"'), prob, species, compile_only=True)
+    with pytest.raises(RuntimeError, match="use_log_ratio"):  # a population average knows no log ratio
+        host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" use_log_ratio="true"'), prob, species, compile_only=True)
+    # include_only_cells_that_went_through_mitosis needs the species Cell::Cell looks up by name (Cell.cpp:40-55)
+    with pytest.raises(RuntimeError, match="nuclear_envelope"):
+        host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" include_only_cells_that_went_through_mitosis="true"'), prob, species, compile_only=True)
+    mitotic = host_api.cellpop_evaluate(prior, lik.replace('stdev="stdev"', 'stdev="stdev" include_only_cells_that_went_through_mitosis="true"'), prob,
+                                        [("nuclear_envelope" if s == "x3" else s) for s in species], compile_only=True)[1]
+    assert "include_only_cells_that_went_through_mitosis=1" in mitotic and "nuclear_envelope_species=3" in mitotic
     # trailing_simulation_time (Experiment.cpp:489, 655-656) moves the end of the integration past the last timepoint
     trail = host_api.cellpop_evaluate(*cellpop_xml(prob, trailing_simulation_time="2.5")[:2], prob, species, compile_only=True)[1]
     assert float(dict(i.split("=", 1) for i in trail.split(";"))["simulation_end_time"]) == float(prob.timepoints[-1]) + 2.5

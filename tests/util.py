@@ -137,6 +137,10 @@ def load_cellpop_golden(name):
                    stdev_ix=opt(q[0]), stdev=float(q[1]), proportional_stdev_ix=opt(q[2]), proportional_stdev=float(q[3]),
                    offset_ix=opt(q[4]), offset=float(q[5]), scale_ix=opt(q[6]), scale=float(q[7]))
             for l, q in enumerate(z["marker_parameters"])])
+    if "include_only_cells_that_went_through_mitosis" in z.files and bool(z["include_only_cells_that_went_through_mitosis"]):
+        extra.update(include_only_cells_that_went_through_mitosis=True)
+    if "nuclear_envelope_species" in z.files:
+        extra.update(nuclear_envelope_species=int(z["nuclear_envelope_species"]))
     if "use_only_nondivided" in z.files and bool(z["use_only_nondivided"]):
         extra.update(use_only_nondivided=True)
     if "log_ratio_denominator" in z.files:
