@@ -189,6 +189,11 @@ __device__ __noinline__ void rhs_eval_lanes(unsigned y_off, unsigned f_off, unsi
 #ifndef CP_GROUP_LOCKSTEP
 #define CP_GROUP_LOCKSTEP 1
 #endif
+// Lock-step in TEAMS of this many warps instead of the whole block (0 = the whole block): every team meets at its own named
+// barrier (bar.red.or with the team's thread count) -- fewer warps wait for the slowest one, fewer warps share a fetch
+#ifndef CP_GROUP_LOCKSTEP_TEAM
+#define CP_GROUP_LOCKSTEP_TEAM 0
+#endif
 // 1: dividing / dying cells (CpArgs: items, per-cell records, event species). The model library of an experiment without
 // divide_cells and without an "apoptosis" species is built with 0 and contains none of that code.
 #ifndef CP_DIVISION
@@ -1858,7 +1863,19 @@ __global__ void __launch_bounds__(BS, CP_GROUP_MIN_BLOCKS) cellpop_group_kernel(
 		// block lock-step: the warps of the block meet before every CP_GROUP_LOCKSTEP_EVERY-th trip (and leave the loop only
 		// there, together), so that they run the same code at nearly the same time and share instruction fetches
 		if (CP_GROUP_LOCKSTEP_EVERY == 1 || (trip++ % CP_GROUP_LOCKSTEP_EVERY) == 0) {
+#if CP_GROUP_LOCKSTEP_TEAM > 0 && (CP_GROUP_WARPS % CP_GROUP_LOCKSTEP_TEAM) == 0 && CP_GROUP_LOCKSTEP_TEAM < CP_GROUP_WARPS
+			{
+				int any;
+				const int team = 1 + (tid / 32) / CP_GROUP_LOCKSTEP_TEAM, pred = (have || !exhausted) ? 1 : 0;
+				asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+				             : "=r"(any)
+				             : "r"(team), "r"(32 * CP_GROUP_LOCKSTEP_TEAM), "r"(pred)
+				             : "memory");
+				if (any == 0) break;
+			}
+#else
 			if (__syncthreads_or((have || !exhausted) ? 1 : 0) == 0) break;
+#endif
 		}
 #else
 		if (!__any_sync(FULL, have || !exhausted)) break;

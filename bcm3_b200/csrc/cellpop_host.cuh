@@ -1148,6 +1148,7 @@ inline int cellpop_module_source(const CellPopState& cp, const std::vector<int>&
 	if (const char* senv = getenv("BCM3B200_CELLPOP_SOLVE_SLOTTED")) o << "#define CP_SOLVE_SLOTTED " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_SOLVE_SKIP")) o << "#define CP_SOLVE_SKIP " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_PIVOT_REDUX")) o << "#define CP_PIVOT_REDUX " << atoi(senv) << "\n";
+	if (const char* senv = getenv("BCM3B200_CELLPOP_LOCKSTEP_TEAM")) o << "#define CP_GROUP_LOCKSTEP_TEAM " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_LOCKSTEP_EVERY")) o << "#define CP_GROUP_LOCKSTEP_EVERY " << atoi(senv) << "\n";
 	if (const char* senv = getenv("BCM3B200_CELLPOP_SJ_UNROLL")) o << "#define CP_SJ_UNROLL " << atoi(senv) << "\n";
 	o << "#include \"cellpop_prelude.cuh\"\n";
